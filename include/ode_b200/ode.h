@@ -1,0 +1,499 @@
+/*
+ * ode_b200 — C ABI of the B200-native ODE 0.12 hot path.
+ *
+ * Two groups of entry points:
+ *
+ *  (1) the drop-in subset of ODE 0.12's public C API (same names, argument
+ *      meaning, struct layouts and error behaviour) for the per-step path
+ *      dSpaceCollide -> dCollide -> dJointCreateContact -> dWorldQuickStep.
+ *      Each declaration cites the reference declaration it replaces
+ *      (paths relative to /root/reference/ode-0.12/include/ode/).
+ *  (2) the added batched-world entry points (dBatch*), SURVEY.md §8(b):
+ *      thousands of independent worlds stepped device-resident, the near
+ *      callback replaced by a data table (dBatchContactPolicy).
+ *
+ * Plain C, no torch types, pointers + sizes only.  The library is built twice,
+ * like the reference: -DdSINGLE (libode_b200_single.so) or -DdDOUBLE
+ * (libode_b200_double.so); dReal is fixed at compile time (common.h:103-112).
+ * There is no CPU fallback: every compute entry point returns an error /
+ * calls the error handler when no CUDA device is usable.
+ */
+#ifndef ODE_B200_ODE_H
+#define ODE_B200_ODE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if !defined(dSINGLE) && !defined(dDOUBLE)
+#define dSINGLE 1
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- scalar / vector types (common.h:103-144) --------------------------- */
+#if defined(dSINGLE)
+typedef float dReal;
+#else
+typedef double dReal;
+#endif
+typedef dReal dVector3[4];    /* 4-wide padded */
+typedef dReal dVector4[4];
+typedef dReal dMatrix3[12];   /* 3 rows x 4, row-major, 4th column padding */
+typedef dReal dQuaternion[4]; /* (w,x,y,z) */
+typedef uint32_t dTriIndex;
+
+#ifndef dInfinity
+#if defined(dSINGLE)
+#define dInfinity ((float)__builtin_inff())
+#else
+#define dInfinity (__builtin_inf())
+#endif
+#endif
+
+/* ---- opaque handles (common.h:222-237) ---------------------------------- */
+typedef struct dxWorld *dWorldID;
+typedef struct dxSpace *dSpaceID;
+typedef struct dxBody *dBodyID;
+typedef struct dxGeom *dGeomID;
+typedef struct dxJoint *dJointID;
+typedef struct dxJointGroup *dJointGroupID;
+typedef struct dxTriMeshData *dTriMeshDataID;
+
+/* ---- enums --------------------------------------------------------------- */
+/* joint type numbers, common.h:251-267 */
+typedef enum {
+  dJointTypeNone = 0, dJointTypeBall, dJointTypeHinge, dJointTypeSlider,
+  dJointTypeContact, dJointTypeUniversal, dJointTypeHinge2, dJointTypeFixed,
+  dJointTypeNull, dJointTypeAMotor, dJointTypeLMotor, dJointTypePlane2D,
+  dJointTypePR, dJointTypePU, dJointTypePiston
+} dJointType;
+
+/* joint parameter names, common.h:303-355: group g, name k -> 0x100*g + k */
+enum {
+  dParamLoStop = 0, dParamHiStop, dParamVel, dParamFMax, dParamFudgeFactor,
+  dParamBounce, dParamCFM, dParamStopERP, dParamStopCFM,
+  dParamSuspensionERP, dParamSuspensionCFM, dParamERP,
+  dParamsInGroup,
+  dParamGroup = 0x100,
+  dParamGroup1 = 0x000, dParamGroup2 = 0x100, dParamGroup3 = 0x200,
+  dParamLoStop1 = 0x000, dParamHiStop1, dParamVel1, dParamFMax1, dParamFudgeFactor1,
+  dParamBounce1, dParamCFM1, dParamStopERP1, dParamStopCFM1,
+  dParamSuspensionERP1, dParamSuspensionCFM1, dParamERP1,
+  dParamLoStop2 = 0x100, dParamHiStop2, dParamVel2, dParamFMax2, dParamFudgeFactor2,
+  dParamBounce2, dParamCFM2, dParamStopERP2, dParamStopCFM2,
+  dParamSuspensionERP2, dParamSuspensionCFM2, dParamERP2,
+  dParamLoStop3 = 0x200, dParamHiStop3, dParamVel3, dParamFMax3, dParamFudgeFactor3,
+  dParamBounce3, dParamCFM3, dParamStopERP3, dParamStopCFM3,
+  dParamSuspensionERP3, dParamSuspensionCFM3, dParamERP3
+};
+
+/* geom class numbers, collision.h:879-902 */
+enum {
+  dSphereClass = 0, dBoxClass, dCapsuleClass, dCylinderClass, dPlaneClass,
+  dRayClass, dConvexClass, dGeomTransformClass, dTriMeshClass, dHeightfieldClass,
+  dFirstSpaceClass,
+  dSimpleSpaceClass = dFirstSpaceClass, dHashSpaceClass, dSweepAndPruneSpaceClass,
+  dQuadTreeSpaceClass,
+  dLastSpaceClass = dQuadTreeSpaceClass,
+  dFirstUserClass, dLastUserClass = dFirstUserClass + 3,
+  dGeomNumClasses
+};
+
+/* contact surface mode bits, contact.h:33-49 */
+enum {
+  dContactMu2 = 0x001, dContactFDir1 = 0x002, dContactBounce = 0x004,
+  dContactSoftERP = 0x008, dContactSoftCFM = 0x010, dContactMotion1 = 0x020,
+  dContactMotion2 = 0x040, dContactMotionN = 0x080, dContactSlip1 = 0x100,
+  dContactSlip2 = 0x200,
+  dContactApprox0 = 0x0000, dContactApprox1_1 = 0x1000, dContactApprox1_2 = 0x2000,
+  dContactApprox1 = 0x3000
+};
+
+/* dCollide flags, collision.h:746 */
+#define CONTACTS_UNIMPORTANT 0x80000000
+
+/* SAP axis orders, collision_space.h:95-101 */
+#define dSAP_AXES_XYZ ((0) | (1 << 2) | (2 << 4))
+#define dSAP_AXES_XZY ((0) | (2 << 2) | (1 << 4))
+#define dSAP_AXES_YXZ ((1) | (0 << 2) | (2 << 4))
+#define dSAP_AXES_YZX ((1) | (2 << 2) | (0 << 4))
+#define dSAP_AXES_ZXY ((2) | (0 << 2) | (1 << 4))
+#define dSAP_AXES_ZYX ((2) | (1 << 2) | (0 << 4))
+
+/* ---- plain structs shared with callers (layout == reference) ------------- */
+/* mass.h:88-92 */
+typedef struct dMass {
+  dReal mass;
+  dVector3 c;
+  dMatrix3 I;
+} dMass;
+
+/* contact.h:52-65 */
+typedef struct dSurfaceParameters {
+  int mode;
+  dReal mu;
+  dReal mu2;
+  dReal bounce;
+  dReal bounce_vel;
+  dReal soft_erp;
+  dReal soft_cfm;
+  dReal motion1, motion2, motionN;
+  dReal slip1, slip2;
+} dSurfaceParameters;
+
+/* contact.h:81-87 */
+typedef struct dContactGeom {
+  dVector3 pos;
+  dVector3 normal;
+  dReal depth;
+  dGeomID g1, g2;
+  int side1, side2;
+} dContactGeom;
+
+/* contact.h:92-96 */
+typedef struct dContact {
+  dSurfaceParameters surface;
+  dContactGeom geom;
+  dVector3 fdir1;
+} dContact;
+
+/* common.h:368-373 */
+typedef struct dJointFeedback {
+  dVector3 f1, t1, f2, t2;
+} dJointFeedback;
+
+/* collision_space.h:49 */
+typedef void dNearCallback(void *data, dGeomID o1, dGeomID o2);
+
+/* ---- init / misc (odeinit.h:119,236; misc.h:45-60; error.h:52-60) --------- */
+int dInitODE2(unsigned int uiInitFlags);
+void dInitODE(void);
+void dCloseODE(void);
+const char *dGetConfiguration(void);
+unsigned long dRand(void);
+unsigned long dRandGetSeed(void);
+void dRandSetSeed(unsigned long s);
+int dRandInt(int n);
+int dTestRand(void);
+typedef void dErrorHandlerFn(int errnum, const char *msg);
+/* simplified handler hook: the reference takes (int, const char*, va_list)
+ * (error.h:43-50); ours receives the formatted message. */
+void dB200SetErrorHandler(dErrorHandlerFn *fn);
+
+/* ---- small math that scene construction needs (odemath.h, rotation.h) ---- */
+int dSafeNormalize3(dVector3 a);
+int dSafeNormalize4(dVector4 a);
+void dNormalize3(dVector3 a);
+void dNormalize4(dVector4 a);
+void dPlaneSpace(const dVector3 n, dVector3 p, dVector3 q);
+int dOrthogonalizeR(dMatrix3 m);
+void dRSetIdentity(dMatrix3 R);
+void dRFromAxisAndAngle(dMatrix3 R, dReal ax, dReal ay, dReal az, dReal angle);
+void dRFromEulerAngles(dMatrix3 R, dReal phi, dReal theta, dReal psi);
+void dQSetIdentity(dQuaternion q);
+void dQFromAxisAndAngle(dQuaternion q, dReal ax, dReal ay, dReal az, dReal angle);
+void dQMultiply0(dQuaternion qa, const dQuaternion qb, const dQuaternion qc);
+void dRfromQ(dMatrix3 R, const dQuaternion q);
+void dQfromR(dQuaternion q, const dMatrix3 R);
+void dDQfromW(dReal dq[4], const dVector3 w, const dQuaternion q);
+int dInvertPDMatrix(const dReal *A, dReal *Ainv, int n);
+
+/* ---- mass (mass.h:43-140) ------------------------------------------------- */
+int dMassCheck(const dMass *m);
+void dMassSetZero(dMass *m);
+void dMassSetParameters(dMass *m, dReal themass, dReal cgx, dReal cgy, dReal cgz,
+                        dReal I11, dReal I22, dReal I33, dReal I12, dReal I13, dReal I23);
+void dMassSetSphere(dMass *m, dReal density, dReal radius);
+void dMassSetSphereTotal(dMass *m, dReal total_mass, dReal radius);
+void dMassSetCapsule(dMass *m, dReal density, int direction, dReal radius, dReal length);
+void dMassSetCapsuleTotal(dMass *m, dReal total_mass, int direction, dReal radius, dReal length);
+void dMassSetBox(dMass *m, dReal density, dReal lx, dReal ly, dReal lz);
+void dMassSetBoxTotal(dMass *m, dReal total_mass, dReal lx, dReal ly, dReal lz);
+void dMassAdjust(dMass *m, dReal newmass);
+void dMassTranslate(dMass *m, dReal x, dReal y, dReal z);
+void dMassRotate(dMass *m, const dMatrix3 R);
+void dMassAdd(dMass *a, const dMass *b);
+
+/* ---- world (objects.h:54-560) --------------------------------------------- */
+dWorldID dWorldCreate(void);
+void dWorldDestroy(dWorldID world);
+void dWorldSetGravity(dWorldID, dReal x, dReal y, dReal z);
+void dWorldGetGravity(dWorldID, dVector3 gravity);
+void dWorldSetERP(dWorldID, dReal erp);
+dReal dWorldGetERP(dWorldID);
+void dWorldSetCFM(dWorldID, dReal cfm);
+dReal dWorldGetCFM(dWorldID);
+int dWorldQuickStep(dWorldID w, dReal stepsize); /* objects.h:352 */
+void dWorldSetQuickStepNumIterations(dWorldID, int num);
+int dWorldGetQuickStepNumIterations(dWorldID);
+void dWorldSetQuickStepW(dWorldID, dReal over_relaxation);
+dReal dWorldGetQuickStepW(dWorldID);
+void dWorldSetContactMaxCorrectingVel(dWorldID, dReal vel);
+dReal dWorldGetContactMaxCorrectingVel(dWorldID);
+void dWorldSetContactSurfaceLayer(dWorldID, dReal depth);
+dReal dWorldGetContactSurfaceLayer(dWorldID);
+void dWorldSetAutoDisableFlag(dWorldID, int do_auto_disable);
+int dWorldGetAutoDisableFlag(dWorldID);
+void dWorldSetAutoDisableLinearThreshold(dWorldID, dReal v);
+void dWorldSetAutoDisableAngularThreshold(dWorldID, dReal v);
+void dWorldSetAutoDisableAverageSamplesCount(dWorldID, unsigned int n);
+void dWorldSetAutoDisableSteps(dWorldID, int steps);
+void dWorldSetAutoDisableTime(dWorldID, dReal time);
+void dWorldSetLinearDamping(dWorldID, dReal scale);
+void dWorldSetAngularDamping(dWorldID, dReal scale);
+void dWorldSetLinearDampingThreshold(dWorldID, dReal threshold);
+void dWorldSetAngularDampingThreshold(dWorldID, dReal threshold);
+void dWorldSetDamping(dWorldID, dReal linear_scale, dReal angular_scale);
+void dWorldSetMaxAngularSpeed(dWorldID, dReal max_speed);
+
+/* ---- body (objects.h:560-1500) -------------------------------------------- */
+dBodyID dBodyCreate(dWorldID);
+void dBodyDestroy(dBodyID);
+dWorldID dBodyGetWorld(dBodyID);
+void dBodySetData(dBodyID, void *data);
+void *dBodyGetData(dBodyID);
+void dBodySetPosition(dBodyID, dReal x, dReal y, dReal z);
+void dBodySetRotation(dBodyID, const dMatrix3 R);
+void dBodySetQuaternion(dBodyID, const dQuaternion q);
+void dBodySetLinearVel(dBodyID, dReal x, dReal y, dReal z);
+void dBodySetAngularVel(dBodyID, dReal x, dReal y, dReal z);
+const dReal *dBodyGetPosition(dBodyID);
+const dReal *dBodyGetRotation(dBodyID);
+const dReal *dBodyGetQuaternion(dBodyID);
+const dReal *dBodyGetLinearVel(dBodyID);
+const dReal *dBodyGetAngularVel(dBodyID);
+void dBodySetMass(dBodyID, const dMass *mass);
+void dBodyGetMass(dBodyID, dMass *mass);
+void dBodyAddForce(dBodyID, dReal fx, dReal fy, dReal fz);
+void dBodyAddTorque(dBodyID, dReal fx, dReal fy, dReal fz);
+void dBodyAddRelForce(dBodyID, dReal fx, dReal fy, dReal fz);
+void dBodyAddRelTorque(dBodyID, dReal fx, dReal fy, dReal fz);
+void dBodyAddForceAtPos(dBodyID, dReal fx, dReal fy, dReal fz, dReal px, dReal py, dReal pz);
+const dReal *dBodyGetForce(dBodyID);
+const dReal *dBodyGetTorque(dBodyID);
+void dBodySetForce(dBodyID, dReal x, dReal y, dReal z);
+void dBodySetTorque(dBodyID, dReal x, dReal y, dReal z);
+void dBodyEnable(dBodyID);
+void dBodyDisable(dBodyID);
+int dBodyIsEnabled(dBodyID);
+void dBodySetGravityMode(dBodyID, int mode);
+int dBodyGetGravityMode(dBodyID);
+void dBodySetFiniteRotationMode(dBodyID, int mode);
+void dBodySetFiniteRotationAxis(dBodyID, dReal x, dReal y, dReal z);
+void dBodySetGyroscopicMode(dBodyID, int enabled);
+int dBodyGetGyroscopicMode(dBodyID);
+void dBodySetAutoDisableFlag(dBodyID, int do_auto_disable);
+int dBodyGetAutoDisableFlag(dBodyID);
+void dBodySetAutoDisableDefaults(dBodyID);
+void dBodySetAutoDisableAverageSamplesCount(dBodyID, unsigned int n);
+void dBodySetLinearDamping(dBodyID, dReal scale);
+void dBodySetAngularDamping(dBodyID, dReal scale);
+void dBodySetDampingDefaults(dBodyID);
+void dBodySetMaxAngularSpeed(dBodyID, dReal max_speed);
+int dBodyGetNumJoints(dBodyID);
+dGeomID dBodyGetFirstGeom(dBodyID);
+dGeomID dBodyGetNextGeom(dGeomID);
+void dBodyGetRelPointPos(dBodyID, dReal px, dReal py, dReal pz, dVector3 result);
+void dBodyVectorToWorld(dBodyID, dReal px, dReal py, dReal pz, dVector3 result);
+
+/* ---- joints (objects.h:1538-2700) ----------------------------------------- */
+dJointGroupID dJointGroupCreate(int max_size);
+void dJointGroupDestroy(dJointGroupID);
+void dJointGroupEmpty(dJointGroupID);
+dJointID dJointCreateContact(dWorldID, dJointGroupID, const dContact *);
+dJointID dJointCreateBall(dWorldID, dJointGroupID);
+dJointID dJointCreateHinge(dWorldID, dJointGroupID);
+dJointID dJointCreateHinge2(dWorldID, dJointGroupID);
+void dJointDestroy(dJointID);
+void dJointAttach(dJointID, dBodyID body1, dBodyID body2);
+void dJointEnable(dJointID);
+void dJointDisable(dJointID);
+int dJointIsEnabled(dJointID);
+dJointType dJointGetType(dJointID);
+dBodyID dJointGetBody(dJointID, int index);
+void dJointSetFeedback(dJointID, dJointFeedback *);
+dJointFeedback *dJointGetFeedback(dJointID);
+void dJointSetBallAnchor(dJointID, dReal x, dReal y, dReal z);
+void dJointSetBallAnchor2(dJointID, dReal x, dReal y, dReal z);
+void dJointSetBallParam(dJointID, int parameter, dReal value);
+void dJointGetBallAnchor(dJointID, dVector3 result);
+void dJointGetBallAnchor2(dJointID, dVector3 result);
+void dJointSetHingeAnchor(dJointID, dReal x, dReal y, dReal z);
+void dJointSetHingeAxis(dJointID, dReal x, dReal y, dReal z);
+void dJointSetHingeParam(dJointID, int parameter, dReal value);
+dReal dJointGetHingeParam(dJointID, int parameter);
+void dJointGetHingeAnchor(dJointID, dVector3 result);
+void dJointGetHingeAnchor2(dJointID, dVector3 result);
+void dJointGetHingeAxis(dJointID, dVector3 result);
+dReal dJointGetHingeAngle(dJointID);
+dReal dJointGetHingeAngleRate(dJointID);
+void dJointSetHinge2Anchor(dJointID, dReal x, dReal y, dReal z);
+void dJointSetHinge2Axis1(dJointID, dReal x, dReal y, dReal z);
+void dJointSetHinge2Axis2(dJointID, dReal x, dReal y, dReal z);
+void dJointSetHinge2Param(dJointID, int parameter, dReal value);
+dReal dJointGetHinge2Param(dJointID, int parameter);
+void dJointGetHinge2Anchor(dJointID, dVector3 result);
+void dJointGetHinge2Anchor2(dJointID, dVector3 result);
+void dJointGetHinge2Axis1(dJointID, dVector3 result);
+void dJointGetHinge2Axis2(dJointID, dVector3 result);
+dReal dJointGetHinge2Angle1(dJointID);
+dReal dJointGetHinge2Angle1Rate(dJointID);
+dReal dJointGetHinge2Angle2Rate(dJointID);
+int dAreConnected(dBodyID, dBodyID);
+int dAreConnectedExcluding(dBodyID body1, dBodyID body2, int joint_type);
+
+/* ---- collision (collision.h, collision_space.h) --------------------------- */
+dSpaceID dSimpleSpaceCreate(dSpaceID space);
+dSpaceID dHashSpaceCreate(dSpaceID space);
+dSpaceID dSweepAndPruneSpaceCreate(dSpaceID space, int axisorder);
+void dSpaceDestroy(dSpaceID);
+void dHashSpaceSetLevels(dSpaceID space, int minlevel, int maxlevel);
+void dHashSpaceGetLevels(dSpaceID space, int *minlevel, int *maxlevel);
+void dSpaceSetCleanup(dSpaceID space, int mode);
+int dSpaceGetCleanup(dSpaceID space);
+void dSpaceSetSublevel(dSpaceID space, int sublevel);
+int dSpaceGetSublevel(dSpaceID space);
+void dSpaceAdd(dSpaceID, dGeomID);
+void dSpaceRemove(dSpaceID, dGeomID);
+int dSpaceQuery(dSpaceID, dGeomID);
+void dSpaceClean(dSpaceID);
+int dSpaceGetNumGeoms(dSpaceID);
+dGeomID dSpaceGetGeom(dSpaceID, int i);
+void dSpaceCollide(dSpaceID space, void *data, dNearCallback *callback);  /* collision_space.h:72-ish / collision.h:795 */
+void dSpaceCollide2(dGeomID space1, dGeomID space2, void *data, dNearCallback *callback);
+int dCollide(dGeomID o1, dGeomID o2, int flags, dContactGeom *contact, int skip); /* collision.h:747 */
+
+void dGeomDestroy(dGeomID);
+void dGeomSetData(dGeomID, void *data);
+void *dGeomGetData(dGeomID);
+void dGeomSetBody(dGeomID, dBodyID);
+dBodyID dGeomGetBody(dGeomID);
+void dGeomSetPosition(dGeomID, dReal x, dReal y, dReal z);
+void dGeomSetRotation(dGeomID, const dMatrix3 R);
+void dGeomSetQuaternion(dGeomID, const dQuaternion Q);
+const dReal *dGeomGetPosition(dGeomID);
+const dReal *dGeomGetRotation(dGeomID);
+void dGeomGetQuaternion(dGeomID, dQuaternion result);
+void dGeomGetAABB(dGeomID, dReal aabb[6]);
+int dGeomIsSpace(dGeomID);
+dSpaceID dGeomGetSpace(dGeomID);
+int dGeomGetClass(dGeomID);
+void dGeomSetCategoryBits(dGeomID, unsigned long bits);
+void dGeomSetCollideBits(dGeomID, unsigned long bits);
+unsigned long dGeomGetCategoryBits(dGeomID);
+unsigned long dGeomGetCollideBits(dGeomID);
+void dGeomEnable(dGeomID);
+void dGeomDisable(dGeomID);
+int dGeomIsEnabled(dGeomID);
+void dGeomSetOffsetPosition(dGeomID, dReal x, dReal y, dReal z);
+void dGeomSetOffsetRotation(dGeomID, const dMatrix3 R);
+void dGeomSetOffsetQuaternion(dGeomID, const dQuaternion Q);
+void dGeomClearOffset(dGeomID);
+int dGeomIsOffset(dGeomID);
+
+dGeomID dCreateSphere(dSpaceID space, dReal radius);
+void dGeomSphereSetRadius(dGeomID sphere, dReal radius);
+dReal dGeomSphereGetRadius(dGeomID sphere);
+dGeomID dCreateBox(dSpaceID space, dReal lx, dReal ly, dReal lz);
+void dGeomBoxSetLengths(dGeomID box, dReal lx, dReal ly, dReal lz);
+void dGeomBoxGetLengths(dGeomID box, dVector3 result);
+dGeomID dCreatePlane(dSpaceID space, dReal a, dReal b, dReal c, dReal d);
+void dGeomPlaneSetParams(dGeomID plane, dReal a, dReal b, dReal c, dReal d);
+void dGeomPlaneGetParams(dGeomID plane, dVector4 result);
+dGeomID dCreateCapsule(dSpaceID space, dReal radius, dReal length);
+void dGeomCapsuleSetParams(dGeomID ccylinder, dReal radius, dReal length);
+void dGeomCapsuleGetParams(dGeomID ccylinder, dReal *radius, dReal *length);
+
+/* ======================================================================== */
+/* (2) batched-world entry points (added; SURVEY.md §8(b) last row)          */
+/* ======================================================================== */
+
+typedef struct dxBatch *dBatchID;
+
+/* One row of the contact-policy table that replaces the near callback on the
+ * batched path.  It expresses what the reference demos' callbacks do
+ * (ode/demo/demo_boxstack.cpp:132-172, demo_crash.cpp:115-141,
+ * demo_buggy.cpp:83-111): optionally skip pairs whose bodies are connected by
+ * a non-contact joint, call dCollide with max_contacts, copy `surface` into
+ * every contact and create+attach one contact joint per contact.
+ * Row selection: first row with (cat(o1)&cat_mask1)&&(cat(o2)&cat_mask2) or the
+ * swapped test; row 0 should be the catch-all {~0,~0}. */
+typedef struct dBatchContactPolicy {
+  unsigned long cat_mask1, cat_mask2;
+  int max_contacts;                 /* flags & 0xffff handed to dCollide */
+  int skip_if_connected;            /* dAreConnectedExcluding(b1,b2,Contact) */
+  int skip_static_pairs;            /* return when neither geom has a body */
+  dSurfaceParameters surface;
+} dBatchContactPolicy;
+
+/* capacity of one world slot; 0 = derive from the bound worlds */
+typedef struct dBatchDesc {
+  int max_contacts_per_world;       /* contact joints per step per world */
+  int device;                       /* CUDA device ordinal */
+  int reserved[6];
+} dBatchDesc;
+
+typedef struct dBatchCounters {
+  long long steps;                  /* world-steps executed */
+  long long body_steps;             /* bodies integrated (enabled bodies in islands) */
+  long long pairs;                  /* near-callback-equivalent pairs */
+  long long contacts;               /* contact joints that entered SOR */
+  long long rows;                   /* constraint rows m summed over islands */
+  long long islands;
+  long long overflow_worlds;        /* world-steps that hit a capacity limit */
+} dBatchCounters;
+
+/* Bind nworlds (world[i], space[i]) pairs into one device-resident batch.
+ * Objects were created through the normal API above; after binding, the
+ * device copy is authoritative until dBatchDownload().  Returns NULL on
+ * failure (message via the error handler), never aborts. */
+dBatchID dBatchCreate(int nworlds, const dWorldID *worlds, const dSpaceID *spaces,
+                      const dBatchDesc *desc);
+void dBatchDestroy(dBatchID);
+int dBatchSetContactPolicy(dBatchID, const dBatchContactPolicy *table, int n);
+/* per-world LCG streams for the SOR row shuffle (misc.cpp:31 is process-global
+ * in the reference; one stream per world here) */
+int dBatchSetSeeds(dBatchID, const uint32_t *seeds);
+int dBatchGetSeeds(dBatchID, uint32_t *seeds);
+/* nsteps x { dSpaceCollide + policy + dWorldQuickStep(h) + dJointGroupEmpty }
+ * for every world.  status_per_world (may be NULL) receives 0 = ok or a
+ * bitmask of dBATCH_ERR_*.  Returns 0 on success. */
+int dBatchCollideAndQuickStep(dBatchID, dReal h, int nsteps, int *status_per_world);
+#define dBATCH_ERR_CONTACT_OVERFLOW 1
+#define dBATCH_ERR_ROW_OVERFLOW 2
+#define dBATCH_ERR_PAIR_OVERFLOW 4
+/* bulk SoA I/O, host buffers: [world][body][k]; body order = creation order.
+ * pos 3, quat 4, lvel 3, avel 3 (13 reals per body). */
+int dBatchNumBodies(dBatchID);            /* per world (max over worlds) */
+int dBatchGetBodyState(dBatchID, dReal *pos3, dReal *quat4, dReal *lvel3, dReal *avel3);
+int dBatchSetBodyState(dBatchID, const dReal *pos3, const dReal *quat4,
+                       const dReal *lvel3, const dReal *avel3);
+/* external force/torque accumulators, [world][body][3] each, added to facc/tacc */
+int dBatchAddForces(dBatchID, const dReal *force3, const dReal *torque3);
+/* copy device state back into the bound dBodyID/dGeomID objects */
+int dBatchDownload(dBatchID);
+int dBatchGetCounters(dBatchID, dBatchCounters *out);
+int dBatchResetCounters(dBatchID);
+/* parity taps for one world's LAST step (tests): callback-order pair list as
+ * geom creation indices, contact records, SOR row count, lambda.
+ * Each returns the number of items available; copies at most cap. */
+int dBatchDebugPairs(dBatchID, int world, int *g1g2, int cap);
+int dBatchDebugContacts(dBatchID, int world, dReal *pos_normal_depth7, int *g1g2, int cap);
+int dBatchDebugLambda(dBatchID, int world, dReal *lambda, int cap);
+/* f1,t1 (6 reals) per contact joint, as dJointSetFeedback would report */
+int dBatchDebugFeedback(dBatchID, int world, dReal *f1t1, int cap);
+/* geom creation indices in space-list order (head first) as of now */
+int dBatchDebugGeomOrder(dBatchID, int world, int *order, int cap);
+/* the CUDA stream the batch launches on (cudaStream_t as void*), so callers can
+ * time with events on the launching stream */
+void *dBatchGetStream(dBatchID);
+/* number of kernel launches issued by the library since load (bench.py) */
+long long dB200KernelLaunchCount(void);
+const char *dB200LastError(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

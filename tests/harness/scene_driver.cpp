@@ -1,0 +1,277 @@
+// scene_driver — runs a scene through the ODE C API and writes a binary trace.
+//
+// The same source is linked twice: against the unmodified reference
+// (oracle/_ref/libode_ref_<prec>.so  -> oracle/_ref/driver_ref_<prec>) and against
+// the product (libode_b200_<prec>.so -> build/driver_b200_<prec>).  With
+// --mode callback both run the classic per-frame loop of the reference demos
+// (ode/demo/demo_boxstack.cpp:553-597): dSpaceCollide + near callback +
+// dWorldQuickStep + dJointGroupEmpty.  With --mode batch (product only, -DHAVE_BATCH)
+// the dBatch* entry points are used and the same trace is produced from the
+// library's parity taps.  --time prints throughput instead of writing a trace
+// (the CPU-baseline leg of bench.py uses this with the reference build).
+//
+// Trace layout (little endian): header {magic 'ODTR', realsize, nworlds, nsteps},
+// then for every step, for every world:
+//   i32 ng, i32 glist[ng]           geom creation indices in space-list order before collide
+//   i32 nb, real state0[nb*13]      pos3 quat4 lvel3 avel3 before the step
+//   i32 np, i32 pairs[2*np]         near-callback (o1,o2) in call order
+//   i32 nc, {i32 g1,g2; real pos3,normal3,depth} x nc   contact joints in creation order
+//   real fb[nc*6]                   joint feedback f1,t1 per contact joint (lambda tap)
+//   real state1[nb*13]              after the step
+//   u32 seed_after
+#include <stdio.h>
+#include <time.h>
+#include <string>
+#include "scenes.h"
+
+struct Trace {
+  FILE *f;
+  void i32(int v) { fwrite(&v, 4, 1, f); }
+  void u32(uint32_t v) { fwrite(&v, 4, 1, f); }
+  void reals(const dReal *p, size_t n) { fwrite(p, sizeof(dReal), n, f); }
+};
+
+struct CbCtx {
+  SceneWorld *sw;
+  ScenePolicy *pol;
+  std::vector<int> pairs;
+  std::vector<int> cg;
+  std::vector<dReal> cdata;
+  std::vector<dJointFeedback *> fbs;
+  long long ncontacts;
+  bool record;
+};
+
+static void near_cb(void *data, dGeomID o1, dGeomID o2) {
+  CbCtx *c = (CbCtx *)data;
+  if (c->record) {
+    c->pairs.push_back((int)(intptr_t)dGeomGetData(o1));
+    c->pairs.push_back((int)(intptr_t)dGeomGetData(o2));
+  }
+  dBodyID b1 = dGeomGetBody(o1), b2 = dGeomGetBody(o2);
+  if (c->pol->skip_if_connected && b1 && b2 && dAreConnectedExcluding(b1, b2, dJointTypeContact)) return;
+  enum { MAXC = 64 };
+  dContact contact[MAXC];
+  int maxc = c->pol->max_contacts;
+  for (int i = 0; i < maxc; i++) {
+    memset(&contact[i], 0, sizeof(dContact));
+    contact[i].surface = c->pol->surface;
+  }
+  int n = dCollide(o1, o2, maxc, &contact[0].geom, sizeof(dContact));
+  for (int i = 0; i < n; i++) {
+    dJointID j = dJointCreateContact(c->sw->world, c->sw->cgroup, &contact[i]);
+    dJointAttach(j, b1, b2);
+    if (c->record) {
+      c->cg.push_back((int)(intptr_t)dGeomGetData(contact[i].geom.g1));
+      c->cg.push_back((int)(intptr_t)dGeomGetData(contact[i].geom.g2));
+      for (int k = 0; k < 3; k++) c->cdata.push_back(contact[i].geom.pos[k]);
+      for (int k = 0; k < 3; k++) c->cdata.push_back(contact[i].geom.normal[k]);
+      c->cdata.push_back(contact[i].geom.depth);
+      dJointFeedback *fb = new dJointFeedback;
+      memset(fb, 0, sizeof(*fb));
+      dJointSetFeedback(j, fb);
+      c->fbs.push_back(fb);
+    }
+  }
+  c->ncontacts += n;
+}
+
+static void dump_state(Trace &t, SceneWorld &sw) {
+  t.i32((int)sw.bodies.size());
+  for (size_t i = 0; i < sw.bodies.size(); i++) {
+    dBodyID b = sw.bodies[i];
+    t.reals(dBodyGetPosition(b), 3);
+    t.reals(dBodyGetQuaternion(b), 4);
+    t.reals(dBodyGetLinearVel(b), 3);
+    t.reals(dBodyGetAngularVel(b), 3);
+  }
+}
+
+static double now_s() {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+int main(int argc, char **argv) {
+  std::string scene = "stack32", out = "", mode = "callback";
+  int nworlds = 1, nsteps = 10, world0 = 0, timing = 0;
+  double h = 0.01;
+  for (int i = 1; i < argc; i++) {
+    std::string a = argv[i];
+    if (a == "--scene") scene = argv[++i];
+    else if (a == "--out") out = argv[++i];
+    else if (a == "--mode") mode = argv[++i];
+    else if (a == "--worlds") nworlds = atoi(argv[++i]);
+    else if (a == "--world0") world0 = atoi(argv[++i]);
+    else if (a == "--steps") nsteps = atoi(argv[++i]);
+    else if (a == "--h") h = atof(argv[++i]);
+    else if (a == "--time") timing = 1;
+    else { fprintf(stderr, "unknown arg %s\n", a.c_str()); return 2; }
+  }
+  dInitODE2(0);
+  std::vector<SceneWorld> worlds(nworlds);
+  ScenePolicy pol;
+  for (int w = 0; w < nworlds; w++)
+    if (scene_build(scene.c_str(), worlds[w], world0 + w, pol)) { fprintf(stderr, "bad scene\n"); return 2; }
+
+  Trace t;
+  t.f = NULL;
+  if (!out.empty()) {
+    t.f = fopen(out.c_str(), "wb");
+    if (!t.f) { perror("open"); return 2; }
+    t.u32(0x5254444f);
+    t.i32((int)sizeof(dReal));
+    t.i32(nworlds);
+    t.i32(nsteps);
+  }
+  long long body_steps = 0, contacts = 0, pairs = 0;
+  double t0 = now_s();
+
+  if (mode == "callback") {
+    CbCtx ctx;
+    ctx.pol = &pol;
+    ctx.ncontacts = 0;
+    ctx.record = t.f != NULL;
+    for (int s = 0; s < nsteps; s++) {
+      for (int w = 0; w < nworlds; w++) {
+        SceneWorld &sw = worlds[w];
+        ctx.sw = &sw;
+        if (t.f) {
+          int ng = dSpaceGetNumGeoms(sw.space);
+          t.i32(ng);
+          for (int i = 0; i < ng; i++) t.i32((int)(intptr_t)dGeomGetData(dSpaceGetGeom(sw.space, i)));
+          dump_state(t, sw);
+        }
+        dRandSetSeed(sw.seed);
+        dSpaceCollide(sw.space, &ctx, &near_cb);
+        dWorldQuickStep(sw.world, (dReal)h);
+        sw.seed = (uint32_t)dRandGetSeed();
+        if (t.f) {
+          t.i32((int)ctx.pairs.size() / 2);
+          fwrite(ctx.pairs.data(), 4, ctx.pairs.size(), t.f);
+          int nc = (int)ctx.cg.size() / 2;
+          t.i32(nc);
+          for (int i = 0; i < nc; i++) {
+            t.i32(ctx.cg[2 * i]);
+            t.i32(ctx.cg[2 * i + 1]);
+            t.reals(&ctx.cdata[7 * i], 7);
+          }
+          for (int i = 0; i < nc; i++) {
+            t.reals(ctx.fbs[i]->f1, 3);
+            t.reals(ctx.fbs[i]->t1, 3);
+            delete ctx.fbs[i];
+          }
+          pairs += ctx.pairs.size() / 2;
+          ctx.pairs.clear(); ctx.cg.clear(); ctx.cdata.clear(); ctx.fbs.clear();
+        }
+        dJointGroupEmpty(sw.cgroup);
+        if (t.f) {
+          for (size_t i = 0; i < sw.bodies.size(); i++) {
+            dBodyID b = sw.bodies[i];
+            t.reals(dBodyGetPosition(b), 3);
+            t.reals(dBodyGetQuaternion(b), 4);
+            t.reals(dBodyGetLinearVel(b), 3);
+            t.reals(dBodyGetAngularVel(b), 3);
+          }
+          t.u32(sw.seed);
+        }
+        body_steps += (long long)sw.bodies.size();
+      }
+    }
+    contacts = ctx.ncontacts;
+  }
+#ifdef HAVE_BATCH
+  else if (mode == "batch") {
+    std::vector<dWorldID> wv(nworlds);
+    std::vector<dSpaceID> sv(nworlds);
+    std::vector<uint32_t> seeds(nworlds);
+    for (int w = 0; w < nworlds; w++) { wv[w] = worlds[w].world; sv[w] = worlds[w].space; seeds[w] = worlds[w].seed; }
+    dBatchDesc desc;
+    memset(&desc, 0, sizeof(desc));
+    dBatchID B = dBatchCreate(nworlds, wv.data(), sv.data(), &desc);
+    if (!B) { fprintf(stderr, "dBatchCreate failed: %s\n", dB200LastError()); return 3; }
+    dBatchContactPolicy bp;
+    memset(&bp, 0, sizeof(bp));
+    bp.cat_mask1 = bp.cat_mask2 = ~0ul;
+    bp.max_contacts = pol.max_contacts;
+    bp.skip_if_connected = pol.skip_if_connected;
+    bp.surface = pol.surface;
+    dBatchSetContactPolicy(B, &bp, 1);
+    dBatchSetSeeds(B, seeds.data());
+    int nb = dBatchNumBodies(B);
+    std::vector<dReal> pos(nworlds * nb * 3), quat(nworlds * nb * 4), lv(nworlds * nb * 3), av(nworlds * nb * 3);
+    std::vector<int> status(nworlds);
+    if (!t.f) {
+      // timing mode: one call, everything device-resident
+      int rc = dBatchCollideAndQuickStep(B, (dReal)h, nsteps, status.data());
+      if (rc) { fprintf(stderr, "step failed: %s\n", dB200LastError()); return 3; }
+      dBatchCounters c;
+      dBatchGetCounters(B, &c);
+      body_steps = c.body_steps; contacts = c.contacts; pairs = c.pairs;
+    } else {
+      std::vector<int> pbuf(2 * 65536), cg(2 * 65536);
+      std::vector<dReal> cd(7 * 65536), lam(3 * 65536);
+      for (int s = 0; s < nsteps; s++) {
+        // the trace is world-major inside a step, so gather per world
+        dBatchGetBodyState(B, pos.data(), quat.data(), lv.data(), av.data());
+        std::vector<dReal> st0(pos.size() + quat.size() + lv.size() + av.size());
+        for (int w = 0; w < nworlds; w++)
+          for (int b = 0; b < nb; b++) {
+            dReal *d = &st0[(size_t)(w * nb + b) * 13];
+            memcpy(d, &pos[(w * nb + b) * 3], 3 * sizeof(dReal));
+            memcpy(d + 3, &quat[(w * nb + b) * 4], 4 * sizeof(dReal));
+            memcpy(d + 7, &lv[(w * nb + b) * 3], 3 * sizeof(dReal));
+            memcpy(d + 10, &av[(w * nb + b) * 3], 3 * sizeof(dReal));
+          }
+        std::vector<std::vector<int> > glists(nworlds);
+        for (int w = 0; w < nworlds; w++) {
+          glists[w].resize(4096);
+          int ng = dBatchDebugGeomOrder(B, w, glists[w].data(), 4096);
+          glists[w].resize(ng);
+        }
+        int rc = dBatchCollideAndQuickStep(B, (dReal)h, 1, status.data());
+        if (rc) { fprintf(stderr, "step failed: %s\n", dB200LastError()); return 3; }
+        dBatchGetBodyState(B, pos.data(), quat.data(), lv.data(), av.data());
+        dBatchGetSeeds(B, seeds.data());
+        for (int w = 0; w < nworlds; w++) {
+          if (status[w]) fprintf(stderr, "world %d step %d status %d\n", w, s, status[w]);
+          t.i32((int)glists[w].size());
+          fwrite(glists[w].data(), 4, glists[w].size(), t.f);
+          t.i32(nb);
+          t.reals(&st0[(size_t)w * nb * 13], (size_t)nb * 13);
+          int np = dBatchDebugPairs(B, w, pbuf.data(), 65536);
+          t.i32(np);
+          fwrite(pbuf.data(), 4, 2 * np, t.f);
+          int nc = dBatchDebugContacts(B, w, cd.data(), cg.data(), 65536);
+          t.i32(nc);
+          for (int i = 0; i < nc; i++) { t.i32(cg[2 * i]); t.i32(cg[2 * i + 1]); t.reals(&cd[7 * i], 7); }
+          int nl = dBatchDebugFeedback(B, w, lam.data(), 65536);
+          (void)nl;
+          t.reals(lam.data(), (size_t)nc * 6);
+          for (int b = 0; b < nb; b++) {
+            t.reals(&pos[(w * nb + b) * 3], 3);
+            t.reals(&quat[(w * nb + b) * 4], 4);
+            t.reals(&lv[(w * nb + b) * 3], 3);
+            t.reals(&av[(w * nb + b) * 3], 3);
+          }
+          t.u32(seeds[w]);
+          body_steps += nb; pairs += np; contacts += nc;
+        }
+      }
+    }
+    dBatchDestroy(B);
+  }
+#endif
+  else { fprintf(stderr, "mode %s not available in this build\n", mode.c_str()); return 2; }
+
+  double dt = now_s() - t0;
+  if (t.f) fclose(t.f);
+  if (timing)
+    printf("{\"scene\":\"%s\",\"mode\":\"%s\",\"worlds\":%d,\"steps\":%d,\"seconds\":%.6f,\"body_steps\":%lld,"
+           "\"contacts\":%lld,\"body_steps_per_sec\":%.1f,\"contacts_per_sec\":%.1f,\"realsize\":%d}\n",
+           scene.c_str(), mode.c_str(), nworlds, nsteps, dt, body_steps, contacts, body_steps / dt, contacts / dt,
+           (int)sizeof(dReal));
+  dCloseODE();
+  return 0;
+}
