@@ -1,0 +1,28 @@
+// ob_backend.h — the narrow seam between the generic batch layer (ob_batch.cpp:
+// marshalling + C ABI) and whatever executes the step.  The product links
+// ob_backend_cuda.cu (device memory + the sm_100a kernels).  tests/hostsim links
+// a test-only backend that runs the same per-element device functions in plain
+// loops on the CPU so their arithmetic can be checked against the reference
+// without a GPU; it is never part of libode_b200_*.so.
+#pragma once
+#include <stddef.h>
+#include "ob_types.h"
+
+struct ObBackend;
+// allocate every array named in `caps` (pointers in caps are ignored); returns 0 on failure
+ObBackend *obk_create(const ObBatchDev &caps, int device, char *err, size_t errlen);
+void obk_destroy(ObBackend *);
+ObBatchDev *obk_arrays(ObBackend *);                       // pointers valid on the execution side
+int obk_h2d(ObBackend *, void *dst, const void *src, size_t bytes);
+int obk_d2h(ObBackend *, void *dst, const void *src, size_t bytes);
+int obk_memset(ObBackend *, void *dst, int value, size_t bytes);
+// nsteps x (collide + step) for all worlds; debug_taps: also fill fback
+int obk_step(ObBackend *, real h, int nsteps, int debug_taps, char *err, size_t errlen);
+int obk_sync(ObBackend *);
+// bulk body-state I/O in API order ([world][creation-index body]); nbody[w] = bodies in world w.
+// Host buffers; a null pointer skips that field.
+int obk_get_state(ObBackend *, real *pos3, real *quat4, real *lvel3, real *avel3);
+int obk_set_state(ObBackend *, const real *pos3, const real *quat4, const real *lvel3, const real *avel3);
+int obk_add_forces(ObBackend *, const real *force3, const real *torque3);
+void *obk_stream(ObBackend *);
+long long obk_launch_count(void);

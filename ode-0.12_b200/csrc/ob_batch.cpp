@@ -1,0 +1,301 @@
+// ob_batch.cpp — the added batched-world entry points (dBatch*, include/ode_b200/ode.h):
+// marshals worlds built through the ODE C API into the device layout of ob_types.h,
+// and exposes bulk I/O, counters and parity taps.  No physics here.
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <vector>
+#include "ob_backend.h"
+#include "ob_host.h"
+
+struct dxBatch {
+  ObBackend *bk;
+  ObBatchDev caps;   // capacities; pointer members are execution-side pointers
+  std::vector<dxWorld *> worlds;
+  std::vector<dxSpace *> spaces;
+  std::vector<std::vector<dxBody *> > bodies;  // [w][batch body index]
+  std::vector<std::vector<dxGeom *> > geoms;   // [w][geom index]
+  std::vector<int> nb, ng;
+  int debug_taps;
+};
+
+static void fill_surface(ObSurface &d, const dSurfaceParameters &s) {
+  d.mode = s.mode; d.mu = s.mu; d.mu2 = s.mu2; d.bounce = s.bounce; d.bounce_vel = s.bounce_vel;
+  d.soft_erp = s.soft_erp; d.soft_cfm = s.soft_cfm; d.motion1 = s.motion1; d.motion2 = s.motion2;
+  d.motionN = s.motionN; d.slip1 = s.slip1; d.slip2 = s.slip2;
+}
+
+void ob_marshal_body(const dxBody *b, ObBodyDyn &d, ObBodyConst &c) {
+  memset(&d, 0, sizeof d);
+  memset(&c, 0, sizeof c);
+  for (int k = 0; k < 3; k++) { d.pos[k] = b->pos[k]; d.lvel[k] = b->lvel[k]; d.avel[k] = b->avel[k]; d.facc[k] = b->facc[k]; d.tacc[k] = b->tacc[k]; }
+  for (int k = 0; k < 4; k++) d.q[k] = b->q[k];
+  for (int k = 0; k < 12; k++) d.R[k] = b->R[k];
+  d.flags = b->flags;
+  d.adis_stepsleft = b->adis_stepsleft;
+  d.adis_timeleft = b->adis_timeleft;
+  c.mass = b->mass.mass; c.invMass = b->invMass; c.max_angular_speed = b->max_angular_speed;
+  for (int k = 0; k < 12; k++) { c.I[k] = b->mass.I[k]; c.invI[k] = b->invI[k]; }
+  for (int k = 0; k < 3; k++) c.finite_rot_axis[k] = b->finite_rot_axis[k];
+  c.damp_lin_scale = b->dampingp.linear_scale; c.damp_ang_scale = b->dampingp.angular_scale;
+  c.damp_lin_thr = b->dampingp.linear_threshold; c.damp_ang_thr = b->dampingp.angular_threshold;
+  c.adis_lin_thr = b->adis.linear_average_threshold; c.adis_ang_thr = b->adis.angular_average_threshold;
+  c.adis_idle_time = b->adis.idle_time; c.adis_idle_steps = b->adis.idle_steps; c.adis_samples = (int)b->adis.average_samples;
+  c.geom_first = -1;
+}
+
+void ob_marshal_geom(dxGeom *g, ObGeom &d) {
+  memset(&d, 0, sizeof d);
+  d.type = g->type;
+  d.body = g->body ? g->body->batch_index : -1;
+  d.cat = (uint32_t)g->category_bits; d.col = (uint32_t)g->collide_bits;
+  d.flags = ((g->gflags & GEOM_ENABLED) ? OB_GEOM_ENABLED : 0) | (g->offset_posr ? OB_GEOM_HAS_OFFSET : 0) |
+            ((g->gflags & GEOM_ZERO_SIZED) ? OB_GEOM_ZERO_SIZED : 0);
+  d.body_next = -1;
+  for (int k = 0; k < 4; k++) d.p[k] = g->p[k];
+  const dxPosR *src = 0;
+  if (g->offset_posr) src = g->offset_posr;
+  else if (!g->body && (g->gflags & GEOM_PLACEABLE)) src = g->final_posr;
+  if (src) { for (int k = 0; k < 3; k++) d.pos[k] = src->pos[k]; for (int k = 0; k < 12; k++) d.R[k] = src->R[k]; }
+  else { d.R[0] = d.R[5] = d.R[10] = 1; }
+}
+
+extern "C" {
+
+dBatchID dBatchCreate(int nworlds, const dWorldID *worlds, const dSpaceID *spaces, const dBatchDesc *desc) {
+  if (nworlds <= 0 || !worlds || !spaces) { ob_set_last_error("dBatchCreate: bad arguments"); return 0; }
+  dxBatch *B = new dxBatch;
+  B->bk = 0; B->debug_taps = 1;
+  B->worlds.assign(worlds, worlds + nworlds);
+  B->spaces.assign(spaces, spaces + nworlds);
+  B->bodies.resize(nworlds); B->geoms.resize(nworlds); B->nb.resize(nworlds); B->ng.resize(nworlds);
+  int NB = 1, NG = 1;
+  for (int w = 0; w < nworlds; w++) {
+    dxWorld *W = worlds[w]; dxSpace *S = spaces[w];
+    if (!W || !S || !S->is_space) { ob_set_last_error("dBatchCreate: world %d: bad world/space", w); delete B; return 0; }
+    if (S->type != dHashSpaceClass && S->type != dSimpleSpaceClass && S->type != dSweepAndPruneSpaceClass) {
+      ob_set_last_error("dBatchCreate: world %d: unsupported space class %d", w, S->type); delete B; return 0;
+    }
+    int i = 0;
+    for (dxBody *b = W->firstbody; b; b = b->next) { b->batch_index = i++; B->bodies[w].push_back(b); }
+    B->nb[w] = i;
+    int ng = S->count;
+    B->geoms[w].resize(ng);
+    int pos = 0;
+    for (dxGeom *g = S->first; g; g = g->next, pos++) {
+      if (g->is_space) { ob_set_last_error("dBatchCreate: world %d: nested spaces are not supported on the batched path", w); delete B; return 0; }
+      if (g->body && g->body->world != W) { ob_set_last_error("dBatchCreate: world %d: geom attached to a body of another world", w); delete B; return 0; }
+      g->batch_index = ng - 1 - pos;
+      B->geoms[w][g->batch_index] = g;
+    }
+    B->ng[w] = ng;
+    NB = std::max(NB, B->nb[w]); NG = std::max(NG, ng);
+  }
+  ObBatchDev caps;
+  memset(&caps, 0, sizeof caps);
+  caps.W = nworlds; caps.NB = NB; caps.NG = NG;
+  caps.NC = (desc && desc->max_contacts_per_world > 0) ? desc->max_contacts_per_world : std::max(64, 16 * NG);
+  caps.NP = std::min(NG * (NG - 1) / 2 + 1, std::max(256, 8 * NG));
+  caps.NR = 3 * caps.NC;
+  caps.npolicy = 1;
+  char err[512] = "";
+  B->bk = obk_create(caps, desc ? desc->device : 0, err, sizeof err);
+  if (!B->bk) { ob_set_last_error("dBatchCreate: %s", err); delete B; return 0; }
+  B->caps = *obk_arrays(B->bk);
+
+  std::vector<ObWorld> hw(nworlds);
+  std::vector<ObBodyDyn> hd((size_t)nworlds * NB);
+  std::vector<ObBodyConst> hc((size_t)nworlds * NB);
+  std::vector<ObGeom> hg((size_t)nworlds * NG);
+  std::vector<int> hl((size_t)nworlds * NG, -1);
+  memset(hd.data(), 0, hd.size() * sizeof(ObBodyDyn));
+  memset(hc.data(), 0, hc.size() * sizeof(ObBodyConst));
+  memset(hg.data(), 0, hg.size() * sizeof(ObGeom));
+  for (int w = 0; w < nworlds; w++) {
+    dxWorld *W = worlds[w]; dxSpace *S = spaces[w];
+    ObWorld &o = hw[w];
+    memset(&o, 0, sizeof o);
+    for (int k = 0; k < 3; k++) o.gravity[k] = W->gravity[k];
+    o.erp = W->global_erp; o.cfm = W->global_cfm; o.sor_w = W->qs_w; o.max_vel = W->contact_max_vel;
+    o.min_depth = W->contact_min_depth; o.iters = W->qs_iterations; o.nb = B->nb[w]; o.ng = B->ng[w];
+    o.seed = 0; o.hash_minlevel = S->minlevel; o.hash_maxlevel = S->maxlevel;
+    o.space_type = S->type == dHashSpaceClass ? OB_SPACE_HASH : (S->type == dSweepAndPruneSpaceClass ? OB_SPACE_SAP : OB_SPACE_SIMPLE);
+    for (int i = 0; i < B->nb[w]; i++) {
+      dxBody *b = B->bodies[w][i];
+      ob_marshal_body(b, hd[(size_t)w * NB + i], hc[(size_t)w * NB + i]);
+      hc[(size_t)w * NB + i].geom_first = b->geom ? b->geom->batch_index : -1;
+    }
+    int pos = 0;
+    for (dxGeom *g = S->first; g; g = g->next, pos++) {
+      ObGeom &d = hg[(size_t)w * NG + g->batch_index];
+      ob_marshal_geom(g, d);
+      d.body_next = g->body_next ? g->body_next->batch_index : -1;
+      hl[(size_t)w * NG + pos] = g->batch_index;
+    }
+    W->bound_batch = B; S->bound_batch = B;
+  }
+  ObPolicy pol;
+  memset(&pol, 0, sizeof pol);
+  pol.cat_mask1 = pol.cat_mask2 = ~0u; pol.max_contacts = 8; pol.skip_if_connected = 1;
+  pol.surface.mode = 0; pol.surface.mu = OB_INF;
+  int rc = 0;
+  rc |= obk_h2d(B->bk, B->caps.world, hw.data(), hw.size() * sizeof(ObWorld));
+  rc |= obk_h2d(B->bk, B->caps.bdyn, hd.data(), hd.size() * sizeof(ObBodyDyn));
+  rc |= obk_h2d(B->bk, B->caps.bconst, hc.data(), hc.size() * sizeof(ObBodyConst));
+  rc |= obk_h2d(B->bk, B->caps.geom, hg.data(), hg.size() * sizeof(ObGeom));
+  rc |= obk_h2d(B->bk, B->caps.glist, hl.data(), hl.size() * sizeof(int));
+  rc |= obk_h2d(B->bk, B->caps.policy, &pol, sizeof pol);
+  rc |= obk_memset(B->bk, B->caps.counters, 0, sizeof(ObCounters));
+  rc |= obk_memset(B->bk, B->caps.npairs, 0, sizeof(int) * nworlds);
+  rc |= obk_memset(B->bk, B->caps.ncontacts, 0, sizeof(int) * nworlds);
+  rc |= obk_memset(B->bk, B->caps.nrows, 0, sizeof(int) * nworlds);
+  if (rc) { ob_set_last_error("dBatchCreate: upload failed"); dBatchDestroy(B); return 0; }
+  return B;
+}
+
+void dBatchDestroy(dBatchID B) {
+  if (!B) return;
+  for (size_t w = 0; w < B->worlds.size(); w++) {
+    if (B->worlds[w]->bound_batch == B) B->worlds[w]->bound_batch = 0;
+    if (B->spaces[w]->bound_batch == B) B->spaces[w]->bound_batch = 0;
+  }
+  if (B->bk) obk_destroy(B->bk);
+  delete B;
+}
+
+int dBatchSetContactPolicy(dBatchID B, const dBatchContactPolicy *table, int n) {
+  if (!B || !table || n != 1) { ob_set_last_error("dBatchSetContactPolicy: exactly one policy row is supported in this build"); return -1; }
+  ObPolicy pol;
+  memset(&pol, 0, sizeof pol);
+  pol.cat_mask1 = (uint32_t)table[0].cat_mask1; pol.cat_mask2 = (uint32_t)table[0].cat_mask2;
+  pol.max_contacts = table[0].max_contacts; pol.skip_if_connected = table[0].skip_if_connected;
+  pol.skip_static_pairs = table[0].skip_static_pairs;
+  fill_surface(pol.surface, table[0].surface);
+  return obk_h2d(B->bk, B->caps.policy, &pol, sizeof pol);
+}
+
+int dBatchSetSeeds(dBatchID B, const uint32_t *seeds) {
+  int W = B->caps.W;
+  std::vector<ObWorld> hw(W);
+  if (obk_d2h(B->bk, hw.data(), B->caps.world, W * sizeof(ObWorld))) return -1;
+  for (int w = 0; w < W; w++) hw[w].seed = seeds[w];
+  return obk_h2d(B->bk, B->caps.world, hw.data(), W * sizeof(ObWorld));
+}
+int dBatchGetSeeds(dBatchID B, uint32_t *seeds) {
+  int W = B->caps.W;
+  std::vector<ObWorld> hw(W);
+  if (obk_d2h(B->bk, hw.data(), B->caps.world, W * sizeof(ObWorld))) return -1;
+  for (int w = 0; w < W; w++) seeds[w] = hw[w].seed;
+  return 0;
+}
+
+int dBatchCollideAndQuickStep(dBatchID B, dReal h, int nsteps, int *status_per_world) {
+  if (!B || !(h > 0) || nsteps < 0) { ob_set_last_error("dBatchCollideAndQuickStep: bad arguments"); return -1; }
+  char err[512] = "";
+  int rc = obk_step(B->bk, h, nsteps, B->debug_taps, err, sizeof err);
+  if (rc) { ob_set_last_error("dBatchCollideAndQuickStep: %s", err); return rc; }
+  if (status_per_world) {
+    int W = B->caps.W;
+    std::vector<ObWorld> hw(W);
+    if (obk_d2h(B->bk, hw.data(), B->caps.world, W * sizeof(ObWorld))) return -1;
+    bool any = false;
+    for (int w = 0; w < W; w++) { status_per_world[w] = hw[w].status; any |= hw[w].status != 0; hw[w].status = 0; }
+    if (any) obk_h2d(B->bk, B->caps.world, hw.data(), W * sizeof(ObWorld));
+  }
+  return 0;
+}
+
+int dBatchNumBodies(dBatchID B) { return B->caps.NB; }
+int dBatchGetBodyState(dBatchID B, dReal *pos3, dReal *quat4, dReal *lvel3, dReal *avel3) {
+  return obk_get_state(B->bk, pos3, quat4, lvel3, avel3);
+}
+int dBatchSetBodyState(dBatchID B, const dReal *pos3, const dReal *quat4, const dReal *lvel3, const dReal *avel3) {
+  return obk_set_state(B->bk, pos3, quat4, lvel3, avel3);
+}
+int dBatchAddForces(dBatchID B, const dReal *force3, const dReal *torque3) { return obk_add_forces(B->bk, force3, torque3); }
+
+int dBatchDownload(dBatchID B) {
+  int W = B->caps.W, NB = B->caps.NB, NG = B->caps.NG;
+  std::vector<ObBodyDyn> hd((size_t)W * NB);
+  std::vector<int> hl((size_t)W * NG);
+  std::vector<ObWorld> hw(W);
+  if (obk_d2h(B->bk, hd.data(), B->caps.bdyn, hd.size() * sizeof(ObBodyDyn))) return -1;
+  if (obk_d2h(B->bk, hl.data(), B->caps.glist, hl.size() * sizeof(int))) return -1;
+  if (obk_d2h(B->bk, hw.data(), B->caps.world, W * sizeof(ObWorld))) return -1;
+  for (int w = 0; w < W; w++) {
+    for (int i = 0; i < B->nb[w]; i++) {
+      dxBody *b = B->bodies[w][i];
+      const ObBodyDyn &d = hd[(size_t)w * NB + i];
+      for (int k = 0; k < 3; k++) { b->pos[k] = d.pos[k]; b->lvel[k] = d.lvel[k]; b->avel[k] = d.avel[k]; b->facc[k] = d.facc[k]; b->tacc[k] = d.tacc[k]; }
+      for (int k = 0; k < 4; k++) b->q[k] = d.q[k];
+      for (int k = 0; k < 12; k++) b->R[k] = d.R[k];
+      b->flags = d.flags; b->adis_stepsleft = d.adis_stepsleft; b->adis_timeleft = d.adis_timeleft;
+    }
+    // rebuild the space's linked list in device order (all geoms clean after a step's collide,
+    // dirty again after its integration: mark the body geoms dirty like dGeomMoved does)
+    dxSpace *S = B->spaces[w];
+    int ng = B->ng[w];
+    S->first = 0;
+    dxGeom **link = &S->first;
+    for (int pos = 0; pos < ng; pos++) {
+      dxGeom *g = B->geoms[w][hl[(size_t)w * NG + pos]];
+      *link = g; g->tome = link; g->next = 0; link = &g->next;
+    }
+  }
+  return 0;
+}
+
+int dBatchGetCounters(dBatchID B, dBatchCounters *out) {
+  ObCounters c;
+  if (obk_d2h(B->bk, &c, B->caps.counters, sizeof c)) return -1;
+  out->steps = (long long)c.steps; out->body_steps = (long long)c.body_steps; out->pairs = (long long)c.pairs;
+  out->contacts = (long long)c.contacts; out->rows = (long long)c.rows; out->islands = (long long)c.islands;
+  out->overflow_worlds = (long long)c.overflow_worlds;
+  return 0;
+}
+int dBatchResetCounters(dBatchID B) { return obk_memset(B->bk, B->caps.counters, 0, sizeof(ObCounters)); }
+
+int dBatchDebugPairs(dBatchID B, int w, int *g1g2, int cap) {
+  int n = 0;
+  if (obk_d2h(B->bk, &n, B->caps.npairs + w, sizeof(int))) return -1;
+  int m = std::min(n, cap);
+  if (m > 0 && obk_d2h(B->bk, g1g2, B->caps.pairs + (size_t)w * B->caps.NP * 2, sizeof(int) * 2 * m)) return -1;
+  return n;
+}
+int dBatchDebugContacts(dBatchID B, int w, dReal *pnd7, int *g1g2, int cap) {
+  int n = 0;
+  if (obk_d2h(B->bk, &n, B->caps.ncontacts + w, sizeof(int))) return -1;
+  int m = std::min(n, cap);
+  if (m <= 0) return n;
+  std::vector<ObContact> c(m);
+  if (obk_d2h(B->bk, c.data(), B->caps.contacts + (size_t)w * B->caps.NC, sizeof(ObContact) * m)) return -1;
+  for (int i = 0; i < m; i++) {
+    for (int k = 0; k < 3; k++) { pnd7[7 * i + k] = c[i].pos[k]; pnd7[7 * i + 3 + k] = c[i].normal[k]; }
+    pnd7[7 * i + 6] = c[i].depth;
+    g1g2[2 * i] = c[i].g1; g1g2[2 * i + 1] = c[i].g2;
+  }
+  return n;
+}
+int dBatchDebugLambda(dBatchID B, int w, dReal *lambda, int cap) {
+  int n = 0;
+  if (obk_d2h(B->bk, &n, B->caps.nrows + w, sizeof(int))) return -1;
+  int m = std::min(n, cap);
+  if (m > 0 && obk_d2h(B->bk, lambda, B->caps.lambda + (size_t)w * B->caps.NR, sizeof(dReal) * m)) return -1;
+  return n;
+}
+int dBatchDebugFeedback(dBatchID B, int w, dReal *f1t1, int cap) {
+  int n = 0;
+  if (obk_d2h(B->bk, &n, B->caps.ncontacts + w, sizeof(int))) return -1;
+  int m = std::min(n, cap);
+  if (m > 0 && obk_d2h(B->bk, f1t1, B->caps.fback + (size_t)w * B->caps.NC * 6, sizeof(dReal) * 6 * m)) return -1;
+  return n;
+}
+int dBatchDebugGeomOrder(dBatchID B, int w, int *order, int cap) {
+  int n = B->ng[w];
+  int m = std::min(n, cap);
+  if (m > 0 && obk_d2h(B->bk, order, B->caps.glist + (size_t)w * B->caps.NG, sizeof(int) * m)) return -1;
+  return n;
+}
+void *dBatchGetStream(dBatchID B) { return obk_stream(B->bk); }
+long long dB200KernelLaunchCount(void) { return obk_launch_count(); }
+}  // extern "C"

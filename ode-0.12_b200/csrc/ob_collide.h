@@ -1,0 +1,588 @@
+// ob_collide.h — AABBs and primitive narrowphase, one geom pair per thread.
+//
+// Each function follows the reference collider it replaces expression by
+// expression (same association order, same compare-branch structure) so that
+// contact counts are exact and contact fields are bit-identical:
+//   computeAABB      ode/src/sphere.cpp:59-67, box.cpp:60-77, plane.cpp:68-96, capsule.cpp:60-74
+//   sphere-sphere    ode/src/sphere.cpp:110-128 + collision_util.cpp:38-67
+//   sphere-box       ode/src/sphere.cpp:131-219
+//   sphere-plane     ode/src/sphere.cpp:222-251
+//   box-box          ode/src/box.cpp:331-742 (intersectRectQuad :187-238, cullPoints :249-311)
+//   box-plane        ode/src/box.cpp:745-878
+//   dCollide         ode/src/collision_kernel.cpp:292-339 (class table + reverse fix-up :167-268)
+// No virtual dispatch: the class pair selects a switch arm.
+#pragma once
+#include "ob_types.h"
+
+struct ObPose {  // world pose + parameters of one geom, gathered per thread
+  int type;
+  real pos[3];
+  real R[12];
+  real p[4];
+};
+
+struct ObCg {  // contact being generated (dContactGeom minus the geom ids)
+  real pos[3];
+  real normal[3];
+  real depth;
+  int side1, side2;
+};
+
+#define OB_MAXC_LOCAL 8   // contacts kept per pair on the primitive path (box-box emits <= 8)
+
+OB_HD void ob_aabb(const ObPose &g, real *aabb) {
+  switch (g.type) {
+    case OB_GEOM_SPHERE: {
+      real r = g.p[0];
+      aabb[0] = g.pos[0] - r; aabb[1] = g.pos[0] + r;
+      aabb[2] = g.pos[1] - r; aabb[3] = g.pos[1] + r;
+      aabb[4] = g.pos[2] - r; aabb[5] = g.pos[2] + r;
+    } break;
+    case OB_GEOM_BOX: {
+      const real *R = g.R; const real *s = g.p;
+      real xr = OB_REAL(0.5) * (ob_fabs(R[0] * s[0]) + ob_fabs(R[1] * s[1]) + ob_fabs(R[2] * s[2]));
+      real yr = OB_REAL(0.5) * (ob_fabs(R[4] * s[0]) + ob_fabs(R[5] * s[1]) + ob_fabs(R[6] * s[2]));
+      real zr = OB_REAL(0.5) * (ob_fabs(R[8] * s[0]) + ob_fabs(R[9] * s[1]) + ob_fabs(R[10] * s[2]));
+      aabb[0] = g.pos[0] - xr; aabb[1] = g.pos[0] + xr;
+      aabb[2] = g.pos[1] - yr; aabb[3] = g.pos[1] + yr;
+      aabb[4] = g.pos[2] - zr; aabb[5] = g.pos[2] + zr;
+    } break;
+    case OB_GEOM_CAPSULE: {
+      // capsule.cpp:60-74: radius + |R(:,2)| * lz/2
+      const real *R = g.R; real radius = g.p[0], lz = g.p[1];
+      real xr = ob_fabs(R[2] * lz) * OB_REAL(0.5) + radius;
+      real yr = ob_fabs(R[6] * lz) * OB_REAL(0.5) + radius;
+      real zr = ob_fabs(R[10] * lz) * OB_REAL(0.5) + radius;
+      aabb[0] = g.pos[0] - xr; aabb[1] = g.pos[0] + xr;
+      aabb[2] = g.pos[1] - yr; aabb[3] = g.pos[1] + yr;
+      aabb[4] = g.pos[2] - zr; aabb[5] = g.pos[2] + zr;
+    } break;
+    case OB_GEOM_PLANE: {
+      const real *p = g.p;
+      aabb[0] = -OB_INF; aabb[1] = OB_INF; aabb[2] = -OB_INF; aabb[3] = OB_INF; aabb[4] = -OB_INF; aabb[5] = OB_INF;
+      if (p[1] == 0.0f && p[2] == 0.0f) {
+        aabb[0] = (p[0] > 0) ? -OB_INF : -p[3];
+        aabb[1] = (p[0] > 0) ? p[3] : OB_INF;
+      } else if (p[0] == 0.0f && p[2] == 0.0f) {
+        aabb[2] = (p[1] > 0) ? -OB_INF : -p[3];
+        aabb[3] = (p[1] > 0) ? p[3] : OB_INF;
+      } else if (p[0] == 0.0f && p[1] == 0.0f) {
+        aabb[4] = (p[2] > 0) ? -OB_INF : -p[3];
+        aabb[5] = (p[2] > 0) ? p[3] : OB_INF;
+      }
+    } break;
+    default:
+      aabb[0] = aabb[2] = aabb[4] = -OB_INF; aabb[1] = aabb[3] = aabb[5] = OB_INF;
+  }
+}
+
+// ---- sphere colliders -----------------------------------------------------------
+OB_HD int ob_collide_spheres(const real *p1, real r1, const real *p2, real r2, ObCg *c) {
+  real t0 = p1[0] - p2[0], t1 = p1[1] - p2[1], t2 = p1[2] - p2[2];
+  real d = ob_sqrt(t0 * t0 + t1 * t1 + t2 * t2);
+  if (d > (r1 + r2)) return 0;
+  if (d <= 0) {
+    c->pos[0] = p1[0]; c->pos[1] = p1[1]; c->pos[2] = p1[2];
+    c->normal[0] = 1; c->normal[1] = 0; c->normal[2] = 0;
+    c->depth = r1 + r2;
+  } else {
+    real d1 = ob_recip(d);
+    c->normal[0] = (p1[0] - p2[0]) * d1;
+    c->normal[1] = (p1[1] - p2[1]) * d1;
+    c->normal[2] = (p1[2] - p2[2]) * d1;
+    real k = OB_REAL(0.5) * (r2 - r1 - d);
+    c->pos[0] = p1[0] + c->normal[0] * k;
+    c->pos[1] = p1[1] + c->normal[1] * k;
+    c->pos[2] = p1[2] + c->normal[2] * k;
+    c->depth = r1 + r2 - d;
+  }
+  return 1;
+}
+
+OB_HD int ob_collide_sphere_box(const ObPose &o1, const ObPose &o2, ObCg *contact) {
+  real l[3], t[3], p[3], q[3], r[3];
+  real depth;
+  int onborder = 0;
+  const real *R2 = o2.R;
+  p[0] = o1.pos[0] - o2.pos[0];
+  p[1] = o1.pos[1] - o2.pos[1];
+  p[2] = o1.pos[2] - o2.pos[2];
+  l[0] = o2.p[0] * OB_REAL(0.5);
+  t[0] = ob_dot14(p, R2);
+  if (t[0] < -l[0]) { t[0] = -l[0]; onborder = 1; }
+  if (t[0] > l[0]) { t[0] = l[0]; onborder = 1; }
+  l[1] = o2.p[1] * OB_REAL(0.5);
+  t[1] = ob_dot14(p, R2 + 1);
+  if (t[1] < -l[1]) { t[1] = -l[1]; onborder = 1; }
+  if (t[1] > l[1]) { t[1] = l[1]; onborder = 1; }
+  t[2] = ob_dot14(p, R2 + 2);
+  l[2] = o2.p[2] * OB_REAL(0.5);
+  if (t[2] < -l[2]) { t[2] = -l[2]; onborder = 1; }
+  if (t[2] > l[2]) { t[2] = l[2]; onborder = 1; }
+  if (!onborder) {
+    real min_distance = l[0] - ob_fabs(t[0]);
+    int mini = 0;
+    for (int i = 1; i < 3; i++) {
+      real face_distance = l[i] - ob_fabs(t[i]);
+      if (face_distance < min_distance) { min_distance = face_distance; mini = i; }
+    }
+    contact->pos[0] = o1.pos[0]; contact->pos[1] = o1.pos[1]; contact->pos[2] = o1.pos[2];
+    real tmp[3] = {0, 0, 0};
+    real sgn = (t[mini] > 0) ? OB_REAL(1.0) : OB_REAL(-1.0);
+    if (mini == 0) tmp[0] = sgn; else if (mini == 1) tmp[1] = sgn; else tmp[2] = sgn;
+    ob_mul0_331(contact->normal, R2, tmp);
+    contact->depth = min_distance + o1.p[0];
+    return 1;
+  }
+  ob_mul0_331(q, R2, t);
+  r[0] = p[0] - q[0]; r[1] = p[1] - q[1]; r[2] = p[2] - q[2];
+  depth = o1.p[0] - ob_sqrt(ob_dot(r, r));
+  if (depth < 0) return 0;
+  contact->pos[0] = q[0] + o2.pos[0];
+  contact->pos[1] = q[1] + o2.pos[1];
+  contact->pos[2] = q[2] + o2.pos[2];
+  contact->normal[0] = r[0]; contact->normal[1] = r[1]; contact->normal[2] = r[2];
+  ob_safe_normalize3(contact->normal);
+  contact->depth = depth;
+  return 1;
+}
+
+OB_HD int ob_collide_sphere_plane(const ObPose &o1, const ObPose &o2, ObCg *contact) {
+  const real *pl = o2.p;
+  real k = ob_dot(o1.pos, pl);
+  real depth = pl[3] - k + o1.p[0];
+  if (depth >= 0) {
+    contact->normal[0] = pl[0]; contact->normal[1] = pl[1]; contact->normal[2] = pl[2];
+    contact->pos[0] = o1.pos[0] - pl[0] * o1.p[0];
+    contact->pos[1] = o1.pos[1] - pl[1] * o1.p[0];
+    contact->pos[2] = o1.pos[2] - pl[2] * o1.p[0];
+    contact->depth = depth;
+    return 1;
+  }
+  return 0;
+}
+
+// ---- box colliders --------------------------------------------------------------
+// dLineClosestApproach, collision_util.cpp:70-92
+OB_HD void ob_line_closest_approach(const real *pa, const real *ua, const real *pb, const real *ub,
+                                    real *alpha, real *beta) {
+  real p[3] = {pb[0] - pa[0], pb[1] - pa[1], pb[2] - pa[2]};
+  real uaub = ob_dot(ua, ub);
+  real q1 = ob_dot(ua, p);
+  real q2 = -ob_dot(ub, p);
+  real d = 1 - uaub * uaub;
+  if (d <= OB_REAL(0.0001)) { *alpha = 0; *beta = 0; }
+  else {
+    d = ob_recip(d);
+    *alpha = (q1 + uaub * q2) * d;
+    *beta = (uaub * q1 + q2) * d;
+  }
+}
+
+// intersectRectQuad, box.cpp:187-238.  ret must hold 16 reals.
+OB_HDN int ob_intersect_rect_quad(const real h[2], real p[8], real ret[16]) {
+  int nq = 4, nr = 0;
+  real buffer[16];
+  real *q = p;
+  real *r = ret;
+  for (int dir = 0; dir <= 1; dir++) {
+    for (int sign = -1; sign <= 1; sign += 2) {
+      real *pq = q;
+      real *pr = r;
+      nr = 0;
+      for (int i = nq; i > 0; i--) {
+        if (sign * pq[dir] < h[dir]) {
+          pr[0] = pq[0]; pr[1] = pq[1];
+          pr += 2; nr++;
+          if (nr & 8) { q = r; goto done; }
+        }
+        real *nextq = (i > 1) ? pq + 2 : q;
+        if ((sign * pq[dir] < h[dir]) ^ (sign * nextq[dir] < h[dir])) {
+          pr[1 - dir] = pq[1 - dir] + (nextq[1 - dir] - pq[1 - dir]) / (nextq[dir] - pq[dir]) * (sign * h[dir] - pq[dir]);
+          pr[dir] = sign * h[dir];
+          pr += 2; nr++;
+          if (nr & 8) { q = r; goto done; }
+        }
+        pq += 2;
+      }
+      q = r;
+      r = (q == ret) ? buffer : ret;
+      nq = nr;
+    }
+  }
+done:
+  if (q != ret) for (int i = 0; i < nr * 2; i++) ret[i] = q[i];
+  return nr;
+}
+
+// glibc-exact atan2f is not available on the device; cullPoints only needs a
+// faithful angle to rank candidates.  We evaluate atan2 in double and round once
+// (SURVEY.md Appendix B); ties with glibc's float routine are measured in tests.
+OB_HD real ob_atan2(real y, real x) { return (real)atan2((double)y, (double)x); }
+
+// cullPoints, box.cpp:249-311
+OB_HDN void ob_cull_points(int n, const real p[], int m, int i0, int iret[]) {
+  int i, j;
+  real a, cx, cy, q;
+  if (n == 1) { cx = p[0]; cy = p[1]; }
+  else if (n == 2) { cx = OB_REAL(0.5) * (p[0] + p[2]); cy = OB_REAL(0.5) * (p[1] + p[3]); }
+  else {
+    a = 0; cx = 0; cy = 0;
+    for (i = 0; i < (n - 1); i++) {
+      q = p[i * 2] * p[i * 2 + 3] - p[i * 2 + 2] * p[i * 2 + 1];
+      a += q;
+      cx += q * (p[i * 2] + p[i * 2 + 2]);
+      cy += q * (p[i * 2 + 1] + p[i * 2 + 3]);
+    }
+    q = p[n * 2 - 2] * p[1] - p[0] * p[n * 2 - 1];
+    a = ob_recip(OB_REAL(3.0) * (a + q));
+    cx = a * (cx + q * (p[n * 2 - 2] + p[0]));
+    cy = a * (cy + q * (p[n * 2 - 1] + p[1]));
+  }
+  real A[8];
+  for (i = 0; i < n; i++) A[i] = ob_atan2(p[i * 2 + 1] - cy, p[i * 2] - cx);
+  int avail[8];
+  for (i = 0; i < n; i++) avail[i] = 1;
+  avail[i0] = 0;
+  iret[0] = i0;
+  int w = 1;
+  for (j = 1; j < m; j++) {
+    a = (real)((double)(real)j * (2 * OB_PI / m) + (double)A[i0]);
+    if ((double)a > OB_PI) a -= (real)(2 * OB_PI);
+    real maxdiff = OB_REAL(1e9), diff;
+    int pick = i0;
+    for (i = 0; i < n; i++) {
+      if (avail[i]) {
+        diff = ob_fabs(A[i] - a);
+        if ((double)diff > OB_PI) diff = (real)(2 * OB_PI - (double)diff);
+        if (diff < maxdiff) { maxdiff = diff; pick = i; }
+      }
+    }
+    avail[pick] = 0;
+    iret[w++] = pick;
+  }
+}
+
+// dBoxBox, box.cpp:331-712.  Returns number of contacts (pos/depth filled), normal, depth, code.
+OB_HDN int ob_box_box(const real *p1, const real *R1, const real *side1, const real *p2, const real *R2,
+                      const real *side2, real *normal, real *depth, int *return_code, int flags, ObCg *contact) {
+  const real fudge_factor = OB_REAL(1.05);
+  real p[3], pp[3], normalC[3] = {0, 0, 0};
+  const real *normalR = 0;
+  real A[3], B[3], R11, R12, R13, R21, R22, R23, R31, R32, R33, Q11, Q12, Q13, Q21, Q22, Q23, Q31, Q32, Q33, s, s2, l,
+      expr1_val;
+  int i, j, invert_normal, code;
+  const int unimportant = (flags & 0x80000000u) != 0;
+
+  p[0] = p2[0] - p1[0]; p[1] = p2[1] - p1[1]; p[2] = p2[2] - p1[2];
+  ob_mul1_331(pp, R1, p);
+  A[0] = side1[0] * OB_REAL(0.5); A[1] = side1[1] * OB_REAL(0.5); A[2] = side1[2] * OB_REAL(0.5);
+  B[0] = side2[0] * OB_REAL(0.5); B[1] = side2[1] * OB_REAL(0.5); B[2] = side2[2] * OB_REAL(0.5);
+
+  R11 = ob_dot44(R1 + 0, R2 + 0); R12 = ob_dot44(R1 + 0, R2 + 1); R13 = ob_dot44(R1 + 0, R2 + 2);
+  R21 = ob_dot44(R1 + 1, R2 + 0); R22 = ob_dot44(R1 + 1, R2 + 1); R23 = ob_dot44(R1 + 1, R2 + 2);
+  R31 = ob_dot44(R1 + 2, R2 + 0); R32 = ob_dot44(R1 + 2, R2 + 1); R33 = ob_dot44(R1 + 2, R2 + 2);
+  Q11 = ob_fabs(R11); Q12 = ob_fabs(R12); Q13 = ob_fabs(R13);
+  Q21 = ob_fabs(R21); Q22 = ob_fabs(R22); Q23 = ob_fabs(R23);
+  Q31 = ob_fabs(R31); Q32 = ob_fabs(R32); Q33 = ob_fabs(R33);
+
+  do {
+#define OB_TST(expr1, expr2, norm, cc)        \
+  expr1_val = (expr1);                        \
+  s2 = ob_fabs(expr1_val) - (expr2);          \
+  if (s2 > 0) return 0;                       \
+  if (s2 > s) {                               \
+    s = s2;                                   \
+    normalR = norm;                           \
+    invert_normal = ((expr1_val) < 0);        \
+    code = (cc);                              \
+    if (unimportant) break;                   \
+  }
+    s = -OB_INF;
+    invert_normal = 0;
+    code = 0;
+    OB_TST(pp[0], (A[0] + B[0] * Q11 + B[1] * Q12 + B[2] * Q13), R1 + 0, 1);
+    OB_TST(pp[1], (A[1] + B[0] * Q21 + B[1] * Q22 + B[2] * Q23), R1 + 1, 2);
+    OB_TST(pp[2], (A[2] + B[0] * Q31 + B[1] * Q32 + B[2] * Q33), R1 + 2, 3);
+    OB_TST(ob_dot41(R2 + 0, p), (A[0] * Q11 + A[1] * Q21 + A[2] * Q31 + B[0]), R2 + 0, 4);
+    OB_TST(ob_dot41(R2 + 1, p), (A[0] * Q12 + A[1] * Q22 + A[2] * Q32 + B[1]), R2 + 1, 5);
+    OB_TST(ob_dot41(R2 + 2, p), (A[0] * Q13 + A[1] * Q23 + A[2] * Q33 + B[2]), R2 + 2, 6);
+#undef OB_TST
+#define OB_TST(expr1, expr2, n1, n2, n3, cc)                        \
+  expr1_val = (expr1);                                              \
+  s2 = ob_fabs(expr1_val) - (expr2);                                \
+  if (s2 > 0) return 0;                                             \
+  l = ob_sqrt((n1) * (n1) + (n2) * (n2) + (n3) * (n3));             \
+  if (l > 0) {                                                      \
+    s2 /= l;                                                        \
+    if (s2 * fudge_factor > s) {                                    \
+      s = s2;                                                       \
+      normalR = 0;                                                  \
+      normalC[0] = (n1) / l; normalC[1] = (n2) / l; normalC[2] = (n3) / l; \
+      invert_normal = ((expr1_val) < 0);                            \
+      code = (cc);                                                  \
+      if (unimportant) break;                                       \
+    }                                                               \
+  }
+    OB_TST(pp[2] * R21 - pp[1] * R31, (A[1] * Q31 + A[2] * Q21 + B[1] * Q13 + B[2] * Q12), 0, -R31, R21, 7);
+    OB_TST(pp[2] * R22 - pp[1] * R32, (A[1] * Q32 + A[2] * Q22 + B[0] * Q13 + B[2] * Q11), 0, -R32, R22, 8);
+    OB_TST(pp[2] * R23 - pp[1] * R33, (A[1] * Q33 + A[2] * Q23 + B[0] * Q12 + B[1] * Q11), 0, -R33, R23, 9);
+    OB_TST(pp[0] * R31 - pp[2] * R11, (A[0] * Q31 + A[2] * Q11 + B[1] * Q23 + B[2] * Q22), R31, 0, -R11, 10);
+    OB_TST(pp[0] * R32 - pp[2] * R12, (A[0] * Q32 + A[2] * Q12 + B[0] * Q23 + B[2] * Q21), R32, 0, -R12, 11);
+    OB_TST(pp[0] * R33 - pp[2] * R13, (A[0] * Q33 + A[2] * Q13 + B[0] * Q22 + B[1] * Q21), R33, 0, -R13, 12);
+    OB_TST(pp[1] * R11 - pp[0] * R21, (A[0] * Q21 + A[1] * Q11 + B[1] * Q33 + B[2] * Q32), -R21, R11, 0, 13);
+    OB_TST(pp[1] * R12 - pp[0] * R22, (A[0] * Q22 + A[1] * Q12 + B[0] * Q33 + B[2] * Q31), -R22, R12, 0, 14);
+    OB_TST(pp[1] * R13 - pp[0] * R23, (A[0] * Q23 + A[1] * Q13 + B[0] * Q32 + B[1] * Q31), -R23, R13, 0, 15);
+#undef OB_TST
+  } while (0);
+
+  if (!code) return 0;
+
+  if (normalR) { normal[0] = normalR[0]; normal[1] = normalR[4]; normal[2] = normalR[8]; }
+  else ob_mul0_331(normal, R1, normalC);
+  if (invert_normal) { normal[0] = -normal[0]; normal[1] = -normal[1]; normal[2] = -normal[2]; }
+  *depth = -s;
+
+  if (code > 6) {
+    // edge-edge contact
+    real pa[3], pb[3], sign;
+    for (i = 0; i < 3; i++) pa[i] = p1[i];
+    for (j = 0; j < 3; j++) {
+      sign = (ob_dot14(normal, R1 + j) > 0) ? OB_REAL(1.0) : OB_REAL(-1.0);
+      for (i = 0; i < 3; i++) pa[i] += sign * A[j] * R1[i * 4 + j];
+    }
+    for (i = 0; i < 3; i++) pb[i] = p2[i];
+    for (j = 0; j < 3; j++) {
+      sign = (ob_dot14(normal, R2 + j) > 0) ? OB_REAL(-1.0) : OB_REAL(1.0);
+      for (i = 0; i < 3; i++) pb[i] += sign * B[j] * R2[i * 4 + j];
+    }
+    real alpha, beta, ua[3], ub[3];
+    for (i = 0; i < 3; i++) ua[i] = R1[((code) - 7) / 3 + i * 4];
+    for (i = 0; i < 3; i++) ub[i] = R2[((code) - 7) % 3 + i * 4];
+    ob_line_closest_approach(pa, ua, pb, ub, &alpha, &beta);
+    for (i = 0; i < 3; i++) pa[i] += ua[i] * alpha;
+    for (i = 0; i < 3; i++) pb[i] += ub[i] * beta;
+    for (i = 0; i < 3; i++) contact[0].pos[i] = OB_REAL(0.5) * (pa[i] + pb[i]);
+    contact[0].depth = *depth;
+    *return_code = code;
+    return 1;
+  }
+
+  // face-something contact
+  const real *Ra, *Rb, *pa, *pb, *Sa, *Sb;
+  if (code <= 3) { Ra = R1; Rb = R2; pa = p1; pb = p2; Sa = A; Sb = B; }
+  else { Ra = R2; Rb = R1; pa = p2; pb = p1; Sa = B; Sb = A; }
+
+  real normal2[3], nr[3], anr[3];
+  if (code <= 3) { normal2[0] = normal[0]; normal2[1] = normal[1]; normal2[2] = normal[2]; }
+  else { normal2[0] = -normal[0]; normal2[1] = -normal[1]; normal2[2] = -normal[2]; }
+  ob_mul1_331(nr, Rb, normal2);
+  anr[0] = ob_fabs(nr[0]); anr[1] = ob_fabs(nr[1]); anr[2] = ob_fabs(nr[2]);
+
+  int lanr, a1, a2;
+  if (anr[1] > anr[0]) {
+    if (anr[1] > anr[2]) { a1 = 0; lanr = 1; a2 = 2; }
+    else { a1 = 0; a2 = 1; lanr = 2; }
+  } else {
+    if (anr[0] > anr[2]) { lanr = 0; a1 = 1; a2 = 2; }
+    else { a1 = 0; a2 = 1; lanr = 2; }
+  }
+
+  real center[3];
+  if (nr[lanr] < 0) { for (i = 0; i < 3; i++) center[i] = pb[i] - pa[i] + Sb[lanr] * Rb[i * 4 + lanr]; }
+  else { for (i = 0; i < 3; i++) center[i] = pb[i] - pa[i] - Sb[lanr] * Rb[i * 4 + lanr]; }
+
+  int codeN, code1, code2;
+  if (code <= 3) codeN = code - 1; else codeN = code - 4;
+  if (codeN == 0) { code1 = 1; code2 = 2; }
+  else if (codeN == 1) { code1 = 0; code2 = 2; }
+  else { code1 = 0; code2 = 1; }
+
+  real quad[8];
+  real c1, c2, m11, m12, m21, m22;
+  c1 = ob_dot14(center, Ra + code1);
+  c2 = ob_dot14(center, Ra + code2);
+  m11 = ob_dot44(Ra + code1, Rb + a1);
+  m12 = ob_dot44(Ra + code1, Rb + a2);
+  m21 = ob_dot44(Ra + code2, Rb + a1);
+  m22 = ob_dot44(Ra + code2, Rb + a2);
+  {
+    real k1 = m11 * Sb[a1], k2 = m21 * Sb[a1], k3 = m12 * Sb[a2], k4 = m22 * Sb[a2];
+    quad[0] = c1 - k1 - k3; quad[1] = c2 - k2 - k4;
+    quad[2] = c1 - k1 + k3; quad[3] = c2 - k2 + k4;
+    quad[4] = c1 + k1 + k3; quad[5] = c2 + k2 + k4;
+    quad[6] = c1 + k1 - k3; quad[7] = c2 + k2 - k4;
+  }
+  real rect[2] = {Sa[code1], Sa[code2]};
+  real ret[16];
+  int n = ob_intersect_rect_quad(rect, quad, ret);
+  if (n < 1) return 0;
+
+  real point[3 * 8];
+  real dep[8];
+  real det1 = ob_recip(m11 * m22 - m12 * m21);
+  m11 *= det1; m12 *= det1; m21 *= det1; m22 *= det1;
+  int cnum = 0;
+  for (j = 0; j < n; j++) {
+    real k1 = m22 * (ret[j * 2] - c1) - m12 * (ret[j * 2 + 1] - c2);
+    real k2 = -m21 * (ret[j * 2] - c1) + m11 * (ret[j * 2 + 1] - c2);
+    for (i = 0; i < 3; i++) point[cnum * 3 + i] = center[i] + k1 * Rb[i * 4 + a1] + k2 * Rb[i * 4 + a2];
+    dep[cnum] = Sa[codeN] - ob_dot(normal2, point + cnum * 3);
+    if (dep[cnum] >= 0) {
+      ret[cnum * 2] = ret[j * 2];
+      ret[cnum * 2 + 1] = ret[j * 2 + 1];
+      cnum++;
+      if ((unsigned)(cnum | 0x80000000u) == ((unsigned)flags & (0xffffu | 0x80000000u))) break;
+    }
+  }
+  if (cnum < 1) return 0;
+
+  int maxc = flags & 0xffff;
+  if (maxc > cnum) maxc = cnum;
+  if (maxc < 1) maxc = 1;
+
+  if (cnum <= maxc) {
+    for (j = 0; j < cnum; j++) {
+      for (i = 0; i < 3; i++) contact[j].pos[i] = point[j * 3 + i] + pa[i];
+      contact[j].depth = dep[j];
+    }
+  } else {
+    int i1 = 0;
+    real maxdepth = dep[0];
+    for (i = 1; i < cnum; i++) if (dep[i] > maxdepth) { maxdepth = dep[i]; i1 = i; }
+    int iret[8];
+    ob_cull_points(cnum, ret, maxc, i1, iret);
+    for (j = 0; j < maxc; j++) {
+      for (i = 0; i < 3; i++) contact[j].pos[i] = point[iret[j] * 3 + i] + pa[i];
+      contact[j].depth = dep[iret[j]];
+    }
+    cnum = maxc;
+  }
+  *return_code = code;
+  return cnum;
+}
+
+OB_HD int ob_collide_box_box(const ObPose &o1, const ObPose &o2, int flags, ObCg *contact) {
+  real normal[3], depth;
+  int code;
+  int num = ob_box_box(o1.pos, o1.R, o1.p, o2.pos, o2.R, o2.p, normal, &depth, &code, flags, contact);
+  for (int i = 0; i < num; i++) {
+    contact[i].normal[0] = -normal[0];
+    contact[i].normal[1] = -normal[1];
+    contact[i].normal[2] = -normal[2];
+  }
+  return num;
+}
+
+// dCollideBoxPlane, box.cpp:745-878
+OB_HDN int ob_collide_box_plane(const ObPose &o1, const ObPose &o2, int flags, ObCg *contact) {
+  int ret = 0;
+  const real *R = o1.R;
+  const real *n = o2.p;
+  const real *side = o1.p;
+  real Q1 = ob_dot14(n, R + 0), Q2 = ob_dot14(n, R + 1), Q3 = ob_dot14(n, R + 2);
+  real A1 = side[0] * Q1, A2 = side[1] * Q2, A3 = side[2] * Q3;
+  real B1 = ob_fabs(A1), B2 = ob_fabs(A2), B3 = ob_fabs(A3);
+  real depth = n[3] + OB_REAL(0.5) * (B1 + B2 + B3) - ob_dot(n, o1.pos);
+  if (depth < 0) return 0;
+  int maxc = flags & 0xffff;
+  if (maxc > 4) maxc = 4;
+  real p[3] = {o1.pos[0], o1.pos[1], o1.pos[2]};
+#define OB_FOO(i, op)                          \
+  p[0] op OB_REAL(0.5) * side[i] * R[0 + i];   \
+  p[1] op OB_REAL(0.5) * side[i] * R[4 + i];   \
+  p[2] op OB_REAL(0.5) * side[i] * R[8 + i];
+#define OB_BAR(i, AA) if (AA > 0) { OB_FOO(i, -=) } else { OB_FOO(i, +=) }
+  OB_BAR(0, A1);
+  OB_BAR(1, A2);
+  OB_BAR(2, A3);
+#undef OB_FOO
+#undef OB_BAR
+  contact[0].pos[0] = p[0]; contact[0].pos[1] = p[1]; contact[0].pos[2] = p[2];
+  contact[0].depth = depth;
+  ret = 1;
+  if (maxc == 1) goto done;
+#define OB_FOO(i, j, op)                           \
+  contact[i].pos[0] = p[0] op side[j] * R[0 + j];  \
+  contact[i].pos[1] = p[1] op side[j] * R[4 + j];  \
+  contact[i].pos[2] = p[2] op side[j] * R[8 + j];
+#define OB_BAR(ctact, sd, AA, BB)                                    \
+  if (depth - BB < 0) goto done;                                     \
+  if (AA > 0) { OB_FOO(ctact, sd, +); } else { OB_FOO(ctact, sd, -); } \
+  contact[ctact].depth = depth - BB;                                 \
+  ret++;
+  if (B1 < B2) {
+    if (B3 < B1) goto use_side_3;
+    else {
+      OB_BAR(1, 0, A1, B1);
+      if (maxc == 2) goto done;
+      if (B2 < B3) goto contact2_2; else goto contact2_3;
+    }
+  } else {
+    if (B3 < B2) {
+    use_side_3:
+      OB_BAR(1, 2, A3, B3);
+      if (maxc == 2) goto done;
+      if (B1 < B2) goto contact2_1; else goto contact2_2;
+    } else {
+      OB_BAR(1, 1, A2, B2);
+      if (maxc == 2) goto done;
+      if (B1 < B3) goto contact2_1; else goto contact2_3;
+    }
+  }
+contact2_1: OB_BAR(2, 0, A1, B1); goto done;
+contact2_2: OB_BAR(2, 1, A2, B2); goto done;
+contact2_3: OB_BAR(2, 2, A3, B3); goto done;
+#undef OB_FOO
+#undef OB_BAR
+done:
+  if (maxc == 4 && ret == 3) {
+    real d4 = contact[1].depth + contact[2].depth - depth;
+    if (d4 > 0) {
+      contact[3].pos[0] = contact[1].pos[0] + contact[2].pos[0] - p[0];
+      contact[3].pos[1] = contact[1].pos[1] + contact[2].pos[1] - p[1];
+      contact[3].pos[2] = contact[1].pos[2] + contact[2].pos[2] - p[2];
+      contact[3].depth = d4;
+      ret++;
+    }
+  }
+  for (int i = 0; i < ret; i++) { contact[i].normal[0] = n[0]; contact[i].normal[1] = n[1]; contact[i].normal[2] = n[2]; }
+  return ret;
+}
+
+// upper bound on contacts a class pair can emit (used to lay out contact slots)
+OB_HD int ob_pair_max_contacts(int t1, int t2, int maxc) {
+  int lo = t1 < t2 ? t1 : t2, hi = t1 < t2 ? t2 : t1;
+  int cap;
+  if (lo == OB_GEOM_SPHERE) cap = (hi == OB_GEOM_SPHERE || hi == OB_GEOM_BOX || hi == OB_GEOM_PLANE || hi == OB_GEOM_CAPSULE) ? 1 : 0;
+  else if (lo == OB_GEOM_BOX && hi == OB_GEOM_BOX) cap = 8;
+  else if (lo == OB_GEOM_BOX && hi == OB_GEOM_PLANE) cap = 4;
+  else if (lo == OB_GEOM_BOX && hi == OB_GEOM_CAPSULE) cap = 1;
+  else if (lo == OB_GEOM_CAPSULE && hi == OB_GEOM_CAPSULE) cap = 2;
+  else if (lo == OB_GEOM_CAPSULE && hi == OB_GEOM_PLANE) cap = 2;
+  else cap = 0;
+  return cap < maxc ? cap : maxc;
+}
+
+// dCollide for primitive class pairs: table lookup + reverse fix-up.
+// Returns the contact count; `swapped` tells the caller g1/g2 were exchanged.
+OB_HD int ob_collide_pair(const ObPose &o1, const ObPose &o2, int flags, ObCg *c, int *swapped) {
+  int t1 = o1.type, t2 = o2.type, n = 0, rev = 0;
+  for (int i = 0; i < OB_MAXC_LOCAL; i++) { c[i].side1 = -1; c[i].side2 = -1; }
+  if (t1 == OB_GEOM_SPHERE && t2 == OB_GEOM_SPHERE) n = ob_collide_spheres(o1.pos, o1.p[0], o2.pos, o2.p[0], c);
+  else if (t1 == OB_GEOM_SPHERE && t2 == OB_GEOM_BOX) n = ob_collide_sphere_box(o1, o2, c);
+  else if (t1 == OB_GEOM_BOX && t2 == OB_GEOM_SPHERE) { n = ob_collide_sphere_box(o2, o1, c); rev = 1; }
+  else if (t1 == OB_GEOM_SPHERE && t2 == OB_GEOM_PLANE) n = ob_collide_sphere_plane(o1, o2, c);
+  else if (t1 == OB_GEOM_PLANE && t2 == OB_GEOM_SPHERE) { n = ob_collide_sphere_plane(o2, o1, c); rev = 1; }
+  else if (t1 == OB_GEOM_BOX && t2 == OB_GEOM_BOX) n = ob_collide_box_box(o1, o2, flags, c);
+  else if (t1 == OB_GEOM_BOX && t2 == OB_GEOM_PLANE) n = ob_collide_box_plane(o1, o2, flags, c);
+  else if (t1 == OB_GEOM_PLANE && t2 == OB_GEOM_BOX) { n = ob_collide_box_plane(o2, o1, flags, c); rev = 1; }
+  if (rev) {
+    for (int i = 0; i < n; i++) {
+      c[i].normal[0] = -c[i].normal[0]; c[i].normal[1] = -c[i].normal[1]; c[i].normal[2] = -c[i].normal[2];
+      int t = c[i].side1; c[i].side1 = c[i].side2; c[i].side2 = t;
+    }
+  }
+  *swapped = rev;
+  return n;
+}

@@ -1,0 +1,148 @@
+// ob_host.h — host-side object model behind the ODE C API handles.
+//
+// This is the mirror of the reference's object model for the hot path only
+// (ode/src/objects.h:38-159, ode/src/collision_kernel.h:96-240,
+// ode/src/joints/joint.h:58-190): worlds, bodies, joints, geoms and spaces with
+// the same linked-list disciplines (push-front everywhere, dirty geoms move to
+// the head), because those list orders ARE the constraint ordering contract
+// (SURVEY.md Appendix A).  No physics is computed here: dSpaceCollide, dCollide
+// and dWorldQuickStep marshal into the device layout (ob_types.h) and launch
+// the CUDA kernels; scene construction and getters/setters are plain host code.
+#pragma once
+#include <stddef.h>
+#include <vector>
+#include "../../include/ode_b200/ode.h"
+#include "ob_types.h"
+
+struct dxJoint;
+struct dxJointNode {
+  dxJoint *joint;   // joint this node belongs to
+  dxBody *body;     // *other* body this node connects to (ode/src/joints/joint.h:45-49)
+  dxJointNode *next;
+};
+
+struct dxAutoDisable {
+  dReal idle_time; int idle_steps; dReal linear_average_threshold, angular_average_threshold;
+  unsigned average_samples;
+};
+struct dxDamping { dReal linear_scale, angular_scale, linear_threshold, angular_threshold; };
+
+struct dxWorld {
+  dxBody *firstbody;
+  dxJoint *firstjoint;
+  int nb, nj;
+  dVector3 gravity;
+  dReal global_erp, global_cfm;
+  dxAutoDisable adis;
+  int body_flags;
+  int qs_iterations; dReal qs_w;
+  dReal contact_max_vel, contact_min_depth;
+  dxDamping dampingp;
+  dReal max_angular_speed;
+  struct dxBatch *bound_batch;   // non-null while a batch owns the device copy
+};
+
+struct dxBody {
+  dxWorld *world;
+  dxBody *next; dxBody **tome;
+  int tag; void *userdata;
+  dxJointNode *firstjoint;
+  unsigned flags;
+  dxGeom *geom;
+  dMass mass;
+  dMatrix3 invI;
+  dReal invMass;
+  dVector3 pos; dMatrix3 R;     // posr
+  dQuaternion q;
+  dVector3 lvel, avel, facc, tacc, finite_rot_axis;
+  dxAutoDisable adis;
+  dReal adis_timeleft; int adis_stepsleft;
+  unsigned average_counter; int average_ready;
+  dxDamping dampingp;
+  dReal max_angular_speed;
+  int batch_index;               // index inside the bound batch world slot
+};
+
+enum { dJOINT_INGROUP = 1, dJOINT_REVERSE = 2, dJOINT_TWOBODIES = 4, dJOINT_DISABLED = 8 };
+
+struct dxLimot {   // dxJointLimitMotor, ode/src/joints/joint.h:196-213
+  dReal vel, fmax, lostop, histop, fudge_factor, normal_cfm, stop_erp, stop_cfm, bounce;
+  int limit; dReal limit_err;
+};
+
+struct dxJoint {
+  dxWorld *world;
+  dxJoint *next; dxJoint **tome;
+  int tag; void *userdata;
+  int type;
+  unsigned flags;
+  dxJointNode node[2];
+  dJointFeedback *feedback;
+  dxJointGroup *group;
+  // contact
+  dContact contact;
+  // ball / hinge / hinge2 (body-frame anchors and axes)
+  dVector3 anchor1, anchor2, axis1, axis2;
+  dQuaternion qrel;
+  dReal erp, cfm;               // ball
+  dxLimot limot, limot2;        // hinge: limot; hinge2: limot (axis 1) + limot2 (axis 2)
+  dReal c0, s0, v1[4], v2[4];   // hinge2
+  dReal susp_erp, susp_cfm;     // hinge2
+};
+
+struct dxJointGroup {
+  std::vector<dxJoint *> joints;   // creation order
+};
+
+enum {  // geom flags, ode/src/collision_kernel.h:64-80
+  GEOM_DIRTY = 1, GEOM_POSR_BAD = 2, GEOM_AABB_BAD = 4, GEOM_PLACEABLE = 8, GEOM_ENABLED = 16, GEOM_ZERO_SIZED = 32
+};
+
+struct dxPosR { dVector3 pos; dMatrix3 R; };
+
+struct dxGeom {
+  int type;
+  int gflags;
+  void *data;
+  dxBody *body;
+  dxGeom *body_next;
+  dxPosR *final_posr;     // body's pos/R when attached without offset
+  dxPosR *offset_posr;
+  dxPosR own_posr;        // storage when not borrowed from the body
+  dxPosR off_storage;
+  dxGeom *next; dxGeom **tome;
+  dxSpace *parent_space;
+  dReal aabb[6];
+  unsigned long category_bits, collide_bits;
+  dReal p[4];             // sphere r | box sides | plane a,b,c,d | capsule r,l
+  int batch_index;
+  bool is_space;
+  virtual ~dxGeom() {}
+};
+
+struct dxSpace : public dxGeom {
+  int count;
+  dxGeom *first;
+  int cleanup, sublevel, lock_count;
+  int minlevel, maxlevel;   // hash space
+  int axisorder;            // SAP
+  struct dxBatch *bound_batch;
+};
+
+// ---- internals shared between ob_host.cpp, ob_batch.cpp, ob_dropin.cpp ---------
+void ob_error(int num, const char *fmt, ...);      // dError: message, then exit(1) unless handled
+void ob_debug(int num, const char *fmt, ...);      // dDebug: message, then abort() unless handled
+void ob_message(int num, const char *fmt, ...);
+void ob_set_last_error(const char *fmt, ...);
+void ob_geom_moved(dxGeom *g);                      // dGeomMoved
+void ob_geom_recompute_posr(dxGeom *g);
+void ob_body_posr(dxBody *b, dxPosR *out);
+extern uint32_t ob_global_seed;
+void ob_joint_init_type(dxJoint *j);             // ob_joints.cpp
+void ob_joint_set_relative_values(dxJoint *j);   // ob_joints.cpp
+
+// drop-in compute entry points implemented over the CUDA backend (ob_dropin.cpp)
+void ob_dropin_space_collide(dxSpace *space, void *data, dNearCallback *cb);
+void ob_dropin_space_collide2(dxGeom *g1, dxGeom *g2, void *data, dNearCallback *cb);
+int ob_dropin_collide(dxGeom *o1, dxGeom *o2, int flags, dContactGeom *contact, int skip);
+int ob_dropin_quickstep(dxWorld *w, dReal h);

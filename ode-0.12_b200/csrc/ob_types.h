@@ -1,0 +1,112 @@
+// ob_types.h — device-resident data layout of a batch of independent worlds.
+//
+// Layout in HBM: every per-world array is one contiguous, 16-byte aligned block
+// ("world slot"), slots are laid out back to back with a fixed stride derived
+// from the batch capacities, so one CTA pulls its world with coalesced 128-bit
+// loads and neighbouring CTAs touch neighbouring memory.  Index conventions
+// carry the reference's ORDER semantics:
+//   * body index  = position in dxWorld::firstbody list (0 = newest body),
+//     so island discovery walks bodies 0..nb-1 (ode/src/util.cpp:420).
+//   * geom index  = creation index inside the bound space; the space's linked
+//     list order is the separate permutation `glist` (head first), rewritten
+//     every step the way dGeomMoved does (ode/src/collision_space.cpp:47-75).
+//   * contact joints are numbered in creation order per step; a body's joint
+//     list is "newest first" (ode/src/ode.cpp:1376-1386).
+#pragma once
+#include "ob_math.h"
+
+enum {  // body flags, ode/src/objects.h:38-48
+  OB_BODY_FINITE_ROT = 1, OB_BODY_FINITE_ROT_AXIS = 2, OB_BODY_DISABLED = 4, OB_BODY_NO_GRAVITY = 8,
+  OB_BODY_AUTO_DISABLE = 16, OB_BODY_LIN_DAMP = 32, OB_BODY_ANG_DAMP = 64, OB_BODY_MAX_ANG_SPEED = 128,
+  OB_BODY_GYROSCOPIC = 256
+};
+enum { OB_GEOM_SPHERE = 0, OB_GEOM_BOX = 1, OB_GEOM_CAPSULE = 2, OB_GEOM_PLANE = 4, OB_GEOM_RAY = 5, OB_GEOM_TRIMESH = 8 };
+enum { OB_GEOM_ENABLED = 1, OB_GEOM_HAS_OFFSET = 2, OB_GEOM_ZERO_SIZED = 4 };
+enum { OB_SPACE_HASH = 0, OB_SPACE_SAP = 1, OB_SPACE_SIMPLE = 2 };
+enum { OB_ERR_CONTACT_OVERFLOW = 1, OB_ERR_ROW_OVERFLOW = 2, OB_ERR_PAIR_OVERFLOW = 4 };
+
+// mutable body state (13 reals of ODE state + cached R + accumulators)
+struct __attribute__((aligned(16))) ObBodyDyn {
+  real pos[3]; uint32_t flags;
+  real q[4];
+  real lvel[3]; int adis_stepsleft;
+  real avel[3]; real adis_timeleft;
+  real facc[4];
+  real tacc[4];
+  real R[12];
+};
+// per-body constants
+struct __attribute__((aligned(16))) ObBodyConst {
+  real mass, invMass, max_angular_speed, pad0;
+  real I[12];     // body-frame inertia (mass.I)
+  real invI[12];  // body-frame inverse inertia
+  real finite_rot_axis[4];
+  real damp_lin_scale, damp_ang_scale, damp_lin_thr, damp_ang_thr;
+  real adis_lin_thr, adis_ang_thr, adis_idle_time; int adis_idle_steps;
+  int adis_samples; int geom_first; int npermjoints; int pad1;
+};
+struct __attribute__((aligned(16))) ObGeom {
+  int type; int body; uint32_t cat, col;        // body = -1: static
+  int flags; int body_next; int pad[2];         // body_next: next geom of the same body (dGeomGetBodyNext)
+  real p[4];                                     // sphere r | box lx,ly,lz | plane a,b,c,d | capsule r,l
+  real pos[4];                                   // static pose or offset pose
+  real R[12];
+};
+struct __attribute__((aligned(16))) ObWorld {
+  real gravity[4];
+  real erp, cfm, sor_w, max_vel;
+  real min_depth; int iters; int nb; int ng;
+  uint32_t seed; int hash_minlevel, hash_maxlevel, space_type;
+  int npermjoints; int status; int pad[2];
+};
+// surface parameters of the contact policy, copied into every contact joint
+struct __attribute__((aligned(16))) ObSurface {
+  int mode; real mu, mu2, bounce;
+  real bounce_vel, soft_erp, soft_cfm, motion1;
+  real motion2, motionN, slip1, slip2;
+};
+struct __attribute__((aligned(16))) ObPolicy {
+  uint32_t cat_mask1, cat_mask2; int max_contacts; int skip_if_connected;
+  int skip_static_pairs; int pad[3];
+  ObSurface surface;
+};
+// one generated contact (dContactGeom-equivalent, 48 B single / 80 B double)
+struct __attribute__((aligned(16))) ObContact {
+  real pos[3]; real depth;
+  real normal[3]; int g1;
+  int g2; int side1, side2; int policy;
+};
+
+struct ObCounters {
+  unsigned long long steps, body_steps, pairs, contacts, rows, islands, overflow_worlds;
+};
+
+// capacities + device pointers, passed by value to every kernel
+struct ObBatchDev {
+  int W;        // worlds
+  int NB;       // bodies per world slot
+  int NG;       // geoms per world slot
+  int NP;       // broadphase pairs per world-step
+  int NC;       // contact joints per world-step (also contact slots)
+  int NR;       // constraint rows per world-step
+  int npolicy;
+  ObWorld *world;        // [W]
+  ObBodyDyn *bdyn;       // [W*NB]
+  ObBodyConst *bconst;   // [W*NB]
+  ObGeom *geom;          // [W*NG]
+  int *glist;            // [W*NG] space-list order (head first), geom indices
+  ObPolicy *policy;      // [npolicy]
+  // per-step products (device scratch, also the parity taps)
+  int *npairs;           // [W]
+  int *pairs;            // [W*NP*2] (o1,o2) geom indices in callback order
+  int *ncontacts;        // [W]
+  ObContact *contacts;   // [W*NC] contact joints in creation order
+  real *rowJ;            // [W*NR*12]
+  real *rowiMJ;          // [W*NR*12]
+  real *rowS;            // [W*NR*4]  b(rhs), Ad*cfm, lo, hi
+  int *rowI;             // [W*NR*4]  findex, b1, b2, joint
+  real *lambda;          // [W*NR]
+  int *nrows;            // [W]
+  real *fback;           // [W*NC*6] f1,t1 per contact joint (debug tap, optional)
+  ObCounters *counters;  // [1]
+};

@@ -1,0 +1,122 @@
+"""Read and compare scene_driver traces (see tests/harness/scene_driver.cpp for the layout).
+
+Exact observables (broadphase pair sequence, contact count, per-contact geom ids,
+space-list order, LCG seed) are compared for equality; floating observables
+(contacts, body state, joint feedback) are reported both as bitwise-equal counts
+and as max relative error  |a-b|_inf / max(1,|b|_inf).
+"""
+import struct
+import sys
+
+import numpy as np
+
+
+def read_trace(path):
+    data = open(path, "rb").read()
+    magic, rs, nworlds, nsteps = struct.unpack_from("<Iiii", data, 0)
+    assert magic == 0x5254444F, "bad trace magic"
+    rt = np.float32 if rs == 4 else np.float64
+    off = 16
+    steps = []
+
+    def take(dtype, n):
+        nonlocal off
+        a = np.frombuffer(data, dtype=dtype, count=n, offset=off)
+        off += a.nbytes
+        return a
+
+    for s in range(nsteps):
+        ws = []
+        for w in range(nworlds):
+            rec = {}
+            ng = int(take(np.int32, 1)[0])
+            rec["glist"] = take(np.int32, ng)
+            nb = int(take(np.int32, 1)[0])
+            rec["state0"] = take(rt, nb * 13).reshape(nb, 13)
+            np_ = int(take(np.int32, 1)[0])
+            rec["pairs"] = take(np.int32, 2 * np_).reshape(np_, 2)
+            nc = int(take(np.int32, 1)[0])
+            cdt = np.dtype([("g", np.int32, 2), ("d", rt, 7)])
+            c = take(cdt, nc)
+            rec["cg"] = c["g"].reshape(nc, 2)
+            rec["cd"] = c["d"].reshape(nc, 7)
+            rec["fb"] = take(rt, nc * 6).reshape(nc, 6)
+            rec["state1"] = take(rt, nb * 13).reshape(nb, 13)
+            rec["seed"] = int(take(np.uint32, 1)[0])
+            ws.append(rec)
+        steps.append(ws)
+    return {"realsize": rs, "nworlds": nworlds, "nsteps": nsteps, "steps": steps}
+
+
+def _relerr(a, b):
+    if a.size == 0:
+        return 0.0
+    a = a.astype(np.float64)
+    b = b.astype(np.float64)
+    m = np.isfinite(a) & np.isfinite(b)
+    if not m.all():
+        if not np.array_equal(np.isnan(a), np.isnan(b)):
+            return float("inf")
+    d = np.abs(np.where(m, a - b, 0.0)).max()
+    return float(d / max(1.0, np.abs(np.where(m, b, 0.0)).max()))
+
+
+def _bits(a):
+    return a.view(np.uint32 if a.dtype == np.float32 else np.uint64)
+
+
+def compare(ta, tb, verbose=False, stop_on_mismatch=True):
+    """Returns a dict of summary statistics. ta = candidate, tb = reference."""
+    assert ta["realsize"] == tb["realsize"] and ta["nworlds"] == tb["nworlds"]
+    n = min(ta["nsteps"], tb["nsteps"])
+    out = {
+        "steps": n, "exact_ok": True, "first_exact_mismatch": None,
+        "pairs": 0, "contacts": 0,
+        "contact_bits_equal": 0, "contact_vals": 0, "state_bits_equal": 0, "state_vals": 0,
+        "fb_bits_equal": 0, "fb_vals": 0,
+        "max_contact_relerr": 0.0, "max_state_relerr": 0.0, "max_fb_relerr": 0.0,
+        "first_state_bit_mismatch": None,
+    }
+    for s in range(n):
+        for w in range(ta["nworlds"]):
+            a, b = ta["steps"][s][w], tb["steps"][s][w]
+            for key in ("glist", "pairs", "cg"):
+                if a[key].shape != b[key].shape or not np.array_equal(a[key], b[key]):
+                    out["exact_ok"] = False
+                    if out["first_exact_mismatch"] is None:
+                        out["first_exact_mismatch"] = (s, w, key)
+                        if verbose:
+                            print("MISMATCH step", s, "world", w, key)
+                            print(" cand:", a[key].tolist()[:40])
+                            print(" ref :", b[key].tolist()[:40])
+            if a["seed"] != b["seed"]:
+                out["exact_ok"] = False
+                if out["first_exact_mismatch"] is None:
+                    out["first_exact_mismatch"] = (s, w, "seed")
+            if not np.array_equal(_bits(a["state0"]), _bits(b["state0"])) and out["first_state_bit_mismatch"] is None:
+                out["first_state_bit_mismatch"] = (s, w, "state0")
+            out["pairs"] += len(b["pairs"])
+            out["contacts"] += len(b["cg"])
+            if a["cd"].shape == b["cd"].shape:
+                out["contact_vals"] += b["cd"].size
+                out["contact_bits_equal"] += int((_bits(a["cd"]) == _bits(b["cd"])).sum())
+                out["max_contact_relerr"] = max(out["max_contact_relerr"], _relerr(a["cd"], b["cd"]))
+                out["fb_vals"] += b["fb"].size
+                out["fb_bits_equal"] += int((_bits(a["fb"]) == _bits(b["fb"])).sum())
+                out["max_fb_relerr"] = max(out["max_fb_relerr"], _relerr(a["fb"], b["fb"]))
+            out["state_vals"] += b["state1"].size
+            eq = _bits(a["state1"]) == _bits(b["state1"])
+            out["state_bits_equal"] += int(eq.sum())
+            if not eq.all() and out["first_state_bit_mismatch"] is None:
+                out["first_state_bit_mismatch"] = (s, w, "state1")
+            out["max_state_relerr"] = max(out["max_state_relerr"], _relerr(a["state1"], b["state1"]))
+        if stop_on_mismatch and not out["exact_ok"]:
+            out["steps"] = s + 1
+            break
+    return out
+
+
+if __name__ == "__main__":
+    r = compare(read_trace(sys.argv[1]), read_trace(sys.argv[2]), verbose=True)
+    for k, v in r.items():
+        print(f"{k}: {v}")

@@ -1,0 +1,410 @@
+// backend_host.cpp — TEST-ONLY execution backend (see ob_backend.h).
+//
+// Runs the per-element device functions of ode-0.12_b200/csrc/ob_*.h in plain
+// sequential loops on the CPU so that their arithmetic and the ordering rules
+// can be compared with the unmodified reference in a container without a GPU.
+// It is linked only into tests/hostsim/libode_b200_hostsim_*.so and is never part
+// of, loaded by, or a fallback for libode_b200_*.so.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <vector>
+#include "../../ode-0.12_b200/csrc/ob_backend.h"
+#include "../../ode-0.12_b200/csrc/ob_broad.h"
+#include "../../ode-0.12_b200/csrc/ob_collide.h"
+#include "../../ode-0.12_b200/csrc/ob_rows.h"
+#include "../../ode-0.12_b200/csrc/ob_solver.h"
+
+struct ObBackend {
+  ObBatchDev d;
+  std::vector<void *> allocs;
+};
+
+template <class T> static T *halloc(ObBackend *b, size_t n) {
+  void *p = calloc(n ? n : 1, sizeof(T));
+  b->allocs.push_back(p);
+  return (T *)p;
+}
+
+ObBackend *obk_create(const ObBatchDev &caps, int, char *, size_t) {
+  ObBackend *b = new ObBackend;
+  b->d = caps;
+  ObBatchDev &d = b->d;
+  size_t W = d.W;
+  d.world = halloc<ObWorld>(b, W);
+  d.bdyn = halloc<ObBodyDyn>(b, W * d.NB);
+  d.bconst = halloc<ObBodyConst>(b, W * d.NB);
+  d.geom = halloc<ObGeom>(b, W * d.NG);
+  d.glist = halloc<int>(b, W * d.NG);
+  d.policy = halloc<ObPolicy>(b, d.npolicy);
+  d.npairs = halloc<int>(b, W);
+  d.pairs = halloc<int>(b, W * d.NP * 2);
+  d.ncontacts = halloc<int>(b, W);
+  d.contacts = halloc<ObContact>(b, W * d.NC);
+  d.rowJ = halloc<real>(b, W * d.NR * 12);
+  d.rowiMJ = halloc<real>(b, W * d.NR * 12);
+  d.rowS = halloc<real>(b, W * d.NR * 4);
+  d.rowI = halloc<int>(b, W * d.NR * 4);
+  d.lambda = halloc<real>(b, W * d.NR);
+  d.nrows = halloc<int>(b, W);
+  d.fback = halloc<real>(b, W * d.NC * 6);
+  d.counters = halloc<ObCounters>(b, 1);
+  return b;
+}
+void obk_destroy(ObBackend *b) { for (size_t i = 0; i < b->allocs.size(); i++) free(b->allocs[i]); delete b; }
+ObBatchDev *obk_arrays(ObBackend *b) { return &b->d; }
+int obk_h2d(ObBackend *, void *dst, const void *src, size_t n) { memcpy(dst, src, n); return 0; }
+int obk_d2h(ObBackend *, void *dst, const void *src, size_t n) { memcpy(dst, src, n); return 0; }
+int obk_memset(ObBackend *, void *dst, int v, size_t n) { memset(dst, v, n); return 0; }
+int obk_sync(ObBackend *) { return 0; }
+void *obk_stream(ObBackend *) { return 0; }
+long long obk_launch_count(void) { return 0; }
+
+int obk_get_state(ObBackend *b, real *pos3, real *quat4, real *lvel3, real *avel3) {
+  ObBatchDev &d = b->d;
+  for (int w = 0; w < d.W; w++) {
+    int nb = d.world[w].nb;
+    for (int c = 0; c < d.NB; c++) {
+      size_t o = (size_t)w * d.NB + c;
+      if (c >= nb) continue;
+      const ObBodyDyn &s = d.bdyn[(size_t)w * d.NB + (nb - 1 - c)];
+      for (int k = 0; k < 3; k++) { if (pos3) pos3[o * 3 + k] = s.pos[k]; if (lvel3) lvel3[o * 3 + k] = s.lvel[k]; if (avel3) avel3[o * 3 + k] = s.avel[k]; }
+      for (int k = 0; k < 4; k++) if (quat4) quat4[o * 4 + k] = s.q[k];
+    }
+  }
+  return 0;
+}
+int obk_set_state(ObBackend *b, const real *pos3, const real *quat4, const real *lvel3, const real *avel3) {
+  ObBatchDev &d = b->d;
+  for (int w = 0; w < d.W; w++) {
+    int nb = d.world[w].nb;
+    for (int c = 0; c < nb; c++) {
+      size_t o = (size_t)w * d.NB + c;
+      ObBodyDyn &s = d.bdyn[(size_t)w * d.NB + (nb - 1 - c)];
+      for (int k = 0; k < 3; k++) { if (pos3) s.pos[k] = pos3[o * 3 + k]; if (lvel3) s.lvel[k] = lvel3[o * 3 + k]; if (avel3) s.avel[k] = avel3[o * 3 + k]; }
+      if (quat4) { for (int k = 0; k < 4; k++) s.q[k] = quat4[o * 4 + k]; ob_safe_normalize4(s.q); ob_RfromQ(s.R, s.q); }
+    }
+  }
+  return 0;
+}
+int obk_add_forces(ObBackend *b, const real *f3, const real *t3) {
+  ObBatchDev &d = b->d;
+  for (int w = 0; w < d.W; w++) {
+    int nb = d.world[w].nb;
+    for (int c = 0; c < nb; c++) {
+      size_t o = (size_t)w * d.NB + c;
+      ObBodyDyn &s = d.bdyn[(size_t)w * d.NB + (nb - 1 - c)];
+      for (int k = 0; k < 3; k++) { if (f3) s.facc[k] += f3[o * 3 + k]; if (t3) s.tacc[k] += t3[o * 3 + k]; }
+    }
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+static void geom_pose(const ObBatchDev &d, int w, int gi, ObPose *o) {
+  const ObGeom &g = d.geom[(size_t)w * d.NG + gi];
+  o->type = g.type;
+  for (int k = 0; k < 4; k++) o->p[k] = g.p[k];
+  if (g.body >= 0) {
+    const ObBodyDyn &b = d.bdyn[(size_t)w * d.NB + g.body];
+    if (g.flags & OB_GEOM_HAS_OFFSET) {
+      ob_mul0_331(o->pos, b.R, g.pos);
+      o->pos[0] += b.pos[0]; o->pos[1] += b.pos[1]; o->pos[2] += b.pos[2];
+      ob_mul0_333(o->R, b.R, g.R);
+      o->R[3] = o->R[7] = o->R[11] = 0;
+    } else {
+      for (int k = 0; k < 3; k++) o->pos[k] = b.pos[k];
+      for (int k = 0; k < 12; k++) o->R[k] = b.R[k];
+    }
+  } else {
+    for (int k = 0; k < 3; k++) o->pos[k] = g.pos[k];
+    for (int k = 0; k < 12; k++) o->R[k] = g.R[k];
+  }
+}
+
+struct PairRec { ObPairKey key; int o1, o2; };
+static bool pair_less(const PairRec &a, const PairRec &b) { return ob_key_less(a.key, b.key); }
+
+static void collide_world(ObBatchDev &d, int w) {
+  ObWorld &W = d.world[w];
+  int ng = W.ng;
+  const int *glist = d.glist + (size_t)w * d.NG;
+  std::vector<ObPose> pose(ng);
+  std::vector<real> aabb(6 * ng);
+  std::vector<ObCellBox> cb(ng);
+  std::vector<int> hr(ng), br(ng), en(ng);
+  int nh = 0, nbig = 0;
+  for (int i = 0; i < ng; i++) {   // i = walk index
+    int gi = glist[i];
+    const ObGeom &g = d.geom[(size_t)w * d.NG + gi];
+    en[i] = (g.flags & OB_GEOM_ENABLED) && !(g.flags & OB_GEOM_ZERO_SIZED);
+    geom_pose(d, w, gi, &pose[i]);
+    ob_aabb(pose[i], &aabb[6 * i]);
+    ob_hash_cellbox(&aabb[6 * i], W.hash_minlevel, W.hash_maxlevel, &cb[i]);
+    hr[i] = nh; br[i] = nbig;
+    if (en[i]) { if (cb[i].level == OB_LEVEL_BIG) nbig++; else nh++; }
+  }
+  std::vector<PairRec> recs;
+  for (int a = 0; a < ng; a++) {
+    if (!en[a]) continue;
+    const ObGeom &ga = d.geom[(size_t)w * d.NG + glist[a]];
+    for (int b = a + 1; b < ng; b++) {
+      if (!en[b]) continue;
+      const ObGeom &gb = d.geom[(size_t)w * d.NG + glist[b]];
+      if (!ob_aabb_pair_filter(ga.body, gb.body, ga.cat, ga.col, gb.cat, gb.col, &aabb[6 * a], &aabb[6 * b])) continue;
+      PairRec r;
+      int first_is_a;
+      if (!ob_hash_pair_key(a, b, cb[a], cb[b], hr[a], hr[b], br[a], br[b], nh, nbig, &r.key, &first_is_a)) continue;
+      r.o1 = first_is_a ? glist[a] : glist[b];
+      r.o2 = first_is_a ? glist[b] : glist[a];
+      recs.push_back(r);
+    }
+  }
+  std::sort(recs.begin(), recs.end(), pair_less);
+  int np = (int)recs.size();
+  if (np > d.NP) { W.status |= OB_ERR_PAIR_OVERFLOW; np = d.NP; }
+  d.npairs[w] = np;
+  int *pairs = d.pairs + (size_t)w * d.NP * 2;
+  for (int i = 0; i < np; i++) { pairs[2 * i] = recs[i].o1; pairs[2 * i + 1] = recs[i].o2; }
+
+  // narrowphase + policy, contact joints in creation order
+  const ObPolicy &pol = d.policy[0];
+  ObContact *cout = d.contacts + (size_t)w * d.NC;
+  int nc = 0;
+  std::vector<int> walk_of(d.NG, -1);
+  for (int i = 0; i < ng; i++) walk_of[glist[i]] = i;
+  for (int i = 0; i < np; i++) {
+    int o1 = pairs[2 * i], o2 = pairs[2 * i + 1];
+    ObCg cg[OB_MAXC_LOCAL];
+    int swapped;
+    int flags = pol.max_contacts > OB_MAXC_LOCAL ? OB_MAXC_LOCAL : pol.max_contacts;
+    int n = ob_collide_pair(pose[walk_of[o1]], pose[walk_of[o2]], flags, cg, &swapped);
+    for (int k = 0; k < n; k++) {
+      if (nc >= d.NC) { W.status |= OB_ERR_CONTACT_OVERFLOW; break; }
+      ObContact &c = cout[nc++];
+      for (int j = 0; j < 3; j++) { c.pos[j] = cg[k].pos[j]; c.normal[j] = cg[k].normal[j]; }
+      c.depth = cg[k].depth; c.g1 = o1; c.g2 = o2; c.side1 = cg[k].side1; c.side2 = cg[k].side2; c.policy = 0;
+    }
+  }
+  d.ncontacts[w] = nc;
+  d.counters->pairs += np;
+}
+
+static void step_world(ObBatchDev &d, int w, real h, int taps) {
+  ObWorld &W = d.world[w];
+  int nb = W.nb, nc = d.ncontacts[w];
+  ObBodyDyn *bd = d.bdyn + (size_t)w * d.NB;
+  const ObBodyConst *bc = d.bconst + (size_t)w * d.NB;
+  const ObGeom *geoms = d.geom + (size_t)w * d.NG;
+  const ObContact *con = d.contacts + (size_t)w * d.NC;
+  const real stepsize1 = ob_recip(h);
+
+  // contact joint -> bodies (dJointAttach: body1==0 -> swap + REVERSE), ode.cpp:1368-1377
+  std::vector<int> jb1(nc), jb2(nc), jrev(nc);
+  for (int j = 0; j < nc; j++) {
+    int b1 = geoms[con[j].g1].body, b2 = geoms[con[j].g2].body;
+    jrev[j] = 0;
+    if (b1 < 0) { b1 = b2; b2 = -1; jrev[j] = 1; }
+    jb1[j] = b1; jb2[j] = b2;
+  }
+  // body joint lists, newest first
+  std::vector<std::vector<int> > adj(nb);   // joint ids
+  for (int j = nc - 1; j >= 0; j--) {
+    if (jb1[j] >= 0) adj[jb1[j]].push_back(j);
+    if (jb2[j] >= 0) adj[jb2[j]].push_back(j);
+  }
+  // auto-disable (util.cpp:99-233), instantaneous-sample mode only
+  for (int b = 0; b < nb; b++) {
+    if (adj[b].empty()) continue;
+    if ((bd[b].flags & (OB_BODY_AUTO_DISABLE | OB_BODY_DISABLED)) != OB_BODY_AUTO_DISABLE) continue;
+    if (bc[b].adis_samples == 0) continue;
+    int idle = 1;
+    real ls = ob_dot(bd[b].lvel, bd[b].lvel);
+    if (ls > bc[b].adis_lin_thr) idle = 0;
+    else { real as = ob_dot(bd[b].avel, bd[b].avel); if (as > bc[b].adis_ang_thr) idle = 0; }
+    if (idle) { bd[b].adis_stepsleft--; bd[b].adis_timeleft -= h; }
+    else { bd[b].adis_stepsleft = bc[b].adis_idle_steps; bd[b].adis_timeleft = bc[b].adis_idle_time; }
+    if (bd[b].adis_stepsleft <= 0 && bd[b].adis_timeleft <= 0) {
+      bd[b].flags |= OB_BODY_DISABLED;
+      for (int k = 0; k < 3; k++) { bd[b].lvel[k] = 0; bd[b].avel[k] = 0; }
+    }
+  }
+  // islands (util.cpp:411-487)
+  std::vector<int> btag(nb, 0), jtag(nc, 0), ibody, ijoint, isz;
+  std::vector<int> stack;
+  for (int bb = 0; bb < nb; bb++) {
+    if (btag[bb]) continue;
+    if (bd[bb].flags & OB_BODY_DISABLED) { btag[bb] = -1; continue; }
+    btag[bb] = 1;
+    size_t b0 = ibody.size(), j0 = ijoint.size();
+    ibody.push_back(bb);
+    int b = bb;
+    while (true) {
+      for (size_t k = 0; k < adj[b].size(); k++) {
+        int j = adj[b][k];
+        if (!jtag[j]) {
+          // isEnabled: at least one attached body with invMass > 0 (joint.cpp:66-71)
+          bool enabled = (bc[jb1[j]].invMass > 0) || (jb2[j] >= 0 && bc[jb2[j]].invMass > 0);
+          if (enabled) {
+            jtag[j] = 1;
+            ijoint.push_back(j);
+            int other = (jb1[j] == b) ? jb2[j] : jb1[j];
+            if (other >= 0 && btag[other] <= 0) {
+              btag[other] = 1;
+              bd[other].flags &= ~OB_BODY_DISABLED;
+              stack.push_back(other);
+            }
+          } else jtag[j] = -1;
+        }
+      }
+      if (stack.empty()) break;
+      b = stack.back(); stack.pop_back();
+      ibody.push_back(b);
+    }
+    isz.push_back((int)(ibody.size() - b0));
+    isz.push_back((int)(ijoint.size() - j0));
+  }
+
+  // per island: dxQuickStepper
+  real *rowJ = d.rowJ + (size_t)w * d.NR * 12, *rowiMJ = d.rowiMJ + (size_t)w * d.NR * 12;
+  real *rowS = d.rowS + (size_t)w * d.NR * 4, *lambda = d.lambda + (size_t)w * d.NR;
+  int *rowI = d.rowI + (size_t)w * d.NR * 4;
+  real *fb = d.fback + (size_t)w * d.NC * 6;
+  int rowbase = 0;
+  size_t bpos = 0, jpos = 0;
+  std::vector<int> moved;   // geoms in dGeomMoved order
+  uint32_t seed = W.seed;
+  for (size_t isl = 0; isl < isz.size() / 2; isl++) {
+    int inb = isz[2 * isl], inj = isz[2 * isl + 1];
+    const int *ib = &ibody[bpos];
+    const int *ij = inj ? &ijoint[jpos] : 0;
+    std::vector<int> tag(nb, -1);
+    for (int i = 0; i < inb; i++) tag[ib[i]] = i;
+    std::vector<real> invIw(12 * inb), tmp1(6 * inb), fc(6 * inb, 0);
+    for (int i = 0; i < inb; i++) {
+      int b = ib[i];
+      ob_body_preamble(bd[b].R, bc[b].I, bc[b].invI, bd[b].avel, bd[b].flags, bc[b].mass, W.gravity, &invIw[12 * i],
+                       bd[b].facc, bd[b].tacc);
+    }
+    // rows
+    std::vector<int> jm(inj), jofs(inj);
+    int m = 0;
+    std::vector<ObSurface> surf(inj);
+    for (int k = 0; k < inj; k++) {
+      surf[k] = d.policy[con[ij[k]].policy].surface;
+      jm[k] = ob_contact_info1(surf[k]);
+      jofs[k] = m;
+      m += jm[k];
+    }
+    if (rowbase + m > d.NR) { W.status |= OB_ERR_ROW_OVERFLOW; m = 0; inj = 0; }
+    real *J = rowJ + (size_t)rowbase * 12, *iMJ = rowiMJ + (size_t)rowbase * 12, *S = rowS + (size_t)rowbase * 4;
+    int *RI = rowI + (size_t)rowbase * 4;
+    real *lam = lambda + rowbase;
+    if (m > 0) {
+      for (int i = 0; i < inb; i++) {
+        int b = ib[i];
+        ob_body_tmp1(bd[b].facc, bd[b].tacc, bd[b].lvel, bd[b].avel, bc[b].invMass, &invIw[12 * i], stepsize1, &tmp1[6 * i]);
+      }
+      std::vector<real> Jcopy;
+      if (taps) Jcopy.resize((size_t)m * 12);
+      for (int k = 0; k < inj; k++) {
+        int j = ij[k];
+        ObRowOut r;
+        ob_rows_defaults(r, jm[k], W.cfm);
+        int b1 = jb1[j], b2 = jb2[j];
+        real zero3[3] = {0, 0, 0};
+        real fdir1[3] = {0, 0, 0};
+        ob_contact_info2(r, jm[k], surf[k], con[j].pos, con[j].normal, con[j].depth, fdir1, jrev[j], bd[b1].pos,
+                         bd[b1].lvel, bd[b1].avel, b2 >= 0, b2 >= 0 ? bd[b2].pos : zero3, b2 >= 0 ? bd[b2].lvel : zero3,
+                         b2 >= 0 ? bd[b2].avel : zero3, stepsize1, W.erp, W.min_depth, W.max_vel);
+        for (int q = 0; q < jm[k]; q++) {
+          int ri = jofs[k] + q;
+          if (taps) memcpy(&Jcopy[(size_t)ri * 12], r.J[q], 12 * sizeof(real));
+          int t1 = tag[b1], t2 = b2 >= 0 ? tag[b2] : -1;
+          real b_out, adcfm;
+          ob_row_finalize(r.J[q], r.c[q], r.cfm[q], t2, &tmp1[6 * t1], t2 >= 0 ? &tmp1[6 * t2] : 0, bc[b1].invMass,
+                          &invIw[12 * t1], b2 >= 0 ? bc[b2].invMass : 0, t2 >= 0 ? &invIw[12 * t2] : 0, stepsize1,
+                          W.sor_w, &iMJ[(size_t)ri * 12], &b_out, &adcfm);
+          memcpy(&J[(size_t)ri * 12], r.J[q], 12 * sizeof(real));
+          S[ri * 4 + 0] = b_out; S[ri * 4 + 1] = adcfm; S[ri * 4 + 2] = r.lo[q]; S[ri * 4 + 3] = r.hi[q];
+          RI[ri * 4 + 0] = r.findex[q] >= 0 ? r.findex[q] + jofs[k] : -1;
+          RI[ri * 4 + 1] = t1; RI[ri * 4 + 2] = t2; RI[ri * 4 + 3] = j;
+          lam[ri] = 0;
+        }
+      }
+      // order (quickstep.cpp:409-424)
+      std::vector<int> order(m);
+      int head = 0, tail = m - 1;
+      for (int i = 0; i < m; i++) { if (RI[i * 4] == -1) order[head++] = i; else order[tail--] = i; }
+      for (int it = 0; it < W.iters; it++) {
+        if ((it & 7) == 0) {
+          for (int i = 1; i < m; i++) {
+            seed = ob_lcg_next(seed);
+            int swapi = ob_randint_fold(seed, (uint32_t)(i + 1));
+            int t = order[i]; order[i] = order[swapi]; order[swapi] = t;
+          }
+        }
+        for (int i = 0; i < m; i++) {
+          int idx = order[i];
+          int t1 = RI[idx * 4 + 1], t2 = RI[idx * 4 + 2], fi = RI[idx * 4];
+          lam[idx] = ob_sor_row(&J[(size_t)idx * 12], &iMJ[(size_t)idx * 12], S[idx * 4], S[idx * 4 + 1], S[idx * 4 + 2],
+                                S[idx * 4 + 3], fi, fi >= 0 ? lam[fi] : 0, lam[idx], &fc[6 * t1], t2 >= 0 ? &fc[6 * t2] : 0);
+        }
+      }
+      if (taps) {
+        for (int k = 0; k < inj; k++) {   // Multiply1_12q1 (quickstep.cpp:70-101)
+          real acc[6] = {0, 0, 0, 0, 0, 0};
+          for (int q = 0; q < jm[k]; q++) {
+            real s = lam[jofs[k] + q];
+            for (int e = 0; e < 6; e++) acc[e] += Jcopy[(size_t)(jofs[k] + q) * 12 + e] * s;
+          }
+          for (int e = 0; e < 6; e++) fb[ij[k] * 6 + e] = acc[e];
+        }
+      }
+    }
+    for (int i = 0; i < inb; i++) {
+      int b = ib[i];
+      ob_body_velocity_update(bd[b].lvel, bd[b].avel, m > 0 ? &fc[6 * i] : 0, bd[b].facc, bd[b].tacc, bc[b].invMass,
+                              &invIw[12 * i], h);
+    }
+    for (int i = 0; i < inb; i++) {
+      int b = ib[i];
+      ob_step_body(bd[b].pos, bd[b].q, bd[b].R, bd[b].lvel, bd[b].avel, bd[b].flags, h, bc[b].max_angular_speed,
+                   bc[b].finite_rot_axis, bc[b].damp_lin_scale, bc[b].damp_ang_scale, bc[b].damp_lin_thr,
+                   bc[b].damp_ang_thr);
+      for (int g = bc[b].geom_first; g >= 0; g = geoms[g].body_next) moved.push_back(g);
+    }
+    for (int i = 0; i < inb; i++) {
+      int b = ib[i];
+      for (int k = 0; k < 4; k++) { bd[b].facc[k] = 0; bd[b].tacc[k] = 0; }
+    }
+    rowbase += m;
+    bpos += isz[2 * isl]; jpos += isz[2 * isl + 1];
+    d.counters->body_steps += inb;
+    d.counters->rows += m;
+    d.counters->contacts += inj;
+    d.counters->islands += 1;
+  }
+  W.seed = seed;
+  d.nrows[w] = rowbase;
+  // space list update: every moved (clean) geom goes to the head, in order (collision_space.cpp:47-75)
+  int *glist = d.glist + (size_t)w * d.NG;
+  int ng = W.ng;
+  std::vector<char> ismoved(d.NG, 0);
+  std::vector<int> nl;
+  for (int i = (int)moved.size() - 1; i >= 0; i--) { nl.push_back(moved[i]); ismoved[moved[i]] = 1; }
+  for (int i = 0; i < ng; i++) if (!ismoved[glist[i]]) nl.push_back(glist[i]);
+  for (int i = 0; i < ng; i++) glist[i] = nl[i];
+  d.counters->steps += 1;
+}
+
+int obk_step(ObBackend *b, real h, int nsteps, int taps, char *, size_t) {
+  ObBatchDev &d = b->d;
+  for (int s = 0; s < nsteps; s++)
+    for (int w = 0; w < d.W; w++) {
+      collide_world(d, w);
+      step_world(d, w, h, taps);
+    }
+  return 0;
+}
