@@ -486,6 +486,17 @@ int dBatchDebugLambda(dBatchID, int world, dReal *lambda, int cap);
 int dBatchDebugFeedback(dBatchID, int world, dReal *f1t1, int cap);
 /* geom creation indices in space-list order (head first) as of now */
 int dBatchDebugGeomOrder(dBatchID, int world, int *order, int cap);
+/* parity taps cost an extra copy of J per row; on by default, switch off for timing */
+int dBatchSetDebugTaps(dBatchID, int enable);
+/* CUDA-event timing on the batch's own launching stream: Start records an event,
+ * Stop records a second one, synchronises and returns the elapsed milliseconds */
+int dBatchTimerStart(dBatchID);
+int dBatchTimerStop(dBatchID, float *ms);
+/* profiling mode: bracket every kernel launch with events and accumulate device
+ * time per kernel (serialises steps; use only to attribute time, not for throughput) */
+int dBatchSetKernelTiming(dBatchID, int enable);
+int dBatchGetKernelTimes(dBatchID, double *ms_per_kernel, long long *launches_per_kernel, int nkernels);
+const char *dBatchKernelName(int k);
 /* the CUDA stream the batch launches on (cudaStream_t as void*), so callers can
  * time with events on the launching stream */
 void *dBatchGetStream(dBatchID);

@@ -25,4 +25,10 @@ int obk_get_state(ObBackend *, real *pos3, real *quat4, real *lvel3, real *avel3
 int obk_set_state(ObBackend *, const real *pos3, const real *quat4, const real *lvel3, const real *avel3);
 int obk_add_forces(ObBackend *, const real *force3, const real *torque3);
 void *obk_stream(ObBackend *);
+int obk_timer_start(ObBackend *);
+int obk_timer_stop(ObBackend *, float *ms);
+#define OBK_NKERNELS 2
+void obk_set_kernel_timing(ObBackend *, int enable);
+void obk_get_kernel_times(ObBackend *, double *ms, long long *launches);
+const char *obk_kernel_name(int k);
 long long obk_launch_count(void);

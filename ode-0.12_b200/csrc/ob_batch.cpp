@@ -296,6 +296,17 @@ int dBatchDebugGeomOrder(dBatchID B, int w, int *order, int cap) {
   if (m > 0 && obk_d2h(B->bk, order, B->caps.glist + (size_t)w * B->caps.NG, sizeof(int) * m)) return -1;
   return n;
 }
+int dBatchSetDebugTaps(dBatchID B, int enable) { B->debug_taps = enable != 0; return 0; }
+int dBatchTimerStart(dBatchID B) { return obk_timer_start(B->bk); }
+int dBatchTimerStop(dBatchID B, float *ms) { return obk_timer_stop(B->bk, ms); }
+int dBatchSetKernelTiming(dBatchID B, int enable) { obk_set_kernel_timing(B->bk, enable); return 0; }
+int dBatchGetKernelTimes(dBatchID B, double *ms, long long *launches, int nk) {
+  double m[OBK_NKERNELS]; long long l[OBK_NKERNELS];
+  obk_get_kernel_times(B->bk, m, l);
+  for (int k = 0; k < nk && k < OBK_NKERNELS; k++) { ms[k] = m[k]; launches[k] = l[k]; }
+  return OBK_NKERNELS;
+}
+const char *dBatchKernelName(int k) { return obk_kernel_name(k); }
 void *dBatchGetStream(dBatchID B) { return obk_stream(B->bk); }
 long long dB200KernelLaunchCount(void) { return obk_launch_count(); }
 }  // extern "C"

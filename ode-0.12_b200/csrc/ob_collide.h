@@ -215,11 +215,6 @@ done:
   return nr;
 }
 
-// glibc-exact atan2f is not available on the device; cullPoints only needs a
-// faithful angle to rank candidates.  We evaluate atan2 in double and round once
-// (SURVEY.md Appendix B); ties with glibc's float routine are measured in tests.
-OB_HD real ob_atan2(real y, real x) { return (real)atan2((double)y, (double)x); }
-
 // cullPoints, box.cpp:249-311
 OB_HDN void ob_cull_points(int n, const real p[], int m, int i0, int iret[]) {
   int i, j;

@@ -1,5 +1,284 @@
-// ob_joints.cpp — ball / hinge / hinge2 host-side bookkeeping (anchors, axes, params).
-// Reference: ode/src/joints/{ball,hinge,hinge2,joint}.cpp.  (filled in incrementally)
+// ob_joints.cpp — host-side bookkeeping of ball / hinge / hinge2 joints: body-frame
+// anchors and axes, limit/motor parameters, angle getters.  Row assembly for these
+// joints happens on the device (ob_rows.h); this file only maintains the parameters
+// the rows are built from, with the reference's exact arithmetic so that the
+// uploaded values are bit-identical.
+// Reference: ode/src/joints/joint.cpp:263-450 (setAnchors/setAxes/getAnchor/getAxis,
+// getHingeAngle, dxJointLimitMotor::init/set/get), ball.cpp, hinge.cpp, hinge2.cpp.
+#include <string.h>
 #include "ob_host.h"
-void ob_joint_init_type(dxJoint *j) { (void)j; }
-void ob_joint_set_relative_values(dxJoint *j) { (void)j; }
+
+static void limot_init(dxLimot &l, dxWorld *w) {
+  l.vel = 0; l.fmax = 0; l.lostop = -OB_INF; l.histop = OB_INF; l.fudge_factor = 1;
+  l.normal_cfm = w->global_cfm; l.stop_erp = w->global_erp; l.stop_cfm = w->global_cfm;
+  l.bounce = 0; l.limit = 0; l.limit_err = 0;
+}
+static void limot_set(dxLimot &l, int num, dReal value) {
+  switch (num) {
+    case dParamLoStop: l.lostop = value; break;
+    case dParamHiStop: l.histop = value; break;
+    case dParamVel: l.vel = value; break;
+    case dParamFMax: if (value >= 0) l.fmax = value; break;
+    case dParamFudgeFactor: if (value >= 0 && value <= 1) l.fudge_factor = value; break;
+    case dParamBounce: l.bounce = value; break;
+    case dParamCFM: l.normal_cfm = value; break;
+    case dParamStopERP: l.stop_erp = value; break;
+    case dParamStopCFM: l.stop_cfm = value; break;
+  }
+}
+static dReal limot_get(const dxLimot &l, int num) {
+  switch (num) {
+    case dParamLoStop: return l.lostop;
+    case dParamHiStop: return l.histop;
+    case dParamVel: return l.vel;
+    case dParamFMax: return l.fmax;
+    case dParamFudgeFactor: return l.fudge_factor;
+    case dParamBounce: return l.bounce;
+    case dParamCFM: return l.normal_cfm;
+    case dParamStopERP: return l.stop_erp;
+    case dParamStopCFM: return l.stop_cfm;
+    default: return 0;
+  }
+}
+
+void ob_joint_init_type(dxJoint *j) {
+  dxWorld *w = j->world;
+  switch (j->type) {
+    case dJointTypeBall:
+      j->erp = w->global_erp; j->cfm = w->global_cfm;
+      break;
+    case dJointTypeHinge:
+      j->axis1[0] = 1; j->axis2[0] = 1;
+      limot_init(j->limot, w);
+      break;
+    case dJointTypeHinge2:
+      j->axis1[0] = 1; j->axis2[1] = 1;
+      j->c0 = 0; j->s0 = 0; j->v1[0] = 1; j->v2[1] = 1;
+      limot_init(j->limot, w); limot_init(j->limot2, w);
+      j->susp_erp = w->global_erp; j->susp_cfm = w->global_cfm;
+      j->flags |= dJOINT_TWOBODIES;
+      break;
+    default: break;
+  }
+}
+
+// joint.cpp:263-296
+static void set_anchors(dxJoint *j, dReal x, dReal y, dReal z, dReal *anchor1, dReal *anchor2) {
+  if (j->node[0].body) {
+    dReal q[4];
+    dxBody *b0 = j->node[0].body, *b1 = j->node[1].body;
+    q[0] = x - b0->pos[0]; q[1] = y - b0->pos[1]; q[2] = z - b0->pos[2]; q[3] = 0;
+    ob_mul1_331(anchor1, b0->R, q);
+    if (b1) {
+      q[0] = x - b1->pos[0]; q[1] = y - b1->pos[1]; q[2] = z - b1->pos[2]; q[3] = 0;
+      ob_mul1_331(anchor2, b1->R, q);
+    } else { anchor2[0] = x; anchor2[1] = y; anchor2[2] = z; }
+  }
+  anchor1[3] = 0; anchor2[3] = 0;
+}
+// joint.cpp:299-331
+static void set_axes(dxJoint *j, dReal x, dReal y, dReal z, dReal *axis1, dReal *axis2) {
+  if (j->node[0].body) {
+    dReal q[4] = {x, y, z, 0};
+    ob_safe_normalize3(q);
+    if (axis1) { ob_mul1_331(axis1, j->node[0].body->R, q); axis1[3] = 0; }
+    if (axis2) {
+      if (j->node[1].body) ob_mul1_331(axis2, j->node[1].body->R, q);
+      else { axis2[0] = x; axis2[1] = y; axis2[2] = z; }
+      axis2[3] = 0;
+    }
+  }
+}
+static void get_anchor(dxJoint *j, dReal *result, const dReal *anchor1) {
+  if (j->node[0].body) {
+    dxBody *b = j->node[0].body;
+    ob_mul0_331(result, b->R, anchor1);
+    result[0] += b->pos[0]; result[1] += b->pos[1]; result[2] += b->pos[2];
+  }
+}
+static void get_anchor2(dxJoint *j, dReal *result, const dReal *anchor2) {
+  if (j->node[1].body) {
+    dxBody *b = j->node[1].body;
+    ob_mul0_331(result, b->R, anchor2);
+    result[0] += b->pos[0]; result[1] += b->pos[1]; result[2] += b->pos[2];
+  } else { result[0] = anchor2[0]; result[1] = anchor2[1]; result[2] = anchor2[2]; }
+}
+static void qmul1(dReal *qa, const dReal *qb, const dReal *qc) {   // dQMultiply1, rotation.cpp:201-208
+  dReal a0 = qb[0] * qc[0] + qb[1] * qc[1] + qb[2] * qc[2] + qb[3] * qc[3];
+  dReal a1 = qb[0] * qc[1] - qb[1] * qc[0] - qb[2] * qc[3] + qb[3] * qc[2];
+  dReal a2 = qb[0] * qc[2] - qb[2] * qc[0] - qb[3] * qc[1] + qb[1] * qc[3];
+  dReal a3 = qb[0] * qc[3] - qb[3] * qc[0] - qb[1] * qc[2] + qb[2] * qc[1];
+  qa[0] = a0; qa[1] = a1; qa[2] = a2; qa[3] = a3;
+}
+static void hinge_initial_rel_rot(dxJoint *j) {   // hinge.cpp computeInitialRelativeRotation
+  if (j->node[0].body) {
+    if (j->node[1].body) qmul1(j->qrel, j->node[0].body->q, j->node[1].body->q);
+    else {
+      const dReal *q = j->node[0].body->q;
+      j->qrel[0] = q[0]; j->qrel[1] = -q[1]; j->qrel[2] = -q[2]; j->qrel[3] = -q[3];
+    }
+  }
+}
+static void hinge2_axis_info(dxJoint *j, dReal *ax1, dReal *ax2, dReal *axCross, dReal *sin_angle, dReal *cos_angle) {
+  ob_mul0_331(ax1, j->node[0].body->R, j->axis1);
+  ob_mul0_331(ax2, j->node[1].body->R, j->axis2);
+  ob_cross(axCross, ax1, ax2);
+  *sin_angle = ob_sqrt(axCross[0] * axCross[0] + axCross[1] * axCross[1] + axCross[2] * axCross[2]);
+  *cos_angle = ob_dot(ax1, ax2);
+}
+static void hinge2_make_v1v2(dxJoint *j) {   // hinge2.cpp makeV1andV2
+  if (j->node[0].body) {
+    dReal ax1[4], ax2[4], v[4];
+    ob_mul0_331(ax1, j->node[0].body->R, j->axis1);
+    ob_mul0_331(ax2, j->node[1].body->R, j->axis2);
+    if ((ax1[0] == 0 && ax1[1] == 0 && ax1[2] == 0) || (ax2[0] == 0 && ax2[1] == 0 && ax2[2] == 0) ||
+        (ax1[0] == ax2[0] && ax1[1] == ax2[1] && ax1[2] == ax2[2])) return;
+    dReal k = ob_dot(ax1, ax2);
+    for (int i = 0; i < 3; i++) ax2[i] -= k * ax1[i];
+    ob_safe_normalize3(ax2);
+    ob_cross(v, ax1, ax2);
+    ob_mul1_331(j->v1, j->node[0].body->R, ax2);
+    ob_mul1_331(j->v2, j->node[0].body->R, v);
+  }
+}
+
+extern "C" {
+// ---- ball ---------------------------------------------------------------------------
+void dJointSetBallAnchor(dJointID j, dReal x, dReal y, dReal z) { set_anchors(j, x, y, z, j->anchor1, j->anchor2); }
+void dJointSetBallAnchor2(dJointID j, dReal x, dReal y, dReal z) { j->anchor2[0] = x; j->anchor2[1] = y; j->anchor2[2] = z; j->anchor2[3] = 0; }
+void dJointGetBallAnchor(dJointID j, dVector3 result) {
+  if (j->flags & dJOINT_REVERSE) get_anchor2(j, result, j->anchor2); else get_anchor(j, result, j->anchor1);
+}
+void dJointGetBallAnchor2(dJointID j, dVector3 result) {
+  if (j->flags & dJOINT_REVERSE) get_anchor(j, result, j->anchor1); else get_anchor2(j, result, j->anchor2);
+}
+void dJointSetBallParam(dJointID j, int parameter, dReal value) {
+  if (parameter == dParamCFM) j->cfm = value; else if (parameter == dParamERP) j->erp = value;
+}
+// ---- hinge --------------------------------------------------------------------------
+void dJointSetHingeAnchor(dJointID j, dReal x, dReal y, dReal z) { set_anchors(j, x, y, z, j->anchor1, j->anchor2); hinge_initial_rel_rot(j); }
+void dJointSetHingeAxis(dJointID j, dReal x, dReal y, dReal z) { set_axes(j, x, y, z, j->axis1, j->axis2); hinge_initial_rel_rot(j); }
+void dJointSetHingeParam(dJointID j, int parameter, dReal value) { limot_set(j->limot, parameter, value); }
+dReal dJointGetHingeParam(dJointID j, int parameter) { return limot_get(j->limot, parameter); }
+void dJointGetHingeAnchor(dJointID j, dVector3 result) {
+  if (j->flags & dJOINT_REVERSE) get_anchor2(j, result, j->anchor2); else get_anchor(j, result, j->anchor1);
+}
+void dJointGetHingeAnchor2(dJointID j, dVector3 result) {
+  if (j->flags & dJOINT_REVERSE) get_anchor(j, result, j->anchor1); else get_anchor2(j, result, j->anchor2);
+}
+void dJointGetHingeAxis(dJointID j, dVector3 result) { if (j->node[0].body) ob_mul0_331(result, j->node[0].body->R, j->axis1); }
+}  // extern "C"
+#include "ob_rows.h"
+extern "C" {
+dReal dJointGetHingeAngle(dJointID j) {
+  if (j->node[0].body) {
+    dReal ang = ob_hinge_angle(j->node[0].body->q, j->node[1].body ? j->node[1].body->q : 0, j->axis1, j->qrel);
+    return (j->flags & dJOINT_REVERSE) ? -ang : ang;
+  }
+  return 0;
+}
+dReal dJointGetHingeAngleRate(dJointID j) {
+  if (j->node[0].body) {
+    dReal axis[4];
+    ob_mul0_331(axis, j->node[0].body->R, j->axis1);
+    dReal rate = ob_dot(axis, j->node[0].body->avel);
+    if (j->node[1].body) rate -= ob_dot(axis, j->node[1].body->avel);
+    if (j->flags & dJOINT_REVERSE) rate = -rate;
+    return rate;
+  }
+  return 0;
+}
+// ---- hinge2 -------------------------------------------------------------------------
+void dJointSetHinge2Anchor(dJointID j, dReal x, dReal y, dReal z) { set_anchors(j, x, y, z, j->anchor1, j->anchor2); hinge2_make_v1v2(j); }
+void dJointSetHinge2Axis1(dJointID j, dReal x, dReal y, dReal z) {
+  if (j->node[0].body) {
+    set_axes(j, x, y, z, j->axis1, 0);
+    dReal ax1[4], ax2[4], ax[4];
+    hinge2_axis_info(j, ax1, ax2, ax, &j->s0, &j->c0);
+  }
+  hinge2_make_v1v2(j);
+}
+void dJointSetHinge2Axis2(dJointID j, dReal x, dReal y, dReal z) {
+  if (j->node[1].body) {
+    set_axes(j, x, y, z, 0, j->axis2);
+    dReal ax1[4], ax2[4], ax[4];
+    hinge2_axis_info(j, ax1, ax2, ax, &j->s0, &j->c0);
+  }
+  hinge2_make_v1v2(j);
+}
+void dJointSetHinge2Param(dJointID j, int parameter, dReal value) {
+  if ((parameter & 0xff00) == 0x100) limot_set(j->limot2, parameter & 0xff, value);
+  else {
+    if (parameter == dParamSuspensionERP) j->susp_erp = value;
+    else if (parameter == dParamSuspensionCFM) j->susp_cfm = value;
+    else limot_set(j->limot, parameter, value);
+  }
+}
+dReal dJointGetHinge2Param(dJointID j, int parameter) {
+  if ((parameter & 0xff00) == 0x100) return limot_get(j->limot2, parameter & 0xff);
+  if (parameter == dParamSuspensionERP) return j->susp_erp;
+  if (parameter == dParamSuspensionCFM) return j->susp_cfm;
+  return limot_get(j->limot, parameter);
+}
+void dJointGetHinge2Anchor(dJointID j, dVector3 result) {
+  if (j->flags & dJOINT_REVERSE) get_anchor2(j, result, j->anchor2); else get_anchor(j, result, j->anchor1);
+}
+void dJointGetHinge2Anchor2(dJointID j, dVector3 result) {
+  if (j->flags & dJOINT_REVERSE) get_anchor(j, result, j->anchor1); else get_anchor2(j, result, j->anchor2);
+}
+void dJointGetHinge2Axis1(dJointID j, dVector3 result) { if (j->node[0].body) ob_mul0_331(result, j->node[0].body->R, j->axis1); }
+void dJointGetHinge2Axis2(dJointID j, dVector3 result) { if (j->node[1].body) ob_mul0_331(result, j->node[1].body->R, j->axis2); }
+dReal dJointGetHinge2Angle1(dJointID j) {
+  if (j->node[0].body) return ob_hinge2_angle(j->node[0].body->R, j->node[1].body->R, j->axis2, j->v1, j->v2);
+  return 0;
+}
+dReal dJointGetHinge2Angle1Rate(dJointID j) {
+  if (j->node[0].body) {
+    dReal axis[4];
+    ob_mul0_331(axis, j->node[0].body->R, j->axis1);
+    dReal rate = ob_dot(axis, j->node[0].body->avel);
+    if (j->node[1].body) rate -= ob_dot(axis, j->node[1].body->avel);
+    return rate;
+  }
+  return 0;
+}
+dReal dJointGetHinge2Angle2Rate(dJointID j) {
+  if (j->node[0].body && j->node[1].body) {
+    dReal axis[4];
+    ob_mul0_331(axis, j->node[1].body->R, j->axis2);
+    dReal rate = ob_dot(axis, j->node[0].body->avel);
+    rate -= ob_dot(axis, j->node[1].body->avel);
+    return rate;
+  }
+  return 0;
+}
+}  // extern "C"
+
+// setRelativeValues, called from dJointAttach (ball.cpp, hinge.cpp, hinge2.cpp)
+void ob_joint_set_relative_values(dxJoint *j) {
+  dReal v[4] = {0, 0, 0, 0};
+  switch (j->type) {
+    case dJointTypeBall:
+      dJointGetBallAnchor(j, v);
+      set_anchors(j, v[0], v[1], v[2], j->anchor1, j->anchor2);
+      break;
+    case dJointTypeHinge:
+      dJointGetHingeAnchor(j, v);
+      set_anchors(j, v[0], v[1], v[2], j->anchor1, j->anchor2);
+      dJointGetHingeAxis(j, v);
+      set_axes(j, v[0], v[1], v[2], j->axis1, j->axis2);
+      hinge_initial_rel_rot(j);
+      break;
+    case dJointTypeHinge2: {
+      dJointGetHinge2Anchor(j, v);
+      set_anchors(j, v[0], v[1], v[2], j->anchor1, j->anchor2);
+      dReal axis[4] = {0, 0, 0, 0};
+      if (j->node[0].body) { dJointGetHinge2Axis1(j, axis); set_axes(j, axis[0], axis[1], axis[2], j->axis1, 0); }
+      if (j->node[0].body) { dJointGetHinge2Axis2(j, axis); set_axes(j, axis[0], axis[1], axis[2], 0, j->axis2); }
+      dReal ax1[4], ax2[4];
+      if (j->node[0].body && j->node[1].body) hinge2_axis_info(j, ax1, ax2, axis, &j->s0, &j->c0);
+      hinge2_make_v1v2(j);
+    } break;
+    default: break;
+  }
+}

@@ -179,6 +179,34 @@ OB_HD void ob_qmul0(real *qa, const real *qb, const real *qc) {
   qa[0] = a0; qa[1] = a1; qa[2] = a2; qa[3] = a3;
 }
 
+// dQMultiply1/2/3 (rotation.cpp:201-228)
+OB_HD void ob_qmul1(real *qa, const real *qb, const real *qc) {
+  real a0 = qb[0] * qc[0] + qb[1] * qc[1] + qb[2] * qc[2] + qb[3] * qc[3];
+  real a1 = qb[0] * qc[1] - qb[1] * qc[0] - qb[2] * qc[3] + qb[3] * qc[2];
+  real a2 = qb[0] * qc[2] - qb[2] * qc[0] - qb[3] * qc[1] + qb[1] * qc[3];
+  real a3 = qb[0] * qc[3] - qb[3] * qc[0] - qb[1] * qc[2] + qb[2] * qc[1];
+  qa[0] = a0; qa[1] = a1; qa[2] = a2; qa[3] = a3;
+}
+OB_HD void ob_qmul2(real *qa, const real *qb, const real *qc) {
+  real a0 = qb[0] * qc[0] + qb[1] * qc[1] + qb[2] * qc[2] + qb[3] * qc[3];
+  real a1 = -qb[0] * qc[1] + qb[1] * qc[0] - qb[2] * qc[3] + qb[3] * qc[2];
+  real a2 = -qb[0] * qc[2] + qb[2] * qc[0] - qb[3] * qc[1] + qb[1] * qc[3];
+  real a3 = -qb[0] * qc[3] + qb[3] * qc[0] - qb[1] * qc[2] + qb[2] * qc[1];
+  qa[0] = a0; qa[1] = a1; qa[2] = a2; qa[3] = a3;
+}
+OB_HD void ob_qmul3(real *qa, const real *qb, const real *qc) {
+  real a0 = qb[0] * qc[0] - qb[1] * qc[1] - qb[2] * qc[2] - qb[3] * qc[3];
+  real a1 = -qb[0] * qc[1] - qb[1] * qc[0] + qb[2] * qc[3] - qb[3] * qc[2];
+  real a2 = -qb[0] * qc[2] - qb[2] * qc[0] + qb[3] * qc[1] - qb[1] * qc[3];
+  real a3 = -qb[0] * qc[3] - qb[3] * qc[0] + qb[1] * qc[2] - qb[2] * qc[1];
+  qa[0] = a0; qa[1] = a1; qa[2] = a2; qa[3] = a3;
+}
+// glibc's atan2f/atan2 are not available on the device.  For dSINGLE we evaluate atan2 in
+// double and round once (a faithful float result) — it only feeds
+// discrete decisions (cullPoints ranking, joint-limit activation), checked against the
+// reference in tests.  For dDOUBLE the CUDA/glibc double routines are both <1 ulp.
+OB_HD real ob_atan2(real y, real x) { return (real)atan2((double)y, (double)x); }
+
 // ---- LCG behind the SOR row shuffle (misc.cpp:33-38, 66-117) -----------------
 OB_HD uint32_t ob_lcg_next(uint32_t s) { return 1664525u * s + 1013904223u; }
 // fold + modulus part of dRandInt applied to an already-advanced state r

@@ -6,13 +6,15 @@
 #pragma once
 #include "ob_types.h"
 
-struct ObRowOut {      // one joint's rows, thread-local
-  real J[6][12];
-  real c[6], cfm[6], lo[6], hi[6];
-  int findex[6];       // joint-local (-1 or row offset inside the joint)
+template <int MAXM> struct ObRowOutT {      // one joint's rows, thread-local
+  real J[MAXM][12];
+  real c[MAXM], cfm[MAXM], lo[MAXM], hi[MAXM];
+  int findex[MAXM];       // joint-local (-1 or row offset inside the joint)
 };
+typedef ObRowOutT<6> ObRowOut;    // any joint
+typedef ObRowOutT<3> ObRowOut3;   // contact joints
 
-OB_HD void ob_rows_defaults(ObRowOut &r, int m, real global_cfm) {
+template <class RO> OB_HD void ob_rows_defaults(RO &r, int m, real global_cfm) {
   for (int i = 0; i < m; i++) {
     for (int j = 0; j < 12; j++) r.J[i][j] = 0;
     r.c[i] = 0; r.cfm[i] = global_cfm; r.lo[i] = -OB_INF; r.hi[i] = OB_INF; r.findex[i] = -1;
@@ -35,7 +37,8 @@ OB_HD int ob_contact_info1(ObSurface &s) {
 
 // getInfo2.  `normal_in` is contact.geom.normal, `reverse` = dJOINT_REVERSE.
 // b1* are node[0].body's state; has_b2 tells whether node[1].body exists.
-OB_HD void ob_contact_info2(ObRowOut &r, int the_m, const ObSurface &sf, const real *cpos, const real *normal_in,
+template <class RO>
+OB_HD void ob_contact_info2(RO &r, int the_m, const ObSurface &sf, const real *cpos, const real *normal_in,
                             real cdepth, const real *fdir1, int reverse, const real *b1pos, const real *b1lvel,
                             const real *b1avel, int has_b2, const real *b2pos, const real *b2lvel,
                             const real *b2avel, real fps, real erp_in, real min_depth, real maxvel) {
@@ -112,5 +115,218 @@ OB_HD void ob_contact_info2(ObRowOut &r, int the_m, const ObSurface &sf, const r
     else { r.lo[2] = -sf.mu; r.hi[2] = sf.mu; }
     if (sf.mode & 0x2000 /*Approx1_2*/) r.findex[2] = 0;
     if (sf.mode & 0x200 /*Slip2*/) r.cfm[2] = sf.slip2;
+  }
+}
+
+// ======================================================================================
+// ball / hinge / hinge2 (ode/src/joints/ball.cpp:48-64, hinge.cpp:53-149, hinge2.cpp:34-180,
+// joint.cpp:85-196 setBall/setBall2, :381-450 hinge angle, :534-733 limit/motor rows)
+
+// getHingeAngle (joint.cpp:396-450); q2 == 0 when the joint has one body
+OB_HD real ob_hinge_angle(const real *q1, const real *q2, const real *axis, const real *q_initial) {
+  real qrel[4];
+  if (q2) { real qq[4]; ob_qmul1(qq, q1, q2); ob_qmul2(qrel, qq, q_initial); }
+  else ob_qmul3(qrel, q1, q_initial);
+  real cost2 = qrel[0];
+  real sint2 = ob_sqrt(qrel[1] * qrel[1] + qrel[2] * qrel[2] + qrel[3] * qrel[3]);
+  real theta = (ob_dot(qrel + 1, axis) >= 0) ? (2 * ob_atan2(sint2, cost2)) : (2 * ob_atan2(sint2, -cost2));
+  if ((double)theta > OB_PI) theta -= (real)(2 * OB_PI);
+  theta = -theta;
+  return theta;
+}
+// dxJointHinge2::measureAngle (hinge2.cpp:34-43)
+OB_HD real ob_hinge2_angle(const real *R1, const real *R2, const real *axis2, const real *v1, const real *v2) {
+  real a1[3], a2[3];
+  ob_mul0_331(a1, R2, axis2);
+  ob_mul1_331(a2, R1, a1);
+  real x = ob_dot(v1, a2);
+  real y = ob_dot(v2, a2);
+  return -ob_atan2(y, x);
+}
+// testRotationalLimit (joint.cpp:534-553)
+OB_HD int ob_limot_test_limit(ObLimot &l, real angle) {
+  if (angle <= l.lostop) { l.limit = 1; l.limit_err = angle - l.lostop; return 1; }
+  else if (angle >= l.histop) { l.limit = 2; l.limit_err = angle - l.histop; return 1; }
+  l.limit = 0;
+  return 0;
+}
+
+struct ObBodyView {   // what row assembly reads from a body
+  const real *pos, *R, *q, *lvel, *avel;
+};
+
+// getInfo1 for permanent joints; mutates limot.limit / limit_err like the reference
+OB_HD int ob_joint_info1(ObJoint &j, const ObBodyView &B1, const ObBodyView *B2) {
+  if (j.type == OB_JOINT_BALL) return 3;
+  if (j.type == OB_JOINT_HINGE) {
+    int m = (j.limot1.fmax > 0) ? 6 : 5;
+    if (((double)j.limot1.lostop >= -OB_PI || (double)j.limot1.histop <= OB_PI) && j.limot1.lostop <= j.limot1.histop) {
+      real angle = ob_hinge_angle(B1.q, B2 ? B2->q : (const real *)0, j.axis1, j.qrel);
+      if (ob_limot_test_limit(j.limot1, angle)) m = 6;
+    }
+    return m;
+  }
+  if (j.type == OB_JOINT_HINGE2) {
+    int m = 4;
+    j.limot1.limit = 0;
+    if (((double)j.limot1.lostop >= -OB_PI || (double)j.limot1.histop <= OB_PI) && j.limot1.lostop <= j.limot1.histop) {
+      real angle = ob_hinge2_angle(B1.R, B2->R, j.axis2, j.v1, j.v2);
+      ob_limot_test_limit(j.limot1, angle);
+    }
+    if (j.limot1.limit || j.limot1.fmax > 0) m++;
+    j.limot2.limit = 0;
+    if (j.limot2.fmax > 0) m++;
+    return m;
+  }
+  return 0;
+}
+
+// setBall (joint.cpp:85-126) into rows 0..2
+template <class RO>
+OB_HD void ob_set_ball(RO &r, const real *anchor1, const real *anchor2, const ObBodyView &B1, const ObBodyView *B2,
+                       real fps, real erp) {
+  real a1[3], a2[3] = {0, 0, 0};
+  r.J[0][0] = 1; r.J[1][1] = 1; r.J[2][2] = 1;
+  ob_mul0_331(a1, B1.R, anchor1);
+  // dSetCrossMatrixMinus(J1a, a1)
+  r.J[0][3 + 1] = a1[2]; r.J[0][3 + 2] = -a1[1];
+  r.J[1][3 + 0] = -a1[2]; r.J[1][3 + 2] = a1[0];
+  r.J[2][3 + 0] = a1[1]; r.J[2][3 + 1] = -a1[0];
+  if (B2) {
+    r.J[0][6] = -1; r.J[1][7] = -1; r.J[2][8] = -1;
+    ob_mul0_331(a2, B2->R, anchor2);
+    // dSetCrossMatrixPlus(J2a, a2)
+    r.J[0][9 + 1] = -a2[2]; r.J[0][9 + 2] = a2[1];
+    r.J[1][9 + 0] = a2[2]; r.J[1][9 + 2] = -a2[0];
+    r.J[2][9 + 0] = -a2[1]; r.J[2][9 + 1] = a2[0];
+  }
+  real k = fps * erp;
+  if (B2) { for (int j = 0; j < 3; j++) r.c[j] = k * (a2[j] + B2->pos[j] - a1[j] - B1.pos[j]); }
+  else { for (int j = 0; j < 3; j++) r.c[j] = k * (anchor2[j] - a1[j] - B1.pos[j]); }
+}
+
+// setBall2 (joint.cpp:134-196) into rows 0..2
+template <class RO>
+OB_HD void ob_set_ball2(RO &r, const real *anchor1, const real *anchor2, const real *axis, real erp1,
+                        const ObBodyView &B1, const ObBodyView *B2, real fps, real erp) {
+  real a1[3], a2[3], q1[3], q2[3];
+  ob_plane_space(axis, q1, q2);
+  for (int i = 0; i < 3; i++) { r.J[0][i] = axis[i]; r.J[1][i] = q1[i]; r.J[2][i] = q2[i]; }
+  ob_mul0_331(a1, B1.R, anchor1);
+  ob_cross(r.J[0] + 3, a1, axis);
+  ob_cross(r.J[1] + 3, a1, q1);
+  ob_cross(r.J[2] + 3, a1, q2);
+  if (B2) {
+    for (int i = 0; i < 3; i++) { r.J[0][6 + i] = -axis[i]; r.J[1][6 + i] = -q1[i]; r.J[2][6 + i] = -q2[i]; }
+    ob_mul0_331(a2, B2->R, anchor2);
+    ob_cross(r.J[0] + 9, a2, axis); for (int i = 9; i < 12; i++) r.J[0][i] = -r.J[0][i];
+    ob_cross(r.J[1] + 9, a2, q1); for (int i = 9; i < 12; i++) r.J[1][i] = -r.J[1][i];
+    ob_cross(r.J[2] + 9, a2, q2); for (int i = 9; i < 12; i++) r.J[2][i] = -r.J[2][i];
+  }
+  real k1 = fps * erp1;
+  real k = fps * erp;
+  for (int i = 0; i < 3; i++) a1[i] += B1.pos[i];
+  real d[3];
+  if (B2) { for (int i = 0; i < 3; i++) a2[i] += B2->pos[i]; for (int i = 0; i < 3; i++) d[i] = a2[i] - a1[i]; }
+  else { for (int i = 0; i < 3; i++) d[i] = anchor2[i] - a1[i]; }
+  r.c[0] = k1 * ob_dot(axis, d);
+  r.c[1] = k * ob_dot(q1, d);
+  r.c[2] = k * ob_dot(q2, d);
+}
+
+// dxJointLimitMotor::addLimot, rotational case (joint.cpp:556-733).  The powered-at-limit
+// side effect (dBodyAddTorque on both bodies, :638-645) is returned in `torque` (applied
+// to body 1 as -torque... see caller): tq1 += -fm*ax1, tq2 += +fm*ax1.  Returns 1 if a row was added.
+template <class RO>
+OB_HD int ob_add_limot_rot(RO &r, int row, const ObLimot &l, const real *ax1, const ObBodyView &B1,
+                           const ObBodyView *B2, real fps, real *side_fm /* out: fm or 0 */) {
+  *side_fm = 0;
+  int powered = l.fmax > 0;
+  if (!(powered || l.limit)) return 0;
+  r.J[row][3] = ax1[0]; r.J[row][4] = ax1[1]; r.J[row][5] = ax1[2];
+  if (B2) { r.J[row][9] = -ax1[0]; r.J[row][10] = -ax1[1]; r.J[row][11] = -ax1[2]; }
+  if (l.limit && (l.lostop == l.histop)) powered = 0;
+  if (powered) {
+    r.cfm[row] = l.normal_cfm;
+    if (!l.limit) { r.c[row] = l.vel; r.lo[row] = -l.fmax; r.hi[row] = l.fmax; }
+    else {
+      real fm = l.fmax;
+      if ((l.vel > 0) || (l.vel == 0 && l.limit == 2)) fm = -fm;
+      if ((l.limit == 1 && l.vel > 0) || (l.limit == 2 && l.vel < 0)) fm *= l.fudge_factor;
+      *side_fm = fm;
+    }
+  }
+  if (l.limit) {
+    real k = fps * l.stop_erp;
+    r.c[row] = -k * l.limit_err;
+    r.cfm[row] = l.stop_cfm;
+    if (l.lostop == l.histop) { r.lo[row] = -OB_INF; r.hi[row] = OB_INF; }
+    else {
+      if (l.limit == 1) { r.lo[row] = 0; r.hi[row] = OB_INF; }
+      else { r.lo[row] = -OB_INF; r.hi[row] = 0; }
+      if (l.bounce > 0) {
+        real vel = ob_dot(B1.avel, ax1);
+        if (B2) vel -= ob_dot(B2->avel, ax1);
+        if (l.limit == 1) { if (vel < 0) { real newc = -l.bounce * vel; if (newc > r.c[row]) r.c[row] = newc; } }
+        else { if (vel > 0) { real newc = -l.bounce * vel; if (newc < r.c[row]) r.c[row] = newc; } }
+      }
+    }
+  }
+  return 1;
+}
+
+// getInfo2 for permanent joints.  erp_io carries the driver's shared Info2.erp, which a ball
+// joint overwrites for every later joint of the island (ball.cpp:60, quickstep.cpp:764-786).
+// side[k] (k<2) returns {fm, ax[3]} of a powered-at-limit motor whose torque must be added
+// to the bodies' tacc before the rhs is formed: tacc1 += -fm*ax, tacc2 += fm*ax.
+template <class RO>
+OB_HD void ob_joint_info2(RO &r, const ObJoint &j, const ObBodyView &B1, const ObBodyView *B2, real fps,
+                          real *erp_io, real side[2][4]) {
+  side[0][0] = 0; side[1][0] = 0;
+  if (j.type == OB_JOINT_BALL) {
+    *erp_io = j.erp;
+    r.cfm[0] = j.cfm; r.cfm[1] = j.cfm; r.cfm[2] = j.cfm;
+    ob_set_ball(r, j.anchor1, j.anchor2, B1, B2, fps, *erp_io);
+  } else if (j.type == OB_JOINT_HINGE) {
+    const real erp = *erp_io;
+    ob_set_ball(r, j.anchor1, j.anchor2, B1, B2, fps, erp);
+    real ax1[3], p[3], q[3];
+    ob_mul0_331(ax1, B1.R, j.axis1);
+    ob_plane_space(ax1, p, q);
+    for (int i = 0; i < 3; i++) { r.J[3][3 + i] = p[i]; r.J[4][3 + i] = q[i]; }
+    if (B2) for (int i = 0; i < 3; i++) { r.J[3][9 + i] = -p[i]; r.J[4][9 + i] = -q[i]; }
+    real ax2[3], b[3];
+    if (B2) ob_mul0_331(ax2, B2->R, j.axis2);
+    else { ax2[0] = j.axis2[0]; ax2[1] = j.axis2[1]; ax2[2] = j.axis2[2]; }
+    ob_cross(b, ax1, ax2);
+    real k = fps * erp;
+    r.c[3] = k * ob_dot(b, p);
+    r.c[4] = k * ob_dot(b, q);
+    real fm;
+    if (ob_add_limot_rot(r, 5, j.limot1, ax1, B1, B2, fps, &fm) && fm != 0) {
+      side[0][0] = fm; side[0][1] = ax1[0]; side[0][2] = ax1[1]; side[0][3] = ax1[2];
+    }
+  } else if (j.type == OB_JOINT_HINGE2) {
+    const real erp = *erp_io;
+    real ax1[3], ax2[3], q[3];
+    ob_mul0_331(ax1, B1.R, j.axis1);
+    ob_mul0_331(ax2, B2->R, j.axis2);
+    ob_cross(q, ax1, ax2);
+    real s = ob_sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
+    real c = ob_dot(ax1, ax2);
+    ob_safe_normalize3(q);
+    ob_set_ball2(r, j.anchor1, j.anchor2, ax1, j.susp_erp, B1, B2, fps, erp);
+    for (int i = 0; i < 3; i++) r.J[3][3 + i] = q[i];
+    if (B2) for (int i = 0; i < 3; i++) r.J[3][9 + i] = -q[i];
+    real k = fps * erp;
+    r.c[3] = k * (j.c0 * s - j.s0 * c);
+    real fm;
+    int added = ob_add_limot_rot(r, 4, j.limot1, ax1, B1, B2, fps, &fm);
+    if (added && fm != 0) { side[0][0] = fm; side[0][1] = ax1[0]; side[0][2] = ax1[1]; side[0][3] = ax1[2]; }
+    int row = 4 + added;
+    if (ob_add_limot_rot(r, row, j.limot2, ax2, B1, B2, fps, &fm) && fm != 0) {
+      side[1][0] = fm; side[1][1] = ax2[0]; side[1][2] = ax2[1]; side[1][3] = ax2[2];
+    }
+    r.cfm[0] = j.susp_cfm;
   }
 }

@@ -70,6 +70,22 @@ struct __attribute__((aligned(16))) ObPolicy {
   int skip_static_pairs; int pad[3];
   ObSurface surface;
 };
+// permanent joints (ball / hinge / hinge2), body-frame parameters as the host API maintains them
+struct __attribute__((aligned(16))) ObLimot {
+  real vel, fmax, lostop, histop;
+  real fudge_factor, normal_cfm, stop_erp, stop_cfm;
+  real bounce; int limit; real limit_err; int pad;
+};
+enum { OB_JOINT_BALL = 1, OB_JOINT_HINGE = 2, OB_JOINT_CONTACT = 4, OB_JOINT_HINGE2 = 6 };   // == dJointType
+enum { OB_JF_DISABLED = 1, OB_JF_REVERSE = 2 };
+struct __attribute__((aligned(16))) ObJoint {
+  int type; int b1, b2; int flags;        // b1/b2 = node[0]/node[1] body index, -1 = none
+  real anchor1[4], anchor2[4], axis1[4], axis2[4], qrel[4];
+  real erp, cfm, susp_erp, susp_cfm;
+  real c0, s0, pad0, pad1;
+  real v1[4], v2[4];
+  ObLimot limot1, limot2;
+};
 // one generated contact (dContactGeom-equivalent, 48 B single / 80 B double)
 struct __attribute__((aligned(16))) ObContact {
   real pos[3]; real depth;
@@ -103,6 +119,7 @@ struct ObBatchDev {
   ObContact *contacts;   // [W*NC] contact joints in creation order
   real *rowJ;            // [W*NR*12]
   real *rowiMJ;          // [W*NR*12]
+  real *rowJc;           // [W*NR*12] unscaled J copy (only written when the feedback tap is on)
   real *rowS;            // [W*NR*4]  b(rhs), Ad*cfm, lo, hi
   int *rowI;             // [W*NR*4]  findex, b1, b2, joint
   real *lambda;          // [W*NR]

@@ -1,0 +1,46 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests", "harness"))
+sys.path.insert(0, ROOT)
+
+GOLDEN = [  # (file stem, scene, steps, worlds, settle) — must match tests/golden/make_golden.sh
+    ("free6", "free6", 20, 1, 0),
+    ("mixed", "mixed", 40, 1, 0),
+    ("mixed_maxc4_settle80", "mixed_maxc4", 40, 1, 80),
+    ("stack32_w2_settle120", "stack32", 12, 2, 120),
+    ("tower64_settle150", "tower64", 8, 1, 150),
+]
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def have_ref():
+    return os.path.exists(os.path.join(ROOT, "oracle", "_ref", "driver_ref_single"))
+
+
+def lib_path(prec="single"):
+    return os.path.join(ROOT, "ode-0.12_b200", "lib", f"libode_b200_{prec}.so")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built():
+    """Build the host-side artefacts once per session if they are missing (CPU only)."""
+    need = [lib_path("single"), os.path.join(ROOT, "tests", "hostsim", "_build", "driver_hostsim_single")]
+    if not all(os.path.exists(p) for p in need):
+        import __graft_entry__
+
+        __graft_entry__.build()
+    yield
+
+
+def assert_bit_exact(r, what=""):
+    assert r["exact_ok"], f"{what}: exact observables differ at {r['first_exact_mismatch']}"
+    assert r["contact_bits_equal"] == r["contact_vals"], f"{what}: contact fields differ (relerr {r['max_contact_relerr']})"
+    assert r["state_bits_equal"] == r["state_vals"], f"{what}: body state differs at {r['first_state_bit_mismatch']} (relerr {r['max_state_relerr']})"
+    assert r["fb_bits_equal"] == r["fb_vals"], f"{what}: joint feedback (lambda tap) differs (relerr {r['max_fb_relerr']})"

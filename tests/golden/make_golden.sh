@@ -1,0 +1,16 @@
+#!/bin/sh
+# Regenerates the golden traces in this directory by running the UNMODIFIED reference
+# (oracle/_ref, built from /root/reference by oracle/Makefile) through
+# tests/harness/scene_driver.cpp.  Traces are the reference's own outputs: callback pair
+# sequence, contacts, joint feedback (lambda tap), body state and LCG seed per step.
+set -e
+cd "$(dirname "$0")/../.."
+for p in single double; do
+  d=oracle/_ref/driver_ref_$p
+  $d --scene free6       --steps 20 --out tests/golden/free6_$p.trace
+  $d --scene mixed       --steps 40 --out tests/golden/mixed_$p.trace
+  $d --scene mixed_maxc4 --steps 40 --settle 80 --out tests/golden/mixed_maxc4_settle80_$p.trace
+  $d --scene stack32     --steps 12 --settle 120 --worlds 2 --out tests/golden/stack32_w2_settle120_$p.trace
+  $d --scene tower64     --steps 8 --settle 150 --out tests/golden/tower64_settle150_$p.trace
+done
+ls -la tests/golden

@@ -95,7 +95,7 @@ static double now_s() {
 
 int main(int argc, char **argv) {
   std::string scene = "stack32", out = "", mode = "callback";
-  int nworlds = 1, nsteps = 10, world0 = 0, timing = 0;
+  int nworlds = 1, nsteps = 10, world0 = 0, timing = 0, settle = 0, maxc_world = 0;
   double h = 0.01;
   for (int i = 1; i < argc; i++) {
     std::string a = argv[i];
@@ -107,6 +107,8 @@ int main(int argc, char **argv) {
     else if (a == "--steps") nsteps = atoi(argv[++i]);
     else if (a == "--h") h = atof(argv[++i]);
     else if (a == "--time") timing = 1;
+    else if (a == "--settle") settle = atoi(argv[++i]);
+    else if (a == "--contacts-cap") maxc_world = atoi(argv[++i]);
     else { fprintf(stderr, "unknown arg %s\n", a.c_str()); return 2; }
   }
   dInitODE2(0);
@@ -132,7 +134,20 @@ int main(int argc, char **argv) {
     CbCtx ctx;
     ctx.pol = &pol;
     ctx.ncontacts = 0;
+    ctx.record = false;
+    for (int s = 0; s < settle; s++)
+      for (int w = 0; w < nworlds; w++) {
+        SceneWorld &sw = worlds[w];
+        ctx.sw = &sw;
+        dRandSetSeed(sw.seed);
+        dSpaceCollide(sw.space, &ctx, &near_cb);
+        dWorldQuickStep(sw.world, (dReal)h);
+        sw.seed = (uint32_t)dRandGetSeed();
+        dJointGroupEmpty(sw.cgroup);
+      }
+    ctx.ncontacts = 0;
     ctx.record = t.f != NULL;
+    t0 = now_s();
     for (int s = 0; s < nsteps; s++) {
       for (int w = 0; w < nworlds; w++) {
         SceneWorld &sw = worlds[w];
@@ -189,6 +204,7 @@ int main(int argc, char **argv) {
     for (int w = 0; w < nworlds; w++) { wv[w] = worlds[w].world; sv[w] = worlds[w].space; seeds[w] = worlds[w].seed; }
     dBatchDesc desc;
     memset(&desc, 0, sizeof(desc));
+    desc.max_contacts_per_world = maxc_world;
     dBatchID B = dBatchCreate(nworlds, wv.data(), sv.data(), &desc);
     if (!B) { fprintf(stderr, "dBatchCreate failed: %s\n", dB200LastError()); return 3; }
     dBatchContactPolicy bp;
@@ -202,6 +218,11 @@ int main(int argc, char **argv) {
     int nb = dBatchNumBodies(B);
     std::vector<dReal> pos(nworlds * nb * 3), quat(nworlds * nb * 4), lv(nworlds * nb * 3), av(nworlds * nb * 3);
     std::vector<int> status(nworlds);
+    if (settle > 0) {
+      if (dBatchCollideAndQuickStep(B, (dReal)h, settle, status.data())) { fprintf(stderr, "settle failed: %s\n", dB200LastError()); return 3; }
+      dBatchResetCounters(B);
+    }
+    t0 = now_s();
     if (!t.f) {
       // timing mode: one call, everything device-resident
       int rc = dBatchCollideAndQuickStep(B, (dReal)h, nsteps, status.data());

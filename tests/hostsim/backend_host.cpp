@@ -44,6 +44,7 @@ ObBackend *obk_create(const ObBatchDev &caps, int, char *, size_t) {
   d.contacts = halloc<ObContact>(b, W * d.NC);
   d.rowJ = halloc<real>(b, W * d.NR * 12);
   d.rowiMJ = halloc<real>(b, W * d.NR * 12);
+  d.rowJc = halloc<real>(b, W * d.NR * 12);
   d.rowS = halloc<real>(b, W * d.NR * 4);
   d.rowI = halloc<int>(b, W * d.NR * 4);
   d.lambda = halloc<real>(b, W * d.NR);
@@ -60,6 +61,11 @@ int obk_memset(ObBackend *, void *dst, int v, size_t n) { memset(dst, v, n); ret
 int obk_sync(ObBackend *) { return 0; }
 void *obk_stream(ObBackend *) { return 0; }
 long long obk_launch_count(void) { return 0; }
+int obk_timer_start(ObBackend *) { return 0; }
+int obk_timer_stop(ObBackend *, float *ms) { *ms = 0; return 0; }
+void obk_set_kernel_timing(ObBackend *, int) {}
+void obk_get_kernel_times(ObBackend *, double *ms, long long *l) { for (int k = 0; k < OBK_NKERNELS; k++) { ms[k] = 0; l[k] = 0; } }
+const char *obk_kernel_name(int) { return "host"; }
 
 int obk_get_state(ObBackend *b, real *pos3, real *quat4, real *lvel3, real *avel3) {
   ObBatchDev &d = b->d;
@@ -310,7 +316,7 @@ static void step_world(ObBatchDev &d, int w, real h, int taps) {
       if (taps) Jcopy.resize((size_t)m * 12);
       for (int k = 0; k < inj; k++) {
         int j = ij[k];
-        ObRowOut r;
+        ObRowOut3 r;
         ob_rows_defaults(r, jm[k], W.cfm);
         int b1 = jb1[j], b2 = jb2[j];
         real zero3[3] = {0, 0, 0};

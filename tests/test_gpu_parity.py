@@ -1,0 +1,81 @@
+"""GPU parity (run on the B200): the CUDA path, called through the C ABI (dBatch*), against the
+reference's golden traces and the live reference build shipped in oracle/_ref, plus
+size-independent properties at BASELINE.json's full batch size."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, assert_bit_exact, have_ref, lib_path
+from run_parity import parity, parity_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("prec", ["single", "double"])
+@pytest.mark.parametrize("stem,scene,steps,worlds,settle", GOLDEN)
+def test_cuda_matches_golden_reference_traces(stem, scene, steps, worlds, settle, prec):
+    g = os.path.join(ROOT, "tests", "golden", f"{stem}_{prec}.trace")
+    r = parity_golden("b200", g, scene, prec, steps, worlds, settle)
+    assert r["steps"] == steps
+    assert_bit_exact(r, f"{stem}/{prec}")
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not shipped")
+@pytest.mark.parametrize("prec", ["single", "double"])
+@pytest.mark.parametrize("scene,steps,worlds", [("stack32", 200, 3), ("block64", 50, 1), ("tower64", 250, 1),
+                                                ("mixed", 200, 2), ("mixed_maxc4", 300, 1)])
+def test_cuda_matches_live_reference(scene, steps, worlds, prec):
+    r = parity("b200", prec, scene, steps, worlds)
+    assert_bit_exact(r, f"{scene}/{prec}")
+
+
+def _batch(lib, scenes, scene, nworlds, cap=0):
+    scenes.ob_scene_build_batch.restype = ctypes.c_void_p
+    scenes.ob_scene_build_batch.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    B = scenes.ob_scene_build_batch(scene.encode(), nworlds, 0, cap, 0)
+    assert B, ctypes.string_at(lib.dB200LastError())
+    return ctypes.c_void_p(B)
+
+
+def _state(lib, B, nworlds):
+    lib.dBatchNumBodies.argtypes = [ctypes.c_void_p]
+    nb = lib.dBatchNumBodies(B)
+    arrs = [np.zeros((nworlds, nb, k), dtype=np.float32) for k in (3, 4, 3, 3)]
+    lib.dBatchGetBodyState.argtypes = [ctypes.c_void_p] + [ctypes.c_void_p] * 4
+    assert lib.dBatchGetBodyState(B, *[a.ctypes.data for a in arrs]) == 0
+    return arrs
+
+
+def test_full_batch_is_deterministic_and_replicates_small_batch():
+    """4096 worlds x config 2: (i) two independent runs give identical bits, (ii) worlds do not
+    interact: world w of the big batch equals world w of a 3-world batch, (iii) no capacity overflow."""
+    lib = ctypes.CDLL(lib_path("single"))
+    scenes = ctypes.CDLL(os.path.join(ROOT, "ode-0.12_b200", "lib", "libob_scenes_single.so"))
+    lib.dB200LastError.restype = ctypes.c_char_p
+    lib.dBatchCollideAndQuickStep.argtypes = [ctypes.c_void_p, ctypes.c_float, ctypes.c_int, ctypes.c_void_p]
+    lib.dBatchDestroy.argtypes = [ctypes.c_void_p]
+    W, steps = 4096, 40
+    results = []
+    for n in (W, W, 3):
+        B = _batch(lib, scenes, "stack32", n, 256)
+        status = np.zeros(n, dtype=np.int32)
+        assert lib.dBatchCollideAndQuickStep(B, 0.01, steps, status.ctypes.data) == 0, lib.dB200LastError()
+        assert not status.any()
+        results.append(_state(lib, B, n))
+        lib.dBatchDestroy(B)
+    for a, b in zip(results[0], results[1]):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    for a, c in zip(results[0], results[2]):
+        assert np.array_equal(a[:3].view(np.uint32), c.view(np.uint32))
+    pos = results[0][0]
+    assert np.isfinite(pos).all() and pos[:, :, 2].min() > -0.5
+
+
+def test_no_gpu_fallback_symbols():
+    """the product library must not contain the test-only host backend"""
+    import subprocess
+
+    out = subprocess.run(["nm", "-D", "--defined-only", lib_path("single")], capture_output=True, text=True).stdout
+    assert "collide_world" not in out and "step_world" not in out

@@ -1,0 +1,29 @@
+"""CPU parity: the per-element device functions (ode-0.12_b200/csrc/ob_*.h), compiled for the
+host and driven sequentially by the TEST-ONLY backend in tests/hostsim, must reproduce the
+unmodified reference bit-for-bit: callback pair order, contacts, space-list order, LCG seed
+(exact by contract) and — stronger than the stated tolerance — body state and joint feedback.
+Golden traces are the reference's own outputs (tests/golden/make_golden.sh)."""
+import os
+
+import pytest
+
+from conftest import GOLDEN, ROOT, assert_bit_exact, have_ref
+from run_parity import parity, parity_golden
+
+
+@pytest.mark.parametrize("prec", ["single", "double"])
+@pytest.mark.parametrize("stem,scene,steps,worlds,settle", GOLDEN)
+def test_hostsim_matches_golden_reference_traces(stem, scene, steps, worlds, settle, prec):
+    g = os.path.join(ROOT, "tests", "golden", f"{stem}_{prec}.trace")
+    r = parity_golden("hostsim", g, scene, prec, steps, worlds, settle)
+    assert r["steps"] == steps
+    assert_bit_exact(r, f"{stem}/{prec}")
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("scene,steps,worlds", [("stack32", 250, 2), ("block64", 60, 1), ("tower64", 300, 1),
+                                                ("mixed_maxc4", 400, 1)])
+def test_hostsim_matches_live_reference(scene, steps, worlds):
+    r = parity("hostsim", "single", scene, steps, worlds)
+    assert r["contacts"] > 0
+    assert_bit_exact(r, scene)
