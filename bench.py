@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's metric on BASELINE.json's config, one JSON line.
+
+metric : body-steps/sec (and contacts solved/sec) of the batched hot path
+         dSpaceCollide + contact policy + dWorldQuickStep(20 it) + dJointGroupEmpty
+workload: configs[1] — 4096 independent worlds x (plane + 32-box stack + 8 spheres),
+         scene `stack32` of tests/harness/scenes.h, settled for SETTLE steps first so the
+         timed steps see the resting pile (~130 contacts / ~400 rows per world).
+A "step" = one pass of that path over all worlds of this rank (weak scaling: every rank
+owns its own 4096 worlds, no data-path collective; NCCL only reduces the metric).
+
+  python bench.py --gpus N --steps K --warmup W            (torchrun for N>1)
+  python bench.py --impl reference ...                      the reference's own CPU code
+                                                            (oracle/_ref) on the host cores
+value  : device-resident throughput (CUDA events on the library's launching stream).
+e2e    : same metric through the C ABI with HOST buffers every step: dBatchAddForces
+         (H2D, pinned staging) + step + dBatchGetBodyState (D2H).
+roofline: dominant kernel k_step, algorithmic bytes (SURVEY.md §8d / DESIGN.md) / its
+         CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+LIBDIR = os.path.join(ROOT, "ode-0.12_b200", "lib")
+SCENE = "stack32"
+WORLDS_PER_GPU = 4096
+SETTLE = 300
+H = 0.01
+CONTACTS_CAP = 256
+# algorithmic bytes per unit, dSINGLE: A body-step, B geom-step, C contact,
+# D row x SOR iteration, ASM row assembly
+A_B, B_B, C_B, D_B, ASM_B = 136, 80, 128, 224, 128
+ITERS = 20
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def load_libs():
+    lib_path = os.path.join(LIBDIR, "libode_b200_single.so")
+    if not os.path.exists(lib_path):
+        raise SystemExit("libode_b200_single.so is missing: run `python __graft_entry__.py` (there is no CPU fallback)")
+    lib = ctypes.CDLL(lib_path, mode=ctypes.RTLD_GLOBAL)
+    scenes = ctypes.CDLL(os.path.join(LIBDIR, "libob_scenes_single.so"))
+    vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+    scenes.ob_scene_build_batch.restype = vp
+    scenes.ob_scene_build_batch.argtypes = [ctypes.c_char_p, ci, ci, ci, ci]
+    lib.dB200LastError.restype = ctypes.c_char_p
+    lib.dBatchCollideAndQuickStep.argtypes = [vp, cf, ci, vp]
+    lib.dBatchTimerStart.argtypes = [vp]
+    lib.dBatchTimerStop.argtypes = [vp, ctypes.POINTER(cf)]
+    lib.dBatchSetDebugTaps.argtypes = [vp, ci]
+    lib.dBatchSetKernelTiming.argtypes = [vp, ci]
+    lib.dBatchGetKernelTimes.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong), ci]
+    lib.dBatchKernelName.restype = ctypes.c_char_p
+    lib.dBatchKernelName.argtypes = [ci]
+    lib.dBatchGetCounters.argtypes = [vp, vp]
+    lib.dBatchResetCounters.argtypes = [vp]
+    lib.dBatchNumBodies.argtypes = [vp]
+    lib.dBatchGetBodyState.argtypes = [vp, vp, vp, vp, vp]
+    lib.dBatchAddForces.argtypes = [vp, vp, vp]
+    lib.dBatchDestroy.argtypes = [vp]
+    lib.dB200KernelLaunchCount.restype = ctypes.c_longlong
+    return lib, scenes
+
+
+def counters(lib, B):
+    c = (ctypes.c_longlong * 7)()
+    lib.dBatchGetCounters(B, ctypes.byref(c))
+    return dict(zip(["steps", "body_steps", "pairs", "contacts", "rows", "islands", "overflow_worlds"], list(c)))
+
+
+def shard(rank, world_size, per_gpu=WORLDS_PER_GPU):
+    """world ids owned by `rank`: contiguous ranges, no overlap (weak scaling)"""
+    return rank * per_gpu, per_gpu
+
+
+def run_b200(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world_size > 1:
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl")
+    lib, scenes = load_libs()
+    world0, nworlds = shard(rank, world_size, args.worlds)
+    B = scenes.ob_scene_build_batch(SCENE.encode(), nworlds, world0, CONTACTS_CAP, local_rank)
+    if not B:
+        raise SystemExit("batch creation failed: " + (lib.dB200LastError() or b"").decode())
+    B = ctypes.c_void_p(B)
+    lib.dBatchSetDebugTaps(B, 0)
+
+    def step(n):
+        if lib.dBatchCollideAndQuickStep(B, H, n, None) != 0:
+            raise SystemExit("step failed: " + lib.dB200LastError().decode())
+
+    def barrier():
+        if dist is not None:
+            import torch
+
+            torch.cuda.synchronize()
+            dist.barrier()
+
+    step(SETTLE)                       # untimed: let the pile come to rest
+    step(max(args.warmup, 3))          # warm-up steps proper
+    lib.dBatchResetCounters(B)
+    l0 = lib.dB200KernelLaunchCount()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    ms = ctypes.c_float()
+    lib.dBatchTimerStart(B)
+    step(args.steps)
+    lib.dBatchTimerStop(B, ctypes.byref(ms))
+    barrier()
+    clocks = sampler.stop()
+    launches = lib.dB200KernelLaunchCount() - l0
+    c = counters(lib, B)
+    elapsed_ms = float(ms.value)
+
+    # per-kernel attribution for the roofline (separate pass, events around every launch)
+    lib.dBatchSetKernelTiming(B, 1)
+    lib.dBatchResetCounters(B)
+    step(args.steps)
+    kms = (ctypes.c_double * 2)()
+    kl = (ctypes.c_longlong * 2)()
+    lib.dBatchGetKernelTimes(B, kms, kl, 2)
+    lib.dBatchSetKernelTiming(B, 0)
+    ck = counters(lib, B)
+    ng_per_world = 41
+    step_bytes = (A_B * ck["body_steps"] + (C_B // 2) * ck["contacts"] + (D_B * ITERS + ASM_B) * ck["rows"]) / max(kl[1], 1)
+    collide_bytes = (B_B * ng_per_world * nworlds * kl[0] + (C_B // 2) * ck["contacts"]) / max(kl[0], 1)
+    t_step = kms[1] / max(kl[1], 1) * 1e-3
+    t_col = kms[0] / max(kl[0], 1) * 1e-3
+    peak, peak_kind = peaks()
+    achieved = step_bytes / t_step / 1e9
+    traffic = None
+    tf = os.path.join(ROOT, "profiles", "k_step_traffic.json")
+    if os.path.exists(tf):
+        traffic = json.load(open(tf)).get("dram_bytes_per_launch")
+
+    # end to end through the C ABI with host buffers every step
+    nb = lib.dBatchNumBodies(B)
+    pos = np.zeros((nworlds, nb, 3), np.float32); quat = np.zeros((nworlds, nb, 4), np.float32)
+    lv = np.zeros((nworlds, nb, 3), np.float32); av = np.zeros((nworlds, nb, 3), np.float32)
+    force = np.zeros((nworlds, nb, 3), np.float32); torque = np.zeros((nworlds, nb, 3), np.float32)
+    rng = np.random.default_rng(rank)
+    lib.dBatchResetCounters(B)
+    e2e_steps = args.steps
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(e2e_steps):
+        force[:, :, 0] = 0.01 * rng.standard_normal((nworlds, nb), dtype=np.float32)
+        lib.dBatchAddForces(B, force.ctypes.data, torque.ctypes.data)
+        step(1)
+        lib.dBatchGetBodyState(B, pos.ctypes.data, quat.ctypes.data, lv.ctypes.data, av.ctypes.data)
+    t_e2e = time.perf_counter() - t0
+    ce = counters(lib, B)
+    assert np.isfinite(pos).all()
+
+    vals = np.array([elapsed_ms, t_e2e], dtype=np.float64)
+    sums = np.array([c["body_steps"], c["contacts"], ce["body_steps"], c["rows"], launches, c["overflow_worlds"]], dtype=np.float64)
+    if dist is not None:
+        import torch
+
+        tv = torch.tensor(vals, device="cuda"); ts = torch.tensor(sums, device="cuda")
+        dist.all_reduce(tv, op=dist.ReduceOp.MAX); dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+        vals, sums = tv.cpu().numpy(), ts.cpu().numpy()
+    if rank == 0:
+        t = vals[0] * 1e-3
+        out = {
+            "metric": "body-steps/sec (batched dSpaceCollide + dWorldQuickStep, 20 SOR iterations)",
+            "value": sums[0] / t, "unit": "body-steps/s",
+            "contacts_solved_per_sec": sums[1] / t,
+            "n_gpus": world_size, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": vals[0] / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"configs[1]: {args.worlds} independent worlds/GPU x (plane + 32-box stack + 8 spheres), "
+                                   f"dHashSpace, boxstack contact policy maxc 8, quickstep 20 it, h={H}, settled {SETTLE} steps",
+                       "worlds_per_gpu": args.worlds, "bodies_per_world": nb, "rows_per_world_step": sums[3] / max(c["steps"] * world_size, 1),
+                       "contacts_per_world_step": sums[1] / max(c["steps"] * world_size, 1),
+                       "cache": "per-step working set (rows written+read) ~%.0f MB/GPU > 126 MB L2" % (c["rows"] / args.steps * 128 * 2 / 1e6 + 70),
+                       "precision": "dSINGLE", "parity": "bit-exact vs reference (tests/)"},
+            "e2e": {"value": sums[2] / vals[1], "unit": "body-steps/s", "h2d_bytes_per_step": int(force.nbytes + torque.nbytes) * world_size,
+                    "d2h_bytes_per_step": int(pos.nbytes + quat.nbytes + lv.nbytes + av.nbytes) * world_size},
+            "gpu_launches": int(sums[4]),
+            "roofline": {"bound": "hbm", "kernel": "k_step", "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": step_bytes,
+                         "kernel_ms": t_step * 1e3, "kernel_share_of_step": t_step / (t_step + t_col),
+                         "k_collide": {"algorithmic_bytes_per_launch": collide_bytes, "kernel_ms": t_col * 1e3,
+                                       "achieved": collide_bytes / t_col / 1e9}},
+            "clocks": clocks,
+            "overflow_worlds": int(sums[5]),
+        }
+        if world_size == 1:
+            out["cpu_baseline"] = cpu_baseline(args, bounded_seconds=20)
+        print(json.dumps(out))
+    lib.dBatchDestroy(B)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def cpu_run(nproc, worlds_each, steps, settle, timeout=900):
+    exe = os.path.join(ROOT, "oracle", "_ref", "driver_ref_single")
+    if not os.path.exists(exe):
+        return None
+    procs = [subprocess.Popen([exe, "--scene", SCENE, "--worlds", str(worlds_each), "--world0", str(i * worlds_each),
+                               "--steps", str(steps), "--settle", str(settle), "--time"], stdout=subprocess.PIPE, text=True)
+             for i in range(nproc)]
+    outs = [json.loads(p.communicate(timeout=timeout)[0].strip().splitlines()[-1]) for p in procs]
+    secs = max(o["seconds"] for o in outs)
+    return {"body_steps": sum(o["body_steps"] for o in outs), "contacts": sum(o["contacts"] for o in outs), "seconds": secs}
+
+
+def cpu_baseline(args, bounded_seconds=20):
+    """the UNMODIFIED reference (oracle/_ref) on this box's host cores: one process per core
+    (ODE has process-global state), a bounded sample of the same workload"""
+    nproc = os.cpu_count() or 1
+    worlds_each = 8
+    steps = 100
+    r = cpu_run(nproc, worlds_each, steps, SETTLE)
+    if r is None:
+        return {"value": None, "unit": "body-steps/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref not present"}
+    return {"value": r["body_steps"] / r["seconds"], "unit": "body-steps/s", "cores": nproc, "kind": "reference",
+            "contacts_solved_per_sec": r["contacts"] / r["seconds"],
+            "sample": f"{nproc} processes x {worlds_each} worlds of {SCENE}, {SETTLE} settle steps untimed + {steps} timed steps"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    nproc = os.cpu_count() or 1
+    worlds_each = 8
+    r = cpu_run(nproc, worlds_each, max(args.steps, 1), SETTLE + max(args.warmup, 3))
+    if r is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref (reference build) not present on this box"}))
+        return
+    v = r["body_steps"] / r["seconds"]
+    sample = f"{nproc} processes x {worlds_each} worlds of {SCENE}, {SETTLE}+{max(args.warmup, 3)} untimed steps, {args.steps} timed"
+    print(json.dumps({
+        "impl": "reference", "metric": "body-steps/sec (batched dSpaceCollide + dWorldQuickStep, 20 SOR iterations)",
+        "value": v, "unit": "body-steps/s", "contacts_solved_per_sec": r["contacts"] / r["seconds"],
+        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": r["seconds"] * 1e3 / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"configs[1] sample: {nproc * worlds_each} worlds x (plane + 32-box stack + 8 spheres), reference ODE 0.12 dSINGLE on host cores"},
+        "cpu_baseline": {"value": v, "unit": "body-steps/s", "cores": nproc, "kind": "reference", "sample": sample},
+        "e2e": {"value": v, "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--worlds", type=int, default=WORLDS_PER_GPU)
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -65,6 +65,12 @@ def _bits(a):
     return a.view(np.uint32 if a.dtype == np.float32 else np.uint64)
 
 
+def _biteq(a, b):
+    """bitwise equality, except that any NaN equals any NaN: x86 SSE produces the default
+    NaN 0xffc00000 for invalid operations, CUDA 0x7fffffff — payloads are not arithmetic"""
+    return (_bits(a) == _bits(b)) | (np.isnan(a) & np.isnan(b))
+
+
 def compare(ta, tb, verbose=False, stop_on_mismatch=True):
     """Returns a dict of summary statistics. ta = candidate, tb = reference."""
     assert ta["realsize"] == tb["realsize"] and ta["nworlds"] == tb["nworlds"]
@@ -93,19 +99,19 @@ def compare(ta, tb, verbose=False, stop_on_mismatch=True):
                 out["exact_ok"] = False
                 if out["first_exact_mismatch"] is None:
                     out["first_exact_mismatch"] = (s, w, "seed")
-            if not np.array_equal(_bits(a["state0"]), _bits(b["state0"])) and out["first_state_bit_mismatch"] is None:
+            if not _biteq(a["state0"], b["state0"]).all() and out["first_state_bit_mismatch"] is None:
                 out["first_state_bit_mismatch"] = (s, w, "state0")
             out["pairs"] += len(b["pairs"])
             out["contacts"] += len(b["cg"])
             if a["cd"].shape == b["cd"].shape:
                 out["contact_vals"] += b["cd"].size
-                out["contact_bits_equal"] += int((_bits(a["cd"]) == _bits(b["cd"])).sum())
+                out["contact_bits_equal"] += int(_biteq(a["cd"], b["cd"]).sum())
                 out["max_contact_relerr"] = max(out["max_contact_relerr"], _relerr(a["cd"], b["cd"]))
                 out["fb_vals"] += b["fb"].size
-                out["fb_bits_equal"] += int((_bits(a["fb"]) == _bits(b["fb"])).sum())
+                out["fb_bits_equal"] += int(_biteq(a["fb"], b["fb"]).sum())
                 out["max_fb_relerr"] = max(out["max_fb_relerr"], _relerr(a["fb"], b["fb"]))
             out["state_vals"] += b["state1"].size
-            eq = _bits(a["state1"]) == _bits(b["state1"])
+            eq = _biteq(a["state1"], b["state1"])
             out["state_bits_equal"] += int(eq.sum())
             if not eq.all() and out["first_state_bit_mismatch"] is None:
                 out["first_state_bit_mismatch"] = (s, w, "state1")
