@@ -35,7 +35,7 @@ SCENE = "stack32"
 WORLDS_PER_GPU = 4096
 SETTLE = 300
 H = 0.01
-CONTACTS_CAP = 256
+CONTACTS_CAP = 192   # stack32 peaks at ~150 contacts/world (measured on the reference); overflow is reported
 # algorithmic bytes per unit, dSINGLE: A body-step, B geom-step, C contact,
 # D row x SOR iteration, ASM row assembly
 A_B, B_B, C_B, D_B, ASM_B = 136, 80, 128, 224, 128
@@ -181,22 +181,37 @@ def run_b200(args):
     lib.dBatchSetKernelTiming(B, 1)
     lib.dBatchResetCounters(B)
     step(args.steps)
-    kms = (ctypes.c_double * 2)()
-    kl = (ctypes.c_longlong * 2)()
-    lib.dBatchGetKernelTimes(B, kms, kl, 2)
+    NK = 8
+    kms = (ctypes.c_double * NK)()
+    kl = (ctypes.c_longlong * NK)()
+    nk = lib.dBatchGetKernelTimes(B, kms, kl, NK)
     lib.dBatchSetKernelTiming(B, 0)
     ck = counters(lib, B)
+    names = [lib.dBatchKernelName(k).decode() for k in range(nk)]
+    kt = {names[k]: kms[k] / max(kl[k], 1) * 1e-3 for k in range(nk)}      # seconds per launch
+    nl = max(kl[0], 1)
     ng_per_world = 41
-    step_bytes = (A_B * ck["body_steps"] + (C_B // 2) * ck["contacts"] + (D_B * ITERS + ASM_B) * ck["rows"]) / max(kl[1], 1)
-    collide_bytes = (B_B * ng_per_world * nworlds * kl[0] + (C_B // 2) * ck["contacts"]) / max(kl[0], 1)
-    t_step = kms[1] / max(kl[1], 1) * 1e-3
-    t_col = kms[0] / max(kl[0], 1) * 1e-3
+    # algorithmic bytes per launch (SURVEY 8d terms): collide = geoms (B) + contacts written (C/2);
+    # prep = bodies read (A/2) + contacts read (C/2) + row assembly; sor = D x iterations per row;
+    # post = bodies read+written (A/2)
+    kbytes = {
+        "k_collide": (B_B * ng_per_world * nworlds * nl + (C_B // 2) * ck["contacts"]) / nl,
+        "k_prep": ((A_B // 2) * ck["body_steps"] + (C_B // 2) * ck["contacts"] + ASM_B * ck["rows"]) / nl,
+        "k_sor": (D_B * ITERS * ck["rows"]) / nl,
+        "k_post": ((A_B // 2) * ck["body_steps"]) / nl,
+    }
+    t_all = sum(kt.values())
+    dom = max(kt, key=kt.get)
     peak, peak_kind = peaks()
+    step_bytes = kbytes[dom]
+    t_step = kt[dom]
     achieved = step_bytes / t_step / 1e9
     traffic = None
-    tf = os.path.join(ROOT, "profiles", "k_step_traffic.json")
+    tf = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
     if os.path.exists(tf):
-        traffic = json.load(open(tf)).get("dram_bytes_per_launch")
+        tj = json.load(open(tf))
+        if tj.get("kernel") == dom:
+            traffic = tj.get("dram_bytes_per_launch")
 
     # end to end through the C ABI with host buffers every step
     nb = lib.dBatchNumBodies(B)
@@ -243,11 +258,13 @@ def run_b200(args):
             "e2e": {"value": sums[2] / vals[1], "unit": "body-steps/s", "h2d_bytes_per_step": int(force.nbytes + torque.nbytes) * world_size,
                     "d2h_bytes_per_step": int(pos.nbytes + quat.nbytes + lv.nbytes + av.nbytes) * world_size},
             "gpu_launches": int(sums[4]),
-            "roofline": {"bound": "hbm", "kernel": "k_step", "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": step_bytes,
-                         "kernel_ms": t_step * 1e3, "kernel_share_of_step": t_step / (t_step + t_col),
-                         "k_collide": {"algorithmic_bytes_per_launch": collide_bytes, "kernel_ms": t_col * 1e3,
-                                       "achieved": collide_bytes / t_col / 1e9}},
+                         "kernel_ms": t_step * 1e3, "kernel_share_of_step": t_step / t_all,
+                         "whole_step": {"algorithmic_bytes": sum(kbytes.values()),
+                                        "achieved": sum(kbytes.values()) / (vals[0] * 1e-3 / args.steps) / 1e9 if world_size == 1 else None},
+                         "kernels": {k: {"ms": kt[k] * 1e3, "algorithmic_bytes_per_launch": kbytes.get(k), "achieved": kbytes.get(k, 0) / kt[k] / 1e9}
+                                     for k in kt}},
             "clocks": clocks,
             "overflow_worlds": int(sums[5]),
         }

@@ -98,6 +98,11 @@ dBatchID dBatchCreate(int nworlds, const dWorldID *worlds, const dSpaceID *space
   caps.NP = std::min(NG * (NG - 1) / 2 + 1, std::max(256, 8 * NG));
   caps.NR = 3 * caps.NC;
   caps.npolicy = 1;
+  {
+    int it = 1;
+    for (int w = 0; w < nworlds; w++) it = std::max(it, worlds[w]->qs_iterations);
+    caps.NEP = (it + 7) / 8;
+  }
   char err[512] = "";
   B->bk = obk_create(caps, desc ? desc->device : 0, err, sizeof err);
   if (!B->bk) { ob_set_last_error("dBatchCreate: %s", err); delete B; return 0; }

@@ -66,6 +66,33 @@ OB_HD void ob_row_finalize(real *J /*12*/, real c, real cfm, int b2 /* -1: none 
   *Adcfm_out = Ad * cfm;
 }
 
+// Same as ob_row_finalize but leaves J unscaled and also returns Ad = w/(diag+cfm); the SOR
+// kernel stores the unscaled J and re-applies `J *= Ad` (quickstep.cpp:393-401) on the fly.
+OB_HD void ob_row_finalize2(const real *J /*12, unscaled*/, real c, real cfm, int b2 /* -1: none */, const real *tmp1_b1,
+                            const real *tmp1_b2, real invM1, const real *invI1, real invM2, const real *invI2,
+                            real stepsize1, real sor_w, real *iMJ /*12*/, real *b_out, real *Adcfm_out, real *Ad_out) {
+  real sum = 0;
+  for (int j = 0; j < 6; j++) sum += J[j] * tmp1_b1[j];
+  if (b2 != -1) for (int j = 0; j < 6; j++) sum += J[6 + j] * tmp1_b2[j];
+  real rhs = c * stepsize1 - sum;
+  cfm *= stepsize1;
+  for (int j = 0; j < 3; j++) iMJ[j] = invM1 * J[j];
+  ob_mul0_331(iMJ + 3, invI1, J + 3);
+  if (b2 != -1) {
+    for (int j = 0; j < 3; j++) iMJ[j + 6] = invM2 * J[j + 6];
+    ob_mul0_331(iMJ + 9, invI2, J + 9);
+  } else {
+    for (int j = 6; j < 12; j++) iMJ[j] = 0;
+  }
+  real s2 = 0;
+  for (int j = 0; j < 6; j++) s2 += iMJ[j] * J[j];
+  if (b2 != -1) for (int k = 6; k < 12; k++) s2 += iMJ[k] * J[k];
+  real Ad = sor_w / (s2 + cfm);
+  *b_out = rhs * Ad;
+  *Adcfm_out = Ad * cfm;
+  *Ad_out = Ad;
+}
+
 // One SOR row update (quickstep.cpp:490-581).  fc1/fc2 point at the 6-vectors of the
 // row's bodies (fc2 = 0 for one-body rows); lam_f = lambda[findex] (ignored if findex<0).
 // Returns the new lambda.

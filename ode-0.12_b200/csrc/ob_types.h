@@ -106,6 +106,7 @@ struct ObBatchDev {
   int NC;       // contact joints per world-step (also contact slots)
   int NR;       // constraint rows per world-step
   int npolicy;
+  int NEP;      // shuffle epochs per step = ceil(max iters / 8)
   ObWorld *world;        // [W]
   ObBodyDyn *bdyn;       // [W*NB]
   ObBodyConst *bconst;   // [W*NB]
@@ -117,7 +118,17 @@ struct ObBatchDev {
   int *pairs;            // [W*NP*2] (o1,o2) geom indices in callback order
   int *ncontacts;        // [W]
   ObContact *contacts;   // [W*NC] contact joints in creation order
-  real *rowJ;            // [W*NR*12]
+  real *rows;            // [W*NR*20] compact rows of the CUDA path (ob_step_kernel.cuh)
+  real *invIw;           // [W*NB*12] world-frame inverse inertia per body (step scratch)
+  real *tmp1;            // [W*NB*8]  v/h + invM*f_ext per body (step scratch)
+  int *stepinfo;         // [W*16] hand-off between k_prep / k_sor / k_post
+  unsigned char *ibody;  // [W*NB] island body order (stepping order)
+  unsigned short *isz;   // [W*NB*4] per island: body start, body count, joint start, joint count
+  unsigned short *jrow;  // [W*(NC+1)] first row of joint k (island joint order)
+  unsigned short *ijoint;// [W*NC] island joint order -> contact joint id
+  unsigned short *sched; // [W*NEP*NR] rows in level order, per shuffle epoch
+  unsigned short *pstart;// [W*NEP*(NR+1)] first slot of every pass, per shuffle epoch
+  real *rowJ;            // [W*NR*12] (host test backend only)
   real *rowiMJ;          // [W*NR*12]
   real *rowJc;           // [W*NR*12] unscaled J copy (only written when the feedback tap is on)
   real *rowS;            // [W*NR*4]  b(rhs), Ad*cfm, lo, hi

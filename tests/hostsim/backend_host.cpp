@@ -351,8 +351,22 @@ static void step_world(ObBatchDev &d, int w, real h, int taps) {
             int t = order[i]; order[i] = order[swapi]; order[swapi] = t;
           }
         }
+        // mirror of the CUDA level schedule (ob_step_kernel.cuh): execute rows level by level;
+        // inside a level in an arbitrary (here: reversed) order — results must not change
+        std::vector<int> lvl(m), lastl(inb, 0), sched;
+        int nlev = 0;
         for (int i = 0; i < m; i++) {
           int idx = order[i];
+          int t1 = RI[idx * 4 + 1], t2 = RI[idx * 4 + 2];
+          int lv = lastl[t1];
+          if (t2 >= 0 && lastl[t2] > lv) lv = lastl[t2];
+          lv++;
+          lastl[t1] = lv; if (t2 >= 0) lastl[t2] = lv;
+          lvl[i] = lv; if (lv > nlev) nlev = lv;
+        }
+        for (int l = 1; l <= nlev; l++) for (int i = m - 1; i >= 0; i--) if (lvl[i] == l) sched.push_back(order[i]);
+        for (int i = 0; i < m; i++) {
+          int idx = getenv("OB_HOST_LEVELS") ? sched[i] : order[i];
           int t1 = RI[idx * 4 + 1], t2 = RI[idx * 4 + 2], fi = RI[idx * 4];
           lam[idx] = ob_sor_row(&J[(size_t)idx * 12], &iMJ[(size_t)idx * 12], S[idx * 4], S[idx * 4 + 1], S[idx * 4 + 2],
                                 S[idx * 4 + 3], fi, fi >= 0 ? lam[fi] : 0, lam[idx], &fc[6 * t1], t2 >= 0 ? &fc[6 * t2] : 0);
