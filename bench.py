@@ -197,6 +197,7 @@ def run_b200(args):
     kbytes = {
         "k_collide": (B_B * ng_per_world * nworlds * nl + (C_B // 2) * ck["contacts"]) / nl,
         "k_prep": ((A_B // 2) * ck["body_steps"] + (C_B // 2) * ck["contacts"] + ASM_B * ck["rows"]) / nl,
+        "k_sched": (8 * 3 * ck["rows"]) / nl,      # row meta read + sched/pstart written per shuffle epoch
         "k_sor": (D_B * ITERS * ck["rows"]) / nl,
         "k_post": ((A_B // 2) * ck["body_steps"]) / nl,
     }

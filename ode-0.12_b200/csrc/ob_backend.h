@@ -27,7 +27,7 @@ int obk_add_forces(ObBackend *, const real *force3, const real *torque3);
 void *obk_stream(ObBackend *);
 int obk_timer_start(ObBackend *);
 int obk_timer_stop(ObBackend *, float *ms);
-#define OBK_NKERNELS 4
+#define OBK_NKERNELS 5
 void obk_set_kernel_timing(ObBackend *, int enable);
 void obk_get_kernel_times(ObBackend *, double *ms, long long *launches);
 const char *obk_kernel_name(int k);

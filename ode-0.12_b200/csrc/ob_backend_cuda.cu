@@ -280,9 +280,9 @@ struct ObBackend {
   real *st_dev;      // packed state staging on the device: pos3|quat4|lvel3|avel3
   real *st_host;     // pinned
   size_t st_elems;   // W*NB
-  size_t smem_collide, smem_prep, smem_sor, smem_post;
-  int grid, grid_step, tile;
-  cudaEvent_t ev[8];   // 0,1: user timer; 2..6 per-kernel timing
+  size_t smem_collide, smem_prep, smem_sched, smem_sor, smem_post;
+  int grid, grid_step, grid_sor, tile;
+  cudaEvent_t ev[8];   // 0,1: user timer; 2..7 per-kernel timing
   int ktiming;
   double kms[OBK_NKERNELS];
   long long klaunch[OBK_NKERNELS];
@@ -353,8 +353,11 @@ ObBackend *obk_create(const ObBatchDev &caps, int device, char *err, size_t errl
     b->tile = G;
     b->smem_prep = prep_tile_smem(d.NB, d.NC, d.NR).total * (32 / G);
     b->smem_sor = sor_tile_smem(d.NB, d.NR).total * (32 / G);
+    b->smem_sched = sched_smem(d.NB, d.NR).total;
     b->smem_post = post_tile_smem(d.NG).total * (32 / G);
     b->grid_step = (int)((W + (32 / G) - 1) / (32 / G));
+    b->grid_sor = b->grid_step;
+    { const char *g = getenv("OB_GRID_SOR"); if (g && atoi(g) > 0 && atoi(g) < b->grid_sor) b->grid_sor = atoi(g); }
   }
   if (d.NB > 254 || d.NG > 255) { snprintf(err, errlen, "world too large for the tile-per-world step kernel (NB=%d NG=%d NR=%d)", d.NB, d.NG, d.NR); goto fail; }
   if (b->smem_collide > (size_t)prop.sharedMemPerBlockOptin || b->smem_prep > (size_t)prop.sharedMemPerBlockOptin ||
@@ -370,6 +373,9 @@ ObBackend *obk_create(const ObBatchDev &caps, int device, char *err, size_t errl
   CK(cudaFuncSetAttribute(k_post<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_post));
   OB_SETSMEM(8) OB_SETSMEM(16) OB_SETSMEM(32)
 #undef OB_SETSMEM
+  CK(cudaFuncSetAttribute(k_sched<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sched));
+  CK(cudaFuncSetAttribute(k_sched<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sched));
+  CK(cudaFuncSetAttribute(k_sched<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sched));
   {
     // grid: every world gets its own CTA up to 16 resident CTAs per SM worth of blocks, beyond that grid-stride
     int cap = prop.multiProcessorCount * 16;
@@ -427,23 +433,28 @@ void obk_set_kernel_timing(ObBackend *b, int enable) {
 void obk_get_kernel_times(ObBackend *b, double *ms, long long *l) {
   for (int k = 0; k < OBK_NKERNELS; k++) { ms[k] = b->kms[k]; l[k] = b->klaunch[k]; }
 }
-const char *obk_kernel_name(int k) { static const char *n[] = {"k_collide", "k_prep", "k_sor", "k_post"}; return k >= 0 && k < 4 ? n[k] : ""; }
+const char *obk_kernel_name(int k) { static const char *n[] = {"k_collide", "k_prep", "k_sched", "k_sor", "k_post"}; return k >= 0 && k < 5 ? n[k] : ""; }
 
 template <int G> static void launch_step(ObBackend *b, real h, int taps) {
   cudaEvent_t *ev = b->ev + 2;
+  const int W = b->d.W;
   if (b->ktiming) cudaEventRecord(ev[0], b->stream);
   k_collide<<<b->grid, OB_THREADS, b->smem_collide, b->stream>>>(b->d);
   if (b->ktiming) cudaEventRecord(ev[1], b->stream);
   k_prep<G><<<b->grid_step, 32, b->smem_prep, b->stream>>>(b->d, h, taps);
   if (b->ktiming) cudaEventRecord(ev[2], b->stream);
-  k_sor<G><<<b->grid_step, 32, b->smem_sor, b->stream>>>(b->d, taps);
+  if (b->d.NB <= 64) k_sched<2><<<W, 32, b->smem_sched, b->stream>>>(b->d, G, taps);
+  else if (b->d.NB <= 128) k_sched<4><<<W, 32, b->smem_sched, b->stream>>>(b->d, G, taps);
+  else k_sched<8><<<W, 32, b->smem_sched, b->stream>>>(b->d, G, taps);
   if (b->ktiming) cudaEventRecord(ev[3], b->stream);
+  k_sor<G><<<b->grid_sor, 32, b->smem_sor, b->stream>>>(b->d, taps);
+  if (b->ktiming) cudaEventRecord(ev[4], b->stream);
   k_post<G><<<b->grid_step, 32, b->smem_post, b->stream>>>(b->d, h);
-  g_launches += 4;
+  g_launches += 5;
   if (b->ktiming) {
-    cudaEventRecord(ev[4], b->stream);
-    if (cudaEventSynchronize(ev[4]) == cudaSuccess)
-      for (int k = 0; k < 4; k++) { float m = 0; cudaEventElapsedTime(&m, ev[k], ev[k + 1]); b->kms[k] += m; b->klaunch[k]++; }
+    cudaEventRecord(ev[5], b->stream);
+    if (cudaEventSynchronize(ev[5]) == cudaSuccess)
+      for (int k = 0; k < 5; k++) { float m = 0; cudaEventElapsedTime(&m, ev[k], ev[k + 1]); b->kms[k] += m; b->klaunch[k]++; }
   }
 }
 

@@ -38,15 +38,11 @@
 __host__ __device__ inline size_t ob_al(size_t x, size_t a) { return (x + a - 1) & ~(a - 1); }
 
 struct PrepTileSmem {   // byte offsets inside one world's shared-memory slice (k_prep)
-  size_t invM, rowb, ord, lvl, X, jb1, jb2, adjstart, cursor, adj, btag, jtag, stack, ibody, ijoint, jrow, isz, last, misc, total;
+  size_t invM, jb1, jb2, adjstart, cursor, adj, btag, jtag, stack, ibody, ijoint, jrow, isz, misc, total;
 };
 __host__ __device__ inline PrepTileSmem prep_tile_smem(int NB, int NC, int NR) {
   PrepTileSmem s; size_t o = 0;
   s.invM = o; o = ob_al(o + sizeof(real) * NB, 16);
-  s.rowb = o; o = ob_al(o + 2 * (size_t)NR, 16);                       // b1,b2 per row
-  s.ord = o; o = ob_al(o + sizeof(unsigned short) * NR, 16);
-  s.lvl = o; o = ob_al(o + sizeof(unsigned short) * NR, 16);           // swap indices, then level per position
-  s.X = o; o = ob_al(o + sizeof(unsigned short) * (NR + 2), 16);       // rows per level -> level ends
   s.jb1 = o; o = ob_al(o + (size_t)NC, 4);
   s.jb2 = o; o = ob_al(o + (size_t)NC, 4);
   s.adjstart = o; o = ob_al(o + sizeof(unsigned short) * (NB + 1), 4);
@@ -59,7 +55,6 @@ __host__ __device__ inline PrepTileSmem prep_tile_smem(int NB, int NC, int NR) {
   s.ijoint = o; o = ob_al(o + sizeof(unsigned short) * NC, 4);
   s.jrow = o; o = ob_al(o + sizeof(unsigned short) * (NC + 1), 4);
   s.isz = o; o = ob_al(o + sizeof(unsigned short) * 4 * NB, 4);
-  s.last = o; o = ob_al(o + sizeof(unsigned short) * NB, 4);
   s.misc = o; o = ob_al(o + sizeof(int) * 8, 16);
   s.total = ob_al(o, 16);
   return s;
@@ -133,10 +128,6 @@ __global__ void __launch_bounds__(32) k_prep(ObBatchDev d, real h, int taps) {
   const unsigned FULL = 0xffffffffu;
   unsigned char *smem = smem_all + (size_t)grp * L.total;
   real *s_invM = (real *)(smem + L.invM);
-  unsigned char *s_rowb = smem + L.rowb;
-  unsigned short *s_ord = (unsigned short *)(smem + L.ord);
-  unsigned short *s_lvl = (unsigned short *)(smem + L.lvl);
-  unsigned short *s_X = (unsigned short *)(smem + L.X);
   unsigned char *s_jb1 = smem + L.jb1, *s_jb2 = smem + L.jb2;
   unsigned short *s_adjstart = (unsigned short *)(smem + L.adjstart);
   unsigned short *s_cursor = (unsigned short *)(smem + L.cursor);
@@ -148,7 +139,6 @@ __global__ void __launch_bounds__(32) k_prep(ObBatchDev d, real h, int taps) {
   unsigned short *s_ijoint = (unsigned short *)(smem + L.ijoint);
   unsigned short *s_jrow = (unsigned short *)(smem + L.jrow);
   unsigned short *s_isz = (unsigned short *)(smem + L.isz);
-  unsigned short *s_last = (unsigned short *)(smem + L.last);
   int *s_misc = (int *)(smem + L.misc);
   const real stepsize1 = ob_recip(h);
 
@@ -159,7 +149,6 @@ __global__ void __launch_bounds__(32) k_prep(ObBatchDev d, real h, int taps) {
     ObWorld &W = d.world[wc];
     const int nb = valid ? W.nb : 0;
     const int nc = valid ? d.ncontacts[wc] : 0;
-    const int iters = W.iters;
     ObBodyDyn *bd = d.bdyn + (size_t)wc * d.NB;
     const ObBodyConst *bc = d.bconst + (size_t)wc * d.NB;
     const ObGeom *geoms = d.geom + (size_t)wc * d.NG;
@@ -344,8 +333,6 @@ __global__ void __launch_bounds__(32) k_prep(ObBatchDev d, real h, int taps) {
           const unsigned fio = (unsigned)(r.findex[q] >= 0 ? q - r.findex[q] : 0);
           const unsigned ub2 = (unsigned)(b2 < 0 ? 255 : b2);
           store_row(rows + (size_t)ri * OB_ROWW, rw, (unsigned)b1 | (ub2 << 8) | (fio << 16));
-          s_rowb[2 * ri] = (unsigned char)b1; s_rowb[2 * ri + 1] = (unsigned char)ub2;
-          s_ord[ri] = (unsigned short)fio;   // parked: "has findex" flag for the initial order below
         }
       }
       if (k < nij) { g_ijoint[k] = s_ijoint[k]; g_jrow[k] = s_jrow[k]; }
@@ -353,57 +340,121 @@ __global__ void __launch_bounds__(32) k_prep(ObBatchDev d, real h, int taps) {
     if (gl == 0 && valid) g_jrow[nij] = (unsigned short)(have_rows ? mtot : 0);
     __syncwarp();
 
-    // ---- (7) per shuffle epoch: the reference's row order, then the level schedule
-    const int nep = (iters + 7) >> 3;
-    const uint32_t seed = W.seed;
-    if (gl == 0) s_misc[5] = 0;
-    // initial order per island (quickstep.cpp:409-424): findex==-1 rows ascending at the head,
-    // the others descending at the tail.  s_ord currently holds the per-row findex flag; the
-    // result goes to s_lvl first, then is copied back (one lane per world).
-    if (gl == 0 && have_rows) {
-      for (int isl = 0; isl < nis; isl++) {
-        const int j0 = s_isz[4 * isl + 2], jn = s_isz[4 * isl + 3];
-        if (!jn) continue;
-        const int r0 = s_jrow[j0], m = s_jrow[j0 + jn] - r0;
-        int head = 0, tail = m - 1;
-        for (int i = 0; i < m; i++) { if (s_ord[r0 + i] == 0) s_lvl[r0 + head++] = (unsigned short)i; else s_lvl[r0 + tail--] = (unsigned short)i; }
-      }
-      for (int i = 0; i < mtot; i++) s_ord[i] = s_lvl[i];
+    // (7) the row order and the level schedule of every shuffle epoch are built by k_sched
+    if (gl == 0 && valid) {
+      si[SI_NIS] = nis; si[SI_NIB] = nib; si[SI_NIJ] = nij; si[SI_MTOT] = mtot; si[SI_HAVEROWS] = have_rows ? 1 : 0;
+      unsigned short *g_isz = d.isz + (size_t)wc * 4 * d.NB;
+      for (int i = 0; i < 4 * nis; i++) g_isz[i] = s_isz[i];
     }
     __syncwarp();
-    const int mtot_max = warp_max_i(mtot);
-    const int nep_max = warp_max_i(valid ? nep : 0);
-    for (int ep = 0; ep < nep_max && ep < d.NEP; ep++) {
-      const bool epv = have_rows && ep < nep;
+  }
+}
+
+
+// =====================================================================================
+// k_sched: one warp per world.  For every shuffle epoch: the reference's row order
+// (quickstep.cpp:409-482, LCG offsets per island as the reference consumes them) and the level
+// schedule derived from it, written as sched[] (rows in level order) + pstart[] (first slot of
+// every pass; a pass = at most G rows of one level).  The level recurrence is a serial chain
+// over the order; it runs with the per-body "last level" table spread over the lanes'
+// registers (body b -> lane b&31, register b>>5) so one step costs two shuffles, not a
+// shared-memory round trip.
+struct SchedSmem { size_t ord, rowb, fio, lvl, X, isl, total; };
+__host__ __device__ inline SchedSmem sched_smem(int NB, int NR) {
+  SchedSmem s; size_t o = 0;
+  s.ord = o; o = ob_al(o + sizeof(unsigned short) * NR, 16);
+  s.rowb = o; o = ob_al(o + sizeof(unsigned short) * NR, 16);
+  s.fio = o; o = ob_al(o + (size_t)NR, 16);
+  s.lvl = o; o = ob_al(o + sizeof(unsigned short) * NR, 16);      // swap indices, then level per position
+  s.X = o; o = ob_al(o + sizeof(int) * (NR + 2), 16);              // rows per level -> level starts -> level ends
+  s.isl = o; o = ob_al(o + sizeof(unsigned short) * 2 * NB, 16);   // (r0, m) per island that has rows
+  s.total = ob_al(o, 16);
+  return s;
+}
+
+template <int NBR>
+__global__ void __launch_bounds__(32) k_sched(ObBatchDev d, int G, int taps) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const SchedSmem L = sched_smem(d.NB, d.NR);
+  unsigned short *s_ord = (unsigned short *)(smem + L.ord);
+  unsigned short *s_rowb = (unsigned short *)(smem + L.rowb);
+  unsigned char *s_fio = smem + L.fio;
+  unsigned short *s_lvl = (unsigned short *)(smem + L.lvl);
+  int *s_X = (int *)(smem + L.X);
+  unsigned short *s_isl = (unsigned short *)(smem + L.isl);
+  const int lane = threadIdx.x;
+  const unsigned FULL = 0xffffffffu;
+  const unsigned lt_mask = (1u << lane) - 1u;
+
+  for (int w = blockIdx.x; w < d.W; w += gridDim.x) {
+    ObWorld &W = d.world[w];
+    int *si = d.stepinfo + (size_t)w * SI_WORDS;
+    const int nis = si[SI_NIS];
+    const bool have_rows = si[SI_HAVEROWS] != 0;
+    const int mtot = have_rows ? si[SI_MTOT] : 0;
+    const int nep = (W.iters + 7) >> 3;
+    const real *rows = d.rows + (size_t)w * d.NR * OB_ROWW;
+    const unsigned short *g_isz = d.isz + (size_t)w * 4 * d.NB;
+    const unsigned short *g_jrow = d.jrow + (size_t)w * (d.NC + 1);
+    if (mtot == 0) {
+      if (lane == 0) for (int ep = 0; ep < d.NEP; ep++) si[SI_NPASS0 + ep] = 0;
+      continue;
+    }
+    // islands that own rows, in island order
+    int nri = 0;
+    if (lane == 0) {
+      for (int isl = 0; isl < nis; isl++) {
+        const int j0 = g_isz[4 * isl + 2], jn = g_isz[4 * isl + 3];
+        if (!jn) continue;
+        const int r0 = g_jrow[j0], m = g_jrow[j0 + jn] - r0;
+        if (m > 0) { s_isl[2 * nri] = (unsigned short)r0; s_isl[2 * nri + 1] = (unsigned short)m; nri++; }
+      }
+    }
+    nri = __shfl_sync(FULL, nri, 0);
+    for (int i = lane; i < mtot; i += 32) {
+      const unsigned meta = *(const unsigned *)(rows + (size_t)i * OB_ROWW + OB_ROWF);
+      s_rowb[i] = (unsigned short)(meta & 0xffffu);
+      s_fio[i] = (unsigned char)((meta >> 16) & 255u);
+    }
+    __syncwarp();
+    // initial order per island (quickstep.cpp:409-424): findex==-1 rows ascending at the head,
+    // the others descending at the tail
+    for (int q = 0; q < nri; q++) {
+      const int r0 = s_isl[2 * q], m = s_isl[2 * q + 1];
+      int head = 0, tail = 0;
+      for (int base = 0; base < m; base += 32) {
+        const int i = base + lane;
+        const bool v = i < m;
+        const bool hf = v && s_fio[r0 + i] == 0;
+        const unsigned bh = __ballot_sync(FULL, hf), bt = __ballot_sync(FULL, v && !hf);
+        if (hf) s_ord[r0 + head + __popc(bh & lt_mask)] = (unsigned short)i;
+        else if (v) s_ord[r0 + m - 1 - (tail + __popc(bt & lt_mask))] = (unsigned short)i;
+        head += __popc(bh); tail += __popc(bt);
+      }
+    }
+    __syncwarp();
+    const uint32_t seed = W.seed;
+    unsigned total_draws = 0;
+    for (int ep = 0; ep < nep && ep < d.NEP; ep++) {
       // (a) shuffle every island's segment (quickstep.cpp:474-481).  The reference runs ALL
       // iterations of island 0 before island 1, so the draws of (island i, epoch e) start at
       // offset  sum_{j<i} nep*(m_j-1) + e*(m_i-1)  of the world's LCG stream.
       unsigned draws_before = 0;
-      for (int isl = 0; isl < nis_max; isl++) {
-        int r0 = 0, m = 0;
-        if (isl < nis && have_rows) {
-          const int j0 = s_isz[4 * isl + 2], jn = s_isz[4 * isl + 3];
-          if (jn) { r0 = s_jrow[j0]; m = s_jrow[j0 + jn] - r0; }
-        }
-        const unsigned my_off = draws_before + (unsigned)ep * (unsigned)(m >= 2 ? m - 1 : 0);
-        if (m >= 2) draws_before += (unsigned)nep * (unsigned)(m - 1);
-        if (!epv) m = 0;
-        const int m_max = warp_max_i(m);
-        if (m_max < 2) continue;
-        {   // swap indices for i = 1..m-1 by all lanes (misc.cpp:66-117), LCG skip-ahead by G
-          uint32_t A, C, A0, C0;
-          ob_lcg_skip(my_off, &A0, &C0);
-          uint32_t s = A0 * seed + C0;
-          ob_lcg_skip((uint32_t)G, &A, &C);
-          for (int q = 0; q <= gl; q++) s = ob_lcg_next(s);
-          for (int base = 1; base < m_max; base += G) {
-            const int i = base + gl;
-            if (i < m) s_lvl[r0 + i] = (unsigned short)ob_randint_fold(s, (uint32_t)(i + 1));
-            s = A * s + C;
-          }
+      for (int q = 0; q < nri; q++) {
+        const int r0 = s_isl[2 * q], m = s_isl[2 * q + 1];
+        if (m < 2) continue;
+        const unsigned my_off = draws_before + (unsigned)ep * (unsigned)(m - 1);
+        draws_before += (unsigned)nep * (unsigned)(m - 1);
+        uint32_t A, C, A0, C0;
+        ob_lcg_skip(my_off + (unsigned)lane + 1u, &A0, &C0);   // lane handles i = lane+1, lane+33, ...
+        uint32_t s = A0 * seed + C0;
+        ob_lcg_skip(32u, &A, &C);
+        for (int i = 1 + lane; i < m; i += 32) {
+          s_lvl[r0 + i] = (unsigned short)ob_randint_fold(s, (uint32_t)(i + 1));
+          s = A * s + C;
         }
         __syncwarp();
-        if (gl == 0) {
+        if (lane == 0) {
           unsigned short *ord = s_ord + r0;
           for (int i = 1; i < m; i++) {
             const int sj = s_lvl[r0 + i];
@@ -412,71 +463,90 @@ __global__ void __launch_bounds__(32) k_prep(ObBatchDev d, real h, int taps) {
         }
         __syncwarp();
       }
-      if (ep == 0) s_misc[5] = (int)draws_before;   // total draws of this step (same every epoch)
-      // (b) level of every position, walking islands and positions in sweep order (one lane)
+      total_draws = draws_before;
+      // (b) level of every position, islands and positions in sweep order
+      int lastreg[NBR];
+#pragma unroll
+      for (int r = 0; r < NBR; r++) lastreg[r] = 0;
+      for (int i = lane; i <= mtot + 1; i += 32) s_X[i] = 0;
+      __syncwarp();
       int nlev = 0;
-      if (gl == 0 && epv) {
-        for (int b = 0; b < nb; b++) s_last[b] = 0;
-        for (int i = 0; i <= mtot + 1; i++) s_X[i] = 0;
-        for (int isl = 0; isl < nis; isl++) {
-          const int j0 = s_isz[4 * isl + 2], jn = s_isz[4 * isl + 3];
-          if (!jn) continue;
-          const int r0 = s_jrow[j0], m = s_jrow[j0 + jn] - r0;
-          for (int k = 0; k < m; k++) {
-            const int idx = r0 + s_ord[r0 + k];
-            const int b1 = s_rowb[2 * idx], b2 = s_rowb[2 * idx + 1];
-            int lv = s_last[b1];
-            if (b2 != 255) { const int l2 = s_last[b2]; lv = l2 > lv ? l2 : lv; }
+      for (int q = 0; q < nri; q++) {
+        const int r0 = s_isl[2 * q], m = s_isl[2 * q + 1];
+        for (int base = 0; base < m; base += 32) {
+          const int kmine = base + lane;
+          unsigned rbm = 0xffffu;
+          if (kmine < m) rbm = s_rowb[r0 + s_ord[r0 + kmine]];
+          int mylv = 0;
+          const int cnt = (m - base) < 32 ? (m - base) : 32;
+          for (int kk = 0; kk < cnt; kk++) {
+            const unsigned rb = __shfl_sync(FULL, rbm, kk);
+            const int b1 = rb & 255, b2 = (rb >> 8) & 255;
+            int v1 = 0, v2 = 0;
+#pragma unroll
+            for (int r = 0; r < NBR; r++) { if ((b1 >> 5) == r) v1 = lastreg[r]; if ((b2 >> 5) == r) v2 = lastreg[r]; }
+            int lv = __shfl_sync(FULL, v1, b1 & 31);
+            if (b2 != 255) { const int l2 = __shfl_sync(FULL, v2, b2 & 31); lv = l2 > lv ? l2 : lv; }
             lv++;
             if (taps & 2) lv = nlev + 1;   // debug: strictly sequential schedule (one row per level)
-            s_last[b1] = (unsigned short)lv;
-            if (b2 != 255) s_last[b2] = (unsigned short)lv;
-            s_lvl[r0 + k] = (unsigned short)lv;      // levels are 1-based
-            s_X[lv]++;
+#pragma unroll
+            for (int r = 0; r < NBR; r++) {
+              if ((b1 >> 5) == r && lane == (b1 & 31)) lastreg[r] = lv;
+              if (b2 != 255 && (b2 >> 5) == r && lane == (b2 & 31)) lastreg[r] = lv;
+            }
+            if (lane == kk) mylv = lv;
             nlev = lv > nlev ? lv : nlev;
           }
+          if (kmine < m) { s_lvl[r0 + kmine] = (unsigned short)mylv; atomicAdd(&s_X[mylv], 1); }
         }
-        // exclusive prefix: s_X[l] = first slot of level l (l = 1..nlev)
-        int a = 0;
-        for (int l = 1; l <= nlev; l++) { const int c = s_X[l]; s_X[l] = (unsigned short)a; a += c; }
-        s_misc[4] = nlev;
       }
       __syncwarp();
-      nlev = epv ? s_misc[4] : 0;
-      // (c) scatter rows into level order (any order inside a level), then the pass table
-      unsigned short *g_sched = d.sched + ((size_t)wc * d.NEP + ep) * d.NR;
-      unsigned short *g_pstart = d.pstart + ((size_t)wc * d.NEP + ep) * (d.NR + 1);
-      if (gl == 0 && epv) {
-        // sequential scatter (keeps s_X as "end of level" afterwards) and pass table:
-        // a pass is a chunk of <= G consecutive slots that does not cross a level boundary
-        for (int isl = 0; isl < nis; isl++) {
-          const int j0 = s_isz[4 * isl + 2], jn = s_isz[4 * isl + 3];
-          if (!jn) continue;
-          const int r0 = s_jrow[j0], m = s_jrow[j0 + jn] - r0;
-          for (int k = 0; k < m; k++) {
-            const int lv = s_lvl[r0 + k];
-            const int pos = s_X[lv]++;
-            g_sched[pos] = (unsigned short)(r0 + s_ord[r0 + k]);
-          }
+      // exclusive prefix over levels 1..nlev: s_X[l] = first slot of level l
+      {
+        int carry = 0;
+        for (int base = 1; base <= nlev; base += 32) {
+          const int l = base + lane;
+          const int c = l <= nlev ? s_X[l] : 0;
+          int x = c;
+          for (int dd = 1; dd < 32; dd <<= 1) { const int y = __shfl_up_sync(FULL, x, dd); if (lane >= dd) x += y; }
+          if (l <= nlev) s_X[l] = carry + x - c;
+          carry += __shfl_sync(FULL, x, 31);
         }
-        int np = 0, start = 0;
-        for (int l = 1; l <= nlev; l++) {
-          const int end = s_X[l];
-          for (int p = start; p < end; p += G) g_pstart[np++] = (unsigned short)p;
-          start = end;
-        }
-        g_pstart[np] = (unsigned short)start;
-        si[SI_NPASS0 + ep] = np;
       }
-      if (gl == 0 && valid && !epv) si[SI_NPASS0 + ep] = 0;
+      __syncwarp();
+      // (c) scatter rows into level order (any order inside a level); afterwards s_X[l] = end of level l
+      unsigned short *g_sched = d.sched + ((size_t)w * d.NEP + ep) * d.NR;
+      unsigned short *g_pstart = d.pstart + ((size_t)w * d.NEP + ep) * (d.NR + 1);
+      for (int q = 0; q < nri; q++) {
+        const int r0 = s_isl[2 * q], m = s_isl[2 * q + 1];
+        for (int k = lane; k < m; k += 32) {
+          const int pos = atomicAdd(&s_X[s_lvl[r0 + k]], 1);
+          g_sched[pos] = (unsigned short)(r0 + s_ord[r0 + k]);
+        }
+      }
+      __syncwarp();
+      // pass table: a pass is a chunk of <= G consecutive slots that does not cross a level boundary
+      {
+        int carry = 0;
+        for (int base = 1; base <= nlev; base += 32) {
+          const int l = base + lane;
+          int start = 0, n = 0;
+          if (l <= nlev) { start = l > 1 ? s_X[l - 1] : 0; n = s_X[l] - start; }
+          const int c = (n + G - 1) / G;
+          int x = c;
+          for (int dd = 1; dd < 32; dd <<= 1) { const int y = __shfl_up_sync(FULL, x, dd); if (lane >= dd) x += y; }
+          const int off = carry + x - c;
+          for (int j = 0; j < c; j++) g_pstart[off + j] = (unsigned short)(start + j * G);
+          carry += __shfl_sync(FULL, x, 31);
+        }
+        if (lane == 0) { g_pstart[carry] = (unsigned short)mtot; si[SI_NPASS0 + ep] = carry; }
+      }
       __syncwarp();
     }
-    (void)mtot_max;
-    if (gl == 0 && valid) {
-      { uint32_t A, C; ob_lcg_skip(have_rows && nep > 0 ? (unsigned)s_misc[5] : 0u, &A, &C); W.seed = A * seed + C; }
-      si[SI_NIS] = nis; si[SI_NIB] = nib; si[SI_NIJ] = nij; si[SI_MTOT] = mtot; si[SI_HAVEROWS] = have_rows ? 1 : 0;
-      unsigned short *g_isz = d.isz + (size_t)wc * 4 * d.NB;
-      for (int i = 0; i < 4 * nis; i++) g_isz[i] = s_isz[i];
+    if (lane == 0) {
+      uint32_t A, C;
+      ob_lcg_skip(total_draws, &A, &C);
+      W.seed = A * seed + C;
     }
     __syncwarp();
   }
@@ -518,20 +588,23 @@ __global__ void __launch_bounds__(32) k_sor(ObBatchDev d, int taps) {
       const unsigned short *pstart = d.pstart + ((size_t)wc * d.NEP + ep) * (d.NR + 1);
       const int np = itv ? si[SI_NPASS0 + ep] : 0;
       const int np_max = warp_max_i(np);
-      // software pipeline: row of pass p+1 is fetched while pass p computes
+      // software pipeline, three stages deep so that no load waits on another load:
+      //   pstart[p+4]  ->  row index of pass p+2  ->  row record of pass p+1  ->  compute pass p
       ObRowReg cur, nxt;
-      int cur_idx = -1, nxt_idx = -1;
+      int cur_idx = -1, i1 = -1;
+      int ps2 = 0, ps3 = 0;
       if (np > 0) {
-        const int p0 = pstart[0], p1 = pstart[1];
-        if (p0 + gl < p1) { nxt_idx = sched[p0 + gl]; load_row(rows + (size_t)nxt_idx * OB_ROWW, nxt); }
+        const int ps0 = pstart[0], ps1 = pstart[1];
+        ps2 = np >= 2 ? pstart[2] : 0; ps3 = np >= 3 ? pstart[3] : 0;
+        if (ps0 + gl < ps1) { cur_idx = sched[ps0 + gl]; load_row(rows + (size_t)cur_idx * OB_ROWW, cur); }
+        if (np >= 2 && ps1 + gl < ps2) i1 = sched[ps1 + gl];
       }
       for (int p = 0; p < np_max; p++) {
-        cur = nxt; cur_idx = nxt_idx;
-        nxt_idx = -1;
-        if (p + 1 < np) {
-          const int q0 = pstart[p + 1], q1 = pstart[p + 2];
-          if (q0 + gl < q1) { nxt_idx = sched[q0 + gl]; load_row(rows + (size_t)nxt_idx * OB_ROWW, nxt); }
-        }
+        // prefetch stage
+        const int ps4 = (p + 4 <= np) ? (int)pstart[p + 4] : 0;
+        int i2 = -1;
+        if (p + 2 < np && ps2 + gl < ps3) i2 = sched[ps2 + gl];
+        if (i1 >= 0) load_row(rows + (size_t)i1 * OB_ROWW, nxt);
         const bool act = p < np && cur_idx >= 0;
         if (taps & 8) __syncwarp();
         if (taps & 4) {   // debug: verify that the rows of this pass touch pairwise disjoint bodies
@@ -594,6 +667,7 @@ __global__ void __launch_bounds__(32) k_sor(ObBatchDev d, int taps) {
 #endif
         }
         __syncwarp();
+        cur = nxt; cur_idx = i1; i1 = i2; ps2 = ps3; ps3 = ps4;
       }
     }
     // cforce per body for k_post; lambda + joint feedback taps (quickstep.cpp:918-957)
