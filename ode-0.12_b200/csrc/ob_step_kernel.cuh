@@ -22,8 +22,8 @@
 // in parallel — reads and writes exactly the values the sequential sweep does, bit for bit.
 // Islands of one world never share bodies, so their sweeps are scheduled together.
 //
-// Row record (24 words): J1l[3] J1a[3] J2a[3] (unscaled) | iMJ1a[3] iMJ2a[3] | Ad b Ad*cfm lo hi
-// | meta (b1, b2, findex offset) | pad.  Every joint type on the path has J2l == -J1l
+// Row record (20 words): J1l[3] J1a[3] J2a[3] (unscaled) | iMJ1a[3] iMJ2a[3] | Ad b Ad*cfm bound
+// | meta (b1, b2, findex offset, bound mode: lo=-hi / lo=0 / hi=0).  Every joint type on the path has J2l == -J1l
 // (contact.cpp:86-93, joint.cpp:91-102,146-163, hinge.cpp:101-116) and iMJ*l == invMass*J*l,
 // so those values are rebuilt per use with the reference's own multiplications.
 #pragma once
@@ -31,8 +31,8 @@
 #include "ob_rows.h"
 #include "ob_solver.h"
 
-#define OB_ROWF 20                                   // reals per row record
-#define OB_ROWW (OB_ROWF + 16 / (int)sizeof(real))   // reals per row incl. the 16-byte meta chunk
+#define OB_ROWF 19                                   // reals per row record
+#define OB_ROWW 20                                   // + one slot holding the 32-bit meta word
 #define OB_MAXEPOCH 8                                // shuffle epochs per step ((iters+7)/8)
 
 __host__ __device__ inline size_t ob_al(size_t x, size_t a) { return (x + a - 1) & ~(a - 1); }
@@ -86,33 +86,43 @@ __device__ __forceinline__ int warp_max_i(int v) {
 
 struct ObRowReg {   // one row in registers
   real v[OB_ROWF];
-  unsigned meta;    // b1 | b2<<8 | findex offset<<16
+  unsigned meta;    // b1 | b2<<8 | findex offset<<16 | bound mode<<24
 };
 __device__ __forceinline__ void load_row(const real *__restrict__ p, ObRowReg &r) {
 #if defined(dSINGLE)
   const float4 *q = (const float4 *)p;
 #pragma unroll
-  for (int i = 0; i < 5; i++) { const float4 t = __ldg(q + i); r.v[4 * i] = t.x; r.v[4 * i + 1] = t.y; r.v[4 * i + 2] = t.z; r.v[4 * i + 3] = t.w; }
-  r.meta = __ldg((const unsigned *)(q + 5));
+  for (int i = 0; i < 4; i++) { const float4 t = __ldg(q + i); r.v[4 * i] = t.x; r.v[4 * i + 1] = t.y; r.v[4 * i + 2] = t.z; r.v[4 * i + 3] = t.w; }
+  const float4 t = __ldg(q + 4);
+  r.v[16] = t.x; r.v[17] = t.y; r.v[18] = t.z; r.meta = __float_as_uint(t.w);
 #else
   const double2 *q = (const double2 *)p;
 #pragma unroll
-  for (int i = 0; i < 10; i++) { const double2 t = __ldg(q + i); r.v[2 * i] = t.x; r.v[2 * i + 1] = t.y; }
-  r.meta = __ldg((const unsigned *)(q + 10));
+  for (int i = 0; i < 9; i++) { const double2 t = __ldg(q + i); r.v[2 * i] = t.x; r.v[2 * i + 1] = t.y; }
+  const double2 t = __ldg(q + 9);
+  r.v[18] = t.x; r.meta = (unsigned)__double2loint(t.y);
 #endif
 }
 __device__ __forceinline__ void store_row(real *p, const real *rw, unsigned meta) {
 #if defined(dSINGLE)
   float4 *q = (float4 *)p;
 #pragma unroll
-  for (int i = 0; i < 5; i++) q[i] = make_float4(rw[4 * i], rw[4 * i + 1], rw[4 * i + 2], rw[4 * i + 3]);
-  ((uint4 *)q)[5] = make_uint4(meta, 0u, 0u, 0u);
+  for (int i = 0; i < 4; i++) q[i] = make_float4(rw[4 * i], rw[4 * i + 1], rw[4 * i + 2], rw[4 * i + 3]);
+  q[4] = make_float4(rw[16], rw[17], rw[18], __uint_as_float(meta));
 #else
   double2 *q = (double2 *)p;
 #pragma unroll
-  for (int i = 0; i < 10; i++) q[i] = make_double2(rw[2 * i], rw[2 * i + 1]);
-  ((uint4 *)q)[10] = make_uint4(meta, 0u, 0u, 0u);
+  for (int i = 0; i < 9; i++) q[i] = make_double2(rw[2 * i], rw[2 * i + 1]);
+  q[9] = make_double2(rw[18], __hiloint2double(0, (int)meta));
 #endif
+}
+// bounds of a row are stored as one value + a mode (all joint types on the path produce one of these)
+__device__ __forceinline__ bool encode_bounds(real lo, real hi, real *v, unsigned *mode) {
+  if (lo == -hi) { *v = hi; *mode = 0; return true; }
+  if (lo == 0) { *v = hi; *mode = 1; return true; }
+  if (hi == 0) { *v = lo; *mode = 2; return true; }
+  *v = hi; *mode = 0;
+  return false;
 }
 
 // per-world hand-off between the three kernels (ObBatchDev::stepinfo), ints
@@ -322,17 +332,19 @@ __global__ void __launch_bounds__(32) k_prep(ObBatchDev d, real h, int taps) {
         const real invM1 = s_invM[b1], invM2 = b2 >= 0 ? s_invM[b2] : (real)0;
         for (int q = 0; q < jm; q++) {
           const int ri = r0 + q;
-          real rw[OB_ROWF];
+          real rw[OB_ROWW];
           for (int e = 0; e < 6; e++) rw[e] = r.J[q][e];
           for (int e = 0; e < 3; e++) rw[6 + e] = r.J[q][9 + e];
           real iMJ[12], b_out, adcfm, Ad;
           ob_row_finalize2(r.J[q], r.c[q], r.cfm[q], b2, t1a, t1b, invM1, iw1, invM2, iw2, stepsize1, W.sor_w, iMJ, &b_out,
                            &adcfm, &Ad);
           for (int e = 0; e < 3; e++) { rw[9 + e] = iMJ[3 + e]; rw[12 + e] = iMJ[9 + e]; }
-          rw[15] = Ad; rw[16] = b_out; rw[17] = adcfm; rw[18] = r.lo[q]; rw[19] = r.hi[q];
+          rw[15] = Ad; rw[16] = b_out; rw[17] = adcfm;
+          unsigned bmode;
+          if (!encode_bounds(r.lo[q], r.hi[q], &rw[18], &bmode)) atomicOr(&W.status, OB_ERR_ROW_OVERFLOW);
           const unsigned fio = (unsigned)(r.findex[q] >= 0 ? q - r.findex[q] : 0);
           const unsigned ub2 = (unsigned)(b2 < 0 ? 255 : b2);
-          store_row(rows + (size_t)ri * OB_ROWW, rw, (unsigned)b1 | (ub2 << 8) | (fio << 16));
+          store_row(rows + (size_t)ri * OB_ROWW, rw, (unsigned)b1 | (ub2 << 8) | (fio << 16) | (bmode << 24));
         }
       }
       if (k < nij) { g_ijoint[k] = s_ijoint[k]; g_jrow[k] = s_jrow[k]; }
@@ -412,7 +424,7 @@ __global__ void __launch_bounds__(32) k_sched(ObBatchDev d, int G, int taps) {
     }
     nri = __shfl_sync(FULL, nri, 0);
     for (int i = lane; i < mtot; i += 32) {
-      const unsigned meta = *(const unsigned *)(rows + (size_t)i * OB_ROWW + OB_ROWF);
+      const unsigned meta = *(const unsigned *)(rows + (size_t)i * OB_ROWW + OB_ROWF);   // low word of the meta slot
       s_rowb[i] = (unsigned short)(meta & 0xffffu);
       s_fio[i] = (unsigned char)((meta >> 16) & 255u);
     }
@@ -482,19 +494,18 @@ __global__ void __launch_bounds__(32) k_sched(ObBatchDev d, int G, int taps) {
           for (int kk = 0; kk < cnt; kk++) {
             const unsigned rb = __shfl_sync(FULL, rbm, kk);
             const int b1 = rb & 255, b2 = (rb >> 8) & 255;
-            int v1 = 0, v2 = 0;
+            const int q1 = b1 >> 5, q2 = b2 >> 5;
+            int v1 = lastreg[0], v2 = lastreg[0];
 #pragma unroll
-            for (int r = 0; r < NBR; r++) { if ((b1 >> 5) == r) v1 = lastreg[r]; if ((b2 >> 5) == r) v2 = lastreg[r]; }
-            int lv = __shfl_sync(FULL, v1, b1 & 31);
-            if (b2 != 255) { const int l2 = __shfl_sync(FULL, v2, b2 & 31); lv = l2 > lv ? l2 : lv; }
+            for (int r = 1; r < NBR; r++) { v1 = (q1 == r) ? lastreg[r] : v1; v2 = (q2 == r) ? lastreg[r] : v2; }
+            int lv = __shfl_sync(FULL, v1, b1);          // source lane = b & 31
+            const int l2 = __shfl_sync(FULL, v2, b2);
+            if (b2 != 255) lv = l2 > lv ? l2 : lv;
             lv++;
-            if (taps & 2) lv = nlev + 1;   // debug: strictly sequential schedule (one row per level)
+            const int qa = (lane == (b1 & 31)) ? q1 : -1, qb = (b2 != 255 && lane == (b2 & 31)) ? q2 : -1;
 #pragma unroll
-            for (int r = 0; r < NBR; r++) {
-              if ((b1 >> 5) == r && lane == (b1 & 31)) lastreg[r] = lv;
-              if (b2 != 255 && (b2 >> 5) == r && lane == (b2 & 31)) lastreg[r] = lv;
-            }
-            if (lane == kk) mylv = lv;
+            for (int r = 0; r < NBR; r++) lastreg[r] = (qa == r || qb == r) ? lv : lastreg[r];
+            mylv = (lane == kk) ? lv : mylv;
             nlev = lv > nlev ? lv : nlev;
           }
           if (kmine < m) { s_lvl[r0 + kmine] = (unsigned short)mylv; atomicAdd(&s_X[mylv], 1); }
@@ -552,6 +563,73 @@ __global__ void __launch_bounds__(32) k_sched(ObBatchDev d, int G, int taps) {
   }
 }
 
+
+// one row update of the sweep (quickstep.cpp:490-581) on a row held in registers
+__device__ __forceinline__ void sor_pass(const ObRowReg &cur, int cur_idx, real *s_fc, real *s_lam, const real *s_invM) {
+  const int b1 = cur.meta & 255, b2r = (cur.meta >> 8) & 255, fio = (cur.meta >> 16) & 255, bmode = cur.meta >> 24;
+  const int b2 = b2r == 255 ? -1 : b2r;
+  const int fi = fio ? cur_idx - fio : -1;
+  const real Ad = cur.v[15], k1 = s_invM[b1];
+  const real bv = cur.v[18];
+  const real lo = bmode == 0 ? -bv : (bmode == 1 ? (real)0 : bv);
+  const real hi = bmode == 2 ? (real)0 : bv;
+  real J[12], iMJ[12];
+  // rebuild what SOR_LCP keeps per row: J scaled by Ad (quickstep.cpp:393-401), iMJ (:117-136)
+#pragma unroll
+  for (int e = 0; e < 3; e++) {
+    iMJ[e] = k1 * cur.v[e];
+    iMJ[3 + e] = cur.v[9 + e];
+    J[e] = cur.v[e] * Ad;
+    J[3 + e] = cur.v[3 + e] * Ad;
+  }
+  real f1[6], f2[6];
+  real *fp1 = s_fc + 8 * b1;
+#if defined(dSINGLE)
+  { const float4 a = *(const float4 *)fp1; const float2 c = *(const float2 *)(fp1 + 4); f1[0] = a.x; f1[1] = a.y; f1[2] = a.z; f1[3] = a.w; f1[4] = c.x; f1[5] = c.y; }
+#else
+  for (int e = 0; e < 6; e++) f1[e] = fp1[e];
+#endif
+  real *fp2 = s_fc;
+  if (b2 >= 0) {
+    const real k2 = s_invM[b2];
+#pragma unroll
+    for (int e = 0; e < 3; e++) {
+      const real j2l = -cur.v[e];
+      iMJ[6 + e] = k2 * j2l;
+      iMJ[9 + e] = cur.v[12 + e];
+      J[6 + e] = j2l * Ad;
+      J[9 + e] = cur.v[6 + e] * Ad;
+    }
+    fp2 = s_fc + 8 * b2;
+#if defined(dSINGLE)
+    { const float4 a = *(const float4 *)fp2; const float2 c = *(const float2 *)(fp2 + 4); f2[0] = a.x; f2[1] = a.y; f2[2] = a.z; f2[3] = a.w; f2[4] = c.x; f2[5] = c.y; }
+#else
+    for (int e = 0; e < 6; e++) f2[e] = fp2[e];
+#endif
+  }
+  const real lam_new = ob_sor_row(J, iMJ, cur.v[16], cur.v[17], lo, hi, fi, fi >= 0 ? s_lam[fi] : (real)0, s_lam[cur_idx], f1,
+                                  b2 >= 0 ? f2 : (real *)0);
+  s_lam[cur_idx] = lam_new;
+#if defined(dSINGLE)
+  *(float4 *)fp1 = make_float4(f1[0], f1[1], f1[2], f1[3]); *(float2 *)(fp1 + 4) = make_float2(f1[4], f1[5]);
+  if (b2 >= 0) { *(float4 *)fp2 = make_float4(f2[0], f2[1], f2[2], f2[3]); *(float2 *)(fp2 + 4) = make_float2(f2[4], f2[5]); }
+#else
+  for (int e = 0; e < 6; e++) fp1[e] = f1[e];
+  if (b2 >= 0) for (int e = 0; e < 6; e++) fp2[e] = f2[e];
+#endif
+}
+// debug (taps & 4): verify that the rows of one pass touch pairwise disjoint bodies
+template <int G>
+__device__ __noinline__ void sor_check_pass(bool act, unsigned meta, int gl, int *status) {
+  const int mb1 = act ? (int)(meta & 255) : -1, mb2 = act ? (int)((meta >> 8) & 255) : -1;
+  for (int l2 = 0; l2 < G; l2++) {
+    const int o1 = __shfl_sync(0xffffffffu, mb1, l2, G), o2 = __shfl_sync(0xffffffffu, mb2, l2, G);
+    if (act && l2 != gl && o1 >= 0) {
+      if (mb1 == o1 || mb1 == o2 || (mb2 != 255 && (mb2 == o1 || mb2 == o2))) atomicOr(status, 256);
+    }
+  }
+}
+
 // =====================================================================================
 template <int G>
 __global__ void __launch_bounds__(32) k_sor(ObBatchDev d, int taps) {
@@ -588,87 +666,37 @@ __global__ void __launch_bounds__(32) k_sor(ObBatchDev d, int taps) {
       const unsigned short *pstart = d.pstart + ((size_t)wc * d.NEP + ep) * (d.NR + 1);
       const int np = itv ? si[SI_NPASS0 + ep] : 0;
       const int np_max = warp_max_i(np);
-      // software pipeline, three stages deep so that no load waits on another load:
-      //   pstart[p+4]  ->  row index of pass p+2  ->  row record of pass p+1  ->  compute pass p
-      ObRowReg cur, nxt;
-      int cur_idx = -1, i1 = -1;
-      int ps2 = 0, ps3 = 0;
+      // software pipeline: pstart[p+5] -> row index of pass p+3 -> row record of pass p+2 (three
+      // register buffers used in rotation) -> compute pass p.  No load waits on another load.
+      ObRowReg A, B, C;
+      int ci = -1, i1 = -1, i2 = -1, ps3 = 0, ps4 = 0;
       if (np > 0) {
-        const int ps0 = pstart[0], ps1 = pstart[1];
-        ps2 = np >= 2 ? pstart[2] : 0; ps3 = np >= 3 ? pstart[3] : 0;
-        if (ps0 + gl < ps1) { cur_idx = sched[ps0 + gl]; load_row(rows + (size_t)cur_idx * OB_ROWW, cur); }
-        if (np >= 2 && ps1 + gl < ps2) i1 = sched[ps1 + gl];
+        const int ps0 = pstart[0], ps1 = pstart[1], ps2 = np >= 2 ? (int)pstart[2] : 0;
+        ps3 = np >= 3 ? (int)pstart[3] : 0; ps4 = np >= 4 ? (int)pstart[4] : 0;
+        if (ps0 + gl < ps1) { ci = sched[ps0 + gl]; load_row(rows + (size_t)ci * OB_ROWW, A); }
+        if (np >= 2 && ps1 + gl < ps2) { i1 = sched[ps1 + gl]; load_row(rows + (size_t)i1 * OB_ROWW, B); }
+        if (np >= 3 && ps2 + gl < ps3) i2 = sched[ps2 + gl];
       }
-      for (int p = 0; p < np_max; p++) {
-        // prefetch stage
-        const int ps4 = (p + 4 <= np) ? (int)pstart[p + 4] : 0;
-        int i2 = -1;
-        if (p + 2 < np && ps2 + gl < ps3) i2 = sched[ps2 + gl];
-        if (i1 >= 0) load_row(rows + (size_t)i1 * OB_ROWW, nxt);
-        const bool act = p < np && cur_idx >= 0;
-        if (taps & 8) __syncwarp();
-        if (taps & 4) {   // debug: verify that the rows of this pass touch pairwise disjoint bodies
-          const int mb1 = act ? (int)(cur.meta & 255) : -1, mb2 = act ? (int)((cur.meta >> 8) & 255) : -1;
-          for (int l2 = 0; l2 < G; l2++) {
-            const int o1 = __shfl_sync(0xffffffffu, mb1, l2, G), o2 = __shfl_sync(0xffffffffu, mb2, l2, G);
-            if (act && l2 != gl && o1 >= 0) {
-              if (mb1 == o1 || mb1 == o2 || (mb2 != 255 && (mb2 == o1 || mb2 == o2))) atomicOr(&d.world[wc].status, 256);
-            }
-          }
-        }
-        if (act) {
-          const int b1 = cur.meta & 255, b2r = (cur.meta >> 8) & 255, fio = (cur.meta >> 16) & 255;
-          const int b2 = b2r == 255 ? -1 : b2r;
-          const int fi = fio ? cur_idx - fio : -1;
-          const real Ad = cur.v[15], k1 = s_invM[b1];
-          real J[12], iMJ[12];
-          // rebuild what SOR_LCP keeps per row: J scaled by Ad (quickstep.cpp:393-401), iMJ (:117-136)
-#pragma unroll
-          for (int e = 0; e < 3; e++) {
-            iMJ[e] = k1 * cur.v[e];
-            iMJ[3 + e] = cur.v[9 + e];
-            J[e] = cur.v[e] * Ad;
-            J[3 + e] = cur.v[3 + e] * Ad;
-          }
-          real f1[6], f2[6];
-          real *fp1 = s_fc + 8 * b1;
-#if defined(dSINGLE)
-          { const float4 a = *(const float4 *)fp1; const float2 c = *(const float2 *)(fp1 + 4); f1[0] = a.x; f1[1] = a.y; f1[2] = a.z; f1[3] = a.w; f1[4] = c.x; f1[5] = c.y; }
-#else
-          for (int e = 0; e < 6; e++) f1[e] = fp1[e];
-#endif
-          real *fp2 = s_fc;
-          if (b2 >= 0) {
-            const real k2 = s_invM[b2];
-#pragma unroll
-            for (int e = 0; e < 3; e++) {
-              const real j2l = -cur.v[e];
-              iMJ[6 + e] = k2 * j2l;
-              iMJ[9 + e] = cur.v[12 + e];
-              J[6 + e] = j2l * Ad;
-              J[9 + e] = cur.v[6 + e] * Ad;
-            }
-            fp2 = s_fc + 8 * b2;
-#if defined(dSINGLE)
-            { const float4 a = *(const float4 *)fp2; const float2 c = *(const float2 *)(fp2 + 4); f2[0] = a.x; f2[1] = a.y; f2[2] = a.z; f2[3] = a.w; f2[4] = c.x; f2[5] = c.y; }
-#else
-            for (int e = 0; e < 6; e++) f2[e] = fp2[e];
-#endif
-          }
-          const real lam_new = ob_sor_row(J, iMJ, cur.v[16], cur.v[17], cur.v[18], cur.v[19], fi, fi >= 0 ? s_lam[fi] : (real)0,
-                                          s_lam[cur_idx], f1, b2 >= 0 ? f2 : (real *)0);
-          s_lam[cur_idx] = lam_new;
-#if defined(dSINGLE)
-          *(float4 *)fp1 = make_float4(f1[0], f1[1], f1[2], f1[3]); *(float2 *)(fp1 + 4) = make_float2(f1[4], f1[5]);
-          if (b2 >= 0) { *(float4 *)fp2 = make_float4(f2[0], f2[1], f2[2], f2[3]); *(float2 *)(fp2 + 4) = make_float2(f2[4], f2[5]); }
-#else
-          for (int e = 0; e < 6; e++) fp1[e] = f1[e];
-          if (b2 >= 0) for (int e = 0; e < 6; e++) fp2[e] = f2[e];
-#endif
-        }
-        __syncwarp();
-        cur = nxt; cur_idx = i1; i1 = i2; ps2 = ps3; ps3 = ps4;
+      int p = 0;
+#define OB_SOR_PASS(CB, LB)                                                                        \
+      {                                                                                            \
+        const int ps5 = (p + 5 <= np) ? (int)pstart[p + 5] : 0;                                    \
+        int i3 = -1;                                                                               \
+        if (p + 3 < np && ps3 + gl < ps4) i3 = sched[ps3 + gl];                                    \
+        if (i2 >= 0) load_row(rows + (size_t)i2 * OB_ROWW, LB);                                    \
+        if (taps & 4) sor_check_pass<G>(p < np && ci >= 0, CB.meta, gl, &d.world[wc].status);      \
+        if (p < np && ci >= 0) sor_pass(CB, ci, s_fc, s_lam, s_invM);                              \
+        __syncwarp();                                                                              \
+        ci = i1; i1 = i2; i2 = i3; ps3 = ps4; ps4 = ps5; p++;                                      \
       }
+      while (p < np_max) {
+        OB_SOR_PASS(A, C)
+        if (p >= np_max) break;
+        OB_SOR_PASS(B, A)
+        if (p >= np_max) break;
+        OB_SOR_PASS(C, B)
+      }
+#undef OB_SOR_PASS
     }
     // cforce per body for k_post; lambda + joint feedback taps (quickstep.cpp:918-957)
     real *g_fc = d.tmp1 + (size_t)wc * d.NB * 8;   // tmp1 is dead after row assembly: reuse as cforce
