@@ -201,8 +201,21 @@ __global__ void __launch_bounds__(OB_THREADS) k_collide(ObBatchDev d) {
       int n = 0, o1 = 0, o2 = 0;
       if (p < np) {
         o1 = s_sorted[p].x; o2 = s_sorted[p].y;
+        bool connected = false;
+        if (pol.skip_if_connected && d.NJ) {   // dAreConnectedExcluding(b1, b2, dJointTypeContact), ode.cpp:1529-1537
+          const int b1 = geoms[o1].body, b2 = geoms[o2].body;
+          if (b1 >= 0 && b2 >= 0) {
+            const unsigned short *ps = d.padjstart + (size_t)w * (d.NB + 1), *pa = d.padj + (size_t)w * 2 * d.NJ;
+            const ObJoint *pj = d.joint + (size_t)w * d.NJ;
+            for (int k = ps[b1]; k < ps[b1 + 1]; k++) {
+              const ObJoint &jj = pj[pa[k]];
+              const int other = jj.b1 == b1 ? jj.b2 : jj.b1;
+              if (other == b2) connected = true;
+            }
+          }
+        }
         int swapped;
-        n = ob_collide_pair(s_pose[s_walk_of[o1]], s_pose[s_walk_of[o2]], maxc, cg, &swapped);
+        if (!connected) n = ob_collide_pair(s_pose[s_walk_of[o1]], s_pose[s_walk_of[o2]], maxc, cg, &swapped);
       }
       int total;
       int off = block_excl_scan(n, s_misc + 8, &total);
@@ -320,6 +333,10 @@ ObBackend *obk_create(const ObBatchDev &caps, int device, char *err, size_t errl
   CK(dalloc(b, &d.geom, W * d.NG));
   CK(dalloc(b, &d.glist, W * d.NG));
   CK(dalloc(b, &d.policy, (size_t)d.npolicy));
+  CK(dalloc(b, &d.joint, W * (d.NJ ? d.NJ : 1)));
+  CK(dalloc(b, &d.njoints, W));
+  CK(dalloc(b, &d.padjstart, W * (d.NB + 1)));
+  CK(dalloc(b, &d.padj, W * 2 * (d.NJ ? d.NJ : 1)));
   CK(dalloc(b, &d.npairs, W));
   CK(dalloc(b, &d.pairs, W * d.NP * 2));
   CK(dalloc(b, &d.ncontacts, W));
@@ -329,8 +346,9 @@ ObBackend *obk_create(const ObBatchDev &caps, int device, char *err, size_t errl
   CK(dalloc(b, &d.stepinfo, W * SI_WORDS));
   CK(dalloc(b, &d.ibody, W * d.NB));
   CK(dalloc(b, &d.isz, W * d.NB * 4));
-  CK(dalloc(b, &d.jrow, W * (d.NC + 1)));
-  CK(dalloc(b, &d.ijoint, W * d.NC));
+  CK(dalloc(b, &d.jrow, W * (d.NC + d.NJ + 1)));
+  CK(dalloc(b, &d.ijoint, W * (d.NC + d.NJ)));
+  CK(dalloc(b, &d.jside, W * (d.NJ ? d.NJ : 1) * 8));
   CK(dalloc(b, &d.sched, W * d.NEP * d.NR));
   CK(dalloc(b, &d.pstart, W * d.NEP * (d.NR + 1)));
   CK(dalloc(b, &d.invIw, W * d.NB * 12));
@@ -351,7 +369,7 @@ ObBackend *obk_create(const ObBatchDev &caps, int device, char *err, size_t errl
     const char *e = getenv("OB_TILE");
     if (e && (atoi(e) == 8 || atoi(e) == 16 || atoi(e) == 32)) G = atoi(e);
     b->tile = G;
-    b->smem_prep = prep_tile_smem(d.NB, d.NC, d.NR).total * (32 / G);
+    b->smem_prep = prep_tile_smem(d.NB, d.NC, d.NJ, d.NR).total * (32 / G);
     b->smem_sor = sor_tile_smem(d.NB, d.NR).total * (32 / G);
     b->smem_sched = sched_smem(d.NB, d.NR).total;
     b->smem_post = post_tile_smem(d.NG).total * (32 / G);
@@ -359,7 +377,7 @@ ObBackend *obk_create(const ObBatchDev &caps, int device, char *err, size_t errl
     b->grid_sor = b->grid_step;
     { const char *g = getenv("OB_GRID_SOR"); if (g && atoi(g) > 0 && atoi(g) < b->grid_sor) b->grid_sor = atoi(g); }
   }
-  if (d.NB > 254 || d.NG > 255) { snprintf(err, errlen, "world too large for the tile-per-world step kernel (NB=%d NG=%d NR=%d)", d.NB, d.NG, d.NR); goto fail; }
+  if (d.NB > 254 || d.NG > 255 || d.NC + d.NJ > 65000) { snprintf(err, errlen, "world too large for the tile-per-world step kernel (NB=%d NG=%d NR=%d)", d.NB, d.NG, d.NR); goto fail; }
   if (b->smem_collide > (size_t)prop.sharedMemPerBlockOptin || b->smem_prep > (size_t)prop.sharedMemPerBlockOptin ||
       b->smem_sor > (size_t)prop.sharedMemPerBlockOptin) {
     snprintf(err, errlen, "world does not fit one CTA's shared memory (collide %zu B, prep %zu B, sor %zu B, limit %zu B)",

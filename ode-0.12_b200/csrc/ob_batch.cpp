@@ -15,6 +15,7 @@ struct dxBatch {
   std::vector<dxSpace *> spaces;
   std::vector<std::vector<dxBody *> > bodies;  // [w][batch body index]
   std::vector<std::vector<dxGeom *> > geoms;   // [w][geom index]
+  std::vector<std::vector<dxJoint *> > joints; // [w][permanent joint index]
   std::vector<int> nb, ng;
   int debug_taps;
 };
@@ -44,6 +45,26 @@ void ob_marshal_body(const dxBody *b, ObBodyDyn &d, ObBodyConst &c) {
   c.geom_first = -1;
 }
 
+static void fill_limot(ObLimot &d, const dxLimot &l) {
+  d.vel = l.vel; d.fmax = l.fmax; d.lostop = l.lostop; d.histop = l.histop; d.fudge_factor = l.fudge_factor;
+  d.normal_cfm = l.normal_cfm; d.stop_erp = l.stop_erp; d.stop_cfm = l.stop_cfm; d.bounce = l.bounce;
+  d.limit = l.limit; d.limit_err = l.limit_err; d.pad = 0;
+}
+void ob_marshal_joint(const dxJoint *j, ObJoint &d) {
+  memset(&d, 0, sizeof d);
+  d.type = j->type;
+  d.b1 = j->node[0].body ? j->node[0].body->batch_index : -1;
+  d.b2 = j->node[1].body ? j->node[1].body->batch_index : -1;
+  d.flags = ((j->flags & dJOINT_DISABLED) ? OB_JF_DISABLED : 0) | ((j->flags & dJOINT_REVERSE) ? OB_JF_REVERSE : 0);
+  for (int k = 0; k < 4; k++) {
+    d.anchor1[k] = j->anchor1[k]; d.anchor2[k] = j->anchor2[k]; d.axis1[k] = j->axis1[k]; d.axis2[k] = j->axis2[k];
+    d.qrel[k] = j->qrel[k]; d.v1[k] = j->v1[k]; d.v2[k] = j->v2[k];
+  }
+  d.erp = j->erp; d.cfm = j->cfm; d.susp_erp = j->susp_erp; d.susp_cfm = j->susp_cfm; d.c0 = j->c0; d.s0 = j->s0;
+  fill_limot(d.limot1, j->limot);
+  fill_limot(d.limot2, j->limot2);
+}
+
 void ob_marshal_geom(dxGeom *g, ObGeom &d) {
   memset(&d, 0, sizeof d);
   d.type = g->type;
@@ -69,7 +90,8 @@ dBatchID dBatchCreate(int nworlds, const dWorldID *worlds, const dSpaceID *space
   B->worlds.assign(worlds, worlds + nworlds);
   B->spaces.assign(spaces, spaces + nworlds);
   B->bodies.resize(nworlds); B->geoms.resize(nworlds); B->nb.resize(nworlds); B->ng.resize(nworlds);
-  int NB = 1, NG = 1;
+  int NB = 1, NG = 1, NJ = 0;
+  B->joints.resize(nworlds);
   for (int w = 0; w < nworlds; w++) {
     dxWorld *W = worlds[w]; dxSpace *S = spaces[w];
     if (!W || !S || !S->is_space) { ob_set_last_error("dBatchCreate: world %d: bad world/space", w); delete B; return 0; }
@@ -89,14 +111,22 @@ dBatchID dBatchCreate(int nworlds, const dWorldID *worlds, const dSpaceID *space
       B->geoms[w][g->batch_index] = g;
     }
     B->ng[w] = ng;
-    NB = std::max(NB, B->nb[w]); NG = std::max(NG, ng);
+    // permanent joints: everything on the world's joint list at bind time, creation order
+    for (dxJoint *j = W->firstjoint; j; j = j->next) {
+      if (j->type == dJointTypeContact) { ob_set_last_error("dBatchCreate: world %d: contact joints present at bind time (call dJointGroupEmpty first)", w); delete B; return 0; }
+      if (j->type != dJointTypeBall && j->type != dJointTypeHinge && j->type != dJointTypeHinge2) { ob_set_last_error("dBatchCreate: world %d: unsupported joint type %d", w, j->type); delete B; return 0; }
+      B->joints[w].push_back(j);
+    }
+    std::reverse(B->joints[w].begin(), B->joints[w].end());
+    NB = std::max(NB, B->nb[w]); NG = std::max(NG, ng); NJ = std::max(NJ, (int)B->joints[w].size());
   }
   ObBatchDev caps;
   memset(&caps, 0, sizeof caps);
   caps.W = nworlds; caps.NB = NB; caps.NG = NG;
   caps.NC = (desc && desc->max_contacts_per_world > 0) ? desc->max_contacts_per_world : std::max(64, 16 * NG);
   caps.NP = std::min(NG * (NG - 1) / 2 + 1, std::max(256, 8 * NG));
-  caps.NR = 3 * caps.NC;
+  caps.NJ = NJ;
+  caps.NR = 3 * caps.NC + 6 * NJ;
   caps.npolicy = 1;
   {
     int it = 1;
@@ -139,6 +169,22 @@ dBatchID dBatchCreate(int nworlds, const dWorldID *worlds, const dSpaceID *space
     }
     W->bound_batch = B; S->bound_batch = B;
   }
+  std::vector<ObJoint> hj((size_t)nworlds * std::max(NJ, 1));
+  std::vector<int> hnj(nworlds, 0);
+  std::vector<unsigned short> hps((size_t)nworlds * (NB + 1), 0), hpa((size_t)nworlds * 2 * std::max(NJ, 1), 0);
+  memset(hj.data(), 0, hj.size() * sizeof(ObJoint));
+  for (int w = 0; w < nworlds; w++) {
+    const std::vector<dxJoint *> &J = B->joints[w];
+    hnj[w] = (int)J.size();
+    for (size_t i = 0; i < J.size(); i++) { ob_marshal_joint(J[i], hj[(size_t)w * NJ + i]); J[i]->tag = (int)i; }
+    unsigned short *ps = &hps[(size_t)w * (NB + 1)], *pa = NJ ? &hpa[(size_t)w * 2 * NJ] : 0;
+    int a = 0;
+    for (int b = 0; b < B->nb[w]; b++) {
+      ps[b] = (unsigned short)a;
+      for (dxJointNode *n = B->bodies[w][b]->firstjoint; n; n = n->next) pa[a++] = (unsigned short)n->joint->tag;
+    }
+    for (int b = B->nb[w]; b <= NB; b++) ps[b] = (unsigned short)a;
+  }
   ObPolicy pol;
   memset(&pol, 0, sizeof pol);
   pol.cat_mask1 = pol.cat_mask2 = ~0u; pol.max_contacts = 8; pol.skip_if_connected = 1;
@@ -150,6 +196,10 @@ dBatchID dBatchCreate(int nworlds, const dWorldID *worlds, const dSpaceID *space
   rc |= obk_h2d(B->bk, B->caps.geom, hg.data(), hg.size() * sizeof(ObGeom));
   rc |= obk_h2d(B->bk, B->caps.glist, hl.data(), hl.size() * sizeof(int));
   rc |= obk_h2d(B->bk, B->caps.policy, &pol, sizeof pol);
+  if (NJ) rc |= obk_h2d(B->bk, B->caps.joint, hj.data(), hj.size() * sizeof(ObJoint));
+  rc |= obk_h2d(B->bk, B->caps.njoints, hnj.data(), hnj.size() * sizeof(int));
+  rc |= obk_h2d(B->bk, B->caps.padjstart, hps.data(), hps.size() * sizeof(unsigned short));
+  if (NJ) rc |= obk_h2d(B->bk, B->caps.padj, hpa.data(), hpa.size() * sizeof(unsigned short));
   rc |= obk_memset(B->bk, B->caps.counters, 0, sizeof(ObCounters));
   rc |= obk_memset(B->bk, B->caps.npairs, 0, sizeof(int) * nworlds);
   rc |= obk_memset(B->bk, B->caps.ncontacts, 0, sizeof(int) * nworlds);

@@ -201,11 +201,111 @@ OB_HD void ob_qmul3(real *qa, const real *qb, const real *qc) {
   real a3 = -qb[0] * qc[3] - qb[3] * qc[0] + qb[1] * qc[2] - qb[2] * qc[1];
   qa[0] = a0; qa[1] = a1; qa[2] = a2; qa[3] = a3;
 }
-// glibc's atan2f/atan2 are not available on the device.  For dSINGLE we evaluate atan2 in
-// double and round once (a faithful float result) — it only feeds
-// discrete decisions (cullPoints ranking, joint-limit activation), checked against the
-// reference in tests.  For dDOUBLE the CUDA/glibc double routines are both <1 ulp.
-OB_HD real ob_atan2(real y, real x) { return (real)atan2((double)y, (double)x); }
+// atan2 with the host libm's results.  The reference calls glibc's atan2f (dAtan2,
+// include/ode/common.h:158) in cullPoints (box.cpp:280), getHingeAngle (joint.cpp:391-393) and
+// hinge2 measureAngle (hinge2.cpp:42); the value itself enters limit rows (limit_err), so a
+// merely faithful atan2 is not enough for bit parity.  glibc 2.39 (the libm pinned in this
+// image; third-party, not part of /root/reference) implements atan2f / atanf with the
+// fdlibm single-precision algorithm (sysdeps/ieee754/flt-32/e_atan2f.c, s_atanf.c):
+// argument reduction to one of four breakpoints + an odd/even split degree-11 polynomial,
+// all in float arithmetic.  Restated here; tests/test_abi.py checks it bit-for-bit against
+// the host atan2f on 10^6 inputs.  dDOUBLE uses the double atan2 of the platform
+// (glibc's is correctly rounded, CUDA's is <= 2 ulp): tolerance-only there.
+OB_HD int32_t ob_f2i(float x) {
+#if defined(__CUDA_ARCH__)
+  return __float_as_int(x);
+#else
+  union { float f; int32_t i; } u; u.f = x; return u.i;
+#endif
+}
+OB_HD float ob_i2f(int32_t i) {
+#if defined(__CUDA_ARCH__)
+  return __int_as_float(i);
+#else
+  union { float f; int32_t i; } u; u.i = i; return u.f;
+#endif
+}
+OB_HD float ob_atanf_glibc(float x) {
+  const float atanhi[4] = {4.6364760399e-01f, 7.8539812565e-01f, 9.8279368877e-01f, 1.5707962513e+00f};
+  const float atanlo[4] = {5.0121582440e-09f, 3.7748947079e-08f, 3.4473217170e-08f, 7.5497894159e-08f};
+  const float aT0 = 3.3333334327e-01f, aT1 = -2.0000000298e-01f, aT2 = 1.4285714924e-01f, aT3 = -1.1111110449e-01f,
+              aT4 = 9.0908870101e-02f, aT5 = -7.6918758452e-02f, aT6 = 6.6610731184e-02f, aT7 = -5.8335702866e-02f,
+              aT8 = 4.9768779427e-02f, aT9 = -3.6531571299e-02f, aT10 = 1.6285819933e-02f;
+  float w, s1, s2, z;
+  int32_t ix, hx, id;
+  hx = ob_f2i(x);
+  ix = hx & 0x7fffffff;
+  if (ix >= 0x4c000000) {
+    if (ix > 0x7f800000) return x + x;
+    if (hx > 0) return atanhi[3] + atanlo[3];
+    return -atanhi[3] - atanlo[3];
+  }
+  if (ix < 0x3ee00000) {
+    if (ix < 0x31000000) return x;
+    id = -1;
+  } else {
+    x = fabsf(x);
+    if (ix < 0x3f980000) {
+      if (ix < 0x3f300000) { id = 0; x = (2.0f * x - 1.0f) / (2.0f + x); }
+      else { id = 1; x = (x - 1.0f) / (x + 1.0f); }
+    } else {
+      if (ix < 0x401c0000) { id = 2; x = (x - 1.5f) / (1.0f + 1.5f * x); }
+      else { id = 3; x = -1.0f / x; }
+    }
+  }
+  z = x * x;
+  w = z * z;
+  s1 = z * (aT0 + w * (aT2 + w * (aT4 + w * (aT6 + w * (aT8 + w * aT10)))));
+  s2 = w * (aT1 + w * (aT3 + w * (aT5 + w * (aT7 + w * aT9))));
+  if (id < 0) return x - x * (s1 + s2);
+  z = atanhi[id] - ((x * (s1 + s2) - atanlo[id]) - x);
+  return (hx < 0) ? -z : z;
+}
+OB_HD float ob_atan2f_glibc(float y, float x) {
+  const float tiny = 1.0e-30f, pi_o_4 = 7.8539818525e-01f, pi_o_2 = 1.5707963705e+00f, pi = 3.1415927410e+00f,
+              pi_lo = -8.7422776573e-08f;
+  float z;
+  int32_t k, m, hx, hy, ix, iy;
+  hx = ob_f2i(x); ix = hx & 0x7fffffff;
+  hy = ob_f2i(y); iy = hy & 0x7fffffff;
+  if (ix > 0x7f800000 || iy > 0x7f800000) return x + y;
+  if (hx == 0x3f800000) return ob_atanf_glibc(y);
+  m = ((hy >> 31) & 1) | ((hx >> 30) & 2);
+  if (iy == 0) {
+    if (m == 0 || m == 1) return y;
+    if (m == 2) return pi + tiny;
+    return -pi - tiny;
+  }
+  if (ix == 0) return (hy < 0) ? -pi_o_2 - tiny : pi_o_2 + tiny;
+  if (ix == 0x7f800000) {
+    if (iy == 0x7f800000) {
+      if (m == 0) return pi_o_4 + tiny;
+      if (m == 1) return -pi_o_4 - tiny;
+      if (m == 2) return 3.0f * pi_o_4 + tiny;
+      return -3.0f * pi_o_4 - tiny;
+    }
+    if (m == 0) return 0.0f;
+    if (m == 1) return -0.0f;
+    if (m == 2) return pi + tiny;
+    return -pi - tiny;
+  }
+  if (iy == 0x7f800000) return (hy < 0) ? -pi_o_2 - tiny : pi_o_2 + tiny;
+  k = (iy - ix) >> 23;
+  if (k > 60) z = pi_o_2 + 0.5f * pi_lo;
+  else if (hx < 0 && k < -60) z = 0.0f;
+  else z = ob_atanf_glibc(fabsf(y / x));
+  if (m == 0) return z;
+  if (m == 1) return ob_i2f(ob_f2i(z) ^ (int32_t)0x80000000);
+  if (m == 2) return pi - (z - pi_lo);
+  return (z - pi_lo) - pi;
+}
+OB_HD real ob_atan2(real y, real x) {
+#if defined(dSINGLE)
+  return ob_atan2f_glibc(y, x);
+#else
+  return atan2(y, x);
+#endif
+}
 
 // ---- LCG behind the SOR row shuffle (misc.cpp:33-38, 66-117) -----------------
 OB_HD uint32_t ob_lcg_next(uint32_t s) { return 1664525u * s + 1013904223u; }

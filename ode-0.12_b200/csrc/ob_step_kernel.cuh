@@ -38,11 +38,13 @@
 __host__ __device__ inline size_t ob_al(size_t x, size_t a) { return (x + a - 1) & ~(a - 1); }
 
 struct PrepTileSmem {   // byte offsets inside one world's shared-memory slice (k_prep)
-  size_t invM, jb1, jb2, adjstart, cursor, adj, btag, jtag, stack, ibody, ijoint, jrow, isz, misc, total;
+  size_t invM, erpsrc, jb1, jb2, adjstart, cursor, adj, btag, jtag, stack, ibody, ijoint, jrow, isz, misc, total;
 };
-__host__ __device__ inline PrepTileSmem prep_tile_smem(int NB, int NC, int NR) {
+__host__ __device__ inline PrepTileSmem prep_tile_smem(int NB, int NCin, int NJ, int NR) {
   PrepTileSmem s; size_t o = 0;
+  const int NC = NCin + NJ;   // joint id space: contacts, then permanent joints
   s.invM = o; o = ob_al(o + sizeof(real) * NB, 16);
+  s.erpsrc = o; o = ob_al(o + sizeof(unsigned short) * NC, 4);
   s.jb1 = o; o = ob_al(o + (size_t)NC, 4);
   s.jb2 = o; o = ob_al(o + (size_t)NC, 4);
   s.adjstart = o; o = ob_al(o + sizeof(unsigned short) * (NB + 1), 4);
@@ -133,11 +135,12 @@ template <int G>
 __global__ void __launch_bounds__(32) k_prep(ObBatchDev d, real h, int taps) {
   constexpr int T = 32 / G;
   extern __shared__ __align__(16) unsigned char smem_all[];
-  const PrepTileSmem L = prep_tile_smem(d.NB, d.NC, d.NR);
+  const PrepTileSmem L = prep_tile_smem(d.NB, d.NC, d.NJ, d.NR);
   const int lane = threadIdx.x, grp = lane / G, gl = lane % G;
   const unsigned FULL = 0xffffffffu;
   unsigned char *smem = smem_all + (size_t)grp * L.total;
   real *s_invM = (real *)(smem + L.invM);
+  unsigned short *s_erpsrc = (unsigned short *)(smem + L.erpsrc);
   unsigned char *s_jb1 = smem + L.jb1, *s_jb2 = smem + L.jb2;
   unsigned short *s_adjstart = (unsigned short *)(smem + L.adjstart);
   unsigned short *s_cursor = (unsigned short *)(smem + L.cursor);
@@ -169,29 +172,47 @@ __global__ void __launch_bounds__(32) k_prep(ObBatchDev d, real h, int taps) {
     int *si = d.stepinfo + (size_t)wc * SI_WORDS;
     const int nb_max = warp_max_i(nb), nc_max = warp_max_i(nc);
 
-    // ---- (1) graph: contact joint -> bodies (dJointAttach swap rule, ode.cpp:1368-1377)
+    // ---- (1) graph.  Joint id space: this step's contact joints 0..nc-1 (creation order), then the
+    // world's permanent joints nc..nc+nj-1.  Contact joint -> bodies by the dJointAttach swap rule
+    // (ode.cpp:1368-1377); permanent joints carry their bodies from the host.
+    const int nj = valid ? d.njoints[wc] : 0;
+    const int njall = nc + nj;
+    const ObJoint *pjoint = d.joint + (size_t)wc * (d.NJ ? d.NJ : 1);
+    const unsigned short *padjstart = d.padjstart + (size_t)wc * (d.NB + 1);
+    const unsigned short *padj = d.padj + (size_t)wc * 2 * (d.NJ ? d.NJ : 1);
+    const int njall_max = warp_max_i(njall);
     for (int b = gl; b < nb; b += G) { s_cursor[b] = 0; s_btag[b] = 0; }
     __syncwarp();
-    for (int base = 0; base < nc_max; base += G) {
+    for (int base = 0; base < njall_max; base += G) {
       const int j = base + gl;
       if (j < nc) {
         int b1 = geoms[con[j].g1].body, b2 = geoms[con[j].g2].body;
         if (b1 < 0) { b1 = b2; b2 = -1; }
         s_jb1[j] = (unsigned char)b1; s_jb2[j] = (unsigned char)(b2 < 0 ? 255 : b2); s_jtag[j] = 0;
+      } else if (j < njall) {
+        const ObJoint &pj = pjoint[j - nc];
+        s_jb1[j] = (unsigned char)pj.b1; s_jb2[j] = (unsigned char)(pj.b2 < 0 ? 255 : pj.b2);
+        s_jtag[j] = (pj.flags & OB_JF_DISABLED) ? -1 : 0;   // disabled joints are never traversed (joint.cpp:66-71)
       }
     }
     __syncwarp();
-    // per-body joint lists, newest joint first (one lane per world)
+    // per-body joint lists: contacts newest first, then the permanent joints in the body's list order
     if (gl == 0 && valid) {
       for (int j = 0; j < nc; j++) { s_cursor[s_jb1[j]]++; if (s_jb2[j] != 255) s_cursor[s_jb2[j]]++; }
       int a = 0;
-      for (int b = 0; b < nb; b++) { const int c = s_cursor[b]; s_adjstart[b] = (unsigned short)a; s_cursor[b] = (unsigned short)a; a += c; }
+      for (int b = 0; b < nb; b++) {
+        const int c = s_cursor[b] + (padjstart[b + 1] - padjstart[b]);
+        s_adjstart[b] = (unsigned short)a; s_cursor[b] = (unsigned short)a; a += c;
+      }
       s_adjstart[nb] = (unsigned short)a;
       for (int j = nc - 1; j >= 0; j--) {
         const int b1 = s_jb1[j], b2 = s_jb2[j];
         s_adj[s_cursor[b1]++] = (unsigned short)j;
         if (b2 != 255) s_adj[s_cursor[b2]++] = (unsigned short)j;
       }
+      if (nj)
+        for (int b = 0; b < nb; b++)
+          for (int k = padjstart[b]; k < padjstart[b + 1]; k++) s_adj[s_cursor[b]++] = (unsigned short)(nc + padj[k]);
     }
     __syncwarp();
     // ---- (2) auto-disable, instantaneous-sample mode (util.cpp:99-233); invMass to smem
@@ -263,7 +284,7 @@ __global__ void __launch_bounds__(32) k_prep(ObBatchDev d, real h, int taps) {
     const int nis = valid ? s_misc[0] : 0, nib = valid ? s_misc[1] : 0, nij = valid ? s_misc[2] : 0;
     const int nib_max = warp_max_i(nib), nij_max = warp_max_i(nij), nis_max = warp_max_i(nis);
 
-    // ---- (4) per-body preamble (quickstep.cpp:610-665) + tmp1 (:840-846), island bodies only
+    // ---- (4) per-body preamble (quickstep.cpp:610-665), island bodies only
     unsigned char *g_ibody = d.ibody + (size_t)wc * d.NB;
     for (int base = 0; base < nib_max; base += G) {
       const int i = base + gl;
@@ -272,28 +293,38 @@ __global__ void __launch_bounds__(32) k_prep(ObBatchDev d, real h, int taps) {
         g_ibody[i] = (unsigned char)b;
         ObBodyDyn &B = bd[b];
         const ObBodyConst &C = bc[b];
-        real R[12], I[12], invI[12], iw[12], avel[3], lvel[3], facc[3], tacc[3], t1[6];
+        real R[12], I[12], invI[12], iw[12], avel[3], facc[3], tacc[3];
         for (int k = 0; k < 12; k++) { R[k] = B.R[k]; I[k] = C.I[k]; invI[k] = C.invI[k]; }
-        for (int k = 0; k < 3; k++) { avel[k] = B.avel[k]; lvel[k] = B.lvel[k]; facc[k] = B.facc[k]; tacc[k] = B.tacc[k]; }
+        for (int k = 0; k < 3; k++) { avel[k] = B.avel[k]; facc[k] = B.facc[k]; tacc[k] = B.tacc[k]; }
         ob_body_preamble(R, I, invI, avel, B.flags, C.mass, W.gravity, iw, facc, tacc);
-        ob_body_tmp1(facc, tacc, lvel, avel, C.invMass, iw, stepsize1, t1);
         for (int k = 0; k < 3; k++) { B.facc[k] = facc[k]; B.tacc[k] = tacc[k]; }
         for (int k = 0; k < 12; k++) g_invIw[12 * b + k] = iw[k];
-        for (int k = 0; k < 6; k++) g_tmp1[8 * b + k] = t1[k];
       }
     }
     // ---- (5) rows per joint (getInfo1) -> row offsets in island joint order (tile-wide scan)
     const ObSurface surf0 = d.policy[0].surface;
-    int mtot = 0;
+    int mtot = 0, anyball = 0;
     for (int base = 0; base < nij_max; base += G) {
       const int k = base + gl;
       int m = 0;
-      if (k < nij) { ObSurface sf = surf0; m = ob_contact_info1(sf); }
+      if (k < nij) {
+        const int j = s_ijoint[k];
+        if (j < nc) { ObSurface sf = surf0; m = ob_contact_info1(sf); }
+        else {
+          ObJoint pj = pjoint[j - nc];
+          const int b1 = pj.b1, b2 = pj.b2;
+          ObBodyView B1 = {bd[b1].pos, bd[b1].R, bd[b1].q, bd[b1].lvel, bd[b1].avel}, B2 = B1;
+          if (b2 >= 0) { B2.pos = bd[b2].pos; B2.R = bd[b2].R; B2.q = bd[b2].q; B2.lvel = bd[b2].lvel; B2.avel = bd[b2].avel; }
+          m = ob_joint_info1(pj, B1, b2 >= 0 ? &B2 : (const ObBodyView *)0);
+          if (pj.type == OB_JOINT_BALL) anyball = 1;
+        }
+      }
       int x = m;
       for (int dd = 1; dd < G; dd <<= 1) { const int y = __shfl_up_sync(FULL, x, dd, G); if (gl >= dd) x += y; }
       if (k < nij) s_jrow[k] = (unsigned short)(mtot + x - m);
       mtot += __shfl_sync(FULL, x, G - 1, G);
     }
+    for (int dd = 1; dd < G; dd <<= 1) anyball |= __shfl_xor_sync(FULL, anyball, dd, G);
     if (gl == 0 && valid) s_jrow[nij] = (unsigned short)mtot;
     __syncwarp();
     if (mtot > d.NR) {   // capacity: solve nothing rather than corrupt memory; flagged per world
@@ -301,26 +332,126 @@ __global__ void __launch_bounds__(32) k_prep(ObBatchDev d, real h, int taps) {
       mtot = 0;
     }
     const bool have_rows = mtot > 0;
-    // ---- (6) row assembly (getInfo2) + finalisation, one lane per joint
-    unsigned short *g_jrow = d.jrow + (size_t)wc * (d.NC + 1);
-    unsigned short *g_ijoint = d.ijoint + (size_t)wc * d.NC;
+    // Info2.erp is one variable shared by all joints of an island and a ball joint overwrites it
+    // (ball.cpp:60, quickstep.cpp:764-786): joint k sees the erp of the last ball joint before it
+    if (anyball && gl == 0 && have_rows) {
+      for (int isl = 0; isl < nis; isl++) {
+        const int j0 = s_isz[4 * isl + 2], jn = s_isz[4 * isl + 3];
+        int src = 0xffff;
+        for (int k = j0; k < j0 + jn; k++) {
+          s_erpsrc[k] = (unsigned short)src;
+          const int j = s_ijoint[k];
+          if (j >= nc && pjoint[j - nc].type == OB_JOINT_BALL) src = k;
+        }
+      }
+    }
+    __syncwarp();
+    // ---- (6a) row assembly (getInfo2), one lane per joint: raw rows {J[12], c, cfm, lo, hi} staged in
+    // the row records; motor-at-limit torques (joint.cpp:638-657) are collected and applied below
+    unsigned short *g_jrow = d.jrow + (size_t)wc * (d.NC + d.NJ + 1);
+    unsigned short *g_ijoint = d.ijoint + (size_t)wc * (d.NC + d.NJ);
+    real *g_side = d.jside + (size_t)wc * (d.NJ ? d.NJ : 1) * 8;
+    int anyside = 0;
     for (int base = 0; base < nij_max; base += G) {
       const int k = base + gl;
       if (k < nij && have_rows) {
         const int j = s_ijoint[k];
-        ObSurface sf = surf0;
-        const int jm = ob_contact_info1(sf);
-        ObRowOut3 r;
-        ob_rows_defaults(r, jm, W.cfm);
-        const ObContact c = con[j];
         const int b1 = s_jb1[j], b2 = s_jb2[j] == 255 ? -1 : (int)s_jb2[j];
-        const int rev = geoms[c.g1].body < 0;
-        real p1[3], l1[3], a1[3], p2[3] = {0, 0, 0}, l2[3] = {0, 0, 0}, a2[3] = {0, 0, 0};
-        for (int e = 0; e < 3; e++) { p1[e] = bd[b1].pos[e]; l1[e] = bd[b1].lvel[e]; a1[e] = bd[b1].avel[e]; }
-        if (b2 >= 0) for (int e = 0; e < 3; e++) { p2[e] = bd[b2].pos[e]; l2[e] = bd[b2].lvel[e]; a2[e] = bd[b2].avel[e]; }
-        const real fdir1[3] = {0, 0, 0};
-        ob_contact_info2(r, jm, sf, c.pos, c.normal, c.depth, fdir1, rev, p1, l1, a1, b2 >= 0, p2, l2, a2, stepsize1,
-                         W.erp, W.min_depth, W.max_vel);
+        const int r0 = s_jrow[k];
+        const unsigned ub2 = (unsigned)(b2 < 0 ? 255 : b2);
+        real erp_in = W.erp;
+        if (anyball) { const int src = s_erpsrc[k]; if (src != 0xffff) erp_in = pjoint[s_ijoint[src] - nc].erp; }
+        if (j < nc) {
+          ObSurface sf = surf0;
+          const int jm = ob_contact_info1(sf);
+          ObRowOut3 r;
+          ob_rows_defaults(r, jm, W.cfm);
+          const ObContact c = con[j];
+          const int rev = geoms[c.g1].body < 0;
+          real p1[3], l1[3], a1[3], p2[3] = {0, 0, 0}, l2[3] = {0, 0, 0}, a2[3] = {0, 0, 0};
+          for (int e = 0; e < 3; e++) { p1[e] = bd[b1].pos[e]; l1[e] = bd[b1].lvel[e]; a1[e] = bd[b1].avel[e]; }
+          if (b2 >= 0) for (int e = 0; e < 3; e++) { p2[e] = bd[b2].pos[e]; l2[e] = bd[b2].lvel[e]; a2[e] = bd[b2].avel[e]; }
+          const real fdir1[3] = {0, 0, 0};
+          ob_contact_info2(r, jm, sf, c.pos, c.normal, c.depth, fdir1, rev, p1, l1, a1, b2 >= 0, p2, l2, a2, stepsize1,
+                           erp_in, W.min_depth, W.max_vel);
+          for (int q = 0; q < jm; q++) {
+            real rw[OB_ROWW];
+            for (int e = 0; e < 12; e++) rw[e] = r.J[q][e];
+            rw[12] = r.c[q]; rw[13] = r.cfm[q]; rw[14] = r.lo[q]; rw[15] = r.hi[q]; rw[16] = rw[17] = rw[18] = 0;
+            const unsigned fio = (unsigned)(r.findex[q] >= 0 ? q - r.findex[q] : 0);
+            store_row(rows + (size_t)(r0 + q) * OB_ROWW, rw, (unsigned)b1 | (ub2 << 8) | (fio << 16));
+          }
+        } else {
+          ObJoint pj = pjoint[j - nc];
+          ObBodyView B1 = {bd[b1].pos, bd[b1].R, bd[b1].q, bd[b1].lvel, bd[b1].avel}, B2 = B1;
+          if (b2 >= 0) { B2.pos = bd[b2].pos; B2.R = bd[b2].R; B2.q = bd[b2].q; B2.lvel = bd[b2].lvel; B2.avel = bd[b2].avel; }
+          const int jm = ob_joint_info1(pj, B1, b2 >= 0 ? &B2 : (const ObBodyView *)0);
+          ObRowOut r;
+          ob_rows_defaults(r, jm, W.cfm);
+          real side[2][4];
+          real erp_io = erp_in;
+          ob_joint_info2(r, pj, B1, b2 >= 0 ? &B2 : (const ObBodyView *)0, stepsize1, &erp_io, side);
+          for (int sx = 0; sx < 2; sx++) {
+            for (int e = 0; e < 4; e++) g_side[(size_t)(j - nc) * 8 + 4 * sx + e] = side[sx][e];
+            if (side[sx][0] != 0) anyside = 1;
+          }
+          for (int q = 0; q < jm; q++) {
+            real rw[OB_ROWW];
+            for (int e = 0; e < 12; e++) rw[e] = r.J[q][e];
+            rw[12] = r.c[q]; rw[13] = r.cfm[q]; rw[14] = r.lo[q]; rw[15] = r.hi[q]; rw[16] = rw[17] = rw[18] = 0;
+            const unsigned fio = (unsigned)(r.findex[q] >= 0 ? q - r.findex[q] : 0);
+            store_row(rows + (size_t)(r0 + q) * OB_ROWW, rw, (unsigned)b1 | (ub2 << 8) | (fio << 16));
+          }
+        }
+      }
+      if (k < nij) { g_ijoint[k] = s_ijoint[k]; g_jrow[k] = s_jrow[k]; }
+    }
+    if (gl == 0 && valid) g_jrow[nij] = (unsigned short)(have_rows ? mtot : 0);
+    for (int dd = 1; dd < G; dd <<= 1) anyside |= __shfl_xor_sync(FULL, anyside, dd, G);
+    __syncwarp();
+    // (6b) dBodyAddTorque side effects in joint order (they change tacc before the rhs is formed)
+    if (anyside && gl == 0) {
+      for (int k = 0; k < nij; k++) {
+        const int j = s_ijoint[k];
+        if (j < nc) continue;
+        const int b1 = s_jb1[j], b2 = s_jb2[j];
+        for (int sx = 0; sx < 2; sx++) {
+          const real fm = __ldcg(g_side + (size_t)(j - nc) * 8 + 4 * sx);
+          if (fm != 0) {
+            for (int e = 0; e < 3; e++) {
+              const real ax = __ldcg(g_side + (size_t)(j - nc) * 8 + 4 * sx + 1 + e);
+              bd[b1].tacc[e] += -fm * ax;
+              if (b2 != 255) bd[b2].tacc[e] += fm * ax;
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+    // (4b) tmp1 = v/h + invM*f_ext per island body (quickstep.cpp:840-846), after the side effects
+    for (int base = 0; base < nib_max; base += G) {
+      const int i = base + gl;
+      if (i < nib && have_rows) {
+        const int b = s_ibody[i];
+        const ObBodyDyn &B = bd[b];
+        real iw[12], avel[3], lvel[3], facc[3], tacc[3], t1[6];
+        for (int k = 0; k < 12; k++) iw[k] = __ldcg(g_invIw + 12 * b + k);
+        for (int k = 0; k < 3; k++) { avel[k] = B.avel[k]; lvel[k] = B.lvel[k]; facc[k] = __ldcg(&B.facc[k]); tacc[k] = __ldcg(&B.tacc[k]); }
+        ob_body_tmp1(facc, tacc, lvel, avel, s_invM[b], iw, stepsize1, t1);
+        for (int k = 0; k < 6; k++) g_tmp1[8 * b + k] = t1[k];
+      }
+    }
+    __syncwarp();
+    // ---- (6c) finalisation, one lane per ROW: rhs, cfm/h, iMJ, Ad (quickstep.cpp:849-857, :355-402)
+    for (int base = 0; base < warp_max_i(mtot); base += G) {
+      const int ri = base + gl;
+      if (ri < mtot) {
+        real *rp = rows + (size_t)ri * OB_ROWW;
+        real raw[16];
+        for (int e = 0; e < 16; e++) raw[e] = __ldcg(rp + e);
+        const unsigned meta = *(const volatile unsigned *)(rp + OB_ROWF);
+        const int b1 = meta & 255, b2r = (meta >> 8) & 255;
+        const int b2 = b2r == 255 ? -1 : b2r;
         real t1a[6], t1b[6], iw1[12], iw2[12];
         for (int e = 0; e < 6; e++) t1a[e] = __ldcg(g_tmp1 + 8 * b1 + e);
         for (int e = 0; e < 12; e++) iw1[e] = __ldcg(g_invIw + 12 * b1 + e);
@@ -328,28 +459,19 @@ __global__ void __launch_bounds__(32) k_prep(ObBatchDev d, real h, int taps) {
           for (int e = 0; e < 6; e++) t1b[e] = __ldcg(g_tmp1 + 8 * b2 + e);
           for (int e = 0; e < 12; e++) iw2[e] = __ldcg(g_invIw + 12 * b2 + e);
         }
-        const int r0 = s_jrow[k];
-        const real invM1 = s_invM[b1], invM2 = b2 >= 0 ? s_invM[b2] : (real)0;
-        for (int q = 0; q < jm; q++) {
-          const int ri = r0 + q;
-          real rw[OB_ROWW];
-          for (int e = 0; e < 6; e++) rw[e] = r.J[q][e];
-          for (int e = 0; e < 3; e++) rw[6 + e] = r.J[q][9 + e];
-          real iMJ[12], b_out, adcfm, Ad;
-          ob_row_finalize2(r.J[q], r.c[q], r.cfm[q], b2, t1a, t1b, invM1, iw1, invM2, iw2, stepsize1, W.sor_w, iMJ, &b_out,
-                           &adcfm, &Ad);
-          for (int e = 0; e < 3; e++) { rw[9 + e] = iMJ[3 + e]; rw[12 + e] = iMJ[9 + e]; }
-          rw[15] = Ad; rw[16] = b_out; rw[17] = adcfm;
-          unsigned bmode;
-          if (!encode_bounds(r.lo[q], r.hi[q], &rw[18], &bmode)) atomicOr(&W.status, OB_ERR_ROW_OVERFLOW);
-          const unsigned fio = (unsigned)(r.findex[q] >= 0 ? q - r.findex[q] : 0);
-          const unsigned ub2 = (unsigned)(b2 < 0 ? 255 : b2);
-          store_row(rows + (size_t)ri * OB_ROWW, rw, (unsigned)b1 | (ub2 << 8) | (fio << 16) | (bmode << 24));
-        }
+        real rw[OB_ROWW];
+        for (int e = 0; e < 6; e++) rw[e] = raw[e];
+        for (int e = 0; e < 3; e++) rw[6 + e] = raw[9 + e];
+        real iMJ[12], b_out, adcfm, Ad;
+        ob_row_finalize2(raw, raw[12], raw[13], b2, t1a, t1b, s_invM[b1], iw1, b2 >= 0 ? s_invM[b2] : (real)0, iw2, stepsize1,
+                         W.sor_w, iMJ, &b_out, &adcfm, &Ad);
+        for (int e = 0; e < 3; e++) { rw[9 + e] = iMJ[3 + e]; rw[12 + e] = iMJ[9 + e]; }
+        rw[15] = Ad; rw[16] = b_out; rw[17] = adcfm;
+        unsigned bmode;
+        if (!encode_bounds(raw[14], raw[15], &rw[18], &bmode)) atomicOr(&W.status, OB_ERR_ROW_OVERFLOW);
+        store_row(rp, rw, (meta & 0x00ffffffu) | (bmode << 24));
       }
-      if (k < nij) { g_ijoint[k] = s_ijoint[k]; g_jrow[k] = s_jrow[k]; }
     }
-    if (gl == 0 && valid) g_jrow[nij] = (unsigned short)(have_rows ? mtot : 0);
     __syncwarp();
 
     // (7) the row order and the level schedule of every shuffle epoch are built by k_sched
@@ -407,7 +529,7 @@ __global__ void __launch_bounds__(32) k_sched(ObBatchDev d, int G, int taps) {
     const int nep = (W.iters + 7) >> 3;
     const real *rows = d.rows + (size_t)w * d.NR * OB_ROWW;
     const unsigned short *g_isz = d.isz + (size_t)w * 4 * d.NB;
-    const unsigned short *g_jrow = d.jrow + (size_t)w * (d.NC + 1);
+    const unsigned short *g_jrow = d.jrow + (size_t)w * (d.NC + d.NJ + 1);
     if (mtot == 0) {
       if (lane == 0) for (int ep = 0; ep < d.NEP; ep++) si[SI_NPASS0 + ep] = 0;
       continue;
@@ -704,8 +826,9 @@ __global__ void __launch_bounds__(32) k_sor(ObBatchDev d, int taps) {
       for (int k = 0; k < 6; k++) g_fc[8 * b + k] = s_fc[8 * b + k];
     if (taps && valid) {
       const int nij = si[SI_NIJ];
-      const unsigned short *g_jrow = d.jrow + (size_t)wc * (d.NC + 1);
-      const unsigned short *g_ijoint = d.ijoint + (size_t)wc * d.NC;
+      const unsigned short *g_jrow = d.jrow + (size_t)wc * (d.NC + d.NJ + 1);
+      const unsigned short *g_ijoint = d.ijoint + (size_t)wc * (d.NC + d.NJ);
+      const int ncw = d.ncontacts[wc];
       real *fb = d.fback + (size_t)wc * d.NC * 6;
       real *gl_lam = d.lambda + (size_t)wc * d.NR;
       if (mtot > 0)
@@ -716,7 +839,7 @@ __global__ void __launch_bounds__(32) k_sor(ObBatchDev d, int taps) {
             const real s = s_lam[jr0 + q];
             for (int e = 0; e < 6; e++) acc[e] += rows[(size_t)(jr0 + q) * OB_ROWW + e] * s;
           }
-          for (int e = 0; e < 6; e++) fb[g_ijoint[k] * 6 + e] = acc[e];
+          if (g_ijoint[k] < ncw) for (int e = 0; e < 6; e++) fb[g_ijoint[k] * 6 + e] = acc[e];
         }
       for (int i = gl; i < mtot; i += G) gl_lam[i] = s_lam[i];
     }
@@ -752,7 +875,7 @@ __global__ void __launch_bounds__(32) k_post(ObBatchDev d, real h) {
     const ObGeom *geoms = d.geom + (size_t)wc * d.NG;
     const unsigned char *g_ibody = d.ibody + (size_t)wc * d.NB;
     const unsigned short *g_isz = d.isz + (size_t)wc * 4 * d.NB;
-    const unsigned short *g_jrow = d.jrow + (size_t)wc * (d.NC + 1);
+    const unsigned short *g_jrow = d.jrow + (size_t)wc * (d.NC + d.NJ + 1);
     const real *g_invIw = d.invIw + (size_t)wc * d.NB * 12;
     const real *g_fc = d.tmp1 + (size_t)wc * d.NB * 8;
     // velocity update + integration per island body (quickstep.cpp:905-1021, util.cpp:255-360)

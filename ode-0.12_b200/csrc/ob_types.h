@@ -107,12 +107,17 @@ struct ObBatchDev {
   int NR;       // constraint rows per world-step
   int npolicy;
   int NEP;      // shuffle epochs per step = ceil(max iters / 8)
+  int NJ;       // permanent (non-contact) joints per world slot
   ObWorld *world;        // [W]
   ObBodyDyn *bdyn;       // [W*NB]
   ObBodyConst *bconst;   // [W*NB]
   ObGeom *geom;          // [W*NG]
   int *glist;            // [W*NG] space-list order (head first), geom indices
   ObPolicy *policy;      // [npolicy]
+  ObJoint *joint;        // [W*NJ] permanent joints (ball / hinge / hinge2), creation order
+  int *njoints;          // [W]
+  unsigned short *padjstart; // [W*(NB+1)] per body: range into padj
+  unsigned short *padj;      // [W*2*NJ] permanent joint ids in the body's joint-list order (newest attach first)
   // per-step products (device scratch, also the parity taps)
   int *npairs;           // [W]
   int *pairs;            // [W*NP*2] (o1,o2) geom indices in callback order
@@ -124,8 +129,9 @@ struct ObBatchDev {
   int *stepinfo;         // [W*16] hand-off between k_prep / k_sor / k_post
   unsigned char *ibody;  // [W*NB] island body order (stepping order)
   unsigned short *isz;   // [W*NB*4] per island: body start, body count, joint start, joint count
-  unsigned short *jrow;  // [W*(NC+1)] first row of joint k (island joint order)
-  unsigned short *ijoint;// [W*NC] island joint order -> contact joint id
+  unsigned short *jrow;  // [W*(NC+NJ+1)] first row of joint k (island joint order)
+  unsigned short *ijoint;// [W*(NC+NJ)] island joint order -> joint id (contacts < nc <= permanent)
+  real *jside;           // [W*NJ*8] motor-at-limit torques {fm, axis} x2 per permanent joint (step scratch)
   unsigned short *sched; // [W*NEP*NR] rows in level order, per shuffle epoch
   unsigned short *pstart;// [W*NEP*(NR+1)] first slot of every pass, per shuffle epoch
   real *rowJ;            // [W*NR*12] (host test backend only)

@@ -13,6 +13,9 @@ GOLDEN = [  # (file stem, scene, steps, worlds, settle) — must match tests/gol
     ("mixed_maxc4_settle80", "mixed_maxc4", 40, 1, 80),
     ("stack32_w2_settle120", "stack32", 12, 2, 120),
     ("tower64_settle150", "tower64", 8, 1, 150),
+    ("chain_settle60", "chain", 30, 1, 60),
+    ("hinges_settle70", "hinges", 30, 1, 70),
+    ("buggy_settle100", "buggy", 30, 1, 100),
 ]
 
 
@@ -37,6 +40,21 @@ def _built():
 
         __graft_entry__.build()
     yield
+
+
+# scenes whose rows depend on atan2 (hinge / hinge2 limit angles).  dSINGLE reproduces glibc's atan2f
+# bit for bit (ob_math.h); for dDOUBLE the device has no bit-identical atan2 (glibc's is correctly
+# rounded, CUDA's is <= 2 ulp), so those scenes are held to the stated tolerance instead:
+# exact discrete observables + |dx|_inf / max(1,|x|_inf) <= 1e-9 over the free-running trace.
+ATAN2_SCENES = ("hinges", "buggy")
+
+
+def assert_parity(r, what, scene, prec, cand):
+    if prec == "double" and cand == "b200" and scene in ATAN2_SCENES:
+        assert r["exact_ok"], f"{what}: exact observables differ at {r['first_exact_mismatch']}"
+        assert r["max_state_relerr"] <= 1e-9 and r["max_contact_relerr"] <= 1e-9, f"{what}: {r['max_state_relerr']}"
+    else:
+        assert_bit_exact(r, what)
 
 
 def assert_bit_exact(r, what=""):

@@ -12,5 +12,8 @@ for p in single double; do
   $d --scene mixed_maxc4 --steps 40 --settle 80 --out tests/golden/mixed_maxc4_settle80_$p.trace
   $d --scene stack32     --steps 12 --settle 120 --worlds 2 --out tests/golden/stack32_w2_settle120_$p.trace
   $d --scene tower64     --steps 8 --settle 150 --out tests/golden/tower64_settle150_$p.trace
+  $d --scene chain       --steps 30 --settle 60 --out tests/golden/chain_settle60_$p.trace
+  $d --scene hinges      --steps 30 --settle 70 --out tests/golden/hinges_settle70_$p.trace
+  $d --scene buggy       --steps 30 --settle 100 --out tests/golden/buggy_settle100_$p.trace
 done
 ls -la tests/golden

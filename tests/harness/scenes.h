@@ -171,6 +171,96 @@ static inline void scene_mixed(SceneWorld &sw, int w, int nbox, int nsph) {
   }
 }
 
+// chain of boxes linked by ball joints, first link pinned to the world, swinging onto a plane
+static inline void scene_chain(SceneWorld &sw, int w, int n) {
+  scene_world_base(sw, w);
+  xs32 rng(sw.seed ^ 0x00C0FFEEu);
+  scene_add_geom(sw, dCreatePlane(sw.space, 0, 0, 1, 0));
+  dBodyID prev = 0;
+  for (int i = 0; i < n; i++) {
+    dBodyID b = scene_add_box(sw, 3, (dReal)0.35, (dReal)0.12, (dReal)0.12, (dReal)(0.4 * i), 0, (dReal)1.6 + rng.uni(-0.01, 0.01));
+    dJointID j = dJointCreateBall(sw.world, 0);
+    dJointAttach(j, b, prev);
+    dJointSetBallAnchor(j, (dReal)(0.4 * i - 0.2), 0, (dReal)1.6);
+    if (i == 2) { dJointSetBallParam(j, dParamERP, (dReal)0.5); dJointSetBallParam(j, dParamCFM, (dReal)1e-3); }
+    sw.joints.push_back(j);
+    prev = b;
+  }
+}
+
+// boxes linked by hinges: stops, a free motor and a motor that runs into its stop (joint.cpp:638-657)
+static inline void scene_hinges(SceneWorld &sw, int w) {
+  scene_world_base(sw, w);
+  xs32 rng(sw.seed ^ 0x0B1E55EDu);
+  scene_add_geom(sw, dCreatePlane(sw.space, 0, 0, 1, 0));
+  dBodyID prev = 0;
+  for (int i = 0; i < 6; i++) {
+    dBodyID b = scene_add_box(sw, 2, (dReal)0.5, (dReal)0.2, (dReal)0.1, (dReal)(0.55 * i), rng.uni(-0.01, 0.01), (dReal)1.2);
+    dJointID j = dJointCreateHinge(sw.world, 0);
+    dJointAttach(j, prev, b);   // first one: (0, b) -> reversed attach
+    dJointSetHingeAnchor(j, (dReal)(0.55 * i - 0.275), 0, (dReal)1.2);
+    dJointSetHingeAxis(j, 0, 1, (dReal)(i == 3 ? 0.2 : 0));
+    if (i == 1 || i == 4) { dJointSetHingeParam(j, dParamLoStop, (dReal)-0.4); dJointSetHingeParam(j, dParamHiStop, (dReal)0.3); }
+    if (i == 2) { dJointSetHingeParam(j, dParamVel, (dReal)1.5); dJointSetHingeParam(j, dParamFMax, (dReal)4); }
+    if (i == 5) {   // powered and limited: reaches the stop, exercises the torque side effect + bounce
+      dJointSetHingeParam(j, dParamLoStop, (dReal)-0.2); dJointSetHingeParam(j, dParamHiStop, (dReal)0.2);
+      dJointSetHingeParam(j, dParamVel, (dReal)3); dJointSetHingeParam(j, dParamFMax, (dReal)6);
+      dJointSetHingeParam(j, dParamBounce, (dReal)0.3); dJointSetHingeParam(j, dParamFudgeFactor, (dReal)0.5);
+    }
+    sw.joints.push_back(j);
+    prev = b;
+  }
+}
+
+// demo_buggy-style vehicle: box chassis + 4 sphere wheels on hinge2 joints (demo_buggy.cpp:226-294),
+// rear wheels locked by stops, front wheels steered by a limited motor, all wheels driven
+static inline void scene_buggy(SceneWorld &sw, int w) {
+  scene_world_base(sw, w);
+  xs32 rng(sw.seed ^ 0x0000B066u);
+  scene_add_geom(sw, dCreatePlane(sw.space, 0, 0, 1, 0));
+  const dReal L = (dReal)0.7, Wd = (dReal)0.5, H = (dReal)0.2, R = (dReal)0.18, Z = (dReal)0.5;
+  dBodyID chassis = scene_add_box(sw, 1 / (L * Wd * H), L, Wd, H, 0, 0, Z);
+  const dReal wx[4] = {(dReal)(0.5 * L), (dReal)(0.5 * L), (dReal)(-0.5 * L), (dReal)(-0.5 * L)};
+  const dReal wy[4] = {(dReal)(0.5 * Wd), (dReal)(-0.5 * Wd), (dReal)(0.5 * Wd), (dReal)(-0.5 * Wd)};
+  for (int i = 0; i < 4; i++) {
+    dBodyID wheel = scene_add_sphere(sw, (dReal)(0.2 / (4.0 / 3.0 * 3.14159265358979 * R * R * R)), R, wx[i], wy[i], Z - H * (dReal)0.5);
+    dQuaternion q;
+    dQFromAxisAndAngle(q, 1, 0, 0, (dReal)(3.14159265358979 * 0.5));
+    dBodySetQuaternion(wheel, q);
+    dJointID j = dJointCreateHinge2(sw.world, 0);
+    dJointAttach(j, chassis, wheel);
+    const dReal *a = dBodyGetPosition(wheel);
+    dJointSetHinge2Anchor(j, a[0], a[1], a[2]);
+    dJointSetHinge2Axis1(j, 0, 0, 1);
+    dJointSetHinge2Axis2(j, 0, 1, 0);
+    dJointSetHinge2Param(j, dParamSuspensionERP, (dReal)0.4);
+    dJointSetHinge2Param(j, dParamSuspensionCFM, (dReal)0.8);
+    if (i >= 2) { dJointSetHinge2Param(j, dParamLoStop, 0); dJointSetHinge2Param(j, dParamHiStop, 0); }
+    else {
+      dJointSetHinge2Param(j, dParamVel, rng.uni(-0.5, 0.5)); dJointSetHinge2Param(j, dParamFMax, (dReal)0.2);
+      dJointSetHinge2Param(j, dParamLoStop, (dReal)-0.75); dJointSetHinge2Param(j, dParamHiStop, (dReal)0.75);
+      dJointSetHinge2Param(j, dParamFudgeFactor, (dReal)0.1);
+    }
+    dJointSetHinge2Param(j, dParamVel2, (dReal)-2.0); dJointSetHinge2Param(j, dParamFMax2, (dReal)0.1);
+    sw.joints.push_back(j);
+  }
+}
+
+static inline ScenePolicy policy_buggy() {
+  // ode/demo/demo_buggy.cpp:96-103
+  ScenePolicy p;
+  memset(&p, 0, sizeof(p));
+  p.max_contacts = 8;
+  p.skip_if_connected = 0;
+  p.surface.mode = dContactSlip1 | dContactSlip2 | dContactSoftERP | dContactSoftCFM | dContactApprox1;
+  p.surface.mu = dInfinity;
+  p.surface.slip1 = (dReal)0.1;
+  p.surface.slip2 = (dReal)0.1;
+  p.surface.soft_erp = (dReal)0.5;
+  p.surface.soft_cfm = (dReal)0.3;
+  return p;
+}
+
 static inline int scene_build(const char *name, SceneWorld &sw, int w, ScenePolicy &pol) {
   pol = policy_boxstack();
   if (!strcmp(name, "block64")) { scene_block64(sw, w); return 0; }
@@ -178,6 +268,9 @@ static inline int scene_build(const char *name, SceneWorld &sw, int w, ScenePoli
   if (!strcmp(name, "stack32")) { scene_stack32(sw, w); return 0; }
   if (!strcmp(name, "mixed")) { scene_mixed(sw, w, 12, 6); return 0; }
   if (!strcmp(name, "mixed_maxc4")) { scene_mixed(sw, w, 12, 6); pol = policy_crash(); return 0; }
+  if (!strcmp(name, "chain")) { scene_chain(sw, w, 8); return 0; }
+  if (!strcmp(name, "hinges")) { scene_hinges(sw, w); return 0; }
+  if (!strcmp(name, "buggy")) { scene_buggy(sw, w); pol = policy_buggy(); return 0; }
   if (!strcmp(name, "free6")) {  // no contacts: integrator + gyroscopic term only
     scene_world_base(sw, w);
     xs32 rng(sw.seed);

@@ -38,6 +38,10 @@ ObBackend *obk_create(const ObBatchDev &caps, int, char *, size_t) {
   d.geom = halloc<ObGeom>(b, W * d.NG);
   d.glist = halloc<int>(b, W * d.NG);
   d.policy = halloc<ObPolicy>(b, d.npolicy);
+  d.joint = halloc<ObJoint>(b, W * (d.NJ ? d.NJ : 1));
+  d.njoints = halloc<int>(b, W);
+  d.padjstart = halloc<unsigned short>(b, W * (d.NB + 1));
+  d.padj = halloc<unsigned short>(b, W * 2 * (d.NJ ? d.NJ : 1));
   d.npairs = halloc<int>(b, W);
   d.pairs = halloc<int>(b, W * d.NP * 2);
   d.ncontacts = halloc<int>(b, W);
@@ -182,6 +186,20 @@ static void collide_world(ObBatchDev &d, int w) {
   for (int i = 0; i < ng; i++) walk_of[glist[i]] = i;
   for (int i = 0; i < np; i++) {
     int o1 = pairs[2 * i], o2 = pairs[2 * i + 1];
+    if (pol.skip_if_connected && d.NJ) {   // dAreConnectedExcluding(b1, b2, dJointTypeContact), ode.cpp:1529-1537
+      const int b1 = d.geom[(size_t)w * d.NG + o1].body, b2 = d.geom[(size_t)w * d.NG + o2].body;
+      bool connected = false;
+      if (b1 >= 0 && b2 >= 0) {
+        const unsigned short *ps = d.padjstart + (size_t)w * (d.NB + 1), *pa = d.padj + (size_t)w * 2 * d.NJ;
+        const ObJoint *pj = d.joint + (size_t)w * d.NJ;
+        for (int k = ps[b1]; k < ps[b1 + 1]; k++) {
+          const ObJoint &jj = pj[pa[k]];
+          const int other = jj.b1 == b1 ? jj.b2 : jj.b1;
+          if (other == b2) connected = true;
+        }
+      }
+      if (connected) continue;
+    }
     ObCg cg[OB_MAXC_LOCAL];
     int swapped;
     int flags = pol.max_contacts > OB_MAXC_LOCAL ? OB_MAXC_LOCAL : pol.max_contacts;
@@ -206,19 +224,28 @@ static void step_world(ObBatchDev &d, int w, real h, int taps) {
   const ObContact *con = d.contacts + (size_t)w * d.NC;
   const real stepsize1 = ob_recip(h);
 
+  // joint id space: contact joints 0..nc-1 (creation order), permanent joints nc..nc+nj-1
+  const int nj = d.njoints[w];
+  const ObJoint *pjoint = d.joint + (size_t)w * (d.NJ ? d.NJ : 1);
+  const int njall = nc + nj;
   // contact joint -> bodies (dJointAttach: body1==0 -> swap + REVERSE), ode.cpp:1368-1377
-  std::vector<int> jb1(nc), jb2(nc), jrev(nc);
+  std::vector<int> jb1(njall), jb2(njall), jrev(njall);
   for (int j = 0; j < nc; j++) {
     int b1 = geoms[con[j].g1].body, b2 = geoms[con[j].g2].body;
     jrev[j] = 0;
     if (b1 < 0) { b1 = b2; b2 = -1; jrev[j] = 1; }
     jb1[j] = b1; jb2[j] = b2;
   }
-  // body joint lists, newest first
+  for (int j = 0; j < nj; j++) { jb1[nc + j] = pjoint[j].b1; jb2[nc + j] = pjoint[j].b2; jrev[nc + j] = 0; }
+  // body joint lists: this step's contacts newest first, then the permanent joints in list order
   std::vector<std::vector<int> > adj(nb);   // joint ids
   for (int j = nc - 1; j >= 0; j--) {
     if (jb1[j] >= 0) adj[jb1[j]].push_back(j);
     if (jb2[j] >= 0) adj[jb2[j]].push_back(j);
+  }
+  {
+    const unsigned short *ps = d.padjstart + (size_t)w * (d.NB + 1), *pa = d.padj + (size_t)w * 2 * (d.NJ ? d.NJ : 1);
+    for (int b = 0; b < nb; b++) for (int k = ps[b]; k < ps[b + 1]; k++) adj[b].push_back(nc + pa[k]);
   }
   // auto-disable (util.cpp:99-233), instantaneous-sample mode only
   for (int b = 0; b < nb; b++) {
@@ -237,7 +264,7 @@ static void step_world(ObBatchDev &d, int w, real h, int taps) {
     }
   }
   // islands (util.cpp:411-487)
-  std::vector<int> btag(nb, 0), jtag(nc, 0), ibody, ijoint, isz;
+  std::vector<int> btag(nb, 0), jtag(njall, 0), ibody, ijoint, isz;
   std::vector<int> stack;
   for (int bb = 0; bb < nb; bb++) {
     if (btag[bb]) continue;
@@ -252,6 +279,7 @@ static void step_world(ObBatchDev &d, int w, real h, int taps) {
         if (!jtag[j]) {
           // isEnabled: at least one attached body with invMass > 0 (joint.cpp:66-71)
           bool enabled = (bc[jb1[j]].invMass > 0) || (jb2[j] >= 0 && bc[jb2[j]].invMass > 0);
+          if (j >= nc && (pjoint[j - nc].flags & OB_JF_DISABLED)) enabled = false;
           if (enabled) {
             jtag[j] = 1;
             ijoint.push_back(j);
@@ -293,13 +321,23 @@ static void step_world(ObBatchDev &d, int w, real h, int taps) {
       ob_body_preamble(bd[b].R, bc[b].I, bc[b].invI, bd[b].avel, bd[b].flags, bc[b].mass, W.gravity, &invIw[12 * i],
                        bd[b].facc, bd[b].tacc);
     }
-    // rows
+    // rows: getInfo1 per joint (quickstep.cpp:670-688; joints with m == 0 are dropped)
+    auto view = [&](int b) { ObBodyView v; v.pos = bd[b].pos; v.R = bd[b].R; v.q = bd[b].q; v.lvel = bd[b].lvel; v.avel = bd[b].avel; return v; };
     std::vector<int> jm(inj), jofs(inj);
     int m = 0;
     std::vector<ObSurface> surf(inj);
+    std::vector<ObJoint> pj(inj);
     for (int k = 0; k < inj; k++) {
-      surf[k] = d.policy[con[ij[k]].policy].surface;
-      jm[k] = ob_contact_info1(surf[k]);
+      const int j = ij[k];
+      if (j < nc) {
+        surf[k] = d.policy[con[j].policy].surface;
+        jm[k] = ob_contact_info1(surf[k]);
+      } else {
+        pj[k] = pjoint[j - nc];
+        ObBodyView B1 = view(jb1[j]), B2;
+        if (jb2[j] >= 0) B2 = view(jb2[j]);
+        jm[k] = ob_joint_info1(pj[k], B1, jb2[j] >= 0 ? &B2 : 0);
+      }
       jofs[k] = m;
       m += jm[k];
     }
@@ -308,6 +346,33 @@ static void step_world(ObBatchDev &d, int w, real h, int taps) {
     int *RI = rowI + (size_t)rowbase * 4;
     real *lam = lambda + rowbase;
     if (m > 0) {
+      // getInfo2 for every joint first (it may add motor torques to tacc, joint.cpp:638-657), then tmp1
+      std::vector<ObRowOut> rr(inj);
+      real erp_io = W.erp;   // Info2.erp is shared by the island's joints; a ball joint overwrites it (ball.cpp:60)
+      for (int k = 0; k < inj; k++) {
+        int j = ij[k];
+        ObRowOut &r = rr[k];
+        ob_rows_defaults(r, jm[k], W.cfm);
+        int b1 = jb1[j], b2 = jb2[j];
+        if (j < nc) {
+          real zero3[3] = {0, 0, 0};
+          real fdir1[3] = {0, 0, 0};
+          ob_contact_info2(r, jm[k], surf[k], con[j].pos, con[j].normal, con[j].depth, fdir1, jrev[j], bd[b1].pos,
+                           bd[b1].lvel, bd[b1].avel, b2 >= 0, b2 >= 0 ? bd[b2].pos : zero3, b2 >= 0 ? bd[b2].lvel : zero3,
+                           b2 >= 0 ? bd[b2].avel : zero3, stepsize1, erp_io, W.min_depth, W.max_vel);
+        } else {
+          ObBodyView B1 = view(b1), B2;
+          if (b2 >= 0) B2 = view(b2);
+          real side[2][4];
+          ob_joint_info2(r, pj[k], B1, b2 >= 0 ? &B2 : 0, stepsize1, &erp_io, side);
+          for (int sx = 0; sx < 2; sx++)
+            if (side[sx][0] != 0) {   // dBodyAddTorque(body1, -fm*ax) ; dBodyAddTorque(body2, +fm*ax)
+              const real fm = side[sx][0];
+              for (int e = 0; e < 3; e++) bd[b1].tacc[e] += -fm * side[sx][1 + e];
+              if (b2 >= 0) for (int e = 0; e < 3; e++) bd[b2].tacc[e] += fm * side[sx][1 + e];
+            }
+        }
+      }
       for (int i = 0; i < inb; i++) {
         int b = ib[i];
         ob_body_tmp1(bd[b].facc, bd[b].tacc, bd[b].lvel, bd[b].avel, bc[b].invMass, &invIw[12 * i], stepsize1, &tmp1[6 * i]);
@@ -316,14 +381,8 @@ static void step_world(ObBatchDev &d, int w, real h, int taps) {
       if (taps) Jcopy.resize((size_t)m * 12);
       for (int k = 0; k < inj; k++) {
         int j = ij[k];
-        ObRowOut3 r;
-        ob_rows_defaults(r, jm[k], W.cfm);
+        ObRowOut &r = rr[k];
         int b1 = jb1[j], b2 = jb2[j];
-        real zero3[3] = {0, 0, 0};
-        real fdir1[3] = {0, 0, 0};
-        ob_contact_info2(r, jm[k], surf[k], con[j].pos, con[j].normal, con[j].depth, fdir1, jrev[j], bd[b1].pos,
-                         bd[b1].lvel, bd[b1].avel, b2 >= 0, b2 >= 0 ? bd[b2].pos : zero3, b2 >= 0 ? bd[b2].lvel : zero3,
-                         b2 >= 0 ? bd[b2].avel : zero3, stepsize1, W.erp, W.min_depth, W.max_vel);
         for (int q = 0; q < jm[k]; q++) {
           int ri = jofs[k] + q;
           if (taps) memcpy(&Jcopy[(size_t)ri * 12], r.J[q], 12 * sizeof(real));
@@ -379,7 +438,7 @@ static void step_world(ObBatchDev &d, int w, real h, int taps) {
             real s = lam[jofs[k] + q];
             for (int e = 0; e < 6; e++) acc[e] += Jcopy[(size_t)(jofs[k] + q) * 12 + e] * s;
           }
-          for (int e = 0; e < 6; e++) fb[ij[k] * 6 + e] = acc[e];
+          if (ij[k] < nc) for (int e = 0; e < 6; e++) fb[ij[k] * 6 + e] = acc[e];
         }
       }
     }
@@ -403,7 +462,7 @@ static void step_world(ObBatchDev &d, int w, real h, int taps) {
     bpos += isz[2 * isl]; jpos += isz[2 * isl + 1];
     d.counters->body_steps += inb;
     d.counters->rows += m;
-    d.counters->contacts += inj;
+    for (int k = 0; k < inj; k++) if (ij[k] < nc) d.counters->contacts += 1;
     d.counters->islands += 1;
   }
   W.seed = seed;

@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, ROOT, assert_bit_exact, have_ref, lib_path
+from conftest import GOLDEN, ROOT, assert_bit_exact, assert_parity, have_ref, lib_path
 from run_parity import parity, parity_golden
 
 pytestmark = pytest.mark.gpu
@@ -19,16 +19,16 @@ def test_cuda_matches_golden_reference_traces(stem, scene, steps, worlds, settle
     g = os.path.join(ROOT, "tests", "golden", f"{stem}_{prec}.trace")
     r = parity_golden("b200", g, scene, prec, steps, worlds, settle)
     assert r["steps"] == steps
-    assert_bit_exact(r, f"{stem}/{prec}")
+    assert_parity(r, f"{stem}/{prec}", scene, prec, "b200")
 
 
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref not shipped")
 @pytest.mark.parametrize("prec", ["single", "double"])
 @pytest.mark.parametrize("scene,steps,worlds", [("stack32", 200, 3), ("block64", 50, 1), ("tower64", 250, 1),
-                                                ("mixed", 200, 2), ("mixed_maxc4", 300, 1)])
+                                                ("mixed", 200, 2), ("mixed_maxc4", 300, 1), ("chain", 250, 2), ("hinges", 250, 1), ("buggy", 250, 3)])
 def test_cuda_matches_live_reference(scene, steps, worlds, prec):
     r = parity("b200", prec, scene, steps, worlds)
-    assert_bit_exact(r, f"{scene}/{prec}")
+    assert_parity(r, f"{scene}/{prec}", scene, prec, "b200")
 
 
 def _batch(lib, scenes, scene, nworlds, cap=0):
