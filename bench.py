@@ -214,19 +214,36 @@ def run_b200(args):
         if tj.get("kernel") == dom:
             traffic = tj.get("dram_bytes_per_launch")
 
-    # end to end through the C ABI with host buffers every step
+    # end to end through the C ABI with HOST buffers every step (page-locked, from dBatchHostAlloc):
+    # external forces H2D -> step -> body state D2H.  The force samples are generated before the
+    # timed region (they stand for the caller's controller output, which is not the library's work).
     nb = lib.dBatchNumBodies(B)
-    pos = np.zeros((nworlds, nb, 3), np.float32); quat = np.zeros((nworlds, nb, 4), np.float32)
-    lv = np.zeros((nworlds, nb, 3), np.float32); av = np.zeros((nworlds, nb, 3), np.float32)
-    force = np.zeros((nworlds, nb, 3), np.float32); torque = np.zeros((nworlds, nb, 3), np.float32)
+    lib.dBatchHostAlloc.restype = ctypes.c_void_p
+    lib.dBatchHostAlloc.argtypes = [ctypes.c_size_t]
+
+    def pinned(shape):
+        n = int(np.prod(shape))
+        ptr = lib.dBatchHostAlloc(n * 4)
+        if not ptr:
+            raise SystemExit("dBatchHostAlloc failed")
+        a = np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_float)), shape=(n,)).reshape(shape)
+        a[...] = 0
+        return a
+
+    pos = pinned((nworlds, nb, 3)); quat = pinned((nworlds, nb, 4))
+    lv = pinned((nworlds, nb, 3)); av = pinned((nworlds, nb, 3))
+    torque = pinned((nworlds, nb, 3))
     rng = np.random.default_rng(rank)
+    forces = [pinned((nworlds, nb, 3)) for _ in range(4)]
+    for f in forces:
+        f[:, :, 0] = 0.01 * rng.standard_normal((nworlds, nb), dtype=np.float32)
+    force = forces[0]
     lib.dBatchResetCounters(B)
     e2e_steps = args.steps
     barrier()
     t0 = time.perf_counter()
     for s in range(e2e_steps):
-        force[:, :, 0] = 0.01 * rng.standard_normal((nworlds, nb), dtype=np.float32)
-        lib.dBatchAddForces(B, force.ctypes.data, torque.ctypes.data)
+        lib.dBatchAddForces(B, forces[s & 3].ctypes.data, torque.ctypes.data)
         step(1)
         lib.dBatchGetBodyState(B, pos.ctypes.data, quat.ctypes.data, lv.ctypes.data, av.ctypes.data)
     t_e2e = time.perf_counter() - t0

@@ -472,6 +472,10 @@ int dBatchSetBodyState(dBatchID, const dReal *pos3, const dReal *quat4,
                        const dReal *lvel3, const dReal *avel3);
 /* external force/torque accumulators, [world][body][3] each, added to facc/tacc */
 int dBatchAddForces(dBatchID, const dReal *force3, const dReal *torque3);
+/* page-locked host memory: buffers from dBatchHostAlloc make the bulk I/O calls above plain
+ * DMA transfers (any other host pointer works too, through the driver's staging copy) */
+void *dBatchHostAlloc(size_t bytes);
+void dBatchHostFree(void *p);
 /* copy device state back into the bound dBodyID/dGeomID objects */
 int dBatchDownload(dBatchID);
 int dBatchGetCounters(dBatchID, dBatchCounters *out);

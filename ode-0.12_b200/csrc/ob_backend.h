@@ -24,6 +24,9 @@ int obk_sync(ObBackend *);
 int obk_get_state(ObBackend *, real *pos3, real *quat4, real *lvel3, real *avel3);
 int obk_set_state(ObBackend *, const real *pos3, const real *quat4, const real *lvel3, const real *avel3);
 int obk_add_forces(ObBackend *, const real *force3, const real *torque3);
+// page-locked host memory for the bulk I/O calls (DMA without a staging copy)
+void *obk_host_alloc(size_t bytes);
+void obk_host_free(void *);
 void *obk_stream(ObBackend *);
 int obk_timer_start(ObBackend *);
 int obk_timer_stop(ObBackend *, float *ms);

@@ -360,7 +360,6 @@ ObBackend *obk_create(const ObBatchDev &caps, int device, char *err, size_t errl
   CK(dalloc(b, &d.counters, (size_t)1));
   b->st_elems = W * d.NB;
   CK(dalloc(b, &b->st_dev, b->st_elems * 13));
-  CK(cudaMallocHost((void **)&b->st_host, b->st_elems * 13 * sizeof(real)));
   b->smem_collide = collide_smem(d.NG, d.NP).total;
   {
     // tile width: G lanes per world, 32/G worlds per warp.  Narrow tiles waste fewer lanes in the
@@ -492,31 +491,33 @@ int obk_step(ObBackend *b, real h, int nsteps, int taps, char *err, size_t errle
   return 0;
 }
 
+// Bulk state I/O copies straight between the caller's buffers and the packed device staging
+// array: with buffers from dBatchHostAlloc (pinned) these are plain DMA transfers, with pageable
+// memory the driver stages them.
 int obk_get_state(ObBackend *b, real *pos3, real *quat4, real *lvel3, real *avel3) {
   cudaSetDevice(b->device);
   const size_t n = b->st_elems;
   real *dp = b->st_dev, *dq = dp + n * 3, *dl = dq + n * 4, *da = dl + n * 3;
   k_pack_state<<<(unsigned)((n + 255) / 256), 256, 0, b->stream>>>(b->d, dp, dq, dl, da);
   g_launches++;
-  if (cudaMemcpyAsync(b->st_host, b->st_dev, n * 13 * sizeof(real), cudaMemcpyDeviceToHost, b->stream) != cudaSuccess) return -1;
-  if (cudaStreamSynchronize(b->stream) != cudaSuccess) return -1;
-  const real *hp = b->st_host, *hq = hp + n * 3, *hl = hq + n * 4, *ha = hl + n * 3;
-  if (pos3) memcpy(pos3, hp, n * 3 * sizeof(real));
-  if (quat4) memcpy(quat4, hq, n * 4 * sizeof(real));
-  if (lvel3) memcpy(lvel3, hl, n * 3 * sizeof(real));
-  if (avel3) memcpy(avel3, ha, n * 3 * sizeof(real));
-  return 0;
+  cudaError_t e = cudaSuccess;
+  if (pos3 && e == cudaSuccess) e = cudaMemcpyAsync(pos3, dp, n * 3 * sizeof(real), cudaMemcpyDeviceToHost, b->stream);
+  if (quat4 && e == cudaSuccess) e = cudaMemcpyAsync(quat4, dq, n * 4 * sizeof(real), cudaMemcpyDeviceToHost, b->stream);
+  if (lvel3 && e == cudaSuccess) e = cudaMemcpyAsync(lvel3, dl, n * 3 * sizeof(real), cudaMemcpyDeviceToHost, b->stream);
+  if (avel3 && e == cudaSuccess) e = cudaMemcpyAsync(avel3, da, n * 3 * sizeof(real), cudaMemcpyDeviceToHost, b->stream);
+  if (e != cudaSuccess) return -1;
+  return cudaStreamSynchronize(b->stream) == cudaSuccess ? 0 : -1;
 }
 int obk_set_state(ObBackend *b, const real *pos3, const real *quat4, const real *lvel3, const real *avel3) {
   cudaSetDevice(b->device);
   const size_t n = b->st_elems;
-  real *hp = b->st_host, *hq = hp + n * 3, *hl = hq + n * 4, *ha = hl + n * 3;
-  if (pos3) memcpy(hp, pos3, n * 3 * sizeof(real));
-  if (quat4) memcpy(hq, quat4, n * 4 * sizeof(real));
-  if (lvel3) memcpy(hl, lvel3, n * 3 * sizeof(real));
-  if (avel3) memcpy(ha, avel3, n * 3 * sizeof(real));
-  if (cudaMemcpyAsync(b->st_dev, b->st_host, n * 13 * sizeof(real), cudaMemcpyHostToDevice, b->stream) != cudaSuccess) return -1;
   real *dp = b->st_dev, *dq = dp + n * 3, *dl = dq + n * 4, *da = dl + n * 3;
+  cudaError_t e = cudaSuccess;
+  if (pos3 && e == cudaSuccess) e = cudaMemcpyAsync(dp, pos3, n * 3 * sizeof(real), cudaMemcpyHostToDevice, b->stream);
+  if (quat4 && e == cudaSuccess) e = cudaMemcpyAsync(dq, quat4, n * 4 * sizeof(real), cudaMemcpyHostToDevice, b->stream);
+  if (lvel3 && e == cudaSuccess) e = cudaMemcpyAsync(dl, lvel3, n * 3 * sizeof(real), cudaMemcpyHostToDevice, b->stream);
+  if (avel3 && e == cudaSuccess) e = cudaMemcpyAsync(da, avel3, n * 3 * sizeof(real), cudaMemcpyHostToDevice, b->stream);
+  if (e != cudaSuccess) return -1;
   k_unpack_state<<<(unsigned)((n + 255) / 256), 256, 0, b->stream>>>(b->d, pos3 ? dp : 0, quat4 ? dq : 0, lvel3 ? dl : 0, avel3 ? da : 0);
   g_launches++;
   return cudaStreamSynchronize(b->stream) == cudaSuccess ? 0 : -1;
@@ -524,11 +525,14 @@ int obk_set_state(ObBackend *b, const real *pos3, const real *quat4, const real 
 int obk_add_forces(ObBackend *b, const real *f3, const real *t3) {
   cudaSetDevice(b->device);
   const size_t n = b->st_elems;
-  real *hf = b->st_host, *ht = hf + n * 3;
-  if (f3) memcpy(hf, f3, n * 3 * sizeof(real));
-  if (t3) memcpy(ht, t3, n * 3 * sizeof(real));
-  if (cudaMemcpyAsync(b->st_dev, b->st_host, n * 6 * sizeof(real), cudaMemcpyHostToDevice, b->stream) != cudaSuccess) return -1;
-  k_add_forces<<<(unsigned)((n + 255) / 256), 256, 0, b->stream>>>(b->d, f3 ? b->st_dev : 0, t3 ? b->st_dev + n * 3 : 0);
+  real *df = b->st_dev, *dt = df + n * 3;
+  cudaError_t e = cudaSuccess;
+  if (f3) e = cudaMemcpyAsync(df, f3, n * 3 * sizeof(real), cudaMemcpyHostToDevice, b->stream);
+  if (t3 && e == cudaSuccess) e = cudaMemcpyAsync(dt, t3, n * 3 * sizeof(real), cudaMemcpyHostToDevice, b->stream);
+  if (e != cudaSuccess) return -1;
+  k_add_forces<<<(unsigned)((n + 255) / 256), 256, 0, b->stream>>>(b->d, f3 ? df : 0, t3 ? dt : 0);
   g_launches++;
   return cudaStreamSynchronize(b->stream) == cudaSuccess ? 0 : -1;
 }
+void *obk_host_alloc(size_t bytes) { void *p = 0; return cudaMallocHost(&p, bytes ? bytes : 1) == cudaSuccess ? p : 0; }
+void obk_host_free(void *p) { if (p) cudaFreeHost(p); }

@@ -268,6 +268,8 @@ int dBatchSetBodyState(dBatchID B, const dReal *pos3, const dReal *quat4, const 
   return obk_set_state(B->bk, pos3, quat4, lvel3, avel3);
 }
 int dBatchAddForces(dBatchID B, const dReal *force3, const dReal *torque3) { return obk_add_forces(B->bk, force3, torque3); }
+void *dBatchHostAlloc(size_t bytes) { return obk_host_alloc(bytes); }
+void dBatchHostFree(void *p) { obk_host_free(p); }
 
 int dBatchDownload(dBatchID B) {
   int W = B->caps.W, NB = B->caps.NB, NG = B->caps.NG;

@@ -98,6 +98,8 @@ int obk_set_state(ObBackend *b, const real *pos3, const real *quat4, const real 
   }
   return 0;
 }
+void *obk_host_alloc(size_t bytes) { return malloc(bytes ? bytes : 1); }
+void obk_host_free(void *p) { free(p); }
 int obk_add_forces(ObBackend *b, const real *f3, const real *t3) {
   ObBatchDev &d = b->d;
   for (int w = 0; w < d.W; w++) {
