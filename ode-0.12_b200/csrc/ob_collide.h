@@ -9,6 +9,7 @@
 //   sphere-plane     ode/src/sphere.cpp:222-251
 //   box-box          ode/src/box.cpp:331-742 (intersectRectQuad :187-238, cullPoints :249-311)
 //   box-plane        ode/src/box.cpp:745-878
+//   capsule-*        ode/src/capsule.cpp:130-411 + collision_util.cpp:107-391
 //   dCollide         ode/src/collision_kernel.cpp:292-339 (class table + reverse fix-up :167-268)
 // No virtual dispatch: the class pair selects a switch arm.
 #pragma once
@@ -545,6 +546,240 @@ done:
   return ret;
 }
 
+// ---- capsule colliders (capsule.cpp:130-411) ------------------------------------
+// dClosestLineSegmentPoints, collision_util.cpp:107-219
+OB_HD void ob_closest_segment_points(const real *a1, const real *a2, const real *b1, const real *b2, real *cp1, real *cp2) {
+  real a1a2[3], b1b2[3], a1b1[3], a1b2[3], a2b1[3], a2b2[3], n[3];
+  real la, lb, k, da1, da2, da3, da4, db1, db2, db3, db4, det;
+  for (int i = 0; i < 3; i++) { a1a2[i] = a2[i] - a1[i]; b1b2[i] = b2[i] - b1[i]; a1b1[i] = b1[i] - a1[i]; }
+  da1 = ob_dot(a1a2, a1b1);
+  db1 = ob_dot(b1b2, a1b1);
+  if (da1 <= 0 && db1 >= 0) { for (int i = 0; i < 3; i++) { cp1[i] = a1[i]; cp2[i] = b1[i]; } return; }
+  for (int i = 0; i < 3; i++) a1b2[i] = b2[i] - a1[i];
+  da2 = ob_dot(a1a2, a1b2);
+  db2 = ob_dot(b1b2, a1b2);
+  if (da2 <= 0 && db2 <= 0) { for (int i = 0; i < 3; i++) { cp1[i] = a1[i]; cp2[i] = b2[i]; } return; }
+  for (int i = 0; i < 3; i++) a2b1[i] = b1[i] - a2[i];
+  da3 = ob_dot(a1a2, a2b1);
+  db3 = ob_dot(b1b2, a2b1);
+  if (da3 >= 0 && db3 >= 0) { for (int i = 0; i < 3; i++) { cp1[i] = a2[i]; cp2[i] = b1[i]; } return; }
+  for (int i = 0; i < 3; i++) a2b2[i] = b2[i] - a2[i];
+  da4 = ob_dot(a1a2, a2b2);
+  db4 = ob_dot(b1b2, a2b2);
+  if (da4 >= 0 && db4 <= 0) { for (int i = 0; i < 3; i++) { cp1[i] = a2[i]; cp2[i] = b2[i]; } return; }
+  la = ob_dot(a1a2, a1a2);
+  if (da1 >= 0 && da3 <= 0) {
+    k = da1 / la;
+    for (int i = 0; i < 3; i++) n[i] = a1b1[i] - k * a1a2[i];
+    if (ob_dot(b1b2, n) >= 0) { for (int i = 0; i < 3; i++) { cp1[i] = a1[i] + k * a1a2[i]; cp2[i] = b1[i]; } return; }
+  }
+  if (da2 >= 0 && da4 <= 0) {
+    k = da2 / la;
+    for (int i = 0; i < 3; i++) n[i] = a1b2[i] - k * a1a2[i];
+    if (ob_dot(b1b2, n) <= 0) { for (int i = 0; i < 3; i++) { cp1[i] = a1[i] + k * a1a2[i]; cp2[i] = b2[i]; } return; }
+  }
+  lb = ob_dot(b1b2, b1b2);
+  if (db1 <= 0 && db2 >= 0) {
+    k = -db1 / lb;
+    for (int i = 0; i < 3; i++) n[i] = -a1b1[i] - k * b1b2[i];
+    if (ob_dot(a1a2, n) >= 0) { for (int i = 0; i < 3; i++) { cp1[i] = a1[i]; cp2[i] = b1[i] + k * b1b2[i]; } return; }
+  }
+  if (db3 <= 0 && db4 >= 0) {
+    k = -db3 / lb;
+    for (int i = 0; i < 3; i++) n[i] = -a2b1[i] - k * b1b2[i];
+    if (ob_dot(a1a2, n) <= 0) { for (int i = 0; i < 3; i++) { cp1[i] = a2[i]; cp2[i] = b1[i] + k * b1b2[i]; } return; }
+  }
+  k = ob_dot(a1a2, b1b2);
+  det = la * lb - k * k;
+  if (det <= 0) { for (int i = 0; i < 3; i++) { cp1[i] = a1[i]; cp2[i] = b1[i]; } return; }
+  det = ob_recip(det);
+  real alpha = (lb * da1 - k * db1) * det;
+  real beta = (k * da1 - la * db1) * det;
+  for (int i = 0; i < 3; i++) { cp1[i] = a1[i] + alpha * a1a2[i]; cp2[i] = b1[i] + beta * b1b2[i]; }
+}
+
+// dClosestLineBoxPoints, collision_util.cpp:244-391
+OB_HD void ob_closest_line_box_points(const real *p1, const real *p2, const real *c, const real *R, const real *side,
+                                      real *lret, real *bret) {
+  real tmp[3], s[3], v[3], sign[3], v2[3], h[3], tanchor[3];
+  int region[3];
+  tmp[0] = p1[0] - c[0]; tmp[1] = p1[1] - c[1]; tmp[2] = p1[2] - c[2];
+  ob_mul1_331(s, R, tmp);
+  tmp[0] = p2[0] - p1[0]; tmp[1] = p2[1] - p1[1]; tmp[2] = p2[2] - p1[2];
+  ob_mul1_331(v, R, tmp);
+  for (int i = 0; i < 3; i++) {
+    if (v[i] < 0) { s[i] = -s[i]; v[i] = -v[i]; sign[i] = -1; }
+    else sign[i] = 1;
+  }
+  for (int i = 0; i < 3; i++) { v2[i] = v[i] * v[i]; h[i] = OB_REAL(0.5) * side[i]; }
+#if defined(dSINGLE)
+  const real tanchor_eps = OB_REAL(1e-19);
+#else
+  const real tanchor_eps = OB_REAL(1e-307);
+#endif
+  for (int i = 0; i < 3; i++) {
+    if (v[i] > tanchor_eps) {
+      if (s[i] < -h[i]) { region[i] = -1; tanchor[i] = (-h[i] - s[i]) / v[i]; }
+      else { region[i] = (s[i] > h[i]); tanchor[i] = (h[i] - s[i]) / v[i]; }
+    } else { region[i] = 0; tanchor[i] = 2; }
+  }
+  real t = 0;
+  real dd2dt = 0;
+  bool done = false;
+  for (int i = 0; i < 3; i++) dd2dt -= (region[i] ? v2[i] : (real)0) * tanchor[i];
+  if (dd2dt >= 0) done = true;
+  if (!done) {
+    do {
+      real next_t = 1;
+      for (int i = 0; i < 3; i++)
+        if (tanchor[i] > t && tanchor[i] < 1 && tanchor[i] < next_t) next_t = tanchor[i];
+      real next_dd2dt = 0;
+      for (int i = 0; i < 3; i++) next_dd2dt += (region[i] ? v2[i] : (real)0) * (next_t - tanchor[i]);
+      if (next_dd2dt >= 0) {
+        real m = (next_dd2dt - dd2dt) / (next_t - t);
+        t -= dd2dt / m;
+        done = true;
+        break;
+      }
+      for (int i = 0; i < 3; i++) {
+        if (tanchor[i] == next_t) { tanchor[i] = (h[i] - s[i]) / v[i]; region[i]++; }
+      }
+      t = next_t;
+      dd2dt = next_dd2dt;
+    } while (t < 1);
+    if (!done) t = 1;
+  }
+  for (int i = 0; i < 3; i++) lret[i] = p1[i] + t * tmp[i];
+  for (int i = 0; i < 3; i++) {
+    tmp[i] = sign[i] * (s[i] + t * v[i]);
+    if (tmp[i] < -h[i]) tmp[i] = -h[i];
+    else if (tmp[i] > h[i]) tmp[i] = h[i];
+  }
+  ob_mul0_331(s, R, tmp);
+  for (int i = 0; i < 3; i++) bret[i] = s[i] + c[i];
+}
+
+// dCollideCapsuleSphere, capsule.cpp:130-161
+OB_HD int ob_collide_capsule_sphere(const ObPose &o1, const ObPose &o2, ObCg *c) {
+  real alpha = o1.R[2] * (o2.pos[0] - o1.pos[0]) + o1.R[6] * (o2.pos[1] - o1.pos[1]) + o1.R[10] * (o2.pos[2] - o1.pos[2]);
+  real lz2 = o1.p[1] * OB_REAL(0.5);
+  if (alpha > lz2) alpha = lz2;
+  if (alpha < -lz2) alpha = -lz2;
+  real p[3];
+  p[0] = o1.pos[0] + alpha * o1.R[2];
+  p[1] = o1.pos[1] + alpha * o1.R[6];
+  p[2] = o1.pos[2] + alpha * o1.R[10];
+  return ob_collide_spheres(p, o1.p[0], o2.pos, o2.p[0], c);
+}
+
+// dCollideCapsuleBox, capsule.cpp:178-231 (dCollideSpheresZeroDist :165-176)
+OB_HD int ob_collide_capsule_box(const ObPose &o1, const ObPose &o2, ObCg *contact) {
+  real p1[3], p2[3];
+  real clen = o1.p[1] * OB_REAL(0.5);
+  p1[0] = o1.pos[0] + clen * o1.R[2]; p1[1] = o1.pos[1] + clen * o1.R[6]; p1[2] = o1.pos[2] + clen * o1.R[10];
+  p2[0] = o1.pos[0] - clen * o1.R[2]; p2[1] = o1.pos[1] - clen * o1.R[6]; p2[2] = o1.pos[2] - clen * o1.R[10];
+  real radius = o1.p[0];
+  const real *c = o2.pos;
+  real pl[3], pb[3];
+  ob_closest_line_box_points(p1, p2, c, o2.R, o2.p, pl, pb);
+#if defined(dSINGLE)
+  const real mindist = OB_REAL(1e-9);
+#else
+  const real mindist = OB_REAL(1e-18);
+#endif
+  real dist = ob_sqrt((pl[0] - pb[0]) * (pl[0] - pb[0]) + (pl[1] - pb[1]) * (pl[1] - pb[1]) + (pl[2] - pb[2]) * (pl[2] - pb[2]));
+  if (dist < mindist) {
+    real normal[3];
+    for (int i = 0; i < 3; i++) normal[i] = pb[i] - c[i];
+    ob_safe_normalize3(normal);
+    contact->normal[0] = normal[0]; contact->normal[1] = normal[1]; contact->normal[2] = normal[2];
+    contact->depth = radius + 0;
+    real k = OB_REAL(0.5) * (0 - radius);
+    contact->pos[0] = pl[0] + contact->normal[0] * k;
+    contact->pos[1] = pl[1] + contact->normal[1] * k;
+    contact->pos[2] = pl[2] + contact->normal[2] * k;
+    return 1;
+  }
+  return ob_collide_spheres(pl, radius, pb, 0, contact);
+}
+
+// dCollideCapsuleCapsule, capsule.cpp:234-349
+OB_HD int ob_collide_capsule_capsule(const ObPose &o1, const ObPose &o2, int flags, ObCg *contact) {
+  const real tolerance = OB_REAL(1e-5);
+  real lz1 = o1.p[1] * OB_REAL(0.5), lz2 = o2.p[1] * OB_REAL(0.5);
+  const real *pos1 = o1.pos, *pos2 = o2.pos;
+  real axis1[3] = {o1.R[2], o1.R[6], o1.R[10]}, axis2[3] = {o2.R[2], o2.R[6], o2.R[10]};
+  real sphere1[3], sphere2[3];
+  real a1a2 = ob_dot(axis1, axis2);
+  real det = OB_REAL(1.0) - a1a2 * a1a2;
+  if (det < tolerance) {
+    if (a1a2 < 0) { axis2[0] = -axis2[0]; axis2[1] = -axis2[1]; axis2[2] = -axis2[2]; }
+    real q[3];
+    for (int i = 0; i < 3; i++) q[i] = pos1[i] - pos2[i];
+    real k = ob_dot(axis1, q);
+    real a1lo = -lz1, a1hi = lz1, a2lo = -lz2 - k, a2hi = lz2 - k;
+    real lo = (a1lo > a2lo) ? a1lo : a2lo;
+    real hi = (a1hi < a2hi) ? a1hi : a2hi;
+    if (lo <= hi) {
+      int num_contacts = flags & 0xffff;
+      if (num_contacts >= 2 && lo < hi) {
+        for (int i = 0; i < 3; i++) sphere1[i] = pos1[i] + lo * axis1[i];
+        for (int i = 0; i < 3; i++) sphere2[i] = pos2[i] + (lo + k) * axis2[i];
+        int n1 = ob_collide_spheres(sphere1, o1.p[0], sphere2, o2.p[0], contact);
+        if (n1) {
+          for (int i = 0; i < 3; i++) sphere1[i] = pos1[i] + hi * axis1[i];
+          for (int i = 0; i < 3; i++) sphere2[i] = pos2[i] + (hi + k) * axis2[i];
+          int n2 = ob_collide_spheres(sphere1, o1.p[0], sphere2, o2.p[0], contact + 1);
+          if (n2) return 2;
+        }
+      }
+      real alpha1 = (lo + hi) * OB_REAL(0.5);
+      real alpha2 = alpha1 + k;
+      for (int i = 0; i < 3; i++) sphere1[i] = pos1[i] + alpha1 * axis1[i];
+      for (int i = 0; i < 3; i++) sphere2[i] = pos2[i] + alpha2 * axis2[i];
+      return ob_collide_spheres(sphere1, o1.p[0], sphere2, o2.p[0], contact);
+    }
+  }
+  real a1[3], a2[3], b1[3], b2[3];
+  for (int i = 0; i < 3; i++) {
+    a1[i] = o1.pos[i] + axis1[i] * lz1; a2[i] = o1.pos[i] - axis1[i] * lz1;
+    b1[i] = o2.pos[i] + axis2[i] * lz2; b2[i] = o2.pos[i] - axis2[i] * lz2;
+  }
+  ob_closest_segment_points(a1, a2, b1, b2, sphere1, sphere2);
+  return ob_collide_spheres(sphere1, o1.p[0], sphere2, o2.p[0], contact);
+}
+
+// dCollideCapsulePlane, capsule.cpp:352-411
+OB_HD int ob_collide_capsule_plane(const ObPose &o1, const ObPose &o2, int flags, ObCg *contact) {
+  const real *pp = o2.p;
+  const real radius = o1.p[0], lz = o1.p[1];
+  real sign = (pp[0] * o1.R[2] + pp[1] * o1.R[6] + pp[2] * o1.R[10] > 0) ? OB_REAL(-1.0) : OB_REAL(1.0);
+  real p[3];
+  p[0] = o1.pos[0] + o1.R[2] * lz * OB_REAL(0.5) * sign;
+  p[1] = o1.pos[1] + o1.R[6] * lz * OB_REAL(0.5) * sign;
+  p[2] = o1.pos[2] + o1.R[10] * lz * OB_REAL(0.5) * sign;
+  real k = ob_dot(p, pp);
+  real depth = pp[3] - k + radius;
+  if (depth < 0) return 0;
+  for (int i = 0; i < 3; i++) { contact->normal[i] = pp[i]; contact->pos[i] = p[i] - pp[i] * radius; }
+  contact->depth = depth;
+  int ncontacts = 1;
+  if ((flags & 0xffff) >= 2) {
+    p[0] = o1.pos[0] - o1.R[2] * lz * OB_REAL(0.5) * sign;
+    p[1] = o1.pos[1] - o1.R[6] * lz * OB_REAL(0.5) * sign;
+    p[2] = o1.pos[2] - o1.R[10] * lz * OB_REAL(0.5) * sign;
+    k = ob_dot(p, pp);
+    depth = pp[3] - k + radius;
+    if (depth >= 0) {
+      ObCg *c2 = contact + 1;
+      for (int i = 0; i < 3; i++) { c2->normal[i] = pp[i]; c2->pos[i] = p[i] - pp[i] * radius; }
+      c2->depth = depth;
+      ncontacts = 2;
+    }
+  }
+  return ncontacts;
+}
+
 // upper bound on contacts a class pair can emit (used to lay out contact slots)
 OB_HD int ob_pair_max_contacts(int t1, int t2, int maxc) {
   int lo = t1 < t2 ? t1 : t2, hi = t1 < t2 ? t2 : t1;
@@ -572,6 +807,13 @@ OB_HD int ob_collide_pair(const ObPose &o1, const ObPose &o2, int flags, ObCg *c
   else if (t1 == OB_GEOM_BOX && t2 == OB_GEOM_BOX) n = ob_collide_box_box(o1, o2, flags, c);
   else if (t1 == OB_GEOM_BOX && t2 == OB_GEOM_PLANE) n = ob_collide_box_plane(o1, o2, flags, c);
   else if (t1 == OB_GEOM_PLANE && t2 == OB_GEOM_BOX) { n = ob_collide_box_plane(o2, o1, flags, c); rev = 1; }
+  else if (t1 == OB_GEOM_CAPSULE && t2 == OB_GEOM_SPHERE) n = ob_collide_capsule_sphere(o1, o2, c);
+  else if (t1 == OB_GEOM_SPHERE && t2 == OB_GEOM_CAPSULE) { n = ob_collide_capsule_sphere(o2, o1, c); rev = 1; }
+  else if (t1 == OB_GEOM_CAPSULE && t2 == OB_GEOM_BOX) n = ob_collide_capsule_box(o1, o2, c);
+  else if (t1 == OB_GEOM_BOX && t2 == OB_GEOM_CAPSULE) { n = ob_collide_capsule_box(o2, o1, c); rev = 1; }
+  else if (t1 == OB_GEOM_CAPSULE && t2 == OB_GEOM_CAPSULE) n = ob_collide_capsule_capsule(o1, o2, flags, c);
+  else if (t1 == OB_GEOM_CAPSULE && t2 == OB_GEOM_PLANE) n = ob_collide_capsule_plane(o1, o2, flags, c);
+  else if (t1 == OB_GEOM_PLANE && t2 == OB_GEOM_CAPSULE) { n = ob_collide_capsule_plane(o2, o1, flags, c); rev = 1; }
   if (rev) {
     for (int i = 0; i < n; i++) {
       c[i].normal[0] = -c[i].normal[0]; c[i].normal[1] = -c[i].normal[1]; c[i].normal[2] = -c[i].normal[2];

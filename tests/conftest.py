@@ -16,6 +16,8 @@ GOLDEN = [  # (file stem, scene, steps, worlds, settle) — must match tests/gol
     ("chain_settle60", "chain", 30, 1, 60),
     ("hinges_settle70", "hinges", 30, 1, 70),
     ("buggy_settle100", "buggy", 30, 1, 100),
+    ("capsmix_settle90", "capsmix", 20, 1, 90),
+    ("ragdoll_settle110", "ragdoll", 12, 1, 110),
 ]
 
 
@@ -46,7 +48,7 @@ def _built():
 # bit for bit (ob_math.h); for dDOUBLE the device has no bit-identical atan2 (glibc's is correctly
 # rounded, CUDA's is <= 2 ulp), so those scenes are held to the stated tolerance instead:
 # exact discrete observables + |dx|_inf / max(1,|x|_inf) <= 1e-9 over the free-running trace.
-ATAN2_SCENES = ("hinges", "buggy")
+ATAN2_SCENES = ("hinges", "buggy", "ragdoll")
 
 
 def assert_parity(r, what, scene, prec, cand):

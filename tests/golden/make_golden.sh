@@ -15,5 +15,7 @@ for p in single double; do
   $d --scene chain       --steps 30 --settle 60 --out tests/golden/chain_settle60_$p.trace
   $d --scene hinges      --steps 30 --settle 70 --out tests/golden/hinges_settle70_$p.trace
   $d --scene buggy       --steps 30 --settle 100 --out tests/golden/buggy_settle100_$p.trace
+  $d --scene capsmix     --steps 20 --settle 90 --out tests/golden/capsmix_settle90_$p.trace
+  $d --scene ragdoll     --steps 12 --settle 110 --out tests/golden/ragdoll_settle110_$p.trace
 done
 ls -la tests/golden

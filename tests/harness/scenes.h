@@ -246,6 +246,96 @@ static inline void scene_buggy(SceneWorld &sw, int w) {
   }
 }
 
+static inline dBodyID scene_add_capsule(SceneWorld &sw, dReal density, dReal r, dReal l, dReal x, dReal y, dReal z) {
+  dBodyID b = dBodyCreate(sw.world);
+  dBodySetPosition(b, x, y, z);
+  dMass m;
+  dMassSetCapsule(&m, density, 3, r, l);
+  dBodySetMass(b, &m);
+  dGeomID g = scene_add_geom(sw, dCreateCapsule(sw.space, r, l));
+  dGeomSetBody(g, b);
+  sw.bodies.push_back(b);
+  return b;
+}
+
+// capsule collider coverage: random capsules / boxes / spheres tumbling onto a plane, plus two
+// pairs of exactly parallel capsules (the two-contact branch of capsule.cpp:262-316)
+static inline void scene_capsmix(SceneWorld &sw, int w) {
+  scene_world_base(sw, w);
+  xs32 rng(sw.seed ^ 0x0CA95017u);
+  scene_add_geom(sw, dCreatePlane(sw.space, 0, 0, 1, 0));
+  for (int i = 0; i < 10; i++) {
+    dBodyID b = scene_add_capsule(sw, 2, rng.uni(0.08, 0.25), rng.uni(0.1, 0.8), rng.uni(-0.8, 0.8), rng.uni(-0.8, 0.8), rng.uni(0.4, 3.5));
+    dQuaternion q = {rng.uni(-1, 1), rng.uni(-1, 1), rng.uni(-1, 1), rng.uni(-1, 1)};
+    dBodySetQuaternion(b, q);
+    dBodySetAngularVel(b, rng.uni(-2, 2), rng.uni(-2, 2), rng.uni(-2, 2));
+  }
+  for (int i = 0; i < 4; i++) {
+    dBodyID b = scene_add_box(sw, 2, rng.uni(0.2, 0.7), rng.uni(0.2, 0.7), rng.uni(0.2, 0.7), rng.uni(-0.8, 0.8), rng.uni(-0.8, 0.8), rng.uni(0.4, 3.5));
+    dQuaternion q = {rng.uni(-1, 1), rng.uni(-1, 1), rng.uni(-1, 1), rng.uni(-1, 1)};
+    dBodySetQuaternion(b, q);
+  }
+  for (int i = 0; i < 4; i++) scene_add_sphere(sw, 2, rng.uni(0.15, 0.4), rng.uni(-0.8, 0.8), rng.uni(-0.8, 0.8), rng.uni(0.4, 3.5));
+  for (int i = 0; i < 2; i++) {   // parallel pairs, axis along x, stacked with a small overlap
+    dMatrix3 R;
+    dRFromAxisAndAngle(R, 0, 1, 0, (dReal)(3.14159265358979 * 0.5));
+    dBodyID a = scene_add_capsule(sw, 2, (dReal)0.15, (dReal)0.6, (dReal)(2.5 + i), (dReal)2.5, (dReal)0.15);
+    dBodyID b = scene_add_capsule(sw, 2, (dReal)0.15, (dReal)0.4, (dReal)(2.55 + i), (dReal)2.5, (dReal)0.44);
+    dBodySetRotation(a, R);
+    dBodySetRotation(b, R);
+  }
+}
+
+// config 4: 20-link ragdoll-like chain (capsule / box links alternating, 19 joints alternating
+// ball / hinge with +-1 rad stops) laid out as a serpentine and dropped onto a 4x4 pile of boxes
+// resting on a plane; crash contact policy (demo_crash.cpp:128-137)
+static inline void scene_ragdoll(SceneWorld &sw, int w) {
+  scene_world_base(sw, w);
+  xs32 rng(sw.seed ^ 0x00D011u);
+  scene_add_geom(sw, dCreatePlane(sw.space, 0, 0, 1, 0));
+  for (int j = 0; j < 4; j++)
+    for (int i = 0; i < 4; i++)
+      scene_add_box(sw, 2, (dReal)0.5, (dReal)0.5, rng.uni(0.3, 0.5), (dReal)((i - 1.5) * 0.56) + rng.uni(-0.02, 0.02),
+                    (dReal)((j - 1.5) * 0.56) + rng.uni(-0.02, 0.02), (dReal)0.26);
+  const dReal L = (dReal)0.3;
+  dBodyID prev = 0;
+  dReal px = 0, py = 0, pz = 0;
+  for (int k = 0; k < 20; k++) {
+    const int r = k / 5, c = k % 5;
+    const dReal x = (dReal)(((r & 1) ? 4 - c : c) * 0.3 - 0.6) + rng.uni(-0.005, 0.005);
+    const dReal y = (dReal)(r * 0.3 - 0.45) + rng.uni(-0.005, 0.005);
+    const dReal z = (dReal)(1.2 + 0.03 * k);
+    dBodyID b;
+    if (k & 1) b = scene_add_box(sw, 2, (dReal)0.26, (dReal)0.12, (dReal)0.1, x, y, z);
+    else {
+      b = scene_add_capsule(sw, 2, (dReal)0.06, (dReal)0.14, x, y, z);
+      dMatrix3 R;
+      dRFromAxisAndAngle(R, 0, 1, 0, (dReal)(3.14159265358979 * 0.5));   // capsule axis (local z) along x
+      dBodySetRotation(b, R);
+    }
+    dBodySetAngularVel(b, rng.uni(-0.5, 0.5), rng.uni(-0.5, 0.5), rng.uni(-0.5, 0.5));
+    if (prev) {
+      const dReal ax = (px + x) * (dReal)0.5, ay = (py + y) * (dReal)0.5, az = (pz + z) * (dReal)0.5;
+      dJointID j;
+      if (k & 1) {
+        j = dJointCreateBall(sw.world, 0);
+        dJointAttach(j, prev, b);
+        dJointSetBallAnchor(j, ax, ay, az);
+      } else {
+        j = dJointCreateHinge(sw.world, 0);
+        dJointAttach(j, prev, b);
+        dJointSetHingeAnchor(j, ax, ay, az);
+        if (c == 0) dJointSetHingeAxis(j, 1, 0, 0); else dJointSetHingeAxis(j, 0, 1, 0);
+        dJointSetHingeParam(j, dParamLoStop, (dReal)-1.0);
+        dJointSetHingeParam(j, dParamHiStop, (dReal)1.0);
+      }
+      sw.joints.push_back(j);
+    }
+    prev = b; px = x; py = y; pz = z;
+    (void)L;
+  }
+}
+
 static inline ScenePolicy policy_buggy() {
   // ode/demo/demo_buggy.cpp:96-103
   ScenePolicy p;
@@ -270,6 +360,8 @@ static inline int scene_build(const char *name, SceneWorld &sw, int w, ScenePoli
   if (!strcmp(name, "mixed_maxc4")) { scene_mixed(sw, w, 12, 6); pol = policy_crash(); return 0; }
   if (!strcmp(name, "chain")) { scene_chain(sw, w, 8); return 0; }
   if (!strcmp(name, "hinges")) { scene_hinges(sw, w); return 0; }
+  if (!strcmp(name, "capsmix")) { scene_capsmix(sw, w); return 0; }
+  if (!strcmp(name, "ragdoll")) { scene_ragdoll(sw, w); pol = policy_crash(); return 0; }
   if (!strcmp(name, "buggy")) { scene_buggy(sw, w); pol = policy_buggy(); return 0; }
   if (!strcmp(name, "free6")) {  // no contacts: integrator + gyroscopic term only
     scene_world_base(sw, w);

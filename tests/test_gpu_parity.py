@@ -25,7 +25,7 @@ def test_cuda_matches_golden_reference_traces(stem, scene, steps, worlds, settle
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref not shipped")
 @pytest.mark.parametrize("prec", ["single", "double"])
 @pytest.mark.parametrize("scene,steps,worlds", [("stack32", 200, 3), ("block64", 50, 1), ("tower64", 250, 1),
-                                                ("mixed", 200, 2), ("mixed_maxc4", 300, 1), ("chain", 250, 2), ("hinges", 250, 1), ("buggy", 250, 3)])
+                                                ("mixed", 200, 2), ("mixed_maxc4", 300, 1), ("chain", 250, 2), ("hinges", 250, 1), ("buggy", 250, 3), ("capsmix", 250, 3), ("ragdoll", 250, 3)])
 def test_cuda_matches_live_reference(scene, steps, worlds, prec):
     r = parity("b200", prec, scene, steps, worlds)
     assert_parity(r, f"{scene}/{prec}", scene, prec, "b200")
