@@ -7,6 +7,7 @@
 #pragma once
 #include <stddef.h>
 #include "ob_types.h"
+#include "ob_collide.h"
 
 struct ObBackend;
 // allocate every array named in `caps` (pointers in caps are ignored); returns 0 on failure
@@ -18,6 +19,13 @@ int obk_d2h(ObBackend *, void *dst, const void *src, size_t bytes);
 int obk_memset(ObBackend *, void *dst, int value, size_t bytes);
 // nsteps x (collide + step) for all worlds; debug_taps: also fill fback
 int obk_step(ObBackend *, real h, int nsteps, int debug_taps, char *err, size_t errlen);
+// one pass of selected phases for all worlds (drop-in path): OBK_PHASE_COLLIDE = broadphase + narrowphase
+// into pairs/contacts, OBK_PHASE_STEP = quickstep over whatever ncontacts/contacts hold
+enum { OBK_PHASE_COLLIDE = 1, OBK_PHASE_STEP = 2 };
+int obk_run_phases(ObBackend *, real h, int phases, int taps, char *err, size_t errlen);
+// dCollide for one pair of posed geoms, outside any batch (one-thread kernel on the GPU).
+// out must hold OB_MAXC_LOCAL contacts.  Returns the contact count or -1.
+int obk_collide_pair(const ObPose *a, const ObPose *b, int flags, ObCg *out, char *err, size_t errlen);
 int obk_sync(ObBackend *);
 // bulk body-state I/O in API order ([world][creation-index body]); nbody[w] = bodies in world w.
 // Host buffers; a null pointer skips that field.

@@ -28,7 +28,6 @@
 #include <vector>
 #include "ob_backend.h"
 #include "ob_broad.h"
-#include "ob_collide.h"
 #include "ob_rows.h"
 #include "ob_solver.h"
 #include "ob_step_kernel.cuh"
@@ -356,7 +355,9 @@ ObBackend *obk_create(const ObBatchDev &caps, int device, char *err, size_t errl
   d.rowJ = d.rowiMJ = d.rowJc = d.rowS = 0; d.rowI = 0;
   CK(dalloc(b, &d.lambda, W * d.NR));
   CK(dalloc(b, &d.nrows, W));
-  CK(dalloc(b, &d.fback, W * d.NC * 6));
+  CK(dalloc(b, &d.fback, W * (d.NC + d.NJ) * 12));
+  d.csurf = 0; d.cfdir1 = 0;
+  if (d.dropin) { CK(dalloc(b, &d.csurf, W * d.NC)); CK(dalloc(b, &d.cfdir1, W * d.NC * 4)); }
   CK(dalloc(b, &d.counters, (size_t)1));
   b->st_elems = W * d.NB;
   CK(dalloc(b, &b->st_dev, b->st_elems * 13));
@@ -452,43 +453,86 @@ void obk_get_kernel_times(ObBackend *b, double *ms, long long *l) {
 }
 const char *obk_kernel_name(int k) { static const char *n[] = {"k_collide", "k_prep", "k_sched", "k_sor", "k_post"}; return k >= 0 && k < 5 ? n[k] : ""; }
 
-template <int G> static void launch_step(ObBackend *b, real h, int taps) {
+template <int G> static void launch_step(ObBackend *b, real h, int taps, int phases) {
   cudaEvent_t *ev = b->ev + 2;
   const int W = b->d.W;
   if (b->ktiming) cudaEventRecord(ev[0], b->stream);
-  k_collide<<<b->grid, OB_THREADS, b->smem_collide, b->stream>>>(b->d);
+  if (phases & OBK_PHASE_COLLIDE) { k_collide<<<b->grid, OB_THREADS, b->smem_collide, b->stream>>>(b->d); g_launches++; }
   if (b->ktiming) cudaEventRecord(ev[1], b->stream);
-  k_prep<G><<<b->grid_step, 32, b->smem_prep, b->stream>>>(b->d, h, taps);
-  if (b->ktiming) cudaEventRecord(ev[2], b->stream);
-  if (b->d.NB <= 64) k_sched<2><<<W, 32, b->smem_sched, b->stream>>>(b->d, G, taps);
-  else if (b->d.NB <= 128) k_sched<4><<<W, 32, b->smem_sched, b->stream>>>(b->d, G, taps);
-  else k_sched<8><<<W, 32, b->smem_sched, b->stream>>>(b->d, G, taps);
-  if (b->ktiming) cudaEventRecord(ev[3], b->stream);
-  k_sor<G><<<b->grid_sor, 32, b->smem_sor, b->stream>>>(b->d, taps);
-  if (b->ktiming) cudaEventRecord(ev[4], b->stream);
-  k_post<G><<<b->grid_step, 32, b->smem_post, b->stream>>>(b->d, h);
-  g_launches += 5;
-  if (b->ktiming) {
+  if (phases & OBK_PHASE_STEP) {
+    k_prep<G><<<b->grid_step, 32, b->smem_prep, b->stream>>>(b->d, h, taps);
+    if (b->ktiming) cudaEventRecord(ev[2], b->stream);
+    if (b->d.NB <= 64) k_sched<2><<<W, 32, b->smem_sched, b->stream>>>(b->d, G, taps);
+    else if (b->d.NB <= 128) k_sched<4><<<W, 32, b->smem_sched, b->stream>>>(b->d, G, taps);
+    else k_sched<8><<<W, 32, b->smem_sched, b->stream>>>(b->d, G, taps);
+    if (b->ktiming) cudaEventRecord(ev[3], b->stream);
+    k_sor<G><<<b->grid_sor, 32, b->smem_sor, b->stream>>>(b->d, taps);
+    if (b->ktiming) cudaEventRecord(ev[4], b->stream);
+    k_post<G><<<b->grid_step, 32, b->smem_post, b->stream>>>(b->d, h);
+    g_launches += 4;
+  }
+  if (b->ktiming && phases == (OBK_PHASE_COLLIDE | OBK_PHASE_STEP)) {
     cudaEventRecord(ev[5], b->stream);
     if (cudaEventSynchronize(ev[5]) == cudaSuccess)
       for (int k = 0; k < 5; k++) { float m = 0; cudaEventElapsedTime(&m, ev[k], ev[k + 1]); b->kms[k] += m; b->klaunch[k]++; }
   }
 }
 
-int obk_step(ObBackend *b, real h, int nsteps, int taps, char *err, size_t errlen) {
+static int run_steps(ObBackend *b, real h, int nsteps, int taps, int phases, char *err, size_t errlen) {
   cudaSetDevice(b->device);
   if (getenv("OB_SEQ")) taps |= 2;
   if (getenv("OB_CHECK")) taps |= 4;
   if (getenv("OB_SYNC2")) taps |= 8;
   for (int s = 0; s < nsteps; s++) {
-    if (b->tile == 8) launch_step<8>(b, h, taps);
-    else if (b->tile == 16) launch_step<16>(b, h, taps);
-    else launch_step<32>(b, h, taps);
+    if (b->tile == 8) launch_step<8>(b, h, taps, phases);
+    else if (b->tile == 16) launch_step<16>(b, h, taps, phases);
+    else launch_step<32>(b, h, taps, phases);
   }
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
   if (e != cudaSuccess) { snprintf(err, errlen, "kernel launch/exec failed: %s", cudaGetErrorString(e)); return -1; }
   return 0;
+}
+int obk_step(ObBackend *b, real h, int nsteps, int taps, char *err, size_t errlen) {
+  return run_steps(b, h, nsteps, taps, OBK_PHASE_COLLIDE | OBK_PHASE_STEP, err, errlen);
+}
+int obk_run_phases(ObBackend *b, real h, int phases, int taps, char *err, size_t errlen) {
+  return run_steps(b, h, 1, taps, phases, err, errlen);
+}
+
+// dCollide outside a batch: one pair, one thread (the per-element collider functions are the same
+// ones k_collide runs; there is no host implementation to fall back to)
+struct PairCtx { ObPose *pose; ObCg *cg; int *n; cudaStream_t stream; bool ok; };
+__global__ void k_collide_pair(const ObPose *pose, int flags, ObCg *out, int *n) {
+  int swapped;
+  ObCg cg[OB_MAXC_LOCAL];
+  const int c = ob_collide_pair(pose[0], pose[1], flags, cg, &swapped);
+  for (int i = 0; i < c; i++) out[i] = cg[i];
+  *n = c;
+}
+int obk_collide_pair(const ObPose *a, const ObPose *b, int flags, ObCg *out, char *err, size_t errlen) {
+  static PairCtx C = {0, 0, 0, 0, false};
+  if (!C.ok) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { snprintf(err, errlen, "no CUDA device available (this library has no CPU fallback)"); return -1; }
+    if (cudaMallocHost((void **)&C.pose, 2 * sizeof(ObPose)) != cudaSuccess || cudaMallocHost((void **)&C.cg, OB_MAXC_LOCAL * sizeof(ObCg)) != cudaSuccess ||
+        cudaMallocHost((void **)&C.n, sizeof(int)) != cudaSuccess || cudaStreamCreateWithFlags(&C.stream, cudaStreamNonBlocking) != cudaSuccess) {
+      snprintf(err, errlen, "obk_collide_pair: allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return -1;
+    }
+    C.ok = true;
+  }
+  C.pose[0] = *a; C.pose[1] = *b;
+  int maxc = flags & 0xffff;
+  if (maxc > OB_MAXC_LOCAL) maxc = OB_MAXC_LOCAL;
+  // page-locked buffers are mapped into the device address space (unified addressing): the kernel reads and writes them directly
+  k_collide_pair<<<1, 1, 0, C.stream>>>(C.pose, (flags & ~0xffff) | maxc, C.cg, C.n);
+  g_launches++;
+  cudaError_t e = cudaStreamSynchronize(C.stream);
+  if (e != cudaSuccess) { snprintf(err, errlen, "k_collide_pair failed: %s", cudaGetErrorString(e)); return -1; }
+  const int n = *C.n;
+  for (int i = 0; i < n; i++) out[i] = C.cg[i];
+  return n;
 }
 
 // Bulk state I/O copies straight between the caller's buffers and the packed device staging

@@ -7,20 +7,10 @@
 #include <vector>
 #include "ob_backend.h"
 #include "ob_host.h"
+#include "ob_batch.h"
 
-struct dxBatch {
-  ObBackend *bk;
-  ObBatchDev caps;   // capacities; pointer members are execution-side pointers
-  std::vector<dxWorld *> worlds;
-  std::vector<dxSpace *> spaces;
-  std::vector<std::vector<dxBody *> > bodies;  // [w][batch body index]
-  std::vector<std::vector<dxGeom *> > geoms;   // [w][geom index]
-  std::vector<std::vector<dxJoint *> > joints; // [w][permanent joint index]
-  std::vector<int> nb, ng;
-  int debug_taps;
-};
 
-static void fill_surface(ObSurface &d, const dSurfaceParameters &s) {
+void ob_fill_surface(ObSurface &d, const dSurfaceParameters &s) {
   d.mode = s.mode; d.mu = s.mu; d.mu2 = s.mu2; d.bounce = s.bounce; d.bounce_vel = s.bounce_vel;
   d.soft_erp = s.soft_erp; d.soft_cfm = s.soft_cfm; d.motion1 = s.motion1; d.motion2 = s.motion2;
   d.motionN = s.motionN; d.slip1 = s.slip1; d.slip2 = s.slip2;
@@ -81,15 +71,81 @@ void ob_marshal_geom(dxGeom *g, ObGeom &d) {
   else { d.R[0] = d.R[5] = d.R[10] = 1; }
 }
 
-extern "C" {
+// Re-marshal the bound worlds into the device layout and upload (everything except the policy
+// table, seeds and per-step scratch).  Contact joints on the world's joint list are skipped: on
+// the batched path they do not exist, on the drop-in path they are uploaded per step.
+int ob_batch_upload(dxBatch *B) {
+  const int nworlds = B->caps.W, NB = B->caps.NB, NG = B->caps.NG, NJ = B->caps.NJ;
+  std::vector<ObWorld> hw(nworlds);
+  std::vector<ObBodyDyn> hd((size_t)nworlds * NB);
+  std::vector<ObBodyConst> hc((size_t)nworlds * NB);
+  std::vector<ObGeom> hg((size_t)nworlds * NG);
+  std::vector<int> hl((size_t)nworlds * NG, -1);
+  memset(hd.data(), 0, hd.size() * sizeof(ObBodyDyn));
+  memset(hc.data(), 0, hc.size() * sizeof(ObBodyConst));
+  memset(hg.data(), 0, hg.size() * sizeof(ObGeom));
+  for (int w = 0; w < nworlds; w++) {
+    dxWorld *W = B->worlds[w]; dxSpace *S = B->spaces[w];
+    ObWorld &o = hw[w];
+    memset(&o, 0, sizeof o);
+    for (int k = 0; k < 3; k++) o.gravity[k] = W->gravity[k];
+    o.erp = W->global_erp; o.cfm = W->global_cfm; o.sor_w = W->qs_w; o.max_vel = W->contact_max_vel;
+    o.min_depth = W->contact_min_depth; o.iters = W->qs_iterations; o.nb = B->nb[w]; o.ng = B->ng[w];
+    o.seed = B->seeds[w]; o.hash_minlevel = S->minlevel; o.hash_maxlevel = S->maxlevel;
+    o.space_type = S->type == dHashSpaceClass ? OB_SPACE_HASH : (S->type == dSweepAndPruneSpaceClass ? OB_SPACE_SAP : OB_SPACE_SIMPLE);
+    for (int i = 0; i < B->nb[w]; i++) {
+      dxBody *b = B->bodies[w][i];
+      ob_marshal_body(b, hd[(size_t)w * NB + i], hc[(size_t)w * NB + i]);
+      hc[(size_t)w * NB + i].geom_first = (b->geom && b->geom->parent_space == S) ? b->geom->batch_index : -1;
+    }
+    int pos = 0;
+    for (dxGeom *g = S->first; g; g = g->next, pos++) {
+      ObGeom &d = hg[(size_t)w * NG + g->batch_index];
+      ob_marshal_geom(g, d);
+      d.body_next = (g->body_next && g->body_next->parent_space == S) ? g->body_next->batch_index : -1;
+      hl[(size_t)w * NG + pos] = g->batch_index;
+    }
+  }
+  std::vector<ObJoint> hj((size_t)nworlds * std::max(NJ, 1));
+  std::vector<int> hnj(nworlds, 0);
+  std::vector<unsigned short> hps((size_t)nworlds * (NB + 1), 0), hpa((size_t)nworlds * 2 * std::max(NJ, 1), 0);
+  memset(hj.data(), 0, hj.size() * sizeof(ObJoint));
+  for (int w = 0; w < nworlds; w++) {
+    const std::vector<dxJoint *> &J = B->joints[w];
+    hnj[w] = (int)J.size();
+    for (size_t i = 0; i < J.size(); i++) { ob_marshal_joint(J[i], hj[(size_t)w * NJ + i]); J[i]->tag = (int)i; }
+    unsigned short *ps = &hps[(size_t)w * (NB + 1)], *pa = &hpa[(size_t)w * 2 * std::max(NJ, 1)];
+    int a = 0;
+    for (int b = 0; b < B->nb[w]; b++) {
+      ps[b] = (unsigned short)a;
+      for (dxJointNode *n = B->bodies[w][b]->firstjoint; n; n = n->next)
+        if (n->joint->type != dJointTypeContact) pa[a++] = (unsigned short)n->joint->tag;
+    }
+    for (int b = B->nb[w]; b <= NB; b++) ps[b] = (unsigned short)a;
+  }
+  int rc = 0;
+  rc |= obk_h2d(B->bk, B->caps.world, hw.data(), hw.size() * sizeof(ObWorld));
+  rc |= obk_h2d(B->bk, B->caps.bdyn, hd.data(), hd.size() * sizeof(ObBodyDyn));
+  rc |= obk_h2d(B->bk, B->caps.bconst, hc.data(), hc.size() * sizeof(ObBodyConst));
+  rc |= obk_h2d(B->bk, B->caps.geom, hg.data(), hg.size() * sizeof(ObGeom));
+  rc |= obk_h2d(B->bk, B->caps.glist, hl.data(), hl.size() * sizeof(int));
+  if (NJ) rc |= obk_h2d(B->bk, B->caps.joint, hj.data(), hj.size() * sizeof(ObJoint));
+  rc |= obk_h2d(B->bk, B->caps.njoints, hnj.data(), hnj.size() * sizeof(int));
+  rc |= obk_h2d(B->bk, B->caps.padjstart, hps.data(), hps.size() * sizeof(unsigned short));
+  if (NJ) rc |= obk_h2d(B->bk, B->caps.padj, hpa.data(), hpa.size() * sizeof(unsigned short));
+  return rc;
+}
 
-dBatchID dBatchCreate(int nworlds, const dWorldID *worlds, const dSpaceID *spaces, const dBatchDesc *desc) {
+// dropin: the batch serves the classic per-call API (ob_dropin.cpp): per-contact surface arrays are
+// allocated, the worlds are not marked as owned by a user batch, contact joints present at bind time are ignored
+dxBatch *ob_batch_create(int nworlds, const dWorldID *worlds, const dSpaceID *spaces, const dBatchDesc *desc, int dropin) {
   if (nworlds <= 0 || !worlds || !spaces) { ob_set_last_error("dBatchCreate: bad arguments"); return 0; }
   dxBatch *B = new dxBatch;
-  B->bk = 0; B->debug_taps = 1;
+  B->bk = 0; B->debug_taps = 1; B->dropin = dropin;
   B->worlds.assign(worlds, worlds + nworlds);
   B->spaces.assign(spaces, spaces + nworlds);
   B->bodies.resize(nworlds); B->geoms.resize(nworlds); B->nb.resize(nworlds); B->ng.resize(nworlds);
+  B->seeds.assign(nworlds, 0);
   int NB = 1, NG = 1, NJ = 0;
   B->joints.resize(nworlds);
   for (int w = 0; w < nworlds; w++) {
@@ -105,7 +161,7 @@ dBatchID dBatchCreate(int nworlds, const dWorldID *worlds, const dSpaceID *space
     B->geoms[w].resize(ng);
     int pos = 0;
     for (dxGeom *g = S->first; g; g = g->next, pos++) {
-      if (g->is_space) { ob_set_last_error("dBatchCreate: world %d: nested spaces are not supported on the batched path", w); delete B; return 0; }
+      if (g->is_space) { ob_set_last_error("dBatchCreate: world %d: nested spaces are not supported on this path", w); delete B; return 0; }
       if (g->body && g->body->world != W) { ob_set_last_error("dBatchCreate: world %d: geom attached to a body of another world", w); delete B; return 0; }
       g->batch_index = ng - 1 - pos;
       B->geoms[w][g->batch_index] = g;
@@ -113,7 +169,10 @@ dBatchID dBatchCreate(int nworlds, const dWorldID *worlds, const dSpaceID *space
     B->ng[w] = ng;
     // permanent joints: everything on the world's joint list at bind time, creation order
     for (dxJoint *j = W->firstjoint; j; j = j->next) {
-      if (j->type == dJointTypeContact) { ob_set_last_error("dBatchCreate: world %d: contact joints present at bind time (call dJointGroupEmpty first)", w); delete B; return 0; }
+      if (j->type == dJointTypeContact) {
+        if (dropin) continue;
+        ob_set_last_error("dBatchCreate: world %d: contact joints present at bind time (call dJointGroupEmpty first)", w); delete B; return 0;
+      }
       if (j->type != dJointTypeBall && j->type != dJointTypeHinge && j->type != dJointTypeHinge2) { ob_set_last_error("dBatchCreate: world %d: unsupported joint type %d", w, j->type); delete B; return 0; }
       B->joints[w].push_back(j);
     }
@@ -128,6 +187,7 @@ dBatchID dBatchCreate(int nworlds, const dWorldID *worlds, const dSpaceID *space
   caps.NJ = NJ;
   caps.NR = 3 * caps.NC + 6 * NJ;
   caps.npolicy = 1;
+  caps.dropin = dropin;
   {
     int it = 1;
     for (int w = 0; w < nworlds; w++) it = std::max(it, worlds[w]->qs_iterations);
@@ -137,69 +197,14 @@ dBatchID dBatchCreate(int nworlds, const dWorldID *worlds, const dSpaceID *space
   B->bk = obk_create(caps, desc ? desc->device : 0, err, sizeof err);
   if (!B->bk) { ob_set_last_error("dBatchCreate: %s", err); delete B; return 0; }
   B->caps = *obk_arrays(B->bk);
-
-  std::vector<ObWorld> hw(nworlds);
-  std::vector<ObBodyDyn> hd((size_t)nworlds * NB);
-  std::vector<ObBodyConst> hc((size_t)nworlds * NB);
-  std::vector<ObGeom> hg((size_t)nworlds * NG);
-  std::vector<int> hl((size_t)nworlds * NG, -1);
-  memset(hd.data(), 0, hd.size() * sizeof(ObBodyDyn));
-  memset(hc.data(), 0, hc.size() * sizeof(ObBodyConst));
-  memset(hg.data(), 0, hg.size() * sizeof(ObGeom));
-  for (int w = 0; w < nworlds; w++) {
-    dxWorld *W = worlds[w]; dxSpace *S = spaces[w];
-    ObWorld &o = hw[w];
-    memset(&o, 0, sizeof o);
-    for (int k = 0; k < 3; k++) o.gravity[k] = W->gravity[k];
-    o.erp = W->global_erp; o.cfm = W->global_cfm; o.sor_w = W->qs_w; o.max_vel = W->contact_max_vel;
-    o.min_depth = W->contact_min_depth; o.iters = W->qs_iterations; o.nb = B->nb[w]; o.ng = B->ng[w];
-    o.seed = 0; o.hash_minlevel = S->minlevel; o.hash_maxlevel = S->maxlevel;
-    o.space_type = S->type == dHashSpaceClass ? OB_SPACE_HASH : (S->type == dSweepAndPruneSpaceClass ? OB_SPACE_SAP : OB_SPACE_SIMPLE);
-    for (int i = 0; i < B->nb[w]; i++) {
-      dxBody *b = B->bodies[w][i];
-      ob_marshal_body(b, hd[(size_t)w * NB + i], hc[(size_t)w * NB + i]);
-      hc[(size_t)w * NB + i].geom_first = b->geom ? b->geom->batch_index : -1;
-    }
-    int pos = 0;
-    for (dxGeom *g = S->first; g; g = g->next, pos++) {
-      ObGeom &d = hg[(size_t)w * NG + g->batch_index];
-      ob_marshal_geom(g, d);
-      d.body_next = g->body_next ? g->body_next->batch_index : -1;
-      hl[(size_t)w * NG + pos] = g->batch_index;
-    }
-    W->bound_batch = B; S->bound_batch = B;
-  }
-  std::vector<ObJoint> hj((size_t)nworlds * std::max(NJ, 1));
-  std::vector<int> hnj(nworlds, 0);
-  std::vector<unsigned short> hps((size_t)nworlds * (NB + 1), 0), hpa((size_t)nworlds * 2 * std::max(NJ, 1), 0);
-  memset(hj.data(), 0, hj.size() * sizeof(ObJoint));
-  for (int w = 0; w < nworlds; w++) {
-    const std::vector<dxJoint *> &J = B->joints[w];
-    hnj[w] = (int)J.size();
-    for (size_t i = 0; i < J.size(); i++) { ob_marshal_joint(J[i], hj[(size_t)w * NJ + i]); J[i]->tag = (int)i; }
-    unsigned short *ps = &hps[(size_t)w * (NB + 1)], *pa = NJ ? &hpa[(size_t)w * 2 * NJ] : 0;
-    int a = 0;
-    for (int b = 0; b < B->nb[w]; b++) {
-      ps[b] = (unsigned short)a;
-      for (dxJointNode *n = B->bodies[w][b]->firstjoint; n; n = n->next) pa[a++] = (unsigned short)n->joint->tag;
-    }
-    for (int b = B->nb[w]; b <= NB; b++) ps[b] = (unsigned short)a;
-  }
+  if (!dropin)
+    for (int w = 0; w < nworlds; w++) { worlds[w]->bound_batch = B; spaces[w]->bound_batch = B; }
   ObPolicy pol;
   memset(&pol, 0, sizeof pol);
   pol.cat_mask1 = pol.cat_mask2 = ~0u; pol.max_contacts = 8; pol.skip_if_connected = 1;
   pol.surface.mode = 0; pol.surface.mu = OB_INF;
-  int rc = 0;
-  rc |= obk_h2d(B->bk, B->caps.world, hw.data(), hw.size() * sizeof(ObWorld));
-  rc |= obk_h2d(B->bk, B->caps.bdyn, hd.data(), hd.size() * sizeof(ObBodyDyn));
-  rc |= obk_h2d(B->bk, B->caps.bconst, hc.data(), hc.size() * sizeof(ObBodyConst));
-  rc |= obk_h2d(B->bk, B->caps.geom, hg.data(), hg.size() * sizeof(ObGeom));
-  rc |= obk_h2d(B->bk, B->caps.glist, hl.data(), hl.size() * sizeof(int));
+  int rc = ob_batch_upload(B);
   rc |= obk_h2d(B->bk, B->caps.policy, &pol, sizeof pol);
-  if (NJ) rc |= obk_h2d(B->bk, B->caps.joint, hj.data(), hj.size() * sizeof(ObJoint));
-  rc |= obk_h2d(B->bk, B->caps.njoints, hnj.data(), hnj.size() * sizeof(int));
-  rc |= obk_h2d(B->bk, B->caps.padjstart, hps.data(), hps.size() * sizeof(unsigned short));
-  if (NJ) rc |= obk_h2d(B->bk, B->caps.padj, hpa.data(), hpa.size() * sizeof(unsigned short));
   rc |= obk_memset(B->bk, B->caps.counters, 0, sizeof(ObCounters));
   rc |= obk_memset(B->bk, B->caps.npairs, 0, sizeof(int) * nworlds);
   rc |= obk_memset(B->bk, B->caps.ncontacts, 0, sizeof(int) * nworlds);
@@ -208,9 +213,15 @@ dBatchID dBatchCreate(int nworlds, const dWorldID *worlds, const dSpaceID *space
   return B;
 }
 
+extern "C" {
+
+dBatchID dBatchCreate(int nworlds, const dWorldID *worlds, const dSpaceID *spaces, const dBatchDesc *desc) {
+  return ob_batch_create(nworlds, worlds, spaces, desc, 0);
+}
+
 void dBatchDestroy(dBatchID B) {
   if (!B) return;
-  for (size_t w = 0; w < B->worlds.size(); w++) {
+  for (size_t w = 0; w < B->worlds.size() && !B->dropin; w++) {
     if (B->worlds[w]->bound_batch == B) B->worlds[w]->bound_batch = 0;
     if (B->spaces[w]->bound_batch == B) B->spaces[w]->bound_batch = 0;
   }
@@ -225,7 +236,7 @@ int dBatchSetContactPolicy(dBatchID B, const dBatchContactPolicy *table, int n) 
   pol.cat_mask1 = (uint32_t)table[0].cat_mask1; pol.cat_mask2 = (uint32_t)table[0].cat_mask2;
   pol.max_contacts = table[0].max_contacts; pol.skip_if_connected = table[0].skip_if_connected;
   pol.skip_static_pairs = table[0].skip_static_pairs;
-  fill_surface(pol.surface, table[0].surface);
+  ob_fill_surface(pol.surface, table[0].surface);
   return obk_h2d(B->bk, B->caps.policy, &pol, sizeof pol);
 }
 
@@ -233,7 +244,7 @@ int dBatchSetSeeds(dBatchID B, const uint32_t *seeds) {
   int W = B->caps.W;
   std::vector<ObWorld> hw(W);
   if (obk_d2h(B->bk, hw.data(), B->caps.world, W * sizeof(ObWorld))) return -1;
-  for (int w = 0; w < W; w++) hw[w].seed = seeds[w];
+  for (int w = 0; w < W; w++) { hw[w].seed = seeds[w]; B->seeds[w] = seeds[w]; }
   return obk_h2d(B->bk, B->caps.world, hw.data(), W * sizeof(ObWorld));
 }
 int dBatchGetSeeds(dBatchID B, uint32_t *seeds) {
@@ -344,7 +355,10 @@ int dBatchDebugFeedback(dBatchID B, int w, dReal *f1t1, int cap) {
   int n = 0;
   if (obk_d2h(B->bk, &n, B->caps.ncontacts + w, sizeof(int))) return -1;
   int m = std::min(n, cap);
-  if (m > 0 && obk_d2h(B->bk, f1t1, B->caps.fback + (size_t)w * B->caps.NC * 6, sizeof(dReal) * 6 * m)) return -1;
+  if (m <= 0) return n;
+  std::vector<dReal> fb((size_t)m * 12);
+  if (obk_d2h(B->bk, fb.data(), B->caps.fback + (size_t)w * (B->caps.NC + B->caps.NJ) * 12, sizeof(dReal) * 12 * m)) return -1;
+  for (int i = 0; i < m; i++) for (int k = 0; k < 6; k++) f1t1[6 * i + k] = fb[(size_t)12 * i + k];
   return n;
 }
 int dBatchDebugGeomOrder(dBatchID B, int w, int *order, int cap) {

@@ -1,0 +1,27 @@
+// ob_batch.h — the batch object shared by ob_batch.cpp (dBatch* entry points) and
+// ob_dropin.cpp (classic per-call API served through a batch of one world).
+#pragma once
+#include <vector>
+#include "ob_backend.h"
+#include "ob_host.h"
+
+struct dxBatch {
+  ObBackend *bk;
+  ObBatchDev caps;   // capacities; pointer members are execution-side pointers
+  std::vector<dxWorld *> worlds;
+  std::vector<dxSpace *> spaces;
+  std::vector<std::vector<dxBody *> > bodies;  // [w][batch body index]
+  std::vector<std::vector<dxGeom *> > geoms;   // [w][geom index]
+  std::vector<std::vector<dxJoint *> > joints; // [w][permanent joint index]
+  std::vector<int> nb, ng;
+  std::vector<uint32_t> seeds;                 // host mirror of the per-world LCG seeds as last set
+  int debug_taps;
+  int dropin;
+};
+
+dxBatch *ob_batch_create(int nworlds, const dWorldID *worlds, const dSpaceID *spaces, const dBatchDesc *desc, int dropin);
+int ob_batch_upload(dxBatch *B);
+void ob_fill_surface(ObSurface &d, const dSurfaceParameters &s);
+void ob_marshal_body(const dxBody *b, ObBodyDyn &d, ObBodyConst &c);
+void ob_marshal_joint(const dxJoint *j, ObJoint &d);
+void ob_marshal_geom(dxGeom *g, ObGeom &d);

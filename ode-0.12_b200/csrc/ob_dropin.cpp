@@ -1,9 +1,317 @@
-// ob_dropin.cpp — the compute entry points of the classic ODE API (dSpaceCollide,
-// dCollide, dWorldQuickStep) served by the CUDA kernels through a batch of one
-// world.  (filled in after the batched path; until then they report an error
-// rather than compute anything on the CPU.)
-#include "ob_host.h"
-void ob_dropin_space_collide(dxSpace *, void *, dNearCallback *) { ob_error(0, "dSpaceCollide: drop-in path not available in this build (use dBatch*)"); }
-void ob_dropin_space_collide2(dxGeom *, dxGeom *, void *, dNearCallback *) { ob_error(0, "dSpaceCollide2: drop-in path not available in this build"); }
-int ob_dropin_collide(dxGeom *, dxGeom *, int, dContactGeom *, int) { ob_error(0, "dCollide: drop-in path not available in this build"); return 0; }
-int ob_dropin_quickstep(dxWorld *, dReal) { ob_error(0, "dWorldQuickStep: drop-in path not available in this build (use dBatch*)"); return 0; }
+// ob_dropin.cpp — the compute entry points of the classic ODE API (dSpaceCollide, dCollide,
+// dWorldQuickStep; ode/src/collision_space.cpp:748, collision_kernel.cpp:292, ode.cpp:1807)
+// served by the CUDA kernels through a hidden batch of ONE world.
+//
+//   dSpaceCollide   : upload the world/space state, run k_collide (broadphase in the reference's
+//                     callback order + narrowphase for every pair with the max-contacts value the
+//                     caller used last time), copy pairs + contacts back, then call the user's
+//                     near callback per pair, in order, on the calling thread.
+//   dCollide        : inside that callback, served from those results when the request matches
+//                     (same pair orientation, same effective max-contacts); otherwise one pair
+//                     is collided on the GPU on demand (k_collide_pair).
+//   dWorldQuickStep : upload state + the contact joints the callback created (with their own
+//                     dSurfaceParameters / fdir1) and run k_prep -> k_sched -> k_sor -> k_post;
+//                     copy body state, the process-global dRand seed and dJointFeedback back, and
+//                     apply dGeomMoved in stepping order on the host lists.
+// Nothing is computed on the CPU here; without a usable GPU these calls raise dError.
+// Semantics are the point of this path, not speed: one small world cannot fill a GPU.
+#include <string.h>
+#include <algorithm>
+#include <map>
+#include <vector>
+#include "ob_batch.h"
+
+struct ObDropin {
+  dxBatch *B;
+  dxWorld *world;      // world stepped through this context (own_world when the space holds no bodies)
+  dxSpace *space;      // space collided through this context (own_space when only a world is stepped)
+  dxWorld *own_world;
+  dxSpace *own_space;
+  int maxc_hint;       // max-contacts value the near callback passed to dCollide last time
+  bool in_collide;     // results below are valid (only while the callbacks run)
+  std::vector<int> pairs;              // (o1,o2) geom indices in callback order
+  std::vector<ObContact> contacts;     // grouped by pair, pair order
+  std::map<std::pair<int, int>, std::pair<int, int> > pair_contacts;   // (o1,o2) -> (first contact, count)
+};
+static std::vector<ObDropin *> g_ctx;
+
+static void ctx_free_batch(ObDropin *c) {
+  if (c->B) { dBatchDestroy(c->B); c->B = 0; }
+}
+static void ctx_drop(size_t i) {
+  ObDropin *c = g_ctx[i];
+  ctx_free_batch(c);
+  g_ctx.erase(g_ctx.begin() + i);
+  if (c->own_world) { dxWorld *w = c->own_world; c->own_world = 0; dWorldDestroy(w); }
+  if (c->own_space) { dxSpace *s = c->own_space; c->own_space = 0; dSpaceDestroy(s); }
+  delete c;
+}
+// called by dWorldDestroy / dGeomDestroy(space) so no context keeps a dangling pointer
+void ob_dropin_forget_world(dxWorld *w) {
+  for (size_t i = 0; i < g_ctx.size();) { if (g_ctx[i]->world == w && g_ctx[i]->own_world != w) ctx_drop(i); else i++; }
+}
+void ob_dropin_forget_space(dxSpace *s) {
+  for (size_t i = 0; i < g_ctx.size();) { if (g_ctx[i]->space == s && g_ctx[i]->own_space != s) ctx_drop(i); else i++; }
+}
+
+static dxWorld *world_of_space(dxSpace *s, bool *mixed) {
+  dxWorld *w = 0;
+  *mixed = false;
+  for (dxGeom *g = s->first; g; g = g->next)
+    if (g->body) { if (!w) w = g->body->world; else if (w != g->body->world) *mixed = true; }
+  return w;
+}
+
+static ObDropin *ctx_new(dxWorld *w, dxSpace *s) {
+  ObDropin *c = new ObDropin;
+  c->B = 0; c->world = w; c->space = s; c->own_world = 0; c->own_space = 0; c->maxc_hint = 8; c->in_collide = false;
+  g_ctx.push_back(c);
+  return c;
+}
+
+// does the bound batch still describe the world/space (same objects, enough capacity)?
+static bool batch_matches(ObDropin *c, int need_contacts) {
+  dxBatch *B = c->B;
+  if (!B) return false;
+  if (need_contacts > B->caps.NC) return false;
+  if ((c->world->qs_iterations + 7) / 8 > B->caps.NEP) return false;
+  int i = 0;
+  for (dxBody *b = c->world->firstbody; b; b = b->next, i++)
+    if (i >= B->nb[0] || B->bodies[0][i] != b || b->batch_index != i) return false;
+  if (i != B->nb[0]) return false;
+  if (c->space->count != B->ng[0]) return false;
+  for (dxGeom *g = c->space->first; g; g = g->next)
+    if (g->is_space || g->batch_index < 0 || g->batch_index >= B->ng[0] || B->geoms[0][g->batch_index] != g) return false;
+  std::vector<dxJoint *> js;
+  for (dxJoint *j = c->world->firstjoint; j; j = j->next) if (j->type != dJointTypeContact) js.push_back(j);
+  std::reverse(js.begin(), js.end());
+  if (js != B->joints[0]) return false;
+  return true;
+}
+
+static bool ctx_ensure(ObDropin *c, int need_contacts, const char *who) {
+  if (batch_matches(c, need_contacts)) return true;
+  ctx_free_batch(c);
+  dBatchDesc desc;
+  memset(&desc, 0, sizeof desc);
+  int cap = std::max(64, 16 * std::max(1, c->space->count));
+  while (cap < need_contacts) cap *= 2;
+  desc.max_contacts_per_world = cap;
+  c->B = ob_batch_create(1, &c->world, &c->space, &desc, 1);
+  if (!c->B) { ob_error(0, "%s: %s", who, dB200LastError()); return false; }
+  return true;
+}
+
+void ob_dropin_space_collide(dxSpace *space, void *data, dNearCallback *cb) {
+  bool mixed;
+  dxWorld *w = world_of_space(space, &mixed);
+  if (mixed) { ob_error(0, "dSpaceCollide: geoms of one space attached to bodies of different worlds are not supported"); return; }
+  ObDropin *c = 0;
+  for (size_t i = 0; i < g_ctx.size(); i++) if (g_ctx[i]->space == space) c = g_ctx[i];
+  if (c && w && c->world != w && c->own_world != c->world) { ob_dropin_forget_space(space); c = 0; }
+  if (!c) {
+    // a context created by dWorldQuickStep for this world (with a placeholder space) is superseded
+    for (size_t i = 0; i < g_ctx.size();) { if (w && g_ctx[i]->world == w && g_ctx[i]->own_space) ctx_drop(i); else i++; }
+    c = ctx_new(w, space);
+    if (!w) { c->own_world = dWorldCreate(); c->world = c->own_world; }
+  } else if (w && c->own_world) {   // bodies appeared in a space that had none
+    dxWorld *ow = c->own_world; ctx_free_batch(c); c->own_world = 0; c->world = w; dWorldDestroy(ow);
+  }
+  if (!ctx_ensure(c, 0, "dSpaceCollide")) return;
+  dxBatch *B = c->B;
+  char err[512] = "";
+  ObPolicy pol;
+  memset(&pol, 0, sizeof pol);
+  pol.cat_mask1 = pol.cat_mask2 = ~0u;
+  pol.max_contacts = c->maxc_hint; pol.skip_if_connected = 0;   // the callback decides, not a policy
+  int rc = ob_batch_upload(B);
+  rc |= obk_h2d(B->bk, B->caps.policy, &pol, sizeof pol);
+  if (rc) { ob_error(0, "dSpaceCollide: upload failed"); return; }
+  if (obk_run_phases(B->bk, 0, OBK_PHASE_COLLIDE, 0, err, sizeof err)) { ob_error(0, "dSpaceCollide: %s", err); return; }
+  int np = 0, nc = 0;
+  ObWorld hw;
+  rc = obk_d2h(B->bk, &np, B->caps.npairs, sizeof(int));
+  rc |= obk_d2h(B->bk, &nc, B->caps.ncontacts, sizeof(int));
+  rc |= obk_d2h(B->bk, &hw, B->caps.world, sizeof hw);
+  if (rc) { ob_error(0, "dSpaceCollide: download failed"); return; }
+  if (hw.status & OB_ERR_PAIR_OVERFLOW) { ob_error(0, "dSpaceCollide: more than %d overlapping pairs", B->caps.NP); return; }
+  c->pairs.resize((size_t)2 * np);
+  c->contacts.resize(nc);
+  if (np) rc |= obk_d2h(B->bk, c->pairs.data(), B->caps.pairs, sizeof(int) * 2 * np);
+  if (nc) rc |= obk_d2h(B->bk, c->contacts.data(), B->caps.contacts, sizeof(ObContact) * nc);
+  if (rc) { ob_error(0, "dSpaceCollide: download failed"); return; }
+  c->pair_contacts.clear();
+  const bool contacts_complete = !(hw.status & OB_ERR_CONTACT_OVERFLOW);
+  if (hw.status) { hw.status = 0; obk_h2d(B->bk, B->caps.world, &hw, sizeof hw); }
+  if (contacts_complete) {
+    int k = 0;
+    for (int p = 0; p < np; p++) {
+      const int o1 = c->pairs[2 * p], o2 = c->pairs[2 * p + 1];
+      const int k0 = k;
+      while (k < nc && c->contacts[k].g1 == o1 && c->contacts[k].g2 == o2) k++;
+      c->pair_contacts[std::make_pair(o1, o2)] = std::make_pair(k0, k - k0);
+    }
+  }
+  // cleanGeoms (collision_space.cpp:405-417): dirty flags cleared, the space is locked while the callbacks run
+  dSpaceClean(space);
+  space->lock_count++;
+  c->in_collide = true;
+  std::vector<int> pairs = c->pairs;   // the callback may re-enter (dSpaceCollide2 on sub-spaces)
+  for (int p = 0; p < np; p++) cb(data, B->geoms[0][pairs[2 * p]], B->geoms[0][pairs[2 * p + 1]]);
+  c->in_collide = false;
+  space->lock_count--;
+}
+
+static void geom_pose_host(dxGeom *g, ObPose *o) {
+  o->type = g->type;
+  for (int i = 0; i < 4; i++) o->p[i] = g->p[i];
+  for (int i = 0; i < 3; i++) o->pos[i] = 0;
+  for (int i = 0; i < 12; i++) o->R[i] = 0;
+  if (g->gflags & GEOM_PLACEABLE) {
+    ob_geom_recompute_posr(g);
+    for (int i = 0; i < 3; i++) o->pos[i] = g->final_posr->pos[i];
+    for (int i = 0; i < 12; i++) o->R[i] = g->final_posr->R[i];
+  }
+}
+
+#define OB_CONTACT_AT(p, skip, i) ((dContactGeom *)(((char *)(p)) + (size_t)(i) * (skip)))
+
+int ob_dropin_collide(dxGeom *o1, dxGeom *o2, int flags, dContactGeom *contact, int skip) {
+  const int want = flags & 0xffff;
+  if (!(o1->gflags & GEOM_ENABLED) || !(o2->gflags & GEOM_ENABLED)) { /* dCollide itself does not test enable flags */ }
+  // (1) inside dSpaceCollide's callback: serve from the batch results when they are the same computation
+  for (size_t i = 0; i < g_ctx.size(); i++) {
+    ObDropin *c = g_ctx[i];
+    if (!c->in_collide || o1->parent_space != c->space || o2->parent_space != c->space) continue;
+    const int cap = ob_pair_max_contacts(o1->type, o2->type, 1 << 15);
+    const int eff_want = std::min(want, std::min(cap, OB_MAXC_LOCAL)), eff_have = std::min(c->maxc_hint, std::min(cap, OB_MAXC_LOCAL));
+    if (want != c->maxc_hint) c->maxc_hint = std::min(want, OB_MAXC_LOCAL);   // next frame's batch narrowphase uses the caller's value
+    std::map<std::pair<int, int>, std::pair<int, int> >::iterator it = c->pair_contacts.find(std::make_pair(o1->batch_index, o2->batch_index));
+    if (it == c->pair_contacts.end() || eff_want != eff_have) break;
+    const int k0 = it->second.first, n = it->second.second;
+    for (int k = 0; k < n; k++) {
+      const ObContact &s = c->contacts[k0 + k];
+      dContactGeom *d = OB_CONTACT_AT(contact, skip, k);
+      for (int e = 0; e < 3; e++) { d->pos[e] = s.pos[e]; d->normal[e] = s.normal[e]; }
+      d->depth = s.depth; d->g1 = o1; d->g2 = o2; d->side1 = s.side1; d->side2 = s.side2;
+    }
+    return n;
+  }
+  // (2) on demand: one pair on the GPU
+  if (ob_pair_max_contacts(o1->type, o2->type, 1 << 15) == 0) return 0;   // no collider for this class pair (collision_kernel.cpp:329)
+  ObPose a, b;
+  geom_pose_host(o1, &a);
+  geom_pose_host(o2, &b);
+  ObCg cg[OB_MAXC_LOCAL];
+  char err[512] = "";
+  const int n = obk_collide_pair(&a, &b, flags, cg, err, sizeof err);
+  if (n < 0) { ob_error(0, "dCollide: %s", err); return 0; }
+  for (int k = 0; k < n; k++) {
+    dContactGeom *d = OB_CONTACT_AT(contact, skip, k);
+    for (int e = 0; e < 3; e++) { d->pos[e] = cg[k].pos[e]; d->normal[e] = cg[k].normal[e]; }
+    d->depth = cg[k].depth; d->g1 = o1; d->g2 = o2; d->side1 = cg[k].side1; d->side2 = cg[k].side2;
+  }
+  return n;
+}
+
+void ob_dropin_space_collide2(dxGeom *, dxGeom *, void *, dNearCallback *) {
+  ob_error(0, "dSpaceCollide2: not available on the drop-in path of this build (use one space per world, or dBatch*)");
+}
+
+int ob_dropin_quickstep(dxWorld *w, dReal h) {
+  ObDropin *c = 0;
+  for (size_t i = 0; i < g_ctx.size(); i++) if (g_ctx[i]->world == w) c = g_ctx[i];
+  if (!c) {
+    // world stepped without a collided space (free bodies / joints only): placeholder space.  If the
+    // world's geoms live in a space that was never collided through this API, bind that one.
+    dxSpace *s = 0;
+    for (dxBody *b = w->firstbody; b && !s; b = b->next) if (b->geom && b->geom->parent_space) s = b->geom->parent_space;
+    c = ctx_new(w, s);
+    if (!s) { c->own_space = dSimpleSpaceCreate(0); c->space = c->own_space; }
+  }
+  // contact joints on the world list, creation order (the list is newest-first, ode.cpp:1162-1177)
+  std::vector<dxJoint *> cj;
+  bool want_fb = false;
+  for (dxJoint *j = w->firstjoint; j; j = j->next) {
+    if (j->feedback) want_fb = true;
+    if (j->type == dJointTypeContact && j->node[0].body) cj.push_back(j);
+  }
+  std::reverse(cj.begin(), cj.end());
+  const int nc = (int)cj.size();
+  if (!ctx_ensure(c, nc, "dWorldQuickStep")) return 0;
+  dxBatch *B = c->B;
+  const ObBatchDev &D = B->caps;
+  B->seeds[0] = ob_global_seed;
+  std::vector<ObContact> hc(std::max(nc, 1));
+  std::vector<ObSurface> hs(std::max(nc, 1));
+  std::vector<dReal> hf((size_t)std::max(nc, 1) * 4, 0);
+  for (int i = 0; i < nc; i++) {
+    const dxJoint *j = cj[i];
+    const dContact &ct = j->contact;
+    ObContact &o = hc[i];
+    memset(&o, 0, sizeof o);
+    for (int e = 0; e < 3; e++) { o.pos[e] = ct.geom.pos[e]; o.normal[e] = ct.geom.normal[e]; }
+    o.depth = ct.geom.depth;
+    o.g1 = (ct.geom.g1 && ct.geom.g1->parent_space == c->space) ? ct.geom.g1->batch_index : -1;
+    o.g2 = (ct.geom.g2 && ct.geom.g2->parent_space == c->space) ? ct.geom.g2->batch_index : -1;
+    o.side1 = j->node[0].body->batch_index;                          // bodies as attached (after the swap rule)
+    o.side2 = j->node[1].body ? j->node[1].body->batch_index : -1;
+    o.policy = (j->flags & dJOINT_REVERSE) ? 1 : 0;
+    ob_fill_surface(hs[i], ct.surface);
+    for (int e = 0; e < 3; e++) hf[(size_t)4 * i + e] = ct.fdir1[e];
+    if (j->node[0].body->world != w) { ob_error(0, "dWorldQuickStep: contact joint attached to a body of another world"); return 0; }
+  }
+  int rc = ob_batch_upload(B);
+  rc |= obk_h2d(B->bk, D.ncontacts, &nc, sizeof(int));
+  if (nc) {
+    rc |= obk_h2d(B->bk, D.contacts, hc.data(), sizeof(ObContact) * nc);
+    rc |= obk_h2d(B->bk, D.csurf, hs.data(), sizeof(ObSurface) * nc);
+    rc |= obk_h2d(B->bk, D.cfdir1, hf.data(), sizeof(dReal) * 4 * nc);
+  }
+  // feedback slots start as all-ones (NaN) so joints that did not enter a solved island keep the caller's values
+  if (want_fb) rc |= obk_memset(B->bk, D.fback, 0xff, sizeof(dReal) * 12 * (size_t)(D.NC + D.NJ));
+  if (rc) { ob_error(0, "dWorldQuickStep: upload failed"); return 0; }
+  char err[512] = "";
+  if (obk_run_phases(B->bk, h, OBK_PHASE_STEP, want_fb ? 1 : 0, err, sizeof err)) { ob_error(0, "dWorldQuickStep: %s", err); return 0; }
+  // results: body state, stepping order (for dGeomMoved), seed, feedback
+  const int nb = B->nb[0];
+  std::vector<ObBodyDyn> hd(std::max(nb, 1));
+  std::vector<unsigned char> ib(std::max(D.NB, 1));
+  std::vector<int> si(SI_WORDS);
+  ObWorld hw;
+  rc = obk_d2h(B->bk, hd.data(), D.bdyn, sizeof(ObBodyDyn) * std::max(nb, 1));
+  rc |= obk_d2h(B->bk, ib.data(), D.ibody, ib.size());
+  rc |= obk_d2h(B->bk, si.data(), D.stepinfo, sizeof(int) * SI_WORDS);
+  rc |= obk_d2h(B->bk, &hw, D.world, sizeof hw);
+  if (rc) { ob_error(0, "dWorldQuickStep: download failed"); return 0; }
+  if (hw.status) {
+    const int st = hw.status;
+    hw.status = 0; obk_h2d(B->bk, D.world, &hw, sizeof hw);
+    ob_error(0, "dWorldQuickStep: capacity exceeded on the device (status %d)", st);
+    return 0;
+  }
+  for (int i = 0; i < nb; i++) {
+    dxBody *b = B->bodies[0][i];
+    const ObBodyDyn &d = hd[i];
+    for (int k = 0; k < 3; k++) { b->pos[k] = d.pos[k]; b->lvel[k] = d.lvel[k]; b->avel[k] = d.avel[k]; b->facc[k] = d.facc[k]; b->tacc[k] = d.tacc[k]; }
+    for (int k = 0; k < 4; k++) b->q[k] = d.q[k];
+    for (int k = 0; k < 12; k++) b->R[k] = d.R[k];
+    b->flags = d.flags; b->adis_stepsleft = d.adis_stepsleft; b->adis_timeleft = d.adis_timeleft;
+  }
+  // dxStepBody: every geom of a stepped body is reported moved, in stepping order (util.cpp:331-337)
+  for (int i = 0; i < si[SI_NIB] && i < nb; i++)
+    for (dxGeom *g = B->bodies[0][ib[i]]->geom; g; g = g->body_next) ob_geom_moved(g);
+  ob_global_seed = hw.seed;
+  if (want_fb) {
+    std::vector<dReal> fb((size_t)(D.NC + D.NJ) * 12);
+    if (obk_d2h(B->bk, fb.data(), D.fback, fb.size() * sizeof(dReal))) { ob_error(0, "dWorldQuickStep: download failed"); return 0; }
+    for (int i = 0; i < nc + (int)B->joints[0].size(); i++) {
+      dxJoint *j = i < nc ? cj[i] : B->joints[0][i - nc];
+      if (!j->feedback) continue;
+      const dReal *s = &fb[(size_t)(i < nc ? i : D.NC + (i - nc)) * 12];
+      if (s[0] != s[0] && s[11] != s[11]) continue;   // untouched slot
+      for (int e = 0; e < 3; e++) { j->feedback->f1[e] = s[e]; j->feedback->t1[e] = s[3 + e]; j->feedback->f2[e] = s[6 + e]; j->feedback->t2[e] = s[9 + e]; }
+    }
+  }
+  return 1;
+}

@@ -340,6 +340,7 @@ dWorldID dWorldCreate(void) {
 static void joint_unlink_bodies(dxJoint *j);
 void dWorldDestroy(dWorldID w) {
   OB_AASSERT(w);
+  ob_dropin_forget_world(w);
   dxBody *b = w->firstbody;
   while (b) { dxBody *nb = b->next; dBodyDestroy(b); b = nb; }
   dxJoint *j = w->firstjoint;
@@ -746,6 +747,7 @@ void dGeomDestroy(dGeomID g) {
   if (g->is_space) {
     dxSpace *s = (dxSpace *)g;
     CHECK_NOT_LOCKED(s);
+    ob_dropin_forget_space(s);
     dxGeom *x, *n;
     for (x = s->first; x; x = n) {
       n = x->next;

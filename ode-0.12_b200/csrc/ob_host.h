@@ -146,3 +146,5 @@ void ob_dropin_space_collide(dxSpace *space, void *data, dNearCallback *cb);
 void ob_dropin_space_collide2(dxGeom *g1, dxGeom *g2, void *data, dNearCallback *cb);
 int ob_dropin_collide(dxGeom *o1, dxGeom *o2, int flags, dContactGeom *contact, int skip);
 int ob_dropin_quickstep(dxWorld *w, dReal h);
+void ob_dropin_forget_world(dxWorld *w);
+void ob_dropin_forget_space(dxSpace *s);

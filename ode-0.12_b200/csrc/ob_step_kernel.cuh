@@ -33,7 +33,6 @@
 
 #define OB_ROWF 19                                   // reals per row record
 #define OB_ROWW 20                                   // + one slot holding the 32-bit meta word
-#define OB_MAXEPOCH 8                                // shuffle epochs per step ((iters+7)/8)
 
 __host__ __device__ inline size_t ob_al(size_t x, size_t a) { return (x + a - 1) & ~(a - 1); }
 
@@ -127,8 +126,6 @@ __device__ __forceinline__ bool encode_bounds(real lo, real hi, real *v, unsigne
   return false;
 }
 
-// per-world hand-off between the three kernels (ObBatchDev::stepinfo), ints
-enum { SI_NIS = 0, SI_NIB, SI_NIJ, SI_MTOT, SI_HAVEROWS, SI_NPASS0, SI_WORDS = SI_NPASS0 + OB_MAXEPOCH };
 
 // =====================================================================================
 template <int G>
@@ -186,8 +183,9 @@ __global__ void __launch_bounds__(32) k_prep(ObBatchDev d, real h, int taps) {
     for (int base = 0; base < njall_max; base += G) {
       const int j = base + gl;
       if (j < nc) {
-        int b1 = geoms[con[j].g1].body, b2 = geoms[con[j].g2].body;
-        if (b1 < 0) { b1 = b2; b2 = -1; }
+        int b1, b2;
+        if (d.dropin) { b1 = con[j].side1; b2 = con[j].side2; }   // drop-in: the caller attached the joint (bodies after the swap rule)
+        else { b1 = geoms[con[j].g1].body; b2 = geoms[con[j].g2].body; if (b1 < 0) { b1 = b2; b2 = -1; } }
         s_jb1[j] = (unsigned char)b1; s_jb2[j] = (unsigned char)(b2 < 0 ? 255 : b2); s_jtag[j] = 0;
       } else if (j < njall) {
         const ObJoint &pj = pjoint[j - nc];
@@ -303,13 +301,14 @@ __global__ void __launch_bounds__(32) k_prep(ObBatchDev d, real h, int taps) {
     }
     // ---- (5) rows per joint (getInfo1) -> row offsets in island joint order (tile-wide scan)
     const ObSurface surf0 = d.policy[0].surface;
+    const ObSurface *csurf = d.csurf ? d.csurf + (size_t)wc * d.NC : (const ObSurface *)0;   // drop-in: per-contact surfaces
     int mtot = 0, anyball = 0;
     for (int base = 0; base < nij_max; base += G) {
       const int k = base + gl;
       int m = 0;
       if (k < nij) {
         const int j = s_ijoint[k];
-        if (j < nc) { ObSurface sf = surf0; m = ob_contact_info1(sf); }
+        if (j < nc) { ObSurface sf = csurf ? csurf[j] : surf0; m = ob_contact_info1(sf); }
         else {
           ObJoint pj = pjoint[j - nc];
           const int b1 = pj.b1, b2 = pj.b2;
@@ -362,16 +361,17 @@ __global__ void __launch_bounds__(32) k_prep(ObBatchDev d, real h, int taps) {
         real erp_in = W.erp;
         if (anyball) { const int src = s_erpsrc[k]; if (src != 0xffff) erp_in = pjoint[s_ijoint[src] - nc].erp; }
         if (j < nc) {
-          ObSurface sf = surf0;
+          ObSurface sf = csurf ? csurf[j] : surf0;
           const int jm = ob_contact_info1(sf);
           ObRowOut3 r;
           ob_rows_defaults(r, jm, W.cfm);
           const ObContact c = con[j];
-          const int rev = geoms[c.g1].body < 0;
+          const int rev = d.dropin ? c.policy : (geoms[c.g1].body < 0);   // dJOINT_REVERSE
           real p1[3], l1[3], a1[3], p2[3] = {0, 0, 0}, l2[3] = {0, 0, 0}, a2[3] = {0, 0, 0};
           for (int e = 0; e < 3; e++) { p1[e] = bd[b1].pos[e]; l1[e] = bd[b1].lvel[e]; a1[e] = bd[b1].avel[e]; }
           if (b2 >= 0) for (int e = 0; e < 3; e++) { p2[e] = bd[b2].pos[e]; l2[e] = bd[b2].lvel[e]; a2[e] = bd[b2].avel[e]; }
-          const real fdir1[3] = {0, 0, 0};
+          real fdir1[3] = {0, 0, 0};
+          if (csurf) for (int e = 0; e < 3; e++) fdir1[e] = d.cfdir1[((size_t)wc * d.NC + j) * 4 + e];
           ob_contact_info2(r, jm, sf, c.pos, c.normal, c.depth, fdir1, rev, p1, l1, a1, b2 >= 0, p2, l2, a2, stepsize1,
                            erp_in, W.min_depth, W.max_vel);
           for (int q = 0; q < jm; q++) {
@@ -829,17 +829,26 @@ __global__ void __launch_bounds__(32) k_sor(ObBatchDev d, int taps) {
       const unsigned short *g_jrow = d.jrow + (size_t)wc * (d.NC + d.NJ + 1);
       const unsigned short *g_ijoint = d.ijoint + (size_t)wc * (d.NC + d.NJ);
       const int ncw = d.ncontacts[wc];
-      real *fb = d.fback + (size_t)wc * d.NC * 6;
+      real *fb = d.fback + (size_t)wc * (d.NC + d.NJ) * 12;
       real *gl_lam = d.lambda + (size_t)wc * d.NR;
       if (mtot > 0)
         for (int k = gl; k < nij; k += G) {
           const int jr0 = g_jrow[k], jm = g_jrow[k + 1] - jr0;
-          real acc[6] = {0, 0, 0, 0, 0, 0};
+          // Multiply1_12q1 (quickstep.cpp:70-101): data = J^T lambda, body 1 then body 2 (J2l == -J1l)
+          real acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+          bool two = false;
           for (int q = 0; q < jm; q++) {
+            const real *rp = rows + (size_t)(jr0 + q) * OB_ROWW;
             const real s = s_lam[jr0 + q];
-            for (int e = 0; e < 6; e++) acc[e] += rows[(size_t)(jr0 + q) * OB_ROWW + e] * s;
+            const unsigned meta = *(const unsigned *)(rp + OB_ROWF);
+            two = ((meta >> 8) & 255u) != 255u;
+            for (int e = 0; e < 6; e++) acc[e] += rp[e] * s;
+            for (int e = 0; e < 3; e++) { acc[6 + e] += (-rp[e]) * s; acc[9 + e] += rp[6 + e] * s; }
           }
-          if (g_ijoint[k] < ncw) for (int e = 0; e < 6; e++) fb[g_ijoint[k] * 6 + e] = acc[e];
+          if (!two) for (int e = 6; e < 12; e++) acc[e] = 0;
+          const int jid = g_ijoint[k];
+          real *o = fb + (size_t)(jid < ncw ? jid : d.NC + (jid - ncw)) * 12;
+          for (int e = 0; e < 12; e++) o[e] = acc[e];
         }
       for (int i = gl; i < mtot; i += G) gl_lam[i] = s_lam[i];
     }

@@ -97,6 +97,10 @@ struct ObCounters {
   unsigned long long steps, body_steps, pairs, contacts, rows, islands, overflow_worlds;
 };
 
+#define OB_MAXEPOCH 8   // shuffle epochs per step ((iters+7)/8)
+// per-world hand-off between the step kernels (ObBatchDev::stepinfo), ints
+enum { SI_NIS = 0, SI_NIB, SI_NIJ, SI_MTOT, SI_HAVEROWS, SI_NPASS0, SI_WORDS = SI_NPASS0 + OB_MAXEPOCH };
+
 // capacities + device pointers, passed by value to every kernel
 struct ObBatchDev {
   int W;        // worlds
@@ -108,6 +112,7 @@ struct ObBatchDev {
   int npolicy;
   int NEP;      // shuffle epochs per step = ceil(max iters / 8)
   int NJ;       // permanent (non-contact) joints per world slot
+  int dropin;   // 1: batch serves the classic per-call API (per-contact surfaces in csurf/cfdir1)
   ObWorld *world;        // [W]
   ObBodyDyn *bdyn;       // [W*NB]
   ObBodyConst *bconst;   // [W*NB]
@@ -141,6 +146,8 @@ struct ObBatchDev {
   int *rowI;             // [W*NR*4]  findex, b1, b2, joint
   real *lambda;          // [W*NR]
   int *nrows;            // [W]
-  real *fback;           // [W*NC*6] f1,t1 per contact joint (debug tap, optional)
+  real *fback;           // [W*(NC+NJ)*12] f1,t1,f2,t2 per joint (contacts, then permanent at NC+k) as dJointFeedback reports them
+  ObSurface *csurf;      // [W*NC] per-contact surface parameters (drop-in path only, else null: policy table)
+  real *cfdir1;          // [W*NC*4] per-contact fdir1 (drop-in path only)
   ObCounters *counters;  // [1]
 };

@@ -47,7 +47,10 @@ def _built():
 # scenes whose rows depend on atan2 (hinge / hinge2 limit angles).  dSINGLE reproduces glibc's atan2f
 # bit for bit (ob_math.h); for dDOUBLE the device has no bit-identical atan2 (glibc's is correctly
 # rounded, CUDA's is <= 2 ulp), so those scenes are held to the stated tolerance instead:
-# exact discrete observables + |dx|_inf / max(1,|x|_inf) <= 1e-9 over the free-running trace.
+# exact discrete observables + |dx|_inf / max(1,|x|_inf) <= 1e-9, over the free-running golden
+# traces and, for the long live comparisons, in lock-step with the reference (every step starts
+# from the reference's pre-step body state, SURVEY 8d parity protocol with K = 1) so that a
+# last-bit difference cannot be amplified by chaotic dynamics into a different contact set.
 ATAN2_SCENES = ("hinges", "buggy", "ragdoll")
 
 

@@ -27,7 +27,7 @@ def driver_path(kind, prec):
     raise ValueError(kind)
 
 
-def run_trace(kind, prec, scene, steps, worlds, out, mode=None, timeout=600, settle=0, contacts_cap=0):
+def run_trace(kind, prec, scene, steps, worlds, out, mode=None, timeout=600, settle=0, contacts_cap=0, resync=None):
     exe = driver_path(kind, prec)
     if mode is None:
         mode = "callback" if kind == "ref" else "batch"
@@ -36,17 +36,21 @@ def run_trace(kind, prec, scene, steps, worlds, out, mode=None, timeout=600, set
         cmd += ["--settle", str(settle)]
     if contacts_cap and kind != "ref":
         cmd += ["--contacts-cap", str(contacts_cap)]
+    if resync and kind != "ref":
+        cmd += ["--resync", resync]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
     if r.returncode != 0:
         raise RuntimeError(f"{' '.join(cmd)} failed rc={r.returncode}\n{r.stdout}\n{r.stderr}")
     return r.stderr
 
 
-def parity(cand, prec, scene, steps, worlds=1, mode=None, settle=0):
+def parity(cand, prec, scene, steps, worlds=1, mode=None, settle=0, lockstep=False):
+    """lockstep: the candidate reloads the reference's pre-step body state before every step
+    (SURVEY 8d parity protocol with K = 1); otherwise both run free from the same start."""
     with tempfile.TemporaryDirectory() as td:
         fr, fc = os.path.join(td, "ref.bin"), os.path.join(td, "cand.bin")
         run_trace("ref", prec, scene, steps, worlds, fr, settle=settle)
-        log = run_trace(cand, prec, scene, steps, worlds, fc, mode=mode, settle=settle)
+        log = run_trace(cand, prec, scene, steps, worlds, fc, mode=mode, settle=settle, resync=fr if lockstep else None)
         res = compare(read_trace(fc), read_trace(fr))
         res["log"] = log[-300:]
         return res
@@ -70,11 +74,12 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--worlds", type=int, default=1)
     ap.add_argument("--mode", default=None)
+    ap.add_argument("--lockstep", action="store_true")
     a = ap.parse_args()
     bad = 0
     for sc in a.scene:
         try:
-            r = parity(a.cand, a.prec, sc, a.steps, a.worlds, a.mode)
+            r = parity(a.cand, a.prec, sc, a.steps, a.worlds, a.mode, lockstep=a.lockstep)
         except Exception as e:  # noqa: BLE001
             print(json.dumps({"scene": sc, "error": str(e)[-600:]}))
             bad += 1

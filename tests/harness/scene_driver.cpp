@@ -94,7 +94,7 @@ static double now_s() {
 }
 
 int main(int argc, char **argv) {
-  std::string scene = "stack32", out = "", mode = "callback";
+  std::string scene = "stack32", out = "", mode = "callback", resync = "";
   int nworlds = 1, nsteps = 10, world0 = 0, timing = 0, settle = 0, maxc_world = 0;
   double h = 0.01;
   for (int i = 1; i < argc; i++) {
@@ -109,6 +109,7 @@ int main(int argc, char **argv) {
     else if (a == "--time") timing = 1;
     else if (a == "--settle") settle = atoi(argv[++i]);
     else if (a == "--contacts-cap") maxc_world = atoi(argv[++i]);
+    else if (a == "--resync") resync = argv[++i];
     else { fprintf(stderr, "unknown arg %s\n", a.c_str()); return 2; }
   }
   dInitODE2(0);
@@ -232,8 +233,39 @@ int main(int argc, char **argv) {
       body_steps = c.body_steps; contacts = c.contacts; pairs = c.pairs;
     } else {
       std::vector<int> pbuf(2 * 65536), cg(2 * 65536);
-      std::vector<dReal> cd(7 * 65536), lam(3 * 65536);
+      std::vector<dReal> cd(7 * 65536), lam(12 * 65536);
+      // lock-step parity (SURVEY 8d "parity protocol", K = 1): before every step load the body state the
+      // reference had before ITS step from a reference trace, so chaos cannot amplify rounding differences
+      FILE *rs = NULL;
+      if (!resync.empty()) {
+        rs = fopen(resync.c_str(), "rb");
+        int hdr[4];
+        if (!rs || fread(hdr, 4, 4, rs) != 4 || hdr[1] != (int)sizeof(dReal) || hdr[2] != nworlds) { fprintf(stderr, "bad --resync trace\n"); return 2; }
+      }
       for (int s = 0; s < nsteps; s++) {
+        if (rs) {
+          for (int w = 0; w < nworlds; w++) {
+            int n;
+            if (fread(&n, 4, 1, rs) != 1) { fprintf(stderr, "resync trace too short\n"); return 2; }
+            fseek(rs, 4L * n, SEEK_CUR);
+            if (fread(&n, 4, 1, rs) != 1 || n != nb) { fprintf(stderr, "resync trace: body count\n"); return 2; }
+            std::vector<dReal> st((size_t)nb * 13);
+            if (fread(st.data(), sizeof(dReal), st.size(), rs) != st.size()) return 2;
+            for (int b = 0; b < nb; b++) {
+              memcpy(&pos[(w * nb + b) * 3], &st[b * 13], 3 * sizeof(dReal));
+              memcpy(&quat[(w * nb + b) * 4], &st[b * 13 + 3], 4 * sizeof(dReal));
+              memcpy(&lv[(w * nb + b) * 3], &st[b * 13 + 7], 3 * sizeof(dReal));
+              memcpy(&av[(w * nb + b) * 3], &st[b * 13 + 10], 3 * sizeof(dReal));
+            }
+            if (fread(&n, 4, 1, rs) != 1) return 2;
+            fseek(rs, 8L * n, SEEK_CUR);                                       // pairs
+            if (fread(&n, 4, 1, rs) != 1) return 2;
+            fseek(rs, (long)n * (8 + 7 * (long)sizeof(dReal)), SEEK_CUR);       // contacts
+            fseek(rs, (long)n * 6 * (long)sizeof(dReal), SEEK_CUR);             // feedback
+            fseek(rs, (long)nb * 13 * (long)sizeof(dReal) + 4, SEEK_CUR);       // state1 + seed
+          }
+          dBatchSetBodyState(B, pos.data(), quat.data(), lv.data(), av.data());
+        }
         // the trace is world-major inside a step, so gather per world
         dBatchGetBodyState(B, pos.data(), quat.data(), lv.data(), av.data());
         std::vector<dReal> st0(pos.size() + quat.size() + lv.size() + av.size());

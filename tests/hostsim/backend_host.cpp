@@ -53,7 +53,11 @@ ObBackend *obk_create(const ObBatchDev &caps, int, char *, size_t) {
   d.rowI = halloc<int>(b, W * d.NR * 4);
   d.lambda = halloc<real>(b, W * d.NR);
   d.nrows = halloc<int>(b, W);
-  d.fback = halloc<real>(b, W * d.NC * 6);
+  d.fback = halloc<real>(b, W * (d.NC + d.NJ) * 12);
+  d.ibody = halloc<unsigned char>(b, W * d.NB);
+  d.stepinfo = halloc<int>(b, W * SI_WORDS);
+  d.csurf = d.dropin ? halloc<ObSurface>(b, W * d.NC) : 0;
+  d.cfdir1 = d.dropin ? halloc<real>(b, W * d.NC * 4) : 0;
   d.counters = halloc<ObCounters>(b, 1);
   return b;
 }
@@ -233,9 +237,10 @@ static void step_world(ObBatchDev &d, int w, real h, int taps) {
   // contact joint -> bodies (dJointAttach: body1==0 -> swap + REVERSE), ode.cpp:1368-1377
   std::vector<int> jb1(njall), jb2(njall), jrev(njall);
   for (int j = 0; j < nc; j++) {
-    int b1 = geoms[con[j].g1].body, b2 = geoms[con[j].g2].body;
+    int b1, b2;
     jrev[j] = 0;
-    if (b1 < 0) { b1 = b2; b2 = -1; jrev[j] = 1; }
+    if (d.dropin) { b1 = con[j].side1; b2 = con[j].side2; jrev[j] = con[j].policy; }
+    else { b1 = geoms[con[j].g1].body; b2 = geoms[con[j].g2].body; if (b1 < 0) { b1 = b2; b2 = -1; jrev[j] = 1; } }
     jb1[j] = b1; jb2[j] = b2;
   }
   for (int j = 0; j < nj; j++) { jb1[nc + j] = pjoint[j].b1; jb2[nc + j] = pjoint[j].b2; jrev[nc + j] = 0; }
@@ -306,7 +311,7 @@ static void step_world(ObBatchDev &d, int w, real h, int taps) {
   real *rowJ = d.rowJ + (size_t)w * d.NR * 12, *rowiMJ = d.rowiMJ + (size_t)w * d.NR * 12;
   real *rowS = d.rowS + (size_t)w * d.NR * 4, *lambda = d.lambda + (size_t)w * d.NR;
   int *rowI = d.rowI + (size_t)w * d.NR * 4;
-  real *fb = d.fback + (size_t)w * d.NC * 6;
+  real *fb = d.fback + (size_t)w * (d.NC + d.NJ) * 12;
   int rowbase = 0;
   size_t bpos = 0, jpos = 0;
   std::vector<int> moved;   // geoms in dGeomMoved order
@@ -332,7 +337,7 @@ static void step_world(ObBatchDev &d, int w, real h, int taps) {
     for (int k = 0; k < inj; k++) {
       const int j = ij[k];
       if (j < nc) {
-        surf[k] = d.policy[con[j].policy].surface;
+        surf[k] = d.csurf ? d.csurf[(size_t)w * d.NC + j] : d.policy[con[j].policy].surface;
         jm[k] = ob_contact_info1(surf[k]);
       } else {
         pj[k] = pjoint[j - nc];
@@ -359,6 +364,7 @@ static void step_world(ObBatchDev &d, int w, real h, int taps) {
         if (j < nc) {
           real zero3[3] = {0, 0, 0};
           real fdir1[3] = {0, 0, 0};
+          if (d.csurf) for (int e = 0; e < 3; e++) fdir1[e] = d.cfdir1[((size_t)w * d.NC + j) * 4 + e];
           ob_contact_info2(r, jm[k], surf[k], con[j].pos, con[j].normal, con[j].depth, fdir1, jrev[j], bd[b1].pos,
                            bd[b1].lvel, bd[b1].avel, b2 >= 0, b2 >= 0 ? bd[b2].pos : zero3, b2 >= 0 ? bd[b2].lvel : zero3,
                            b2 >= 0 ? bd[b2].avel : zero3, stepsize1, erp_io, W.min_depth, W.max_vel);
@@ -434,13 +440,15 @@ static void step_world(ObBatchDev &d, int w, real h, int taps) {
         }
       }
       if (taps) {
-        for (int k = 0; k < inj; k++) {   // Multiply1_12q1 (quickstep.cpp:70-101)
-          real acc[6] = {0, 0, 0, 0, 0, 0};
+        for (int k = 0; k < inj; k++) {   // Multiply1_12q1 (quickstep.cpp:70-101), body 1 then body 2
+          real acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
           for (int q = 0; q < jm[k]; q++) {
             real s = lam[jofs[k] + q];
-            for (int e = 0; e < 6; e++) acc[e] += Jcopy[(size_t)(jofs[k] + q) * 12 + e] * s;
+            for (int e = 0; e < 12; e++) acc[e] += Jcopy[(size_t)(jofs[k] + q) * 12 + e] * s;
           }
-          if (ij[k] < nc) for (int e = 0; e < 6; e++) fb[ij[k] * 6 + e] = acc[e];
+          if (jb2[ij[k]] < 0) for (int e = 6; e < 12; e++) acc[e] = 0;
+          real *o = fb + (size_t)(ij[k] < nc ? ij[k] : d.NC + (ij[k] - nc)) * 12;
+          for (int e = 0; e < 12; e++) o[e] = acc[e];
         }
       }
     }
@@ -468,6 +476,8 @@ static void step_world(ObBatchDev &d, int w, real h, int taps) {
     d.counters->islands += 1;
   }
   W.seed = seed;
+  for (size_t i = 0; i < ibody.size(); i++) d.ibody[(size_t)w * d.NB + i] = (unsigned char)ibody[i];
+  d.stepinfo[(size_t)w * SI_WORDS + SI_NIB] = (int)ibody.size();
   d.nrows[w] = rowbase;
   // space list update: every moved (clean) geom goes to the head, in order (collision_space.cpp:47-75)
   int *glist = d.glist + (size_t)w * d.NG;
@@ -480,6 +490,18 @@ static void step_world(ObBatchDev &d, int w, real h, int taps) {
   d.counters->steps += 1;
 }
 
+int obk_run_phases(ObBackend *b, real h, int phases, int taps, char *, size_t) {
+  ObBatchDev &d = b->d;
+  for (int w = 0; w < d.W; w++) {
+    if (phases & OBK_PHASE_COLLIDE) collide_world(d, w);
+    if (phases & OBK_PHASE_STEP) step_world(d, w, h, taps);
+  }
+  return 0;
+}
+int obk_collide_pair(const ObPose *a, const ObPose *b, int flags, ObCg *out, char *, size_t) {
+  int swapped;
+  return ob_collide_pair(*a, *b, flags, out, &swapped);
+}
 int obk_step(ObBackend *b, real h, int nsteps, int taps, char *, size_t) {
   ObBatchDev &d = b->d;
   for (int s = 0; s < nsteps; s++)

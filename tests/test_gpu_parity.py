@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, ROOT, assert_bit_exact, assert_parity, have_ref, lib_path
+from conftest import ATAN2_SCENES, GOLDEN, ROOT, assert_bit_exact, assert_parity, have_ref, lib_path
 from run_parity import parity, parity_golden
 
 pytestmark = pytest.mark.gpu
@@ -27,8 +27,21 @@ def test_cuda_matches_golden_reference_traces(stem, scene, steps, worlds, settle
 @pytest.mark.parametrize("scene,steps,worlds", [("stack32", 200, 3), ("block64", 50, 1), ("tower64", 250, 1),
                                                 ("mixed", 200, 2), ("mixed_maxc4", 300, 1), ("chain", 250, 2), ("hinges", 250, 1), ("buggy", 250, 3), ("capsmix", 250, 3), ("ragdoll", 250, 3)])
 def test_cuda_matches_live_reference(scene, steps, worlds, prec):
-    r = parity("b200", prec, scene, steps, worlds)
+    # dDOUBLE scenes with atan2 on the path: lock-step protocol (SURVEY 8d, K = 1), see conftest.ATAN2_SCENES
+    r = parity("b200", prec, scene, steps, worlds, lockstep=(prec == "double" and scene in ATAN2_SCENES))
     assert_parity(r, f"{scene}/{prec}", scene, prec, "b200")
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not shipped")
+@pytest.mark.parametrize("prec", ["single", "double"])
+@pytest.mark.parametrize("scene,steps,worlds", [("stack32", 60, 2), ("mixed_maxc4", 120, 1), ("chain", 100, 1), ("capsmix", 100, 1), ("block64", 20, 1)])
+def test_dropin_classic_api_matches_live_reference(scene, steps, worlds, prec):
+    """the drop-in boundary: unchanged user code (dSpaceCollide + near callback calling dCollide /
+    dJointCreateContact / dJointSetFeedback + dWorldQuickStep + dJointGroupEmpty) linked against
+    libode_b200 runs on the GPU kernels and reproduces the reference's trace bit for bit."""
+    r = parity("b200", prec, scene, steps, worlds, mode="callback")
+    assert r["pairs"] > 0
+    assert_bit_exact(r, f"dropin/{scene}/{prec}")
 
 
 def _batch(lib, scenes, scene, nworlds, cap=0):

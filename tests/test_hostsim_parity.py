@@ -27,3 +27,13 @@ def test_hostsim_matches_live_reference(scene, steps, worlds):
     r = parity("hostsim", "single", scene, steps, worlds)
     assert r["contacts"] > 0
     assert_bit_exact(r, scene)
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("scene,steps,worlds", [("stack32", 80, 2), ("mixed_maxc4", 150, 1), ("hinges", 150, 1), ("buggy", 120, 2), ("ragdoll", 100, 1)])
+def test_hostsim_dropin_callback_loop_matches_live_reference(scene, steps, worlds):
+    """host logic of the drop-in path (ob_dropin.cpp): the classic loop dSpaceCollide + near callback
+    (dCollide, dJointCreateContact, dJointAttach, dJointSetFeedback) + dWorldQuickStep +
+    dJointGroupEmpty, same driver source as the reference's, must give the same trace."""
+    r = parity("hostsim", "single", scene, steps, worlds, mode="callback")
+    assert_bit_exact(r, f"dropin/{scene}")
