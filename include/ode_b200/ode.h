@@ -432,7 +432,8 @@ typedef struct dBatchContactPolicy {
 typedef struct dBatchDesc {
   int max_contacts_per_world;       /* contact joints per step per world */
   int device;                       /* CUDA device ordinal */
-  int reserved[6];
+  int max_pairs_per_world;          /* near-callback pairs per step per world (0: 12 x geoms) */
+  int reserved[5];
 } dBatchDesc;
 
 typedef struct dBatchCounters {

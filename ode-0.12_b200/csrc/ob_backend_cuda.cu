@@ -38,7 +38,7 @@ static long long g_launches = 0;
 // ------------------------------------------------------------------------------------
 // shared-memory layouts (one function for host sizing and device carving)
 struct CollideSmem {
-  size_t pose, aabb, cb, gid, body, cat, col, en, hr, br, walk_of, key, o12, sorted, misc, total;
+  size_t pose, aabb, cb, gid, body, cat, col, en, hr, br, walk_of, sapkey, sapinit, sappos, sapwalk, key, o12, sorted, misc, total;
 };
 __host__ __device__ inline size_t ob_al16(size_t x) { return (x + 15) & ~(size_t)15; }
 __host__ __device__ inline CollideSmem collide_smem(int NG, int NP) {
@@ -54,6 +54,10 @@ __host__ __device__ inline CollideSmem collide_smem(int NG, int NP) {
   s.hr = o; o = ob_al16(o + sizeof(int) * NG);
   s.br = o; o = ob_al16(o + sizeof(int) * NG);
   s.walk_of = o; o = ob_al16(o + sizeof(int) * NG);
+  s.sapkey = o; o = ob_al16(o + sizeof(float) * (NG + 1));
+  s.sapinit = o; o = ob_al16(o + sizeof(int) * (NG + 1));
+  s.sappos = o; o = ob_al16(o + sizeof(int) * (NG + 1));
+  s.sapwalk = o; o = ob_al16(o + sizeof(int) * (NG + 1));
   s.key = o; o = ob_al16(o + sizeof(ObPairKey) * NP);
   s.o12 = o; o = ob_al16(o + sizeof(int2) * NP);
   s.sorted = o; o = ob_al16(o + sizeof(int2) * NP);
@@ -116,6 +120,10 @@ __global__ void __launch_bounds__(OB_THREADS) k_collide(ObBatchDev d) {
   int *s_hr = (int *)(smem + L.hr);
   int *s_br = (int *)(smem + L.br);
   int *s_walk_of = (int *)(smem + L.walk_of);
+  float *s_sapkey = (float *)(smem + L.sapkey);
+  int *s_sapinit = (int *)(smem + L.sapinit);
+  int *s_sappos = (int *)(smem + L.sappos);
+  int *s_sapwalk = (int *)(smem + L.sapwalk);
   ObPairKey *s_key = (ObPairKey *)(smem + L.key);
   int2 *s_o12 = (int2 *)(smem + L.o12);
   int2 *s_sorted = (int2 *)(smem + L.sorted);
@@ -129,9 +137,15 @@ __global__ void __launch_bounds__(OB_THREADS) k_collide(ObBatchDev d) {
     const ObBodyDyn *bd = d.bdyn + (size_t)w * d.NB;
     const int *glist = d.glist + (size_t)w * d.NG;
     if (tid < 8) s_misc[tid] = 0;
+    const int stype = W.space_type;
+    // SAP: cleanGeoms appends the DirtyList to the GeomList (collision_sapspace.cpp:394-423), so the walk
+    // order is glist rotated by sap_ndirty; the cleaned order is written back below
+    const int rot = stype == OB_SPACE_SAP ? W.sap_ndirty : 0;
+    int ax0 = 0, ax1 = 2, ax2 = 4;
+    if (stype == OB_SPACE_SAP) ob_sap_axes(W.sap_axes, &ax0, &ax1, &ax2);
     // (1) pose, AABB, cell box per geom in walk order
     for (int i = tid; i < ng; i += nt) {
-      int gi = glist[i];
+      int gi = glist[i + rot < ng ? i + rot : i + rot - ng];
       const ObGeom g = geoms[gi];
       s_gid[i] = gi; s_body[i] = g.body; s_cat[i] = g.cat; s_col[i] = g.col;
       s_walk_of[gi] = i;
@@ -145,16 +159,23 @@ __global__ void __launch_bounds__(OB_THREADS) k_collide(ObBatchDev d) {
       ObCellBox cb;
       cb.level = 0;
       for (int k = 0; k < 6; k++) cb.db[k] = 0;
-      ob_hash_cellbox(ab, W.hash_minlevel, W.hash_maxlevel, &cb);
+      if (stype == OB_SPACE_HASH) ob_hash_cellbox(ab, W.hash_minlevel, W.hash_maxlevel, &cb);
+      else if (stype == OB_SPACE_SAP && ab[ax0 + 1] == OB_INF) cb.level = OB_LEVEL_BIG;   // TmpInfGeomList (:446-449)
       s_cb[i] = cb;
     }
     __syncthreads();
-    // (2) ranks among hashed / big geoms in walk order
+    if (stype == OB_SPACE_SAP) {
+      int *gl = d.glist + (size_t)w * d.NG;
+      for (int i = tid; i < ng; i += nt) gl[i] = s_gid[i];
+      if (tid == 0) W.sap_ndirty = 0;
+    }
+    // (2) ranks among hashed / big geoms in walk order (SAP: finite / infinite on axis 0)
     for (int i = tid; i < ng; i += nt) {
       int h = 0, b = 0;
       for (int j = 0; j < i; j++)
         if (s_en[j]) { if (s_cb[j].level == OB_LEVEL_BIG) b++; else h++; }
       s_hr[i] = h; s_br[i] = b;
+      if (s_en[i] && s_cb[i].level != OB_LEVEL_BIG) { s_sapwalk[h] = i; s_sapkey[h] = (float)s_aabb[6 * i + ax0]; }
       if (i == ng - 1) {
         if (s_en[i]) { if (s_cb[i].level == OB_LEVEL_BIG) b++; else h++; }
         s_misc[1] = h; s_misc[2] = b;
@@ -162,15 +183,62 @@ __global__ void __launch_bounds__(OB_THREADS) k_collide(ObBatchDev d) {
     }
     __syncthreads();
     const int nh = s_misc[1], nbig = s_misc[2];
-    // (3) candidate pairs: collideAABBs filter + first-encounter key
+    // (2b) SAP: sorted position of every finite geom = RadixSort's output order (ob_broad.h)
+    if (stype == OB_SPACE_SAP && nh > 0) {
+      int *st = d.sapstate + (size_t)w * (d.NG + 3);
+      const int nbk = nh + 1;                       // + FLT_MAX sentinel, element index nh
+      const bool valid = st[0] != 0 && st[1] == nbk;
+      if (tid == 0) s_sapkey[nh] = 3.402823466e+38f;
+      for (int p = tid; p < nbk; p += nt) { if (valid) s_sapinit[st[2 + p]] = p; else s_sapinit[p] = p; }
+      __syncthreads();
+      for (int p = 1 + tid; p < nbk; p += nt) {
+        const int e = valid ? st[2 + p] : p, e0 = valid ? st[1 + p] : p - 1;
+        if (s_sapkey[e] < s_sapkey[e0]) s_misc[4] = 1;   // not already sorted
+      }
+      __syncthreads();
+      const bool unsorted = s_misc[4] != 0;
+      for (int t = tid; t < nbk; t += nt) {
+        int pos = s_sapinit[t];
+        if (unsorted) {
+          const uint32_t ot = ob_sap_keyorder(s_sapkey[t]);
+          pos = 0;
+          for (int u = 0; u < nbk; u++)
+            if (u != t && ob_sap_precedes(ob_sap_keyorder(s_sapkey[u]), ot, s_sapinit[u], s_sapinit[t])) pos++;
+        }
+        s_sappos[t] = pos;
+      }
+      __syncthreads();
+      if (unsorted) for (int t = tid; t < nbk; t += nt) st[2 + s_sappos[t]] = t;
+      if (tid == 0) { st[1] = nbk; if (unsorted) st[0] = 1; else if (!valid) st[0] = 0; }
+    }
+    // (3) candidate pairs: the space's filter + the sequence key of the pair's callback
     for (int idx = tid; idx < ng * ng; idx += nt) {
       int a = idx / ng, b = idx - a * ng;
       if (a >= b || !s_en[a] || !s_en[b]) continue;
-      if (!ob_aabb_pair_filter(s_body[a], s_body[b], s_cat[a], s_col[a], s_cat[b], s_col[b], s_aabb + 6 * a, s_aabb + 6 * b))
-        continue;
       ObPairKey key;
       int first_is_a;
-      if (!ob_hash_pair_key(a, b, s_cb[a], s_cb[b], s_hr[a], s_hr[b], s_br[a], s_br[b], nh, nbig, &key, &first_is_a)) continue;
+      if (stype == OB_SPACE_HASH) {
+        if (!ob_aabb_pair_filter(s_body[a], s_body[b], s_cat[a], s_col[a], s_cat[b], s_col[b], s_aabb + 6 * a, s_aabb + 6 * b))
+          continue;
+        if (!ob_hash_pair_key(a, b, s_cb[a], s_cb[b], s_hr[a], s_hr[b], s_br[a], s_br[b], nh, nbig, &key, &first_is_a)) continue;
+      } else if (stype == OB_SPACE_SAP) {
+        if (!ob_pair_filter_noaabb(s_body[a], s_body[b], s_cat[a], s_col[a], s_cat[b], s_col[b])) continue;
+        const bool ia = s_cb[a].level == OB_LEVEL_BIG, ib = s_cb[b].level == OB_LEVEL_BIG;
+        for (int k = 0; k < 7; k++) key.k[k] = 0;
+        if (!ia && !ib) {
+          const int pa = s_sappos[s_hr[a]], pb = s_sappos[s_hr[b]];
+          first_is_a = pa < pb;
+          const int K = first_is_a ? a : b, J = first_is_a ? b : a;
+          if (!ob_sap_sweep_test(s_sapkey[s_hr[J]], s_aabb + 6 * K, s_aabb + 6 * J, ax0, ax1, ax2)) continue;
+          key.k[1] = first_is_a ? pa : pb; key.k[2] = first_is_a ? pb : pa;
+        } else if (ia && ib) { key.k[0] = 1; key.k[1] = s_br[a]; key.k[3] = s_br[b]; first_is_a = 1; }
+        else { key.k[0] = 1; key.k[1] = ia ? s_br[a] : s_br[b]; key.k[2] = 1; key.k[3] = ia ? s_hr[b] : s_hr[a]; first_is_a = ia; }
+      } else {   // dxSimpleSpace::collide (collision_space.cpp:247-268): nested walk of the list
+        if (!ob_aabb_pair_filter(s_body[a], s_body[b], s_cat[a], s_col[a], s_cat[b], s_col[b], s_aabb + 6 * a, s_aabb + 6 * b))
+          continue;
+        for (int k = 0; k < 7; k++) key.k[k] = 0;
+        key.k[1] = a; key.k[2] = b; first_is_a = 1;
+      }
       int slot = atomicAdd(&s_misc[0], 1);
       if (slot < d.NP) {
         s_key[slot] = key;
@@ -331,6 +399,7 @@ ObBackend *obk_create(const ObBatchDev &caps, int device, char *err, size_t errl
   CK(dalloc(b, &d.bconst, W * d.NB));
   CK(dalloc(b, &d.geom, W * d.NG));
   CK(dalloc(b, &d.glist, W * d.NG));
+  CK(dalloc(b, &d.sapstate, W * (d.NG + 3)));
   CK(dalloc(b, &d.policy, (size_t)d.npolicy));
   CK(dalloc(b, &d.joint, W * (d.NJ ? d.NJ : 1)));
   CK(dalloc(b, &d.njoints, W));

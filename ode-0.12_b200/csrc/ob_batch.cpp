@@ -105,6 +105,13 @@ int ob_batch_upload(dxBatch *B) {
       d.body_next = (g->body_next && g->body_next->parent_space == S) ? g->body_next->batch_index : -1;
       hl[(size_t)w * NG + pos] = g->batch_index;
     }
+    if (S->type == dSweepAndPruneSpaceClass) {   // order state of a SAP space: DirtyList then GeomList
+      pos = 0;
+      for (size_t i = 0; i < S->sap_dirty.size(); i++) hl[(size_t)w * NG + pos++] = S->sap_dirty[i]->batch_index;
+      for (size_t i = 0; i < S->sap_geoms.size(); i++) hl[(size_t)w * NG + pos++] = S->sap_geoms[i]->batch_index;
+      o.sap_ndirty = (int)S->sap_dirty.size();
+      o.sap_axes = S->axisorder;
+    }
   }
   std::vector<ObJoint> hj((size_t)nworlds * std::max(NJ, 1));
   std::vector<int> hnj(nworlds, 0);
@@ -183,7 +190,7 @@ dxBatch *ob_batch_create(int nworlds, const dWorldID *worlds, const dSpaceID *sp
   memset(&caps, 0, sizeof caps);
   caps.W = nworlds; caps.NB = NB; caps.NG = NG;
   caps.NC = (desc && desc->max_contacts_per_world > 0) ? desc->max_contacts_per_world : std::max(64, 16 * NG);
-  caps.NP = std::min(NG * (NG - 1) / 2 + 1, std::max(256, 8 * NG));
+  caps.NP = (desc && desc->max_pairs_per_world > 0) ? desc->max_pairs_per_world : std::min(NG * (NG - 1) / 2 + 1, std::max(256, 12 * NG));
   caps.NJ = NJ;
   caps.NR = 3 * caps.NC + 6 * NJ;
   caps.npolicy = 1;
@@ -303,6 +310,16 @@ int dBatchDownload(dBatchID B) {
     // dirty again after its integration: mark the body geoms dirty like dGeomMoved does)
     dxSpace *S = B->spaces[w];
     int ng = B->ng[w];
+    if (S->type == dSweepAndPruneSpaceClass) {
+      const int nd = hw[w].sap_ndirty;
+      S->sap_dirty.clear(); S->sap_geoms.clear();
+      for (int pos = 0; pos < ng; pos++) {
+        dxGeom *g = B->geoms[w][hl[(size_t)w * NG + pos]];
+        if (pos < nd) { g->sap_didx = pos; g->sap_gidx = -1; g->gflags |= GEOM_DIRTY | GEOM_AABB_BAD; S->sap_dirty.push_back(g); }
+        else { g->sap_didx = -1; g->sap_gidx = pos - nd; g->gflags &= ~(GEOM_DIRTY | GEOM_AABB_BAD); S->sap_geoms.push_back(g); }
+      }
+      continue;
+    }
     S->first = 0;
     dxGeom **link = &S->first;
     for (int pos = 0; pos < ng; pos++) {

@@ -121,3 +121,43 @@ OB_HD bool ob_hash_pair_key(int wa, int wb, const ObCellBox &ca, const ObCellBox
   }
   return true;
 }
+
+// ---- dxSAPSpace::collide (collision_sapspace.cpp:425-496) and dxSimpleSpace::collide -------------
+// (collision_space.cpp:247-268), order-exact.
+//
+// SAP: TmpGeomList = enabled geoms with a finite axis-0 maximum, in GeomList order; the others go to
+// TmpInfGeomList.  BoxPruning (:521-567) sorts float-cast axis-0 minima (+ an FLT_MAX sentinel) with
+// RadixSort (:600-830) and sweeps.  RadixSort's output, as a function of its inputs:
+//   * it starts from the permutation the previous call returned (or identity when that is invalid:
+//     first call, or the element count changed, :109-129);
+//   * if the keys read in that order are already non-decreasing it returns that order unchanged (:633-687);
+//   * otherwise the result is the stable LSB-radix order: by IEEE bit pattern, negatives (descending
+//     bits) before non-negatives (ascending bits), equal keys in starting order EXCEPT equal negative
+//     keys, which come out reversed (the MSB pass writes negatives back to front, :751-824).
+// The sweep visits sorted position k, then every later position j while key[j] <= max0[k]
+// (:537-566), so pair (k, j) has sequence key (0, k, j).  Infinite geoms: (1, m, 0, n) against later
+// infinite ones, then (1, m, 1, t) against every finite one in TmpGeomList order (:478-493).
+OB_HD uint32_t ob_sap_keyorder(float f) {
+  const uint32_t u = (uint32_t)ob_f2i(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+// does element u come before element t in RadixSort's output (full-sort case)?
+OB_HD bool ob_sap_precedes(uint32_t ou, uint32_t ot, int init_u, int init_t) {
+  if (ou != ot) return ou < ot;
+  return (ou & 0x80000000u) ? init_u < init_t : init_u > init_t;   // equal negative keys: reversed
+}
+OB_HD void ob_sap_axes(int axisorder, int *ax0, int *ax1, int *ax2) {
+  *ax0 = ((axisorder) & 3) << 1; *ax1 = ((axisorder >> 2) & 3) << 1; *ax2 = ((axisorder >> 4) & 3) << 1;
+}
+// collideGeomsNoAABBs filter (:234-258) minus the callback
+OB_HD bool ob_pair_filter_noaabb(int body1, int body2, uint32_t cat1, uint32_t col1, uint32_t cat2, uint32_t col2) {
+  if (body1 == body2 && body1 >= 0) return false;
+  return ((cat1 & col2) || (cat2 & col1)) != 0;
+}
+// finite x finite: K = geom at the earlier sorted position, J = the later one
+OB_HD bool ob_sap_sweep_test(float key_j, const real *aabb_k, const real *aabb_j, int ax0, int ax1, int ax2) {
+  if (!((real)key_j <= aabb_k[ax0 + 1])) return false;
+  if (!(aabb_k[ax1 + 1] >= aabb_j[ax1] && aabb_j[ax1 + 1] >= aabb_k[ax1])) return false;
+  if (!(aabb_k[ax2 + 1] >= aabb_j[ax2] && aabb_j[ax2 + 1] >= aabb_k[ax2])) return false;
+  return true;
+}

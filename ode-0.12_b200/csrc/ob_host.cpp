@@ -688,12 +688,24 @@ void ob_geom_moved(dxGeom *geom) {   // dGeomMoved, collision_space.cpp:47-75
   while (parent && (geom->gflags & GEOM_DIRTY) == 0) {
     CHECK_NOT_LOCKED(parent);
     geom->gflags |= GEOM_DIRTY | GEOM_AABB_BAD;
-    // dxSpace::dirty: unlink, push-front
-    if (geom->next) geom->next->tome = geom->tome;
-    *geom->tome = geom->next;
-    geom->next = parent->first; geom->tome = &parent->first;
-    if (parent->first) parent->first->tome = &geom->next;
-    parent->first = geom;
+    if (parent->type == dSweepAndPruneSpaceClass) {
+      // dxSAPSpace::dirty (collision_sapspace.cpp:363-387): swap-remove from GeomList, append to DirtyList
+      if (geom->sap_didx < 0) {
+        std::vector<dxGeom *> &G = parent->sap_geoms;
+        dxGeom *last = G.back();
+        G[geom->sap_gidx] = last; last->sap_gidx = geom->sap_gidx;
+        G.pop_back();
+        geom->sap_gidx = -1; geom->sap_didx = (int)parent->sap_dirty.size();
+        parent->sap_dirty.push_back(geom);
+      }
+    } else {
+      // dxSpace::dirty: unlink, push-front
+      if (geom->next) geom->next->tome = geom->tome;
+      *geom->tome = geom->next;
+      geom->next = parent->first; geom->tome = &parent->first;
+      if (parent->first) parent->first->tome = &geom->next;
+      parent->first = geom;
+    }
     geom = parent;
     parent = parent->parent_space;
   }
@@ -712,6 +724,25 @@ void ob_geom_recompute_posr(dxGeom *g) {   // recomputePosr/computePosr, collisi
     g->gflags &= ~GEOM_POSR_BAD;
   }
 }
+void ob_space_clean(dxSpace *s) {
+  // cleanGeoms (collision_space.cpp:405-417, collision_sapspace.cpp:394-423): AABBs are recomputed on
+  // the device inside dSpaceCollide; here only the dirty bookkeeping is done, which is what ordering depends on.
+  if (s->type == dSweepAndPruneSpaceClass) {
+    for (size_t i = 0; i < s->sap_dirty.size(); i++) {
+      dxGeom *g = s->sap_dirty[i];
+      if (g->is_space) ob_space_clean((dxSpace *)g);
+      g->gflags &= ~(GEOM_DIRTY | GEOM_AABB_BAD);
+      g->sap_didx = -1; g->sap_gidx = (int)s->sap_geoms.size();
+      s->sap_geoms.push_back(g);
+    }
+    s->sap_dirty.clear();
+    return;
+  }
+  for (dxGeom *g = s->first; g && (g->gflags & GEOM_DIRTY); g = g->next) {
+    if (g->is_space) ob_space_clean((dxSpace *)g);
+    g->gflags &= ~(GEOM_DIRTY | GEOM_AABB_BAD);
+  }
+}
 extern "C" {
 static void geom_init(dxGeom *g, dSpaceID space, int is_placeable, int type) {
   g->type = type;
@@ -727,6 +758,7 @@ static void geom_init(dxGeom *g, dSpaceID space, int is_placeable, int type) {
   g->category_bits = ~0ul; g->collide_bits = ~0ul;
   g->p[0] = g->p[1] = g->p[2] = g->p[3] = 0;
   g->batch_index = -1;
+  g->sap_didx = g->sap_gidx = -1;
   g->is_space = false;
   if (space) dSpaceAdd(space, g);
 }
@@ -965,6 +997,10 @@ static void space_add(dxSpace *s, dxGeom *g) {   // dxSpace::add, collision_spac
   s->first = g;
   s->count++;
   g->gflags |= GEOM_DIRTY | GEOM_AABB_BAD;
+  if (s->type == dSweepAndPruneSpaceClass) {   // dxSAPSpace::add, collision_sapspace.cpp:303-321
+    g->sap_didx = (int)s->sap_dirty.size(); g->sap_gidx = -1;
+    s->sap_dirty.push_back(g);
+  }
   ob_geom_moved(s);
 }
 static void space_remove(dxSpace *s, dxGeom *g) {   // dxSpace::remove, :185-206
@@ -973,23 +1009,29 @@ static void space_remove(dxSpace *s, dxGeom *g) {   // dxSpace::remove, :185-206
   if (g->next) g->next->tome = g->tome;
   *g->tome = g->next;
   s->count--;
+  if (s->type == dSweepAndPruneSpaceClass) {   // dxSAPSpace::remove, :323-361 (swap with the last element)
+    std::vector<dxGeom *> &L = g->sap_didx >= 0 ? s->sap_dirty : s->sap_geoms;
+    const int idx = g->sap_didx >= 0 ? g->sap_didx : g->sap_gidx;
+    dxGeom *last = L.back();
+    L[idx] = last;
+    if (g->sap_didx >= 0) last->sap_didx = idx; else last->sap_gidx = idx;
+    L.pop_back();
+    g->sap_didx = g->sap_gidx = -1;
+  }
   g->next = 0; g->tome = 0; g->parent_space = 0;
   ob_geom_moved(s);
 }
 void dSpaceAdd(dSpaceID s, dGeomID g) { OB_UASSERT(s && s->is_space, "argument not a space"); space_add(s, g); }
 void dSpaceRemove(dSpaceID s, dGeomID g) { OB_UASSERT(s && s->is_space, "argument not a space"); space_remove(s, g); }
 int dSpaceQuery(dSpaceID s, dGeomID g) { return g->parent_space == s; }
-void dSpaceClean(dSpaceID s) {
-  // cleanGeoms (collision_space.cpp:405-417): AABBs are recomputed on the device inside
-  // dSpaceCollide; here only the dirty flags are cleared, which is what ordering depends on.
-  for (dxGeom *g = s->first; g && (g->gflags & GEOM_DIRTY); g = g->next) {
-    if (g->is_space) dSpaceClean((dxSpace *)g);
-    g->gflags &= ~(GEOM_DIRTY | GEOM_AABB_BAD);
-  }
-}
+void dSpaceClean(dSpaceID s) { ob_space_clean(s); }
 int dSpaceGetNumGeoms(dSpaceID s) { return s->count; }
 dGeomID dSpaceGetGeom(dSpaceID s, int i) {
   OB_UASSERT(i >= 0 && i < s->count, "index out of range");
+  if (s->type == dSweepAndPruneSpaceClass) {   // dxSAPSpace::getGeom, collision_sapspace.cpp:292-301
+    const int nd = (int)s->sap_dirty.size();
+    return i < nd ? s->sap_dirty[i] : s->sap_geoms[i - nd];
+  }
   dxGeom *g = s->first;
   for (int j = 0; j < i; j++) g = g ? g->next : 0;
   return g;

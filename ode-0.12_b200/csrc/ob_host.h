@@ -116,6 +116,7 @@ struct dxGeom {
   unsigned long category_bits, collide_bits;
   dReal p[4];             // sphere r | box sides | plane a,b,c,d | capsule r,l
   int batch_index;
+  int sap_didx, sap_gidx;   // position in the parent SAP space's DirtyList / GeomList (-1: not in that list)
   bool is_space;
   virtual ~dxGeom() {}
 };
@@ -126,6 +127,9 @@ struct dxSpace : public dxGeom {
   int cleanup, sublevel, lock_count;
   int minlevel, maxlevel;   // hash space
   int axisorder;            // SAP
+  // SAP space only (collision_sapspace.cpp:140-160): the two arrays whose order defines the sweep's
+  // tie-breaking; `first/next` stays a plain membership list for these spaces
+  std::vector<dxGeom *> sap_dirty, sap_geoms;
   struct dxBatch *bound_batch;
 };
 
@@ -136,6 +140,7 @@ void ob_message(int num, const char *fmt, ...);
 void ob_set_last_error(const char *fmt, ...);
 void ob_geom_moved(dxGeom *g);                      // dGeomMoved
 void ob_geom_recompute_posr(dxGeom *g);
+void ob_space_clean(dxSpace *s);                    // cleanGeoms
 void ob_body_posr(dxBody *b, dxPosR *out);
 extern uint32_t ob_global_seed;
 void ob_joint_init_type(dxJoint *j);             // ob_joints.cpp

@@ -927,18 +927,39 @@ __global__ void __launch_bounds__(32) k_post(ObBatchDev d, real h) {
     for (int g = gl; g < d.NG; g += G) s_flag[g] = 0;
     __syncwarp();
     const int nm = valid ? s_misc[0] : 0;
-    for (int i = gl; i < nm; i += G) s_flag[s_moved[i]] = 1;
+    const bool sap = valid && W.space_type == OB_SPACE_SAP;
     for (int i = gl; i < ng; i += G) s_old[i] = (unsigned short)glist[i];
     __syncwarp();
-    for (int i = gl; i < ng; i += G) {
-      const int g = s_old[i];
-      if (!s_flag[g]) {
-        int before = 0;
-        for (int j2 = 0; j2 < i; j2++) before += s_flag[s_old[j2]] ? 0 : 1;
-        glist[nm + before] = g;
+    if (sap) {
+      // dxSAPSpace::dirty per moved geom (collision_sapspace.cpp:363-387): swap-remove from the GeomList,
+      // append to the DirtyList; stored as DirtyList followed by GeomList.  (All geoms are clean here:
+      // k_collide ran cleanGeoms.)  The removals form a serial chain, one lane walks it.
+      if (gl == 0) {
+        for (int i = 0; i < ng; i++) s_flag[s_old[i]] = (unsigned char)i;   // position in the GeomList
+        int n = ng;
+        for (int i = 0; i < nm; i++) {
+          const int g = s_moved[i], idx = s_flag[g], last = s_old[n - 1];
+          s_old[idx] = (unsigned short)last; s_flag[last] = (unsigned char)idx;
+          n--;
+        }
+        W.sap_ndirty = nm;
       }
+      __syncwarp();
+      for (int i = gl; i < nm; i += G) glist[i] = s_moved[i];
+      for (int i = gl; i < ng - nm; i += G) glist[nm + i] = s_old[i];
+    } else {
+      for (int i = gl; i < nm; i += G) s_flag[s_moved[i]] = 1;
+      __syncwarp();
+      for (int i = gl; i < ng; i += G) {
+        const int g = s_old[i];
+        if (!s_flag[g]) {
+          int before = 0;
+          for (int j2 = 0; j2 < i; j2++) before += s_flag[s_old[j2]] ? 0 : 1;
+          glist[nm + before] = g;
+        }
+      }
+      for (int i = gl; i < nm; i += G) glist[nm - 1 - i] = s_moved[i];
     }
-    for (int i = gl; i < nm; i += G) glist[nm - 1 - i] = s_moved[i];
     if (gl == 0 && valid) {
       d.nrows[w] = mtot;
       atomicAdd(&d.counters->steps, 1ull);

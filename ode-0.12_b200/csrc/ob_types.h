@@ -57,7 +57,9 @@ struct __attribute__((aligned(16))) ObWorld {
   real erp, cfm, sor_w, max_vel;
   real min_depth; int iters; int nb; int ng;
   uint32_t seed; int hash_minlevel, hash_maxlevel, space_type;
-  int npermjoints; int status; int pad[2];
+  int npermjoints; int status;
+  int sap_ndirty;   // SAP space: glist = DirtyList (first sap_ndirty entries) followed by GeomList
+  int sap_axes;     // SAP space: axis order code (dSAP_AXES_*, collision_sapspace.cpp:273-275)
 };
 // surface parameters of the contact policy, copied into every contact joint
 struct __attribute__((aligned(16))) ObSurface {
@@ -118,6 +120,7 @@ struct ObBatchDev {
   ObBodyConst *bconst;   // [W*NB]
   ObGeom *geom;          // [W*NG]
   int *glist;            // [W*NG] space-list order (head first), geom indices
+  int *sapstate;         // [W*(NG+3)] SAP radix-sort context carried across steps: valid, nb, ranks[NG+1]
   ObPolicy *policy;      // [npolicy]
   ObJoint *joint;        // [W*NJ] permanent joints (ball / hinge / hinge2), creation order
   int *njoints;          // [W]

@@ -18,6 +18,9 @@ GOLDEN = [  # (file stem, scene, steps, worlds, settle) — must match tests/gol
     ("buggy_settle100", "buggy", 30, 1, 100),
     ("capsmix_settle90", "capsmix", 20, 1, 90),
     ("ragdoll_settle110", "ragdoll", 12, 1, 110),
+    ("block64_sap_settle20", "block64@sap", 6, 1, 20),
+    ("mixed_sapz_settle60", "mixed@sapz", 30, 1, 60),
+    ("mixed_simple_settle60", "mixed@simple", 30, 1, 60),
 ]
 
 
@@ -55,7 +58,7 @@ ATAN2_SCENES = ("hinges", "buggy", "ragdoll")
 
 
 def assert_parity(r, what, scene, prec, cand):
-    if prec == "double" and cand == "b200" and scene in ATAN2_SCENES:
+    if prec == "double" and cand == "b200" and scene.split("@")[0] in ATAN2_SCENES:
         assert r["exact_ok"], f"{what}: exact observables differ at {r['first_exact_mismatch']}"
         assert r["max_state_relerr"] <= 1e-9 and r["max_contact_relerr"] <= 1e-9, f"{what}: {r['max_state_relerr']}"
     else:

@@ -17,5 +17,8 @@ for p in single double; do
   $d --scene buggy       --steps 30 --settle 100 --out tests/golden/buggy_settle100_$p.trace
   $d --scene capsmix     --steps 20 --settle 90 --out tests/golden/capsmix_settle90_$p.trace
   $d --scene ragdoll     --steps 12 --settle 110 --out tests/golden/ragdoll_settle110_$p.trace
+  $d --scene block64@sap --steps 6 --settle 20 --out tests/golden/block64_sap_settle20_$p.trace
+  $d --scene mixed@sapz  --steps 30 --settle 60 --out tests/golden/mixed_sapz_settle60_$p.trace
+  $d --scene mixed@simple --steps 30 --settle 60 --out tests/golden/mixed_simple_settle60_$p.trace
 done
 ls -la tests/golden

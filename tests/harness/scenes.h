@@ -69,9 +69,13 @@ static inline dBodyID scene_add_sphere(SceneWorld &sw, dReal density, dReal r, d
   return b;
 }
 
-static inline void scene_world_base(SceneWorld &sw, int w, bool sap = false) {
+// space class used by scene_world_base: 0 hash (default), 1 SAP (XYZ), 2 simple, 3 SAP (ZXY)
+static int g_scene_space_kind = 0;
+static inline void scene_world_base(SceneWorld &sw, int w) {
   sw.world = dWorldCreate();
-  sw.space = sap ? dSweepAndPruneSpaceCreate(0, dSAP_AXES_XYZ) : dHashSpaceCreate(0);
+  sw.space = g_scene_space_kind == 1 ? dSweepAndPruneSpaceCreate(0, dSAP_AXES_XYZ)
+           : g_scene_space_kind == 3 ? dSweepAndPruneSpaceCreate(0, dSAP_AXES_ZXY)
+           : g_scene_space_kind == 2 ? dSimpleSpaceCreate(0) : dHashSpaceCreate(0);
   sw.cgroup = dJointGroupCreate(0);
   sw.seed = scene_world_seed(w);
   dWorldSetGravity(sw.world, 0, 0, (dReal)-9.81);
@@ -351,7 +355,18 @@ static inline ScenePolicy policy_buggy() {
   return p;
 }
 
-static inline int scene_build(const char *name, SceneWorld &sw, int w, ScenePolicy &pol) {
+static inline int scene_build(const char *name_in, SceneWorld &sw, int w, ScenePolicy &pol) {
+  // suffixes select the space class: NAME@sap, NAME@sapz (axis order ZXY), NAME@simple
+  char name[64];
+  strncpy(name, name_in, sizeof name - 1); name[sizeof name - 1] = 0;
+  g_scene_space_kind = 0;
+  if (char *at = strchr(name, '@')) {
+    if (!strcmp(at, "@sap")) g_scene_space_kind = 1;
+    else if (!strcmp(at, "@sapz")) g_scene_space_kind = 3;
+    else if (!strcmp(at, "@simple")) g_scene_space_kind = 2;
+    else return -1;
+    *at = 0;
+  }
   pol = policy_boxstack();
   if (!strcmp(name, "block64")) { scene_block64(sw, w); return 0; }
   if (!strcmp(name, "tower64")) { scene_tower64(sw, w); return 0; }

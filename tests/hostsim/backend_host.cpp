@@ -37,6 +37,7 @@ ObBackend *obk_create(const ObBatchDev &caps, int, char *, size_t) {
   d.bconst = halloc<ObBodyConst>(b, W * d.NB);
   d.geom = halloc<ObGeom>(b, W * d.NG);
   d.glist = halloc<int>(b, W * d.NG);
+  d.sapstate = halloc<int>(b, W * (d.NG + 3));
   d.policy = halloc<ObPolicy>(b, d.npolicy);
   d.joint = halloc<ObJoint>(b, W * (d.NJ ? d.NJ : 1));
   d.njoints = halloc<int>(b, W);
@@ -145,7 +146,18 @@ static bool pair_less(const PairRec &a, const PairRec &b) { return ob_key_less(a
 static void collide_world(ObBatchDev &d, int w) {
   ObWorld &W = d.world[w];
   int ng = W.ng;
-  const int *glist = d.glist + (size_t)w * d.NG;
+  int *glist = d.glist + (size_t)w * d.NG;
+  const int stype = W.space_type;
+  int ax0 = 0, ax1 = 2, ax2 = 4;
+  if (stype == OB_SPACE_SAP) {
+    ob_sap_axes(W.sap_axes, &ax0, &ax1, &ax2);
+    // cleanGeoms: GeomList += DirtyList
+    std::vector<int> cleaned;
+    for (int i = W.sap_ndirty; i < ng; i++) cleaned.push_back(glist[i]);
+    for (int i = 0; i < W.sap_ndirty; i++) cleaned.push_back(glist[i]);
+    for (int i = 0; i < ng; i++) glist[i] = cleaned[i];
+    W.sap_ndirty = 0;
+  }
   std::vector<ObPose> pose(ng);
   std::vector<real> aabb(6 * ng);
   std::vector<ObCellBox> cb(ng);
@@ -157,9 +169,39 @@ static void collide_world(ObBatchDev &d, int w) {
     en[i] = (g.flags & OB_GEOM_ENABLED) && !(g.flags & OB_GEOM_ZERO_SIZED);
     geom_pose(d, w, gi, &pose[i]);
     ob_aabb(pose[i], &aabb[6 * i]);
-    ob_hash_cellbox(&aabb[6 * i], W.hash_minlevel, W.hash_maxlevel, &cb[i]);
+    cb[i].level = 0;
+    if (stype == OB_SPACE_HASH) ob_hash_cellbox(&aabb[6 * i], W.hash_minlevel, W.hash_maxlevel, &cb[i]);
+    else if (stype == OB_SPACE_SAP && aabb[6 * i + ax0 + 1] == OB_INF) cb[i].level = OB_LEVEL_BIG;
     hr[i] = nh; br[i] = nbig;
     if (en[i]) { if (cb[i].level == OB_LEVEL_BIG) nbig++; else nh++; }
+  }
+  // SAP: sorted position of every finite geom (RadixSort's output order, ob_broad.h)
+  std::vector<float> sapkey(nh + 1);
+  std::vector<int> sappos(nh + 1), sapinit(nh + 1);
+  if (stype == OB_SPACE_SAP && nh > 0) {
+    for (int i = 0; i < ng; i++) if (en[i] && cb[i].level != OB_LEVEL_BIG) sapkey[hr[i]] = (float)aabb[6 * i + ax0];
+    sapkey[nh] = 3.402823466e+38f;
+    int *st = d.sapstate + (size_t)w * (d.NG + 3);
+    const int nbk = nh + 1;
+    const bool valid = st[0] != 0 && st[1] == nbk;
+    for (int p = 0; p < nbk; p++) { if (valid) sapinit[st[2 + p]] = p; else sapinit[p] = p; }
+    bool unsorted = false;
+    for (int p = 1; p < nbk; p++) {
+      const int e = valid ? st[2 + p] : p, e0 = valid ? st[1 + p] : p - 1;
+      if (sapkey[e] < sapkey[e0]) unsorted = true;
+    }
+    for (int t = 0; t < nbk; t++) {
+      int pos = sapinit[t];
+      if (unsorted) {
+        pos = 0;
+        for (int u = 0; u < nbk; u++)
+          if (u != t && ob_sap_precedes(ob_sap_keyorder(sapkey[u]), ob_sap_keyorder(sapkey[t]), sapinit[u], sapinit[t])) pos++;
+      }
+      sappos[t] = pos;
+    }
+    if (unsorted) { for (int t = 0; t < nbk; t++) st[2 + sappos[t]] = t; st[0] = 1; }
+    else if (!valid) st[0] = 0;
+    st[1] = nbk;
   }
   std::vector<PairRec> recs;
   for (int a = 0; a < ng; a++) {
@@ -168,10 +210,28 @@ static void collide_world(ObBatchDev &d, int w) {
     for (int b = a + 1; b < ng; b++) {
       if (!en[b]) continue;
       const ObGeom &gb = d.geom[(size_t)w * d.NG + glist[b]];
-      if (!ob_aabb_pair_filter(ga.body, gb.body, ga.cat, ga.col, gb.cat, gb.col, &aabb[6 * a], &aabb[6 * b])) continue;
       PairRec r;
       int first_is_a;
-      if (!ob_hash_pair_key(a, b, cb[a], cb[b], hr[a], hr[b], br[a], br[b], nh, nbig, &r.key, &first_is_a)) continue;
+      if (stype == OB_SPACE_HASH) {
+        if (!ob_aabb_pair_filter(ga.body, gb.body, ga.cat, ga.col, gb.cat, gb.col, &aabb[6 * a], &aabb[6 * b])) continue;
+        if (!ob_hash_pair_key(a, b, cb[a], cb[b], hr[a], hr[b], br[a], br[b], nh, nbig, &r.key, &first_is_a)) continue;
+      } else if (stype == OB_SPACE_SAP) {
+        if (!ob_pair_filter_noaabb(ga.body, gb.body, ga.cat, ga.col, gb.cat, gb.col)) continue;
+        const bool ia = cb[a].level == OB_LEVEL_BIG, ib = cb[b].level == OB_LEVEL_BIG;
+        for (int k = 0; k < 7; k++) r.key.k[k] = 0;
+        if (!ia && !ib) {
+          const int pa = sappos[hr[a]], pb = sappos[hr[b]];
+          first_is_a = pa < pb;
+          const int K = first_is_a ? a : b, J = first_is_a ? b : a;
+          if (!ob_sap_sweep_test(sapkey[hr[J]], &aabb[6 * K], &aabb[6 * J], ax0, ax1, ax2)) continue;
+          r.key.k[1] = first_is_a ? pa : pb; r.key.k[2] = first_is_a ? pb : pa;
+        } else if (ia && ib) { r.key.k[0] = 1; r.key.k[1] = br[a]; r.key.k[3] = br[b]; first_is_a = 1; }
+        else { r.key.k[0] = 1; r.key.k[1] = ia ? br[a] : br[b]; r.key.k[2] = 1; r.key.k[3] = ia ? hr[b] : hr[a]; first_is_a = ia; }
+      } else {
+        if (!ob_aabb_pair_filter(ga.body, gb.body, ga.cat, ga.col, gb.cat, gb.col, &aabb[6 * a], &aabb[6 * b])) continue;
+        for (int k = 0; k < 7; k++) r.key.k[k] = 0;
+        r.key.k[1] = a; r.key.k[2] = b; first_is_a = 1;
+      }
       r.o1 = first_is_a ? glist[a] : glist[b];
       r.o2 = first_is_a ? glist[b] : glist[a];
       recs.push_back(r);
@@ -484,8 +544,21 @@ static void step_world(ObBatchDev &d, int w, real h, int taps) {
   int ng = W.ng;
   std::vector<char> ismoved(d.NG, 0);
   std::vector<int> nl;
-  for (int i = (int)moved.size() - 1; i >= 0; i--) { nl.push_back(moved[i]); ismoved[moved[i]] = 1; }
-  for (int i = 0; i < ng; i++) if (!ismoved[glist[i]]) nl.push_back(glist[i]);
+  if (W.space_type == OB_SPACE_SAP) {
+    // dxSAPSpace::dirty per moved geom (collision_sapspace.cpp:363-387); stored as DirtyList + GeomList
+    std::vector<int> G(glist, glist + ng), posof(d.NG, -1);
+    for (int i = 0; i < ng; i++) posof[G[i]] = i;
+    for (size_t i = 0; i < moved.size(); i++) {
+      const int g = moved[i], idx = posof[g], last = G.back();
+      G[idx] = last; posof[last] = idx; G.pop_back();
+      nl.push_back(g);
+    }
+    for (size_t i = 0; i < G.size(); i++) nl.push_back(G[i]);
+    W.sap_ndirty = (int)moved.size();
+  } else {
+    for (int i = (int)moved.size() - 1; i >= 0; i--) { nl.push_back(moved[i]); ismoved[moved[i]] = 1; }
+    for (int i = 0; i < ng; i++) if (!ismoved[glist[i]]) nl.push_back(glist[i]);
+  }
   for (int i = 0; i < ng; i++) glist[i] = nl[i];
   d.counters->steps += 1;
 }
