@@ -406,6 +406,31 @@ dGeomID dCreateCapsule(dSpaceID space, dReal radius, dReal length);
 void dGeomCapsuleSetParams(dGeomID ccylinder, dReal radius, dReal length);
 void dGeomCapsuleGetParams(dGeomID ccylinder, dReal *radius, dReal *length);
 
+/* ---- trimesh (collision_trimesh.h:51-153).  Vertex and index arrays are COPIED at build time
+ * (the reference borrows them); per-triangle callbacks are not supported by the GPU colliders. */
+typedef int dTriCallback(dGeomID TriMesh, dGeomID RefObject, int TriangleIndex);
+typedef void dTriArrayCallback(dGeomID TriMesh, dGeomID RefObject, const int *TriIndices, int TriCount);
+typedef int dTriRayCallback(dGeomID TriMesh, dGeomID Ray, int TriangleIndex, dReal u, dReal v);
+dTriMeshDataID dGeomTriMeshDataCreate(void);
+void dGeomTriMeshDataDestroy(dTriMeshDataID g);
+void dGeomTriMeshDataBuildSingle(dTriMeshDataID g, const void *Vertices, int VertexStride, int VertexCount,
+                                 const void *Indices, int IndexCount, int TriStride);
+void dGeomTriMeshDataBuildSingle1(dTriMeshDataID g, const void *Vertices, int VertexStride, int VertexCount,
+                                  const void *Indices, int IndexCount, int TriStride, const void *Normals);
+void dGeomTriMeshDataBuildDouble(dTriMeshDataID g, const void *Vertices, int VertexStride, int VertexCount,
+                                 const void *Indices, int IndexCount, int TriStride);
+void dGeomTriMeshDataBuildDouble1(dTriMeshDataID g, const void *Vertices, int VertexStride, int VertexCount,
+                                  const void *Indices, int IndexCount, int TriStride, const void *Normals);
+void dGeomTriMeshDataBuildSimple(dTriMeshDataID g, const dReal *Vertices, int VertexCount,
+                                 const dTriIndex *Indices, int IndexCount);
+void dGeomTriMeshDataPreprocess(dTriMeshDataID g);
+void dGeomTriMeshDataUpdate(dTriMeshDataID g);
+dGeomID dCreateTriMesh(dSpaceID space, dTriMeshDataID Data, dTriCallback *Callback,
+                       dTriArrayCallback *ArrayCallback, dTriRayCallback *RayCallback);
+void dGeomTriMeshSetData(dGeomID g, dTriMeshDataID Data);
+dTriMeshDataID dGeomTriMeshGetData(dGeomID g);
+int dGeomTriMeshGetTriangleCount(dGeomID g);
+
 /* ======================================================================== */
 /* (2) batched-world entry points (added; SURVEY.md §8(b) last row)          */
 /* ======================================================================== */
@@ -465,6 +490,7 @@ int dBatchCollideAndQuickStep(dBatchID, dReal h, int nsteps, int *status_per_wor
 #define dBATCH_ERR_CONTACT_OVERFLOW 1
 #define dBATCH_ERR_ROW_OVERFLOW 2
 #define dBATCH_ERR_PAIR_OVERFLOW 4
+#define dBATCH_ERR_BVH_STACK 8        /* trimesh tree deeper than the traversal stack */
 /* bulk SoA I/O, host buffers: [world][body][k]; body order = creation order.
  * pos 3, quat 4, lvel 3, avel 3 (13 reals per body). */
 int dBatchNumBodies(dBatchID);            /* per world (max over worlds) */

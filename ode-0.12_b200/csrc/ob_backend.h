@@ -25,7 +25,11 @@ enum { OBK_PHASE_COLLIDE = 1, OBK_PHASE_STEP = 2 };
 int obk_run_phases(ObBackend *, real h, int phases, int taps, char *err, size_t errlen);
 // dCollide for one pair of posed geoms, outside any batch (one-thread kernel on the GPU).
 // out must hold OB_MAXC_LOCAL contacts.  Returns the contact count or -1.
-int obk_collide_pair(const ObPose *a, const ObPose *b, int flags, ObCg *out, char *err, size_t errlen);
+// meshes2: trimesh data of a / b (ObPose::mesh must be 0 / 1), or null when neither is a trimesh
+int obk_collide_pair(const ObPose *a, const ObPose *b, int flags, ObCg *out, const ObMeshDev *meshes2, char *err, size_t errlen);
+// copy one trimesh (vertices, triangles, tree) to the execution side; io->aabbc/aabbe are kept, pointers filled
+int obk_mesh_upload(const float *verts, int nverts, const int *tris, int ntris, const ObBvNode *nodes, int device, ObMeshDev *io);
+void obk_mesh_free(ObMeshDev *m);
 int obk_sync(ObBackend *);
 // bulk body-state I/O in API order ([world][creation-index body]); nbody[w] = bodies in world w.
 // Host buffers; a null pointer skips that field.

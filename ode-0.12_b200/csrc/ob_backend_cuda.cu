@@ -87,6 +87,7 @@ __device__ inline int block_excl_scan(int v, int *s_w, int *total) {
 
 __device__ inline void geom_pose_dev(const ObGeom &g, const ObBodyDyn *bd, ObPose *o) {
   o->type = g.type;
+  o->mesh = g.mesh;
   for (int k = 0; k < 4; k++) o->p[k] = g.p[k];
   if (g.body >= 0) {
     const ObBodyDyn &b = bd[g.body];
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(OB_THREADS) k_collide(ObBatchDev d) {
       geom_pose_dev(g, bd, &p);
       s_pose[i] = p;
       real ab[6];
-      ob_aabb(p, ab);
+      ob_aabb(p, ab, d.meshes);
       for (int k = 0; k < 6; k++) s_aabb[6 * i + k] = ab[k];
       ObCellBox cb;
       cb.level = 0;
@@ -282,7 +283,9 @@ __global__ void __launch_bounds__(OB_THREADS) k_collide(ObBatchDev d) {
           }
         }
         int swapped;
-        if (!connected) n = ob_collide_pair(s_pose[s_walk_of[o1]], s_pose[s_walk_of[o2]], maxc, cg, &swapped);
+        int bverr = 0;
+        if (!connected) n = ob_collide_pair(s_pose[s_walk_of[o1]], s_pose[s_walk_of[o2]], maxc, cg, &swapped, d.meshes, &bverr);
+        if (bverr) atomicOr(&W.status, OB_ERR_BVH_STACK);
       }
       int total;
       int off = block_excl_scan(n, s_misc + 8, &total);
@@ -401,6 +404,7 @@ ObBackend *obk_create(const ObBatchDev &caps, int device, char *err, size_t errl
   CK(dalloc(b, &d.glist, W * d.NG));
   CK(dalloc(b, &d.sapstate, W * (d.NG + 3)));
   CK(dalloc(b, &d.policy, (size_t)d.npolicy));
+  CK(dalloc(b, &d.meshes, (size_t)(d.nmesh ? d.nmesh : 1)));
   CK(dalloc(b, &d.joint, W * (d.NJ ? d.NJ : 1)));
   CK(dalloc(b, &d.njoints, W));
   CK(dalloc(b, &d.padjstart, W * (d.NB + 1)));
@@ -572,14 +576,15 @@ int obk_run_phases(ObBackend *b, real h, int phases, int taps, char *err, size_t
 // dCollide outside a batch: one pair, one thread (the per-element collider functions are the same
 // ones k_collide runs; there is no host implementation to fall back to)
 struct PairCtx { ObPose *pose; ObCg *cg; int *n; cudaStream_t stream; bool ok; };
-__global__ void k_collide_pair(const ObPose *pose, int flags, ObCg *out, int *n) {
-  int swapped;
+__global__ void k_collide_pair(const ObPose *pose, int flags, ObCg *out, int *n, ObMeshDev m0, ObMeshDev m1) {
+  int swapped, bverr = 0;
   ObCg cg[OB_MAXC_LOCAL];
-  const int c = ob_collide_pair(pose[0], pose[1], flags, cg, &swapped);
+  ObMeshDev meshes[2] = {m0, m1};
+  const int c = ob_collide_pair(pose[0], pose[1], flags, cg, &swapped, meshes, &bverr);
   for (int i = 0; i < c; i++) out[i] = cg[i];
-  *n = c;
+  *n = bverr ? -2 : c;
 }
-int obk_collide_pair(const ObPose *a, const ObPose *b, int flags, ObCg *out, char *err, size_t errlen) {
+int obk_collide_pair(const ObPose *a, const ObPose *b, int flags, ObCg *out, const ObMeshDev *meshes2, char *err, size_t errlen) {
   static PairCtx C = {0, 0, 0, 0, false};
   if (!C.ok) {
     int ndev = 0;
@@ -594,14 +599,40 @@ int obk_collide_pair(const ObPose *a, const ObPose *b, int flags, ObCg *out, cha
   C.pose[0] = *a; C.pose[1] = *b;
   int maxc = flags & 0xffff;
   if (maxc > OB_MAXC_LOCAL) maxc = OB_MAXC_LOCAL;
+  ObMeshDev m0, m1;
+  memset(&m0, 0, sizeof m0); memset(&m1, 0, sizeof m1);
+  if (meshes2) { m0 = meshes2[0]; m1 = meshes2[1]; }
   // page-locked buffers are mapped into the device address space (unified addressing): the kernel reads and writes them directly
-  k_collide_pair<<<1, 1, 0, C.stream>>>(C.pose, (flags & ~0xffff) | maxc, C.cg, C.n);
+  k_collide_pair<<<1, 1, 0, C.stream>>>(C.pose, (flags & ~0xffff) | maxc, C.cg, C.n, m0, m1);
   g_launches++;
   cudaError_t e = cudaStreamSynchronize(C.stream);
   if (e != cudaSuccess) { snprintf(err, errlen, "k_collide_pair failed: %s", cudaGetErrorString(e)); return -1; }
   const int n = *C.n;
+  if (n == -2) { snprintf(err, errlen, "trimesh tree deeper than the traversal stack"); return -1; }
   for (int i = 0; i < n; i++) out[i] = C.cg[i];
   return n;
+}
+
+int obk_mesh_upload(const float *verts, int nverts, const int *tris, int ntris, const ObBvNode *nodes, int device, ObMeshDev *io) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return -1;
+  if (cudaSetDevice(device) != cudaSuccess) return -1;
+  float *dv = 0; int *dt = 0; ObBvNode *dn = 0;
+  if (cudaMalloc((void **)&dv, sizeof(float) * 3 * (size_t)nverts) != cudaSuccess) return -1;
+  if (cudaMalloc((void **)&dt, sizeof(int) * 3 * (size_t)ntris) != cudaSuccess) { cudaFree(dv); return -1; }
+  if (cudaMalloc((void **)&dn, sizeof(ObBvNode) * (size_t)(ntris - 1)) != cudaSuccess) { cudaFree(dv); cudaFree(dt); return -1; }
+  cudaError_t e = cudaMemcpy(dv, verts, sizeof(float) * 3 * (size_t)nverts, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dt, tris, sizeof(int) * 3 * (size_t)ntris, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dn, nodes, sizeof(ObBvNode) * (size_t)(ntris - 1), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(dv); cudaFree(dt); cudaFree(dn); return -1; }
+  io->verts = dv; io->tris = dt; io->nodes = dn; io->nverts = nverts; io->ntris = ntris;
+  return 0;
+}
+void obk_mesh_free(ObMeshDev *m) {
+  if (m->verts) cudaFree((void *)m->verts);
+  if (m->tris) cudaFree((void *)m->tris);
+  if (m->nodes) cudaFree((void *)m->nodes);
+  m->verts = 0; m->tris = 0; m->nodes = 0;
 }
 
 // Bulk state I/O copies straight between the caller's buffers and the packed device staging

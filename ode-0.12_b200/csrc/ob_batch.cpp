@@ -8,6 +8,7 @@
 #include "ob_backend.h"
 #include "ob_host.h"
 #include "ob_batch.h"
+#include "ob_trimesh_host.h"
 
 
 void ob_fill_surface(ObSurface &d, const dSurfaceParameters &s) {
@@ -102,6 +103,11 @@ int ob_batch_upload(dxBatch *B) {
     for (dxGeom *g = S->first; g; g = g->next, pos++) {
       ObGeom &d = hg[(size_t)w * NG + g->batch_index];
       ob_marshal_geom(g, d);
+      if (g->type == dTriMeshClass) {
+        d.mesh = -1;
+        for (size_t mi = 0; mi < B->meshes.size(); mi++) if (B->meshes[mi] == g->tmdata) d.mesh = (int)mi;
+        if (d.mesh < 0) d.flags &= ~OB_GEOM_ENABLED;   // data changed after binding: the drop-in layer rebinds, see batch_matches
+      }
       d.body_next = (g->body_next && g->body_next->parent_space == S) ? g->body_next->batch_index : -1;
       hl[(size_t)w * NG + pos] = g->batch_index;
     }
@@ -186,8 +192,17 @@ dxBatch *ob_batch_create(int nworlds, const dWorldID *worlds, const dSpaceID *sp
     std::reverse(B->joints[w].begin(), B->joints[w].end());
     NB = std::max(NB, B->nb[w]); NG = std::max(NG, ng); NJ = std::max(NJ, (int)B->joints[w].size());
   }
+  for (int w = 0; w < nworlds; w++)
+    for (dxGeom *g = spaces[w]->first; g; g = g->next)
+      if (g->type == dTriMeshClass) {
+        if (!g->tmdata || g->tmdata->ntris < 2) { ob_set_last_error("dBatchCreate: world %d: trimesh geom without built data", w); delete B; return 0; }
+        bool have = false;
+        for (size_t mi = 0; mi < B->meshes.size(); mi++) have |= B->meshes[mi] == g->tmdata;
+        if (!have) B->meshes.push_back(g->tmdata);
+      }
   ObBatchDev caps;
   memset(&caps, 0, sizeof caps);
+  caps.nmesh = (int)B->meshes.size();
   caps.W = nworlds; caps.NB = NB; caps.NG = NG;
   caps.NC = (desc && desc->max_contacts_per_world > 0) ? desc->max_contacts_per_world : std::max(64, 16 * NG);
   caps.NP = (desc && desc->max_pairs_per_world > 0) ? desc->max_pairs_per_world : std::min(NG * (NG - 1) / 2 + 1, std::max(256, 12 * NG));
@@ -210,7 +225,17 @@ dxBatch *ob_batch_create(int nworlds, const dWorldID *worlds, const dSpaceID *sp
   memset(&pol, 0, sizeof pol);
   pol.cat_mask1 = pol.cat_mask2 = ~0u; pol.max_contacts = 8; pol.skip_if_connected = 1;
   pol.surface.mode = 0; pol.surface.mu = OB_INF;
-  int rc = ob_batch_upload(B);
+  int rc = 0;
+  if (!B->meshes.empty()) {
+    std::vector<ObMeshDev> mt(B->meshes.size());
+    for (size_t mi = 0; mi < mt.size(); mi++) {
+      const ObMeshDev *md = ob_trimesh_device(B->meshes[mi], desc ? desc->device : 0);
+      if (!md) { ob_set_last_error("dBatchCreate: trimesh upload failed"); dBatchDestroy(B); return 0; }
+      mt[mi] = *md;
+    }
+    rc |= obk_h2d(B->bk, B->caps.meshes, mt.data(), mt.size() * sizeof(ObMeshDev));
+  }
+  rc |= ob_batch_upload(B);
   rc |= obk_h2d(B->bk, B->caps.policy, &pol, sizeof pol);
   rc |= obk_memset(B->bk, B->caps.counters, 0, sizeof(ObCounters));
   rc |= obk_memset(B->bk, B->caps.npairs, 0, sizeof(int) * nworlds);

@@ -14,6 +14,7 @@ struct dxBatch {
   std::vector<std::vector<dxGeom *> > geoms;   // [w][geom index]
   std::vector<std::vector<dxJoint *> > joints; // [w][permanent joint index]
   std::vector<int> nb, ng;
+  std::vector<struct dxTriMeshData *> meshes; // distinct trimesh data objects referenced by the bound geoms (device table order)
   std::vector<uint32_t> seeds;                 // host mirror of the per-world LCG seeds as last set
   int debug_taps;
   int dropin;

@@ -14,24 +14,10 @@
 // No virtual dispatch: the class pair selects a switch arm.
 #pragma once
 #include "ob_types.h"
+#include "ob_collide_types.h"
+#include "ob_trimesh.h"
 
-struct ObPose {  // world pose + parameters of one geom, gathered per thread
-  int type;
-  real pos[3];
-  real R[12];
-  real p[4];
-};
-
-struct ObCg {  // contact being generated (dContactGeom minus the geom ids)
-  real pos[3];
-  real normal[3];
-  real depth;
-  int side1, side2;
-};
-
-#define OB_MAXC_LOCAL 8   // contacts kept per pair on the primitive path (box-box emits <= 8)
-
-OB_HD void ob_aabb(const ObPose &g, real *aabb) {
+OB_HD void ob_aabb(const ObPose &g, real *aabb, const ObMeshDev *meshes = 0) {
   switch (g.type) {
     case OB_GEOM_SPHERE: {
       real r = g.p[0];
@@ -71,6 +57,19 @@ OB_HD void ob_aabb(const ObPose &g, real *aabb) {
         aabb[4] = (p[2] > 0) ? -OB_INF : -p[3];
         aabb[5] = (p[2] > 0) ? p[3] : OB_INF;
       }
+    } break;
+    case OB_GEOM_TRIMESH: {
+      // dxTriMesh::computeAABB, collision_trimesh_opcode.cpp:668-692
+      const ObMeshDev &d = meshes[g.mesh];
+      const real *R = g.R;
+      real c[3];
+      ob_mul0_331(c, R, d.aabbc);
+      real xrange = ob_fabs(R[0] * d.aabbe[0]) + ob_fabs(R[1] * d.aabbe[1]) + ob_fabs(R[2] * d.aabbe[2]);
+      real yrange = ob_fabs(R[4] * d.aabbe[0]) + ob_fabs(R[5] * d.aabbe[1]) + ob_fabs(R[6] * d.aabbe[2]);
+      real zrange = ob_fabs(R[8] * d.aabbe[0]) + ob_fabs(R[9] * d.aabbe[1]) + ob_fabs(R[10] * d.aabbe[2]);
+      aabb[0] = c[0] + g.pos[0] - xrange; aabb[1] = c[0] + g.pos[0] + xrange;
+      aabb[2] = c[1] + g.pos[1] - yrange; aabb[3] = c[1] + g.pos[1] + yrange;
+      aabb[4] = c[2] + g.pos[2] - zrange; aabb[5] = c[2] + g.pos[2] + zrange;
     } break;
     default:
       aabb[0] = aabb[2] = aabb[4] = -OB_INF; aabb[1] = aabb[3] = aabb[5] = OB_INF;
@@ -790,14 +789,17 @@ OB_HD int ob_pair_max_contacts(int t1, int t2, int maxc) {
   else if (lo == OB_GEOM_BOX && hi == OB_GEOM_CAPSULE) cap = 1;
   else if (lo == OB_GEOM_CAPSULE && hi == OB_GEOM_CAPSULE) cap = 2;
   else if (lo == OB_GEOM_CAPSULE && hi == OB_GEOM_PLANE) cap = 2;
+  else if (hi == OB_GEOM_TRIMESH && (lo == OB_GEOM_SPHERE)) cap = 1 << 15;   // bounded by the caller's max_contacts only
   else cap = 0;
   return cap < maxc ? cap : maxc;
 }
 
 // dCollide for primitive class pairs: table lookup + reverse fix-up.
 // Returns the contact count; `swapped` tells the caller g1/g2 were exchanged.
-OB_HD int ob_collide_pair(const ObPose &o1, const ObPose &o2, int flags, ObCg *c, int *swapped) {
+OB_HD int ob_collide_pair(const ObPose &o1, const ObPose &o2, int flags, ObCg *c, int *swapped, const ObMeshDev *meshes = 0,
+                          int *bverr = 0) {
   int t1 = o1.type, t2 = o2.type, n = 0, rev = 0;
+  int bve = 0;
   for (int i = 0; i < OB_MAXC_LOCAL; i++) { c[i].side1 = -1; c[i].side2 = -1; }
   if (t1 == OB_GEOM_SPHERE && t2 == OB_GEOM_SPHERE) n = ob_collide_spheres(o1.pos, o1.p[0], o2.pos, o2.p[0], c);
   else if (t1 == OB_GEOM_SPHERE && t2 == OB_GEOM_BOX) n = ob_collide_sphere_box(o1, o2, c);
@@ -814,6 +816,9 @@ OB_HD int ob_collide_pair(const ObPose &o1, const ObPose &o2, int flags, ObCg *c
   else if (t1 == OB_GEOM_CAPSULE && t2 == OB_GEOM_CAPSULE) n = ob_collide_capsule_capsule(o1, o2, flags, c);
   else if (t1 == OB_GEOM_CAPSULE && t2 == OB_GEOM_PLANE) n = ob_collide_capsule_plane(o1, o2, flags, c);
   else if (t1 == OB_GEOM_PLANE && t2 == OB_GEOM_CAPSULE) { n = ob_collide_capsule_plane(o2, o1, flags, c); rev = 1; }
+  else if (t1 == OB_GEOM_TRIMESH && t2 == OB_GEOM_SPHERE) n = ob_collide_trimesh_sphere(o1, o2, meshes[o1.mesh], flags, c, &bve);
+  else if (t1 == OB_GEOM_SPHERE && t2 == OB_GEOM_TRIMESH) { n = ob_collide_trimesh_sphere(o2, o1, meshes[o2.mesh], flags, c, &bve); rev = 1; }
+  if (bve && bverr) *bverr = 1;
   if (rev) {
     for (int i = 0; i < n; i++) {
       c[i].normal[0] = -c[i].normal[0]; c[i].normal[1] = -c[i].normal[1]; c[i].normal[2] = -c[i].normal[2];

@@ -20,6 +20,7 @@
 #include <map>
 #include <vector>
 #include "ob_batch.h"
+#include "ob_trimesh_host.h"
 
 struct ObDropin {
   dxBatch *B;
@@ -82,6 +83,12 @@ static bool batch_matches(ObDropin *c, int need_contacts) {
   if (c->space->count != B->ng[0]) return false;
   for (dxGeom *g = c->space->first; g; g = g->next)
     if (g->is_space || g->batch_index < 0 || g->batch_index >= B->ng[0] || B->geoms[0][g->batch_index] != g) return false;
+  for (dxGeom *g = c->space->first; g; g = g->next)
+    if (g->type == dTriMeshClass) {
+      bool have = false;
+      for (size_t mi = 0; mi < B->meshes.size(); mi++) have |= B->meshes[mi] == g->tmdata && !g->tmdata->dev.empty();
+      if (!have) return false;
+    }
   std::vector<dxJoint *> js;
   for (dxJoint *j = c->world->firstjoint; j; j = j->next) if (j->type != dJointTypeContact) js.push_back(j);
   std::reverse(js.begin(), js.end());
@@ -164,6 +171,7 @@ void ob_dropin_space_collide(dxSpace *space, void *data, dNearCallback *cb) {
 
 static void geom_pose_host(dxGeom *g, ObPose *o) {
   o->type = g->type;
+  o->mesh = 0;
   for (int i = 0; i < 4; i++) o->p[i] = g->p[i];
   for (int i = 0; i < 3; i++) o->pos[i] = 0;
   for (int i = 0; i < 12; i++) o->R[i] = 0;
@@ -204,7 +212,17 @@ int ob_dropin_collide(dxGeom *o1, dxGeom *o2, int flags, dContactGeom *contact, 
   geom_pose_host(o2, &b);
   ObCg cg[OB_MAXC_LOCAL];
   char err[512] = "";
-  const int n = obk_collide_pair(&a, &b, flags, cg, err, sizeof err);
+  ObMeshDev m2[2];
+  memset(m2, 0, sizeof m2);
+  dxGeom *og[2] = {o1, o2};
+  ObPose *op[2] = {&a, &b};
+  for (int k = 0; k < 2; k++)
+    if (og[k]->type == dTriMeshClass) {
+      const ObMeshDev *md = og[k]->tmdata ? ob_trimesh_device(og[k]->tmdata, 0) : 0;
+      if (!md) { ob_error(0, "dCollide: trimesh data missing or upload failed"); return 0; }
+      m2[k] = *md; op[k]->mesh = k;
+    }
+  const int n = obk_collide_pair(&a, &b, flags, cg, m2, err, sizeof err);
   if (n < 0) { ob_error(0, "dCollide: %s", err); return 0; }
   for (int k = 0; k < n; k++) {
     dContactGeom *d = OB_CONTACT_AT(contact, skip, k);

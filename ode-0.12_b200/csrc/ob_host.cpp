@@ -2,6 +2,7 @@
 // See ob_host.h.  Reference behaviour cited per function group.
 #include "ob_host.h"
 #include "ob_collide.h"
+#include "ob_trimesh_host.h"
 #include "ob_solver.h"
 #include <stdarg.h>
 #include <stdio.h>
@@ -40,8 +41,6 @@ void ob_set_last_error(const char *fmt, ...) {
   char buf[1024]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
   g_last_error = buf;
 }
-#define OB_UASSERT(c, msg) do { if (!(c)) ob_debug(2 /*d_ERR_UASSERT*/, msg " in %s()", __FUNCTION__); } while (0)
-#define OB_AASSERT(c) OB_UASSERT(c, "Bad argument(s)")
 
 // ---------------------------------------------------------------------------------
 // init / RNG (ode/src/odeinit.cpp, ode/src/misc.cpp:31-117)
@@ -758,10 +757,14 @@ static void geom_init(dxGeom *g, dSpaceID space, int is_placeable, int type) {
   g->category_bits = ~0ul; g->collide_bits = ~0ul;
   g->p[0] = g->p[1] = g->p[2] = g->p[3] = 0;
   g->batch_index = -1;
+  g->tmdata = 0;
   g->sap_didx = g->sap_gidx = -1;
   g->is_space = false;
   if (space) dSpaceAdd(space, g);
 }
+}  // extern "C"
+dxGeom *ob_geom_create(dxSpace *space, int is_placeable, int type) { dxGeom *g = new dxGeom; geom_init(g, space, is_placeable, type); return g; }
+extern "C" {
 static void geom_body_remove(dxGeom *g) {
   if (g->body) {
     dxGeom **last = &g->body->geom, *x = g->body->geom;
@@ -918,7 +921,11 @@ void dGeomGetAABB(dGeomID g, dReal aabb[6]) {
   if (g->is_space) { for (int i = 0; i < 6; i++) aabb[i] = (i & 1) ? OB_INF : -OB_INF; return; }
   ObPose o;
   geom_host_pose(g, &o);
-  ob_aabb(o, aabb);
+  o.mesh = 0;
+  ObMeshDev md;
+  memset(&md, 0, sizeof md);
+  if (g->type == dTriMeshClass && g->tmdata) for (int k = 0; k < 3; k++) { md.aabbc[k] = g->tmdata->aabbc[k]; md.aabbe[k] = g->tmdata->aabbe[k]; }
+  ob_aabb(o, aabb, &md);
 }
 
 dGeomID dCreateSphere(dSpaceID space, dReal radius) {

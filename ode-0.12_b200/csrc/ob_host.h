@@ -115,6 +115,7 @@ struct dxGeom {
   dReal aabb[6];
   unsigned long category_bits, collide_bits;
   dReal p[4];             // sphere r | box sides | plane a,b,c,d | capsule r,l
+  struct dxTriMeshData *tmdata;   // trimesh geoms: the shared mesh data
   int batch_index;
   int sap_didx, sap_gidx;   // position in the parent SAP space's DirtyList / GeomList (-1: not in that list)
   bool is_space;
@@ -138,7 +139,10 @@ void ob_error(int num, const char *fmt, ...);      // dError: message, then exit
 void ob_debug(int num, const char *fmt, ...);      // dDebug: message, then abort() unless handled
 void ob_message(int num, const char *fmt, ...);
 void ob_set_last_error(const char *fmt, ...);
+#define OB_UASSERT(c, msg) do { if (!(c)) ob_debug(2 /*d_ERR_UASSERT*/, msg " in %s()", __FUNCTION__); } while (0)
+#define OB_AASSERT(c) OB_UASSERT(c, "Bad argument(s)")
 void ob_geom_moved(dxGeom *g);                      // dGeomMoved
+dxGeom *ob_geom_create(dxSpace *space, int is_placeable, int type);
 void ob_geom_recompute_posr(dxGeom *g);
 void ob_space_clean(dxSpace *s);                    // cleanGeoms
 void ob_body_posr(dxBody *b, dxPosR *out);

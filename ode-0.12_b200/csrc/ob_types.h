@@ -23,7 +23,7 @@ enum {  // body flags, ode/src/objects.h:38-48
 enum { OB_GEOM_SPHERE = 0, OB_GEOM_BOX = 1, OB_GEOM_CAPSULE = 2, OB_GEOM_PLANE = 4, OB_GEOM_RAY = 5, OB_GEOM_TRIMESH = 8 };
 enum { OB_GEOM_ENABLED = 1, OB_GEOM_HAS_OFFSET = 2, OB_GEOM_ZERO_SIZED = 4 };
 enum { OB_SPACE_HASH = 0, OB_SPACE_SAP = 1, OB_SPACE_SIMPLE = 2 };
-enum { OB_ERR_CONTACT_OVERFLOW = 1, OB_ERR_ROW_OVERFLOW = 2, OB_ERR_PAIR_OVERFLOW = 4 };
+enum { OB_ERR_CONTACT_OVERFLOW = 1, OB_ERR_ROW_OVERFLOW = 2, OB_ERR_PAIR_OVERFLOW = 4, OB_ERR_BVH_STACK = 8 };
 
 // mutable body state (13 reals of ODE state + cached R + accumulators)
 struct __attribute__((aligned(16))) ObBodyDyn {
@@ -47,7 +47,7 @@ struct __attribute__((aligned(16))) ObBodyConst {
 };
 struct __attribute__((aligned(16))) ObGeom {
   int type; int body; uint32_t cat, col;        // body = -1: static
-  int flags; int body_next; int pad[2];         // body_next: next geom of the same body (dGeomGetBodyNext)
+  int flags; int body_next; int mesh; int pad;  // body_next: next geom of the same body (dGeomGetBodyNext); mesh: trimesh data index
   real p[4];                                     // sphere r | box lx,ly,lz | plane a,b,c,d | capsule r,l
   real pos[4];                                   // static pose or offset pose
   real R[12];
@@ -122,6 +122,8 @@ struct ObBatchDev {
   int *glist;            // [W*NG] space-list order (head first), geom indices
   int *sapstate;         // [W*(NG+3)] SAP radix-sort context carried across steps: valid, nb, ranks[NG+1]
   ObPolicy *policy;      // [npolicy]
+  struct ObMeshDev *meshes;   // [nmesh] trimesh data table (ob_trimesh.h); geoms refer to it by index
+  int nmesh;
   ObJoint *joint;        // [W*NJ] permanent joints (ball / hinge / hinge2), creation order
   int *njoints;          // [W]
   unsigned short *padjstart; // [W*(NB+1)] per body: range into padj

@@ -340,6 +340,51 @@ static inline void scene_ragdoll(SceneWorld &sw, int w) {
   }
 }
 
+// ---- trimesh scenes ---------------------------------------------------------------------------
+// One shared dTriMeshData per (n, spacing) in the process, like config 3's shared terrain: an n x n
+// vertex grid, two triangles per cell, height = amp*sin(fx*x)*cos(fy*y) + noise (hashed per vertex).
+struct SceneTerrain { int n; double spacing; dTriMeshDataID data; std::vector<float> verts; std::vector<dTriIndex> idx; };
+static inline dTriMeshDataID scene_terrain_data(int n, double spacing, double amp, double fx, double fy, double noise) {
+  static std::vector<SceneTerrain *> cache;
+  for (size_t i = 0; i < cache.size(); i++) if (cache[i]->n == n && cache[i]->spacing == spacing) return cache[i]->data;
+  SceneTerrain *t = new SceneTerrain;
+  t->n = n; t->spacing = spacing;
+  xs32 rng(7);
+  const double half = 0.5 * (n - 1) * spacing;
+  for (int j = 0; j < n; j++)
+    for (int i = 0; i < n; i++) {
+      const double x = i * spacing - half, y = j * spacing - half;
+      const double z = amp * sin(fx * x) * cos(fy * y) + noise * ((rng.next() >> 8) * (1.0 / 16777216.0) - 0.5);
+      t->verts.push_back((float)x); t->verts.push_back((float)y); t->verts.push_back((float)z);
+    }
+  for (int j = 0; j + 1 < n; j++)
+    for (int i = 0; i + 1 < n; i++) {
+      const dTriIndex a = (dTriIndex)(j * n + i), b = a + 1, c = a + n, d = c + 1;
+      t->idx.push_back(a); t->idx.push_back(b); t->idx.push_back(c);
+      t->idx.push_back(b); t->idx.push_back(d); t->idx.push_back(c);
+    }
+  t->data = dGeomTriMeshDataCreate();
+  dGeomTriMeshDataBuildSingle(t->data, t->verts.data(), 3 * sizeof(float), n * n, t->idx.data(), (int)t->idx.size(), 3 * sizeof(dTriIndex));
+  cache.push_back(t);
+  return t->data;
+}
+
+// spheres of assorted sizes dropped on a rotated, translated terrain mesh (dCollideSTL + the BVH order)
+static inline void scene_terrain_spheres(SceneWorld &sw, int w) {
+  scene_world_base(sw, w);
+  xs32 rng(sw.seed ^ 0x7E44A1u);
+  scene_add_geom(sw, dCreatePlane(sw.space, 0, 0, 1, (dReal)-3));
+  dGeomID mesh = scene_add_geom(sw, dCreateTriMesh(sw.space, scene_terrain_data(25, 0.5, 0.45, 0.9, 0.7, 0.12), 0, 0, 0));
+  dMatrix3 R;
+  dRFromAxisAndAngle(R, (dReal)0.1, (dReal)-0.05, 1, (dReal)0.6);
+  dGeomSetRotation(mesh, R);
+  dGeomSetPosition(mesh, (dReal)0.3, (dReal)-0.2, (dReal)0.1);
+  for (int i = 0; i < 14; i++) {
+    dBodyID b = scene_add_sphere(sw, 2, rng.uni(0.12, 0.7), rng.uni(-4, 4), rng.uni(-4, 4), rng.uni(1.5, 5));
+    dBodySetLinearVel(b, rng.uni(-1, 1), rng.uni(-1, 1), 0);
+  }
+}
+
 static inline ScenePolicy policy_buggy() {
   // ode/demo/demo_buggy.cpp:96-103
   ScenePolicy p;
@@ -375,6 +420,7 @@ static inline int scene_build(const char *name_in, SceneWorld &sw, int w, SceneP
   if (!strcmp(name, "mixed_maxc4")) { scene_mixed(sw, w, 12, 6); pol = policy_crash(); return 0; }
   if (!strcmp(name, "chain")) { scene_chain(sw, w, 8); return 0; }
   if (!strcmp(name, "hinges")) { scene_hinges(sw, w); return 0; }
+  if (!strcmp(name, "terrain_spheres")) { scene_terrain_spheres(sw, w); return 0; }
   if (!strcmp(name, "capsmix")) { scene_capsmix(sw, w); return 0; }
   if (!strcmp(name, "ragdoll")) { scene_ragdoll(sw, w); pol = policy_crash(); return 0; }
   if (!strcmp(name, "buggy")) { scene_buggy(sw, w); pol = policy_buggy(); return 0; }

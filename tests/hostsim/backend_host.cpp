@@ -39,6 +39,7 @@ ObBackend *obk_create(const ObBatchDev &caps, int, char *, size_t) {
   d.glist = halloc<int>(b, W * d.NG);
   d.sapstate = halloc<int>(b, W * (d.NG + 3));
   d.policy = halloc<ObPolicy>(b, d.npolicy);
+  d.meshes = halloc<ObMeshDev>(b, d.nmesh ? d.nmesh : 1);
   d.joint = halloc<ObJoint>(b, W * (d.NJ ? d.NJ : 1));
   d.njoints = halloc<int>(b, W);
   d.padjstart = halloc<unsigned short>(b, W * (d.NB + 1));
@@ -122,6 +123,7 @@ int obk_add_forces(ObBackend *b, const real *f3, const real *t3) {
 static void geom_pose(const ObBatchDev &d, int w, int gi, ObPose *o) {
   const ObGeom &g = d.geom[(size_t)w * d.NG + gi];
   o->type = g.type;
+  o->mesh = g.mesh;
   for (int k = 0; k < 4; k++) o->p[k] = g.p[k];
   if (g.body >= 0) {
     const ObBodyDyn &b = d.bdyn[(size_t)w * d.NB + g.body];
@@ -168,7 +170,7 @@ static void collide_world(ObBatchDev &d, int w) {
     const ObGeom &g = d.geom[(size_t)w * d.NG + gi];
     en[i] = (g.flags & OB_GEOM_ENABLED) && !(g.flags & OB_GEOM_ZERO_SIZED);
     geom_pose(d, w, gi, &pose[i]);
-    ob_aabb(pose[i], &aabb[6 * i]);
+    ob_aabb(pose[i], &aabb[6 * i], d.meshes);
     cb[i].level = 0;
     if (stype == OB_SPACE_HASH) ob_hash_cellbox(&aabb[6 * i], W.hash_minlevel, W.hash_maxlevel, &cb[i]);
     else if (stype == OB_SPACE_SAP && aabb[6 * i + ax0 + 1] == OB_INF) cb[i].level = OB_LEVEL_BIG;
@@ -269,7 +271,9 @@ static void collide_world(ObBatchDev &d, int w) {
     ObCg cg[OB_MAXC_LOCAL];
     int swapped;
     int flags = pol.max_contacts > OB_MAXC_LOCAL ? OB_MAXC_LOCAL : pol.max_contacts;
-    int n = ob_collide_pair(pose[walk_of[o1]], pose[walk_of[o2]], flags, cg, &swapped);
+    int bverr = 0;
+    int n = ob_collide_pair(pose[walk_of[o1]], pose[walk_of[o2]], flags, cg, &swapped, d.meshes, &bverr);
+    if (bverr) W.status |= OB_ERR_BVH_STACK;
     for (int k = 0; k < n; k++) {
       if (nc >= d.NC) { W.status |= OB_ERR_CONTACT_OVERFLOW; break; }
       ObContact &c = cout[nc++];
@@ -571,10 +575,24 @@ int obk_run_phases(ObBackend *b, real h, int phases, int taps, char *, size_t) {
   }
   return 0;
 }
-int obk_collide_pair(const ObPose *a, const ObPose *b, int flags, ObCg *out, char *, size_t) {
-  int swapped;
-  return ob_collide_pair(*a, *b, flags, out, &swapped);
+int obk_collide_pair(const ObPose *a, const ObPose *b, int flags, ObCg *out, const ObMeshDev *meshes2, char *, size_t) {
+  int swapped, bverr = 0;
+  int maxc = flags & 0xffff;
+  if (maxc > OB_MAXC_LOCAL) maxc = OB_MAXC_LOCAL;
+  const int n = ob_collide_pair(*a, *b, (flags & ~0xffff) | maxc, out, &swapped, meshes2, &bverr);
+  return bverr ? -1 : n;
 }
+int obk_mesh_upload(const float *verts, int nverts, const int *tris, int ntris, const ObBvNode *nodes, int, ObMeshDev *io) {
+  float *v = (float *)malloc(sizeof(float) * 3 * (size_t)nverts);
+  int *t = (int *)malloc(sizeof(int) * 3 * (size_t)ntris);
+  ObBvNode *n = (ObBvNode *)malloc(sizeof(ObBvNode) * (size_t)(ntris - 1));
+  memcpy(v, verts, sizeof(float) * 3 * (size_t)nverts);
+  memcpy(t, tris, sizeof(int) * 3 * (size_t)ntris);
+  memcpy(n, nodes, sizeof(ObBvNode) * (size_t)(ntris - 1));
+  io->verts = v; io->tris = t; io->nodes = n; io->nverts = nverts; io->ntris = ntris;
+  return 0;
+}
+void obk_mesh_free(ObMeshDev *m) { free((void *)m->verts); free((void *)m->tris); free((void *)m->nodes); m->verts = 0; m->tris = 0; m->nodes = 0; }
 int obk_step(ObBackend *b, real h, int nsteps, int taps, char *, size_t) {
   ObBatchDev &d = b->d;
   for (int s = 0; s < nsteps; s++)
