@@ -16,6 +16,7 @@
 #include "ob_types.h"
 #include "ob_collide_types.h"
 #include "ob_trimesh.h"
+#include "ob_trimesh_box.h"
 
 OB_HD void ob_aabb(const ObPose &g, real *aabb, const ObMeshDev *meshes = 0) {
   switch (g.type) {
@@ -789,7 +790,7 @@ OB_HD int ob_pair_max_contacts(int t1, int t2, int maxc) {
   else if (lo == OB_GEOM_BOX && hi == OB_GEOM_CAPSULE) cap = 1;
   else if (lo == OB_GEOM_CAPSULE && hi == OB_GEOM_CAPSULE) cap = 2;
   else if (lo == OB_GEOM_CAPSULE && hi == OB_GEOM_PLANE) cap = 2;
-  else if (hi == OB_GEOM_TRIMESH && (lo == OB_GEOM_SPHERE)) cap = 1 << 15;   // bounded by the caller's max_contacts only
+  else if (hi == OB_GEOM_TRIMESH && (lo == OB_GEOM_SPHERE || lo == OB_GEOM_BOX)) cap = 1 << 15;   // bounded by the caller's max_contacts only
   else cap = 0;
   return cap < maxc ? cap : maxc;
 }
@@ -818,6 +819,8 @@ OB_HD int ob_collide_pair(const ObPose &o1, const ObPose &o2, int flags, ObCg *c
   else if (t1 == OB_GEOM_PLANE && t2 == OB_GEOM_CAPSULE) { n = ob_collide_capsule_plane(o2, o1, flags, c); rev = 1; }
   else if (t1 == OB_GEOM_TRIMESH && t2 == OB_GEOM_SPHERE) n = ob_collide_trimesh_sphere(o1, o2, meshes[o1.mesh], flags, c, &bve);
   else if (t1 == OB_GEOM_SPHERE && t2 == OB_GEOM_TRIMESH) { n = ob_collide_trimesh_sphere(o2, o1, meshes[o2.mesh], flags, c, &bve); rev = 1; }
+  else if (t1 == OB_GEOM_TRIMESH && t2 == OB_GEOM_BOX) n = ob_collide_trimesh_box(o1, o2, meshes[o1.mesh], flags, c, &bve);
+  else if (t1 == OB_GEOM_BOX && t2 == OB_GEOM_TRIMESH) { n = ob_collide_trimesh_box(o2, o1, meshes[o2.mesh], flags, c, &bve); rev = 1; }
   if (bve && bverr) *bverr = 1;
   if (rev) {
     for (int i = 0; i < n; i++) {

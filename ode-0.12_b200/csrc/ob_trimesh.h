@@ -9,6 +9,7 @@
 //   sphere  : dCollideSTL  ode/src/collision_trimesh_sphere.cpp:244-538 over
 //             SphereCollider::_CollideNoPrimitiveTest OPCODE/OPC_SphereCollider.cpp:474-488
 //             (primitive tests are off, collision_trimesh_opcode.cpp:46)
+//   box     : ob_trimesh_box.h
 // Traversal is pos-then-neg depth first with an explicit stack; a volume that fully contains a node
 // box dumps the whole subtree (OPC_VolumeCollider.cpp:70-80).  Triangles are consumed in visit order
 // until the caller's max-contacts is reached, as the reference does.
@@ -35,13 +36,16 @@ struct ObBvIter {
   int overflow;
 };
 OB_HD void ob_bv_begin(ObBvIter &it) { it.sp = 0; it.overflow = 0; it.stack[it.sp++] = 0u; }
-// next touched triangle in the reference's visit order, or -1.  Q: overlap(node), contains(node)
+// next touched triangle in the reference's visit order, or -1.  Q: overlap(node), contains(node), prim(mesh, tri)
 template <class Q>
 OB_HD int ob_bv_next(const ObMeshDev &m, ObBvIter &it, const Q &q) {
   while (it.sp > 0) {
     const uint32_t item = it.stack[--it.sp];
     const uint32_t dump = item & OB_BV_DUMP, ref = item & ~OB_BV_DUMP;
-    if (ref & 1u) return (int)(ref >> 1);
+    if (ref & 1u) {   // leaf: primitive test unless the subtree is being dumped
+      if (dump || q.prim(m, (int)(ref >> 1))) return (int)(ref >> 1);
+      continue;
+    }
     const ObBvNode nd = m.nodes[ref >> 1];
     uint32_t d = dump;
     if (!d) {
@@ -99,6 +103,7 @@ struct ObSphereQuery {
     else { s = tmp - n.e[2]; if (s > 0.0f) { d += s * s; if (d > r2) return false; } }
     return d <= r2;
   }
+  OB_HD bool prim(const ObMeshDev &, int) const { return true; }   // SetPrimitiveTests(false)
   OB_HD float sqd(float px, float py, float pz) const {
     return ((c[0] - px) * (c[0] - px) + (c[1] - py) * (c[1] - py) + (c[2] - pz) * (c[2] - pz));
   }

@@ -21,6 +21,9 @@ GOLDEN = [  # (file stem, scene, steps, worlds, settle) — must match tests/gol
     ("block64_sap_settle20", "block64@sap", 6, 1, 20),
     ("mixed_sapz_settle60", "mixed@sapz", 30, 1, 60),
     ("mixed_simple_settle60", "mixed@simple", 30, 1, 60),
+    ("terrain_spheres_settle70", "terrain_spheres", 25, 1, 70),
+    ("terrain_boxes_settle70", "terrain_boxes", 15, 1, 70),
+    ("buggy_terrain_w2_settle90", "buggy_terrain", 30, 2, 90),
 ]
 
 
@@ -54,7 +57,7 @@ def _built():
 # traces and, for the long live comparisons, in lock-step with the reference (every step starts
 # from the reference's pre-step body state, SURVEY 8d parity protocol with K = 1) so that a
 # last-bit difference cannot be amplified by chaotic dynamics into a different contact set.
-ATAN2_SCENES = ("hinges", "buggy", "ragdoll")
+ATAN2_SCENES = ("hinges", "buggy", "ragdoll", "buggy_terrain")
 
 
 def assert_parity(r, what, scene, prec, cand):

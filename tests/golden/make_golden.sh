@@ -20,5 +20,8 @@ for p in single double; do
   $d --scene block64@sap --steps 6 --settle 20 --out tests/golden/block64_sap_settle20_$p.trace
   $d --scene mixed@sapz  --steps 30 --settle 60 --out tests/golden/mixed_sapz_settle60_$p.trace
   $d --scene mixed@simple --steps 30 --settle 60 --out tests/golden/mixed_simple_settle60_$p.trace
+  $d --scene terrain_spheres --steps 25 --settle 70 --out tests/golden/terrain_spheres_settle70_$p.trace
+  $d --scene terrain_boxes --steps 15 --settle 70 --out tests/golden/terrain_boxes_settle70_$p.trace
+  $d --scene buggy_terrain --steps 30 --settle 90 --worlds 2 --out tests/golden/buggy_terrain_w2_settle90_$p.trace
 done
 ls -la tests/golden

@@ -385,6 +385,60 @@ static inline void scene_terrain_spheres(SceneWorld &sw, int w) {
   }
 }
 
+// boxes (and a few spheres) tumbling on the terrain mesh: dCollideBTL (all three clipping cases)
+static inline void scene_terrain_boxes(SceneWorld &sw, int w) {
+  scene_world_base(sw, w);
+  xs32 rng(sw.seed ^ 0xB0C5E5u);
+  scene_add_geom(sw, dCreatePlane(sw.space, 0, 0, 1, (dReal)-3));
+  dGeomID mesh = scene_add_geom(sw, dCreateTriMesh(sw.space, scene_terrain_data(25, 0.5, 0.45, 0.9, 0.7, 0.12), 0, 0, 0));
+  dGeomSetPosition(mesh, (dReal)-0.1, (dReal)0.25, 0);
+  for (int i = 0; i < 10; i++) {
+    dBodyID b = scene_add_box(sw, 2, rng.uni(0.2, 1.2), rng.uni(0.2, 1.2), rng.uni(0.2, 0.9), rng.uni(-3.5, 3.5), rng.uni(-3.5, 3.5), rng.uni(1.2, 4));
+    dQuaternion q = {rng.uni(-1, 1), rng.uni(-1, 1), rng.uni(-1, 1), rng.uni(-1, 1)};
+    dBodySetQuaternion(b, q);
+    dBodySetAngularVel(b, rng.uni(-2, 2), rng.uni(-2, 2), rng.uni(-2, 2));
+  }
+  for (int i = 0; i < 4; i++) scene_add_sphere(sw, 2, rng.uni(0.15, 0.5), rng.uni(-3, 3), rng.uni(-3, 3), rng.uni(1.5, 4));
+}
+
+// config 3: demo_buggy-style vehicle (box chassis + 4 sphere wheels on hinge2, demo_buggy.cpp:226-294)
+// dropped on a shared trimesh terrain (n x n vertex grid, 1 m spacing,
+// 0.5*sin(0.07x)*cos(0.05y) + 0.15*noise); world w spawns on a lattice over the terrain
+static inline void scene_buggy_terrain(SceneWorld &sw, int w, int n) {
+  scene_world_base(sw, w);
+  xs32 rng(sw.seed ^ 0x00C0B066u);
+  scene_add_geom(sw, dCreateTriMesh(sw.space, scene_terrain_data(n, 1.0, 0.5, 0.07, 0.05, 0.15), 0, 0, 0));
+  const int lat = (n - 8) / 4 > 1 ? (n - 8) / 4 : 1;
+  const dReal ox = (dReal)(((w % lat) - 0.5 * (lat - 1)) * 4.0) + rng.uni(-0.5, 0.5);
+  const dReal oy = (dReal)((((w / lat) % lat) - 0.5 * (lat - 1)) * 4.0) + rng.uni(-0.5, 0.5);
+  const dReal L = (dReal)0.7, Wd = (dReal)0.5, H = (dReal)0.2, R = (dReal)0.18, Z = (dReal)1.1;
+  dBodyID chassis = scene_add_box(sw, 1 / (L * Wd * H), L, Wd, H, ox, oy, Z);
+  const dReal wx[4] = {(dReal)(0.5 * L), (dReal)(0.5 * L), (dReal)(-0.5 * L), (dReal)(-0.5 * L)};
+  const dReal wy[4] = {(dReal)(0.5 * Wd), (dReal)(-0.5 * Wd), (dReal)(0.5 * Wd), (dReal)(-0.5 * Wd)};
+  for (int i = 0; i < 4; i++) {
+    dBodyID wheel = scene_add_sphere(sw, (dReal)(0.2 / (4.0 / 3.0 * 3.14159265358979 * R * R * R)), R, ox + wx[i], oy + wy[i], Z - H * (dReal)0.5);
+    dQuaternion q;
+    dQFromAxisAndAngle(q, 1, 0, 0, (dReal)(3.14159265358979 * 0.5));
+    dBodySetQuaternion(wheel, q);
+    dJointID j = dJointCreateHinge2(sw.world, 0);
+    dJointAttach(j, chassis, wheel);
+    const dReal *a = dBodyGetPosition(wheel);
+    dJointSetHinge2Anchor(j, a[0], a[1], a[2]);
+    dJointSetHinge2Axis1(j, 0, 0, 1);
+    dJointSetHinge2Axis2(j, 0, 1, 0);
+    dJointSetHinge2Param(j, dParamSuspensionERP, (dReal)0.4);
+    dJointSetHinge2Param(j, dParamSuspensionCFM, (dReal)0.8);
+    if (i >= 2) { dJointSetHinge2Param(j, dParamLoStop, 0); dJointSetHinge2Param(j, dParamHiStop, 0); }
+    else {
+      dJointSetHinge2Param(j, dParamVel, rng.uni(-0.5, 0.5)); dJointSetHinge2Param(j, dParamFMax, (dReal)0.2);
+      dJointSetHinge2Param(j, dParamLoStop, (dReal)-0.75); dJointSetHinge2Param(j, dParamHiStop, (dReal)0.75);
+      dJointSetHinge2Param(j, dParamFudgeFactor, (dReal)0.1);
+    }
+    dJointSetHinge2Param(j, dParamVel2, (dReal)-3.0); dJointSetHinge2Param(j, dParamFMax2, (dReal)0.1);
+    sw.joints.push_back(j);
+  }
+}
+
 static inline ScenePolicy policy_buggy() {
   // ode/demo/demo_buggy.cpp:96-103
   ScenePolicy p;
@@ -420,6 +474,9 @@ static inline int scene_build(const char *name_in, SceneWorld &sw, int w, SceneP
   if (!strcmp(name, "mixed_maxc4")) { scene_mixed(sw, w, 12, 6); pol = policy_crash(); return 0; }
   if (!strcmp(name, "chain")) { scene_chain(sw, w, 8); return 0; }
   if (!strcmp(name, "hinges")) { scene_hinges(sw, w); return 0; }
+  if (!strcmp(name, "buggy_terrain")) { scene_buggy_terrain(sw, w, 48); pol = policy_buggy(); pol.max_contacts = 10; return 0; }
+  if (!strcmp(name, "buggy_terrain256")) { scene_buggy_terrain(sw, w, 256); pol = policy_buggy(); pol.max_contacts = 10; return 0; }
+  if (!strcmp(name, "terrain_boxes")) { scene_terrain_boxes(sw, w); return 0; }
   if (!strcmp(name, "terrain_spheres")) { scene_terrain_spheres(sw, w); return 0; }
   if (!strcmp(name, "capsmix")) { scene_capsmix(sw, w); return 0; }
   if (!strcmp(name, "ragdoll")) { scene_ragdoll(sw, w); pol = policy_crash(); return 0; }

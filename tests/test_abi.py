@@ -18,7 +18,7 @@ def declared_symbols():
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
     txt = "\n".join(l for l in txt.splitlines() if not l.lstrip().startswith("#"))
     names = re.findall(r"\b(d[A-Z]\w+|dB200\w+)\s*\(", txt)
-    skip = {"dNearCallback", "dErrorHandlerFn"}
+    skip = {"dNearCallback", "dErrorHandlerFn", "dTriCallback", "dTriArrayCallback", "dTriRayCallback"}
     return sorted(set(n for n in names if n not in skip))
 
 
