@@ -31,11 +31,26 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 LIBDIR = os.path.join(ROOT, "ode-0.12_b200", "lib")
+# BASELINE.json configs that shard over independent worlds.  The headline (default) is configs[1];
+# --config 3 / 4 time configs[2] / configs[3] with the same harness.  (configs[0] is one small world:
+# latency only; configs[4] is the large single world.)
+CONFIGS = {
+    2: dict(scene="stack32", worlds=4096, settle=300, cap=192, geoms=41,
+            desc="configs[1]: {W} independent worlds/GPU x (plane + 32-box stack + 8 spheres), dHashSpace, boxstack contact policy maxc 8"),
+    3: dict(scene="buggy_terrain256", worlds=65536, settle=200, cap=48, geoms=6,
+            desc="configs[2]: {W} independent worlds/GPU x (hinge2 buggy: box chassis + 4 sphere wheels) on one shared 256x256-vertex "
+                 "trimesh terrain (130050 triangles, OPCODE-equivalent colliders), dHashSpace, buggy contact policy maxc 10"),
+    4: dict(scene="ragdoll", worlds=16384, settle=150, cap=160, geoms=37,
+            desc="configs[3]: {W} independent worlds/GPU x (20-link capsule/box chain on 19 ball/hinge joints + 16-box pile), dHashSpace, "
+                 "crash contact policy maxc 4"),
+}
 SCENE = "stack32"
 WORLDS_PER_GPU = 4096
 SETTLE = 300
 H = 0.01
 CONTACTS_CAP = 192   # stack32 peaks at ~150 contacts/world (measured on the reference); overflow is reported
+GEOMS_PER_WORLD = 41
+CONFIG_DESC = CONFIGS[2]["desc"]
 # algorithmic bytes per unit, dSINGLE: A body-step, B geom-step, C contact,
 # D row x SOR iteration, ASM row assembly
 A_B, B_B, C_B, D_B, ASM_B = 136, 80, 128, 224, 128
@@ -130,6 +145,18 @@ def shard(rank, world_size, per_gpu=WORLDS_PER_GPU):
     return rank * per_gpu, per_gpu
 
 
+def reduce_metrics(dist, vals, sums, device):
+    """the only inter-rank traffic of the benchmark: MAX of the timings, SUM of the counters (worlds are
+    independent, so the data path has no collective).  dist=None: single process."""
+    if dist is None:
+        return vals, sums
+    import torch
+
+    tv = torch.tensor(vals, device=device); ts = torch.tensor(sums, device=device)
+    dist.all_reduce(tv, op=dist.ReduceOp.MAX); dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+    return tv.cpu().numpy(), ts.cpu().numpy()
+
+
 def run_b200(args):
     rank = int(os.environ.get("RANK", "0"))
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
@@ -190,7 +217,7 @@ def run_b200(args):
     names = [lib.dBatchKernelName(k).decode() for k in range(nk)]
     kt = {names[k]: kms[k] / max(kl[k], 1) * 1e-3 for k in range(nk)}      # seconds per launch
     nl = max(kl[0], 1)
-    ng_per_world = 41
+    ng_per_world = GEOMS_PER_WORLD
     # algorithmic bytes per launch (SURVEY 8d terms): collide = geoms (B) + contacts written (C/2);
     # prep = bodies read (A/2) + contacts read (C/2) + row assembly; sor = D x iterations per row;
     # post = bodies read+written (A/2)
@@ -252,12 +279,7 @@ def run_b200(args):
 
     vals = np.array([elapsed_ms, t_e2e], dtype=np.float64)
     sums = np.array([c["body_steps"], c["contacts"], ce["body_steps"], c["rows"], launches, c["overflow_worlds"]], dtype=np.float64)
-    if dist is not None:
-        import torch
-
-        tv = torch.tensor(vals, device="cuda"); ts = torch.tensor(sums, device="cuda")
-        dist.all_reduce(tv, op=dist.ReduceOp.MAX); dist.all_reduce(ts, op=dist.ReduceOp.SUM)
-        vals, sums = tv.cpu().numpy(), ts.cpu().numpy()
+    vals, sums = reduce_metrics(dist, vals, sums, "cuda")
     if rank == 0:
         t = vals[0] * 1e-3
         out = {
@@ -267,8 +289,7 @@ def run_b200(args):
             "n_gpus": world_size, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": vals[0] / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"configs[1]: {args.worlds} independent worlds/GPU x (plane + 32-box stack + 8 spheres), "
-                                   f"dHashSpace, boxstack contact policy maxc 8, quickstep 20 it, h={H}, settled {SETTLE} steps",
+            "config": {"workload": CONFIG_DESC.format(W=args.worlds) + f", quickstep 20 it, h={H}, settled {SETTLE} steps",
                        "worlds_per_gpu": args.worlds, "bodies_per_world": nb, "rows_per_world_step": sums[3] / max(c["steps"] * world_size, 1),
                        "contacts_per_world_step": sums[1] / max(c["steps"] * world_size, 1),
                        "cache": "per-step working set (rows written+read) ~%.0f MB/GPU > 126 MB L2" % (c["rows"] / args.steps * 128 * 2 / 1e6 + 70),
@@ -338,7 +359,7 @@ def run_reference(args):
         "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": r["seconds"] * 1e3 / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"configs[1] sample: {nproc * worlds_each} worlds x (plane + 32-box stack + 8 spheres), reference ODE 0.12 dSINGLE on host cores"},
+        "config": {"workload": "sample of " + CONFIG_DESC.format(W=nproc * worlds_each) + ", reference ODE 0.12 dSINGLE on host cores"},
         "cpu_baseline": {"value": v, "unit": "body-steps/s", "cores": nproc, "kind": "reference", "sample": sample},
         "e2e": {"value": v, "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -350,8 +371,13 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--worlds", type=int, default=WORLDS_PER_GPU)
+    ap.add_argument("--worlds", type=int, default=0)
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
     a = ap.parse_args()
+    cfg = CONFIGS[a.config]
+    SCENE, SETTLE, CONTACTS_CAP, GEOMS_PER_WORLD, CONFIG_DESC = cfg["scene"], cfg["settle"], cfg["cap"], cfg["geoms"], cfg["desc"]
+    if a.worlds <= 0:
+        a.worlds = cfg["worlds"]
     if a.impl == "reference":
         run_reference(a)
     else:

@@ -107,7 +107,11 @@ __device__ inline void geom_pose_dev(const ObGeom &g, const ObBodyDyn *bd, ObPos
 }
 
 // ------------------------------------------------------------------------------------
+// MESH: the batch has trimesh geoms (narrowphase with the BVH colliders, up to OB_MAXC_LOCAL contacts per
+// pair); otherwise the primitive-only narrowphase with 8 contact slots per pair (box-box emits at most 8)
+template <bool MESH>
 __global__ void __launch_bounds__(OB_THREADS) k_collide(ObBatchDev d) {
+  constexpr int CGCAP = MESH ? OB_MAXC_LOCAL : 8;
   extern __shared__ __align__(16) unsigned char smem[];
   const CollideSmem L = collide_smem(d.NG, d.NP);
   ObPose *s_pose = (ObPose *)(smem + L.pose);
@@ -262,10 +266,10 @@ __global__ void __launch_bounds__(OB_THREADS) k_collide(ObBatchDev d) {
     // (5) narrowphase per pair in callback order, ordered compaction into contact joints
     const ObPolicy pol = d.policy[0];
     ObContact *cout = d.contacts + (size_t)w * d.NC;
-    const int maxc = pol.max_contacts > OB_MAXC_LOCAL ? OB_MAXC_LOCAL : pol.max_contacts;
+    const int maxc = pol.max_contacts > CGCAP ? CGCAP : pol.max_contacts;
     for (int base = 0; base < np; base += nt) {
       int p = base + tid;
-      ObCg cg[OB_MAXC_LOCAL];
+      ObCg cg[CGCAP];
       int n = 0, o1 = 0, o2 = 0;
       if (p < np) {
         o1 = s_sorted[p].x; o2 = s_sorted[p].y;
@@ -284,7 +288,7 @@ __global__ void __launch_bounds__(OB_THREADS) k_collide(ObBatchDev d) {
         }
         int swapped;
         int bverr = 0;
-        if (!connected) n = ob_collide_pair(s_pose[s_walk_of[o1]], s_pose[s_walk_of[o2]], maxc, cg, &swapped, d.meshes, &bverr);
+        if (!connected) n = ob_collide_pair_t<MESH, CGCAP>(s_pose[s_walk_of[o1]], s_pose[s_walk_of[o2]], maxc, cg, &swapped, d.meshes, &bverr);
         if (bverr) atomicOr(&W.status, OB_ERR_BVH_STACK);
       }
       int total;
@@ -457,7 +461,8 @@ ObBackend *obk_create(const ObBatchDev &caps, int device, char *err, size_t errl
              b->smem_collide, b->smem_prep, b->smem_sor, (size_t)prop.sharedMemPerBlockOptin);
     goto fail;
   }
-  CK(cudaFuncSetAttribute(k_collide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_collide));
+  CK(cudaFuncSetAttribute(k_collide<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_collide));
+  CK(cudaFuncSetAttribute(k_collide<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_collide));
 #define OB_SETSMEM(GG) \
   CK(cudaFuncSetAttribute(k_prep<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_prep)); \
   CK(cudaFuncSetAttribute(k_sor<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sor)); \
@@ -469,7 +474,7 @@ ObBackend *obk_create(const ObBatchDev &caps, int device, char *err, size_t errl
   CK(cudaFuncSetAttribute(k_sched<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sched));
   {
     // grid: every world gets its own CTA up to 16 resident CTAs per SM worth of blocks, beyond that grid-stride
-    int cap = prop.multiProcessorCount * 16;
+    int cap = prop.multiProcessorCount * 32;
     b->grid = (int)W < cap ? (int)W : cap;
   }
   return b;
@@ -530,7 +535,13 @@ template <int G> static void launch_step(ObBackend *b, real h, int taps, int pha
   cudaEvent_t *ev = b->ev + 2;
   const int W = b->d.W;
   if (b->ktiming) cudaEventRecord(ev[0], b->stream);
-  if (phases & OBK_PHASE_COLLIDE) { k_collide<<<b->grid, OB_THREADS, b->smem_collide, b->stream>>>(b->d); g_launches++; }
+  if (phases & OBK_PHASE_COLLIDE) {
+    // CTA width follows the world size: the widest loop is the ng*ng candidate-pair scan
+    const int ct = b->d.NG <= 8 ? 32 : (b->d.NG <= 20 ? 64 : OB_THREADS);
+    if (b->d.nmesh) k_collide<true><<<b->grid, ct, b->smem_collide, b->stream>>>(b->d);
+    else k_collide<false><<<b->grid, ct, b->smem_collide, b->stream>>>(b->d);
+    g_launches++;
+  }
   if (b->ktiming) cudaEventRecord(ev[1], b->stream);
   if (phases & OBK_PHASE_STEP) {
     k_prep<G><<<b->grid_step, 32, b->smem_prep, b->stream>>>(b->d, h, taps);

@@ -797,11 +797,12 @@ OB_HD int ob_pair_max_contacts(int t1, int t2, int maxc) {
 
 // dCollide for primitive class pairs: table lookup + reverse fix-up.
 // Returns the contact count; `swapped` tells the caller g1/g2 were exchanged.
-OB_HD int ob_collide_pair(const ObPose &o1, const ObPose &o2, int flags, ObCg *c, int *swapped, const ObMeshDev *meshes = 0,
-                          int *bverr = 0) {
+// MESH = false compiles the trimesh arms out (kernels for worlds without trimesh geoms); CGCAP = size of c[]
+template <bool MESH, int CGCAP>
+OB_HD int ob_collide_pair_t(const ObPose &o1, const ObPose &o2, int flags, ObCg *c, int *swapped, const ObMeshDev *meshes, int *bverr) {
   int t1 = o1.type, t2 = o2.type, n = 0, rev = 0;
   int bve = 0;
-  for (int i = 0; i < OB_MAXC_LOCAL; i++) { c[i].side1 = -1; c[i].side2 = -1; }
+  for (int i = 0; i < CGCAP; i++) { c[i].side1 = -1; c[i].side2 = -1; }
   if (t1 == OB_GEOM_SPHERE && t2 == OB_GEOM_SPHERE) n = ob_collide_spheres(o1.pos, o1.p[0], o2.pos, o2.p[0], c);
   else if (t1 == OB_GEOM_SPHERE && t2 == OB_GEOM_BOX) n = ob_collide_sphere_box(o1, o2, c);
   else if (t1 == OB_GEOM_BOX && t2 == OB_GEOM_SPHERE) { n = ob_collide_sphere_box(o2, o1, c); rev = 1; }
@@ -817,10 +818,10 @@ OB_HD int ob_collide_pair(const ObPose &o1, const ObPose &o2, int flags, ObCg *c
   else if (t1 == OB_GEOM_CAPSULE && t2 == OB_GEOM_CAPSULE) n = ob_collide_capsule_capsule(o1, o2, flags, c);
   else if (t1 == OB_GEOM_CAPSULE && t2 == OB_GEOM_PLANE) n = ob_collide_capsule_plane(o1, o2, flags, c);
   else if (t1 == OB_GEOM_PLANE && t2 == OB_GEOM_CAPSULE) { n = ob_collide_capsule_plane(o2, o1, flags, c); rev = 1; }
-  else if (t1 == OB_GEOM_TRIMESH && t2 == OB_GEOM_SPHERE) n = ob_collide_trimesh_sphere(o1, o2, meshes[o1.mesh], flags, c, &bve);
-  else if (t1 == OB_GEOM_SPHERE && t2 == OB_GEOM_TRIMESH) { n = ob_collide_trimesh_sphere(o2, o1, meshes[o2.mesh], flags, c, &bve); rev = 1; }
-  else if (t1 == OB_GEOM_TRIMESH && t2 == OB_GEOM_BOX) n = ob_collide_trimesh_box(o1, o2, meshes[o1.mesh], flags, c, &bve);
-  else if (t1 == OB_GEOM_BOX && t2 == OB_GEOM_TRIMESH) { n = ob_collide_trimesh_box(o2, o1, meshes[o2.mesh], flags, c, &bve); rev = 1; }
+  else if (MESH && t1 == OB_GEOM_TRIMESH && t2 == OB_GEOM_SPHERE) n = ob_collide_trimesh_sphere(o1, o2, meshes[o1.mesh], flags, c, &bve);
+  else if (MESH && t1 == OB_GEOM_SPHERE && t2 == OB_GEOM_TRIMESH) { n = ob_collide_trimesh_sphere(o2, o1, meshes[o2.mesh], flags, c, &bve); rev = 1; }
+  else if (MESH && t1 == OB_GEOM_TRIMESH && t2 == OB_GEOM_BOX) n = ob_collide_trimesh_box(o1, o2, meshes[o1.mesh], flags, c, &bve);
+  else if (MESH && t1 == OB_GEOM_BOX && t2 == OB_GEOM_TRIMESH) { n = ob_collide_trimesh_box(o2, o1, meshes[o2.mesh], flags, c, &bve); rev = 1; }
   if (bve && bverr) *bverr = 1;
   if (rev) {
     for (int i = 0; i < n; i++) {
@@ -830,4 +831,8 @@ OB_HD int ob_collide_pair(const ObPose &o1, const ObPose &o2, int flags, ObCg *c
   }
   *swapped = rev;
   return n;
+}
+OB_HD int ob_collide_pair(const ObPose &o1, const ObPose &o2, int flags, ObCg *c, int *swapped, const ObMeshDev *meshes = 0,
+                          int *bverr = 0) {
+  return ob_collide_pair_t<true, OB_MAXC_LOCAL>(o1, o2, flags, c, swapped, meshes, bverr);
 }
