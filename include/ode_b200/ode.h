@@ -458,7 +458,12 @@ typedef struct dBatchDesc {
   int max_contacts_per_world;       /* contact joints per step per world */
   int device;                       /* CUDA device ordinal */
   int max_pairs_per_world;          /* near-callback pairs per step per world (0: 12 x geoms) */
-  int reserved[5];
+  int large_world;                  /* 1: run the (single) world on the grid-wide large-world path: device SAP
+                                     * sweep + graph-coloured SOR (one CTA cannot hold it).  Chosen automatically
+                                     * for a single world with more than 254 bodies.  Contact joints only,
+                                     * dSweepAndPruneSpace only; SOR order differs from the reference's random
+                                     * order, so trajectories match it within a tolerance, not bit for bit. */
+  int reserved[4];
 } dBatchDesc;
 
 typedef struct dBatchCounters {
@@ -492,7 +497,8 @@ int dBatchCollideAndQuickStep(dBatchID, dReal h, int nsteps, int *status_per_wor
 #define dBATCH_ERR_PAIR_OVERFLOW 4
 #define dBATCH_ERR_BVH_STACK 8        /* trimesh tree deeper than the traversal stack */
 /* bulk SoA I/O, host buffers: [world][body][k]; body order = creation order.
- * pos 3, quat 4, lvel 3, avel 3 (13 reals per body). */
+ * pos 3, quat 4, lvel 3, avel 3 (13 reals per body).  Set stores the quaternion as given
+ * (it must be unit; the rotation matrix is rebuilt from it), so Get -> Set restores bit for bit. */
 int dBatchNumBodies(dBatchID);            /* per world (max over worlds) */
 int dBatchGetBodyState(dBatchID, dReal *pos3, dReal *quat4, dReal *lvel3, dReal *avel3);
 int dBatchSetBodyState(dBatchID, const dReal *pos3, const dReal *quat4,
@@ -528,6 +534,14 @@ int dBatchTimerStop(dBatchID, float *ms);
 int dBatchSetKernelTiming(dBatchID, int enable);
 int dBatchGetKernelTimes(dBatchID, double *ms_per_kernel, long long *launches_per_kernel, int nkernels);
 const char *dBatchKernelName(int k);
+/* large-world path (dBatchDesc.large_world): figures of the last step and, while kernel timing is
+ * on, CUDA-event time per phase summed over steps_timed steps:
+ * phase_ms = {geoms + radix sort, pair sweep, narrowphase, colouring, row assembly, SOR, integration} */
+typedef struct dBatchLargeWorldStats {
+  int pairs, contacts, contact_pairs, solved_contacts, colours, colouring_rounds, sor_launches, steps_timed;
+  double phase_ms[7];
+} dBatchLargeWorldStats;
+int dBatchGetLargeWorldStats(dBatchID, dBatchLargeWorldStats *out);   /* -1 for a batch of small worlds */
 /* the CUDA stream the batch launches on (cudaStream_t as void*), so callers can
  * time with events on the launching stream */
 void *dBatchGetStream(dBatchID);

@@ -47,3 +47,7 @@ void obk_set_kernel_timing(ObBackend *, int enable);
 void obk_get_kernel_times(ObBackend *, double *ms, long long *launches);
 const char *obk_kernel_name(int k);
 long long obk_launch_count(void);
+// large-world path: last step's {pairs, contacts, contact pairs, solved contacts, colours, colouring rounds, SOR launches, steps timed}
+// and the per-phase CUDA-event times accumulated while kernel timing is on
+// {geoms+sort, pairs, narrowphase, colouring, assembly, SOR, integration}.  Returns -1 for a small-world batch.
+int obk_large_stats(ObBackend *, int *ints8, double *ms8);

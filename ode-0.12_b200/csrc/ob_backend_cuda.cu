@@ -30,6 +30,7 @@
 #include "ob_broad.h"
 #include "ob_rows.h"
 #include "ob_solver.h"
+#include "ob_large.h"
 #include "ob_step_kernel.cuh"
 
 #define OB_THREADS 128
@@ -341,8 +342,8 @@ __global__ void k_unpack_state(ObBatchDev d, const real *pos3, const real *quat4
     if (avel3) s.avel[k] = avel3[(size_t)i * 3 + k];
   }
   if (quat4) {
+    // q is stored as given (must be unit): a state read with dBatchGetBodyState restores bit for bit
     for (int k = 0; k < 4; k++) s.q[k] = quat4[(size_t)i * 4 + k];
-    ob_safe_normalize4(s.q);
     ob_RfromQ(s.R, s.q);
   }
 }
@@ -373,6 +374,13 @@ struct ObBackend {
   int ktiming;
   double kms[OBK_NKERNELS];
   long long klaunch[OBK_NKERNELS];
+  // one large world (ob_large.h)
+  int large;
+  ObLargeDev L;
+  int *lw_host;        // pinned: scalars + segment table read back for launch sizing
+  int lw_rounds, lw_ncol, lw_stat[8];
+  double lw_ms[8];     // geoms+sort, pairs, narrow, colour, assemble, sor, post (CUDA events, when kernel timing is on)
+  cudaEvent_t lw_ev[9];
 };
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { snprintf(err, errlen, "%s: %s", #call, cudaGetErrorString(e_)); goto fail; } } while (0)
@@ -384,6 +392,7 @@ template <class T> static cudaError_t dalloc(ObBackend *b, T **p, size_t n) {
   *p = (T *)q;
   return e;
 }
+#include "ob_large_kernels.cuh"
 
 ObBackend *obk_create(const ObBatchDev &caps, int device, char *err, size_t errlen) {
   ObBackend *b = new ObBackend;
@@ -395,12 +404,21 @@ ObBackend *obk_create(const ObBatchDev &caps, int device, char *err, size_t errl
   const size_t W = d.W;
   int ndev = 0;
   cudaDeviceProp prop;
-  if (d.NB > 32000 || d.NC > 32000 || d.NR > 65000) { snprintf(err, errlen, "world too large for the CTA-per-world path (NB=%d NC=%d NR=%d)", d.NB, d.NC, d.NR); goto fail2; }
+  b->large = d.large; b->lw_host = 0; b->lw_rounds = 0; b->lw_ncol = 0;
+  for (int k = 0; k < 8; k++) b->lw_stat[k] = 0;
+  memset(&b->L, 0, sizeof b->L);
+  for (int k = 0; k < 9; k++) b->lw_ev[k] = 0;
+  for (int k = 0; k < 8; k++) b->lw_ms[k] = 0;
+  if (!d.large && (d.NB > 32000 || d.NC > 32000 || d.NR > 65000)) { snprintf(err, errlen, "world too large for the CTA-per-world path (NB=%d NC=%d NR=%d)", d.NB, d.NC, d.NR); goto fail2; }
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { snprintf(err, errlen, "no CUDA device available (this library has no CPU fallback)"); goto fail2; }
   CK(cudaSetDevice(device));
   CK(cudaGetDeviceProperties(&prop, device));
   CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
   for (int k = 0; k < 8; k++) CK(cudaEventCreate(&b->ev[k]));
+  if (d.large) {
+    if (lw_create(b, err, errlen)) goto fail;
+    return b;
+  }
   CK(dalloc(b, &d.world, W));
   CK(dalloc(b, &d.bdyn, W * d.NB));
   CK(dalloc(b, &d.bconst, W * d.NB));
@@ -481,6 +499,7 @@ ObBackend *obk_create(const ObBatchDev &caps, int device, char *err, size_t errl
 fail:
   for (size_t i = 0; i < b->allocs.size(); i++) cudaFree(b->allocs[i]);
   if (b->st_host) cudaFreeHost(b->st_host);
+  if (b->lw_host) cudaFreeHost(b->lw_host);
   if (b->stream) cudaStreamDestroy(b->stream);
 fail2:
   delete b;
@@ -492,6 +511,8 @@ void obk_destroy(ObBackend *b) {
   cudaStreamSynchronize(b->stream);
   for (size_t i = 0; i < b->allocs.size(); i++) cudaFree(b->allocs[i]);
   if (b->st_host) cudaFreeHost(b->st_host);
+  if (b->lw_host) cudaFreeHost(b->lw_host);
+  for (int k = 0; k < 9; k++) if (b->lw_ev[k]) cudaEventDestroy(b->lw_ev[k]);
   for (int k = 0; k < 8; k++) if (b->ev[k]) cudaEventDestroy(b->ev[k]);
   cudaStreamDestroy(b->stream);
   delete b;
@@ -524,10 +545,17 @@ int obk_timer_stop(ObBackend *b, float *ms) {
 }
 void obk_set_kernel_timing(ObBackend *b, int enable) {
   b->ktiming = enable;
+  for (int k = 0; k < 8; k++) b->lw_ms[k] = 0;
+  b->lw_stat[7] = 0;
   for (int k = 0; k < OBK_NKERNELS; k++) { b->kms[k] = 0; b->klaunch[k] = 0; }
 }
 void obk_get_kernel_times(ObBackend *b, double *ms, long long *l) {
   for (int k = 0; k < OBK_NKERNELS; k++) { ms[k] = b->kms[k]; l[k] = b->klaunch[k]; }
+}
+int obk_large_stats(ObBackend *b, int *ints8, double *ms8) {
+  if (!b->large) return -1;
+  for (int k = 0; k < 8; k++) { ints8[k] = b->lw_stat[k]; ms8[k] = b->lw_ms[k]; }
+  return 0;
 }
 const char *obk_kernel_name(int k) { static const char *n[] = {"k_collide", "k_prep", "k_sched", "k_sor", "k_post"}; return k >= 0 && k < 5 ? n[k] : ""; }
 
@@ -567,6 +595,11 @@ static int run_steps(ObBackend *b, real h, int nsteps, int taps, int phases, cha
   if (getenv("OB_SEQ")) taps |= 2;
   if (getenv("OB_CHECK")) taps |= 4;
   if (getenv("OB_SYNC2")) taps |= 8;
+  if (b->large) {
+    if (phases != (OBK_PHASE_COLLIDE | OBK_PHASE_STEP)) { snprintf(err, errlen, "the large-world path runs whole steps only"); return -1; }
+    for (int s = 0; s < nsteps; s++) if (lw_step(b, h, taps, err, errlen)) return -1;
+    return 0;
+  }
   for (int s = 0; s < nsteps; s++) {
     if (b->tile == 8) launch_step<8>(b, h, taps, phases);
     else if (b->tile == 16) launch_step<16>(b, h, taps, phases);

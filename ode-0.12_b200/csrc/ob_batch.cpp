@@ -75,6 +75,8 @@ void ob_marshal_geom(dxGeom *g, ObGeom &d) {
 // Re-marshal the bound worlds into the device layout and upload (everything except the policy
 // table, seeds and per-step scratch).  Contact joints on the world's joint list are skipped: on
 // the batched path they do not exist, on the drop-in path they are uploaded per step.
+static int ob_batch_upload_check_large(dxBatch *) { return 0; }
+
 int ob_batch_upload(dxBatch *B) {
   const int nworlds = B->caps.W, NB = B->caps.NB, NG = B->caps.NG, NJ = B->caps.NJ;
   std::vector<ObWorld> hw(nworlds);
@@ -142,6 +144,7 @@ int ob_batch_upload(dxBatch *B) {
   rc |= obk_h2d(B->bk, B->caps.bconst, hc.data(), hc.size() * sizeof(ObBodyConst));
   rc |= obk_h2d(B->bk, B->caps.geom, hg.data(), hg.size() * sizeof(ObGeom));
   rc |= obk_h2d(B->bk, B->caps.glist, hl.data(), hl.size() * sizeof(int));
+  if (B->caps.large) return rc;   // no permanent joints on the large-world path
   if (NJ) rc |= obk_h2d(B->bk, B->caps.joint, hj.data(), hj.size() * sizeof(ObJoint));
   rc |= obk_h2d(B->bk, B->caps.njoints, hnj.data(), hnj.size() * sizeof(int));
   rc |= obk_h2d(B->bk, B->caps.padjstart, hps.data(), hps.size() * sizeof(unsigned short));
@@ -205,7 +208,15 @@ dxBatch *ob_batch_create(int nworlds, const dWorldID *worlds, const dSpaceID *sp
   caps.nmesh = (int)B->meshes.size();
   caps.W = nworlds; caps.NB = NB; caps.NG = NG;
   caps.NC = (desc && desc->max_contacts_per_world > 0) ? desc->max_contacts_per_world : std::max(64, 16 * NG);
-  caps.NP = (desc && desc->max_pairs_per_world > 0) ? desc->max_pairs_per_world : std::min(NG * (NG - 1) / 2 + 1, std::max(256, 12 * NG));
+  caps.NP = (desc && desc->max_pairs_per_world > 0) ? desc->max_pairs_per_world : (int)std::min((long long)NG * (NG - 1) / 2 + 1, (long long)std::max(256, 12 * NG));
+  caps.large = (!dropin && nworlds == 1 && ((desc && desc->large_world) || NB > 254 || NG > 255)) ? 1 : 0;
+  if (caps.large) {
+    // the grid-wide path (ob_large.h): contact joints only, SAP space, every body enabled
+    if (NJ) { ob_set_last_error("dBatchCreate: the large-world path supports contact joints only (%d permanent joints bound)", NJ); delete B; return 0; }
+    if (spaces[0]->type != dSweepAndPruneSpaceClass) { ob_set_last_error("dBatchCreate: the large-world path implements dSweepAndPruneSpace only"); delete B; return 0; }
+    for (int i = 0; i < B->nb[0]; i++)
+      if (B->bodies[0][i]->flags & (OB_BODY_DISABLED | OB_BODY_AUTO_DISABLE)) { ob_set_last_error("dBatchCreate: the large-world path does not support disabled / auto-disabling bodies"); delete B; return 0; }
+  }
   caps.NJ = NJ;
   caps.NR = 3 * caps.NC + 6 * NJ;
   caps.npolicy = 1;
@@ -242,6 +253,7 @@ dxBatch *ob_batch_create(int nworlds, const dWorldID *worlds, const dSpaceID *sp
   rc |= obk_memset(B->bk, B->caps.ncontacts, 0, sizeof(int) * nworlds);
   rc |= obk_memset(B->bk, B->caps.nrows, 0, sizeof(int) * nworlds);
   if (rc) { ob_set_last_error("dBatchCreate: upload failed"); dBatchDestroy(B); return 0; }
+  if (caps.large && ob_batch_upload_check_large(B)) { dBatchDestroy(B); return 0; }
   return B;
 }
 
@@ -388,6 +400,7 @@ int dBatchDebugContacts(dBatchID B, int w, dReal *pnd7, int *g1g2, int cap) {
 }
 int dBatchDebugLambda(dBatchID B, int w, dReal *lambda, int cap) {
   int n = 0;
+  if (B->caps.large) return 0;
   if (obk_d2h(B->bk, &n, B->caps.nrows + w, sizeof(int))) return -1;
   int m = std::min(n, cap);
   if (m > 0 && obk_d2h(B->bk, lambda, B->caps.lambda + (size_t)w * B->caps.NR, sizeof(dReal) * m)) return -1;
@@ -398,6 +411,7 @@ int dBatchDebugFeedback(dBatchID B, int w, dReal *f1t1, int cap) {
   if (obk_d2h(B->bk, &n, B->caps.ncontacts + w, sizeof(int))) return -1;
   int m = std::min(n, cap);
   if (m <= 0) return n;
+  if (B->caps.large) { memset(f1t1, 0, sizeof(dReal) * 6 * (size_t)m); return n; }   // no feedback tap on the large-world path
   std::vector<dReal> fb((size_t)m * 12);
   if (obk_d2h(B->bk, fb.data(), B->caps.fback + (size_t)w * (B->caps.NC + B->caps.NJ) * 12, sizeof(dReal) * 12 * m)) return -1;
   for (int i = 0; i < m; i++) for (int k = 0; k < 6; k++) f1t1[6 * i + k] = fb[(size_t)12 * i + k];
@@ -420,6 +434,14 @@ int dBatchGetKernelTimes(dBatchID B, double *ms, long long *launches, int nk) {
   return OBK_NKERNELS;
 }
 const char *dBatchKernelName(int k) { return obk_kernel_name(k); }
+int dBatchGetLargeWorldStats(dBatchID B, dBatchLargeWorldStats *out) {
+  int iv[8]; double ms[8];
+  if (!B || !out || obk_large_stats(B->bk, iv, ms)) return -1;
+  out->pairs = iv[0]; out->contacts = iv[1]; out->contact_pairs = iv[2]; out->solved_contacts = iv[3];
+  out->colours = iv[4]; out->colouring_rounds = iv[5]; out->sor_launches = iv[6]; out->steps_timed = iv[7];
+  for (int k = 0; k < 7; k++) out->phase_ms[k] = ms[k];
+  return 0;
+}
 void *dBatchGetStream(dBatchID B) { return obk_stream(B->bk); }
 long long dB200KernelLaunchCount(void) { return obk_launch_count(); }
 }  // extern "C"

@@ -1,0 +1,681 @@
+// ob_large_kernels.cuh — grid-wide kernels of the large-world path (ob_large.h explains the design).
+// Included by ob_backend_cuda.cu after the definition of ObBackend.
+//
+// Per step (all launches on the backend's stream, three small device->host reads for launch sizing):
+//   k_lw_geom      thread/geom   pose, AABB, sort key                       (collision_kernel.cpp:454-465, sapspace.cpp:441-452)
+//   lw_radix_sort  4 passes      stable LSD radix sort of (key, geom)       (RadixSort, sapspace.cpp:600-830)
+//   k_lw_gather    thread/geom   sorted boxes
+//   k_lw_sweep<0>  thread/geom   count pairs   } BoxPruning sweep + infinite-geom list (sapspace.cpp:478-493, :537-566)
+//   lw_scan                      offsets       }
+//   k_lw_sweep<1>  thread/geom   fill pairs    }
+//   k_lw_narrow    thread/pair   dCollide -> contacts in fixed per-pair slots
+//   lw_scan x2                   contact creation index, contact-pair compaction
+//   k_lw_cpairs    thread/pair   contact pairs (body1, body2, contacts)
+//   k_lw_col_*     rounds        deterministic greedy colouring (hashed priorities)
+//   lw_radix_sort  2 passes      pairs by (colour, contacts descending); k_lw_segtab: segment table
+//   k_lw_body_pre  thread/body   quickstep.cpp:610-665, :840-846
+//   k_lw_assemble  thread/pair   contact.cpp:74-256 + quickstep.cpp:849-857, :117-136, :370-402 -> SoA rows
+//   k_lw_sor       iters x colours launches, thread/pair: quickstep.cpp:490-581 over the pair's rows
+//   k_lw_body_post thread/body   quickstep.cpp:905-975, util.cpp:255-360
+#pragma once
+#include "ob_large.h"
+
+#define LW_T 128
+static inline unsigned lw_blocks(size_t n, int t = LW_T) { return (unsigned)((n + t - 1) / t); }
+
+// ---- exclusive scan of uint32 (out[n] = total) -------------------------------------------------
+#define LW_SCAN_T 256
+#define LW_SCAN_E 4
+__global__ void __launch_bounds__(LW_SCAN_T) k_lw_scan1(const uint32_t *in, uint32_t *out, uint32_t *bsum, int n, int single) {
+  __shared__ uint32_t s_w[LW_SCAN_T / 32];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const size_t base = ((size_t)blockIdx.x * LW_SCAN_T + tid) * LW_SCAN_E;
+  uint32_t v[LW_SCAN_E], sum = 0;
+#pragma unroll
+  for (int e = 0; e < LW_SCAN_E; e++) { v[e] = base + e < (size_t)n ? in[base + e] : 0u; sum += v[e]; }
+  uint32_t x = sum;
+  for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+  if (lane == 31) s_w[wid] = x;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t t = lane < LW_SCAN_T / 32 ? s_w[lane] : 0u;
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, t, d); if (lane >= d) t += y; }
+    if (lane < LW_SCAN_T / 32) s_w[lane] = t;
+  }
+  __syncthreads();
+  uint32_t run = (wid ? s_w[wid - 1] : 0u) + x - sum;
+#pragma unroll
+  for (int e = 0; e < LW_SCAN_E; e++) { if (base + e < (size_t)n) out[base + e] = run; run += v[e]; }
+  if (tid == LW_SCAN_T - 1) {
+    bsum[blockIdx.x] = s_w[LW_SCAN_T / 32 - 1];
+    if (single) out[n] = s_w[LW_SCAN_T / 32 - 1];
+  }
+}
+__global__ void __launch_bounds__(LW_SCAN_T) k_lw_scan_add(uint32_t *out, const uint32_t *bscan, int n, int nblk) {
+  const size_t base = ((size_t)blockIdx.x * LW_SCAN_T + threadIdx.x) * LW_SCAN_E;
+  const uint32_t add = bscan[blockIdx.x];
+#pragma unroll
+  for (int e = 0; e < LW_SCAN_E; e++) if (base + e < (size_t)n) out[base + e] += add;
+  if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = bscan[nblk];
+}
+// tmp: scratch of at least 2*(n/1024+2)+... words (levels shrink by 1024x)
+static void lw_scan(cudaStream_t st, const uint32_t *in, uint32_t *out, int n, uint32_t *tmp) {
+  const int per = LW_SCAN_T * LW_SCAN_E;
+  const int nblk = n > 0 ? (n + per - 1) / per : 1;
+  k_lw_scan1<<<nblk, LW_SCAN_T, 0, st>>>(in, out, tmp, n, nblk == 1);
+  g_launches++;
+  if (nblk > 1) {
+    uint32_t *bscan = tmp + nblk + 1;
+    lw_scan(st, tmp, bscan, nblk, bscan + nblk + 2);
+    k_lw_scan_add<<<nblk, LW_SCAN_T, 0, st>>>(out, bscan, n, nblk);
+    g_launches++;
+  }
+}
+
+// ---- stable LSD radix sort, 8-bit digits, (uint32 key, int value) ----------------------------------
+#define LW_RS_T 256
+#define LW_RS_E 8
+__global__ void __launch_bounds__(LW_RS_T) k_lw_rs_hist(const uint32_t *key, int n, int shift, uint32_t *bh, int nblk) {
+  __shared__ uint32_t s_h[256];
+  s_h[threadIdx.x] = 0;
+  __syncthreads();
+  const size_t base = (size_t)blockIdx.x * LW_RS_T * LW_RS_E;
+  for (int r = 0; r < LW_RS_E; r++) {
+    const size_t e = base + (size_t)r * LW_RS_T + threadIdx.x;
+    if (e < (size_t)n) atomicAdd(&s_h[(key[e] >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  bh[(size_t)threadIdx.x * nblk + blockIdx.x] = s_h[threadIdx.x];
+}
+__global__ void __launch_bounds__(LW_RS_T) k_lw_rs_scatter(const uint32_t *key, const int *val, uint32_t *key2, int *val2, int n,
+                                                          int shift, const uint32_t *bhscan, int nblk) {
+  __shared__ uint32_t s_base[256], s_run[256];
+  __shared__ unsigned short s_wc[LW_RS_T / 32][256];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  s_base[tid] = bhscan[(size_t)tid * nblk + blockIdx.x];
+  s_run[tid] = 0;
+  for (int w = 0; w < LW_RS_T / 32; w++) s_wc[w][tid] = 0;
+  __syncthreads();
+  const size_t base = (size_t)blockIdx.x * LW_RS_T * LW_RS_E;
+  for (int r = 0; r < LW_RS_E; r++) {
+    const size_t e = base + (size_t)r * LW_RS_T + tid;
+    const bool act = e < (size_t)n;
+    uint32_t k = 0; int v = 0;
+    if (act) { k = key[e]; v = val[e]; }
+    const unsigned d = act ? ((k >> shift) & 255u) : 256u;
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    const int rank_w = __popc(peers & ((1u << lane) - 1u));
+    if (act && rank_w == 0) s_wc[wid][d] = (unsigned short)__popc(peers);
+    __syncthreads();
+    if (act) {
+      uint32_t pre = s_run[d];
+      for (int w = 0; w < wid; w++) pre += s_wc[w][d];
+      const size_t dst = (size_t)s_base[d] + pre + rank_w;
+      key2[dst] = k; val2[dst] = v;
+    }
+    __syncthreads();
+    {
+      uint32_t t = 0;
+      for (int w = 0; w < LW_RS_T / 32; w++) { t += s_wc[w][tid]; s_wc[w][tid] = 0; }
+      s_run[tid] += t;
+    }
+    __syncthreads();
+  }
+}
+// sorts (key[0], val[0]) using the [1] buffers; returns the index (0/1) of the buffers holding the result
+static int lw_radix_sort(cudaStream_t st, uint32_t *key[2], int *val[2], int n, int npasses, uint32_t *tmp) {
+  const int per = LW_RS_T * LW_RS_E;
+  const int nblk = n > 0 ? (n + per - 1) / per : 1;
+  int cur = 0;
+  for (int p = 0; p < npasses; p++) {
+    uint32_t *bh = tmp, *bhs = tmp + 256 * (size_t)nblk + 1;
+    k_lw_rs_hist<<<nblk, LW_RS_T, 0, st>>>(key[cur], n, 8 * p, bh, nblk);
+    lw_scan(st, bh, bhs, 256 * nblk, bhs + 256 * (size_t)nblk + 2);
+    k_lw_rs_scatter<<<nblk, LW_RS_T, 0, st>>>(key[cur], val[cur], key[cur ^ 1], val[cur ^ 1], n, 8 * p, bhs, nblk);
+    g_launches += 2;
+    cur ^= 1;
+  }
+  return cur;
+}
+
+// ---- geoms ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(LW_T) k_lw_geom(ObBatchDev d, ObLargeDev L) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const ObWorld &W = d.world[0];
+  if (g >= W.ng) return;
+  const ObGeom G = d.geom[g];
+  ObPose p;
+  geom_pose_dev(G, d.bdyn, &p);
+  L.pose[g] = p;
+  real ab[6];
+  ob_aabb(p, ab, d.meshes);
+  for (int k = 0; k < 6; k++) L.aabb[(size_t)g * 6 + k] = ab[k];
+  int ax0, ax1, ax2;
+  ob_sap_axes(W.sap_axes, &ax0, &ax1, &ax2);
+  float minf;
+  const int en = (G.flags & OB_GEOM_ENABLED) && !(G.flags & OB_GEOM_ZERO_SIZED);
+  L.gkey[0][g] = ob_lw_geomkey(ab, en, ax0, &minf);
+  L.gidx[0][g] = g;
+}
+__global__ void __launch_bounds__(LW_T) k_lw_gather(ObBatchDev d, ObLargeDev L, const uint32_t *skey, const int *sidx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const ObWorld &W = d.world[0];
+  const int ng = W.ng;
+  if (i >= ng) return;
+  const uint32_t key = skey[i];
+  const int g = sidx[i];
+  int ax0, ax1, ax2;
+  ob_sap_axes(W.sap_axes, &ax0, &ax1, &ax2);
+  const real *ab = L.aabb + (size_t)g * 6;
+  const ObGeom &G = d.geom[g];
+  ObLwBox b;
+  b.maxx = ab[ax0 + 1]; b.miny = ab[ax1]; b.maxy = ab[ax1 + 1]; b.minz = ab[ax2]; b.maxz = ab[ax2 + 1];
+  b.minx = (float)ab[ax0]; b.body = G.body; b.cat = G.cat; b.col = G.col; b.geom = g; b.pad[0] = b.pad[1] = 0;
+  L.sbox[i] = b;
+  const uint32_t nxt = i + 1 < ng ? skey[i + 1] : OB_LW_KEY_OFF;
+  if (key < OB_LW_KEY_BIG && (i + 1 == ng || nxt >= OB_LW_KEY_BIG)) L.scal[LW_NFIN] = i + 1;
+  if (key == OB_LW_KEY_BIG && (i + 1 == ng || nxt != OB_LW_KEY_BIG)) L.scal[LW_NBIG] = i + 1;   // end of the infinite list (start = NFIN)
+}
+
+// ---- pairs ---------------------------------------------------------------------------------------
+// cnt / off layout: [0, ng) sweep hits of sorted position i; [ng, 2ng) hits of i against the infinite
+// list; [2ng] infinite x infinite.  Pair orientation: the geom met first is o1 (sapspace.cpp:478-493, :553).
+template <int FILL>
+__global__ void __launch_bounds__(LW_T) k_lw_sweep(ObBatchDev d, ObLargeDev L) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ng = d.world[0].ng;
+  const int nfin = L.scal[LW_NFIN];
+  const int bigend = L.scal[LW_NBIG] > nfin ? L.scal[LW_NBIG] : nfin;
+  const int *sidx = L.gidx[0];   // the 4-pass sort leaves the result in buffer 0
+  if (i == 0) {   // infinite x infinite (collideGeomsNoAABBs on the TmpInfGeomList, :479-485)
+    uint32_t h = 0;
+    const size_t o = FILL ? L.off[2 * ng] : 0;
+    for (int a = nfin; a < bigend; a++)
+      for (int b = a + 1; b < bigend; b++) {
+        const int ga = sidx[a], gb = sidx[b];
+        const ObGeom &A = d.geom[ga], &B = d.geom[gb];
+        if (ob_pair_filter_noaabb(A.body, B.body, A.cat, A.col, B.cat, B.col)) {
+          if (FILL && o + h < (size_t)L.NP) { L.pairs[2 * (o + h)] = ga; L.pairs[2 * (o + h) + 1] = gb; }
+          h++;
+        }
+      }
+    if (!FILL) L.cnt[2 * ng] = h;
+    if (FILL) {
+      uint32_t np = L.off[2 * ng + 1];
+      if (np > (uint32_t)L.NP) { np = (uint32_t)L.NP; atomicOr(&d.world[0].status, OB_ERR_PAIR_OVERFLOW); }
+      L.scal[LW_NP] = (int)np;
+    }
+  }
+  if (i >= ng) return;
+  if (i >= nfin) { if (!FILL) { L.cnt[i] = 0; L.cnt[ng + i] = 0; } return; }
+  const ObLwBox K = L.sbox[i];
+  uint32_t h = 0;
+  size_t o = FILL ? L.off[i] : 0;
+  for (int j = i + 1; j < nfin; j++) {
+    const ObLwBox &J = L.sbox[j];
+    if (!((real)J.minx <= K.maxx)) break;
+    if (ob_lw_sweep_hit(K, J)) {
+      if (FILL && o + h < (size_t)L.NP) { L.pairs[2 * (o + h)] = K.geom; L.pairs[2 * (o + h) + 1] = J.geom; }
+      h++;
+    }
+  }
+  if (!FILL) L.cnt[i] = h;
+  h = 0;
+  o = FILL ? L.off[ng + i] : 0;
+  for (int a = nfin; a < bigend; a++) {   // collideGeomsNoAABBs: no AABB test against the infinite list (:486-491)
+    const int ga = sidx[a];
+    const ObGeom &A = d.geom[ga];
+    if (ob_pair_filter_noaabb(A.body, K.body, A.cat, A.col, K.cat, K.col)) {
+      if (FILL && o + h < (size_t)L.NP) { L.pairs[2 * (o + h)] = ga; L.pairs[2 * (o + h) + 1] = K.geom; }
+      h++;
+    }
+  }
+  if (!FILL) L.cnt[ng + i] = h;
+}
+
+template <bool MESH>
+__global__ void __launch_bounds__(LW_T) k_lw_narrow(ObBatchDev d, ObLargeDev L, int np, int maxc) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= np) return;
+  const int o1 = L.pairs[2 * p], o2 = L.pairs[2 * p + 1];
+  ObCg cg[OB_LW_MAXC];
+  int swapped, bverr = 0;
+  const int n = ob_collide_pair_t<MESH, OB_LW_MAXC>(L.pose[o1], L.pose[o2], maxc, cg, &swapped, d.meshes, &bverr);
+  if (bverr) atomicOr(&d.world[0].status, OB_ERR_BVH_STACK);
+  ObContact *out = L.pc + (size_t)p * maxc;
+  for (int k = 0; k < n; k++) {
+    ObContact c;
+    for (int e = 0; e < 3; e++) { c.pos[e] = cg[k].pos[e]; c.normal[e] = cg[k].normal[e]; }
+    c.depth = cg[k].depth; c.g1 = o1; c.g2 = o2; c.side1 = cg[k].side1; c.side2 = cg[k].side2; c.policy = 0;
+    out[k] = c;
+  }
+  L.ncp[p] = (uint32_t)n;
+  const int b1 = d.geom[o1].body, b2 = d.geom[o2].body;
+  L.cpflag[p] = (n > 0 && (b1 >= 0 || b2 >= 0)) ? 1u : 0u;
+}
+__global__ void __launch_bounds__(LW_T) k_lw_cpairs(ObBatchDev d, ObLargeDev L, int np, int maxc, int taps) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p == 0) {
+    L.scal[LW_NCONTACTS] = (int)L.coff[np];
+    L.scal[LW_NCP] = (int)L.cpoff[np];
+    d.npairs[0] = np;
+    d.ncontacts[0] = (int)L.coff[np] < d.NC ? (int)L.coff[np] : d.NC;
+  }
+  if (p >= np) return;
+  const int n = (int)L.ncp[p];
+  if (L.cpflag[p]) {
+    const int o1 = L.pairs[2 * p], o2 = L.pairs[2 * p + 1];
+    int b1 = d.geom[o1].body, b2 = d.geom[o2].body, rev = 0;
+    if (b1 < 0) { b1 = b2; b2 = -1; rev = 1; }   // dJointAttach swap rule (ode.cpp:1368-1377)
+    ObLwPair P;
+    P.b1 = b1; P.b2 = b2; P.info = n | (rev << 8) | (255 << 16); P.src = p;
+    L.cp[0][L.cpoff[p]] = P;
+  }
+  if (taps) {
+    const size_t o = L.coff[p];
+    for (int k = 0; k < n; k++) if (o + k < (size_t)d.NC) d.contacts[o + k] = L.pc[(size_t)p * maxc + k];
+  }
+}
+
+// ---- colouring ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(LW_T) k_lw_col_claim(ObLargeDev L, int ncp, uint32_t round) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= ncp) return;
+  const ObLwPair P = L.cp[0][p];
+  if ((P.info >> 16) != 255) return;
+  const unsigned long long pr = ob_lw_prio((uint32_t)p, round);
+  atomicMin(&L.claim[P.b1], pr);
+  if (P.b2 >= 0) atomicMin(&L.claim[P.b2], pr);
+}
+__global__ void __launch_bounds__(LW_T) k_lw_col_take(ObLargeDev L, int ncp, uint32_t round) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  bool left = false;
+  if (p < ncp) {
+    ObLwPair P = L.cp[0][p];
+    if ((P.info >> 16) == 255) {
+      const unsigned long long pr = ob_lw_prio((uint32_t)p, round);
+      if (L.claim[P.b1] == pr && (P.b2 < 0 || L.claim[P.b2] == pr)) {
+        unsigned long long u = L.used[P.b1];
+        if (P.b2 >= 0) u |= L.used[P.b2];
+        int c = ob_lw_first_free(u);
+        if (c >= OB_LW_MAXCOL) { c = OB_LW_MAXCOL - 1; atomicOr(&L.scal[LW_ERR], 1); }
+        L.used[P.b1] |= 1ull << c;
+        if (P.b2 >= 0) L.used[P.b2] |= 1ull << c;
+        L.cp[0][p].info = (P.info & 0xffff) | (c << 16);
+      } else left = true;
+    }
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, left);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(&L.scal[LW_UNCOLOURED], __popc(m));
+}
+__global__ void __launch_bounds__(LW_T) k_lw_pairkey(ObLargeDev L, int ncp) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= ncp) return;
+  const int info = L.cp[0][p].info;
+  L.pkey[0][p] = (uint32_t)(((info >> 16) & 255) * 8 + (8 - (info & 255)));
+  L.pidx[0][p] = p;
+}
+__global__ void __launch_bounds__(LW_T) k_lw_pairgather(ObLargeDev L, int ncp, const int *sidx) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= ncp) return;
+  L.cp[1][p] = L.cp[0][sidx[p]];
+}
+// segment table from the sorted keys: one block of 512 threads
+__global__ void __launch_bounds__(512) k_lw_segtab(ObLargeDev L, int ncp, const uint32_t *skey) {
+  __shared__ int s_lb[OB_LW_MAXCOL * 8 + 1];
+  const int t = threadIdx.x;
+  {   // lower_bound(t) in skey[0..ncp)
+    int lo = 0, hi = ncp;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (skey[mid] < (uint32_t)t) lo = mid + 1; else hi = mid; }
+    s_lb[t] = lo;
+    if (t == 0) s_lb[OB_LW_MAXCOL * 8] = ncp;
+  }
+  __syncthreads();
+  if (t == 0) {
+    int cbase = 0, ncol = 0;
+    for (int c = 0; c < OB_LW_MAXCOL; c++) {
+      int *row = L.segtab + c * (2 + OB_LW_MAXC);
+      const int start = s_lb[c * 8], count = s_lb[c * 8 + 8] - start;
+      row[0] = start; row[1] = count;
+      for (int k = 0; k < OB_LW_MAXC; k++) {
+        row[2 + k] = cbase;
+        cbase += s_lb[c * 8 + (8 - k)] - start;   // pairs of this colour with more than k contacts
+      }
+      if (count > 0) ncol = c + 1;
+    }
+    L.scal[LW_NCOL] = ncol;
+    L.scal[LW_NSOLVED] = cbase;
+  }
+}
+
+// ---- solver ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(LW_T) k_lw_body_pre(ObBatchDev d, ObLargeDev L, real h) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const ObWorld &W = d.world[0];
+  if (b >= W.nb) return;
+  ObBodyDyn &B = d.bdyn[b];
+  const ObBodyConst &C = d.bconst[b];
+  const real stepsize1 = ob_recip(h);
+  real R[12], I[12], invI[12], iw[12], avel[3], lvel[3], facc[3], tacc[3], t1[6];
+  for (int k = 0; k < 12; k++) { R[k] = B.R[k]; I[k] = C.I[k]; invI[k] = C.invI[k]; }
+  for (int k = 0; k < 3; k++) { avel[k] = B.avel[k]; lvel[k] = B.lvel[k]; facc[k] = B.facc[k]; tacc[k] = B.tacc[k]; }
+  ob_body_preamble(R, I, invI, avel, B.flags, C.mass, W.gravity, iw, facc, tacc);
+  for (int k = 0; k < 3; k++) { B.facc[k] = facc[k]; B.tacc[k] = tacc[k]; }
+  for (int k = 0; k < 12; k++) d.invIw[(size_t)12 * b + k] = iw[k];
+  ob_body_tmp1(facc, tacc, lvel, avel, C.invMass, iw, stepsize1, t1);
+  for (int k = 0; k < 6; k++) d.tmp1[(size_t)8 * b + k] = t1[k];
+  for (int k = 0; k < 8; k++) L.fc[(size_t)8 * b + k] = 0;
+  L.invM[b] = C.invMass;
+  L.hasrow[b] = 0;
+}
+
+__device__ __forceinline__ void lw_store_row(const ObLargeDev &L, int q, size_t cs, const real *rw, unsigned meta) {
+#if defined(dSINGLE)
+#pragma unroll
+  for (int s = 0; s < 4; s++) *(float4 *)(L.rows + ob_lw_row_index(q, s, L.NC, cs)) = make_float4(rw[4 * s], rw[4 * s + 1], rw[4 * s + 2], rw[4 * s + 3]);
+  *(float4 *)(L.rows + ob_lw_row_index(q, 4, L.NC, cs)) = make_float4(rw[16], rw[17], rw[18], __uint_as_float(meta));
+#else
+#pragma unroll
+  for (int s = 0; s < 9; s++) *(double2 *)(L.rows + ob_lw_row_index(q, s, L.NC, cs)) = make_double2(rw[2 * s], rw[2 * s + 1]);
+  *(double2 *)(L.rows + ob_lw_row_index(q, 9, L.NC, cs)) = make_double2(rw[18], __hiloint2double(0, (int)meta));
+#endif
+}
+__device__ __forceinline__ void lw_load_row(const ObLargeDev &L, int q, size_t cs, real *rw, unsigned *meta) {
+#if defined(dSINGLE)
+#pragma unroll
+  for (int s = 0; s < 4; s++) {
+    const float4 t = __ldg((const float4 *)(L.rows + ob_lw_row_index(q, s, L.NC, cs)));
+    rw[4 * s] = t.x; rw[4 * s + 1] = t.y; rw[4 * s + 2] = t.z; rw[4 * s + 3] = t.w;
+  }
+  const float4 t = __ldg((const float4 *)(L.rows + ob_lw_row_index(q, 4, L.NC, cs)));
+  rw[16] = t.x; rw[17] = t.y; rw[18] = t.z; *meta = __float_as_uint(t.w);
+#else
+#pragma unroll
+  for (int s = 0; s < 9; s++) {
+    const double2 t = __ldg((const double2 *)(L.rows + ob_lw_row_index(q, s, L.NC, cs)));
+    rw[2 * s] = t.x; rw[2 * s + 1] = t.y;
+  }
+  const double2 t = __ldg((const double2 *)(L.rows + ob_lw_row_index(q, 9, L.NC, cs)));
+  rw[18] = t.x; *meta = (unsigned)__double2loint(t.y);
+#endif
+}
+
+__global__ void __launch_bounds__(LW_T) k_lw_assemble(ObBatchDev d, ObLargeDev L, int ncp, int maxc, int m, real h) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= ncp) return;
+  const ObWorld &W = d.world[0];
+  const ObLwPair P = L.cp[1][p];
+  const int nc = P.info & 255, rev = (P.info >> 8) & 1, col = (P.info >> 16) & 255;
+  const int *seg = L.segtab + col * (2 + OB_LW_MAXC);
+  const int i = p - seg[0];
+  const real stepsize1 = ob_recip(h);
+  ObSurface surf = d.policy[0].surface;
+  ob_contact_info1(surf);
+  const int b1 = P.b1, b2 = P.b2;
+  real p1[3], l1[3], a1[3], t1a[6], iw1[12], p2[3] = {0, 0, 0}, l2[3] = {0, 0, 0}, a2[3] = {0, 0, 0}, t1b[6] = {0, 0, 0, 0, 0, 0}, iw2[12];
+  for (int e = 0; e < 3; e++) { p1[e] = d.bdyn[b1].pos[e]; l1[e] = d.bdyn[b1].lvel[e]; a1[e] = d.bdyn[b1].avel[e]; }
+  for (int e = 0; e < 6; e++) t1a[e] = d.tmp1[(size_t)8 * b1 + e];
+  for (int e = 0; e < 12; e++) iw1[e] = d.invIw[(size_t)12 * b1 + e];
+  real k2 = 0;
+  for (int e = 0; e < 12; e++) iw2[e] = 0;
+  if (b2 >= 0) {
+    for (int e = 0; e < 3; e++) { p2[e] = d.bdyn[b2].pos[e]; l2[e] = d.bdyn[b2].lvel[e]; a2[e] = d.bdyn[b2].avel[e]; }
+    for (int e = 0; e < 6; e++) t1b[e] = d.tmp1[(size_t)8 * b2 + e];
+    for (int e = 0; e < 12; e++) iw2[e] = d.invIw[(size_t)12 * b2 + e];
+    k2 = L.invM[b2];
+    L.hasrow[b2] = 1;
+  }
+  L.hasrow[b1] = 1;
+  const real k1 = L.invM[b1];
+  for (int k = 0; k < nc; k++) {
+    const size_t cs = (size_t)seg[2 + k] + i;
+    if (cs >= (size_t)L.NC) { atomicOr(&d.world[0].status, OB_ERR_CONTACT_OVERFLOW); break; }
+    const ObContact c = L.pc[(size_t)P.src * maxc + k];
+    real rw[3][OB_LW_ROWW];
+    unsigned meta[3];
+    if (!ob_lw_contact_rows(c, rev, surf, m, W, p1, l1, a1, t1a, iw1, k1, b2 >= 0, p2, l2, a2, t1b, iw2, k2, stepsize1, rw, meta))
+      atomicOr(&d.world[0].status, OB_ERR_ROW_OVERFLOW);
+    for (int q = 0; q < m; q++) {
+      lw_store_row(L, q, cs, rw[q], meta[q]);
+      L.lambda[(size_t)q * L.NC + cs] = 0;
+    }
+  }
+}
+
+template <int M>
+__global__ void __launch_bounds__(LW_T) k_lw_sor(ObLargeDev L, int col) {
+  const int *seg = L.segtab + col * (2 + OB_LW_MAXC);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= seg[1]) return;
+  const ObLwPair P = L.cp[1][seg[0] + i];
+  const int nc = P.info & 255, b1 = P.b1, b2 = P.b2;
+  real f1[6], f2[6] = {0, 0, 0, 0, 0, 0};
+  real *fp1 = L.fc + (size_t)8 * b1, *fp2 = L.fc + (size_t)8 * (b2 >= 0 ? b2 : b1);
+  for (int e = 0; e < 6; e++) f1[e] = fp1[e];
+  const real k1 = L.invM[b1];
+  real k2 = 0;
+  if (b2 >= 0) { for (int e = 0; e < 6; e++) f2[e] = fp2[e]; k2 = L.invM[b2]; }
+  for (int k = 0; k < nc; k++) {
+    const size_t cs = (size_t)seg[2 + k] + i;
+    if (cs >= (size_t)L.NC) break;
+    real lam[M];
+#pragma unroll
+    for (int q = 0; q < M; q++) {
+      real rw[OB_LW_ROWW];
+      unsigned meta;
+      lw_load_row(L, q, cs, rw, &meta);
+      const int fio = (meta >> 16) & 255;
+      real lam_f = 0;
+#pragma unroll
+      for (int r = 0; r < M; r++) if (fio && r == q - fio) lam_f = lam[r];
+      real *lp = L.lambda + (size_t)q * L.NC + cs;
+      lam[q] = ob_lw_row_update(rw, meta, k1, k2, b2 >= 0, lam_f, *lp, f1, f2);
+      *lp = lam[q];
+    }
+  }
+  for (int e = 0; e < 6; e++) fp1[e] = f1[e];
+  if (b2 >= 0) for (int e = 0; e < 6; e++) fp2[e] = f2[e];
+}
+
+__global__ void __launch_bounds__(LW_T) k_lw_body_post(ObBatchDev d, ObLargeDev L, real h) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const ObWorld &W = d.world[0];
+  if (b == 0) {
+    d.nrows[0] = 0;
+    atomicAdd(&d.counters->steps, 1ull);
+    atomicAdd(&d.counters->body_steps, (unsigned long long)W.nb);
+    atomicAdd(&d.counters->pairs, (unsigned long long)L.scal[LW_NP]);
+    atomicAdd(&d.counters->contacts, (unsigned long long)L.scal[LW_NSOLVED]);
+    if (W.status || L.scal[LW_ERR]) atomicAdd(&d.counters->overflow_worlds, 1ull);
+  }
+  if (b >= W.nb) return;
+  ObBodyDyn &B = d.bdyn[b];
+  const ObBodyConst &C = d.bconst[b];
+  real pos[3], q[4], R[12], lvel[3], avel[3], facc[3], tacc[3], iw[12], fcb[6];
+  for (int k = 0; k < 3; k++) { pos[k] = B.pos[k]; lvel[k] = B.lvel[k]; avel[k] = B.avel[k]; facc[k] = B.facc[k]; tacc[k] = B.tacc[k]; }
+  for (int k = 0; k < 4; k++) q[k] = B.q[k];
+  for (int k = 0; k < 12; k++) iw[k] = d.invIw[(size_t)12 * b + k];
+  for (int k = 0; k < 6; k++) fcb[k] = L.fc[(size_t)8 * b + k];
+  ob_body_velocity_update(lvel, avel, L.hasrow[b] ? fcb : (real *)0, facc, tacc, C.invMass, iw, h);
+  real fra[3] = {C.finite_rot_axis[0], C.finite_rot_axis[1], C.finite_rot_axis[2]};
+  ob_step_body(pos, q, R, lvel, avel, B.flags, h, C.max_angular_speed, fra, C.damp_lin_scale, C.damp_ang_scale, C.damp_lin_thr,
+               C.damp_ang_thr);
+  for (int k = 0; k < 3; k++) { B.pos[k] = pos[k]; B.lvel[k] = lvel[k]; B.avel[k] = avel[k]; }
+  for (int k = 0; k < 4; k++) { B.q[k] = q[k]; B.facc[k] = 0; B.tacc[k] = 0; }
+  for (int k = 0; k < 12; k++) B.R[k] = R[k];
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+#define LWCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { snprintf(err, errlen, "%s: %s", #call, cudaGetErrorString(e_)); return -1; } } while (0)
+#define LW_HOST_WORDS (LW_WORDS + OB_LW_MAXCOL * (2 + OB_LW_MAXC))
+
+static int lw_create(ObBackend *b, char *err, size_t errlen) {
+  ObBatchDev &d = b->d;
+  ObLargeDev &L = b->L;
+  if (d.W != 1) { snprintf(err, errlen, "the large-world path takes exactly one world"); return -1; }
+  L.NG = d.NG; L.NB = d.NB; L.NP = d.NP; L.NC = d.NC;
+  const size_t NG = d.NG, NB = d.NB, NP = d.NP, NC = d.NC;
+  LWCK(dalloc(b, &d.world, (size_t)1));
+  LWCK(dalloc(b, &d.bdyn, NB));
+  LWCK(dalloc(b, &d.bconst, NB));
+  LWCK(dalloc(b, &d.geom, NG));
+  LWCK(dalloc(b, &d.glist, NG));
+  LWCK(dalloc(b, &d.policy, (size_t)d.npolicy));
+  LWCK(dalloc(b, &d.meshes, (size_t)(d.nmesh ? d.nmesh : 1)));
+  LWCK(dalloc(b, &d.njoints, (size_t)1));
+  LWCK(dalloc(b, &d.npairs, (size_t)1));
+  LWCK(dalloc(b, &d.pairs, NP * 2));
+  LWCK(dalloc(b, &d.ncontacts, (size_t)1));
+  LWCK(dalloc(b, &d.contacts, NC));
+  LWCK(dalloc(b, &d.invIw, NB * 12));
+  LWCK(dalloc(b, &d.tmp1, NB * 8));
+  LWCK(dalloc(b, &d.nrows, (size_t)1));
+  LWCK(dalloc(b, &d.counters, (size_t)1));
+  d.joint = 0; d.padjstart = 0; d.padj = 0; d.sapstate = 0; d.rows = 0; d.stepinfo = 0; d.ibody = 0; d.isz = 0; d.jrow = 0;
+  d.ijoint = 0; d.jside = 0; d.sched = 0; d.pstart = 0; d.rowJ = d.rowiMJ = d.rowJc = d.rowS = 0; d.rowI = 0; d.lambda = 0;
+  d.fback = 0; d.csurf = 0; d.cfdir1 = 0;
+  b->st_elems = NB;
+  LWCK(dalloc(b, &b->st_dev, NB * 13));
+  LWCK(dalloc(b, &L.pose, NG));
+  LWCK(dalloc(b, &L.aabb, NG * 6));
+  for (int k = 0; k < 2; k++) { LWCK(dalloc(b, &L.gkey[k], NG)); LWCK(dalloc(b, &L.gidx[k], NG)); }
+  LWCK(dalloc(b, &L.sbox, NG));
+  LWCK(dalloc(b, &L.scal, (size_t)LW_WORDS));
+  LWCK(dalloc(b, &L.cnt, 2 * NG + 2));
+  LWCK(dalloc(b, &L.off, 2 * NG + 2));
+  L.pairs = d.pairs;
+  LWCK(dalloc(b, &L.pc, NP * OB_LW_MAXC));
+  LWCK(dalloc(b, &L.ncp, NP + 1));
+  LWCK(dalloc(b, &L.coff, NP + 1));
+  LWCK(dalloc(b, &L.cpflag, NP + 1));
+  LWCK(dalloc(b, &L.cpoff, NP + 1));
+  for (int k = 0; k < 2; k++) { LWCK(dalloc(b, &L.cp[k], NP)); LWCK(dalloc(b, &L.pkey[k], NP)); LWCK(dalloc(b, &L.pidx[k], NP)); }
+  LWCK(dalloc(b, &L.claim, NB));
+  LWCK(dalloc(b, &L.used, NB));
+  LWCK(dalloc(b, &L.segtab, (size_t)OB_LW_MAXCOL * (2 + OB_LW_MAXC)));
+  LWCK(dalloc(b, &L.rows, (size_t)3 * OB_LW_SLOTS * OB_LW_SLOTW * NC));
+  LWCK(dalloc(b, &L.lambda, 3 * NC));
+  LWCK(dalloc(b, &L.fc, NB * 8));
+  LWCK(dalloc(b, &L.invM, NB));
+  LWCK(dalloc(b, &L.hasrow, NB));
+  L.tmp_words = (NP > 2 * NG ? NP : 2 * NG) / 2 + 65536;
+  LWCK(dalloc(b, &L.tmp, L.tmp_words));
+  LWCK(cudaMallocHost((void **)&b->lw_host, sizeof(int) * LW_HOST_WORDS));
+  for (int k = 0; k < 9; k++) LWCK(cudaEventCreate(&b->lw_ev[k]));
+  return 0;
+}
+
+static int lw_step(ObBackend *b, real h, int taps, char *err, size_t errlen) {
+  ObBatchDev &d = b->d;
+  ObLargeDev &L = b->L;
+  cudaStream_t st = b->stream;
+  int *hs = b->lw_host;
+  // world + policy as the device holds them (small reads; also orders this step after any upload)
+  ObWorld hw; ObPolicy hp;
+  LWCK(cudaMemcpyAsync(&hw, d.world, sizeof hw, cudaMemcpyDeviceToHost, st));
+  LWCK(cudaMemcpyAsync(&hp, d.policy, sizeof hp, cudaMemcpyDeviceToHost, st));
+  LWCK(cudaStreamSynchronize(st));
+  const int ng = hw.ng, nb = hw.nb;
+  if (hw.space_type != OB_SPACE_SAP) { snprintf(err, errlen, "the large-world path implements dSweepAndPruneSpace only"); return -1; }
+  const int maxc = hp.max_contacts > OB_LW_MAXC ? OB_LW_MAXC : (hp.max_contacts < 1 ? 1 : hp.max_contacts);
+  ObSurface sf = hp.surface;
+  const int m = ob_contact_info1(sf);
+  const bool tm = b->ktiming != 0;
+  int evi = 0;
+#define LW_MARK() do { if (tm) cudaEventRecord(b->lw_ev[evi], st); evi++; } while (0)
+  LW_MARK();
+  // (1) geoms, sort by axis-0 minimum
+  LWCK(cudaMemsetAsync(L.scal, 0, sizeof(int) * LW_WORDS, st));
+  k_lw_geom<<<lw_blocks(ng), LW_T, 0, st>>>(d, L);
+  const int gcur = lw_radix_sort(st, L.gkey, L.gidx, ng, 4, L.tmp);
+  if (gcur != 0) { snprintf(err, errlen, "internal: sort parity"); return -1; }
+  k_lw_gather<<<lw_blocks(ng), LW_T, 0, st>>>(d, L, L.gkey[0], L.gidx[0]);
+  g_launches += 2;
+  LW_MARK();
+  // (2) pairs: count, scan, fill
+  k_lw_sweep<0><<<lw_blocks(ng), LW_T, 0, st>>>(d, L);
+  lw_scan(st, L.cnt, L.off, 2 * ng + 1, L.tmp);
+  k_lw_sweep<1><<<lw_blocks(ng), LW_T, 0, st>>>(d, L);
+  g_launches += 2;
+  LWCK(cudaMemcpyAsync(hs, L.scal, sizeof(int) * LW_WORDS, cudaMemcpyDeviceToHost, st));
+  LWCK(cudaStreamSynchronize(st));
+  const int np = hs[LW_NP];
+  LW_MARK();
+  // (3) narrowphase, contact pairs
+  if (np > 0) {
+    if (d.nmesh) k_lw_narrow<true><<<lw_blocks(np), LW_T, 0, st>>>(d, L, np, maxc);
+    else k_lw_narrow<false><<<lw_blocks(np), LW_T, 0, st>>>(d, L, np, maxc);
+    g_launches++;
+  }
+  lw_scan(st, L.ncp, L.coff, np, L.tmp);
+  lw_scan(st, L.cpflag, L.cpoff, np, L.tmp);
+  k_lw_cpairs<<<lw_blocks(np > 0 ? np : 1), LW_T, 0, st>>>(d, L, np, maxc, taps);
+  g_launches++;
+  LWCK(cudaMemcpyAsync(hs, L.scal, sizeof(int) * LW_WORDS, cudaMemcpyDeviceToHost, st));
+  LWCK(cudaStreamSynchronize(st));
+  const int ncp = hs[LW_NCP];
+  LW_MARK();
+  // (4) colouring: rounds of claim / take until every pair has a colour
+  int ncol = 0, rounds = 0;
+  if (ncp > 0) {
+    LWCK(cudaMemsetAsync(L.used, 0, sizeof(unsigned long long) * nb, st));
+    int left = ncp;
+    while (left > 0) {
+      for (int r = 0; r < 4; r++, rounds++) {
+        LWCK(cudaMemsetAsync(L.claim, 0xff, sizeof(unsigned long long) * nb, st));
+        LWCK(cudaMemsetAsync(L.scal + LW_UNCOLOURED, 0, sizeof(int), st));
+        k_lw_col_claim<<<lw_blocks(ncp), LW_T, 0, st>>>(L, ncp, (uint32_t)rounds);
+        k_lw_col_take<<<lw_blocks(ncp), LW_T, 0, st>>>(L, ncp, (uint32_t)rounds);
+        g_launches += 2;
+      }
+      LWCK(cudaMemcpyAsync(hs, L.scal, sizeof(int) * LW_WORDS, cudaMemcpyDeviceToHost, st));
+      LWCK(cudaStreamSynchronize(st));
+      left = hs[LW_UNCOLOURED];
+      if (rounds > 4096) { snprintf(err, errlen, "colouring did not converge"); return -1; }
+    }
+    if (hs[LW_ERR]) { snprintf(err, errlen, "more than %d colours needed (a body with more than %d contact pairs)", OB_LW_MAXCOL, OB_LW_MAXCOL / 2); return -1; }
+    k_lw_pairkey<<<lw_blocks(ncp), LW_T, 0, st>>>(L, ncp);
+    const int pcur = lw_radix_sort(st, L.pkey, L.pidx, ncp, 2, L.tmp);
+    if (pcur != 0) { snprintf(err, errlen, "internal: sort parity"); return -1; }
+    k_lw_pairgather<<<lw_blocks(ncp), LW_T, 0, st>>>(L, ncp, L.pidx[0]);
+    k_lw_segtab<<<1, 512, 0, st>>>(L, ncp, L.pkey[0]);
+    g_launches += 3;
+    LWCK(cudaMemcpyAsync(hs, L.scal, sizeof(int) * LW_WORDS, cudaMemcpyDeviceToHost, st));
+    LWCK(cudaMemcpyAsync(hs + LW_WORDS, L.segtab, sizeof(int) * OB_LW_MAXCOL * (2 + OB_LW_MAXC), cudaMemcpyDeviceToHost, st));
+    LWCK(cudaStreamSynchronize(st));
+    ncol = hs[LW_NCOL];
+    if (hs[LW_NSOLVED] > L.NC) { snprintf(err, errlen, "contact capacity exceeded (%d > %d): raise dBatchDesc.max_contacts_per_world", hs[LW_NSOLVED], L.NC); return -1; }
+  }
+  b->lw_rounds = rounds; b->lw_ncol = ncol;
+  LW_MARK();
+  // (5) bodies, rows
+  k_lw_body_pre<<<lw_blocks(nb), LW_T, 0, st>>>(d, L, h);
+  g_launches++;
+  if (ncp > 0) { k_lw_assemble<<<lw_blocks(ncp), LW_T, 0, st>>>(d, L, ncp, maxc, m, h); g_launches++; }
+  LW_MARK();
+  // (6) SOR: colours in ascending order, every iteration
+  int sor_launches = 0;
+  for (int it = 0; it < hw.iters && ncp > 0; it++)
+    for (int c = 0; c < ncol; c++) {
+      const int cnt = hs[LW_WORDS + c * (2 + OB_LW_MAXC) + 1];
+      if (cnt <= 0) continue;
+      if (m == 3) k_lw_sor<3><<<lw_blocks(cnt), LW_T, 0, st>>>(L, c);
+      else if (m == 2) k_lw_sor<2><<<lw_blocks(cnt), LW_T, 0, st>>>(L, c);
+      else k_lw_sor<1><<<lw_blocks(cnt), LW_T, 0, st>>>(L, c);
+      g_launches++; sor_launches++;
+    }
+  LW_MARK();
+  // (7) integrate
+  k_lw_body_post<<<lw_blocks(nb), LW_T, 0, st>>>(d, L, h);
+  g_launches++;
+  LW_MARK();
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) { snprintf(err, errlen, "large-world step failed: %s", cudaGetErrorString(e)); return -1; }
+  if (tm) for (int k = 0; k + 1 < evi && k < 8; k++) { float ms = 0; cudaEventElapsedTime(&ms, b->lw_ev[k], b->lw_ev[k + 1]); b->lw_ms[k] += ms; }
+  b->lw_stat[0] = np; b->lw_stat[1] = hs[LW_NCONTACTS]; b->lw_stat[2] = ncp; b->lw_stat[3] = ncp > 0 ? hs[LW_NSOLVED] : 0;
+  b->lw_stat[4] = ncol; b->lw_stat[5] = rounds; b->lw_stat[6] = sor_launches; if (tm) b->lw_stat[7]++;
+  if (getenv("OB_LW_VERBOSE")) fprintf(stderr, "lw: pairs %d contacts %d cpairs %d solved %d colours %d rounds %d sor launches %d\n", np, hs[LW_NCONTACTS], ncp, b->lw_stat[3], ncol, rounds, sor_launches);
+#undef LW_MARK
+  return 0;
+}

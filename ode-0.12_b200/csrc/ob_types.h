@@ -115,6 +115,7 @@ struct ObBatchDev {
   int NEP;      // shuffle epochs per step = ceil(max iters / 8)
   int NJ;       // permanent (non-contact) joints per world slot
   int dropin;   // 1: batch serves the classic per-call API (per-contact surfaces in csurf/cfdir1)
+  int large;    // 1: one large world on the grid-wide path (ob_large.h); W == 1
   ObWorld *world;        // [W]
   ObBodyDyn *bdyn;       // [W*NB]
   ObBodyConst *bconst;   // [W*NB]

@@ -23,5 +23,7 @@ for p in single double; do
   $d --scene terrain_spheres --steps 25 --settle 70 --out tests/golden/terrain_spheres_settle70_$p.trace
   $d --scene terrain_boxes --steps 15 --settle 70 --out tests/golden/terrain_boxes_settle70_$p.trace
   $d --scene buggy_terrain --steps 30 --settle 90 --worlds 2 --out tests/golden/buggy_terrain_w2_settle90_$p.trace
+  # large-world path (config 5): reference trace used in lock-step (--resync) by tests/test_large_world.py
+  $d --scene pile_5x5x8 --steps 10 --settle 60 --out tests/golden/pile_5x5x8_large_settle60_$p.trace
 done
 ls -la tests/golden

@@ -27,7 +27,7 @@ def driver_path(kind, prec):
     raise ValueError(kind)
 
 
-def run_trace(kind, prec, scene, steps, worlds, out, mode=None, timeout=600, settle=0, contacts_cap=0, resync=None):
+def run_trace(kind, prec, scene, steps, worlds, out, mode=None, timeout=900, settle=0, contacts_cap=0, resync=None, large=False):
     exe = driver_path(kind, prec)
     if mode is None:
         mode = "callback" if kind == "ref" else "batch"
@@ -38,6 +38,8 @@ def run_trace(kind, prec, scene, steps, worlds, out, mode=None, timeout=600, set
         cmd += ["--contacts-cap", str(contacts_cap)]
     if resync and kind != "ref":
         cmd += ["--resync", resync]
+    if large and kind != "ref":
+        cmd += ["--large"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
     if r.returncode != 0:
         raise RuntimeError(f"{' '.join(cmd)} failed rc={r.returncode}\n{r.stdout}\n{r.stderr}")

@@ -21,6 +21,7 @@
 //   u32 seed_after
 #include <stdio.h>
 #include <time.h>
+#include <algorithm>
 #include <string>
 #include "scenes.h"
 
@@ -87,6 +88,33 @@ static void dump_state(Trace &t, SceneWorld &sw) {
   }
 }
 
+// --resync: read the pre-step body state of every world for the next step from a reference trace
+struct Resync {
+  FILE *f;
+  Resync() : f(NULL) {}
+  bool open(const std::string &path, int nworlds) {
+    f = fopen(path.c_str(), "rb");
+    int hdr[4];
+    return f && fread(hdr, 4, 4, f) == 4 && hdr[1] == (int)sizeof(dReal) && hdr[2] == nworlds;
+  }
+  // st: [nb*13] of world w; call for w = 0..nworlds-1 in order, once per step
+  bool next(int nb, std::vector<dReal> &st) {
+    int n;
+    if (fread(&n, 4, 1, f) != 1) return false;
+    fseek(f, 4L * n, SEEK_CUR);
+    if (fread(&n, 4, 1, f) != 1 || n != nb) return false;
+    st.resize((size_t)nb * 13);
+    if (fread(st.data(), sizeof(dReal), st.size(), f) != st.size()) return false;
+    if (fread(&n, 4, 1, f) != 1) return false;
+    fseek(f, 8L * n, SEEK_CUR);                                       // pairs
+    if (fread(&n, 4, 1, f) != 1) return false;
+    fseek(f, (long)n * (8 + 7 * (long)sizeof(dReal)), SEEK_CUR);       // contacts
+    fseek(f, (long)n * 6 * (long)sizeof(dReal), SEEK_CUR);             // feedback
+    fseek(f, (long)nb * 13 * (long)sizeof(dReal) + 4, SEEK_CUR);       // state1 + seed
+    return true;
+  }
+};
+
 static double now_s() {
   struct timespec ts;
   clock_gettime(CLOCK_MONOTONIC, &ts);
@@ -95,7 +123,8 @@ static double now_s() {
 
 int main(int argc, char **argv) {
   std::string scene = "stack32", out = "", mode = "callback", resync = "";
-  int nworlds = 1, nsteps = 10, world0 = 0, timing = 0, settle = 0, maxc_world = 0;
+  int nworlds = 1, nsteps = 10, world0 = 0, timing = 0, settle = 0, maxc_world = 0, large = 0;
+  uint32_t seed_xor = 0;
   double h = 0.01;
   for (int i = 1; i < argc; i++) {
     std::string a = argv[i];
@@ -110,6 +139,8 @@ int main(int argc, char **argv) {
     else if (a == "--settle") settle = atoi(argv[++i]);
     else if (a == "--contacts-cap") maxc_world = atoi(argv[++i]);
     else if (a == "--resync") resync = argv[++i];
+    else if (a == "--seed-xor") seed_xor = (uint32_t)strtoul(argv[++i], 0, 0);   // other SOR shuffle stream, same scene
+    else if (a == "--large") large = 1;                                          // force the large-world path (batch mode)
     else { fprintf(stderr, "unknown arg %s\n", a.c_str()); return 2; }
   }
   dInitODE2(0);
@@ -117,6 +148,7 @@ int main(int argc, char **argv) {
   ScenePolicy pol;
   for (int w = 0; w < nworlds; w++)
     if (scene_build(scene.c_str(), worlds[w], world0 + w, pol)) { fprintf(stderr, "bad scene\n"); return 2; }
+  for (int w = 0; w < nworlds; w++) worlds[w].seed ^= seed_xor;
 
   Trace t;
   t.f = NULL;
@@ -148,11 +180,24 @@ int main(int argc, char **argv) {
       }
     ctx.ncontacts = 0;
     ctx.record = t.f != NULL;
+    Resync rsc;
+    if (!resync.empty() && !rsc.open(resync, nworlds)) { fprintf(stderr, "bad --resync trace\n"); return 2; }
     t0 = now_s();
     for (int s = 0; s < nsteps; s++) {
       for (int w = 0; w < nworlds; w++) {
         SceneWorld &sw = worlds[w];
         ctx.sw = &sw;
+        if (rsc.f) {
+          std::vector<dReal> st;
+          if (!rsc.next((int)sw.bodies.size(), st)) { fprintf(stderr, "resync trace too short\n"); return 2; }
+          for (size_t i = 0; i < sw.bodies.size(); i++) {
+            const dReal *p = &st[i * 13];
+            dBodySetPosition(sw.bodies[i], p[0], p[1], p[2]);
+            dBodySetQuaternion(sw.bodies[i], p + 3);
+            dBodySetLinearVel(sw.bodies[i], p[7], p[8], p[9]);
+            dBodySetAngularVel(sw.bodies[i], p[10], p[11], p[12]);
+          }
+        }
         if (t.f) {
           int ng = dSpaceGetNumGeoms(sw.space);
           t.i32(ng);
@@ -206,6 +251,7 @@ int main(int argc, char **argv) {
     dBatchDesc desc;
     memset(&desc, 0, sizeof(desc));
     desc.max_contacts_per_world = maxc_world;
+    desc.large_world = large;
     dBatchID B = dBatchCreate(nworlds, wv.data(), sv.data(), &desc);
     if (!B) { fprintf(stderr, "dBatchCreate failed: %s\n", dB200LastError()); return 3; }
     dBatchContactPolicy bp;
@@ -232,37 +278,24 @@ int main(int argc, char **argv) {
       dBatchGetCounters(B, &c);
       body_steps = c.body_steps; contacts = c.contacts; pairs = c.pairs;
     } else {
-      std::vector<int> pbuf(2 * 65536), cg(2 * 65536);
-      std::vector<dReal> cd(7 * 65536), lam(12 * 65536);
+      const int tapcap = std::max(65536, 16 * nb);
+      std::vector<int> pbuf(2 * (size_t)tapcap), cg(2 * (size_t)tapcap);
+      std::vector<dReal> cd(7 * (size_t)tapcap), lam(12 * (size_t)tapcap);
       // lock-step parity (SURVEY 8d "parity protocol", K = 1): before every step load the body state the
       // reference had before ITS step from a reference trace, so chaos cannot amplify rounding differences
-      FILE *rs = NULL;
-      if (!resync.empty()) {
-        rs = fopen(resync.c_str(), "rb");
-        int hdr[4];
-        if (!rs || fread(hdr, 4, 4, rs) != 4 || hdr[1] != (int)sizeof(dReal) || hdr[2] != nworlds) { fprintf(stderr, "bad --resync trace\n"); return 2; }
-      }
+      Resync rsc;
+      if (!resync.empty() && !rsc.open(resync, nworlds)) { fprintf(stderr, "bad --resync trace\n"); return 2; }
       for (int s = 0; s < nsteps; s++) {
-        if (rs) {
+        if (rsc.f) {
           for (int w = 0; w < nworlds; w++) {
-            int n;
-            if (fread(&n, 4, 1, rs) != 1) { fprintf(stderr, "resync trace too short\n"); return 2; }
-            fseek(rs, 4L * n, SEEK_CUR);
-            if (fread(&n, 4, 1, rs) != 1 || n != nb) { fprintf(stderr, "resync trace: body count\n"); return 2; }
-            std::vector<dReal> st((size_t)nb * 13);
-            if (fread(st.data(), sizeof(dReal), st.size(), rs) != st.size()) return 2;
+            std::vector<dReal> st;
+            if (!rsc.next(nb, st)) { fprintf(stderr, "resync trace too short / body count\n"); return 2; }
             for (int b = 0; b < nb; b++) {
               memcpy(&pos[(w * nb + b) * 3], &st[b * 13], 3 * sizeof(dReal));
               memcpy(&quat[(w * nb + b) * 4], &st[b * 13 + 3], 4 * sizeof(dReal));
               memcpy(&lv[(w * nb + b) * 3], &st[b * 13 + 7], 3 * sizeof(dReal));
               memcpy(&av[(w * nb + b) * 3], &st[b * 13 + 10], 3 * sizeof(dReal));
             }
-            if (fread(&n, 4, 1, rs) != 1) return 2;
-            fseek(rs, 8L * n, SEEK_CUR);                                       // pairs
-            if (fread(&n, 4, 1, rs) != 1) return 2;
-            fseek(rs, (long)n * (8 + 7 * (long)sizeof(dReal)), SEEK_CUR);       // contacts
-            fseek(rs, (long)n * 6 * (long)sizeof(dReal), SEEK_CUR);             // feedback
-            fseek(rs, (long)nb * 13 * (long)sizeof(dReal) + 4, SEEK_CUR);       // state1 + seed
           }
           dBatchSetBodyState(B, pos.data(), quat.data(), lv.data(), av.data());
         }
@@ -279,8 +312,8 @@ int main(int argc, char **argv) {
           }
         std::vector<std::vector<int> > glists(nworlds);
         for (int w = 0; w < nworlds; w++) {
-          glists[w].resize(4096);
-          int ng = dBatchDebugGeomOrder(B, w, glists[w].data(), 4096);
+          glists[w].resize(std::max(4096, nb + 64));
+          int ng = dBatchDebugGeomOrder(B, w, glists[w].data(), (int)glists[w].size());
           glists[w].resize(ng);
         }
         int rc = dBatchCollideAndQuickStep(B, (dReal)h, 1, status.data());
@@ -293,13 +326,13 @@ int main(int argc, char **argv) {
           fwrite(glists[w].data(), 4, glists[w].size(), t.f);
           t.i32(nb);
           t.reals(&st0[(size_t)w * nb * 13], (size_t)nb * 13);
-          int np = dBatchDebugPairs(B, w, pbuf.data(), 65536);
+          int np = dBatchDebugPairs(B, w, pbuf.data(), tapcap);
           t.i32(np);
           fwrite(pbuf.data(), 4, 2 * np, t.f);
-          int nc = dBatchDebugContacts(B, w, cd.data(), cg.data(), 65536);
+          int nc = dBatchDebugContacts(B, w, cd.data(), cg.data(), tapcap);
           t.i32(nc);
           for (int i = 0; i < nc; i++) { t.i32(cg[2 * i]); t.i32(cg[2 * i + 1]); t.reals(&cd[7 * i], 7); }
-          int nl = dBatchDebugFeedback(B, w, lam.data(), 65536);
+          int nl = dBatchDebugFeedback(B, w, lam.data(), tapcap);
           (void)nl;
           t.reals(lam.data(), (size_t)nc * 6);
           for (int b = 0; b < nb; b++) {

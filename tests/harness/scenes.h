@@ -6,6 +6,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
@@ -439,6 +440,30 @@ static inline void scene_buggy_terrain(SceneWorld &sw, int w, int n) {
   }
 }
 
+// config 5: nx*ny*nz bodies, alternating spheres (r 0.25) and boxes (0.5^3), jittered lattice (1 m in x/y,
+// 0.62 m in z) dropped into a walled box (floor + 4 wall planes); dSweepAndPruneSpace, crash policy.
+// One world; scene name pile_NXxNYxNZ.
+static inline void scene_pile(SceneWorld &sw, int w, int nx, int ny, int nz) {
+  g_scene_space_kind = 1;
+  scene_world_base(sw, w);
+  xs32 rng(sw.seed ^ 0x0091E5u);
+  const dReal hx = (dReal)(0.5 * nx + 0.5), hy = (dReal)(0.5 * ny + 0.5);
+  scene_add_geom(sw, dCreatePlane(sw.space, 0, 0, 1, 0));
+  scene_add_geom(sw, dCreatePlane(sw.space, 1, 0, 0, -hx));
+  scene_add_geom(sw, dCreatePlane(sw.space, -1, 0, 0, -hx));
+  scene_add_geom(sw, dCreatePlane(sw.space, 0, 1, 0, -hy));
+  scene_add_geom(sw, dCreatePlane(sw.space, 0, -1, 0, -hy));
+  for (int k = 0; k < nz; k++)
+    for (int j = 0; j < ny; j++)
+      for (int i = 0; i < nx; i++) {
+        const dReal x = (dReal)(i - 0.5 * (nx - 1)) + rng.uni(-0.1, 0.1);
+        const dReal y = (dReal)(j - 0.5 * (ny - 1)) + rng.uni(-0.1, 0.1);
+        const dReal z = (dReal)(0.4 + 0.62 * k) + rng.uni(-0.02, 0.02);
+        if ((i + j + k) & 1) scene_add_sphere(sw, 1, (dReal)0.25, x, y, z);
+        else scene_add_box(sw, 1, (dReal)0.5, (dReal)0.5, (dReal)0.5, x, y, z);
+      }
+}
+
 static inline ScenePolicy policy_buggy() {
   // ode/demo/demo_buggy.cpp:96-103
   ScenePolicy p;
@@ -481,6 +506,10 @@ static inline int scene_build(const char *name_in, SceneWorld &sw, int w, SceneP
   if (!strcmp(name, "capsmix")) { scene_capsmix(sw, w); return 0; }
   if (!strcmp(name, "ragdoll")) { scene_ragdoll(sw, w); pol = policy_crash(); return 0; }
   if (!strcmp(name, "buggy")) { scene_buggy(sw, w); pol = policy_buggy(); return 0; }
+  {
+    int nx, ny, nz;
+    if (sscanf(name, "pile_%dx%dx%d", &nx, &ny, &nz) == 3 && nx > 0 && ny > 0 && nz > 0) { scene_pile(sw, w, nx, ny, nz); pol = policy_crash(); return 0; }
+  }
   if (!strcmp(name, "free6")) {  // no contacts: integrator + gyroscopic term only
     scene_world_base(sw, w);
     xs32 rng(sw.seed);

@@ -122,6 +122,71 @@ def compare(ta, tb, verbose=False, stop_on_mismatch=True):
     return out
 
 
+def compare_large(ta, tb):
+    """Large-world comparison (candidate ta vs reference tb), SURVEY 8d parity protocol in lock-step:
+    * broadphase pairs compared as SETS — the reference's callback order depends on RadixSort
+      temporal-coherence state tied to its island stepping order, which the large-world path does not
+      carry.  Orientation (which geom is o1) must match too, except for pairs whose float axis-0 minima
+      tie exactly (`pairs_flipped`, reported; the reference breaks such ties by that same state);
+    * contacts of the equally oriented pairs, after a stable sort by (g1, g2) (the order inside a pair
+      is the collider's): geom ids exact, pos/normal/depth bitwise;
+    * body state after the step vs the reference: max relative error |a-b|_inf / max(1,|b|_inf) and RMS
+      of the per-body velocity difference (the coloured SOR order differs from the reference's random order)."""
+    assert ta["realsize"] == tb["realsize"] and ta["nworlds"] == tb["nworlds"] == 1
+    n = min(ta["nsteps"], tb["nsteps"])
+    out = {"steps": n, "pairs": 0, "contacts": 0, "pair_sets_equal": True, "pairs_flipped": 0, "contact_ids_equal": True,
+           "contact_bits_equal": 0, "contact_vals": 0, "state0_bits_equal": True,
+           "max_pos_relerr": 0.0, "max_vel_relerr": 0.0, "rms_dv": 0.0, "rms_dw": 0.0, "first_mismatch": None}
+    sdv = sdw = 0.0
+    nbod = 0
+    for s in range(n):
+        a, b = ta["steps"][s][0], tb["steps"][s][0]
+        if not _biteq(a["state0"], b["state0"]).all():
+            out["state0_bits_equal"] = False
+        pa = set(map(tuple, a["pairs"].tolist()))
+        pb = set(map(tuple, b["pairs"].tolist()))
+        out["pairs"] += len(b["pairs"])
+        flipped = {(y, x) for (x, y) in pa - pb}
+        if flipped != pb - pa or len(pa) != len(a["pairs"]) or len(pb) != len(b["pairs"]):
+            out["pair_sets_equal"] = False
+            if out["first_mismatch"] is None:
+                out["first_mismatch"] = (s, "pairs", sorted(pa - pb)[:5], sorted(pb - pa)[:5])
+        out["pairs_flipped"] += len(flipped)
+        out["contacts"] += len(b["cg"])
+
+        def keep(rec, drop):
+            if not drop or len(rec["cg"]) == 0:
+                return rec["cg"], rec["cd"]
+            m = np.array([tuple(g) not in drop for g in rec["cg"].tolist()], dtype=bool)
+            return rec["cg"][m], rec["cd"][m]
+
+        acg, acd = keep(a, pa - pb)
+        bcg, bcd = keep(b, pb - pa)
+        if acg.shape != bcg.shape:
+            out["contact_ids_equal"] = False
+            if out["first_mismatch"] is None:
+                out["first_mismatch"] = (s, "ncontacts", len(acg), len(bcg))
+        else:
+            ia = np.lexsort((np.arange(len(acg)), acg[:, 1], acg[:, 0]))
+            ib = np.lexsort((np.arange(len(bcg)), bcg[:, 1], bcg[:, 0]))
+            if not np.array_equal(acg[ia], bcg[ib]):
+                out["contact_ids_equal"] = False
+                if out["first_mismatch"] is None:
+                    out["first_mismatch"] = (s, "contact ids")
+            else:
+                out["contact_vals"] += bcd.size
+                out["contact_bits_equal"] += int(_biteq(acd[ia], bcd[ib]).sum())
+        out["max_pos_relerr"] = max(out["max_pos_relerr"], _relerr(a["state1"][:, :7], b["state1"][:, :7]))
+        out["max_vel_relerr"] = max(out["max_vel_relerr"], _relerr(a["state1"][:, 7:], b["state1"][:, 7:]))
+        x, y = a["state1"].astype(np.float64), b["state1"].astype(np.float64)
+        sdv += float(((x[:, 7:10] - y[:, 7:10]) ** 2).sum())
+        sdw += float(((x[:, 10:13] - y[:, 10:13]) ** 2).sum())
+        nbod += len(x)
+    out["rms_dv"] = (sdv / max(nbod, 1)) ** 0.5
+    out["rms_dw"] = (sdw / max(nbod, 1)) ** 0.5
+    return out
+
+
 if __name__ == "__main__":
     r = compare(read_trace(sys.argv[1]), read_trace(sys.argv[2]), verbose=True)
     for k, v in r.items():

@@ -61,6 +61,7 @@ ObBackend *obk_create(const ObBatchDev &caps, int, char *, size_t) {
   d.csurf = d.dropin ? halloc<ObSurface>(b, W * d.NC) : 0;
   d.cfdir1 = d.dropin ? halloc<real>(b, W * d.NC * 4) : 0;
   d.counters = halloc<ObCounters>(b, 1);
+  if (d.large) { d.invIw = halloc<real>(b, (size_t)d.NB * 12); d.tmp1 = halloc<real>(b, (size_t)d.NB * 8); }
   return b;
 }
 void obk_destroy(ObBackend *b) { for (size_t i = 0; i < b->allocs.size(); i++) free(b->allocs[i]); delete b; }
@@ -76,6 +77,12 @@ int obk_timer_stop(ObBackend *, float *ms) { *ms = 0; return 0; }
 void obk_set_kernel_timing(ObBackend *, int) {}
 void obk_get_kernel_times(ObBackend *, double *ms, long long *l) { for (int k = 0; k < OBK_NKERNELS; k++) { ms[k] = 0; l[k] = 0; } }
 const char *obk_kernel_name(int) { return "host"; }
+static int g_lw_stat[8];
+int obk_large_stats(ObBackend *b, int *ints8, double *ms8) {
+  if (!b->d.large) return -1;
+  for (int k = 0; k < 8; k++) { ints8[k] = g_lw_stat[k]; ms8[k] = 0; }
+  return 0;
+}
 
 int obk_get_state(ObBackend *b, real *pos3, real *quat4, real *lvel3, real *avel3) {
   ObBatchDev &d = b->d;
@@ -99,7 +106,7 @@ int obk_set_state(ObBackend *b, const real *pos3, const real *quat4, const real 
       size_t o = (size_t)w * d.NB + c;
       ObBodyDyn &s = d.bdyn[(size_t)w * d.NB + (nb - 1 - c)];
       for (int k = 0; k < 3; k++) { if (pos3) s.pos[k] = pos3[o * 3 + k]; if (lvel3) s.lvel[k] = lvel3[o * 3 + k]; if (avel3) s.avel[k] = avel3[o * 3 + k]; }
-      if (quat4) { for (int k = 0; k < 4; k++) s.q[k] = quat4[o * 4 + k]; ob_safe_normalize4(s.q); ob_RfromQ(s.R, s.q); }
+      if (quat4) { for (int k = 0; k < 4; k++) s.q[k] = quat4[o * 4 + k]; ob_RfromQ(s.R, s.q); }
     }
   }
   return 0;
@@ -141,6 +148,8 @@ static void geom_pose(const ObBatchDev &d, int w, int gi, ObPose *o) {
     for (int k = 0; k < 12; k++) o->R[k] = g.R[k];
   }
 }
+
+#include "large_host.h"
 
 struct PairRec { ObPairKey key; int o1, o2; };
 static bool pair_less(const PairRec &a, const PairRec &b) { return ob_key_less(a.key, b.key); }
@@ -569,6 +578,7 @@ static void step_world(ObBatchDev &d, int w, real h, int taps) {
 
 int obk_run_phases(ObBackend *b, real h, int phases, int taps, char *, size_t) {
   ObBatchDev &d = b->d;
+  if (d.large) return -1;
   for (int w = 0; w < d.W; w++) {
     if (phases & OBK_PHASE_COLLIDE) collide_world(d, w);
     if (phases & OBK_PHASE_STEP) step_world(d, w, h, taps);
@@ -593,8 +603,18 @@ int obk_mesh_upload(const float *verts, int nverts, const int *tris, int ntris, 
   return 0;
 }
 void obk_mesh_free(ObMeshDev *m) { free((void *)m->verts); free((void *)m->tris); free((void *)m->nodes); m->verts = 0; m->tris = 0; m->nodes = 0; }
-int obk_step(ObBackend *b, real h, int nsteps, int taps, char *, size_t) {
+int obk_step(ObBackend *b, real h, int nsteps, int taps, char *err, size_t errlen) {
   ObBatchDev &d = b->d;
+  if (d.large) {
+    for (int s = 0; s < nsteps; s++) {
+      LargeHostStats st;
+      const int rc = large_step_host(d, h, taps, &st);
+      if (rc) { snprintf(err, errlen, "large-world step failed (%d)", rc); return -1; }
+      g_lw_stat[0] = st.np; g_lw_stat[1] = st.ncontacts; g_lw_stat[2] = st.ncp; g_lw_stat[3] = st.nsolved; g_lw_stat[4] = st.ncol; g_lw_stat[5] = st.rounds;
+      if (getenv("OB_LW_VERBOSE")) fprintf(stderr, "lw: pairs %d contacts %d cpairs %d colours %d rounds %d\n", st.np, st.ncontacts, st.ncp, st.ncol, st.rounds);
+    }
+    return 0;
+  }
   for (int s = 0; s < nsteps; s++)
     for (int w = 0; w < d.W; w++) {
       collide_world(d, w);
