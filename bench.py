@@ -315,6 +315,131 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+LARGE = dict(scene="pile_100x100x20", settle=300, cpu_scene="pile_24x24x20", cpu_settle=200, cpu_steps=10,
+             desc="configs[4]: one world, {NB} bodies (50/50 spheres r 0.25 / boxes 0.5^3) piled in a walled box, dSweepAndPruneSpace, "
+                  "crash contact policy maxc 4, graph-coloured SOR")
+PHASES = ["geoms+sort", "pair sweep", "narrowphase", "colouring", "row assembly", "sor", "integration"]
+
+
+class LargeStats(ctypes.Structure):
+    _fields_ = [("pairs", ctypes.c_int), ("contacts", ctypes.c_int), ("contact_pairs", ctypes.c_int), ("solved_contacts", ctypes.c_int),
+                ("colours", ctypes.c_int), ("colouring_rounds", ctypes.c_int), ("sor_launches", ctypes.c_int), ("steps_timed", ctypes.c_int),
+                ("phase_ms", ctypes.c_double * 7)]
+
+
+def run_large(args):
+    """configs[4]: one large world on one GPU (the path does not shard without an exchange step per colour:
+    ranks > 0 exit).  value = device-resident body-steps/s; roofline on the SOR phase
+    (iterations x colours launches of k_lw_sor), algorithmic bytes D x iterations per row."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    lib, scenes = load_libs()
+    lib.dBatchGetLargeWorldStats.argtypes = [ctypes.c_void_p, ctypes.POINTER(LargeStats)]
+    scene = args.scene or LARGE["scene"]
+    B = scenes.ob_scene_build_batch(scene.encode(), 1, 0, 0, int(os.environ.get("LOCAL_RANK", "0")))
+    if not B:
+        raise SystemExit("batch creation failed: " + (lib.dB200LastError() or b"").decode())
+    B = ctypes.c_void_p(B)
+    lib.dBatchSetDebugTaps(B, 0)
+    status = np.zeros(1, dtype=np.int32)
+
+    def step(n):
+        if lib.dBatchCollideAndQuickStep(B, H, n, status.ctypes.data) != 0:
+            raise SystemExit("step failed: " + lib.dB200LastError().decode())
+        if status[0]:
+            raise SystemExit(f"capacity overflow, status {status[0]}")
+
+    settle = args.settle if args.settle >= 0 else LARGE["settle"]
+    step(settle)
+    step(max(args.warmup, 3))
+    lib.dBatchResetCounters(B)
+    l0 = lib.dB200KernelLaunchCount()
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    sampler.start()
+    ms = ctypes.c_float()
+    lib.dBatchTimerStart(B)
+    step(args.steps)
+    lib.dBatchTimerStop(B, ctypes.byref(ms))
+    clocks = sampler.stop()
+    launches = lib.dB200KernelLaunchCount() - l0
+    c = counters(lib, B)
+    t = float(ms.value) * 1e-3
+    # per-phase attribution (CUDA events between the phases, separate pass)
+    lib.dBatchSetKernelTiming(B, 1)
+    lib.dBatchResetCounters(B)
+    step(args.steps)
+    st = LargeStats()
+    lib.dBatchGetLargeWorldStats(B, ctypes.byref(st))
+    lib.dBatchSetKernelTiming(B, 0)
+    ck = counters(lib, B)
+    nst = max(st.steps_timed, 1)
+    ph = {PHASES[k]: st.phase_ms[k] / nst for k in range(7)}
+    nb = lib.dBatchNumBodies(B)
+    rows_per_step = 3 * ck["contacts"] / nst
+    sor_bytes = D_B * ITERS * rows_per_step
+    peak, peak_kind = peaks()
+    step_bytes = (A_B * nb + B_B * (nb + 5) + C_B * ck["contacts"] / nst + (D_B * ITERS + ASM_B) * rows_per_step)
+    achieved = sor_bytes / (ph["sor"] * 1e-3) / 1e9
+    # end to end with host buffers
+    lib.dBatchHostAlloc.restype = ctypes.c_void_p
+    lib.dBatchHostAlloc.argtypes = [ctypes.c_size_t]
+
+    def pinned(shape):
+        n = int(np.prod(shape))
+        ptr = lib.dBatchHostAlloc(n * 4)
+        a = np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_float)), shape=(n,)).reshape(shape)
+        a[...] = 0
+        return a
+
+    pos = pinned((nb, 3)); quat = pinned((nb, 4)); lv = pinned((nb, 3)); av = pinned((nb, 3)); torque = pinned((nb, 3))
+    rng = np.random.default_rng(0)
+    forces = [pinned((nb, 3)) for _ in range(4)]
+    for f in forces:
+        f[:, 0] = 0.01 * rng.standard_normal(nb, dtype=np.float32)
+    lib.dBatchResetCounters(B)
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        lib.dBatchAddForces(B, forces[s & 3].ctypes.data, torque.ctypes.data)
+        step(1)
+        lib.dBatchGetBodyState(B, pos.ctypes.data, quat.ctypes.data, lv.ctypes.data, av.ctypes.data)
+    t_e2e = time.perf_counter() - t0
+    ce = counters(lib, B)
+    assert np.isfinite(pos).all()
+    out = {
+        "metric": "body-steps/sec (dSpaceCollide + dWorldQuickStep, 20 SOR iterations)", "value": c["body_steps"] / t, "unit": "body-steps/s",
+        "contacts_solved_per_sec": c["contacts"] / t, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": t * 1e3 / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": LARGE["desc"].format(NB=nb) + f", scene {scene}, quickstep 20 it, h={H}, settled {settle} steps",
+                   "bodies": nb, "pairs_per_step": st.pairs, "contacts_per_step": st.contacts, "rows_per_step": rows_per_step,
+                   "colours": st.colours, "colouring_rounds": st.colouring_rounds, "sor_launches_per_step": st.sor_launches,
+                   "cache": "rows %.0f MB/step streamed every iteration (> 126 MB L2 at full size)" % (rows_per_step * 80 / 1e6),
+                   "precision": "dSINGLE", "parity": "pairs+contacts exact, state within stated tolerance vs reference; bitwise vs sequential mirror (tests/test_large_world.py)"},
+        "e2e": {"value": ce["body_steps"] / t_e2e, "unit": "body-steps/s", "h2d_bytes_per_step": int(forces[0].nbytes + torque.nbytes),
+                "d2h_bytes_per_step": int(pos.nbytes + quat.nbytes + lv.nbytes + av.nbytes)},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "k_lw_sor (x%d launches/step)" % st.sor_launches, "achieved": achieved, "peak": peak,
+                     "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "algorithmic_bytes_per_launch": sor_bytes / max(st.sor_launches, 1), "kernel_ms": ph["sor"] / max(st.sor_launches, 1),
+                     "kernel_share_of_step": ph["sor"] / max(sum(ph.values()), 1e-9),
+                     "whole_step": {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (t / args.steps) / 1e9},
+                     "phases_ms": ph},
+        "clocks": clocks, "overflow_worlds": c["overflow_worlds"],
+    }
+    if not args.no_cpu:
+        exe = os.path.join(ROOT, "oracle", "_ref", "driver_ref_single")
+        if os.path.exists(exe):
+            r = json.loads(subprocess.run([exe, "--scene", LARGE["cpu_scene"], "--steps", str(LARGE["cpu_steps"]), "--settle", str(LARGE["cpu_settle"]),
+                                           "--time"], capture_output=True, text=True, timeout=1800).stdout.strip().splitlines()[-1])
+            out["cpu_baseline"] = {"value": r["body_steps_per_sec"], "unit": "body-steps/s", "cores": 1, "kind": "reference",
+                                   "contacts_solved_per_sec": r["contacts_per_sec"],
+                                   "sample": f"1 process (one world cannot use more), scene {LARGE['cpu_scene']} (same pile, smaller footprint), "
+                                             f"{LARGE['cpu_settle']} settle steps untimed + {LARGE['cpu_steps']} timed"}
+    print(json.dumps(out))
+    lib.dBatchDestroy(B)
+
+
 def cpu_run(nproc, worlds_each, steps, settle, timeout=900):
     exe = os.path.join(ROOT, "oracle", "_ref", "driver_ref_single")
     if not os.path.exists(exe):
@@ -372,8 +497,16 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--worlds", type=int, default=0)
-    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS) + [5])
+    ap.add_argument("--scene", default="")
+    ap.add_argument("--settle", type=int, default=-1)
+    ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()
+    if a.config == 5:
+        if a.impl == "reference":
+            raise SystemExit("--config 5 reports the reference inside its own line (cpu_baseline)")
+        run_large(a)
+        sys.exit(0)
     cfg = CONFIGS[a.config]
     SCENE, SETTLE, CONTACTS_CAP, GEOMS_PER_WORLD, CONFIG_DESC = cfg["scene"], cfg["settle"], cfg["cap"], cfg["geoms"], cfg["desc"]
     if a.worlds <= 0:
