@@ -378,7 +378,7 @@ struct ObBackend {
   int large;
   ObLargeDev L;
   int *lw_host;        // pinned: scalars + segment table read back for launch sizing
-  int lw_rounds, lw_ncol, lw_stat[8];
+  int lw_rounds, lw_ncol, lw_stat[8], lw_sor_grid[3];
   double lw_ms[8];     // geoms+sort, pairs, narrow, colour, assemble, sor, post (CUDA events, when kernel timing is on)
   cudaEvent_t lw_ev[9];
 };

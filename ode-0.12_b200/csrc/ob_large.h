@@ -45,6 +45,10 @@
 #define OB_LW_SLOTW 2
 #endif
 #define OB_LW_ROWW 20
+#define OB_LW_HITBUF 16
+#if !defined(__CUDACC__)
+struct int4 { int x, y, z, w; };
+#endif
 
 struct __attribute__((aligned(16))) ObLwBox { real maxx, miny, maxy, minz, maxz; float minx; int body; uint32_t cat, col; int geom; int pad[2]; };
 struct __attribute__((aligned(16))) ObLwPair { int b1, b2; int info; int src; };   // info = nc | rev<<8 | colour<<16 ; src = geom-pair index
@@ -56,7 +60,12 @@ struct ObLargeDev {
   real *aabb;                  // [NG*6]
   uint32_t *gkey[2];           // [NG] radix sort ping-pong
   int *gidx[2];
-  ObLwBox *sbox;               // [NG] sorted order
+  ObLwBox *sbox;               // [NG] sorted order (host mirror layout; the kernels use the split arrays below)
+  float *sminx;                // [NG] sorted: float-cast axis-0 minimum (the sweep's stop test reads only this)
+  real *smaxx;                 // [NG] axis-0 maximum
+  real *syz;                   // [NG*4] miny maxy minz maxz
+  int4 *smeta;                 // [NG] body, category bits, collide bits, geom index
+  int *hits;                   // [NG*OB_LW_HITBUF] first hits of every sorted position, recorded by the counting pass
   int *scal;                   // device scalars, see LW_* below
   // pairs
   uint32_t *cnt;               // [2*NG+2] per sorted geom: sweep hits, then hits against the infinite list
@@ -82,7 +91,7 @@ struct ObLargeDev {
   uint32_t *tmp;               // scan / sort scratch
   size_t tmp_words;
 };
-enum { LW_NFIN = 0, LW_NBIG, LW_NP, LW_NCONTACTS, LW_NCP, LW_UNCOLOURED, LW_NCOL, LW_ERR, LW_NSOLVED, LW_WORDS = 16 };
+enum { LW_NFIN = 0, LW_NBIG, LW_NP, LW_NCONTACTS, LW_NCP, LW_UNCOLOURED, LW_NCOL, LW_ERR, LW_NSOLVED, LW_BARRIER, LW_LEFT0 /* 16 per-round counters */, LW_WORDS = 32 };
 
 // ---- broadphase --------------------------------------------------------------------------------
 // sort key of one geom (collision_sapspace.cpp:441-452, :531-535): float-cast axis-0 minimum
@@ -105,8 +114,11 @@ OB_HD uint32_t ob_lw_hash(uint32_t x) {
   x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
   return x;
 }
+// priority of a pair in a round (lower wins).  The top byte counts DOWN with the round, so a claim left
+// in the table by an earlier round always loses against any claim of the current round: the claim table
+// needs no clearing between rounds (it is cleared once per step; at most 255 rounds).
 OB_HD unsigned long long ob_lw_prio(uint32_t pair, uint32_t round) {
-  return ((unsigned long long)ob_lw_hash(pair * 0x9E3779B9u + round) << 32) | pair;
+  return ((unsigned long long)(254u - (round & 255u)) << 56) | ((unsigned long long)(ob_lw_hash(pair * 0x9E3779B9u + round) >> 8) << 32) | pair;
 }
 OB_HD int ob_lw_first_free(unsigned long long used) {   // lowest clear bit, OB_LW_MAXCOL if none
   for (int c = 0; c < OB_LW_MAXCOL; c++) if (!((used >> c) & 1ull)) return c;

@@ -171,7 +171,9 @@ __global__ void __launch_bounds__(LW_T) k_lw_gather(ObBatchDev d, ObLargeDev L, 
   ObLwBox b;
   b.maxx = ab[ax0 + 1]; b.miny = ab[ax1]; b.maxy = ab[ax1 + 1]; b.minz = ab[ax2]; b.maxz = ab[ax2 + 1];
   b.minx = (float)ab[ax0]; b.body = G.body; b.cat = G.cat; b.col = G.col; b.geom = g; b.pad[0] = b.pad[1] = 0;
-  L.sbox[i] = b;
+  L.sminx[i] = b.minx; L.smaxx[i] = b.maxx;
+  L.syz[(size_t)4 * i] = b.miny; L.syz[(size_t)4 * i + 1] = b.maxy; L.syz[(size_t)4 * i + 2] = b.minz; L.syz[(size_t)4 * i + 3] = b.maxz;
+  L.smeta[i] = make_int4(G.body, (int)G.cat, (int)G.col, g);
   const uint32_t nxt = i + 1 < ng ? skey[i + 1] : OB_LW_KEY_OFF;
   if (key < OB_LW_KEY_BIG && (i + 1 == ng || nxt >= OB_LW_KEY_BIG)) L.scal[LW_NFIN] = i + 1;
   if (key == OB_LW_KEY_BIG && (i + 1 == ng || nxt != OB_LW_KEY_BIG)) L.scal[LW_NBIG] = i + 1;   // end of the infinite list (start = NFIN)
@@ -208,25 +210,56 @@ __global__ void __launch_bounds__(LW_T) k_lw_sweep(ObBatchDev d, ObLargeDev L) {
   }
   if (i >= ng) return;
   if (i >= nfin) { if (!FILL) { L.cnt[i] = 0; L.cnt[ng + i] = 0; } return; }
-  const ObLwBox K = L.sbox[i];
-  uint32_t h = 0;
-  size_t o = FILL ? L.off[i] : 0;
-  for (int j = i + 1; j < nfin; j++) {
-    const ObLwBox &J = L.sbox[j];
-    if (!((real)J.minx <= K.maxx)) break;
-    if (ob_lw_sweep_hit(K, J)) {
-      if (FILL && o + h < (size_t)L.NP) { L.pairs[2 * (o + h)] = K.geom; L.pairs[2 * (o + h) + 1] = J.geom; }
+  const real Kmaxx = L.smaxx[i];
+  const real Kminy = L.syz[(size_t)4 * i], Kmaxy = L.syz[(size_t)4 * i + 1], Kminz = L.syz[(size_t)4 * i + 2], Kmaxz = L.syz[(size_t)4 * i + 3];
+  const int4 Km = L.smeta[i];
+  int *hb = L.hits + (size_t)i * OB_LW_HITBUF;
+  if (!FILL) {
+    // counting pass: BoxPruning's inner loop (:545-560); the first OB_LW_HITBUF hits are remembered
+    uint32_t h = 0;
+    for (int j = i + 1; j < nfin; j++) {
+      if (!((real)L.sminx[j] <= Kmaxx)) break;
+#if defined(dSINGLE)
+      const float4 yz = *(const float4 *)(L.syz + (size_t)4 * j);
+      const real Jminy = yz.x, Jmaxy = yz.y, Jminz = yz.z, Jmaxz = yz.w;
+#else
+      const double2 y2 = *(const double2 *)(L.syz + (size_t)4 * j), z2 = *(const double2 *)(L.syz + (size_t)4 * j + 2);
+      const real Jminy = y2.x, Jmaxy = y2.y, Jminz = z2.x, Jmaxz = z2.y;
+#endif
+      if (!(Kmaxy >= Jminy && Jmaxy >= Kminy)) continue;
+      if (!(Kmaxz >= Jminz && Jmaxz >= Kminz)) continue;
+      const int4 Jm = L.smeta[j];
+      if (!ob_pair_filter_noaabb(Km.x, Jm.x, (uint32_t)Km.y, (uint32_t)Km.z, (uint32_t)Jm.y, (uint32_t)Jm.z)) continue;
+      if (h < OB_LW_HITBUF) hb[h] = Jm.w;
       h++;
     }
+    L.cnt[i] = h;
+  } else {
+    const uint32_t n = L.cnt[i];
+    const size_t o = L.off[i];
+    if (n <= OB_LW_HITBUF) {
+      for (uint32_t h = 0; h < n; h++) if (o + h < (size_t)L.NP) { L.pairs[2 * (o + h)] = Km.w; L.pairs[2 * (o + h) + 1] = hb[h]; }
+    } else {
+      uint32_t h = 0;
+      for (int j = i + 1; j < nfin; j++) {
+        if (!((real)L.sminx[j] <= Kmaxx)) break;
+        const real Jminy = L.syz[(size_t)4 * j], Jmaxy = L.syz[(size_t)4 * j + 1], Jminz = L.syz[(size_t)4 * j + 2], Jmaxz = L.syz[(size_t)4 * j + 3];
+        if (!(Kmaxy >= Jminy && Jmaxy >= Kminy)) continue;
+        if (!(Kmaxz >= Jminz && Jmaxz >= Kminz)) continue;
+        const int4 Jm = L.smeta[j];
+        if (!ob_pair_filter_noaabb(Km.x, Jm.x, (uint32_t)Km.y, (uint32_t)Km.z, (uint32_t)Jm.y, (uint32_t)Jm.z)) continue;
+        if (o + h < (size_t)L.NP) { L.pairs[2 * (o + h)] = Km.w; L.pairs[2 * (o + h) + 1] = Jm.w; }
+        h++;
+      }
+    }
   }
-  if (!FILL) L.cnt[i] = h;
-  h = 0;
-  o = FILL ? L.off[ng + i] : 0;
+  uint32_t h = 0;
+  const size_t o = FILL ? L.off[ng + i] : 0;
   for (int a = nfin; a < bigend; a++) {   // collideGeomsNoAABBs: no AABB test against the infinite list (:486-491)
     const int ga = sidx[a];
     const ObGeom &A = d.geom[ga];
-    if (ob_pair_filter_noaabb(A.body, K.body, A.cat, A.col, K.cat, K.col)) {
-      if (FILL && o + h < (size_t)L.NP) { L.pairs[2 * (o + h)] = ga; L.pairs[2 * (o + h) + 1] = K.geom; }
+    if (ob_pair_filter_noaabb(A.body, Km.x, A.cat, A.col, (uint32_t)Km.y, (uint32_t)Km.z)) {
+      if (FILL && o + h < (size_t)L.NP) { L.pairs[2 * (o + h)] = ga; L.pairs[2 * (o + h) + 1] = Km.w; }
       h++;
     }
   }
@@ -306,7 +339,7 @@ __global__ void __launch_bounds__(LW_T) k_lw_col_take(ObLargeDev L, int ncp, uin
     }
   }
   const unsigned m = __ballot_sync(0xffffffffu, left);
-  if ((threadIdx.x & 31) == 0 && m) atomicAdd(&L.scal[LW_UNCOLOURED], __popc(m));
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(&L.scal[LW_LEFT0 + (round & 15u)], __popc(m));
 }
 __global__ void __launch_bounds__(LW_T) k_lw_pairkey(ObLargeDev L, int ncp) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -442,19 +475,30 @@ __global__ void __launch_bounds__(LW_T) k_lw_assemble(ObBatchDev d, ObLargeDev L
   }
 }
 
+// one contact pair: its contacts in order, the rows of a contact in order.  fc and lambda go through L2
+// (ld.cg / st.cg): inside the persistent kernel other SMs wrote them in an earlier colour.
 template <int M>
-__global__ void __launch_bounds__(LW_T) k_lw_sor(ObLargeDev L, int col) {
-  const int *seg = L.segtab + col * (2 + OB_LW_MAXC);
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= seg[1]) return;
+__device__ __forceinline__ void lw_sor_pair(const ObLargeDev &L, const int *seg, int i) {
   const ObLwPair P = L.cp[1][seg[0] + i];
   const int nc = P.info & 255, b1 = P.b1, b2 = P.b2;
   real f1[6], f2[6] = {0, 0, 0, 0, 0, 0};
   real *fp1 = L.fc + (size_t)8 * b1, *fp2 = L.fc + (size_t)8 * (b2 >= 0 ? b2 : b1);
-  for (int e = 0; e < 6; e++) f1[e] = fp1[e];
+#if defined(dSINGLE)
+  { const float4 a = __ldcg((const float4 *)fp1); const float2 c = __ldcg((const float2 *)(fp1 + 4)); f1[0] = a.x; f1[1] = a.y; f1[2] = a.z; f1[3] = a.w; f1[4] = c.x; f1[5] = c.y; }
+#else
+  for (int e = 0; e < 6; e++) f1[e] = __ldcg(fp1 + e);
+#endif
   const real k1 = L.invM[b1];
   real k2 = 0;
-  if (b2 >= 0) { for (int e = 0; e < 6; e++) f2[e] = fp2[e]; k2 = L.invM[b2]; }
+  if (b2 >= 0) {
+#if defined(dSINGLE)
+    const float4 a = __ldcg((const float4 *)fp2); const float2 c = __ldcg((const float2 *)(fp2 + 4));
+    f2[0] = a.x; f2[1] = a.y; f2[2] = a.z; f2[3] = a.w; f2[4] = c.x; f2[5] = c.y;
+#else
+    for (int e = 0; e < 6; e++) f2[e] = __ldcg(fp2 + e);
+#endif
+    k2 = L.invM[b2];
+  }
   for (int k = 0; k < nc; k++) {
     const size_t cs = (size_t)seg[2 + k] + i;
     if (cs >= (size_t)L.NC) break;
@@ -469,12 +513,51 @@ __global__ void __launch_bounds__(LW_T) k_lw_sor(ObLargeDev L, int col) {
 #pragma unroll
       for (int r = 0; r < M; r++) if (fio && r == q - fio) lam_f = lam[r];
       real *lp = L.lambda + (size_t)q * L.NC + cs;
-      lam[q] = ob_lw_row_update(rw, meta, k1, k2, b2 >= 0, lam_f, *lp, f1, f2);
-      *lp = lam[q];
+      lam[q] = ob_lw_row_update(rw, meta, k1, k2, b2 >= 0, lam_f, __ldcg(lp), f1, f2);
+      __stcg(lp, lam[q]);
     }
   }
-  for (int e = 0; e < 6; e++) fp1[e] = f1[e];
-  if (b2 >= 0) for (int e = 0; e < 6; e++) fp2[e] = f2[e];
+#if defined(dSINGLE)
+  __stcg((float4 *)fp1, make_float4(f1[0], f1[1], f1[2], f1[3])); __stcg((float2 *)(fp1 + 4), make_float2(f1[4], f1[5]));
+  if (b2 >= 0) { __stcg((float4 *)fp2, make_float4(f2[0], f2[1], f2[2], f2[3])); __stcg((float2 *)(fp2 + 4), make_float2(f2[4], f2[5])); }
+#else
+  for (int e = 0; e < 6; e++) __stcg(fp1 + e, f1[e]);
+  if (b2 >= 0) for (int e = 0; e < 6; e++) __stcg(fp2 + e, f2[e]);
+#endif
+}
+// one launch per (iteration, colour): debugging path (OB_LW_SOR_LAUNCHES=1)
+template <int M>
+__global__ void __launch_bounds__(LW_T) k_lw_sor(ObLargeDev L, int col) {
+  const int *seg = L.segtab + col * (2 + OB_LW_MAXC);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= seg[1]) return;
+  lw_sor_pair<M>(L, seg, i);
+}
+// the whole SOR phase in one cooperative launch: every CTA walks (iteration, colour) and the grid meets
+// at a barrier after every colour (arrive counter in global memory, monotonically increasing)
+#define LW_SOR_T 256
+__device__ __forceinline__ void lw_grid_barrier(unsigned *bar, unsigned target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    while (*(volatile unsigned *)bar < target) { }
+    __threadfence();
+  }
+  __syncthreads();
+}
+template <int M>
+__global__ void __launch_bounds__(LW_SOR_T) k_lw_sor_all(ObLargeDev L, int iters, int ncol, unsigned *bar) {
+  unsigned epoch = 0;
+  const int stride = gridDim.x * blockDim.x;
+  for (int it = 0; it < iters; it++)
+    for (int c = 0; c < ncol; c++) {
+      const int *seg = L.segtab + c * (2 + OB_LW_MAXC);
+      const int cnt = seg[1];
+      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += stride) lw_sor_pair<M>(L, seg, i);
+      epoch++;
+      lw_grid_barrier(bar, epoch * gridDim.x);
+    }
 }
 
 __global__ void __launch_bounds__(LW_T) k_lw_body_post(ObBatchDev d, ObLargeDev L, real h) {
@@ -539,7 +622,12 @@ static int lw_create(ObBackend *b, char *err, size_t errlen) {
   LWCK(dalloc(b, &L.pose, NG));
   LWCK(dalloc(b, &L.aabb, NG * 6));
   for (int k = 0; k < 2; k++) { LWCK(dalloc(b, &L.gkey[k], NG)); LWCK(dalloc(b, &L.gidx[k], NG)); }
-  LWCK(dalloc(b, &L.sbox, NG));
+  L.sbox = 0;
+  LWCK(dalloc(b, &L.sminx, NG));
+  LWCK(dalloc(b, &L.smaxx, NG));
+  LWCK(dalloc(b, &L.syz, NG * 4));
+  LWCK(dalloc(b, &L.smeta, NG));
+  LWCK(dalloc(b, &L.hits, NG * OB_LW_HITBUF));
   LWCK(dalloc(b, &L.scal, (size_t)LW_WORDS));
   LWCK(dalloc(b, &L.cnt, 2 * NG + 2));
   LWCK(dalloc(b, &L.off, 2 * NG + 2));
@@ -562,6 +650,17 @@ static int lw_create(ObBackend *b, char *err, size_t errlen) {
   LWCK(dalloc(b, &L.tmp, L.tmp_words));
   LWCK(cudaMallocHost((void **)&b->lw_host, sizeof(int) * LW_HOST_WORDS));
   for (int k = 0; k < 9; k++) LWCK(cudaEventCreate(&b->lw_ev[k]));
+  {   // persistent SOR kernel: as many CTAs as are co-resident
+    cudaDeviceProp prop;
+    LWCK(cudaGetDeviceProperties(&prop, b->device));
+    if (!prop.cooperativeLaunch) { snprintf(err, errlen, "device does not support cooperative launches"); return -1; }
+    int per = 0;
+    LWCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_lw_sor_all<1>, LW_SOR_T, 0)); b->lw_sor_grid[0] = per * prop.multiProcessorCount;
+    LWCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_lw_sor_all<2>, LW_SOR_T, 0)); b->lw_sor_grid[1] = per * prop.multiProcessorCount;
+    LWCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_lw_sor_all<3>, LW_SOR_T, 0)); b->lw_sor_grid[2] = per * prop.multiProcessorCount;
+    const char *e = getenv("OB_LW_SOR_CTAS_PER_SM");
+    if (e && atoi(e) > 0) for (int k = 0; k < 3; k++) if (atoi(e) * prop.multiProcessorCount < b->lw_sor_grid[k]) b->lw_sor_grid[k] = atoi(e) * prop.multiProcessorCount;
+  }
   return 0;
 }
 
@@ -619,19 +718,20 @@ static int lw_step(ObBackend *b, real h, int taps, char *err, size_t errlen) {
   int ncol = 0, rounds = 0;
   if (ncp > 0) {
     LWCK(cudaMemsetAsync(L.used, 0, sizeof(unsigned long long) * nb, st));
+    LWCK(cudaMemsetAsync(L.claim, 0xff, sizeof(unsigned long long) * nb, st));
     int left = ncp;
     while (left > 0) {
-      for (int r = 0; r < 4; r++, rounds++) {
-        LWCK(cudaMemsetAsync(L.claim, 0xff, sizeof(unsigned long long) * nb, st));
-        LWCK(cudaMemsetAsync(L.scal + LW_UNCOLOURED, 0, sizeof(int), st));
+      const int chunk = rounds == 0 ? 12 : 4;   // rounds between two looks at the remaining count
+      LWCK(cudaMemsetAsync(L.scal + LW_LEFT0, 0, sizeof(int) * 16, st));
+      for (int r = 0; r < chunk; r++, rounds++) {
         k_lw_col_claim<<<lw_blocks(ncp), LW_T, 0, st>>>(L, ncp, (uint32_t)rounds);
         k_lw_col_take<<<lw_blocks(ncp), LW_T, 0, st>>>(L, ncp, (uint32_t)rounds);
         g_launches += 2;
       }
       LWCK(cudaMemcpyAsync(hs, L.scal, sizeof(int) * LW_WORDS, cudaMemcpyDeviceToHost, st));
       LWCK(cudaStreamSynchronize(st));
-      left = hs[LW_UNCOLOURED];
-      if (rounds > 4096) { snprintf(err, errlen, "colouring did not converge"); return -1; }
+      left = hs[LW_LEFT0 + ((rounds - 1) & 15)];
+      if (rounds > 240) { snprintf(err, errlen, "colouring did not converge"); return -1; }
     }
     if (hs[LW_ERR]) { snprintf(err, errlen, "more than %d colours needed (a body with more than %d contact pairs)", OB_LW_MAXCOL, OB_LW_MAXCOL / 2); return -1; }
     k_lw_pairkey<<<lw_blocks(ncp), LW_T, 0, st>>>(L, ncp);
@@ -655,6 +755,15 @@ static int lw_step(ObBackend *b, real h, int taps, char *err, size_t errlen) {
   LW_MARK();
   // (6) SOR: colours in ascending order, every iteration
   int sor_launches = 0;
+  if (ncp > 0 && hw.iters > 0 && !getenv("OB_LW_SOR_LAUNCHES")) {
+    LWCK(cudaMemsetAsync(L.scal + LW_BARRIER, 0, sizeof(int), st));
+    unsigned *bar = (unsigned *)(L.scal + LW_BARRIER);
+    int iters = hw.iters, nc_ = ncol;
+    void *kargs[] = {(void *)&L, (void *)&iters, (void *)&nc_, (void *)&bar};
+    const void *fn = m == 3 ? (const void *)k_lw_sor_all<3> : (m == 2 ? (const void *)k_lw_sor_all<2> : (const void *)k_lw_sor_all<1>);
+    LWCK(cudaLaunchCooperativeKernel(fn, dim3(b->lw_sor_grid[m - 1]), dim3(LW_SOR_T), kargs, 0, st));
+    g_launches++; sor_launches = 1;
+  } else
   for (int it = 0; it < hw.iters && ncp > 0; it++)
     for (int c = 0; c < ncol; c++) {
       const int cnt = hs[LW_WORDS + c * (2 + OB_LW_MAXC) + 1];

@@ -134,7 +134,7 @@ static int large_step_host(ObBatchDev &d, real h, int taps, LargeHostStats *stat
       } else left++;
     }
     rounds++;
-    if (rounds > 4096) return -1;
+    if (rounds > 240) return -1;
   }
   if (colerr) return -2;
   // (5) order pairs by (colour, contacts descending), stable
