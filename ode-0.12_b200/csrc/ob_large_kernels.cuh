@@ -483,6 +483,15 @@ __device__ __forceinline__ void lw_sor_pair(const ObLargeDev &L, const int *seg,
   const int nc = P.info & 255, b1 = P.b1, b2 = P.b2;
   real f1[6], f2[6] = {0, 0, 0, 0, 0, 0};
   real *fp1 = L.fc + (size_t)8 * b1, *fp2 = L.fc + (size_t)8 * (b2 >= 0 ? b2 : b1);
+  // contacts in order; the rows of contact k+1 are loaded (registers) while contact k is applied
+  real rwA[M][OB_LW_ROWW], rwB[M][OB_LW_ROWW], lamA[M], lamB[M];
+  unsigned metaA[M], metaB[M];
+#define LW_LOAD(RW, META, LAM, KK)                                                                                   \
+  {                                                                                                                  \
+    const size_t cs_ = (size_t)seg[2 + (KK)] + i;                                                                    \
+    _Pragma("unroll") for (int q = 0; q < M; q++) { lw_load_row(L, q, cs_, RW[q], &META[q]); LAM[q] = __ldcg(L.lambda + (size_t)q * L.NC + cs_); } \
+  }
+  LW_LOAD(rwA, metaA, lamA, 0)   // every contact pair has at least one contact: no need to wait for P
 #if defined(dSINGLE)
   { const float4 a = __ldcg((const float4 *)fp1); const float2 c = __ldcg((const float2 *)(fp1 + 4)); f1[0] = a.x; f1[1] = a.y; f1[2] = a.z; f1[3] = a.w; f1[4] = c.x; f1[5] = c.y; }
 #else
@@ -499,24 +508,27 @@ __device__ __forceinline__ void lw_sor_pair(const ObLargeDev &L, const int *seg,
 #endif
     k2 = L.invM[b2];
   }
-  for (int k = 0; k < nc; k++) {
-    const size_t cs = (size_t)seg[2 + k] + i;
-    if (cs >= (size_t)L.NC) break;
-    real lam[M];
-#pragma unroll
-    for (int q = 0; q < M; q++) {
-      real rw[OB_LW_ROWW];
-      unsigned meta;
-      lw_load_row(L, q, cs, rw, &meta);
-      const int fio = (meta >> 16) & 255;
-      real lam_f = 0;
-#pragma unroll
-      for (int r = 0; r < M; r++) if (fio && r == q - fio) lam_f = lam[r];
-      real *lp = L.lambda + (size_t)q * L.NC + cs;
-      lam[q] = ob_lw_row_update(rw, meta, k1, k2, b2 >= 0, lam_f, __ldcg(lp), f1, f2);
-      __stcg(lp, lam[q]);
+#define LW_APPLY(RW, META, LAM, KK)                                                                                  \
+  {                                                                                                                  \
+    const size_t cs_ = (size_t)seg[2 + (KK)] + i;                                                                    \
+    _Pragma("unroll") for (int q = 0; q < M; q++) {                                                                  \
+      const int fio = (META[q] >> 16) & 255;                                                                         \
+      real lam_f = 0;                                                                                                \
+      _Pragma("unroll") for (int r = 0; r < M; r++) if (fio && r == q - fio) lam_f = LAM[r];                         \
+      LAM[q] = ob_lw_row_update(RW[q], META[q], k1, k2, b2 >= 0, lam_f, LAM[q], f1, f2);                             \
+      __stcg(L.lambda + (size_t)q * L.NC + cs_, LAM[q]);                                                             \
+    }                                                                                                                \
+  }
+  for (int k = 0; k < nc; k += 2) {
+    if (k + 1 < nc) LW_LOAD(rwB, metaB, lamB, k + 1)
+    LW_APPLY(rwA, metaA, lamA, k)
+    if (k + 1 < nc) {
+      if (k + 2 < nc) LW_LOAD(rwA, metaA, lamA, k + 2)
+      LW_APPLY(rwB, metaB, lamB, k + 1)
     }
   }
+#undef LW_LOAD
+#undef LW_APPLY
 #if defined(dSINGLE)
   __stcg((float4 *)fp1, make_float4(f1[0], f1[1], f1[2], f1[3])); __stcg((float2 *)(fp1 + 4), make_float2(f1[4], f1[5]));
   if (b2 >= 0) { __stcg((float4 *)fp2, make_float4(f2[0], f2[1], f2[2], f2[3])); __stcg((float2 *)(fp2 + 4), make_float2(f2[4], f2[5])); }
@@ -546,15 +558,38 @@ __device__ __forceinline__ void lw_grid_barrier(unsigned *bar, unsigned target) 
   }
   __syncthreads();
 }
+// pull the rows a pair will read into L2 (no registers held): issued for the NEXT colour before the
+// grid barrier, so that after the barrier the sweep's row loads are L2 hits
+template <int M>
+__device__ __forceinline__ void lw_prefetch_pair(const ObLargeDev &L, const int *seg, int i) {
+  const int nc = L.cp[1][seg[0] + i].info & 255;
+  for (int k = 0; k < nc; k++) {
+    const size_t cs = (size_t)seg[2 + k] + i;
+#pragma unroll
+    for (int q = 0; q < M; q++) {
+#pragma unroll
+      for (int s2 = 0; s2 < OB_LW_SLOTS; s2++) asm volatile("prefetch.global.L2 [%0];" ::"l"(L.rows + ob_lw_row_index(q, s2, L.NC, cs)));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(L.lambda + (size_t)q * L.NC + cs));
+    }
+  }
+}
 template <int M>
 __global__ void __launch_bounds__(LW_SOR_T) k_lw_sor_all(ObLargeDev L, int iters, int ncol, unsigned *bar) {
   unsigned epoch = 0;
   const int stride = gridDim.x * blockDim.x;
+  // warp tiles of 32 consecutive pairs are dealt round-robin over the CTAs: pairs are sorted by contact
+  // count, so consecutive tiles are equally heavy and every SM gets the same share of the bytes
+  const int t = ((threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 32 + (threadIdx.x & 31);
   for (int it = 0; it < iters; it++)
     for (int c = 0; c < ncol; c++) {
       const int *seg = L.segtab + c * (2 + OB_LW_MAXC);
       const int cnt = seg[1];
-      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += stride) lw_sor_pair<M>(L, seg, i);
+      for (int i = t; i < cnt; i += stride) lw_sor_pair<M>(L, seg, i);
+      if (c + 1 < ncol || it + 1 < iters) {
+        const int *segn = L.segtab + (c + 1 < ncol ? c + 1 : 0) * (2 + OB_LW_MAXC);
+        const int cntn = segn[1];
+        for (int i = t; i < cntn; i += stride) lw_prefetch_pair<M>(L, segn, i);
+      }
       epoch++;
       lw_grid_barrier(bar, epoch * gridDim.x);
     }

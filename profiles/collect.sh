@@ -1,0 +1,23 @@
+#!/bin/sh
+# Runs ON THE GPU BOX (gpurun -- sh profiles/collect.sh TAG): bench lines for every config, the ncu launch
+# list of the default bench command and one `--set full` capture per dominant kernel.  Outputs go to
+# gpurun_out/; profiles/summarize.py (run in the build container) turns them into the tracked summaries.
+TAG=${1:-r01}
+O=gpurun_out
+mkdir -p $O
+python bench.py --steps 30 --warmup 3 > $O/bench_${TAG}_c2.json 2> $O/bench_${TAG}_c2.err
+python bench.py --config 3 --steps 30 --warmup 3 > $O/bench_${TAG}_c3.json 2> $O/bench_${TAG}_c3.err
+python bench.py --config 4 --steps 30 --warmup 3 > $O/bench_${TAG}_c4.json 2> $O/bench_${TAG}_c4.err
+python bench.py --config 5 --steps 20 --warmup 3 > $O/bench_${TAG}_c5.json 2> $O/bench_${TAG}_c5.err
+python bench.py --impl reference --steps 30 --warmup 3 > $O/bench_${TAG}_ref.json 2> $O/bench_${TAG}_ref.err
+# launch list of the same command as the default bench (numbers printed under ncu are never bench values)
+ncu --metrics gpu__time_duration.sum --clock-control none -s 1600 -c 400 --csv --log-file $O/launches_${TAG}_c2.csv \
+    python bench.py --steps 30 --warmup 3 > $O/ncu_${TAG}_c2.log 2>&1
+D=ode-0.12_b200/lib/driver_b200_single
+for k in k_sor k_collide k_prep k_sched k_post; do
+  ncu --set full --clock-control none --import-source on -k regex:$k -s 305 -c 1 -f -o $O/prof_${TAG}_$k \
+      $D --scene stack32 --worlds 4096 --steps 10 --settle 300 --mode batch --time > $O/ncu_${TAG}_$k.log 2>&1
+done
+ncu --set full --clock-control none --import-source on -k regex:k_lw_sor_all -s 300 -c 1 -f -o $O/prof_${TAG}_k_lw_sor_all \
+    $D --scene pile_100x100x20 --steps 3 --settle 300 --mode batch --time > $O/ncu_${TAG}_k_lw_sor_all.log 2>&1
+ls -la $O | tail -30
