@@ -405,6 +405,16 @@ void dGeomPlaneGetParams(dGeomID plane, dVector4 result);
 dGeomID dCreateCapsule(dSpaceID space, dReal radius, dReal length);
 void dGeomCapsuleSetParams(dGeomID ccylinder, dReal radius, dReal length);
 void dGeomCapsuleGetParams(dGeomID ccylinder, dReal *radius, dReal *length);
+/* rays: include/ode/collision.h:1025-1067, ode/src/ray.cpp:91-189 */
+dGeomID dCreateRay(dSpaceID space, dReal length);
+void dGeomRaySetLength(dGeomID ray, dReal length);
+dReal dGeomRayGetLength(dGeomID ray);
+void dGeomRaySet(dGeomID ray, dReal px, dReal py, dReal pz, dReal dx, dReal dy, dReal dz);
+void dGeomRayGet(dGeomID ray, dVector3 start, dVector3 dir);
+void dGeomRaySetParams(dGeomID g, int FirstContact, int BackfaceCull);
+void dGeomRayGetParams(dGeomID g, int *FirstContact, int *BackfaceCull);
+void dGeomRaySetClosestHit(dGeomID g, int closestHit);
+int dGeomRayGetClosestHit(dGeomID g);
 
 /* ---- trimesh (collision_trimesh.h:51-153).  Vertex and index arrays are COPIED at build time
  * (the reference borrows them); per-triangle callbacks are not supported by the GPU colliders. */

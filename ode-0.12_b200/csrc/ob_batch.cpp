@@ -64,6 +64,7 @@ void ob_marshal_geom(dxGeom *g, ObGeom &d) {
   d.flags = ((g->gflags & GEOM_ENABLED) ? OB_GEOM_ENABLED : 0) | (g->offset_posr ? OB_GEOM_HAS_OFFSET : 0) |
             ((g->gflags & GEOM_ZERO_SIZED) ? OB_GEOM_ZERO_SIZED : 0);
   d.body_next = -1;
+  if (g->type == dRayClass) d.mesh = ob_ray_flags(g);   // rays carry their mode bits where trimeshes carry the data index
   for (int k = 0; k < 4; k++) d.p[k] = g->p[k];
   const dxPosR *src = 0;
   if (g->offset_posr) src = g->offset_posr;
@@ -179,6 +180,7 @@ dxBatch *ob_batch_create(int nworlds, const dWorldID *worlds, const dSpaceID *sp
     for (dxGeom *g = S->first; g; g = g->next, pos++) {
       if (g->is_space) { ob_set_last_error("dBatchCreate: world %d: nested spaces are not supported on this path", w); delete B; return 0; }
       if (g->body && g->body->world != W) { ob_set_last_error("dBatchCreate: world %d: geom attached to a body of another world", w); delete B; return 0; }
+      if (g->type == dRayClass && !dropin) { ob_set_last_error("dBatchCreate: world %d: ray geoms are served by dSpaceCollide / dCollide (a ray contact is a query result, not a contact joint)", w); delete B; return 0; }
       g->batch_index = ng - 1 - pos;
       B->geoms[w][g->batch_index] = g;
     }

@@ -72,6 +72,15 @@ OB_HD void ob_aabb(const ObPose &g, real *aabb, const ObMeshDev *meshes = 0) {
       aabb[2] = c[1] + g.pos[1] - yrange; aabb[3] = c[1] + g.pos[1] + yrange;
       aabb[4] = c[2] + g.pos[2] - zrange; aabb[5] = c[2] + g.pos[2] + zrange;
     } break;
+    case OB_GEOM_RAY: {
+      // dxRay::computeAABB, ray.cpp:56-88
+      const real length = g.p[0];
+      for (int k = 0; k < 3; k++) {
+        const real e = g.pos[k] + g.R[4 * k + 2] * length;
+        if (g.pos[k] < e) { aabb[2 * k] = g.pos[k]; aabb[2 * k + 1] = e; }
+        else { aabb[2 * k] = e; aabb[2 * k + 1] = g.pos[k]; }
+      }
+    } break;
     default:
       aabb[0] = aabb[2] = aabb[4] = -OB_INF; aabb[1] = aabb[3] = aabb[5] = OB_INF;
   }
@@ -780,6 +789,158 @@ OB_HD int ob_collide_capsule_plane(const ObPose &o1, const ObPose &o2, int flags
   return ncontacts;
 }
 
+// ---- ray colliders (ode/src/ray.cpp) ----------------------------------------------------------
+// ray pose: pos = origin, R(:,2) = direction, p[0] = length.  o1 = ray.
+// ray_sphere_helper, ray.cpp:192-232; mode 1 = use the exit point
+OB_HD int ob_ray_sphere_helper(const ObPose &ray, const real *sphere_pos, real radius, ObCg *contact, int mode) {
+  real q[3] = {ray.pos[0] - sphere_pos[0], ray.pos[1] - sphere_pos[1], ray.pos[2] - sphere_pos[2]};
+  const real B = ob_dot14(q, ray.R + 2);
+  const real C = ob_dot(q, q) - radius * radius;
+  real k = B * B - C;
+  if (k < 0) return 0;
+  k = ob_sqrt(k);
+  real alpha;
+  if (mode && C >= 0) {
+    alpha = -B + k;
+    if (alpha < 0) return 0;
+  } else {
+    alpha = -B - k;
+    if (alpha < 0) {
+      alpha = -B + k;
+      if (alpha < 0) return 0;
+    }
+  }
+  if (alpha > ray.p[0]) return 0;
+  contact->pos[0] = ray.pos[0] + alpha * ray.R[2];
+  contact->pos[1] = ray.pos[1] + alpha * ray.R[6];
+  contact->pos[2] = ray.pos[2] + alpha * ray.R[10];
+  const real nsign = (C < 0 || mode) ? OB_REAL(-1.0) : OB_REAL(1.0);
+  contact->normal[0] = nsign * (contact->pos[0] - sphere_pos[0]);
+  contact->normal[1] = nsign * (contact->pos[1] - sphere_pos[1]);
+  contact->normal[2] = nsign * (contact->pos[2] - sphere_pos[2]);
+  ob_safe_normalize3(contact->normal);
+  contact->depth = alpha;
+  return 1;
+}
+// dCollideRaySphere, ray.cpp:235-251
+OB_HD int ob_collide_ray_sphere(const ObPose &o1, const ObPose &o2, ObCg *contact) {
+  return ob_ray_sphere_helper(o1, o2.pos, o2.p[0], contact, 0);
+}
+// dCollideRayBox, ray.cpp:254-350
+OB_HD int ob_collide_ray_box(const ObPose &ray, const ObPose &box, ObCg *contact) {
+  real tmp[3], s[3], v[3], sign[3];
+  tmp[0] = ray.pos[0] - box.pos[0]; tmp[1] = ray.pos[1] - box.pos[1]; tmp[2] = ray.pos[2] - box.pos[2];
+  ob_mul1_331(s, box.R, tmp);
+  tmp[0] = ray.R[2]; tmp[1] = ray.R[6]; tmp[2] = ray.R[10];
+  ob_mul1_331(v, box.R, tmp);
+  for (int i = 0; i < 3; i++) {
+    if (v[i] < 0) { s[i] = -s[i]; v[i] = -v[i]; sign[i] = 1; }
+    else sign[i] = -1;
+  }
+  real h[3] = {OB_REAL(0.5) * box.p[0], OB_REAL(0.5) * box.p[1], OB_REAL(0.5) * box.p[2]};
+  if ((s[0] < -h[0] && v[0] <= 0) || s[0] > h[0] || (s[1] < -h[1] && v[1] <= 0) || s[1] > h[1] ||
+      (s[2] < -h[2] && v[2] <= 0) || s[2] > h[2] || (v[0] == 0 && v[1] == 0 && v[2] == 0))
+    return 0;
+  real lo = -OB_INF, hi = OB_INF;
+  int nlo = 0, nhi = 0;
+  for (int i = 0; i < 3; i++) {
+    if (v[i] != 0) {
+      real k = (-h[i] - s[i]) / v[i];
+      if (k > lo) { lo = k; nlo = i; }
+      k = (h[i] - s[i]) / v[i];
+      if (k < hi) { hi = k; nhi = i; }
+    }
+  }
+  if (lo > hi) return 0;
+  real alpha;
+  int n;
+  if (lo >= 0) { alpha = lo; n = nlo; }
+  else { alpha = hi; n = nhi; }
+  if (alpha < 0 || alpha > ray.p[0]) return 0;
+  contact->pos[0] = ray.pos[0] + alpha * ray.R[2];
+  contact->pos[1] = ray.pos[1] + alpha * ray.R[6];
+  contact->pos[2] = ray.pos[2] + alpha * ray.R[10];
+  contact->normal[0] = box.R[0 * 4 + n] * sign[n];
+  contact->normal[1] = box.R[1 * 4 + n] * sign[n];
+  contact->normal[2] = box.R[2 * 4 + n] * sign[n];
+  contact->depth = alpha;
+  return 1;
+}
+// dCollideRayCapsule, ray.cpp:353-470
+OB_HD int ob_collide_ray_capsule(const ObPose &ray, const ObPose &ccyl, ObCg *contact) {
+  const real radius = ccyl.p[0], lz2 = ccyl.p[1] * OB_REAL(0.5);
+  real cs[3], q[3], r[3], C, k;
+  cs[0] = ray.pos[0] - ccyl.pos[0]; cs[1] = ray.pos[1] - ccyl.pos[1]; cs[2] = ray.pos[2] - ccyl.pos[2];
+  k = ob_dot41(ccyl.R + 2, cs);
+  q[0] = k * ccyl.R[2] - cs[0]; q[1] = k * ccyl.R[6] - cs[1]; q[2] = k * ccyl.R[10] - cs[2];
+  C = ob_dot(q, q) - radius * radius;
+  int inside_ccyl = 0;
+  if (C < 0) {
+    if (k < -lz2) k = -lz2;
+    else if (k > lz2) k = lz2;
+    r[0] = ccyl.pos[0] + k * ccyl.R[2]; r[1] = ccyl.pos[1] + k * ccyl.R[6]; r[2] = ccyl.pos[2] + k * ccyl.R[10];
+    if ((ray.pos[0] - r[0]) * (ray.pos[0] - r[0]) + (ray.pos[1] - r[1]) * (ray.pos[1] - r[1]) + (ray.pos[2] - r[2]) * (ray.pos[2] - r[2]) <
+        radius * radius)
+      inside_ccyl = 1;
+  }
+  if (!inside_ccyl && C < 0) {
+    if (k < 0) k = -lz2; else k = lz2;
+  } else {
+    const real uv = ob_dot44(ccyl.R + 2, ray.R + 2);
+    r[0] = uv * ccyl.R[2] - ray.R[2]; r[1] = uv * ccyl.R[6] - ray.R[6]; r[2] = uv * ccyl.R[10] - ray.R[10];
+    real A = ob_dot(r, r);
+    const real B = 2 * ob_dot(q, r);
+    k = B * B - 4 * A * C;
+    if (k < 0) {
+      if (!inside_ccyl) return 0;
+      if (uv < 0) k = -lz2; else k = lz2;
+    } else {
+      k = ob_sqrt(k);
+      A = ob_recip(2 * A);
+      real alpha = (-B - k) * A;
+      if (alpha < 0) {
+        alpha = (-B + k) * A;
+        if (alpha < 0) return 0;
+      }
+      if (alpha > ray.p[0]) return 0;
+      contact->pos[0] = ray.pos[0] + alpha * ray.R[2];
+      contact->pos[1] = ray.pos[1] + alpha * ray.R[6];
+      contact->pos[2] = ray.pos[2] + alpha * ray.R[10];
+      q[0] = contact->pos[0] - ccyl.pos[0]; q[1] = contact->pos[1] - ccyl.pos[1]; q[2] = contact->pos[2] - ccyl.pos[2];
+      k = ob_dot14(q, ccyl.R + 2);
+      const real nsign = inside_ccyl ? OB_REAL(-1.0) : OB_REAL(1.0);
+      if (k >= -lz2 && k <= lz2) {
+        contact->normal[0] = nsign * (contact->pos[0] - (ccyl.pos[0] + k * ccyl.R[2]));
+        contact->normal[1] = nsign * (contact->pos[1] - (ccyl.pos[1] + k * ccyl.R[6]));
+        contact->normal[2] = nsign * (contact->pos[2] - (ccyl.pos[2] + k * ccyl.R[10]));
+        ob_safe_normalize3(contact->normal);
+        contact->depth = alpha;
+        return 1;
+      }
+      if (k < 0) k = -lz2; else k = lz2;
+    }
+  }
+  q[0] = ccyl.pos[0] + k * ccyl.R[2]; q[1] = ccyl.pos[1] + k * ccyl.R[6]; q[2] = ccyl.pos[2] + k * ccyl.R[10];
+  return ob_ray_sphere_helper(ray, q, radius, contact, inside_ccyl);
+}
+// dCollideRayPlane, ray.cpp:473-502
+OB_HD int ob_collide_ray_plane(const ObPose &ray, const ObPose &plane, ObCg *contact) {
+  real alpha = plane.p[3] - ob_dot(plane.p, ray.pos);
+  const real nsign = (alpha > 0) ? OB_REAL(-1.0) : OB_REAL(1.0);
+  const real k = ob_dot14(plane.p, ray.R + 2);
+  if (k == 0) return 0;
+  alpha /= k;
+  if (alpha < 0 || alpha > ray.p[0]) return 0;
+  contact->pos[0] = ray.pos[0] + alpha * ray.R[2];
+  contact->pos[1] = ray.pos[1] + alpha * ray.R[6];
+  contact->pos[2] = ray.pos[2] + alpha * ray.R[10];
+  contact->normal[0] = nsign * plane.p[0];
+  contact->normal[1] = nsign * plane.p[1];
+  contact->normal[2] = nsign * plane.p[2];
+  contact->depth = alpha;
+  return 1;
+}
+
 // upper bound on contacts a class pair can emit (used to lay out contact slots)
 OB_HD int ob_pair_max_contacts(int t1, int t2, int maxc) {
   int lo = t1 < t2 ? t1 : t2, hi = t1 < t2 ? t2 : t1;
@@ -790,7 +951,8 @@ OB_HD int ob_pair_max_contacts(int t1, int t2, int maxc) {
   else if (lo == OB_GEOM_BOX && hi == OB_GEOM_CAPSULE) cap = 1;
   else if (lo == OB_GEOM_CAPSULE && hi == OB_GEOM_CAPSULE) cap = 2;
   else if (lo == OB_GEOM_CAPSULE && hi == OB_GEOM_PLANE) cap = 2;
-  else if (hi == OB_GEOM_TRIMESH && (lo == OB_GEOM_SPHERE || lo == OB_GEOM_BOX)) cap = 1 << 15;   // bounded by the caller's max_contacts only
+  else if (hi == OB_GEOM_TRIMESH && (lo == OB_GEOM_SPHERE || lo == OB_GEOM_BOX || lo == OB_GEOM_RAY)) cap = 1 << 15;   // bounded by the caller's max_contacts only
+  else if (hi == OB_GEOM_RAY && (lo == OB_GEOM_SPHERE || lo == OB_GEOM_BOX || lo == OB_GEOM_CAPSULE || lo == OB_GEOM_PLANE)) cap = 1;
   else cap = 0;
   return cap < maxc ? cap : maxc;
 }
@@ -818,6 +980,16 @@ OB_HD int ob_collide_pair_t(const ObPose &o1, const ObPose &o2, int flags, ObCg 
   else if (t1 == OB_GEOM_CAPSULE && t2 == OB_GEOM_CAPSULE) n = ob_collide_capsule_capsule(o1, o2, flags, c);
   else if (t1 == OB_GEOM_CAPSULE && t2 == OB_GEOM_PLANE) n = ob_collide_capsule_plane(o1, o2, flags, c);
   else if (t1 == OB_GEOM_PLANE && t2 == OB_GEOM_CAPSULE) { n = ob_collide_capsule_plane(o2, o1, flags, c); rev = 1; }
+  else if (t1 == OB_GEOM_RAY && t2 == OB_GEOM_SPHERE) n = ob_collide_ray_sphere(o1, o2, c);
+  else if (t1 == OB_GEOM_SPHERE && t2 == OB_GEOM_RAY) { n = ob_collide_ray_sphere(o2, o1, c); rev = 1; }
+  else if (t1 == OB_GEOM_RAY && t2 == OB_GEOM_BOX) n = ob_collide_ray_box(o1, o2, c);
+  else if (t1 == OB_GEOM_BOX && t2 == OB_GEOM_RAY) { n = ob_collide_ray_box(o2, o1, c); rev = 1; }
+  else if (t1 == OB_GEOM_RAY && t2 == OB_GEOM_CAPSULE) n = ob_collide_ray_capsule(o1, o2, c);
+  else if (t1 == OB_GEOM_CAPSULE && t2 == OB_GEOM_RAY) { n = ob_collide_ray_capsule(o2, o1, c); rev = 1; }
+  else if (t1 == OB_GEOM_RAY && t2 == OB_GEOM_PLANE) n = ob_collide_ray_plane(o1, o2, c);
+  else if (t1 == OB_GEOM_PLANE && t2 == OB_GEOM_RAY) { n = ob_collide_ray_plane(o2, o1, c); rev = 1; }
+  else if (MESH && t1 == OB_GEOM_TRIMESH && t2 == OB_GEOM_RAY) n = ob_collide_trimesh_ray(o1, o2, meshes[o1.mesh], flags, c, &bve);
+  else if (MESH && t1 == OB_GEOM_RAY && t2 == OB_GEOM_TRIMESH) { n = ob_collide_trimesh_ray(o2, o1, meshes[o2.mesh], flags, c, &bve); rev = 1; }
   else if (MESH && t1 == OB_GEOM_TRIMESH && t2 == OB_GEOM_SPHERE) n = ob_collide_trimesh_sphere(o1, o2, meshes[o1.mesh], flags, c, &bve);
   else if (MESH && t1 == OB_GEOM_SPHERE && t2 == OB_GEOM_TRIMESH) { n = ob_collide_trimesh_sphere(o2, o1, meshes[o2.mesh], flags, c, &bve); rev = 1; }
   else if (MESH && t1 == OB_GEOM_TRIMESH && t2 == OB_GEOM_BOX) n = ob_collide_trimesh_box(o1, o2, meshes[o1.mesh], flags, c, &bve);

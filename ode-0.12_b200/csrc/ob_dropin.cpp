@@ -171,7 +171,7 @@ void ob_dropin_space_collide(dxSpace *space, void *data, dNearCallback *cb) {
 
 static void geom_pose_host(dxGeom *g, ObPose *o) {
   o->type = g->type;
-  o->mesh = 0;
+  o->mesh = g->type == dRayClass ? ob_ray_flags(g) : 0;
   for (int i = 0; i < 4; i++) o->p[i] = g->p[i];
   for (int i = 0; i < 3; i++) o->pos[i] = 0;
   for (int i = 0; i < 12; i++) o->R[i] = 0;

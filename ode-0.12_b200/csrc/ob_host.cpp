@@ -763,6 +763,9 @@ static void geom_init(dxGeom *g, dSpaceID space, int is_placeable, int type) {
   if (space) dSpaceAdd(space, g);
 }
 }  // extern "C"
+int ob_ray_flags(const dxGeom *g) {
+  return ((g->gflags & RAY_FIRSTCONTACT) ? 1 : 0) | ((g->gflags & RAY_BACKFACECULL) ? 2 : 0) | ((g->gflags & RAY_CLOSEST_HIT) ? 4 : 0);
+}
 dxGeom *ob_geom_create(dxSpace *space, int is_placeable, int type) { dxGeom *g = new dxGeom; geom_init(g, space, is_placeable, type); return g; }
 extern "C" {
 static void geom_body_remove(dxGeom *g) {
@@ -922,6 +925,7 @@ void dGeomGetAABB(dGeomID g, dReal aabb[6]) {
   ObPose o;
   geom_host_pose(g, &o);
   o.mesh = 0;
+  if (g->type == dRayClass) o.mesh = ob_ray_flags(g);
   ObMeshDev md;
   memset(&md, 0, sizeof md);
   if (g->type == dTriMeshClass && g->tmdata) for (int k = 0; k < 3; k++) { md.aabbc[k] = g->tmdata->aabbc[k]; md.aabbe[k] = g->tmdata->aabbe[k]; }
@@ -963,6 +967,36 @@ void dGeomCapsuleSetParams(dGeomID g, dReal radius, dReal length) {
   g->p[0] = radius; g->p[1] = length; zero_sized(g, !radius); ob_geom_moved(g);
 }
 void dGeomCapsuleGetParams(dGeomID g, dReal *radius, dReal *length) { *radius = g->p[0]; *length = g->p[1]; }
+// rays (ode/src/ray.cpp:49-189): p[0] = length, direction = column 2 of the rotation; the three mode flags
+// live in gflags like the reference's RAY_* bits (collision_kernel.h:79-81)
+dGeomID dCreateRay(dSpaceID space, dReal length) {
+  dxGeom *g = new dxGeom; geom_init(g, space, 1, dRayClass);
+  g->p[0] = length; return g;
+}
+void dGeomRaySetLength(dGeomID g, dReal length) { g->p[0] = length; ob_geom_moved(g); }
+dReal dGeomRayGetLength(dGeomID g) { return g->p[0]; }
+void dGeomRaySet(dGeomID g, dReal px, dReal py, dReal pz, dReal dx, dReal dy, dReal dz) {
+  ob_geom_recompute_posr(g);
+  dReal *rot = g->final_posr->R, *pos = g->final_posr->pos;   // for a ray on a body without offset this IS the body's pose, as in the reference
+  pos[0] = px; pos[1] = py; pos[2] = pz;
+  dReal n[3] = {dx, dy, dz};
+  ob_safe_normalize3(n);
+  rot[0 * 4 + 2] = n[0]; rot[1 * 4 + 2] = n[1]; rot[2 * 4 + 2] = n[2];
+  ob_geom_moved(g);
+}
+void dGeomRayGet(dGeomID g, dVector3 start, dVector3 dir) {
+  ob_geom_recompute_posr(g);
+  for (int k = 0; k < 3; k++) { start[k] = g->final_posr->pos[k]; dir[k] = g->final_posr->R[k * 4 + 2]; }
+}
+void dGeomRaySetParams(dGeomID g, int FirstContact, int BackfaceCull) {
+  if (FirstContact) g->gflags |= RAY_FIRSTCONTACT; else g->gflags &= ~RAY_FIRSTCONTACT;
+  if (BackfaceCull) g->gflags |= RAY_BACKFACECULL; else g->gflags &= ~RAY_BACKFACECULL;
+}
+void dGeomRayGetParams(dGeomID g, int *FirstContact, int *BackfaceCull) {
+  *FirstContact = (g->gflags & RAY_FIRSTCONTACT) != 0; *BackfaceCull = (g->gflags & RAY_BACKFACECULL) != 0;
+}
+void dGeomRaySetClosestHit(dGeomID g, int closestHit) { if (closestHit) g->gflags |= RAY_CLOSEST_HIT; else g->gflags &= ~RAY_CLOSEST_HIT; }
+int dGeomRayGetClosestHit(dGeomID g) { return (g->gflags & RAY_CLOSEST_HIT) != 0; }
 
 // spaces
 static dxSpace *space_create(dSpaceID parent, int type) {

@@ -95,10 +95,13 @@ struct dxJointGroup {
 };
 
 enum {  // geom flags, ode/src/collision_kernel.h:64-80
-  GEOM_DIRTY = 1, GEOM_POSR_BAD = 2, GEOM_AABB_BAD = 4, GEOM_PLACEABLE = 8, GEOM_ENABLED = 16, GEOM_ZERO_SIZED = 32
+  GEOM_DIRTY = 1, GEOM_POSR_BAD = 2, GEOM_AABB_BAD = 4, GEOM_PLACEABLE = 8, GEOM_ENABLED = 16, GEOM_ZERO_SIZED = 32,
+  RAY_FIRSTCONTACT = 0x10000, RAY_BACKFACECULL = 0x20000, RAY_CLOSEST_HIT = 0x40000   // collision_kernel.h:79-81
 };
 
 struct dxPosR { dVector3 pos; dMatrix3 R; };
+struct dxGeom;
+int ob_ray_flags(const dxGeom *g);   // RAY_* gflags -> OB_RAY_* bits (ob_trimesh.h)
 
 struct dxGeom {
   int type;

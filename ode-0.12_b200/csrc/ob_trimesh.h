@@ -270,3 +270,131 @@ OB_HD int ob_collide_trimesh_sphere(const ObPose &o1, const ObPose &o2, const Ob
   if (it.overflow) *bverr = 1;
   return out;
 }
+
+
+// ---- ray query: dCollideRTL, collision_trimesh_ray.cpp:37-150 over RayCollider::_SegmentStab
+// (OPCODE/OPC_RayCollider.cpp:263-460, :550-568, OPC_RayAABBOverlap.h, OPC_RayTriOverlap.h).
+// o1 = trimesh, o2 = ray (o2.p[0] = length, o2.mesh = OB_RAY_* flag bits).
+enum { OB_RAY_FIRSTCONTACT = 1, OB_RAY_BACKFACECULL = 2, OB_RAY_CLOSEST_HIT = 4 };
+struct ObRayQuery {
+  float dir[3], org[3];        // model space
+  float data[3], data2[3], fdir[3];
+  float maxdist;
+  int culling;
+  // result of the last successful primitive test (mStabbedFace)
+  mutable float dist, u, v;
+  OB_HD bool overlap(const ObBvNode &n) const {   // SegmentAABBOverlap
+    const float Dx = data2[0] - n.c[0]; if (fabsf(Dx) > n.e[0] + fdir[0]) return false;
+    const float Dy = data2[1] - n.c[1]; if (fabsf(Dy) > n.e[1] + fdir[1]) return false;
+    const float Dz = data2[2] - n.c[2]; if (fabsf(Dz) > n.e[2] + fdir[2]) return false;
+    float f;
+    f = data[1] * Dz - data[2] * Dy; if (fabsf(f) > n.e[1] * fdir[2] + n.e[2] * fdir[1]) return false;
+    f = data[2] * Dx - data[0] * Dz; if (fabsf(f) > n.e[0] * fdir[2] + n.e[2] * fdir[0]) return false;
+    f = data[0] * Dy - data[1] * Dx; if (fabsf(f) > n.e[0] * fdir[1] + n.e[1] * fdir[0]) return false;
+    return true;
+  }
+  OB_HD bool contains(const ObBvNode &) const { return false; }
+  // SEGMENT_PRIM: RayTriOverlap (integer-representation compares, IceFPU.h:40) + distance < segment length
+  OB_HD bool prim(const ObMeshDev &m, int tri) const {
+    const float *v0 = m.verts + 3 * (size_t)m.tris[3 * (size_t)tri], *v1 = m.verts + 3 * (size_t)m.tris[3 * (size_t)tri + 1],
+                *v2 = m.verts + 3 * (size_t)m.tris[3 * (size_t)tri + 2];
+    const float e1[3] = {v1[0] - v0[0], v1[1] - v0[1], v1[2] - v0[2]}, e2[3] = {v2[0] - v0[0], v2[1] - v0[1], v2[2] - v0[2]};
+    const float pv[3] = {dir[1] * e2[2] - dir[2] * e2[1], dir[2] * e2[0] - dir[0] * e2[2], dir[0] * e2[1] - dir[1] * e2[0]};
+    const float det = e1[0] * pv[0] + e1[1] * pv[1] + e1[2] * pv[2];
+    const float LOCAL_EPSILON = 0.000001f;
+    if (culling) {
+      if (det < LOCAL_EPSILON) return false;
+      const float tv[3] = {org[0] - v0[0], org[1] - v0[1], org[2] - v0[2]};
+      u = tv[0] * pv[0] + tv[1] * pv[1] + tv[2] * pv[2];
+      if (((uint32_t)ob_f2i(u) & 0x80000000u) || (uint32_t)ob_f2i(u) > (uint32_t)ob_f2i(det)) return false;
+      const float qv[3] = {tv[1] * e1[2] - tv[2] * e1[1], tv[2] * e1[0] - tv[0] * e1[2], tv[0] * e1[1] - tv[1] * e1[0]};
+      v = dir[0] * qv[0] + dir[1] * qv[1] + dir[2] * qv[2];
+      if (((uint32_t)ob_f2i(v) & 0x80000000u) || u + v > det) return false;
+      dist = e2[0] * qv[0] + e2[1] * qv[1] + e2[2] * qv[2];
+      if ((uint32_t)ob_f2i(dist) & 0x80000000u) return false;
+      const float ood = 1.0f / det;
+      dist *= ood; u *= ood; v *= ood;
+    } else {
+      if (det > -LOCAL_EPSILON && det < LOCAL_EPSILON) return false;
+      const float ood = 1.0f / det;
+      const float tv[3] = {org[0] - v0[0], org[1] - v0[1], org[2] - v0[2]};
+      u = (tv[0] * pv[0] + tv[1] * pv[1] + tv[2] * pv[2]) * ood;
+      if (((uint32_t)ob_f2i(u) & 0x80000000u) || (uint32_t)ob_f2i(u) > 0x3f800000u) return false;
+      const float qv[3] = {tv[1] * e1[2] - tv[2] * e1[1], tv[2] * e1[0] - tv[0] * e1[2], tv[0] * e1[1] - tv[1] * e1[0]};
+      v = (dir[0] * qv[0] + dir[1] * qv[1] + dir[2] * qv[2]) * ood;
+      if (((uint32_t)ob_f2i(v) & 0x80000000u) || u + v > 1.0f) return false;
+      dist = (e2[0] * qv[0] + e2[1] * qv[1] + e2[2] * qv[2]) * ood;
+      if ((uint32_t)ob_f2i(dist) & 0x80000000u) return false;
+    }
+    return (uint32_t)ob_f2i(dist) < (uint32_t)ob_f2i(maxdist);
+  }
+};
+
+OB_HD int ob_collide_trimesh_ray(const ObPose &o1, const ObPose &o2, const ObMeshDev &m, int flags, ObCg *contact, int *bverr) {
+  const int maxc = flags & 0xffff;
+  const real *TLPosition = o1.pos, *TLRotation = o1.R;
+  const real Length = o2.p[0];
+  const int first = (o2.mesh & OB_RAY_FIRSTCONTACT) != 0, closest = (o2.mesh & OB_RAY_CLOSEST_HIT) != 0;
+  const real Origin[3] = {o2.pos[0], o2.pos[1], o2.pos[2]}, Direction[3] = {o2.R[2], o2.R[6], o2.R[10]};
+  ObRayQuery q;
+  q.culling = (o2.mesh & OB_RAY_BACKFACECULL) != 0;
+  q.maxdist = (float)Length;
+  q.dist = q.u = q.v = 0;
+  {
+    // InitQuery (:339-361): mDir = Matrix3x3(world) * dir, mOrigin = orig * InvertPRMatrix(world)
+    const float wd[3] = {(float)Direction[0], (float)Direction[1], (float)Direction[2]};
+    for (int i = 0; i < 3; i++) q.dir[i] = (float)TLRotation[i] * wd[0] + (float)TLRotation[4 + i] * wd[1] + (float)TLRotation[8 + i] * wd[2];
+    q.org[0] = (float)Origin[0]; q.org[1] = (float)Origin[1]; q.org[2] = (float)Origin[2];
+    ObInvPR inv;
+    ob_inv_pr(TLPosition, TLRotation, &inv);
+    ob_point_mul(inv, q.org);
+    for (int i = 0; i < 3; i++) {   // :426-434
+      q.data[i] = (0.5f * q.dir[i]) * q.maxdist;
+      q.data2[i] = q.org[i] + q.data[i];
+      q.fdir[i] = fabsf(q.data[i]);
+    }
+  }
+  // the stab: every hit in visit order, or only the closest one (strict <, ties keep the first), or the first
+  ObBvIter it;
+  ob_bv_begin(it);
+  int out = 0;
+  int ctri = -1; float cdist = 0;
+  for (;;) {
+    if (!closest && out == maxc) break;
+    const int tri = ob_bv_next(m, it, q);
+    if (tri < 0) break;
+    int use = tri; float T = q.dist;
+    if (closest) {
+      if (ctri < 0 || q.dist < cdist) { ctri = tri; cdist = q.dist; }
+      if (first) break;
+      continue;
+    }
+    real dv[3][3];
+    ob_fetch_triangle(m, use, TLPosition, TLRotation, dv);
+    real vu[3] = {dv[1][0] - dv[0][0], dv[1][1] - dv[0][1], dv[1][2] - dv[0][2]};
+    real vv[3] = {dv[2][0] - dv[0][0], dv[2][1] - dv[0][1], dv[2][2] - dv[0][2]};
+    ob_cross(contact[out].normal, vv, vu);   // reversed
+    if (ob_safe_normalize3(contact[out].normal)) {
+      const real Tr = (real)T;
+      for (int e = 0; e < 3; e++) contact[out].pos[e] = Origin[e] + (Direction[e] * Tr);
+      contact[out].depth = Tr; contact[out].side1 = use; contact[out].side2 = -1;
+      out++;
+    }
+    if (first) break;
+  }
+  if (closest && ctri >= 0 && maxc > 0) {
+    real dv[3][3];
+    ob_fetch_triangle(m, ctri, TLPosition, TLRotation, dv);
+    real vu[3] = {dv[1][0] - dv[0][0], dv[1][1] - dv[0][1], dv[1][2] - dv[0][2]};
+    real vv[3] = {dv[2][0] - dv[0][0], dv[2][1] - dv[0][1], dv[2][2] - dv[0][2]};
+    ob_cross(contact[0].normal, vv, vu);
+    if (ob_safe_normalize3(contact[0].normal)) {
+      const real Tr = (real)cdist;
+      for (int e = 0; e < 3; e++) contact[0].pos[e] = Origin[e] + (Direction[e] * Tr);
+      contact[0].depth = Tr; contact[0].side1 = ctri; contact[0].side2 = -1;
+      out = 1;
+    }
+  }
+  if (it.overflow && bverr) *bverr = 1;
+  return out;
+}
