@@ -24,6 +24,14 @@ GOLDEN = [  # (file stem, scene, steps, worlds, settle) — must match tests/gol
     ("terrain_spheres_settle70", "terrain_spheres", 25, 1, 70),
     ("terrain_boxes_settle70", "terrain_boxes", 15, 1, 70),
     ("buggy_terrain_w2_settle90", "buggy_terrain", 30, 2, 90),
+    ("terrain_capsules_settle70", "terrain_capsules", 20, 1, 70),
+]
+
+
+# reference traces replayed through the DROP-IN path (classic callback loop); scenes with ray geoms only
+# exist there: a ray contact is a query result for the caller, not a contact joint
+GOLDEN_CALLBACK = [
+    ("raycast_settle40", "raycast", 20, 1, 40),
 ]
 
 

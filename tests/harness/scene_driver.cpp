@@ -59,9 +59,13 @@ static void near_cb(void *data, dGeomID o1, dGeomID o2) {
     contact[i].surface = c->pol->surface;
   }
   int n = dCollide(o1, o2, maxc, &contact[0].geom, sizeof(dContact));
+  const bool ray = dGeomGetClass(o1) == dRayClass || dGeomGetClass(o2) == dRayClass;   // query result, not a contact joint
   for (int i = 0; i < n; i++) {
-    dJointID j = dJointCreateContact(c->sw->world, c->sw->cgroup, &contact[i]);
-    dJointAttach(j, b1, b2);
+    dJointID j = 0;
+    if (!ray) {
+      j = dJointCreateContact(c->sw->world, c->sw->cgroup, &contact[i]);
+      dJointAttach(j, b1, b2);
+    }
     if (c->record) {
       c->cg.push_back((int)(intptr_t)dGeomGetData(contact[i].geom.g1));
       c->cg.push_back((int)(intptr_t)dGeomGetData(contact[i].geom.g2));
@@ -70,11 +74,11 @@ static void near_cb(void *data, dGeomID o1, dGeomID o2) {
       c->cdata.push_back(contact[i].geom.depth);
       dJointFeedback *fb = new dJointFeedback;
       memset(fb, 0, sizeof(*fb));
-      dJointSetFeedback(j, fb);
+      if (j) dJointSetFeedback(j, fb);
       c->fbs.push_back(fb);
     }
   }
-  c->ncontacts += n;
+  if (!ray) c->ncontacts += n;
 }
 
 static void dump_state(Trace &t, SceneWorld &sw) {

@@ -402,6 +402,25 @@ static inline void scene_terrain_boxes(SceneWorld &sw, int w) {
   for (int i = 0; i < 4; i++) scene_add_sphere(sw, 2, rng.uni(0.15, 0.5), rng.uni(-3, 3), rng.uni(-3, 3), rng.uni(1.5, 4));
 }
 
+// capsules (and a few boxes) tumbling on the terrain mesh: dCollideCCTL (collision_trimesh_ccylinder.cpp)
+static inline void scene_terrain_capsules(SceneWorld &sw, int w) {
+  scene_world_base(sw, w);
+  xs32 rng(sw.seed ^ 0xCA95E5u);
+  scene_add_geom(sw, dCreatePlane(sw.space, 0, 0, 1, (dReal)-3));
+  dGeomID mesh = scene_add_geom(sw, dCreateTriMesh(sw.space, scene_terrain_data(25, 0.5, 0.45, 0.9, 0.7, 0.12), 0, 0, 0));
+  dMatrix3 R;
+  dRFromAxisAndAngle(R, (dReal)-0.1, (dReal)0.15, 1, (dReal)-0.5);
+  dGeomSetRotation(mesh, R);
+  dGeomSetPosition(mesh, (dReal)0.15, (dReal)0.1, (dReal)-0.05);
+  for (int i = 0; i < 12; i++) {
+    dBodyID b = scene_add_capsule(sw, 2, rng.uni(0.1, 0.35), rng.uni(0.2, 1.2), rng.uni(-3.5, 3.5), rng.uni(-3.5, 3.5), rng.uni(1.2, 4));
+    dQuaternion q = {rng.uni(-1, 1), rng.uni(-1, 1), rng.uni(-1, 1), rng.uni(-1, 1)};
+    dBodySetQuaternion(b, q);
+    dBodySetAngularVel(b, rng.uni(-2, 2), rng.uni(-2, 2), rng.uni(-2, 2));
+  }
+  for (int i = 0; i < 3; i++) scene_add_box(sw, 2, rng.uni(0.3, 0.8), rng.uni(0.3, 0.8), rng.uni(0.3, 0.8), rng.uni(-3, 3), rng.uni(-3, 3), rng.uni(1.5, 4));
+}
+
 // config 3: demo_buggy-style vehicle (box chassis + 4 sphere wheels on hinge2, demo_buggy.cpp:226-294)
 // dropped on a shared trimesh terrain (n x n vertex grid, 1 m spacing,
 // 0.5*sin(0.07x)*cos(0.05y) + 0.15*noise); world w spawns on a lattice over the terrain
@@ -464,6 +483,58 @@ static inline void scene_pile(SceneWorld &sw, int w, int nx, int ny, int nz) {
       }
 }
 
+// ray colliders (ray.cpp, collision_trimesh_ray.cpp): bodies of every primitive class tumbling over a plane
+// and a rotated terrain mesh, watched by rays — free-standing ones in every mode (all hits / first contact /
+// closest hit, with and without backface culling) and "sensor" rays riding on bodies (raycar style,
+// RC/car.cpp:353-371).  The near callback records ray contacts and creates no joints for them.
+static inline void scene_raycast(SceneWorld &sw, int w) {
+  scene_world_base(sw, w);
+  xs32 rng(sw.seed ^ 0x00BA7CA5u);
+  scene_add_geom(sw, dCreatePlane(sw.space, 0, 0, 1, (dReal)-1.5));
+  dGeomID mesh = scene_add_geom(sw, dCreateTriMesh(sw.space, scene_terrain_data(25, 0.5, 0.45, 0.9, 0.7, 0.12), 0, 0, 0));
+  dMatrix3 R;
+  dRFromAxisAndAngle(R, (dReal)0.2, (dReal)0.1, 1, (dReal)0.4);
+  dGeomSetRotation(mesh, R);
+  dGeomSetPosition(mesh, (dReal)0.2, (dReal)-0.1, (dReal)0.05);
+  std::vector<dBodyID> carriers;
+  for (int i = 0; i < 5; i++) {
+    dBodyID b = scene_add_box(sw, 2, rng.uni(0.3, 0.9), rng.uni(0.3, 0.9), rng.uni(0.2, 0.6), rng.uni(-3, 3), rng.uni(-3, 3), rng.uni(1.2, 3));
+    dQuaternion q = {rng.uni(-1, 1), rng.uni(-1, 1), rng.uni(-1, 1), rng.uni(-1, 1)};
+    dBodySetQuaternion(b, q);
+    dBodySetAngularVel(b, rng.uni(-1, 1), rng.uni(-1, 1), rng.uni(-1, 1));
+    carriers.push_back(b);
+  }
+  for (int i = 0; i < 4; i++) scene_add_sphere(sw, 2, rng.uni(0.2, 0.5), rng.uni(-3, 3), rng.uni(-3, 3), rng.uni(1.5, 3));
+  for (int i = 0; i < 4; i++) {
+    dBodyID b = scene_add_capsule(sw, 2, rng.uni(0.12, 0.3), rng.uni(0.3, 0.9), rng.uni(-3, 3), rng.uni(-3, 3), rng.uni(1.5, 3));
+    dQuaternion q = {rng.uni(-1, 1), rng.uni(-1, 1), rng.uni(-1, 1), rng.uni(-1, 1)};
+    dBodySetQuaternion(b, q);
+  }
+  // free-standing rays, mode = i % 6
+  for (int i = 0; i < 42; i++) {
+    dGeomID r = scene_add_geom(sw, dCreateRay(sw.space, rng.uni(2, 9)));
+    const dReal px = rng.uni(-4, 4), py = rng.uni(-4, 4), pz = rng.uni(-0.5, 5);
+    if (i < 18) dGeomRaySet(r, px, py, pz, rng.uni(-0.6, 0.6), rng.uni(-0.6, 0.6), (dReal)((i / 6) & 1 ? 1 : -1));
+    else if (i < 30) dGeomRaySet(r, px, py, rng.uni(0.1, 1.0), rng.uni(-1, 1), rng.uni(-1, 1), rng.uni(-0.15, 0.15));   // skim the settled bodies
+    else dGeomRaySet(r, px, py, pz, rng.uni(-1, 1), rng.uni(-1, 1), rng.uni(-1, 1));
+    const int mode = i % 6;
+    dGeomRaySetParams(r, mode == 1 || mode == 4, mode >= 3);
+    dGeomRaySetClosestHit(r, mode == 2 || mode == 5);
+  }
+  // sensor rays on bodies: straight down the body's -z through an offset rotation, and one without offset
+  for (size_t i = 0; i < carriers.size(); i++) {
+    dGeomID r = scene_add_geom(sw, dCreateRay(sw.space, (dReal)2.5));
+    dGeomSetBody(r, carriers[i]);
+    if (i != 1) {
+      dMatrix3 Ro;
+      dRFromAxisAndAngle(Ro, 1, 0, 0, (dReal)3.14159265358979);
+      dGeomSetOffsetRotation(r, Ro);
+      dGeomSetOffsetPosition(r, rng.uni(-0.1, 0.1), rng.uni(-0.1, 0.1), 0);
+    }
+    dGeomRaySetClosestHit(r, i & 1);
+  }
+}
+
 static inline ScenePolicy policy_buggy() {
   // ode/demo/demo_buggy.cpp:96-103
   ScenePolicy p;
@@ -502,8 +573,10 @@ static inline int scene_build(const char *name_in, SceneWorld &sw, int w, SceneP
   if (!strcmp(name, "buggy_terrain")) { scene_buggy_terrain(sw, w, 48); pol = policy_buggy(); pol.max_contacts = 10; return 0; }
   if (!strcmp(name, "buggy_terrain256")) { scene_buggy_terrain(sw, w, 256); pol = policy_buggy(); pol.max_contacts = 10; return 0; }
   if (!strcmp(name, "terrain_boxes")) { scene_terrain_boxes(sw, w); return 0; }
+  if (!strcmp(name, "terrain_capsules")) { scene_terrain_capsules(sw, w); return 0; }
   if (!strcmp(name, "terrain_spheres")) { scene_terrain_spheres(sw, w); return 0; }
   if (!strcmp(name, "capsmix")) { scene_capsmix(sw, w); return 0; }
+  if (!strcmp(name, "raycast")) { scene_raycast(sw, w); return 0; }
   if (!strcmp(name, "ragdoll")) { scene_ragdoll(sw, w); pol = policy_crash(); return 0; }
   if (!strcmp(name, "buggy")) { scene_buggy(sw, w); pol = policy_buggy(); return 0; }
   {

@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import ATAN2_SCENES, GOLDEN, ROOT, assert_bit_exact, assert_parity, have_ref, lib_path
+from conftest import ATAN2_SCENES, GOLDEN, GOLDEN_CALLBACK, ROOT, assert_bit_exact, assert_parity, have_ref, lib_path
 from run_parity import parity, parity_golden
 
 pytestmark = pytest.mark.gpu
@@ -22,12 +22,22 @@ def test_cuda_matches_golden_reference_traces(stem, scene, steps, worlds, settle
     assert_parity(r, f"{stem}/{prec}", scene, prec, "b200")
 
 
+@pytest.mark.parametrize("prec", ["single", "double"])
+@pytest.mark.parametrize("stem,scene,steps,worlds,settle", GOLDEN_CALLBACK)
+def test_cuda_dropin_matches_golden_reference_traces(stem, scene, steps, worlds, settle, prec):
+    """ray colliders in every mode + capsule-trimesh on the GPU, through dSpaceCollide / dCollide"""
+    g = os.path.join(ROOT, "tests", "golden", f"{stem}_{prec}.trace")
+    r = parity_golden("b200", g, scene, prec, steps, worlds, settle, mode="callback")
+    assert r["steps"] == steps and r["contacts"] > 0
+    assert_bit_exact(r, f"{stem}/{prec}")
+
+
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref not shipped")
 @pytest.mark.parametrize("prec", ["single", "double"])
 @pytest.mark.parametrize("scene,steps,worlds", [("stack32", 200, 3), ("block64", 50, 1), ("tower64", 250, 1),
                                                 ("mixed", 200, 2), ("mixed_maxc4", 300, 1), ("chain", 250, 2), ("hinges", 250, 1), ("buggy", 250, 3), ("capsmix", 250, 3), ("ragdoll", 250, 3),
                                                 ("block64@sap", 50, 1), ("stack32@sap", 200, 3), ("tower64@sapz", 250, 1), ("capsmix@simple", 200, 2),
-                                                ("terrain_spheres", 300, 3), ("terrain_boxes", 250, 2), ("buggy_terrain", 300, 4)])
+                                                ("terrain_spheres", 300, 3), ("terrain_boxes", 250, 2), ("buggy_terrain", 300, 4), ("terrain_capsules", 300, 2)])
 def test_cuda_matches_live_reference(scene, steps, worlds, prec):
     # dDOUBLE scenes with atan2 on the path: lock-step protocol (SURVEY 8d, K = 1), see conftest.ATAN2_SCENES
     r = parity("b200", prec, scene, steps, worlds, lockstep=(prec == "double" and scene.split("@")[0] in ATAN2_SCENES))
@@ -37,7 +47,8 @@ def test_cuda_matches_live_reference(scene, steps, worlds, prec):
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref not shipped")
 @pytest.mark.parametrize("prec", ["single", "double"])
 @pytest.mark.parametrize("scene,steps,worlds", [("stack32", 60, 2), ("mixed_maxc4", 120, 1), ("chain", 100, 1), ("capsmix", 100, 1), ("block64", 20, 1),
-                                                ("stack32@sap", 60, 2), ("mixed@simple", 100, 1), ("terrain_boxes", 80, 1), ("buggy_terrain", 100, 1)])
+                                                ("stack32@sap", 60, 2), ("mixed@simple", 100, 1), ("terrain_boxes", 80, 1), ("buggy_terrain", 100, 1),
+                                                ("raycast", 150, 2)])
 def test_dropin_classic_api_matches_live_reference(scene, steps, worlds, prec):
     """the drop-in boundary: unchanged user code (dSpaceCollide + near callback calling dCollide /
     dJointCreateContact / dJointSetFeedback + dWorldQuickStep + dJointGroupEmpty) linked against
