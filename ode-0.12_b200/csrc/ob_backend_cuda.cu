@@ -601,6 +601,8 @@ static int run_steps(ObBackend *b, real h, int nsteps, int taps, int phases, cha
     return 0;
   }
   for (int s = 0; s < nsteps; s++) {
+    // parity tap: joints that enter no island (attached to no body / to disabled bodies) report zero feedback
+    if ((taps & 1) && !b->d.dropin && b->d.fback) cudaMemsetAsync(b->d.fback, 0, sizeof(real) * 12 * (size_t)b->d.W * (b->d.NC + b->d.NJ), b->stream);
     if (b->tile == 8) launch_step<8>(b, h, taps, phases);
     else if (b->tile == 16) launch_step<16>(b, h, taps, phases);
     else launch_step<32>(b, h, taps, phases);
@@ -661,7 +663,12 @@ int obk_mesh_upload(const float *verts, int nverts, const int *tris, int ntris, 
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return -1;
   if (cudaSetDevice(device) != cudaSuccess) return -1;
-  float *dv = 0; int *dt = 0; ObBvNode *dn = 0;
+  float *dv = 0; int *dt = 0; ObBvNode *dn = 0; int *df = 0;
+  std::vector<int> vfirst((size_t)(nverts > 0 ? nverts : 1), -1);
+  for (int c = 0; c < 3 * ntris; c++) { const int vi = tris[c]; if (vi >= 0 && vi < nverts && vfirst[vi] < 0) vfirst[vi] = c; }
+  if (cudaMalloc((void **)&df, sizeof(int) * vfirst.size()) != cudaSuccess) return -1;
+  if (cudaMemcpy(df, vfirst.data(), sizeof(int) * vfirst.size(), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(df); return -1; }
+  io->vfirst = df;
   if (cudaMalloc((void **)&dv, sizeof(float) * 3 * (size_t)nverts) != cudaSuccess) return -1;
   if (cudaMalloc((void **)&dt, sizeof(int) * 3 * (size_t)ntris) != cudaSuccess) { cudaFree(dv); return -1; }
   if (cudaMalloc((void **)&dn, sizeof(ObBvNode) * (size_t)(ntris - 1)) != cudaSuccess) { cudaFree(dv); cudaFree(dt); return -1; }
@@ -676,7 +683,8 @@ void obk_mesh_free(ObMeshDev *m) {
   if (m->verts) cudaFree((void *)m->verts);
   if (m->tris) cudaFree((void *)m->tris);
   if (m->nodes) cudaFree((void *)m->nodes);
-  m->verts = 0; m->tris = 0; m->nodes = 0;
+  if (m->vfirst) cudaFree((void *)m->vfirst);
+  m->verts = 0; m->tris = 0; m->nodes = 0; m->vfirst = 0;
 }
 
 // Bulk state I/O copies straight between the caller's buffers and the packed device staging

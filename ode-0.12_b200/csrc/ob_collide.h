@@ -952,7 +952,7 @@ OB_HD int ob_pair_max_contacts(int t1, int t2, int maxc) {
   else if (lo == OB_GEOM_BOX && hi == OB_GEOM_CAPSULE) cap = 1;
   else if (lo == OB_GEOM_CAPSULE && hi == OB_GEOM_CAPSULE) cap = 2;
   else if (lo == OB_GEOM_CAPSULE && hi == OB_GEOM_PLANE) cap = 2;
-  else if (hi == OB_GEOM_TRIMESH && (lo == OB_GEOM_SPHERE || lo == OB_GEOM_BOX || lo == OB_GEOM_CAPSULE || lo == OB_GEOM_RAY)) cap = 1 << 15;   // bounded by the caller's max_contacts only
+  else if (hi == OB_GEOM_TRIMESH && (lo == OB_GEOM_SPHERE || lo == OB_GEOM_BOX || lo == OB_GEOM_CAPSULE || lo == OB_GEOM_PLANE || lo == OB_GEOM_RAY)) cap = 1 << 15;   // bounded by the caller's max_contacts only
   else if (hi == OB_GEOM_RAY && (lo == OB_GEOM_SPHERE || lo == OB_GEOM_BOX || lo == OB_GEOM_CAPSULE || lo == OB_GEOM_PLANE)) cap = 1;
   else cap = 0;
   return cap < maxc ? cap : maxc;
@@ -989,6 +989,8 @@ OB_HD int ob_collide_pair_t(const ObPose &o1, const ObPose &o2, int flags, ObCg 
   else if (t1 == OB_GEOM_CAPSULE && t2 == OB_GEOM_RAY) { n = ob_collide_ray_capsule(o2, o1, c); rev = 1; }
   else if (t1 == OB_GEOM_RAY && t2 == OB_GEOM_PLANE) n = ob_collide_ray_plane(o1, o2, c);
   else if (t1 == OB_GEOM_PLANE && t2 == OB_GEOM_RAY) { n = ob_collide_ray_plane(o2, o1, c); rev = 1; }
+  else if (MESH && t1 == OB_GEOM_TRIMESH && t2 == OB_GEOM_PLANE) n = ob_collide_trimesh_plane(o1, o2, meshes[o1.mesh], (flags & ~0xffff) | ((flags & 0xffff) < CGCAP ? (flags & 0xffff) : CGCAP), c);
+  else if (MESH && t1 == OB_GEOM_PLANE && t2 == OB_GEOM_TRIMESH) { n = ob_collide_trimesh_plane(o2, o1, meshes[o2.mesh], (flags & ~0xffff) | ((flags & 0xffff) < CGCAP ? (flags & 0xffff) : CGCAP), c); rev = 1; }
   else if (MESH && t1 == OB_GEOM_TRIMESH && t2 == OB_GEOM_CAPSULE) n = ob_collide_trimesh_capsule(o1, o2, meshes[o1.mesh], flags, c, &bve);
   else if (MESH && t1 == OB_GEOM_CAPSULE && t2 == OB_GEOM_TRIMESH) { n = ob_collide_trimesh_capsule(o2, o1, meshes[o2.mesh], flags, c, &bve); rev = 1; }
   else if (MESH && t1 == OB_GEOM_TRIMESH && t2 == OB_GEOM_RAY) n = ob_collide_trimesh_ray(o1, o2, meshes[o1.mesh], flags, c, &bve);

@@ -196,7 +196,8 @@ __global__ void __launch_bounds__(32) k_prep(ObBatchDev d, real h, int taps) {
     __syncwarp();
     // per-body joint lists: contacts newest first, then the permanent joints in the body's list order
     if (gl == 0 && valid) {
-      for (int j = 0; j < nc; j++) { s_cursor[s_jb1[j]]++; if (s_jb2[j] != 255) s_cursor[s_jb2[j]]++; }
+      // a contact between two body-less geoms is a joint attached to nothing (ode.cpp:1348-1399): it is on no body's list
+      for (int j = 0; j < nc; j++) { if (s_jb1[j] == 255) continue; s_cursor[s_jb1[j]]++; if (s_jb2[j] != 255) s_cursor[s_jb2[j]]++; }
       int a = 0;
       for (int b = 0; b < nb; b++) {
         const int c = s_cursor[b] + (padjstart[b + 1] - padjstart[b]);
@@ -205,6 +206,7 @@ __global__ void __launch_bounds__(32) k_prep(ObBatchDev d, real h, int taps) {
       s_adjstart[nb] = (unsigned short)a;
       for (int j = nc - 1; j >= 0; j--) {
         const int b1 = s_jb1[j], b2 = s_jb2[j];
+        if (b1 == 255) continue;
         s_adj[s_cursor[b1]++] = (unsigned short)j;
         if (b2 != 255) s_adj[s_cursor[b2]++] = (unsigned short)j;
       }

@@ -26,6 +26,7 @@ struct ObMeshDev {     // one dTriMeshData on the execution side
   const ObBvNode *nodes;   // [ntris-1]
   int nverts, ntris;
   real aabbc[3], aabbe[3];   // model-space AABB centre / extents (collision_trimesh_opcode.cpp:123-157)
+  const int *vfirst;   // [nverts] flattened corner index (3*tri + corner) of the vertex's first use, -1 if unused
 };
 
 #define OB_BV_STACK 96
@@ -397,4 +398,34 @@ OB_HD int ob_collide_trimesh_ray(const ObPose &o1, const ObPose &o2, const ObMes
   }
   if (it.overflow && bverr) *bverr = 1;
   return out;
+}
+
+
+// ---- dCollideTrimeshPlane, collision_trimesh_plane.cpp:38-168: every mesh vertex, in triangle order, each
+// vertex once (the reference's VertexUseCache bit set == "this corner is the vertex's first use", which is a
+// property of the index list and is precomputed at upload: ObMeshDev::vfirst).  o1 = trimesh, o2 = plane.
+OB_HD int ob_collide_trimesh_plane(const ObPose &o1, const ObPose &o2, const ObMeshDev &m, int flags, ObCg *contact) {
+  const int contact_max = flags & 0xffff;
+  int count = 0;
+  for (int t = 0; t < m.ntris; ++t) {
+    for (int v = 0; v < 3; ++v) {
+      const int vi = m.tris[3 * (size_t)t + v];
+      if (m.vfirst[vi] != 3 * t + v) continue;
+      const float *p = m.verts + 3 * (size_t)vi;
+      const real iv[3] = {(real)p[0], (real)p[1], (real)p[2]};
+      real vertex[3];
+      ob_mul0_331(vertex, o1.R, iv);
+      vertex[0] += o1.pos[0]; vertex[1] += o1.pos[1]; vertex[2] += o1.pos[2];
+      const real alpha = o2.p[3] - ob_dot(o2.p, vertex);
+      if (alpha > 0) {
+        ObCg &c = contact[count];
+        c.pos[0] = vertex[0]; c.pos[1] = vertex[1]; c.pos[2] = vertex[2];
+        c.normal[0] = o2.p[0]; c.normal[1] = o2.p[1]; c.normal[2] = o2.p[2];
+        c.depth = alpha; c.side1 = t; c.side2 = -1;
+        ++count;
+        if (count >= contact_max) return count;
+      }
+    }
+  }
+  return count;
 }

@@ -25,6 +25,7 @@ GOLDEN = [  # (file stem, scene, steps, worlds, settle) — must match tests/gol
     ("terrain_boxes_settle70", "terrain_boxes", 15, 1, 70),
     ("buggy_terrain_w2_settle90", "buggy_terrain", 30, 2, 90),
     ("terrain_capsules_settle70", "terrain_capsules", 20, 1, 70),
+    ("terrain_plane_settle60", "terrain_plane", 20, 1, 60),
 ]
 
 

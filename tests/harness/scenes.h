@@ -421,6 +421,18 @@ static inline void scene_terrain_capsules(SceneWorld &sw, int w) {
   for (int i = 0; i < 3; i++) scene_add_box(sw, 2, rng.uni(0.3, 0.8), rng.uni(0.3, 0.8), rng.uni(0.3, 0.8), rng.uni(-3, 3), rng.uni(-3, 3), rng.uni(1.5, 4));
 }
 
+// a terrain mesh cut by a tilted plane (dCollideTrimeshPlane: static mesh vertices below the plane -> contact
+// joints attached to no body, which the stepper must ignore) with spheres and boxes rolling on both
+static inline void scene_terrain_plane(SceneWorld &sw, int w) {
+  scene_world_base(sw, w);
+  xs32 rng(sw.seed ^ 0x91A4E5u);
+  scene_add_geom(sw, dCreatePlane(sw.space, (dReal)0.05, (dReal)-0.03, 1, (dReal)0.1));
+  dGeomID mesh = scene_add_geom(sw, dCreateTriMesh(sw.space, scene_terrain_data(25, 0.5, 0.45, 0.9, 0.7, 0.12), 0, 0, 0));
+  dGeomSetPosition(mesh, (dReal)0.1, (dReal)-0.2, (dReal)0.0);
+  for (int i = 0; i < 6; i++) scene_add_sphere(sw, 2, rng.uni(0.2, 0.5), rng.uni(-3, 3), rng.uni(-3, 3), rng.uni(1.5, 3));
+  for (int i = 0; i < 4; i++) scene_add_box(sw, 2, rng.uni(0.3, 0.8), rng.uni(0.3, 0.8), rng.uni(0.3, 0.8), rng.uni(-3, 3), rng.uni(-3, 3), rng.uni(1.5, 3));
+}
+
 // config 3: demo_buggy-style vehicle (box chassis + 4 sphere wheels on hinge2, demo_buggy.cpp:226-294)
 // dropped on a shared trimesh terrain (n x n vertex grid, 1 m spacing,
 // 0.5*sin(0.07x)*cos(0.05y) + 0.15*noise); world w spawns on a lattice over the terrain
@@ -573,6 +585,7 @@ static inline int scene_build(const char *name_in, SceneWorld &sw, int w, SceneP
   if (!strcmp(name, "buggy_terrain")) { scene_buggy_terrain(sw, w, 48); pol = policy_buggy(); pol.max_contacts = 10; return 0; }
   if (!strcmp(name, "buggy_terrain256")) { scene_buggy_terrain(sw, w, 256); pol = policy_buggy(); pol.max_contacts = 10; return 0; }
   if (!strcmp(name, "terrain_boxes")) { scene_terrain_boxes(sw, w); return 0; }
+  if (!strcmp(name, "terrain_plane")) { scene_terrain_plane(sw, w); return 0; }
   if (!strcmp(name, "terrain_capsules")) { scene_terrain_capsules(sw, w); return 0; }
   if (!strcmp(name, "terrain_spheres")) { scene_terrain_spheres(sw, w); return 0; }
   if (!strcmp(name, "capsmix")) { scene_capsmix(sw, w); return 0; }

@@ -599,10 +599,13 @@ int obk_mesh_upload(const float *verts, int nverts, const int *tris, int ntris, 
   memcpy(v, verts, sizeof(float) * 3 * (size_t)nverts);
   memcpy(t, tris, sizeof(int) * 3 * (size_t)ntris);
   memcpy(n, nodes, sizeof(ObBvNode) * (size_t)(ntris - 1));
-  io->verts = v; io->tris = t; io->nodes = n; io->nverts = nverts; io->ntris = ntris;
+  int *vf = (int *)malloc(sizeof(int) * (size_t)(nverts > 0 ? nverts : 1));
+  for (int i = 0; i < nverts; i++) vf[i] = -1;
+  for (int c = 0; c < 3 * ntris; c++) { const int vi = tris[c]; if (vi >= 0 && vi < nverts && vf[vi] < 0) vf[vi] = c; }
+  io->verts = v; io->tris = t; io->nodes = n; io->nverts = nverts; io->ntris = ntris; io->vfirst = vf;
   return 0;
 }
-void obk_mesh_free(ObMeshDev *m) { free((void *)m->verts); free((void *)m->tris); free((void *)m->nodes); m->verts = 0; m->tris = 0; m->nodes = 0; }
+void obk_mesh_free(ObMeshDev *m) { free((void *)m->verts); free((void *)m->tris); free((void *)m->nodes); free((void *)m->vfirst); m->verts = 0; m->tris = 0; m->nodes = 0; m->vfirst = 0; }
 int obk_step(ObBackend *b, real h, int nsteps, int taps, char *err, size_t errlen) {
   ObBatchDev &d = b->d;
   if (d.large) {
@@ -615,10 +618,12 @@ int obk_step(ObBackend *b, real h, int nsteps, int taps, char *err, size_t errle
     }
     return 0;
   }
-  for (int s = 0; s < nsteps; s++)
+  for (int s = 0; s < nsteps; s++) {
+    if ((taps & 1) && !d.dropin) memset(d.fback, 0, sizeof(real) * 12 * (size_t)d.W * (d.NC + d.NJ));
     for (int w = 0; w < d.W; w++) {
       collide_world(d, w);
       step_world(d, w, h, taps);
     }
+  }
   return 0;
 }
