@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(OB_THREADS) k_collide(ObBatchDev d) {
   int *s_misc = (int *)(smem + L.misc);   // [0]=npairs raw, [1]=nh, [2]=nbig, [3]=contact base, [8..40]=scan scratch
   const int tid = threadIdx.x, nt = blockDim.x;
 
-  for (int w = blockIdx.x; w < d.W; w += gridDim.x) {
+  for (int w = d.wbeg + blockIdx.x; w < d.wend; w += gridDim.x) {
     ObWorld &W = d.world[w];
     const int ng = W.ng;
     const ObGeom *geoms = d.geom + (size_t)w * d.NG;
@@ -368,7 +368,13 @@ struct ObBackend {
   real *st_dev;      // packed state staging on the device: pos3|quat4|lvel3|avel3
   real *st_host;     // pinned
   size_t st_elems;   // W*NB
-  size_t smem_collide, smem_prep, smem_sched, smem_sor, smem_post;
+  size_t smem_collide, smem_prep, smem_sched, smem_sched_lane, smem_sor, smem_post;
+  int sched_lane;   // 1: k_sched_lane (one lane per world) fits shared memory
+  // independent worlds are stepped in nchunks chunks, each on its own stream: the chunks drift apart, so the
+  // ALU-bound collide of one chunk overlaps the latency-bound SOR of another instead of running back to back
+  int nchunks;
+  cudaStream_t cstream[8];
+  cudaEvent_t cev[9];
   int grid, grid_step, grid_sor, tile;
   cudaEvent_t ev[8];   // 0,1: user timer; 2..7 per-kernel timing
   int ktiming;
@@ -404,6 +410,9 @@ ObBackend *obk_create(const ObBatchDev &caps, int device, char *err, size_t errl
   const size_t W = d.W;
   int ndev = 0;
   cudaDeviceProp prop;
+  b->nchunks = 1;
+  for (int k = 0; k < 8; k++) b->cstream[k] = 0;
+  for (int k = 0; k < 9; k++) b->cev[k] = 0;
   b->large = d.large; b->lw_host = 0; b->lw_rounds = 0; b->lw_ncol = 0;
   for (int k = 0; k < 8; k++) b->lw_stat[k] = 0;
   memset(&b->L, 0, sizeof b->L);
@@ -415,6 +424,9 @@ ObBackend *obk_create(const ObBatchDev &caps, int device, char *err, size_t errl
   CK(cudaGetDeviceProperties(&prop, device));
   CK(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
   for (int k = 0; k < 8; k++) CK(cudaEventCreate(&b->ev[k]));
+  for (int k = 0; k < 8; k++) CK(cudaStreamCreateWithFlags(&b->cstream[k], cudaStreamNonBlocking));
+  for (int k = 0; k < 9; k++) CK(cudaEventCreateWithFlags(&b->cev[k], cudaEventDisableTiming));
+  d.wbeg = 0; d.wend = d.W;
   if (d.large) {
     if (lw_create(b, err, errlen)) goto fail;
     return b;
@@ -490,6 +502,17 @@ ObBackend *obk_create(const ObBatchDev &caps, int device, char *err, size_t errl
   CK(cudaFuncSetAttribute(k_sched<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sched));
   CK(cudaFuncSetAttribute(k_sched<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sched));
   CK(cudaFuncSetAttribute(k_sched<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sched));
+  b->smem_sched_lane = sched_lane_smem(d.NB, d.NR).total;
+  // measured on B200: one lane per world wins for many small worlds (config 3: 65536 worlds x 56 rows, 0.70 -> 0.43 ms),
+  // the warp per world for fewer, larger ones (config 2: 4096 x 377 rows, 0.40 vs 2.7 ms: too few warps to hide the chain latency)
+  b->sched_lane = b->smem_sched_lane <= (size_t)prop.sharedMemPerBlockOptin && ((W >= 8192 && d.NR <= 256) || getenv("OB_SCHED_LANE")) && !getenv("OB_SCHED_WARP");
+  if (b->sched_lane) CK(cudaFuncSetAttribute(k_sched_lane, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sched_lane));
+  {
+    int nch = 1;   // measured on B200 (configs 2-4): 2-8 chunks change the step time by -4 % .. +10 %, so off unless OB_CHUNKS asks
+    const char *e = getenv("OB_CHUNKS");
+    if (e && atoi(e) >= 1 && atoi(e) <= 8) nch = atoi(e);
+    b->nchunks = nch;
+  }
   {
     // grid: every world gets its own CTA up to 16 resident CTAs per SM worth of blocks, beyond that grid-stride
     int cap = prop.multiProcessorCount * 32;
@@ -514,6 +537,8 @@ void obk_destroy(ObBackend *b) {
   if (b->lw_host) cudaFreeHost(b->lw_host);
   for (int k = 0; k < 9; k++) if (b->lw_ev[k]) cudaEventDestroy(b->lw_ev[k]);
   for (int k = 0; k < 8; k++) if (b->ev[k]) cudaEventDestroy(b->ev[k]);
+  for (int k = 0; k < 8; k++) if (b->cstream[k]) cudaStreamDestroy(b->cstream[k]);
+  for (int k = 0; k < 9; k++) if (b->cev[k]) cudaEventDestroy(b->cev[k]);
   cudaStreamDestroy(b->stream);
   delete b;
 }
@@ -559,34 +584,69 @@ int obk_large_stats(ObBackend *b, int *ints8, double *ms8) {
 }
 const char *obk_kernel_name(int k) { static const char *n[] = {"k_collide", "k_prep", "k_sched", "k_sor", "k_post"}; return k >= 0 && k < 5 ? n[k] : ""; }
 
-template <int G> static void launch_step(ObBackend *b, real h, int taps, int phases) {
+// one step of the world range [w0, w1) on stream st
+template <int G> static void launch_step(ObBackend *b, real h, int taps, int phases, int w0, int w1, cudaStream_t st, bool timing) {
   cudaEvent_t *ev = b->ev + 2;
-  const int W = b->d.W;
-  if (b->ktiming) cudaEventRecord(ev[0], b->stream);
+  constexpr int T = 32 / G;
+  ObBatchDev d = b->d;
+  d.wbeg = w0; d.wend = w1;
+  const int W = w1 - w0;
+  const int cap = b->grid;   // resident-CTA cap computed for the whole batch
+  if (timing) cudaEventRecord(ev[0], st);
   if (phases & OBK_PHASE_COLLIDE) {
     // CTA width follows the world size: the widest loop is the ng*ng candidate-pair scan
-    const int ct = b->d.NG <= 8 ? 32 : (b->d.NG <= 20 ? 64 : OB_THREADS);
-    if (b->d.nmesh) k_collide<true><<<b->grid, ct, b->smem_collide, b->stream>>>(b->d);
-    else k_collide<false><<<b->grid, ct, b->smem_collide, b->stream>>>(b->d);
+    const int ct = d.NG <= 8 ? 32 : (d.NG <= 20 ? 64 : OB_THREADS);
+    const int grid = W < cap ? W : cap;
+    if (d.nmesh) k_collide<true><<<grid, ct, b->smem_collide, st>>>(d);
+    else k_collide<false><<<grid, ct, b->smem_collide, st>>>(d);
     g_launches++;
   }
-  if (b->ktiming) cudaEventRecord(ev[1], b->stream);
+  if (timing) cudaEventRecord(ev[1], st);
   if (phases & OBK_PHASE_STEP) {
-    k_prep<G><<<b->grid_step, 32, b->smem_prep, b->stream>>>(b->d, h, taps);
-    if (b->ktiming) cudaEventRecord(ev[2], b->stream);
-    if (b->d.NB <= 64) k_sched<2><<<W, 32, b->smem_sched, b->stream>>>(b->d, G, taps);
-    else if (b->d.NB <= 128) k_sched<4><<<W, 32, b->smem_sched, b->stream>>>(b->d, G, taps);
-    else k_sched<8><<<W, 32, b->smem_sched, b->stream>>>(b->d, G, taps);
-    if (b->ktiming) cudaEventRecord(ev[3], b->stream);
-    k_sor<G><<<b->grid_sor, 32, b->smem_sor, b->stream>>>(b->d, taps);
-    if (b->ktiming) cudaEventRecord(ev[4], b->stream);
-    k_post<G><<<b->grid_step, 32, b->smem_post, b->stream>>>(b->d, h);
+    const int gstep = (W + T - 1) / T;
+    int gsor = gstep;
+    if (b->grid_sor < b->grid_step) gsor = gsor < b->grid_sor ? gsor : b->grid_sor;
+    k_prep<G><<<gstep, 32, b->smem_prep, st>>>(d, h, taps);
+    if (timing) cudaEventRecord(ev[2], st);
+    if (b->sched_lane) k_sched_lane<<<(W + 31) / 32, 32, b->smem_sched_lane, st>>>(d, G);
+    else if (d.NB <= 64) k_sched<2><<<W, 32, b->smem_sched, st>>>(d, G, taps);
+    else if (d.NB <= 128) k_sched<4><<<W, 32, b->smem_sched, st>>>(d, G, taps);
+    else k_sched<8><<<W, 32, b->smem_sched, st>>>(d, G, taps);
+    if (timing) cudaEventRecord(ev[3], st);
+    k_sor<G><<<gsor, 32, b->smem_sor, st>>>(d, taps);
+    if (timing) cudaEventRecord(ev[4], st);
+    k_post<G><<<gstep, 32, b->smem_post, st>>>(d, h);
     g_launches += 4;
   }
-  if (b->ktiming && phases == (OBK_PHASE_COLLIDE | OBK_PHASE_STEP)) {
-    cudaEventRecord(ev[5], b->stream);
+  if (timing && phases == (OBK_PHASE_COLLIDE | OBK_PHASE_STEP)) {
+    cudaEventRecord(ev[5], st);
     if (cudaEventSynchronize(ev[5]) == cudaSuccess)
       for (int k = 0; k < 5; k++) { float m = 0; cudaEventElapsedTime(&m, ev[k], ev[k + 1]); b->kms[k] += m; b->klaunch[k]++; }
+  }
+}
+template <int G> static void launch_steps(ObBackend *b, real h, int nsteps, int taps, int phases) {
+  const int W = b->d.W;
+  // per-kernel timing and the parity taps run unchunked on the main stream
+  const int nch = (b->ktiming || (taps & 1) || b->d.dropin || nsteps < 2) ? 1 : b->nchunks;
+  if (nch <= 1) {
+    for (int s = 0; s < nsteps; s++) {
+      // parity tap: joints that enter no island (attached to no body / to disabled bodies) report zero feedback
+      if ((taps & 1) && !b->d.dropin && b->d.fback) cudaMemsetAsync(b->d.fback, 0, sizeof(real) * 12 * (size_t)W * (b->d.NC + b->d.NJ), b->stream);
+      launch_step<G>(b, h, taps, phases, 0, W, b->stream, b->ktiming != 0);
+    }
+    return;
+  }
+  // fork: every chunk stream starts after what is already queued on the main stream; worlds are independent,
+  // so the chunks never wait for each other between steps; join: the main stream waits for all of them
+  cudaEventRecord(b->cev[8], b->stream);
+  const int per = ((W + nch - 1) / nch + 31) / 32 * 32;   // multiple of 32 keeps warp tiles whole
+  for (int c = 0; c < nch; c++) {
+    const int w0 = c * per, w1 = (c + 1) * per < W ? (c + 1) * per : W;
+    if (w0 >= w1) continue;
+    cudaStreamWaitEvent(b->cstream[c], b->cev[8], 0);
+    for (int s = 0; s < nsteps; s++) launch_step<G>(b, h, taps, phases, w0, w1, b->cstream[c], false);
+    cudaEventRecord(b->cev[c], b->cstream[c]);
+    cudaStreamWaitEvent(b->stream, b->cev[c], 0);
   }
 }
 
@@ -600,13 +660,9 @@ static int run_steps(ObBackend *b, real h, int nsteps, int taps, int phases, cha
     for (int s = 0; s < nsteps; s++) if (lw_step(b, h, taps, err, errlen)) return -1;
     return 0;
   }
-  for (int s = 0; s < nsteps; s++) {
-    // parity tap: joints that enter no island (attached to no body / to disabled bodies) report zero feedback
-    if ((taps & 1) && !b->d.dropin && b->d.fback) cudaMemsetAsync(b->d.fback, 0, sizeof(real) * 12 * (size_t)b->d.W * (b->d.NC + b->d.NJ), b->stream);
-    if (b->tile == 8) launch_step<8>(b, h, taps, phases);
-    else if (b->tile == 16) launch_step<16>(b, h, taps, phases);
-    else launch_step<32>(b, h, taps, phases);
-  }
+  if (b->tile == 8) launch_steps<8>(b, h, nsteps, taps, phases);
+  else if (b->tile == 16) launch_steps<16>(b, h, nsteps, taps, phases);
+  else launch_steps<32>(b, h, nsteps, taps, phases);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
   if (e != cudaSuccess) { snprintf(err, errlen, "kernel launch/exec failed: %s", cudaGetErrorString(e)); return -1; }

@@ -152,9 +152,9 @@ __global__ void __launch_bounds__(32) k_prep(ObBatchDev d, real h, int taps) {
   int *s_misc = (int *)(smem + L.misc);
   const real stepsize1 = ob_recip(h);
 
-  for (int wbase = blockIdx.x * T; wbase < d.W; wbase += gridDim.x * T) {
+  for (int wbase = d.wbeg + blockIdx.x * T; wbase < d.wend; wbase += gridDim.x * T) {
     const int w = wbase + grp;
-    const bool valid = w < d.W;
+    const bool valid = w < d.wend;
     const int wc = valid ? w : 0;
     ObWorld &W = d.world[wc];
     const int nb = valid ? W.nb : 0;
@@ -522,7 +522,7 @@ __global__ void __launch_bounds__(32) k_sched(ObBatchDev d, int G, int taps) {
   const unsigned FULL = 0xffffffffu;
   const unsigned lt_mask = (1u << lane) - 1u;
 
-  for (int w = blockIdx.x; w < d.W; w += gridDim.x) {
+  for (int w = d.wbeg + blockIdx.x; w < d.wend; w += gridDim.x) {
     ObWorld &W = d.world[w];
     int *si = d.stepinfo + (size_t)w * SI_WORDS;
     const int nis = si[SI_NIS];
@@ -688,6 +688,142 @@ __global__ void __launch_bounds__(32) k_sched(ObBatchDev d, int G, int taps) {
 }
 
 
+// k_sched_lane: the same products as k_sched, but ONE LANE PER WORLD.  Everything k_sched does is a serial
+// chain per world (the m-1 dependent swaps of the shuffle, the level recurrence over the order), which a
+// warp per world executes with 31 idle lanes; here 32 worlds advance in lock-step, each lane in its own
+// column of shared memory (element i of lane l at [i*32 + l]: bank == lane, conflict-free for any index).
+// Used when the per-warp working set fits shared memory (ob_backend_cuda.cu), else k_sched.
+struct SchedLaneSmem { size_t ord, rowb, lvl, X, fio, last, isl, total; };
+__host__ __device__ inline SchedLaneSmem sched_lane_smem(int NB, int NR) {
+  SchedLaneSmem s; size_t o = 0;
+  s.ord = o; o = ob_al(o + sizeof(unsigned short) * 32 * NR, 16);
+  s.rowb = o; o = ob_al(o + sizeof(unsigned short) * 32 * NR, 16);
+  s.lvl = o; o = ob_al(o + sizeof(unsigned short) * 32 * NR, 16);
+  s.X = o; o = ob_al(o + sizeof(unsigned short) * 32 * (NR + 2), 16);
+  s.fio = o; o = ob_al(o + (size_t)32 * NR, 16);
+  s.last = o; o = ob_al(o + sizeof(unsigned short) * 32 * (NB + 1), 16);
+  s.isl = o; o = ob_al(o + sizeof(unsigned short) * 32 * 2 * NB, 16);
+  s.total = ob_al(o, 16);
+  return s;
+}
+__global__ void __launch_bounds__(32) k_sched_lane(ObBatchDev d, int G) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const SchedLaneSmem L = sched_lane_smem(d.NB, d.NR);
+  const int lane = threadIdx.x;
+  unsigned short *s_ord = (unsigned short *)(smem + L.ord) + lane;
+  unsigned short *s_rowb = (unsigned short *)(smem + L.rowb) + lane;
+  unsigned short *s_lvl = (unsigned short *)(smem + L.lvl) + lane;
+  unsigned short *s_X = (unsigned short *)(smem + L.X) + lane;
+  unsigned char *s_fio = smem + L.fio + lane;
+  unsigned short *s_last = (unsigned short *)(smem + L.last) + lane;
+  unsigned short *s_isl = (unsigned short *)(smem + L.isl) + lane;
+#define LN(a, i) a[(size_t)(i) * 32]
+  for (int wbase = d.wbeg + blockIdx.x * 32; wbase < d.wend; wbase += gridDim.x * 32) {
+    const int w = wbase + lane;
+    if (w >= d.wend) continue;
+    ObWorld &W = d.world[w];
+    int *si = d.stepinfo + (size_t)w * SI_WORDS;
+    const int nis = si[SI_NIS];
+    const int mtot = si[SI_HAVEROWS] ? si[SI_MTOT] : 0;
+    const int nep = (W.iters + 7) >> 3;
+    if (mtot == 0) { for (int ep = 0; ep < d.NEP; ep++) si[SI_NPASS0 + ep] = 0; continue; }
+    const real *rows = d.rows + (size_t)w * d.NR * OB_ROWW;
+    const unsigned short *g_isz = d.isz + (size_t)w * 4 * d.NB;
+    const unsigned short *g_jrow = d.jrow + (size_t)w * (d.NC + d.NJ + 1);
+    const int nb = W.nb;
+    int nri = 0;
+    for (int isl = 0; isl < nis; isl++) {
+      const int j0 = g_isz[4 * isl + 2], jn = g_isz[4 * isl + 3];
+      if (!jn) continue;
+      const int r0 = g_jrow[j0], m = g_jrow[j0 + jn] - r0;
+      if (m > 0) { LN(s_isl, 2 * nri) = (unsigned short)r0; LN(s_isl, 2 * nri + 1) = (unsigned short)m; nri++; }
+    }
+    for (int i = 0; i < mtot; i++) {
+      const unsigned meta = *(const unsigned *)(rows + (size_t)i * OB_ROWW + OB_ROWF);
+      LN(s_rowb, i) = (unsigned short)(meta & 0xffffu);
+      LN(s_fio, i) = (unsigned char)((meta >> 16) & 255u);
+    }
+    // initial order per island (quickstep.cpp:409-424)
+    for (int q = 0; q < nri; q++) {
+      const int r0 = LN(s_isl, 2 * q), m = LN(s_isl, 2 * q + 1);
+      int head = 0, tail = 0;
+      for (int i = 0; i < m; i++) {
+        if (LN(s_fio, r0 + i) == 0) LN(s_ord, r0 + head++) = (unsigned short)i;
+        else LN(s_ord, r0 + m - 1 - tail++) = (unsigned short)i;
+      }
+    }
+    const uint32_t seed = W.seed;
+    unsigned total_draws = 0;
+    for (int ep = 0; ep < nep && ep < d.NEP; ep++) {
+      // (a) shuffle (quickstep.cpp:474-481); draw offsets as in k_sched
+      unsigned draws_before = 0;
+      for (int q = 0; q < nri; q++) {
+        const int r0 = LN(s_isl, 2 * q), m = LN(s_isl, 2 * q + 1);
+        if (m < 2) continue;
+        const unsigned my_off = draws_before + (unsigned)ep * (unsigned)(m - 1);
+        draws_before += (unsigned)nep * (unsigned)(m - 1);
+        uint32_t A, C;
+        ob_lcg_skip(my_off, &A, &C);
+        uint32_t s = A * seed + C;
+        for (int i = 1; i < m; i++) {
+          s = 1664525u * s + 1013904223u;
+          const int sj = ob_randint_fold(s, (uint32_t)(i + 1));
+          const unsigned short t = LN(s_ord, r0 + i); LN(s_ord, r0 + i) = LN(s_ord, r0 + sj); LN(s_ord, r0 + sj) = t;
+        }
+      }
+      total_draws = draws_before;
+      // (b) levels
+      for (int b = 0; b < nb; b++) LN(s_last, b) = 0;
+      for (int i = 0; i <= mtot + 1; i++) LN(s_X, i) = 0;
+      int nlev = 0;
+      for (int q = 0; q < nri; q++) {
+        const int r0 = LN(s_isl, 2 * q), m = LN(s_isl, 2 * q + 1);
+        for (int k = 0; k < m; k++) {
+          const unsigned rb = LN(s_rowb, r0 + LN(s_ord, r0 + k));
+          const int b1 = rb & 255, b2 = (rb >> 8) & 255;
+          int lv = LN(s_last, b1);
+          if (b2 != 255) { const int l2 = LN(s_last, b2); lv = l2 > lv ? l2 : lv; }
+          lv++;
+          LN(s_last, b1) = (unsigned short)lv;
+          if (b2 != 255) LN(s_last, b2) = (unsigned short)lv;
+          LN(s_lvl, r0 + k) = (unsigned short)lv;
+          LN(s_X, lv) = LN(s_X, lv) + 1;
+          nlev = lv > nlev ? lv : nlev;
+        }
+      }
+      {
+        int run = 0;
+        for (int l = 1; l <= nlev; l++) { const int c = LN(s_X, l); LN(s_X, l) = (unsigned short)run; run += c; }
+      }
+      // (c) rows into level order; afterwards X[l] = end of level l
+      unsigned short *g_sched = d.sched + ((size_t)w * d.NEP + ep) * d.NR;
+      unsigned short *g_pstart = d.pstart + ((size_t)w * d.NEP + ep) * (d.NR + 1);
+      for (int q = 0; q < nri; q++) {
+        const int r0 = LN(s_isl, 2 * q), m = LN(s_isl, 2 * q + 1);
+        for (int k = 0; k < m; k++) {
+          const int lv = LN(s_lvl, r0 + k);
+          const int pos = LN(s_X, lv);
+          LN(s_X, lv) = (unsigned short)(pos + 1);
+          g_sched[pos] = (unsigned short)(r0 + LN(s_ord, r0 + k));
+        }
+      }
+      int total = 0, start = 0;
+      for (int l = 1; l <= nlev; l++) {
+        const int end = LN(s_X, l);
+        for (int p0 = start; p0 < end; p0 += G) g_pstart[total++] = (unsigned short)p0;
+        start = end;
+      }
+      g_pstart[total] = (unsigned short)mtot;
+      si[SI_NPASS0 + ep] = total;
+    }
+    uint32_t A, C;
+    ob_lcg_skip(total_draws, &A, &C);
+    W.seed = A * seed + C;
+  }
+#undef LN
+}
+
+
 // one row update of the sweep (quickstep.cpp:490-581) on a row held in registers
 __device__ __forceinline__ void sor_pass(const ObRowReg &cur, int cur_idx, real *s_fc, real *s_lam, const real *s_invM) {
   const int b1 = cur.meta & 255, b2r = (cur.meta >> 8) & 255, fio = (cur.meta >> 16) & 255, bmode = cur.meta >> 24;
@@ -766,9 +902,9 @@ __global__ void __launch_bounds__(32) k_sor(ObBatchDev d, int taps) {
   real *s_lam = (real *)(smem + L.lam);
   real *s_invM = (real *)(smem + L.invM);
 
-  for (int wbase = blockIdx.x * T; wbase < d.W; wbase += gridDim.x * T) {
+  for (int wbase = d.wbeg + blockIdx.x * T; wbase < d.wend; wbase += gridDim.x * T) {
     const int w = wbase + grp;
-    const bool valid = w < d.W;
+    const bool valid = w < d.wend;
     const int wc = valid ? w : 0;
     const int *si = d.stepinfo + (size_t)wc * SI_WORDS;
     const int nb = valid ? d.world[wc].nb : 0;
@@ -871,9 +1007,9 @@ __global__ void __launch_bounds__(32) k_post(ObBatchDev d, real h) {
   unsigned short *s_old = (unsigned short *)(smem + L.old);
   int *s_misc = (int *)(smem + L.misc);
 
-  for (int wbase = blockIdx.x * T; wbase < d.W; wbase += gridDim.x * T) {
+  for (int wbase = d.wbeg + blockIdx.x * T; wbase < d.wend; wbase += gridDim.x * T) {
     const int w = wbase + grp;
-    const bool valid = w < d.W;
+    const bool valid = w < d.wend;
     const int wc = valid ? w : 0;
     ObWorld &W = d.world[wc];
     const int *si = d.stepinfo + (size_t)wc * SI_WORDS;

@@ -116,6 +116,7 @@ struct ObBatchDev {
   int NJ;       // permanent (non-contact) joints per world slot
   int dropin;   // 1: batch serves the classic per-call API (per-contact surfaces in csurf/cfdir1)
   int large;    // 1: one large world on the grid-wide path (ob_large.h); W == 1
+  int wbeg, wend;   // world range [wbeg, wend) of THIS launch (a chunk of the batch; chunks run on their own streams)
   ObWorld *world;        // [W]
   ObBodyDyn *bdyn;       // [W*NB]
   ObBodyConst *bconst;   // [W*NB]

@@ -60,6 +60,16 @@ def test_dropin_classic_api_matches_live_reference(scene, steps, worlds, prec):
     assert_bit_exact(r, f"dropin/{scene}/{prec}")
 
 
+@pytest.mark.parametrize("stem,scene,steps,worlds,settle", [g for g in GOLDEN if g[1] in ("stack32", "ragdoll", "buggy_terrain", "mixed_maxc4", "tower64", "hinges")])
+def test_lane_per_world_scheduler_matches_golden(stem, scene, steps, worlds, settle, monkeypatch):
+    """k_sched_lane (one lane per world, used for batches of >= 512 worlds) forced on small batches"""
+    monkeypatch.setenv("OB_SCHED_LANE", "1")
+    g = os.path.join(ROOT, "tests", "golden", f"{stem}_single.trace")
+    r = parity_golden("b200", g, scene, "single", steps, worlds, settle)
+    assert r["steps"] == steps
+    assert_parity(r, f"{stem}/lane", scene, "single", "b200")
+
+
 def _batch(lib, scenes, scene, nworlds, cap=0):
     scenes.ob_scene_build_batch.restype = ctypes.c_void_p
     scenes.ob_scene_build_batch.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
