@@ -28,6 +28,12 @@ int obk_run_phases(ObBackend *, real h, int phases, int taps, char *err, size_t 
 // meshes2: trimesh data of a / b (ObPose::mesh must be 0 / 1), or null when neither is a trimesh
 int obk_collide_pair(const ObPose *a, const ObPose *b, int flags, ObCg *out, const ObMeshDev *meshes2, char *err, size_t errlen);
 // copy one trimesh (vertices, triangles, tree) to the execution side; io->aabbc/aabbe are kept, pointers filled
+// dSpaceCollide2 (geom x space): nq posed query geoms against the geoms of world slot 0 (already uploaded).
+// qmesh[q] carries the model-space AABB when query q is a trimesh (pose.mesh must be 0).  qbody = body index in
+// the bound world or -2 (a body of another world / none: -1).  hit[q*NG + g] = 1 when collideAABBs
+// (collision_space_internal.h:48-82) would call the near callback for (geom g of the space, query q).
+int obk_collide2(ObBackend *, const ObPose *q, const int *qbody, const uint32_t *qcat, const uint32_t *qcol, const ObMeshDev *qmesh,
+                 int nq, unsigned char *hit, char *err, size_t errlen);
 int obk_mesh_upload(const float *verts, int nverts, const int *tris, int ntris, const ObBvNode *nodes, int device, ObMeshDev *io);
 void obk_mesh_free(ObMeshDev *m);
 int obk_sync(ObBackend *);

@@ -715,6 +715,47 @@ int obk_collide_pair(const ObPose *a, const ObPose *b, int flags, ObCg *out, con
   return n;
 }
 
+// dSpaceCollide2: thread per (space geom, query geom)
+struct ObQueryGeom { ObPose pose; ObMeshDev mesh; int body; uint32_t cat, col; int pad; };
+__global__ void k_collide2(ObBatchDev d, const ObQueryGeom *q, int nq, unsigned char *hit) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ng = d.world[0].ng;
+  if (idx >= ng * nq) return;
+  const int qi = idx / ng, g = idx - qi * ng;
+  const ObGeom G = d.geom[g];
+  unsigned char h = 0;
+  if ((G.flags & OB_GEOM_ENABLED) && !(G.flags & OB_GEOM_ZERO_SIZED)) {   // GEOM_ENABLED(g), collision_kernel.h:75
+    ObPose p;
+    geom_pose_dev(G, d.bdyn, &p);
+    real a[6], b[6];
+    ob_aabb(p, a, d.meshes);
+    ob_aabb(q[qi].pose, b, &q[qi].mesh);
+    h = ob_aabb_pair_filter(G.body, q[qi].body, G.cat, G.col, q[qi].cat, q[qi].col, a, b) ? 1 : 0;
+  }
+  hit[(size_t)qi * d.NG + g] = h;
+}
+int obk_collide2(ObBackend *b, const ObPose *q, const int *qbody, const uint32_t *qcat, const uint32_t *qcol, const ObMeshDev *qmesh,
+                 int nq, unsigned char *hit, char *err, size_t errlen) {
+  cudaSetDevice(b->device);
+  std::vector<ObQueryGeom> hq(nq);
+  for (int i = 0; i < nq; i++) { hq[i].pose = q[i]; hq[i].mesh = qmesh[i]; hq[i].body = qbody[i]; hq[i].cat = qcat[i]; hq[i].col = qcol[i]; hq[i].pad = 0; }
+  ObQueryGeom *dq = 0; unsigned char *dh = 0;
+  const size_t nh = (size_t)nq * b->d.NG;
+  cudaError_t e = cudaMalloc((void **)&dq, sizeof(ObQueryGeom) * nq);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&dh, nh);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dq, hq.data(), sizeof(ObQueryGeom) * nq, cudaMemcpyHostToDevice, b->stream);
+  if (e == cudaSuccess) {
+    k_collide2<<<(unsigned)((nh + 127) / 128), 128, 0, b->stream>>>(b->d, dq, nq, dh);
+    g_launches++;
+    e = cudaMemcpyAsync(hit, dh, nh, cudaMemcpyDeviceToHost, b->stream);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
+  if (dq) cudaFree(dq);
+  if (dh) cudaFree(dh);
+  if (e != cudaSuccess) { snprintf(err, errlen, "k_collide2 failed: %s", cudaGetErrorString(e)); return -1; }
+  return 0;
+}
+
 int obk_mesh_upload(const float *verts, int nverts, const int *tris, int ntris, const ObBvNode *nodes, int device, ObMeshDev *io) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return -1;

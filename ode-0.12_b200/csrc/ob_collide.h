@@ -946,14 +946,14 @@ OB_HD int ob_collide_ray_plane(const ObPose &ray, const ObPose &plane, ObCg *con
 OB_HD int ob_pair_max_contacts(int t1, int t2, int maxc) {
   int lo = t1 < t2 ? t1 : t2, hi = t1 < t2 ? t2 : t1;
   int cap;
-  if (lo == OB_GEOM_SPHERE) cap = (hi == OB_GEOM_SPHERE || hi == OB_GEOM_BOX || hi == OB_GEOM_PLANE || hi == OB_GEOM_CAPSULE) ? 1 : 0;
+  if (hi == OB_GEOM_RAY) cap = (lo == OB_GEOM_SPHERE || lo == OB_GEOM_BOX || lo == OB_GEOM_CAPSULE || lo == OB_GEOM_PLANE) ? 1 : 0;
+  else if (hi == OB_GEOM_TRIMESH) cap = (lo == OB_GEOM_SPHERE || lo == OB_GEOM_BOX || lo == OB_GEOM_CAPSULE || lo == OB_GEOM_PLANE || lo == OB_GEOM_RAY) ? (1 << 15) : 0;   // bounded by the caller's max_contacts only
+  else if (lo == OB_GEOM_SPHERE) cap = (hi == OB_GEOM_SPHERE || hi == OB_GEOM_BOX || hi == OB_GEOM_PLANE || hi == OB_GEOM_CAPSULE) ? 1 : 0;
   else if (lo == OB_GEOM_BOX && hi == OB_GEOM_BOX) cap = 8;
   else if (lo == OB_GEOM_BOX && hi == OB_GEOM_PLANE) cap = 4;
   else if (lo == OB_GEOM_BOX && hi == OB_GEOM_CAPSULE) cap = 1;
   else if (lo == OB_GEOM_CAPSULE && hi == OB_GEOM_CAPSULE) cap = 2;
   else if (lo == OB_GEOM_CAPSULE && hi == OB_GEOM_PLANE) cap = 2;
-  else if (hi == OB_GEOM_TRIMESH && (lo == OB_GEOM_SPHERE || lo == OB_GEOM_BOX || lo == OB_GEOM_CAPSULE || lo == OB_GEOM_PLANE || lo == OB_GEOM_RAY)) cap = 1 << 15;   // bounded by the caller's max_contacts only
-  else if (hi == OB_GEOM_RAY && (lo == OB_GEOM_SPHERE || lo == OB_GEOM_BOX || lo == OB_GEOM_CAPSULE || lo == OB_GEOM_PLANE)) cap = 1;
   else cap = 0;
   return cap < maxc ? cap : maxc;
 }

@@ -109,10 +109,11 @@ static bool ctx_ensure(ObDropin *c, int need_contacts, const char *who) {
   return true;
 }
 
-void ob_dropin_space_collide(dxSpace *space, void *data, dNearCallback *cb) {
+// the context (bound batch of one world) that serves `space`, created or re-bound as needed
+static ObDropin *ctx_for_space(dxSpace *space, const char *who) {
   bool mixed;
   dxWorld *w = world_of_space(space, &mixed);
-  if (mixed) { ob_error(0, "dSpaceCollide: geoms of one space attached to bodies of different worlds are not supported"); return; }
+  if (mixed) { ob_error(0, "%s: geoms of one space attached to bodies of different worlds are not supported", who); return 0; }
   ObDropin *c = 0;
   for (size_t i = 0; i < g_ctx.size(); i++) if (g_ctx[i]->space == space) c = g_ctx[i];
   if (c && w && c->world != w && c->own_world != c->world) { ob_dropin_forget_space(space); c = 0; }
@@ -124,7 +125,13 @@ void ob_dropin_space_collide(dxSpace *space, void *data, dNearCallback *cb) {
   } else if (w && c->own_world) {   // bodies appeared in a space that had none
     dxWorld *ow = c->own_world; ctx_free_batch(c); c->own_world = 0; c->world = w; dWorldDestroy(ow);
   }
-  if (!ctx_ensure(c, 0, "dSpaceCollide")) return;
+  if (!ctx_ensure(c, 0, who)) return 0;
+  return c;
+}
+
+void ob_dropin_space_collide(dxSpace *space, void *data, dNearCallback *cb) {
+  ObDropin *c = ctx_for_space(space, "dSpaceCollide");
+  if (!c) return;
   dxBatch *B = c->B;
   char err[512] = "";
   ObPolicy pol;
@@ -232,8 +239,80 @@ int ob_dropin_collide(dxGeom *o1, dxGeom *o2, int flags, dContactGeom *contact, 
   return n;
 }
 
-void ob_dropin_space_collide2(dxGeom *, dxGeom *, void *, dNearCallback *) {
-  ob_error(0, "dSpaceCollide2: not available on the drop-in path of this build (use one space per world, or dBatch*)");
+// dxSpace::collide2 (collision_space.cpp:269-286, :586-604, collision_sapspace.cpp:498-518): every enabled geom of
+// the space, in list order, against the query geoms; AABBs and the collideAABBs filter run on the GPU (k_collide2).
+// swap: call cb(query, member) instead of cb(member, query) (swap_callback, collision_space.cpp:764-769).
+static void space_collide2(dxSpace *space, const std::vector<dxGeom *> &queries, void *data, dNearCallback *cb, bool swap) {
+  if (queries.empty()) return;
+  ObDropin *c = ctx_for_space(space, "dSpaceCollide2");
+  if (!c) return;
+  dxBatch *B = c->B;
+  if (ob_batch_upload(B)) { ob_error(0, "dSpaceCollide2: upload failed"); return; }
+  const int nq = (int)queries.size(), NG = B->caps.NG;
+  std::vector<ObPose> qp(nq);
+  std::vector<ObMeshDev> qm(nq);
+  std::vector<int> qb(nq);
+  std::vector<uint32_t> qcat(nq), qcol(nq);
+  for (int i = 0; i < nq; i++) {
+    dxGeom *g = queries[i];
+    if (g->is_space) { ob_error(0, "dSpaceCollide2: nested spaces are not supported on this path"); return; }
+    geom_pose_host(g, &qp[i]);
+    memset(&qm[i], 0, sizeof(ObMeshDev));
+    if (g->type == dTriMeshClass) {
+      if (!g->tmdata) { ob_error(0, "dSpaceCollide2: trimesh geom without data"); return; }
+      for (int k = 0; k < 3; k++) { qm[i].aabbc[k] = g->tmdata->aabbc[k]; qm[i].aabbe[k] = g->tmdata->aabbe[k]; }
+      qp[i].mesh = 0;
+    }
+    qb[i] = !g->body ? -1 : (g->body->world == c->world && g->body->batch_index >= 0 && g->body->batch_index < B->nb[0] &&
+                             B->bodies[0][g->body->batch_index] == g->body ? g->body->batch_index : -2);
+    qcat[i] = (uint32_t)g->category_bits; qcol[i] = (uint32_t)g->collide_bits;
+  }
+  std::vector<unsigned char> hit((size_t)nq * NG);
+  char err[512] = "";
+  if (obk_collide2(B->bk, qp.data(), qb.data(), qcat.data(), qcol.data(), qm.data(), nq, hit.data(), err, sizeof err)) { ob_error(0, "dSpaceCollide2: %s", err); return; }
+  dSpaceClean(space);
+  // member order: the space's list (SAP: GeomList, which cleanGeoms just completed)
+  std::vector<dxGeom *> members;
+  if (space->type == dSweepAndPruneSpaceClass) members = space->sap_geoms;
+  else for (dxGeom *g = space->first; g; g = g->next) members.push_back(g);
+  space->lock_count++;
+  for (int i = 0; i < nq; i++)
+    for (size_t k = 0; k < members.size(); k++) {
+      dxGeom *g = members[k];
+      if (g->batch_index < 0 || !hit[(size_t)i * NG + g->batch_index] || g == queries[i]) continue;
+      if (swap) cb(data, queries[i], g); else cb(data, g, queries[i]);
+    }
+  space->lock_count--;
+}
+
+// dSpaceCollide2, collision_space.cpp:772-833 (spaces are flat here: sublevels are all 0)
+void ob_dropin_space_collide2(dxGeom *g1, dxGeom *g2, void *data, dNearCallback *cb) {
+  dxSpace *s1 = g1->is_space ? (dxSpace *)g1 : 0, *s2 = g2->is_space ? (dxSpace *)g2 : 0;
+  if (s1 && s2) {
+    if (s1 == s2) { ob_dropin_space_collide(s1, data, cb); return; }
+    // iterate through the space that has the fewest geoms, calling collide2 in the other space for each one
+    std::vector<dxGeom *> q;
+    if (s1->count < s2->count) {
+      for (dxGeom *g = s1->first; g; g = g->next) q.push_back(g);
+      space_collide2(s2, q, data, cb, true);
+    } else {
+      for (dxGeom *g = s2->first; g; g = g->next) q.push_back(g);
+      space_collide2(s1, q, data, cb, false);
+    }
+  } else if (s1) {
+    space_collide2(s1, std::vector<dxGeom *>(1, g2), data, cb, false);
+  } else if (s2) {
+    space_collide2(s2, std::vector<dxGeom *>(1, g1), data, cb, true);
+  } else {
+    // two geoms: collideAABBs; served by a one-geom query against a throw-away space would cost more than it
+    // is worth: the callback's dCollide is the computation, the AABB pre-test only prunes
+    if (g1->body == g2->body && g1->body) return;
+    if ((((unsigned long)g1->category_bits & (unsigned long)g2->collide_bits) || ((unsigned long)g2->category_bits & (unsigned long)g1->collide_bits)) == 0) return;
+    dReal a[6], b[6];
+    dGeomGetAABB(g1, a); dGeomGetAABB(g2, b);
+    if (a[0] > b[1] || a[1] < b[0] || a[2] > b[3] || a[3] < b[2] || a[4] > b[5] || a[5] < b[4]) return;
+    cb(data, g1, g2);
+  }
 }
 
 int ob_dropin_quickstep(dxWorld *w, dReal h) {

@@ -33,6 +33,7 @@ GOLDEN = [  # (file stem, scene, steps, worlds, settle) — must match tests/gol
 # exist there: a ray contact is a query result for the caller, not a contact joint
 GOLDEN_CALLBACK = [
     ("raycast_settle40", "raycast", 20, 1, 40),
+    ("raycast2_settle40", "raycast2", 20, 1, 40),   # rays in a second space: dSpaceCollide2 (space x space, geom x space)
 ]
 
 

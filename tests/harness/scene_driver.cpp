@@ -81,6 +81,16 @@ static void near_cb(void *data, dGeomID o1, dGeomID o2) {
   if (!ray) c->ncontacts += n;
 }
 
+// scenes with a second space: dSpaceCollide2 in its three forms (space x space, geom x space, space x geom)
+static void collide_second_space(SceneWorld &sw, CbCtx &ctx) {
+  if (!sw.space2) return;
+  dSpaceCollide2((dGeomID)sw.space, (dGeomID)sw.space2, &ctx, &near_cb);
+  const int n2 = dSpaceGetNumGeoms(sw.space2);
+  for (int i = 0; i < 3 && i < n2; i++) dSpaceCollide2(dSpaceGetGeom(sw.space2, i), (dGeomID)sw.space, &ctx, &near_cb);
+  for (int i = 3; i < 6 && i < n2; i++) dSpaceCollide2((dGeomID)sw.space, dSpaceGetGeom(sw.space2, i), &ctx, &near_cb);
+  if (n2 > 7) dSpaceCollide2(dSpaceGetGeom(sw.space2, 6), dSpaceGetGeom(sw.space, 2), &ctx, &near_cb);
+}
+
 static void dump_state(Trace &t, SceneWorld &sw) {
   t.i32((int)sw.bodies.size());
   for (size_t i = 0; i < sw.bodies.size(); i++) {
@@ -178,6 +188,7 @@ int main(int argc, char **argv) {
         ctx.sw = &sw;
         dRandSetSeed(sw.seed);
         dSpaceCollide(sw.space, &ctx, &near_cb);
+        collide_second_space(sw, ctx);
         dWorldQuickStep(sw.world, (dReal)h);
         sw.seed = (uint32_t)dRandGetSeed();
         dJointGroupEmpty(sw.cgroup);
@@ -210,6 +221,7 @@ int main(int argc, char **argv) {
         }
         dRandSetSeed(sw.seed);
         dSpaceCollide(sw.space, &ctx, &near_cb);
+        collide_second_space(sw, ctx);
         dWorldQuickStep(sw.world, (dReal)h);
         sw.seed = (uint32_t)dRandGetSeed();
         if (t.f) {

@@ -15,6 +15,7 @@
 struct SceneWorld {
   dWorldID world;
   dSpaceID space;
+  dSpaceID space2;               // optional second space (query geoms), collided with dSpaceCollide2
   dJointGroupID cgroup;
   std::vector<dBodyID> bodies;   // creation order
   std::vector<dGeomID> geoms;    // creation order (index stored in geom data)
@@ -74,6 +75,7 @@ static inline dBodyID scene_add_sphere(SceneWorld &sw, dReal density, dReal r, d
 static int g_scene_space_kind = 0;
 static inline void scene_world_base(SceneWorld &sw, int w) {
   sw.world = dWorldCreate();
+  sw.space2 = 0;
   sw.space = g_scene_space_kind == 1 ? dSweepAndPruneSpaceCreate(0, dSAP_AXES_XYZ)
            : g_scene_space_kind == 3 ? dSweepAndPruneSpaceCreate(0, dSAP_AXES_ZXY)
            : g_scene_space_kind == 2 ? dSimpleSpaceCreate(0) : dHashSpaceCreate(0);
@@ -499,8 +501,11 @@ static inline void scene_pile(SceneWorld &sw, int w, int nx, int ny, int nz) {
 // and a rotated terrain mesh, watched by rays — free-standing ones in every mode (all hits / first contact /
 // closest hit, with and without backface culling) and "sensor" rays riding on bodies (raycar style,
 // RC/car.cpp:353-371).  The near callback records ray contacts and creates no joints for them.
-static inline void scene_raycast(SceneWorld &sw, int w) {
+static inline void scene_raycast(SceneWorld &sw, int w, int two_spaces) {
   scene_world_base(sw, w);
+  // two_spaces: the rays live in their own space and are collided with dSpaceCollide2 (space x space, geom x space)
+  if (two_spaces) sw.space2 = two_spaces == 2 ? dHashSpaceCreate(0) : dSimpleSpaceCreate(0);
+  dSpaceID rs = two_spaces ? sw.space2 : sw.space;
   xs32 rng(sw.seed ^ 0x00BA7CA5u);
   scene_add_geom(sw, dCreatePlane(sw.space, 0, 0, 1, (dReal)-1.5));
   dGeomID mesh = scene_add_geom(sw, dCreateTriMesh(sw.space, scene_terrain_data(25, 0.5, 0.45, 0.9, 0.7, 0.12), 0, 0, 0));
@@ -524,7 +529,7 @@ static inline void scene_raycast(SceneWorld &sw, int w) {
   }
   // free-standing rays, mode = i % 6
   for (int i = 0; i < 42; i++) {
-    dGeomID r = scene_add_geom(sw, dCreateRay(sw.space, rng.uni(2, 9)));
+    dGeomID r = scene_add_geom(sw, dCreateRay(rs, rng.uni(2, 9)));
     const dReal px = rng.uni(-4, 4), py = rng.uni(-4, 4), pz = rng.uni(-0.5, 5);
     if (i < 18) dGeomRaySet(r, px, py, pz, rng.uni(-0.6, 0.6), rng.uni(-0.6, 0.6), (dReal)((i / 6) & 1 ? 1 : -1));
     else if (i < 30) dGeomRaySet(r, px, py, rng.uni(0.1, 1.0), rng.uni(-1, 1), rng.uni(-1, 1), rng.uni(-0.15, 0.15));   // skim the settled bodies
@@ -535,7 +540,7 @@ static inline void scene_raycast(SceneWorld &sw, int w) {
   }
   // sensor rays on bodies: straight down the body's -z through an offset rotation, and one without offset
   for (size_t i = 0; i < carriers.size(); i++) {
-    dGeomID r = scene_add_geom(sw, dCreateRay(sw.space, (dReal)2.5));
+    dGeomID r = scene_add_geom(sw, dCreateRay(rs, (dReal)2.5));
     dGeomSetBody(r, carriers[i]);
     if (i != 1) {
       dMatrix3 Ro;
@@ -589,7 +594,9 @@ static inline int scene_build(const char *name_in, SceneWorld &sw, int w, SceneP
   if (!strcmp(name, "terrain_capsules")) { scene_terrain_capsules(sw, w); return 0; }
   if (!strcmp(name, "terrain_spheres")) { scene_terrain_spheres(sw, w); return 0; }
   if (!strcmp(name, "capsmix")) { scene_capsmix(sw, w); return 0; }
-  if (!strcmp(name, "raycast")) { scene_raycast(sw, w); return 0; }
+  if (!strcmp(name, "raycast")) { scene_raycast(sw, w, 0); return 0; }
+  if (!strcmp(name, "raycast2")) { scene_raycast(sw, w, 1); return 0; }
+  if (!strcmp(name, "raycast2h")) { scene_raycast(sw, w, 2); return 0; }
   if (!strcmp(name, "ragdoll")) { scene_ragdoll(sw, w); pol = policy_crash(); return 0; }
   if (!strcmp(name, "buggy")) { scene_buggy(sw, w); pol = policy_buggy(); return 0; }
   {

@@ -592,6 +592,26 @@ int obk_collide_pair(const ObPose *a, const ObPose *b, int flags, ObCg *out, con
   const int n = ob_collide_pair(*a, *b, (flags & ~0xffff) | maxc, out, &swapped, meshes2, &bverr);
   return bverr ? -1 : n;
 }
+int obk_collide2(ObBackend *b, const ObPose *q, const int *qbody, const uint32_t *qcat, const uint32_t *qcol, const ObMeshDev *qmesh,
+                 int nq, unsigned char *hit, char *, size_t) {
+  ObBatchDev &d = b->d;
+  const int ng = d.world[0].ng;
+  for (int qi = 0; qi < nq; qi++)
+    for (int g = 0; g < ng; g++) {
+      const ObGeom &G = d.geom[g];
+      unsigned char h = 0;
+      if ((G.flags & OB_GEOM_ENABLED) && !(G.flags & OB_GEOM_ZERO_SIZED)) {
+        ObPose p;
+        geom_pose(d, 0, g, &p);
+        real a[6], bb[6];
+        ob_aabb(p, a, d.meshes);
+        ob_aabb(q[qi], bb, &qmesh[qi]);
+        h = ob_aabb_pair_filter(G.body, qbody[qi], G.cat, G.col, qcat[qi], qcol[qi], a, bb) ? 1 : 0;
+      }
+      hit[(size_t)qi * d.NG + g] = h;
+    }
+  return 0;
+}
 int obk_mesh_upload(const float *verts, int nverts, const int *tris, int ntris, const ObBvNode *nodes, int, ObMeshDev *io) {
   float *v = (float *)malloc(sizeof(float) * 3 * (size_t)nverts);
   int *t = (int *)malloc(sizeof(int) * 3 * (size_t)ntris);
