@@ -306,6 +306,9 @@ dJointID dJointCreateContact(dWorldID, dJointGroupID, const dContact *);
 dJointID dJointCreateBall(dWorldID, dJointGroupID);
 dJointID dJointCreateHinge(dWorldID, dJointGroupID);
 dJointID dJointCreateHinge2(dWorldID, dJointGroupID);
+dJointID dJointCreateSlider(dWorldID, dJointGroupID);   /* include/ode/objects.h:1571, ode/src/joints/slider.cpp */
+dJointID dJointCreateUniversal(dWorldID, dJointGroupID);   /* include/ode/objects.h:1592, ode/src/joints/universal.cpp */
+dJointID dJointCreateFixed(dWorldID, dJointGroupID);    /* include/ode/objects.h:1616, ode/src/joints/fixed.cpp */
 void dJointDestroy(dJointID);
 void dJointAttach(dJointID, dBodyID body1, dBodyID body2);
 void dJointEnable(dJointID);
@@ -315,6 +318,29 @@ dJointType dJointGetType(dJointID);
 dBodyID dJointGetBody(dJointID, int index);
 void dJointSetFeedback(dJointID, dJointFeedback *);
 dJointFeedback *dJointGetFeedback(dJointID);
+void dJointSetSliderAxis(dJointID, dReal x, dReal y, dReal z);
+void dJointSetSliderAxisDelta(dJointID, dReal x, dReal y, dReal z, dReal ax, dReal ay, dReal az);
+void dJointGetSliderAxis(dJointID, dVector3 result);
+void dJointSetSliderParam(dJointID, int parameter, dReal value);
+dReal dJointGetSliderParam(dJointID, int parameter);
+dReal dJointGetSliderPosition(dJointID);
+dReal dJointGetSliderPositionRate(dJointID);
+void dJointAddSliderForce(dJointID, dReal force);
+void dJointSetUniversalAnchor(dJointID, dReal x, dReal y, dReal z);
+void dJointSetUniversalAxis1(dJointID, dReal x, dReal y, dReal z);
+void dJointSetUniversalAxis2(dJointID, dReal x, dReal y, dReal z);
+void dJointGetUniversalAnchor(dJointID, dVector3 result);
+void dJointGetUniversalAnchor2(dJointID, dVector3 result);
+void dJointGetUniversalAxis1(dJointID, dVector3 result);
+void dJointGetUniversalAxis2(dJointID, dVector3 result);
+void dJointSetUniversalParam(dJointID, int parameter, dReal value);
+dReal dJointGetUniversalParam(dJointID, int parameter);
+void dJointGetUniversalAngles(dJointID, dReal *angle1, dReal *angle2);
+dReal dJointGetUniversalAngle1(dJointID);
+dReal dJointGetUniversalAngle2(dJointID);
+void dJointSetFixed(dJointID);
+void dJointSetFixedParam(dJointID, int parameter, dReal value);
+dReal dJointGetFixedParam(dJointID, int parameter);
 void dJointSetBallAnchor(dJointID, dReal x, dReal y, dReal z);
 void dJointSetBallAnchor2(dJointID, dReal x, dReal y, dReal z);
 void dJointSetBallParam(dJointID, int parameter, dReal value);

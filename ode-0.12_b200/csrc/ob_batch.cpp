@@ -51,6 +51,8 @@ void ob_marshal_joint(const dxJoint *j, ObJoint &d) {
     d.anchor1[k] = j->anchor1[k]; d.anchor2[k] = j->anchor2[k]; d.axis1[k] = j->axis1[k]; d.axis2[k] = j->axis2[k];
     d.qrel[k] = j->qrel[k]; d.v1[k] = j->v1[k]; d.v2[k] = j->v2[k];
   }
+  if (j->type == dJointTypeUniversal) for (int k = 0; k < 4; k++) d.v1[k] = j->qrel2[k];   // ObJoint::v1 doubles as qrel2
+  if (j->type == dJointTypeSlider || j->type == dJointTypeFixed) for (int k = 0; k < 3; k++) d.anchor1[k] = j->offset[k];   // ObJoint::anchor1 doubles as the offset
   d.erp = j->erp; d.cfm = j->cfm; d.susp_erp = j->susp_erp; d.susp_cfm = j->susp_cfm; d.c0 = j->c0; d.s0 = j->s0;
   fill_limot(d.limot1, j->limot);
   fill_limot(d.limot2, j->limot2);
@@ -191,7 +193,7 @@ dxBatch *ob_batch_create(int nworlds, const dWorldID *worlds, const dSpaceID *sp
         if (dropin) continue;
         ob_set_last_error("dBatchCreate: world %d: contact joints present at bind time (call dJointGroupEmpty first)", w); delete B; return 0;
       }
-      if (j->type != dJointTypeBall && j->type != dJointTypeHinge && j->type != dJointTypeHinge2) { ob_set_last_error("dBatchCreate: world %d: unsupported joint type %d", w, j->type); delete B; return 0; }
+      if (j->type != dJointTypeBall && j->type != dJointTypeHinge && j->type != dJointTypeHinge2 && j->type != dJointTypeSlider && j->type != dJointTypeFixed && j->type != dJointTypeUniversal) { ob_set_last_error("dBatchCreate: world %d: unsupported joint type %d", w, j->type); delete B; return 0; }
       B->joints[w].push_back(j);
     }
     std::reverse(B->joints[w].begin(), B->joints[w].end());

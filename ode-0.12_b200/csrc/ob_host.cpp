@@ -611,6 +611,9 @@ dJointID dJointCreateContact(dWorldID w, dJointGroupID group, const dContact *c)
 dJointID dJointCreateBall(dWorldID w, dJointGroupID g) { return create_joint(w, g, dJointTypeBall); }
 dJointID dJointCreateHinge(dWorldID w, dJointGroupID g) { return create_joint(w, g, dJointTypeHinge); }
 dJointID dJointCreateHinge2(dWorldID w, dJointGroupID g) { return create_joint(w, g, dJointTypeHinge2); }
+dJointID dJointCreateSlider(dWorldID w, dJointGroupID g) { return create_joint(w, g, dJointTypeSlider); }
+dJointID dJointCreateFixed(dWorldID w, dJointGroupID g) { return create_joint(w, g, dJointTypeFixed); }
+dJointID dJointCreateUniversal(dWorldID w, dJointGroupID g) { return create_joint(w, g, dJointTypeUniversal); }
 static void joint_free(dxJoint *j) {
   if (j->world) {
     joint_unlink_bodies(j);

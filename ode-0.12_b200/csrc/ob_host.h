@@ -88,6 +88,8 @@ struct dxJoint {
   dxLimot limot, limot2;        // hinge: limot; hinge2: limot (axis 1) + limot2 (axis 2)
   dReal c0, s0, v1[4], v2[4];   // hinge2
   dReal susp_erp, susp_cfm;     // hinge2
+  dVector3 offset;              // slider / fixed: centre of body 1 w.r.t. body 2 (slider.cpp computeOffset, fixed.cpp dJointSetFixed)
+  dQuaternion qrel2;            // universal: second initial relative rotation (qrel = qrel1)
 };
 
 struct dxJointGroup {

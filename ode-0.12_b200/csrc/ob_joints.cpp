@@ -58,6 +58,17 @@ void ob_joint_init_type(dxJoint *j) {
       j->susp_erp = w->global_erp; j->susp_cfm = w->global_cfm;
       j->flags |= dJOINT_TWOBODIES;
       break;
+    case dJointTypeSlider:
+      j->axis1[0] = 1;
+      limot_init(j->limot, w);
+      break;
+    case dJointTypeFixed:
+      j->erp = w->global_erp; j->cfm = w->global_cfm;
+      break;
+    case dJointTypeUniversal:
+      j->axis1[0] = 1; j->axis2[1] = 1;
+      limot_init(j->limot, w); limot_init(j->limot2, w);
+      break;
     default: break;
   }
 }
@@ -254,6 +265,159 @@ dReal dJointGetHinge2Angle2Rate(dJointID j) {
 }
 }  // extern "C"
 
+// ---- slider (slider.cpp) and fixed (fixed.cpp) ----------------------------------------------------
+static void slider_compute_offset(dxJoint *j) {   // dxJointSlider::computeOffset
+  if (j->node[1].body) {
+    dReal c[4];
+    for (int i = 0; i < 3; i++) c[i] = j->node[0].body->pos[i] - j->node[1].body->pos[i];
+    c[3] = 0;
+    ob_mul1_331(j->offset, j->node[1].body->R, c);
+  } else if (j->node[0].body) {
+    for (int i = 0; i < 3; i++) j->offset[i] = j->node[0].body->pos[i];
+  }
+}
+extern "C" {
+void dJointSetSliderAxis(dJointID j, dReal x, dReal y, dReal z) {
+  set_axes(j, x, y, z, j->axis1, 0);
+  slider_compute_offset(j);
+  hinge_initial_rel_rot(j);   // same computeInitialRelativeRotation as the hinge (slider.cpp)
+}
+void dJointSetSliderAxisDelta(dJointID j, dReal x, dReal y, dReal z, dReal dx, dReal dy, dReal dz) {
+  set_axes(j, x, y, z, j->axis1, 0);
+  slider_compute_offset(j);
+  if (!j->node[1].body) { j->offset[0] += dx; j->offset[1] += dy; j->offset[2] += dz; }
+  hinge_initial_rel_rot(j);
+}
+void dJointGetSliderAxis(dJointID j, dVector3 result) { if (j->node[0].body) ob_mul0_331(result, j->node[0].body->R, j->axis1); }
+void dJointSetSliderParam(dJointID j, int parameter, dReal value) { limot_set(j->limot, parameter, value); }
+dReal dJointGetSliderParam(dJointID j, int parameter) { return limot_get(j->limot, parameter); }
+dReal dJointGetSliderPosition(dJointID j) {
+  dReal ax1[4], q[4];
+  ob_mul0_331(ax1, j->node[0].body->R, j->axis1);
+  if (j->node[1].body) {
+    ob_mul0_331(q, j->node[1].body->R, j->offset);
+    for (int i = 0; i < 3; i++) q[i] = j->node[0].body->pos[i] - q[i] - j->node[1].body->pos[i];
+  } else {
+    for (int i = 0; i < 3; i++) q[i] = j->node[0].body->pos[i] - j->offset[i];
+    if (j->flags & dJOINT_REVERSE) { ax1[0] = -ax1[0]; ax1[1] = -ax1[1]; ax1[2] = -ax1[2]; }
+  }
+  return ob_dot(ax1, q);
+}
+dReal dJointGetSliderPositionRate(dJointID j) {
+  dReal ax1[4];
+  ob_mul0_331(ax1, j->node[0].body->R, j->axis1);
+  if (j->node[1].body) return ob_dot(ax1, j->node[0].body->lvel) - ob_dot(ax1, j->node[1].body->lvel);
+  dReal rate = ob_dot(ax1, j->node[0].body->lvel);
+  if (j->flags & dJOINT_REVERSE) rate = -rate;
+  return rate;
+}
+void dJointAddSliderForce(dJointID j, dReal force) {
+  dReal axis[4] = {0, 0, 0, 0};
+  if (j->flags & dJOINT_REVERSE) force -= force;   // sic (slider.cpp:316-317)
+  dJointGetSliderAxis(j, axis);
+  axis[0] *= force; axis[1] *= force; axis[2] *= force;
+  if (j->node[0].body) dBodyAddForce(j->node[0].body, axis[0], axis[1], axis[2]);
+  if (j->node[1].body) dBodyAddForce(j->node[1].body, -axis[0], -axis[1], -axis[2]);
+  if (j->node[0].body && j->node[1].body) {
+    dReal ltd[4], c[4];
+    for (int i = 0; i < 3; i++) c[i] = (dReal)0.5 * (j->node[1].body->pos[i] - j->node[0].body->pos[i]);
+    ob_cross(ltd, c, axis);
+    dBodyAddTorque(j->node[0].body, ltd[0], ltd[1], ltd[2]);
+    dBodyAddTorque(j->node[1].body, ltd[0], ltd[1], ltd[2]);
+  }
+}
+void dJointSetFixed(dJointID j) {
+  if (j->node[0].body) {
+    if (j->node[1].body) {
+      dReal ofs[4];
+      for (int i = 0; i < 3; i++) ofs[i] = j->node[0].body->pos[i] - j->node[1].body->pos[i];
+      ofs[3] = 0;
+      ob_mul1_331(j->offset, j->node[0].body->R, ofs);
+    } else {
+      for (int i = 0; i < 3; i++) j->offset[i] = j->node[0].body->pos[i];
+    }
+  }
+  hinge_initial_rel_rot(j);   // dxJointFixed::computeInitialRelativeRotation is the same computation
+}
+void dJointSetFixedParam(dJointID j, int parameter, dReal value) {
+  if (parameter == dParamCFM) j->cfm = value; else if (parameter == dParamERP) j->erp = value;
+}
+dReal dJointGetFixedParam(dJointID j, int parameter) {
+  if (parameter == dParamCFM) return j->cfm;
+  if (parameter == dParamERP) return j->erp;
+  return 0;
+}
+}  // extern "C"
+
+// ---- universal (universal.cpp) -------------------------------------------------------------------------
+static void universal_axes(dxJoint *j, dReal *ax1, dReal *ax2) {
+  ob_mul0_331(ax1, j->node[0].body->R, j->axis1);
+  if (j->node[1].body) ob_mul0_331(ax2, j->node[1].body->R, j->axis2);
+  else { ax2[0] = j->axis2[0]; ax2[1] = j->axis2[1]; ax2[2] = j->axis2[2]; }
+}
+static void universal_initial_rel_rots(dxJoint *j) {   // computeInitialRelativeRotations :364-391
+  if (j->node[0].body) {
+    dReal ax1[4], ax2[4], R[12], qcross[4];
+    universal_axes(j, ax1, ax2);
+    memset(R, 0, sizeof R);
+    ob_Rfrom2axes(R, ax1[0], ax1[1], ax1[2], ax2[0], ax2[1], ax2[2]);
+    ob_QfromR(qcross, R);
+    qmul1(j->qrel, j->node[0].body->q, qcross);
+    ob_Rfrom2axes(R, ax2[0], ax2[1], ax2[2], ax1[0], ax1[1], ax1[2]);
+    ob_QfromR(qcross, R);
+    if (j->node[1].body) qmul1(j->qrel2, j->node[1].body->q, qcross);
+    else for (int i = 0; i < 4; i++) j->qrel2[i] = qcross[i];
+  }
+}
+static void universal_fill(const dxJoint *j, ObJoint &o) {   // what the angle functions of ob_rows.h read
+  memset(&o, 0, sizeof o);
+  for (int k = 0; k < 4; k++) { o.axis1[k] = j->axis1[k]; o.axis2[k] = j->axis2[k]; o.qrel[k] = j->qrel[k]; o.v1[k] = j->qrel2[k]; }
+}
+extern "C" {
+void dJointSetUniversalAnchor(dJointID j, dReal x, dReal y, dReal z) { set_anchors(j, x, y, z, j->anchor1, j->anchor2); universal_initial_rel_rots(j); }
+void dJointSetUniversalAxis1(dJointID j, dReal x, dReal y, dReal z) {
+  if (j->flags & dJOINT_REVERSE) set_axes(j, x, y, z, 0, j->axis2); else set_axes(j, x, y, z, j->axis1, 0);
+  universal_initial_rel_rots(j);
+}
+void dJointSetUniversalAxis2(dJointID j, dReal x, dReal y, dReal z) {
+  if (j->flags & dJOINT_REVERSE) set_axes(j, x, y, z, j->axis1, 0); else set_axes(j, x, y, z, 0, j->axis2);
+  universal_initial_rel_rots(j);
+}
+void dJointGetUniversalAnchor(dJointID j, dVector3 result) {
+  if (j->flags & dJOINT_REVERSE) get_anchor2(j, result, j->anchor2); else get_anchor(j, result, j->anchor1);
+}
+void dJointGetUniversalAnchor2(dJointID j, dVector3 result) {
+  if (j->flags & dJOINT_REVERSE) get_anchor(j, result, j->anchor1); else get_anchor2(j, result, j->anchor2);
+}
+void dJointGetUniversalAxis1(dJointID j, dVector3 result) {
+  if (j->flags & dJOINT_REVERSE) { if (j->node[1].body) ob_mul0_331(result, j->node[1].body->R, j->axis2); else { result[0] = j->axis2[0]; result[1] = j->axis2[1]; result[2] = j->axis2[2]; } }
+  else if (j->node[0].body) ob_mul0_331(result, j->node[0].body->R, j->axis1);
+}
+void dJointGetUniversalAxis2(dJointID j, dVector3 result) {
+  if (j->flags & dJOINT_REVERSE) { if (j->node[0].body) ob_mul0_331(result, j->node[0].body->R, j->axis1); }
+  else if (j->node[1].body) ob_mul0_331(result, j->node[1].body->R, j->axis2);
+  else { result[0] = j->axis2[0]; result[1] = j->axis2[1]; result[2] = j->axis2[2]; }
+}
+void dJointSetUniversalParam(dJointID j, int parameter, dReal value) {
+  if ((parameter & 0xff00) == 0x100) limot_set(j->limot2, parameter & 0xff, value); else limot_set(j->limot, parameter, value);
+}
+dReal dJointGetUniversalParam(dJointID j, int parameter) {
+  if ((parameter & 0xff00) == 0x100) return limot_get(j->limot2, parameter & 0xff);
+  return limot_get(j->limot, parameter);
+}
+void dJointGetUniversalAngles(dJointID j, dReal *angle1, dReal *angle2) {
+  *angle1 = 0; *angle2 = 0;
+  if (!j->node[0].body) return;
+  ObJoint o;
+  universal_fill(j, o);
+  dReal a1, a2;
+  ob_universal_angles(o, j->node[0].body->R, j->node[0].body->q, j->node[1].body ? j->node[1].body->R : 0, j->node[1].body ? j->node[1].body->q : 0, &a1, &a2);
+  if (j->flags & dJOINT_REVERSE) { *angle1 = a2; *angle2 = -a1; } else { *angle1 = a1; *angle2 = a2; }   // universal.cpp:642-655
+}
+dReal dJointGetUniversalAngle1(dJointID j) { dReal a, b; dJointGetUniversalAngles(j, &a, &b); return a; }
+dReal dJointGetUniversalAngle2(dJointID j) { dReal a, b; dJointGetUniversalAngles(j, &a, &b); return b; }
+}  // extern "C"
+
 // setRelativeValues, called from dJointAttach (ball.cpp, hinge.cpp, hinge2.cpp)
 void ob_joint_set_relative_values(dxJoint *j) {
   dReal v[4] = {0, 0, 0, 0};
@@ -278,6 +442,20 @@ void ob_joint_set_relative_values(dxJoint *j) {
       dReal ax1[4], ax2[4];
       if (j->node[0].body && j->node[1].body) hinge2_axis_info(j, ax1, ax2, axis, &j->s0, &j->c0);
       hinge2_make_v1v2(j);
+    } break;
+    case dJointTypeSlider:
+      slider_compute_offset(j);
+      hinge_initial_rel_rot(j);
+      break;
+    case dJointTypeUniversal: {   // universal.cpp setRelativeValues
+      dJointGetUniversalAnchor(j, v);
+      set_anchors(j, v[0], v[1], v[2], j->anchor1, j->anchor2);
+      dReal ax1[4] = {0, 0, 0, 0}, ax2[4] = {0, 0, 0, 0};
+      dJointGetUniversalAxis1(j, ax1);
+      dJointGetUniversalAxis2(j, ax2);
+      if (j->flags & dJOINT_REVERSE) { set_axes(j, ax1[0], ax1[1], ax1[2], 0, j->axis2); set_axes(j, ax2[0], ax2[1], ax2[2], j->axis1, 0); }
+      else { set_axes(j, ax1[0], ax1[1], ax1[2], j->axis1, 0); set_axes(j, ax2[0], ax2[1], ax2[2], 0, j->axis2); }
+      universal_initial_rel_rots(j);
     } break;
     default: break;
   }

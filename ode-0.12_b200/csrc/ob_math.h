@@ -122,6 +122,56 @@ OB_HD int ob_safe_normalize3(real *a) {
   a[0] *= l; a[1] *= l; a[2] *= l;
   return 1;
 }
+// dRFrom2Axes (rotation.cpp:94-133); returns 0 (R untouched) for a zero-length vector
+OB_HD int ob_Rfrom2axes(real *R, real ax, real ay, real az, real bx, real by, real bz) {
+  real l = ob_sqrt(ax * ax + ay * ay + az * az);
+  if (l <= OB_REAL(0.0)) return 0;
+  l = ob_recip(l);
+  ax *= l; ay *= l; az *= l;
+  const real k = ax * bx + ay * by + az * bz;
+  bx -= k * ax; by -= k * ay; bz -= k * az;
+  l = ob_sqrt(bx * bx + by * by + bz * bz);
+  if (l <= OB_REAL(0.0)) return 0;
+  l = ob_recip(l);
+  bx *= l; by *= l; bz *= l;
+  R[0] = ax; R[4] = ay; R[8] = az;
+  R[1] = bx; R[5] = by; R[9] = bz;
+  R[2] = -by * az + ay * bz;
+  R[6] = -bz * ax + az * bx;
+  R[10] = -bx * ay + ax * by;
+  R[3] = R[7] = R[11] = OB_REAL(0.0);
+  return 1;
+}
+// dQfromR (rotation.cpp:258-307)
+OB_HD void ob_QfromR(real *q, const real *R) {
+  real tr = R[0] + R[5] + R[10], s;
+  if (tr >= 0) {
+    s = ob_sqrt(tr + 1);
+    q[0] = OB_REAL(0.5) * s;
+    s = OB_REAL(0.5) * ob_recip(s);
+    q[1] = (R[9] - R[6]) * s; q[2] = (R[2] - R[8]) * s; q[3] = (R[4] - R[1]) * s;
+    return;
+  }
+  int c;
+  if (R[5] > R[0]) c = (R[10] > R[5]) ? 2 : 1;
+  else c = (R[10] > R[0]) ? 2 : 0;
+  if (c == 0) {
+    s = ob_sqrt((R[0] - (R[5] + R[10])) + 1);
+    q[1] = OB_REAL(0.5) * s;
+    s = OB_REAL(0.5) * ob_recip(s);
+    q[2] = (R[1] + R[4]) * s; q[3] = (R[8] + R[2]) * s; q[0] = (R[9] - R[6]) * s;
+  } else if (c == 1) {
+    s = ob_sqrt((R[5] - (R[10] + R[0])) + 1);
+    q[2] = OB_REAL(0.5) * s;
+    s = OB_REAL(0.5) * ob_recip(s);
+    q[3] = (R[6] + R[9]) * s; q[1] = (R[1] + R[4]) * s; q[0] = (R[2] - R[8]) * s;
+  } else {
+    s = ob_sqrt((R[10] - (R[0] + R[5])) + 1);
+    q[3] = OB_REAL(0.5) * s;
+    s = OB_REAL(0.5) * ob_recip(s);
+    q[1] = (R[8] + R[2]) * s; q[2] = (R[6] + R[9]) * s; q[0] = (R[4] - R[1]) * s;
+  }
+}
 // _dSafeNormalize4 (odemath.cpp:119-139)
 OB_HD int ob_safe_normalize4(real *a) {
   real l = ob_dot(a, a) + a[3] * a[3];

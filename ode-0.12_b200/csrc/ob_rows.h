@@ -134,6 +134,40 @@ OB_HD real ob_hinge_angle(const real *q1, const real *q2, const real *axis, cons
   theta = -theta;
   return theta;
 }
+// getHingeAngleFromRelativeQuat (joint.cpp:381-420)
+OB_HD real ob_hinge_angle_from_qrel(const real *qrel, const real *axis) {
+  real cost2 = qrel[0];
+  real sint2 = ob_sqrt(qrel[1] * qrel[1] + qrel[2] * qrel[2] + qrel[3] * qrel[3]);
+  real theta = (ob_dot(qrel + 1, axis) >= 0) ? (2 * ob_atan2(sint2, cost2)) : (2 * ob_atan2(sint2, -cost2));
+  if ((double)theta > OB_PI) theta -= (real)(2 * OB_PI);
+  theta = -theta;
+  return theta;
+}
+// dxJointUniversal::getAxes / getAngles (universal.cpp:52-169); qrel1 = ObJoint::qrel, qrel2 = ObJoint::v1
+OB_HD void ob_universal_axes(const ObJoint &j, const real *R1, const real *R2, real *ax1, real *ax2) {
+  ob_mul0_331(ax1, R1, j.axis1);
+  if (R2) ob_mul0_331(ax2, R2, j.axis2);
+  else { ax2[0] = j.axis2[0]; ax2[1] = j.axis2[1]; ax2[2] = j.axis2[2]; }
+}
+OB_HD void ob_universal_angles(const ObJoint &j, const real *R1, const real *q1, const real *R2, const real *q2, real *angle1, real *angle2) {
+  real ax1[3], ax2[3], R[12], qcross[4], qq[4], qrel[4];
+  ob_universal_axes(j, R1, R2, ax1, ax2);
+  for (int i = 0; i < 12; i++) R[i] = 0;
+  ob_Rfrom2axes(R, ax1[0], ax1[1], ax1[2], ax2[0], ax2[1], ax2[2]);
+  ob_QfromR(qcross, R);
+  ob_qmul1(qq, q1, qcross);
+  ob_qmul2(qrel, qq, j.qrel);
+  *angle1 = ob_hinge_angle_from_qrel(qrel, j.axis1);
+  real qcross2[4];
+  qrel[0] = 0;
+  qrel[1] = ax1[0] + ax2[0]; qrel[2] = ax1[1] + ax2[1]; qrel[3] = ax1[2] + ax2[2];
+  const real l = ob_recip(ob_sqrt(qrel[1] * qrel[1] + qrel[2] * qrel[2] + qrel[3] * qrel[3]));
+  qrel[1] *= l; qrel[2] *= l; qrel[3] *= l;
+  ob_qmul0(qcross2, qrel, qcross);
+  if (q2) { ob_qmul1(qq, q2, qcross2); ob_qmul2(qrel, qq, j.v1); }
+  else ob_qmul2(qrel, qcross2, j.v1);
+  *angle2 = -ob_hinge_angle_from_qrel(qrel, j.axis2);
+}
 // dxJointHinge2::measureAngle (hinge2.cpp:34-43)
 OB_HD real ob_hinge2_angle(const real *R1, const real *R2, const real *axis2, const real *v1, const real *v2) {
   real a1[3], a2[3];
@@ -155,6 +189,20 @@ struct ObBodyView {   // what row assembly reads from a body
   const real *pos, *R, *q, *lvel, *avel;
 };
 
+// dJointGetSliderPosition (slider.cpp:44-83)
+OB_HD real ob_slider_position(const ObJoint &j, const ObBodyView &B1, const ObBodyView *B2) {
+  real ax1[3], q[3];
+  ob_mul0_331(ax1, B1.R, j.axis1);
+  if (B2) {
+    ob_mul0_331(q, B2->R, j.anchor1);
+    for (int i = 0; i < 3; i++) q[i] = B1.pos[i] - q[i] - B2->pos[i];
+  } else {
+    q[0] = B1.pos[0] - j.anchor1[0]; q[1] = B1.pos[1] - j.anchor1[1]; q[2] = B1.pos[2] - j.anchor1[2];
+    if (j.flags & OB_JF_REVERSE) { ax1[0] = -ax1[0]; ax1[1] = -ax1[1]; ax1[2] = -ax1[2]; }
+  }
+  return ob_dot(ax1, q);
+}
+
 // getInfo1 for permanent joints; mutates limot.limit / limit_err like the reference
 OB_HD int ob_joint_info1(ObJoint &j, const ObBodyView &B1, const ObBodyView *B2) {
   if (j.type == OB_JOINT_BALL) return 3;
@@ -163,6 +211,32 @@ OB_HD int ob_joint_info1(ObJoint &j, const ObBodyView &B1, const ObBodyView *B2)
     if (((double)j.limot1.lostop >= -OB_PI || (double)j.limot1.histop <= OB_PI) && j.limot1.lostop <= j.limot1.histop) {
       real angle = ob_hinge_angle(B1.q, B2 ? B2->q : (const real *)0, j.axis1, j.qrel);
       if (ob_limot_test_limit(j.limot1, angle)) m = 6;
+    }
+    return m;
+  }
+  if (j.type == OB_JOINT_FIXED) return 6;
+  if (j.type == OB_JOINT_UNIVERSAL) {   // universal.cpp:265-292
+    int m = 4;
+    const bool limiting1 = ((double)j.limot1.lostop >= -OB_PI || (double)j.limot1.histop <= OB_PI) && j.limot1.lostop <= j.limot1.histop;
+    const bool limiting2 = ((double)j.limot2.lostop >= -OB_PI || (double)j.limot2.histop <= OB_PI) && j.limot2.lostop <= j.limot2.histop;
+    j.limot1.limit = 0; j.limot2.limit = 0;
+    if (limiting1 || limiting2) {
+      real angle1, angle2;
+      ob_universal_angles(j, B1.R, B1.q, B2 ? B2->R : (const real *)0, B2 ? B2->q : (const real *)0, &angle1, &angle2);
+      if (limiting1) ob_limot_test_limit(j.limot1, angle1);
+      if (limiting2) ob_limot_test_limit(j.limot2, angle2);
+    }
+    if (j.limot1.limit || j.limot1.fmax > 0) m++;
+    if (j.limot2.limit || j.limot2.fmax > 0) m++;
+    return m;
+  }
+  if (j.type == OB_JOINT_SLIDER) {   // slider.cpp:116-145
+    int m = (j.limot1.fmax > 0) ? 6 : 5;
+    j.limot1.limit = 0;
+    if ((j.limot1.lostop > -OB_INF || j.limot1.histop < OB_INF) && j.limot1.lostop <= j.limot1.histop) {
+      const real pos = ob_slider_position(j, B1, B2);
+      if (pos <= j.limot1.lostop) { j.limot1.limit = 1; j.limot1.limit_err = pos - j.limot1.lostop; m = 6; }
+      else if (pos >= j.limot1.histop) { j.limot1.limit = 2; j.limot1.limit_err = pos - j.limot1.histop; m = 6; }
     }
     return m;
   }
@@ -275,6 +349,99 @@ OB_HD int ob_add_limot_rot(RO &r, int row, const ObLimot &l, const real *ax1, co
   return 1;
 }
 
+// dxJointLimitMotor::addLimot, linear case (joint.cpp:556-733 with rotational == 0): the row acts along ax1
+// on the linear velocities; with two bodies the force is applied half way between the centres ("linear torque
+// decoupling", ltd = c x ax1 in both angular blocks).  Powered at a limit: side_fm returns fm; the caller adds
+// force -fm*ax1 / +fm*ax1 and torque -fm*ltd to BOTH bodies (:646-657).
+template <class RO>
+OB_HD int ob_add_limot_lin(RO &r, int row, const ObLimot &l, const real *ax1, const ObBodyView &B1, const ObBodyView *B2,
+                           real fps, real *side_fm, real *ltd) {
+  *side_fm = 0;
+  ltd[0] = ltd[1] = ltd[2] = 0;
+  int powered = l.fmax > 0;
+  if (!(powered || l.limit)) return 0;
+  r.J[row][0] = ax1[0]; r.J[row][1] = ax1[1]; r.J[row][2] = ax1[2];
+  if (B2) {
+    r.J[row][6] = -ax1[0]; r.J[row][7] = -ax1[1]; r.J[row][8] = -ax1[2];
+    real c[3];
+    c[0] = OB_REAL(0.5) * (B2->pos[0] - B1.pos[0]);
+    c[1] = OB_REAL(0.5) * (B2->pos[1] - B1.pos[1]);
+    c[2] = OB_REAL(0.5) * (B2->pos[2] - B1.pos[2]);
+    ob_cross(ltd, c, ax1);
+    for (int i = 0; i < 3; i++) { r.J[row][3 + i] = ltd[i]; r.J[row][9 + i] = ltd[i]; }
+  }
+  if (l.limit && (l.lostop == l.histop)) powered = 0;
+  if (powered) {
+    r.cfm[row] = l.normal_cfm;
+    if (!l.limit) { r.c[row] = l.vel; r.lo[row] = -l.fmax; r.hi[row] = l.fmax; }
+    else {
+      real fm = l.fmax;
+      if ((l.vel > 0) || (l.vel == 0 && l.limit == 2)) fm = -fm;
+      if ((l.limit == 1 && l.vel > 0) || (l.limit == 2 && l.vel < 0)) fm *= l.fudge_factor;
+      *side_fm = fm;
+    }
+  }
+  if (l.limit) {
+    real k = fps * l.stop_erp;
+    r.c[row] = -k * l.limit_err;
+    r.cfm[row] = l.stop_cfm;
+    if (l.lostop == l.histop) { r.lo[row] = -OB_INF; r.hi[row] = OB_INF; }
+    else {
+      if (l.limit == 1) { r.lo[row] = 0; r.hi[row] = OB_INF; }
+      else { r.lo[row] = -OB_INF; r.hi[row] = 0; }
+      if (l.bounce > 0) {
+        real vel = ob_dot(B1.lvel, ax1);
+        if (B2) vel -= ob_dot(B2->lvel, ax1);
+        if (l.limit == 1) { if (vel < 0) { real newc = -l.bounce * vel; if (newc > r.c[row]) r.c[row] = newc; } }
+        else { if (vel > 0) { real newc = -l.bounce * vel; if (newc < r.c[row]) r.c[row] = newc; } }
+      }
+    }
+  }
+  return 1;
+}
+
+// setFixedOrientation (joint.cpp:202-255): three angular rows from start_row
+template <class RO>
+OB_HD void ob_set_fixed_orientation(RO &r, int start_row, const real *qrel, const ObBodyView &B1, const ObBodyView *B2, real fps, real erp) {
+  r.J[start_row][3] = 1; r.J[start_row + 1][4] = 1; r.J[start_row + 2][5] = 1;
+  if (B2) { r.J[start_row][9] = -1; r.J[start_row + 1][10] = -1; r.J[start_row + 2][11] = -1; }
+  real qerr[4], e[3];
+  if (B2) { real qq[4]; ob_qmul1(qq, B1.q, B2->q); ob_qmul2(qerr, qq, qrel); }
+  else ob_qmul3(qerr, B1.q, qrel);
+  if (qerr[0] < 0) { qerr[1] = -qerr[1]; qerr[2] = -qerr[2]; qerr[3] = -qerr[3]; }
+  ob_mul0_331(e, B1.R, qerr + 1);
+  const real k = fps * erp;
+  r.c[start_row] = 2 * k * e[0];
+  r.c[start_row + 1] = 2 * k * e[1];
+  r.c[start_row + 2] = 2 * k * e[2];
+}
+
+// the bodies' accumulators after a joint's powered-at-limit motor side effects (joint.cpp:638-657), in the
+// order the reference applies them.  side[k] = {fm, v[3]}: rotational limots (hinge, hinge2, universal):
+// torque -fm*v on body 1, +fm*v on body 2; slider: side[0] = force (-fm*ax1 / +fm*ax1), side[1] = the
+// decoupling torque, -fm*ltd on BOTH bodies.
+OB_HD void ob_apply_joint_side(int jtype, const real side[2][4], real *facc1, real *tacc1, real *facc2, real *tacc2) {
+  if (jtype == OB_JOINT_SLIDER) {
+    const real fm = side[0][0];
+    if (fm != 0) {
+      for (int e = 0; e < 3; e++) facc1[e] += -fm * side[0][1 + e];
+      if (facc2) {
+        for (int e = 0; e < 3; e++) facc2[e] += fm * side[0][1 + e];
+        for (int e = 0; e < 3; e++) tacc1[e] += -fm * side[1][1 + e];
+        for (int e = 0; e < 3; e++) tacc2[e] += -fm * side[1][1 + e];
+      }
+    }
+    return;
+  }
+  for (int sx = 0; sx < 2; sx++) {
+    const real fm = side[sx][0];
+    if (fm != 0) {
+      for (int e = 0; e < 3; e++) tacc1[e] += -fm * side[sx][1 + e];
+      if (tacc2) for (int e = 0; e < 3; e++) tacc2[e] += fm * side[sx][1 + e];
+    }
+  }
+}
+
 // getInfo2 for permanent joints.  erp_io carries the driver's shared Info2.erp, which a ball
 // joint overwrites for every later joint of the island (ball.cpp:60, quickstep.cpp:764-786).
 // side[k] (k<2) returns {fm, ax[3]} of a powered-at-limit motor whose torque must be added
@@ -305,6 +472,79 @@ OB_HD void ob_joint_info2(RO &r, const ObJoint &j, const ObBodyView &B1, const O
     real fm;
     if (ob_add_limot_rot(r, 5, j.limot1, ax1, B1, B2, fps, &fm) && fm != 0) {
       side[0][0] = fm; side[0][1] = ax1[0]; side[0][2] = ax1[1]; side[0][3] = ax1[2];
+    }
+  } else if (j.type == OB_JOINT_UNIVERSAL) {   // universal.cpp:296-361
+    const real erp = *erp_io;
+    ob_set_ball(r, j.anchor1, j.anchor2, B1, B2, fps, erp);
+    real ax1[3], ax2[3], ax2t[3], p[3];
+    ob_universal_axes(j, B1.R, B2 ? B2->R : (const real *)0, ax1, ax2);
+    const real k = ob_dot(ax1, ax2);
+    ax2t[0] = ax2[0] - k * ax1[0]; ax2t[1] = ax2[1] - k * ax1[1]; ax2t[2] = ax2[2] - k * ax1[2];
+    ob_cross(p, ax1, ax2t);
+    ob_safe_normalize3(p);
+    for (int i = 0; i < 3; i++) r.J[3][3 + i] = p[i];
+    if (B2) for (int i = 0; i < 3; i++) r.J[3][9 + i] = -p[i];
+    r.c[3] = fps * erp * -k;
+    real fm;
+    const int added = ob_add_limot_rot(r, 4, j.limot1, ax1, B1, B2, fps, &fm);
+    if (added && fm != 0) { side[0][0] = fm; side[0][1] = ax1[0]; side[0][2] = ax1[1]; side[0][3] = ax1[2]; }
+    if (ob_add_limot_rot(r, 4 + added, j.limot2, ax2, B1, B2, fps, &fm) && fm != 0) {
+      side[1][0] = fm; side[1][1] = ax2[0]; side[1][2] = ax2[1]; side[1][3] = ax2[2];
+    }
+  } else if (j.type == OB_JOINT_FIXED) {   // fixed.cpp:57-100
+    ob_set_fixed_orientation(r, 3, j.qrel, B1, B2, fps, *erp_io);   // uses the erp that was current BEFORE this joint
+    r.J[0][0] = 1; r.J[1][1] = 1; r.J[2][2] = 1;
+    *erp_io = j.erp;
+    r.cfm[0] = j.cfm; r.cfm[1] = j.cfm; r.cfm[2] = j.cfm;
+    real ofs[3];
+    ob_mul0_331(ofs, B1.R, j.anchor1);
+    if (B2) {
+      // dSetCrossMatrixPlus(J1a, ofs)
+      r.J[0][3 + 1] = -ofs[2]; r.J[0][3 + 2] = ofs[1];
+      r.J[1][3 + 0] = ofs[2]; r.J[1][3 + 2] = -ofs[0];
+      r.J[2][3 + 0] = -ofs[1]; r.J[2][3 + 1] = ofs[0];
+      r.J[0][6] = -1; r.J[1][7] = -1; r.J[2][8] = -1;
+    }
+    const real k = fps * *erp_io;
+    if (B2) { for (int i = 0; i < 3; i++) r.c[i] = k * (B2->pos[i] - B1.pos[i] + ofs[i]); }
+    else { for (int i = 0; i < 3; i++) r.c[i] = k * (j.anchor1[i] - B1.pos[i]); }
+  } else if (j.type == OB_JOINT_SLIDER) {   // slider.cpp:149-227
+    const real erp = *erp_io;
+    real c[3] = {0, 0, 0};
+    if (B2) for (int i = 0; i < 3; i++) c[i] = B2->pos[i] - B1.pos[i];
+    ob_set_fixed_orientation(r, 0, j.qrel, B1, B2, fps, erp);
+    real ax1[3], p[3], q[3];
+    ob_mul0_331(ax1, B1.R, j.axis1);
+    ob_plane_space(ax1, p, q);
+    if (B2) {
+      real tmp[3];
+      ob_cross(tmp, c, p);
+      tmp[0] *= OB_REAL(0.5); tmp[1] *= OB_REAL(0.5); tmp[2] *= OB_REAL(0.5);
+      for (int i = 0; i < 3; i++) { r.J[3][3 + i] = tmp[i]; r.J[3][9 + i] = tmp[i]; }
+      ob_cross(tmp, c, q);
+      tmp[0] *= OB_REAL(0.5); tmp[1] *= OB_REAL(0.5); tmp[2] *= OB_REAL(0.5);
+      for (int i = 0; i < 3; i++) { r.J[4][3 + i] = tmp[i]; r.J[4][9 + i] = tmp[i]; }
+      for (int i = 0; i < 3; i++) { r.J[3][6 + i] = -p[i]; r.J[4][6 + i] = -q[i]; }
+    }
+    for (int i = 0; i < 3; i++) { r.J[3][i] = p[i]; r.J[4][i] = q[i]; }
+    const real k = fps * erp;
+    if (B2) {
+      real ofs[3];
+      ob_mul0_331(ofs, B2->R, j.anchor1);
+      for (int i = 0; i < 3; i++) c[i] += ofs[i];
+      r.c[3] = k * ob_dot(p, c);
+      r.c[4] = k * ob_dot(q, c);
+    } else {
+      real ofs[3];
+      for (int i = 0; i < 3; i++) ofs[i] = j.anchor1[i] - B1.pos[i];
+      r.c[3] = k * ob_dot(p, ofs);
+      r.c[4] = k * ob_dot(q, ofs);
+      if (j.flags & OB_JF_REVERSE) for (int i = 0; i < 3; i++) ax1[i] = -ax1[i];
+    }
+    real fm, ltd[3];
+    if (ob_add_limot_lin(r, 5, j.limot1, ax1, B1, B2, fps, &fm, ltd) && fm != 0) {
+      side[0][0] = fm; side[0][1] = ax1[0]; side[0][2] = ax1[1]; side[0][3] = ax1[2];
+      side[1][0] = fm; side[1][1] = ltd[0]; side[1][2] = ltd[1]; side[1][3] = ltd[2];
     }
   } else if (j.type == OB_JOINT_HINGE2) {
     const real erp = *erp_io;

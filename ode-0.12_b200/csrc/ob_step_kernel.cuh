@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(32) k_prep(ObBatchDev d, real h, int taps) {
           ObBodyView B1 = {bd[b1].pos, bd[b1].R, bd[b1].q, bd[b1].lvel, bd[b1].avel}, B2 = B1;
           if (b2 >= 0) { B2.pos = bd[b2].pos; B2.R = bd[b2].R; B2.q = bd[b2].q; B2.lvel = bd[b2].lvel; B2.avel = bd[b2].avel; }
           m = ob_joint_info1(pj, B1, b2 >= 0 ? &B2 : (const ObBodyView *)0);
-          if (pj.type == OB_JOINT_BALL) anyball = 1;
+          if (pj.type == OB_JOINT_BALL || pj.type == OB_JOINT_FIXED) anyball = 1;   // joints that overwrite Info2.erp (ball.cpp:59, fixed.cpp:72)
         }
       }
       int x = m;
@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(32) k_prep(ObBatchDev d, real h, int taps) {
         for (int k = j0; k < j0 + jn; k++) {
           s_erpsrc[k] = (unsigned short)src;
           const int j = s_ijoint[k];
-          if (j >= nc && pjoint[j - nc].type == OB_JOINT_BALL) src = k;
+          if (j >= nc && (pjoint[j - nc].type == OB_JOINT_BALL || pjoint[j - nc].type == OB_JOINT_FIXED)) src = k;
         }
       }
     }
@@ -411,22 +411,16 @@ __global__ void __launch_bounds__(32) k_prep(ObBatchDev d, real h, int taps) {
     if (gl == 0 && valid) g_jrow[nij] = (unsigned short)(have_rows ? mtot : 0);
     for (int dd = 1; dd < G; dd <<= 1) anyside |= __shfl_xor_sync(FULL, anyside, dd, G);
     __syncwarp();
-    // (6b) dBodyAddTorque side effects in joint order (they change tacc before the rhs is formed)
+    // (6b) dBodyAddTorque / dBodyAddForce side effects in joint order (they change the accumulators before the rhs is formed)
     if (anyside && gl == 0) {
       for (int k = 0; k < nij; k++) {
         const int j = s_ijoint[k];
         if (j < nc) continue;
         const int b1 = s_jb1[j], b2 = s_jb2[j];
-        for (int sx = 0; sx < 2; sx++) {
-          const real fm = __ldcg(g_side + (size_t)(j - nc) * 8 + 4 * sx);
-          if (fm != 0) {
-            for (int e = 0; e < 3; e++) {
-              const real ax = __ldcg(g_side + (size_t)(j - nc) * 8 + 4 * sx + 1 + e);
-              bd[b1].tacc[e] += -fm * ax;
-              if (b2 != 255) bd[b2].tacc[e] += fm * ax;
-            }
-          }
-        }
+        real side[2][4];
+        for (int sx = 0; sx < 2; sx++) for (int e = 0; e < 4; e++) side[sx][e] = __ldcg(g_side + (size_t)(j - nc) * 8 + 4 * sx + e);
+        if (side[0][0] == 0 && side[1][0] == 0) continue;
+        ob_apply_joint_side(pjoint[j - nc].type, side, bd[b1].facc, bd[b1].tacc, b2 != 255 ? bd[b2].facc : (real *)0, b2 != 255 ? bd[b2].tacc : (real *)0);
       }
     }
     __syncwarp();

@@ -78,11 +78,11 @@ struct __attribute__((aligned(16))) ObLimot {
   real fudge_factor, normal_cfm, stop_erp, stop_cfm;
   real bounce; int limit; real limit_err; int pad;
 };
-enum { OB_JOINT_BALL = 1, OB_JOINT_HINGE = 2, OB_JOINT_CONTACT = 4, OB_JOINT_HINGE2 = 6 };   // == dJointType
+enum { OB_JOINT_BALL = 1, OB_JOINT_HINGE = 2, OB_JOINT_SLIDER = 3, OB_JOINT_CONTACT = 4, OB_JOINT_UNIVERSAL = 5, OB_JOINT_HINGE2 = 6, OB_JOINT_FIXED = 7 };   // == dJointType
 enum { OB_JF_DISABLED = 1, OB_JF_REVERSE = 2 };
 struct __attribute__((aligned(16))) ObJoint {
   int type; int b1, b2; int flags;        // b1/b2 = node[0]/node[1] body index, -1 = none
-  real anchor1[4], anchor2[4], axis1[4], axis2[4], qrel[4];
+  real anchor1[4], anchor2[4], axis1[4], axis2[4], qrel[4];   // slider / fixed: anchor1 = offset; universal: qrel = qrel1, v1 = qrel2
   real erp, cfm, susp_erp, susp_cfm;
   real c0, s0, pad0, pad1;
   real v1[4], v2[4];

@@ -26,6 +26,8 @@ GOLDEN = [  # (file stem, scene, steps, worlds, settle) — must match tests/gol
     ("buggy_terrain_w2_settle90", "buggy_terrain", 30, 2, 90),
     ("terrain_capsules_settle70", "terrain_capsules", 20, 1, 70),
     ("terrain_plane_settle60", "terrain_plane", 20, 1, 60),
+    ("sliders_settle60", "sliders", 30, 1, 60),
+    ("universals_settle60", "universals", 30, 1, 60),
 ]
 
 
@@ -67,7 +69,7 @@ def _built():
 # traces and, for the long live comparisons, in lock-step with the reference (every step starts
 # from the reference's pre-step body state, SURVEY 8d parity protocol with K = 1) so that a
 # last-bit difference cannot be amplified by chaotic dynamics into a different contact set.
-ATAN2_SCENES = ("hinges", "buggy", "ragdoll", "buggy_terrain")
+ATAN2_SCENES = ("hinges", "buggy", "ragdoll", "buggy_terrain", "universals")
 
 
 def assert_parity(r, what, scene, prec, cand):

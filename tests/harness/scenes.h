@@ -253,6 +253,100 @@ static inline void scene_buggy(SceneWorld &sw, int w) {
   }
 }
 
+// slider and fixed joints (slider.cpp, fixed.cpp) mixed with ball / hinge joints in one island: a fixed joint
+// overwrites the island's shared Info2.erp like a ball does (fixed.cpp:72), sliders with stops, a free motor, a
+// motor driven into its stop (force + torque-decoupling side effects, joint.cpp:646-657), a slider and a fixed
+// joint attached to the world, one of them with the bodies given in reversed order
+static inline void scene_sliders(SceneWorld &sw, int w) {
+  scene_world_base(sw, w);
+  xs32 rng(sw.seed ^ 0x0051DE5u);
+  scene_add_geom(sw, dCreatePlane(sw.space, 0, 0, 1, 0));
+  dBodyID prev = 0;
+  for (int i = 0; i < 7; i++) {
+    dBodyID b = scene_add_box(sw, 2, (dReal)0.4, (dReal)0.25, (dReal)0.2, (dReal)(0.6 * i), rng.uni(-0.02, 0.02), (dReal)(1.0 + 0.05 * i));
+    dQuaternion q = {1, rng.uni(-0.1, 0.1), rng.uni(-0.1, 0.1), rng.uni(-0.1, 0.1)};
+    dBodySetQuaternion(b, q);
+    dJointID j;
+    if (i == 0) {           // slider to the world, bodies reversed: dJOINT_REVERSE
+      j = dJointCreateSlider(sw.world, 0);
+      dJointAttach(j, 0, b);
+      dJointSetSliderAxis(j, (dReal)0.1, 0, 1);
+      dJointSetSliderParam(j, dParamLoStop, (dReal)-0.3); dJointSetSliderParam(j, dParamHiStop, (dReal)0.15);
+      dJointSetSliderParam(j, dParamBounce, (dReal)0.4);
+    } else if (i == 1 || i == 4) {   // two-body sliders: stops / motor into the stop
+      j = dJointCreateSlider(sw.world, 0);
+      dJointAttach(j, prev, b);
+      dJointSetSliderAxis(j, 1, (dReal)(i == 4 ? 0.3 : 0), (dReal)0.2);
+      dJointSetSliderParam(j, dParamLoStop, (dReal)-0.1); dJointSetSliderParam(j, dParamHiStop, (dReal)0.12);
+      if (i == 4) {
+        dJointSetSliderParam(j, dParamVel, (dReal)1.0); dJointSetSliderParam(j, dParamFMax, (dReal)8);
+        dJointSetSliderParam(j, dParamFudgeFactor, (dReal)0.4); dJointSetSliderParam(j, dParamStopERP, (dReal)0.5);
+        dJointSetSliderParam(j, dParamStopCFM, (dReal)1e-3);
+      }
+    } else if (i == 2) {    // fixed, own erp/cfm
+      j = dJointCreateFixed(sw.world, 0);
+      dJointAttach(j, prev, b);
+      dJointSetFixed(j);
+      dJointSetFixedParam(j, dParamERP, (dReal)0.6); dJointSetFixedParam(j, dParamCFM, (dReal)1e-4);
+    } else if (i == 3) {    // hinge after the fixed joint: sees the fixed joint's erp
+      j = dJointCreateHinge(sw.world, 0);
+      dJointAttach(j, prev, b);
+      dJointSetHingeAnchor(j, (dReal)(0.6 * i - 0.3), 0, (dReal)1.1);
+      dJointSetHingeAxis(j, 0, 1, 0);
+    } else if (i == 5) {    // free slider motor
+      j = dJointCreateSlider(sw.world, 0);
+      dJointAttach(j, b, prev);
+      dJointSetSliderAxis(j, 0, 1, 0);
+      dJointSetSliderParam(j, dParamVel, (dReal)-0.5); dJointSetSliderParam(j, dParamFMax, (dReal)3);
+    } else {                // ball, then a second chain end welded to the world below
+      j = dJointCreateBall(sw.world, 0);
+      dJointAttach(j, prev, b);
+      dJointSetBallAnchor(j, (dReal)(0.6 * i - 0.3), 0, (dReal)1.25);
+    }
+    sw.joints.push_back(j);
+    prev = b;
+  }
+  // a separate box welded to the world (one-body fixed joint), hit by a falling sphere
+  dBodyID wb = scene_add_box(sw, 2, (dReal)0.5, (dReal)0.5, (dReal)0.3, (dReal)-1.5, 0, (dReal)0.8);
+  dJointID jf = dJointCreateFixed(sw.world, 0);
+  dJointAttach(jf, wb, 0);
+  dJointSetFixed(jf);
+  sw.joints.push_back(jf);
+  scene_add_sphere(sw, 3, (dReal)0.25, (dReal)-1.45, (dReal)0.05, (dReal)2.5);
+  scene_add_sphere(sw, 3, (dReal)0.2, (dReal)1.3, (dReal)0.02, (dReal)2.8);
+}
+
+// universal joints (universal.cpp): free, with stops on both axes (getAngles: dRFrom2Axes + dQfromR + atan2),
+// with a motor on axis 2, attached to the world, and one with the bodies given in reversed order
+static inline void scene_universals(SceneWorld &sw, int w) {
+  scene_world_base(sw, w);
+  xs32 rng(sw.seed ^ 0x00041E5u);
+  scene_add_geom(sw, dCreatePlane(sw.space, 0, 0, 1, 0));
+  dBodyID prev = 0;
+  for (int i = 0; i < 6; i++) {
+    dBodyID b = scene_add_box(sw, 2, (dReal)0.45, (dReal)0.2, (dReal)0.15, (dReal)(0.55 * i), rng.uni(-0.02, 0.02), (dReal)1.4);
+    dBodySetAngularVel(b, rng.uni(-1, 1), rng.uni(-1, 1), rng.uni(-1, 1));
+    dJointID j = dJointCreateUniversal(sw.world, 0);
+    if (i == 3) dJointAttach(j, b, prev); else if (i == 0) dJointAttach(j, 0, b); else dJointAttach(j, prev, b);
+    dJointSetUniversalAnchor(j, (dReal)(0.55 * i - 0.275), 0, (dReal)1.4);
+    dJointSetUniversalAxis1(j, 0, 1, (dReal)(i == 2 ? 0.3 : 0));
+    dJointSetUniversalAxis2(j, 0, (dReal)(i == 4 ? 0.2 : 0), 1);
+    if (i == 1 || i == 3 || i == 5) {
+      dJointSetUniversalParam(j, dParamLoStop, (dReal)-0.3); dJointSetUniversalParam(j, dParamHiStop, (dReal)0.25);
+      dJointSetUniversalParam(j, dParamLoStop2, (dReal)-0.2); dJointSetUniversalParam(j, dParamHiStop2, (dReal)0.35);
+      if (i == 5) dJointSetUniversalParam(j, dParamBounce, (dReal)0.3);
+    }
+    if (i == 2) { dJointSetUniversalParam(j, dParamVel2, (dReal)1.2); dJointSetUniversalParam(j, dParamFMax2, (dReal)2); }
+    if (i == 3) {   // powered into its stop
+      dJointSetUniversalParam(j, dParamVel, (dReal)2.0); dJointSetUniversalParam(j, dParamFMax, (dReal)3);
+      dJointSetUniversalParam(j, dParamFudgeFactor, (dReal)0.5);
+    }
+    sw.joints.push_back(j);
+    prev = b;
+  }
+  scene_add_sphere(sw, 3, (dReal)0.2, (dReal)1.0, (dReal)0.03, (dReal)2.6);
+}
+
 static inline dBodyID scene_add_capsule(SceneWorld &sw, dReal density, dReal r, dReal l, dReal x, dReal y, dReal z) {
   dBodyID b = dBodyCreate(sw.world);
   dBodySetPosition(b, x, y, z);
@@ -587,6 +681,8 @@ static inline int scene_build(const char *name_in, SceneWorld &sw, int w, SceneP
   if (!strcmp(name, "mixed_maxc4")) { scene_mixed(sw, w, 12, 6); pol = policy_crash(); return 0; }
   if (!strcmp(name, "chain")) { scene_chain(sw, w, 8); return 0; }
   if (!strcmp(name, "hinges")) { scene_hinges(sw, w); return 0; }
+  if (!strcmp(name, "sliders")) { scene_sliders(sw, w); return 0; }
+  if (!strcmp(name, "universals")) { scene_universals(sw, w); return 0; }
   if (!strcmp(name, "buggy_terrain")) { scene_buggy_terrain(sw, w, 48); pol = policy_buggy(); pol.max_contacts = 10; return 0; }
   if (!strcmp(name, "buggy_terrain256")) { scene_buggy_terrain(sw, w, 256); pol = policy_buggy(); pol.max_contacts = 10; return 0; }
   if (!strcmp(name, "terrain_boxes")) { scene_terrain_boxes(sw, w); return 0; }

@@ -446,12 +446,9 @@ static void step_world(ObBatchDev &d, int w, real h, int taps) {
           if (b2 >= 0) B2 = view(b2);
           real side[2][4];
           ob_joint_info2(r, pj[k], B1, b2 >= 0 ? &B2 : 0, stepsize1, &erp_io, side);
-          for (int sx = 0; sx < 2; sx++)
-            if (side[sx][0] != 0) {   // dBodyAddTorque(body1, -fm*ax) ; dBodyAddTorque(body2, +fm*ax)
-              const real fm = side[sx][0];
-              for (int e = 0; e < 3; e++) bd[b1].tacc[e] += -fm * side[sx][1 + e];
-              if (b2 >= 0) for (int e = 0; e < 3; e++) bd[b2].tacc[e] += fm * side[sx][1 + e];
-            }
+          if ((side[0][0] != 0 || side[1][0] != 0) && getenv("OB_HOST_VERBOSE")) fprintf(stderr, "side effect: joint type %d fm %g\n", pj[k].type, (double)side[0][0]);
+          if (side[0][0] != 0 || side[1][0] != 0)
+            ob_apply_joint_side(pj[k].type, side, bd[b1].facc, bd[b1].tacc, b2 >= 0 ? bd[b2].facc : (real *)0, b2 >= 0 ? bd[b2].tacc : (real *)0);
         }
       }
       for (int i = 0; i < inb; i++) {
