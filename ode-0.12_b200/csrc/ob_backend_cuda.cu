@@ -369,6 +369,7 @@ struct ObBackend {
   real *st_host;     // pinned
   size_t st_elems;   // W*NB
   size_t smem_collide, smem_prep, smem_sched, smem_sched_lane, smem_sor, smem_post;
+  int sor_deep;     // 1: k_sor with the deep index prefetch (worlds with many rows)
   int sched_lane;   // 1: k_sched_lane (one lane per world) fits shared memory
   // independent worlds are stepped in nchunks chunks, each on its own stream: the chunks drift apart, so the
   // ALU-bound collide of one chunk overlaps the latency-bound SOR of another instead of running back to back
@@ -495,13 +496,16 @@ ObBackend *obk_create(const ObBatchDev &caps, int device, char *err, size_t errl
   CK(cudaFuncSetAttribute(k_collide<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_collide));
 #define OB_SETSMEM(GG) \
   CK(cudaFuncSetAttribute(k_prep<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_prep)); \
-  CK(cudaFuncSetAttribute(k_sor<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sor)); \
+  CK(cudaFuncSetAttribute(k_sor<GG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sor)); \
+  CK(cudaFuncSetAttribute(k_sor<GG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sor)); \
   CK(cudaFuncSetAttribute(k_post<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_post));
   OB_SETSMEM(8) OB_SETSMEM(16) OB_SETSMEM(32)
 #undef OB_SETSMEM
   CK(cudaFuncSetAttribute(k_sched<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sched));
   CK(cudaFuncSetAttribute(k_sched<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sched));
   CK(cudaFuncSetAttribute(k_sched<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sched));
+  b->sor_deep = d.NR > 256 ? 1 : 0;
+  { const char *e = getenv("OB_SOR_DEEP"); if (e) b->sor_deep = atoi(e) != 0; }
   b->smem_sched_lane = sched_lane_smem(d.NB, d.NR).total;
   // measured on B200: one lane per world wins for many small worlds (config 3: 65536 worlds x 56 rows, 0.70 -> 0.43 ms),
   // the warp per world for fewer, larger ones (config 2: 4096 x 377 rows, 0.40 vs 2.7 ms: too few warps to hide the chain latency)
@@ -595,7 +599,8 @@ template <int G> static void launch_step(ObBackend *b, real h, int taps, int pha
   if (timing) cudaEventRecord(ev[0], st);
   if (phases & OBK_PHASE_COLLIDE) {
     // CTA width follows the world size: the widest loop is the ng*ng candidate-pair scan
-    const int ct = d.NG <= 8 ? 32 : (d.NG <= 20 ? 64 : OB_THREADS);
+    int ct = d.NG <= 8 ? 32 : (d.NG <= 20 ? 64 : OB_THREADS);
+    { static const char *e = getenv("OB_COLLIDE_THREADS"); if (e && (atoi(e) == 32 || atoi(e) == 64 || atoi(e) == 96 || atoi(e) == 128)) ct = atoi(e); }
     const int grid = W < cap ? W : cap;
     if (d.nmesh) k_collide<true><<<grid, ct, b->smem_collide, st>>>(d);
     else k_collide<false><<<grid, ct, b->smem_collide, st>>>(d);
@@ -613,7 +618,8 @@ template <int G> static void launch_step(ObBackend *b, real h, int taps, int pha
     else if (d.NB <= 128) k_sched<4><<<W, 32, b->smem_sched, st>>>(d, G, taps);
     else k_sched<8><<<W, 32, b->smem_sched, st>>>(d, G, taps);
     if (timing) cudaEventRecord(ev[3], st);
-    k_sor<G><<<gsor, 32, b->smem_sor, st>>>(d, taps);
+    if (b->sor_deep) k_sor<G, true><<<gsor, 32, b->smem_sor, st>>>(d, taps);
+    else k_sor<G, false><<<gsor, 32, b->smem_sor, st>>>(d, taps);
     if (timing) cudaEventRecord(ev[4], st);
     k_post<G><<<gstep, 32, b->smem_post, st>>>(d, h);
     g_launches += 4;

@@ -70,6 +70,17 @@ def test_lane_per_world_scheduler_matches_golden(stem, scene, steps, worlds, set
     assert_parity(r, f"{stem}/lane", scene, "single", "b200")
 
 
+@pytest.mark.parametrize("deep", ["0", "1"])
+@pytest.mark.parametrize("stem,scene,steps,worlds,settle", [g for g in GOLDEN if g[1] in ("stack32", "ragdoll", "buggy_terrain", "sliders")])
+def test_both_sor_pipelines_match_golden(stem, scene, steps, worlds, settle, deep, monkeypatch):
+    """k_sor<G, DEEP>: the deep index prefetch (worlds with > 256 row slots) and the shallow one, forced either way"""
+    monkeypatch.setenv("OB_SOR_DEEP", deep)
+    g = os.path.join(ROOT, "tests", "golden", f"{stem}_single.trace")
+    r = parity_golden("b200", g, scene, "single", steps, worlds, settle)
+    assert r["steps"] == steps
+    assert_parity(r, f"{stem}/deep{deep}", scene, "single", "b200")
+
+
 def _batch(lib, scenes, scene, nworlds, cap=0):
     scenes.ob_scene_build_batch.restype = ctypes.c_void_p
     scenes.ob_scene_build_batch.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
