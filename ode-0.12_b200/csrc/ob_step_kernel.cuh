@@ -887,7 +887,8 @@ __device__ __noinline__ void sor_check_pass(bool act, unsigned meta, int gl, int
 // =====================================================================================
 // DEEP: index prefetch five passes ahead (worlds with many rows: the sweep is long and the pipeline's
 // prologue is amortised); otherwise the shallow pipeline with its short prologue (many tiny worlds).
-// Measured on B200: config 2 (377 rows/world) 1.07 -> 0.97 ms with DEEP, config 3 (56 rows/world) 5.19 -> 5.59 ms.
+// Measured on B200: config 2 (377 rows/world) 1.07 -> 0.93 ms with DEEP (index 6 passes, rows 3 passes ahead, four
+// row buffers), config 3 (56 rows/world) 5.19 -> 5.59 ms.
 template <int G, bool DEEP>
 __global__ void __launch_bounds__(32) k_sor(ObBatchDev d, int taps) {
   constexpr int T = 32 / G;
@@ -925,37 +926,41 @@ __global__ void __launch_bounds__(32) k_sor(ObBatchDev d, int taps) {
       const int np_max = warp_max_i(np);
       if constexpr (DEEP) {
       // software pipeline, no load waits on another load issued less than three passes earlier:
-      // pstart[p+9] -> row index of pass p+5 -> row record of pass p+2 (three register buffers used in
+      // pstart[p+10] -> row index of pass p+6 -> row record of pass p+3 (four register buffers used in
       // rotation) -> compute pass p.  (With one pass of slack the pass time settles at the L2 latency of
       // the index loads instead of the update's own dependent chain.)
 #define OB_PS(K) (((K) <= np) ? (int)pstart[K] : 0)
 #define OB_IDX(K, PA, PB) (((K) < np && (PA) + gl < (PB)) ? (int)sched[(PA) + gl] : -1)
-      ObRowReg A, B, C;
-      int ci = -1, i1 = -1, i2 = -1, i3 = -1, i4 = -1, ps5 = 0, ps6 = 0, ps7 = 0, ps8 = 0;
+      ObRowReg A, B, C, D;
+      int ci = -1, i1 = -1, i2 = -1, i3 = -1, i4 = -1, i5 = -1, ps6 = 0, ps7 = 0, ps8 = 0, ps9 = 0;
       if (np > 0) {
-        const int ps0 = OB_PS(0), ps1 = OB_PS(1), ps2 = OB_PS(2), ps3 = OB_PS(3), ps4 = OB_PS(4);
-        ps5 = OB_PS(5); ps6 = OB_PS(6); ps7 = OB_PS(7); ps8 = OB_PS(8);
-        ci = OB_IDX(0, ps0, ps1); i1 = OB_IDX(1, ps1, ps2); i2 = OB_IDX(2, ps2, ps3); i3 = OB_IDX(3, ps3, ps4); i4 = OB_IDX(4, ps4, ps5);
+        const int ps0 = OB_PS(0), ps1 = OB_PS(1), ps2 = OB_PS(2), ps3 = OB_PS(3), ps4 = OB_PS(4), ps5 = OB_PS(5);
+        ps6 = OB_PS(6); ps7 = OB_PS(7); ps8 = OB_PS(8); ps9 = OB_PS(9);
+        ci = OB_IDX(0, ps0, ps1); i1 = OB_IDX(1, ps1, ps2); i2 = OB_IDX(2, ps2, ps3); i3 = OB_IDX(3, ps3, ps4);
+        i4 = OB_IDX(4, ps4, ps5); i5 = OB_IDX(5, ps5, ps6);
         if (ci >= 0) load_row(rows + (size_t)ci * OB_ROWW, A);
         if (i1 >= 0) load_row(rows + (size_t)i1 * OB_ROWW, B);
+        if (i2 >= 0) load_row(rows + (size_t)i2 * OB_ROWW, C);
       }
       int p = 0;
 #define OB_SOR_PASS(CB, LB)                                                                        \
       {                                                                                            \
-        const int ps9 = OB_PS(p + 9);                                                              \
-        const int i5 = OB_IDX(p + 5, ps5, ps6);                                                    \
-        if (i2 >= 0) load_row(rows + (size_t)i2 * OB_ROWW, LB);                                    \
+        const int ps10 = OB_PS(p + 10);                                                            \
+        const int i6 = OB_IDX(p + 6, ps6, ps7);                                                    \
+        if (i3 >= 0) load_row(rows + (size_t)i3 * OB_ROWW, LB);                                    \
         if (taps & 4) sor_check_pass<G>(p < np && ci >= 0, CB.meta, gl, &d.world[wc].status);      \
         if (p < np && ci >= 0) sor_pass(CB, ci, s_fc, s_lam, s_invM);                              \
         __syncwarp();                                                                              \
-        ci = i1; i1 = i2; i2 = i3; i3 = i4; i4 = i5; ps5 = ps6; ps6 = ps7; ps7 = ps8; ps8 = ps9; p++; \
+        ci = i1; i1 = i2; i2 = i3; i3 = i4; i4 = i5; i5 = i6; ps6 = ps7; ps7 = ps8; ps8 = ps9; ps9 = ps10; p++; \
       }
       while (p < np_max) {
-        OB_SOR_PASS(A, C)
+        OB_SOR_PASS(A, D)
         if (p >= np_max) break;
         OB_SOR_PASS(B, A)
         if (p >= np_max) break;
         OB_SOR_PASS(C, B)
+        if (p >= np_max) break;
+        OB_SOR_PASS(D, C)
       }
 #undef OB_SOR_PASS
 #undef OB_PS
