@@ -70,6 +70,17 @@ def test_lane_per_world_scheduler_matches_golden(stem, scene, steps, worlds, set
     assert_parity(r, f"{stem}/lane", scene, "single", "b200")
 
 
+@pytest.mark.parametrize("tile", ["4", "16", "32"])
+@pytest.mark.parametrize("stem,scene,steps,worlds,settle", [g for g in GOLDEN if g[1] in ("stack32", "ragdoll", "buggy_terrain", "universals", "tower64")])
+def test_every_tile_width_matches_golden(stem, scene, steps, worlds, settle, tile, monkeypatch):
+    """G lanes per world in k_prep / k_sor / k_post: 4 (tiny worlds, large batches), 8 (default for >= 1024 worlds), 16, 32"""
+    monkeypatch.setenv("OB_TILE", tile)
+    g = os.path.join(ROOT, "tests", "golden", f"{stem}_single.trace")
+    r = parity_golden("b200", g, scene, "single", steps, worlds, settle)
+    assert r["steps"] == steps
+    assert_parity(r, f"{stem}/tile{tile}", scene, "single", "b200")
+
+
 @pytest.mark.parametrize("deep", ["0", "1"])
 @pytest.mark.parametrize("stem,scene,steps,worlds,settle", [g for g in GOLDEN if g[1] in ("stack32", "ragdoll", "buggy_terrain", "sliders")])
 def test_both_sor_pipelines_match_golden(stem, scene, steps, worlds, settle, deep, monkeypatch):
