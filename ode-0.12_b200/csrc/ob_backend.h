@@ -34,7 +34,7 @@ int obk_collide_pair(const ObPose *a, const ObPose *b, int flags, ObCg *out, con
 // (collision_space_internal.h:48-82) would call the near callback for (geom g of the space, query q).
 int obk_collide2(ObBackend *, const ObPose *q, const int *qbody, const uint32_t *qcat, const uint32_t *qcol, const ObMeshDev *qmesh,
                  int nq, unsigned char *hit, char *err, size_t errlen);
-int obk_mesh_upload(const float *verts, int nverts, const int *tris, int ntris, const ObBvNode *nodes, int device, ObMeshDev *io);
+int obk_mesh_upload(const float *verts, int nverts, const int *tris, int ntris, const ObBvNode *nodes, const unsigned char *useflags /* [ntris] or null */, int device, ObMeshDev *io);
 void obk_mesh_free(ObMeshDev *m);
 int obk_sync(ObBackend *);
 // bulk body-state I/O in API order ([world][creation-index body]); nbody[w] = bodies in world w.

@@ -764,7 +764,7 @@ int obk_collide2(ObBackend *b, const ObPose *q, const int *qbody, const uint32_t
   return 0;
 }
 
-int obk_mesh_upload(const float *verts, int nverts, const int *tris, int ntris, const ObBvNode *nodes, int device, ObMeshDev *io) {
+int obk_mesh_upload(const float *verts, int nverts, const int *tris, int ntris, const ObBvNode *nodes, const unsigned char *useflags, int device, ObMeshDev *io) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return -1;
   if (cudaSetDevice(device) != cudaSuccess) return -1;
@@ -774,6 +774,13 @@ int obk_mesh_upload(const float *verts, int nverts, const int *tris, int ntris, 
   if (cudaMalloc((void **)&df, sizeof(int) * vfirst.size()) != cudaSuccess) return -1;
   if (cudaMemcpy(df, vfirst.data(), sizeof(int) * vfirst.size(), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(df); return -1; }
   io->vfirst = df;
+  io->useflags = 0;
+  if (useflags) {
+    unsigned char *du = 0;
+    if (cudaMalloc((void **)&du, (size_t)ntris) != cudaSuccess) return -1;
+    if (cudaMemcpy(du, useflags, (size_t)ntris, cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(du); return -1; }
+    io->useflags = du;
+  }
   if (cudaMalloc((void **)&dv, sizeof(float) * 3 * (size_t)nverts) != cudaSuccess) return -1;
   if (cudaMalloc((void **)&dt, sizeof(int) * 3 * (size_t)ntris) != cudaSuccess) { cudaFree(dv); return -1; }
   if (cudaMalloc((void **)&dn, sizeof(ObBvNode) * (size_t)(ntris - 1)) != cudaSuccess) { cudaFree(dv); cudaFree(dt); return -1; }
@@ -789,7 +796,8 @@ void obk_mesh_free(ObMeshDev *m) {
   if (m->tris) cudaFree((void *)m->tris);
   if (m->nodes) cudaFree((void *)m->nodes);
   if (m->vfirst) cudaFree((void *)m->vfirst);
-  m->verts = 0; m->tris = 0; m->nodes = 0; m->vfirst = 0;
+  if (m->useflags) cudaFree((void *)m->useflags);
+  m->verts = 0; m->tris = 0; m->nodes = 0; m->vfirst = 0; m->useflags = 0;
 }
 
 // Bulk state I/O copies straight between the caller's buffers and the packed device staging

@@ -27,6 +27,7 @@ struct ObMeshDev {     // one dTriMeshData on the execution side
   int nverts, ntris;
   real aabbc[3], aabbe[3];   // model-space AABB centre / extents (collision_trimesh_opcode.cpp:123-157)
   const int *vfirst;   // [nverts] flattened corner index (3*tri + corner) of the vertex's first use, -1 if unused
+  const unsigned char *useflags;   // [ntris] dxTriMeshData::UseFlags (kEdge0..2 = 1,2,4; kVert0..2 = 8,16,32), null = kUseAll
 };
 
 #define OB_BV_STACK 96

@@ -17,6 +17,7 @@
 // on the host exactly where the reference does it; the per-step queries run on the GPU (ob_trimesh.h).
 #include <float.h>
 #include <string.h>
+#include <algorithm>
 #include <vector>
 #include "ob_backend.h"
 #include "ob_host.h"
@@ -90,6 +91,7 @@ static int build_common(dxTriMeshData *d, int nverts, int ntris) {
   b.cur = 1;
   b.build(0, b.idx.data(), ntris);
   d->nodes.swap(b.nodes);
+  d->useflags.clear();
   for (size_t i = 0; i < d->dev.size(); i++) obk_mesh_free(&d->dev[i].m);
   d->dev.clear();
   return 0;
@@ -102,7 +104,7 @@ const ObMeshDev *ob_trimesh_device(dxTriMeshData *d, int device) {
   c.device = device;
   memset(&c.m, 0, sizeof c.m);
   for (int k = 0; k < 3; k++) { c.m.aabbc[k] = d->aabbc[k]; c.m.aabbe[k] = d->aabbe[k]; }
-  if (obk_mesh_upload(d->verts.data(), d->nverts, d->tris.data(), d->ntris, d->nodes.data(), device, &c.m)) return 0;
+  if (obk_mesh_upload(d->verts.data(), d->nverts, d->tris.data(), d->ntris, d->nodes.data(), d->useflags.empty() ? 0 : d->useflags.data(), device, &c.m)) return 0;
   d->dev.push_back(c);
   return &d->dev.back().m;
 }
@@ -173,7 +175,65 @@ void dGeomTriMeshDataBuildSimple(dTriMeshDataID d, const dReal *Vertices, int Ve
   dGeomTriMeshDataBuildDouble(d, Vertices, 4 * sizeof(dReal), VertexCount, Indices, IndexCount, 3 * sizeof(dTriIndex));
 #endif
 }
-void dGeomTriMeshDataPreprocess(dTriMeshDataID) {}   // edge/vertex use flags: only read by the capsule collider
+// dxTriMeshData::Preprocess (collision_trimesh_opcode.cpp:256-363): per triangle, which edges and vertices the
+// capsule collider should test.  Edges shared by two triangles are paired after sorting (the reference's qsort
+// on (VertIdx1, VertIdx2); glibc's is a stable merge sort, so equal records keep their order); convex and
+// boundary edges mark their edge + vertices, and finally every vertex of a concave edge is cleared wherever it
+// is used (done here with a vertex set instead of the reference's all-pairs loop: same result).
+void dGeomTriMeshDataPreprocess(dTriMeshDataID d) {
+  if (!d || !d->useflags.empty() || d->ntris <= 0) return;
+  struct Edge { int v1, v2, tri; unsigned char ef, f1, f2; bool concave; };
+  const int nt = d->ntris, ne = 3 * nt;
+  std::vector<Edge> rec(ne);
+  static const unsigned char EF[3] = {1, 2, 4}, VF[3] = {8, 16, 32};
+  for (int t = 0; t < nt; t++)
+    for (int e = 0; e < 3; e++) {
+      Edge &r = rec[3 * t + e];
+      r.ef = EF[e]; r.f1 = VF[e]; r.f2 = VF[(e + 1) % 3];
+      r.v1 = d->tris[3 * (size_t)t + e]; r.v2 = d->tris[3 * (size_t)t + (e + 1) % 3];
+      if (r.v1 > r.v2) { int tv = r.v1; r.v1 = r.v2; r.v2 = tv; unsigned char tf = r.f1; r.f1 = r.f2; r.f2 = tf; }
+      r.tri = t; r.concave = false;
+    }
+  std::stable_sort(rec.begin(), rec.end(), [](const Edge &a, const Edge &b) { return a.v1 == b.v1 ? a.v2 < b.v2 : a.v1 < b.v1; });
+  d->useflags.assign(nt, 0);
+  auto vert = [&](int tri, int k) { return d->verts.data() + 3 * (size_t)d->tris[3 * (size_t)tri + k]; };
+  auto opposite = [&](const Edge &r) {   // GetOppositeVert
+    if ((r.f1 == 8 && r.f2 == 16) || (r.f1 == 16 && r.f2 == 8)) return vert(r.tri, 2);
+    if ((r.f1 == 16 && r.f2 == 32) || (r.f1 == 32 && r.f2 == 16)) return vert(r.tri, 0);
+    return vert(r.tri, 1);
+  };
+  for (int i = 0; i < ne; i++) {
+    Edge &r1 = rec[i];
+    if (i < ne - 1 && r1.v1 == rec[i + 1].v1 && r1.v2 == rec[i + 1].v2) {
+      const Edge &r2 = rec[i + 1];
+      const float *p0 = vert(r1.tri, 0), *p1 = vert(r1.tri, 1), *p2 = vert(r1.tri, 2);
+      const float a[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]}, b[3] = {p0[0] - p1[0], p0[1] - p1[1], p0[2] - p1[2]};
+      float n[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+      float M = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
+      if (M) { M = 1.0f / sqrtf(M); n[0] *= M; n[1] *= M; n[2] *= M; }
+      const float *o1 = opposite(r1), *o2 = opposite(r2);
+      float dv[3] = {o2[0] - o1[0], o2[1] - o1[1], o2[2] - o1[2]};
+      float M2 = dv[0] * dv[0] + dv[1] * dv[1] + dv[2] * dv[2];
+      if (M2) { M2 = 1.0f / sqrtf(M2); dv[0] *= M2; dv[1] *= M2; dv[2] *= M2; }
+      const float dot = n[0] * dv[0] + n[1] * dv[1] + n[2] * dv[2];
+      if (dot >= -0.000001f) r1.concave = true;
+      else d->useflags[r1.tri] |= r1.f1 | r1.f2 | r1.ef;
+      i++;
+    } else {
+      d->useflags[r1.tri] |= r1.f1 | r1.f2 | r1.ef;
+    }
+  }
+  std::vector<char> cv(d->nverts > 0 ? d->nverts : 1, 0);
+  bool any = false;
+  for (int i = 0; i < ne; i++) if (rec[i].concave) { cv[rec[i].v1] = 1; cv[rec[i].v2] = 1; any = true; }
+  if (any)
+    for (int j = 0; j < ne; j++) {
+      if (cv[rec[j].v1]) d->useflags[rec[j].tri] &= (unsigned char)~rec[j].f1;
+      if (cv[rec[j].v2]) d->useflags[rec[j].tri] &= (unsigned char)~rec[j].f2;
+    }
+  for (size_t i = 0; i < d->dev.size(); i++) obk_mesh_free(&d->dev[i].m);   // device copies are rebuilt with the flags
+  d->dev.clear();
+}
 void dGeomTriMeshDataUpdate(dTriMeshDataID) {}
 
 dGeomID dCreateTriMesh(dSpaceID space, dTriMeshDataID Data, dTriCallback *Callback, dTriArrayCallback *ArrayCallback, dTriRayCallback *RayCallback) {

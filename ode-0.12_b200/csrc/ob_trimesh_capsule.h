@@ -6,8 +6,8 @@
 // = LARGEST negative depth), the capsule's axis segment shifted by the radius along the best normal
 // clipped against the triangle plane and its three edge planes (:738-910) -> two contacts per triangle.
 // The local contact list is finally de-duplicated (_OptimizeLocalContacts :238-264) and copied out.
-// Edge / vertex use flags: dGeomTriMeshDataPreprocess is not implemented here, which is the reference's
-// state when the application never calls it (UseFlags == NULL -> kUseAll, :1089).
+// Edge / vertex use flags (dGeomTriMeshDataPreprocess, ob_trimesh_build.cpp) select the axes per triangle;
+// without preprocessing every axis is tested (UseFlags == NULL -> kUseAll, :1089).
 #pragma once
 #include "ob_trimesh_box.h"
 
@@ -77,8 +77,8 @@ OB_HD void ob_cctl_axis(const real *v1, const real *v2, const real *v3, const re
 }
 OB_HD real ob_len2_3(const real *a) { return a[0] * a[0] + a[1] * a[1] + a[2] * a[2]; }
 
-// _cldTestSeparatingAxesOfCapsule :466-735 (use flags = kUseAll)
-OB_HDN bool ob_cctl_separating_axes(ObCctlData &D, const real *v0, const real *v1, const real *v2) {
+// _cldTestSeparatingAxesOfCapsule :466-735; flags = the triangle's use flags (edge e: 1<<e, vertex e: 8<<e)
+OB_HDN bool ob_cctl_separating_axes(ObCctlData &D, const real *v0, const real *v1, const real *v2, unsigned flags) {
   const real hl = D.size * OB_REAL(0.5) - D.radius;
   real vCp0[3], vCp1[3];
   for (int k = 0; k < 3; k++) { vCp0[k] = D.capPos[k] + D.capAxis[k] * hl; vCp1[k] = D.capPos[k] - D.capAxis[k] * hl; }
@@ -92,26 +92,32 @@ OB_HDN bool ob_cctl_separating_axes(ObCctlData &D, const real *v0, const real *v
   const real *E[3] = {D.E0, D.E1, D.E2};
   const real *V[3] = {v0, v1, v2};
   for (int e = 0; e < 3; e++) {   // axes C x E_e
+    if (!(flags & (1u << e))) continue;
     ob_cross(vAxis, D.capAxis, E[e]);
     if (ob_len2_3(vAxis) > fEpsilon) if (!ob_cctl_test_axis(D, vAxis, 2 + e, false)) return false;
   }
   for (int e = 0; e < 3; e++) {   // ((Cp0 - V_e) x E_e) x E_e
+    if (!(flags & (1u << e))) continue;
     ob_cctl_axis(vCp0, V[e], E[e], E[e], vAxis);
     if (ob_len2_3(vAxis) > fEpsilon) if (!ob_cctl_test_axis(D, vAxis, 5 + e, false)) return false;
   }
   for (int e = 0; e < 3; e++) {   // ((Cp1 - V_e) x E_e) x E_e
+    if (!(flags & (1u << e))) continue;
     ob_cctl_axis(vCp1, V[e], E[e], E[e], vAxis);
     if (ob_len2_3(vAxis) > fEpsilon) if (!ob_cctl_test_axis(D, vAxis, 8 + e, false)) return false;
   }
   for (int e = 0; e < 3; e++) {   // ((V_e - Cp0) x C) x C
+    if (!(flags & (8u << e))) continue;
     ob_cctl_axis(V[e], vCp0, D.capAxis, D.capAxis, vAxis);
     if (ob_len2_3(vAxis) > fEpsilon) if (!ob_cctl_test_axis(D, vAxis, 11 + e, false)) return false;
   }
   for (int e = 0; e < 3; e++) {   // V_e - Cp0
+    if (!(flags & (8u << e))) continue;
     vAxis[0] = V[e][0] - vCp0[0]; vAxis[1] = V[e][1] - vCp0[1]; vAxis[2] = V[e][2] - vCp0[2];
     if (ob_len2_3(vAxis) > fEpsilon) if (!ob_cctl_test_axis(D, vAxis, 14 + e, false)) return false;
   }
   for (int e = 0; e < 3; e++) {   // V_e - Cp1
+    if (!(flags & (8u << e))) continue;
     vAxis[0] = V[e][0] - vCp1[0]; vAxis[1] = V[e][1] - vCp1[1]; vAxis[2] = V[e][2] - vCp1[2];
     if (ob_len2_3(vAxis) > fEpsilon) if (!ob_cctl_test_axis(D, vAxis, 17 + e, false)) return false;
   }
@@ -119,7 +125,7 @@ OB_HDN bool ob_cctl_separating_axes(ObCctlData &D, const real *v0, const real *v
 }
 
 // _cldTestOneTriangleVSCapsule :738-910
-OB_HDN void ob_cctl_one_triangle(ObCctlData &D, const real *v0, const real *v1, const real *v2) {
+OB_HDN void ob_cctl_one_triangle(ObCctlData &D, const real *v0, const real *v1, const real *v2, unsigned flags) {
   for (int k = 0; k < 3; k++) { D.E0[k] = v1[k] - v0[k]; D.E1[k] = v2[k] - v1[k]; D.E2[k] = v0[k] - v2[k]; }
   real mE0[3] = {v0[0] - v1[0], v0[1] - v1[1], v0[2] - v1[2]};
   ob_cross(D.N, D.E1, mE0);
@@ -127,7 +133,7 @@ OB_HDN void ob_cctl_one_triangle(ObCctlData &D, const real *v0, const real *v1, 
   const real plDistance = -ob_dot(v0, D.N);
   const real dist = D.N[0] * D.capPos[0] + D.N[1] * D.capPos[1] + D.N[2] * D.capPos[2] + plDistance;
   if (dist < 0) return;   // capsule must be over the positive side of the triangle
-  if (!ob_cctl_separating_axes(D, v0, v1, v2)) return;
+  if (!ob_cctl_separating_axes(D, v0, v1, v2, flags)) return;
   if (D.bestAxis == 0) return;
   const real hl = D.size * OB_REAL(0.5) - D.radius;
   real ct[3], p0[3], p1[3];
@@ -189,7 +195,7 @@ OB_HD int ob_collide_trimesh_capsule(const ObPose &o1, const ObPose &o2, const O
     if (tri < 0) break;
     real dv[3][3];
     ob_fetch_triangle(m, tri, o1.pos, o1.R, dv);
-    ob_cctl_one_triangle(D, dv[0], dv[1], dv[2]);
+    ob_cctl_one_triangle(D, dv[0], dv[1], dv[2], m.useflags ? (unsigned)m.useflags[tri] : 0xFFu);
     for (; ct0 < D.ct; ct0++) D.ltri[ct0] = tri;
     if (D.ct >= maxc) break;
   }

@@ -8,6 +8,7 @@ struct dxTriMeshData {
   std::vector<float> verts;      // [nverts*3] as OPCODE sees them (float)
   std::vector<int> tris;         // [ntris*3]
   std::vector<ObBvNode> nodes;   // [ntris-1] no-leaf tree, root = 0
+  std::vector<unsigned char> useflags;   // [ntris] edge / vertex use flags (dGeomTriMeshDataPreprocess), empty = never preprocessed
   int nverts, ntris;
   dReal aabbc[3], aabbe[3];
   struct DevCopy { int device; ObMeshDev m; };

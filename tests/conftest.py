@@ -26,6 +26,7 @@ GOLDEN = [  # (file stem, scene, steps, worlds, settle) — must match tests/gol
     ("buggy_terrain_w2_settle90", "buggy_terrain", 30, 2, 90),
     ("terrain_capsules_settle70", "terrain_capsules", 20, 1, 70),
     ("terrain_plane_settle60", "terrain_plane", 20, 1, 60),
+    ("terrain_capsules_pre_settle70", "terrain_capsules_pre", 20, 1, 70),   # dGeomTriMeshDataPreprocess: edge / vertex use flags
     ("sliders_settle60", "sliders", 30, 1, 60),
     ("universals_settle60", "universals", 30, 1, 60),
 ]

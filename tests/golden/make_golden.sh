@@ -25,6 +25,7 @@ for p in single double; do
   $d --scene buggy_terrain --steps 30 --settle 90 --worlds 2 --out tests/golden/buggy_terrain_w2_settle90_$p.trace
   $d --scene terrain_capsules --steps 20 --settle 70 --out tests/golden/terrain_capsules_settle70_$p.trace
   $d --scene terrain_plane --steps 20 --settle 60 --out tests/golden/terrain_plane_settle60_$p.trace
+  $d --scene terrain_capsules_pre --steps 20 --settle 70 --out tests/golden/terrain_capsules_pre_settle70_$p.trace
   $d --scene sliders --steps 30 --settle 60 --out tests/golden/sliders_settle60_$p.trace
   $d --scene universals --steps 30 --settle 60 --out tests/golden/universals_settle60_$p.trace
   # drop-in (callback) path only: ray colliders + capsule-trimesh

@@ -440,12 +440,12 @@ static inline void scene_ragdoll(SceneWorld &sw, int w) {
 // ---- trimesh scenes ---------------------------------------------------------------------------
 // One shared dTriMeshData per (n, spacing) in the process, like config 3's shared terrain: an n x n
 // vertex grid, two triangles per cell, height = amp*sin(fx*x)*cos(fy*y) + noise (hashed per vertex).
-struct SceneTerrain { int n; double spacing; dTriMeshDataID data; std::vector<float> verts; std::vector<dTriIndex> idx; };
-static inline dTriMeshDataID scene_terrain_data(int n, double spacing, double amp, double fx, double fy, double noise) {
+struct SceneTerrain { int n; double spacing; int pre; dTriMeshDataID data; std::vector<float> verts; std::vector<dTriIndex> idx; };
+static inline dTriMeshDataID scene_terrain_data(int n, double spacing, double amp, double fx, double fy, double noise, int preprocess = 0) {
   static std::vector<SceneTerrain *> cache;
-  for (size_t i = 0; i < cache.size(); i++) if (cache[i]->n == n && cache[i]->spacing == spacing) return cache[i]->data;
+  for (size_t i = 0; i < cache.size(); i++) if (cache[i]->n == n && cache[i]->spacing == spacing && cache[i]->pre == preprocess) return cache[i]->data;
   SceneTerrain *t = new SceneTerrain;
-  t->n = n; t->spacing = spacing;
+  t->n = n; t->spacing = spacing; t->pre = preprocess;
   xs32 rng(7);
   const double half = 0.5 * (n - 1) * spacing;
   for (int j = 0; j < n; j++)
@@ -462,6 +462,7 @@ static inline dTriMeshDataID scene_terrain_data(int n, double spacing, double am
     }
   t->data = dGeomTriMeshDataCreate();
   dGeomTriMeshDataBuildSingle(t->data, t->verts.data(), 3 * sizeof(float), n * n, t->idx.data(), (int)t->idx.size(), 3 * sizeof(dTriIndex));
+  if (preprocess) dGeomTriMeshDataPreprocess(t->data);   // edge / vertex use flags for the capsule collider
   cache.push_back(t);
   return t->data;
 }
@@ -499,11 +500,11 @@ static inline void scene_terrain_boxes(SceneWorld &sw, int w) {
 }
 
 // capsules (and a few boxes) tumbling on the terrain mesh: dCollideCCTL (collision_trimesh_ccylinder.cpp)
-static inline void scene_terrain_capsules(SceneWorld &sw, int w) {
+static inline void scene_terrain_capsules(SceneWorld &sw, int w, int preprocess) {
   scene_world_base(sw, w);
   xs32 rng(sw.seed ^ 0xCA95E5u);
   scene_add_geom(sw, dCreatePlane(sw.space, 0, 0, 1, (dReal)-3));
-  dGeomID mesh = scene_add_geom(sw, dCreateTriMesh(sw.space, scene_terrain_data(25, 0.5, 0.45, 0.9, 0.7, 0.12), 0, 0, 0));
+  dGeomID mesh = scene_add_geom(sw, dCreateTriMesh(sw.space, scene_terrain_data(25, 0.5, 0.45, 0.9, 0.7, 0.12, preprocess), 0, 0, 0));
   dMatrix3 R;
   dRFromAxisAndAngle(R, (dReal)-0.1, (dReal)0.15, 1, (dReal)-0.5);
   dGeomSetRotation(mesh, R);
@@ -687,7 +688,8 @@ static inline int scene_build(const char *name_in, SceneWorld &sw, int w, SceneP
   if (!strcmp(name, "buggy_terrain256")) { scene_buggy_terrain(sw, w, 256); pol = policy_buggy(); pol.max_contacts = 10; return 0; }
   if (!strcmp(name, "terrain_boxes")) { scene_terrain_boxes(sw, w); return 0; }
   if (!strcmp(name, "terrain_plane")) { scene_terrain_plane(sw, w); return 0; }
-  if (!strcmp(name, "terrain_capsules")) { scene_terrain_capsules(sw, w); return 0; }
+  if (!strcmp(name, "terrain_capsules")) { scene_terrain_capsules(sw, w, 0); return 0; }
+  if (!strcmp(name, "terrain_capsules_pre")) { scene_terrain_capsules(sw, w, 1); return 0; }
   if (!strcmp(name, "terrain_spheres")) { scene_terrain_spheres(sw, w); return 0; }
   if (!strcmp(name, "capsmix")) { scene_capsmix(sw, w); return 0; }
   if (!strcmp(name, "raycast")) { scene_raycast(sw, w, 0); return 0; }

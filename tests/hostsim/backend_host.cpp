@@ -609,7 +609,7 @@ int obk_collide2(ObBackend *b, const ObPose *q, const int *qbody, const uint32_t
     }
   return 0;
 }
-int obk_mesh_upload(const float *verts, int nverts, const int *tris, int ntris, const ObBvNode *nodes, int, ObMeshDev *io) {
+int obk_mesh_upload(const float *verts, int nverts, const int *tris, int ntris, const ObBvNode *nodes, const unsigned char *useflags, int, ObMeshDev *io) {
   float *v = (float *)malloc(sizeof(float) * 3 * (size_t)nverts);
   int *t = (int *)malloc(sizeof(int) * 3 * (size_t)ntris);
   ObBvNode *n = (ObBvNode *)malloc(sizeof(ObBvNode) * (size_t)(ntris - 1));
@@ -620,9 +620,11 @@ int obk_mesh_upload(const float *verts, int nverts, const int *tris, int ntris, 
   for (int i = 0; i < nverts; i++) vf[i] = -1;
   for (int c = 0; c < 3 * ntris; c++) { const int vi = tris[c]; if (vi >= 0 && vi < nverts && vf[vi] < 0) vf[vi] = c; }
   io->verts = v; io->tris = t; io->nodes = n; io->nverts = nverts; io->ntris = ntris; io->vfirst = vf;
+  io->useflags = 0;
+  if (useflags) { unsigned char *u = (unsigned char *)malloc((size_t)ntris); memcpy(u, useflags, (size_t)ntris); io->useflags = u; }
   return 0;
 }
-void obk_mesh_free(ObMeshDev *m) { free((void *)m->verts); free((void *)m->tris); free((void *)m->nodes); free((void *)m->vfirst); m->verts = 0; m->tris = 0; m->nodes = 0; m->vfirst = 0; }
+void obk_mesh_free(ObMeshDev *m) { free((void *)m->verts); free((void *)m->tris); free((void *)m->nodes); free((void *)m->vfirst); free((void *)m->useflags); m->useflags = 0; m->verts = 0; m->tris = 0; m->nodes = 0; m->vfirst = 0; }
 int obk_step(ObBackend *b, real h, int nsteps, int taps, char *err, size_t errlen) {
   ObBatchDev &d = b->d;
   if (d.large) {
