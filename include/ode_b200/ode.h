@@ -160,6 +160,8 @@ typedef struct dContact {
 } dContact;
 
 /* common.h:368-373 */
+enum { dAMotorUser = 0, dAMotorEuler = 1 };   /* include/ode/common.h:261-264 */
+
 typedef struct dJointFeedback {
   dVector3 f1, t1, f2, t2;
 } dJointFeedback;
@@ -308,7 +310,9 @@ dJointID dJointCreateHinge(dWorldID, dJointGroupID);
 dJointID dJointCreateHinge2(dWorldID, dJointGroupID);
 dJointID dJointCreateSlider(dWorldID, dJointGroupID);   /* include/ode/objects.h:1571, ode/src/joints/slider.cpp */
 dJointID dJointCreateUniversal(dWorldID, dJointGroupID);   /* include/ode/objects.h:1592, ode/src/joints/universal.cpp */
-dJointID dJointCreateFixed(dWorldID, dJointGroupID);    /* include/ode/objects.h:1616, ode/src/joints/fixed.cpp */
+dJointID dJointCreateFixed(dWorldID, dJointGroupID);
+dJointID dJointCreateAMotor(dWorldID, dJointGroupID);   /* include/ode/objects.h:1634, ode/src/joints/amotor.cpp */
+dJointID dJointCreateLMotor(dWorldID, dJointGroupID);   /* include/ode/objects.h:1643, ode/src/joints/lmotor.cpp */    /* include/ode/objects.h:1616, ode/src/joints/fixed.cpp */
 void dJointDestroy(dJointID);
 void dJointAttach(dJointID, dBodyID body1, dBodyID body2);
 void dJointEnable(dJointID);
@@ -338,6 +342,23 @@ dReal dJointGetUniversalParam(dJointID, int parameter);
 void dJointGetUniversalAngles(dJointID, dReal *angle1, dReal *angle2);
 dReal dJointGetUniversalAngle1(dJointID);
 dReal dJointGetUniversalAngle2(dJointID);
+void dJointSetAMotorNumAxes(dJointID, int num);
+void dJointSetAMotorAxis(dJointID, int anum, int rel, dReal x, dReal y, dReal z);
+void dJointSetAMotorAngle(dJointID, int anum, dReal angle);
+void dJointSetAMotorParam(dJointID, int parameter, dReal value);
+void dJointSetAMotorMode(dJointID, int mode);
+int dJointGetAMotorNumAxes(dJointID);
+void dJointGetAMotorAxis(dJointID, int anum, dVector3 result);
+int dJointGetAMotorAxisRel(dJointID, int anum);
+dReal dJointGetAMotorAngle(dJointID, int anum);
+dReal dJointGetAMotorParam(dJointID, int parameter);
+int dJointGetAMotorMode(dJointID);
+void dJointSetLMotorNumAxes(dJointID, int num);
+void dJointSetLMotorAxis(dJointID, int anum, int rel, dReal x, dReal y, dReal z);
+void dJointSetLMotorParam(dJointID, int parameter, dReal value);
+int dJointGetLMotorNumAxes(dJointID);
+void dJointGetLMotorAxis(dJointID, int anum, dVector3 result);
+dReal dJointGetLMotorParam(dJointID, int parameter);
 void dJointSetFixed(dJointID);
 void dJointSetFixedParam(dJointID, int parameter, dReal value);
 dReal dJointGetFixedParam(dJointID, int parameter);

@@ -455,7 +455,7 @@ ObBackend *obk_create(const ObBatchDev &caps, int device, char *err, size_t errl
   CK(dalloc(b, &d.isz, W * d.NB * 4));
   CK(dalloc(b, &d.jrow, W * (d.NC + d.NJ + 1)));
   CK(dalloc(b, &d.ijoint, W * (d.NC + d.NJ)));
-  CK(dalloc(b, &d.jside, W * (d.NJ ? d.NJ : 1) * 8));
+  CK(dalloc(b, &d.jside, W * (d.NJ ? d.NJ : 1) * 4 * OB_NSIDE));
   CK(dalloc(b, &d.sched, W * d.NEP * d.NR));
   CK(dalloc(b, &d.pstart, W * d.NEP * (d.NR + 1)));
   CK(dalloc(b, &d.invIw, W * d.NB * 12));

@@ -56,6 +56,12 @@ void ob_marshal_joint(const dxJoint *j, ObJoint &d) {
   d.erp = j->erp; d.cfm = j->cfm; d.susp_erp = j->susp_erp; d.susp_cfm = j->susp_cfm; d.c0 = j->c0; d.s0 = j->s0;
   fill_limot(d.limot1, j->limot);
   fill_limot(d.limot2, j->limot2);
+  fill_limot(d.limot3, j->limot3);
+  if (j->type == dJointTypeAMotor || j->type == dJointTypeLMotor) {
+    d.flags |= (j->num << 8) | ((j->mode == dAMotorEuler ? 1 : 0) << 12) | (j->rel[0] << 16) | (j->rel[1] << 20) | (j->rel[2] << 24);
+    for (int k = 0; k < 3; k++) { d.anchor1[k] = j->axis3[k]; d.anchor2[k] = j->reference1[k]; d.v1[k] = j->reference2[k]; d.qrel[k] = j->angle[k]; }
+    d.qrel[3] = 0;
+  }
 }
 
 void ob_marshal_geom(dxGeom *g, ObGeom &d) {
@@ -193,7 +199,7 @@ dxBatch *ob_batch_create(int nworlds, const dWorldID *worlds, const dSpaceID *sp
         if (dropin) continue;
         ob_set_last_error("dBatchCreate: world %d: contact joints present at bind time (call dJointGroupEmpty first)", w); delete B; return 0;
       }
-      if (j->type != dJointTypeBall && j->type != dJointTypeHinge && j->type != dJointTypeHinge2 && j->type != dJointTypeSlider && j->type != dJointTypeFixed && j->type != dJointTypeUniversal) { ob_set_last_error("dBatchCreate: world %d: unsupported joint type %d", w, j->type); delete B; return 0; }
+      if (j->type != dJointTypeBall && j->type != dJointTypeHinge && j->type != dJointTypeHinge2 && j->type != dJointTypeSlider && j->type != dJointTypeFixed && j->type != dJointTypeUniversal && j->type != dJointTypeAMotor && j->type != dJointTypeLMotor) { ob_set_last_error("dBatchCreate: world %d: unsupported joint type %d", w, j->type); delete B; return 0; }
       B->joints[w].push_back(j);
     }
     std::reverse(B->joints[w].begin(), B->joints[w].end());

@@ -614,6 +614,8 @@ dJointID dJointCreateHinge2(dWorldID w, dJointGroupID g) { return create_joint(w
 dJointID dJointCreateSlider(dWorldID w, dJointGroupID g) { return create_joint(w, g, dJointTypeSlider); }
 dJointID dJointCreateFixed(dWorldID w, dJointGroupID g) { return create_joint(w, g, dJointTypeFixed); }
 dJointID dJointCreateUniversal(dWorldID w, dJointGroupID g) { return create_joint(w, g, dJointTypeUniversal); }
+dJointID dJointCreateAMotor(dWorldID w, dJointGroupID g) { return create_joint(w, g, dJointTypeAMotor); }
+dJointID dJointCreateLMotor(dWorldID w, dJointGroupID g) { return create_joint(w, g, dJointTypeLMotor); }
 static void joint_free(dxJoint *j) {
   if (j->world) {
     joint_unlink_bodies(j);

@@ -90,6 +90,11 @@ struct dxJoint {
   dReal susp_erp, susp_cfm;     // hinge2
   dVector3 offset;              // slider / fixed: centre of body 1 w.r.t. body 2 (slider.cpp computeOffset, fixed.cpp dJointSetFixed)
   dQuaternion qrel2;            // universal: second initial relative rotation (qrel = qrel1)
+  // amotor / lmotor: axes are axis1, axis2, axis3
+  int num, mode, rel[3];
+  dVector3 axis3, reference1, reference2;
+  dxLimot limot3;
+  dReal angle[3];
 };
 
 struct dxJointGroup {

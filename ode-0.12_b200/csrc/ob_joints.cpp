@@ -69,6 +69,11 @@ void ob_joint_init_type(dxJoint *j) {
       j->axis1[0] = 1; j->axis2[1] = 1;
       limot_init(j->limot, w); limot_init(j->limot2, w);
       break;
+    case dJointTypeAMotor:
+    case dJointTypeLMotor:
+      j->num = 0; j->mode = dAMotorUser;
+      limot_init(j->limot, w); limot_init(j->limot2, w); limot_init(j->limot3, w);
+      break;
     default: break;
   }
 }
@@ -416,6 +421,66 @@ void dJointGetUniversalAngles(dJointID j, dReal *angle1, dReal *angle2) {
 }
 dReal dJointGetUniversalAngle1(dJointID j) { dReal a, b; dJointGetUniversalAngles(j, &a, &b); return a; }
 dReal dJointGetUniversalAngle2(dJointID j) { dReal a, b; dJointGetUniversalAngles(j, &a, &b); return b; }
+}  // extern "C"
+
+// ---- amotor (amotor.cpp) and lmotor (lmotor.cpp) -----------------------------------------------------------
+static dReal *motor_axis(dxJoint *j, int anum) { return anum == 0 ? j->axis1 : (anum == 1 ? j->axis2 : j->axis3); }
+static dxLimot &motor_limot(dxJoint *j, int anum) { return anum == 0 ? j->limot : (anum == 1 ? j->limot2 : j->limot3); }
+static void amotor_set_euler_reference(dxJoint *j) {   // setEulerReferenceVectors :128-158
+  if (j->node[0].body && j->node[1].body) {
+    dReal r[4];
+    ob_mul0_331(r, j->node[1].body->R, j->axis3);
+    ob_mul1_331(j->reference1, j->node[0].body->R, r);
+    ob_mul0_331(r, j->node[0].body->R, j->axis1);
+    ob_mul1_331(j->reference2, j->node[1].body->R, r);
+  } else if (j->node[0].body) {
+    dReal r[4] = {j->axis3[0], j->axis3[1], j->axis3[2], j->axis3[3]};
+    ob_mul1_331(j->reference1, j->node[0].body->R, r);
+    ob_mul0_331(r, j->node[0].body->R, j->axis1);
+    j->reference2[0] += r[0]; j->reference2[1] += r[1]; j->reference2[2] += r[2];   // sic
+  }
+}
+static void motor_set_axis(dxJoint *j, int anum, int rel, dReal x, dReal y, dReal z, bool amotor) {
+  if (anum < 0) anum = 0;
+  if (anum > 2) anum = 2;
+  if (!j->node[1].body && rel == 2) rel = 1;
+  j->rel[anum] = rel;
+  dReal r[4] = {x, y, z, 0};
+  dReal *axis = motor_axis(j, anum);
+  if (rel > 0) {
+    if (rel == 1) ob_mul1_331(axis, j->node[0].body->R, r);
+    else if (j->node[1].body) ob_mul1_331(axis, j->node[1].body->R, r);
+    else { axis[0] = r[0]; axis[1] = r[1]; axis[2] = r[2]; axis[3] = r[3]; }
+  } else { axis[0] = r[0]; axis[1] = r[1]; axis[2] = r[2]; }
+  ob_safe_normalize3(axis);
+  if (amotor && j->mode == dAMotorEuler) amotor_set_euler_reference(j);
+}
+static void motor_get_axis(dxJoint *j, int anum, dReal *result) {
+  if (anum < 0) anum = 0;
+  if (anum > 2) anum = 2;
+  const dReal *axis = motor_axis(j, anum);
+  if (j->rel[anum] == 1) ob_mul0_331(result, j->node[0].body->R, axis);
+  else if (j->rel[anum] == 2 && j->node[1].body) ob_mul0_331(result, j->node[1].body->R, axis);
+  else { result[0] = axis[0]; result[1] = axis[1]; result[2] = axis[2]; }
+}
+extern "C" {
+void dJointSetAMotorNumAxes(dJointID j, int num) { if (j->mode == dAMotorEuler) j->num = 3; else j->num = num < 0 ? 0 : (num > 3 ? 3 : num); }
+void dJointSetAMotorAxis(dJointID j, int anum, int rel, dReal x, dReal y, dReal z) { motor_set_axis(j, anum, rel, x, y, z, true); }
+void dJointSetAMotorAngle(dJointID j, int anum, dReal angle) { if (j->mode == dAMotorUser) { if (anum < 0) anum = 0; if (anum > 2) anum = 2; j->angle[anum] = angle; } }
+void dJointSetAMotorParam(dJointID j, int parameter, dReal value) { int anum = parameter >> 8; if (anum < 0) anum = 0; if (anum > 2) anum = 2; limot_set(motor_limot(j, anum), parameter & 0xff, value); }
+void dJointSetAMotorMode(dJointID j, int mode) { j->mode = mode; if (mode == dAMotorEuler) { j->num = 3; amotor_set_euler_reference(j); } }
+int dJointGetAMotorNumAxes(dJointID j) { return j->num; }
+void dJointGetAMotorAxis(dJointID j, int anum, dVector3 result) { motor_get_axis(j, anum, result); }
+int dJointGetAMotorAxisRel(dJointID j, int anum) { if (anum < 0) anum = 0; if (anum > 2) anum = 2; return j->rel[anum]; }
+dReal dJointGetAMotorAngle(dJointID j, int anum) { if (anum < 0) anum = 0; if (anum > 2) anum = 2; return j->angle[anum]; }
+dReal dJointGetAMotorParam(dJointID j, int parameter) { int anum = parameter >> 8; if (anum < 0) anum = 0; if (anum > 2) anum = 2; return limot_get(motor_limot(j, anum), parameter & 0xff); }
+int dJointGetAMotorMode(dJointID j) { return j->mode; }
+void dJointSetLMotorNumAxes(dJointID j, int num) { j->num = num < 0 ? 0 : (num > 3 ? 3 : num); }
+void dJointSetLMotorAxis(dJointID j, int anum, int rel, dReal x, dReal y, dReal z) { motor_set_axis(j, anum, rel, x, y, z, false); }
+void dJointSetLMotorParam(dJointID j, int parameter, dReal value) { int anum = parameter >> 8; if (anum < 0) anum = 0; if (anum > 2) anum = 2; limot_set(motor_limot(j, anum), parameter & 0xff, value); }
+int dJointGetLMotorNumAxes(dJointID j) { return j->num; }
+void dJointGetLMotorAxis(dJointID j, int anum, dVector3 result) { if (anum < 0) anum = 0; if (anum > 2) anum = 2; const dReal *a = motor_axis(j, anum); result[0] = a[0]; result[1] = a[1]; result[2] = a[2]; }
+dReal dJointGetLMotorParam(dJointID j, int parameter) { int anum = parameter >> 8; if (anum < 0) anum = 0; if (anum > 2) anum = 2; return limot_get(motor_limot(j, anum), parameter & 0xff); }
 }  // extern "C"
 
 // setRelativeValues, called from dJointAttach (ball.cpp, hinge.cpp, hinge2.cpp)

@@ -203,6 +203,39 @@ OB_HD real ob_slider_position(const ObJoint &j, const ObBodyView &B1, const ObBo
   return ob_dot(ax1, q);
 }
 
+// dxJointAMotor::computeGlobalAxes / computeEulerAngles (amotor.cpp:51-126); lmotor.cpp:44-66 is the non-Euler branch
+OB_HD void ob_motor_axis(const ObJoint &j, int i, const real *axis, const ObBodyView &B1, const ObBodyView *B2, real *out) {
+  const int rel = OB_JM_REL(j.flags, i);
+  if (rel == 1) ob_mul0_331(out, B1.R, axis);
+  else if (rel == 2) { if (B2) ob_mul0_331(out, B2->R, axis); else { out[0] = 0; out[1] = 0; out[2] = 0; } }   // reference: left uninitialised
+  else { out[0] = axis[0]; out[1] = axis[1]; out[2] = axis[2]; }
+}
+OB_HD void ob_amotor_axes(const ObJoint &j, const ObBodyView &B1, const ObBodyView *B2, real ax[3][3]) {
+  if (OB_JM_MODE(j.flags) == 1) {
+    ob_mul0_331(ax[0], B1.R, j.axis1);
+    if (B2) ob_mul0_331(ax[2], B2->R, j.anchor1);
+    else { ax[2][0] = j.anchor1[0]; ax[2][1] = j.anchor1[1]; ax[2][2] = j.anchor1[2]; }
+    ob_cross(ax[1], ax[2], ax[0]);
+    ob_safe_normalize3(ax[1]);
+  } else {
+    const int num = OB_JM_NUM(j.flags);
+    const real *axs[3] = {j.axis1, j.axis2, j.anchor1};
+    for (int i = 0; i < 3; i++) { ax[i][0] = ax[i][1] = ax[i][2] = 0; if (i < num) ob_motor_axis(j, i, axs[i], B1, B2, ax[i]); }
+  }
+}
+OB_HD void ob_amotor_euler_angles(const ObJoint &j, const ObBodyView &B1, const ObBodyView *B2, real ax[3][3], real *angle) {
+  real ref1[3], ref2[3], q[3];
+  ob_mul0_331(ref1, B1.R, j.anchor2);
+  if (B2) ob_mul0_331(ref2, B2->R, j.v1);
+  else { ref2[0] = j.v1[0]; ref2[1] = j.v1[1]; ref2[2] = j.v1[2]; }
+  ob_cross(q, ax[0], ref1);
+  angle[0] = -ob_atan2(ob_dot(ax[2], q), ob_dot(ax[2], ref1));
+  ob_cross(q, ax[0], ax[1]);
+  angle[1] = -ob_atan2(ob_dot(ax[2], ax[0]), ob_dot(ax[2], q));
+  ob_cross(q, ax[1], ax[2]);
+  angle[2] = -ob_atan2(ob_dot(ref2, ax[1]), ob_dot(ref2, q));
+}
+
 // getInfo1 for permanent joints; mutates limot.limit / limit_err like the reference
 OB_HD int ob_joint_info1(ObJoint &j, const ObBodyView &B1, const ObBodyView *B2) {
   if (j.type == OB_JOINT_BALL) return 3;
@@ -215,6 +248,27 @@ OB_HD int ob_joint_info1(ObJoint &j, const ObBodyView &B1, const ObBodyView *B2)
     return m;
   }
   if (j.type == OB_JOINT_FIXED) return 6;
+  if (j.type == OB_JOINT_LMOTOR) {   // lmotor.cpp:75-86
+    int m = 0;
+    const int num = OB_JM_NUM(j.flags);
+    if (num > 0 && j.limot1.fmax > 0) m++;
+    if (num > 1 && j.limot2.fmax > 0) m++;
+    if (num > 2 && j.limot3.fmax > 0) m++;
+    return m;
+  }
+  if (j.type == OB_JOINT_AMOTOR) {   // amotor.cpp:150-172
+    const int num = OB_JM_NUM(j.flags);
+    real angle[3] = {j.qrel[0], j.qrel[1], j.qrel[2]};
+    if (OB_JM_MODE(j.flags) == 1 /* dAMotorEuler */) {
+      real ax[3][3];
+      ob_amotor_axes(j, B1, B2, ax);
+      ob_amotor_euler_angles(j, B1, B2, ax, angle);
+    }
+    int m = 0;
+    ObLimot *lm[3] = {&j.limot1, &j.limot2, &j.limot3};
+    for (int i = 0; i < num; i++) if (ob_limot_test_limit(*lm[i], angle[i]) || lm[i]->fmax > 0) m++;
+    return m;
+  }
   if (j.type == OB_JOINT_UNIVERSAL) {   // universal.cpp:265-292
     int m = 4;
     const bool limiting1 = ((double)j.limot1.lostop >= -OB_PI || (double)j.limot1.histop <= OB_PI) && j.limot1.lostop <= j.limot1.histop;
@@ -420,7 +474,7 @@ OB_HD void ob_set_fixed_orientation(RO &r, int start_row, const real *qrel, cons
 // order the reference applies them.  side[k] = {fm, v[3]}: rotational limots (hinge, hinge2, universal):
 // torque -fm*v on body 1, +fm*v on body 2; slider: side[0] = force (-fm*ax1 / +fm*ax1), side[1] = the
 // decoupling torque, -fm*ltd on BOTH bodies.
-OB_HD void ob_apply_joint_side(int jtype, const real side[2][4], real *facc1, real *tacc1, real *facc2, real *tacc2) {
+OB_HD void ob_apply_joint_side(int jtype, const real side[OB_NSIDE][4], real *facc1, real *tacc1, real *facc2, real *tacc2) {
   if (jtype == OB_JOINT_SLIDER) {
     const real fm = side[0][0];
     if (fm != 0) {
@@ -433,7 +487,7 @@ OB_HD void ob_apply_joint_side(int jtype, const real side[2][4], real *facc1, re
     }
     return;
   }
-  for (int sx = 0; sx < 2; sx++) {
+  for (int sx = 0; sx < OB_NSIDE; sx++) {
     const real fm = side[sx][0];
     if (fm != 0) {
       for (int e = 0; e < 3; e++) tacc1[e] += -fm * side[sx][1 + e];
@@ -448,8 +502,8 @@ OB_HD void ob_apply_joint_side(int jtype, const real side[2][4], real *facc1, re
 // to the bodies' tacc before the rhs is formed: tacc1 += -fm*ax, tacc2 += fm*ax.
 template <class RO>
 OB_HD void ob_joint_info2(RO &r, const ObJoint &j, const ObBodyView &B1, const ObBodyView *B2, real fps,
-                          real *erp_io, real side[2][4]) {
-  side[0][0] = 0; side[1][0] = 0;
+                          real *erp_io, real side[OB_NSIDE][4]) {
+  for (int sx = 0; sx < OB_NSIDE; sx++) side[sx][0] = 0;
   if (j.type == OB_JOINT_BALL) {
     *erp_io = j.erp;
     r.cfm[0] = j.cfm; r.cfm[1] = j.cfm; r.cfm[2] = j.cfm;
@@ -490,6 +544,33 @@ OB_HD void ob_joint_info2(RO &r, const ObJoint &j, const ObBodyView &B1, const O
     if (added && fm != 0) { side[0][0] = fm; side[0][1] = ax1[0]; side[0][2] = ax1[1]; side[0][3] = ax1[2]; }
     if (ob_add_limot_rot(r, 4 + added, j.limot2, ax2, B1, B2, fps, &fm) && fm != 0) {
       side[1][0] = fm; side[1][1] = ax2[0]; side[1][2] = ax2[1]; side[1][3] = ax2[2];
+    }
+  } else if (j.type == OB_JOINT_AMOTOR) {   // amotor.cpp:175-206
+    real ax[3][3], c01[3], c12[3];
+    ob_amotor_axes(j, B1, B2, ax);
+    const real *axp[3] = {ax[0], ax[1], ax[2]};
+    if (OB_JM_MODE(j.flags) == 1) {
+      ob_cross(c01, ax[0], ax[1]); axp[2] = c01;
+      ob_cross(c12, ax[1], ax[2]); axp[0] = c12;
+    }
+    const ObLimot *lm[3] = {&j.limot1, &j.limot2, &j.limot3};
+    const int num = OB_JM_NUM(j.flags);
+    int row = 0;
+    for (int i = 0; i < num; i++) {
+      real fm;
+      const int added = ob_add_limot_rot(r, row, *lm[i], axp[i], B1, B2, fps, &fm);
+      if (added && fm != 0) { side[i][0] = fm; side[i][1] = axp[i][0]; side[i][2] = axp[i][1]; side[i][3] = axp[i][2]; }
+      row += added;
+    }
+  } else if (j.type == OB_JOINT_LMOTOR) {   // lmotor.cpp:89-99 (its limots never reach a limit state: no side effects)
+    const real *axs[3] = {j.axis1, j.axis2, j.anchor1};
+    const ObLimot *lm[3] = {&j.limot1, &j.limot2, &j.limot3};
+    const int num = OB_JM_NUM(j.flags);
+    int row = 0;
+    for (int i = 0; i < num; i++) {
+      real ax[3], fm, ltd[3];
+      ob_motor_axis(j, i, axs[i], B1, B2, ax);
+      row += ob_add_limot_lin(r, row, *lm[i], ax, B1, B2, fps, &fm, ltd);
     }
   } else if (j.type == OB_JOINT_FIXED) {   // fixed.cpp:57-100
     ob_set_fixed_orientation(r, 3, j.qrel, B1, B2, fps, *erp_io);   // uses the erp that was current BEFORE this joint

@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(32) k_prep(ObBatchDev d, real h, int taps) {
     // the row records; motor-at-limit torques (joint.cpp:638-657) are collected and applied below
     unsigned short *g_jrow = d.jrow + (size_t)wc * (d.NC + d.NJ + 1);
     unsigned short *g_ijoint = d.ijoint + (size_t)wc * (d.NC + d.NJ);
-    real *g_side = d.jside + (size_t)wc * (d.NJ ? d.NJ : 1) * 8;
+    real *g_side = d.jside + (size_t)wc * (d.NJ ? d.NJ : 1) * 4 * OB_NSIDE;
     int anyside = 0;
     for (int base = 0; base < nij_max; base += G) {
       const int k = base + gl;
@@ -390,11 +390,11 @@ __global__ void __launch_bounds__(32) k_prep(ObBatchDev d, real h, int taps) {
           const int jm = ob_joint_info1(pj, B1, b2 >= 0 ? &B2 : (const ObBodyView *)0);
           ObRowOut r;
           ob_rows_defaults(r, jm, W.cfm);
-          real side[2][4];
+          real side[OB_NSIDE][4];
           real erp_io = erp_in;
           ob_joint_info2(r, pj, B1, b2 >= 0 ? &B2 : (const ObBodyView *)0, stepsize1, &erp_io, side);
-          for (int sx = 0; sx < 2; sx++) {
-            for (int e = 0; e < 4; e++) g_side[(size_t)(j - nc) * 8 + 4 * sx + e] = side[sx][e];
+          for (int sx = 0; sx < OB_NSIDE; sx++) {
+            for (int e = 0; e < 4; e++) g_side[(size_t)(j - nc) * 4 * OB_NSIDE + 4 * sx + e] = side[sx][e];
             if (side[sx][0] != 0) anyside = 1;
           }
           for (int q = 0; q < jm; q++) {
@@ -417,9 +417,10 @@ __global__ void __launch_bounds__(32) k_prep(ObBatchDev d, real h, int taps) {
         const int j = s_ijoint[k];
         if (j < nc) continue;
         const int b1 = s_jb1[j], b2 = s_jb2[j];
-        real side[2][4];
-        for (int sx = 0; sx < 2; sx++) for (int e = 0; e < 4; e++) side[sx][e] = __ldcg(g_side + (size_t)(j - nc) * 8 + 4 * sx + e);
-        if (side[0][0] == 0 && side[1][0] == 0) continue;
+        real side[OB_NSIDE][4];
+        bool any = false;
+        for (int sx = 0; sx < OB_NSIDE; sx++) { for (int e = 0; e < 4; e++) side[sx][e] = __ldcg(g_side + (size_t)(j - nc) * 4 * OB_NSIDE + 4 * sx + e); any |= side[sx][0] != 0; }
+        if (!any) continue;
         ob_apply_joint_side(pjoint[j - nc].type, side, bd[b1].facc, bd[b1].tacc, b2 != 255 ? bd[b2].facc : (real *)0, b2 != 255 ? bd[b2].tacc : (real *)0);
       }
     }

@@ -29,6 +29,7 @@ GOLDEN = [  # (file stem, scene, steps, worlds, settle) — must match tests/gol
     ("terrain_capsules_pre_settle70", "terrain_capsules_pre", 20, 1, 70),   # dGeomTriMeshDataPreprocess: edge / vertex use flags
     ("sliders_settle60", "sliders", 30, 1, 60),
     ("universals_settle60", "universals", 30, 1, 60),
+    ("motors_settle60", "motors", 30, 1, 60),
 ]
 
 
@@ -70,7 +71,7 @@ def _built():
 # traces and, for the long live comparisons, in lock-step with the reference (every step starts
 # from the reference's pre-step body state, SURVEY 8d parity protocol with K = 1) so that a
 # last-bit difference cannot be amplified by chaotic dynamics into a different contact set.
-ATAN2_SCENES = ("hinges", "buggy", "ragdoll", "buggy_terrain", "universals")
+ATAN2_SCENES = ("hinges", "buggy", "ragdoll", "buggy_terrain", "universals", "motors")
 
 
 def assert_parity(r, what, scene, prec, cand):

@@ -347,6 +347,70 @@ static inline void scene_universals(SceneWorld &sw, int w) {
   scene_add_sphere(sw, 3, (dReal)0.2, (dReal)1.0, (dReal)0.03, (dReal)2.6);
 }
 
+// angular / linear motors (amotor.cpp, lmotor.cpp): an Euler-mode amotor with stops next to a ball joint (the
+// ragdoll idiom), a user-mode amotor to the world whose user-set angle sits beyond its stop while powered
+// (motor-at-limit torque side effect on up to three axes), lmotors with axes relative to the world, body 1 and body 2
+static inline void scene_motors(SceneWorld &sw, int w) {
+  scene_world_base(sw, w);
+  xs32 rng(sw.seed ^ 0x0A4070u);
+  scene_add_geom(sw, dCreatePlane(sw.space, 0, 0, 1, 0));
+  dBodyID b[5];
+  for (int i = 0; i < 5; i++) {
+    b[i] = scene_add_box(sw, 2, (dReal)0.4, (dReal)0.2, (dReal)0.2, (dReal)(0.5 * i), rng.uni(-0.02, 0.02), (dReal)1.3);
+    dBodySetAngularVel(b[i], rng.uni(-1.5, 1.5), rng.uni(-1.5, 1.5), rng.uni(-1.5, 1.5));
+  }
+  // b0-b1: ball + Euler amotor with stops
+  dJointID j = dJointCreateBall(sw.world, 0);
+  dJointAttach(j, b[0], b[1]);
+  dJointSetBallAnchor(j, (dReal)0.25, 0, (dReal)1.3);
+  sw.joints.push_back(j);
+  j = dJointCreateAMotor(sw.world, 0);
+  dJointAttach(j, b[0], b[1]);
+  dJointSetAMotorMode(j, dAMotorEuler);
+  dJointSetAMotorAxis(j, 0, 1, 1, 0, 0);
+  dJointSetAMotorAxis(j, 2, 2, 0, 0, 1);
+  dJointSetAMotorParam(j, dParamLoStop, (dReal)-0.3); dJointSetAMotorParam(j, dParamHiStop, (dReal)0.3);
+  dJointSetAMotorParam(j, dParamLoStop2, (dReal)-0.2); dJointSetAMotorParam(j, dParamHiStop2, (dReal)0.25);
+  dJointSetAMotorParam(j, dParamLoStop3, (dReal)-0.4); dJointSetAMotorParam(j, dParamHiStop3, (dReal)0.15);
+  dJointSetAMotorParam(j, dParamBounce2, (dReal)0.3);
+  sw.joints.push_back(j);
+  // b1-b2: hinge + 3-axis lmotor (axes relative to world / body 1 / body 2)
+  j = dJointCreateHinge(sw.world, 0);
+  dJointAttach(j, b[1], b[2]);
+  dJointSetHingeAnchor(j, (dReal)0.75, 0, (dReal)1.3);
+  dJointSetHingeAxis(j, 0, 1, 0);
+  sw.joints.push_back(j);
+  j = dJointCreateLMotor(sw.world, 0);
+  dJointAttach(j, b[1], b[2]);
+  dJointSetLMotorNumAxes(j, 3);
+  dJointSetLMotorAxis(j, 0, 0, 1, 0, 0);
+  dJointSetLMotorAxis(j, 1, 1, 0, 1, (dReal)0.2);
+  dJointSetLMotorAxis(j, 2, 2, 0, 0, 1);
+  dJointSetLMotorParam(j, dParamVel, (dReal)0.2); dJointSetLMotorParam(j, dParamFMax, (dReal)1.5);
+  dJointSetLMotorParam(j, dParamVel3, (dReal)-0.1); dJointSetLMotorParam(j, dParamFMax3, (dReal)0.8);
+  sw.joints.push_back(j);
+  // b3 - world: user-mode amotor, powered, angle beyond the stop on axis 0, plain motor on axis 1
+  j = dJointCreateAMotor(sw.world, 0);
+  dJointAttach(j, b[3], 0);
+  dJointSetAMotorNumAxes(j, 2);
+  dJointSetAMotorAxis(j, 0, 1, 0, 0, 1);
+  dJointSetAMotorAxis(j, 1, 0, 1, 0, 0);
+  dJointSetAMotorAngle(j, 0, (dReal)0.5);
+  dJointSetAMotorParam(j, dParamLoStop, (dReal)-0.3); dJointSetAMotorParam(j, dParamHiStop, (dReal)0.3);
+  dJointSetAMotorParam(j, dParamVel, (dReal)1.0); dJointSetAMotorParam(j, dParamFMax, (dReal)2.0);
+  dJointSetAMotorParam(j, dParamFudgeFactor, (dReal)0.5);
+  dJointSetAMotorParam(j, dParamVel2, (dReal)-2.0); dJointSetAMotorParam(j, dParamFMax2, (dReal)1.0);
+  sw.joints.push_back(j);
+  // b4 - world: one-body lmotor holding the box up against gravity along z, free otherwise
+  j = dJointCreateLMotor(sw.world, 0);
+  dJointAttach(j, b[4], 0);
+  dJointSetLMotorNumAxes(j, 1);
+  dJointSetLMotorAxis(j, 0, 0, 0, 0, 1);
+  dJointSetLMotorParam(j, dParamVel, (dReal)0.3); dJointSetLMotorParam(j, dParamFMax, (dReal)1.0);
+  sw.joints.push_back(j);
+  scene_add_sphere(sw, 3, (dReal)0.2, (dReal)0.6, (dReal)0.03, (dReal)2.6);
+}
+
 static inline dBodyID scene_add_capsule(SceneWorld &sw, dReal density, dReal r, dReal l, dReal x, dReal y, dReal z) {
   dBodyID b = dBodyCreate(sw.world);
   dBodySetPosition(b, x, y, z);
@@ -684,6 +748,7 @@ static inline int scene_build(const char *name_in, SceneWorld &sw, int w, SceneP
   if (!strcmp(name, "hinges")) { scene_hinges(sw, w); return 0; }
   if (!strcmp(name, "sliders")) { scene_sliders(sw, w); return 0; }
   if (!strcmp(name, "universals")) { scene_universals(sw, w); return 0; }
+  if (!strcmp(name, "motors")) { scene_motors(sw, w); return 0; }
   if (!strcmp(name, "buggy_terrain")) { scene_buggy_terrain(sw, w, 48); pol = policy_buggy(); pol.max_contacts = 10; return 0; }
   if (!strcmp(name, "buggy_terrain256")) { scene_buggy_terrain(sw, w, 256); pol = policy_buggy(); pol.max_contacts = 10; return 0; }
   if (!strcmp(name, "terrain_boxes")) { scene_terrain_boxes(sw, w); return 0; }

@@ -444,10 +444,10 @@ static void step_world(ObBatchDev &d, int w, real h, int taps) {
         } else {
           ObBodyView B1 = view(b1), B2;
           if (b2 >= 0) B2 = view(b2);
-          real side[2][4];
+          real side[OB_NSIDE][4];
           ob_joint_info2(r, pj[k], B1, b2 >= 0 ? &B2 : 0, stepsize1, &erp_io, side);
-          if ((side[0][0] != 0 || side[1][0] != 0) && getenv("OB_HOST_VERBOSE")) fprintf(stderr, "side effect: joint type %d fm %g\n", pj[k].type, (double)side[0][0]);
-          if (side[0][0] != 0 || side[1][0] != 0)
+          if ((side[0][0] != 0 || side[1][0] != 0 || side[2][0] != 0) && getenv("OB_HOST_VERBOSE")) fprintf(stderr, "side effect: joint type %d fm %g\n", pj[k].type, (double)side[0][0]);
+          if (side[0][0] != 0 || side[1][0] != 0 || side[2][0] != 0)
             ob_apply_joint_side(pj[k].type, side, bd[b1].facc, bd[b1].tacc, b2 >= 0 ? bd[b2].facc : (real *)0, b2 >= 0 ? bd[b2].tacc : (real *)0);
         }
       }
