@@ -556,6 +556,11 @@ int dBatchCollideAndQuickStep(dBatchID, dReal h, int nsteps, int *status_per_wor
 /* bulk SoA I/O, host buffers: [world][body][k]; body order = creation order.
  * pos 3, quat 4, lvel 3, avel 3 (13 reals per body).  Set stores the quaternion as given
  * (it must be unit; the rotation matrix is rebuilt from it), so Get -> Set restores bit for bit. */
+/* order state for snapshots (opaque ints): the space list order, SAP sort ranks and dirty counts that the
+ * next step's callback order depends on besides body state and seeds */
+int dBatchOrderStateSize(dBatchID);
+int dBatchGetOrderState(dBatchID, int *buf);
+int dBatchSetOrderState(dBatchID, const int *buf);
 int dBatchNumBodies(dBatchID);            /* per world (max over worlds) */
 int dBatchGetBodyState(dBatchID, dReal *pos3, dReal *quat4, dReal *lvel3, dReal *avel3);
 int dBatchSetBodyState(dBatchID, const dReal *pos3, const dReal *quat4,

@@ -433,6 +433,35 @@ int dBatchDebugGeomOrder(dBatchID B, int w, int *order, int cap) {
   if (m > 0 && obk_d2h(B->bk, order, B->caps.glist + (size_t)w * B->caps.NG, sizeof(int) * m)) return -1;
   return n;
 }
+// Order state: what the next step's callback / row order depends on besides body state and seeds — the space
+// list order (rewritten every step like dGeomMoved does), the SAP space's RadixSort ranks and dirty count.
+// An opaque int blob for snapshots: [W*NG glist][W*(NG+3) sapstate][W sap_ndirty].
+int dBatchOrderStateSize(dBatchID B) {
+  const ObBatchDev &D = B->caps;
+  return D.W * D.NG + (D.sapstate ? D.W * (D.NG + 3) : 0) + D.W;
+}
+int dBatchGetOrderState(dBatchID B, int *buf) {
+  const ObBatchDev &D = B->caps;
+  size_t o = 0;
+  if (obk_d2h(B->bk, buf + o, D.glist, sizeof(int) * (size_t)D.W * D.NG)) return -1;
+  o += (size_t)D.W * D.NG;
+  if (D.sapstate) { if (obk_d2h(B->bk, buf + o, D.sapstate, sizeof(int) * (size_t)D.W * (D.NG + 3))) return -1; o += (size_t)D.W * (D.NG + 3); }
+  std::vector<ObWorld> hw(D.W);
+  if (obk_d2h(B->bk, hw.data(), D.world, D.W * sizeof(ObWorld))) return -1;
+  for (int w = 0; w < D.W; w++) buf[o + w] = hw[w].sap_ndirty;
+  return 0;
+}
+int dBatchSetOrderState(dBatchID B, const int *buf) {
+  const ObBatchDev &D = B->caps;
+  size_t o = 0;
+  if (obk_h2d(B->bk, D.glist, buf + o, sizeof(int) * (size_t)D.W * D.NG)) return -1;
+  o += (size_t)D.W * D.NG;
+  if (D.sapstate) { if (obk_h2d(B->bk, D.sapstate, buf + o, sizeof(int) * (size_t)D.W * (D.NG + 3))) return -1; o += (size_t)D.W * (D.NG + 3); }
+  std::vector<ObWorld> hw(D.W);
+  if (obk_d2h(B->bk, hw.data(), D.world, D.W * sizeof(ObWorld))) return -1;
+  for (int w = 0; w < D.W; w++) hw[w].sap_ndirty = buf[o + w];
+  return obk_h2d(B->bk, D.world, hw.data(), D.W * sizeof(ObWorld));
+}
 int dBatchSetDebugTaps(dBatchID B, int enable) { B->debug_taps = enable != 0; return 0; }
 int dBatchTimerStart(dBatchID B) { return obk_timer_start(B->bk); }
 int dBatchTimerStop(dBatchID B, float *ms) { return obk_timer_stop(B->bk, ms); }

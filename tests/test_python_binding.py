@@ -1,0 +1,69 @@
+"""ode-0.12_b200/python/ode_b200.py (Python binding over the batched API + binary snapshot).
+CPU: bound to the TEST-ONLY host build (tests/hostsim) so the binding's marshalling is exercised without a
+GPU; GPU: the same against the product library."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, lib_path
+
+sys.path.insert(0, os.path.join(ROOT, "ode-0.12_b200", "python"))
+import ode_b200 as ode  # noqa: E402
+
+HOSTSIM = os.path.join(ROOT, "tests", "hostsim", "_build", "libode_b200_hostsim_single.so")
+
+
+def _scene(lib, n):
+    worlds = []
+    rng = np.random.default_rng(5)
+    for w in range(n):
+        W = ode.World(lib)
+        W.add_plane(0, 0, 1, 0)
+        for i in range(6):
+            W.add_box((0.1 * rng.standard_normal(), 0.1 * rng.standard_normal(), 0.4 + 0.55 * i), (0.5, 0.4, 0.3), density=2.0)
+        W.add_sphere((0.3, 0.1, 4.0), 0.25)
+        W.add_capsule((-0.4, 0.2, 4.5), 0.15, 0.5)
+        worlds.append(W)
+    return worlds
+
+
+def _run(libpath):
+    lib = ode.load(libpath)
+    out = {}
+    b = ode.Batch(lib, _scene(lib, 3))
+    b.set_contact_policy(max_contacts=8, mode=ode.ContactBounce | ode.ContactSoftCFM, bounce=0.1, bounce_vel=0.1, soft_cfm=0.01)
+    b.set_seeds(np.array([11, 22, 33], dtype=np.uint32))
+    assert not b.step(0.01, 60).any()
+    snap = os.path.join(os.environ.get("TMPDIR", "/tmp"), "ob_snapshot_%d.npz" % os.getpid())
+    b.save(snap)
+    assert not b.step(0.01, 40).any()
+    out["final"] = b.get_state()
+    out["counters"] = b.counters()
+    # a fresh batch restored from the snapshot continues bit for bit
+    b2 = ode.Batch(lib, _scene(lib, 3))
+    b2.set_contact_policy(max_contacts=8, mode=ode.ContactBounce | ode.ContactSoftCFM, bounce=0.1, bounce_vel=0.1, soft_cfm=0.01)
+    b2.load(snap)
+    assert not b2.step(0.01, 40).any()
+    out["restored"] = b2.get_state()
+    os.remove(snap)
+    b.destroy(); b2.destroy()
+    return out
+
+
+def _check(o):
+    pos = o["final"][0]
+    assert pos.shape == (3, 8, 3) and np.isfinite(pos).all() and pos[:, :, 2].min() > 0.05
+    assert o["counters"]["contacts"] > 0 and o["counters"]["overflow_worlds"] == 0
+    for a, b in zip(o["final"], o["restored"]):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_binding_and_snapshot_on_host_build():
+    _check(_run(HOSTSIM))
+
+
+@pytest.mark.gpu
+def test_binding_and_snapshot_on_gpu():
+    _check(_run(lib_path("single")))
