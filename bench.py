@@ -273,9 +273,22 @@ def run_b200(args):
         lib.dBatchAddForces(B, forces[s & 3].ctypes.data, torque.ctypes.data)
         step(1)
         lib.dBatchGetBodyState(B, pos.ctypes.data, quat.ctypes.data, lv.ctypes.data, av.ctypes.data)
-    t_e2e = time.perf_counter() - t0
+    t_e2e = max_over_ranks(time.perf_counter() - t0)
     ce = counters(lib, B)
     assert np.isfinite(pos).all()
+    if dist is not None:
+        # every rank must hold the same world after the same steps: compare a checksum of the body state
+        import torch
+
+        h64 = int(np.frombuffer(np.ascontiguousarray(pos).tobytes(), dtype=np.uint32).astype(np.uint64).sum() & 0x7FFFFFFFFFFFFFFF)
+        hv = torch.tensor([h64, -h64], dtype=torch.int64, device="cuda")
+        dist.all_reduce(hv, op=dist.ReduceOp.MAX)
+        if int(hv[0].item()) != -int(hv[1].item()):
+            raise SystemExit("split ranks disagree on the body state")
+        if rank != 0:
+            lib.dBatchDestroy(B)
+            dist.destroy_process_group()
+            return
 
     vals = np.array([elapsed_ms, t_e2e], dtype=np.float64)
     sums = np.array([c["body_steps"], c["contacts"], ce["body_steps"], c["rows"], launches, c["overflow_worlds"]], dtype=np.float64)
@@ -328,16 +341,25 @@ class LargeStats(ctypes.Structure):
 
 
 def run_large(args):
-    """configs[4]: one large world on one GPU (the path does not shard without an exchange step per colour:
-    ranks > 0 exit).  value = device-resident body-steps/s; roofline on the SOR phase
-    (iterations x colours launches of k_lw_sor), algorithmic bytes D x iterations per row."""
+    """configs[4]: one large world.  N = 1: one GPU.  N > 1 (torchrun, one process per GPU): every rank holds the whole
+    world, the SOR phase is split over the ranks with the fc exchange over NVLink inside the kernel
+    (dBatchSplitExport / dBatchSplitAttach) -- total work is fixed, "scaling": "strong"; NCCL only gathers
+    the 128-byte buffer descriptions once and reduces the timing.  value = device-resident body-steps/s (max over ranks
+    of the CUDA-event time); roofline on the SOR phase, algorithmic bytes D x iterations per row."""
     rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world_size > 1:
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl")
     lib, scenes = load_libs()
     lib.dBatchGetLargeWorldStats.argtypes = [ctypes.c_void_p, ctypes.POINTER(LargeStats)]
     scene = args.scene or LARGE["scene"]
-    B = scenes.ob_scene_build_batch(scene.encode(), 1, 0, 0, int(os.environ.get("LOCAL_RANK", "0")))
+    B = scenes.ob_scene_build_batch(scene.encode(), 1, 0, 0, local_rank)
     if not B:
         raise SystemExit("batch creation failed: " + (lib.dB200LastError() or b"").decode())
     B = ctypes.c_void_p(B)
@@ -350,21 +372,54 @@ def run_large(args):
         if status[0]:
             raise SystemExit(f"capacity overflow, status {status[0]}")
 
+    def barrier():
+        if dist is not None:
+            import torch
+
+            torch.cuda.synchronize()
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+
+        tv = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+        return float(tv.item())
+
+    if dist is not None:
+        import torch
+
+        lib.dBatchSplitExport.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        lib.dBatchSplitAttach.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        hb = ctypes.create_string_buffer(128)
+        if lib.dBatchSplitExport(B, hb) != 0:
+            raise SystemExit("split export failed: " + lib.dB200LastError().decode())
+        mine = torch.frombuffer(bytearray(hb.raw), dtype=torch.uint8).cuda()
+        allh = [torch.empty_like(mine) for _ in range(world_size)]
+        dist.all_gather(allh, mine)
+        blob = b"".join(t_.cpu().numpy().tobytes() for t_ in allh)
+        if lib.dBatchSplitAttach(B, rank, world_size, blob) != 0:
+            raise SystemExit("split attach failed: " + lib.dB200LastError().decode())
+        barrier()
     settle = args.settle if args.settle >= 0 else LARGE["settle"]
     step(settle)
     step(max(args.warmup, 3))
     lib.dBatchResetCounters(B)
     l0 = lib.dB200KernelLaunchCount()
-    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    sampler = ClockSampler(local_rank)
     sampler.start()
+    barrier()
     ms = ctypes.c_float()
     lib.dBatchTimerStart(B)
     step(args.steps)
     lib.dBatchTimerStop(B, ctypes.byref(ms))
+    barrier()
     clocks = sampler.stop()
     launches = lib.dB200KernelLaunchCount() - l0
     c = counters(lib, B)
-    t = float(ms.value) * 1e-3
+    t = max_over_ranks(float(ms.value)) * 1e-3
     # per-phase attribution (CUDA events between the phases, separate pass)
     lib.dBatchSetKernelTiming(B, 1)
     lib.dBatchResetCounters(B)
@@ -403,17 +458,32 @@ def run_large(args):
         lib.dBatchAddForces(B, forces[s & 3].ctypes.data, torque.ctypes.data)
         step(1)
         lib.dBatchGetBodyState(B, pos.ctypes.data, quat.ctypes.data, lv.ctypes.data, av.ctypes.data)
-    t_e2e = time.perf_counter() - t0
+    t_e2e = max_over_ranks(time.perf_counter() - t0)
     ce = counters(lib, B)
     assert np.isfinite(pos).all()
+    if dist is not None:
+        # every rank must hold the same world after the same steps: compare a checksum of the body state
+        import torch
+
+        h64 = int(np.frombuffer(np.ascontiguousarray(pos).tobytes(), dtype=np.uint32).astype(np.uint64).sum() & 0x7FFFFFFFFFFFFFFF)
+        hv = torch.tensor([h64, -h64], dtype=torch.int64, device="cuda")
+        dist.all_reduce(hv, op=dist.ReduceOp.MAX)
+        if int(hv[0].item()) != -int(hv[1].item()):
+            raise SystemExit("split ranks disagree on the body state")
+        if rank != 0:
+            lib.dBatchDestroy(B)
+            dist.destroy_process_group()
+            return
     out = {
         "metric": "body-steps/sec (dSpaceCollide + dWorldQuickStep, 20 SOR iterations)", "value": c["body_steps"] / t, "unit": "body-steps/s",
-        "contacts_solved_per_sec": c["contacts"] / t, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "contacts_solved_per_sec": c["contacts"] / t, "n_gpus": world_size, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": t * 1e3 / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": LARGE["desc"].format(NB=nb) + f", scene {scene}, quickstep 20 it, h={H}, settled {settle} steps",
                    "bodies": nb, "pairs_per_step": st.pairs, "contacts_per_step": st.contacts, "rows_per_step": rows_per_step,
                    "colours": st.colours, "colouring_rounds": st.colouring_rounds, "sor_launches_per_step": st.sor_launches,
+                   "parallelism": "one GPU" if world_size == 1 else f"SOR phase split over {world_size} GPUs (fc exchange over NVLink peer stores inside "
+                                  "k_lw_sor_split, flag barrier per colour); the phases before it run on every rank",
                    "cache": "rows %.0f MB/step streamed every iteration (> 126 MB L2 at full size)" % (rows_per_step * 80 / 1e6),
                    "precision": "dSINGLE", "parity": "pairs+contacts exact, state within stated tolerance vs reference; bitwise vs sequential mirror (tests/test_large_world.py)"},
         "e2e": {"value": ce["body_steps"] / t_e2e, "unit": "body-steps/s", "h2d_bytes_per_step": int(forces[0].nbytes + torque.nbytes),
@@ -427,7 +497,7 @@ def run_large(args):
                      "phases_ms": ph},
         "clocks": clocks, "overflow_worlds": c["overflow_worlds"],
     }
-    if not args.no_cpu:
+    if not args.no_cpu and world_size == 1:
         exe = os.path.join(ROOT, "oracle", "_ref", "driver_ref_single")
         if os.path.exists(exe):
             r = json.loads(subprocess.run([exe, "--scene", LARGE["cpu_scene"], "--steps", str(LARGE["cpu_steps"]), "--settle", str(LARGE["cpu_settle"]),
@@ -438,6 +508,8 @@ def run_large(args):
                                              f"{LARGE['cpu_settle']} settle steps untimed + {LARGE['cpu_steps']} timed"}
     print(json.dumps(out))
     lib.dBatchDestroy(B)
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 def cpu_run(nproc, worlds_each, steps, settle, timeout=900):

@@ -604,6 +604,21 @@ typedef struct dBatchLargeWorldStats {
   double phase_ms[7];
 } dBatchLargeWorldStats;
 int dBatchGetLargeWorldStats(dBatchID, dBatchLargeWorldStats *out);   /* -1 for a batch of small worlds */
+/* One large world over the GPUs of one box (BASELINE.json configs[4] "2/4/8-GPU split").
+ * One process per GPU; every rank builds the SAME world and binds it into a large-world batch of its own.
+ * Broadphase, narrowphase, colouring and row assembly are deterministic and run on every rank; the SOR
+ * phase -- the reference's SOR_LCP (ode/src/quickstep.cpp:342-584) as the coloured sweep -- is dealt over
+ * the ranks: each rank sweeps its share of every colour's contact pairs and stores the constraint forces
+ * it produced into every rank's array through NVLink peer mappings, inside the kernel, with a flag barrier
+ * per colour.  All ranks end every step with the same body state, bit for bit the single-GPU result.
+ *   dBatchSplitExport: fills a D_BATCH_SPLIT_HANDLE_BYTES description of this rank's exchange buffer
+ *                      (CUDA IPC handle); the caller gathers the ranks' descriptions (any transport).
+ *   dBatchSplitAttach: all descriptions in rank order.  From then on dBatchCollideAndQuickStep must be
+ *                      called by every rank with the same arguments; a rank that stays away makes the
+ *                      others fail with an error after OB_LW_SPLIT_TIMEOUT_MS (default 5000), not hang. */
+#define D_BATCH_SPLIT_HANDLE_BYTES 128
+int dBatchSplitExport(dBatchID, void *handle);
+int dBatchSplitAttach(dBatchID, int rank, int nranks, const void *handles);
 /* the CUDA stream the batch launches on (cudaStream_t as void*), so callers can
  * time with events on the launching stream */
 void *dBatchGetStream(dBatchID);

@@ -57,3 +57,9 @@ long long obk_launch_count(void);
 // and the per-phase CUDA-event times accumulated while kernel timing is on
 // {geoms+sort, pairs, narrowphase, colouring, assembly, SOR, integration}.  Returns -1 for a small-world batch.
 int obk_large_stats(ObBackend *, int *ints8, double *ms8);
+// large-world path over several GPUs of one box (one rank per GPU, every rank holds the whole world): the SOR
+// phase is dealt over the ranks, fc is exchanged through peer mappings inside the kernel (ObLwSplit, ob_large.h).
+// export: 128-byte description of this rank's fc + flag buffer; attach: all ranks' exports in rank order.
+#define OBK_SPLIT_HANDLE_BYTES 128
+int obk_split_export(ObBackend *, void *handle128, char *err, size_t errlen);
+int obk_split_attach(ObBackend *, int rank, int nranks, const void *handles, char *err, size_t errlen);

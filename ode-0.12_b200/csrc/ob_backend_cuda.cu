@@ -30,6 +30,7 @@
 #include "ob_broad.h"
 #include "ob_rows.h"
 #include "ob_solver.h"
+#include <unistd.h>
 #include "ob_large.h"
 #include "ob_step_kernel.cuh"
 
@@ -388,6 +389,12 @@ struct ObBackend {
   int lw_rounds, lw_ncol, lw_stat[8], lw_sor_grid[3];
   double lw_ms[8];     // geoms+sort, pairs, narrow, colour, assemble, sor, post (CUDA events, when kernel timing is on)
   cudaEvent_t lw_ev[9];
+  // SOR phase split over the GPUs of one box (ObLwSplit): flag words behind fc in ONE allocation (one IPC handle)
+  unsigned *lw_flags;
+  size_t lw_flags_off;          // bytes from L.fc to lw_flags
+  int lw_split_on, lw_split_grid[3], lw_split_threads;
+  ObLwSplit lw_split;
+  void *lw_peer_base[OB_LW_MAXRANKS];   // cudaIpcOpenMemHandle mappings to close
 };
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { snprintf(err, errlen, "%s: %s", #call, cudaGetErrorString(e_)); goto fail; } } while (0)
@@ -414,6 +421,8 @@ ObBackend *obk_create(const ObBatchDev &caps, int device, char *err, size_t errl
   b->nchunks = 1;
   for (int k = 0; k < 8; k++) b->cstream[k] = 0;
   for (int k = 0; k < 9; k++) b->cev[k] = 0;
+  b->lw_flags = 0; b->lw_flags_off = 0; b->lw_split_on = 0; memset(&b->lw_split, 0, sizeof b->lw_split);
+  for (int k = 0; k < OB_LW_MAXRANKS; k++) b->lw_peer_base[k] = 0;
   b->large = d.large; b->lw_host = 0; b->lw_rounds = 0; b->lw_ncol = 0;
   for (int k = 0; k < 8; k++) b->lw_stat[k] = 0;
   memset(&b->L, 0, sizeof b->L);
@@ -525,6 +534,7 @@ ObBackend *obk_create(const ObBatchDev &caps, int device, char *err, size_t errl
   }
   return b;
 fail:
+  for (int k = 0; k < OB_LW_MAXRANKS; k++) if (b->lw_peer_base[k]) cudaIpcCloseMemHandle(b->lw_peer_base[k]);
   for (size_t i = 0; i < b->allocs.size(); i++) cudaFree(b->allocs[i]);
   if (b->st_host) cudaFreeHost(b->st_host);
   if (b->lw_host) cudaFreeHost(b->lw_host);
@@ -537,6 +547,7 @@ fail2:
 void obk_destroy(ObBackend *b) {
   cudaSetDevice(b->device);
   cudaStreamSynchronize(b->stream);
+  for (int k = 0; k < OB_LW_MAXRANKS; k++) if (b->lw_peer_base[k]) cudaIpcCloseMemHandle(b->lw_peer_base[k]);
   for (size_t i = 0; i < b->allocs.size(); i++) cudaFree(b->allocs[i]);
   if (b->st_host) cudaFreeHost(b->st_host);
   if (b->lw_host) cudaFreeHost(b->lw_host);

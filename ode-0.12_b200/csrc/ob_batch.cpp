@@ -481,6 +481,18 @@ int dBatchGetLargeWorldStats(dBatchID B, dBatchLargeWorldStats *out) {
   for (int k = 0; k < 7; k++) out->phase_ms[k] = ms[k];
   return 0;
 }
+int dBatchSplitExport(dBatchID B, void *handle) {
+  char err[256] = "";
+  if (!B || !handle) return -1;
+  if (obk_split_export(B->bk, handle, err, sizeof err)) { ob_set_last_error("dBatchSplitExport: %s", err); return -1; }
+  return 0;
+}
+int dBatchSplitAttach(dBatchID B, int rank, int nranks, const void *handles) {
+  char err[256] = "";
+  if (!B || !handles) return -1;
+  if (obk_split_attach(B->bk, rank, nranks, handles, err, sizeof err)) { ob_set_last_error("dBatchSplitAttach: %s", err); return -1; }
+  return 0;
+}
 void *dBatchGetStream(dBatchID B) { return obk_stream(B->bk); }
 long long dB200KernelLaunchCount(void) { return obk_launch_count(); }
 }  // extern "C"

@@ -91,6 +91,27 @@ struct ObLargeDev {
   uint32_t *tmp;               // scan / sort scratch
   size_t tmp_words;
 };
+// ---- split of the SOR phase over the GPUs of one box -------------------
+// Every rank (one process per GPU) holds the whole world and runs the phases before the solver
+// redundantly: they are deterministic, so all ranks hold the same pairs, colours and rows.  In the SOR
+// phase the pairs of a colour are dealt over the ranks; a rank writes the fc[] it produced into EVERY
+// rank's fc array (stores through NVLink peer mappings) and the ranks meet at a flag barrier after each
+// colour, so after the barrier each rank's fc equals the single-GPU array bit for bit.
+#define OB_LW_MAXRANKS 8
+#define OB_LW_FLAG_WORDS 64      // per rank: [0..7] phase reached by rank r, [16] local release word, [17] timeout flag
+#define OB_LW_FLAG_RELEASE 16
+#define OB_LW_FLAG_TIMEOUT 17
+struct ObLwSplit {
+  int rank, nranks;
+  unsigned base;                       // phase number before this launch (monotonic over the steps, equal on all ranks)
+  unsigned timeout_ms;
+  real *fc[OB_LW_MAXRANKS];            // every rank's fc array as mapped into THIS process (fc[rank] == ObLargeDev::fc)
+  unsigned *flags[OB_LW_MAXRANKS];     // every rank's flag words (flags[rank] is local)
+};
+// which rank sweeps warp tile `tile` (32 consecutive pairs of a colour): tiles are dealt round-robin, like the
+// single-GPU kernel deals them over its CTAs, so every rank gets the same mix of heavy and light pairs
+OB_HD int ob_lw_split_owner(int pair_in_colour, int nranks) { return (pair_in_colour >> 5) % nranks; }
+
 enum { LW_NFIN = 0, LW_NBIG, LW_NP, LW_NCONTACTS, LW_NCP, LW_UNCOLOURED, LW_NCOL, LW_ERR, LW_NSOLVED, LW_BARRIER, LW_LEFT0 /* 16 per-round counters */, LW_WORDS = 32 };
 
 // ---- broadphase --------------------------------------------------------------------------------

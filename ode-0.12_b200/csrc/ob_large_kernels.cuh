@@ -477,8 +477,8 @@ __global__ void __launch_bounds__(LW_T) k_lw_assemble(ObBatchDev d, ObLargeDev L
 
 // one contact pair: its contacts in order, the rows of a contact in order.  fc and lambda go through L2
 // (ld.cg / st.cg): inside the persistent kernel other SMs wrote them in an earlier colour.
-template <int M>
-__device__ __forceinline__ void lw_sor_pair(const ObLargeDev &L, const int *seg, int i) {
+template <int M, bool SPLIT = false>
+__device__ __forceinline__ void lw_sor_pair(const ObLargeDev &L, const int *seg, int i, const ObLwSplit *S = 0) {
   const ObLwPair P = L.cp[1][seg[0] + i];
   const int nc = P.info & 255, b1 = P.b1, b2 = P.b2;
   real f1[6], f2[6] = {0, 0, 0, 0, 0, 0};
@@ -529,6 +529,21 @@ __device__ __forceinline__ void lw_sor_pair(const ObLargeDev &L, const int *seg,
   }
 #undef LW_LOAD
 #undef LW_APPLY
+  if (SPLIT) {
+    // the split sweep: this rank's result goes into every rank's fc array (own copy included); the
+    // peer copies are plain stores through the NVLink mapping, made visible by the flag barrier
+    for (int r = 0; r < S->nranks; r++) {
+      real *q1 = S->fc[r] + (size_t)8 * b1, *q2 = S->fc[r] + (size_t)8 * (b2 >= 0 ? b2 : b1);
+#if defined(dSINGLE)
+      __stcg((float4 *)q1, make_float4(f1[0], f1[1], f1[2], f1[3])); __stcg((float2 *)(q1 + 4), make_float2(f1[4], f1[5]));
+      if (b2 >= 0) { __stcg((float4 *)q2, make_float4(f2[0], f2[1], f2[2], f2[3])); __stcg((float2 *)(q2 + 4), make_float2(f2[4], f2[5])); }
+#else
+      for (int e = 0; e < 6; e++) __stcg(q1 + e, f1[e]);
+      if (b2 >= 0) for (int e = 0; e < 6; e++) __stcg(q2 + e, f2[e]);
+#endif
+    }
+    return;
+  }
 #if defined(dSINGLE)
   __stcg((float4 *)fp1, make_float4(f1[0], f1[1], f1[2], f1[3])); __stcg((float2 *)(fp1 + 4), make_float2(f1[4], f1[5]));
   if (b2 >= 0) { __stcg((float4 *)fp2, make_float4(f2[0], f2[1], f2[2], f2[3])); __stcg((float2 *)(fp2 + 4), make_float2(f2[4], f2[5])); }
@@ -592,6 +607,65 @@ __global__ void __launch_bounds__(LW_SOR_T) k_lw_sor_all(ObLargeDev L, int iters
       }
       epoch++;
       lw_grid_barrier(bar, epoch * gridDim.x);
+    }
+}
+
+// ---- the SOR phase split over the GPUs of one box (ObLwSplit, ob_large.h) -------------------------
+// Barrier of all CTAs of all ranks.  Every CTA arrives at the local counter behind a system-scope fence
+// (its peer stores of fc are ordered before the arrival); CTA 0 waits for the local arrivals, raises this
+// rank's phase word in every peer's flag array, waits until every peer has raised its own here, and then
+// releases the local CTAs.  A wait that outlasts timeout_ms (a rank that never launched) raises the
+// timeout flag, after which no barrier waits any more: the step finishes and the host reports the error.
+__device__ __forceinline__ unsigned long long lw_globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ void lw_split_barrier(unsigned *bar, unsigned local_target, const ObLwSplit &S, unsigned phase) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    volatile unsigned *mine = (volatile unsigned *)S.flags[S.rank];
+    __threadfence_system();
+    atomicAdd(bar, 1u);
+    if (blockIdx.x == 0) {
+      while (*(volatile unsigned *)bar < local_target) { }
+      __threadfence_system();
+      for (int r = 0; r < S.nranks; r++) if (r != S.rank) *((volatile unsigned *)S.flags[r] + S.rank) = phase;
+      const unsigned long long t0 = lw_globaltimer();
+      for (int r = 0; r < S.nranks; r++) {
+        if (r == S.rank) continue;
+        while ((int)(mine[r] - phase) < 0 && !mine[OB_LW_FLAG_TIMEOUT]) {
+          if (lw_globaltimer() - t0 > (unsigned long long)S.timeout_ms * 1000000ull) mine[OB_LW_FLAG_TIMEOUT] = 1;
+        }
+      }
+      __threadfence_system();
+      mine[OB_LW_FLAG_RELEASE] = phase;
+    } else {
+      while ((int)(mine[OB_LW_FLAG_RELEASE] - phase) < 0) { }
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+}
+template <int M>
+__global__ void __launch_bounds__(LW_SOR_T) k_lw_sor_split(ObLargeDev L, ObLwSplit S, int iters, int ncol, unsigned *bar) {
+  unsigned epoch = 0, phase = S.base;
+  // the ranks' grids form one virtual grid with this rank's CTAs at positions rank, rank + nranks, ...:
+  // warp tile w of a colour is swept by rank w % nranks (ob_lw_split_owner)
+  const int vgrid = gridDim.x * S.nranks, vblock = blockIdx.x * S.nranks + S.rank;
+  const int stride = vgrid * blockDim.x;
+  const int t = ((threadIdx.x >> 5) * vgrid + vblock) * 32 + (threadIdx.x & 31);
+  // entry: no rank may store into a peer's fc before that peer's k_lw_body_pre has initialised it
+  epoch++; phase++;
+  lw_split_barrier(bar, epoch * gridDim.x, S, phase);
+  for (int it = 0; it < iters; it++)
+    for (int c = 0; c < ncol; c++) {
+      const int *seg = L.segtab + c * (2 + OB_LW_MAXC);
+      const int cnt = seg[1];
+      for (int i = t; i < cnt; i += stride) lw_sor_pair<M, true>(L, seg, i, &S);
+      if (c + 1 < ncol || it + 1 < iters) {
+        const int *segn = L.segtab + (c + 1 < ncol ? c + 1 : 0) * (2 + OB_LW_MAXC);
+        const int cntn = segn[1];
+        for (int i = t; i < cntn; i += stride) lw_prefetch_pair<M>(L, segn, i);
+      }
+      epoch++; phase++;
+      lw_split_barrier(bar, epoch * gridDim.x, S, phase);
     }
 }
 
@@ -678,7 +752,12 @@ static int lw_create(ObBackend *b, char *err, size_t errlen) {
   LWCK(dalloc(b, &L.segtab, (size_t)OB_LW_MAXCOL * (2 + OB_LW_MAXC)));
   LWCK(dalloc(b, &L.rows, (size_t)3 * OB_LW_SLOTS * OB_LW_SLOTW * NC));
   LWCK(dalloc(b, &L.lambda, 3 * NC));
-  LWCK(dalloc(b, &L.fc, NB * 8));
+  {   // fc and the split barrier's flag words share one allocation, so that one IPC handle exports both
+    const size_t fcb = (NB * 8 * sizeof(real) + 255) & ~(size_t)255;
+    unsigned char *raw = 0;
+    LWCK(dalloc(b, &raw, fcb + OB_LW_FLAG_WORDS * sizeof(unsigned)));
+    L.fc = (real *)raw; b->lw_flags = (unsigned *)(raw + fcb); b->lw_flags_off = fcb;
+  }
   LWCK(dalloc(b, &L.invM, NB));
   LWCK(dalloc(b, &L.hasrow, NB));
   L.tmp_words = (NP > 2 * NG ? NP : 2 * NG) / 2 + 65536;
@@ -695,7 +774,89 @@ static int lw_create(ObBackend *b, char *err, size_t errlen) {
     LWCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_lw_sor_all<3>, LW_SOR_T, 0)); b->lw_sor_grid[2] = per * prop.multiProcessorCount;
     const char *e = getenv("OB_LW_SOR_CTAS_PER_SM");
     if (e && atoi(e) > 0) for (int k = 0; k < 3; k++) if (atoi(e) * prop.multiProcessorCount < b->lw_sor_grid[k]) b->lw_sor_grid[k] = atoi(e) * prop.multiProcessorCount;
+    // the split kernel (several GPUs): same sizing; OB_LW_SOR_THREADS narrows its CTAs (two ranks on ONE GPU
+    // must be co-resident: the loop-back test uses 128 threads and one CTA per SM for each)
+    const char *t = getenv("OB_LW_SOR_THREADS");
+    b->lw_split_threads = t && atoi(t) >= 32 && atoi(t) <= LW_SOR_T ? atoi(t) & ~31 : LW_SOR_T;
+    LWCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_lw_sor_split<1>, b->lw_split_threads, 0)); b->lw_split_grid[0] = per * prop.multiProcessorCount;
+    LWCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_lw_sor_split<2>, b->lw_split_threads, 0)); b->lw_split_grid[1] = per * prop.multiProcessorCount;
+    LWCK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_lw_sor_split<3>, b->lw_split_threads, 0)); b->lw_split_grid[2] = per * prop.multiProcessorCount;
+    if (e && atoi(e) > 0) for (int k = 0; k < 3; k++) if (atoi(e) * prop.multiProcessorCount < b->lw_split_grid[k]) b->lw_split_grid[k] = atoi(e) * prop.multiProcessorCount;
   }
+  return 0;
+}
+
+// ---- split over GPUs: export / attach ------------------------------------------------------------
+// What a rank publishes about its fc + flag allocation.  Ranks in other processes map it with the IPC
+// handle; a rank in the same process (loop-back tests, or one process driving several GPUs) uses the
+// pointer itself.  128 bytes, opaque to the caller (dBatchSplitExport / dBatchSplitAttach).
+struct ObLwSplitHandle {
+  int pid, device;
+  unsigned long long ptr;        // L.fc in the exporting process
+  unsigned long long alloc_off;  // L.fc - base of the cudaMalloc block the IPC handle names
+  unsigned long long flags_off;  // flag words - L.fc
+  unsigned long long nb;         // body capacity (must match)
+  cudaIpcMemHandle_t ipc;        // 64 bytes
+  unsigned char pad[128 - 40 - sizeof(cudaIpcMemHandle_t)];
+};
+static_assert(sizeof(ObLwSplitHandle) == OBK_SPLIT_HANDLE_BYTES, "split handle is 128 bytes");
+
+int obk_split_export(ObBackend *b, void *handle128, char *err, size_t errlen) {
+  if (!b->large) { snprintf(err, errlen, "only the large-world path splits over GPUs"); return -1; }
+  cudaSetDevice(b->device);
+  ObLwSplitHandle H;
+  memset(&H, 0, sizeof H);
+  H.pid = (int)getpid(); H.device = b->device; H.ptr = (unsigned long long)(uintptr_t)b->L.fc; H.flags_off = b->lw_flags_off; H.nb = (unsigned long long)b->L.NB;
+  // the IPC handle names the whole block cudaMalloc carved the buffer from: find our offset in it
+  typedef int (*getrange_t)(unsigned long long *, size_t *, unsigned long long);
+  void *fn = 0;
+  cudaDriverEntryPointQueryResult qr;
+  LWCK(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr));
+  unsigned long long base = 0; size_t size = 0;
+  if (!fn || ((getrange_t)fn)(&base, &size, H.ptr) != 0) { snprintf(err, errlen, "cuMemGetAddressRange failed"); return -1; }
+  H.alloc_off = H.ptr - base;
+  LWCK(cudaIpcGetMemHandle(&H.ipc, (void *)(uintptr_t)base));
+  memcpy(handle128, &H, sizeof H);
+  return 0;
+}
+
+int obk_split_attach(ObBackend *b, int rank, int nranks, const void *handles, char *err, size_t errlen) {
+  if (!b->large) { snprintf(err, errlen, "only the large-world path splits over GPUs"); return -1; }
+  if (nranks < 1 || nranks > OB_LW_MAXRANKS || rank < 0 || rank >= nranks) { snprintf(err, errlen, "bad rank %d of %d (at most %d ranks)", rank, nranks, OB_LW_MAXRANKS); return -1; }
+  if (b->lw_split_on) { snprintf(err, errlen, "the batch is already attached to a split"); return -1; }
+  cudaSetDevice(b->device);
+  const ObLwSplitHandle *H = (const ObLwSplitHandle *)handles;
+  ObLwSplit S;
+  memset(&S, 0, sizeof S);
+  S.rank = rank; S.nranks = nranks; S.base = 0;
+  const char *to = getenv("OB_LW_SPLIT_TIMEOUT_MS");
+  S.timeout_ms = to && atoi(to) > 0 ? (unsigned)atoi(to) : 5000u;
+  for (int r = 0; r < nranks; r++) {
+    if (H[r].nb != (unsigned long long)b->L.NB || H[r].flags_off != b->lw_flags_off) { snprintf(err, errlen, "rank %d holds a world of another size", r); return -1; }
+    real *fc = 0;
+    if (r == rank) {
+      if (H[r].ptr != (unsigned long long)(uintptr_t)b->L.fc || H[r].pid != (int)getpid()) { snprintf(err, errlen, "handle %d is not this batch's own export", r); return -1; }
+      fc = b->L.fc;
+    } else if (H[r].pid == (int)getpid()) {
+      if (H[r].device != b->device) {
+        cudaError_t e = cudaDeviceEnablePeerAccess(H[r].device, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        else if (e != cudaSuccess) { snprintf(err, errlen, "no peer access from device %d to %d: %s", b->device, H[r].device, cudaGetErrorString(e)); return -1; }
+      }
+      fc = (real *)(uintptr_t)H[r].ptr;
+    } else {
+      void *base = 0;
+      LWCK(cudaIpcOpenMemHandle(&base, H[r].ipc, cudaIpcMemLazyEnablePeerAccess));
+      b->lw_peer_base[r] = base;
+      fc = (real *)((unsigned char *)base + H[r].alloc_off);
+    }
+    S.fc[r] = fc;
+    S.flags[r] = (unsigned *)((unsigned char *)fc + H[r].flags_off);
+  }
+  LWCK(cudaMemsetAsync(b->lw_flags, 0, OB_LW_FLAG_WORDS * sizeof(unsigned), b->stream));
+  LWCK(cudaStreamSynchronize(b->stream));
+  b->lw_split = S;
+  b->lw_split_on = nranks > 1;
   return 0;
 }
 
@@ -796,6 +957,14 @@ static int lw_step(ObBackend *b, real h, int taps, char *err, size_t errlen) {
     int iters = hw.iters, nc_ = ncol;
     void *kargs[] = {(void *)&L, (void *)&iters, (void *)&nc_, (void *)&bar};
     const void *fn = m == 3 ? (const void *)k_lw_sor_all<3> : (m == 2 ? (const void *)k_lw_sor_all<2> : (const void *)k_lw_sor_all<1>);
+    if (b->lw_split_on) {
+      ObLwSplit S = b->lw_split;
+      void *sargs[] = {(void *)&L, (void *)&S, (void *)&iters, (void *)&nc_, (void *)&bar};
+      const void *sfn = m == 3 ? (const void *)k_lw_sor_split<3> : (m == 2 ? (const void *)k_lw_sor_split<2> : (const void *)k_lw_sor_split<1>);
+      LWCK(cudaLaunchCooperativeKernel(sfn, dim3(b->lw_split_grid[m - 1]), dim3(b->lw_split_threads), sargs, 0, st));
+      b->lw_split.base += 1u + (unsigned)iters * (unsigned)nc_;   // the same on every rank: the phases before the solver are replicated
+      LWCK(cudaMemcpyAsync(hs + LW_ERR, b->lw_flags + OB_LW_FLAG_TIMEOUT, sizeof(int), cudaMemcpyDeviceToHost, st));
+    } else
     LWCK(cudaLaunchCooperativeKernel(fn, dim3(b->lw_sor_grid[m - 1]), dim3(LW_SOR_T), kargs, 0, st));
     g_launches++; sor_launches = 1;
   } else
@@ -816,6 +985,7 @@ static int lw_step(ObBackend *b, real h, int taps, char *err, size_t errlen) {
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) { snprintf(err, errlen, "large-world step failed: %s", cudaGetErrorString(e)); return -1; }
+  if (b->lw_split_on && sor_launches && hs[LW_ERR]) { snprintf(err, errlen, "split SOR: a peer rank did not reach the barrier within the timeout (rank %d of %d)", b->lw_split.rank, b->lw_split.nranks); return -1; }
   if (tm) for (int k = 0; k + 1 < evi && k < 8; k++) { float ms = 0; cudaEventElapsedTime(&ms, b->lw_ev[k], b->lw_ev[k + 1]); b->lw_ms[k] += ms; }
   b->lw_stat[0] = np; b->lw_stat[1] = hs[LW_NCONTACTS]; b->lw_stat[2] = ncp; b->lw_stat[3] = ncp > 0 ? hs[LW_NSOLVED] : 0;
   b->lw_stat[4] = ncol; b->lw_stat[5] = rounds; b->lw_stat[6] = sor_launches; if (tm) b->lw_stat[7]++;

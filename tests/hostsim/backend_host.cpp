@@ -9,16 +9,21 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <atomic>
 #include <vector>
 #include "../../ode-0.12_b200/csrc/ob_backend.h"
+#include "../../ode-0.12_b200/csrc/ob_large.h"
 #include "../../ode-0.12_b200/csrc/ob_broad.h"
 #include "../../ode-0.12_b200/csrc/ob_collide.h"
 #include "../../ode-0.12_b200/csrc/ob_rows.h"
 #include "../../ode-0.12_b200/csrc/ob_solver.h"
 
+struct LargeHostSplit;
 struct ObBackend {
   ObBatchDev d;
   std::vector<void *> allocs;
+  LargeHostSplit *split;      // large world split over ranks (threads here), see large_host.h
+  void *split_fc, *split_flags;
 };
 
 template <class T> static T *halloc(ObBackend *b, size_t n) {
@@ -29,7 +34,7 @@ template <class T> static T *halloc(ObBackend *b, size_t n) {
 
 ObBackend *obk_create(const ObBatchDev &caps, int, char *, size_t) {
   ObBackend *b = new ObBackend;
-  b->d = caps;
+  b->d = caps; b->split = 0; b->split_fc = 0; b->split_flags = 0;
   ObBatchDev &d = b->d;
   size_t W = d.W;
   d.world = halloc<ObWorld>(b, W);
@@ -630,7 +635,8 @@ int obk_step(ObBackend *b, real h, int nsteps, int taps, char *err, size_t errle
   if (d.large) {
     for (int s = 0; s < nsteps; s++) {
       LargeHostStats st;
-      const int rc = large_step_host(d, h, taps, &st);
+      const int rc = large_step_host(d, h, taps, &st, b->split);
+      if (rc == -7) { snprintf(err, errlen, "split SOR: a peer rank did not reach the barrier within the timeout"); return -1; }
       if (rc) { snprintf(err, errlen, "large-world step failed (%d)", rc); return -1; }
       g_lw_stat[0] = st.np; g_lw_stat[1] = st.ncontacts; g_lw_stat[2] = st.ncp; g_lw_stat[3] = st.nsolved; g_lw_stat[4] = st.ncol; g_lw_stat[5] = st.rounds;
       if (getenv("OB_LW_VERBOSE")) fprintf(stderr, "lw: pairs %d contacts %d cpairs %d colours %d rounds %d\n", st.np, st.ncontacts, st.ncp, st.ncol, st.rounds);
@@ -646,3 +652,35 @@ int obk_step(ObBackend *b, real h, int nsteps, int taps, char *err, size_t errle
   }
   return 0;
 }
+
+// split mirror: the "handle" is the exporting batch's fc / flag pointers (ranks are threads of one process)
+struct HostSplitHandle { void *fc; void *flags; unsigned long long nb; };
+int obk_split_export(ObBackend *b, void *handle128, char *err, size_t errlen) {
+  if (!b->d.large) { snprintf(err, errlen, "only the large-world path splits over GPUs"); return -1; }
+  if (!b->split_fc) {
+    b->split_fc = halloc<real>(b, (size_t)b->d.NB * 6);
+    b->split_flags = new std::atomic<unsigned>[OB_LW_FLAG_WORDS];
+    for (int k = 0; k < OB_LW_FLAG_WORDS; k++) ((std::atomic<unsigned> *)b->split_flags)[k].store(0);
+  }
+  memset(handle128, 0, OBK_SPLIT_HANDLE_BYTES);
+  HostSplitHandle H = {b->split_fc, b->split_flags, (unsigned long long)b->d.NB};
+  memcpy(handle128, &H, sizeof H);
+  return 0;
+}
+int obk_split_attach(ObBackend *b, int rank, int nranks, const void *handles, char *err, size_t errlen) {
+  if (!b->d.large || !b->split_fc) { snprintf(err, errlen, "export before attach (large-world batches only)"); return -1; }
+  if (nranks < 1 || nranks > OB_LW_MAXRANKS || rank < 0 || rank >= nranks) { snprintf(err, errlen, "bad rank %d of %d", rank, nranks); return -1; }
+  LargeHostSplit *S = new LargeHostSplit;
+  S->rank = rank; S->nranks = nranks; S->base = 0;
+  S->timeout_ms = getenv("OB_LW_SPLIT_TIMEOUT_MS") ? (unsigned)atoi(getenv("OB_LW_SPLIT_TIMEOUT_MS")) : 20000u;
+  for (int r = 0; r < nranks; r++) {
+    HostSplitHandle H;
+    memcpy(&H, (const unsigned char *)handles + (size_t)r * OBK_SPLIT_HANDLE_BYTES, sizeof H);
+    if (H.nb != (unsigned long long)b->d.NB) { snprintf(err, errlen, "rank %d holds a world of another size", r); delete S; return -1; }
+    S->fc[r] = (real *)H.fc; S->flags[r] = (std::atomic<unsigned> *)H.flags;
+  }
+  if (S->fc[rank] != b->split_fc) { snprintf(err, errlen, "handle %d is not this batch's own export", rank); delete S; return -1; }
+  b->split = nranks > 1 ? S : 0;
+  return 0;
+}
+

@@ -11,7 +11,31 @@
 
 struct LargeHostStats { int np, ncontacts, ncp, ncol, rounds, nsolved; };
 
-static int large_step_host(ObBatchDev &d, real h, int taps, LargeHostStats *stats) {
+// Mirror of the split SOR phase (ObLwSplit, ob_large.h): each rank is a batch of its own, stepped by its own
+// host thread; the ranks write their fc results into every rank's array and meet at a flag barrier after each
+// colour -- the protocol of k_lw_sor_split / lw_split_barrier with std::atomic flag words.
+#include <atomic>
+#include <chrono>
+struct LargeHostSplit {
+  int rank, nranks;
+  unsigned base, timeout_ms;
+  real *fc[OB_LW_MAXRANKS];                       // [nb*6] per rank
+  std::atomic<unsigned> *flags[OB_LW_MAXRANKS];   // [OB_LW_FLAG_WORDS] per rank
+};
+static bool large_host_barrier(LargeHostSplit &S, unsigned phase) {
+  std::atomic<unsigned> *mine = S.flags[S.rank];
+  for (int r = 0; r < S.nranks; r++) if (r != S.rank) S.flags[r][S.rank].store(phase, std::memory_order_release);
+  const std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  for (int r = 0; r < S.nranks; r++) {
+    if (r == S.rank) continue;
+    while ((int)(mine[r].load(std::memory_order_acquire) - phase) < 0 && !mine[OB_LW_FLAG_TIMEOUT].load()) {
+      if (std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count() > (long long)S.timeout_ms) mine[OB_LW_FLAG_TIMEOUT].store(1);
+    }
+  }
+  return !mine[OB_LW_FLAG_TIMEOUT].load();
+}
+
+static int large_step_host(ObBatchDev &d, real h, int taps, LargeHostStats *stats, LargeHostSplit *split = 0) {
   ObWorld &W = d.world[0];
   const int ng = W.ng, nb = W.nb;
   if (W.space_type != OB_SPACE_SAP) return -1;
@@ -147,7 +171,9 @@ static int large_step_host(ObBatchDev &d, real h, int taps, LargeHostStats *stat
   for (int p = 0; p < ncpairs; p++) ncol = std::max(ncol, ((scp[p].info >> 16) & 255) + 1);
   // (6) bodies
   const real stepsize1 = ob_recip(h);
-  std::vector<real> fc((size_t)nb * 6, (real)0);
+  std::vector<real> fc_own(split ? (size_t)0 : (size_t)nb * 6, (real)0);
+  real *fc = split ? split->fc[split->rank] : fc_own.data();
+  if (split) for (size_t k = 0; k < (size_t)nb * 6; k++) fc[k] = 0;
   std::vector<int> hasrow(nb, 0);
   for (int b = 0; b < nb; b++) {
     ObBodyDyn &B = d.bdyn[b];
@@ -187,6 +213,39 @@ static int large_step_host(ObBatchDev &d, real h, int taps, LargeHostStats *stat
   }
   rstart[ncpairs] = rows.size();
   std::vector<real> lam(rows.size(), (real)0);
+  // (8') split over ranks: the pairs of a colour are dealt over the ranks by warp tile (ob_lw_split_owner), results
+  // go into every rank's fc, barrier after every colour (and one before the first store: the peers' fc must be cleared)
+  if (split && ncpairs > 0 && W.iters > 0) {
+    LargeHostSplit &S = *split;
+    unsigned phase = S.base;
+    bool ok = large_host_barrier(S, ++phase);
+    std::vector<int> colstart(ncol + 1, ncpairs);
+    for (int p = ncpairs - 1; p >= 0; p--) colstart[(scp[p].info >> 16) & 255] = p;
+    for (int c = ncol - 1; c >= 0; c--) if (colstart[c] > colstart[c + 1]) colstart[c] = colstart[c + 1];
+    for (int it = 0; it < W.iters; it++)
+      for (int c = 0; c < ncol; c++) {
+        for (int p = colstart[c]; p < colstart[c + 1]; p++) {
+          if (ob_lw_split_owner(p - colstart[c], S.nranks) != S.rank) continue;
+          const ObLwPair &P = scp[p];
+          const int nc = P.info & 255, b1 = P.b1, b2 = P.b2;
+          real f1[6], f2[6] = {0, 0, 0, 0, 0, 0};
+          for (int e = 0; e < 6; e++) { f1[e] = fc[(size_t)6 * b1 + e]; if (b2 >= 0) f2[e] = fc[(size_t)6 * b2 + e]; }
+          const real k1 = d.bconst[b1].invMass, k2 = b2 >= 0 ? d.bconst[b2].invMass : (real)0;
+          for (int k = 0; k < nc; k++)
+            for (int q = 0; q < m; q++) {
+              const size_t ri = rstart[p] + (size_t)k * m + q;
+              const int fio = (rows[ri].meta >> 16) & 255;
+              const real lam_f = fio ? lam[ri - fio] : (real)0;
+              lam[ri] = ob_lw_row_update(rows[ri].v, rows[ri].meta, k1, k2, b2 >= 0, lam_f, lam[ri], f1, b2 >= 0 ? f2 : (real *)0);
+            }
+          for (int r = 0; r < S.nranks; r++)
+            for (int e = 0; e < 6; e++) { S.fc[r][(size_t)6 * b1 + e] = f1[e]; if (b2 >= 0) S.fc[r][(size_t)6 * b2 + e] = f2[e]; }
+        }
+        ok = large_host_barrier(S, ++phase) && ok;
+      }
+    S.base = phase;
+    if (!ok) return -7;
+  } else
   // (8) SOR: sequential Gauss-Seidel in (colour, pair, contact, row) order
   for (int it = 0; it < W.iters; it++)
     for (int p = 0; p < ncpairs; p++) {
