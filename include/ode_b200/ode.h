@@ -269,6 +269,7 @@ const dReal *dBodyGetAngularVel(dBodyID);
 void dBodySetMass(dBodyID, const dMass *mass);
 void dBodyGetMass(dBodyID, dMass *mass);
 void dBodyAddForce(dBodyID, dReal fx, dReal fy, dReal fz);
+void dBodyGetRelPointVel(dBodyID, dReal px, dReal py, dReal pz, dVector3 result);   /* include/ode/objects.h:1113 */
 void dBodyAddTorque(dBodyID, dReal fx, dReal fy, dReal fz);
 void dBodyAddRelForce(dBodyID, dReal fx, dReal fy, dReal fz);
 void dBodyAddRelTorque(dBodyID, dReal fx, dReal fy, dReal fz);
@@ -313,6 +314,10 @@ dJointID dJointCreateUniversal(dWorldID, dJointGroupID);   /* include/ode/object
 dJointID dJointCreateFixed(dWorldID, dJointGroupID);
 dJointID dJointCreateAMotor(dWorldID, dJointGroupID);   /* include/ode/objects.h:1634, ode/src/joints/amotor.cpp */
 dJointID dJointCreateLMotor(dWorldID, dJointGroupID);   /* include/ode/objects.h:1643, ode/src/joints/lmotor.cpp */    /* include/ode/objects.h:1616, ode/src/joints/fixed.cpp */
+dJointID dJointCreatePR(dWorldID, dJointGroupID);        /* include/ode/objects.h:1586, ode/src/joints/pr.cpp */
+dJointID dJointCreatePU(dWorldID, dJointGroupID);        /* include/ode/objects.h:1594, ode/src/joints/pu.cpp */
+dJointID dJointCreatePiston(dWorldID, dJointGroupID);    /* include/ode/objects.h:1603, ode/src/joints/piston.cpp */
+dJointID dJointCreatePlane2D(dWorldID, dJointGroupID);   /* include/ode/objects.h:1637, ode/src/joints/plane2d.cpp */
 void dJointDestroy(dJointID);
 void dJointAttach(dJointID, dBodyID body1, dBodyID body2);
 void dJointEnable(dJointID);
@@ -330,6 +335,64 @@ dReal dJointGetSliderParam(dJointID, int parameter);
 dReal dJointGetSliderPosition(dJointID);
 dReal dJointGetSliderPositionRate(dJointID);
 void dJointAddSliderForce(dJointID, dReal force);
+/* plane2d (include/ode/objects.h:2332-2346): body 1 is kept in the plane z = 0 of the static environment;
+ * optional motors along x, y and about z.  A second body is refused by dBatchCreate / dWorldQuickStep. */
+void dJointSetPlane2DXParam(dJointID, int parameter, dReal value);
+void dJointSetPlane2DYParam(dJointID, int parameter, dReal value);
+void dJointSetPlane2DAngleParam(dJointID, int parameter, dReal value);
+/* piston (include/ode/objects.h:2169-2215, 2790-2870): prismatic + rotoide about the same axis; parameter
+ * group 1 = prismatic limit-motor, group 2 (dParamLoStop2 ...) = rotoide */
+void dJointSetPistonAnchor(dJointID, dReal x, dReal y, dReal z);
+void dJointSetPistonAnchorOffset(dJointID, dReal x, dReal y, dReal z, dReal dx, dReal dy, dReal dz);
+void dJointGetPistonAnchor(dJointID, dVector3 result);
+void dJointGetPistonAnchor2(dJointID, dVector3 result);
+void dJointSetPistonAxis(dJointID, dReal x, dReal y, dReal z);
+void dJointGetPistonAxis(dJointID, dVector3 result);
+void dJointSetPistonParam(dJointID, int parameter, dReal value);
+dReal dJointGetPistonParam(dJointID, int parameter);
+dReal dJointGetPistonPosition(dJointID);
+dReal dJointGetPistonPositionRate(dJointID);
+dReal dJointGetPistonAngle(dJointID);
+dReal dJointGetPistonAngleRate(dJointID);
+void dJointAddPistonForce(dJointID, dReal force);
+/* PR, prismatic + rotoide about different axes (include/ode/objects.h:2035-2062, 2640-2700):
+ * axis 1 = prismatic, axis 2 = rotoide */
+void dJointSetPRAnchor(dJointID, dReal x, dReal y, dReal z);
+void dJointSetPRAxis1(dJointID, dReal x, dReal y, dReal z);
+void dJointSetPRAxis2(dJointID, dReal x, dReal y, dReal z);
+void dJointGetPRAnchor(dJointID, dVector3 result);
+void dJointGetPRAxis1(dJointID, dVector3 result);
+void dJointGetPRAxis2(dJointID, dVector3 result);
+void dJointSetPRParam(dJointID, int parameter, dReal value);
+dReal dJointGetPRParam(dJointID, int parameter);
+dReal dJointGetPRPosition(dJointID);
+dReal dJointGetPRPositionRate(dJointID);
+dReal dJointGetPRAngle(dJointID);
+dReal dJointGetPRAngleRate(dJointID);
+void dJointAddPRTorque(dJointID, dReal torque);
+/* PU, prismatic + universal (include/ode/objects.h:2072-2160, 2700-2790): axes 1, 2 = universal, axis 3 (P) =
+ * prismatic; parameter groups 1, 2 = the universal axes, group 3 (dParamLoStop3 ...) = prismatic */
+void dJointSetPUAnchor(dJointID, dReal x, dReal y, dReal z);
+void dJointSetPUAnchorDelta(dJointID, dReal x, dReal y, dReal z, dReal dx, dReal dy, dReal dz);
+void dJointSetPUAnchorOffset(dJointID, dReal x, dReal y, dReal z, dReal dx, dReal dy, dReal dz);
+void dJointSetPUAxis1(dJointID, dReal x, dReal y, dReal z);
+void dJointSetPUAxis2(dJointID, dReal x, dReal y, dReal z);
+void dJointSetPUAxis3(dJointID, dReal x, dReal y, dReal z);
+void dJointSetPUAxisP(dJointID, dReal x, dReal y, dReal z);
+void dJointGetPUAnchor(dJointID, dVector3 result);
+void dJointGetPUAxis1(dJointID, dVector3 result);
+void dJointGetPUAxis2(dJointID, dVector3 result);
+void dJointGetPUAxis3(dJointID, dVector3 result);
+void dJointGetPUAxisP(dJointID, dVector3 result);
+void dJointSetPUParam(dJointID, int parameter, dReal value);
+dReal dJointGetPUParam(dJointID, int parameter);
+void dJointGetPUAngles(dJointID, dReal *angle1, dReal *angle2);
+dReal dJointGetPUAngle1(dJointID);
+dReal dJointGetPUAngle2(dJointID);
+dReal dJointGetPUAngle1Rate(dJointID);
+dReal dJointGetPUAngle2Rate(dJointID);
+dReal dJointGetPUPosition(dJointID);
+dReal dJointGetPUPositionRate(dJointID);
 void dJointSetUniversalAnchor(dJointID, dReal x, dReal y, dReal z);
 void dJointSetUniversalAxis1(dJointID, dReal x, dReal y, dReal z);
 void dJointSetUniversalAxis2(dJointID, dReal x, dReal y, dReal z);

@@ -51,7 +51,9 @@ void ob_marshal_joint(const dxJoint *j, ObJoint &d) {
     d.anchor1[k] = j->anchor1[k]; d.anchor2[k] = j->anchor2[k]; d.axis1[k] = j->axis1[k]; d.axis2[k] = j->axis2[k];
     d.qrel[k] = j->qrel[k]; d.v1[k] = j->v1[k]; d.v2[k] = j->v2[k];
   }
+  if (j->type == dJointTypePU) for (int k = 0; k < 4; k++) { d.v1[k] = j->qrel2[k]; d.v2[k] = j->axis3[k]; }   // universal part as below; v2 = axisP1
   if (j->type == dJointTypeUniversal) for (int k = 0; k < 4; k++) d.v1[k] = j->qrel2[k];   // ObJoint::v1 doubles as qrel2
+  if (j->type == dJointTypePR) for (int k = 0; k < 4; k++) { d.anchor1[k] = k < 3 ? j->offset[k] : 0; d.v1[k] = j->axis3[k]; }   // offset -> anchor1, axisP1 -> v1
   if (j->type == dJointTypeSlider || j->type == dJointTypeFixed) for (int k = 0; k < 3; k++) d.anchor1[k] = j->offset[k];   // ObJoint::anchor1 doubles as the offset
   d.erp = j->erp; d.cfm = j->cfm; d.susp_erp = j->susp_erp; d.susp_cfm = j->susp_cfm; d.c0 = j->c0; d.s0 = j->s0;
   fill_limot(d.limot1, j->limot);
@@ -199,7 +201,9 @@ dxBatch *ob_batch_create(int nworlds, const dWorldID *worlds, const dSpaceID *sp
         if (dropin) continue;
         ob_set_last_error("dBatchCreate: world %d: contact joints present at bind time (call dJointGroupEmpty first)", w); delete B; return 0;
       }
-      if (j->type != dJointTypeBall && j->type != dJointTypeHinge && j->type != dJointTypeHinge2 && j->type != dJointTypeSlider && j->type != dJointTypeFixed && j->type != dJointTypeUniversal && j->type != dJointTypeAMotor && j->type != dJointTypeLMotor) { ob_set_last_error("dBatchCreate: world %d: unsupported joint type %d", w, j->type); delete B; return 0; }
+      if (j->type != dJointTypeBall && j->type != dJointTypeHinge && j->type != dJointTypeHinge2 && j->type != dJointTypeSlider && j->type != dJointTypeFixed && j->type != dJointTypeUniversal && j->type != dJointTypeAMotor && j->type != dJointTypeLMotor && j->type != dJointTypePlane2D && j->type != dJointTypePiston && j->type != dJointTypePR && j->type != dJointTypePU) { ob_set_last_error("dBatchCreate: world %d: unsupported joint type %d", w, j->type); delete B; return 0; }
+      // plane2d constrains body 1 against the static environment (plane2d.cpp:95-118 never fills J2); a second body is refused
+      if (j->type == dJointTypePlane2D && j->node[1].body) { ob_set_last_error("dBatchCreate: world %d: a plane2d joint takes one body", w); delete B; return 0; }
       B->joints[w].push_back(j);
     }
     std::reverse(B->joints[w].begin(), B->joints[w].end());

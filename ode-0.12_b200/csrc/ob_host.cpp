@@ -475,6 +475,13 @@ void dBodySetMass(dBodyID b, const dMass *mass) {
 void dBodyGetMass(dBodyID b, dMass *mass) { memcpy(mass, &b->mass, sizeof(dMass)); }
 void dBodyAddForce(dBodyID b, dReal fx, dReal fy, dReal fz) { b->facc[0] += fx; b->facc[1] += fy; b->facc[2] += fz; }
 void dBodyAddTorque(dBodyID b, dReal fx, dReal fy, dReal fz) { b->tacc[0] += fx; b->tacc[1] += fy; b->tacc[2] += fz; }
+void dBodyGetRelPointVel(dBodyID b, dReal px, dReal py, dReal pz, dVector3 result) {   // ode.cpp: lvel + avel x (R * prel)
+  dReal prel[4] = {px, py, pz, 0}, p[4], c[4];
+  ob_mul0_331(p, b->R, prel);
+  ob_cross(c, b->avel, p);
+  result[0] = b->lvel[0]; result[1] = b->lvel[1]; result[2] = b->lvel[2];
+  result[0] += c[0]; result[1] += c[1]; result[2] += c[2];
+}
 void dBodyAddRelForce(dBodyID b, dReal fx, dReal fy, dReal fz) {
   dReal t1[3] = {fx, fy, fz}, t2[3];
   ob_mul0_331(t2, b->R, t1);
@@ -616,6 +623,10 @@ dJointID dJointCreateFixed(dWorldID w, dJointGroupID g) { return create_joint(w,
 dJointID dJointCreateUniversal(dWorldID w, dJointGroupID g) { return create_joint(w, g, dJointTypeUniversal); }
 dJointID dJointCreateAMotor(dWorldID w, dJointGroupID g) { return create_joint(w, g, dJointTypeAMotor); }
 dJointID dJointCreateLMotor(dWorldID w, dJointGroupID g) { return create_joint(w, g, dJointTypeLMotor); }
+dJointID dJointCreatePlane2D(dWorldID w, dJointGroupID g) { return create_joint(w, g, dJointTypePlane2D); }
+dJointID dJointCreatePiston(dWorldID w, dJointGroupID g) { return create_joint(w, g, dJointTypePiston); }
+dJointID dJointCreatePR(dWorldID w, dJointGroupID g) { return create_joint(w, g, dJointTypePR); }
+dJointID dJointCreatePU(dWorldID w, dJointGroupID g) { return create_joint(w, g, dJointTypePU); }
 static void joint_free(dxJoint *j) {
   if (j->world) {
     joint_unlink_bodies(j);

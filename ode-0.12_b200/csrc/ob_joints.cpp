@@ -69,6 +69,21 @@ void ob_joint_init_type(dxJoint *j) {
       j->axis1[0] = 1; j->axis2[1] = 1;
       limot_init(j->limot, w); limot_init(j->limot2, w);
       break;
+    case dJointTypePlane2D:   // limot = x motor, limot2 = y motor, limot3 = angle motor (plane2d.cpp:54-60)
+      limot_init(j->limot, w); limot_init(j->limot2, w); limot_init(j->limot3, w);
+      break;
+    case dJointTypePiston:    // limot = prismatic, limot2 = rotoide (piston.cpp:37-50)
+      j->axis1[0] = 1; j->axis2[0] = 1;
+      limot_init(j->limot, w); limot_init(j->limot2, w);
+      break;
+    case dJointTypePR:        // axis1/axis2 = axisR1/axisR2, axis3 = axisP1, offset = anchor w.r.t. body 1 (pr.cpp:36-64)
+      j->axis1[0] = 1; j->axis2[0] = 1; j->axis3[1] = 1;
+      limot_init(j->limot, w); limot_init(j->limot2, w);
+      break;
+    case dJointTypePU:        // universal fields + axis3 = axisP1; limot / limot2 = universal axes, limot3 = prismatic (pu.cpp:31-72)
+      j->axis1[1] = 1; j->axis2[2] = 1; j->axis3[0] = 1;
+      limot_init(j->limot, w); limot_init(j->limot2, w); limot_init(j->limot3, w);
+      break;
     case dJointTypeAMotor:
     case dJointTypeLMotor:
       j->num = 0; j->mode = dAMotorUser;
@@ -481,6 +496,243 @@ void dJointSetLMotorParam(dJointID j, int parameter, dReal value) { int anum = p
 int dJointGetLMotorNumAxes(dJointID j) { return j->num; }
 void dJointGetLMotorAxis(dJointID j, int anum, dVector3 result) { if (anum < 0) anum = 0; if (anum > 2) anum = 2; const dReal *a = motor_axis(j, anum); result[0] = a[0]; result[1] = a[1]; result[2] = a[2]; }
 dReal dJointGetLMotorParam(dJointID j, int parameter) { int anum = parameter >> 8; if (anum < 0) anum = 0; if (anum > 2) anum = 2; return limot_get(motor_limot(j, anum), parameter & 0xff); }
+
+// ---- plane2d (plane2d.cpp), piston (piston.cpp), PR (pr.cpp) ------------------------------------------
+void dJointSetPlane2DXParam(dJointID j, int parameter, dReal value) { limot_set(j->limot, parameter, value); }
+void dJointSetPlane2DYParam(dJointID j, int parameter, dReal value) { limot_set(j->limot2, parameter, value); }
+void dJointSetPlane2DAngleParam(dJointID j, int parameter, dReal value) { limot_set(j->limot3, parameter, value); }
+
+static void get_axis(dxJoint *j, dReal *result, const dReal *axis) {   // joint.cpp getAxis
+  if (j->node[0].body) ob_mul0_331(result, j->node[0].body->R, axis);
+}
+// dJointGetPistonPosition (piston.cpp:54-107) / dJointGetPRPosition (pr.cpp:75-125)
+static dReal prismatic_position(dxJoint *j, const dReal *anchor1, const dReal *axisP) {
+  if (!j->node[0].body) return 0;
+  dxBody *b0 = j->node[0].body, *b1 = j->node[1].body;
+  dReal q[4], ax[4];
+  ob_mul0_331(q, b0->R, anchor1);
+  if (b1) {
+    dReal a2[4];
+    ob_mul0_331(a2, b1->R, j->anchor2);
+    for (int i = 0; i < 3; i++) q[i] = (b0->pos[i] + q[i]) - (b1->pos[i] + a2[i]);
+  } else {
+    for (int i = 0; i < 3; i++) q[i] = (b0->pos[i] + q[i]) - j->anchor2[i];
+    if (j->flags & dJOINT_REVERSE) { q[0] = -q[0]; q[1] = -q[1]; q[2] = -q[2]; }
+  }
+  ob_mul0_331(ax, b0->R, axisP);
+  return ob_dot(ax, q);
+}
+static dReal rotoide_angle(dxJoint *j) {
+  if (!j->node[0].body) return 0;
+  dReal ang = ob_hinge_angle(j->node[0].body->q, j->node[1].body ? j->node[1].body->q : 0, j->axis1, j->qrel);
+  return (j->flags & dJOINT_REVERSE) ? -ang : ang;
+}
+static dReal rotoide_rate(dxJoint *j) {
+  if (!j->node[0].body) return 0;
+  dReal axis[4];
+  ob_mul0_331(axis, j->node[0].body->R, j->axis1);
+  dReal rate = ob_dot(axis, j->node[0].body->avel);
+  if (j->node[1].body) rate -= ob_dot(axis, j->node[1].body->avel);
+  if (j->flags & dJOINT_REVERSE) rate = -rate;
+  return rate;
+}
+static void two_limot_set(dxJoint *j, int parameter, dReal value) {   // group 2 (0x100) = rotoide, else prismatic
+  if ((parameter & 0xff00) == 0x100) limot_set(j->limot2, parameter & 0xff, value);
+  else limot_set(j->limot, parameter, value);
+}
+static dReal two_limot_get(dxJoint *j, int parameter) {
+  if ((parameter & 0xff00) == 0x100) return limot_get(j->limot2, parameter & 0xff);
+  return limot_get(j->limot, parameter);
+}
+
+void dJointSetPistonAnchor(dJointID j, dReal x, dReal y, dReal z) {
+  set_anchors(j, x, y, z, j->anchor1, j->anchor2);
+  hinge_initial_rel_rot(j);
+}
+void dJointSetPistonAnchorOffset(dJointID j, dReal x, dReal y, dReal z, dReal dx, dReal dy, dReal dz) {   // piston.cpp:434-466
+  if (j->flags & dJOINT_REVERSE) { dx = -dx; dy = -dy; dz = -dz; }
+  dxBody *b0 = j->node[0].body;
+  if (b0) { b0->pos[0] -= dx; b0->pos[1] -= dy; b0->pos[2] -= dz; }
+  set_anchors(j, x, y, z, j->anchor1, j->anchor2);
+  if (b0) { b0->pos[0] += dx; b0->pos[1] += dy; b0->pos[2] += dz; }
+  hinge_initial_rel_rot(j);
+}
+void dJointGetPistonAnchor(dJointID j, dVector3 result) {
+  if (j->flags & dJOINT_REVERSE) get_anchor2(j, result, j->anchor2);
+  else get_anchor(j, result, j->anchor1);
+}
+void dJointGetPistonAnchor2(dJointID j, dVector3 result) {
+  if (j->flags & dJOINT_REVERSE) get_anchor(j, result, j->anchor1);
+  else get_anchor2(j, result, j->anchor2);
+}
+void dJointSetPistonAxis(dJointID j, dReal x, dReal y, dReal z) {
+  set_axes(j, x, y, z, j->axis1, j->axis2);
+  hinge_initial_rel_rot(j);
+}
+void dJointGetPistonAxis(dJointID j, dVector3 result) { get_axis(j, result, j->axis1); }
+void dJointSetPistonParam(dJointID j, int parameter, dReal value) { two_limot_set(j, parameter, value); }
+dReal dJointGetPistonParam(dJointID j, int parameter) { return two_limot_get(j, parameter); }
+dReal dJointGetPistonPosition(dJointID j) { return prismatic_position(j, j->anchor1, j->axis1); }
+dReal dJointGetPistonPositionRate(dJointID j) {   // piston.cpp:110-133
+  dReal ax[4];
+  ob_mul0_331(ax, j->node[0].body->R, j->axis1);
+  if (j->node[1].body) return ob_dot(ax, j->node[0].body->lvel) - ob_dot(ax, j->node[1].body->lvel);
+  dReal rate = ob_dot(ax, j->node[0].body->lvel);
+  return (j->flags & dJOINT_REVERSE) ? -rate : rate;
+}
+dReal dJointGetPistonAngle(dJointID j) { return rotoide_angle(j); }
+dReal dJointGetPistonAngleRate(dJointID j) { return rotoide_rate(j); }
+void dJointAddPistonForce(dJointID j, dReal force) {   // piston.cpp:586-664
+  if (j->flags & dJOINT_REVERSE) force -= force;   // sic
+  dReal axis[4] = {0, 0, 0, 0};
+  get_axis(j, axis, j->axis1);
+  axis[0] *= force; axis[1] *= force; axis[2] *= force;
+  dxBody *b0 = j->node[0].body, *b1 = j->node[1].body;
+  if (b0) dBodyAddForce(b0, axis[0], axis[1], axis[2]);
+  if (b1) dBodyAddForce(b1, -axis[0], -axis[1], -axis[2]);
+  if (b0 && b1) {
+    dReal ltd[4], c[4];
+    ob_mul0_331(c, b0->R, j->anchor1);
+    ob_cross(ltd, c, axis);
+    dBodyAddTorque(b0, ltd[0], ltd[1], ltd[2]);
+    ob_mul0_331(c, b1->R, j->anchor2);
+    ob_cross(ltd, c, axis);
+    dBodyAddTorque(b1, ltd[0], ltd[1], ltd[2]);
+  }
+}
+
+void dJointSetPRAnchor(dJointID j, dReal x, dReal y, dReal z) { set_anchors(j, x, y, z, j->offset, j->anchor2); }
+void dJointSetPRAxis1(dJointID j, dReal x, dReal y, dReal z) {
+  set_axes(j, x, y, z, j->axis3, 0);
+  hinge_initial_rel_rot(j);
+}
+void dJointSetPRAxis2(dJointID j, dReal x, dReal y, dReal z) {
+  set_axes(j, x, y, z, j->axis1, j->axis2);
+  hinge_initial_rel_rot(j);
+}
+void dJointGetPRAnchor(dJointID j, dVector3 result) {
+  if (j->node[1].body) get_anchor2(j, result, j->anchor2);
+  else { result[0] = j->anchor2[0]; result[1] = j->anchor2[1]; result[2] = j->anchor2[2]; }
+}
+void dJointGetPRAxis1(dJointID j, dVector3 result) { get_axis(j, result, j->axis3); }
+void dJointGetPRAxis2(dJointID j, dVector3 result) { get_axis(j, result, j->axis1); }
+void dJointSetPRParam(dJointID j, int parameter, dReal value) { two_limot_set(j, parameter, value); }
+dReal dJointGetPRParam(dJointID j, int parameter) { return two_limot_get(j, parameter); }
+dReal dJointGetPRPosition(dJointID j) { return prismatic_position(j, j->offset, j->axis3); }
+dReal dJointGetPRPositionRate(dJointID j) {   // pr.cpp:128-160
+  dReal ax[4];
+  ob_mul0_331(ax, j->node[0].body->R, j->axis3);
+  if (j->node[1].body) {
+    dVector3 lv2;
+    dBodyGetRelPointVel(j->node[1].body, j->anchor2[0], j->anchor2[1], j->anchor2[2], lv2);
+    return ob_dot(ax, j->node[0].body->lvel) - ob_dot(ax, lv2);
+  }
+  dReal rate = ob_dot(ax, j->node[0].body->lvel);
+  return (j->flags & dJOINT_REVERSE) ? -rate : rate;
+}
+dReal dJointGetPRAngle(dJointID j) { return rotoide_angle(j); }
+dReal dJointGetPRAngleRate(dJointID j) { return rotoide_rate(j); }
+void dJointAddPRTorque(dJointID j, dReal torque) {   // pr.cpp:563-583
+  dReal axis[4] = {0, 0, 0, 0};
+  if (j->flags & dJOINT_REVERSE) torque = -torque;
+  get_axis(j, axis, j->axis1);
+  axis[0] *= torque; axis[1] *= torque; axis[2] *= torque;
+  if (j->node[0].body) dBodyAddTorque(j->node[0].body, axis[0], axis[1], axis[2]);
+  if (j->node[1].body) dBodyAddTorque(j->node[1].body, -axis[0], -axis[1], -axis[2]);
+}
+
+// ---- PU, prismatic + universal (pu.cpp; the universal part is dxJointUniversal's) -----------------------
+void dJointSetPUAnchor(dJointID j, dReal x, dReal y, dReal z) { set_anchors(j, x, y, z, j->anchor1, j->anchor2); universal_initial_rel_rots(j); }
+void dJointSetPUAnchorDelta(dJointID j, dReal x, dReal y, dReal z, dReal dx, dReal dy, dReal dz) {   // pu.cpp:418-440
+  dxBody *b0 = j->node[0].body;
+  if (b0) { b0->pos[0] += dx; b0->pos[1] += dy; b0->pos[2] += dz; }
+  set_anchors(j, x, y, z, j->anchor1, j->anchor2);
+  if (b0) { b0->pos[0] -= dx; b0->pos[1] -= dy; b0->pos[2] -= dz; }
+  universal_initial_rel_rots(j);
+}
+void dJointSetPUAnchorOffset(dJointID j, dReal x, dReal y, dReal z, dReal dx, dReal dy, dReal dz) {   // pu.cpp:473-503
+  if (j->flags & dJOINT_REVERSE) { dx = -dx; dy = -dy; dz = -dz; }
+  dxBody *b0 = j->node[0].body;
+  if (b0) { b0->pos[0] -= dx; b0->pos[1] -= dy; b0->pos[2] -= dz; }
+  set_anchors(j, x, y, z, j->anchor1, j->anchor2);
+  if (b0) { b0->pos[0] += dx; b0->pos[1] += dy; b0->pos[2] += dz; }
+  universal_initial_rel_rots(j);
+}
+void dJointSetPUAxis1(dJointID j, dReal x, dReal y, dReal z) { dJointSetUniversalAxis1(j, x, y, z); }
+void dJointSetPUAxis2(dJointID j, dReal x, dReal y, dReal z) { dJointSetUniversalAxis2(j, x, y, z); }
+void dJointSetPUAxis3(dJointID j, dReal x, dReal y, dReal z) {
+  set_axes(j, x, y, z, j->axis3, 0);
+  universal_initial_rel_rots(j);
+}
+void dJointSetPUAxisP(dJointID j, dReal x, dReal y, dReal z) { dJointSetPUAxis3(j, x, y, z); }
+void dJointGetPUAnchor(dJointID j, dVector3 result) {
+  if (j->node[1].body) get_anchor2(j, result, j->anchor2);
+  else { result[0] = j->anchor2[0]; result[1] = j->anchor2[1]; result[2] = j->anchor2[2]; }
+}
+void dJointGetPUAxis1(dJointID j, dVector3 result) { dJointGetUniversalAxis1(j, result); }
+void dJointGetPUAxis2(dJointID j, dVector3 result) { dJointGetUniversalAxis2(j, result); }
+void dJointGetPUAxis3(dJointID j, dVector3 result) { get_axis(j, result, j->axis3); }
+void dJointGetPUAxisP(dJointID j, dVector3 result) { dJointGetPUAxis3(j, result); }
+void dJointSetPUParam(dJointID j, int parameter, dReal value) {
+  switch (parameter & 0xff00) {
+    case 0x000: limot_set(j->limot, parameter, value); break;
+    case 0x100: limot_set(j->limot2, parameter & 0xff, value); break;
+    case 0x200: limot_set(j->limot3, parameter & 0xff, value); break;
+  }
+}
+dReal dJointGetPUParam(dJointID j, int parameter) {
+  switch (parameter & 0xff00) {
+    case 0x000: return limot_get(j->limot, parameter);
+    case 0x100: return limot_get(j->limot2, parameter & 0xff);
+    case 0x200: return limot_get(j->limot3, parameter & 0xff);
+  }
+  return 0;
+}
+void dJointGetPUAngles(dJointID j, dReal *angle1, dReal *angle2) {   // pu.cpp:545-553: swapped, not negated, when reversed
+  *angle1 = 0; *angle2 = 0;
+  if (!j->node[0].body) return;
+  ObJoint o;
+  universal_fill(j, o);
+  dReal a1, a2;
+  ob_universal_angles(o, j->node[0].body->R, j->node[0].body->q, j->node[1].body ? j->node[1].body->R : 0, j->node[1].body ? j->node[1].body->q : 0, &a1, &a2);
+  if (j->flags & dJOINT_REVERSE) { *angle2 = a1; *angle1 = a2; } else { *angle1 = a1; *angle2 = a2; }
+}
+dReal dJointGetPUAngle1(dJointID j) { dReal a, b; dJointGetPUAngles(j, &a, &b); return a; }
+dReal dJointGetPUAngle2(dJointID j) { dReal a, b; dJointGetPUAngles(j, &a, &b); return b; }
+static dReal pu_angle_rate(dxJoint *j, int second) {   // pu.cpp:575-615
+  if (!j->node[0].body) return 0;
+  dReal axis[4] = {0, 0, 0, 0};
+  if (second) dJointGetUniversalAxis2(j, axis); else dJointGetUniversalAxis1(j, axis);
+  dReal rate = ob_dot(axis, j->node[0].body->avel);
+  if (j->node[1].body) rate -= ob_dot(axis, j->node[1].body->avel);
+  return rate;
+}
+dReal dJointGetPUAngle1Rate(dJointID j) { return pu_angle_rate(j, 0); }
+dReal dJointGetPUAngle2Rate(dJointID j) { return pu_angle_rate(j, 1); }
+dReal dJointGetPUPosition(dJointID j) { return prismatic_position(j, j->anchor1, j->axis3); }
+dReal dJointGetPUPositionRate(dJointID j) {   // pu.cpp:128-180
+  dxBody *b0 = j->node[0].body, *b1 = j->node[1].body;
+  if (!b0) return 0;
+  dReal r[4], anchor2[4] = {0, 0, 0, 0}, lvel1[4], axP1[4];
+  if (b1) {
+    ob_mul0_331(anchor2, b1->R, j->anchor2);
+    for (int i = 0; i < 3; i++) r[i] = b0->pos[i] - (anchor2[i] + b1->pos[i]);
+  } else {
+    for (int i = 0; i < 3; i++) r[i] = b0->pos[i] - j->anchor2[i];
+  }
+  ob_cross(lvel1, r, b0->avel);
+  for (int i = 0; i < 3; i++) lvel1[i] = lvel1[i] + b0->lvel[i];
+  ob_mul0_331(axP1, b0->R, j->axis3);
+  if (b1) {
+    dReal lvel2[4], tmp[4];
+    ob_cross(lvel2, anchor2, b1->avel);
+    for (int i = 0; i < 3; i++) tmp[i] = lvel2[i] + b1->lvel[i];
+    for (int i = 0; i < 3; i++) lvel1[i] = lvel1[i] - tmp[i];
+    return ob_dot(axP1, lvel1);
+  }
+  dReal rate = ob_dot(axP1, lvel1);
+  return (j->flags & dJOINT_REVERSE) ? -rate : rate;
+}
 }  // extern "C"
 
 // setRelativeValues, called from dJointAttach (ball.cpp, hinge.cpp, hinge2.cpp)
@@ -520,6 +772,34 @@ void ob_joint_set_relative_values(dxJoint *j) {
       dJointGetUniversalAxis2(j, ax2);
       if (j->flags & dJOINT_REVERSE) { set_axes(j, ax1[0], ax1[1], ax1[2], 0, j->axis2); set_axes(j, ax2[0], ax2[1], ax2[2], j->axis1, 0); }
       else { set_axes(j, ax1[0], ax1[1], ax1[2], j->axis1, 0); set_axes(j, ax2[0], ax2[1], ax2[2], 0, j->axis2); }
+      universal_initial_rel_rots(j);
+    } break;
+    case dJointTypePiston:   // piston.cpp:682-693
+      dJointGetPistonAnchor(j, v);
+      set_anchors(j, v[0], v[1], v[2], j->anchor1, j->anchor2);
+      dJointGetPistonAxis(j, v);
+      set_axes(j, v[0], v[1], v[2], j->axis1, j->axis2);
+      hinge_initial_rel_rot(j);
+      break;
+    case dJointTypePR:       // pr.cpp:598-613
+      dJointGetPRAnchor(j, v);
+      set_anchors(j, v[0], v[1], v[2], j->offset, j->anchor2);
+      dJointGetPRAxis1(j, v);
+      set_axes(j, v[0], v[1], v[2], j->axis3, 0);
+      dJointGetPRAxis2(j, v);
+      set_axes(j, v[0], v[1], v[2], j->axis1, j->axis2);
+      hinge_initial_rel_rot(j);
+      break;
+    case dJointTypePU: {     // pu.cpp:826-852 (sic: the prismatic axis goes through the axis2 slot of setAxes)
+      dJointGetPUAnchor(j, v);
+      set_anchors(j, v[0], v[1], v[2], j->anchor1, j->anchor2);
+      dReal ax1[4] = {0, 0, 0, 0}, ax2[4] = {0, 0, 0, 0}, ax3[4] = {0, 0, 0, 0};
+      dJointGetPUAxis1(j, ax1);
+      dJointGetPUAxis2(j, ax2);
+      dJointGetPUAxis3(j, ax3);
+      if (j->flags & dJOINT_REVERSE) { set_axes(j, ax1[0], ax1[1], ax1[2], 0, j->axis2); set_axes(j, ax2[0], ax2[1], ax2[2], j->axis1, 0); }
+      else { set_axes(j, ax1[0], ax1[1], ax1[2], j->axis1, 0); set_axes(j, ax2[0], ax2[1], ax2[2], 0, j->axis2); }
+      set_axes(j, ax3[0], ax3[1], ax3[2], 0, j->axis3);
       universal_initial_rel_rots(j);
     } break;
     default: break;

@@ -621,11 +621,13 @@ __device__ __forceinline__ void lw_split_barrier(unsigned *bar, unsigned local_t
   __syncthreads();
   if (threadIdx.x == 0) {
     volatile unsigned *mine = (volatile unsigned *)S.flags[S.rank];
+    // the ONE system-scope fence of the barrier: it returns when this CTA's peer stores have been performed at the
+    // peers, so everything ordered after it (the arrival, CTA 0's flag stores) reaches a peer after the data
     __threadfence_system();
     atomicAdd(bar, 1u);
     if (blockIdx.x == 0) {
       while (*(volatile unsigned *)bar < local_target) { }
-      __threadfence_system();
+      __threadfence();
       for (int r = 0; r < S.nranks; r++) if (r != S.rank) *((volatile unsigned *)S.flags[r] + S.rank) = phase;
       const unsigned long long t0 = lw_globaltimer();
       for (int r = 0; r < S.nranks; r++) {
@@ -634,12 +636,13 @@ __device__ __forceinline__ void lw_split_barrier(unsigned *bar, unsigned local_t
           if (lw_globaltimer() - t0 > (unsigned long long)S.timeout_ms * 1000000ull) mine[OB_LW_FLAG_TIMEOUT] = 1;
         }
       }
-      __threadfence_system();
+      // the peers' data arrived in this GPU's L2 before their flags did; the sweep reads fc with ld.cg (L2)
+      __threadfence();
       mine[OB_LW_FLAG_RELEASE] = phase;
     } else {
       while ((int)(mine[OB_LW_FLAG_RELEASE] - phase) < 0) { }
     }
-    __threadfence_system();
+    __threadfence();
   }
   __syncthreads();
 }

@@ -204,6 +204,27 @@ OB_HD real ob_slider_position(const ObJoint &j, const ObBodyView &B1, const ObBo
 }
 
 // dxJointAMotor::computeGlobalAxes / computeEulerAngles (amotor.cpp:51-126); lmotor.cpp:44-66 is the non-Euler branch
+// dJointGetPistonPosition / dJointGetPRPosition (piston.cpp:54-107, pr.cpp:75-125): the anchor (offset) carried by
+// body 1 relative to anchor2, along the prismatic axis carried by body 1
+OB_HD real ob_prismatic_position(const ObJoint &j, const real *anchor1, const real *axisP, const ObBodyView &B1, const ObBodyView *B2) {
+  real q[3], ax[3];
+  ob_mul0_331(q, B1.R, anchor1);
+  if (B2) {
+    real a2[3];
+    ob_mul0_331(a2, B2->R, j.anchor2);
+    q[0] = (B1.pos[0] + q[0]) - (B2->pos[0] + a2[0]);
+    q[1] = (B1.pos[1] + q[1]) - (B2->pos[1] + a2[1]);
+    q[2] = (B1.pos[2] + q[2]) - (B2->pos[2] + a2[2]);
+  } else {
+    q[0] = (B1.pos[0] + q[0]) - j.anchor2[0];
+    q[1] = (B1.pos[1] + q[1]) - j.anchor2[1];
+    q[2] = (B1.pos[2] + q[2]) - j.anchor2[2];
+    if (j.flags & OB_JF_REVERSE) { q[0] = -q[0]; q[1] = -q[1]; q[2] = -q[2]; }
+  }
+  ob_mul0_331(ax, B1.R, axisP);
+  return ob_dot(ax, q);
+}
+
 OB_HD void ob_motor_axis(const ObJoint &j, int i, const real *axis, const ObBodyView &B1, const ObBodyView *B2, real *out) {
   const int rel = OB_JM_REL(j.flags, i);
   if (rel == 1) ob_mul0_331(out, B1.R, axis);
@@ -292,6 +313,52 @@ OB_HD int ob_joint_info1(ObJoint &j, const ObBodyView &B1, const ObBodyView *B2)
       if (pos <= j.limot1.lostop) { j.limot1.limit = 1; j.limot1.limit_err = pos - j.limot1.lostop; m = 6; }
       else if (pos >= j.limot1.histop) { j.limot1.limit = 2; j.limot1.limit_err = pos - j.limot1.histop; m = 6; }
     }
+    return m;
+  }
+  if (j.type == OB_JOINT_PLANE2D) {   // plane2d.cpp:70-82
+    int m = 3;
+    if (j.limot1.fmax > 0) m++;
+    if (j.limot2.fmax > 0) m++;
+    if (j.limot3.fmax > 0) m++;
+    return m;
+  }
+  if (j.type == OB_JOINT_PISTON || j.type == OB_JOINT_PR) {   // piston.cpp:181-217, pr.cpp:196-232; limot1 = prismatic, limot2 = rotoide
+    int m = 4;
+    j.limot1.limit = 0;
+    if ((j.limot1.lostop > -OB_INF || j.limot1.histop < OB_INF) && j.limot1.lostop <= j.limot1.histop) {
+      const real pos = ob_prismatic_position(j, j.anchor1, j.type == OB_JOINT_PR ? j.v1 : j.axis1, B1, B2);
+      ob_limot_test_limit(j.limot1, pos);
+    }
+    if (j.limot1.limit || j.limot1.fmax > 0) m++;
+    j.limot2.limit = 0;
+    const bool limiting = j.type == OB_JOINT_PR ? ((double)j.limot2.lostop >= -OB_PI || (double)j.limot2.histop <= OB_PI)
+                                                : (j.limot2.lostop > -OB_INF || j.limot2.histop < OB_INF);
+    if (limiting && j.limot2.lostop <= j.limot2.histop) {
+      const real angle = ob_hinge_angle(B1.q, B2 ? B2->q : (const real *)0, j.axis1, j.qrel);
+      ob_limot_test_limit(j.limot2, angle);
+    }
+    if (j.limot2.limit || j.limot2.fmax > 0) m++;
+    return m;
+  }
+  if (j.type == OB_JOINT_PU) {   // pu.cpp:188-232; limot1 / limot2 = universal axes, limot3 = prismatic
+    int m = 3;
+    j.limot3.limit = 0;
+    if ((j.limot3.lostop > -OB_INF || j.limot3.histop < OB_INF) && j.limot3.lostop <= j.limot3.histop) {
+      const real pos = ob_prismatic_position(j, j.anchor1, j.v2, B1, B2);
+      ob_limot_test_limit(j.limot3, pos);
+    }
+    if (j.limot3.limit || j.limot3.fmax > 0) m++;
+    const bool limiting1 = ((double)j.limot1.lostop >= -OB_PI || (double)j.limot1.histop <= OB_PI) && j.limot1.lostop <= j.limot1.histop;
+    const bool limiting2 = ((double)j.limot2.lostop >= -OB_PI || (double)j.limot2.histop <= OB_PI) && j.limot2.lostop <= j.limot2.histop;
+    j.limot1.limit = 0; j.limot2.limit = 0;
+    if (limiting1 || limiting2) {
+      real angle1, angle2;
+      ob_universal_angles(j, B1.R, B1.q, B2 ? B2->R : (const real *)0, B2 ? B2->q : (const real *)0, &angle1, &angle2);
+      if (limiting1) ob_limot_test_limit(j.limot1, angle1);
+      if (limiting2) ob_limot_test_limit(j.limot2, angle2);
+    }
+    if (j.limot1.limit || j.limot1.fmax > 0) m++;
+    if (j.limot2.limit || j.limot2.fmax > 0) m++;
     return m;
   }
   if (j.type == OB_JOINT_HINGE2) {
@@ -475,7 +542,7 @@ OB_HD void ob_set_fixed_orientation(RO &r, int start_row, const real *qrel, cons
 // torque -fm*v on body 1, +fm*v on body 2; slider: side[0] = force (-fm*ax1 / +fm*ax1), side[1] = the
 // decoupling torque, -fm*ltd on BOTH bodies.
 OB_HD void ob_apply_joint_side(int jtype, const real side[OB_NSIDE][4], real *facc1, real *tacc1, real *facc2, real *tacc2) {
-  if (jtype == OB_JOINT_SLIDER) {
+  if (jtype == OB_JOINT_SLIDER || jtype == OB_JOINT_PISTON || jtype == OB_JOINT_PR) {
     const real fm = side[0][0];
     if (fm != 0) {
       for (int e = 0; e < 3; e++) facc1[e] += -fm * side[0][1 + e];
@@ -485,13 +552,31 @@ OB_HD void ob_apply_joint_side(int jtype, const real side[OB_NSIDE][4], real *fa
         for (int e = 0; e < 3; e++) tacc2[e] += -fm * side[1][1 + e];
       }
     }
+    // piston / PR: the rotoide motor follows the prismatic one (slot 2)
+    const real fr = side[2][0];
+    if (fr != 0) {
+      for (int e = 0; e < 3; e++) tacc1[e] += -fr * side[2][1 + e];
+      if (tacc2) for (int e = 0; e < 3; e++) tacc2[e] += fr * side[2][1 + e];
+    }
     return;
   }
-  for (int sx = 0; sx < OB_NSIDE; sx++) {
+  const int nrot = jtype == OB_JOINT_PU ? 2 : OB_NSIDE;
+  for (int sx = 0; sx < nrot; sx++) {
     const real fm = side[sx][0];
     if (fm != 0) {
       for (int e = 0; e < 3; e++) tacc1[e] += -fm * side[sx][1 + e];
       if (tacc2) for (int e = 0; e < 3; e++) tacc2[e] += fm * side[sx][1 + e];
+    }
+  }
+  if (jtype == OB_JOINT_PU) {   // the prismatic motor comes last: slot 2 = force, slot 3 = decoupling torque
+    const real fm = side[2][0];
+    if (fm != 0) {
+      for (int e = 0; e < 3; e++) facc1[e] += -fm * side[2][1 + e];
+      if (facc2) {
+        for (int e = 0; e < 3; e++) facc2[e] += fm * side[2][1 + e];
+        for (int e = 0; e < 3; e++) tacc1[e] += -fm * side[3][1 + e];
+        for (int e = 0; e < 3; e++) tacc2[e] += -fm * side[3][1 + e];
+      }
     }
   }
 }
@@ -626,6 +711,122 @@ OB_HD void ob_joint_info2(RO &r, const ObJoint &j, const ObBodyView &B1, const O
     if (ob_add_limot_lin(r, 5, j.limot1, ax1, B1, B2, fps, &fm, ltd) && fm != 0) {
       side[0][0] = fm; side[0][1] = ax1[0]; side[0][2] = ax1[1]; side[0][3] = ax1[2];
       side[1][0] = fm; side[1][1] = ltd[0]; side[1][2] = ltd[1]; side[1][3] = ltd[2];
+    }
+  } else if (j.type == OB_JOINT_PU) {   // pu.cpp:236-380
+    const real k = fps * *erp_io;
+    real axP[3], dist[3], wanchor2[3] = {0, 0, 0};
+    ob_mul0_331(axP, B1.R, j.v2);
+    if (B2) {
+      ob_mul0_331(wanchor2, B2->R, j.anchor2);
+      for (int i = 0; i < 3; i++) dist[i] = wanchor2[i] + B2->pos[i] - B1.pos[i];
+    } else if (j.flags & OB_JF_REVERSE) {
+      for (int i = 0; i < 3; i++) dist[i] = B1.pos[i] - j.anchor2[i];
+    } else {
+      for (int i = 0; i < 3; i++) dist[i] = j.anchor2[i] - B1.pos[i];
+    }
+    real ax1[3], ax2[3], q[3], p[3];
+    ob_universal_axes(j, B1.R, B2 ? B2->R : (const real *)0, ax1, ax2);
+    const real val = ob_dot(ax1, ax2);
+    q[0] = ax2[0] - val * ax1[0]; q[1] = ax2[1] - val * ax1[1]; q[2] = ax2[2] - val * ax1[2];
+    ob_cross(p, ax1, q);
+    ob_safe_normalize3(p);
+    for (int i = 0; i < 3; i++) r.J[0][3 + i] = p[i];
+    if (B2) for (int i = 0; i < 3; i++) r.J[0][9 + i] = -p[i];
+    r.c[0] = k * -val;
+    ob_cross(q, ax1, axP);
+    ob_cross(&r.J[1][3], dist, ax1);
+    ob_cross(&r.J[2][3], dist, q);
+    for (int i = 0; i < 3; i++) { r.J[1][i] = ax1[i]; r.J[2][i] = q[i]; }
+    if (B2) {
+      ob_cross(&r.J[1][9], ax1, wanchor2);
+      ob_cross(&r.J[2][9], q, wanchor2);
+      for (int i = 0; i < 3; i++) { r.J[1][6 + i] = -ax1[i]; r.J[2][6 + i] = -q[i]; }
+    }
+    real err[3];
+    ob_mul0_331(err, B1.R, j.anchor1);
+    for (int i = 0; i < 3; i++) err[i] = dist[i] - err[i];
+    r.c[1] = k * ob_dot(ax1, err);
+    r.c[2] = k * ob_dot(q, err);
+    real fm, ltd[3];
+    int row = 3;
+    int added = ob_add_limot_rot(r, row, j.limot1, ax1, B1, B2, fps, &fm);
+    if (added && fm != 0) { side[0][0] = fm; side[0][1] = ax1[0]; side[0][2] = ax1[1]; side[0][3] = ax1[2]; }
+    row += added;
+    added = ob_add_limot_rot(r, row, j.limot2, ax2, B1, B2, fps, &fm);
+    if (added && fm != 0) { side[1][0] = fm; side[1][1] = ax2[0]; side[1][2] = ax2[1]; side[1][3] = ax2[2]; }
+    row += added;
+    if (!B2 && (j.flags & OB_JF_REVERSE)) { axP[0] = -axP[0]; axP[1] = -axP[1]; axP[2] = -axP[2]; }
+    if (ob_add_limot_lin(r, row, j.limot3, axP, B1, B2, fps, &fm, ltd) && fm != 0) {
+      side[2][0] = fm; side[2][1] = axP[0]; side[2][2] = axP[1]; side[2][3] = axP[2];
+      side[3][0] = fm; side[3][1] = ltd[0]; side[3][2] = ltd[1]; side[3][3] = ltd[2];
+    }
+  } else if (j.type == OB_JOINT_PLANE2D) {   // plane2d.cpp:87-147 (body 1 against the static environment)
+    r.J[0][2] = 1; r.J[1][3] = 1; r.J[2][4] = 1;
+    const real eps = fps * *erp_io;
+    r.c[0] = eps * -B1.pos[2];
+    const real ex[3] = {1, 0, 0}, ey[3] = {0, 1, 0}, ez[3] = {0, 0, 1};
+    real fm, ltd[3];
+    int row = 3;
+    // the reference keeps the row numbers from getInfo1 (x, y, angle in this order, each only when its fmax > 0)
+    if (j.limot1.fmax > 0) row += ob_add_limot_lin(r, row, j.limot1, ex, B1, B2, fps, &fm, ltd);
+    if (j.limot2.fmax > 0) row += ob_add_limot_lin(r, row, j.limot2, ey, B1, B2, fps, &fm, ltd);
+    if (j.limot3.fmax > 0) row += ob_add_limot_rot(r, row, j.limot3, ez, B1, B2, fps, &fm);
+  } else if (j.type == OB_JOINT_PISTON || j.type == OB_JOINT_PR) {   // piston.cpp:220-421, pr.cpp:236-390
+    const bool pr = j.type == OB_JOINT_PR;
+    const real k = fps * *erp_io;
+    real dist[3], lanchor2[3] = {0, 0, 0};
+    if (B2) {
+      ob_mul0_331(lanchor2, B2->R, j.anchor2);
+      for (int i = 0; i < 3; i++) dist[i] = lanchor2[i] + B2->pos[i] - B1.pos[i];
+    } else if (j.flags & OB_JF_REVERSE) {
+      for (int i = 0; i < 3; i++) dist[i] = B1.pos[i] - j.anchor2[i];
+    } else {
+      for (int i = 0; i < 3; i++) dist[i] = j.anchor2[i] - B1.pos[i];
+    }
+    real ax1[3], axP[3], p[3], q[3], ax2[3], b[3];
+    ob_mul0_331(ax1, B1.R, j.axis1);           // rotoide axis (piston: also the prismatic axis)
+    if (pr) {
+      ob_mul0_331(axP, B1.R, j.v1);            // prismatic axis
+      ob_cross(q, ax1, axP);
+      for (int i = 0; i < 3; i++) p[i] = axP[i];
+    } else {
+      for (int i = 0; i < 3; i++) axP[i] = ax1[i];
+      ob_plane_space(ax1, p, q);
+    }
+    // rows 0, 1: no relative rotation about p and q
+    for (int i = 0; i < 3; i++) { r.J[0][3 + i] = p[i]; r.J[1][3 + i] = q[i]; }
+    if (B2) {
+      for (int i = 0; i < 3; i++) { r.J[0][9 + i] = -p[i]; r.J[1][9 + i] = -q[i]; }
+      ob_mul0_331(ax2, B2->R, j.axis2);
+    } else { ax2[0] = j.axis2[0]; ax2[1] = j.axis2[1]; ax2[2] = j.axis2[2]; }
+    ob_cross(b, ax1, ax2);
+    r.c[0] = k * ob_dot(p, b);
+    r.c[1] = k * ob_dot(q, b);
+    // rows 2, 3: no relative translation across the prismatic axis (piston: p, q; PR: the rotoide axis and q)
+    const real *u2 = pr ? ax1 : p;
+    ob_cross(&r.J[2][3], dist, u2);
+    ob_cross(&r.J[3][3], dist, q);
+    for (int i = 0; i < 3; i++) { r.J[2][i] = u2[i]; r.J[3][i] = q[i]; }
+    if (B2) {
+      ob_cross(&r.J[2][9], pr ? ax2 : p, lanchor2);
+      ob_cross(&r.J[3][9], q, lanchor2);
+      for (int i = 0; i < 3; i++) { r.J[2][6 + i] = -u2[i]; r.J[3][6 + i] = -q[i]; }
+    }
+    real err[3];
+    ob_mul0_331(err, B1.R, j.anchor1);
+    for (int i = 0; i < 3; i++) err[i] = dist[i] - err[i];
+    r.c[2] = k * ob_dot(u2, err);
+    r.c[3] = k * ob_dot(q, err);
+    real axm[3] = {axP[0], axP[1], axP[2]};
+    if (!B2 && (j.flags & OB_JF_REVERSE)) { axm[0] = -axP[0]; axm[1] = -axP[1]; axm[2] = -axP[2]; }
+    real fm, ltd[3];
+    const int added = ob_add_limot_lin(r, 4, j.limot1, axm, B1, B2, fps, &fm, ltd);
+    if (added && fm != 0) {
+      side[0][0] = fm; side[0][1] = axm[0]; side[0][2] = axm[1]; side[0][3] = axm[2];
+      side[1][0] = fm; side[1][1] = ltd[0]; side[1][2] = ltd[1]; side[1][3] = ltd[2];
+    }
+    if (ob_add_limot_rot(r, 4 + added, j.limot2, ax1, B1, B2, fps, &fm) && fm != 0) {
+      side[2][0] = fm; side[2][1] = ax1[0]; side[2][2] = ax1[1]; side[2][3] = ax1[2];
     }
   } else if (j.type == OB_JOINT_HINGE2) {
     const real erp = *erp_io;

@@ -78,17 +78,17 @@ struct __attribute__((aligned(16))) ObLimot {
   real fudge_factor, normal_cfm, stop_erp, stop_cfm;
   real bounce; int limit; real limit_err; int pad;
 };
-enum { OB_JOINT_BALL = 1, OB_JOINT_HINGE = 2, OB_JOINT_SLIDER = 3, OB_JOINT_CONTACT = 4, OB_JOINT_UNIVERSAL = 5, OB_JOINT_HINGE2 = 6, OB_JOINT_FIXED = 7, OB_JOINT_AMOTOR = 9, OB_JOINT_LMOTOR = 10 };   // == dJointType
+enum { OB_JOINT_BALL = 1, OB_JOINT_HINGE = 2, OB_JOINT_SLIDER = 3, OB_JOINT_CONTACT = 4, OB_JOINT_UNIVERSAL = 5, OB_JOINT_HINGE2 = 6, OB_JOINT_FIXED = 7, OB_JOINT_AMOTOR = 9, OB_JOINT_LMOTOR = 10, OB_JOINT_PLANE2D = 11, OB_JOINT_PR = 12, OB_JOINT_PU = 13, OB_JOINT_PISTON = 14 };   // == dJointType
 enum { OB_JF_DISABLED = 1, OB_JF_REVERSE = 2 };
 // motor joints (amotor / lmotor) pack their small integers into ObJoint::flags: num<<8 | mode<<12 | rel0<<16 | rel1<<20 | rel2<<24;
 // axes: axis1, axis2, anchor1; amotor: reference1 = anchor2, reference2 = v1, user-mode angles = qrel[0..2]
 #define OB_JM_NUM(f) (((f) >> 8) & 15)
 #define OB_JM_MODE(f) (((f) >> 12) & 15)
 #define OB_JM_REL(f, i) (((f) >> (16 + 4 * (i))) & 15)
-#define OB_NSIDE 3   // motor side-effect slots per joint
+#define OB_NSIDE 4   // motor side-effect slots per joint (PU: two rotational motors + force and decoupling torque of the prismatic one)
 struct __attribute__((aligned(16))) ObJoint {
   int type; int b1, b2; int flags;        // b1/b2 = node[0]/node[1] body index, -1 = none
-  real anchor1[4], anchor2[4], axis1[4], axis2[4], qrel[4];   // slider / fixed: anchor1 = offset; universal: qrel = qrel1, v1 = qrel2
+  real anchor1[4], anchor2[4], axis1[4], axis2[4], qrel[4];   // slider / fixed / PR: anchor1 = offset; universal: qrel = qrel1, v1 = qrel2; PR: axis1/axis2 = axisR1/axisR2, v1 = axisP1; PU: universal fields + v2 = axisP1, limot3 = prismatic; plane2d: limot1..3 = x, y, angle motors
   real erp, cfm, susp_erp, susp_cfm;
   real c0, s0, pad0, pad1;
   real v1[4], v2[4];

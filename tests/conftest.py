@@ -30,6 +30,8 @@ GOLDEN = [  # (file stem, scene, steps, worlds, settle) — must match tests/gol
     ("sliders_settle60", "sliders", 30, 1, 60),
     ("universals_settle60", "universals", 30, 1, 60),
     ("motors_settle60", "motors", 30, 1, 60),
+    ("pistons_settle60", "pistons", 30, 1, 60),   # piston / PR / plane2d joints
+    ("pus_settle60", "pus", 30, 1, 60),           # PU joints
 ]
 
 
@@ -71,7 +73,7 @@ def _built():
 # traces and, for the long live comparisons, in lock-step with the reference (every step starts
 # from the reference's pre-step body state, SURVEY 8d parity protocol with K = 1) so that a
 # last-bit difference cannot be amplified by chaotic dynamics into a different contact set.
-ATAN2_SCENES = ("hinges", "buggy", "ragdoll", "buggy_terrain", "universals", "motors")
+ATAN2_SCENES = ("hinges", "buggy", "ragdoll", "buggy_terrain", "universals", "motors", "pistons", "pus")
 
 
 def assert_parity(r, what, scene, prec, cand):

@@ -316,6 +316,162 @@ static inline void scene_sliders(SceneWorld &sw, int w) {
   scene_add_sphere(sw, 3, (dReal)0.2, (dReal)1.3, (dReal)0.02, (dReal)2.8);
 }
 
+// piston, PR and plane2d joints (piston.cpp, pr.cpp, plane2d.cpp): a chain hanging from the world by a reversed
+// one-body piston with stops on both limit-motors; two-body pistons / PR joints with prismatic stops, rotoide stops,
+// a rotoide motor, a prismatic motor driven into its stop (force + torque-decoupling + nothing for the rotoide);
+// one body kept in the plane z = const by a plane2d joint with all three motors, one with none
+static inline void scene_pistons(SceneWorld &sw, int w) {
+  scene_world_base(sw, w);
+  xs32 rng(sw.seed ^ 0x0915704u);
+  scene_add_geom(sw, dCreatePlane(sw.space, 0, 0, 1, 0));
+  dBodyID prev = 0;
+  for (int i = 0; i < 7; i++) {
+    dBodyID b = scene_add_box(sw, 2, (dReal)0.4, (dReal)0.25, (dReal)0.2, (dReal)(0.6 * i), rng.uni(-0.02, 0.02), (dReal)(1.2 + 0.05 * i));
+    dQuaternion q = {1, rng.uni(-0.1, 0.1), rng.uni(-0.1, 0.1), rng.uni(-0.1, 0.1)};
+    dBodySetQuaternion(b, q);
+    dJointID j;
+    if (i == 0) {           // piston to the world, bodies reversed
+      j = dJointCreatePiston(sw.world, 0);
+      dJointAttach(j, 0, b);
+      dJointSetPistonAnchor(j, 0, 0, (dReal)1.5);
+      dJointSetPistonAxis(j, (dReal)0.1, 0, 1);
+      dJointSetPistonParam(j, dParamLoStop, (dReal)-0.2); dJointSetPistonParam(j, dParamHiStop, (dReal)0.1);
+      dJointSetPistonParam(j, dParamBounce, (dReal)0.3);
+      dJointSetPistonParam(j, dParamLoStop2, (dReal)-0.4); dJointSetPistonParam(j, dParamHiStop2, (dReal)0.3);
+    } else if (i == 1 || i == 4) {   // two-body pistons: stops / prismatic motor into its stop + rotoide motor
+      j = dJointCreatePiston(sw.world, 0);
+      dJointAttach(j, prev, b);
+      dJointSetPistonAnchor(j, (dReal)(0.6 * i - 0.3), (dReal)0.05, (dReal)1.3);
+      dJointSetPistonAxis(j, 1, (dReal)(i == 4 ? 0.3 : 0), (dReal)0.2);
+      dJointSetPistonParam(j, dParamLoStop, (dReal)-0.1); dJointSetPistonParam(j, dParamHiStop, (dReal)0.12);
+      if (i == 4) {
+        dJointSetPistonParam(j, dParamVel, (dReal)1.0); dJointSetPistonParam(j, dParamFMax, (dReal)8);
+        dJointSetPistonParam(j, dParamFudgeFactor, (dReal)0.4); dJointSetPistonParam(j, dParamStopERP, (dReal)0.5);
+        dJointSetPistonParam(j, dParamStopCFM, (dReal)1e-3);
+        dJointSetPistonParam(j, dParamVel2, (dReal)-0.8); dJointSetPistonParam(j, dParamFMax2, (dReal)2);
+        dJointSetPistonParam(j, dParamLoStop2, (dReal)-0.15); dJointSetPistonParam(j, dParamHiStop2, (dReal)0.2);   // rotoide motor into its stop
+        dJointSetPistonParam(j, dParamFudgeFactor2, (dReal)0.7);
+      } else {
+        dJointSetPistonParam(j, dParamLoStop2, (dReal)-0.05); dJointSetPistonParam(j, dParamHiStop2, (dReal)0.05);
+        dJointSetPistonParam(j, dParamBounce2, (dReal)0.5);
+      }
+    } else if (i == 2 || i == 5) {   // PR: prismatic axis and rotoide axis differ
+      j = dJointCreatePR(sw.world, 0);
+      if (i == 5) dJointAttach(j, b, prev); else dJointAttach(j, prev, b);
+      dJointSetPRAnchor(j, (dReal)(0.6 * i - 0.3), 0, (dReal)1.35);
+      dJointSetPRAxis1(j, (dReal)0.2, 0, 1);
+      dJointSetPRAxis2(j, 0, 1, (dReal)(i == 5 ? 0.1 : 0));
+      dJointSetPRParam(j, dParamLoStop, (dReal)-0.08); dJointSetPRParam(j, dParamHiStop, (dReal)0.06);
+      if (i == 5) {
+        dJointSetPRParam(j, dParamVel, (dReal)-0.6); dJointSetPRParam(j, dParamFMax, (dReal)5);
+        dJointSetPRParam(j, dParamLoStop2, (dReal)-0.2); dJointSetPRParam(j, dParamHiStop2, (dReal)0.25);
+      } else {
+        dJointSetPRParam(j, dParamVel2, (dReal)0.7); dJointSetPRParam(j, dParamFMax2, (dReal)1.5);
+      }
+    } else if (i == 3) {    // hinge in between
+      j = dJointCreateHinge(sw.world, 0);
+      dJointAttach(j, prev, b);
+      dJointSetHingeAnchor(j, (dReal)(0.6 * i - 0.3), 0, (dReal)1.3);
+      dJointSetHingeAxis(j, 0, 1, 0);
+    } else {                // ball
+      j = dJointCreateBall(sw.world, 0);
+      dJointAttach(j, prev, b);
+      dJointSetBallAnchor(j, (dReal)(0.6 * i - 0.3), 0, (dReal)1.45);
+    }
+    sw.joints.push_back(j);
+    prev = b;
+  }
+  // PR to the world, reversed, with a prismatic motor
+  {
+    dBodyID b = scene_add_box(sw, 2, (dReal)0.3, (dReal)0.3, (dReal)0.3, (dReal)-1.2, (dReal)0.8, (dReal)1.0);
+    dJointID j = dJointCreatePR(sw.world, 0);
+    dJointAttach(j, 0, b);
+    dJointSetPRAnchor(j, (dReal)-1.2, (dReal)0.8, (dReal)1.4);
+    dJointSetPRAxis1(j, 0, 0, 1);
+    dJointSetPRAxis2(j, 1, 0, 0);
+    dJointSetPRParam(j, dParamLoStop, (dReal)-0.3); dJointSetPRParam(j, dParamHiStop, (dReal)0.05);
+    dJointSetPRParam(j, dParamVel, (dReal)0.4); dJointSetPRParam(j, dParamFMax, (dReal)30);
+    sw.joints.push_back(j);
+  }
+  // plane2d: two boxes sliding on the plane z = 0 ... they rest on the ground plane geom; spheres drop on them
+  for (int k = 0; k < 2; k++) {
+    dBodyID b = scene_add_box(sw, 2, (dReal)0.5, (dReal)0.4, (dReal)0.3, (dReal)(-1.5 + 0.9 * k), (dReal)-0.9, (dReal)0.16);
+    dBodySetLinearVel(b, (dReal)(0.5 - k), (dReal)0.3, 0);
+    dBodySetAngularVel(b, 0, 0, (dReal)(1.0 + k));
+    dJointID j = dJointCreatePlane2D(sw.world, 0);
+    dJointAttach(j, b, 0);
+    if (k == 0) {
+      dJointSetPlane2DXParam(j, dParamVel, (dReal)0.3); dJointSetPlane2DXParam(j, dParamFMax, (dReal)4);
+      dJointSetPlane2DYParam(j, dParamVel, (dReal)-0.2); dJointSetPlane2DYParam(j, dParamFMax, (dReal)2);
+      dJointSetPlane2DAngleParam(j, dParamVel, (dReal)0.9); dJointSetPlane2DAngleParam(j, dParamFMax, (dReal)1);
+    } else {
+      dJointSetPlane2DYParam(j, dParamVel, (dReal)0.5); dJointSetPlane2DYParam(j, dParamFMax, (dReal)3);
+    }
+    sw.joints.push_back(j);
+    scene_add_sphere(sw, 3, (dReal)0.15, (dReal)(-1.45 + 0.9 * k), (dReal)-0.85, (dReal)(1.5 + 0.4 * k));
+  }
+  scene_add_sphere(sw, 3, (dReal)0.2, (dReal)1.3, (dReal)0.02, (dReal)2.8);
+}
+
+// PU joints (pu.cpp: prismatic + universal): a chain hanging from the world by a reversed one-body PU; two-body PUs
+// with prismatic stops, universal-axis stops, motors on each of the three limit-motors (one driven into its stop),
+// bodies given in both orders; a hinge and a ball in between so the shared Info2.erp varies
+static inline void scene_pus(SceneWorld &sw, int w) {
+  scene_world_base(sw, w);
+  xs32 rng(sw.seed ^ 0x0009055u);
+  scene_add_geom(sw, dCreatePlane(sw.space, 0, 0, 1, 0));
+  dBodyID prev = 0;
+  for (int i = 0; i < 7; i++) {
+    dBodyID b = scene_add_box(sw, 2, (dReal)0.4, (dReal)0.25, (dReal)0.2, (dReal)(0.6 * i), rng.uni(-0.02, 0.02), (dReal)(1.2 + 0.05 * i));
+    dQuaternion q = {1, rng.uni(-0.1, 0.1), rng.uni(-0.1, 0.1), rng.uni(-0.1, 0.1)};
+    dBodySetQuaternion(b, q);
+    dJointID j;
+    if (i == 3) {
+      j = dJointCreateHinge(sw.world, 0);
+      dJointAttach(j, prev, b);
+      dJointSetHingeAnchor(j, (dReal)(0.6 * i - 0.3), 0, (dReal)1.3);
+      dJointSetHingeAxis(j, 0, 1, 0);
+    } else if (i == 6) {
+      j = dJointCreateBall(sw.world, 0);
+      dJointAttach(j, prev, b);
+      dJointSetBallAnchor(j, (dReal)(0.6 * i - 0.3), 0, (dReal)1.45);
+    } else {
+      j = dJointCreatePU(sw.world, 0);
+      if (i == 0) dJointAttach(j, 0, b);            // world, reversed
+      else if (i == 5) dJointAttach(j, b, prev);
+      else dJointAttach(j, prev, b);
+      dJointSetPUAnchor(j, (dReal)(0.6 * i - 0.3), (dReal)0.03, (dReal)(i == 0 ? 1.6 : 1.3));
+      dJointSetPUAxis1(j, 0, 1, (dReal)0.1);
+      dJointSetPUAxis2(j, (dReal)0.1, 0, 1);
+      dJointSetPUAxisP(j, 1, (dReal)(i == 4 ? 0.2 : 0), (dReal)(i == 0 ? 0.5 : 0.1));
+      dJointSetPUParam(j, dParamLoStop3, (dReal)-0.1); dJointSetPUParam(j, dParamHiStop3, (dReal)0.08);
+      if (i == 0) {
+        dJointSetPUParam(j, dParamBounce3, (dReal)0.3);
+        dJointSetPUParam(j, dParamLoStop1, (dReal)-0.3); dJointSetPUParam(j, dParamHiStop1, (dReal)0.2);
+      } else if (i == 1) {
+        dJointSetPUParam(j, dParamLoStop1, (dReal)-0.1); dJointSetPUParam(j, dParamHiStop1, (dReal)0.1);
+        dJointSetPUParam(j, dParamLoStop2, (dReal)-0.15); dJointSetPUParam(j, dParamHiStop2, (dReal)0.05);
+        dJointSetPUParam(j, dParamBounce2, (dReal)0.4);
+      } else if (i == 2) {     // prismatic motor driven into its stop
+        dJointSetPUParam(j, dParamVel3, (dReal)0.9); dJointSetPUParam(j, dParamFMax3, (dReal)7);
+        dJointSetPUParam(j, dParamFudgeFactor3, (dReal)0.5); dJointSetPUParam(j, dParamStopERP3, (dReal)0.4);
+      } else if (i == 4) {     // universal motors, axis 1 into its stop
+        dJointSetPUParam(j, dParamVel1, (dReal)-0.7); dJointSetPUParam(j, dParamFMax1, (dReal)1.5);
+        dJointSetPUParam(j, dParamLoStop1, (dReal)-0.2); dJointSetPUParam(j, dParamHiStop1, (dReal)0.2);
+        dJointSetPUParam(j, dParamVel2, (dReal)0.5); dJointSetPUParam(j, dParamFMax2, (dReal)0.8);
+      } else {                 // i == 5: reversed body order, stops on axis 2 + free prismatic motor
+        dJointSetPUParam(j, dParamLoStop2, (dReal)-0.25); dJointSetPUParam(j, dParamHiStop2, (dReal)0.15);
+        dJointSetPUParam(j, dParamVel3, (dReal)-0.3); dJointSetPUParam(j, dParamFMax3, (dReal)2);
+        dJointSetPUParam(j, dParamLoStop3, -dInfinity); dJointSetPUParam(j, dParamHiStop3, dInfinity);
+      }
+    }
+    sw.joints.push_back(j);
+    prev = b;
+  }
+  scene_add_sphere(sw, 3, (dReal)0.25, (dReal)0.3, (dReal)0.05, (dReal)2.5);
+  scene_add_sphere(sw, 3, (dReal)0.2, (dReal)2.3, (dReal)0.02, (dReal)2.8);
+}
+
 // universal joints (universal.cpp): free, with stops on both axes (getAngles: dRFrom2Axes + dQfromR + atan2),
 // with a motor on axis 2, attached to the world, and one with the bodies given in reversed order
 static inline void scene_universals(SceneWorld &sw, int w) {
@@ -747,6 +903,8 @@ static inline int scene_build(const char *name_in, SceneWorld &sw, int w, SceneP
   if (!strcmp(name, "chain")) { scene_chain(sw, w, 8); return 0; }
   if (!strcmp(name, "hinges")) { scene_hinges(sw, w); return 0; }
   if (!strcmp(name, "sliders")) { scene_sliders(sw, w); return 0; }
+  if (!strcmp(name, "pistons")) { scene_pistons(sw, w); return 0; }
+  if (!strcmp(name, "pus")) { scene_pus(sw, w); return 0; }
   if (!strcmp(name, "universals")) { scene_universals(sw, w); return 0; }
   if (!strcmp(name, "motors")) { scene_motors(sw, w); return 0; }
   if (!strcmp(name, "buggy_terrain")) { scene_buggy_terrain(sw, w, 48); pol = policy_buggy(); pol.max_contacts = 10; return 0; }
