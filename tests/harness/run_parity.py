@@ -58,11 +58,12 @@ def parity(cand, prec, scene, steps, worlds=1, mode=None, settle=0, lockstep=Fal
         return res
 
 
-def parity_golden(cand, golden_path, scene, prec, steps, worlds=1, settle=0, mode=None):
-    """Compare a candidate driver against a committed reference trace (tests/golden)."""
+def parity_golden(cand, golden_path, scene, prec, steps, worlds=1, settle=0, mode=None, lockstep=False):
+    """Compare a candidate driver against a committed reference trace (tests/golden).
+    lockstep: every step starts from the golden trace's pre-step body state (SURVEY 8d protocol, K = 1)."""
     with tempfile.TemporaryDirectory() as td:
         fc = os.path.join(td, "cand.bin")
-        log = run_trace(cand, prec, scene, steps, worlds, fc, settle=settle, mode=mode)
+        log = run_trace(cand, prec, scene, steps, worlds, fc, settle=settle, mode=mode, resync=golden_path if lockstep else None)
         res = compare(read_trace(fc), read_trace(golden_path))
         res["log"] = log[-300:]
         return res

@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import ATAN2_SCENES, GOLDEN, GOLDEN_CALLBACK, ROOT, assert_bit_exact, assert_parity, have_ref, lib_path
+from conftest import ATAN2_LOCKSTEP_GOLDEN, ATAN2_SCENES, GOLDEN, GOLDEN_CALLBACK, ROOT, assert_bit_exact, assert_parity, have_ref, lib_path
 from run_parity import parity, parity_golden
 
 pytestmark = pytest.mark.gpu
@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("stem,scene,steps,worlds,settle", GOLDEN)
 def test_cuda_matches_golden_reference_traces(stem, scene, steps, worlds, settle, prec):
     g = os.path.join(ROOT, "tests", "golden", f"{stem}_{prec}.trace")
-    r = parity_golden("b200", g, scene, prec, steps, worlds, settle)
+    r = parity_golden("b200", g, scene, prec, steps, worlds, settle, lockstep=(prec == "double" and scene in ATAN2_LOCKSTEP_GOLDEN))
     assert r["steps"] == steps
     assert_parity(r, f"{stem}/{prec}", scene, prec, "b200")
 
