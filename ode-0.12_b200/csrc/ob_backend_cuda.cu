@@ -505,7 +505,8 @@ ObBackend *obk_create(const ObBatchDev &caps, int device, char *err, size_t errl
   CK(cudaFuncSetAttribute(k_collide<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_collide));
   CK(cudaFuncSetAttribute(k_collide<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_collide));
 #define OB_SETSMEM(GG) \
-  CK(cudaFuncSetAttribute(k_prep<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_prep)); \
+  CK(cudaFuncSetAttribute(k_prep<GG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_prep)); \
+  CK(cudaFuncSetAttribute(k_prep<GG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_prep)); \
   CK(cudaFuncSetAttribute(k_sor<GG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sor)); \
   CK(cudaFuncSetAttribute(k_sor<GG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sor)); \
   CK(cudaFuncSetAttribute(k_post<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_post));
@@ -623,7 +624,8 @@ template <int G> static void launch_step(ObBackend *b, real h, int taps, int pha
     const int gstep = (W + T - 1) / T;
     int gsor = gstep;
     if (b->grid_sor < b->grid_step) gsor = gsor < b->grid_sor ? gsor : b->grid_sor;
-    k_prep<G><<<gstep, 32, b->smem_prep, st>>>(d, h, taps);
+    if (d.NJ > 0) k_prep<G, true><<<gstep, 32, b->smem_prep, st>>>(d, h, taps);
+    else k_prep<G, false><<<gstep, 32, b->smem_prep, st>>>(d, h, taps);
     if (timing) cudaEventRecord(ev[2], st);
     if (b->sched_lane) k_sched_lane<<<(W + 31) / 32, 32, b->smem_sched_lane, st>>>(d, G);
     else if (d.NB <= 64) k_sched<2><<<W, 32, b->smem_sched, st>>>(d, G, taps);

@@ -128,7 +128,8 @@ __device__ __forceinline__ bool encode_bounds(real lo, real hi, real *v, unsigne
 
 
 // =====================================================================================
-template <int G>
+// PJ = false: the batch has no permanent joints (contact joints only), the getInfo1/2 code of every joint type is compiled out
+template <int G, bool PJ>
 __global__ void __launch_bounds__(32) k_prep(ObBatchDev d, real h, int taps) {
   constexpr int T = 32 / G;
   extern __shared__ __align__(16) unsigned char smem_all[];
@@ -310,7 +311,7 @@ __global__ void __launch_bounds__(32) k_prep(ObBatchDev d, real h, int taps) {
       int m = 0;
       if (k < nij) {
         const int j = s_ijoint[k];
-        if (j < nc) { ObSurface sf = csurf ? csurf[j] : surf0; m = ob_contact_info1(sf); }
+        if (!PJ || j < nc) { ObSurface sf = csurf ? csurf[j] : surf0; m = ob_contact_info1(sf); }
         else {
           ObJoint pj = pjoint[j - nc];
           const int b1 = pj.b1, b2 = pj.b2;
@@ -362,7 +363,7 @@ __global__ void __launch_bounds__(32) k_prep(ObBatchDev d, real h, int taps) {
         const unsigned ub2 = (unsigned)(b2 < 0 ? 255 : b2);
         real erp_in = W.erp;
         if (anyball) { const int src = s_erpsrc[k]; if (src != 0xffff) erp_in = pjoint[s_ijoint[src] - nc].erp; }
-        if (j < nc) {
+        if (!PJ || j < nc) {
           ObSurface sf = csurf ? csurf[j] : surf0;
           const int jm = ob_contact_info1(sf);
           ObRowOut3 r;
@@ -412,7 +413,7 @@ __global__ void __launch_bounds__(32) k_prep(ObBatchDev d, real h, int taps) {
     for (int dd = 1; dd < G; dd <<= 1) anyside |= __shfl_xor_sync(FULL, anyside, dd, G);
     __syncwarp();
     // (6b) dBodyAddTorque / dBodyAddForce side effects in joint order (they change the accumulators before the rhs is formed)
-    if (anyside && gl == 0) {
+    if (PJ && anyside && gl == 0) {
       for (int k = 0; k < nij; k++) {
         const int j = s_ijoint[k];
         if (j < nc) continue;
