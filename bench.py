@@ -313,7 +313,7 @@ def run_b200(args):
             "clocks": clocks,
             "overflow_worlds": int(sums[5]),
         }
-        if world_size == 1:
+        if world_size == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(args, bounded_seconds=20)
         print(json.dumps(out))
     lib.dBatchDestroy(B)

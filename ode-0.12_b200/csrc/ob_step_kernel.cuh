@@ -491,7 +491,7 @@ __global__ void __launch_bounds__(32) k_prep(ObBatchDev d, real h, int taps) {
 // over the order; it runs with the per-body "last level" table spread over the lanes'
 // registers (body b -> lane b&31, register b>>5) so one step costs two shuffles, not a
 // shared-memory round trip.
-struct SchedSmem { size_t ord, rowb, fio, lvl, X, isl, total; };
+struct SchedSmem { size_t ord, rowb, fio, lvl, X, isl, last, total; };
 __host__ __device__ inline SchedSmem sched_smem(int NB, int NR) {
   SchedSmem s; size_t o = 0;
   s.ord = o; o = ob_al(o + sizeof(unsigned short) * NR, 16);
@@ -500,6 +500,7 @@ __host__ __device__ inline SchedSmem sched_smem(int NB, int NR) {
   s.lvl = o; o = ob_al(o + sizeof(unsigned short) * NR, 16);      // swap indices, then level per position
   s.X = o; o = ob_al(o + sizeof(int) * (NR + 2), 16);              // rows per level -> level starts -> level ends
   s.isl = o; o = ob_al(o + sizeof(unsigned short) * 2 * NB, 16);   // (r0, m) per island that has rows
+  s.last = o; o = ob_al(o + sizeof(int) * 257, 16);                // level of the last row on every body (+ slot 255/256: "no body 2")
   s.total = ob_al(o, 16);
   return s;
 }
@@ -514,6 +515,7 @@ __global__ void __launch_bounds__(32) k_sched(ObBatchDev d, int G, int taps) {
   unsigned short *s_lvl = (unsigned short *)(smem + L.lvl);
   int *s_X = (int *)(smem + L.X);
   unsigned short *s_isl = (unsigned short *)(smem + L.isl);
+  int *s_last = (int *)(smem + L.last);
   const int lane = threadIdx.x;
   const unsigned FULL = 0xffffffffu;
   const unsigned lt_mask = (1u << lane) - 1u;
@@ -588,48 +590,48 @@ __global__ void __launch_bounds__(32) k_sched(ObBatchDev d, int G, int taps) {
         __syncwarp();
         if (lane == 0) {
           unsigned short *ord = s_ord + r0;
+          int sj = s_lvl[r0 + 1];
           for (int i = 1; i < m; i++) {
-            const int sj = s_lvl[r0 + i];
-            const unsigned short t = ord[i]; ord[i] = ord[sj]; ord[sj] = t;
+            const int sjn = s_lvl[r0 + (i + 1 < m ? i + 1 : i)];   // the next swap index is fetched ahead of the dependent chain
+            const unsigned short t = ord[i], u = ord[sj];
+            ord[i] = u; ord[sj] = t;
+            sj = sjn;
           }
         }
         __syncwarp();
       }
       total_draws = draws_before;
-      // (b) level of every position, islands and positions in sweep order
-      int lastreg[NBR];
-#pragma unroll
-      for (int r = 0; r < NBR; r++) lastreg[r] = 0;
+      // (b) level of every position, islands and positions in sweep order.  The recurrence
+      // level(k) = 1 + max(last[b1], last[b2]) is one dependent chain per world: every lane runs it in lock-step on
+      // the shared `last` table (uniform addresses: broadcast loads, same-value stores), ~10 instructions per row;
+      // the rows' body bytes are gathered into s_lvl in parallel first and fetched one row ahead of the chain
       for (int i = lane; i <= mtot + 1; i += 32) s_X[i] = 0;
+      for (int i = lane; i < 257; i += 32) s_last[i] = 0;
+      for (int q = 0; q < nri; q++) {
+        const int r0 = s_isl[2 * q], m = s_isl[2 * q + 1];
+        for (int k = lane; k < m; k += 32) s_lvl[r0 + k] = s_rowb[r0 + s_ord[r0 + k]];
+      }
       __syncwarp();
       int nlev = 0;
       for (int q = 0; q < nri; q++) {
         const int r0 = s_isl[2 * q], m = s_isl[2 * q + 1];
-        for (int base = 0; base < m; base += 32) {
-          const int kmine = base + lane;
-          unsigned rbm = 0xffffu;
-          if (kmine < m) rbm = s_rowb[r0 + s_ord[r0 + kmine]];
-          int mylv = 0;
-          const int cnt = (m - base) < 32 ? (m - base) : 32;
-          for (int kk = 0; kk < cnt; kk++) {
-            const unsigned rb = __shfl_sync(FULL, rbm, kk);
-            const int b1 = rb & 255, b2 = (rb >> 8) & 255;
-            const int q1 = b1 >> 5, q2 = b2 >> 5;
-            int v1 = lastreg[0], v2 = lastreg[0];
-#pragma unroll
-            for (int r = 1; r < NBR; r++) { v1 = (q1 == r) ? lastreg[r] : v1; v2 = (q2 == r) ? lastreg[r] : v2; }
-            int lv = __shfl_sync(FULL, v1, b1);          // source lane = b & 31
-            const int l2 = __shfl_sync(FULL, v2, b2);
-            if (b2 != 255) lv = l2 > lv ? l2 : lv;
-            lv++;
-            const int qa = (lane == (b1 & 31)) ? q1 : -1, qb = (b2 != 255 && lane == (b2 & 31)) ? q2 : -1;
-#pragma unroll
-            for (int r = 0; r < NBR; r++) lastreg[r] = (qa == r || qb == r) ? lv : lastreg[r];
-            mylv = (lane == kk) ? lv : mylv;
-            nlev = lv > nlev ? lv : nlev;
-          }
-          if (kmine < m) { s_lvl[r0 + kmine] = (unsigned short)mylv; atomicAdd(&s_X[mylv], 1); }
+        unsigned rb = s_lvl[r0];
+        for (int k = 0; k < m; k++) {
+          const unsigned rbn = s_lvl[r0 + (k + 1 < m ? k + 1 : k)];
+          const int b1 = rb & 255, b2 = (rb >> 8) & 255;      // b2 == 255: slot 255 is read (always 0) and slot 256 written
+          const int l1 = s_last[b1], l2 = s_last[b2];
+          const int lv = (l2 > l1 ? l2 : l1) + 1;
+          s_last[b1] = lv;
+          s_last[b2 + (b2 == 255)] = lv;
+          s_lvl[r0 + k] = (unsigned short)lv;
+          nlev = lv > nlev ? lv : nlev;
+          rb = rbn;
         }
+      }
+      __syncwarp();
+      for (int q = 0; q < nri; q++) {
+        const int r0 = s_isl[2 * q], m = s_isl[2 * q + 1];
+        for (int k = lane; k < m; k += 32) atomicAdd(&s_X[s_lvl[r0 + k]], 1);
       }
       __syncwarp();
       // exclusive prefix over levels 1..nlev: s_X[l] = first slot of level l
