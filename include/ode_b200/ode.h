@@ -211,6 +211,8 @@ void dMassSetSphere(dMass *m, dReal density, dReal radius);
 void dMassSetSphereTotal(dMass *m, dReal total_mass, dReal radius);
 void dMassSetCapsule(dMass *m, dReal density, int direction, dReal radius, dReal length);
 void dMassSetCapsuleTotal(dMass *m, dReal total_mass, int direction, dReal radius, dReal length);
+void dMassSetCylinder(dMass *m, dReal density, int direction, dReal radius, dReal length);          /* include/ode/mass.h:60 */
+void dMassSetCylinderTotal(dMass *m, dReal total_mass, int direction, dReal radius, dReal length);   /* include/ode/mass.h:62 */
 void dMassSetBox(dMass *m, dReal density, dReal lx, dReal ly, dReal lz);
 void dMassSetBoxTotal(dMass *m, dReal total_mass, dReal lx, dReal ly, dReal lz);
 void dMassAdjust(dMass *m, dReal newmass);
@@ -515,6 +517,11 @@ void dGeomPlaneGetParams(dGeomID plane, dVector4 result);
 dGeomID dCreateCapsule(dSpaceID space, dReal radius, dReal length);
 void dGeomCapsuleSetParams(dGeomID ccylinder, dReal radius, dReal length);
 void dGeomCapsuleGetParams(dGeomID ccylinder, dReal *radius, dReal *length);
+/* flat-ended cylinder, include/ode/collision.h:1063-1065 (ode/src/cylinder.cpp); colliders against plane, sphere
+ * and box (ode/src/collision_cylinder_{plane,sphere,box}.cpp) */
+dGeomID dCreateCylinder(dSpaceID space, dReal radius, dReal length);
+void dGeomCylinderSetParams(dGeomID cylinder, dReal radius, dReal length);
+void dGeomCylinderGetParams(dGeomID cylinder, dReal *radius, dReal *length);
 /* rays: include/ode/collision.h:1025-1067, ode/src/ray.cpp:91-189 */
 dGeomID dCreateRay(dSpaceID space, dReal length);
 void dGeomRaySetLength(dGeomID ray, dReal length);

@@ -46,6 +46,16 @@ OB_HD void ob_aabb(const ObPose &g, real *aabb, const ObMeshDev *meshes = 0) {
       aabb[2] = g.pos[1] - yr; aabb[3] = g.pos[1] + yr;
       aabb[4] = g.pos[2] - zr; aabb[5] = g.pos[2] + zr;
     } break;
+    case OB_GEOM_CYLINDER: {
+      // dxCylinder::computeAABB, cylinder.cpp:60-78
+      const real *R = g.R; const real radius = g.p[0], lz = g.p[1];
+      real xr = ob_fabs(R[0] * radius) + ob_fabs(R[1] * radius) + OB_REAL(0.5) * ob_fabs(R[2] * lz);
+      real yr = ob_fabs(R[4] * radius) + ob_fabs(R[5] * radius) + OB_REAL(0.5) * ob_fabs(R[6] * lz);
+      real zr = ob_fabs(R[8] * radius) + ob_fabs(R[9] * radius) + OB_REAL(0.5) * ob_fabs(R[10] * lz);
+      aabb[0] = g.pos[0] - xr; aabb[1] = g.pos[0] + xr;
+      aabb[2] = g.pos[1] - yr; aabb[3] = g.pos[1] + yr;
+      aabb[4] = g.pos[2] - zr; aabb[5] = g.pos[2] + zr;
+    } break;
     case OB_GEOM_PLANE: {
       const real *p = g.p;
       aabb[0] = -OB_INF; aabb[1] = OB_INF; aabb[2] = -OB_INF; aabb[3] = OB_INF; aabb[4] = -OB_INF; aabb[5] = OB_INF;
@@ -790,6 +800,397 @@ OB_HD int ob_collide_capsule_plane(const ObPose &o1, const ObPose &o2, int flags
   return ncontacts;
 }
 
+// ---- flat-ended cylinder colliders --------------------------------------------------------------
+// cylinder pose: p[0] = radius, p[1] = length, axis = column 2 of the rotation.
+#if defined(dSINGLE)
+#define OB_CYL_TOL OB_REAL(0.0001)
+#else
+#define OB_CYL_TOL OB_REAL(0.0000001)
+#endif
+// dCollideCylinderPlane, collision_cylinder_plane.cpp:38-266 (o1 = cylinder, o2 = plane)
+OB_HDN int ob_collide_cylinder_plane(const ObPose &o1, const ObPose &o2, int flags, ObCg *contact) {
+  const int maxc = flags & 0xffff;
+  int n = 0;
+  const real radius = o1.p[0], length = o1.p[1];
+  const real *cylpos = o1.pos, *pv = o2.p;
+  const real vDir1[3] = {o1.R[2], o1.R[6], o1.R[10]};
+  real s = length * OB_REAL(0.5);
+  real G1Pos1[3], G1Pos2[3];
+  for (int i = 0; i < 3; i++) { G1Pos2[i] = vDir1[i] * s + cylpos[i]; G1Pos1[i] = vDir1[i] * -s + cylpos[i]; }
+  s = vDir1[0] * pv[0] + vDir1[1] * pv[1] + vDir1[2] * pv[2];
+  if (s < 0) s += OB_REAL(1.0); else s -= OB_REAL(1.0);
+#define OB_CYLPL_EMIT(COND)                                                                       \
+  {                                                                                               \
+    ObCg *c = contact + n;                                                                        \
+    c->depth = pv[3] - ob_dot(pv, c->pos);                                                        \
+    if (c->depth COND 0) {                                                                        \
+      c->normal[0] = pv[0]; c->normal[1] = pv[1]; c->normal[2] = pv[2];                           \
+      c->side1 = -1; c->side2 = -1;                                                               \
+      n++;                                                                                        \
+      if (n >= maxc) return n;                                                                    \
+    }                                                                                             \
+  }
+  if (s < OB_CYL_TOL && s > (-OB_CYL_TOL)) {
+    // the axis is parallel to the normal: the deeper disc touches with up to four rim points
+    real P[3];
+    s = pv[3] - ob_dot(pv, G1Pos1);
+    real t = pv[3] - ob_dot(pv, G1Pos2);
+    if (s >= t) { if (s >= 0) { P[0] = G1Pos1[0]; P[1] = G1Pos1[1]; P[2] = G1Pos1[2]; } else return n; }
+    else { if (t >= 0) { P[0] = G1Pos2[0]; P[1] = G1Pos2[1]; P[2] = G1Pos2[2]; } else return n; }
+    real V1[3], V2[3];
+    if (vDir1[0] < OB_CYL_TOL && vDir1[0] > (-OB_CYL_TOL)) { V1[0] = vDir1[0] + OB_REAL(1.0); V1[1] = vDir1[1]; V1[2] = vDir1[2]; }
+    else { V1[0] = vDir1[0]; V1[1] = vDir1[1] + OB_REAL(1.0); V1[2] = vDir1[2]; }
+    ob_cross(V2, V1, vDir1);
+    t = ob_sqrt(V2[0] * V2[0] + V2[1] * V2[1] + V2[2] * V2[2]);
+    t = radius / t;
+    V2[0] *= t; V2[1] *= t; V2[2] *= t;
+    ob_cross(V1, V2, vDir1);
+    for (int i = 0; i < 3; i++) contact[n].pos[i] = P[i] + V1[i];
+    OB_CYLPL_EMIT(>)
+    for (int i = 0; i < 3; i++) contact[n].pos[i] = P[i] - V1[i];
+    OB_CYLPL_EMIT(>)
+    for (int i = 0; i < 3; i++) contact[n].pos[i] = P[i] + V2[i];
+    OB_CYLPL_EMIT(>)
+    for (int i = 0; i < 3; i++) contact[n].pos[i] = P[i] - V2[i];
+    OB_CYLPL_EMIT(>)
+  } else {
+    real C[3];
+    const real t = ob_dot(pv, vDir1);
+    for (int i = 0; i < 3; i++) C[i] = vDir1[i] * t - pv[i];
+    s = ob_sqrt(C[0] * C[0] + C[1] * C[1] + C[2] * C[2]);
+    s = radius / s;
+    C[0] *= s; C[1] *= s; C[2] *= s;
+    for (int i = 0; i < 3; i++) contact[n].pos[i] = C[i] + G1Pos1[i];
+    OB_CYLPL_EMIT(>=)
+    for (int i = 0; i < 3; i++) contact[n].pos[i] = C[i] + G1Pos2[i];
+    {   // the second depth is written out term by term in the reference (:250)
+      ObCg *c = contact + n;
+      c->depth = pv[3] - pv[0] * c->pos[0] - pv[1] * c->pos[1] - pv[2] * c->pos[2];
+      if (c->depth >= 0) {
+        c->normal[0] = pv[0]; c->normal[1] = pv[1]; c->normal[2] = pv[2];
+        c->side1 = -1; c->side2 = -1;
+        n++;
+        if (n >= maxc) return n;
+      }
+    }
+  }
+#undef OB_CYLPL_EMIT
+  return n;
+}
+
+// dCollideCylinderSphere, collision_cylinder_sphere.cpp:51-277 (o1 = cylinder, o2 = sphere); one contact or none
+OB_HDN int ob_collide_cylinder_sphere(const ObPose &o1, const ObPose &o2, ObCg *contact) {
+  const real radius = o1.p[0], length = o1.p[1], radius2 = o2.p[0];
+  const real *cylpos = o1.pos, *sp = o2.pos;
+  const real vDir1[3] = {o1.R[2], o1.R[6], o1.R[10]};
+  real s = length * OB_REAL(0.5);
+  real G1Pos1[3], G1Pos2[3], C[3];
+  for (int i = 0; i < 3; i++) { G1Pos2[i] = vDir1[i] * s + cylpos[i]; G1Pos1[i] = vDir1[i] * -s + cylpos[i]; }
+  s = (sp[0] - G1Pos1[0]) * vDir1[0] - (G1Pos1[1] - sp[1]) * vDir1[1] - (G1Pos1[2] - sp[2]) * vDir1[2];
+  if (s < (-radius2) || s > (length + radius2)) return 0;
+  for (int i = 0; i < 3; i++) C[i] = s * vDir1[i] + G1Pos1[i] - sp[i];
+  const real t = ob_sqrt(C[0] * C[0] + C[1] * C[1] + C[2] * C[2]);
+  if (t > (radius + radius2)) return 0;
+  contact->side1 = -1; contact->side2 = -1;
+  if (t > radius && (s < 0 || s > length)) {
+    // the sphere touches a rim
+    const real *G = s <= 0 ? G1Pos1 : G1Pos2;
+    const real ds = s <= 0 ? s : s - length;
+    contact->depth = radius2 - ob_sqrt(ds * ds + (t - radius) * (t - radius));
+    if (contact->depth < 0) return 0;
+    for (int i = 0; i < 3; i++) contact->pos[i] = C[i] / t * -radius + G[i];
+    for (int i = 0; i < 3; i++) contact->normal[i] = (contact->pos[i] - sp[i]) / (radius2 - contact->depth);
+    return 1;
+  } else if ((radius - t) <= s && (radius - t) <= (length - s)) {
+    // the sphere touches the mantle
+    contact->depth = (radius2 + radius) - t;
+    if (contact->depth < 0) return 0;
+    if (t > (radius2 + OB_CYL_TOL)) {
+      C[0] /= t; C[1] /= t; C[2] /= t;
+      for (int i = 0; i < 3; i++) { contact->pos[i] = C[i] * radius2 + sp[i]; contact->normal[i] = C[i]; }
+    } else {
+      for (int i = 0; i < 3; i++) { contact->pos[i] = C[i] + sp[i]; contact->normal[i] = C[i] / t; }
+    }
+    return 1;
+  } else {
+    // the sphere touches a disc
+    if (s <= (length * OB_REAL(0.5))) {
+      contact->depth = s + radius2;
+      if (contact->depth < 0) return 0;
+      for (int i = 0; i < 3; i++) { contact->pos[i] = radius2 * vDir1[i] + sp[i]; contact->normal[i] = vDir1[i]; }
+    } else {
+      contact->depth = (radius2 + length - s);
+      if (contact->depth < 0) return 0;
+      for (int i = 0; i < 3; i++) { contact->pos[i] = radius2 * -vDir1[i] + sp[i]; contact->normal[i] = -vDir1[i]; }
+    }
+    return 1;
+  }
+}
+
+// dCollideCylinderBox, collision_cylinder_box.cpp (o1 = cylinder, o2 = box): separating axes (3 box axes, the cylinder
+// axis, 3 cross products, 8 vertex axes, 2 x 12 edge-circle axes), then either the cylinder's nearest mantle line
+// clipped to the box (two contacts) or the box's nearest face clipped to the cylinder's cap octagon.
+struct ObCylBox {
+  real cylR[12], cylPos[3], cylAxis[3], radius, size;
+  real boxR[12], boxPos[3], boxHalf[3], vert[8][3];
+  real diff[3], normal[3], bestDepth, bestrb, bestrc;
+  int bestAxis;
+};
+// the octagon's outward normals in the cap frame: -cos / -sin of pi/8 + i*pi/4 accumulated in dReal as :186-196 does
+// (glibc values of this image; gcc folds the same constants at -O2)
+OB_HD void ob_cyl_segment_normal(int i, real *n) {
+#if defined(dSINGLE)
+  const float t[8][2] = {{-0.923879504f, -0.382683456f}, {-0.382683426f, -0.923879504f}, {0.382683516f, -0.923879504f}, {0.923879623f, -0.382683277f}, {0.923879445f, 0.382683665f}, {0.382683128f, 0.923879683f}, {-0.382683605f, 0.923879445f}, {-0.923879564f, 0.382683426f}};
+#else
+  const double t[8][2] = {{-0.92387953251128674, -0.38268343236508978}, {-0.38268343236508984, -0.92387953251128674}, {0.38268343236508973, -0.92387953251128674}, {0.92387953251128674, -0.38268343236508989}, {0.92387953251128685, 0.38268343236508967}, {0.38268343236509034, 0.92387953251128652}, {-0.38268343236508917, 0.92387953251128696}, {-0.92387953251128652, 0.38268343236509039}};
+#endif
+  n[0] = t[i][0]; n[1] = t[i][1]; n[2] = 0;
+}
+// _cldTestAxis :206-286
+OB_HDN int ob_cylbox_test_axis(ObCylBox &D, real *vIn, int iAxis) {
+  const real fL = ob_sqrt(vIn[0] * vIn[0] + vIn[1] * vIn[1] + vIn[2] * vIn[2]);
+  if (fL < OB_REAL(1e-5)) return 1;
+  ob_safe_normalize3(vIn);
+  const real fdot1 = ob_dot(D.cylAxis, vIn);
+  real frc;
+  if (fdot1 > OB_REAL(1.0)) frc = D.size * OB_REAL(0.5);
+  else if (fdot1 < OB_REAL(-1.0)) frc = D.size * OB_REAL(0.5);
+  else frc = ob_fabs(fdot1 * (D.size * OB_REAL(0.5))) + D.radius * ob_sqrt(OB_REAL(1.0) - (fdot1 * fdot1));
+  real frb = ob_fabs(ob_dot41(D.boxR + 0, vIn)) * D.boxHalf[0];
+  frb += ob_fabs(ob_dot41(D.boxR + 1, vIn)) * D.boxHalf[1];
+  frb += ob_fabs(ob_dot41(D.boxR + 2, vIn)) * D.boxHalf[2];
+  const real fd = ob_dot(D.diff, vIn);
+  real fDepth = frc + frb;
+  if (ob_fabs(fd) > fDepth) return 0;
+  fDepth -= ob_fabs(fd);
+  if (fDepth < D.bestDepth) {
+    D.bestDepth = fDepth;
+    D.normal[0] = vIn[0]; D.normal[1] = vIn[1]; D.normal[2] = vIn[2];
+    D.bestAxis = iAxis; D.bestrb = frb; D.bestrc = frc;
+    if (fd > 0) { D.normal[0] = -D.normal[0]; D.normal[1] = -D.normal[1]; D.normal[2] = -D.normal[2]; }
+  }
+  return 1;
+}
+// _cldTestEdgeCircleAxis :289-333
+OB_HDN int ob_cylbox_test_edge_circle(ObCylBox &D, const real *vcc, const real *v0, const real *v1, int iAxis) {
+  real dirE[3] = {v1[0] - v0[0], v1[1] - v0[1], v1[2] - v0[2]};
+  ob_safe_normalize3(dirE);
+  const real fdot2 = ob_dot(dirE, D.cylAxis);
+  if (ob_fabs(fdot2) < OB_REAL(1e-5)) return 1;
+  real t1[3] = {vcc[0] - v0[0], vcc[1] - v0[1], vcc[2] - v0[2]};
+  const real fdot1 = ob_dot(t1, D.cylAxis);
+  real vpnt[3];
+  for (int i = 0; i < 3; i++) vpnt[i] = v0[i] + dirE[i] * (fdot1 / fdot2);
+  real tangent[3], axis[3];
+  for (int i = 0; i < 3; i++) t1[i] = vcc[i] - vpnt[i];
+  ob_cross(tangent, t1, D.cylAxis);
+  ob_cross(axis, tangent, dirE);
+  return ob_cylbox_test_axis(D, axis, iAxis);
+}
+// dClipEdgeToPlane, collision_util.cpp:471-509
+OB_HD int ob_clip_edge_to_plane(real *e0, real *e1, const real *pl) {
+  const real d0 = pl[0] * e0[0] + pl[1] * e0[1] + pl[2] * e0[2] + pl[3];
+  const real d1 = pl[0] * e1[0] + pl[1] * e1[1] + pl[2] * e1[2] + pl[3];
+  if (d0 < 0 && d1 < 0) return 0;
+  else if (d0 > 0 && d1 > 0) return 1;
+  else if ((d0 > 0 && d1 < 0) || (d0 < 0 && d1 > 0)) {
+    real ip[3];
+    for (int i = 0; i < 3; i++) ip[i] = e0[i] - (e0[i] - e1[i]) * d0 / (d0 - d1);
+    if (d0 < 0) { e0[0] = ip[0]; e0[1] = ip[1]; e0[2] = ip[2]; }
+    else { e1[0] = ip[0]; e1[1] = ip[1]; e1[2] = ip[2]; }
+    return 1;
+  }
+  return 1;
+}
+// dClipPolyToPlane, collision_util.cpp:512-557
+OB_HDN int ob_clip_poly_to_plane(const real (*in)[3], int ctIn, real (*out)[3], const real *pl) {
+  int ctOut = 0;
+  int i0 = ctIn - 1;
+  for (int i1 = 0; i1 < ctIn; i0 = i1, i1++) {
+    const real d0 = pl[0] * in[i0][0] + pl[1] * in[i0][1] + pl[2] * in[i0][2] + pl[3];
+    const real d1 = pl[0] * in[i1][0] + pl[1] * in[i1][1] + pl[2] * in[i1][2] + pl[3];
+    if (d0 >= 0) { out[ctOut][0] = in[i0][0]; out[ctOut][1] = in[i0][1]; out[ctOut][2] = in[i0][2]; ctOut++; }
+    if ((d0 > 0 && d1 < 0) || (d0 < 0 && d1 > 0)) {
+      for (int i = 0; i < 3; i++) out[ctOut][i] = in[i0][i] - (in[i0][i] - in[i1][i]) * d0 / (d0 - d1);
+      ctOut++;
+    }
+  }
+  return ctOut;
+}
+// dMatrix3Inv, collision_util.h:192-213 -- including its operator precedence: only the second product of the
+// three "cofactors" without parentheses is divided by the determinant
+OB_HD void ob_matrix3_inv_ref(const real *ma, real *dst) {
+  const real det = ma[0] * (ma[5] * ma[10] - ma[9] * ma[6]) - ma[1] * (ma[4] * ma[10] - ma[8] * ma[6]) + ma[2] * (ma[4] * ma[9] - ma[8] * ma[5]);
+  for (int i = 0; i < 12; i++) dst[i] = 0;
+  if (ob_fabs(det) < OB_REAL(0.0005)) { dst[0] = 1; dst[5] = 1; dst[10] = 1; return; }
+  dst[0] = ma[5] * ma[10] - ma[6] * ma[9] / det;
+  dst[1] = -(ma[1] * ma[10] - ma[9] * ma[2]) / det;
+  dst[2] = ma[1] * ma[6] - ma[5] * ma[2] / det;
+  dst[4] = -(ma[4] * ma[10] - ma[6] * ma[8]) / det;
+  dst[5] = ma[0] * ma[10] - ma[8] * ma[2] / det;
+  dst[6] = -(ma[0] * ma[6] - ma[4] * ma[2]) / det;
+  dst[8] = ma[4] * ma[9] - ma[8] * ma[5] / det;
+  dst[9] = -(ma[0] * ma[9] - ma[8] * ma[1]) / det;
+  dst[10] = ma[0] * ma[5] - ma[1] * ma[4] / det;
+}
+OB_HDN int ob_collide_cylinder_box(const ObPose &o1, const ObPose &o2, int flags, ObCg *contact) {
+  const int maxc = flags & 0xffff;
+  ObCylBox D;
+  // _cldInitCylinderBox :100-203
+  for (int i = 0; i < 12; i++) { D.cylR[i] = o1.R[i]; D.boxR[i] = o2.R[i]; }
+  for (int i = 0; i < 3; i++) { D.cylPos[i] = o1.pos[i]; D.boxPos[i] = o2.pos[i]; D.cylAxis[i] = o1.R[4 * i + 2]; D.boxHalf[i] = o2.p[i] * OB_REAL(0.5); }
+  D.radius = o1.p[0]; D.size = o1.p[1];
+  {
+    const real sx[8] = {-1, 1, -1, 1, 1, 1, -1, -1}, sy[8] = {1, 1, -1, -1, 1, -1, -1, 1}, sz[8] = {-1, -1, -1, -1, 1, 1, 1, 1};
+    for (int i = 0; i < 8; i++) {
+      const real v[3] = {sx[i] < 0 ? -D.boxHalf[0] : D.boxHalf[0], sy[i] < 0 ? -D.boxHalf[1] : D.boxHalf[1], sz[i] < 0 ? -D.boxHalf[2] : D.boxHalf[2]};
+      real t[3];
+      ob_mul0_331(t, D.boxR, v);
+      for (int k = 0; k < 3; k++) D.vert[i][k] = t[k] + D.boxPos[k];
+    }
+  }
+  for (int i = 0; i < 3; i++) { D.diff[i] = D.cylPos[i] - D.boxPos[i]; D.normal[i] = 0; }
+  D.bestDepth = OB_INF; D.bestrb = 0; D.bestrc = 0; D.bestAxis = 0;
+  int n = 0;
+  // _cldTestSeparatingAxes :336-573
+  {
+    real ax[3];
+    const real eps = OB_REAL(1e-6);
+    for (int a = 0; a < 3; a++) {
+      ax[0] = D.boxR[a]; ax[1] = D.boxR[4 + a]; ax[2] = D.boxR[8 + a];
+      if (!ob_cylbox_test_axis(D, ax, 1 + a)) return 0;
+    }
+    ax[0] = D.cylAxis[0]; ax[1] = D.cylAxis[1]; ax[2] = D.cylAxis[2];
+    if (!ob_cylbox_test_axis(D, ax, 4)) return 0;
+    for (int a = 0; a < 3; a++) {
+      const real col[3] = {D.boxR[a], D.boxR[4 + a], D.boxR[8 + a]};
+      ob_cross(ax, D.cylAxis, col);     // dVector3CrossMat3Col(m, col, v, r): r = v x m(:,col)
+      if (ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2] > eps) { if (!ob_cylbox_test_axis(D, ax, 5 + a)) return 0; }
+    }
+    for (int i = 0; i < 8; i++) {
+      real t1[3] = {D.vert[i][0] - D.cylPos[0], D.vert[i][1] - D.cylPos[1], D.vert[i][2] - D.cylPos[2]}, t2[3];
+      ob_cross(t2, D.cylAxis, t1);
+      ob_cross(ax, D.cylAxis, t2);
+      if (ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2] > eps) { if (!ob_cylbox_test_axis(D, ax, 8 + i)) return 0; }
+    }
+    const unsigned char ea[12] = {1, 1, 2, 2, 4, 4, 0, 5, 5, 2, 4, 6}, eb[12] = {0, 3, 3, 0, 1, 7, 7, 3, 6, 6, 5, 7};
+    real vcc[3];
+    for (int i = 0; i < 3; i++) vcc[i] = D.cylPos[i] + D.cylAxis[i] * (D.size * OB_REAL(0.5));
+    for (int e = 0; e < 12; e++) if (!ob_cylbox_test_edge_circle(D, vcc, D.vert[ea[e]], D.vert[eb[e]], 16 + e)) return 0;
+    for (int i = 0; i < 3; i++) vcc[i] = D.cylPos[i] - D.cylAxis[i] * (D.size * OB_REAL(0.5));
+    for (int e = 0; e < 12; e++) if (!ob_cylbox_test_edge_circle(D, vcc, D.vert[ea[e]], D.vert[eb[e]], 28 + e)) return 0;
+  }
+  if (D.bestAxis == 0) return 0;
+  const real fdot = ob_dot(D.normal, D.cylAxis);
+  if (ob_fabs(fdot) < OB_REAL(0.9)) {
+    // _cldClipCylinderToBox :576-717
+    real vN[3];
+    const real ft = ob_dot(D.cylAxis, D.normal);
+    for (int i = 0; i < 3; i++) vN[i] = D.normal[i] - D.cylAxis[i] * ft;
+    ob_safe_normalize3(vN);
+    real cpt[3], ep0[3], ep1[3];
+    for (int i = 0; i < 3; i++) cpt[i] = D.cylPos[i] + vN[i] * D.radius;
+    for (int i = 0; i < 3; i++) { ep0[i] = cpt[i] + D.cylAxis[i] * (D.size * OB_REAL(0.5)); ep1[i] = cpt[i] - D.cylAxis[i] * (D.size * OB_REAL(0.5)); }
+    for (int i = 0; i < 3; i++) { ep0[i] -= D.boxPos[i]; ep1[i] -= D.boxPos[i]; }
+    for (int k = 0; k < 6; k++) {
+      const int a = k % 3;
+      real pl[4] = {D.boxR[a], D.boxR[4 + a], D.boxR[8 + a], D.boxHalf[a]};
+      if (k >= 3) { pl[0] = -pl[0]; pl[1] = -pl[1]; pl[2] = -pl[2]; }
+      if (!ob_clip_edge_to_plane(ep0, ep1, pl)) return 0;
+    }
+    real d0 = D.bestrb + ob_dot(ep0, D.normal), d1 = D.bestrb + ob_dot(ep1, D.normal);
+    if (d0 < 0) d0 = 0;
+    if (d1 < 0) d1 = 0;
+    for (int i = 0; i < 3; i++) { ep0[i] += D.boxPos[i]; ep1[i] += D.boxPos[i]; }
+    ObCg *c = contact + n;
+    c->depth = d0; c->side1 = -1; c->side2 = -1;
+    for (int i = 0; i < 3; i++) { c->normal[i] = -D.normal[i]; c->pos[i] = ep0[i]; }
+    n++;
+    if (n != maxc) {
+      c = contact + n;
+      c->depth = d1; c->side1 = -1; c->side2 = -1;
+      for (int i = 0; i < 3; i++) { c->normal[i] = -D.normal[i]; c->pos[i] = ep1[i]; }
+      n++;
+    }
+    return n;
+  }
+  // _cldClipBoxToCylinder :720-982
+  real circlePos[3], circleN[3] = {0, 0, 0};
+  if (ob_dot(D.cylAxis, D.normal) > OB_REAL(0.0)) {
+    for (int i = 0; i < 3; i++) circlePos[i] = D.cylPos[i] + D.cylAxis[i] * (D.size * OB_REAL(0.5));
+    circleN[2] = OB_REAL(-1.0);
+  } else {
+    for (int i = 0; i < 3; i++) circlePos[i] = D.cylPos[i] - D.cylAxis[i] * (D.size * OB_REAL(0.5));
+    circleN[2] = OB_REAL(1.0);
+  }
+  real vNr[3], inv[12];
+  ob_matrix3_inv_ref(D.boxR, inv);
+  ob_mul0_331(vNr, inv, D.normal);
+  const real an[3] = {ob_fabs(vNr[0]), ob_fabs(vNr[1]), ob_fabs(vNr[2])};
+  int iB0, iB1, iB2;
+  if (an[1] > an[0]) {
+    if (an[0] > an[2]) { iB0 = 1; iB1 = 0; iB2 = 2; }
+    else if (an[1] > an[2]) { iB0 = 1; iB1 = 2; iB2 = 0; }
+    else { iB0 = 2; iB1 = 1; iB2 = 0; }
+  } else {
+    if (an[1] > an[2]) { iB0 = 0; iB1 = 1; iB2 = 2; }
+    else if (an[0] > an[2]) { iB0 = 0; iB1 = 2; iB2 = 1; }
+    else { iB0 = 2; iB1 = 0; iB2 = 1; }
+  }
+  real center[3];
+  {
+    const real col[3] = {D.boxR[iB0], D.boxR[4 + iB0], D.boxR[8 + iB0]};
+    if (vNr[iB0] > 0) { for (int i = 0; i < 3; i++) center[i] = D.boxPos[i] - D.boxHalf[iB0] * col[i]; }
+    else { for (int i = 0; i < 3; i++) center[i] = D.boxPos[i] + D.boxHalf[iB0] * col[i]; }
+  }
+  real pts[4][3], A1[16][3], A2[16][3];
+  for (int i = 0; i < 16; i++) for (int k = 0; k < 3; k++) { A1[i][k] = 0; A2[i][k] = 0; }
+  {
+    const real a1[3] = {D.boxR[iB1], D.boxR[4 + iB1], D.boxR[8 + iB1]}, a2[3] = {D.boxR[iB2], D.boxR[4 + iB2], D.boxR[8 + iB2]};
+    for (int k = 0; k < 3; k++) {
+      pts[0][k] = center[k] + D.boxHalf[iB1] * a1[k] - D.boxHalf[iB2] * a2[k];
+      pts[1][k] = center[k] - D.boxHalf[iB1] * a1[k] - D.boxHalf[iB2] * a2[k];
+      pts[2][k] = center[k] - D.boxHalf[iB1] * a1[k] + D.boxHalf[iB2] * a2[k];
+      pts[3][k] = center[k] + D.boxHalf[iB1] * a1[k] + D.boxHalf[iB2] * a2[k];
+    }
+  }
+  real cinv[12];
+  ob_matrix3_inv_ref(D.cylR, cinv);
+  for (int i = 0; i < 4; i++) {
+    const real t[3] = {pts[i][0] - circlePos[0], pts[i][1] - circlePos[1], pts[i][2] - circlePos[2]};
+    ob_mul0_331(pts[i], cinv, t);
+  }
+  int c1 = 0, c2 = 0;
+  {
+    const real pl[4] = {circleN[0], circleN[1], circleN[2], OB_REAL(0.0)};
+    c1 = ob_clip_poly_to_plane(pts, 4, A1, pl);
+  }
+  for (int sgm = 0; sgm < 8; sgm++) {
+    real pl[4];
+    ob_cyl_segment_normal(sgm, pl);
+    pl[3] = D.radius;
+    if (0 == (sgm % 2)) c2 = ob_clip_poly_to_plane(A1, c1, A2, pl);
+    else c1 = ob_clip_poly_to_plane(A2, c2, A1, pl);
+  }
+  // eight segments: the result is in A1 (nCircleSegment % 2 == 0 after the loop)
+  for (int i = 0; i < c1; i++) {
+    real vp[3];
+    ob_mul0_331(vp, D.cylR, A1[i]);
+    vp[0] += circlePos[0]; vp[1] += circlePos[1]; vp[2] += circlePos[2];
+    const real t[3] = {vp[0] - D.cylPos[0], vp[1] - D.cylPos[1], vp[2] - D.cylPos[2]};
+    const real ftmpdot = ob_dot(t, D.normal);
+    const real fd = D.bestrc - ftmpdot;
+    if (fd > OB_REAL(0.0)) {
+      ObCg *c = contact + n;
+      c->depth = fd; c->side1 = -1; c->side2 = -1;
+      for (int k = 0; k < 3; k++) { c->normal[k] = -D.normal[k]; c->pos[k] = vp[k]; }
+      n++;
+      if (n == maxc) break;
+    }
+  }
+  return n;
+}
+
 // ---- ray colliders (ode/src/ray.cpp) ----------------------------------------------------------
 // ray pose: pos = origin, R(:,2) = direction, p[0] = length.  o1 = ray.
 // ray_sphere_helper, ray.cpp:192-232; mode 1 = use the exit point
@@ -948,7 +1349,9 @@ OB_HD int ob_pair_max_contacts(int t1, int t2, int maxc) {
   int cap;
   if (hi == OB_GEOM_RAY) cap = (lo == OB_GEOM_SPHERE || lo == OB_GEOM_BOX || lo == OB_GEOM_CAPSULE || lo == OB_GEOM_PLANE) ? 1 : 0;
   else if (hi == OB_GEOM_TRIMESH) cap = (lo == OB_GEOM_SPHERE || lo == OB_GEOM_BOX || lo == OB_GEOM_CAPSULE || lo == OB_GEOM_PLANE || lo == OB_GEOM_RAY) ? (1 << 15) : 0;   // bounded by the caller's max_contacts only
-  else if (lo == OB_GEOM_SPHERE) cap = (hi == OB_GEOM_SPHERE || hi == OB_GEOM_BOX || hi == OB_GEOM_PLANE || hi == OB_GEOM_CAPSULE) ? 1 : 0;
+  else if (lo == OB_GEOM_SPHERE) cap = (hi == OB_GEOM_SPHERE || hi == OB_GEOM_BOX || hi == OB_GEOM_PLANE || hi == OB_GEOM_CAPSULE || hi == OB_GEOM_CYLINDER) ? 1 : 0;
+  else if (lo == OB_GEOM_CYLINDER && hi == OB_GEOM_PLANE) cap = 4;
+  else if (lo == OB_GEOM_BOX && hi == OB_GEOM_CYLINDER) cap = 16;   // a clipped face polygon: bounded by the caller's max_contacts / the contact buffer
   else if (lo == OB_GEOM_BOX && hi == OB_GEOM_BOX) cap = 8;
   else if (lo == OB_GEOM_BOX && hi == OB_GEOM_PLANE) cap = 4;
   else if (lo == OB_GEOM_BOX && hi == OB_GEOM_CAPSULE) cap = 1;
@@ -981,6 +1384,12 @@ OB_HD int ob_collide_pair_t(const ObPose &o1, const ObPose &o2, int flags, ObCg 
   else if (t1 == OB_GEOM_CAPSULE && t2 == OB_GEOM_CAPSULE) n = ob_collide_capsule_capsule(o1, o2, flags, c);
   else if (t1 == OB_GEOM_CAPSULE && t2 == OB_GEOM_PLANE) n = ob_collide_capsule_plane(o1, o2, flags, c);
   else if (t1 == OB_GEOM_PLANE && t2 == OB_GEOM_CAPSULE) { n = ob_collide_capsule_plane(o2, o1, flags, c); rev = 1; }
+  else if (t1 == OB_GEOM_CYLINDER && t2 == OB_GEOM_PLANE) n = ob_collide_cylinder_plane(o1, o2, flags, c);
+  else if (t1 == OB_GEOM_PLANE && t2 == OB_GEOM_CYLINDER) { n = ob_collide_cylinder_plane(o2, o1, flags, c); rev = 1; }
+  else if (t1 == OB_GEOM_CYLINDER && t2 == OB_GEOM_BOX) n = ob_collide_cylinder_box(o1, o2, (flags & ~0xffff) | ((flags & 0xffff) < CGCAP ? (flags & 0xffff) : CGCAP), c);
+  else if (t1 == OB_GEOM_BOX && t2 == OB_GEOM_CYLINDER) { n = ob_collide_cylinder_box(o2, o1, (flags & ~0xffff) | ((flags & 0xffff) < CGCAP ? (flags & 0xffff) : CGCAP), c); rev = 1; }
+  else if (t1 == OB_GEOM_CYLINDER && t2 == OB_GEOM_SPHERE) n = ob_collide_cylinder_sphere(o1, o2, c);
+  else if (t1 == OB_GEOM_SPHERE && t2 == OB_GEOM_CYLINDER) { n = ob_collide_cylinder_sphere(o2, o1, c); rev = 1; }
   else if (t1 == OB_GEOM_RAY && t2 == OB_GEOM_SPHERE) n = ob_collide_ray_sphere(o1, o2, c);
   else if (t1 == OB_GEOM_SPHERE && t2 == OB_GEOM_RAY) { n = ob_collide_ray_sphere(o2, o1, c); rev = 1; }
   else if (t1 == OB_GEOM_RAY && t2 == OB_GEOM_BOX) n = ob_collide_ray_box(o1, o2, c);

@@ -262,6 +262,18 @@ void dMassSetCapsule(dMass *m, dReal density, int direction, dReal radius, dReal
   m->MI(0, 0) = Ia; m->MI(1, 1) = Ia; m->MI(2, 2) = Ia;
   m->MI(direction - 1, direction - 1) = Ib;
 }
+void dMassSetCylinderTotal(dMass *m, dReal total_mass, int direction, dReal radius, dReal length) {   // mass.cpp:180-198
+  OB_UASSERT(direction >= 1 && direction <= 3, "bad direction number");
+  dMassSetZero(m);
+  const dReal r2 = radius * radius;
+  m->mass = total_mass;
+  const dReal I = total_mass * (OB_REAL(0.25) * r2 + (OB_REAL(1.0) / OB_REAL(12.0)) * length * length);
+  m->MI(0, 0) = I; m->MI(1, 1) = I; m->MI(2, 2) = I;
+  m->MI(direction - 1, direction - 1) = total_mass * OB_REAL(0.5) * r2;
+}
+void dMassSetCylinder(dMass *m, dReal density, int direction, dReal radius, dReal length) {
+  dMassSetCylinderTotal(m, (dReal)(OB_PI * radius * radius * length * density), direction, radius, length);
+}
 void dMassAdjust(dMass *m, dReal newmass) {
   dReal scale = newmass / m->mass;
   m->mass = newmass;
@@ -983,6 +995,15 @@ void dGeomCapsuleSetParams(dGeomID g, dReal radius, dReal length) {
   g->p[0] = radius; g->p[1] = length; zero_sized(g, !radius); ob_geom_moved(g);
 }
 void dGeomCapsuleGetParams(dGeomID g, dReal *radius, dReal *length) { *radius = g->p[0]; *length = g->p[1]; }
+// flat-ended cylinder (ode/src/cylinder.cpp:49-101): p[0] = radius, p[1] = length along the local z axis
+dGeomID dCreateCylinder(dSpaceID space, dReal radius, dReal length) {
+  dxGeom *g = new dxGeom; geom_init(g, space, 1, dCylinderClass);
+  g->p[0] = radius; g->p[1] = length; zero_sized(g, !radius || !length); return g;
+}
+void dGeomCylinderSetParams(dGeomID g, dReal radius, dReal length) {
+  g->p[0] = radius; g->p[1] = length; zero_sized(g, !radius || !length); ob_geom_moved(g);
+}
+void dGeomCylinderGetParams(dGeomID g, dReal *radius, dReal *length) { *radius = g->p[0]; *length = g->p[1]; }
 // rays (ode/src/ray.cpp:49-189): p[0] = length, direction = column 2 of the rotation; the three mode flags
 // live in gflags like the reference's RAY_* bits (collision_kernel.h:79-81)
 dGeomID dCreateRay(dSpaceID space, dReal length) {

@@ -20,7 +20,7 @@ enum {  // body flags, ode/src/objects.h:38-48
   OB_BODY_AUTO_DISABLE = 16, OB_BODY_LIN_DAMP = 32, OB_BODY_ANG_DAMP = 64, OB_BODY_MAX_ANG_SPEED = 128,
   OB_BODY_GYROSCOPIC = 256
 };
-enum { OB_GEOM_SPHERE = 0, OB_GEOM_BOX = 1, OB_GEOM_CAPSULE = 2, OB_GEOM_PLANE = 4, OB_GEOM_RAY = 5, OB_GEOM_TRIMESH = 8 };
+enum { OB_GEOM_SPHERE = 0, OB_GEOM_BOX = 1, OB_GEOM_CAPSULE = 2, OB_GEOM_CYLINDER = 3, OB_GEOM_PLANE = 4, OB_GEOM_RAY = 5, OB_GEOM_TRIMESH = 8 };
 enum { OB_GEOM_ENABLED = 1, OB_GEOM_HAS_OFFSET = 2, OB_GEOM_ZERO_SIZED = 4 };
 enum { OB_SPACE_HASH = 0, OB_SPACE_SAP = 1, OB_SPACE_SIMPLE = 2 };
 enum { OB_ERR_CONTACT_OVERFLOW = 1, OB_ERR_ROW_OVERFLOW = 2, OB_ERR_PAIR_OVERFLOW = 4, OB_ERR_BVH_STACK = 8 };

@@ -45,10 +45,15 @@ def main(tag):
         shutil.copy(lc, os.path.join(PROF, f"{tag}_launches_c2.csv"))
     dom = {}
     for f in sorted(os.listdir(OUT)):
-        if not (f.startswith(f"prof_{tag}_") and f.endswith(".ncu-rep")):
+        # raw-metrics CSV written on the GPU box by collect.sh (export_rep), or a report brought back whole
+        if f.startswith(f"raw_{tag}_") and f.endswith(".csv"):
+            kern = f[len(f"raw_{tag}_"):-len(".csv")]
+            raw = open(os.path.join(OUT, f)).read()
+        elif f.startswith(f"prof_{tag}_") and f.endswith(".ncu-rep"):
+            kern = f[len(f"prof_{tag}_"):-len(".ncu-rep")]
+            raw = subprocess.run(["ncu", "-i", os.path.join(OUT, f), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        else:
             continue
-        kern = f[len(f"prof_{tag}_"):-len(".ncu-rep")]
-        raw = subprocess.run(["ncu", "-i", os.path.join(OUT, f), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(io.StringIO(raw)))
         if len(rows) < 3:
             continue

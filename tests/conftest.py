@@ -32,6 +32,7 @@ GOLDEN = [  # (file stem, scene, steps, worlds, settle) — must match tests/gol
     ("motors_settle60", "motors", 30, 1, 60),
     ("pistons_settle60", "pistons", 30, 1, 60),   # piston / PR / plane2d joints
     ("pus_settle60", "pus", 30, 1, 60),           # PU joints
+    ("cylmix_settle90", "cylmix", 20, 1, 90),     # flat cylinders vs plane / sphere / box
 ]
 
 

@@ -579,6 +579,53 @@ static inline dBodyID scene_add_capsule(SceneWorld &sw, dReal density, dReal r, 
   return b;
 }
 
+static inline dBodyID scene_add_cylinder(SceneWorld &sw, dReal density, dReal r, dReal l, dReal x, dReal y, dReal z) {
+  dBodyID b = dBodyCreate(sw.world);
+  dBodySetPosition(b, x, y, z);
+  dMass m;
+  dMassSetCylinder(&m, density, 3, r, l);
+  dBodySetMass(b, &m);
+  dGeomID g = scene_add_geom(sw, dCreateCylinder(sw.space, r, l));
+  dGeomSetBody(g, b);
+  sw.bodies.push_back(b);
+  return b;
+}
+
+// flat cylinder colliders (collision_cylinder_plane.cpp, collision_cylinder_sphere.cpp): random cylinders and spheres
+// tumbling onto a plane, two cylinders standing exactly upright (the axis-parallel four-point branch), spheres dropped
+// on discs, rims and mantles.  Cylinder-cylinder pairs have no collider in the reference build (no libccd): they
+// reach the near callback and produce no contacts, here too.  `boxes`: also boxes (collision_cylinder_box.cpp)
+static inline void scene_cylmix_impl(SceneWorld &sw, int w, bool boxes) {
+  scene_world_base(sw, w);
+  xs32 rng(sw.seed ^ 0x00C71u);
+  scene_add_geom(sw, dCreatePlane(sw.space, 0, 0, 1, 0));
+  for (int i = 0; i < 8; i++) {
+    dBodyID b = scene_add_cylinder(sw, 2, rng.uni(0.1, 0.3), rng.uni(0.1, 0.8), rng.uni(-0.8, 0.8), rng.uni(-0.8, 0.8), rng.uni(0.4, 3.5));
+    dQuaternion q = {rng.uni(-1, 1), rng.uni(-1, 1), rng.uni(-1, 1), rng.uni(-1, 1)};
+    dBodySetQuaternion(b, q);
+    dBodySetAngularVel(b, rng.uni(-2, 2), rng.uni(-2, 2), rng.uni(-2, 2));
+  }
+  for (int i = 0; i < 2; i++) scene_add_cylinder(sw, 2, (dReal)0.3, (dReal)0.4, (dReal)(1.6 + 0.9 * i), (dReal)1.5, (dReal)(0.19 + 0.4 * i));   // upright
+  for (int i = 0; i < 6; i++) scene_add_sphere(sw, 2, rng.uni(0.12, 0.35), rng.uni(-0.8, 0.8), rng.uni(-0.8, 0.8), rng.uni(0.4, 3.5));
+  scene_add_sphere(sw, 3, (dReal)0.15, (dReal)1.62, (dReal)1.53, (dReal)1.2);     // onto the upright cylinder's disc
+  scene_add_sphere(sw, 3, (dReal)0.2, (dReal)(2.5 + 0.31), (dReal)1.5, (dReal)1.6);   // onto a rim
+  if (boxes) {
+    for (int i = 0; i < 5; i++) {
+      dBodyID b = scene_add_box(sw, 2, rng.uni(0.2, 0.7), rng.uni(0.2, 0.7), rng.uni(0.2, 0.7), rng.uni(-0.8, 0.8), rng.uni(-0.8, 0.8), rng.uni(0.4, 3.5));
+      dQuaternion q = {rng.uni(-1, 1), rng.uni(-1, 1), rng.uni(-1, 1), rng.uni(-1, 1)};
+      dBodySetQuaternion(b, q);
+    }
+    scene_add_box(sw, 2, (dReal)1.2, (dReal)1.2, (dReal)0.3, (dReal)-2.0, (dReal)-1.5, (dReal)0.16);        // a slab ...
+    scene_add_cylinder(sw, 2, (dReal)0.25, (dReal)0.5, (dReal)-2.0, (dReal)-1.5, (dReal)0.58);              // ... with a cylinder standing on it
+    dBodyID lying = scene_add_cylinder(sw, 2, (dReal)0.2, (dReal)0.9, (dReal)-1.9, (dReal)-1.4, (dReal)1.2);  // and one lying across
+    dMatrix3 R;
+    dRFromAxisAndAngle(R, 0, 1, 0, (dReal)(3.14159265358979 * 0.5));
+    dBodySetRotation(lying, R);
+  }
+}
+static inline void scene_cylspheres(SceneWorld &sw, int w) { scene_cylmix_impl(sw, w, false); }
+static inline void scene_cylmix(SceneWorld &sw, int w) { scene_cylmix_impl(sw, w, true); }
+
 // capsule collider coverage: random capsules / boxes / spheres tumbling onto a plane, plus two
 // pairs of exactly parallel capsules (the two-contact branch of capsule.cpp:262-316)
 static inline void scene_capsmix(SceneWorld &sw, int w) {
@@ -905,6 +952,8 @@ static inline int scene_build(const char *name_in, SceneWorld &sw, int w, SceneP
   if (!strcmp(name, "sliders")) { scene_sliders(sw, w); return 0; }
   if (!strcmp(name, "pistons")) { scene_pistons(sw, w); return 0; }
   if (!strcmp(name, "pus")) { scene_pus(sw, w); return 0; }
+  if (!strcmp(name, "cylspheres")) { scene_cylspheres(sw, w); return 0; }
+  if (!strcmp(name, "cylmix")) { scene_cylmix(sw, w); return 0; }
   if (!strcmp(name, "universals")) { scene_universals(sw, w); return 0; }
   if (!strcmp(name, "motors")) { scene_motors(sw, w); return 0; }
   if (!strcmp(name, "buggy_terrain")) { scene_buggy_terrain(sw, w, 48); pol = policy_buggy(); pol.max_contacts = 10; return 0; }
