@@ -893,8 +893,13 @@ __device__ __noinline__ void sor_check_pass(bool act, unsigned meta, int gl, int
 // prologue is amortised); otherwise the shallow pipeline with its short prologue (many tiny worlds).
 // Measured on B200: config 2 (377 rows/world) 1.07 -> 0.93 ms with DEEP (index 6 passes, rows 3 passes ahead, four
 // row buffers), config 3 (56 rows/world) 5.19 -> 5.59 ms.
+// Tiny worlds (G = 4, shallow pipeline): 186 registers leave 10 warps per SM and the sweep waits on its own dependent
+// chain (ncu r01z: 11 % of the warp slots active); OB_SOR4_MINBLOCKS asks ptxas for <= 128 registers = 16 warps per SM.
+#ifndef OB_SOR4_MINBLOCKS
+#define OB_SOR4_MINBLOCKS 16
+#endif
 template <int G, bool DEEP>
-__global__ void __launch_bounds__(32) k_sor(ObBatchDev d, int taps) {
+__global__ void __launch_bounds__(32, (G == 4 && !DEEP) ? OB_SOR4_MINBLOCKS : 1) k_sor(ObBatchDev d, int taps) {
   constexpr int T = 32 / G;
   extern __shared__ __align__(16) unsigned char smem_all[];
   const SorTileSmem L = sor_tile_smem(d.NB, d.NR);
