@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(OB_THREADS) k_collide(ObBatchDev d) {
   }
 }
 
-#define OB_TILE_WPC 16   // worlds per CTA of k_collide_tile
+#define OB_TILE_WPC 8   // worlds per CTA of k_collide_tile
 struct CollideTileSmem { size_t np, cb, first, scan, cls, perm, stoff, cnt, stage, total; };
 __host__ __device__ inline CollideTileSmem collide_tile_smem(int NG, int NP, int WPC, int stage_cap) {
   CollideTileSmem s; size_t o = 0;

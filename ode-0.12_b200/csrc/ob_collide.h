@@ -1325,6 +1325,51 @@ OB_HD int ob_collide_ray_capsule(const ObPose &ray, const ObPose &ccyl, ObCg *co
   q[0] = ccyl.pos[0] + k * ccyl.R[2]; q[1] = ccyl.pos[1] + k * ccyl.R[6]; q[2] = ccyl.pos[2] + k * ccyl.R[10];
   return ob_ray_sphere_helper(ray, q, radius, contact, inside_ccyl);
 }
+// dCollideRayCylinder, ray.cpp:500-620 (ray vs flat cylinder: caps when the ray is parallel to the axis, else the
+// mantle between the caps)
+OB_HD int ob_collide_ray_cylinder(const ObPose &ray, const ObPose &cyl, ObCg *contact) {
+  contact->side1 = -1; contact->side2 = -1;
+  const real half_length = cyl.p[1] * OB_REAL(0.5), radius = cyl.p[0], length = ray.p[0];
+  real q[3], r[3];
+  for (int i = 0; i < 3; i++) r[i] = ray.pos[i] - cyl.pos[i];
+  real d = ob_dot41(cyl.R + 2, r);
+  for (int i = 0; i < 3; i++) q[i] = (d * cyl.R[i * 4 + 2]) - r[i];
+  const real C = ob_dot(q, q) - (radius * radius);
+  const real uv = ob_dot44(cyl.R + 2, ray.R + 2);
+  for (int i = 0; i < 3; i++) r[i] = (uv * cyl.R[i * 4 + 2]) - ray.R[i * 4 + 2];
+  real A = ob_dot(r, r);
+  const real B = 2 * ob_dot(q, r);
+  real k = B * B - 4 * A * C;
+  if (k < OB_EPSILON && C <= 0) {
+    // the ray is parallel to the axis and inside the infinite cylinder: it can only meet a cap
+    const real uvsign = (uv < 0) ? OB_REAL(-1.0) : OB_REAL(1.0);
+    const real internal = (d >= -half_length && d <= +half_length) ? OB_REAL(-1.0) : OB_REAL(1.0);
+    if (((uv > 0) && (d + (uvsign * length) < half_length * internal)) || ((uv < 0) && (d + (uvsign * length) > half_length * internal))) return 0;
+    contact->depth = ((-uvsign * d) - (internal * half_length));
+    for (int i = 0; i < 3; i++) { contact->pos[i] = ray.pos[i] + (contact->depth * ray.R[i * 4 + 2]); contact->normal[i] = uvsign * (cyl.R[i * 4 + 2]); }
+    return 1;
+  }
+  if (k > 0) {
+    k = ob_sqrt(k);
+    A = ob_recip(2 * A);
+    real alpha = (-B - k) * A;
+    if (alpha < 0) alpha = (-B + k) * A;
+    if (alpha >= 0 && alpha <= length) {
+      for (int i = 0; i < 3; i++) contact->pos[i] = ray.pos[i] + (alpha * ray.R[i * 4 + 2]);
+      for (int i = 0; i < 3; i++) q[i] = contact->pos[i] - cyl.pos[i];
+      d = ob_dot14(q, cyl.R + 2);
+      if (d >= -half_length && d <= +half_length) {
+        const real nsign = (C < 0) ? OB_REAL(-1.0) : OB_REAL(1.0);
+        for (int i = 0; i < 3; i++) contact->normal[i] = nsign * (contact->pos[i] - (cyl.pos[i] + d * cyl.R[i * 4 + 2]));
+        ob_safe_normalize3(contact->normal);
+        contact->depth = alpha;
+        return 1;
+      }
+    }
+  }
+  return 0;
+}
+
 // dCollideRayPlane, ray.cpp:473-502
 OB_HD int ob_collide_ray_plane(const ObPose &ray, const ObPose &plane, ObCg *contact) {
   real alpha = plane.p[3] - ob_dot(plane.p, ray.pos);
@@ -1347,7 +1392,7 @@ OB_HD int ob_collide_ray_plane(const ObPose &ray, const ObPose &plane, ObCg *con
 OB_HD int ob_pair_max_contacts(int t1, int t2, int maxc) {
   int lo = t1 < t2 ? t1 : t2, hi = t1 < t2 ? t2 : t1;
   int cap;
-  if (hi == OB_GEOM_RAY) cap = (lo == OB_GEOM_SPHERE || lo == OB_GEOM_BOX || lo == OB_GEOM_CAPSULE || lo == OB_GEOM_PLANE) ? 1 : 0;
+  if (hi == OB_GEOM_RAY) cap = (lo == OB_GEOM_SPHERE || lo == OB_GEOM_BOX || lo == OB_GEOM_CAPSULE || lo == OB_GEOM_CYLINDER || lo == OB_GEOM_PLANE) ? 1 : 0;
   else if (hi == OB_GEOM_TRIMESH) cap = (lo == OB_GEOM_SPHERE || lo == OB_GEOM_BOX || lo == OB_GEOM_CAPSULE || lo == OB_GEOM_PLANE || lo == OB_GEOM_RAY) ? (1 << 15) : 0;   // bounded by the caller's max_contacts only
   else if (lo == OB_GEOM_SPHERE) cap = (hi == OB_GEOM_SPHERE || hi == OB_GEOM_BOX || hi == OB_GEOM_PLANE || hi == OB_GEOM_CAPSULE || hi == OB_GEOM_CYLINDER) ? 1 : 0;
   else if (lo == OB_GEOM_CYLINDER && hi == OB_GEOM_PLANE) cap = 4;
@@ -1396,6 +1441,8 @@ OB_HD int ob_collide_pair_t(const ObPose &o1, const ObPose &o2, int flags, ObCg 
   else if (t1 == OB_GEOM_BOX && t2 == OB_GEOM_RAY) { n = ob_collide_ray_box(o2, o1, c); rev = 1; }
   else if (t1 == OB_GEOM_RAY && t2 == OB_GEOM_CAPSULE) n = ob_collide_ray_capsule(o1, o2, c);
   else if (t1 == OB_GEOM_CAPSULE && t2 == OB_GEOM_RAY) { n = ob_collide_ray_capsule(o2, o1, c); rev = 1; }
+  else if (t1 == OB_GEOM_RAY && t2 == OB_GEOM_CYLINDER) n = ob_collide_ray_cylinder(o1, o2, c);
+  else if (t1 == OB_GEOM_CYLINDER && t2 == OB_GEOM_RAY) { n = ob_collide_ray_cylinder(o2, o1, c); rev = 1; }
   else if (t1 == OB_GEOM_RAY && t2 == OB_GEOM_PLANE) n = ob_collide_ray_plane(o1, o2, c);
   else if (t1 == OB_GEOM_PLANE && t2 == OB_GEOM_RAY) { n = ob_collide_ray_plane(o2, o1, c); rev = 1; }
   else if (MESH && t1 == OB_GEOM_TRIMESH && t2 == OB_GEOM_PLANE) n = ob_collide_trimesh_plane(o1, o2, meshes[o1.mesh], (flags & ~0xffff) | ((flags & 0xffff) < CGCAP ? (flags & 0xffff) : CGCAP), c);

@@ -53,6 +53,11 @@ OB_HD real ob_fabs(real x) {
 #endif
 }
 OB_HD real ob_recip(real x) { return OB_REAL(1.0) / x; }
+#if defined(dSINGLE)
+#define OB_EPSILON 1.1920928955078125e-7f      // FLT_EPSILON (dEpsilon, ode/src/config.h:93)
+#else
+#define OB_EPSILON 2.2204460492503131e-16      // DBL_EPSILON (config.h:95)
+#endif
 OB_HD real ob_recipsqrt(real x) { return OB_REAL(1.0) / ob_sqrt(x); }
 
 // a.b with strides (odemath.h:175-178): a0*b0 + a1*b1 + a2*b2, left to right

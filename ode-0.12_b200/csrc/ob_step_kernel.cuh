@@ -129,6 +129,8 @@ __device__ __forceinline__ bool encode_bounds(real lo, real hi, real *v, unsigne
 
 // =====================================================================================
 // PJ = false: the batch has no permanent joints (contact joints only), the getInfo1/2 code of every joint type is compiled out
+// (tried on B200: capping the contact-only variant at 128 registers for 16 warps per SM instead of 11 -- spills in the row
+// assembly, config 2 k_prep 0.43 -> 0.58 ms; kept at 168 registers)
 template <int G, bool PJ>
 __global__ void __launch_bounds__(32) k_prep(ObBatchDev d, real h, int taps) {
   constexpr int T = 32 / G;
@@ -893,13 +895,10 @@ __device__ __noinline__ void sor_check_pass(bool act, unsigned meta, int gl, int
 // prologue is amortised); otherwise the shallow pipeline with its short prologue (many tiny worlds).
 // Measured on B200: config 2 (377 rows/world) 1.07 -> 0.93 ms with DEEP (index 6 passes, rows 3 passes ahead, four
 // row buffers), config 3 (56 rows/world) 5.19 -> 5.59 ms.
-// Tiny worlds (G = 4, shallow pipeline): 186 registers leave 10 warps per SM and the sweep waits on its own dependent
-// chain (ncu r01z: 11 % of the warp slots active); OB_SOR4_MINBLOCKS asks ptxas for <= 128 registers = 16 warps per SM.
-#ifndef OB_SOR4_MINBLOCKS
-#define OB_SOR4_MINBLOCKS 16
-#endif
+// (tried on B200: capping k_sor<4, false> at 128 registers for 16 warps per SM instead of 10 -- 176 B of spills in the
+// sweep loop, config 3 k_sor 3.07 -> 4.04 ms; kept at 186 registers)
 template <int G, bool DEEP>
-__global__ void __launch_bounds__(32, (G == 4 && !DEEP) ? OB_SOR4_MINBLOCKS : 1) k_sor(ObBatchDev d, int taps) {
+__global__ void __launch_bounds__(32) k_sor(ObBatchDev d, int taps) {
   constexpr int T = 32 / G;
   extern __shared__ __align__(16) unsigned char smem_all[];
   const SorTileSmem L = sor_tile_smem(d.NB, d.NR);

@@ -41,6 +41,7 @@ GOLDEN = [  # (file stem, scene, steps, worlds, settle) — must match tests/gol
 GOLDEN_CALLBACK = [
     ("raycast_settle40", "raycast", 20, 1, 40),
     ("raycast2_settle40", "raycast2", 20, 1, 40),   # rays in a second space: dSpaceCollide2 (space x space, geom x space)
+    ("raycyl_settle40", "raycyl", 20, 1, 40),       # ray-cylinder (mantle and cap branches)
 ]
 
 

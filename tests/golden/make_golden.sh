@@ -35,6 +35,7 @@ for p in single double; do
   # drop-in (callback) path only: ray colliders + capsule-trimesh
   $d --scene raycast --steps 20 --settle 40 --out tests/golden/raycast_settle40_$p.trace
   $d --scene raycast2 --steps 20 --settle 40 --out tests/golden/raycast2_settle40_$p.trace
+  $d --scene raycyl --steps 20 --settle 40 --out tests/golden/raycyl_settle40_$p.trace
   # large-world path (config 5): reference trace used in lock-step (--resync) by tests/test_large_world.py
   $d --scene pile_5x5x8 --steps 10 --settle 60 --out tests/golden/pile_5x5x8_large_settle60_$p.trace
 done

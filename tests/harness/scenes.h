@@ -863,7 +863,7 @@ static inline void scene_pile(SceneWorld &sw, int w, int nx, int ny, int nz) {
 // and a rotated terrain mesh, watched by rays — free-standing ones in every mode (all hits / first contact /
 // closest hit, with and without backface culling) and "sensor" rays riding on bodies (raycar style,
 // RC/car.cpp:353-371).  The near callback records ray contacts and creates no joints for them.
-static inline void scene_raycast(SceneWorld &sw, int w, int two_spaces) {
+static inline void scene_raycast(SceneWorld &sw, int w, int two_spaces, bool cylinders = false) {
   scene_world_base(sw, w);
   // two_spaces: the rays live in their own space and are collided with dSpaceCollide2 (space x space, geom x space)
   if (two_spaces) sw.space2 = two_spaces == 2 ? dHashSpaceCreate(0) : dSimpleSpaceCreate(0);
@@ -888,6 +888,23 @@ static inline void scene_raycast(SceneWorld &sw, int w, int two_spaces) {
     dBodyID b = scene_add_capsule(sw, 2, rng.uni(0.12, 0.3), rng.uni(0.3, 0.9), rng.uni(-3, 3), rng.uni(-3, 3), rng.uni(1.5, 3));
     dQuaternion q = {rng.uni(-1, 1), rng.uni(-1, 1), rng.uni(-1, 1), rng.uni(-1, 1)};
     dBodySetQuaternion(b, q);
+  }
+  if (cylinders) {   // ray.cpp dCollideRayCylinder: tumbling ones, one standing upright under vertical rays, one lying
+    // (static geoms hung in the air: a cylinder BODY would land on the terrain mesh, and cylinder-trimesh is not built)
+    for (int i = 0; i < 8; i++) {
+      dGeomID c = scene_add_geom(sw, dCreateCylinder(sw.space, rng.uni(0.3, 0.8), rng.uni(0.4, 1.6)));
+      dGeomSetPosition(c, rng.uni(-4, 4), rng.uni(-4, 4), rng.uni(0.5, 4));
+      dQuaternion q = {rng.uni(-1, 1), rng.uni(-1, 1), rng.uni(-1, 1), rng.uni(-1, 1)};
+      dReal l = (dReal)sqrt((double)(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]));
+      for (int k = 0; k < 4; k++) q[k] /= l;
+      dGeomSetQuaternion(c, q);
+    }
+    dGeomID c0 = scene_add_geom(sw, dCreateCylinder(sw.space, (dReal)0.6, (dReal)1.0));
+    dGeomSetPosition(c0, (dReal)3.5, (dReal)3.5, (dReal)-1.0);
+    for (int i = 0; i < 4; i++) {   // exactly parallel to the axis: the cap branch, from above, below, inside and beside
+      dGeomID r = scene_add_geom(sw, dCreateRay(rs, (dReal)(i == 2 ? 0.3 : 4)));
+      dGeomRaySet(r, (dReal)(3.5 + 0.1 * i), (dReal)(i == 3 ? 4.3 : 3.4), (dReal)(i == 1 ? -3 : (i == 2 ? -1.1 : 2)), 0, 0, (dReal)(i == 1 ? 1 : -1));
+    }
   }
   // free-standing rays, mode = i % 6
   for (int i = 0; i < 42; i++) {
@@ -967,6 +984,7 @@ static inline int scene_build(const char *name_in, SceneWorld &sw, int w, SceneP
   if (!strcmp(name, "raycast")) { scene_raycast(sw, w, 0); return 0; }
   if (!strcmp(name, "raycast2")) { scene_raycast(sw, w, 1); return 0; }
   if (!strcmp(name, "raycast2h")) { scene_raycast(sw, w, 2); return 0; }
+  if (!strcmp(name, "raycyl")) { scene_raycast(sw, w, 0, true); return 0; }
   if (!strcmp(name, "ragdoll")) { scene_ragdoll(sw, w); pol = policy_crash(); return 0; }
   if (!strcmp(name, "buggy")) { scene_buggy(sw, w); pol = policy_buggy(); return 0; }
   {

@@ -48,7 +48,7 @@ def test_cuda_matches_live_reference(scene, steps, worlds, prec):
 @pytest.mark.parametrize("prec", ["single", "double"])
 @pytest.mark.parametrize("scene,steps,worlds", [("stack32", 60, 2), ("mixed_maxc4", 120, 1), ("chain", 100, 1), ("capsmix", 100, 1), ("block64", 20, 1),
                                                 ("stack32@sap", 60, 2), ("mixed@simple", 100, 1), ("terrain_boxes", 80, 1), ("buggy_terrain", 100, 1),
-                                                ("raycast", 150, 2), ("raycast2", 120, 2), ("raycast2h", 120, 1), ("sliders", 150, 1), ("universals", 150, 1), ("motors", 150, 1), ("pistons", 150, 1), ("pus", 150, 1), ("cylmix", 150, 1)])
+                                                ("raycast", 150, 2), ("raycast2", 120, 2), ("raycast2h", 120, 1), ("raycyl", 120, 1), ("sliders", 150, 1), ("universals", 150, 1), ("motors", 150, 1), ("pistons", 150, 1), ("pus", 150, 1), ("cylmix", 150, 1)])
 def test_dropin_classic_api_matches_live_reference(scene, steps, worlds, prec):
     """the drop-in boundary: unchanged user code (dSpaceCollide + near callback calling dCollide /
     dJointCreateContact / dJointSetFeedback + dWorldQuickStep + dJointGroupEmpty) linked against
