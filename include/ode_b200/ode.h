@@ -22,6 +22,7 @@
 #define ODE_B200_ODE_H
 
 #include <stddef.h>
+#include <stdio.h>
 #include <stdint.h>
 
 #if !defined(dSINGLE) && !defined(dDOUBLE)
@@ -201,6 +202,10 @@ void dRfromQ(dMatrix3 R, const dQuaternion q);
 void dQfromR(dQuaternion q, const dMatrix3 R);
 void dDQfromW(dReal dq[4], const dVector3 w, const dQuaternion q);
 int dInvertPDMatrix(const dReal *A, dReal *Ainv, int n);
+
+/* ---- export (include/ode/export-dif.h:31, ode/src/export-dif.cpp): text dump of a world in the reference's
+ * "Dynamics Interchange Format v0.1"; every name is prefixed with `world_name` */
+void dWorldExportDIF(dWorldID w, FILE *file, const char *world_name);
 
 /* ---- mass (mass.h:43-140) ------------------------------------------------- */
 int dMassCheck(const dMass *m);

@@ -22,6 +22,8 @@
 #include "ob_batch.h"
 #include "ob_trimesh_host.h"
 
+void ob_joints_prestep_bookkeeping(dxWorld *w);   // ob_joints.cpp
+
 struct ObDropin {
   dxBatch *B;
   dxWorld *world;      // world stepped through this context (own_world when the space holds no bodies)
@@ -358,6 +360,7 @@ int ob_dropin_quickstep(dxWorld *w, dReal h) {
     for (int e = 0; e < 3; e++) hf[(size_t)4 * i + e] = ct.fdir1[e];
     if (j->node[0].body->world != w) { ob_error(0, "dWorldQuickStep: contact joint attached to a body of another world"); return 0; }
   }
+  ob_joints_prestep_bookkeeping(w);
   int rc = ob_batch_upload(B);
   rc |= obk_h2d(B->bk, D.ncontacts, &nc, sizeof(int));
   if (nc) {

@@ -735,6 +735,27 @@ dReal dJointGetPUPositionRate(dJointID j) {   // pu.cpp:128-180
 }
 }  // extern "C"
 
+// Host-visible side effects of getInfo1 that the device does not write back: an Euler-mode amotor stores the angles it
+// measured in the joint (amotor.cpp:150-160, read back by dJointGetAMotorAngle and dWorldExportDIF).  Called by the
+// drop-in dWorldQuickStep with the pre-step body state; same function as the device uses, so the values are the same bits.
+void ob_marshal_joint(const dxJoint *j, ObJoint &d);
+void ob_joints_prestep_bookkeeping(dxWorld *w) {
+  for (dxJoint *j = w->firstjoint; j; j = j->next) {
+    if (j->type != dJointTypeAMotor || j->mode != dAMotorEuler || (j->flags & dJOINT_DISABLED)) continue;
+    dxBody *b0 = j->node[0].body, *b1 = j->node[1].body;
+    if (!b0) continue;
+    if ((b0->flags & OB_BODY_DISABLED) && (!b1 || (b1->flags & OB_BODY_DISABLED))) continue;
+    ObJoint o;
+    ob_marshal_joint(j, o);
+    ObBodyView B1 = {b0->pos, b0->R, b0->q, b0->lvel, b0->avel}, B2 = B1;
+    if (b1) { B2.pos = b1->pos; B2.R = b1->R; B2.q = b1->q; B2.lvel = b1->lvel; B2.avel = b1->avel; }
+    real ax[3][3], ang[3];
+    ob_amotor_axes(o, B1, b1 ? &B2 : (const ObBodyView *)0, ax);
+    ob_amotor_euler_angles(o, B1, b1 ? &B2 : (const ObBodyView *)0, ax, ang);
+    j->angle[0] = ang[0]; j->angle[1] = ang[1]; j->angle[2] = ang[2];
+  }
+}
+
 // setRelativeValues, called from dJointAttach (ball.cpp, hinge.cpp, hinge2.cpp)
 void ob_joint_set_relative_values(dxJoint *j) {
   dReal v[4] = {0, 0, 0, 0};

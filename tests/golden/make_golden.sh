@@ -39,4 +39,8 @@ for p in single double; do
   # large-world path (config 5): reference trace used in lock-step (--resync) by tests/test_large_world.py
   $d --scene pile_5x5x8 --steps 10 --settle 60 --out tests/golden/pile_5x5x8_large_settle60_$p.trace
 done
+# dWorldExportDIF text dumps written by the reference (tests/test_export_dif.py)
+oracle/_ref/driver_ref_single --scene pistons --steps 25 --settle 20 --export-dif tests/golden/pistons_single.dif > /dev/null
+oracle/_ref/driver_ref_double --scene motors --steps 25 --settle 20 --export-dif tests/golden/motors_double.dif > /dev/null
+oracle/_ref/driver_ref_single --scene cylmix --steps 25 --settle 20 --export-dif tests/golden/cylmix_single.dif > /dev/null
 ls -la tests/golden

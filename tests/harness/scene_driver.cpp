@@ -136,7 +136,7 @@ static double now_s() {
 }
 
 int main(int argc, char **argv) {
-  std::string scene = "stack32", out = "", mode = "callback", resync = "";
+  std::string scene = "stack32", out = "", mode = "callback", resync = "", export_dif = "";
   int nworlds = 1, nsteps = 10, world0 = 0, timing = 0, settle = 0, maxc_world = 0, large = 0;
   uint32_t seed_xor = 0;
   double h = 0.01;
@@ -154,6 +154,7 @@ int main(int argc, char **argv) {
     else if (a == "--contacts-cap") maxc_world = atoi(argv[++i]);
     else if (a == "--resync") resync = argv[++i];
     else if (a == "--seed-xor") seed_xor = (uint32_t)strtoul(argv[++i], 0, 0);   // other SOR shuffle stream, same scene
+    else if (a == "--export-dif") export_dif = argv[++i];                        // callback mode: dWorldExportDIF of every world inside the last step (contact joints alive)
     else if (a == "--large") large = 1;                                          // force the large-world path (batch mode)
     else { fprintf(stderr, "unknown arg %s\n", a.c_str()); return 2; }
   }
@@ -222,6 +223,14 @@ int main(int argc, char **argv) {
         dRandSetSeed(sw.seed);
         dSpaceCollide(sw.space, &ctx, &near_cb);
         collide_second_space(sw, ctx);
+        if (!export_dif.empty() && s == nsteps - 1) {   // inside the last step: the contact joints of this step are alive
+          FILE *ef = fopen(export_dif.c_str(), w == 0 ? "w" : "a");
+          if (!ef) { perror("export"); return 2; }
+          char prefix[32];
+          snprintf(prefix, sizeof prefix, "w%d_", w);
+          dWorldExportDIF(sw.world, ef, prefix);
+          fclose(ef);
+        }
         dWorldQuickStep(sw.world, (dReal)h);
         sw.seed = (uint32_t)dRandGetSeed();
         if (t.f) {
