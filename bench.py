@@ -242,7 +242,8 @@ def run_b200(args):
     tf = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
     if os.path.exists(tf):
         tj = json.load(open(tf))
-        if tj.get("kernel") == dom:
+        # the capture is of configs[1] (stack32 x 4096 worlds, the bench's capacities): only that workload may quote it
+        if tj.get("kernel") == dom and SCENE == "stack32" and nworlds == 4096:
             traffic = tj.get("dram_bytes_per_launch")
 
     # end to end through the C ABI with HOST buffers every step (page-locked, from dBatchHostAlloc):

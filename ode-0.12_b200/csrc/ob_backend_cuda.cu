@@ -684,6 +684,7 @@ struct ObBackend {
   real *st_host;     // pinned
   size_t st_elems;   // W*NB
   size_t smem_collide, smem_prep, smem_sched, smem_sched_lane, smem_sor, smem_post, smem_collide_tile;
+  int prep_tile;                      // tile width of k_prep (defaults to `tile`)
   int collide_tile, tile_stage_cap;   // k_collide_tile serves the batch (worlds of <= 8 geoms)
   int sor_deep;     // 1: k_sor with the deep index prefetch (worlds with many rows)
   int sched_lane;   // 1: k_sched_lane (one lane per world) fits shared memory
@@ -802,7 +803,11 @@ ObBackend *obk_create(const ObBatchDev &caps, int device, char *err, size_t errl
     const char *e = getenv("OB_TILE");
     if (e && (atoi(e) == 4 || atoi(e) == 8 || atoi(e) == 16 || atoi(e) == 32)) G = atoi(e);
     b->tile = G;
-    b->smem_prep = prep_tile_smem(d.NB, d.NC, d.NJ, d.NR).total * (32 / G);
+    // row assembly (k_prep) has its own tile width: it is a throughput kernel (lane per joint / row) that waits on
+    // scattered loads, so more, narrower-batched warps can pay even where the sweep prefers few lanes per world
+    b->prep_tile = G;
+    { const char *pe = getenv("OB_PREP_TILE"); if (pe && (atoi(pe) == 4 || atoi(pe) == 8 || atoi(pe) == 16 || atoi(pe) == 32)) b->prep_tile = atoi(pe); }
+    b->smem_prep = prep_tile_smem(d.NB, d.NC, d.NJ, d.NR).total * (32 / b->prep_tile);
     b->smem_sor = sor_tile_smem(d.NB, d.NR).total * (32 / G);
     b->smem_sched = sched_smem(d.NB, d.NR).total;
     b->smem_post = post_tile_smem(d.NG).total * (32 / G);
@@ -956,8 +961,10 @@ template <int G> static void launch_step(ObBackend *b, real h, int taps, int pha
     const int gstep = (W + T - 1) / T;
     int gsor = gstep;
     if (b->grid_sor < b->grid_step) gsor = gsor < b->grid_sor ? gsor : b->grid_sor;
-    if (d.NJ > 0) k_prep<G, true><<<gstep, 32, b->smem_prep, st>>>(d, h, taps);
-    else k_prep<G, false><<<gstep, 32, b->smem_prep, st>>>(d, h, taps);
+#define OB_LAUNCH_PREP(GP) { const int gp = (W + (32 / GP) - 1) / (32 / GP); \
+      if (d.NJ > 0) k_prep<GP, true><<<gp, 32, b->smem_prep, st>>>(d, h, taps); else k_prep<GP, false><<<gp, 32, b->smem_prep, st>>>(d, h, taps); }
+    if (b->prep_tile == 4) OB_LAUNCH_PREP(4) else if (b->prep_tile == 8) OB_LAUNCH_PREP(8) else if (b->prep_tile == 16) OB_LAUNCH_PREP(16) else OB_LAUNCH_PREP(32)
+#undef OB_LAUNCH_PREP
     if (timing) cudaEventRecord(ev[2], st);
     if (b->sched_lane) k_sched_lane<<<(W + 31) / 32, 32, b->smem_sched_lane, st>>>(d, G);
     else if (d.NB <= 64) k_sched<2><<<W, 32, b->smem_sched, st>>>(d, G, taps);
