@@ -1,0 +1,185 @@
+// ob_api_extra.cpp — the remaining small entry points of the reference's public C API for the object families this
+// library serves (include/ode/objects.h, collision.h, rotation.h, misc.h, mass.h): accessors, force helpers, joint
+// conveniences, rotation utilities.  Host bookkeeping only; each function follows the reference's arithmetic so that
+// what it stores or returns is bit-identical (tests/test_api_probe.py runs the same probe program against both).
+#include <string.h>
+#include "ob_host.h"
+#include "ob_rows.h"
+
+void ob_marshal_joint(const dxJoint *j, ObJoint &d);
+
+extern "C" {
+// ---- bodies (ode/src/ode.cpp:640-1110) ------------------------------------------------------------------
+void dBodyAddForceAtRelPos(dBodyID b, dReal fx, dReal fy, dReal fz, dReal px, dReal py, dReal pz) {
+  dReal prel[4] = {px, py, pz, 0}, f[4] = {fx, fy, fz, 0}, p[4], c[4];
+  ob_mul0_331(p, b->R, prel);
+  b->facc[0] += f[0]; b->facc[1] += f[1]; b->facc[2] += f[2];
+  ob_cross(c, p, f);
+  b->tacc[0] += c[0]; b->tacc[1] += c[1]; b->tacc[2] += c[2];
+}
+void dBodyAddRelForceAtPos(dBodyID b, dReal fx, dReal fy, dReal fz, dReal px, dReal py, dReal pz) {
+  dReal frel[4] = {fx, fy, fz, 0}, f[4], q[4], c[4];
+  ob_mul0_331(f, b->R, frel);
+  b->facc[0] += f[0]; b->facc[1] += f[1]; b->facc[2] += f[2];
+  q[0] = px - b->pos[0]; q[1] = py - b->pos[1]; q[2] = pz - b->pos[2];
+  ob_cross(c, q, f);
+  b->tacc[0] += c[0]; b->tacc[1] += c[1]; b->tacc[2] += c[2];
+}
+void dBodyAddRelForceAtRelPos(dBodyID b, dReal fx, dReal fy, dReal fz, dReal px, dReal py, dReal pz) {
+  dReal frel[4] = {fx, fy, fz, 0}, prel[4] = {px, py, pz, 0}, f[4], p[4], c[4];
+  ob_mul0_331(f, b->R, frel);
+  ob_mul0_331(p, b->R, prel);
+  b->facc[0] += f[0]; b->facc[1] += f[1]; b->facc[2] += f[2];
+  ob_cross(c, p, f);
+  b->tacc[0] += c[0]; b->tacc[1] += c[1]; b->tacc[2] += c[2];
+}
+void dBodyCopyPosition(dBodyID b, dVector3 pos) { pos[0] = b->pos[0]; pos[1] = b->pos[1]; pos[2] = b->pos[2]; }
+void dBodyCopyQuaternion(dBodyID b, dQuaternion q) { q[0] = b->q[0]; q[1] = b->q[1]; q[2] = b->q[2]; q[3] = b->q[3]; }
+void dBodyCopyRotation(dBodyID b, dMatrix3 R) { for (int i = 0; i < 12; i++) R[i] = b->R[i]; }
+dReal dBodyGetLinearDamping(dBodyID b) { return b->dampingp.linear_scale; }
+dReal dBodyGetAngularDamping(dBodyID b) { return b->dampingp.angular_scale; }
+dReal dBodyGetLinearDampingThreshold(dBodyID b) { return ob_sqrt(b->dampingp.linear_threshold); }
+dReal dBodyGetAngularDampingThreshold(dBodyID b) { return ob_sqrt(b->dampingp.angular_threshold); }
+void dBodySetLinearDampingThreshold(dBodyID b, dReal t) { b->dampingp.linear_threshold = t * t; }
+void dBodySetAngularDampingThreshold(dBodyID b, dReal t) { b->dampingp.angular_threshold = t * t; }
+void dBodySetDamping(dBodyID b, dReal linear_scale, dReal angular_scale) { dBodySetLinearDamping(b, linear_scale); dBodySetAngularDamping(b, angular_scale); }
+dReal dBodyGetAutoDisableLinearThreshold(dBodyID b) { return ob_sqrt(b->adis.linear_average_threshold); }
+dReal dBodyGetAutoDisableAngularThreshold(dBodyID b) { return ob_sqrt(b->adis.angular_average_threshold); }
+void dBodySetAutoDisableLinearThreshold(dBodyID b, dReal t) { b->adis.linear_average_threshold = t * t; }
+void dBodySetAutoDisableAngularThreshold(dBodyID b, dReal t) { b->adis.angular_average_threshold = t * t; }
+int dBodyGetAutoDisableAverageSamplesCount(dBodyID b) { return (int)b->adis.average_samples; }
+int dBodyGetAutoDisableSteps(dBodyID b) { return b->adis.idle_steps; }
+void dBodySetAutoDisableSteps(dBodyID b, int steps) { b->adis.idle_steps = steps; }
+dReal dBodyGetAutoDisableTime(dBodyID b) { return b->adis.idle_time; }
+void dBodySetAutoDisableTime(dBodyID b, dReal time) { b->adis.idle_time = time; }
+int dBodyGetFiniteRotationMode(dBodyID b) { return (b->flags & OB_BODY_FINITE_ROT) != 0; }
+void dBodyGetFiniteRotationAxis(dBodyID b, dVector3 result) { result[0] = b->finite_rot_axis[0]; result[1] = b->finite_rot_axis[1]; result[2] = b->finite_rot_axis[2]; }
+dReal dBodyGetMaxAngularSpeed(dBodyID b) { return b->max_angular_speed; }
+dJointID dBodyGetJoint(dBodyID b, int index) {
+  int i = 0;
+  for (dxJointNode *n = b->firstjoint; n; n = n->next, i++) if (i == index) return n->joint;
+  return 0;
+}
+
+// ---- worlds (ode/src/ode.cpp:1840-2010) -----------------------------------------------------------------
+dReal dWorldGetLinearDamping(dWorldID w) { return w->dampingp.linear_scale; }
+dReal dWorldGetAngularDamping(dWorldID w) { return w->dampingp.angular_scale; }
+dReal dWorldGetLinearDampingThreshold(dWorldID w) { return ob_sqrt(w->dampingp.linear_threshold); }
+dReal dWorldGetAngularDampingThreshold(dWorldID w) { return ob_sqrt(w->dampingp.angular_threshold); }
+dReal dWorldGetMaxAngularSpeed(dWorldID w) { return w->max_angular_speed; }
+dReal dWorldGetAutoDisableLinearThreshold(dWorldID w) { return ob_sqrt(w->adis.linear_average_threshold); }
+dReal dWorldGetAutoDisableAngularThreshold(dWorldID w) { return ob_sqrt(w->adis.angular_average_threshold); }
+int dWorldGetAutoDisableAverageSamplesCount(dWorldID w) { return (int)w->adis.average_samples; }
+int dWorldGetAutoDisableSteps(dWorldID w) { return w->adis.idle_steps; }
+dReal dWorldGetAutoDisableTime(dWorldID w) { return w->adis.idle_time; }
+// step working memory is device memory owned by the batch: the reference's arena controls are accepted and ignored
+int dWorldUseSharedWorkingMemory(dWorldID, dWorldID) { return 1; }
+void dWorldCleanupWorkingMemory(dWorldID) {}
+int dWorldSetStepMemoryReservationPolicy(dWorldID, const void *) { return 1; }
+int dWorldSetStepMemoryManager(dWorldID, const void *) { return 1; }
+
+// ---- joints (ode/src/ode.cpp:1380-1560, joints/*.cpp) -----------------------------------------------------
+void dJointSetData(dJointID j, void *data) { j->userdata = data; }
+void *dJointGetData(dJointID j) { return j->userdata; }
+int dJointGetNumBodies(dJointID j) { return !j->node[0].body ? 0 : (!j->node[1].body ? 1 : 2); }
+dJointID dConnectingJoint(dBodyID in_b1, dBodyID in_b2) {
+  dBodyID b1 = in_b1 ? in_b1 : in_b2, b2 = in_b1 ? in_b2 : in_b1;
+  for (dxJointNode *n = b1->firstjoint; n; n = n->next) if (n->body == b2) return n->joint;
+  return 0;
+}
+int dConnectingJointList(dBodyID in_b1, dBodyID in_b2, dJointID *out_list) {
+  dBodyID b1 = in_b1 ? in_b1 : in_b2, b2 = in_b1 ? in_b2 : in_b1;
+  int n_out = 0;
+  for (dxJointNode *n = b1->firstjoint; n; n = n->next) if (n->body == b2) out_list[n_out++] = n->joint;
+  return n_out;
+}
+dReal dJointGetBallParam(dJointID j, int parameter) {   // ball.cpp:132-150
+  if (parameter == dParamCFM) return j->cfm;
+  if (parameter == dParamERP) return j->erp;
+  return 0;
+}
+void dJointAddHingeTorque(dJointID j, dReal torque) {   // hinge.cpp:326-345
+  dReal axis[4] = {0, 0, 0, 0};
+  if (j->flags & dJOINT_REVERSE) torque = -torque;
+  if (j->node[0].body) ob_mul0_331(axis, j->node[0].body->R, j->axis1);
+  axis[0] *= torque; axis[1] *= torque; axis[2] *= torque;
+  if (j->node[0].body) dBodyAddTorque(j->node[0].body, axis[0], axis[1], axis[2]);
+  if (j->node[1].body) dBodyAddTorque(j->node[1].body, -axis[0], -axis[1], -axis[2]);
+}
+static void universal_axis(dxJoint *j, int second, dReal *axis) {   // getAxis / getAxis2 (joint.cpp)
+  if (!second) { if (j->node[0].body) ob_mul0_331(axis, j->node[0].body->R, j->axis1); }
+  else if (j->node[1].body) ob_mul0_331(axis, j->node[1].body->R, j->axis2);
+  else { axis[0] = j->axis2[0]; axis[1] = j->axis2[1]; axis[2] = j->axis2[2]; }
+}
+static dReal universal_rate(dxJoint *j, int second) {   // universal.cpp:682-727
+  if (!j->node[0].body) return 0;
+  dReal axis[4] = {0, 0, 0, 0};
+  universal_axis(j, (j->flags & dJOINT_REVERSE) ? !second : second, axis);
+  dReal rate = ob_dot(axis, j->node[0].body->avel);
+  if (j->node[1].body) rate -= ob_dot(axis, j->node[1].body->avel);
+  return rate;
+}
+dReal dJointGetUniversalAngle1Rate(dJointID j) { return universal_rate(j, 0); }
+dReal dJointGetUniversalAngle2Rate(dJointID j) { return universal_rate(j, 1); }
+void dJointAddUniversalTorques(dJointID j, dReal torque1, dReal torque2) {   // universal.cpp:729-753
+  dReal a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0};
+  if (j->flags & dJOINT_REVERSE) { const dReal t = torque1; torque1 = -torque2; torque2 = -t; }
+  universal_axis(j, 0, a1);
+  universal_axis(j, 1, a2);
+  a1[0] = a1[0] * torque1 + a2[0] * torque2;
+  a1[1] = a1[1] * torque1 + a2[1] * torque2;
+  a1[2] = a1[2] * torque1 + a2[2] * torque2;
+  if (j->node[0].body) dBodyAddTorque(j->node[0].body, a1[0], a1[1], a1[2]);
+  if (j->node[1].body) dBodyAddTorque(j->node[1].body, -a1[0], -a1[1], -a1[2]);
+}
+void dJointAddAMotorTorques(dJointID j, dReal torque1, dReal torque2, dReal torque3) {   // amotor.cpp:476-511
+  if (j->num == 0 || !j->node[0].body) return;
+  dxBody *b0 = j->node[0].body, *b1 = j->node[1].body;
+  ObJoint o;
+  ob_marshal_joint(j, o);
+  ObBodyView B1 = {b0->pos, b0->R, b0->q, b0->lvel, b0->avel}, B2 = B1;
+  if (b1) { B2.pos = b1->pos; B2.R = b1->R; B2.q = b1->q; B2.lvel = b1->lvel; B2.avel = b1->avel; }
+  real ax[3][3];
+  ob_amotor_axes(o, B1, b1 ? &B2 : (const ObBodyView *)0, ax);
+  ax[0][0] *= torque1; ax[0][1] *= torque1; ax[0][2] *= torque1;
+  if (j->num >= 2) {
+    ax[0][0] += ax[1][0] * torque2; ax[0][1] += ax[1][1] * torque2; ax[0][2] += ax[1][2] * torque2;
+    if (j->num >= 3) { ax[0][0] += ax[2][0] * torque3; ax[0][1] += ax[2][1] * torque3; ax[0][2] += ax[2][2] * torque3; }
+  }
+  dBodyAddTorque(b0, ax[0][0], ax[0][1], ax[0][2]);
+  if (b1) dBodyAddTorque(b1, -ax[0][0], -ax[0][1], -ax[0][2]);
+}
+
+// ---- geoms (ode/src/collision_kernel.cpp:640-700, 1130-1200) -----------------------------------------------
+void dGeomCopyPosition(dGeomID g, dVector3 pos) { const dReal *p = dGeomGetPosition(g); pos[0] = p[0]; pos[1] = p[1]; pos[2] = p[2]; }
+void dGeomCopyRotation(dGeomID g, dMatrix3 R) { const dReal *r = dGeomGetRotation(g); for (int i = 0; i < 12; i++) R[i] = r[i]; }
+static const dReal g_zero3[4] = {0, 0, 0, 0};
+static const dReal g_ident[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+const dReal *dGeomGetOffsetPosition(dGeomID g) { return g->offset_posr ? g->offset_posr->pos : g_zero3; }
+const dReal *dGeomGetOffsetRotation(dGeomID g) { return g->offset_posr ? g->offset_posr->R : g_ident; }
+void dGeomCopyOffsetPosition(dGeomID g, dVector3 pos) { const dReal *p = dGeomGetOffsetPosition(g); pos[0] = p[0]; pos[1] = p[1]; pos[2] = p[2]; }
+void dGeomCopyOffsetRotation(dGeomID g, dMatrix3 R) { const dReal *r = dGeomGetOffsetRotation(g); for (int i = 0; i < 12; i++) R[i] = r[i]; }
+void dGeomGetOffsetQuaternion(dGeomID g, dQuaternion result) {
+  if (g->offset_posr) ob_QfromR(result, g->offset_posr->R);
+  else { result[0] = 1; result[1] = 0; result[2] = 0; result[3] = 0; }
+}
+void dInfiniteAABB(dGeomID, dReal aabb[6]) { aabb[0] = -dInfinity; aabb[1] = dInfinity; aabb[2] = -dInfinity; aabb[3] = dInfinity; aabb[4] = -dInfinity; aabb[5] = dInfinity; }
+
+// ---- rotation / random / mass utilities (rotation.cpp, misc.cpp, mass.cpp) ------------------------------------
+void dQMultiply1(dQuaternion qa, const dQuaternion qb, const dQuaternion qc) { ob_qmul1(qa, qb, qc); }
+void dQMultiply2(dQuaternion qa, const dQuaternion qb, const dQuaternion qc) { ob_qmul2(qa, qb, qc); }
+void dQMultiply3(dQuaternion qa, const dQuaternion qb, const dQuaternion qc) { ob_qmul3(qa, qb, qc); }
+void dRFrom2Axes(dMatrix3 R, dReal ax, dReal ay, dReal az, dReal bx, dReal by, dReal bz) { ob_Rfrom2axes(R, ax, ay, az, bx, by, bz); }
+void dRFromZAxis(dMatrix3 R, dReal ax, dReal ay, dReal az) {   // rotation.cpp:136-156
+  dReal n[4] = {ax, ay, az, 0}, p[4], q[4];
+  ob_safe_normalize3(n);
+  ob_plane_space(n, p, q);
+  R[0] = p[0]; R[4] = p[1]; R[8] = p[2];
+  R[1] = q[0]; R[5] = q[1]; R[9] = q[2];
+  R[2] = n[0]; R[6] = n[1]; R[10] = n[2];
+  R[3] = 0; R[7] = 0; R[11] = 0;
+}
+dReal dRandReal(void) { return ((dReal)dRand()) / ((dReal)0xffffffff); }
+void dMassSetCappedCylinder(dMass *m, dReal density, int direction, dReal radius, dReal length) { dMassSetCapsule(m, density, direction, radius, length); }
+void dMassSetCappedCylinderTotal(dMass *m, dReal total_mass, int direction, dReal radius, dReal length) { dMassSetCapsuleTotal(m, total_mass, direction, radius, length); }
+}  // extern "C"

@@ -806,6 +806,9 @@ ObBackend *obk_create(const ObBatchDev &caps, int device, char *err, size_t errl
     // row assembly (k_prep) has its own tile width: it is a throughput kernel (lane per joint / row) that waits on
     // scattered loads, so more, narrower-batched warps can pay even where the sweep prefers few lanes per world
     b->prep_tile = G;
+    // measured on B200: contact-only worlds with hundreds of rows (config 2) 0.44 -> 0.38 ms with one world per warp;
+    // jointed / tiny worlds (configs 3, 4) are fastest at the sweep's own width (config 3: 1.26 / 1.35 / 1.50 / 2.17 ms at 4 / 8 / 16 / 32)
+    if (d.NJ == 0 && d.NC >= 96) b->prep_tile = 32;
     { const char *pe = getenv("OB_PREP_TILE"); if (pe && (atoi(pe) == 4 || atoi(pe) == 8 || atoi(pe) == 16 || atoi(pe) == 32)) b->prep_tile = atoi(pe); }
     b->smem_prep = prep_tile_smem(d.NB, d.NC, d.NJ, d.NR).total * (32 / b->prep_tile);
     b->smem_sor = sor_tile_smem(d.NB, d.NR).total * (32 / G);
