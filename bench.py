@@ -171,7 +171,7 @@ def run_b200(args):
         import torch.distributed as dist
 
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib, scenes = load_libs()
     world0, nworlds = shard(rank, world_size, args.worlds)
     B = scenes.ob_scene_build_batch(SCENE.encode(), nworlds, world0, CONTACTS_CAP, local_rank)
@@ -349,7 +349,7 @@ def run_large(args):
         import torch.distributed as dist
 
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib, scenes = load_libs()
     lib.dBatchGetLargeWorldStats.argtypes = [ctypes.c_void_p, ctypes.POINTER(LargeStats)]
     scene = args.scene or LARGE["scene"]

@@ -203,6 +203,78 @@ void dQfromR(dQuaternion q, const dMatrix3 R);
 void dDQfromW(dReal dq[4], const dVector3 w, const dQuaternion q);
 int dInvertPDMatrix(const dReal *A, dReal *Ainv, int n);
 
+/* ---- further accessors and conveniences of the reference API (ob_api_extra.cpp); the line numbers are those of the
+ * reference's include/ode/objects.h unless another header is named ------------------------------------------------ */
+void dBodyAddForceAtRelPos(dBodyID, dReal fx, dReal fy, dReal fz, dReal px, dReal py, dReal pz);      /* :1040 */
+void dBodyAddRelForceAtPos(dBodyID, dReal fx, dReal fy, dReal fz, dReal px, dReal py, dReal pz);      /* :1042 */
+void dBodyAddRelForceAtRelPos(dBodyID, dReal fx, dReal fy, dReal fz, dReal px, dReal py, dReal pz);   /* :1044 */
+void dBodyCopyPosition(dBodyID body, dVector3 pos);            /* :940 */
+void dBodyCopyRotation(dBodyID, dMatrix3 R);                   /* :957 */
+void dBodyCopyQuaternion(dBodyID body, dQuaternion quat);      /* :974 */
+dReal dBodyGetLinearDamping(dBodyID b);                        /* :1351 */
+dReal dBodyGetAngularDamping(dBodyID b);                       /* :1368 */
+dReal dBodyGetLinearDampingThreshold(dBodyID b);
+dReal dBodyGetAngularDampingThreshold(dBodyID b);
+void dBodySetLinearDampingThreshold(dBodyID b, dReal threshold);
+void dBodySetAngularDampingThreshold(dBodyID b, dReal threshold);
+void dBodySetDamping(dBodyID b, dReal linear_scale, dReal angular_scale);
+dReal dBodyGetAutoDisableLinearThreshold(dBodyID);             /* :753 */
+void dBodySetAutoDisableLinearThreshold(dBodyID, dReal linear_average_threshold);
+dReal dBodyGetAutoDisableAngularThreshold(dBodyID);
+void dBodySetAutoDisableAngularThreshold(dBodyID, dReal angular_average_threshold);
+int dBodyGetAutoDisableAverageSamplesCount(dBodyID);
+int dBodyGetAutoDisableSteps(dBodyID);
+void dBodySetAutoDisableSteps(dBodyID, int steps);
+dReal dBodyGetAutoDisableTime(dBodyID);
+void dBodySetAutoDisableTime(dBodyID, dReal time);
+int dBodyGetFiniteRotationMode(dBodyID);                       /* :1209 */
+void dBodyGetFiniteRotationAxis(dBodyID, dVector3 result);
+dReal dBodyGetMaxAngularSpeed(dBodyID b);
+dJointID dBodyGetJoint(dBodyID, int index);                    /* :1231 */
+dReal dWorldGetLinearDamping(dWorldID w);                      /* :663 */
+dReal dWorldGetAngularDamping(dWorldID w);
+dReal dWorldGetLinearDampingThreshold(dWorldID w);
+dReal dWorldGetAngularDampingThreshold(dWorldID w);
+dReal dWorldGetMaxAngularSpeed(dWorldID w);
+dReal dWorldGetAutoDisableLinearThreshold(dWorldID);           /* :487 */
+dReal dWorldGetAutoDisableAngularThreshold(dWorldID);
+int dWorldGetAutoDisableAverageSamplesCount(dWorldID);
+int dWorldGetAutoDisableSteps(dWorldID);
+dReal dWorldGetAutoDisableTime(dWorldID);
+/* step working memory lives on the device and belongs to the batch: the arena controls (:157-290) are accepted, return
+ * success and change nothing; the info structs are taken as opaque pointers */
+int dWorldUseSharedWorkingMemory(dWorldID w, dWorldID from_world);
+void dWorldCleanupWorkingMemory(dWorldID w);
+int dWorldSetStepMemoryReservationPolicy(dWorldID w, const void *policyinfo);
+int dWorldSetStepMemoryManager(dWorldID w, const void *memfuncs);
+void dJointSetData(dJointID, void *data);                      /* :1722 */
+void *dJointGetData(dJointID);
+int dJointGetNumBodies(dJointID);                              /* :1678 */
+dJointID dConnectingJoint(dBodyID, dBodyID);                   /* :2940 */
+int dConnectingJointList(dBodyID, dBodyID, dJointID *);
+dReal dJointGetBallParam(dJointID, int parameter);             /* :2369 */
+void dJointAddHingeTorque(dJointID joint, dReal torque);       /* :1857 */
+dReal dJointGetUniversalAngle1Rate(dJointID);                  /* :2578 */
+dReal dJointGetUniversalAngle2Rate(dJointID);
+void dJointAddUniversalTorques(dJointID joint, dReal torque1, dReal torque2);               /* :2028 */
+void dJointAddAMotorTorques(dJointID, dReal torque1, dReal torque2, dReal torque3);         /* :2301 */
+void dGeomCopyPosition(dGeomID geom, dVector3 pos);            /* collision.h:194 */
+void dGeomCopyRotation(dGeomID geom, dMatrix3 R);
+const dReal *dGeomGetOffsetPosition(dGeomID geom);             /* collision.h:680 */
+void dGeomCopyOffsetPosition(dGeomID geom, dVector3 pos);
+const dReal *dGeomGetOffsetRotation(dGeomID geom);
+void dGeomCopyOffsetRotation(dGeomID geom, dMatrix3 R);
+void dGeomGetOffsetQuaternion(dGeomID geom, dQuaternion result);
+void dInfiniteAABB(dGeomID geom, dReal aabb[6]);               /* collision.h:1481 */
+void dQMultiply1(dQuaternion qa, const dQuaternion qb, const dQuaternion qc);   /* rotation.h:55-57 */
+void dQMultiply2(dQuaternion qa, const dQuaternion qb, const dQuaternion qc);
+void dQMultiply3(dQuaternion qa, const dQuaternion qb, const dQuaternion qc);
+void dRFrom2Axes(dMatrix3 R, dReal ax, dReal ay, dReal az, dReal bx, dReal by, dReal bz);   /* rotation.h:41 */
+void dRFromZAxis(dMatrix3 R, dReal ax, dReal ay, dReal az);                                 /* rotation.h:44 */
+dReal dRandReal(void);                                         /* misc.h:54 */
+void dMassSetCappedCylinder(dMass *m, dReal density, int direction, dReal radius, dReal length);        /* mass.h:84, deprecated alias of the capsule */
+void dMassSetCappedCylinderTotal(dMass *m, dReal total_mass, int direction, dReal radius, dReal length);
+
 /* ---- export (include/ode/export-dif.h:31, ode/src/export-dif.cpp): text dump of a world in the reference's
  * "Dynamics Interchange Format v0.1"; every name is prefixed with `world_name` */
 void dWorldExportDIF(dWorldID w, FILE *file, const char *world_name);
