@@ -272,6 +272,18 @@ void dQMultiply3(dQuaternion qa, const dQuaternion qb, const dQuaternion qc);
 void dRFrom2Axes(dMatrix3 R, dReal ax, dReal ay, dReal az, dReal bx, dReal by, dReal bz);   /* rotation.h:41 */
 void dRFromZAxis(dMatrix3 R, dReal ax, dReal ay, dReal az);                                 /* rotation.h:44 */
 dReal dRandReal(void);                                         /* misc.h:54 */
+void dMakeRandomVector(dReal *A, int n, dReal range);          /* misc.h:60-75 */
+void dMakeRandomMatrix(dReal *A, int n, int m, dReal range);
+void dClearUpperTriangle(dReal *A, int n);
+dReal dMaxDifference(const dReal *A, const dReal *B, int n, int m);
+dReal dMaxDifferenceLowerTriangle(const dReal *A, const dReal *B, int n);
+int dAllocateODEDataForThread(unsigned int uiAllocateFlags);   /* odeinit.h:190 */
+void dCleanupODEAllDataForThread(void);
+dReal dGeomSpherePointDepth(dGeomID sphere, dReal x, dReal y, dReal z);    /* collision.h:851 */
+dReal dGeomBoxPointDepth(dGeomID box, dReal x, dReal y, dReal z);
+dReal dGeomPlanePointDepth(dGeomID plane, dReal x, dReal y, dReal z);
+dReal dGeomCapsulePointDepth(dGeomID ccylinder, dReal x, dReal y, dReal z);
+void dJointAddHinge2Torques(dJointID joint, dReal torque1, dReal torque2);   /* objects.h:1997 */
 void dMassSetCappedCylinder(dMass *m, dReal density, int direction, dReal radius, dReal length);        /* mass.h:84, deprecated alias of the capsule */
 void dMassSetCappedCylinderTotal(dMass *m, dReal total_mass, int direction, dReal radius, dReal length);
 

@@ -180,6 +180,78 @@ void dRFromZAxis(dMatrix3 R, dReal ax, dReal ay, dReal az) {   // rotation.cpp:1
   R[3] = 0; R[7] = 0; R[11] = 0;
 }
 dReal dRandReal(void) { return ((dReal)dRand()) / ((dReal)0xffffffff); }
+#define OB_PAD(a) (((a) > 1) ? ((((a) - 1) | 3) + 1) : (a))   // dPAD, common.h
+void dMakeRandomVector(dReal *A, int n, dReal range) { for (int i = 0; i < n; i++) A[i] = (dRandReal() * OB_REAL(2.0) - OB_REAL(1.0)) * range; }
+void dMakeRandomMatrix(dReal *A, int n, int m, dReal range) {
+  const int skip = OB_PAD(m);
+  dReal *row = A;
+  for (int i = 0; i < n; row += skip, ++i) for (int j = 0; j < m; ++j) row[j] = (dRandReal() * OB_REAL(2.0) - OB_REAL(1.0)) * range;
+}
+void dClearUpperTriangle(dReal *A, int n) {
+  const int skip = OB_PAD(n);
+  dReal *row = A;
+  for (int i = 0; i < n; row += skip, ++i) for (int j = i + 1; j < n; ++j) row[j] = 0;
+}
+dReal dMaxDifference(const dReal *A, const dReal *B, int n, int m) {
+  const int skip = OB_PAD(m);
+  dReal mx = 0;
+  for (int i = 0; i < n; A += skip, B += skip, ++i) for (int j = 0; j < m; ++j) { const dReal d = ob_fabs(A[j] - B[j]); if (d > mx) mx = d; }
+  return mx;
+}
+dReal dMaxDifferenceLowerTriangle(const dReal *A, const dReal *B, int n) {
+  const int skip = OB_PAD(n);
+  dReal mx = 0;
+  for (int i = 0; i < n; A += skip, B += skip, ++i) for (int j = 0; j <= i; ++j) { const dReal d = ob_fabs(A[j] - B[j]); if (d > mx) mx = d; }
+  return mx;
+}
+int dAllocateODEDataForThread(unsigned int) { return 1; }   // odeinit.h: no per-thread data in this library
+void dCleanupODEAllDataForThread(void) {}
+// point depth queries (sphere.cpp:95, plane.cpp:141, capsule.cpp:104, box.cpp:109): positive inside
+dReal dGeomSpherePointDepth(dGeomID g, dReal x, dReal y, dReal z) {
+  const dReal *pos = dGeomGetPosition(g);
+  return g->p[0] - ob_sqrt((x - pos[0]) * (x - pos[0]) + (y - pos[1]) * (y - pos[1]) + (z - pos[2]) * (z - pos[2]));
+}
+dReal dGeomPlanePointDepth(dGeomID g, dReal x, dReal y, dReal z) { return g->p[3] - g->p[0] * x - g->p[1] * y - g->p[2] * z; }
+dReal dGeomCapsulePointDepth(dGeomID g, dReal x, dReal y, dReal z) {
+  const dReal *pos = dGeomGetPosition(g), *R = dGeomGetRotation(g);
+  dReal a[3] = {x - pos[0], y - pos[1], z - pos[2]};
+  dReal beta = ob_dot14(a, R + 2);
+  const dReal lz2 = g->p[1] * OB_REAL(0.5);
+  if (beta < -lz2) beta = -lz2; else if (beta > lz2) beta = lz2;
+  a[0] = pos[0] + beta * R[0 * 4 + 2]; a[1] = pos[1] + beta * R[1 * 4 + 2]; a[2] = pos[2] + beta * R[2 * 4 + 2];
+  return g->p[0] - ob_sqrt((x - a[0]) * (x - a[0]) + (y - a[1]) * (y - a[1]) + (z - a[2]) * (z - a[2]));
+}
+dReal dGeomBoxPointDepth(dGeomID g, dReal x, dReal y, dReal z) {
+  const dReal *pos = dGeomGetPosition(g), *R = dGeomGetRotation(g);
+  dReal p[4] = {x - pos[0], y - pos[1], z - pos[2], 0}, q[4], dist[6];
+  ob_mul1_331(q, R, p);
+  bool inside = true;
+  for (int i = 0; i < 3; i++) {
+    const dReal side = g->p[i] * OB_REAL(0.5);
+    dist[i] = side - q[i]; dist[i + 3] = side + q[i];
+    if (dist[i] < 0 || dist[i + 3] < 0) inside = false;
+  }
+  if (inside) {
+    dReal smallest = (dReal)(unsigned)-1;
+    for (int i = 0; i < 6; i++) if (dist[i] < smallest) smallest = dist[i];
+    return smallest;
+  }
+  dReal largest = 0;
+  for (int i = 0; i < 6; i++) if (dist[i] > largest) largest = dist[i];
+  return -largest;
+}
+void dJointAddHinge2Torques(dJointID j, dReal torque1, dReal torque2) {   // hinge2.cpp:393-410
+  if (j->node[0].body && j->node[1].body) {
+    dReal a1[4], a2[4];
+    ob_mul0_331(a1, j->node[0].body->R, j->axis1);
+    ob_mul0_331(a2, j->node[1].body->R, j->axis2);
+    a1[0] = a1[0] * torque1 + a2[0] * torque2;
+    a1[1] = a1[1] * torque1 + a2[1] * torque2;
+    a1[2] = a1[2] * torque1 + a2[2] * torque2;
+    dBodyAddTorque(j->node[0].body, a1[0], a1[1], a1[2]);
+    dBodyAddTorque(j->node[1].body, -a1[0], -a1[1], -a1[2]);
+  }
+}
 void dMassSetCappedCylinder(dMass *m, dReal density, int direction, dReal radius, dReal length) { dMassSetCapsule(m, density, direction, radius, length); }
 void dMassSetCappedCylinderTotal(dMass *m, dReal total_mass, int direction, dReal radius, dReal length) { dMassSetCapsuleTotal(m, total_mass, direction, radius, length); }
 }  // extern "C"

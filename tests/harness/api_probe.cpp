@@ -125,6 +125,23 @@ int main() {
   dMassSetCappedCylinder(&m, (dReal)2.5, 2, (dReal)0.3, (dReal)1.2); pr1("ccmass", m.mass); pr("ccI", m.I, 12);
   dMassSetCappedCylinderTotal(&m, (dReal)4, 3, (dReal)0.2, (dReal)0.9); pr("ccIt", m.I, 12);
   dMassSetCylinder(&m, (dReal)1.5, 1, (dReal)0.25, (dReal)0.8); pr1("cylmass", m.mass); pr("cylI", m.I, 12);
+  // second batch: matrix helpers, point depths, hinge2 torques
+  dReal A[12], Bm[12];
+  dMakeRandomVector(v3, 3, (dReal)2.5); pr("rvec", v3, 3);
+  dMakeRandomMatrix(A, 3, 3, (dReal)1.5); dMakeRandomMatrix(Bm, 3, 3, (dReal)1.5);
+  pr1("maxdiff", dMaxDifference(A, Bm, 3, 3)); pr1("maxdiffL", dMaxDifferenceLowerTriangle(A, Bm, 3));
+  dClearUpperTriangle(A, 3); pr("cleared", A, 12 - 1);
+  dGeomID gs = dCreateSphere(s, (dReal)0.4), gc = dCreateCapsule(s, (dReal)0.2, (dReal)0.8), gp = dCreatePlane(s, 0, (dReal)0.6, (dReal)0.8, (dReal)0.3);
+  dGeomSetPosition(gs, (dReal)0.2, (dReal)0.1, (dReal)0.5); dGeomSetBody(gc, b[2]);
+  pr1("sdepth", dGeomSpherePointDepth(gs, (dReal)0.3, (dReal)0.2, (dReal)0.6)); pr1("pdepth", dGeomPlanePointDepth(gp, 1, 2, (dReal)-0.5));
+  pr1("cdepth", dGeomCapsulePointDepth(gc, (dReal)1.5, (dReal)0.3, (dReal)1.7)); pr1("cdepth2", dGeomCapsulePointDepth(gc, 3, 0, 0));
+  pr1("bdepth_in", dGeomBoxPointDepth(g, v3[0] * 0 + dGeomGetPosition(g)[0] + (dReal)0.01, dGeomGetPosition(g)[1], dGeomGetPosition(g)[2]));
+  pr1("bdepth_out", dGeomBoxPointDepth(g, 2, 2, 2));
+  dJointID j2 = dJointCreateHinge2(w, 0);
+  dJointAttach(j2, b[0], b[1]); dJointSetHinge2Anchor(j2, (dReal)0.2, (dReal)0.1, 1); dJointSetHinge2Axis1(j2, 0, 0, 1); dJointSetHinge2Axis2(j2, 0, 1, (dReal)0.1);
+  for (int i = 0; i < 3; i++) { dBodySetForce(b[i], 0, 0, 0); dBodySetTorque(b[i], 0, 0, 0); }
+  dJointAddHinge2Torques(j2, (dReal)0.6, (dReal)-0.3); body_acc("h2T0", b[0]); body_acc("h2T1", b[1]);
+  printf("thr %d\n", dAllocateODEDataForThread(0xffffffffu));
   printf("wsm %d %d %d\n", dWorldUseSharedWorkingMemory(w, 0), dWorldSetStepMemoryReservationPolicy(w, 0), dWorldSetStepMemoryManager(w, 0));
   dWorldCleanupWorkingMemory(w);
   dCloseODE();
