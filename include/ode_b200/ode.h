@@ -231,6 +231,9 @@ int dBodyGetFiniteRotationMode(dBodyID);                       /* :1209 */
 void dBodyGetFiniteRotationAxis(dBodyID, dVector3 result);
 dReal dBodyGetMaxAngularSpeed(dBodyID b);
 dJointID dBodyGetJoint(dBodyID, int index);                    /* :1231 */
+void dBodySetDynamic(dBodyID);                                 /* :1245 */
+void dBodySetKinematic(dBodyID);                               /* :1254 */
+int dBodyIsKinematic(dBodyID);                                 /* :1261 */
 dReal dWorldGetLinearDamping(dWorldID w);                      /* :663 */
 dReal dWorldGetAngularDamping(dWorldID w);
 dReal dWorldGetLinearDampingThreshold(dWorldID w);
@@ -254,6 +257,8 @@ dJointID dConnectingJoint(dBodyID, dBodyID);                   /* :2940 */
 int dConnectingJointList(dBodyID, dBodyID, dJointID *);
 dReal dJointGetBallParam(dJointID, int parameter);             /* :2369 */
 void dJointAddHingeTorque(dJointID joint, dReal torque);       /* :1857 */
+void dJointSetHingeAnchorDelta(dJointID, dReal x, dReal y, dReal z, dReal ax, dReal ay, dReal az);   /* :1812 */
+void dJointSetHingeAxisOffset(dJointID j, dReal x, dReal y, dReal z, dReal angle);                   /* :1840 */
 dReal dJointGetUniversalAngle1Rate(dJointID);                  /* :2578 */
 dReal dJointGetUniversalAngle2Rate(dJointID);
 void dJointAddUniversalTorques(dJointID joint, dReal torque1, dReal torque2);               /* :2028 */

@@ -55,6 +55,11 @@ void dBodySetAutoDisableTime(dBodyID b, dReal time) { b->adis.idle_time = time; 
 int dBodyGetFiniteRotationMode(dBodyID b) { return (b->flags & OB_BODY_FINITE_ROT) != 0; }
 void dBodyGetFiniteRotationAxis(dBodyID b, dVector3 result) { result[0] = b->finite_rot_axis[0]; result[1] = b->finite_rot_axis[1]; result[2] = b->finite_rot_axis[2]; }
 dReal dBodyGetMaxAngularSpeed(dBodyID b) { return b->max_angular_speed; }
+// kinematic bodies (ode.cpp:834-852): infinite mass -- the inverse mass and inertia are zero, nothing else is special;
+// the row assembly, the solver and the integrator read them like any other body's
+void dBodySetKinematic(dBodyID b) { for (int i = 0; i < 12; i++) b->invI[i] = 0; b->invMass = 0; }
+void dBodySetDynamic(dBodyID b) { dBodySetMass(b, &b->mass); }
+int dBodyIsKinematic(dBodyID b) { return b->invMass == 0; }
 dJointID dBodyGetJoint(dBodyID b, int index) {
   int i = 0;
   for (dxJointNode *n = b->firstjoint; n; n = n->next, i++) if (i == index) return n->joint;

@@ -191,6 +191,28 @@ void dJointSetHingeAnchor(dJointID j, dReal x, dReal y, dReal z) { set_anchors(j
 void dJointSetHingeAxis(dJointID j, dReal x, dReal y, dReal z) { set_axes(j, x, y, z, j->axis1, j->axis2); hinge_initial_rel_rot(j); }
 void dJointSetHingeParam(dJointID j, int parameter, dReal value) { limot_set(j->limot, parameter, value); }
 dReal dJointGetHingeParam(dJointID j, int parameter) { return limot_get(j->limot, parameter); }
+void dJointSetHingeAnchorDelta(dJointID j, dReal x, dReal y, dReal z, dReal dx, dReal dy, dReal dz) {   // hinge.cpp:163-199
+  if (j->node[0].body) {
+    dxBody *b0 = j->node[0].body, *b1 = j->node[1].body;
+    dReal q[4] = {x - b0->pos[0], y - b0->pos[1], z - b0->pos[2], 0};
+    ob_mul1_331(j->anchor1, b0->R, q);
+    if (b1) {
+      q[0] = x - b1->pos[0]; q[1] = y - b1->pos[1]; q[2] = z - b1->pos[2]; q[3] = 0;
+      ob_mul1_331(j->anchor2, b1->R, q);
+    } else { j->anchor2[0] = x + dx; j->anchor2[1] = y + dy; j->anchor2[2] = z + dz; }
+  }
+  j->anchor1[3] = 0; j->anchor2[3] = 0;
+  hinge_initial_rel_rot(j);
+}
+void dJointSetHingeAxisOffset(dJointID j, dReal x, dReal y, dReal z, dReal dangle) {   // hinge.cpp:213-230
+  set_axes(j, x, y, z, j->axis1, j->axis2);
+  hinge_initial_rel_rot(j);
+  if (j->flags & dJOINT_REVERSE) dangle = -dangle;
+  dQuaternion qAngle, qOffset;
+  dQFromAxisAndAngle(qAngle, x, y, z, dangle);
+  ob_qmul3(qOffset, qAngle, j->qrel);
+  j->qrel[0] = qOffset[0]; j->qrel[1] = qOffset[1]; j->qrel[2] = qOffset[2]; j->qrel[3] = qOffset[3];
+}
 void dJointGetHingeAnchor(dJointID j, dVector3 result) {
   if (j->flags & dJOINT_REVERSE) get_anchor2(j, result, j->anchor2); else get_anchor(j, result, j->anchor1);
 }

@@ -33,6 +33,7 @@ GOLDEN = [  # (file stem, scene, steps, worlds, settle) — must match tests/gol
     ("pistons_settle60", "pistons", 30, 1, 60),   # piston / PR / plane2d joints
     ("pus_settle60", "pus", 30, 1, 60),           # PU joints
     ("cylmix_settle90", "cylmix", 20, 1, 90),     # flat cylinders vs plane / sphere / box
+    ("kinematic_settle60", "kinematic", 30, 1, 60),   # dBodySetKinematic bodies pushing a pile, hinged to a dynamic body
 ]
 
 

@@ -141,6 +141,11 @@ int main() {
   dJointAttach(j2, b[0], b[1]); dJointSetHinge2Anchor(j2, (dReal)0.2, (dReal)0.1, 1); dJointSetHinge2Axis1(j2, 0, 0, 1); dJointSetHinge2Axis2(j2, 0, 1, (dReal)0.1);
   for (int i = 0; i < 3; i++) { dBodySetForce(b[i], 0, 0, 0); dBodySetTorque(b[i], 0, 0, 0); }
   dJointAddHinge2Torques(j2, (dReal)0.6, (dReal)-0.3); body_acc("h2T0", b[0]); body_acc("h2T1", b[1]);
+  dJointID jh2 = dJointCreateHinge(w, 0), jh3 = dJointCreateHinge(w, 0);
+  dJointAttach(jh2, b[1], 0); dJointSetHingeAnchorDelta(jh2, (dReal)0.5, (dReal)0.2, (dReal)1.3, (dReal)0.1, (dReal)-0.05, (dReal)0.2);
+  dJointGetHingeAnchor(jh2, v3); pr("hdelta_a1", v3, 3); dJointGetHingeAnchor2(jh2, v3); pr("hdelta_a2", v3, 3);
+  dJointAttach(jh3, b[1], b[2]); dJointSetHingeAnchor(jh3, 1, 0, (dReal)1.2); dJointSetHingeAxisOffset(jh3, (dReal)0.2, 1, (dReal)0.1, (dReal)0.35);
+  pr1("hoff_angle", dJointGetHingeAngle(jh3)); dJointGetHingeAxis(jh3, v3); pr("hoff_axis", v3, 3);
   printf("thr %d\n", dAllocateODEDataForThread(0xffffffffu));
   printf("wsm %d %d %d\n", dWorldUseSharedWorkingMemory(w, 0), dWorldSetStepMemoryReservationPolicy(w, 0), dWorldSetStepMemoryManager(w, 0));
   dWorldCleanupWorkingMemory(w);

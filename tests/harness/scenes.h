@@ -472,6 +472,33 @@ static inline void scene_pus(SceneWorld &sw, int w) {
   scene_add_sphere(sw, 3, (dReal)0.2, (dReal)2.3, (dReal)0.02, (dReal)2.8);
 }
 
+// kinematic bodies (dBodySetKinematic: zero inverse mass / inertia, ode.cpp:841-846): a kinematic slab sweeping through
+// a loose pile at constant velocity while spinning slowly, a kinematic sphere dropping at constant speed onto a box, a
+// hinge between a kinematic and a dynamic body; one body is switched back with dBodySetDynamic
+static inline void scene_kinematic(SceneWorld &sw, int w) {
+  scene_world_base(sw, w);
+  xs32 rng(sw.seed ^ 0x00C1AEu);
+  scene_add_geom(sw, dCreatePlane(sw.space, 0, 0, 1, 0));
+  dBodyID slab = scene_add_box(sw, 2, (dReal)0.3, (dReal)1.6, (dReal)0.5, (dReal)-1.6, 0, (dReal)0.3);
+  dBodySetKinematic(slab);
+  dBodySetLinearVel(slab, (dReal)0.8, 0, 0);
+  dBodySetAngularVel(slab, 0, 0, (dReal)0.3);
+  for (int i = 0; i < 10; i++) scene_add_box(sw, 2, rng.uni(0.2, 0.5), rng.uni(0.2, 0.5), rng.uni(0.2, 0.5), rng.uni(-0.8, 0.8), rng.uni(-0.6, 0.6), (dReal)(0.3 + 0.45 * (i % 3)));
+  for (int i = 0; i < 4; i++) scene_add_sphere(sw, 2, rng.uni(0.15, 0.3), rng.uni(-0.8, 0.8), rng.uni(-0.6, 0.6), rng.uni(1.6, 2.2));
+  dBodyID ball = scene_add_sphere(sw, 3, (dReal)0.2, (dReal)0.1, (dReal)0.05, (dReal)2.8);
+  dBodySetKinematic(ball);
+  dBodySetLinearVel(ball, 0, 0, (dReal)-0.9);
+  dBodyID arm = scene_add_box(sw, 2, (dReal)0.6, (dReal)0.1, (dReal)0.1, (dReal)-1.3, 0, (dReal)0.9);
+  dJointID j = dJointCreateHinge(sw.world, 0);
+  dJointAttach(j, slab, arm);
+  dJointSetHingeAnchor(j, (dReal)-1.6, 0, (dReal)0.9);
+  dJointSetHingeAxis(j, 0, 1, 0);
+  sw.joints.push_back(j);
+  dBodyID back = scene_add_box(sw, 2, (dReal)0.3, (dReal)0.3, (dReal)0.3, (dReal)1.5, (dReal)1.2, (dReal)1.5);
+  dBodySetKinematic(back);
+  dBodySetDynamic(back);
+}
+
 // universal joints (universal.cpp): free, with stops on both axes (getAngles: dRFrom2Axes + dQfromR + atan2),
 // with a motor on axis 2, attached to the world, and one with the bodies given in reversed order
 static inline void scene_universals(SceneWorld &sw, int w) {
@@ -969,6 +996,7 @@ static inline int scene_build(const char *name_in, SceneWorld &sw, int w, SceneP
   if (!strcmp(name, "sliders")) { scene_sliders(sw, w); return 0; }
   if (!strcmp(name, "pistons")) { scene_pistons(sw, w); return 0; }
   if (!strcmp(name, "pus")) { scene_pus(sw, w); return 0; }
+  if (!strcmp(name, "kinematic")) { scene_kinematic(sw, w); return 0; }
   if (!strcmp(name, "cylspheres")) { scene_cylspheres(sw, w); return 0; }
   if (!strcmp(name, "cylmix")) { scene_cylmix(sw, w); return 0; }
   if (!strcmp(name, "universals")) { scene_universals(sw, w); return 0; }
