@@ -270,6 +270,9 @@ void dGeomCopyOffsetPosition(dGeomID geom, dVector3 pos);
 const dReal *dGeomGetOffsetRotation(dGeomID geom);
 void dGeomCopyOffsetRotation(dGeomID geom, dMatrix3 R);
 void dGeomGetOffsetQuaternion(dGeomID geom, dQuaternion result);
+void dGeomSetOffsetWorldPosition(dGeomID geom, dReal x, dReal y, dReal z);    /* collision.h:616 */
+void dGeomSetOffsetWorldRotation(dGeomID geom, const dMatrix3 R);             /* collision.h:632 */
+void dGeomSetOffsetWorldQuaternion(dGeomID geom, const dQuaternion Q);        /* collision.h:648 */
 void dInfiniteAABB(dGeomID geom, dReal aabb[6]);               /* collision.h:1481 */
 void dQMultiply1(dQuaternion qa, const dQuaternion qb, const dQuaternion qc);   /* rotation.h:55-57 */
 void dQMultiply2(dQuaternion qa, const dQuaternion qb, const dQuaternion qc);

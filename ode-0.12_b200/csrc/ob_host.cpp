@@ -928,6 +928,43 @@ void dGeomSetOffsetQuaternion(dGeomID g, const dQuaternion quat) {
   ob_RfromQ(g->offset_posr->R, quat);
   ob_geom_moved(g);
 }
+// offset given in WORLD coordinates (collision_kernel.cpp:1080-1134): the body-relative offset that puts the geom there
+static void world_offset_posr(const dxBody *b, const dReal *wpos, const dReal *wR, dxPosR *off) {   // getWorldOffsetPosr :441-452
+  dMatrix3 inv;
+  memcpy(inv, b->R, sizeof(dMatrix3));
+  dReal t;
+  t = inv[0 + 4 * 1]; inv[0 + 4 * 1] = inv[1 + 4 * 0]; inv[1 + 4 * 0] = t;
+  t = inv[2 + 4 * 0]; inv[2 + 4 * 0] = inv[0 + 4 * 2]; inv[0 + 4 * 2] = t;
+  t = inv[1 + 4 * 2]; inv[1 + 4 * 2] = inv[2 + 4 * 1]; inv[2 + 4 * 1] = t;
+  ob_mul0_333(off->R, inv, wR);
+  const dReal wo[4] = {wpos[0] - b->pos[0], wpos[1] - b->pos[1], wpos[2] - b->pos[2], 0};
+  ob_mul0_331(off->pos, inv, wo);
+}
+void dGeomSetOffsetWorldPosition(dGeomID g, dReal x, dReal y, dReal z) {
+  CHECK_NOT_LOCKED(g->parent_space);
+  if (!g->offset_posr) geom_create_offset(g);
+  const dReal prel[4] = {x - g->body->pos[0], y - g->body->pos[1], z - g->body->pos[2], 0};   // dBodyGetPosRelPoint, ode.cpp:730-740
+  ob_mul1_331(g->offset_posr->pos, g->body->R, prel);
+  ob_geom_moved(g);
+}
+void dGeomSetOffsetWorldRotation(dGeomID g, const dMatrix3 R) {
+  CHECK_NOT_LOCKED(g->parent_space);
+  if (!g->offset_posr) geom_create_offset(g);
+  ob_geom_recompute_posr(g);
+  dVector3 wpos = {g->final_posr->pos[0], g->final_posr->pos[1], g->final_posr->pos[2], 0};
+  world_offset_posr(g->body, wpos, R, g->offset_posr);
+  ob_geom_moved(g);
+}
+void dGeomSetOffsetWorldQuaternion(dGeomID g, const dQuaternion quat) {
+  CHECK_NOT_LOCKED(g->parent_space);
+  if (!g->offset_posr) geom_create_offset(g);
+  ob_geom_recompute_posr(g);
+  dVector3 wpos = {g->final_posr->pos[0], g->final_posr->pos[1], g->final_posr->pos[2], 0};
+  dMatrix3 wR;
+  ob_RfromQ(wR, quat);
+  world_offset_posr(g->body, wpos, wR, g->offset_posr);
+  ob_geom_moved(g);
+}
 void dGeomClearOffset(dGeomID g) {
   if (g->offset_posr) {
     g->offset_posr = 0;

@@ -44,6 +44,7 @@ done
 oracle/_ref/driver_ref_single --scene pistons --steps 25 --settle 20 --export-dif tests/golden/pistons_single.dif > /dev/null
 oracle/_ref/driver_ref_double --scene motors --steps 25 --settle 20 --export-dif tests/golden/motors_double.dif > /dev/null
 oracle/_ref/driver_ref_single --scene cylmix --steps 25 --settle 20 --export-dif tests/golden/cylmix_single.dif > /dev/null
+oracle/_ref/driver_ref_double --scene cylmix --steps 25 --settle 20 --export-dif tests/golden/cylmix_double.dif > /dev/null
 # accessor probe (tests/test_api_probe.py): output of the probe linked against the reference
 oracle/_ref/api_probe_ref_single > tests/golden/api_probe_single.txt
 oracle/_ref/api_probe_ref_double > tests/golden/api_probe_double.txt

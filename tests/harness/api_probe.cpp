@@ -3,6 +3,7 @@
 // library); tests/test_api_probe.py requires identical output.  Public C API only, no stepping: runs without a GPU.
 #include <stdio.h>
 #include <string.h>
+#include <math.h>
 #include <stdint.h>
 #ifdef PROBE_REFERENCE_HEADERS
 #include <ode/ode.h>
@@ -146,6 +147,13 @@ int main() {
   dJointGetHingeAnchor(jh2, v3); pr("hdelta_a1", v3, 3); dJointGetHingeAnchor2(jh2, v3); pr("hdelta_a2", v3, 3);
   dJointAttach(jh3, b[1], b[2]); dJointSetHingeAnchor(jh3, 1, 0, (dReal)1.2); dJointSetHingeAxisOffset(jh3, (dReal)0.2, 1, (dReal)0.1, (dReal)0.35);
   pr1("hoff_angle", dJointGetHingeAngle(jh3)); dJointGetHingeAxis(jh3, v3); pr("hoff_axis", v3, 3);
+  dGeomID gw = dCreateBox(s, (dReal)0.2, (dReal)0.3, (dReal)0.4);
+  dGeomSetBody(gw, b[2]);
+  dGeomSetOffsetWorldPosition(gw, (dReal)1.7, (dReal)0.4, (dReal)1.9); pr("gwo_pos", dGeomGetOffsetPosition(gw), 3); pr("gwo_wpos", dGeomGetPosition(gw), 3);
+  dMatrix3 Rw; dRFromAxisAndAngle(Rw, 1, (dReal)0.5, (dReal)-0.3, (dReal)1.1);
+  dGeomSetOffsetWorldRotation(gw, Rw); pr("gwo_R", dGeomGetOffsetRotation(gw), 12); pr("gwo_pos2", dGeomGetOffsetPosition(gw), 3); pr("gwo_wR", dGeomGetRotation(gw), 12);
+  dQuaternion qw = {(dReal)0.7, (dReal)-0.1, (dReal)0.6, (dReal)0.2}; { dReal l = (dReal)sqrt((double)(qw[0]*qw[0]+qw[1]*qw[1]+qw[2]*qw[2]+qw[3]*qw[3])); for (int k = 0; k < 4; k++) qw[k] /= l; }
+  dGeomSetOffsetWorldQuaternion(gw, qw); pr("gwo_R2", dGeomGetOffsetRotation(gw), 12); pr("gwo_pos3", dGeomGetOffsetPosition(gw), 3);
   printf("thr %d\n", dAllocateODEDataForThread(0xffffffffu));
   printf("wsm %d %d %d\n", dWorldUseSharedWorkingMemory(w, 0), dWorldSetStepMemoryReservationPolicy(w, 0), dWorldSetStepMemoryManager(w, 0));
   dWorldCleanupWorkingMemory(w);

@@ -13,11 +13,11 @@ import tempfile
 
 import pytest
 
-from conftest import ROOT, have_ref
+from conftest import ATAN2_SCENES, ROOT, have_ref
 from run_parity import driver_path
 
 SCENES = ["stack32", "mixed", "hinges", "buggy", "ragdoll", "capsmix", "sliders", "universals", "motors", "pistons", "pus", "cylmix", "raycyl"]
-GOLDEN = [("pistons", "single"), ("motors", "double"), ("cylmix", "single")]   # tests/golden/*.dif, written by the reference (make_golden.sh)
+GOLDEN = [("pistons", "single"), ("motors", "double"), ("cylmix", "single"), ("cylmix", "double")]   # tests/golden/*.dif, written by the reference (make_golden.sh)
 
 
 def _export(kind, prec, scene, path, steps=25, settle=20):
@@ -57,6 +57,8 @@ def test_hostsim_dif_equals_golden(scene, prec):
 @pytest.mark.gpu
 @pytest.mark.parametrize("scene,prec", GOLDEN)
 def test_cuda_dif_equals_golden(scene, prec):
+    if prec == "double" and scene in ATAN2_SCENES:
+        pytest.skip("dDOUBLE atan2 scenes are tolerance-class on the GPU (conftest.ATAN2_SCENES): a 15-digit text dump after 45 free-running steps cannot be byte-equal")
     _check_golden("b200", scene, prec)
 
 
