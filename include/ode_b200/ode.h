@@ -231,6 +231,7 @@ int dBodyGetFiniteRotationMode(dBodyID);                       /* :1209 */
 void dBodyGetFiniteRotationAxis(dBodyID, dVector3 result);
 dReal dBodyGetMaxAngularSpeed(dBodyID b);
 dJointID dBodyGetJoint(dBodyID, int index);                    /* :1231 */
+void dBodySetMovedCallback(dBodyID b, void (*callback)(dBodyID));   /* :1308; drop-in path: called after the step, stepping order */
 void dBodySetDynamic(dBodyID);                                 /* :1245 */
 void dBodySetKinematic(dBodyID);                               /* :1254 */
 int dBodyIsKinematic(dBodyID);                                 /* :1261 */

@@ -60,6 +60,10 @@ dReal dBodyGetMaxAngularSpeed(dBodyID b) { return b->max_angular_speed; }
 void dBodySetKinematic(dBodyID b) { for (int i = 0; i < 12; i++) b->invI[i] = 0; b->invMass = 0; }
 void dBodySetDynamic(dBodyID b) { dBodySetMass(b, &b->mass); }
 int dBodyIsKinematic(dBodyID b) { return b->invMass == 0; }
+// the reference calls it from dxStepBody (util.cpp:338-340) for every body it stepped; here the drop-in dWorldQuickStep
+// calls it for the same bodies in the same order AFTER the whole step came back from the GPU (the callback sees the
+// final, damped state of all bodies).  The batched path never calls into user code.
+void dBodySetMovedCallback(dBodyID b, void (*callback)(dBodyID)) { b->moved_callback = callback; }
 dJointID dBodyGetJoint(dBodyID b, int index) {
   int i = 0;
   for (dxJointNode *n = b->firstjoint; n; n = n->next, i++) if (i == index) return n->joint;

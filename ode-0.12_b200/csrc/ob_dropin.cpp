@@ -401,6 +401,10 @@ int ob_dropin_quickstep(dxWorld *w, dReal h) {
   // dxStepBody: every geom of a stepped body is reported moved, in stepping order (util.cpp:331-337)
   for (int i = 0; i < si[SI_NIB] && i < nb; i++)
     for (dxGeom *g = B->bodies[0][ib[i]]->geom; g; g = g->body_next) ob_geom_moved(g);
+  for (int i = 0; i < si[SI_NIB] && i < nb; i++) {   // moved callbacks, stepping order (util.cpp:338-340)
+    dxBody *b = B->bodies[0][ib[i]];
+    if (b->moved_callback) b->moved_callback(b);
+  }
   ob_global_seed = hw.seed;
   if (want_fb) {
     std::vector<dReal> fb((size_t)(D.NC + D.NJ) * 12);

@@ -61,6 +61,7 @@ struct dxBody {
   dxDamping dampingp;
   dReal max_angular_speed;
   int batch_index;               // index inside the bound batch world slot
+  void (*moved_callback)(dxBody *);   // dBodySetMovedCallback (ode.cpp:1119): drop-in path, after every step that moved the body
 };
 
 enum { dJOINT_INGROUP = 1, dJOINT_REVERSE = 2, dJOINT_TWOBODIES = 4, dJOINT_DISABLED = 8 };

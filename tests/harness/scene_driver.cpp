@@ -135,8 +135,12 @@ static double now_s() {
   return ts.tv_sec + 1e-9 * ts.tv_nsec;
 }
 
+// --moved-log: every body reports through dBodySetMovedCallback; the log holds, per step, the order of the calls
+static FILE *g_moved_log = NULL;
+static void moved_cb(dBodyID b) { if (g_moved_log) fprintf(g_moved_log, " %d", (int)(intptr_t)dBodyGetData(b)); }
+
 int main(int argc, char **argv) {
-  std::string scene = "stack32", out = "", mode = "callback", resync = "", export_dif = "";
+  std::string scene = "stack32", out = "", mode = "callback", resync = "", export_dif = "", moved_log = "";
   int nworlds = 1, nsteps = 10, world0 = 0, timing = 0, settle = 0, maxc_world = 0, large = 0;
   uint32_t seed_xor = 0;
   double h = 0.01;
@@ -154,6 +158,7 @@ int main(int argc, char **argv) {
     else if (a == "--contacts-cap") maxc_world = atoi(argv[++i]);
     else if (a == "--resync") resync = argv[++i];
     else if (a == "--seed-xor") seed_xor = (uint32_t)strtoul(argv[++i], 0, 0);   // other SOR shuffle stream, same scene
+    else if (a == "--moved-log") moved_log = argv[++i];                          // callback mode: order of the body moved-callbacks per step
     else if (a == "--export-dif") export_dif = argv[++i];                        // callback mode: dWorldExportDIF of every world inside the last step (contact joints alive)
     else if (a == "--large") large = 1;                                          // force the large-world path (batch mode)
     else { fprintf(stderr, "unknown arg %s\n", a.c_str()); return 2; }
@@ -165,6 +170,11 @@ int main(int argc, char **argv) {
     if (scene_build(scene.c_str(), worlds[w], world0 + w, pol)) { fprintf(stderr, "bad scene\n"); return 2; }
   for (int w = 0; w < nworlds; w++) worlds[w].seed ^= seed_xor;
 
+  if (!moved_log.empty()) {
+    g_moved_log = fopen(moved_log.c_str(), "w");
+    for (int w = 0; w < nworlds; w++)
+      for (size_t i = 0; i < worlds[w].bodies.size(); i++) { dBodySetData(worlds[w].bodies[i], (void *)(intptr_t)i); dBodySetMovedCallback(worlds[w].bodies[i], &moved_cb); }
+  }
   Trace t;
   t.f = NULL;
   if (!out.empty()) {
@@ -232,6 +242,7 @@ int main(int argc, char **argv) {
           fclose(ef);
         }
         dWorldQuickStep(sw.world, (dReal)h);
+        if (g_moved_log) fprintf(g_moved_log, "\n");
         sw.seed = (uint32_t)dRandGetSeed();
         if (t.f) {
           t.i32((int)ctx.pairs.size() / 2);
@@ -378,6 +389,7 @@ int main(int argc, char **argv) {
 
   double dt = now_s() - t0;
   if (t.f) fclose(t.f);
+  if (g_moved_log) fclose(g_moved_log);
   if (timing)
     printf("{\"scene\":\"%s\",\"mode\":\"%s\",\"worlds\":%d,\"steps\":%d,\"seconds\":%.6f,\"body_steps\":%lld,"
            "\"contacts\":%lld,\"body_steps_per_sec\":%.1f,\"contacts_per_sec\":%.1f,\"realsize\":%d}\n",
