@@ -275,6 +275,9 @@ void dGeomSetOffsetWorldPosition(dGeomID geom, dReal x, dReal y, dReal z);    /*
 void dGeomSetOffsetWorldRotation(dGeomID geom, const dMatrix3 R);             /* collision.h:632 */
 void dGeomSetOffsetWorldQuaternion(dGeomID geom, const dQuaternion Q);        /* collision.h:648 */
 void dInfiniteAABB(dGeomID geom, dReal aabb[6]);               /* collision.h:1481 */
+dTriMeshDataID dGeomTriMeshGetTriMeshDataID(dGeomID g);        /* collision_trimesh.h:180 */
+void dGeomTriMeshGetTriangle(dGeomID g, int index, dVector3 *v0, dVector3 *v1, dVector3 *v2);   /* collision_trimesh.h:198, world coordinates */
+void dGeomTriMeshGetPoint(dGeomID g, int index, dReal u, dReal v, dVector3 out);                 /* collision_trimesh.h:204 */
 void dQMultiply1(dQuaternion qa, const dQuaternion qb, const dQuaternion qc);   /* rotation.h:55-57 */
 void dQMultiply2(dQuaternion qa, const dQuaternion qb, const dQuaternion qc);
 void dQMultiply3(dQuaternion qa, const dQuaternion qb, const dQuaternion qc);

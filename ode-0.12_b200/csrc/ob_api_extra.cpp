@@ -5,6 +5,7 @@
 #include <string.h>
 #include "ob_host.h"
 #include "ob_rows.h"
+#include "ob_trimesh_host.h"
 
 void ob_marshal_joint(const dxJoint *j, ObJoint &d);
 
@@ -171,6 +172,31 @@ void dGeomCopyOffsetRotation(dGeomID g, dMatrix3 R) { const dReal *r = dGeomGetO
 void dGeomGetOffsetQuaternion(dGeomID g, dQuaternion result) {
   if (g->offset_posr) ob_QfromR(result, g->offset_posr->R);
   else { result[0] = 1; result[1] = 0; result[2] = 0; result[3] = 0; }
+}
+// trimesh accessors (collision_trimesh_opcode.cpp:820-882, collision_trimesh_internal.h:394-411, :585-592)
+dTriMeshDataID dGeomTriMeshGetTriMeshDataID(dGeomID g) { return g->tmdata; }
+static void fetch_triangle(dxGeom *g, int index, dReal out[3][4]) {
+  const dReal *pos = dGeomGetPosition(g), *R = dGeomGetRotation(g);
+  const dxTriMeshData *d = g->tmdata;
+  for (int i = 0; i < 3; i++) {
+    const float *vf = &d->verts[(size_t)3 * d->tris[(size_t)3 * index + i]];
+    const dReal v[4] = {vf[0], vf[1], vf[2], 0};
+    ob_mul0_331(out[i], R, v);
+    out[i][0] += pos[0]; out[i][1] += pos[1]; out[i][2] += pos[2]; out[i][3] = 0;
+  }
+}
+void dGeomTriMeshGetTriangle(dGeomID g, int index, dVector3 *v0, dVector3 *v1, dVector3 *v2) {
+  dReal v[3][4];
+  fetch_triangle(g, index, v);
+  if (v0) for (int k = 0; k < 4; k++) (*v0)[k] = v[0][k];
+  if (v1) for (int k = 0; k < 4; k++) (*v1)[k] = v[1][k];
+  if (v2) for (int k = 0; k < 4; k++) (*v2)[k] = v[2][k];
+}
+void dGeomTriMeshGetPoint(dGeomID g, int index, dReal u, dReal v, dVector3 out) {
+  dReal dv[3][4];
+  fetch_triangle(g, index, dv);
+  const dReal w = OB_REAL(1.0) - u - v;
+  for (int k = 0; k < 4; k++) out[k] = (dv[0][k] * w) + (dv[1][k] * u) + (dv[2][k] * v);
 }
 void dInfiniteAABB(dGeomID, dReal aabb[6]) { aabb[0] = -dInfinity; aabb[1] = dInfinity; aabb[2] = -dInfinity; aabb[3] = dInfinity; aabb[4] = -dInfinity; aabb[5] = dInfinity; }
 

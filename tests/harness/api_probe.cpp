@@ -154,6 +154,17 @@ int main() {
   dGeomSetOffsetWorldRotation(gw, Rw); pr("gwo_R", dGeomGetOffsetRotation(gw), 12); pr("gwo_pos2", dGeomGetOffsetPosition(gw), 3); pr("gwo_wR", dGeomGetRotation(gw), 12);
   dQuaternion qw = {(dReal)0.7, (dReal)-0.1, (dReal)0.6, (dReal)0.2}; { dReal l = (dReal)sqrt((double)(qw[0]*qw[0]+qw[1]*qw[1]+qw[2]*qw[2]+qw[3]*qw[3])); for (int k = 0; k < 4; k++) qw[k] /= l; }
   dGeomSetOffsetWorldQuaternion(gw, qw); pr("gwo_R2", dGeomGetOffsetRotation(gw), 12); pr("gwo_pos3", dGeomGetOffsetPosition(gw), 3);
+  // trimesh accessors on a small rotated mesh
+  static float tverts[5 * 3] = {0, 0, 0, 1, 0, (float)0.2, 0, 1, (float)0.1, 1, 1, (float)-0.3, (float)0.5, (float)0.5, 1};
+  static dTriIndex tidx[4 * 3] = {0, 1, 2, 1, 3, 2, 0, 4, 1, 2, 3, 4};
+  dTriMeshDataID td = dGeomTriMeshDataCreate();
+  dGeomTriMeshDataBuildSingle(td, tverts, 3 * sizeof(float), 5, tidx, 12, 3 * sizeof(dTriIndex));
+  dGeomID tm = dCreateTriMesh(s, td, 0, 0, 0);
+  dGeomSetPosition(tm, (dReal)0.3, (dReal)-0.2, (dReal)0.7); dGeomSetRotation(tm, Rw);
+  printf("tmdata %d\n", dGeomTriMeshGetTriMeshDataID(tm) == td);
+  dVector3 t0, t1, t2;
+  dGeomTriMeshGetTriangle(tm, 2, &t0, &t1, &t2); pr("tri2_v0", t0, 4); pr("tri2_v1", t1, 4); pr("tri2_v2", t2, 4);
+  dGeomTriMeshGetPoint(tm, 3, (dReal)0.25, (dReal)0.6, v3); pr("tri3_pt", v3, 3);
   printf("thr %d\n", dAllocateODEDataForThread(0xffffffffu));
   printf("wsm %d %d %d\n", dWorldUseSharedWorkingMemory(w, 0), dWorldSetStepMemoryReservationPolicy(w, 0), dWorldSetStepMemoryManager(w, 0));
   dWorldCleanupWorkingMemory(w);

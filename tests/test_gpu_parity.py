@@ -134,6 +134,41 @@ def test_full_batch_is_deterministic_and_replicates_small_batch():
     assert np.isfinite(pos).all() and pos[:, :, 2].min() > -0.5
 
 
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not shipped")
+@pytest.mark.parametrize("scene,W,cap,steps", [("stack32", 4096, 256, 60), ("buggy_terrain256", 65536, 48, 60), ("ragdoll", 16384, 160, 40)])
+def test_sampled_worlds_of_the_full_batch_equal_the_reference(scene, W, cap, steps):
+    """BASELINE.json configs[1..3] at their FULL batch size (the kernels' many-worlds-per-CTA / per-warp mappings, grid
+    caps, world ranges): after `steps` free-running steps, worlds sampled from the start, the middle and the end of the
+    batch hold bit for bit the body state the unmodified reference computes for the same world ids (dSINGLE)."""
+    import subprocess
+    import tempfile
+    from run_parity import driver_path
+    from tracecmp import read_trace
+
+    lib = ctypes.CDLL(lib_path("single"))
+    scenes = ctypes.CDLL(os.path.join(ROOT, "ode-0.12_b200", "lib", "libob_scenes_single.so"))
+    lib.dB200LastError.restype = ctypes.c_char_p
+    lib.dBatchCollideAndQuickStep.argtypes = [ctypes.c_void_p, ctypes.c_float, ctypes.c_int, ctypes.c_void_p]
+    lib.dBatchDestroy.argtypes = [ctypes.c_void_p]
+    B = _batch(lib, scenes, scene, W, cap)
+    status = np.zeros(W, dtype=np.int32)
+    assert lib.dBatchCollideAndQuickStep(B, 0.01, steps, status.ctypes.data) == 0, lib.dB200LastError()
+    assert not status.any()
+    pos, quat, lv, av = _state(lib, B, W)
+    lib.dBatchDestroy(B)
+    with tempfile.TemporaryDirectory() as td:
+        for w0 in (0, W // 2 - 1, W - 2):
+            f = os.path.join(td, f"ref_{w0}.bin")
+            subprocess.run([driver_path("ref", "single"), "--scene", scene, "--worlds", "2", "--world0", str(w0), "--steps", str(steps), "--out", f],
+                           check=True, capture_output=True, timeout=900)
+            last = read_trace(f)["steps"][-1]
+            for k in range(2):
+                st = last[k]["state1"]
+                nb = st.shape[0]
+                got = np.concatenate([pos[w0 + k, :nb], quat[w0 + k, :nb], lv[w0 + k, :nb], av[w0 + k, :nb]], axis=1)
+                assert np.array_equal(got.view(np.uint32), np.ascontiguousarray(st).view(np.uint32)), f"{scene}: world {w0 + k} of {W} differs from the reference"
+
+
 def test_no_gpu_fallback_symbols():
     """the product library must not contain the test-only host backend"""
     import subprocess
