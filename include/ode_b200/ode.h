@@ -263,6 +263,8 @@ void dJointSetHingeAxisOffset(dJointID j, dReal x, dReal y, dReal z, dReal angle
 dReal dJointGetUniversalAngle1Rate(dJointID);                  /* :2578 */
 dReal dJointGetUniversalAngle2Rate(dJointID);
 void dJointAddUniversalTorques(dJointID joint, dReal torque1, dReal torque2);               /* :2028 */
+void dJointSetUniversalAxis1Offset(dJointID, dReal x, dReal y, dReal z, dReal offset1, dReal offset2);   /* :1948 */
+void dJointSetUniversalAxis2Offset(dJointID, dReal x, dReal y, dReal z, dReal offset1, dReal offset2);   /* :1968 */
 void dJointAddAMotorTorques(dJointID, dReal torque1, dReal torque2, dReal torque3);         /* :2301 */
 void dGeomCopyPosition(dGeomID geom, dVector3 pos);            /* collision.h:194 */
 void dGeomCopyRotation(dGeomID geom, dMatrix3 R);

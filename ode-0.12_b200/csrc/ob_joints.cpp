@@ -425,6 +425,40 @@ void dJointSetUniversalAxis2(dJointID j, dReal x, dReal y, dReal z) {
   if (j->flags & dJOINT_REVERSE) set_axes(j, x, y, z, j->axis1, 0); else set_axes(j, x, y, z, 0, j->axis2);
   universal_initial_rel_rots(j);
 }
+// axis setters that also declare the current pose to be at angles (offset1, offset2) (universal.cpp:418-478, :493-548)
+static void universal_offset_rel_rots(dxJoint *j, const dReal *a1, const dReal *a2, dReal offset1, dReal offset2) {
+  dQuaternion qAngle, qcross, qOffset;
+  dMatrix3 R;
+  memset(R, 0, sizeof R);
+  dQFromAxisAndAngle(qAngle, a1[0], a1[1], a1[2], offset1);
+  ob_Rfrom2axes(R, a1[0], a1[1], a1[2], a2[0], a2[1], a2[2]);
+  ob_QfromR(qcross, R);
+  dQMultiply0(qOffset, qAngle, qcross);
+  qmul1(j->qrel, j->node[0].body->q, qOffset);
+  dQFromAxisAndAngle(qAngle, a2[0], a2[1], a2[2], offset2);
+  ob_Rfrom2axes(R, a2[0], a2[1], a2[2], a1[0], a1[1], a1[2]);
+  ob_QfromR(qcross, R);
+  qmul1(qOffset, qAngle, qcross);
+  if (j->node[1].body) qmul1(j->qrel2, j->node[1].body->q, qOffset);
+  else for (int i = 0; i < 4; i++) j->qrel2[i] = qcross[i];
+}
+void dJointSetUniversalAxis1Offset(dJointID j, dReal x, dReal y, dReal z, dReal offset1, dReal offset2) {
+  if (j->flags & dJOINT_REVERSE) { set_axes(j, x, y, z, 0, j->axis2); offset1 = -offset1; offset2 = -offset2; }
+  else set_axes(j, x, y, z, j->axis1, 0);
+  universal_initial_rel_rots(j);
+  dReal ax1[4], ax2[4];
+  universal_axes(j, ax1, ax2);
+  const dReal in[3] = {x, y, z};           // the caller's axis, not the stored normalised one
+  universal_offset_rel_rots(j, in, ax2, offset1, offset2);
+}
+void dJointSetUniversalAxis2Offset(dJointID j, dReal x, dReal y, dReal z, dReal offset1, dReal offset2) {
+  if (j->flags & dJOINT_REVERSE) { set_axes(j, x, y, z, j->axis1, 0); offset1 = -offset2; offset2 = -offset1; }   // sic (:503-504)
+  else set_axes(j, x, y, z, 0, j->axis2);
+  universal_initial_rel_rots(j);
+  dReal ax1[4], ax2[4];
+  universal_axes(j, ax1, ax2);
+  universal_offset_rel_rots(j, ax1, ax2, offset1, offset2);
+}
 void dJointGetUniversalAnchor(dJointID j, dVector3 result) {
   if (j->flags & dJOINT_REVERSE) get_anchor2(j, result, j->anchor2); else get_anchor(j, result, j->anchor1);
 }

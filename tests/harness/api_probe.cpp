@@ -165,6 +165,13 @@ int main() {
   dVector3 t0, t1, t2;
   dGeomTriMeshGetTriangle(tm, 2, &t0, &t1, &t2); pr("tri2_v0", t0, 4); pr("tri2_v1", t1, 4); pr("tri2_v2", t2, 4);
   dGeomTriMeshGetPoint(tm, 3, (dReal)0.25, (dReal)0.6, v3); pr("tri3_pt", v3, 3);
+  dJointID ju2 = dJointCreateUniversal(w, 0), ju3 = dJointCreateUniversal(w, 0);
+  dJointAttach(ju2, b[0], b[2]); dJointSetUniversalAnchor(ju2, (dReal)0.6, 0, (dReal)1.2);
+  dJointSetUniversalAxis2(ju2, 0, 1, (dReal)0.1); dJointSetUniversalAxis1Offset(ju2, 1, (dReal)0.1, 0, (dReal)0.3, (dReal)-0.2);
+  dReal ua1, ua2; dJointGetUniversalAngles(ju2, &ua1, &ua2); pr1("uoff1_a1", ua1); pr1("uoff1_a2", ua2);
+  dJointAttach(ju3, 0, b[1]); dJointSetUniversalAnchor(ju3, (dReal)0.6, 0, (dReal)1.2);
+  dJointSetUniversalAxis1(ju3, 1, 0, (dReal)0.2); dJointSetUniversalAxis2Offset(ju3, 0, 1, 0, (dReal)0.25, (dReal)0.15);
+  dJointGetUniversalAngles(ju3, &ua1, &ua2); pr1("uoff2_a1", ua1); pr1("uoff2_a2", ua2);
   printf("thr %d\n", dAllocateODEDataForThread(0xffffffffu));
   printf("wsm %d %d %d\n", dWorldUseSharedWorkingMemory(w, 0), dWorldSetStepMemoryReservationPolicy(w, 0), dWorldSetStepMemoryManager(w, 0));
   dWorldCleanupWorkingMemory(w);
