@@ -277,6 +277,9 @@ void dGeomSetOffsetWorldPosition(dGeomID geom, dReal x, dReal y, dReal z);    /*
 void dGeomSetOffsetWorldRotation(dGeomID geom, const dMatrix3 R);             /* collision.h:632 */
 void dGeomSetOffsetWorldQuaternion(dGeomID geom, const dQuaternion Q);        /* collision.h:648 */
 void dInfiniteAABB(dGeomID geom, dReal aabb[6]);               /* collision.h:1481 */
+int dSpaceGetClass(dSpaceID space);                            /* collision_space.h:175 */
+void dSpaceSetManualCleanup(dSpaceID space, int mode);         /* collision_space.h:112 */
+int dSpaceGetManualCleanup(dSpaceID space);
 dTriMeshDataID dGeomTriMeshGetTriMeshDataID(dGeomID g);        /* collision_trimesh.h:180 */
 void dGeomTriMeshGetTriangle(dGeomID g, int index, dVector3 *v0, dVector3 *v1, dVector3 *v2);   /* collision_trimesh.h:198, world coordinates */
 void dGeomTriMeshGetPoint(dGeomID g, int index, dReal u, dReal v, dVector3 out);                 /* collision_trimesh.h:204 */
@@ -422,6 +425,7 @@ dJointID dJointCreateLMotor(dWorldID, dJointGroupID);   /* include/ode/objects.h
 dJointID dJointCreatePR(dWorldID, dJointGroupID);        /* include/ode/objects.h:1586, ode/src/joints/pr.cpp */
 dJointID dJointCreatePU(dWorldID, dJointGroupID);        /* include/ode/objects.h:1594, ode/src/joints/pu.cpp */
 dJointID dJointCreatePiston(dWorldID, dJointGroupID);    /* include/ode/objects.h:1603, ode/src/joints/piston.cpp */
+dJointID dJointCreateNull(dWorldID, dJointGroupID);      /* include/ode/objects.h:1625, ode/src/joints/null.cpp */
 dJointID dJointCreatePlane2D(dWorldID, dJointGroupID);   /* include/ode/objects.h:1637, ode/src/joints/plane2d.cpp */
 void dJointDestroy(dJointID);
 void dJointAttach(dJointID, dBodyID body1, dBodyID body2);
@@ -453,6 +457,7 @@ void dJointGetPistonAnchor(dJointID, dVector3 result);
 void dJointGetPistonAnchor2(dJointID, dVector3 result);
 void dJointSetPistonAxis(dJointID, dReal x, dReal y, dReal z);
 void dJointGetPistonAxis(dJointID, dVector3 result);
+void dJointSetPistonAxisDelta(dJointID j, dReal x, dReal y, dReal z, dReal ax, dReal ay, dReal az);   /* :2204 */
 void dJointSetPistonParam(dJointID, int parameter, dReal value);
 dReal dJointGetPistonParam(dJointID, int parameter);
 dReal dJointGetPistonPosition(dJointID);

@@ -198,6 +198,9 @@ void dGeomTriMeshGetPoint(dGeomID g, int index, dReal u, dReal v, dVector3 out) 
   const dReal w = OB_REAL(1.0) - u - v;
   for (int k = 0; k < 4; k++) out[k] = (dv[0][k] * w) + (dv[1][k] * u) + (dv[2][k] * v);
 }
+int dSpaceGetClass(dSpaceID space) { return space->type; }                       // collision_space.cpp:740
+void dSpaceSetManualCleanup(dSpaceID space, int mode) { space->manual_cleanup = mode != 0; }   // :679; spaces here are flat: the flag is only stored
+int dSpaceGetManualCleanup(dSpaceID space) { return space->manual_cleanup; }
 void dInfiniteAABB(dGeomID, dReal aabb[6]) { aabb[0] = -dInfinity; aabb[1] = dInfinity; aabb[2] = -dInfinity; aabb[3] = dInfinity; aabb[4] = -dInfinity; aabb[5] = dInfinity; }
 
 // ---- rotation / random / mass utilities (rotation.cpp, misc.cpp, mass.cpp) ------------------------------------

@@ -201,7 +201,7 @@ dxBatch *ob_batch_create(int nworlds, const dWorldID *worlds, const dSpaceID *sp
         if (dropin) continue;
         ob_set_last_error("dBatchCreate: world %d: contact joints present at bind time (call dJointGroupEmpty first)", w); delete B; return 0;
       }
-      if (j->type != dJointTypeBall && j->type != dJointTypeHinge && j->type != dJointTypeHinge2 && j->type != dJointTypeSlider && j->type != dJointTypeFixed && j->type != dJointTypeUniversal && j->type != dJointTypeAMotor && j->type != dJointTypeLMotor && j->type != dJointTypePlane2D && j->type != dJointTypePiston && j->type != dJointTypePR && j->type != dJointTypePU) { ob_set_last_error("dBatchCreate: world %d: unsupported joint type %d", w, j->type); delete B; return 0; }
+      if (j->type != dJointTypeBall && j->type != dJointTypeHinge && j->type != dJointTypeHinge2 && j->type != dJointTypeSlider && j->type != dJointTypeFixed && j->type != dJointTypeUniversal && j->type != dJointTypeAMotor && j->type != dJointTypeLMotor && j->type != dJointTypePlane2D && j->type != dJointTypePiston && j->type != dJointTypePR && j->type != dJointTypePU && j->type != dJointTypeNull) { ob_set_last_error("dBatchCreate: world %d: unsupported joint type %d", w, j->type); delete B; return 0; }
       // plane2d constrains body 1 against the static environment (plane2d.cpp:95-118 never fills J2); a second body is refused
       if (j->type == dJointTypePlane2D && j->node[1].body) { ob_set_last_error("dBatchCreate: world %d: a plane2d joint takes one body", w); delete B; return 0; }
       B->joints[w].push_back(j);

@@ -635,6 +635,7 @@ dJointID dJointCreateFixed(dWorldID w, dJointGroupID g) { return create_joint(w,
 dJointID dJointCreateUniversal(dWorldID w, dJointGroupID g) { return create_joint(w, g, dJointTypeUniversal); }
 dJointID dJointCreateAMotor(dWorldID w, dJointGroupID g) { return create_joint(w, g, dJointTypeAMotor); }
 dJointID dJointCreateLMotor(dWorldID w, dJointGroupID g) { return create_joint(w, g, dJointTypeLMotor); }
+dJointID dJointCreateNull(dWorldID w, dJointGroupID g) { return create_joint(w, g, dJointTypeNull); }   // joints/null.cpp: no rows, but it joins its bodies into one island
 dJointID dJointCreatePlane2D(dWorldID w, dJointGroupID g) { return create_joint(w, g, dJointTypePlane2D); }
 dJointID dJointCreatePiston(dWorldID w, dJointGroupID g) { return create_joint(w, g, dJointTypePiston); }
 dJointID dJointCreatePR(dWorldID w, dJointGroupID g) { return create_joint(w, g, dJointTypePR); }
@@ -1077,7 +1078,7 @@ static dxSpace *space_create(dSpaceID parent, int type) {
   dxSpace *s = new dxSpace;
   geom_init(s, 0, 0, type);
   s->is_space = true;
-  s->count = 0; s->first = 0; s->cleanup = 1; s->sublevel = 0; s->lock_count = 0;
+  s->count = 0; s->first = 0; s->cleanup = 1; s->sublevel = 0; s->lock_count = 0; s->manual_cleanup = 0;
   s->minlevel = -3; s->maxlevel = 10; s->axisorder = 0; s->bound_batch = 0;
   if (parent) dSpaceAdd(parent, s);
   return s;

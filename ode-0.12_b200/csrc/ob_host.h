@@ -136,7 +136,7 @@ struct dxGeom {
 struct dxSpace : public dxGeom {
   int count;
   dxGeom *first;
-  int cleanup, sublevel, lock_count;
+  int cleanup, sublevel, lock_count, manual_cleanup;
   int minlevel, maxlevel;   // hash space
   int axisorder;            // SAP
   // SAP space only (collision_sapspace.cpp:140-160): the two arrays whose order defines the sweep's

@@ -626,6 +626,15 @@ void dJointSetPistonAxis(dJointID j, dReal x, dReal y, dReal z) {
   hinge_initial_rel_rot(j);
 }
 void dJointGetPistonAxis(dJointID j, dVector3 result) { get_axis(j, result, j->axis1); }
+void dJointSetPistonAxisDelta(dJointID j, dReal x, dReal y, dReal z, dReal dx, dReal dy, dReal dz) {   // piston.cpp:508-539
+  set_axes(j, x, y, z, j->axis1, j->axis2);
+  hinge_initial_rel_rot(j);
+  dReal c[4] = {0, 0, 0, 0};
+  dxBody *b0 = j->node[0].body, *b1 = j->node[1].body;
+  if (b1) { c[0] = (b0->pos[0] - b1->pos[0] - dx); c[1] = (b0->pos[1] - b1->pos[1] - dy); c[2] = (b0->pos[2] - b1->pos[2] - dz); }
+  else if (b0) { c[0] = b0->pos[0] - dx; c[1] = b0->pos[1] - dy; c[2] = b0->pos[2] - dz; }
+  ob_mul1_331(j->anchor1, b0->R, c);
+}
 void dJointSetPistonParam(dJointID j, int parameter, dReal value) { two_limot_set(j, parameter, value); }
 dReal dJointGetPistonParam(dJointID j, int parameter) { return two_limot_get(j, parameter); }
 dReal dJointGetPistonPosition(dJointID j) { return prismatic_position(j, j->anchor1, j->axis1); }

@@ -34,6 +34,7 @@ GOLDEN = [  # (file stem, scene, steps, worlds, settle) — must match tests/gol
     ("pus_settle60", "pus", 30, 1, 60),           # PU joints
     ("cylmix_settle90", "cylmix", 20, 1, 90),     # flat cylinders vs plane / sphere / box
     ("kinematic_settle60", "kinematic", 30, 1, 60),   # dBodySetKinematic bodies pushing a pile, hinged to a dynamic body
+    ("nulljoint_settle60", "nulljoint", 30, 1, 60),   # null joints merge islands (order of the dRandInt draws)
 ]
 
 

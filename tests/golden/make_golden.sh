@@ -33,6 +33,7 @@ for p in single double; do
   $d --scene pus --steps 30 --settle 60 --out tests/golden/pus_settle60_$p.trace
   $d --scene cylmix --steps 20 --settle 90 --out tests/golden/cylmix_settle90_$p.trace
   $d --scene kinematic --steps 30 --settle 60 --out tests/golden/kinematic_settle60_$p.trace
+  $d --scene nulljoint --steps 30 --settle 60 --out tests/golden/nulljoint_settle60_$p.trace
   # drop-in (callback) path only: ray colliders + capsule-trimesh
   $d --scene raycast --steps 20 --settle 40 --out tests/golden/raycast_settle40_$p.trace
   $d --scene raycast2 --steps 20 --settle 40 --out tests/golden/raycast2_settle40_$p.trace

@@ -499,6 +499,27 @@ static inline void scene_kinematic(SceneWorld &sw, int w) {
   dBodySetDynamic(back);
 }
 
+// null joints (joints/null.cpp): no constraint rows, but a null joint puts its two bodies into ONE island, which changes
+// the island order, hence the order of the dRandInt draws and every later bit: two separate piles tied by a null joint
+static inline void scene_nulljoint(SceneWorld &sw, int w) {
+  scene_world_base(sw, w);
+  xs32 rng(sw.seed ^ 0x0000A11u);
+  scene_add_geom(sw, dCreatePlane(sw.space, 0, 0, 1, 0));
+  dBodyID first[2] = {0, 0};
+  for (int pile = 0; pile < 2; pile++)
+    for (int i = 0; i < 6; i++) {
+      dBodyID b = scene_add_box(sw, 2, rng.uni(0.2, 0.5), rng.uni(0.2, 0.5), rng.uni(0.2, 0.5), (dReal)(-2 + 4 * pile) + rng.uni(-0.2, 0.2), rng.uni(-0.2, 0.2), (dReal)(0.3 + 0.5 * i));
+      if (i == 2) first[pile] = b;
+    }
+  dJointID j = dJointCreateNull(sw.world, 0);
+  dJointAttach(j, first[0], first[1]);
+  sw.joints.push_back(j);
+  dJointID j1 = dJointCreateNull(sw.world, 0);   // and one to the world
+  dJointAttach(j1, sw.bodies[0], 0);
+  sw.joints.push_back(j1);
+  for (int i = 0; i < 3; i++) scene_add_sphere(sw, 2, rng.uni(0.15, 0.3), rng.uni(-0.5, 0.5), (dReal)1.5, rng.uni(0.5, 2));
+}
+
 // universal joints (universal.cpp): free, with stops on both axes (getAngles: dRFrom2Axes + dQfromR + atan2),
 // with a motor on axis 2, attached to the world, and one with the bodies given in reversed order
 static inline void scene_universals(SceneWorld &sw, int w) {
@@ -997,6 +1018,7 @@ static inline int scene_build(const char *name_in, SceneWorld &sw, int w, SceneP
   if (!strcmp(name, "pistons")) { scene_pistons(sw, w); return 0; }
   if (!strcmp(name, "pus")) { scene_pus(sw, w); return 0; }
   if (!strcmp(name, "kinematic")) { scene_kinematic(sw, w); return 0; }
+  if (!strcmp(name, "nulljoint")) { scene_nulljoint(sw, w); return 0; }
   if (!strcmp(name, "cylspheres")) { scene_cylspheres(sw, w); return 0; }
   if (!strcmp(name, "cylmix")) { scene_cylmix(sw, w); return 0; }
   if (!strcmp(name, "universals")) { scene_universals(sw, w); return 0; }
