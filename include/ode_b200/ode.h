@@ -630,6 +630,18 @@ void dGeomCapsuleGetParams(dGeomID ccylinder, dReal *radius, dReal *length);
 dGeomID dCreateCylinder(dSpaceID space, dReal radius, dReal length);
 void dGeomCylinderSetParams(dGeomID cylinder, dReal radius, dReal length);
 void dGeomCylinderGetParams(dGeomID cylinder, dReal *radius, dReal *length);
+
+/* Geom transforms (reference: include/ode/collision.h:1086-1092, ode/src/collision_transform.cpp).  A transform
+ * geom T encapsulates one geom that is in no space and on no body; T collides as that geom posed at T o local.
+ * Encapsulated classes served: sphere, box, capsule, cylinder.  Contacts report the encapsulated geom in g1/g2
+ * unless dGeomTransformSetInfo(T, 1). */
+dGeomID dCreateGeomTransform(dSpaceID space);
+void dGeomTransformSetGeom(dGeomID g, dGeomID obj);
+dGeomID dGeomTransformGetGeom(dGeomID g);
+void dGeomTransformSetCleanup(dGeomID g, int mode);
+int dGeomTransformGetCleanup(dGeomID g);
+void dGeomTransformSetInfo(dGeomID g, int mode);
+int dGeomTransformGetInfo(dGeomID g);
 /* rays: include/ode/collision.h:1025-1067, ode/src/ray.cpp:91-189 */
 dGeomID dCreateRay(dSpaceID space, dReal length);
 void dGeomRaySetLength(dGeomID ray, dReal length);

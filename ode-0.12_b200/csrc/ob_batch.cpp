@@ -68,16 +68,32 @@ void ob_marshal_joint(const dxJoint *j, ObJoint &d) {
 
 void ob_marshal_geom(dxGeom *g, ObGeom &d) {
   memset(&d, 0, sizeof d);
-  d.type = g->type;
+  // a geom transform is uploaded as its encapsulated geom: class, parameters and zero-size flag of the inner geom,
+  // everything else (body, bits, enable flag) of the transform; the inner geom's own pose is the "offset"
+  // (computeFinalTx, collision_transform.cpp:101-108, is the same arithmetic as computePosr)
+  dxGeom *sh = ob_geom_shape(g);
+  const bool xf = g->type == dGeomTransformClass;
+  if (xf) {
+    if (!sh) { ob_error(0, "geom transform without an encapsulated geom is not served on this path"); sh = g; }
+    else if (sh->type != dSphereClass && sh->type != dBoxClass && sh->type != dCapsuleClass && sh->type != dCylinderClass)
+      ob_error(0, "geom transform: encapsulated geom class %d is not served on this path (sphere, box, capsule, cylinder are)", sh->type);
+    else if (g->offset_posr) ob_error(0, "geom transform with its own offset is not served on this path");
+    if (sh->parent_space || sh->body) ob_debug(2, "GeomTransform encapsulated object must not be in a space or attached to a body");
+  }
+  d.type = sh->type;
   d.body = g->body ? g->body->batch_index : -1;
   d.cat = (uint32_t)g->category_bits; d.col = (uint32_t)g->collide_bits;
-  d.flags = ((g->gflags & GEOM_ENABLED) ? OB_GEOM_ENABLED : 0) | (g->offset_posr ? OB_GEOM_HAS_OFFSET : 0) |
-            ((g->gflags & GEOM_ZERO_SIZED) ? OB_GEOM_ZERO_SIZED : 0);
+  d.flags = ((g->gflags & GEOM_ENABLED) ? OB_GEOM_ENABLED : 0) | ((g->offset_posr || (xf && g->body)) ? OB_GEOM_HAS_OFFSET : 0) |
+            ((sh->gflags & GEOM_ZERO_SIZED) ? OB_GEOM_ZERO_SIZED : 0);
   d.body_next = -1;
   if (g->type == dRayClass) d.mesh = ob_ray_flags(g);   // rays carry their mode bits where trimeshes carry the data index
-  for (int k = 0; k < 4; k++) d.p[k] = g->p[k];
+  if (xf) d.mesh = OB_POSE_XFORM;
+  for (int k = 0; k < 4; k++) d.p[k] = sh->p[k];
   const dxPosR *src = 0;
-  if (g->offset_posr) src = g->offset_posr;
+  dxPosR composed;
+  if (xf && g->body) src = sh->final_posr;
+  else if (xf) { ob_geom_final_pose(g, &composed); src = &composed; }
+  else if (g->offset_posr) src = g->offset_posr;
   else if (!g->body && (g->gflags & GEOM_PLACEABLE)) src = g->final_posr;
   if (src) { for (int k = 0; k < 3; k++) d.pos[k] = src->pos[k]; for (int k = 0; k < 12; k++) d.R[k] = src->R[k]; }
   else { d.R[0] = d.R[5] = d.R[10] = 1; }

@@ -179,17 +179,18 @@ void ob_dropin_space_collide(dxSpace *space, void *data, dNearCallback *cb) {
 }
 
 static void geom_pose_host(dxGeom *g, ObPose *o) {
-  o->type = g->type;
-  o->mesh = g->type == dRayClass ? ob_ray_flags(g) : 0;
-  for (int i = 0; i < 4; i++) o->p[i] = g->p[i];
-  for (int i = 0; i < 3; i++) o->pos[i] = 0;
-  for (int i = 0; i < 12; i++) o->R[i] = 0;
-  if (g->gflags & GEOM_PLACEABLE) {
-    ob_geom_recompute_posr(g);
-    for (int i = 0; i < 3; i++) o->pos[i] = g->final_posr->pos[i];
-    for (int i = 0; i < 12; i++) o->R[i] = g->final_posr->R[i];
-  }
+  dxGeom *sh = ob_geom_shape(g);   // geom transform: the encapsulated geom at T o local (collision_transform.cpp:101-108)
+  o->type = sh->type;
+  o->mesh = g->type == dRayClass ? ob_ray_flags(g) : (g->type == dGeomTransformClass ? OB_POSE_XFORM : 0);
+  for (int i = 0; i < 4; i++) o->p[i] = sh->p[i];
+  dxPosR f;
+  ob_geom_final_pose(g, &f);
+  for (int i = 0; i < 3; i++) o->pos[i] = f.pos[i];
+  for (int i = 0; i < 12; i++) o->R[i] = f.R[i];
 }
+// g1 / g2 of a generated contact: the encapsulated geom of a transform unless its info mode is on (collision_transform.cpp:143-151)
+static inline dxGeom *contact_geom(dxGeom *g) { return (g->type == dGeomTransformClass && !g->xf_info) ? g->xf_obj : g; }
+static inline int shape_type(dxGeom *g) { dxGeom *sh = ob_geom_shape(g); return sh ? sh->type : -1; }
 
 #define OB_CONTACT_AT(p, skip, i) ((dContactGeom *)(((char *)(p)) + (size_t)(i) * (skip)))
 
@@ -200,7 +201,7 @@ int ob_dropin_collide(dxGeom *o1, dxGeom *o2, int flags, dContactGeom *contact, 
   for (size_t i = 0; i < g_ctx.size(); i++) {
     ObDropin *c = g_ctx[i];
     if (!c->in_collide || o1->parent_space != c->space || o2->parent_space != c->space) continue;
-    const int cap = ob_pair_max_contacts(o1->type, o2->type, 1 << 15);
+    const int cap = ob_pair_max_contacts(shape_type(o1), shape_type(o2), 1 << 15);
     const int eff_want = std::min(want, std::min(cap, OB_MAXC_LOCAL)), eff_have = std::min(c->maxc_hint, std::min(cap, OB_MAXC_LOCAL));
     if (want != c->maxc_hint) c->maxc_hint = std::min(want, OB_MAXC_LOCAL);   // next frame's batch narrowphase uses the caller's value
     std::map<std::pair<int, int>, std::pair<int, int> >::iterator it = c->pair_contacts.find(std::make_pair(o1->batch_index, o2->batch_index));
@@ -210,12 +211,13 @@ int ob_dropin_collide(dxGeom *o1, dxGeom *o2, int flags, dContactGeom *contact, 
       const ObContact &s = c->contacts[k0 + k];
       dContactGeom *d = OB_CONTACT_AT(contact, skip, k);
       for (int e = 0; e < 3; e++) { d->pos[e] = s.pos[e]; d->normal[e] = s.normal[e]; }
-      d->depth = s.depth; d->g1 = o1; d->g2 = o2; d->side1 = s.side1; d->side2 = s.side2;
+      d->depth = s.depth; d->g1 = contact_geom(o1); d->g2 = contact_geom(o2); d->side1 = s.side1; d->side2 = s.side2;
     }
     return n;
   }
   // (2) on demand: one pair on the GPU
-  if (ob_pair_max_contacts(o1->type, o2->type, 1 << 15) == 0) return 0;   // no collider for this class pair (collision_kernel.cpp:329)
+  if ((o1->type == dGeomTransformClass && !o1->xf_obj) || (o2->type == dGeomTransformClass && !o2->xf_obj)) return 0;   // collision_transform.cpp:122
+  if (ob_pair_max_contacts(shape_type(o1), shape_type(o2), 1 << 15) == 0) return 0;   // no collider for this class pair (collision_kernel.cpp:329)
   ObPose a, b;
   geom_pose_host(o1, &a);
   geom_pose_host(o2, &b);
@@ -236,7 +238,7 @@ int ob_dropin_collide(dxGeom *o1, dxGeom *o2, int flags, dContactGeom *contact, 
   for (int k = 0; k < n; k++) {
     dContactGeom *d = OB_CONTACT_AT(contact, skip, k);
     for (int e = 0; e < 3; e++) { d->pos[e] = cg[k].pos[e]; d->normal[e] = cg[k].normal[e]; }
-    d->depth = cg[k].depth; d->g1 = o1; d->g2 = o2; d->side1 = cg[k].side1; d->side2 = cg[k].side2;
+    d->depth = cg[k].depth; d->g1 = contact_geom(o1); d->g2 = contact_geom(o2); d->side1 = cg[k].side1; d->side2 = cg[k].side2;
   }
   return n;
 }

@@ -166,6 +166,14 @@ void geom_fields(Dif &d, dxGeom *g) {
     case dPlaneClass: d.str("type", "plane"); d.vec("normal", g->p); d.r("d", g->p[3]); break;
     case dRayClass: d.str("type", "ray"); d.r("length", g->p[0]); break;
     case dTriMeshClass: d.str("type", "trimesh"); break;
+    case dGeomTransformClass: {   // printGeomTransform, export-dif.cpp:429-443 (closing brace without a comma, as there)
+      dxGeom *g2 = g->xf_obj;
+      dQuaternion q;
+      dGeomGetQuaternion(g2, q);
+      d.str("type", "transform"); d.vec("pos", dGeomGetPosition(g2)); d.vec("q", q, 4);
+      d.open("geometry = {"); geom_fields(d, g2); d.depth--; d.line("}");
+      break;
+    }
     default: break;
   }
 }

@@ -752,6 +752,22 @@ void ob_geom_recompute_posr(dxGeom *g) {   // recomputePosr/computePosr, collisi
     g->gflags &= ~GEOM_POSR_BAD;
   }
 }
+dxGeom *ob_geom_shape(dxGeom *g) { return g->type == dGeomTransformClass ? g->xf_obj : g; }
+void ob_geom_final_pose(dxGeom *g, dxPosR *out) {
+  memset(out, 0, sizeof *out);
+  if (!(g->gflags & GEOM_PLACEABLE)) return;
+  ob_geom_recompute_posr(g);
+  if (g->type == dGeomTransformClass && g->xf_obj) {   // computeFinalTx, collision_transform.cpp:101-108
+    const dxPosR *in = g->xf_obj->final_posr;
+    ob_mul0_331(out->pos, g->final_posr->R, in->pos);
+    out->pos[0] += g->final_posr->pos[0]; out->pos[1] += g->final_posr->pos[1]; out->pos[2] += g->final_posr->pos[2];
+    ob_mul0_333(out->R, g->final_posr->R, in->R);
+    out->R[3] = out->R[7] = out->R[11] = 0;
+    return;
+  }
+  for (int i = 0; i < 3; i++) out->pos[i] = g->final_posr->pos[i];
+  for (int i = 0; i < 12; i++) out->R[i] = g->final_posr->R[i];
+}
 void ob_space_clean(dxSpace *s) {
   // cleanGeoms (collision_space.cpp:405-417, collision_sapspace.cpp:394-423): AABBs are recomputed on
   // the device inside dSpaceCollide; here only the dirty bookkeeping is done, which is what ordering depends on.
@@ -787,6 +803,7 @@ static void geom_init(dxGeom *g, dSpaceID space, int is_placeable, int type) {
   g->p[0] = g->p[1] = g->p[2] = g->p[3] = 0;
   g->batch_index = -1;
   g->tmdata = 0;
+  g->xf_obj = 0; g->xf_cleanup = 0; g->xf_info = 0;
   g->sap_didx = g->sap_gidx = -1;
   g->is_space = false;
   if (space) dSpaceAdd(space, g);
@@ -823,6 +840,7 @@ void dGeomDestroy(dGeomID g) {
   }
   if (g->parent_space) dSpaceRemove(g->parent_space, g);
   geom_body_remove(g);
+  if (g->type == dGeomTransformClass && g->xf_obj && g->xf_cleanup) dGeomDestroy(g->xf_obj);   // ~dxGeomTransform, collision_transform.cpp:75-78
   delete g;
 }
 void dGeomSetData(dGeomID g, void *data) { g->data = data; }
@@ -978,16 +996,17 @@ int dGeomIsOffset(dGeomID g) { return g->offset_posr != 0; }
 
 // host-side AABB (only used by dGeomGetAABB; the hot path computes AABBs on the device)
 static void geom_host_pose(dxGeom *g, ObPose *o) {
-  o->type = g->type;
-  for (int i = 0; i < 4; i++) o->p[i] = g->p[i];
-  if (g->gflags & GEOM_PLACEABLE) {
-    ob_geom_recompute_posr(g);
-    for (int i = 0; i < 3; i++) o->pos[i] = g->final_posr->pos[i];
-    for (int i = 0; i < 12; i++) o->R[i] = g->final_posr->R[i];
-  } else { for (int i = 0; i < 3; i++) o->pos[i] = 0; for (int i = 0; i < 12; i++) o->R[i] = 0; }
+  dxGeom *sh = ob_geom_shape(g);
+  o->type = sh->type;
+  for (int i = 0; i < 4; i++) o->p[i] = sh->p[i];
+  dxPosR f;
+  ob_geom_final_pose(g, &f);
+  for (int i = 0; i < 3; i++) o->pos[i] = f.pos[i];
+  for (int i = 0; i < 12; i++) o->R[i] = f.R[i];
 }
 void dGeomGetAABB(dGeomID g, dReal aabb[6]) {
   if (g->is_space) { for (int i = 0; i < 6; i++) aabb[i] = (i & 1) ? OB_INF : -OB_INF; return; }
+  if (!ob_geom_shape(g)) { for (int i = 0; i < 6; i++) aabb[i] = 0; return; }   // empty transform, collision_transform.cpp:83-86
   ObPose o;
   geom_host_pose(g, &o);
   o.mesh = 0;
@@ -1042,6 +1061,20 @@ void dGeomCylinderSetParams(dGeomID g, dReal radius, dReal length) {
   g->p[0] = radius; g->p[1] = length; zero_sized(g, !radius || !length); ob_geom_moved(g);
 }
 void dGeomCylinderGetParams(dGeomID g, dReal *radius, dReal *length) { *radius = g->p[0]; *length = g->p[1]; }
+// geom transforms (ode/src/collision_transform.cpp:59-250).  The encapsulated geom must be one of the primitive
+// classes this path serves inside a transform; anything else is refused when the transform is marshalled.
+dGeomID dCreateGeomTransform(dSpaceID space) { dxGeom *g = new dxGeom; geom_init(g, space, 1, dGeomTransformClass); return g; }
+#define OB_XF_CHECK(g) OB_UASSERT((g) && (g)->type == dGeomTransformClass, "argument not a geom transform")
+void dGeomTransformSetGeom(dGeomID g, dGeomID obj) {
+  OB_XF_CHECK(g);
+  if (g->xf_obj && g->xf_cleanup) dGeomDestroy(g->xf_obj);
+  g->xf_obj = obj;
+}
+dGeomID dGeomTransformGetGeom(dGeomID g) { OB_XF_CHECK(g); return g->xf_obj; }
+void dGeomTransformSetCleanup(dGeomID g, int mode) { OB_XF_CHECK(g); g->xf_cleanup = mode; }
+int dGeomTransformGetCleanup(dGeomID g) { OB_XF_CHECK(g); return g->xf_cleanup; }
+void dGeomTransformSetInfo(dGeomID g, int mode) { OB_XF_CHECK(g); g->xf_info = mode; }
+int dGeomTransformGetInfo(dGeomID g) { OB_XF_CHECK(g); return g->xf_info; }
 // rays (ode/src/ray.cpp:49-189): p[0] = length, direction = column 2 of the rotation; the three mode flags
 // live in gflags like the reference's RAY_* bits (collision_kernel.h:79-81)
 dGeomID dCreateRay(dSpaceID space, dReal length) {

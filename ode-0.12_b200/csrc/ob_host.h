@@ -127,6 +127,7 @@ struct dxGeom {
   unsigned long category_bits, collide_bits;
   dReal p[4];             // sphere r | box sides | plane a,b,c,d | capsule r,l
   struct dxTriMeshData *tmdata;   // trimesh geoms: the shared mesh data
+  dxGeom *xf_obj; int xf_cleanup, xf_info;   // geom transform (collision_transform.cpp:44-47): encapsulated geom, cleanup mode, info mode
   int batch_index;
   int sap_didx, sap_gidx;   // position in the parent SAP space's DirtyList / GeomList (-1: not in that list)
   bool is_space;
@@ -155,6 +156,10 @@ void ob_set_last_error(const char *fmt, ...);
 void ob_geom_moved(dxGeom *g);                      // dGeomMoved
 dxGeom *ob_geom_create(dxSpace *space, int is_placeable, int type);
 void ob_geom_recompute_posr(dxGeom *g);
+// geom transforms: the geom whose shape stands for g on the device (g itself unless g is a transform), and the pose
+// it collides at (computeFinalTx, collision_transform.cpp:101-108).  ob_geom_shape returns 0 for an empty transform.
+dxGeom *ob_geom_shape(dxGeom *g);
+void ob_geom_final_pose(dxGeom *g, dxPosR *out);
 void ob_space_clean(dxSpace *s);                    // cleanGeoms
 void ob_body_posr(dxBody *b, dxPosR *out);
 extern uint32_t ob_global_seed;

@@ -22,6 +22,9 @@ enum {  // body flags, ode/src/objects.h:38-48
 };
 enum { OB_GEOM_SPHERE = 0, OB_GEOM_BOX = 1, OB_GEOM_CAPSULE = 2, OB_GEOM_CYLINDER = 3, OB_GEOM_PLANE = 4, OB_GEOM_RAY = 5, OB_GEOM_TRIMESH = 8 };
 enum { OB_GEOM_ENABLED = 1, OB_GEOM_HAS_OFFSET = 2, OB_GEOM_ZERO_SIZED = 4 };
+// ObGeom::mesh / ObPose::mesh of a primitive (non-trimesh, non-ray) geom: set when the record stands for a geom
+// transform (dCreateGeomTransform) served as its encapsulated geom; only the collider dispatch order depends on it
+#define OB_POSE_XFORM 0x40000000
 enum { OB_SPACE_HASH = 0, OB_SPACE_SAP = 1, OB_SPACE_SIMPLE = 2 };
 enum { OB_ERR_CONTACT_OVERFLOW = 1, OB_ERR_ROW_OVERFLOW = 2, OB_ERR_PAIR_OVERFLOW = 4, OB_ERR_BVH_STACK = 8 };
 

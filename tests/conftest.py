@@ -35,6 +35,7 @@ GOLDEN = [  # (file stem, scene, steps, worlds, settle) — must match tests/gol
     ("cylmix_settle90", "cylmix", 20, 1, 90),     # flat cylinders vs plane / sphere / box
     ("kinematic_settle60", "kinematic", 30, 1, 60),   # dBodySetKinematic bodies pushing a pile, hinged to a dynamic body
     ("nulljoint_settle60", "nulljoint", 30, 1, 60),   # null joints merge islands (order of the dRandInt draws)
+    ("transforms_settle80", "transforms", 25, 1, 80),   # geom transforms: composite bodies (T x X, X x T, T x T collider order), static transform
 ]
 
 

@@ -34,6 +34,7 @@ for p in single double; do
   $d --scene cylmix --steps 20 --settle 90 --out tests/golden/cylmix_settle90_$p.trace
   $d --scene kinematic --steps 30 --settle 60 --out tests/golden/kinematic_settle60_$p.trace
   $d --scene nulljoint --steps 30 --settle 60 --out tests/golden/nulljoint_settle60_$p.trace
+  $d --scene transforms --steps 25 --settle 80 --out tests/golden/transforms_settle80_$p.trace
   # drop-in (callback) path only: ray colliders + capsule-trimesh
   $d --scene raycast --steps 20 --settle 40 --out tests/golden/raycast_settle40_$p.trace
   $d --scene raycast2 --steps 20 --settle 40 --out tests/golden/raycast2_settle40_$p.trace
@@ -46,6 +47,7 @@ oracle/_ref/driver_ref_single --scene pistons --steps 25 --settle 20 --export-di
 oracle/_ref/driver_ref_double --scene motors --steps 25 --settle 20 --export-dif tests/golden/motors_double.dif > /dev/null
 oracle/_ref/driver_ref_single --scene cylmix --steps 25 --settle 20 --export-dif tests/golden/cylmix_single.dif > /dev/null
 oracle/_ref/driver_ref_double --scene cylmix --steps 25 --settle 20 --export-dif tests/golden/cylmix_double.dif > /dev/null
+oracle/_ref/driver_ref_single --scene transforms --steps 25 --settle 20 --export-dif tests/golden/transforms_single.dif > /dev/null
 # accessor probe (tests/test_api_probe.py): output of the probe linked against the reference
 oracle/_ref/api_probe_ref_single > tests/golden/api_probe_single.txt
 oracle/_ref/api_probe_ref_double > tests/golden/api_probe_double.txt

@@ -172,6 +172,17 @@ int main() {
   dJointAttach(ju3, 0, b[1]); dJointSetUniversalAnchor(ju3, (dReal)0.6, 0, (dReal)1.2);
   dJointSetUniversalAxis1(ju3, 1, 0, (dReal)0.2); dJointSetUniversalAxis2Offset(ju3, 0, 1, 0, (dReal)0.25, (dReal)0.15);
   dJointGetUniversalAngles(ju3, &ua1, &ua2); pr1("uoff2_a1", ua1); pr1("uoff2_a2", ua2);
+  // geom transform: accessors, class, AABB of the encapsulated geom at T o local (with and without a body)
+  dGeomID xin = dCreateCapsule(0, (dReal)0.15, (dReal)0.7), xt = dCreateGeomTransform(s);
+  printf("xf0 %d %d %d %d\n", dGeomGetClass(xt) == dGeomTransformClass, dGeomTransformGetGeom(xt) == 0, dGeomTransformGetCleanup(xt), dGeomTransformGetInfo(xt));
+  dReal xab[6]; dGeomGetAABB(xt, xab); pr("xf_aabb_empty", xab, 6);
+  dGeomTransformSetGeom(xt, xin); dGeomTransformSetCleanup(xt, 1); dGeomTransformSetInfo(xt, 1);
+  printf("xf1 %d %d %d\n", dGeomTransformGetGeom(xt) == xin, dGeomTransformGetCleanup(xt), dGeomTransformGetInfo(xt));
+  dGeomSetPosition(xin, (dReal)0.2, (dReal)-0.1, (dReal)0.35); dGeomSetRotation(xin, Rw);
+  dGeomSetPosition(xt, (dReal)-1.3, (dReal)0.8, (dReal)2.1); dGeomSetQuaternion(xt, qw);
+  dGeomGetAABB(xt, xab); pr("xf_aabb_static", xab, 6);
+  dGeomSetBody(xt, b[1]); dGeomGetAABB(xt, xab); pr("xf_aabb_body", xab, 6); pr("xf_pos", dGeomGetPosition(xt), 3);
+  dGeomDestroy(xt);
   printf("thr %d\n", dAllocateODEDataForThread(0xffffffffu));
   printf("wsm %d %d %d\n", dWorldUseSharedWorkingMemory(w, 0), dWorldSetStepMemoryReservationPolicy(w, 0), dWorldSetStepMemoryManager(w, 0));
   dWorldCleanupWorkingMemory(w);

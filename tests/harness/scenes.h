@@ -671,6 +671,85 @@ static inline void scene_cylmix_impl(SceneWorld &sw, int w, bool boxes) {
     dBodySetRotation(lying, R);
   }
 }
+// geom transforms (collision_transform.cpp): composite bodies in the manner of demo_boxstack's 'x' objects - three
+// transform geoms per body encapsulating a sphere, a box and a capsule or cylinder at their own local poses, mass
+// assembled with dMassRotate / dMassTranslate / dMassAdd and recentred - tumbling onto a plane among plain boxes and
+// spheres, plus a static transform (no body) around a tilted box.  Covers T x X, X x T and T x T collider order.
+// The encapsulated geoms carry their transform's data id, so traces name the same geom in every mode.
+static inline dGeomID scene_add_xf(SceneWorld &sw, dGeomID inner, int info) {
+  dGeomID t = scene_add_geom(sw, dCreateGeomTransform(sw.space));
+  dGeomTransformSetCleanup(t, 1);
+  dGeomTransformSetInfo(t, info);
+  dGeomTransformSetGeom(t, inner);
+  dGeomSetData(inner, dGeomGetData(t));
+  return t;
+}
+static inline void scene_transforms(SceneWorld &sw, int w) {
+  scene_world_base(sw, w);
+  xs32 rng(sw.seed ^ 0x7F0A3u);
+  scene_add_geom(sw, dCreatePlane(sw.space, 0, 0, 1, 0));
+  for (int i = 0; i < 7; i++) {
+    dBodyID b = dBodyCreate(sw.world);
+    dBodySetPosition(b, rng.uni(-1.2, 1.2), rng.uni(-1.2, 1.2), (dReal)(0.8 + 0.75 * i));
+    dQuaternion q = {rng.uni(-1, 1), rng.uni(-1, 1), rng.uni(-1, 1), rng.uni(-1, 1)};
+    dBodySetQuaternion(b, q);
+    dMass m, m2;
+    dMassSetZero(&m);
+    dGeomID inner[3], t[3];
+    dReal dpos[3][3];
+    for (int k = 0; k < 3; k++) for (int e = 0; e < 3; e++) dpos[k][e] = rng.uni(-0.3, 0.3);
+    for (int k = 0; k < 3; k++) {
+      if (k == 0) {
+        dReal r = rng.uni(0.08, 0.3);
+        inner[k] = dCreateSphere(0, r);
+        dMassSetSphere(&m2, 2, r);
+      } else if (k == 1) {
+        dReal lx = rng.uni(0.15, 0.6), ly = rng.uni(0.15, 0.6), lz = rng.uni(0.15, 0.6);
+        inner[k] = dCreateBox(0, lx, ly, lz);
+        dMassSetBox(&m2, 2, lx, ly, lz);
+      } else if (i & 1) {
+        dReal r = rng.uni(0.06, 0.15), l = rng.uni(0.2, 0.9);
+        inner[k] = dCreateCapsule(0, r, l);
+        dMassSetCapsule(&m2, 2, 3, r, l);
+      } else {
+        dReal r = rng.uni(0.1, 0.25), l = rng.uni(0.15, 0.6);
+        inner[k] = dCreateCylinder(0, r, l);
+        dMassSetCylinder(&m2, 2, 3, r, l);
+      }
+      t[k] = scene_add_xf(sw, inner[k], (i + k) % 3 == 0);
+      dGeomSetPosition(inner[k], dpos[k][0], dpos[k][1], dpos[k][2]);
+      dMatrix3 Rtx;
+      dRFromAxisAndAngle(Rtx, rng.uni(-1, 1), rng.uni(-1, 1), rng.uni(-1, 1), rng.uni(-5, 5));
+      dGeomSetRotation(inner[k], Rtx);
+      dMassRotate(&m2, Rtx);
+      dMassTranslate(&m2, dpos[k][0], dpos[k][1], dpos[k][2]);
+      dMassAdd(&m, &m2);
+    }
+    // move all encapsulated objects so that the centre of mass is (0,0,0), as the demo does
+    for (int k = 0; k < 3; k++) dGeomSetPosition(inner[k], dpos[k][0] - m.c[0], dpos[k][1] - m.c[1], dpos[k][2] - m.c[2]);
+    dMassTranslate(&m, -m.c[0], -m.c[1], -m.c[2]);
+    for (int k = 0; k < 3; k++) dGeomSetBody(t[k], b);
+    dBodySetMass(b, &m);
+    sw.bodies.push_back(b);
+  }
+  for (int i = 0; i < 4; i++) {
+    dBodyID b = scene_add_box(sw, 2, rng.uni(0.2, 0.6), rng.uni(0.2, 0.6), rng.uni(0.2, 0.6), rng.uni(-1.0, 1.0), rng.uni(-1.0, 1.0), rng.uni(0.4, 4.0));
+    dQuaternion q = {rng.uni(-1, 1), rng.uni(-1, 1), rng.uni(-1, 1), rng.uni(-1, 1)};
+    dBodySetQuaternion(b, q);
+  }
+  for (int i = 0; i < 4; i++) scene_add_sphere(sw, 2, rng.uni(0.12, 0.3), rng.uni(-1.0, 1.0), rng.uni(-1.0, 1.0), rng.uni(0.4, 4.0));
+  // static ramp: a transform without a body, itself placed and rotated, around a box with its own local pose
+  dGeomID rb = dCreateBox(0, (dReal)1.6, (dReal)1.2, (dReal)0.2);
+  dGeomID rt = scene_add_xf(sw, rb, 1);
+  dMatrix3 R1, R2;
+  dRFromAxisAndAngle(R1, 0, 1, 0, (dReal)0.35);
+  dGeomSetRotation(rb, R1);
+  dGeomSetPosition(rb, (dReal)0.1, (dReal)-0.05, (dReal)0.2);
+  dRFromAxisAndAngle(R2, 0, 0, 1, (dReal)0.6);
+  dGeomSetRotation(rt, R2);
+  dGeomSetPosition(rt, (dReal)0.3, (dReal)0.2, (dReal)0.15);
+}
+
 static inline void scene_cylspheres(SceneWorld &sw, int w) { scene_cylmix_impl(sw, w, false); }
 static inline void scene_cylmix(SceneWorld &sw, int w) { scene_cylmix_impl(sw, w, true); }
 
@@ -1019,6 +1098,7 @@ static inline int scene_build(const char *name_in, SceneWorld &sw, int w, SceneP
   if (!strcmp(name, "pus")) { scene_pus(sw, w); return 0; }
   if (!strcmp(name, "kinematic")) { scene_kinematic(sw, w); return 0; }
   if (!strcmp(name, "nulljoint")) { scene_nulljoint(sw, w); return 0; }
+  if (!strcmp(name, "transforms")) { scene_transforms(sw, w); return 0; }
   if (!strcmp(name, "cylspheres")) { scene_cylspheres(sw, w); return 0; }
   if (!strcmp(name, "cylmix")) { scene_cylmix(sw, w); return 0; }
   if (!strcmp(name, "universals")) { scene_universals(sw, w); return 0; }

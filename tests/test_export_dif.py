@@ -16,8 +16,8 @@ import pytest
 from conftest import ATAN2_SCENES, ROOT, have_ref
 from run_parity import driver_path
 
-SCENES = ["stack32", "mixed", "hinges", "buggy", "ragdoll", "capsmix", "sliders", "universals", "motors", "pistons", "pus", "cylmix", "raycyl"]
-GOLDEN = [("pistons", "single"), ("motors", "double"), ("cylmix", "single"), ("cylmix", "double")]   # tests/golden/*.dif, written by the reference (make_golden.sh)
+SCENES = ["stack32", "mixed", "hinges", "buggy", "ragdoll", "capsmix", "sliders", "universals", "motors", "pistons", "pus", "cylmix", "raycyl", "transforms"]
+GOLDEN = [("pistons", "single"), ("motors", "double"), ("cylmix", "single"), ("cylmix", "double"), ("transforms", "single")]   # tests/golden/*.dif, written by the reference (make_golden.sh)
 
 
 def _export(kind, prec, scene, path, steps=25, settle=20):
