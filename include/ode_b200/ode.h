@@ -408,6 +408,18 @@ dGeomID dBodyGetFirstGeom(dBodyID);
 dGeomID dBodyGetNextGeom(dGeomID);
 void dBodyGetRelPointPos(dBodyID, dReal px, dReal py, dReal pz, dVector3 result);
 void dBodyVectorToWorld(dBodyID, dReal px, dReal py, dReal pz, dVector3 result);
+void dBodyVectorFromWorld(dBodyID, dReal px, dReal py, dReal pz, dVector3 result);   /* include/ode/objects.h:1154 */
+void dBodyGetPointVel(dBodyID, dReal px, dReal py, dReal pz, dVector3 result);       /* include/ode/objects.h:1121 */
+void dBodyGetPosRelPoint(dBodyID, dReal px, dReal py, dReal pz, dVector3 result);    /* include/ode/objects.h:1132 */
+void dWorldImpulseToForce(dWorldID, dReal stepsize, dReal ix, dReal iy, dReal iz, dVector3 force);   /* ode.cpp:1828-1838 */
+/* geom-frame conversions, collision_kernel.cpp:784-866 (non-placeable geoms return the argument) */
+void dGeomGetRelPointPos(dGeomID geom, dReal px, dReal py, dReal pz, dVector3 result);
+void dGeomGetPosRelPoint(dGeomID geom, dReal px, dReal py, dReal pz, dVector3 result);
+void dGeomVectorToWorld(dGeomID geom, dReal px, dReal py, dReal pz, dVector3 result);
+void dGeomVectorFromWorld(dGeomID geom, dReal px, dReal py, dReal pz, dVector3 result);
+/* collision_util.cpp:109-219; misc.cpp:128-136 */
+void dClosestLineSegmentPoints(const dVector3 a1, const dVector3 a2, const dVector3 b1, const dVector3 b2, dVector3 cp1, dVector3 cp2);
+void dPrintMatrix(const dReal *A, int n, int m, char *fmt, FILE *f);
 
 /* ---- joints (objects.h:1538-2700) ----------------------------------------- */
 dJointGroupID dJointGroupCreate(int max_size);

@@ -2,9 +2,11 @@
 // library serves (include/ode/objects.h, collision.h, rotation.h, misc.h, mass.h): accessors, force helpers, joint
 // conveniences, rotation utilities.  Host bookkeeping only; each function follows the reference's arithmetic so that
 // what it stores or returns is bit-identical (tests/test_api_probe.py runs the same probe program against both).
+#include <stdio.h>
 #include <string.h>
 #include "ob_host.h"
 #include "ob_rows.h"
+#include "ob_collide.h"
 #include "ob_trimesh_host.h"
 
 void ob_marshal_joint(const dxJoint *j, ObJoint &d);
@@ -288,6 +290,66 @@ void dJointAddHinge2Torques(dJointID j, dReal torque1, dReal torque2) {   // hin
     a1[2] = a1[2] * torque1 + a2[2] * torque2;
     dBodyAddTorque(j->node[0].body, a1[0], a1[1], a1[2]);
     dBodyAddTorque(j->node[1].body, -a1[0], -a1[1], -a1[2]);
+  }
+}
+// body / geom frame conversions (ode.cpp:714-765, collision_kernel.cpp:784-866)
+void dBodyGetPointVel(dBodyID b, dReal px, dReal py, dReal pz, dVector3 result) {
+  OB_AASSERT(b);
+  dReal p[4] = {px - b->pos[0], py - b->pos[1], pz - b->pos[2], 0}, c[4];
+  result[0] = b->lvel[0]; result[1] = b->lvel[1]; result[2] = b->lvel[2];
+  ob_cross(c, b->avel, p);
+  result[0] += c[0]; result[1] += c[1]; result[2] += c[2];
+}
+void dBodyGetPosRelPoint(dBodyID b, dReal px, dReal py, dReal pz, dVector3 result) {
+  OB_AASSERT(b);
+  dReal prel[4] = {px - b->pos[0], py - b->pos[1], pz - b->pos[2], 0};
+  ob_mul1_331(result, b->R, prel);
+}
+void dBodyVectorFromWorld(dBodyID b, dReal px, dReal py, dReal pz, dVector3 result) {
+  OB_AASSERT(b);
+  dReal p[4] = {px, py, pz, 0};
+  ob_mul1_331(result, b->R, p);
+}
+void dWorldImpulseToForce(dWorldID w, dReal stepsize, dReal ix, dReal iy, dReal iz, dVector3 force) {
+  OB_AASSERT(w);
+  stepsize = OB_REAL(1.0) / stepsize;
+  force[0] = stepsize * ix; force[1] = stepsize * iy; force[2] = stepsize * iz;
+}
+static bool geom_frame(dGeomID g, dReal px, dReal py, dReal pz, dVector3 result) {   // non-placeable: identity
+  OB_AASSERT(g);
+  if (!(g->gflags & GEOM_PLACEABLE)) { result[0] = px; result[1] = py; result[2] = pz; return false; }
+  ob_geom_recompute_posr(g);
+  return true;
+}
+void dGeomGetRelPointPos(dGeomID g, dReal px, dReal py, dReal pz, dVector3 result) {
+  if (!geom_frame(g, px, py, pz, result)) return;
+  dReal prel[4] = {px, py, pz, 0}, p[4];
+  ob_mul0_331(p, g->final_posr->R, prel);
+  result[0] = p[0] + g->final_posr->pos[0]; result[1] = p[1] + g->final_posr->pos[1]; result[2] = p[2] + g->final_posr->pos[2];
+}
+void dGeomGetPosRelPoint(dGeomID g, dReal px, dReal py, dReal pz, dVector3 result) {
+  if (!geom_frame(g, px, py, pz, result)) return;
+  dReal prel[4] = {px - g->final_posr->pos[0], py - g->final_posr->pos[1], pz - g->final_posr->pos[2], 0};
+  ob_mul1_331(result, g->final_posr->R, prel);
+}
+void dGeomVectorToWorld(dGeomID g, dReal px, dReal py, dReal pz, dVector3 result) {
+  if (!geom_frame(g, px, py, pz, result)) return;
+  dReal p[4] = {px, py, pz, 0};
+  ob_mul0_331(result, g->final_posr->R, p);
+}
+void dGeomVectorFromWorld(dGeomID g, dReal px, dReal py, dReal pz, dVector3 result) {
+  if (!geom_frame(g, px, py, pz, result)) return;
+  dReal p[4] = {px, py, pz, 0};
+  ob_mul1_331(result, g->final_posr->R, p);
+}
+void dClosestLineSegmentPoints(const dVector3 a1, const dVector3 a2, const dVector3 b1, const dVector3 b2, dVector3 cp1, dVector3 cp2) {
+  ob_closest_segment_points(a1, a2, b1, b2, cp1, cp2);   // the same function the capsule colliders run on the device
+}
+void dPrintMatrix(const dReal *A, int n, int m, char *fmt, FILE *f) {   // misc.cpp:128-136, rows padded to a multiple of 4
+  const int skip = m > 1 ? ((m - 1) | 3) + 1 : m;
+  for (int i = 0; i < n; i++, A += skip) {
+    for (int j = 0; j < m; j++) fprintf(f, fmt, A[j]);
+    fprintf(f, "\n");
   }
 }
 void dMassSetCappedCylinder(dMass *m, dReal density, int direction, dReal radius, dReal length) { dMassSetCapsule(m, density, direction, radius, length); }

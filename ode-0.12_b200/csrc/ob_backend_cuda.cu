@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(OB_THREADS) k_collide(ObBatchDev d) {
         }
         int swapped;
         int bverr = 0;
-        if (!connected) n = ob_collide_pair_t<MESH, CGCAP>(s_pose[s_walk_of[o1]], s_pose[s_walk_of[o2]], maxc, cg, &swapped, d.meshes, &bverr);
+        if (!connected) n = ob_collide_pair_xf_t<MESH, CGCAP>(&s_pose[s_walk_of[o1]], &s_pose[s_walk_of[o2]], d.any_xf, maxc, cg, &swapped, d.meshes, &bverr);
         if (bverr) atomicOr(&W.status, OB_ERR_BVH_STACK);
       }
       int total;
@@ -573,7 +573,7 @@ __global__ void __launch_bounds__(32 * WPC) k_collide_tile(ObBatchDev d, int sta
           }
         }
         int swapped, bverr = 0;
-        if (!connected) n = ob_collide_pair_t<MESH, CGCAP>(pose_v[walk_v[o12.x]], pose_v[walk_v[o12.y]], maxc, cg, &swapped, d.meshes, &bverr);
+        if (!connected) n = ob_collide_pair_xf_t<MESH, CGCAP>(&pose_v[walk_v[o12.x]], &pose_v[walk_v[o12.y]], d.any_xf, maxc, cg, &swapped, d.meshes, &bverr);
         if (bverr) atomicOr(&d.world[wv].status, OB_ERR_BVH_STACK);
         int off = 0;
         if (n > 0) {

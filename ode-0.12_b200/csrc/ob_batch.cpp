@@ -114,6 +114,7 @@ int ob_batch_upload(dxBatch *B) {
   memset(hd.data(), 0, hd.size() * sizeof(ObBodyDyn));
   memset(hc.data(), 0, hc.size() * sizeof(ObBodyConst));
   memset(hg.data(), 0, hg.size() * sizeof(ObGeom));
+  int any_xf = 0;
   for (int w = 0; w < nworlds; w++) {
     dxWorld *W = B->worlds[w]; dxSpace *S = B->spaces[w];
     ObWorld &o = hw[w];
@@ -132,6 +133,7 @@ int ob_batch_upload(dxBatch *B) {
     for (dxGeom *g = S->first; g; g = g->next, pos++) {
       ObGeom &d = hg[(size_t)w * NG + g->batch_index];
       ob_marshal_geom(g, d);
+      if (g->type == dGeomTransformClass) any_xf = 1;
       if (g->type == dTriMeshClass) {
         d.mesh = -1;
         for (size_t mi = 0; mi < B->meshes.size(); mi++) if (B->meshes[mi] == g->tmdata) d.mesh = (int)mi;
@@ -166,6 +168,7 @@ int ob_batch_upload(dxBatch *B) {
     for (int b = B->nb[w]; b <= NB; b++) ps[b] = (unsigned short)a;
   }
   int rc = 0;
+  B->caps.any_xf = any_xf; obk_arrays(B->bk)->any_xf = any_xf;   // kernel parameter, not device memory
   rc |= obk_h2d(B->bk, B->caps.world, hw.data(), hw.size() * sizeof(ObWorld));
   rc |= obk_h2d(B->bk, B->caps.bdyn, hd.data(), hd.size() * sizeof(ObBodyDyn));
   rc |= obk_h2d(B->bk, B->caps.bconst, hc.data(), hc.size() * sizeof(ObBodyConst));

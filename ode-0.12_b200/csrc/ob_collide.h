@@ -1410,14 +1410,7 @@ OB_HD int ob_pair_max_contacts(int t1, int t2, int maxc) {
 // Returns the contact count; `swapped` tells the caller g1/g2 were exchanged.
 // MESH = false compiles the trimesh arms out (kernels for worlds without trimesh geoms); CGCAP = size of c[]
 template <bool MESH, int CGCAP>
-OB_HD int ob_collide_pair_t(const ObPose &a1, const ObPose &a2, int flags, ObCg *c, int *swapped, const ObMeshDev *meshes, int *bverr) {
-  // Geom transforms (collision_transform.cpp:115-160; setAllColliders(dGeomTransformClass, ..) collision_kernel.cpp:254):
-  // a transform arrives here as its encapsulated geom posed at T o local, tagged OB_POSE_XFORM.  The transform class
-  // sorts above every other class, so dCollide(X, T) = reverse(dCollideTransform(T, X)) = reverse(dCollide(inner, X)),
-  // and dCollide(T1, T2) = dCollide(inner1, T2) = reverse(dCollide(inner2, inner1)): whenever the second geom is a
-  // transform the pair is collided the other way round and reversed once more.
-  const bool x2 = a2.type != OB_GEOM_TRIMESH && a2.type != OB_GEOM_RAY && (a2.mesh & OB_POSE_XFORM);
-  const ObPose &o1 = x2 ? a2 : a1, &o2 = x2 ? a1 : a2;
+OB_HD int ob_collide_pair_t(const ObPose &o1, const ObPose &o2, int flags, ObCg *c, int *swapped, const ObMeshDev *meshes, int *bverr) {
   int t1 = o1.type, t2 = o2.type, n = 0, rev = 0;
   int bve = 0;
   for (int i = 0; i < CGCAP; i++) { c[i].side1 = -1; c[i].side2 = -1; }
@@ -1463,7 +1456,6 @@ OB_HD int ob_collide_pair_t(const ObPose &a1, const ObPose &a2, int flags, ObCg 
   else if (MESH && t1 == OB_GEOM_TRIMESH && t2 == OB_GEOM_BOX) n = ob_collide_trimesh_box(o1, o2, meshes[o1.mesh], flags, c, &bve);
   else if (MESH && t1 == OB_GEOM_BOX && t2 == OB_GEOM_TRIMESH) { n = ob_collide_trimesh_box(o2, o1, meshes[o2.mesh], flags, c, &bve); rev = 1; }
   if (bve && bverr) *bverr = 1;
-  if (x2) rev ^= 1;
   if (rev) {
     for (int i = 0; i < n; i++) {
       c[i].normal[0] = -c[i].normal[0]; c[i].normal[1] = -c[i].normal[1]; c[i].normal[2] = -c[i].normal[2];
@@ -1473,7 +1465,31 @@ OB_HD int ob_collide_pair_t(const ObPose &a1, const ObPose &a2, int flags, ObCg 
   *swapped = rev;
   return n;
 }
+// Geom transforms (collision_transform.cpp:115-160; setAllColliders(dGeomTransformClass, ..), collision_kernel.cpp:267):
+// a transform arrives as its encapsulated geom posed at T o local, tagged OB_POSE_XFORM.  The transform class's table
+// entries give dCollide(X, T) = reverse(dCollideTransform(T, X)) = reverse(dCollide(inner, X)) and dCollide(T1, T2) =
+// dCollide(inner1, T2) = reverse(dCollide(inner2, inner1)): whenever the SECOND geom is a transform the pair is
+// collided the other way round and reversed once more (box-box is not symmetric bit for bit).  any_xf is the
+// batch-wide "some geom is a transform" flag (ObBatchDev::any_xf), uniform per launch, so batches without transforms
+// pay one uniform branch and no dependent load.
+OB_HD bool ob_pose_is_xform(const ObPose &p) { return p.type != OB_GEOM_TRIMESH && p.type != OB_GEOM_RAY && (p.mesh & OB_POSE_XFORM); }
+template <bool MESH, int CGCAP>
+OB_HD int ob_collide_pair_xf_t(const ObPose *a1, const ObPose *a2, int any_xf, int flags, ObCg *c, int *swapped, const ObMeshDev *meshes, int *bverr) {
+  bool flip = false;
+  if (any_xf) {
+    if (ob_pose_is_xform(*a2)) { const ObPose *t = a1; a1 = a2; a2 = t; flip = true; }
+  }
+  const int n = ob_collide_pair_t<MESH, CGCAP>(*a1, *a2, flags, c, swapped, meshes, bverr);
+  if (flip) {
+    for (int i = 0; i < n; i++) {
+      c[i].normal[0] = -c[i].normal[0]; c[i].normal[1] = -c[i].normal[1]; c[i].normal[2] = -c[i].normal[2];
+      int t = c[i].side1; c[i].side1 = c[i].side2; c[i].side2 = t;
+    }
+    *swapped ^= 1;
+  }
+  return n;
+}
 OB_HD int ob_collide_pair(const ObPose &o1, const ObPose &o2, int flags, ObCg *c, int *swapped, const ObMeshDev *meshes = 0,
                           int *bverr = 0) {
-  return ob_collide_pair_t<true, OB_MAXC_LOCAL>(o1, o2, flags, c, swapped, meshes, bverr);
+  return ob_collide_pair_xf_t<true, OB_MAXC_LOCAL>(&o1, &o2, 1, flags, c, swapped, meshes, bverr);
 }

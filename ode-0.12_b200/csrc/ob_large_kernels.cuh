@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(LW_T) k_lw_narrow(ObBatchDev d, ObLargeDev L, 
   const int o1 = L.pairs[2 * p], o2 = L.pairs[2 * p + 1];
   ObCg cg[OB_LW_MAXC];
   int swapped, bverr = 0;
-  const int n = ob_collide_pair_t<MESH, OB_LW_MAXC>(L.pose[o1], L.pose[o2], maxc, cg, &swapped, d.meshes, &bverr);
+  const int n = ob_collide_pair_xf_t<MESH, OB_LW_MAXC>(&L.pose[o1], &L.pose[o2], d.any_xf, maxc, cg, &swapped, d.meshes, &bverr);
   if (bverr) atomicOr(&d.world[0].status, OB_ERR_BVH_STACK);
   ObContact *out = L.pc + (size_t)p * maxc;
   for (int k = 0; k < n; k++) {

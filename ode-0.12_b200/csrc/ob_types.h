@@ -135,6 +135,7 @@ struct ObBatchDev {
   ObPolicy *policy;      // [npolicy]
   struct ObMeshDev *meshes;   // [nmesh] trimesh data table (ob_trimesh.h); geoms refer to it by index
   int nmesh;
+  int any_xf;   // some geom of the batch is a geom transform (OB_POSE_XFORM): set by every upload, uniform per launch
   ObJoint *joint;        // [W*NJ] permanent joints (ball / hinge / hinge2), creation order
   int *njoints;          // [W]
   unsigned short *padjstart; // [W*(NB+1)] per body: range into padj

@@ -183,6 +183,21 @@ int main() {
   dGeomGetAABB(xt, xab); pr("xf_aabb_static", xab, 6);
   dGeomSetBody(xt, b[1]); dGeomGetAABB(xt, xab); pr("xf_aabb_body", xab, 6); pr("xf_pos", dGeomGetPosition(xt), 3);
   dGeomDestroy(xt);
+  // frame conversions, impulse to force, closest segment points, dPrintMatrix
+  dBodyGetPointVel(b[1], (dReal)0.4, (dReal)-0.7, (dReal)1.9, v3); pr("bpointvel", v3, 3);
+  dBodyGetPosRelPoint(b[1], (dReal)0.4, (dReal)-0.7, (dReal)1.9, v3); pr("bposrel", v3, 3);
+  dBodyVectorFromWorld(b[1], (dReal)0.3, (dReal)0.9, (dReal)-0.2, v3); pr("bvecfrom", v3, 3);
+  dWorldImpulseToForce(w, (dReal)0.013, (dReal)0.3, (dReal)-1.1, (dReal)2.7, v3); pr("imp2f", v3, 3);
+  dGeomGetRelPointPos(gw, (dReal)0.1, (dReal)0.2, (dReal)-0.3, v3); pr("grelpt", v3, 3);
+  dGeomGetPosRelPoint(gw, (dReal)0.1, (dReal)0.2, (dReal)-0.3, v3); pr("gposrel", v3, 3);
+  dGeomVectorToWorld(gw, (dReal)0.1, (dReal)0.2, (dReal)-0.3, v3); pr("gvecto", v3, 3);
+  dGeomVectorFromWorld(gw, (dReal)0.1, (dReal)0.2, (dReal)-0.3, v3); pr("gvecfrom", v3, 3);
+  { dGeomID pl = dCreatePlane(s, 0, 0, 1, 0); dGeomGetRelPointPos(pl, 1, 2, 3, v3); pr("plrelpt", v3, 3); dGeomVectorFromWorld(pl, 1, 2, 3, v3); pr("plvec", v3, 3); dGeomDestroy(pl); }
+  { dVector3 sa1 = {0, 0, 0}, sa2 = {1, (dReal)0.2, 0}, sb1 = {(dReal)0.3, 1, (dReal)0.4}, sb2 = {(dReal)0.6, (dReal)-0.5, (dReal)0.1}, c1, c2;
+    dClosestLineSegmentPoints(sa1, sa2, sb1, sb2, c1, c2); pr("clsp1", c1, 3); pr("clsp2", c2, 3);
+    dVector3 sb3 = {2, 1, 1}, sb4 = {3, 2, (dReal)1.5};
+    dClosestLineSegmentPoints(sa1, sa2, sb3, sb4, c1, c2); pr("clsp3", c1, 3); pr("clsp4", c2, 3); }
+  { char fmt[] = "%8.3f "; dPrintMatrix(Rw, 3, 3, fmt, stdout); }
   printf("thr %d\n", dAllocateODEDataForThread(0xffffffffu));
   printf("wsm %d %d %d\n", dWorldUseSharedWorkingMemory(w, 0), dWorldSetStepMemoryReservationPolicy(w, 0), dWorldSetStepMemoryManager(w, 0));
   dWorldCleanupWorkingMemory(w);

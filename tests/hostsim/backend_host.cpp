@@ -286,7 +286,7 @@ static void collide_world(ObBatchDev &d, int w) {
     int swapped;
     int flags = pol.max_contacts > OB_MAXC_LOCAL ? OB_MAXC_LOCAL : pol.max_contacts;
     int bverr = 0;
-    int n = ob_collide_pair(pose[walk_of[o1]], pose[walk_of[o2]], flags, cg, &swapped, d.meshes, &bverr);
+    int n = ob_collide_pair_xf_t<true, OB_MAXC_LOCAL>(&pose[walk_of[o1]], &pose[walk_of[o2]], d.any_xf, flags, cg, &swapped, d.meshes, &bverr);
     if (bverr) W.status |= OB_ERR_BVH_STACK;
     for (int k = 0; k < n; k++) {
       if (nc >= d.NC) { W.status |= OB_ERR_CONTACT_OVERFLOW; break; }

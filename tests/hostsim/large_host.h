@@ -108,8 +108,8 @@ static int large_step_host(ObBatchDev &d, real h, int taps, LargeHostStats *stat
     const int o1 = pairs[2 * p], o2 = pairs[2 * p + 1];
     ObCg cg[OB_LW_MAXC];
     int swapped, bverr = 0;
-    const int n = d.nmesh ? ob_collide_pair_t<true, OB_LW_MAXC>(pose[o1], pose[o2], maxc, cg, &swapped, d.meshes, &bverr)
-                          : ob_collide_pair_t<false, OB_LW_MAXC>(pose[o1], pose[o2], maxc, cg, &swapped, d.meshes, &bverr);
+    const int n = d.nmesh ? ob_collide_pair_xf_t<true, OB_LW_MAXC>(&pose[o1], &pose[o2], d.any_xf, maxc, cg, &swapped, d.meshes, &bverr)
+                          : ob_collide_pair_xf_t<false, OB_LW_MAXC>(&pose[o1], &pose[o2], d.any_xf, maxc, cg, &swapped, d.meshes, &bverr);
     if (bverr) W.status |= OB_ERR_BVH_STACK;
     for (int k = 0; k < n; k++) {
       ObContact c;
