@@ -536,6 +536,7 @@ int dJointGetAMotorNumAxes(dJointID);
 void dJointGetAMotorAxis(dJointID, int anum, dVector3 result);
 int dJointGetAMotorAxisRel(dJointID, int anum);
 dReal dJointGetAMotorAngle(dJointID, int anum);
+dReal dJointGetAMotorAngleRate(dJointID, int anum);   /* objects.h; amotor.cpp:445-451: dDebug("not yet implemented") in the reference, here too */
 dReal dJointGetAMotorParam(dJointID, int parameter);
 int dJointGetAMotorMode(dJointID);
 void dJointSetLMotorNumAxes(dJointID, int num);
@@ -682,6 +683,7 @@ void dGeomTriMeshDataBuildDouble1(dTriMeshDataID g, const void *Vertices, int Ve
                                   const void *Indices, int IndexCount, int TriStride, const void *Normals);
 void dGeomTriMeshDataBuildSimple(dTriMeshDataID g, const dReal *Vertices, int VertexCount,
                                  const dTriIndex *Indices, int IndexCount);
+void dGeomTriMeshDataBuildSimple1(dTriMeshDataID g, const dReal *Vertices, int VertexCount, const dTriIndex *Indices, int IndexCount, const int *Normals);   /* collision_trimesh.h:127 */
 void dGeomTriMeshDataPreprocess(dTriMeshDataID g);
 void dGeomTriMeshDataUpdate(dTriMeshDataID g);
 dGeomID dCreateTriMesh(dSpaceID space, dTriMeshDataID Data, dTriCallback *Callback,

@@ -111,7 +111,7 @@ __device__ inline void geom_pose_dev(const ObGeom &g, const ObBodyDyn *bd, ObPos
 // ------------------------------------------------------------------------------------
 // MESH: the batch has trimesh geoms (narrowphase with the BVH colliders, up to OB_MAXC_LOCAL contacts per
 // pair); otherwise the primitive-only narrowphase with 8 contact slots per pair (box-box emits at most 8)
-template <bool MESH>
+template <bool MESH, bool XF>
 __global__ void __launch_bounds__(OB_THREADS) k_collide(ObBatchDev d) {
   constexpr int CGCAP = MESH ? OB_MAXC_LOCAL : 8;
   extern __shared__ __align__(16) unsigned char smem[];
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(OB_THREADS) k_collide(ObBatchDev d) {
         }
         int swapped;
         int bverr = 0;
-        if (!connected) n = ob_collide_pair_xf_t<MESH, CGCAP>(&s_pose[s_walk_of[o1]], &s_pose[s_walk_of[o2]], d.any_xf, maxc, cg, &swapped, d.meshes, &bverr);
+        if (!connected) n = ob_collide_pair_sel_t<MESH, CGCAP, XF>(&s_pose[s_walk_of[o1]], &s_pose[s_walk_of[o2]], maxc, cg, &swapped, d.meshes, &bverr);
         if (bverr) atomicOr(&W.status, OB_ERR_BVH_STACK);
       }
       int total;
@@ -342,7 +342,7 @@ __host__ __device__ inline CollideTileSmem collide_tile_smem(int NG, int NP, int
 // own world (poses, AABBs, ordered pair list: phases 1-4, warp-synchronous), then the pairs of all WPC worlds are
 // pooled, grouped by collider class so that a warp runs ONE collider on full lanes, and their contacts go through a
 // shared-memory staging area into the per-world contact arrays in callback order (phase 5).
-template <bool MESH, int WPC>
+template <bool MESH, bool XF, int WPC>
 __global__ void __launch_bounds__(32 * WPC) k_collide_tile(ObBatchDev d, int stage_cap) {
   constexpr int CGCAP = MESH ? OB_MAXC_LOCAL : 8;
   extern __shared__ __align__(16) unsigned char smem[];
@@ -573,7 +573,7 @@ __global__ void __launch_bounds__(32 * WPC) k_collide_tile(ObBatchDev d, int sta
           }
         }
         int swapped, bverr = 0;
-        if (!connected) n = ob_collide_pair_xf_t<MESH, CGCAP>(&pose_v[walk_v[o12.x]], &pose_v[walk_v[o12.y]], d.any_xf, maxc, cg, &swapped, d.meshes, &bverr);
+        if (!connected) n = ob_collide_pair_sel_t<MESH, CGCAP, XF>(&pose_v[walk_v[o12.x]], &pose_v[walk_v[o12.y]], maxc, cg, &swapped, d.meshes, &bverr);
         if (bverr) atomicOr(&d.world[wv].status, OB_ERR_BVH_STACK);
         int off = 0;
         if (n > 0) {
@@ -825,8 +825,9 @@ ObBackend *obk_create(const ObBatchDev &caps, int device, char *err, size_t errl
              b->smem_collide, b->smem_prep, b->smem_sor, (size_t)prop.sharedMemPerBlockOptin);
     goto fail;
   }
-  CK(cudaFuncSetAttribute(k_collide<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_collide));
-  CK(cudaFuncSetAttribute(k_collide<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_collide));
+  CK(cudaFuncSetAttribute(k_collide<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_collide));
+  CK(cudaFuncSetAttribute(k_collide<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_collide));
+  CK(cudaFuncSetAttribute(k_collide<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_collide));
   // small worlds: OB_TILE_WPC worlds per CTA with a pooled, class-grouped narrowphase (k_collide_tile)
   b->collide_tile = 0;
   if (d.NG <= 8 && !getenv("OB_COLLIDE_NOTILE")) {
@@ -835,8 +836,9 @@ ObBackend *obk_create(const ObBatchDev &caps, int device, char *err, size_t errl
     b->smem_collide_tile = (size_t)OB_TILE_WPC * collide_smem(d.NG, d.NP).total + collide_tile_smem(d.NG, d.NP, OB_TILE_WPC, b->tile_stage_cap).total;
     if (b->smem_collide_tile <= (size_t)prop.sharedMemPerBlockOptin && (long long)OB_TILE_WPC * d.NP < 65000) {
       b->collide_tile = 1;
-      CK(cudaFuncSetAttribute(k_collide_tile<false, OB_TILE_WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_collide_tile));
-      CK(cudaFuncSetAttribute(k_collide_tile<true, OB_TILE_WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_collide_tile));
+      CK(cudaFuncSetAttribute(k_collide_tile<false, false, OB_TILE_WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_collide_tile));
+      CK(cudaFuncSetAttribute(k_collide_tile<true, false, OB_TILE_WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_collide_tile));
+      CK(cudaFuncSetAttribute(k_collide_tile<true, true, OB_TILE_WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_collide_tile));
     }
   }
 #define OB_SETSMEM(GG) \
@@ -953,10 +955,13 @@ template <int G> static void launch_step(ObBackend *b, real h, int taps, int pha
     if (b->collide_tile) {
       const int tiles = (W + OB_TILE_WPC - 1) / OB_TILE_WPC;
       const int tgrid = tiles < cap ? tiles : cap;
-      if (d.nmesh) k_collide_tile<true, OB_TILE_WPC><<<tgrid, 32 * OB_TILE_WPC, b->smem_collide_tile, st>>>(d, b->tile_stage_cap);
-      else k_collide_tile<false, OB_TILE_WPC><<<tgrid, 32 * OB_TILE_WPC, b->smem_collide_tile, st>>>(d, b->tile_stage_cap);
-    } else if (d.nmesh) k_collide<true><<<grid, ct, b->smem_collide, st>>>(d);
-    else k_collide<false><<<grid, ct, b->smem_collide, st>>>(d);
+      // batches with geom transforms run the <MESH = true, XF = true> instantiation (a superset: the mesh arms only fire for trimesh geoms)
+      if (d.any_xf) k_collide_tile<true, true, OB_TILE_WPC><<<tgrid, 32 * OB_TILE_WPC, b->smem_collide_tile, st>>>(d, b->tile_stage_cap);
+      else if (d.nmesh) k_collide_tile<true, false, OB_TILE_WPC><<<tgrid, 32 * OB_TILE_WPC, b->smem_collide_tile, st>>>(d, b->tile_stage_cap);
+      else k_collide_tile<false, false, OB_TILE_WPC><<<tgrid, 32 * OB_TILE_WPC, b->smem_collide_tile, st>>>(d, b->tile_stage_cap);
+    } else if (d.any_xf) k_collide<true, true><<<grid, ct, b->smem_collide, st>>>(d);
+    else if (d.nmesh) k_collide<true, false><<<grid, ct, b->smem_collide, st>>>(d);
+    else k_collide<false, false><<<grid, ct, b->smem_collide, st>>>(d);
     g_launches++;
   }
   if (timing) cudaEventRecord(ev[1], st);

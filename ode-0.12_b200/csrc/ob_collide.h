@@ -1473,21 +1473,31 @@ OB_HD int ob_collide_pair_t(const ObPose &o1, const ObPose &o2, int flags, ObCg 
 // batch-wide "some geom is a transform" flag (ObBatchDev::any_xf), uniform per launch, so batches without transforms
 // pay one uniform branch and no dependent load.
 OB_HD bool ob_pose_is_xform(const ObPose &p) { return p.type != OB_GEOM_TRIMESH && p.type != OB_GEOM_RAY && (p.mesh & OB_POSE_XFORM); }
+// The reversed path is a real (not inlined) call: batches without transforms keep exactly the code they had, behind
+// one uniform branch on the kernel parameter, and the rare path does not double the size of the collide kernels.
+template <bool MESH, int CGCAP>
+OB_HDN int ob_collide_pair_flipped_t(const ObPose *a1, const ObPose *a2, int flags, ObCg *c, int *swapped, const ObMeshDev *meshes, int *bverr) {
+  const int n = ob_collide_pair_t<MESH, CGCAP>(*a2, *a1, flags, c, swapped, meshes, bverr);
+  for (int i = 0; i < n; i++) {
+    c[i].normal[0] = -c[i].normal[0]; c[i].normal[1] = -c[i].normal[1]; c[i].normal[2] = -c[i].normal[2];
+    int t = c[i].side1; c[i].side1 = c[i].side2; c[i].side2 = t;
+  }
+  *swapped ^= 1;
+  return n;
+}
 template <bool MESH, int CGCAP>
 OB_HD int ob_collide_pair_xf_t(const ObPose *a1, const ObPose *a2, int any_xf, int flags, ObCg *c, int *swapped, const ObMeshDev *meshes, int *bverr) {
-  bool flip = false;
-  if (any_xf) {
-    if (ob_pose_is_xform(*a2)) { const ObPose *t = a1; a1 = a2; a2 = t; flip = true; }
-  }
-  const int n = ob_collide_pair_t<MESH, CGCAP>(*a1, *a2, flags, c, swapped, meshes, bverr);
-  if (flip) {
-    for (int i = 0; i < n; i++) {
-      c[i].normal[0] = -c[i].normal[0]; c[i].normal[1] = -c[i].normal[1]; c[i].normal[2] = -c[i].normal[2];
-      int t = c[i].side1; c[i].side1 = c[i].side2; c[i].side2 = t;
-    }
-    *swapped ^= 1;
-  }
-  return n;
+  if (any_xf && ob_pose_is_xform(*a2)) return ob_collide_pair_flipped_t<MESH, CGCAP>(a1, a2, flags, c, swapped, meshes, bverr);
+  return ob_collide_pair_t<MESH, CGCAP>(*a1, *a2, flags, c, swapped, meshes, bverr);
+}
+// XF is a compile-time property of the launch (kernels are instantiated <MESH, XF>; a batch with transforms runs the
+// <true, true> instantiation): measured on B200, even a never-taken call to the flipped path cost k_collide 2 % (config 2)
+// to 7 % (config 4) through register allocation (80 -> 96 registers), so batches without transforms run the code they
+// had before (profiles/job_ab.sh).
+template <bool MESH, int CGCAP, bool XF>
+OB_HD int ob_collide_pair_sel_t(const ObPose *a1, const ObPose *a2, int flags, ObCg *c, int *swapped, const ObMeshDev *meshes, int *bverr) {
+  if (XF) return ob_collide_pair_xf_t<MESH, CGCAP>(a1, a2, 1, flags, c, swapped, meshes, bverr);
+  return ob_collide_pair_t<MESH, CGCAP>(*a1, *a2, flags, c, swapped, meshes, bverr);
 }
 OB_HD int ob_collide_pair(const ObPose &o1, const ObPose &o2, int flags, ObCg *c, int *swapped, const ObMeshDev *meshes = 0,
                           int *bverr = 0) {

@@ -543,6 +543,7 @@ void dJointSetAMotorMode(dJointID j, int mode) { j->mode = mode; if (mode == dAM
 int dJointGetAMotorNumAxes(dJointID j) { return j->num; }
 void dJointGetAMotorAxis(dJointID j, int anum, dVector3 result) { motor_get_axis(j, anum, result); }
 int dJointGetAMotorAxisRel(dJointID j, int anum) { if (anum < 0) anum = 0; if (anum > 2) anum = 2; return j->rel[anum]; }
+dReal dJointGetAMotorAngleRate(dJointID, int) { ob_debug(0, "not yet implemented"); return 0; }   // amotor.cpp:445-451: the reference aborts the same way
 dReal dJointGetAMotorAngle(dJointID j, int anum) { if (anum < 0) anum = 0; if (anum > 2) anum = 2; return j->angle[anum]; }
 dReal dJointGetAMotorParam(dJointID j, int parameter) { int anum = parameter >> 8; if (anum < 0) anum = 0; if (anum > 2) anum = 2; return limot_get(motor_limot(j, anum), parameter & 0xff); }
 int dJointGetAMotorMode(dJointID j) { return j->mode; }

@@ -266,14 +266,14 @@ __global__ void __launch_bounds__(LW_T) k_lw_sweep(ObBatchDev d, ObLargeDev L) {
   if (!FILL) L.cnt[ng + i] = h;
 }
 
-template <bool MESH>
+template <bool MESH, bool XF>
 __global__ void __launch_bounds__(LW_T) k_lw_narrow(ObBatchDev d, ObLargeDev L, int np, int maxc) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= np) return;
   const int o1 = L.pairs[2 * p], o2 = L.pairs[2 * p + 1];
   ObCg cg[OB_LW_MAXC];
   int swapped, bverr = 0;
-  const int n = ob_collide_pair_xf_t<MESH, OB_LW_MAXC>(&L.pose[o1], &L.pose[o2], d.any_xf, maxc, cg, &swapped, d.meshes, &bverr);
+  const int n = ob_collide_pair_sel_t<MESH, OB_LW_MAXC, XF>(&L.pose[o1], &L.pose[o2], maxc, cg, &swapped, d.meshes, &bverr);
   if (bverr) atomicOr(&d.world[0].status, OB_ERR_BVH_STACK);
   ObContact *out = L.pc + (size_t)p * maxc;
   for (int k = 0; k < n; k++) {
@@ -901,8 +901,9 @@ static int lw_step(ObBackend *b, real h, int taps, char *err, size_t errlen) {
   LW_MARK();
   // (3) narrowphase, contact pairs
   if (np > 0) {
-    if (d.nmesh) k_lw_narrow<true><<<lw_blocks(np), LW_T, 0, st>>>(d, L, np, maxc);
-    else k_lw_narrow<false><<<lw_blocks(np), LW_T, 0, st>>>(d, L, np, maxc);
+    if (d.any_xf) k_lw_narrow<true, true><<<lw_blocks(np), LW_T, 0, st>>>(d, L, np, maxc);
+    else if (d.nmesh) k_lw_narrow<true, false><<<lw_blocks(np), LW_T, 0, st>>>(d, L, np, maxc);
+    else k_lw_narrow<false, false><<<lw_blocks(np), LW_T, 0, st>>>(d, L, np, maxc);
     g_launches++;
   }
   lw_scan(st, L.ncp, L.coff, np, L.tmp);

@@ -175,6 +175,14 @@ void dGeomTriMeshDataBuildSimple(dTriMeshDataID d, const dReal *Vertices, int Ve
   dGeomTriMeshDataBuildDouble(d, Vertices, 4 * sizeof(dReal), VertexCount, Indices, IndexCount, 3 * sizeof(dTriIndex));
 #endif
 }
+void dGeomTriMeshDataBuildSimple1(dTriMeshDataID d, const dReal *Vertices, int VertexCount, const dTriIndex *Indices, int IndexCount, const int *Normals) {
+  // collision_trimesh_opcode.cpp:484-498: as BuildSimple, with per-face normals handed to the *1 builder
+#if defined(dSINGLE)
+  dGeomTriMeshDataBuildSingle1(d, Vertices, 4 * sizeof(dReal), VertexCount, Indices, IndexCount, 3 * sizeof(dTriIndex), Normals);
+#else
+  dGeomTriMeshDataBuildDouble1(d, Vertices, 4 * sizeof(dReal), VertexCount, Indices, IndexCount, 3 * sizeof(dTriIndex), Normals);
+#endif
+}
 // dxTriMeshData::Preprocess (collision_trimesh_opcode.cpp:256-363): per triangle, which edges and vertices the
 // capsule collider should test.  Edges shared by two triangles are paired after sorting (the reference's qsort
 // on (VertIdx1, VertIdx2); glibc's is a stable merge sort, so equal records keep their order); convex and
