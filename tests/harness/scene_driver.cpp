@@ -60,6 +60,14 @@ static void near_cb(void *data, dGeomID o1, dGeomID o2) {
   }
   int n = dCollide(o1, o2, maxc, &contact[0].geom, sizeof(dContact));
   const bool ray = dGeomGetClass(o1) == dRayClass || dGeomGetClass(o2) == dRayClass;   // query result, not a contact joint
+  // contact geom identity (collision_kernel.cpp:331-343, collision_transform.cpp:143-151): g1 / g2 name the geoms of the
+  // call, a geom transform being replaced by its encapsulated geom unless its info mode is on
+  for (int i = 0; i < n; i++) {
+    dGeomID e[2] = {o1, o2};
+    for (int k = 0; k < 2; k++)
+      if (dGeomGetClass(e[k]) == dGeomTransformClass && !dGeomTransformGetInfo(e[k])) e[k] = dGeomTransformGetGeom(e[k]);
+    if (contact[i].geom.g1 != e[0] || contact[i].geom.g2 != e[1]) { fprintf(stderr, "contact %d: g1 / g2 do not name the expected geoms\n", i); exit(3); }
+  }
   for (int i = 0; i < n; i++) {
     dJointID j = 0;
     if (!ray) {
