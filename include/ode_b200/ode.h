@@ -322,6 +322,8 @@ void dMassSetCylinderTotal(dMass *m, dReal total_mass, int direction, dReal radi
 void dMassSetBox(dMass *m, dReal density, dReal lx, dReal ly, dReal lz);
 void dMassSetBoxTotal(dMass *m, dReal total_mass, dReal lx, dReal ly, dReal lz);
 void dMassAdjust(dMass *m, dReal newmass);
+void dMassSetTrimesh(dMass *m, dReal density, dGeomID g);             /* include/ode/mass.h:83, mass.cpp:234-427 */
+void dMassSetTrimeshTotal(dMass *m, dReal total_mass, dGeomID g);     /* include/ode/mass.h:84 */
 void dMassTranslate(dMass *m, dReal x, dReal y, dReal z);
 void dMassRotate(dMass *m, const dMatrix3 R);
 void dMassAdd(dMass *a, const dMass *b);

@@ -352,6 +352,90 @@ void dPrintMatrix(const dReal *A, int n, int m, char *fmt, FILE *f) {   // misc.
     fprintf(f, "\n");
   }
 }
+// dMassSetTrimesh (mass.cpp:234-427): Mirtich's polyhedral mass properties ("Fast and Accurate Computation of Polyhedral
+// Mass Properties", jgt 1(2) 1996) over the triangles in world coordinates.  Per face: projection integrals over the
+// plane of the two minor axes (A, B) of the normal, face integrals from them, volume integrals accumulated; every
+// expression keeps the reference's operand order so that the result is the same bit for bit.
+namespace {
+struct ObProj { dReal P1, Pa, Pb, Paa, Pab, Pbb, Paaa, Paab, Pabb, Pbbb; };
+static void mirtich_projection(const dVector3 *v, int A, int B, ObProj &P) {
+  memset(&P, 0, sizeof P);
+  for (int j = 0; j < 3; j++) {   // edges v[j] -> v[j+1]
+    const int jn = j == 2 ? 0 : j + 1;
+    const dReal a0 = v[j][A], b0 = v[j][B], a1 = v[jn][A], b1 = v[jn][B];
+    const dReal da = a1 - a0, db = b1 - b0;
+    const dReal a0_2 = a0 * a0, a0_3 = a0_2 * a0, a0_4 = a0_3 * a0;
+    const dReal b0_2 = b0 * b0, b0_3 = b0_2 * b0, b0_4 = b0_3 * b0;
+    const dReal a1_2 = a1 * a1, a1_3 = a1_2 * a1, b1_2 = b1 * b1, b1_3 = b1_2 * b1;
+    const dReal C1 = a1 + a0;
+    const dReal Ca = a1 * C1 + a0_2, Caa = a1 * Ca + a0_3, Caaa = a1 * Caa + a0_4;
+    const dReal Cb = b1 * (b1 + b0) + b0_2, Cbb = b1 * Cb + b0_3, Cbbb = b1 * Cbb + b0_4;
+    const dReal Cab = 3 * a1_2 + 2 * a1 * a0 + a0_2, Kab = a1_2 + 2 * a1 * a0 + 3 * a0_2;
+    const dReal Caab = a0 * Cab + 4 * a1_3, Kaab = a1 * Kab + 4 * a0_3;
+    const dReal Cabb = 4 * b1_3 + 3 * b1_2 * b0 + 2 * b1 * b0_2 + b0_3;
+    const dReal Kabb = b1_3 + 2 * b1_2 * b0 + 3 * b1 * b0_2 + 4 * b0_3;
+    P.P1 += db * C1; P.Pa += db * Ca; P.Paa += db * Caa; P.Paaa += db * Caaa;
+    P.Pb += da * Cb; P.Pbb += da * Cbb; P.Pbbb += da * Cbbb;
+    P.Pab += db * (b1 * Cab + b0 * Kab);
+    P.Paab += db * (b1 * Caab + b0 * Kaab);
+    P.Pabb += da * (a1 * Cabb + a0 * Kabb);
+  }
+  P.P1 /= 2.0; P.Pa /= 6.0; P.Paa /= 12.0; P.Paaa /= 20.0;
+  P.Pb /= -6.0; P.Pbb /= -12.0; P.Pbbb /= -20.0;
+  P.Pab /= 24.0; P.Paab /= 60.0; P.Pabb /= -60.0;
+}
+}  // namespace
+void dMassSetTrimesh(dMass *m, dReal density, dGeomID g) {
+  OB_AASSERT(m);
+  OB_UASSERT(g && g->type == dTriMeshClass, "argument not a trimesh");
+  dMassSetZero(m);
+  const int ntri = dGeomTriMeshGetTriangleCount(g);
+  dReal T0 = 0, T1[3] = {0, 0, 0}, T2[3] = {0, 0, 0}, TP[3] = {0, 0, 0};
+  for (int i = 0; i < ntri; i++) {
+    dVector3 v[3], n, ea, eb;
+    dGeomTriMeshGetTriangle(g, i, &v[0], &v[1], &v[2]);
+    for (int k = 0; k < 3; k++) { ea[k] = v[1][k] - v[0][k]; eb[k] = v[2][k] - v[0][k]; }
+    ob_cross(n, eb, ea);
+    const dReal nx = ob_fabs(n[0]), ny = ob_fabs(n[1]), nz = ob_fabs(n[2]);
+    const int C = (nx > ny && nx > nz) ? 0 : ((ny > nz) ? 1 : 2);
+    if (n[C] == 0) continue;   // a triangle the pose transform degenerated
+    const int A = (C + 1) % 3, B = (A + 1) % 3;
+    ObProj P;
+    mirtich_projection(v, A, B, P);
+    const dReal nA = n[A], nB = n[B];
+    const dReal w = -ob_dot(n, v[0]);
+    const dReal k1 = 1 / n[C], k2 = k1 * k1, k3 = k2 * k1, k4 = k3 * k1;
+    const dReal Fa = k1 * P.Pa, Fb = k1 * P.Pb;
+    const dReal Fc = -k2 * (nA * P.Pa + nB * P.Pb + w * P.P1);
+    const dReal Faa = k1 * P.Paa, Fbb = k1 * P.Pbb;
+    const dReal Fcc = k3 * ((nA * nA) * P.Paa + 2 * nA * nB * P.Pab + (nB * nB) * P.Pbb + w * (2 * (nA * P.Pa + nB * P.Pb) + w * P.P1));
+    const dReal Faaa = k1 * P.Paaa, Fbbb = k1 * P.Pbbb;
+    const dReal Fccc = -k4 * ((nA * nA * nA) * P.Paaa + 3 * (nA * nA) * nB * P.Paab + 3 * nA * (nB * nB) * P.Pabb + (nB * nB * nB) * P.Pbbb +
+                              3 * w * ((nA * nA) * P.Paa + 2 * nA * nB * P.Pab + (nB * nB) * P.Pbb) + w * w * (3 * (nA * P.Pa + nB * P.Pb) + w * P.P1));
+    const dReal Faab = k1 * P.Paab;
+    const dReal Fbbc = -k2 * (nA * P.Pabb + nB * P.Pbbb + w * P.Pbb);
+    const dReal Fcca = k3 * ((nA * nA) * P.Paaa + 2 * nA * nB * P.Paab + (nB * nB) * P.Pabb + w * (2 * (nA * P.Paa + nB * P.Pab) + w * P.Pa));
+    T0 += n[0] * ((A == 0) ? Fa : ((B == 0) ? Fb : Fc));
+    T1[A] += n[A] * Faa; T1[B] += n[B] * Fbb; T1[C] += n[C] * Fcc;
+    T2[A] += n[A] * Faaa; T2[B] += n[B] * Fbbb; T2[C] += n[C] * Fccc;
+    TP[A] += n[A] * Faab; TP[B] += n[B] * Fbbc; TP[C] += n[C] * Fcca;
+  }
+  for (int k = 0; k < 3; k++) { T1[k] /= 2; T2[k] /= 3; TP[k] /= 2; }
+  m->mass = density * T0;
+  m->I[0] = density * (T2[1] + T2[2]);
+  m->I[5] = density * (T2[2] + T2[0]);
+  m->I[10] = density * (T2[0] + T2[1]);
+  m->I[1] = m->I[4] = -density * TP[0];
+  m->I[9] = m->I[6] = -density * TP[1];
+  m->I[8] = m->I[2] = -density * TP[2];
+  dMassTranslate(m, T1[0] / T0, T1[1] / T0, T1[2] / T0);   // as the reference does (its SF bug 1729095 fix)
+}
+void dMassSetTrimeshTotal(dMass *m, dReal total_mass, dGeomID g) {
+  OB_AASSERT(m);
+  OB_UASSERT(g && g->type == dTriMeshClass, "argument not a trimesh");
+  dMassSetTrimesh(m, 1.0, g);
+  dMassAdjust(m, total_mass);
+}
 void dMassSetCappedCylinder(dMass *m, dReal density, int direction, dReal radius, dReal length) { dMassSetCapsule(m, density, direction, radius, length); }
 void dMassSetCappedCylinderTotal(dMass *m, dReal total_mass, int direction, dReal radius, dReal length) { dMassSetCapsuleTotal(m, total_mass, direction, radius, length); }
 }  // extern "C"

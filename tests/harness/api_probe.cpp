@@ -198,6 +198,17 @@ int main() {
     dVector3 sb3 = {2, 1, 1}, sb4 = {3, 2, (dReal)1.5};
     dClosestLineSegmentPoints(sa1, sa2, sb3, sb4, c1, c2); pr("clsp3", c1, 3); pr("clsp4", c2, 3); }
   { char fmt[] = "%8.3f "; dPrintMatrix(Rw, 3, 3, fmt, stdout); }
+  // dMassSetTrimesh / Total on the rotated open mesh above and on a closed tetrahedron
+  { dMass mt; dMassSetTrimesh(&mt, (dReal)2.5, tm); pr1("mtm_mass", mt.mass); pr("mtm_c", mt.c, 3); pr("mtm_I", mt.I, 12);
+    static float qv[4 * 3] = {0, 0, 0, (float)1.1, 0, 0, 0, (float)0.9, 0, (float)0.2, (float)0.3, (float)1.3};
+    static dTriIndex qi[4 * 3] = {0, 2, 1, 0, 1, 3, 1, 2, 3, 2, 0, 3};
+    dTriMeshDataID qd = dGeomTriMeshDataCreate();
+    dGeomTriMeshDataBuildSingle(qd, qv, 3 * sizeof(float), 4, qi, 12, 3 * sizeof(dTriIndex));
+    dGeomID qm = dCreateTriMesh(0, qd, 0, 0, 0);
+    dGeomSetPosition(qm, (dReal)-0.4, (dReal)0.25, (dReal)0.6); dGeomSetQuaternion(qm, qw);
+    dMassSetTrimesh(&mt, (dReal)1.7, qm); pr1("mtet_mass", mt.mass); pr("mtet_c", mt.c, 3); pr("mtet_I", mt.I, 12);
+    dMassSetTrimeshTotal(&mt, (dReal)3.2, qm); pr1("mtett_mass", mt.mass); pr("mtett_I", mt.I, 12);
+    dGeomDestroy(qm); dGeomTriMeshDataDestroy(qd); }
   printf("thr %d\n", dAllocateODEDataForThread(0xffffffffu));
   printf("wsm %d %d %d\n", dWorldUseSharedWorkingMemory(w, 0), dWorldSetStepMemoryReservationPolicy(w, 0), dWorldSetStepMemoryManager(w, 0));
   dWorldCleanupWorkingMemory(w);
