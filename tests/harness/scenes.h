@@ -750,6 +750,18 @@ static inline void scene_transforms(SceneWorld &sw, int w) {
   dGeomSetPosition(rt, (dReal)0.3, (dReal)0.2, (dReal)0.15);
 }
 
+// the same with ray geoms in the space (drop-in path only): ray x transform and transform x ray in both callback orders
+static inline void scene_transforms_rays(SceneWorld &sw, int w) {
+  scene_transforms(sw, w);
+  xs32 rng(sw.seed ^ 0x5A17Eu);
+  for (int i = 0; i < 8; i++) {
+    dGeomID r = scene_add_geom(sw, dCreateRay(sw.space, rng.uni(2, 7)));
+    if (i < 5) dGeomRaySet(r, rng.uni(-1.2, 1.2), rng.uni(-1.2, 1.2), (dReal)6, rng.uni(-0.2, 0.2), rng.uni(-0.2, 0.2), -1);
+    else dGeomRaySet(r, (dReal)-3, rng.uni(-1, 1), rng.uni(0.1, 0.6), 1, rng.uni(-0.2, 0.2), rng.uni(-0.05, 0.1));
+    if (i & 1) dGeomRaySetClosestHit(r, 1);
+  }
+}
+
 static inline void scene_cylspheres(SceneWorld &sw, int w) { scene_cylmix_impl(sw, w, false); }
 static inline void scene_cylmix(SceneWorld &sw, int w) { scene_cylmix_impl(sw, w, true); }
 
@@ -1098,6 +1110,7 @@ static inline int scene_build(const char *name_in, SceneWorld &sw, int w, SceneP
   if (!strcmp(name, "pus")) { scene_pus(sw, w); return 0; }
   if (!strcmp(name, "kinematic")) { scene_kinematic(sw, w); return 0; }
   if (!strcmp(name, "nulljoint")) { scene_nulljoint(sw, w); return 0; }
+  if (!strcmp(name, "transforms_rays")) { scene_transforms_rays(sw, w); return 0; }
   if (!strcmp(name, "transforms")) { scene_transforms(sw, w); return 0; }
   if (!strcmp(name, "cylspheres")) { scene_cylspheres(sw, w); return 0; }
   if (!strcmp(name, "cylmix")) { scene_cylmix(sw, w); return 0; }
