@@ -1,0 +1,657 @@
+// ob_kern_collide.cu — broadphase + narrowphase kernels of the batched path (k_collide, k_collide_tile), the
+// one-pair kernel behind dCollide and the dSpaceCollide2 filter kernel.
+#include "ob_backend_cuda.h"
+
+// ------------------------------------------------------------------------------------
+// MESH: the batch has trimesh geoms (narrowphase with the BVH colliders, up to OB_MAXC_LOCAL contacts per
+// pair); otherwise the primitive-only narrowphase with 8 contact slots per pair (box-box emits at most 8)
+template <bool MESH, bool XF>
+__global__ void __launch_bounds__(OB_THREADS) k_collide(ObBatchDev d) {
+  constexpr int CGCAP = MESH ? OB_MAXC_LOCAL : 8;
+  extern __shared__ __align__(16) unsigned char smem[];
+  const CollideSmem L = collide_smem(d.NG, d.NP);
+  ObPose *s_pose = (ObPose *)(smem + L.pose);
+  real *s_aabb = (real *)(smem + L.aabb);
+  ObCellBox *s_cb = (ObCellBox *)(smem + L.cb);
+  int *s_gid = (int *)(smem + L.gid);
+  int *s_body = (int *)(smem + L.body);
+  uint32_t *s_cat = (uint32_t *)(smem + L.cat);
+  uint32_t *s_col = (uint32_t *)(smem + L.col);
+  int *s_en = (int *)(smem + L.en);
+  int *s_hr = (int *)(smem + L.hr);
+  int *s_br = (int *)(smem + L.br);
+  int *s_walk_of = (int *)(smem + L.walk_of);
+  float *s_sapkey = (float *)(smem + L.sapkey);
+  int *s_sapinit = (int *)(smem + L.sapinit);
+  int *s_sappos = (int *)(smem + L.sappos);
+  int *s_sapwalk = (int *)(smem + L.sapwalk);
+  ObPairKey *s_key = (ObPairKey *)(smem + L.key);
+  int2 *s_o12 = (int2 *)(smem + L.o12);
+  int2 *s_sorted = (int2 *)(smem + L.sorted);
+  int *s_misc = (int *)(smem + L.misc);   // [0]=npairs raw, [1]=nh, [2]=nbig, [3]=contact base, [8..40]=scan scratch
+  const int tid = threadIdx.x, nt = blockDim.x;
+
+  for (int w = d.wbeg + blockIdx.x; w < d.wend; w += gridDim.x) {
+    ObWorld &W = d.world[w];
+    const int ng = W.ng;
+    const ObGeom *geoms = d.geom + (size_t)w * d.NG;
+    const ObBodyDyn *bd = d.bdyn + (size_t)w * d.NB;
+    const int *glist = d.glist + (size_t)w * d.NG;
+    if (tid < 8) s_misc[tid] = 0;
+    const int stype = W.space_type;
+    // SAP: cleanGeoms appends the DirtyList to the GeomList (collision_sapspace.cpp:394-423), so the walk
+    // order is glist rotated by sap_ndirty; the cleaned order is written back below
+    const int rot = stype == OB_SPACE_SAP ? W.sap_ndirty : 0;
+    int ax0 = 0, ax1 = 2, ax2 = 4;
+    if (stype == OB_SPACE_SAP) ob_sap_axes(W.sap_axes, &ax0, &ax1, &ax2);
+    // (1) pose, AABB, cell box per geom in walk order
+    for (int i = tid; i < ng; i += nt) {
+      int gi = glist[i + rot < ng ? i + rot : i + rot - ng];
+      const ObGeom g = geoms[gi];
+      s_gid[i] = gi; s_body[i] = g.body; s_cat[i] = g.cat; s_col[i] = g.col;
+      s_walk_of[gi] = i;
+      s_en[i] = (g.flags & OB_GEOM_ENABLED) && !(g.flags & OB_GEOM_ZERO_SIZED);
+      ObPose p;
+      geom_pose_dev(g, bd, &p);
+      s_pose[i] = p;
+      real ab[6];
+      ob_aabb(p, ab, d.meshes);
+      for (int k = 0; k < 6; k++) s_aabb[6 * i + k] = ab[k];
+      ObCellBox cb;
+      cb.level = 0;
+      for (int k = 0; k < 6; k++) cb.db[k] = 0;
+      if (stype == OB_SPACE_HASH) ob_hash_cellbox(ab, W.hash_minlevel, W.hash_maxlevel, &cb);
+      else if (stype == OB_SPACE_SAP && ab[ax0 + 1] == OB_INF) cb.level = OB_LEVEL_BIG;   // TmpInfGeomList (:446-449)
+      s_cb[i] = cb;
+    }
+    __syncthreads();
+    if (stype == OB_SPACE_SAP) {
+      int *gl = d.glist + (size_t)w * d.NG;
+      for (int i = tid; i < ng; i += nt) gl[i] = s_gid[i];
+      if (tid == 0) W.sap_ndirty = 0;
+    }
+    // (2) ranks among hashed / big geoms in walk order (SAP: finite / infinite on axis 0)
+    for (int i = tid; i < ng; i += nt) {
+      int h = 0, b = 0;
+      for (int j = 0; j < i; j++)
+        if (s_en[j]) { if (s_cb[j].level == OB_LEVEL_BIG) b++; else h++; }
+      s_hr[i] = h; s_br[i] = b;
+      if (s_en[i] && s_cb[i].level != OB_LEVEL_BIG) { s_sapwalk[h] = i; s_sapkey[h] = (float)s_aabb[6 * i + ax0]; }
+      if (i == ng - 1) {
+        if (s_en[i]) { if (s_cb[i].level == OB_LEVEL_BIG) b++; else h++; }
+        s_misc[1] = h; s_misc[2] = b;
+      }
+    }
+    __syncthreads();
+    const int nh = s_misc[1], nbig = s_misc[2];
+    // (2b) SAP: sorted position of every finite geom = RadixSort's output order (ob_broad.h)
+    if (stype == OB_SPACE_SAP && nh > 0) {
+      int *st = d.sapstate + (size_t)w * (d.NG + 3);
+      const int nbk = nh + 1;                       // + FLT_MAX sentinel, element index nh
+      const bool valid = st[0] != 0 && st[1] == nbk;
+      if (tid == 0) s_sapkey[nh] = 3.402823466e+38f;
+      for (int p = tid; p < nbk; p += nt) { if (valid) s_sapinit[st[2 + p]] = p; else s_sapinit[p] = p; }
+      __syncthreads();
+      for (int p = 1 + tid; p < nbk; p += nt) {
+        const int e = valid ? st[2 + p] : p, e0 = valid ? st[1 + p] : p - 1;
+        if (s_sapkey[e] < s_sapkey[e0]) s_misc[4] = 1;   // not already sorted
+      }
+      __syncthreads();
+      const bool unsorted = s_misc[4] != 0;
+      for (int t = tid; t < nbk; t += nt) {
+        int pos = s_sapinit[t];
+        if (unsorted) {
+          const uint32_t ot = ob_sap_keyorder(s_sapkey[t]);
+          pos = 0;
+          for (int u = 0; u < nbk; u++)
+            if (u != t && ob_sap_precedes(ob_sap_keyorder(s_sapkey[u]), ot, s_sapinit[u], s_sapinit[t])) pos++;
+        }
+        s_sappos[t] = pos;
+      }
+      __syncthreads();
+      if (unsorted) for (int t = tid; t < nbk; t += nt) st[2 + s_sappos[t]] = t;
+      if (tid == 0) { st[1] = nbk; if (unsorted) st[0] = 1; else if (!valid) st[0] = 0; }
+    }
+    // (3) candidate pairs: the space's filter + the sequence key of the pair's callback
+    for (int idx = tid; idx < ng * ng; idx += nt) {
+      int a = idx / ng, b = idx - a * ng;
+      if (a >= b || !s_en[a] || !s_en[b]) continue;
+      ObPairKey key;
+      int first_is_a;
+      if (stype == OB_SPACE_HASH) {
+        if (!ob_aabb_pair_filter(s_body[a], s_body[b], s_cat[a], s_col[a], s_cat[b], s_col[b], s_aabb + 6 * a, s_aabb + 6 * b))
+          continue;
+        if (!ob_hash_pair_key(a, b, s_cb[a], s_cb[b], s_hr[a], s_hr[b], s_br[a], s_br[b], nh, nbig, &key, &first_is_a)) continue;
+      } else if (stype == OB_SPACE_SAP) {
+        if (!ob_pair_filter_noaabb(s_body[a], s_body[b], s_cat[a], s_col[a], s_cat[b], s_col[b])) continue;
+        const bool ia = s_cb[a].level == OB_LEVEL_BIG, ib = s_cb[b].level == OB_LEVEL_BIG;
+        for (int k = 0; k < 7; k++) key.k[k] = 0;
+        if (!ia && !ib) {
+          const int pa = s_sappos[s_hr[a]], pb = s_sappos[s_hr[b]];
+          first_is_a = pa < pb;
+          const int K = first_is_a ? a : b, J = first_is_a ? b : a;
+          if (!ob_sap_sweep_test(s_sapkey[s_hr[J]], s_aabb + 6 * K, s_aabb + 6 * J, ax0, ax1, ax2)) continue;
+          key.k[1] = first_is_a ? pa : pb; key.k[2] = first_is_a ? pb : pa;
+        } else if (ia && ib) { key.k[0] = 1; key.k[1] = s_br[a]; key.k[3] = s_br[b]; first_is_a = 1; }
+        else { key.k[0] = 1; key.k[1] = ia ? s_br[a] : s_br[b]; key.k[2] = 1; key.k[3] = ia ? s_hr[b] : s_hr[a]; first_is_a = ia; }
+      } else {   // dxSimpleSpace::collide (collision_space.cpp:247-268): nested walk of the list
+        if (!ob_aabb_pair_filter(s_body[a], s_body[b], s_cat[a], s_col[a], s_cat[b], s_col[b], s_aabb + 6 * a, s_aabb + 6 * b))
+          continue;
+        for (int k = 0; k < 7; k++) key.k[k] = 0;
+        key.k[1] = a; key.k[2] = b; first_is_a = 1;
+      }
+      int slot = atomicAdd(&s_misc[0], 1);
+      if (slot < d.NP) {
+        s_key[slot] = key;
+        s_o12[slot] = first_is_a ? make_int2(s_gid[a], s_gid[b]) : make_int2(s_gid[b], s_gid[a]);
+      }
+    }
+    __syncthreads();
+    int np = s_misc[0];
+    if (np > d.NP) { np = d.NP; if (tid == 0) atomicOr(&W.status, OB_ERR_PAIR_OVERFLOW); }
+    // (4) order: rank of every pair = number of pairs with a smaller key (keys are unique)
+    int *gpairs = d.pairs + (size_t)w * d.NP * 2;
+    for (int p = tid; p < np; p += nt) {
+      const ObPairKey kp = s_key[p];
+      int rank = 0;
+      for (int q = 0; q < np; q++) rank += ob_key_less(s_key[q], kp) ? 1 : 0;
+      s_sorted[rank] = s_o12[p];
+      gpairs[2 * rank] = s_o12[p].x; gpairs[2 * rank + 1] = s_o12[p].y;
+    }
+    __syncthreads();
+    // (5) narrowphase per pair in callback order, ordered compaction into contact joints
+    const ObPolicy pol = d.policy[0];
+    ObContact *cout = d.contacts + (size_t)w * d.NC;
+    const int maxc = pol.max_contacts > CGCAP ? CGCAP : pol.max_contacts;
+    for (int base = 0; base < np; base += nt) {
+      int p = base + tid;
+      ObCg cg[CGCAP];
+      int n = 0, o1 = 0, o2 = 0;
+      if (p < np) {
+        o1 = s_sorted[p].x; o2 = s_sorted[p].y;
+        bool connected = false;
+        if (pol.skip_if_connected && d.NJ) {   // dAreConnectedExcluding(b1, b2, dJointTypeContact), ode.cpp:1529-1537
+          const int b1 = geoms[o1].body, b2 = geoms[o2].body;
+          if (b1 >= 0 && b2 >= 0) {
+            const unsigned short *ps = d.padjstart + (size_t)w * (d.NB + 1), *pa = d.padj + (size_t)w * 2 * d.NJ;
+            const ObJoint *pj = d.joint + (size_t)w * d.NJ;
+            for (int k = ps[b1]; k < ps[b1 + 1]; k++) {
+              const ObJoint &jj = pj[pa[k]];
+              const int other = jj.b1 == b1 ? jj.b2 : jj.b1;
+              if (other == b2) connected = true;
+            }
+          }
+        }
+        int swapped;
+        int bverr = 0;
+        if (!connected) n = ob_collide_pair_sel_t<MESH, CGCAP, XF>(&s_pose[s_walk_of[o1]], &s_pose[s_walk_of[o2]], maxc, cg, &swapped, d.meshes, &bverr);
+        if (bverr) atomicOr(&W.status, OB_ERR_BVH_STACK);
+      }
+      int total;
+      int off = block_excl_scan(n, s_misc + 8, &total);
+      int cbase = s_misc[3];
+      for (int k = 0; k < n; k++) {
+        int j = cbase + off + k;
+        if (j < d.NC) {
+          ObContact c;
+          for (int e = 0; e < 3; e++) { c.pos[e] = cg[k].pos[e]; c.normal[e] = cg[k].normal[e]; }
+          c.depth = cg[k].depth; c.g1 = o1; c.g2 = o2; c.side1 = cg[k].side1; c.side2 = cg[k].side2; c.policy = 0;
+          cout[j] = c;
+        }
+      }
+      __syncthreads();
+      if (tid == 0) s_misc[3] = cbase + total;
+      __syncthreads();
+    }
+    if (tid == 0) {
+      int nc = s_misc[3];
+      if (nc > d.NC) { nc = d.NC; atomicOr(&W.status, OB_ERR_CONTACT_OVERFLOW); }
+      d.ncontacts[w] = nc;
+      d.npairs[w] = np;
+      atomicAdd(&d.counters->pairs, (unsigned long long)np);
+    }
+    __syncthreads();
+  }
+}
+
+#define OB_TILE_WPC 8   // worlds per CTA of k_collide_tile
+struct CollideTileSmem { size_t np, cb, first, scan, cls, perm, stoff, cnt, stage, total; };
+__host__ __device__ inline CollideTileSmem collide_tile_smem(int NG, int NP, int WPC, int stage_cap) {
+  CollideTileSmem s; size_t o = 0;
+  s.np = o; o = ob_al16(o + sizeof(int) * (WPC + 1));
+  s.cb = o; o = ob_al16(o + sizeof(int) * WPC);
+  s.first = o; o = ob_al16(o + sizeof(int) * WPC);
+  s.scan = o; o = ob_al16(o + sizeof(int) * 40);
+  s.cls = o; o = ob_al16(o + sizeof(int) * 8);
+  s.perm = o; o = ob_al16(o + sizeof(unsigned short) * WPC * NP);
+  s.stoff = o; o = ob_al16(o + sizeof(unsigned short) * WPC * NP);
+  s.cnt = o; o = ob_al16(o + (size_t)WPC * NP);
+  s.stage = o; o = ob_al16(o + sizeof(ObCg) * stage_cap);
+  s.total = o;
+  return s;
+}
+// k_collide_tile: the same products as k_collide for batches of SMALL worlds (a handful of geoms, e.g. the buggies of
+// BASELINE.json configs[2]).  With one warp per world the narrowphase runs on 5-9 lanes of 32 (ncu, r01z: 89 % of the
+// kernel's warp instructions execute with <= 4 active threads).  Here a CTA takes WPC worlds: every warp stages its
+// own world (poses, AABBs, ordered pair list: phases 1-4, warp-synchronous), then the pairs of all WPC worlds are
+// pooled, grouped by collider class so that a warp runs ONE collider on full lanes, and their contacts go through a
+// shared-memory staging area into the per-world contact arrays in callback order (phase 5).
+template <bool MESH, bool XF, int WPC>
+__global__ void __launch_bounds__(32 * WPC) k_collide_tile(ObBatchDev d, int stage_cap) {
+  constexpr int CGCAP = MESH ? OB_MAXC_LOCAL : 8;
+  extern __shared__ __align__(16) unsigned char smem[];
+  const CollideSmem L = collide_smem(d.NG, d.NP);
+  const int warp = threadIdx.x >> 5;
+  unsigned char *sm = smem + (size_t)warp * L.total;
+  ObPose *s_pose = (ObPose *)(sm + L.pose);
+  real *s_aabb = (real *)(sm + L.aabb);
+  ObCellBox *s_cb = (ObCellBox *)(sm + L.cb);
+  int *s_gid = (int *)(sm + L.gid);
+  int *s_body = (int *)(sm + L.body);
+  uint32_t *s_cat = (uint32_t *)(sm + L.cat);
+  uint32_t *s_col = (uint32_t *)(sm + L.col);
+  int *s_en = (int *)(sm + L.en);
+  int *s_hr = (int *)(sm + L.hr);
+  int *s_br = (int *)(sm + L.br);
+  int *s_walk_of = (int *)(sm + L.walk_of);
+  float *s_sapkey = (float *)(sm + L.sapkey);
+  int *s_sapinit = (int *)(sm + L.sapinit);
+  int *s_sappos = (int *)(sm + L.sappos);
+  int *s_sapwalk = (int *)(sm + L.sapwalk);
+  ObPairKey *s_key = (ObPairKey *)(sm + L.key);
+  int2 *s_o12 = (int2 *)(sm + L.o12);
+  int2 *s_sorted = (int2 *)(sm + L.sorted);
+  int *s_misc = (int *)(sm + L.misc);   // [0]=npairs raw, [1]=nh, [2]=nbig, [3]=contact base, [8..40]=scan scratch
+  const int tid = threadIdx.x & 31, nt = 32;
+  // CTA-wide area behind the WPC per-world slices
+  const CollideTileSmem T = collide_tile_smem(d.NG, d.NP, WPC, stage_cap);
+  unsigned char *cm = smem + (size_t)WPC * L.total;
+  int *c_np = (int *)(cm + T.np);                    // [WPC+1] prefix of the worlds' pair counts
+  int *c_cb = (int *)(cm + T.cb);                    // [WPC] contacts written so far per world
+  int *c_first = (int *)(cm + T.first);              // [WPC] scan value at a world's first pair of the chunk
+  int *c_scan = (int *)(cm + T.scan);                // [40] block_excl_scan scratch
+  int *c_cls = (int *)(cm + T.cls);                  // [8] pairs per collider class -> class starts -> fill cursors; [7] = staged contacts
+  unsigned short *c_perm = (unsigned short *)(cm + T.perm);     // [WPC*NP] class-grouped order -> pooled pair
+  unsigned short *c_stoff = (unsigned short *)(cm + T.stoff);   // [WPC*NP] staging offset of a pooled pair
+  unsigned char *c_n = cm + T.cnt;                              // [WPC*NP] contacts of a pooled pair
+  ObCg *c_stage = (ObCg *)(cm + T.stage);                       // [stage_cap]
+
+  for (int wb = d.wbeg + blockIdx.x * WPC; wb < d.wend; wb += gridDim.x * WPC) {
+    const int w = wb + warp;
+    const bool valid = w < d.wend;
+    int np = 0;
+    if (valid) {
+    ObWorld &W = d.world[w];
+    const int ng = W.ng;
+    const ObGeom *geoms = d.geom + (size_t)w * d.NG;
+    const ObBodyDyn *bd = d.bdyn + (size_t)w * d.NB;
+    const int *glist = d.glist + (size_t)w * d.NG;
+    if (tid < 8) s_misc[tid] = 0;
+    const int stype = W.space_type;
+    // SAP: cleanGeoms appends the DirtyList to the GeomList (collision_sapspace.cpp:394-423), so the walk
+    // order is glist rotated by sap_ndirty; the cleaned order is written back below
+    const int rot = stype == OB_SPACE_SAP ? W.sap_ndirty : 0;
+    int ax0 = 0, ax1 = 2, ax2 = 4;
+    if (stype == OB_SPACE_SAP) ob_sap_axes(W.sap_axes, &ax0, &ax1, &ax2);
+    // (1) pose, AABB, cell box per geom in walk order
+    for (int i = tid; i < ng; i += nt) {
+      int gi = glist[i + rot < ng ? i + rot : i + rot - ng];
+      const ObGeom g = geoms[gi];
+      s_gid[i] = gi; s_body[i] = g.body; s_cat[i] = g.cat; s_col[i] = g.col;
+      s_walk_of[gi] = i;
+      s_en[i] = (g.flags & OB_GEOM_ENABLED) && !(g.flags & OB_GEOM_ZERO_SIZED);
+      ObPose p;
+      geom_pose_dev(g, bd, &p);
+      s_pose[i] = p;
+      real ab[6];
+      ob_aabb(p, ab, d.meshes);
+      for (int k = 0; k < 6; k++) s_aabb[6 * i + k] = ab[k];
+      ObCellBox cb;
+      cb.level = 0;
+      for (int k = 0; k < 6; k++) cb.db[k] = 0;
+      if (stype == OB_SPACE_HASH) ob_hash_cellbox(ab, W.hash_minlevel, W.hash_maxlevel, &cb);
+      else if (stype == OB_SPACE_SAP && ab[ax0 + 1] == OB_INF) cb.level = OB_LEVEL_BIG;   // TmpInfGeomList (:446-449)
+      s_cb[i] = cb;
+    }
+    __syncwarp();
+    if (stype == OB_SPACE_SAP) {
+      int *gl = d.glist + (size_t)w * d.NG;
+      for (int i = tid; i < ng; i += nt) gl[i] = s_gid[i];
+      if (tid == 0) W.sap_ndirty = 0;
+    }
+    // (2) ranks among hashed / big geoms in walk order (SAP: finite / infinite on axis 0)
+    for (int i = tid; i < ng; i += nt) {
+      int h = 0, b = 0;
+      for (int j = 0; j < i; j++)
+        if (s_en[j]) { if (s_cb[j].level == OB_LEVEL_BIG) b++; else h++; }
+      s_hr[i] = h; s_br[i] = b;
+      if (s_en[i] && s_cb[i].level != OB_LEVEL_BIG) { s_sapwalk[h] = i; s_sapkey[h] = (float)s_aabb[6 * i + ax0]; }
+      if (i == ng - 1) {
+        if (s_en[i]) { if (s_cb[i].level == OB_LEVEL_BIG) b++; else h++; }
+        s_misc[1] = h; s_misc[2] = b;
+      }
+    }
+    __syncwarp();
+    const int nh = s_misc[1], nbig = s_misc[2];
+    // (2b) SAP: sorted position of every finite geom = RadixSort's output order (ob_broad.h)
+    if (stype == OB_SPACE_SAP && nh > 0) {
+      int *st = d.sapstate + (size_t)w * (d.NG + 3);
+      const int nbk = nh + 1;                       // + FLT_MAX sentinel, element index nh
+      const bool valid = st[0] != 0 && st[1] == nbk;
+      if (tid == 0) s_sapkey[nh] = 3.402823466e+38f;
+      for (int p = tid; p < nbk; p += nt) { if (valid) s_sapinit[st[2 + p]] = p; else s_sapinit[p] = p; }
+      __syncwarp();
+      for (int p = 1 + tid; p < nbk; p += nt) {
+        const int e = valid ? st[2 + p] : p, e0 = valid ? st[1 + p] : p - 1;
+        if (s_sapkey[e] < s_sapkey[e0]) s_misc[4] = 1;   // not already sorted
+      }
+      __syncwarp();
+      const bool unsorted = s_misc[4] != 0;
+      for (int t = tid; t < nbk; t += nt) {
+        int pos = s_sapinit[t];
+        if (unsorted) {
+          const uint32_t ot = ob_sap_keyorder(s_sapkey[t]);
+          pos = 0;
+          for (int u = 0; u < nbk; u++)
+            if (u != t && ob_sap_precedes(ob_sap_keyorder(s_sapkey[u]), ot, s_sapinit[u], s_sapinit[t])) pos++;
+        }
+        s_sappos[t] = pos;
+      }
+      __syncwarp();
+      if (unsorted) for (int t = tid; t < nbk; t += nt) st[2 + s_sappos[t]] = t;
+      if (tid == 0) { st[1] = nbk; if (unsorted) st[0] = 1; else if (!valid) st[0] = 0; }
+    }
+    // (3) candidate pairs: the space's filter + the sequence key of the pair's callback
+    for (int idx = tid; idx < ng * ng; idx += nt) {
+      int a = idx / ng, b = idx - a * ng;
+      if (a >= b || !s_en[a] || !s_en[b]) continue;
+      ObPairKey key;
+      int first_is_a;
+      if (stype == OB_SPACE_HASH) {
+        if (!ob_aabb_pair_filter(s_body[a], s_body[b], s_cat[a], s_col[a], s_cat[b], s_col[b], s_aabb + 6 * a, s_aabb + 6 * b))
+          continue;
+        if (!ob_hash_pair_key(a, b, s_cb[a], s_cb[b], s_hr[a], s_hr[b], s_br[a], s_br[b], nh, nbig, &key, &first_is_a)) continue;
+      } else if (stype == OB_SPACE_SAP) {
+        if (!ob_pair_filter_noaabb(s_body[a], s_body[b], s_cat[a], s_col[a], s_cat[b], s_col[b])) continue;
+        const bool ia = s_cb[a].level == OB_LEVEL_BIG, ib = s_cb[b].level == OB_LEVEL_BIG;
+        for (int k = 0; k < 7; k++) key.k[k] = 0;
+        if (!ia && !ib) {
+          const int pa = s_sappos[s_hr[a]], pb = s_sappos[s_hr[b]];
+          first_is_a = pa < pb;
+          const int K = first_is_a ? a : b, J = first_is_a ? b : a;
+          if (!ob_sap_sweep_test(s_sapkey[s_hr[J]], s_aabb + 6 * K, s_aabb + 6 * J, ax0, ax1, ax2)) continue;
+          key.k[1] = first_is_a ? pa : pb; key.k[2] = first_is_a ? pb : pa;
+        } else if (ia && ib) { key.k[0] = 1; key.k[1] = s_br[a]; key.k[3] = s_br[b]; first_is_a = 1; }
+        else { key.k[0] = 1; key.k[1] = ia ? s_br[a] : s_br[b]; key.k[2] = 1; key.k[3] = ia ? s_hr[b] : s_hr[a]; first_is_a = ia; }
+      } else {   // dxSimpleSpace::collide (collision_space.cpp:247-268): nested walk of the list
+        if (!ob_aabb_pair_filter(s_body[a], s_body[b], s_cat[a], s_col[a], s_cat[b], s_col[b], s_aabb + 6 * a, s_aabb + 6 * b))
+          continue;
+        for (int k = 0; k < 7; k++) key.k[k] = 0;
+        key.k[1] = a; key.k[2] = b; first_is_a = 1;
+      }
+      int slot = atomicAdd(&s_misc[0], 1);
+      if (slot < d.NP) {
+        s_key[slot] = key;
+        s_o12[slot] = first_is_a ? make_int2(s_gid[a], s_gid[b]) : make_int2(s_gid[b], s_gid[a]);
+      }
+    }
+    __syncwarp();
+    np = s_misc[0];
+    if (np > d.NP) { np = d.NP; if (tid == 0) atomicOr(&W.status, OB_ERR_PAIR_OVERFLOW); }
+    // (4) order: rank of every pair = number of pairs with a smaller key (keys are unique)
+    int *gpairs = d.pairs + (size_t)w * d.NP * 2;
+    for (int p = tid; p < np; p += nt) {
+      const ObPairKey kp = s_key[p];
+      int rank = 0;
+      for (int q = 0; q < np; q++) rank += ob_key_less(s_key[q], kp) ? 1 : 0;
+      s_sorted[rank] = s_o12[p];
+      gpairs[2 * rank] = s_o12[p].x; gpairs[2 * rank + 1] = s_o12[p].y;
+    }
+    __syncwarp();
+    }   // valid
+    // (5) narrowphase over the pooled pairs of the CTA's worlds
+    const ObPolicy pol = d.policy[0];
+    const int maxc = pol.max_contacts > CGCAP ? CGCAP : pol.max_contacts;
+    const int nthr = 32 * WPC;
+    if (tid == 0) c_np[warp + 1] = np;
+    if (threadIdx.x < 8) c_cls[threadIdx.x] = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) { c_np[0] = 0; for (int v = 0; v < WPC; v++) { c_np[v + 1] += c_np[v]; c_cb[v] = 0; } }
+    __syncthreads();
+    const int total = c_np[WPC];
+    // (5a) group the pooled pairs by collider class (order inside a class is irrelevant: results are staged)
+    for (int f = threadIdx.x; f < total; f += nthr) {
+      int v = 0;
+      while (f >= c_np[v + 1]) v++;
+      const unsigned char *smv = smem + (size_t)v * L.total;
+      const int2 o12 = ((const int2 *)(smv + L.sorted))[f - c_np[v]];
+      const ObGeom *gv = d.geom + (size_t)(wb + v) * d.NG;
+      const int t1 = gv[o12.x].type, t2 = gv[o12.y].type;
+      const int lo = t1 < t2 ? t1 : t2, hi = t1 < t2 ? t2 : t1;
+      int cls = hi == OB_GEOM_TRIMESH ? (lo == OB_GEOM_SPHERE ? 1 : (lo == OB_GEOM_BOX ? 2 : 3)) : ((lo == OB_GEOM_BOX && hi == OB_GEOM_BOX) ? 4 : 5);
+      if (pol.skip_if_connected && d.NJ && gv[o12.x].body >= 0 && gv[o12.y].body >= 0) cls = 0;   // mostly jointed pairs: the cheap test
+      c_n[f] = (unsigned char)cls;
+      atomicAdd(&c_cls[cls], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { int run = 0; for (int k = 0; k < 7; k++) { const int c = c_cls[k]; c_cls[k] = run; run += c; } c_cls[7] = 0; }
+    __syncthreads();
+    for (int f = threadIdx.x; f < total; f += nthr) c_perm[atomicAdd(&c_cls[c_n[f]], 1)] = (unsigned short)f;
+    __syncthreads();
+    // (5b) one pair per thread in class order; contacts into the staging area
+    for (int s0 = 0; s0 < total; s0 += nthr) {
+      const int sidx = s0 + threadIdx.x;
+      if (sidx < total) {
+        const int f = c_perm[sidx];
+        int v = 0;
+        while (f >= c_np[v + 1]) v++;
+        const int wv = wb + v;
+        const unsigned char *smv = smem + (size_t)v * L.total;
+        const int2 o12 = ((const int2 *)(smv + L.sorted))[f - c_np[v]];
+        const ObPose *pose_v = (const ObPose *)(smv + L.pose);
+        const int *walk_v = (const int *)(smv + L.walk_of);
+        const ObGeom *gv = d.geom + (size_t)wv * d.NG;
+        ObCg cg[CGCAP];
+        int n = 0;
+        bool connected = false;
+        if (pol.skip_if_connected && d.NJ) {   // dAreConnectedExcluding(b1, b2, dJointTypeContact), ode.cpp:1529-1537
+          const int b1 = gv[o12.x].body, b2 = gv[o12.y].body;
+          if (b1 >= 0 && b2 >= 0) {
+            const unsigned short *ps = d.padjstart + (size_t)wv * (d.NB + 1), *pa = d.padj + (size_t)wv * 2 * d.NJ;
+            const ObJoint *pj = d.joint + (size_t)wv * d.NJ;
+            for (int k = ps[b1]; k < ps[b1 + 1]; k++) {
+              const ObJoint &jj = pj[pa[k]];
+              const int other = jj.b1 == b1 ? jj.b2 : jj.b1;
+              if (other == b2) connected = true;
+            }
+          }
+        }
+        int swapped, bverr = 0;
+        if (!connected) n = ob_collide_pair_sel_t<MESH, CGCAP, XF>(&pose_v[walk_v[o12.x]], &pose_v[walk_v[o12.y]], maxc, cg, &swapped, d.meshes, &bverr);
+        if (bverr) atomicOr(&d.world[wv].status, OB_ERR_BVH_STACK);
+        int off = 0;
+        if (n > 0) {
+          off = atomicAdd(&c_cls[7], n);
+          if (off + n > stage_cap) { atomicOr(&d.world[wv].status, OB_ERR_CONTACT_OVERFLOW); n = 0; }
+        }
+        for (int k = 0; k < n; k++) c_stage[off + k] = cg[k];
+        c_stoff[f] = (unsigned short)off;
+        c_n[f] = (unsigned char)n;
+      }
+    }
+    __syncthreads();
+    // (5c) ordered compaction: pooled pairs in (world, callback) order, contacts in pair order
+    for (int base = 0; base < total; base += nthr) {
+      const int f = base + threadIdx.x;
+      const int n = f < total ? c_n[f] : 0;
+      int tot;
+      const int off = block_excl_scan(n, c_scan, &tot);
+      int v = 0;
+      if (f < total) {
+        while (f >= c_np[v + 1]) v++;
+        const int firstf = c_np[v] > base ? c_np[v] : base;
+        if (f == firstf) c_first[v] = off;
+      }
+      __syncthreads();
+      int j0 = 0;
+      if (f < total) {
+        j0 = c_cb[v] + off - c_first[v];
+        const unsigned char *smv = smem + (size_t)v * L.total;
+        const int2 o12 = ((const int2 *)(smv + L.sorted))[f - c_np[v]];
+        ObContact *cout = d.contacts + (size_t)(wb + v) * d.NC;
+        const ObCg *src = c_stage + c_stoff[f];
+        for (int k = 0; k < n; k++) {
+          const int j = j0 + k;
+          if (j < d.NC) {
+            ObContact c;
+            for (int e = 0; e < 3; e++) { c.pos[e] = src[k].pos[e]; c.normal[e] = src[k].normal[e]; }
+            c.depth = src[k].depth; c.g1 = o12.x; c.g2 = o12.y; c.side1 = src[k].side1; c.side2 = src[k].side2; c.policy = 0;
+            cout[j] = c;
+          }
+        }
+      }
+      __syncthreads();
+      if (f < total) {
+        const int lastf = (c_np[v + 1] < base + nthr ? c_np[v + 1] : base + nthr) - 1;
+        if (f == lastf) c_cb[v] = j0 + n;
+      }
+      __syncthreads();
+    }
+    if (tid == 0 && valid) {
+      int nc = c_cb[warp];
+      if (nc > d.NC) { nc = d.NC; atomicOr(&d.world[w].status, OB_ERR_CONTACT_OVERFLOW); }
+      d.ncontacts[w] = nc;
+      d.npairs[w] = np;
+      atomicAdd(&d.counters->pairs, (unsigned long long)np);
+    }
+    __syncthreads();
+  }
+}
+
+
+int obk_collide_setup(ObBackend *b, const cudaDeviceProp &prop, char *err, size_t errlen) {
+  ObBatchDev &d = b->d;
+  b->smem_collide = collide_smem(d.NG, d.NP).total;
+  if (b->smem_collide > (size_t)prop.sharedMemPerBlockOptin) {
+    snprintf(err, errlen, "world does not fit one CTA's shared memory (collide %zu B, limit %zu B)", b->smem_collide, (size_t)prop.sharedMemPerBlockOptin);
+    goto fail;
+  }
+  CK(cudaFuncSetAttribute(k_collide<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_collide));
+  CK(cudaFuncSetAttribute(k_collide<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_collide));
+  CK(cudaFuncSetAttribute(k_collide<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_collide));
+  // small worlds: OB_TILE_WPC worlds per CTA with a pooled, class-grouped narrowphase (k_collide_tile)
+  b->collide_tile = 0;
+  if (d.NG <= 8 && !getenv("OB_COLLIDE_NOTILE")) {
+    long long cap = (long long)OB_TILE_WPC * d.NC;
+    b->tile_stage_cap = (int)(cap < 60000 ? cap : 60000);
+    b->smem_collide_tile = (size_t)OB_TILE_WPC * collide_smem(d.NG, d.NP).total + collide_tile_smem(d.NG, d.NP, OB_TILE_WPC, b->tile_stage_cap).total;
+    if (b->smem_collide_tile <= (size_t)prop.sharedMemPerBlockOptin && (long long)OB_TILE_WPC * d.NP < 65000) {
+      b->collide_tile = 1;
+      CK(cudaFuncSetAttribute(k_collide_tile<false, false, OB_TILE_WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_collide_tile));
+      CK(cudaFuncSetAttribute(k_collide_tile<true, false, OB_TILE_WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_collide_tile));
+      CK(cudaFuncSetAttribute(k_collide_tile<true, true, OB_TILE_WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_collide_tile));
+    }
+  }
+  return 0;
+fail:
+  return -1;
+}
+
+void obk_collide_launch(ObBackend *b, const ObBatchDev &d, int W, int cap, cudaStream_t st) {
+    // CTA width follows the world size: the widest loop is the ng*ng candidate-pair scan
+    int ct = d.NG <= 8 ? 32 : (d.NG <= 20 ? 64 : OB_THREADS);
+    { static const char *e = getenv("OB_COLLIDE_THREADS"); if (e && (atoi(e) == 32 || atoi(e) == 64 || atoi(e) == 96 || atoi(e) == 128)) ct = atoi(e); }
+    const int grid = W < cap ? W : cap;
+    if (b->collide_tile) {
+      const int tiles = (W + OB_TILE_WPC - 1) / OB_TILE_WPC;
+      const int tgrid = tiles < cap ? tiles : cap;
+      // batches with geom transforms run the <MESH = true, XF = true> instantiation (a superset: the mesh arms only fire for trimesh geoms)
+      if (d.any_xf) k_collide_tile<true, true, OB_TILE_WPC><<<tgrid, 32 * OB_TILE_WPC, b->smem_collide_tile, st>>>(d, b->tile_stage_cap);
+      else if (d.nmesh) k_collide_tile<true, false, OB_TILE_WPC><<<tgrid, 32 * OB_TILE_WPC, b->smem_collide_tile, st>>>(d, b->tile_stage_cap);
+      else k_collide_tile<false, false, OB_TILE_WPC><<<tgrid, 32 * OB_TILE_WPC, b->smem_collide_tile, st>>>(d, b->tile_stage_cap);
+    } else if (d.any_xf) k_collide<true, true><<<grid, ct, b->smem_collide, st>>>(d);
+    else if (d.nmesh) k_collide<true, false><<<grid, ct, b->smem_collide, st>>>(d);
+    else k_collide<false, false><<<grid, ct, b->smem_collide, st>>>(d);
+  g_launches++;
+}
+
+// dCollide outside a batch: one pair, one thread (the per-element collider functions are the same
+// ones k_collide runs; there is no host implementation to fall back to)
+struct PairCtx { ObPose *pose; ObCg *cg; int *n; cudaStream_t stream; bool ok; };
+__global__ void k_collide_pair(const ObPose *pose, int flags, ObCg *out, int *n, ObMeshDev m0, ObMeshDev m1) {
+  int swapped, bverr = 0;
+  ObCg cg[OB_MAXC_LOCAL];
+  ObMeshDev meshes[2] = {m0, m1};
+  const int c = ob_collide_pair(pose[0], pose[1], flags, cg, &swapped, meshes, &bverr);
+  for (int i = 0; i < c; i++) out[i] = cg[i];
+  *n = bverr ? -2 : c;
+}
+int obk_collide_pair(const ObPose *a, const ObPose *b, int flags, ObCg *out, const ObMeshDev *meshes2, char *err, size_t errlen) {
+  static PairCtx C = {0, 0, 0, 0, false};
+  if (!C.ok) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { snprintf(err, errlen, "no CUDA device available (this library has no CPU fallback)"); return -1; }
+    if (cudaMallocHost((void **)&C.pose, 2 * sizeof(ObPose)) != cudaSuccess || cudaMallocHost((void **)&C.cg, OB_MAXC_LOCAL * sizeof(ObCg)) != cudaSuccess ||
+        cudaMallocHost((void **)&C.n, sizeof(int)) != cudaSuccess || cudaStreamCreateWithFlags(&C.stream, cudaStreamNonBlocking) != cudaSuccess) {
+      snprintf(err, errlen, "obk_collide_pair: allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return -1;
+    }
+    C.ok = true;
+  }
+  C.pose[0] = *a; C.pose[1] = *b;
+  int maxc = flags & 0xffff;
+  if (maxc > OB_MAXC_LOCAL) maxc = OB_MAXC_LOCAL;
+  ObMeshDev m0, m1;
+  memset(&m0, 0, sizeof m0); memset(&m1, 0, sizeof m1);
+  if (meshes2) { m0 = meshes2[0]; m1 = meshes2[1]; }
+  // page-locked buffers are mapped into the device address space (unified addressing): the kernel reads and writes them directly
+  k_collide_pair<<<1, 1, 0, C.stream>>>(C.pose, (flags & ~0xffff) | maxc, C.cg, C.n, m0, m1);
+  g_launches++;
+  cudaError_t e = cudaStreamSynchronize(C.stream);
+  if (e != cudaSuccess) { snprintf(err, errlen, "k_collide_pair failed: %s", cudaGetErrorString(e)); return -1; }
+  const int n = *C.n;
+  if (n == -2) { snprintf(err, errlen, "trimesh tree deeper than the traversal stack"); return -1; }
+  for (int i = 0; i < n; i++) out[i] = C.cg[i];
+  return n;
+}
+
+// dSpaceCollide2: thread per (space geom, query geom)
+struct ObQueryGeom { ObPose pose; ObMeshDev mesh; int body; uint32_t cat, col; int pad; };
+__global__ void k_collide2(ObBatchDev d, const ObQueryGeom *q, int nq, unsigned char *hit) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ng = d.world[0].ng;
+  if (idx >= ng * nq) return;
+  const int qi = idx / ng, g = idx - qi * ng;
+  const ObGeom G = d.geom[g];
+  unsigned char h = 0;
+  if ((G.flags & OB_GEOM_ENABLED) && !(G.flags & OB_GEOM_ZERO_SIZED)) {   // GEOM_ENABLED(g), collision_kernel.h:75
+    ObPose p;
+    geom_pose_dev(G, d.bdyn, &p);
+    real a[6], b[6];
+    ob_aabb(p, a, d.meshes);
+    ob_aabb(q[qi].pose, b, &q[qi].mesh);
+    h = ob_aabb_pair_filter(G.body, q[qi].body, G.cat, G.col, q[qi].cat, q[qi].col, a, b) ? 1 : 0;
+  }
+  hit[(size_t)qi * d.NG + g] = h;
+}
+int obk_collide2(ObBackend *b, const ObPose *q, const int *qbody, const uint32_t *qcat, const uint32_t *qcol, const ObMeshDev *qmesh,
+                 int nq, unsigned char *hit, char *err, size_t errlen) {
+  cudaSetDevice(b->device);
+  std::vector<ObQueryGeom> hq(nq);
+  for (int i = 0; i < nq; i++) { hq[i].pose = q[i]; hq[i].mesh = qmesh[i]; hq[i].body = qbody[i]; hq[i].cat = qcat[i]; hq[i].col = qcol[i]; hq[i].pad = 0; }
+  ObQueryGeom *dq = 0; unsigned char *dh = 0;
+  const size_t nh = (size_t)nq * b->d.NG;
+  cudaError_t e = cudaMalloc((void **)&dq, sizeof(ObQueryGeom) * nq);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&dh, nh);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dq, hq.data(), sizeof(ObQueryGeom) * nq, cudaMemcpyHostToDevice, b->stream);
+  if (e == cudaSuccess) {
+    k_collide2<<<(unsigned)((nh + 127) / 128), 128, 0, b->stream>>>(b->d, dq, nq, dh);
+    g_launches++;
+    e = cudaMemcpyAsync(hit, dh, nh, cudaMemcpyDeviceToHost, b->stream);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
+  if (dq) cudaFree(dq);
+  if (dh) cudaFree(dh);
+  if (e != cudaSuccess) { snprintf(err, errlen, "k_collide2 failed: %s", cudaGetErrorString(e)); return -1; }
+  return 0;
+}

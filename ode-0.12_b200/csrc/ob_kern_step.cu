@@ -1,0 +1,139 @@
+// ob_kern_step.cu — the quickstep kernels (ob_step_kernel.cuh): tile widths, shared-memory sizes, kernel attributes and
+// the four launches of one step (k_prep, k_sched*, k_sor*, k_post).
+#include "ob_backend_cuda.h"
+#include "ob_step_kernel.cuh"
+
+int obk_stepk_setup(ObBackend *b, const cudaDeviceProp &prop, char *err, size_t errlen) {
+  ObBatchDev &d = b->d;
+  const size_t W = d.W;
+  {
+    // tile width: G lanes per world, 32/G worlds per warp.  Narrow tiles waste fewer lanes in the
+    // dependency rounds of the SOR sweep; wide tiles finish one world sooner.  Heuristic on batch size.
+    int G = W >= 1024 ? 8 : (W >= 256 ? 16 : 32);
+    if (W >= 4096 && d.NB <= 8) G = 4;   // tiny worlds (config 3: 5 bodies, <= 3 rows per level): 8 worlds per warp, 10.5 -> 8.3 ms/step
+    const char *e = getenv("OB_TILE");
+    if (e && (atoi(e) == 4 || atoi(e) == 8 || atoi(e) == 16 || atoi(e) == 32)) G = atoi(e);
+    b->tile = G;
+    // row assembly (k_prep) has its own tile width: it is a throughput kernel (lane per joint / row) that waits on
+    // scattered loads, so more, narrower-batched warps can pay even where the sweep prefers few lanes per world
+    b->prep_tile = G;
+    // measured on B200: contact-only worlds with hundreds of rows (config 2) 0.44 -> 0.38 ms with one world per warp;
+    // jointed / tiny worlds (configs 3, 4) are fastest at the sweep's own width (config 3: 1.26 / 1.35 / 1.50 / 2.17 ms at 4 / 8 / 16 / 32)
+    if (d.NJ == 0 && d.NC >= 96) b->prep_tile = 32;
+    { const char *pe = getenv("OB_PREP_TILE"); if (pe && (atoi(pe) == 4 || atoi(pe) == 8 || atoi(pe) == 16 || atoi(pe) == 32)) b->prep_tile = atoi(pe); }
+    b->smem_prep = prep_tile_smem(d.NB, d.NC, d.NJ, d.NR).total * (32 / b->prep_tile);
+    b->smem_sor = sor_tile_smem(d.NB, d.NR).total * (32 / G);
+    b->smem_sched = sched_smem(d.NB, d.NR).total;
+    b->smem_post = post_tile_smem(d.NG).total * (32 / G);
+    b->grid_step = (int)((W + (32 / G) - 1) / (32 / G));
+    b->grid_sor = b->grid_step;
+    { const char *g = getenv("OB_GRID_SOR"); if (g && atoi(g) > 0 && atoi(g) < b->grid_sor) b->grid_sor = atoi(g); }
+  }
+  if (d.NB > 254 || d.NG > 255 || d.NC + d.NJ > 65000) { snprintf(err, errlen, "world too large for the tile-per-world step kernel (NB=%d NG=%d NR=%d)", d.NB, d.NG, d.NR); goto fail; }
+  if (b->smem_prep > (size_t)prop.sharedMemPerBlockOptin || b->smem_sor > (size_t)prop.sharedMemPerBlockOptin) {
+    snprintf(err, errlen, "world does not fit one CTA's shared memory (prep %zu B, sor %zu B, limit %zu B)",
+             b->smem_prep, b->smem_sor, (size_t)prop.sharedMemPerBlockOptin);
+    goto fail;
+  }
+#define OB_SETSMEM(GG) \
+  CK(cudaFuncSetAttribute(k_prep<GG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_prep)); \
+  CK(cudaFuncSetAttribute(k_prep<GG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_prep)); \
+  CK(cudaFuncSetAttribute(k_sor<GG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sor)); \
+  CK(cudaFuncSetAttribute(k_sor<GG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sor)); \
+  CK(cudaFuncSetAttribute(k_post<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_post));
+  OB_SETSMEM(4) OB_SETSMEM(8) OB_SETSMEM(16) OB_SETSMEM(32)
+#undef OB_SETSMEM
+  CK(cudaFuncSetAttribute(k_sched<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sched));
+  CK(cudaFuncSetAttribute(k_sched<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sched));
+  CK(cudaFuncSetAttribute(k_sched<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sched));
+  b->sor_deep = d.NR > 256 ? 1 : 0;
+  { const char *e = getenv("OB_SOR_DEEP"); if (e) b->sor_deep = atoi(e) != 0; }
+  b->smem_sched_lane = sched_lane_smem(d.NB, d.NR).total;
+  // measured on B200: one lane per world wins for many small worlds (config 3: 65536 worlds x 56 rows, 0.70 -> 0.43 ms),
+  // the warp per world for fewer, larger ones (config 2: 4096 x 377 rows, 0.40 vs 2.7 ms: too few warps to hide the chain latency)
+  b->sched_lane = b->smem_sched_lane <= (size_t)prop.sharedMemPerBlockOptin && ((W >= 8192 && d.NR <= 256) || getenv("OB_SCHED_LANE")) && !getenv("OB_SCHED_WARP");
+  if (b->sched_lane) CK(cudaFuncSetAttribute(k_sched_lane, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sched_lane));
+  {
+    // k_sched_tile: lanes per world by batch size (enough warps to hide the serial chains' latency, few enough lanes
+    // per world that a warp instruction of the chains advances several worlds)
+    int gs = W >= 2048 ? 8 : (W >= 512 ? 16 : 0);
+    const char *e = getenv("OB_SCHED_TILE");
+    if (e) gs = atoi(e);
+    if (gs != 2 && gs != 4 && gs != 8 && gs != 16) gs = 0;
+    if (gs && !(e == 0 && b->sched_lane)) {
+      b->smem_sched_tile = sched_tile_smem(d.NB, d.NR).total * (32 / gs);
+      if (b->smem_sched_tile <= (size_t)prop.sharedMemPerBlockOptin) {
+        b->sched_gs = gs;
+        if (gs == 2) CK(cudaFuncSetAttribute(k_sched_tile<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sched_tile));
+        if (gs == 4) CK(cudaFuncSetAttribute(k_sched_tile<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sched_tile));
+        if (gs == 8) CK(cudaFuncSetAttribute(k_sched_tile<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sched_tile));
+        if (gs == 16) CK(cudaFuncSetAttribute(k_sched_tile<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sched_tile));
+      }
+    }
+  }
+  {
+    // k_sor_ring: on unless the caller pins one of the register-pipelined variants (OB_SOR_DEEP) or OB_SOR_RING=0
+    const char *e = getenv("OB_SOR_RING");
+    const bool want = e ? atoi(e) != 0 : getenv("OB_SOR_DEEP") == 0;
+    b->smem_sor_ring = sor_ring_smem(d.NB, d.NR, b->tile).total * (32 / b->tile);
+    if (want && b->smem_sor_ring <= (size_t)prop.sharedMemPerBlockOptin) {
+      int per_sm = 0;
+#define OB_RING_SETUP(GG) { CK(cudaFuncSetAttribute(k_sor_ring<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sor_ring)); \
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sor_ring<GG>, 32, b->smem_sor_ring)); }
+      if (b->tile == 4) OB_RING_SETUP(4) else if (b->tile == 8) OB_RING_SETUP(8) else if (b->tile == 16) OB_RING_SETUP(16) else OB_RING_SETUP(32)
+#undef OB_RING_SETUP
+      if (per_sm > 0) { b->sor_ring = 1; b->ring_resident = per_sm * prop.multiProcessorCount; }
+    }
+    const char *l2 = getenv("OB_SOR_L2MB");
+    if (l2 && atof(l2) > 0) b->l2_target_bytes = atof(l2) * 1e6;
+    CK(cudaMallocHost((void **)&b->cnt_host, sizeof(ObCounters)));
+    memset(b->cnt_host, 0, sizeof(ObCounters));
+  }
+  return 0;
+fail:
+  return -1;
+}
+
+template <int G> static void stepk_launch_t(ObBackend *b, const ObBatchDev &d, real h, int taps, int W, cudaStream_t st, cudaEvent_t *ev, bool timing) {
+  constexpr int T = 32 / G;
+    const int gstep = (W + T - 1) / T;
+    int gsor = gstep;
+    if (b->grid_sor < b->grid_step) gsor = gsor < b->grid_sor ? gsor : b->grid_sor;
+#define OB_LAUNCH_PREP(GP) { const int gp = (W + (32 / GP) - 1) / (32 / GP); \
+      if (d.NJ > 0) k_prep<GP, true><<<gp, 32, b->smem_prep, st>>>(d, h, taps); else k_prep<GP, false><<<gp, 32, b->smem_prep, st>>>(d, h, taps); }
+    if (b->prep_tile == 4) OB_LAUNCH_PREP(4) else if (b->prep_tile == 8) OB_LAUNCH_PREP(8) else if (b->prep_tile == 16) OB_LAUNCH_PREP(16) else OB_LAUNCH_PREP(32)
+#undef OB_LAUNCH_PREP
+    if (timing) cudaEventRecord(ev[2], st);
+    if (b->sched_gs == 2) k_sched_tile<2><<<(W + 15) / 16, 32, b->smem_sched_tile, st>>>(d, G);
+    else if (b->sched_gs == 4) k_sched_tile<4><<<(W + 7) / 8, 32, b->smem_sched_tile, st>>>(d, G);
+    else if (b->sched_gs == 8) k_sched_tile<8><<<(W + 3) / 4, 32, b->smem_sched_tile, st>>>(d, G);
+    else if (b->sched_gs == 16) k_sched_tile<16><<<(W + 1) / 2, 32, b->smem_sched_tile, st>>>(d, G);
+    else if (b->sched_lane) k_sched_lane<<<(W + 31) / 32, 32, b->smem_sched_lane, st>>>(d, G);
+    else if (d.NB <= 64) k_sched<2><<<W, 32, b->smem_sched, st>>>(d, G, taps);
+    else if (d.NB <= 128) k_sched<4><<<W, 32, b->smem_sched, st>>>(d, G, taps);
+    else k_sched<8><<<W, 32, b->smem_sched, st>>>(d, G, taps);
+    if (timing) cudaEventRecord(ev[3], st);
+    if (b->sor_ring) {
+      // persistent grid: as many CTAs as stay resident, fewer when the rows of the worlds in flight would not fit the L2
+      // (rows/world measured from the counters; capacity-based guess before the first read-back), whole waves
+      const double rows_w = b->avg_rows > 0 ? b->avg_rows : 0.65 * d.NR;
+      const double world_bytes = rows_w * OB_ROWW * sizeof(real) + 1.0;
+      long long cap = (long long)(b->l2_target_bytes / world_bytes) / T;
+      if (cap > b->ring_resident) cap = b->ring_resident;
+      if (cap < 1) cap = 1;
+      { static const char *e = getenv("OB_GRID_SOR"); if (e && atoi(e) > 0) cap = atoi(e); }
+      const int waves = (int)((gstep + cap - 1) / cap);
+      const int gring = (gstep + waves - 1) / waves;
+      k_sor_ring<G><<<gring, 32, b->smem_sor_ring, st>>>(d, taps);
+    } else if (b->sor_deep) k_sor<G, true><<<gsor, 32, b->smem_sor, st>>>(d, taps);
+    else k_sor<G, false><<<gsor, 32, b->smem_sor, st>>>(d, taps);
+    if (timing) cudaEventRecord(ev[4], st);
+    k_post<G><<<gstep, 32, b->smem_post, st>>>(d, h);
+  g_launches += 4;
+}
+void obk_stepk_launch(ObBackend *b, const ObBatchDev &d, real h, int taps, int W, cudaStream_t st, cudaEvent_t *ev, bool timing) {
+  if (b->tile == 4) stepk_launch_t<4>(b, d, h, taps, W, st, ev, timing);
+  else if (b->tile == 8) stepk_launch_t<8>(b, d, h, taps, W, st, ev, timing);
+  else if (b->tile == 16) stepk_launch_t<16>(b, d, h, taps, W, st, ev, timing);
+  else stepk_launch_t<32>(b, d, h, taps, W, st, ev, timing);
+}

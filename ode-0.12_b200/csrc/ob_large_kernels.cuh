@@ -704,7 +704,7 @@ __global__ void __launch_bounds__(LW_T) k_lw_body_post(ObBatchDev d, ObLargeDev 
 #define LWCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { snprintf(err, errlen, "%s: %s", #call, cudaGetErrorString(e_)); return -1; } } while (0)
 #define LW_HOST_WORDS (LW_WORDS + OB_LW_MAXCOL * (2 + OB_LW_MAXC))
 
-static int lw_create(ObBackend *b, char *err, size_t errlen) {
+int lw_create(ObBackend *b, char *err, size_t errlen) {
   ObBatchDev &d = b->d;
   ObLargeDev &L = b->L;
   if (d.W != 1) { snprintf(err, errlen, "the large-world path takes exactly one world"); return -1; }
@@ -863,7 +863,7 @@ int obk_split_attach(ObBackend *b, int rank, int nranks, const void *handles, ch
   return 0;
 }
 
-static int lw_step(ObBackend *b, real h, int taps, char *err, size_t errlen) {
+int lw_step(ObBackend *b, real h, int taps, char *err, size_t errlen) {
   ObBatchDev &d = b->d;
   ObLargeDev &L = b->L;
   cudaStream_t st = b->stream;

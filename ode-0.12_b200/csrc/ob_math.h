@@ -16,7 +16,7 @@
 
 #if defined(__CUDACC__)
 #define OB_HD __host__ __device__ __forceinline__
-#define OB_HDN __host__ __device__ __noinline__
+#define OB_HDN static __host__ __device__ __noinline__
 #else
 #define OB_HD inline
 #define OB_HDN inline

@@ -31,8 +31,6 @@
 #include "ob_rows.h"
 #include "ob_solver.h"
 
-#define OB_ROWF 19                                   // reals per row record
-#define OB_ROWW 20                                   // + one slot holding the 32-bit meta word
 
 __host__ __device__ inline size_t ob_al(size_t x, size_t a) { return (x + a - 1) & ~(a - 1); }
 
@@ -824,6 +822,216 @@ __global__ void __launch_bounds__(32) k_sched_lane(ObBatchDev d, int G) {
 }
 
 
+// k_sched_tile<GS>: the same products as k_sched, GS lanes per world and 32/GS worlds per warp.  What k_sched spends
+// its instructions on are the two serial chains per epoch (the m-1 dependent swaps of the shuffle and the level
+// recurrence): a warp per world issues them as warp instructions with one live lane (ncu r01z: 237 M warp
+// instructions, 70 % issue-active, as many as the whole sweep).  Here lane 0 of every tile runs its world's chain, so
+// one warp instruction advances 32/GS worlds; the data-parallel parts (draws, gather, scatter, pass table) use the
+// tile's GS lanes.  k_sched_lane is the GS = 1 end of the same idea (too few warps for batches of big worlds).
+struct SchedTileSmem { size_t ord, rowb, fio, lvl, X, isl, last, total; };
+__host__ __device__ inline SchedTileSmem sched_tile_smem(int NB, int NR) {
+  SchedTileSmem s; size_t o = 0;
+  s.ord = o; o = ob_al(o + sizeof(unsigned short) * NR, 16);
+  s.rowb = o; o = ob_al(o + sizeof(unsigned short) * NR, 16);
+  s.fio = o; o = ob_al(o + (size_t)NR, 16);
+  s.lvl = o; o = ob_al(o + sizeof(unsigned short) * NR, 16);      // swap indices, then body bytes, then level per position
+  s.X = o; o = ob_al(o + sizeof(int) * (NR + 2), 16);              // rows per level -> level starts -> level ends
+  s.isl = o; o = ob_al(o + sizeof(unsigned short) * 2 * NB, 16);   // (r0, m) per island that has rows
+  s.last = o; o = ob_al(o + sizeof(unsigned short) * 258, 16);     // level of the last row on every body (+ slots 255/256: "no body 2")
+  s.total = ob_al(o, 16);
+  return s;
+}
+template <int GS>
+__global__ void __launch_bounds__(32) k_sched_tile(ObBatchDev d, int G) {
+  constexpr int T = 32 / GS;
+  extern __shared__ __align__(16) unsigned char smem_all[];
+  const SchedTileSmem L = sched_tile_smem(d.NB, d.NR);
+  const int lane = threadIdx.x, grp = lane / GS, gl = lane % GS;
+  unsigned char *smem = smem_all + (size_t)grp * L.total;
+  unsigned short *s_ord = (unsigned short *)(smem + L.ord);
+  unsigned short *s_rowb = (unsigned short *)(smem + L.rowb);
+  unsigned char *s_fio = smem + L.fio;
+  unsigned short *s_lvl = (unsigned short *)(smem + L.lvl);
+  int *s_X = (int *)(smem + L.X);
+  unsigned short *s_isl = (unsigned short *)(smem + L.isl);
+  unsigned short *s_last = (unsigned short *)(smem + L.last);
+  const unsigned FULL = 0xffffffffu;
+  const unsigned gmask = GS == 32 ? FULL : ((1u << GS) - 1u);
+  const unsigned lt_mask = (1u << gl) - 1u;
+  const int gsh = grp * GS;
+
+  for (int wbase = d.wbeg + blockIdx.x * T; wbase < d.wend; wbase += gridDim.x * T) {
+    const int w = wbase + grp;
+    const bool valid = w < d.wend;
+    const int wc = valid ? w : d.wbeg;
+    ObWorld &W = d.world[wc];
+    int *si = d.stepinfo + (size_t)wc * SI_WORDS;
+    const int nis = valid ? si[SI_NIS] : 0;
+    const int mtot = (valid && si[SI_HAVEROWS]) ? si[SI_MTOT] : 0;
+    int nep = valid ? (W.iters + 7) >> 3 : 0;
+    if (nep > d.NEP) nep = d.NEP;
+    const real *rows = d.rows + (size_t)wc * d.NR * OB_ROWW;
+    const unsigned short *g_isz = d.isz + (size_t)wc * 4 * d.NB;
+    const unsigned short *g_jrow = d.jrow + (size_t)wc * (d.NC + d.NJ + 1);
+    if (valid && mtot == 0 && gl == 0) for (int ep = 0; ep < d.NEP; ep++) si[SI_NPASS0 + ep] = 0;
+    // islands that own rows, in island order
+    int nri = 0;
+    if (gl == 0 && mtot > 0) {
+      for (int isl = 0; isl < nis; isl++) {
+        const int j0 = g_isz[4 * isl + 2], jn = g_isz[4 * isl + 3];
+        if (!jn) continue;
+        const int r0 = g_jrow[j0], m = g_jrow[j0 + jn] - r0;
+        if (m > 0) { s_isl[2 * nri] = (unsigned short)r0; s_isl[2 * nri + 1] = (unsigned short)m; nri++; }
+      }
+    }
+    nri = __shfl_sync(FULL, nri, 0, GS);
+    for (int i = gl; i < mtot; i += GS) {
+      const unsigned meta = *(const unsigned *)(rows + (size_t)i * OB_ROWW + OB_ROWF);   // low word of the meta slot
+      s_rowb[i] = (unsigned short)(meta & 0xffffu);
+      s_fio[i] = (unsigned char)((meta >> 16) & 255u);
+    }
+    __syncwarp();
+    // initial order per island (quickstep.cpp:409-424): findex==-1 rows ascending at the head, the others descending at the tail
+    const int nri_max = warp_max_i(nri);
+    for (int q = 0; q < nri_max; q++) {
+      const int r0 = q < nri ? s_isl[2 * q] : 0, m = q < nri ? s_isl[2 * q + 1] : 0;
+      const int m_max = warp_max_i(m);
+      int head = 0, tail = 0;
+      for (int base = 0; base < m_max; base += GS) {
+        const int i = base + gl;
+        const bool v = i < m;
+        const bool hf = v && s_fio[r0 + i] == 0;
+        const unsigned bh = (__ballot_sync(FULL, hf) >> gsh) & gmask, bt = (__ballot_sync(FULL, v && !hf) >> gsh) & gmask;
+        if (hf) s_ord[r0 + head + __popc(bh & lt_mask)] = (unsigned short)i;
+        else if (v) s_ord[r0 + m - 1 - (tail + __popc(bt & lt_mask))] = (unsigned short)i;
+        head += __popc(bh); tail += __popc(bt);
+      }
+    }
+    __syncwarp();
+    const uint32_t seed = W.seed;
+    unsigned total_draws = 0;
+    for (int q = 0; q < nri; q++) { const int m = s_isl[2 * q + 1]; if (m >= 2) total_draws += (unsigned)nep * (unsigned)(m - 1); }
+    const int nep_max = warp_max_i(mtot > 0 ? nep : 0);
+    for (int ep = 0; ep < nep_max; ep++) {
+      const bool epv = mtot > 0 && ep < nep;
+      const int nri_e = epv ? nri : 0, mtot_e = epv ? mtot : 0;
+      // (a) shuffle every island's segment (quickstep.cpp:474-481).  The reference runs ALL iterations of island 0
+      // before island 1, so the draws of (island i, epoch e) start at offset sum_{j<i} nep*(m_j-1) + e*(m_i-1)
+      {
+        unsigned draws_before = 0;
+        for (int q = 0; q < nri_e; q++) {
+          const int r0 = s_isl[2 * q], m = s_isl[2 * q + 1];
+          if (m < 2) continue;
+          const unsigned my_off = draws_before + (unsigned)ep * (unsigned)(m - 1);
+          draws_before += (unsigned)nep * (unsigned)(m - 1);
+          uint32_t A, C, A0, C0;
+          ob_lcg_skip(my_off + (unsigned)gl + 1u, &A0, &C0);   // lane handles i = gl+1, gl+1+GS, ...
+          uint32_t s = A0 * seed + C0;
+          ob_lcg_skip((unsigned)GS, &A, &C);
+          for (int i = 1 + gl; i < m; i += GS) {
+            s_lvl[r0 + i] = (unsigned short)ob_randint_fold(s, (uint32_t)(i + 1));
+            s = A * s + C;
+          }
+        }
+      }
+      __syncwarp();
+      if (gl == 0) {
+        for (int q = 0; q < nri_e; q++) {
+          const int r0 = s_isl[2 * q], m = s_isl[2 * q + 1];
+          if (m < 2) continue;
+          unsigned short *ord = s_ord + r0;
+          int sj = s_lvl[r0 + 1];
+          for (int i = 1; i < m; i++) {
+            const int sjn = s_lvl[r0 + (i + 1 < m ? i + 1 : i)];   // the next swap index is fetched ahead of the dependent chain
+            const unsigned short t = ord[i], u = ord[sj];
+            ord[i] = u; ord[sj] = t;
+            sj = sjn;
+          }
+        }
+      }
+      __syncwarp();
+      // (b) level of every position, islands and positions in sweep order: level(k) = 1 + max(last[b1], last[b2])
+      for (int i = gl; i <= mtot_e + 1; i += GS) s_X[i] = 0;
+      if (epv) for (int i = gl; i < 258; i += GS) s_last[i] = 0;
+      for (int q = 0; q < nri_e; q++) {
+        const int r0 = s_isl[2 * q], m = s_isl[2 * q + 1];
+        for (int k = gl; k < m; k += GS) s_lvl[r0 + k] = s_rowb[r0 + s_ord[r0 + k]];
+      }
+      __syncwarp();
+      int nlev = 0;
+      if (gl == 0) {
+        for (int q = 0; q < nri_e; q++) {
+          const int r0 = s_isl[2 * q], m = s_isl[2 * q + 1];
+          unsigned rb = s_lvl[r0];
+          for (int k = 0; k < m; k++) {
+            const unsigned rbn = s_lvl[r0 + (k + 1 < m ? k + 1 : k)];
+            const int b1 = rb & 255, b2 = (rb >> 8) & 255;      // b2 == 255: slot 255 is read (always 0) and slot 256 written
+            const int l1 = s_last[b1], l2 = s_last[b2];
+            const int lv = (l2 > l1 ? l2 : l1) + 1;
+            s_last[b1] = (unsigned short)lv;
+            s_last[b2 + (b2 == 255)] = (unsigned short)lv;
+            s_lvl[r0 + k] = (unsigned short)lv;
+            s_X[lv] = s_X[lv] + 1;                               // rows per level (off the dependent chain)
+            nlev = lv > nlev ? lv : nlev;
+            rb = rbn;
+          }
+        }
+      }
+      nlev = __shfl_sync(FULL, nlev, 0, GS);
+      __syncwarp();
+      const int nlev_max = warp_max_i(nlev);
+      // exclusive prefix over levels 1..nlev: s_X[l] = first slot of level l
+      {
+        int carry = 0;
+        for (int base = 1; base <= nlev_max; base += GS) {
+          const int l = base + gl;
+          const int c = l <= nlev ? s_X[l] : 0;
+          int x = c;
+          for (int dd = 1; dd < GS; dd <<= 1) { const int y = __shfl_up_sync(FULL, x, dd, GS); if (gl >= dd) x += y; }
+          if (l <= nlev) s_X[l] = carry + x - c;
+          carry += __shfl_sync(FULL, x, GS - 1, GS);
+        }
+      }
+      __syncwarp();
+      // (c) scatter rows into level order (any order inside a level); afterwards s_X[l] = end of level l
+      unsigned short *g_sched = d.sched + ((size_t)wc * d.NEP + ep) * d.NR;
+      unsigned short *g_pstart = d.pstart + ((size_t)wc * d.NEP + ep) * (d.NR + 1);
+      for (int q = 0; q < nri_e; q++) {
+        const int r0 = s_isl[2 * q], m = s_isl[2 * q + 1];
+        for (int k = gl; k < m; k += GS) {
+          const int pos = atomicAdd(&s_X[s_lvl[r0 + k]], 1);
+          g_sched[pos] = (unsigned short)(r0 + s_ord[r0 + k]);
+        }
+      }
+      __syncwarp();
+      // pass table: a pass is a chunk of <= G consecutive slots that does not cross a level boundary
+      {
+        int carry = 0;
+        for (int base = 1; base <= nlev_max; base += GS) {
+          const int l = base + gl;
+          int start = 0, n = 0;
+          if (l <= nlev) { start = l > 1 ? s_X[l - 1] : 0; n = s_X[l] - start; }
+          const int c = (n + G - 1) / G;
+          int x = c;
+          for (int dd = 1; dd < GS; dd <<= 1) { const int y = __shfl_up_sync(FULL, x, dd, GS); if (gl >= dd) x += y; }
+          const int off = carry + x - c;
+          for (int j = 0; j < c; j++) g_pstart[off + j] = (unsigned short)(start + j * G);
+          carry += __shfl_sync(FULL, x, GS - 1, GS);
+        }
+        if (gl == 0 && epv) { g_pstart[carry] = (unsigned short)mtot; si[SI_NPASS0 + ep] = carry; }
+      }
+      __syncwarp();
+    }
+    if (gl == 0 && mtot > 0) {
+      uint32_t A, C;
+      ob_lcg_skip(total_draws, &A, &C);
+      W.seed = A * seed + C;
+    }
+    __syncwarp();
+  }
+}
+
+
 // one row update of the sweep (quickstep.cpp:490-581) on a row held in registers
 __device__ __forceinline__ void sor_pass(const ObRowReg &cur, int cur_idx, real *s_fc, real *s_lam, const real *s_invM) {
   const int b1 = cur.meta & 255, b2r = (cur.meta >> 8) & 255, fio = (cur.meta >> 16) & 255, bmode = cur.meta >> 24;
@@ -887,6 +1095,43 @@ __device__ __noinline__ void sor_check_pass(bool act, unsigned meta, int gl, int
     if (act && l2 != gl && o1 >= 0) {
       if (mb1 == o1 || mb1 == o2 || (mb2 != 255 && (mb2 == o1 || mb2 == o2))) atomicOr(status, 256);
     }
+  }
+}
+
+// after the sweeps: cforce per body for k_post; lambda + joint feedback taps (quickstep.cpp:918-957)
+template <int G>
+__device__ __forceinline__ void sor_epilogue(const ObBatchDev &d, int taps, int wc, bool valid, int gl, int nb, int mtot, const int *si,
+                                             const real *rows, const real *s_fc, const real *s_lam) {
+  real *g_fc = d.tmp1 + (size_t)wc * d.NB * 8;   // tmp1 is dead after row assembly: reuse as cforce
+  for (int b = gl; b < nb; b += G)
+    for (int k = 0; k < 6; k++) g_fc[8 * b + k] = s_fc[8 * b + k];
+  if (taps && valid) {
+    const int nij = si[SI_NIJ];
+    const unsigned short *g_jrow = d.jrow + (size_t)wc * (d.NC + d.NJ + 1);
+    const unsigned short *g_ijoint = d.ijoint + (size_t)wc * (d.NC + d.NJ);
+    const int ncw = d.ncontacts[wc];
+    real *fb = d.fback + (size_t)wc * (d.NC + d.NJ) * 12;
+    real *gl_lam = d.lambda + (size_t)wc * d.NR;
+    if (mtot > 0)
+      for (int k = gl; k < nij; k += G) {
+        const int jr0 = g_jrow[k], jm = g_jrow[k + 1] - jr0;
+        // Multiply1_12q1 (quickstep.cpp:70-101): data = J^T lambda, body 1 then body 2 (J2l == -J1l)
+        real acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        bool two = false;
+        for (int q = 0; q < jm; q++) {
+          const real *rp = rows + (size_t)(jr0 + q) * OB_ROWW;
+          const real s = s_lam[jr0 + q];
+          const unsigned meta = *(const unsigned *)(rp + OB_ROWF);
+          two = ((meta >> 8) & 255u) != 255u;
+          for (int e = 0; e < 6; e++) acc[e] += rp[e] * s;
+          for (int e = 0; e < 3; e++) { acc[6 + e] += (-rp[e]) * s; acc[9 + e] += rp[6 + e] * s; }
+        }
+        if (!two) for (int e = 6; e < 12; e++) acc[e] = 0;
+        const int jid = g_ijoint[k];
+        real *o = fb + (size_t)(jid < ncw ? jid : d.NC + (jid - ncw)) * 12;
+        for (int e = 0; e < 12; e++) o[e] = acc[e];
+      }
+    for (int i = gl; i < mtot; i += G) gl_lam[i] = s_lam[i];
   }
 }
 
@@ -1007,38 +1252,157 @@ __global__ void __launch_bounds__(32) k_sor(ObBatchDev d, int taps) {
 #undef OB_SOR_PASS
       }
     }
-    // cforce per body for k_post; lambda + joint feedback taps (quickstep.cpp:918-957)
-    real *g_fc = d.tmp1 + (size_t)wc * d.NB * 8;   // tmp1 is dead after row assembly: reuse as cforce
-    for (int b = gl; b < nb; b += G)
-      for (int k = 0; k < 6; k++) g_fc[8 * b + k] = s_fc[8 * b + k];
-    if (taps && valid) {
-      const int nij = si[SI_NIJ];
-      const unsigned short *g_jrow = d.jrow + (size_t)wc * (d.NC + d.NJ + 1);
-      const unsigned short *g_ijoint = d.ijoint + (size_t)wc * (d.NC + d.NJ);
-      const int ncw = d.ncontacts[wc];
-      real *fb = d.fback + (size_t)wc * (d.NC + d.NJ) * 12;
-      real *gl_lam = d.lambda + (size_t)wc * d.NR;
-      if (mtot > 0)
-        for (int k = gl; k < nij; k += G) {
-          const int jr0 = g_jrow[k], jm = g_jrow[k + 1] - jr0;
-          // Multiply1_12q1 (quickstep.cpp:70-101): data = J^T lambda, body 1 then body 2 (J2l == -J1l)
-          real acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-          bool two = false;
-          for (int q = 0; q < jm; q++) {
-            const real *rp = rows + (size_t)(jr0 + q) * OB_ROWW;
-            const real s = s_lam[jr0 + q];
-            const unsigned meta = *(const unsigned *)(rp + OB_ROWF);
-            two = ((meta >> 8) & 255u) != 255u;
-            for (int e = 0; e < 6; e++) acc[e] += rp[e] * s;
-            for (int e = 0; e < 3; e++) { acc[6 + e] += (-rp[e]) * s; acc[9 + e] += rp[6 + e] * s; }
-          }
-          if (!two) for (int e = 6; e < 12; e++) acc[e] = 0;
-          const int jid = g_ijoint[k];
-          real *o = fb + (size_t)(jid < ncw ? jid : d.NC + (jid - ncw)) * 12;
-          for (int e = 0; e < 12; e++) o[e] = acc[e];
-        }
-      for (int i = gl; i < mtot; i += G) gl_lam[i] = s_lam[i];
+    sor_epilogue<G>(d, taps, wc, valid, gl, nb, mtot, si, rows, s_fc, s_lam);
+    __syncwarp();
+  }
+}
+
+// =====================================================================================
+// k_sor_ring<G>: the same sweep as k_sor, with the row records streamed through a shared-memory ring by cp.async
+// (LDGSTS) instead of register buffers.  ncu of k_sor<8, DEEP> (r01z): 228 registers, 1.7 warps per scheduler, 27 %
+// issue-active with long-scoreboard on top -- the register pipeline (index six passes ahead, rows three passes ahead)
+// cannot be made deeper without spilling, so the pass time settles at (memory latency) / 3.  Here
+//   * the epoch's schedule (row index per slot + pass starts) is staged in shared memory once per epoch (it is reused
+//     by the epoch's 8 iterations), so finding the row of pass p + D - 1 is two LDS, not a chain of global loads;
+//   * every lane copies ITS row of pass p + D - 1 straight from global/L2 into its own ring slot (5 x 16 B, .cg) and
+//     waits only for its own group of pass p (cp.async.wait_group): no register staging, no cross-lane hand-off,
+//     prefetch depth D - 1 = 5 passes, continuous across the iterations of an epoch (virtual pass counter);
+//   * the kernel is launched as a persistent grid sized by the host so that the rows of the worlds in flight fit the
+//     L2 (ob_backend_cuda.cu): the 20 iterations then re-read them from L2 instead of HBM.
+// The arithmetic of a row update is sor_pass(), unchanged: bit-identical results.
+#define OB_RING_D 6
+struct SorRingSmem { size_t fc, lam, invM, idx, ps, ring, total; };
+__host__ __device__ inline SorRingSmem sor_ring_smem(int NB, int NR, int G) {
+  SorRingSmem s; size_t o = 0;
+  s.fc = o; o = ob_al(o + sizeof(real) * 8 * NB, 16);
+  s.lam = o; o = ob_al(o + sizeof(real) * NR, 16);
+  s.invM = o; o = ob_al(o + sizeof(real) * NB, 16);
+  s.idx = o; o = ob_al(o + sizeof(unsigned short) * NR, 16);
+  s.ps = o; o = ob_al(o + sizeof(unsigned short) * (NR + 2), 16);
+  s.ring = o; o = ob_al(o + sizeof(real) * OB_ROWW * OB_RING_D * G, 16);
+  s.total = ob_al(o, 16);
+  return s;
+}
+__device__ __forceinline__ void ob_cp_async16(void *smem_dst, const void *gsrc) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void ob_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void ob_cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void load_row_smem(const real *p, ObRowReg &r) {
+#if defined(dSINGLE)
+  const float4 *q = (const float4 *)p;
+#pragma unroll
+  for (int i = 0; i < 4; i++) { const float4 t = q[i]; r.v[4 * i] = t.x; r.v[4 * i + 1] = t.y; r.v[4 * i + 2] = t.z; r.v[4 * i + 3] = t.w; }
+  const float4 t = q[4];
+  r.v[16] = t.x; r.v[17] = t.y; r.v[18] = t.z; r.meta = __float_as_uint(t.w);
+#else
+  const double2 *q = (const double2 *)p;
+#pragma unroll
+  for (int i = 0; i < 9; i++) { const double2 t = q[i]; r.v[2 * i] = t.x; r.v[2 * i + 1] = t.y; }
+  const double2 t = q[9];
+  r.v[18] = t.x; r.meta = (unsigned)__double2loint(t.y);
+#endif
+}
+
+template <int G>
+__global__ void __launch_bounds__(32) k_sor_ring(ObBatchDev d, int taps) {
+  constexpr int T = 32 / G, D = OB_RING_D;
+  constexpr int ROWB = OB_ROWW * (int)sizeof(real);
+  extern __shared__ __align__(16) unsigned char smem_all[];
+  const SorRingSmem L = sor_ring_smem(d.NB, d.NR, G);
+  const int lane = threadIdx.x, grp = lane / G, gl = lane % G;
+  unsigned char *smem = smem_all + (size_t)grp * L.total;
+  real *s_fc = (real *)(smem + L.fc);
+  real *s_lam = (real *)(smem + L.lam);
+  real *s_invM = (real *)(smem + L.invM);
+  unsigned short *s_idx = (unsigned short *)(smem + L.idx);
+  unsigned short *s_ps = (unsigned short *)(smem + L.ps);
+  unsigned char *s_ring = smem + L.ring + (size_t)gl * ROWB;   // this lane's column of the ring: slot k at k * G * ROWB
+
+  for (int wbase = d.wbeg + blockIdx.x * T; wbase < d.wend; wbase += gridDim.x * T) {
+    const int w = wbase + grp;
+    const bool valid = w < d.wend;
+    const int wc = valid ? w : d.wbeg;
+    const int *si = d.stepinfo + (size_t)wc * SI_WORDS;
+    const int nb = valid ? d.world[wc].nb : 0;
+    const int iters = valid ? d.world[wc].iters : 0;
+    const int mtot = valid && si[SI_HAVEROWS] ? si[SI_MTOT] : 0;
+    const ObBodyConst *bc = d.bconst + (size_t)wc * d.NB;
+    const real *rows = d.rows + (size_t)wc * d.NR * OB_ROWW;
+    for (int b = gl; b < nb; b += G) {
+      s_invM[b] = bc[b].invMass;
+      for (int k = 0; k < 8; k++) s_fc[8 * b + k] = 0;
     }
+    for (int i = gl; i < mtot; i += G) s_lam[i] = 0;
+    int nep = mtot > 0 ? (iters + 7) >> 3 : 0;
+    if (nep > d.NEP) nep = d.NEP;
+    const int nep_max = warp_max_i(nep);
+    for (int ep = 0; ep < nep_max; ep++) {
+      const bool epv = ep < nep;
+      const int np = epv ? si[SI_NPASS0 + ep] : 0;
+      int nit = epv ? iters - 8 * ep : 0;
+      if (nit > 8) nit = 8;
+      // stage the epoch's schedule
+      __syncwarp();
+      {
+        const unsigned short *sched = d.sched + ((size_t)wc * d.NEP + ep) * d.NR;
+        const unsigned short *pstart = d.pstart + ((size_t)wc * d.NEP + ep) * (d.NR + 1);
+        if (epv) {
+          for (int i = gl; i < mtot; i += G) s_idx[i] = sched[i];
+          for (int i = gl; i <= np; i += G) s_ps[i] = pstart[i];
+        }
+      }
+      __syncwarp();
+      const int vtot = np * nit;               // passes of this tile in this epoch (virtual pass v = it * np + p)
+      const int vmax = warp_max_i(vtot);
+      int pf_p = 0, pf_v = 0, pf_slot = 0;      // prefetcher: pass within the iteration, virtual pass, ring slot
+      int pf_s = 0;                             // first slot of pass pf_p
+#define OB_RING_ISSUE()                                                                            \
+      {                                                                                            \
+        if (pf_v < vtot) {                                                                         \
+          const int pe_ = s_ps[pf_p + 1];                                                          \
+          if (pf_s + gl < pe_) {                                                                   \
+            const unsigned char *src_ = (const unsigned char *)(rows + (size_t)s_idx[pf_s + gl] * OB_ROWW); \
+            unsigned char *dst_ = s_ring + (size_t)pf_slot * (G * ROWB);                           \
+            _Pragma("unroll") for (int c_ = 0; c_ < ROWB / 16; c_++) ob_cp_async16(dst_ + 16 * c_, src_ + 16 * c_); \
+          }                                                                                        \
+          pf_s = pe_;                                                                              \
+          if (++pf_p == np) { pf_p = 0; pf_s = 0; }                                                \
+        }                                                                                          \
+        ob_cp_async_commit();                                                                      \
+        pf_v++;                                                                                    \
+        if (++pf_slot == D) pf_slot = 0;                                                           \
+      }
+      for (int k = 0; k < D - 1; k++) OB_RING_ISSUE()
+      int c_p = 0, c_slot = 0, c_s = 0;
+      for (int v = 0; v < vmax; v++) {
+        OB_RING_ISSUE()
+        ob_cp_async_wait<D - 1>();   // this lane's copy of pass v has landed (groups complete in order)
+        bool act = false;
+        int ci = 0;
+        ObRowReg cur;
+        cur.meta = 0;
+        if (v < vtot) {
+          const int ce = s_ps[c_p + 1];
+          if (c_s + gl < ce) {
+            act = true;
+            ci = s_idx[c_s + gl];
+            load_row_smem((const real *)(s_ring + (size_t)c_slot * (G * ROWB)), cur);
+          }
+          c_s = ce;
+          if (++c_p == np) { c_p = 0; c_s = 0; }
+        }
+        if (taps & 4) sor_check_pass<G>(act, cur.meta, gl, &d.world[wc].status);
+        if (act) sor_pass(cur, ci, s_fc, s_lam, s_invM);
+        if (++c_slot == D) c_slot = 0;
+        __syncwarp();
+      }
+      ob_cp_async_wait<0>();
+#undef OB_RING_ISSUE
+    }
+    __syncwarp();
+    sor_epilogue<G>(d, taps, wc, valid, gl, nb, mtot, si, rows, s_fc, s_lam);
     __syncwarp();
   }
 }
@@ -1147,11 +1511,19 @@ __global__ void __launch_bounds__(32) k_post(ObBatchDev d, real h) {
       }
       for (int i = gl; i < nm; i += G) glist[nm - 1 - i] = s_moved[i];
     }
+    // contacts solved = contact joints that entered an island with rows (permanent joints are not contacts)
+    int ncj = 0;
+    if (have_rows) {
+      const unsigned short *g_ijoint = d.ijoint + (size_t)wc * (d.NC + d.NJ);
+      const int ncw = d.ncontacts[wc];
+      for (int k = gl; k < nij; k += G) ncj += g_ijoint[k] < ncw ? 1 : 0;
+    }
+    for (int dd = 1; dd < G; dd <<= 1) ncj += __shfl_xor_sync(0xffffffffu, ncj, dd, G);
     if (gl == 0 && valid) {
       d.nrows[w] = mtot;
       atomicAdd(&d.counters->steps, 1ull);
       atomicAdd(&d.counters->body_steps, (unsigned long long)nib);
-      atomicAdd(&d.counters->contacts, (unsigned long long)(have_rows ? nij : 0));
+      atomicAdd(&d.counters->contacts, (unsigned long long)ncj);
       atomicAdd(&d.counters->rows, (unsigned long long)mtot);
       atomicAdd(&d.counters->islands, (unsigned long long)nis);
       if (W.status) atomicAdd(&d.counters->overflow_worlds, 1ull);
