@@ -47,14 +47,7 @@ CONFIGS = {
             desc="configs[3]: {W} independent worlds/GPU x (20-link capsule/box chain on 19 ball/hinge joints + 16-box pile), dHashSpace, "
                  "crash contact policy maxc 4"),
 }
-SCENE = "stack32"
-WORLDS_PER_GPU = 4096
-SETTLE = 300
 H = 0.01
-CONTACTS_CAP = 192   # stack32 peaks at ~150 contacts/world (measured on the reference); overflow is reported
-GEOMS_PER_WORLD = 41
-CONFIG_DESC = CONFIGS[2]["desc"]
-CPU_SAMPLE = None    # (processes, worlds per process, timed steps) of the reference arm; None = one process per host core x 8 worlds
 # algorithmic bytes per unit, dSINGLE: A body-step, B geom-step, C contact,
 # D row x SOR iteration, ASM row assembly
 A_B, B_B, C_B, D_B, ASM_B = 136, 80, 128, 224, 128
@@ -144,7 +137,7 @@ def counters(lib, B):
     return dict(zip(["steps", "body_steps", "pairs", "contacts", "rows", "islands", "overflow_worlds"], list(c)))
 
 
-def shard(rank, world_size, per_gpu=WORLDS_PER_GPU):
+def shard(rank, world_size, per_gpu):
     """world ids owned by `rank`: contiguous ranges, no overlap (weak scaling)"""
     return rank * per_gpu, per_gpu
 
@@ -161,19 +154,38 @@ def reduce_metrics(dist, vals, sums, device):
     return tv.cpu().numpy(), ts.cpu().numpy()
 
 
-def run_b200(args):
-    rank = int(os.environ.get("RANK", "0"))
-    world_size = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    dist = None
-    if world_size > 1:
-        import torch
-        import torch.distributed as dist
+class Ctx:
+    """process-wide state of one bench run: rank layout, the NCCL group (N > 1) and the loaded libraries"""
 
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    lib, scenes = load_libs()
-    world0, nworlds = shard(rank, world_size, args.worlds)
+    def __init__(self):
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world_size = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.dist = None
+        if self.world_size > 1:
+            import torch
+            import torch.distributed as dist
+
+            torch.cuda.set_device(self.local_rank)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            self.dist = dist
+        self.lib, self.scenes = load_libs()
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.destroy_process_group()
+
+
+def measure_batched(ctx, cfg_id, steps, warmup, worlds=0, strong=False, cpu=False, args=None):
+    """one configuration of independent worlds (CONFIGS[cfg_id]) on this rank's GPU; returns the JSON dict on rank 0.
+    strong=True: `worlds` is the TOTAL over all ranks (fixed work, each rank owns worlds/N); else worlds per GPU."""
+    cfg = CONFIGS[cfg_id]
+    SCENE, SETTLE, CONTACTS_CAP, GEOMS_PER_WORLD, CONFIG_DESC = cfg["scene"], cfg["settle"], cfg["cap"], cfg["geoms"], cfg["desc"]
+    rank, world_size, local_rank, dist, lib, scenes = ctx.rank, ctx.world_size, ctx.local_rank, ctx.dist, ctx.lib, ctx.scenes
+    per_gpu = worlds if worlds > 0 else cfg["worlds"]
+    if strong:
+        per_gpu = (per_gpu + world_size - 1) // world_size
+    world0, nworlds = shard(rank, world_size, per_gpu)
     B = scenes.ob_scene_build_batch(SCENE.encode(), nworlds, world0, CONTACTS_CAP, local_rank)
     if not B:
         raise SystemExit("batch creation failed: " + (lib.dB200LastError() or b"").decode())
@@ -192,7 +204,7 @@ def run_b200(args):
             dist.barrier()
 
     step(SETTLE)                       # untimed: let the pile come to rest
-    step(max(args.warmup, 3))          # warm-up steps proper
+    step(max(warmup, 3))          # warm-up steps proper
     lib.dBatchResetCounters(B)
     l0 = lib.dB200KernelLaunchCount()
     sampler = ClockSampler(local_rank)
@@ -200,7 +212,7 @@ def run_b200(args):
     barrier()
     ms = ctypes.c_float()
     lib.dBatchTimerStart(B)
-    step(args.steps)
+    step(steps)
     lib.dBatchTimerStop(B, ctypes.byref(ms))
     barrier()
     clocks = sampler.stop()
@@ -211,7 +223,7 @@ def run_b200(args):
     # per-kernel attribution for the roofline (separate pass, events around every launch)
     lib.dBatchSetKernelTiming(B, 1)
     lib.dBatchResetCounters(B)
-    step(args.steps)
+    step(steps)
     NK = 8
     kms = (ctypes.c_double * NK)()
     kl = (ctypes.c_longlong * NK)()
@@ -271,7 +283,7 @@ def run_b200(args):
         f[:, :, 0] = 0.01 * rng.standard_normal((nworlds, nb), dtype=np.float32)
     force = forces[0]
     lib.dBatchResetCounters(B)
-    e2e_steps = args.steps
+    e2e_steps = steps
     barrier()
     t0 = time.perf_counter()
     for s in range(e2e_steps):
@@ -285,21 +297,22 @@ def run_b200(args):
     vals = np.array([elapsed_ms, t_e2e], dtype=np.float64)
     sums = np.array([c["body_steps"], c["contacts"], ce["body_steps"], c["rows"], launches, c["overflow_worlds"]], dtype=np.float64)
     vals, sums = reduce_metrics(dist, vals, sums, "cuda")
+    out = None
     if rank == 0:
         t = vals[0] * 1e-3
         out = {
             "metric": "body-steps/sec (batched dSpaceCollide + dWorldQuickStep, 20 SOR iterations)",
             "value": sums[0] / t, "unit": "body-steps/s",
             "contacts_solved_per_sec": sums[1] / t,
-            "n_gpus": world_size, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": vals[0] / args.steps, "higher_is_better": True, "scaling": "weak",
+            "n_gpus": world_size, "steps": steps, "warmup": max(warmup, 3),
+            "ms_per_step": vals[0] / steps, "higher_is_better": True, "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": CONFIG_DESC.format(W=args.worlds) + f", quickstep 20 it, h={H}, settled {SETTLE} steps",
-                       "worlds_per_gpu": args.worlds, "bodies_per_world": nb, "rows_per_world_step": sums[3] / max(c["steps"] * world_size, 1),
+            "config": {"workload": CONFIG_DESC.format(W=per_gpu) + f", quickstep 20 it, h={H}, settled {SETTLE} steps",
+                       "worlds_per_gpu": per_gpu, "bodies_per_world": nb, "rows_per_world_step": sums[3] / max(c["steps"] * world_size, 1),
                        "contacts_per_world_step": sums[1] / max(c["steps"] * world_size, 1),
                        "cache": (lambda mb: ("per-step working set (rows written+read) ~%.0f MB/GPU > 126 MB L2" % mb) if mb > 126 else
                                  ("per-step working set ~%.1f MB fits the L2 and is not flushed: this configuration measures the latency of "
-                                  "one island's dependent row updates, not a stream" % mb))(c["rows"] / args.steps * 128 * 2 / 1e6 + 70 * nworlds / 4096),
+                                  "one island's dependent row updates, not a stream" % mb))(c["rows"] / steps * 128 * 2 / 1e6 + 70 * nworlds / 4096),
                        "precision": "dSINGLE", "parity": "bit-exact vs reference (tests/)"},
             "e2e": {"value": sums[2] / vals[1], "unit": "body-steps/s", "h2d_bytes_per_step": int(force.nbytes + torque.nbytes) * world_size,
                     "d2h_bytes_per_step": int(pos.nbytes + quat.nbytes + lv.nbytes + av.nbytes) * world_size},
@@ -308,18 +321,16 @@ def run_b200(args):
                          "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": step_bytes,
                          "kernel_ms": t_step * 1e3, "kernel_share_of_step": t_step / t_all,
                          "whole_step": {"algorithmic_bytes": sum(kbytes.values()),
-                                        "achieved": sum(kbytes.values()) / (vals[0] * 1e-3 / args.steps) / 1e9 if world_size == 1 else None},
+                                        "achieved": sum(kbytes.values()) / (vals[0] * 1e-3 / steps) / 1e9 if world_size == 1 else None},
                          "kernels": {k: {"ms": kt[k] * 1e3, "algorithmic_bytes_per_launch": kbytes.get(k), "achieved": kbytes.get(k, 0) / kt[k] / 1e9}
                                      for k in kt}},
             "clocks": clocks,
             "overflow_worlds": int(sums[5]),
         }
-        if world_size == 1 and not args.no_cpu:
-            out["cpu_baseline"] = cpu_baseline(args, bounded_seconds=20)
-        print(json.dumps(out))
+        if world_size == 1 and cpu:
+            out["cpu_baseline"] = cpu_baseline(cfg)
     lib.dBatchDestroy(B)
-    if dist is not None:
-        dist.destroy_process_group()
+    return out
 
 
 LARGE = dict(scene="pile_100x100x20", settle=300, cpu_scene="pile_24x24x20", cpu_settle=200, cpu_steps=10,
@@ -334,25 +345,15 @@ class LargeStats(ctypes.Structure):
                 ("phase_ms", ctypes.c_double * 7)]
 
 
-def run_large(args):
+def measure_large(ctx, steps, warmup, scene="", settle=-1, cpu=False):
     """configs[4]: one large world.  N = 1: one GPU.  N > 1 (torchrun, one process per GPU): every rank holds the whole
     world, the SOR phase is split over the ranks with the fc exchange over NVLink inside the kernel
     (dBatchSplitExport / dBatchSplitAttach) -- total work is fixed, "scaling": "strong"; NCCL only gathers
     the 128-byte buffer descriptions once and reduces the timing.  value = device-resident body-steps/s (max over ranks
     of the CUDA-event time); roofline on the SOR phase, algorithmic bytes D x iterations per row."""
-    rank = int(os.environ.get("RANK", "0"))
-    world_size = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    dist = None
-    if world_size > 1:
-        import torch
-        import torch.distributed as dist
-
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    lib, scenes = load_libs()
+    rank, world_size, local_rank, dist, lib, scenes = ctx.rank, ctx.world_size, ctx.local_rank, ctx.dist, ctx.lib, ctx.scenes
     lib.dBatchGetLargeWorldStats.argtypes = [ctypes.c_void_p, ctypes.POINTER(LargeStats)]
-    scene = args.scene or LARGE["scene"]
+    scene = scene or LARGE["scene"]
     B = scenes.ob_scene_build_batch(scene.encode(), 1, 0, 0, local_rank)
     if not B:
         raise SystemExit("batch creation failed: " + (lib.dB200LastError() or b"").decode())
@@ -397,9 +398,9 @@ def run_large(args):
         if lib.dBatchSplitAttach(B, rank, world_size, blob) != 0:
             raise SystemExit("split attach failed: " + lib.dB200LastError().decode())
         barrier()
-    settle = args.settle if args.settle >= 0 else LARGE["settle"]
+    settle = settle if settle >= 0 else LARGE["settle"]
     step(settle)
-    step(max(args.warmup, 3))
+    step(max(warmup, 3))
     lib.dBatchResetCounters(B)
     l0 = lib.dB200KernelLaunchCount()
     sampler = ClockSampler(local_rank)
@@ -407,7 +408,7 @@ def run_large(args):
     barrier()
     ms = ctypes.c_float()
     lib.dBatchTimerStart(B)
-    step(args.steps)
+    step(steps)
     lib.dBatchTimerStop(B, ctypes.byref(ms))
     barrier()
     clocks = sampler.stop()
@@ -417,7 +418,7 @@ def run_large(args):
     # per-phase attribution (CUDA events between the phases, separate pass)
     lib.dBatchSetKernelTiming(B, 1)
     lib.dBatchResetCounters(B)
-    step(args.steps)
+    step(steps)
     st = LargeStats()
     lib.dBatchGetLargeWorldStats(B, ctypes.byref(st))
     lib.dBatchSetKernelTiming(B, 0)
@@ -448,7 +449,7 @@ def run_large(args):
         f[:, 0] = 0.01 * rng.standard_normal(nb, dtype=np.float32)
     lib.dBatchResetCounters(B)
     t0 = time.perf_counter()
-    for s in range(args.steps):
+    for s in range(steps):
         lib.dBatchAddForces(B, forces[s & 3].ctypes.data, torque.ctypes.data)
         step(1)
         lib.dBatchGetBodyState(B, pos.ctypes.data, quat.ctypes.data, lv.ctypes.data, av.ctypes.data)
@@ -466,12 +467,11 @@ def run_large(args):
             raise SystemExit("split ranks disagree on the body state")
         if rank != 0:
             lib.dBatchDestroy(B)
-            dist.destroy_process_group()
-            return
+            return None
     out = {
         "metric": "body-steps/sec (dSpaceCollide + dWorldQuickStep, 20 SOR iterations)", "value": c["body_steps"] / t, "unit": "body-steps/s",
-        "contacts_solved_per_sec": c["contacts"] / t, "n_gpus": world_size, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": t * 1e3 / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "contacts_solved_per_sec": c["contacts"] / t, "n_gpus": world_size, "steps": steps, "warmup": max(warmup, 3),
+        "ms_per_step": t * 1e3 / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": LARGE["desc"].format(NB=nb) + f", scene {scene}, quickstep 20 it, h={H}, settled {settle} steps",
                    "bodies": nb, "pairs_per_step": st.pairs, "contacts_per_step": st.contacts, "rows_per_step": rows_per_step,
@@ -487,11 +487,11 @@ def run_large(args):
                      "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                      "algorithmic_bytes_per_launch": sor_bytes / max(st.sor_launches, 1), "kernel_ms": ph["sor"] / max(st.sor_launches, 1),
                      "kernel_share_of_step": ph["sor"] / max(sum(ph.values()), 1e-9),
-                     "whole_step": {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (t / args.steps) / 1e9},
+                     "whole_step": {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (t / steps) / 1e9},
                      "phases_ms": ph},
         "clocks": clocks, "overflow_worlds": c["overflow_worlds"],
     }
-    if not args.no_cpu and world_size == 1:
+    if cpu and world_size == 1:
         exe = os.path.join(ROOT, "oracle", "_ref", "driver_ref_single")
         if os.path.exists(exe):
             r = json.loads(subprocess.run([exe, "--scene", LARGE["cpu_scene"], "--steps", str(LARGE["cpu_steps"]), "--settle", str(LARGE["cpu_settle"]),
@@ -500,17 +500,17 @@ def run_large(args):
                                    "contacts_solved_per_sec": r["contacts_per_sec"],
                                    "sample": f"1 process (one world cannot use more), scene {LARGE['cpu_scene']} (same pile, smaller footprint), "
                                              f"{LARGE['cpu_settle']} settle steps untimed + {LARGE['cpu_steps']} timed"}
-    print(json.dumps(out))
     lib.dBatchDestroy(B)
-    if dist is not None:
-        dist.destroy_process_group()
+    return out
 
 
-def cpu_run(nproc, worlds_each, steps, settle, timeout=900):
+def cpu_run(scene, nproc, worlds_each, steps, settle, timeout=1700):
+    """the unmodified reference (oracle/_ref/driver_ref_single: classic dSpaceCollide + near callback + dWorldQuickStep
+    loop over its worlds) in nproc processes, worlds [i*worlds_each, (i+1)*worlds_each) each"""
     exe = os.path.join(ROOT, "oracle", "_ref", "driver_ref_single")
     if not os.path.exists(exe):
         return None
-    procs = [subprocess.Popen([exe, "--scene", SCENE, "--worlds", str(worlds_each), "--world0", str(i * worlds_each),
+    procs = [subprocess.Popen([exe, "--scene", scene, "--worlds", str(worlds_each), "--world0", str(i * worlds_each),
                                "--steps", str(steps), "--settle", str(settle), "--time"], stdout=subprocess.PIPE, text=True)
              for i in range(nproc)]
     outs = [json.loads(p.communicate(timeout=timeout)[0].strip().splitlines()[-1]) for p in procs]
@@ -518,39 +518,88 @@ def cpu_run(nproc, worlds_each, steps, settle, timeout=900):
     return {"body_steps": sum(o["body_steps"] for o in outs), "contacts": sum(o["contacts"] for o in outs), "seconds": secs}
 
 
-def cpu_baseline(args, bounded_seconds=20):
-    """the UNMODIFIED reference (oracle/_ref) on this box's host cores: one process per core
-    (ODE has process-global state), a bounded sample of the same workload"""
-    nproc, worlds_each, steps = CPU_SAMPLE if CPU_SAMPLE else (os.cpu_count() or 1, 8, 100)
-    r = cpu_run(nproc, worlds_each, steps, SETTLE)
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_baseline(cfg):
+    """cpu_baseline leg of the b200 arm: a BOUNDED sample of the same workload on this box's host cores (one process per
+    core -- ODE keeps process-global state -- x 8 worlds, 100 timed steps after the settle)"""
+    nproc, worlds_each, steps = cfg.get("cpu") or (host_cores(), 8, 100)
+    r = cpu_run(cfg["scene"], nproc, worlds_each, steps, cfg["settle"])
     if r is None:
         return {"value": None, "unit": "body-steps/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref not present"}
     return {"value": r["body_steps"] / r["seconds"], "unit": "body-steps/s", "cores": nproc, "kind": "reference",
             "contacts_solved_per_sec": r["contacts"] / r["seconds"],
-            "sample": f"{nproc} processes x {worlds_each} worlds of {SCENE}, {SETTLE} settle steps untimed + {steps} timed steps"}
+            "sample": f"{nproc} processes x {worlds_each} worlds of {cfg['scene']}, {cfg['settle']} settle steps untimed + {steps} timed steps"}
 
 
 def run_reference(args):
+    """--impl reference: the reference's own CPU implementation on ALL host cores over the SAME configuration as the b200
+    arm: N x worlds_per_gpu worlds (N = WORLD_SIZE), dealt over one process per core.  A timed window shorter than about a
+    second is noise on a shared host, so the K timed steps are repeated back to back (R x K steps in one timed region)
+    until the window is >= 1 s; value = body-steps of the whole window / its duration."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    nproc, worlds_each = CPU_SAMPLE[:2] if CPU_SAMPLE else (os.cpu_count() or 1, 8)
-    r = cpu_run(nproc, worlds_each, max(args.steps, 1), SETTLE + max(args.warmup, 3))
-    if r is None:
+    n_gpus = int(os.environ.get("WORLD_SIZE", "1"))
+    cfg = CONFIGS[args.config]
+    per_gpu = args.worlds if args.worlds > 0 else cfg["worlds"]
+    total = per_gpu * n_gpus
+    nproc = min(host_cores(), total)
+    worlds_each = (total + nproc - 1) // nproc
+    K = max(args.steps, 1)
+    warm = max(args.warmup, 3)
+    # repeats from a quick calibration: 2 worlds per process, 20 steps of the settled scene
+    cal = cpu_run(cfg["scene"], nproc, min(2, worlds_each), 20, cfg["settle"])
+    if cal is None:
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref (reference build) not present on this box"}))
         return
+    est_step = cal["seconds"] / 20 * worlds_each / min(2, worlds_each)
+    R = max(1, int(np.ceil(1.2 / max(est_step * K, 1e-9))))
+    R = min(R, 50)
+    r = cpu_run(cfg["scene"], nproc, worlds_each, K * R, cfg["settle"] + warm)
     v = r["body_steps"] / r["seconds"]
-    sample = f"{nproc} processes x {worlds_each} worlds of {SCENE}, {SETTLE}+{max(args.warmup, 3)} untimed steps, {args.steps} timed"
+    sample = (f"FULL configuration: {nproc} processes x {worlds_each} worlds = {nproc * worlds_each} worlds of {cfg['scene']} "
+              f"({n_gpus} x {per_gpu}), {cfg['settle']}+{warm} untimed steps, {R} x {K} = {K * R} timed steps in one {r['seconds']:.2f} s window")
     print(json.dumps({
         "impl": "reference", "metric": "body-steps/sec (batched dSpaceCollide + dWorldQuickStep, 20 SOR iterations)",
         "value": v, "unit": "body-steps/s", "contacts_solved_per_sec": r["contacts"] / r["seconds"],
-        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": r["seconds"] * 1e3 / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "n_gpus": n_gpus, "steps": K, "warmup": warm,
+        "ms_per_step": r["seconds"] * 1e3 / (K * R), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "sample of " + CONFIG_DESC.format(W=nproc * worlds_each) + ", reference ODE 0.12 dSINGLE on host cores"},
+        "config": {"workload": cfg["desc"].format(W=per_gpu) + f", quickstep 20 it, h={H}, settled {cfg['settle']} steps",
+                   "worlds_per_gpu": per_gpu, "worlds_total": nproc * worlds_each, "timed_steps_total": K * R,
+                   "precision": "dSINGLE", "implementation": "reference ODE 0.12 (oracle/_ref, unmodified) on the host cores"},
         "cpu_baseline": {"value": v, "unit": "body-steps/s", "cores": nproc, "kind": "reference", "sample": sample},
         "e2e": {"value": v, "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def brief(d):
+    """the part of a configuration's line that other_configs carries"""
+    if d is None:
+        return None
+    r = d.get("roofline", {})
+    out = {k: d[k] for k in ("value", "unit", "ms_per_step", "n_gpus", "steps", "warmup", "scaling", "contacts_solved_per_sec", "overflow_worlds") if k in d}
+    out["workload"] = d["config"]["workload"]
+    out["e2e"] = d["e2e"]["value"]
+    ws = r.get("whole_step", {})
+    out["whole_step_algorithmic_GBps"] = ws.get("achieved")
+    out["whole_step_frac_of_hbm_peak"] = (ws["achieved"] / r["peak"]) if ws.get("achieved") and r.get("peak") else None
+    if "kernels" in r:
+        out["kernels_ms"] = {k: v["ms"] for k, v in r["kernels"].items()}
+    if "phases_ms" in r:
+        out["phases_ms"] = r["phases_ms"]
+    for k in ("rows_per_world_step", "contacts_per_world_step", "bodies", "contacts_per_step", "colours", "parallelism"):
+        if k in d["config"]:
+            out[k] = d["config"][k]
+    if "cpu_baseline" in d:
+        out["cpu_baseline"] = d["cpu_baseline"]
+    return out
 
 
 if __name__ == "__main__":
@@ -564,18 +613,33 @@ if __name__ == "__main__":
     ap.add_argument("--scene", default="")
     ap.add_argument("--settle", type=int, default=-1)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-other", action="store_true", help="skip the other_configs block of the default line")
+    ap.add_argument("--strong", action="store_true", help="--worlds is the total over all GPUs (fixed work)")
     a = ap.parse_args()
-    if a.config == 5:
-        if a.impl == "reference":
-            raise SystemExit("--config 5 reports the reference inside its own line (cpu_baseline)")
-        run_large(a)
-        sys.exit(0)
-    cfg = CONFIGS[a.config]
-    SCENE, SETTLE, CONTACTS_CAP, GEOMS_PER_WORLD, CONFIG_DESC = cfg["scene"], cfg["settle"], cfg["cap"], cfg["geoms"], cfg["desc"]
-    CPU_SAMPLE = cfg.get("cpu")
-    if a.worlds <= 0:
-        a.worlds = cfg["worlds"]
     if a.impl == "reference":
+        if a.config == 5:
+            raise SystemExit("--config 5 reports the reference inside its own line (cpu_baseline)")
         run_reference(a)
+        sys.exit(0)
+    ctx = Ctx()
+    if a.config == 5:
+        out = measure_large(ctx, a.steps, a.warmup, a.scene, a.settle, cpu=not a.no_cpu)
     else:
-        run_b200(a)
+        out = measure_batched(ctx, a.config, a.steps, a.warmup, a.worlds, strong=a.strong, cpu=not a.no_cpu)
+        if a.config == 2 and not a.no_other and not a.strong and a.worlds <= 0:
+            # the other BASELINE.json configurations ride in the same line (driver-measured): shorter runs of the same harness.
+            # N > 1: configs[1] again as STRONG scaling (the named 4096 worlds over N GPUs) and configs[4] split over the GPUs.
+            ks, kw = max(10, a.steps // 3), 3
+            other = {}
+            if ctx.world_size > 1:
+                other["configs[1] strong (4096 worlds total)"] = brief(measure_batched(ctx, 2, ks, kw, CONFIGS[2]["worlds"], strong=True))
+            other["configs[2]"] = brief(measure_batched(ctx, 3, ks, kw))
+            other["configs[3]"] = brief(measure_batched(ctx, 4, ks, kw))
+            other["configs[4]"] = brief(measure_large(ctx, ks, kw, cpu=(not a.no_cpu and ctx.world_size == 1)))
+            if ctx.world_size == 1:
+                other["configs[0]"] = brief(measure_batched(ctx, 1, 200, 5, cpu=not a.no_cpu))
+            if out is not None:
+                out["other_configs"] = other
+    if out is not None:
+        print(json.dumps(out))
+    ctx.close()

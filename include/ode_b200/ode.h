@@ -830,6 +830,12 @@ int dBatchSplitAttach(dBatchID, int rank, int nranks, const void *handles);
 void *dBatchGetStream(dBatchID);
 /* number of kernel launches issued by the library since load (bench.py) */
 long long dB200KernelLaunchCount(void);
+/* Diagnostics for the libm restatements of ob_math.h (atan2f, sinf, cosf as glibc 2.39 computes them; the reference calls
+ * them through dAtan2 / dSin / dCos, include/ode/common.h:150-160).  fn: 0 atan2f(a, b), 1 sinf(a), 2 cosf(a).
+ * dB200LibmHost evaluates the restatement compiled for the host, dB200LibmDevice the same source on the GPU (needs a
+ * device; returns -1 without one).  tests/test_abi.py compares both with the platform's libm bit for bit. */
+int dB200LibmHost(int fn, int n, const float *a, const float *b, float *out);
+int dB200LibmDevice(int fn, int n, const float *a, const float *b, float *out);
 const char *dB200LastError(void);
 
 #ifdef __cplusplus

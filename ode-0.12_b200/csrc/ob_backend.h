@@ -53,6 +53,8 @@ void obk_set_kernel_timing(ObBackend *, int enable);
 void obk_get_kernel_times(ObBackend *, double *ms, long long *launches);
 const char *obk_kernel_name(int k);
 long long obk_launch_count(void);
+// ob_math.h libm restatements evaluated on the device (fn: 0 atan2f, 1 sinf, 2 cosf); -1 without a device
+int obk_libm(int fn, int n, const float *a, const float *b, float *out);
 // large-world path: last step's {pairs, contacts, contact pairs, solved contacts, colours, colouring rounds, SOR launches, steps timed}
 // and the per-phase CUDA-event times accumulated while kernel timing is on
 // {geoms+sort, pairs, narrowphase, colouring, assembly, SOR, integration}.  Returns -1 for a small-world batch.

@@ -69,8 +69,8 @@ ObBackend *obk_create(const ObBatchDev &caps, int device, char *err, size_t errl
   ObBackend *b = new ObBackend;
   b->d = caps; b->device = device; b->stream = 0; b->st_dev = 0; b->st_host = 0;
   b->ktiming = 0;
-  b->sched_gs = 0; b->smem_sched_tile = 0; b->sor_ring = 0; b->smem_sor_ring = 0; b->ring_resident = 0; b->avg_rows = 0; b->cnt_host = 0;
-  b->l2_target_bytes = 80e6;
+  b->sched_gs = 0; b->smem_sched_tile = 0; b->sor_ring = 0; b->smem_sor_ring = 0; b->ring_resident = 0; b->ring_depth = 0; b->sor_pair = 0; b->smem_sor_pair = 0; b->pair_resident = 0; b->avg_rows = 0; b->cnt_host = 0;
+  b->l2_target_bytes = 1e12;   // r02a on B200: limiting the worlds in flight to an L2-sized set costs whole waves (1.72 -> 2.5 -> 3.2 ms at 100 / 60 / 40 MB); off unless OB_SOR_L2MB asks
   for (int k = 0; k < OBK_NKERNELS; k++) { b->kms[k] = 0; b->klaunch[k] = 0; }
   for (int k = 0; k < 8; k++) b->ev[k] = 0;
   ObBatchDev &d = b->d;
@@ -368,3 +368,26 @@ int obk_add_forces(ObBackend *b, const real *f3, const real *t3) {
 }
 void *obk_host_alloc(size_t bytes) { void *p = 0; return cudaMallocHost(&p, bytes ? bytes : 1) == cudaSuccess ? p : 0; }
 void obk_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+
+// diagnostics: the libm restatements of ob_math.h on the device
+__global__ void k_libm(int fn, int n, const float *a, const float *b, float *out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = fn == 0 ? ob_atan2f_glibc(a[i], b[i]) : (fn == 1 ? ob_sinf_glibc(a[i]) : ob_cosf_glibc(a[i]));
+}
+int obk_libm(int fn, int n, const float *a, const float *b, float *out) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || n <= 0) return -1;
+  float *da = 0, *db = 0, *dout = 0;
+  const size_t nb = sizeof(float) * (size_t)n;
+  cudaError_t e = cudaMalloc((void **)&da, nb);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&db, nb);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&dout, nb);
+  if (e == cudaSuccess) e = cudaMemcpy(da, a, nb, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(db, b ? b : a, nb, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) { k_libm<<<(unsigned)((n + 255) / 256), 256>>>(fn, n, da, db, dout); g_launches++; e = cudaMemcpy(out, dout, nb, cudaMemcpyDeviceToHost); }
+  if (da) cudaFree(da);
+  if (db) cudaFree(db);
+  if (dout) cudaFree(dout);
+  return e == cudaSuccess ? 0 : -1;
+}

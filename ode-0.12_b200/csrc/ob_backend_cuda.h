@@ -43,7 +43,7 @@ __host__ __device__ inline CollideSmem collide_smem(int NG, int NP) {
   s.sapinit = o; o = ob_al16(o + sizeof(int) * (NG + 1));
   s.sappos = o; o = ob_al16(o + sizeof(int) * (NG + 1));
   s.sapwalk = o; o = ob_al16(o + sizeof(int) * (NG + 1));
-  s.key = o; o = ob_al16(o + sizeof(ObPairKey) * NP);
+  { const size_t kb = sizeof(ObPairKey) * NP, cb = sizeof(int) * 2 * OB_THREADS; s.key = o; o = ob_al16(o + (kb > cb ? kb : cb)); }   // keys; reused by the narrowphase for per-pair counts / offsets of a chunk
   s.o12 = o; o = ob_al16(o + sizeof(int2) * NP);
   s.sorted = o; o = ob_al16(o + sizeof(int2) * NP);
   s.misc = o; o = ob_al16(o + sizeof(int) * 64);
@@ -110,6 +110,10 @@ struct ObBackend {
   int sor_ring;     // 1: k_sor_ring (rows through a cp.async shared-memory ring, persistent L2-sized grid)
   size_t smem_sor_ring;
   int ring_resident;        // CTAs of k_sor_ring that fit the device at once
+  int ring_depth;           // slots of the row ring (6 or 4; 0: ring kernel not in use)
+  int sor_pair;             // > 0: k_sor_pair (two lanes per row) with this ring depth
+  size_t smem_sor_pair;
+  int pair_resident;
   double avg_rows;          // measured rows per world-step (counters read back at every sync point), 0 = unknown
   ObCounters *cnt_host;     // pinned copy of the device counters
   double l2_target_bytes;   // rows of the worlds in flight are kept below this (OB_SOR_L2MB)

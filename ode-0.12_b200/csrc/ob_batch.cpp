@@ -518,4 +518,9 @@ int dBatchSplitAttach(dBatchID B, int rank, int nranks, const void *handles) {
 }
 void *dBatchGetStream(dBatchID B) { return obk_stream(B->bk); }
 long long dB200KernelLaunchCount(void) { return obk_launch_count(); }
+int dB200LibmHost(int fn, int n, const float *a, const float *b, float *out) {
+  for (int i = 0; i < n; i++) out[i] = fn == 0 ? ob_atan2f_glibc(a[i], b[i]) : (fn == 1 ? ob_sinf_glibc(a[i]) : ob_cosf_glibc(a[i]));
+  return 0;
+}
+int dB200LibmDevice(int fn, int n, const float *a, const float *b, float *out) { return obk_libm(fn, n, a, b, out); }
 }  // extern "C"

@@ -30,7 +30,9 @@ struct ObDropin {
   dxSpace *space;      // space collided through this context (own_space when only a world is stepped)
   dxWorld *own_world;
   dxSpace *own_space;
-  int maxc_hint;       // max-contacts value the near callback passed to dCollide last time
+  int maxc_hint;       // max-contacts value the near callback passed to dCollide last time (NEXT frame's narrowphase runs with it)
+  int maxc_used;       // max-contacts value this frame's batched narrowphase actually ran with (what the cached contacts obey)
+  int kcap;            // per-pair contact capacity of the collide kernel that produced them (8 without trimeshes, else OB_MAXC_LOCAL)
   bool in_collide;     // results below are valid (only while the callbacks run)
   std::vector<int> pairs;              // (o1,o2) geom indices in callback order
   std::vector<ObContact> contacts;     // grouped by pair, pair order
@@ -67,7 +69,7 @@ static dxWorld *world_of_space(dxSpace *s, bool *mixed) {
 
 static ObDropin *ctx_new(dxWorld *w, dxSpace *s) {
   ObDropin *c = new ObDropin;
-  c->B = 0; c->world = w; c->space = s; c->own_world = 0; c->own_space = 0; c->maxc_hint = 8; c->in_collide = false;
+  c->B = 0; c->world = w; c->space = s; c->own_world = 0; c->own_space = 0; c->maxc_hint = 8; c->maxc_used = 8; c->kcap = 8; c->in_collide = false;
   g_ctx.push_back(c);
   return c;
 }
@@ -140,6 +142,8 @@ void ob_dropin_space_collide(dxSpace *space, void *data, dNearCallback *cb) {
   memset(&pol, 0, sizeof pol);
   pol.cat_mask1 = pol.cat_mask2 = ~0u;
   pol.max_contacts = c->maxc_hint; pol.skip_if_connected = 0;   // the callback decides, not a policy
+  c->maxc_used = c->maxc_hint;
+  c->kcap = (B->caps.nmesh || B->caps.any_xf) ? OB_MAXC_LOCAL : 8;   // CGCAP of the k_collide instantiation that serves this batch
   int rc = ob_batch_upload(B);
   rc |= obk_h2d(B->bk, B->caps.policy, &pol, sizeof pol);
   if (rc) { ob_error(0, "dSpaceCollide: upload failed"); return; }
@@ -202,11 +206,14 @@ int ob_dropin_collide(dxGeom *o1, dxGeom *o2, int flags, dContactGeom *contact, 
     ObDropin *c = g_ctx[i];
     if (!c->in_collide || o1->parent_space != c->space || o2->parent_space != c->space) continue;
     const int cap = ob_pair_max_contacts(shape_type(o1), shape_type(o2), 1 << 15);
-    const int eff_want = std::min(want, std::min(cap, OB_MAXC_LOCAL)), eff_have = std::min(c->maxc_hint, std::min(cap, OB_MAXC_LOCAL));
-    if (want != c->maxc_hint) c->maxc_hint = std::min(want, OB_MAXC_LOCAL);   // next frame's batch narrowphase uses the caller's value
+    // the cached contacts were computed with maxc_used (clamped by the kernel's per-pair capacity), not with this call's
+    // value: they are served only when both give the same computation; anything else goes to the on-demand path
+    const int eff_want = std::min(want, std::min(cap, OB_MAXC_LOCAL)), eff_have = std::min(c->maxc_used, std::min(cap, c->kcap));
+    if (want != c->maxc_hint) c->maxc_hint = std::min(want, OB_MAXC_LOCAL);   // NEXT frame's batch narrowphase uses the caller's value
     std::map<std::pair<int, int>, std::pair<int, int> >::iterator it = c->pair_contacts.find(std::make_pair(o1->batch_index, o2->batch_index));
     if (it == c->pair_contacts.end() || eff_want != eff_have) break;
     const int k0 = it->second.first, n = it->second.second;
+    if (n > want) break;   // never write past the caller's array
     for (int k = 0; k < n; k++) {
       const ObContact &s = c->contacts[k0 + k];
       dContactGeom *d = OB_CONTACT_AT(contact, skip, k);
@@ -233,6 +240,10 @@ int ob_dropin_collide(dxGeom *o1, dxGeom *o2, int flags, dContactGeom *contact, 
       if (!md) { ob_error(0, "dCollide: trimesh data missing or upload failed"); return 0; }
       m2[k] = *md; op[k]->mesh = k;
     }
+  if (want > OB_MAXC_LOCAL && ob_pair_max_contacts(shape_type(o1), shape_type(o2), 1 << 15) > OB_MAXC_LOCAL) {
+    static bool warned = false;   // the reference returns up to `want` contacts for these pairs; this build stops at OB_MAXC_LOCAL (ode.h)
+    if (!warned) { warned = true; ob_message(0, "dCollide: %d contacts requested, at most %d per pair are generated (documented limit)", want, OB_MAXC_LOCAL); }
+  }
   const int n = obk_collide_pair(&a, &b, flags, cg, m2, err, sizeof err);
   if (n < 0) { ob_error(0, "dCollide: %s", err); return 0; }
   for (int k = 0; k < n; k++) {

@@ -56,7 +56,9 @@ int obk_stepk_setup(ObBackend *b, const cudaDeviceProp &prop, char *err, size_t 
   {
     // k_sched_tile: lanes per world by batch size (enough warps to hide the serial chains' latency, few enough lanes
     // per world that a warp instruction of the chains advances several worlds)
-    int gs = W >= 2048 ? 8 : (W >= 512 ? 16 : 0);
+    // measured on B200 (r02a, configs[1]): 0.95 / 0.55 / 0.39 ms at 4 / 8 / 16 lanes per world against 0.39 ms for the warp per
+    // world -- the chains are latency-bound, fewer warps lose what fewer instructions gain; off unless OB_SCHED_TILE asks
+    int gs = 0;
     const char *e = getenv("OB_SCHED_TILE");
     if (e) gs = atoi(e);
     if (gs != 2 && gs != 4 && gs != 8 && gs != 16) gs = 0;
@@ -72,17 +74,62 @@ int obk_stepk_setup(ObBackend *b, const cudaDeviceProp &prop, char *err, size_t 
     }
   }
   {
-    // k_sor_ring: on unless the caller pins one of the register-pipelined variants (OB_SOR_DEEP) or OB_SOR_RING=0
+    // k_sor_ring: on unless the caller pins one of the register-pipelined variants (OB_SOR_DEEP) or OB_SOR_RING=0.
+    // Ring depth: 6 slots (rows 5 passes ahead) when every CTA of the batch still stays resident, else 4
     const char *e = getenv("OB_SOR_RING");
     const bool want = e ? atoi(e) != 0 : getenv("OB_SOR_DEEP") == 0;
-    b->smem_sor_ring = sor_ring_smem(d.NB, d.NR, b->tile).total * (32 / b->tile);
-    if (want && b->smem_sor_ring <= (size_t)prop.sharedMemPerBlockOptin) {
-      int per_sm = 0;
-#define OB_RING_SETUP(GG) { CK(cudaFuncSetAttribute(k_sor_ring<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sor_ring)); \
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sor_ring<GG>, 32, b->smem_sor_ring)); }
-      if (b->tile == 4) OB_RING_SETUP(4) else if (b->tile == 8) OB_RING_SETUP(8) else if (b->tile == 16) OB_RING_SETUP(16) else OB_RING_SETUP(32)
+    const int Tw = 32 / b->tile;
+    const int need = (int)((W + Tw - 1) / Tw);
+    b->ring_depth = 0;
+    if (want) {
+      const int depths[2] = {6, 4};
+      int best_res = 0;
+      for (int k = 0; k < 2; k++) {
+        const int D = depths[k];
+        { const char *de = getenv("OB_RING_DEPTH"); if (de && atoi(de) != D) continue; }
+        const size_t sm = sor_ring_smem(d.NB, d.NR, b->tile, D).total * Tw;
+        if (sm > (size_t)prop.sharedMemPerBlockOptin) continue;
+        int per_sm = 0;
+#define OB_RING_SETUP(GG, DD) { CK(cudaFuncSetAttribute(k_sor_ring<GG, DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+          CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sor_ring<GG, DD>, 32, sm)); }
+#define OB_RING_SETUP_G(DD) { if (b->tile == 4) OB_RING_SETUP(4, DD) else if (b->tile == 8) OB_RING_SETUP(8, DD) else if (b->tile == 16) OB_RING_SETUP(16, DD) else OB_RING_SETUP(32, DD) }
+        if (D == 6) OB_RING_SETUP_G(6) else OB_RING_SETUP_G(4)
+#undef OB_RING_SETUP_G
 #undef OB_RING_SETUP
-      if (per_sm > 0) { b->sor_ring = 1; b->ring_resident = per_sm * prop.multiProcessorCount; }
+        const int res = per_sm * prop.multiProcessorCount;
+        if (res <= 0) continue;
+        // take the deeper ring unless it costs residency the batch needs
+        if (b->ring_depth == 0 || (best_res < need && res > best_res)) { b->ring_depth = D; b->smem_sor_ring = sm; b->ring_resident = res; best_res = res; }
+      }
+      b->sor_ring = b->ring_depth != 0;
+    }
+    // k_sor_pair: two lanes per row (2 * tile lanes per world), on top of the ring's machinery; ring depth 5, or 4 when that keeps more CTAs resident
+    b->sor_pair = 0;
+    {
+      const char *pe = getenv("OB_SOR_PAIR");
+      const bool wantp = b->sor_ring && b->tile <= 16 && (pe ? atoi(pe) != 0 : true);
+      if (wantp) {
+        const int GP = 2 * b->tile, Tp = 32 / GP;
+        const int needp = (int)((W + Tp - 1) / Tp);
+        int best = 0;
+        const int depths[2] = {5, 4};
+        for (int k = 0; k < 2; k++) {
+          const int D = depths[k];
+          { const char *de = getenv("OB_PAIR_DEPTH"); if (de && atoi(de) != D) continue; }
+          const size_t sm = sor_ring_smem(d.NB, d.NR, b->tile, D).total * Tp;
+          if (sm > (size_t)prop.sharedMemPerBlockOptin) continue;
+          int per_sm = 0;
+#define OB_PAIR_SETUP(GG, DD) { CK(cudaFuncSetAttribute(k_sor_pair<GG, DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sor_pair<GG, DD>, 32, sm)); }
+#define OB_PAIR_SETUP_G(DD) { if (GP == 8) OB_PAIR_SETUP(8, DD) else if (GP == 16) OB_PAIR_SETUP(16, DD) else OB_PAIR_SETUP(32, DD) }
+          if (D == 5) OB_PAIR_SETUP_G(5) else OB_PAIR_SETUP_G(4)
+#undef OB_PAIR_SETUP_G
+#undef OB_PAIR_SETUP
+          const int res = per_sm * prop.multiProcessorCount;
+          if (res <= 0) continue;
+          if (b->sor_pair == 0 || (best < needp && res > best)) { b->sor_pair = D; b->smem_sor_pair = sm; b->pair_resident = res; best = res; }
+        }
+      }
     }
     const char *l2 = getenv("OB_SOR_L2MB");
     if (l2 && atof(l2) > 0) b->l2_target_bytes = atof(l2) * 1e6;
@@ -113,7 +160,18 @@ template <int G> static void stepk_launch_t(ObBackend *b, const ObBatchDev &d, r
     else if (d.NB <= 128) k_sched<4><<<W, 32, b->smem_sched, st>>>(d, G, taps);
     else k_sched<8><<<W, 32, b->smem_sched, st>>>(d, G, taps);
     if (timing) cudaEventRecord(ev[3], st);
-    if (b->sor_ring) {
+    if (b->sor_pair) {
+      constexpr int GP = G <= 16 ? 2 * G : 32, Tp = 32 / GP;
+      const int gp = (W + Tp - 1) / Tp;
+      long long cap = b->pair_resident > 0 ? b->pair_resident : gp;
+      { static const char *e = getenv("OB_GRID_SOR"); if (e && atoi(e) > 0) cap = atoi(e); }
+      const int waves = (int)((gp + cap - 1) / cap);
+      const int gpair = (gp + waves - 1) / waves;
+      if (G <= 16) {
+        if (b->sor_pair == 5) k_sor_pair<GP, 5><<<gpair, 32, b->smem_sor_pair, st>>>(d, taps);
+        else k_sor_pair<GP, 4><<<gpair, 32, b->smem_sor_pair, st>>>(d, taps);
+      }
+    } else if (b->sor_ring) {
       // persistent grid: as many CTAs as stay resident, fewer when the rows of the worlds in flight would not fit the L2
       // (rows/world measured from the counters; capacity-based guess before the first read-back), whole waves
       const double rows_w = b->avg_rows > 0 ? b->avg_rows : 0.65 * d.NR;
@@ -124,7 +182,8 @@ template <int G> static void stepk_launch_t(ObBackend *b, const ObBatchDev &d, r
       { static const char *e = getenv("OB_GRID_SOR"); if (e && atoi(e) > 0) cap = atoi(e); }
       const int waves = (int)((gstep + cap - 1) / cap);
       const int gring = (gstep + waves - 1) / waves;
-      k_sor_ring<G><<<gring, 32, b->smem_sor_ring, st>>>(d, taps);
+      if (b->ring_depth == 6) k_sor_ring<G, 6><<<gring, 32, b->smem_sor_ring, st>>>(d, taps);
+      else k_sor_ring<G, 4><<<gring, 32, b->smem_sor_ring, st>>>(d, taps);
     } else if (b->sor_deep) k_sor<G, true><<<gsor, 32, b->smem_sor, st>>>(d, taps);
     else k_sor<G, false><<<gsor, 32, b->smem_sor, st>>>(d, taps);
     if (timing) cudaEventRecord(ev[4], st);

@@ -362,6 +362,94 @@ OB_HD real ob_atan2(real y, real x) {
 #endif
 }
 
+// sinf / cosf with the host libm's results: dxStepBody's finite-rotation integrator (util.cpp:288-330) calls dSin / dCos
+// (sinf / cosf in dSINGLE) on the half rotation angle, and the value lands in the body's quaternion.  glibc 2.39
+// (sysdeps/ieee754/flt-32/s_sinf.c, s_cosf.c, s_sincosf.h — the ARM optimized-routines algorithm; third-party, not part
+// of /root/reference) evaluates both in DOUBLE precision: |x| < pi/4 a degree-7 / degree-8 polynomial, |x| < 120 a
+// multiply-and-round quadrant reduction, beyond that a 2/pi bit-table reduction.  x86-64 libm dispatches (ifunc) to its
+// FMA build on every CPU with FMA3, i.e. the polynomial and the reduction contract a*b+c; restated here with explicit
+// fma() in exactly those places.  Checked against the host's sinf / cosf on ALL 2^32 float inputs (0 mismatches with
+// fma, tests/test_abi.py runs a sampled version; the coefficient table was read back from this image's libm.so.6).
+// dDOUBLE uses the platform's sin / cos (glibc's and CUDA's differ in the last bits): tolerance class, like atan2.
+OB_HD double ob_fma64(double a, double b, double c) {
+#if defined(__CUDA_ARCH__)
+  return fma(a, b, c);
+#else
+  return __builtin_fma(a, b, c);
+#endif
+}
+OB_HD uint32_t ob_abstop12(float x) { return ((uint32_t)ob_f2i(x) >> 20) & 0x7ffu; }
+// sign folded into the polynomial's coefficients (table entry 1 of __sincosf_table negates the cosine part)
+OB_HD float ob_sincosf_poly(double x, double x2, int neg, int n) {
+  const double sg = neg ? -1.0 : 1.0;
+  if ((n & 1) == 0) {
+    const double S1 = -0.16666654943701084 /* 0x1.555545995a603p-3 */, S2 = 0.008332178146138854 /* 0x1.1107605230bc4p-7 */, S3 = -0.00019517298981385725 /* 0x1.994eb3774cf24p-13 */;
+    const double x3 = x * x2, s1 = ob_fma64(x2, S3, S2), x7 = x3 * x2, s = ob_fma64(x3, S1, x);
+    return (float)ob_fma64(x7, s1, s);
+  } else {
+    const double C0 = sg * 1.0 /* 0x1p0 */, C1 = sg * -0.49999999725108224 /* 0x1.ffffffd0c621cp-2 */, C2 = sg * 0.041666623324344516 /* 0x1.55553e1068f19p-5 */, C3 = sg * -0.001388676379437604 /* 0x1.6c087e89a359dp-10 */,
+                 C4 = sg * 2.4390450703564542e-05 /* 0x1.99343027bf8c3p-16 */;
+    const double x4 = x2 * x2, c2 = ob_fma64(x2, C4, C3), c1 = ob_fma64(x2, C1, C0), x6 = x4 * x2, c = ob_fma64(x4, C2, c1);
+    return (float)ob_fma64(x6, c2, c);
+  }
+}
+OB_HD double ob_sincosf_reduce(float y, int *np, int *signp) {
+  const double hpi_inv = 10680707.430881744 /* 0x1.45F306DC9C883p+23 */, hpi = 1.5707963267948966 /* 0x1.921FB54442D18p0 */;
+  *signp = 0;
+  if (ob_abstop12(y) < ob_abstop12(120.0f)) {
+    const double x = (double)y, r = x * hpi_inv;
+    const int n = ((int32_t)r + 0x800000) >> 24;
+    *np = n;
+    return ob_fma64(-(double)n, hpi, x);
+  }
+  const uint32_t inv_pio4[24] = {0xa2, 0xa2f9, 0xa2f983, 0xa2f9836e, 0xf9836e4e, 0x836e4e44, 0x6e4e4415, 0x4e441529, 0x441529fc, 0x1529fc27,
+                                 0x29fc2757, 0xfc2757d1, 0x2757d1f5, 0x57d1f534, 0xd1f534dd, 0xf534ddc0, 0x34ddc0db, 0xddc0db62, 0xc0db6295,
+                                 0xdb629599, 0x6295993c, 0x95993c43, 0x993c4390, 0x3c439041};
+  uint32_t xi = (uint32_t)ob_f2i(y);
+  *signp = (int)(xi >> 31);
+  const uint32_t *arr = &inv_pio4[(xi >> 26) & 15];
+  const int shift = (xi >> 23) & 7;
+  uint64_t n, res0, res1, res2;
+  xi = (xi & 0xffffff) | 0x800000;
+  xi <<= shift;
+  res0 = (uint64_t)(uint32_t)(xi * arr[0]);
+  res1 = (uint64_t)xi * arr[4];
+  res2 = (uint64_t)xi * arr[8];
+  res0 = (res2 >> 32) | (res0 << 32);
+  res0 += res1;
+  n = (res0 + (1ULL << 61)) >> 62;
+  res0 -= n << 62;
+  const double x = (double)(int64_t)res0;
+  *np = (int)n;
+  return x * 3.4061215800865545e-19 /* 0x1.921FB54442D18p-62 */;
+}
+OB_HD float ob_sinf_glibc(float y) {
+  if (ob_abstop12(y) < ob_abstop12(0.785398185f)) {
+    if (ob_abstop12(y) < ob_abstop12(0.000244140625f)) return y;
+    const double x = (double)y;
+    return ob_sincosf_poly(x, x * x, 0, 0);
+  }
+  if (!(ob_abstop12(y) < ob_abstop12(ob_i2f(0x7f800000)))) return y - y;   // inf / nan -> nan
+  int n, sign;
+  const double x = ob_sincosf_reduce(y, &n, &sign);
+  const int q = n + sign;
+  const double s = ((q & 3) == 1 || (q & 3) == 2) ? -1.0 : 1.0;
+  return ob_sincosf_poly(x * s, x * x, (q & 2) != 0, n);
+}
+OB_HD float ob_cosf_glibc(float y) {
+  if (ob_abstop12(y) < ob_abstop12(0.785398185f)) {
+    if (ob_abstop12(y) < ob_abstop12(0.000244140625f)) return 1.0f;
+    const double x = (double)y;
+    return ob_sincosf_poly(x, x * x, 0, 1);
+  }
+  if (!(ob_abstop12(y) < ob_abstop12(ob_i2f(0x7f800000)))) return y - y;
+  int n, sign;
+  const double x = ob_sincosf_reduce(y, &n, &sign);
+  const int q = n + sign;
+  const double s = ((q & 3) == 1 || (q & 3) == 2) ? -1.0 : 1.0;
+  return ob_sincosf_poly(x * s, x * x, (q & 2) != 0, n ^ 1);
+}
+
 // ---- LCG behind the SOR row shuffle (misc.cpp:33-38, 66-117) -----------------
 OB_HD uint32_t ob_lcg_next(uint32_t s) { return 1664525u * s + 1013904223u; }
 // fold + modulus part of dRandInt applied to an already-advanced state r

@@ -140,14 +140,14 @@ OB_HD void ob_body_velocity_update(real *lvel, real *avel, const real *cforce /*
 OB_HD real ob_sinc(real x) {
   if ((double)ob_fabs(x) < 1.0e-4) return OB_REAL(1.0) - x * x * OB_REAL(0.166666666666666666667);
 #if defined(dSINGLE)
-  return sinf(x) / x;
+  return ob_sinf_glibc(x) / x;
 #else
   return sin(x) / x;
 #endif
 }
 OB_HD real ob_cos(real x) {
 #if defined(dSINGLE)
-  return cosf(x);
+  return ob_cosf_glibc(x);
 #else
   return cos(x);
 #endif

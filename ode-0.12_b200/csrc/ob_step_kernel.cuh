@@ -929,23 +929,28 @@ __global__ void __launch_bounds__(32) k_sched_tile(ObBatchDev d, int G) {
           uint32_t s = A0 * seed + C0;
           ob_lcg_skip((unsigned)GS, &A, &C);
           for (int i = 1 + gl; i < m; i += GS) {
-            s_lvl[r0 + i] = (unsigned short)ob_randint_fold(s, (uint32_t)(i + 1));
+            s_lvl[r0 + i] = (unsigned short)(r0 + ob_randint_fold(s, (uint32_t)(i + 1)));   // absolute position of the swap partner
             s = A * s + C;
           }
         }
+        // the first position of every island swaps with itself: the chain below needs no island boundaries
+        for (int q = gl; q < nri_e; q += GS) s_lvl[s_isl[2 * q]] = s_isl[2 * q];
       }
       __syncwarp();
-      if (gl == 0) {
-        for (int q = 0; q < nri_e; q++) {
-          const int r0 = s_isl[2 * q], m = s_isl[2 * q + 1];
-          if (m < 2) continue;
-          unsigned short *ord = s_ord + r0;
-          int sj = s_lvl[r0 + 1];
-          for (int i = 1; i < m; i++) {
-            const int sjn = s_lvl[r0 + (i + 1 < m ? i + 1 : i)];   // the next swap index is fetched ahead of the dependent chain
-            const unsigned short t = ord[i], u = ord[sj];
-            ord[i] = u; ord[sj] = t;
-            sj = sjn;
+      // the m-1 dependent swaps of every island, as ONE flat loop over the world's positions with a warp-uniform trip count:
+      // the leader lanes of the warp's tiles stay converged, one warp instruction advances every tile's chain
+      // (r02b: with per-island loops of different lengths the leaders drifted apart, 1.4 live lanes per instruction)
+      {
+        const int kmax = warp_max_i(mtot_e);
+        if (gl == 0) {
+          int tg = mtot_e > 0 ? (int)s_lvl[0] : 0;
+          for (int k = 0; k < kmax; k++) {
+            const bool on = k < mtot_e;
+            const int kk = on ? k : 0, tj = on ? tg : 0;
+            const int tgn = s_lvl[(on && k + 1 < mtot_e) ? k + 1 : kk];   // the next partner is fetched ahead of the dependent chain
+            const unsigned short t = s_ord[kk], u = s_ord[tj];
+            if (on) { s_ord[kk] = u; s_ord[tj] = t; }
+            tg = tgn;
           }
         }
       }
@@ -959,20 +964,26 @@ __global__ void __launch_bounds__(32) k_sched_tile(ObBatchDev d, int G) {
       }
       __syncwarp();
       int nlev = 0;
-      if (gl == 0) {
-        for (int q = 0; q < nri_e; q++) {
-          const int r0 = s_isl[2 * q], m = s_isl[2 * q + 1];
-          unsigned rb = s_lvl[r0];
-          for (int k = 0; k < m; k++) {
-            const unsigned rbn = s_lvl[r0 + (k + 1 < m ? k + 1 : k)];
+      {
+        // islands own disjoint bodies and rows [r0, r0 + m) are contiguous in island order, so the recurrence is one flat
+        // loop over the world's positions; warp-uniform trip count as above
+        const int kmax = warp_max_i(mtot_e);
+        if (gl == 0) {
+          unsigned rb = mtot_e > 0 ? (unsigned)s_lvl[0] : 0u;
+          for (int k = 0; k < kmax; k++) {
+            const bool on = k < mtot_e;
+            const int kk = on ? k : 0;
+            const unsigned rbn = s_lvl[(on && k + 1 < mtot_e) ? k + 1 : kk];
             const int b1 = rb & 255, b2 = (rb >> 8) & 255;      // b2 == 255: slot 255 is read (always 0) and slot 256 written
             const int l1 = s_last[b1], l2 = s_last[b2];
             const int lv = (l2 > l1 ? l2 : l1) + 1;
-            s_last[b1] = (unsigned short)lv;
-            s_last[b2 + (b2 == 255)] = (unsigned short)lv;
-            s_lvl[r0 + k] = (unsigned short)lv;
-            s_X[lv] = s_X[lv] + 1;                               // rows per level (off the dependent chain)
-            nlev = lv > nlev ? lv : nlev;
+            if (on) {
+              s_last[b1] = (unsigned short)lv;
+              s_last[b2 + (b2 == 255)] = (unsigned short)lv;
+              s_lvl[kk] = (unsigned short)lv;
+              s_X[lv] = s_X[lv] + 1;                             // rows per level (off the dependent chain)
+              nlev = lv > nlev ? lv : nlev;
+            }
             rb = rbn;
           }
         }
@@ -1101,7 +1112,7 @@ __device__ __noinline__ void sor_check_pass(bool act, unsigned meta, int gl, int
 // after the sweeps: cforce per body for k_post; lambda + joint feedback taps (quickstep.cpp:918-957)
 template <int G>
 __device__ __forceinline__ void sor_epilogue(const ObBatchDev &d, int taps, int wc, bool valid, int gl, int nb, int mtot, const int *si,
-                                             const real *rows, const real *s_fc, const real *s_lam) {
+                                             const real *rows, const real *s_fc, const real *s_lam, int fcs = 8) {
   real *g_fc = d.tmp1 + (size_t)wc * d.NB * 8;   // tmp1 is dead after row assembly: reuse as cforce
   for (int b = gl; b < nb; b += G)
     for (int k = 0; k < 6; k++) g_fc[8 * b + k] = s_fc[8 * b + k];
@@ -1258,28 +1269,32 @@ __global__ void __launch_bounds__(32) k_sor(ObBatchDev d, int taps) {
 }
 
 // =====================================================================================
-// k_sor_ring<G>: the same sweep as k_sor, with the row records streamed through a shared-memory ring by cp.async
-// (LDGSTS) instead of register buffers.  ncu of k_sor<8, DEEP> (r01z): 228 registers, 1.7 warps per scheduler, 27 %
-// issue-active with long-scoreboard on top -- the register pipeline (index six passes ahead, rows three passes ahead)
-// cannot be made deeper without spilling, so the pass time settles at (memory latency) / 3.  Here
-//   * the epoch's schedule (row index per slot + pass starts) is staged in shared memory once per epoch (it is reused
-//     by the epoch's 8 iterations), so finding the row of pass p + D - 1 is two LDS, not a chain of global loads;
-//   * every lane copies ITS row of pass p + D - 1 straight from global/L2 into its own ring slot (5 x 16 B, .cg) and
-//     waits only for its own group of pass p (cp.async.wait_group): no register staging, no cross-lane hand-off,
-//     prefetch depth D - 1 = 5 passes, continuous across the iterations of an epoch (virtual pass counter);
-//   * the kernel is launched as a persistent grid sized by the host so that the rows of the worlds in flight fit the
-//     L2 (ob_backend_cuda.cu): the 20 iterations then re-read them from L2 instead of HBM.
-// The arithmetic of a row update is sor_pass(), unchanged: bit-identical results.
-#define OB_RING_D 6
-struct SorRingSmem { size_t fc, lam, invM, idx, ps, ring, total; };
-__host__ __device__ inline SorRingSmem sor_ring_smem(int NB, int NR, int G) {
+// k_sor_ring<G, D>: the same sweep as k_sor, restructured around what actually bounds it.  ncu of k_sor<8, DEEP> (r01z)
+// and of the first ring version (r02a/b) agree: one pass costs a warp ~1050 cycles for ~190 instructions although the
+// math of a row update is ~60 flops -- the warp executes ONE long dependent chain per pass (schedule lookup -> row
+// record -> meta decode -> invM / fc addresses -> fc loads -> J*Ad, invM*J products -> dot products -> clamp -> update
+// -> stores), and with 4096 worlds = 1024 warps there are < 2 warps per scheduler to hide it behind.  So:
+//   * rows come through a shared-memory ring filled by cp.async (LDGSTS): every lane copies ITS row of pass v + D - 1
+//     straight from global/L2 into its own ring slot and later waits only for its own groups -- no register staging,
+//     no cross-lane hand-off; the prefetcher also leaves the row's index in a header slot, so the consumer never looks
+//     at the schedule;
+//   * the epoch's schedule is staged in shared memory once per epoch (reused by its 8 iterations) as ONE u16 array:
+//     row index | 0x8000 on the first slot of a pass -- the pass length is a ballot away, the pass table is not kept;
+//   * SOFTWARE PIPELINE over passes: while pass v waits for its fc / lambda loads, the warp decodes the row of pass
+//     v + 1 (ring -> registers, J*Ad, invM*J, bounds, addresses).  Only fc and lambda carry a dependency from pass to
+//     pass, so the dependent chain of a pass shrinks to  fc loads -> dots -> clamp -> update -> stores;
+//   * no branches in the pass: one-body rows and idle lanes run the same instructions on harmless operands, their
+//     results are dropped by selects and predicated stores (a select never lets a garbage NaN through).
+// The arithmetic of a row update is ob_sor_row()'s, operation for operation (same products, same association order):
+// bit-identical results, checked by the parity suite and the OB_CHECK pass-disjointness tap.
+struct SorRingSmem { size_t fc, lam, idx, hdr, ring, total; };
+__host__ __device__ inline SorRingSmem sor_ring_smem(int NB, int NR, int G, int D) {
   SorRingSmem s; size_t o = 0;
-  s.fc = o; o = ob_al(o + sizeof(real) * 8 * NB, 16);
+  s.fc = o; o = ob_al(o + sizeof(real) * 8 * NB, 16);                      // per body: fc[6], invMass, unused
   s.lam = o; o = ob_al(o + sizeof(real) * NR, 16);
-  s.invM = o; o = ob_al(o + sizeof(real) * NB, 16);
-  s.idx = o; o = ob_al(o + sizeof(unsigned short) * NR, 16);
-  s.ps = o; o = ob_al(o + sizeof(unsigned short) * (NR + 2), 16);
-  s.ring = o; o = ob_al(o + sizeof(real) * OB_ROWW * OB_RING_D * G, 16);
+  s.idx = o; o = ob_al(o + sizeof(unsigned short) * (NR + G + 2), 16);     // schedule of the epoch + sentinels
+  s.hdr = o; o = ob_al(o + sizeof(unsigned short) * D * G, 16);            // row index of every ring slot (0xffff: idle)
+  s.ring = o; o = ob_al(o + sizeof(real) * OB_ROWW * D * G, 16);
   s.total = ob_al(o, 16);
   return s;
 }
@@ -1287,38 +1302,78 @@ __device__ __forceinline__ void ob_cp_async16(void *smem_dst, const void *gsrc) 
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void ob_cp_async16_sa(unsigned sa, const void *gsrc) {   // destination given as a shared-window address
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void ob_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N> __device__ __forceinline__ void ob_cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void load_row_smem(const real *p, ObRowReg &r) {
+
+// operands of one row update, prepared one pass ahead of their use
+struct ObRowPrep {
+  real Js[9];       // J1l, J1a, J2a scaled by Ad (quickstep.cpp:393-401); J2l*Ad == -Js[0..2]
+  real iM1[3];      // invM1 * J1l      (iMJ of body 2's linear part is invM2 * (-J1l) == -iM2[])
+  real iM2[3];      // invM2 * J1l
+  real iMa[6];      // iMJ1a, iMJ2a as stored
+  real b, adcfm, lo, hi;
+  int o1, o2;       // word offsets of the bodies' fc in s_fc (o2 == o1 for one-body rows)
+  int li, lf;       // lambda index of the row, of its friction normal (== li when none)
+  bool act, has2, fric;
+};
+__device__ __forceinline__ void sor_prep(const real *slot, int ci, const real *s_fc, ObRowPrep &P) {
+  ObRowReg r;
 #if defined(dSINGLE)
-  const float4 *q = (const float4 *)p;
+  const float4 *q = (const float4 *)slot;
 #pragma unroll
   for (int i = 0; i < 4; i++) { const float4 t = q[i]; r.v[4 * i] = t.x; r.v[4 * i + 1] = t.y; r.v[4 * i + 2] = t.z; r.v[4 * i + 3] = t.w; }
-  const float4 t = q[4];
-  r.v[16] = t.x; r.v[17] = t.y; r.v[18] = t.z; r.meta = __float_as_uint(t.w);
+  { const float4 t = q[4]; r.v[16] = t.x; r.v[17] = t.y; r.v[18] = t.z; r.meta = __float_as_uint(t.w); }
 #else
-  const double2 *q = (const double2 *)p;
+  const double2 *q = (const double2 *)slot;
 #pragma unroll
   for (int i = 0; i < 9; i++) { const double2 t = q[i]; r.v[2 * i] = t.x; r.v[2 * i + 1] = t.y; }
-  const double2 t = q[9];
-  r.v[18] = t.x; r.meta = (unsigned)__double2loint(t.y);
+  { const double2 t = q[9]; r.v[18] = t.x; r.meta = (unsigned)__double2loint(t.y); }
 #endif
+  P.act = ci != 0xffff;
+  const unsigned meta = P.act ? r.meta : 0u;
+  const int b1 = meta & 255, b2r = (meta >> 8) & 255, fio = (meta >> 16) & 255, bmode = meta >> 24;
+  P.has2 = b2r != 255;
+  P.fric = fio != 0;
+  const int b2 = P.has2 ? b2r : b1;
+  P.o1 = 8 * b1; P.o2 = 8 * b2;
+  P.li = P.act ? ci : 0;
+  P.lf = P.fric ? P.li - fio : P.li;
+  const real Ad = r.v[15], k1 = s_fc[8 * b1 + 6], k2 = s_fc[8 * b2 + 6];
+  const real bv = r.v[18];
+  P.lo = bmode == 0 ? -bv : (bmode == 1 ? (real)0 : bv);
+  P.hi = bmode == 2 ? (real)0 : bv;
+  P.b = r.v[16]; P.adcfm = r.v[17];
+#pragma unroll
+  for (int e = 0; e < 9; e++) P.Js[e] = r.v[e] * Ad;
+#pragma unroll
+  for (int e = 0; e < 3; e++) { P.iM1[e] = k1 * r.v[e]; P.iM2[e] = k2 * r.v[e]; }
+#pragma unroll
+  for (int e = 0; e < 6; e++) P.iMa[e] = r.v[9 + e];
 }
 
-template <int G>
+template <int G, int D>
 __global__ void __launch_bounds__(32) k_sor_ring(ObBatchDev d, int taps) {
-  constexpr int T = 32 / G, D = OB_RING_D;
+  constexpr int T = 32 / G;
   constexpr int ROWB = OB_ROWW * (int)sizeof(real);
   extern __shared__ __align__(16) unsigned char smem_all[];
-  const SorRingSmem L = sor_ring_smem(d.NB, d.NR, G);
-  const int lane = threadIdx.x, grp = lane / G, gl = lane % G;
+  const SorRingSmem L = sor_ring_smem(d.NB, d.NR, G, D);
+  int lane = threadIdx.x;
+  asm volatile("" : "+r"(lane));   // opaque: keeps lane-derived values in registers instead of re-reading SR_TID.X inside the pass (r02c: S2R + short-scoreboard stalls)
+  const int grp = lane / G, gl = lane % G;
+  const unsigned FULL = 0xffffffffu;
+  const unsigned gmask = G == 32 ? FULL : ((1u << G) - 1u);
+  const int gsh = grp * G;
   unsigned char *smem = smem_all + (size_t)grp * L.total;
   real *s_fc = (real *)(smem + L.fc);
   real *s_lam = (real *)(smem + L.lam);
-  real *s_invM = (real *)(smem + L.invM);
   unsigned short *s_idx = (unsigned short *)(smem + L.idx);
-  unsigned short *s_ps = (unsigned short *)(smem + L.ps);
-  unsigned char *s_ring = smem + L.ring + (size_t)gl * ROWB;   // this lane's column of the ring: slot k at k * G * ROWB
+  unsigned short *s_hdr = (unsigned short *)(smem + L.hdr) + gl;   // this lane's column: slot k at k * G
+  unsigned char *s_ring = smem + L.ring + (size_t)gl * ROWB;       // this lane's column of the ring: slot k at k * G * ROWB
+  unsigned ring_sa = (unsigned)__cvta_generic_to_shared(s_ring);   // the same as a shared-window address, converted once (cp.async destination)
+  asm volatile("" : "+r"(ring_sa));
 
   for (int wbase = d.wbeg + blockIdx.x * T; wbase < d.wend; wbase += gridDim.x * T) {
     const int w = wbase + grp;
@@ -1330,9 +1385,10 @@ __global__ void __launch_bounds__(32) k_sor_ring(ObBatchDev d, int taps) {
     const int mtot = valid && si[SI_HAVEROWS] ? si[SI_MTOT] : 0;
     const ObBodyConst *bc = d.bconst + (size_t)wc * d.NB;
     const real *rows = d.rows + (size_t)wc * d.NR * OB_ROWW;
-    for (int b = gl; b < nb; b += G) {
-      s_invM[b] = bc[b].invMass;
+    for (int b = gl; b < d.NB; b += G) {
+#pragma unroll
       for (int k = 0; k < 8; k++) s_fc[8 * b + k] = 0;
+      if (b < nb) s_fc[8 * b + 6] = bc[b].invMass;
     }
     for (int i = gl; i < mtot; i += G) s_lam[i] = 0;
     int nep = mtot > 0 ? (iters + 7) >> 3 : 0;
@@ -1343,66 +1399,304 @@ __global__ void __launch_bounds__(32) k_sor_ring(ObBatchDev d, int taps) {
       const int np = epv ? si[SI_NPASS0 + ep] : 0;
       int nit = epv ? iters - 8 * ep : 0;
       if (nit > 8) nit = 8;
-      // stage the epoch's schedule
+      // stage the epoch's schedule: row index per slot, bit 15 on the first slot of every pass, sentinels behind the end
       __syncwarp();
-      {
+      if (epv) {
         const unsigned short *sched = d.sched + ((size_t)wc * d.NEP + ep) * d.NR;
+        for (int i = gl; i < mtot; i += G) s_idx[i] = sched[i];
+        for (int i = gl; i <= G + 1; i += G) s_idx[mtot + i] = 0x8000;
+      }
+      __syncwarp();
+      if (epv) {
         const unsigned short *pstart = d.pstart + ((size_t)wc * d.NEP + ep) * (d.NR + 1);
-        if (epv) {
-          for (int i = gl; i < mtot; i += G) s_idx[i] = sched[i];
-          for (int i = gl; i <= np; i += G) s_ps[i] = pstart[i];
-        }
+        for (int i = gl; i < np; i += G) s_idx[pstart[i]] |= 0x8000;
       }
       __syncwarp();
       const int vtot = np * nit;               // passes of this tile in this epoch (virtual pass v = it * np + p)
       const int vmax = warp_max_i(vtot);
-      int pf_p = 0, pf_v = 0, pf_slot = 0;      // prefetcher: pass within the iteration, virtual pass, ring slot
-      int pf_s = 0;                             // first slot of pass pf_p
+      int pf_v = 0, pf_slot = 0, pf_s = 0;      // prefetcher: virtual pass, ring slot, first schedule slot of the pass
+      // one prefetch step: find the row of this lane in the next pass, start its copy, leave its index in the header
 #define OB_RING_ISSUE()                                                                            \
       {                                                                                            \
-        if (pf_v < vtot) {                                                                         \
-          const int pe_ = s_ps[pf_p + 1];                                                          \
-          if (pf_s + gl < pe_) {                                                                   \
-            const unsigned char *src_ = (const unsigned char *)(rows + (size_t)s_idx[pf_s + gl] * OB_ROWW); \
-            unsigned char *dst_ = s_ring + (size_t)pf_slot * (G * ROWB);                           \
-            _Pragma("unroll") for (int c_ = 0; c_ < ROWB / 16; c_++) ob_cp_async16(dst_ + 16 * c_, src_ + 16 * c_); \
-          }                                                                                        \
-          pf_s = pe_;                                                                              \
-          if (++pf_p == np) { pf_p = 0; pf_s = 0; }                                                \
+        const bool on_ = pf_v < vtot;                                                              \
+        const unsigned me_ = on_ ? (unsigned)s_idx[pf_s + gl] : 0u;                                \
+        const unsigned nx_ = on_ ? (unsigned)s_idx[pf_s + gl + 1] : 0x8000u;                       \
+        const unsigned bits_ = (__ballot_sync(FULL, (nx_ & 0x8000u) != 0) >> gsh) & gmask;         \
+        const int len_ = __ffs(bits_);           /* slots of this pass: next start within G slots */ \
+        const bool mine_ = on_ && gl < len_;                                                       \
+        const unsigned ri_ = me_ & 0x7fffu;                                                        \
+        if (mine_) {                                                                               \
+          const unsigned char *src_ = (const unsigned char *)(rows + (size_t)ri_ * OB_ROWW);       \
+          const unsigned dst_ = ring_sa + (unsigned)pf_slot * (unsigned)(G * ROWB);                 \
+          _Pragma("unroll") for (int c_ = 0; c_ < ROWB / 16; c_++) ob_cp_async16_sa(dst_ + 16u * c_, src_ + 16 * c_); \
         }                                                                                          \
+        s_hdr[pf_slot * G] = (unsigned short)(mine_ ? ri_ : 0xffffu);                              \
         ob_cp_async_commit();                                                                      \
+        if (on_) { pf_s += len_; if (pf_s >= mtot) pf_s = 0; }                                     \
         pf_v++;                                                                                    \
         if (++pf_slot == D) pf_slot = 0;                                                           \
       }
+#pragma unroll 1
       for (int k = 0; k < D - 1; k++) OB_RING_ISSUE()
-      int c_p = 0, c_slot = 0, c_s = 0;
-      for (int v = 0; v < vmax; v++) {
-        OB_RING_ISSUE()
-        ob_cp_async_wait<D - 1>();   // this lane's copy of pass v has landed (groups complete in order)
-        bool act = false;
-        int ci = 0;
-        ObRowReg cur;
-        cur.meta = 0;
-        if (v < vtot) {
-          const int ce = s_ps[c_p + 1];
-          if (c_s + gl < ce) {
-            act = true;
-            ci = s_idx[c_s + gl];
-            load_row_smem((const real *)(s_ring + (size_t)c_slot * (G * ROWB)), cur);
-          }
-          c_s = ce;
-          if (++c_p == np) { c_p = 0; c_s = 0; }
-        }
-        if (taps & 4) sor_check_pass<G>(act, cur.meta, gl, &d.world[wc].status);
-        if (act) sor_pass(cur, ci, s_fc, s_lam, s_invM);
-        if (++c_slot == D) c_slot = 0;
-        __syncwarp();
+      ObRowPrep pa, pb;
+      ob_cp_async_wait<D - 2>();                // group 0 has landed
+      sor_prep((const real *)s_ring, (int)s_hdr[0], s_fc, pa);
+      int n_slot = 1;                           // ring slot of pass v + 1
+      // one pass: CUR is applied, NXT is decoded meanwhile; the loop alternates (pa, pb) / (pb, pa) so no operand set is copied
+#define OB_RING_PASS(CUR, NXT)                                                                     \
+      {                                                                                            \
+        OB_RING_ISSUE()                                                                            \
+        /* (B) this pass's dependent loads: fc of both bodies, lambda, lambda of the friction normal */ \
+        real f1[6], f2[6];                                                                         \
+        const real *fp1 = s_fc + CUR.o1, *fp2 = s_fc + CUR.o2;                                     \
+        OB_LOAD_FC(f1, fp1) OB_LOAD_FC(f2, fp2)                                                    \
+        const real old_lambda = s_lam[CUR.li], lam_f = s_lam[CUR.lf];                              \
+        /* (C) meanwhile: decode the row of the next pass */                                       \
+        ob_cp_async_wait<D - 2>();              /* this lane's copy of pass v + 1 has landed (groups complete in order) */ \
+        sor_prep((const real *)(s_ring + (size_t)n_slot * (G * ROWB)), (int)s_hdr[n_slot * G], s_fc, NXT); \
+        if (++n_slot == D) n_slot = 0;                                                             \
+        if (taps & 4) sor_check_pass<G>(CUR.act, (unsigned)(CUR.o1 >> 3) | ((CUR.has2 ? (unsigned)(CUR.o2 >> 3) : 255u) << 8), gl, &d.world[wc].status); \
+        /* (D) the update, ob_sor_row() operation for operation (quickstep.cpp:490-581) */         \
+        real delta = CUR.b - old_lambda * CUR.adcfm;                                               \
+        delta -= f1[0] * CUR.Js[0] + f1[1] * CUR.Js[1] + f1[2] * CUR.Js[2] + f1[3] * CUR.Js[3] + f1[4] * CUR.Js[4] + f1[5] * CUR.Js[5]; \
+        const real delta2 = delta - (f2[0] * -CUR.Js[0] + f2[1] * -CUR.Js[1] + f2[2] * -CUR.Js[2] + f2[3] * CUR.Js[6] + f2[4] * CUR.Js[7] + f2[5] * CUR.Js[8]); \
+        delta = CUR.has2 ? delta2 : delta;                                                         \
+        const real hf = ob_fabs(CUR.hi * lam_f);                                                   \
+        const real hi_act = CUR.fric ? hf : CUR.hi, lo_act = CUR.fric ? -hf : CUR.lo;              \
+        const real new_lambda = old_lambda + delta;                                                \
+        real out = new_lambda;                                                                     \
+        if (new_lambda < lo_act) { delta = lo_act - old_lambda; out = lo_act; }                    \
+        else if (new_lambda > hi_act) { delta = hi_act - old_lambda; out = hi_act; }               \
+        f1[0] += delta * CUR.iM1[0]; f1[1] += delta * CUR.iM1[1]; f1[2] += delta * CUR.iM1[2];     \
+        f1[3] += delta * CUR.iMa[0]; f1[4] += delta * CUR.iMa[1]; f1[5] += delta * CUR.iMa[2];     \
+        f2[0] += delta * -CUR.iM2[0]; f2[1] += delta * -CUR.iM2[1]; f2[2] += delta * -CUR.iM2[2];  \
+        f2[3] += delta * CUR.iMa[3]; f2[4] += delta * CUR.iMa[4]; f2[5] += delta * CUR.iMa[5];     \
+        if (CUR.act) {                                                                             \
+          s_lam[CUR.li] = out;                                                                     \
+          OB_STORE_FC(s_fc + CUR.o1, f1)                                                           \
+          if (CUR.has2) OB_STORE_FC(s_fc + CUR.o2, f2)                                             \
+        }                                                                                          \
+        __syncwarp();                                                                              \
       }
+#if defined(dSINGLE)
+#define OB_LOAD_FC(F, P) { const float4 a_ = *(const float4 *)(P); const float2 c_ = *(const float2 *)((P) + 4); F[0] = a_.x; F[1] = a_.y; F[2] = a_.z; F[3] = a_.w; F[4] = c_.x; F[5] = c_.y; }
+#define OB_STORE_FC(P, F) { real *w_ = (P); *(float4 *)w_ = make_float4(F[0], F[1], F[2], F[3]); *(float2 *)(w_ + 4) = make_float2(F[4], F[5]); }
+#else
+#define OB_LOAD_FC(F, P) { _Pragma("unroll") for (int e_ = 0; e_ < 6; e_++) F[e_] = (P)[e_]; }
+#define OB_STORE_FC(P, F) { real *w_ = (P); _Pragma("unroll") for (int e_ = 0; e_ < 6; e_++) w_[e_] = F[e_]; }
+#endif
+#pragma unroll 1
+      for (int v = 0; v < vmax; v += 2) {
+        OB_RING_PASS(pa, pb)
+        if (v + 1 >= vmax) break;
+        OB_RING_PASS(pb, pa)
+      }
+#undef OB_RING_PASS
+#undef OB_LOAD_FC
+#undef OB_STORE_FC
       ob_cp_async_wait<0>();
 #undef OB_RING_ISSUE
     }
     __syncwarp();
-    sor_epilogue<G>(d, taps, wc, valid, gl, nb, mtot, si, rows, s_fc, s_lam);
+    sor_epilogue<G>(d, taps, wc, valid, gl, nb, mtot, si, rows, s_fc, s_lam, 8);
+    __syncwarp();
+  }
+}
+
+// =====================================================================================
+// k_sor_pair<G, D>: k_sor_ring with TWO LANES PER ROW (G lanes per world = G/2 rows per pass; lane 2r works on body 1 of the
+// pass's r-th row, lane 2r+1 on body 2).  The ring kernel showed what bounds the sweep on configs[1]: 4096 worlds x 4 per
+// warp = 1024 warps, 1.7 per scheduler, every one of them an in-order chain of ~215 instructions per pass at ~5 cycles
+// each (ncu r02c/r02d: wait + short-scoreboard + branch stalls, 0.29 IPC per scheduler, memory idle).  Splitting a row
+// over a lane pair halves the chain a lane runs (half the decode, one 6-term dot product, one 6-vector update) and
+// doubles the warps that hide it.  The arithmetic is unchanged: lane A forms fc1.J1, lane B fc2.J2 (same association
+// order), one shuffle exchanges them and BOTH lanes evaluate  delta -= dot1; delta -= dot2; clamp  exactly as
+// ob_sor_row() does, so they agree bit for bit and each applies delta to its own body.
+// Row copies: lane A starts the copy of the row's first 48 bytes, lane B of the last 32; a lane may read its partner's
+// part only after the partner's wait_group AND a __syncwarp, so the wait for pass v + 2 sits in iteration v (the pass's
+// closing __syncwarp publishes it) and the decode of pass v + 1 runs one iteration behind the wait.  D >= 4.
+struct ObHalfPrep {
+  real Jo[6];       // this lane's half of the row's J, scaled by Ad (body 2: linear part negated)
+  real iMo[6];      // this lane's half of iMJ (body 2: linear part negated)
+  real b, adcfm, lo, hi;
+  int off;          // word offset of this lane's body in s_fc
+  int li, lf;       // lambda index of the row, of its friction normal (== li when none)
+  bool act, has2, fric;
+};
+__device__ __forceinline__ void sor_prep_half(const real *slot, int ci, int h, const real *s_fc, ObHalfPrep &P) {
+  // words: [0-2 J1l][3-5 J1a][6-8 J2a][9-11 iMJ1a][12-14 iMJ2a][15 Ad][16 b][17 Ad*cfm][18 bound][19 meta]
+  real lin[3], ang[3], ima[3];
+#pragma unroll
+  for (int e = 0; e < 3; e++) { lin[e] = slot[e]; ang[e] = h ? slot[6 + e] : slot[3 + e]; ima[e] = h ? slot[12 + e] : slot[9 + e]; }
+  const real Ad = slot[15], bv = slot[18];
+  P.b = slot[16]; P.adcfm = slot[17];
+#if defined(dSINGLE)
+  const unsigned rmeta = __float_as_uint(slot[19]);
+#else
+  const unsigned rmeta = (unsigned)__double2loint(slot[19]);
+#endif
+  P.act = ci != 0xffff;
+  const unsigned meta = P.act ? rmeta : 0u;
+  const int b1 = meta & 255, b2r = (meta >> 8) & 255, fio = (meta >> 16) & 255, bmode = meta >> 24;
+  P.has2 = b2r != 255;
+  P.fric = fio != 0;
+  const int bo = (h && P.has2) ? b2r : b1;
+  P.off = 8 * bo;
+  P.li = P.act ? ci : 0;
+  P.lf = P.fric ? P.li - fio : P.li;
+  const real k = s_fc[8 * bo + 6];
+  P.lo = bmode == 0 ? -bv : (bmode == 1 ? (real)0 : bv);
+  P.hi = bmode == 2 ? (real)0 : bv;
+#pragma unroll
+  for (int e = 0; e < 3; e++) {
+    const real l = h ? -lin[e] : lin[e];      // J2l == -J1l
+    P.Jo[e] = l * Ad;                          // (-x) * Ad == -(x * Ad): same bits as the reference's J2l * Ad
+    P.Jo[3 + e] = ang[e] * Ad;
+    P.iMo[e] = k * l;                          // invM2 * (-J1l)
+    P.iMo[3 + e] = ima[e];
+  }
+}
+
+template <int G, int D>
+__global__ void __launch_bounds__(32) k_sor_pair(ObBatchDev d, int taps) {
+  constexpr int T = 32 / G, R = G / 2;
+  constexpr int ROWB = OB_ROWW * (int)sizeof(real);
+  extern __shared__ __align__(16) unsigned char smem_all[];
+  const SorRingSmem L = sor_ring_smem(d.NB, d.NR, R, D);
+  int lane = threadIdx.x;
+  asm volatile("" : "+r"(lane));
+  const int grp = lane / G, gl = lane % G, r = gl >> 1, h = gl & 1;
+  const unsigned FULL = 0xffffffffu;
+  const unsigned gmask = G == 32 ? FULL : ((1u << G) - 1u);
+  const int gsh = grp * G;
+  unsigned char *smem = smem_all + (size_t)grp * L.total;
+  real *s_fc = (real *)(smem + L.fc);
+  real *s_lam = (real *)(smem + L.lam);
+  unsigned short *s_idx = (unsigned short *)(smem + L.idx);
+  unsigned short *s_hdr = (unsigned short *)(smem + L.hdr) + r;    // this row slot's column: ring slot k at k * R
+  unsigned char *s_ring = smem + L.ring + (size_t)r * ROWB;        // this row slot's column of the ring: ring slot k at k * R * ROWB
+  unsigned ring_sa = (unsigned)__cvta_generic_to_shared(s_ring) + (h ? 48u : 0u);   // lane A copies bytes [0, 48), lane B [48, ROWB)
+  asm volatile("" : "+r"(ring_sa));
+
+  for (int wbase = d.wbeg + blockIdx.x * T; wbase < d.wend; wbase += gridDim.x * T) {
+    const int w = wbase + grp;
+    const bool valid = w < d.wend;
+    const int wc = valid ? w : d.wbeg;
+    const int *si = d.stepinfo + (size_t)wc * SI_WORDS;
+    const int nb = valid ? d.world[wc].nb : 0;
+    const int iters = valid ? d.world[wc].iters : 0;
+    const int mtot = valid && si[SI_HAVEROWS] ? si[SI_MTOT] : 0;
+    const ObBodyConst *bc = d.bconst + (size_t)wc * d.NB;
+    const real *rows = d.rows + (size_t)wc * d.NR * OB_ROWW;
+    for (int b = gl; b < d.NB; b += G) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) s_fc[8 * b + k] = 0;
+      if (b < nb) s_fc[8 * b + 6] = bc[b].invMass;
+    }
+    for (int i = gl; i < mtot; i += G) s_lam[i] = 0;
+    int nep = mtot > 0 ? (iters + 7) >> 3 : 0;
+    if (nep > d.NEP) nep = d.NEP;
+    const int nep_max = warp_max_i(nep);
+    for (int ep = 0; ep < nep_max; ep++) {
+      const bool epv = ep < nep;
+      const int np = epv ? si[SI_NPASS0 + ep] : 0;
+      int nit = epv ? iters - 8 * ep : 0;
+      if (nit > 8) nit = 8;
+      __syncwarp();
+      if (epv) {
+        const unsigned short *sched = d.sched + ((size_t)wc * d.NEP + ep) * d.NR;
+        for (int i = gl; i < mtot; i += G) s_idx[i] = sched[i];
+        for (int i = gl; i <= R + 1; i += G) s_idx[mtot + i] = 0x8000;
+      }
+      __syncwarp();
+      if (epv) {
+        const unsigned short *pstart = d.pstart + ((size_t)wc * d.NEP + ep) * (d.NR + 1);
+        for (int i = gl; i < np; i += G) s_idx[pstart[i]] |= 0x8000;
+      }
+      __syncwarp();
+      const int vtot = np * nit;
+      const int vmax = warp_max_i(vtot);
+      int pf_v = 0, pf_slot = 0, pf_s = 0;
+#define OB_PAIR_ISSUE()                                                                            \
+      {                                                                                            \
+        const bool on_ = pf_v < vtot;                                                              \
+        const unsigned me_ = on_ ? (unsigned)s_idx[pf_s + r] : 0u;                                 \
+        const unsigned nx_ = on_ ? (unsigned)s_idx[pf_s + r + 1] : 0x8000u;                        \
+        const unsigned bits_ = (__ballot_sync(FULL, h == 0 && (nx_ & 0x8000u) != 0) >> gsh) & gmask; \
+        const int len_ = (__ffs(bits_) + 1) >> 1;   /* rows of this pass: first even lane whose next slot starts a pass */ \
+        const bool mine_ = on_ && r < len_;                                                        \
+        const unsigned ri_ = me_ & 0x7fffu;                                                        \
+        if (mine_) {                                                                               \
+          const unsigned char *src_ = (const unsigned char *)(rows + (size_t)ri_ * OB_ROWW) + (h ? 48 : 0); \
+          const unsigned dst_ = ring_sa + (unsigned)pf_slot * (unsigned)(R * ROWB);                \
+          if (h == 0) { _Pragma("unroll") for (int c_ = 0; c_ < 3; c_++) ob_cp_async16_sa(dst_ + 16u * c_, src_ + 16 * c_); } \
+          else { _Pragma("unroll") for (int c_ = 0; c_ < (ROWB - 48) / 16; c_++) ob_cp_async16_sa(dst_ + 16u * c_, src_ + 16 * c_); } \
+        }                                                                                          \
+        if (h == 0) s_hdr[pf_slot * R] = (unsigned short)(mine_ ? ri_ : 0xffffu);                  \
+        ob_cp_async_commit();                                                                      \
+        if (on_) { pf_s += len_; if (pf_s >= mtot) pf_s = 0; }                                     \
+        pf_v++;                                                                                    \
+        if (++pf_slot == D) pf_slot = 0;                                                           \
+      }
+#pragma unroll 1
+      for (int k = 0; k < D - 1; k++) OB_PAIR_ISSUE()
+      ObHalfPrep pa, pb;
+      ob_cp_async_wait<D - 3>();                // groups 0 and 1 have landed (this lane's parts)
+      __syncwarp();                             // ... and the partner's
+      sor_prep_half((const real *)s_ring, (int)s_hdr[0], h, s_fc, pa);
+      int n_slot = 1;
+#define OB_PAIR_PASS(CUR, NXT)                                                                     \
+      {                                                                                            \
+        OB_PAIR_ISSUE()                                                                            \
+        real f[6];                                                                                 \
+        const real *fp = s_fc + CUR.off;                                                           \
+        OB_LOAD_FC(f, fp)                                                                          \
+        const real old_lambda = s_lam[CUR.li], lam_f = s_lam[CUR.lf];                              \
+        ob_cp_async_wait<D - 3>();              /* pass v + 2 landed; published by this pass's closing __syncwarp */ \
+        sor_prep_half((const real *)(s_ring + (size_t)n_slot * (R * ROWB)), (int)s_hdr[n_slot * R], h, s_fc, NXT); \
+        if (++n_slot == D) n_slot = 0;                                                             \
+        const real dot = f[0] * CUR.Jo[0] + f[1] * CUR.Jo[1] + f[2] * CUR.Jo[2] + f[3] * CUR.Jo[3] + f[4] * CUR.Jo[4] + f[5] * CUR.Jo[5]; \
+        const real oth = __shfl_xor_sync(FULL, dot, 1);                                            \
+        const real d1 = h ? oth : dot, d2 = h ? dot : oth;                                         \
+        real delta = CUR.b - old_lambda * CUR.adcfm;                                               \
+        delta -= d1;                                                                               \
+        const real delta2 = delta - d2;                                                            \
+        delta = CUR.has2 ? delta2 : delta;                                                         \
+        const real hf = ob_fabs(CUR.hi * lam_f);                                                   \
+        const real hi_act = CUR.fric ? hf : CUR.hi, lo_act = CUR.fric ? -hf : CUR.lo;              \
+        const real new_lambda = old_lambda + delta;                                                \
+        real out = new_lambda;                                                                     \
+        if (new_lambda < lo_act) { delta = lo_act - old_lambda; out = lo_act; }                    \
+        else if (new_lambda > hi_act) { delta = hi_act - old_lambda; out = hi_act; }               \
+        f[0] += delta * CUR.iMo[0]; f[1] += delta * CUR.iMo[1]; f[2] += delta * CUR.iMo[2];        \
+        f[3] += delta * CUR.iMo[3]; f[4] += delta * CUR.iMo[4]; f[5] += delta * CUR.iMo[5];        \
+        if (CUR.act && (h == 0 || CUR.has2)) {                                                     \
+          if (h == 0) s_lam[CUR.li] = out;                                                         \
+          OB_STORE_FC(s_fc + CUR.off, f)                                                           \
+        }                                                                                          \
+        __syncwarp();                                                                              \
+      }
+#if defined(dSINGLE)
+#define OB_LOAD_FC(F, P) { const float4 a_ = *(const float4 *)(P); const float2 c_ = *(const float2 *)((P) + 4); F[0] = a_.x; F[1] = a_.y; F[2] = a_.z; F[3] = a_.w; F[4] = c_.x; F[5] = c_.y; }
+#define OB_STORE_FC(P, F) { real *w_ = (P); *(float4 *)w_ = make_float4(F[0], F[1], F[2], F[3]); *(float2 *)(w_ + 4) = make_float2(F[4], F[5]); }
+#else
+#define OB_LOAD_FC(F, P) { _Pragma("unroll") for (int e_ = 0; e_ < 6; e_++) F[e_] = (P)[e_]; }
+#define OB_STORE_FC(P, F) { real *w_ = (P); _Pragma("unroll") for (int e_ = 0; e_ < 6; e_++) w_[e_] = F[e_]; }
+#endif
+#pragma unroll 1
+      for (int v = 0; v < vmax; v += 2) {
+        OB_PAIR_PASS(pa, pb)
+        if (v + 1 >= vmax) break;
+        OB_PAIR_PASS(pb, pa)
+      }
+#undef OB_PAIR_PASS
+#undef OB_LOAD_FC
+#undef OB_STORE_FC
+      ob_cp_async_wait<0>();
+#undef OB_PAIR_ISSUE
+    }
+    __syncwarp();
+    sor_epilogue<G>(d, taps, wc, valid, gl, nb, mtot, si, rows, s_fc, s_lam, 8);
     __syncwarp();
   }
 }

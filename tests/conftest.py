@@ -36,6 +36,9 @@ GOLDEN = [  # (file stem, scene, steps, worlds, settle) — must match tests/gol
     ("kinematic_settle60", "kinematic", 30, 1, 60),   # dBodySetKinematic bodies pushing a pile, hinged to a dynamic body
     ("nulljoint_settle60", "nulljoint", 30, 1, 60),   # null joints merge islands (order of the dRandInt draws)
     ("transforms_settle80", "transforms", 25, 1, 80),   # geom transforms: composite bodies (T x X, X x T, T x T collider order), static transform
+    ("bodyflags_settle50", "bodyflags", 30, 1, 50),     # finite rotation (both modes: glibc-exact sinf / cosf), damping + thresholds, max angular speed, gravity mode, gyroscopic off, contact max-correcting-vel / surface layer
+    ("autodisable_settle150", "autodisable", 30, 1, 150),   # auto-disable (instantaneous samples) + re-enabling through the island walk
+    ("contactmodes_settle60", "contactmodes", 30, 1, 60),   # Mu2, Motion1/2/N, Slip1/2, Bounce, SoftERP/CFM, Approx1_2
 ]
 
 
@@ -45,6 +48,8 @@ GOLDEN_CALLBACK = [
     ("raycast_settle40", "raycast", 20, 1, 40),
     ("raycast2_settle40", "raycast2", 20, 1, 40),   # rays in a second space: dSpaceCollide2 (space x space, geom x space)
     ("raycyl_settle40", "raycyl", 20, 1, 40),       # ray-cylinder (mantle and cap branches)
+    ("contactmodes_fdir1_settle60", "contactmodes_fdir1", 25, 1, 60),   # dContactFDir1: per-contact first friction direction set by the callback
+    ("mixed_varmaxc_settle40", "mixed_varmaxc", 30, 1, 40),             # max-contacts differs from dCollide call to call (cached batch results vs on-demand pairs)
 ]
 
 
@@ -78,7 +83,8 @@ def _built():
 # traces and, for the long live comparisons, in lock-step with the reference (every step starts
 # from the reference's pre-step body state, SURVEY 8d parity protocol with K = 1) so that a
 # last-bit difference cannot be amplified by chaotic dynamics into a different contact set.
-ATAN2_SCENES = ("hinges", "buggy", "ragdoll", "buggy_terrain", "universals", "motors", "pistons", "pus")
+ATAN2_SCENES = ("hinges", "buggy", "ragdoll", "buggy_terrain", "universals", "motors", "pistons", "pus",
+                "bodyflags")   # bodyflags: finite rotation calls sin / cos (dDOUBLE: platform libm, same tolerance class; dSINGLE: glibc-exact restatement)
 
 
 # dDOUBLE on the GPU, scenes whose limit-motors bounce off their stops (restitution turns a last-bit atan2 difference

@@ -35,10 +35,15 @@ for p in single double; do
   $d --scene kinematic --steps 30 --settle 60 --out tests/golden/kinematic_settle60_$p.trace
   $d --scene nulljoint --steps 30 --settle 60 --out tests/golden/nulljoint_settle60_$p.trace
   $d --scene transforms --steps 25 --settle 80 --out tests/golden/transforms_settle80_$p.trace
-  # drop-in (callback) path only: ray colliders + capsule-trimesh
+  $d --scene bodyflags --steps 30 --settle 50 --out tests/golden/bodyflags_settle50_$p.trace
+  $d --scene autodisable --steps 30 --settle 150 --out tests/golden/autodisable_settle150_$p.trace
+  $d --scene contactmodes --steps 30 --settle 60 --out tests/golden/contactmodes_settle60_$p.trace
+  # drop-in (callback) path only: ray colliders + capsule-trimesh, FDir1, per-call max-contacts
   $d --scene raycast --steps 20 --settle 40 --out tests/golden/raycast_settle40_$p.trace
   $d --scene raycast2 --steps 20 --settle 40 --out tests/golden/raycast2_settle40_$p.trace
   $d --scene raycyl --steps 20 --settle 40 --out tests/golden/raycyl_settle40_$p.trace
+  $d --scene contactmodes_fdir1 --steps 25 --settle 60 --out tests/golden/contactmodes_fdir1_settle60_$p.trace
+  $d --scene mixed_varmaxc --steps 30 --settle 40 --out tests/golden/mixed_varmaxc_settle40_$p.trace
   # large-world path (config 5): reference trace used in lock-step (--resync) by tests/test_large_world.py
   $d --scene pile_5x5x8 --steps 10 --settle 60 --out tests/golden/pile_5x5x8_large_settle60_$p.trace
 done

@@ -41,6 +41,7 @@ struct CbCtx {
   std::vector<dJointFeedback *> fbs;
   long long ncontacts;
   bool record;
+  unsigned calls, frame;   // near-callback invocations so far, frames so far (ScenePolicy::varmaxc)
 };
 
 static void near_cb(void *data, dGeomID o1, dGeomID o2) {
@@ -54,11 +55,26 @@ static void near_cb(void *data, dGeomID o1, dGeomID o2) {
   enum { MAXC = 64 };
   dContact contact[MAXC];
   int maxc = c->pol->max_contacts;
+  // varmaxc: a different max-contacts value from call to call and from frame to frame (an application that budgets contacts per
+  // pair type); exercises dCollide against results the batched narrowphase computed with another value
+  if (c->pol->varmaxc) maxc = 2 + (int)((c->calls * 5 + c->frame * 3) % 7);
+  c->calls++;
   for (int i = 0; i < maxc; i++) {
     memset(&contact[i], 0, sizeof(dContact));
     contact[i].surface = c->pol->surface;
   }
   int n = dCollide(o1, o2, maxc, &contact[0].geom, sizeof(dContact));
+  if (c->pol->fdir1)
+    for (int i = 0; i < n; i++) {
+      // first friction direction: the world x axis projected into the contact plane (falls back to y for normals along x), unit length
+      const dReal *nn = contact[i].geom.normal;
+      dVector3 a = {1, 0, 0, 0};
+      if (nn[0] > (dReal)0.9 || nn[0] < (dReal)-0.9) { a[0] = 0; a[1] = 1; }
+      const dReal k = a[0] * nn[0] + a[1] * nn[1] + a[2] * nn[2];
+      dVector3 t = {a[0] - k * nn[0], a[1] - k * nn[1], a[2] - k * nn[2], 0};
+      dNormalize3(t);
+      contact[i].fdir1[0] = t[0]; contact[i].fdir1[1] = t[1]; contact[i].fdir1[2] = t[2];
+    }
   const bool ray = dGeomGetClass(o1) == dRayClass || dGeomGetClass(o2) == dRayClass;   // query result, not a contact joint
   // contact geom identity (collision_kernel.cpp:331-343, collision_transform.cpp:143-151): g1 / g2 name the geoms of the
   // call, a geom transform being replaced by its encapsulated geom unless its info mode is on
@@ -201,7 +217,8 @@ int main(int argc, char **argv) {
     ctx.pol = &pol;
     ctx.ncontacts = 0;
     ctx.record = false;
-    for (int s = 0; s < settle; s++)
+    ctx.calls = 0; ctx.frame = 0;
+    for (int s = 0; s < settle; s++, ctx.frame++)
       for (int w = 0; w < nworlds; w++) {
         SceneWorld &sw = worlds[w];
         ctx.sw = &sw;
@@ -217,7 +234,7 @@ int main(int argc, char **argv) {
     Resync rsc;
     if (!resync.empty() && !rsc.open(resync, nworlds)) { fprintf(stderr, "bad --resync trace\n"); return 2; }
     t0 = now_s();
-    for (int s = 0; s < nsteps; s++) {
+    for (int s = 0; s < nsteps; s++, ctx.frame++) {
       for (int w = 0; w < nworlds; w++) {
         SceneWorld &sw = worlds[w];
         ctx.sw = &sw;

@@ -28,6 +28,9 @@ struct ScenePolicy {
   int max_contacts;
   int skip_if_connected;
   dSurfaceParameters surface;
+  // knobs only a near callback can express (classic loop; the batched path's policy table has no equivalent):
+  int fdir1;     // 1: dContactFDir1 with a first friction direction computed from the contact normal
+  int varmaxc;   // 1: the max-contacts value passed to dCollide varies from call to call
 };
 
 struct xs32 {  // scene jitter RNG (not ODE's)
@@ -1085,6 +1088,87 @@ static inline ScenePolicy policy_buggy() {
   return p;
 }
 
+
+// Body-level switches of dxStepBody / the quickstep preamble that no other scene turns on: finite rotation (both modes,
+// util.cpp:288-330), linear / angular damping with thresholds (:337-359), max angular speed (:258-268), gravity mode off,
+// gyroscopic term off (quickstep.cpp:633-652), and the world's contact correction limits (contact.cpp:130-141:
+// dWorldSetContactMaxCorrectingVel / dWorldSetContactSurfaceLayer).  Tumbling boxes and spheres dropped on a plane.
+static inline void scene_bodyflags(SceneWorld &sw, int w) {
+  scene_world_base(sw, w);
+  xs32 rng(sw.seed ^ 0x0BADF00Du);
+  dWorldSetContactMaxCorrectingVel(sw.world, (dReal)1.5);
+  dWorldSetContactSurfaceLayer(sw.world, (dReal)0.002);
+  dWorldSetLinearDamping(sw.world, (dReal)0.002);           // defaults copied into every body created afterwards
+  dWorldSetAngularDampingThreshold(sw.world, (dReal)0.05);
+  scene_add_geom(sw, dCreatePlane(sw.space, 0, 0, 1, 0));
+  for (int i = 0; i < 14; i++) {
+    dBodyID b = (i % 3 == 2) ? scene_add_sphere(sw, 2, rng.uni(0.2, 0.45), rng.uni(-1.2, 1.2), rng.uni(-1.2, 1.2), rng.uni(0.6, 4))
+                             : scene_add_box(sw, 2, rng.uni(0.25, 0.8), rng.uni(0.25, 0.8), rng.uni(0.25, 0.8), rng.uni(-1.2, 1.2), rng.uni(-1.2, 1.2), rng.uni(0.6, 4));
+    dQuaternion q = {rng.uni(-1, 1), rng.uni(-1, 1), rng.uni(-1, 1), rng.uni(-1, 1)};
+    dBodySetQuaternion(b, q);
+    dBodySetAngularVel(b, rng.uni(-6, 6), rng.uni(-6, 6), rng.uni(-6, 6));
+    dBodySetLinearVel(b, rng.uni(-1, 1), rng.uni(-1, 1), rng.uni(-1, 1));
+    switch (i % 7) {
+      case 0: dBodySetFiniteRotationMode(b, 1); break;                                              // finite rotation about the whole angular velocity
+      case 1: dBodySetFiniteRotationMode(b, 1); dBodySetFiniteRotationAxis(b, 0, 0, 1); break;     // finite about z, infinitesimal for the rest
+      case 2: dBodySetLinearDamping(b, (dReal)0.02); dBodySetAngularDamping(b, (dReal)0.05); dBodySetLinearDampingThreshold(b, (dReal)0.3); break;
+      case 3: dBodySetMaxAngularSpeed(b, (dReal)2.5); break;
+      case 4: dBodySetGravityMode(b, 0); dBodySetLinearVel(b, 0, 0, (dReal)-0.8); break;
+      case 5: dBodySetGyroscopicMode(b, 0); break;
+      default: dBodySetFiniteRotationMode(b, 1); dBodySetFiniteRotationAxis(b, (dReal)0.6, 0, (dReal)0.8); dBodySetAngularDamping(b, (dReal)0.01); dBodySetMaxAngularSpeed(b, 4); break;
+    }
+  }
+}
+
+// Auto-disable (util.cpp:99-233, instantaneous-sample mode) and re-enabling through the island walk (util.cpp:447-451):
+// a small pile settles and falls asleep body by body; late spheres land on it and wake it; one body has auto-disable off,
+// one was put to sleep by hand, one has its own thresholds.
+static inline void scene_autodisable(SceneWorld &sw, int w) {
+  scene_world_base(sw, w);
+  xs32 rng(sw.seed ^ 0x51EE9u);
+  dWorldSetAutoDisableFlag(sw.world, 1);
+  dWorldSetAutoDisableLinearThreshold(sw.world, (dReal)0.05);
+  dWorldSetAutoDisableAngularThreshold(sw.world, (dReal)0.05);
+  dWorldSetAutoDisableSteps(sw.world, 8);
+  dWorldSetAutoDisableTime(sw.world, (dReal)0.05);
+  scene_add_geom(sw, dCreatePlane(sw.space, 0, 0, 1, 0));
+  for (int i = 0; i < 9; i++) {
+    dBodyID b = scene_add_box(sw, 3, rng.uni(0.4, 0.7), rng.uni(0.4, 0.7), rng.uni(0.3, 0.5),
+                              (dReal)((i % 3 - 1) * 0.75) + rng.uni(-0.03, 0.03), (dReal)((i / 3 - 1) * 0.75) + rng.uni(-0.03, 0.03), (dReal)0.3);
+    if (i == 4) dBodySetAutoDisableFlag(b, 0);
+    if (i == 7) { dBodySetAutoDisableLinearThreshold(b, (dReal)0.5); dBodySetAutoDisableSteps(b, 2); dBodySetAutoDisableTime(b, 0); }
+    if (i == 8) dBodyDisable(b);
+  }
+  for (int i = 0; i < 4; i++) scene_add_box(sw, 3, (dReal)0.5, (dReal)0.5, (dReal)0.4, (dReal)((i % 2) * 0.8 - 0.4), (dReal)((i / 2) * 0.8 - 0.4), (dReal)0.85);
+  // late arrivals: they fall for 0.7 .. 1.6 s and hit the sleeping pile
+  for (int i = 0; i < 4; i++) scene_add_sphere(sw, 4, (dReal)0.22, rng.uni(-0.7, 0.7), rng.uni(-0.7, 0.7), (dReal)(3.5 + 3.0 * i));
+}
+
+// Contact surface modes no other policy uses (contact.cpp:74-256): Mu2, Motion1 / Motion2 / MotionN (conveyor-belt
+// terms in the right-hand side), Slip1 / Slip2 with non-zero slip, Bounce, SoftERP + SoftCFM, pyramid approximation on
+// direction 2 only.  The callback variant adds FDir1 (ScenePolicy::fdir1).
+static inline ScenePolicy policy_contactmodes(int fdir1) {
+  ScenePolicy p;
+  memset(&p, 0, sizeof(p));
+  p.max_contacts = 6;
+  p.skip_if_connected = 1;
+  p.surface.mode = dContactMu2 | dContactMotion1 | dContactMotion2 | dContactMotionN | dContactSlip1 | dContactSlip2 | dContactBounce |
+                   dContactSoftERP | dContactSoftCFM | dContactApprox1_2 | (fdir1 ? dContactFDir1 : 0);
+  p.surface.mu = (dReal)0.9;
+  p.surface.mu2 = (dReal)0.3;
+  p.surface.bounce = (dReal)0.3;
+  p.surface.bounce_vel = (dReal)0.2;
+  p.surface.soft_erp = (dReal)0.6;
+  p.surface.soft_cfm = (dReal)0.003;
+  p.surface.motion1 = (dReal)0.4;
+  p.surface.motion2 = (dReal)-0.25;
+  p.surface.motionN = (dReal)0.05;
+  p.surface.slip1 = (dReal)0.02;
+  p.surface.slip2 = (dReal)0.05;
+  p.fdir1 = fdir1;
+  return p;
+}
+
 static inline int scene_build(const char *name_in, SceneWorld &sw, int w, ScenePolicy &pol) {
   // suffixes select the space class: NAME@sap, NAME@sapz (axis order ZXY), NAME@simple
   char name[64];
@@ -1103,6 +1187,11 @@ static inline int scene_build(const char *name_in, SceneWorld &sw, int w, SceneP
   if (!strcmp(name, "stack32")) { scene_stack32(sw, w); return 0; }
   if (!strcmp(name, "mixed")) { scene_mixed(sw, w, 12, 6); return 0; }
   if (!strcmp(name, "mixed_maxc4")) { scene_mixed(sw, w, 12, 6); pol = policy_crash(); return 0; }
+  if (!strcmp(name, "mixed_varmaxc")) { scene_mixed(sw, w, 12, 6); pol.varmaxc = 1; return 0; }   // callback loop only
+  if (!strcmp(name, "bodyflags")) { scene_bodyflags(sw, w); return 0; }
+  if (!strcmp(name, "autodisable")) { scene_autodisable(sw, w); return 0; }
+  if (!strcmp(name, "contactmodes")) { scene_mixed(sw, w, 10, 5); pol = policy_contactmodes(0); return 0; }
+  if (!strcmp(name, "contactmodes_fdir1")) { scene_mixed(sw, w, 10, 5); pol = policy_contactmodes(1); return 0; }   // callback loop only
   if (!strcmp(name, "chain")) { scene_chain(sw, w, 8); return 0; }
   if (!strcmp(name, "hinges")) { scene_hinges(sw, w); return 0; }
   if (!strcmp(name, "sliders")) { scene_sliders(sw, w); return 0; }

@@ -128,3 +128,48 @@ def test_mass_and_inverse_inertia_match_reference_bitwise(prec, rt):
             assert lib.dInvertPDMatrix(m1.I, inv, 3) == 1
             outs.append(bytes(m1) + bytes(m2) + bytes(m3) + bytes(R) + bytes(inv))
         assert outs[0] == outs[1]
+
+
+def _libm_inputs(n, seed):
+    rng = np.random.default_rng(seed)
+    a = np.concatenate([rng.uniform(-4, 4, n // 4), rng.uniform(-130, 130, n // 4), rng.standard_normal(n // 4) * 1e-3,
+                        (rng.standard_normal(n // 4) * 10.0 ** rng.integers(-30, 30, n // 4))]).astype(np.float32)
+    a[:8] = [0.0, -0.0, 0.78539816, 0.78539822, 120.0, 119.99999, 1e-5, 3.14159265]
+    b = rng.permutation(a).astype(np.float32)
+    return a, b
+
+
+def _libm_reference(fn, a, b):
+    libm = ctypes.CDLL("libm.so.6")
+    f = [libm.atan2f, libm.sinf, libm.cosf][fn]
+    f.restype = ctypes.c_float
+    f.argtypes = [ctypes.c_float] * (2 if fn == 0 else 1)
+    return np.array([f(float(x), float(y)) if fn == 0 else f(float(x)) for x, y in zip(a, b)], dtype=np.float32)
+
+
+@pytest.mark.parametrize("fn", [0, 1, 2])
+def test_libm_restatements_match_the_platform_libm_bitwise(fn):
+    """ob_math.h restates glibc 2.39's atan2f / sinf / cosf (what dAtan2 / dSin / dCos resolve to in the reference's dSINGLE
+    build); the host-compiled restatement must equal the platform libm bit for bit (the exhaustive 2^32 check of sinf / cosf
+    was run once offline: 0 mismatches)."""
+    lib = ctypes.CDLL(lib_path("single"))
+    a, b = _libm_inputs(40000, 7 + fn)
+    out = np.zeros_like(a)
+    lib.dB200LibmHost.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    assert lib.dB200LibmHost(fn, len(a), a.ctypes.data, b.ctypes.data, out.ctypes.data) == 0
+    ref = _libm_reference(fn, a, b)
+    same = (out.view(np.uint32) == ref.view(np.uint32)) | (np.isnan(out) & np.isnan(ref))
+    assert same.all(), f"{(~same).sum()} mismatches, first at {a[~same][:3]}"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fn", [0, 1, 2])
+def test_libm_restatements_on_the_device_match_the_platform_libm_bitwise(fn):
+    lib = ctypes.CDLL(lib_path("single"))
+    a, b = _libm_inputs(40000, 17 + fn)
+    out = np.zeros_like(a)
+    lib.dB200LibmDevice.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    assert lib.dB200LibmDevice(fn, len(a), a.ctypes.data, b.ctypes.data, out.ctypes.data) == 0
+    ref = _libm_reference(fn, a, b)
+    same = (out.view(np.uint32) == ref.view(np.uint32)) | (np.isnan(out) & np.isnan(ref))
+    assert same.all(), f"{(~same).sum()} mismatches, first at {a[~same][:3]}"
