@@ -135,6 +135,8 @@ ObBackend *obk_create(const ObBatchDev &caps, int device, char *err, size_t errl
   d.csurf = 0; d.cfdir1 = 0;
   if (d.dropin) { CK(dalloc(b, &d.csurf, W * d.NC)); CK(dalloc(b, &d.cfdir1, W * d.NC * 4)); }
   CK(dalloc(b, &d.counters, (size_t)1));
+  d.adisbuf = 0; d.adisctl = 0;
+  if (d.NADIS > 0) { CK(dalloc(b, &d.adisbuf, W * d.NB * d.NADIS * 6)); CK(dalloc(b, &d.adisctl, W * d.NB * 2)); }
   b->st_elems = W * d.NB;
   CK(dalloc(b, &b->st_dev, b->st_elems * 13));
   if (obk_stepk_setup(b, prop, err, errlen)) goto fail;

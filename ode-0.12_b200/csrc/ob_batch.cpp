@@ -174,6 +174,21 @@ int ob_batch_upload(dxBatch *B) {
   rc |= obk_h2d(B->bk, B->caps.bconst, hc.data(), hc.size() * sizeof(ObBodyConst));
   rc |= obk_h2d(B->bk, B->caps.geom, hg.data(), hg.size() * sizeof(ObGeom));
   rc |= obk_h2d(B->bk, B->caps.glist, hl.data(), hl.size() * sizeof(int));
+  if (B->caps.NADIS > 0) {   // averaged auto-disable: sample ring buffers + (write index, full flag) per body
+    const int NA = B->caps.NADIS;
+    std::vector<dReal> hb((size_t)nworlds * NB * NA * 6, 0);
+    std::vector<int> hcw((size_t)nworlds * NB * 2, 0);
+    for (int w = 0; w < nworlds; w++)
+      for (int i = 0; i < B->nb[w]; i++) {
+        const dxBody *b = B->bodies[w][i];
+        const size_t bi = (size_t)w * NB + i;
+        if ((int)b->adis.average_samples > NA) { ob_set_last_error("a body's auto-disable sample count (%u) was raised above the bound batch's buffer depth (%d): re-create the batch", b->adis.average_samples, NA); return -1; }
+        for (size_t k = 0; k < b->average_buf.size(); k++) hb[bi * NA * 6 + k] = b->average_buf[k];
+        hcw[bi * 2] = (int)b->average_counter; hcw[bi * 2 + 1] = b->average_ready;
+      }
+    rc |= obk_h2d(B->bk, B->caps.adisbuf, hb.data(), hb.size() * sizeof(dReal));
+    rc |= obk_h2d(B->bk, B->caps.adisctl, hcw.data(), hcw.size() * sizeof(int));
+  }
   if (B->caps.large) return rc;   // no permanent joints on the large-world path
   if (NJ) rc |= obk_h2d(B->bk, B->caps.joint, hj.data(), hj.size() * sizeof(ObJoint));
   rc |= obk_h2d(B->bk, B->caps.njoints, hnj.data(), hnj.size() * sizeof(int));
@@ -251,6 +266,9 @@ dxBatch *ob_batch_create(int nworlds, const dWorldID *worlds, const dSpaceID *sp
       if (B->bodies[0][i]->flags & (OB_BODY_DISABLED | OB_BODY_AUTO_DISABLE)) { ob_set_last_error("dBatchCreate: the large-world path does not support disabled / auto-disabling bodies"); delete B; return 0; }
   }
   caps.NJ = NJ;
+  caps.NADIS = 0;   // deepest auto-disable sample buffer among the bound bodies (only averaging bodies, average_samples > 1, need one)
+  for (int w = 0; w < nworlds; w++)
+    for (int i = 0; i < B->nb[w]; i++) { const int n = (int)B->bodies[w][i]->adis.average_samples; if (n > 1 && n > caps.NADIS) caps.NADIS = n; }
   caps.NR = 3 * caps.NC + 6 * NJ;
   caps.npolicy = 1;
   caps.dropin = dropin;
@@ -367,10 +385,22 @@ int dBatchDownload(dBatchID B) {
   if (obk_d2h(B->bk, hd.data(), B->caps.bdyn, hd.size() * sizeof(ObBodyDyn))) return -1;
   if (obk_d2h(B->bk, hl.data(), B->caps.glist, hl.size() * sizeof(int))) return -1;
   if (obk_d2h(B->bk, hw.data(), B->caps.world, W * sizeof(ObWorld))) return -1;
+  const int NA = B->caps.NADIS;
+  std::vector<dReal> hb((size_t)(NA > 0 ? (size_t)W * NB * NA * 6 : 0));
+  std::vector<int> hcw((size_t)(NA > 0 ? (size_t)W * NB * 2 : 0));
+  if (NA > 0) {
+    if (obk_d2h(B->bk, hb.data(), B->caps.adisbuf, hb.size() * sizeof(dReal))) return -1;
+    if (obk_d2h(B->bk, hcw.data(), B->caps.adisctl, hcw.size() * sizeof(int))) return -1;
+  }
   for (int w = 0; w < W; w++) {
     for (int i = 0; i < B->nb[w]; i++) {
       dxBody *b = B->bodies[w][i];
       const ObBodyDyn &d = hd[(size_t)w * NB + i];
+      if (NA > 0) {
+        const size_t bi = (size_t)w * NB + i;
+        for (size_t k = 0; k < b->average_buf.size() && k < (size_t)NA * 6; k++) b->average_buf[k] = hb[bi * NA * 6 + k];
+        b->average_counter = (unsigned)hcw[bi * 2]; b->average_ready = hcw[bi * 2 + 1];
+      }
       for (int k = 0; k < 3; k++) { b->pos[k] = d.pos[k]; b->lvel[k] = d.lvel[k]; b->avel[k] = d.avel[k]; b->facc[k] = d.facc[k]; b->tacc[k] = d.tacc[k]; }
       for (int k = 0; k < 4; k++) b->q[k] = d.q[k];
       for (int k = 0; k < 12; k++) b->R[k] = d.R[k];

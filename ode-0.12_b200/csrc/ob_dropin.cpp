@@ -81,8 +81,10 @@ static bool batch_matches(ObDropin *c, int need_contacts) {
   if (need_contacts > B->caps.NC) return false;
   if ((c->world->qs_iterations + 7) / 8 > B->caps.NEP) return false;
   int i = 0;
-  for (dxBody *b = c->world->firstbody; b; b = b->next, i++)
+  for (dxBody *b = c->world->firstbody; b; b = b->next, i++) {
     if (i >= B->nb[0] || B->bodies[0][i] != b || b->batch_index != i) return false;
+    if (b->adis.average_samples > 1 && (int)b->adis.average_samples > B->caps.NADIS) return false;   // deeper sample buffer than the batch has
+  }
   if (i != B->nb[0]) return false;
   if (c->space->count != B->ng[0]) return false;
   for (dxGeom *g = c->space->first; g; g = g->next)
@@ -403,6 +405,14 @@ int ob_dropin_quickstep(dxWorld *w, dReal h) {
     ob_error(0, "dWorldQuickStep: capacity exceeded on the device (status %d)", st);
     return 0;
   }
+  const int NA = D.NADIS;   // averaged auto-disable: the sample buffers live in the host bodies between calls
+  std::vector<dReal> hb((size_t)(NA > 0 ? (size_t)nb * NA * 6 : 0));
+  std::vector<int> hcw((size_t)(NA > 0 ? (size_t)nb * 2 : 0));
+  if (NA > 0 && nb > 0) {
+    rc = obk_d2h(B->bk, hb.data(), D.adisbuf, hb.size() * sizeof(dReal));
+    rc |= obk_d2h(B->bk, hcw.data(), D.adisctl, hcw.size() * sizeof(int));
+    if (rc) { ob_error(0, "dWorldQuickStep: download failed"); return 0; }
+  }
   for (int i = 0; i < nb; i++) {
     dxBody *b = B->bodies[0][i];
     const ObBodyDyn &d = hd[i];
@@ -410,6 +420,10 @@ int ob_dropin_quickstep(dxWorld *w, dReal h) {
     for (int k = 0; k < 4; k++) b->q[k] = d.q[k];
     for (int k = 0; k < 12; k++) b->R[k] = d.R[k];
     b->flags = d.flags; b->adis_stepsleft = d.adis_stepsleft; b->adis_timeleft = d.adis_timeleft;
+    if (NA > 0) {
+      for (size_t k = 0; k < b->average_buf.size() && k < (size_t)NA * 6; k++) b->average_buf[k] = hb[(size_t)i * NA * 6 + k];
+      b->average_counter = (unsigned)hcw[2 * i]; b->average_ready = hcw[2 * i + 1];
+    }
   }
   // dxStepBody: every geom of a stepped body is reported moved, in stepping order (util.cpp:331-337)
   for (int i = 0; i < si[SI_NIB] && i < nb; i++)

@@ -540,6 +540,7 @@ void dBodySetGyroscopicMode(dBodyID b, int enabled) { if (enabled) b->flags |= O
 int dBodyGetGyroscopicMode(dBodyID b) { return (b->flags & OB_BODY_GYROSCOPIC) != 0; }
 void dBodySetAutoDisableAverageSamplesCount(dBodyID b, unsigned int n) {
   b->adis.average_samples = n; b->average_counter = 0; b->average_ready = 0;
+  b->average_buf.assign(n > 1 ? (size_t)6 * n : 0, 0);   // buffers are reallocated and the averaging restarts (ode.cpp:1050-1075)
 }
 void dBodySetAutoDisableFlag(dBodyID b, int do_auto_disable) {
   if (!do_auto_disable) {
@@ -555,6 +556,7 @@ void dBodySetAutoDisableDefaults(dBodyID b) {
   dxWorld *w = b->world;
   b->adis = w->adis;
   dBodySetAutoDisableFlag(b, w->body_flags & OB_BODY_AUTO_DISABLE);
+  dBodySetAutoDisableAverageSamplesCount(b, w->adis.average_samples);   // (re)allocates the sample buffers, restarts the averaging (ode.cpp:1094-1101)
 }
 void dBodySetDampingDefaults(dBodyID b) {
   dxWorld *w = b->world;

@@ -58,6 +58,7 @@ struct dxBody {
   dxAutoDisable adis;
   dReal adis_timeleft; int adis_stepsleft;
   unsigned average_counter; int average_ready;
+  std::vector<dReal> average_buf;   // [average_samples][6] lvel / avel samples (dxBody::average_lvel_buffer / average_avel_buffer, objects.h)
   dxDamping dampingp;
   dReal max_angular_speed;
   int batch_index;               // index inside the bound batch world slot

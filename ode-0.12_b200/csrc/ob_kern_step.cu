@@ -58,7 +58,8 @@ int obk_stepk_setup(ObBackend *b, const cudaDeviceProp &prop, char *err, size_t 
     // per world that a warp instruction of the chains advances several worlds)
     // measured on B200 (r02a, configs[1]): 0.95 / 0.55 / 0.39 ms at 4 / 8 / 16 lanes per world against 0.39 ms for the warp per
     // world -- the chains are latency-bound, fewer warps lose what fewer instructions gain; off unless OB_SCHED_TILE asks
-    int gs = 0;
+    // r02e (flat serial loops, build without --split-compile): 0.31 ms at 16 lanes per world against 0.39 ms for the warp per world
+    int gs = W >= 2048 ? 16 : 0;
     const char *e = getenv("OB_SCHED_TILE");
     if (e) gs = atoi(e);
     if (gs != 2 && gs != 4 && gs != 8 && gs != 16) gs = 0;
@@ -77,7 +78,9 @@ int obk_stepk_setup(ObBackend *b, const cudaDeviceProp &prop, char *err, size_t 
     // k_sor_ring: on unless the caller pins one of the register-pipelined variants (OB_SOR_DEEP) or OB_SOR_RING=0.
     // Ring depth: 6 slots (rows 5 passes ahead) when every CTA of the batch still stays resident, else 4
     const char *e = getenv("OB_SOR_RING");
-    const bool want = e ? atoi(e) != 0 : getenv("OB_SOR_DEEP") == 0;
+    // measured (r02e): configs[1] 0.94 vs 0.93 ms, configs[3] 2.82 vs 3.10 ms (ring vs register pipeline) at 8 lanes per world;
+    // tiny worlds at 4 lanes per world (configs[2]) 4.08 vs 3.10 ms: the ring's per-pass bookkeeping outweighs its prefetch there
+    const bool want = e ? atoi(e) != 0 : (getenv("OB_SOR_DEEP") == 0 && b->tile >= 8);
     const int Tw = 32 / b->tile;
     const int need = (int)((W + Tw - 1) / Tw);
     b->ring_depth = 0;
@@ -107,7 +110,7 @@ int obk_stepk_setup(ObBackend *b, const cudaDeviceProp &prop, char *err, size_t 
     b->sor_pair = 0;
     {
       const char *pe = getenv("OB_SOR_PAIR");
-      const bool wantp = b->sor_ring && b->tile <= 16 && (pe ? atoi(pe) != 0 : true);
+      const bool wantp = b->sor_ring && b->tile <= 16 && (pe ? atoi(pe) != 0 : false);   // r02e: 1.04 ms against the ring's 0.94 on configs[1] (shared-memory pipe at 65 %): opt-in
       if (wantp) {
         const int GP = 2 * b->tile, Tp = 32 / GP;
         const int needp = (int)((W + Tp - 1) / Tp);

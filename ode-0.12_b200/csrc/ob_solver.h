@@ -137,6 +137,51 @@ OB_HD void ob_body_velocity_update(real *lvel, real *avel, const real *cforce /*
   avel[0] = avel[0] + t[0]; avel[1] = avel[1] + t[1]; avel[2] = avel[2] + t[2];
 }
 
+// dInternalHandleAutoDisabling for one body that has joints (util.cpp:99-233).  samples == 1 is the instantaneous mode;
+// samples > 1 averages the last `samples` velocity samples: buf = [samples][6] (lvel, avel) ring buffer of this body,
+// ctl = {write index, buffer-full flag}; the body cannot go idle before the buffer has filled once.
+// Returns true when the body was put to sleep (flags / velocities already updated).
+OB_HD bool ob_auto_disable(ObBodyDyn &B, const ObBodyConst &C, real h, real *buf, int *ctl) {
+  if ((B.flags & (OB_BODY_AUTO_DISABLE | OB_BODY_DISABLED)) != OB_BODY_AUTO_DISABLE) return false;
+  const int ns = C.adis_samples;
+  if (ns == 0) return false;
+  int idle = 0;
+  real al[3], aa[3];
+  bool ready = true;
+  if (ns > 1 && buf) {
+    int cnt = ctl[0];
+    if (cnt >= ns) { ctl[1] = 0; cnt = 0; }   // the reference's sanity reset (only reachable after the count was lowered)
+    for (int k = 0; k < 3; k++) { buf[6 * cnt + k] = B.lvel[k]; buf[6 * cnt + 3 + k] = B.avel[k]; }
+    cnt++;
+    if (cnt >= ns) { cnt = 0; ctl[1] = 1; }
+    ctl[0] = cnt;
+    ready = ctl[1] != 0;
+    if (ready) {
+      for (int k = 0; k < 3; k++) { al[k] = buf[k]; aa[k] = buf[3 + k]; }
+      for (int i = 1; i < ns; i++)
+        for (int k = 0; k < 3; k++) { al[k] += buf[6 * i + k]; aa[k] += buf[6 * i + 3 + k]; }
+      const real r1 = OB_REAL(1.0) / (real)ns;
+      for (int k = 0; k < 3; k++) { al[k] *= r1; aa[k] *= r1; }
+    }
+  } else {
+    for (int k = 0; k < 3; k++) { al[k] = B.lvel[k]; aa[k] = B.avel[k]; }
+  }
+  if (ready) {
+    idle = 1;
+    const real ls = ob_dot(al, al);
+    if (ls > C.adis_lin_thr) idle = 0;
+    else { const real as = ob_dot(aa, aa); if (as > C.adis_ang_thr) idle = 0; }
+  }
+  if (idle) { B.adis_stepsleft--; B.adis_timeleft -= h; }
+  else { B.adis_stepsleft = C.adis_idle_steps; B.adis_timeleft = C.adis_idle_time; }
+  if (B.adis_stepsleft <= 0 && B.adis_timeleft <= 0) {
+    B.flags |= OB_BODY_DISABLED;
+    for (int k = 0; k < 3; k++) { B.lvel[k] = 0; B.avel[k] = 0; }
+    return true;
+  }
+  return false;
+}
+
 OB_HD real ob_sinc(real x) {
   if ((double)ob_fabs(x) < 1.0e-4) return OB_REAL(1.0) - x * x * OB_REAL(0.166666666666666666667);
 #if defined(dSINGLE)

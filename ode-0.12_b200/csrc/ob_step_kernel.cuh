@@ -216,26 +216,16 @@ __global__ void __launch_bounds__(32) k_prep(ObBatchDev d, real h, int taps) {
           for (int k = padjstart[b]; k < padjstart[b + 1]; k++) s_adj[s_cursor[b]++] = (unsigned short)(nc + padj[k]);
     }
     __syncwarp();
-    // ---- (2) auto-disable, instantaneous-sample mode (util.cpp:99-233); invMass to smem
+    // ---- (2) auto-disable (util.cpp:99-233: instantaneous or averaged samples, ob_auto_disable); invMass to smem
     for (int base = 0; base < nb_max; base += G) {
       const int b = base + gl;
       if (b < nb) {
         const ObBodyConst &C = bc[b];
         s_invM[b] = C.invMass;
         ObBodyDyn &B = bd[b];
-        const unsigned fl = B.flags;
-        if (s_adjstart[b + 1] != s_adjstart[b] && (fl & (OB_BODY_AUTO_DISABLE | OB_BODY_DISABLED)) == OB_BODY_AUTO_DISABLE &&
-            C.adis_samples != 0) {
-          int idle = 1;
-          const real ls = ob_dot(B.lvel, B.lvel);
-          if (ls > C.adis_lin_thr) idle = 0;
-          else { const real as = ob_dot(B.avel, B.avel); if (as > C.adis_ang_thr) idle = 0; }
-          if (idle) { B.adis_stepsleft--; B.adis_timeleft -= h; }
-          else { B.adis_stepsleft = C.adis_idle_steps; B.adis_timeleft = C.adis_idle_time; }
-          if (B.adis_stepsleft <= 0 && B.adis_timeleft <= 0) {
-            B.flags = fl | OB_BODY_DISABLED;
-            for (int k = 0; k < 3; k++) { B.lvel[k] = 0; B.avel[k] = 0; }
-          }
+        if (s_adjstart[b + 1] != s_adjstart[b]) {   // bodies without joints never fall asleep (util.cpp:104)
+          const size_t bi = (size_t)wc * d.NB + b;
+          ob_auto_disable(B, C, h, d.NADIS ? d.adisbuf + bi * d.NADIS * 6 : (real *)0, d.NADIS ? d.adisctl + bi * 2 : (int *)0);
         }
         if (B.flags & OB_BODY_DISABLED) s_btag[b] = -2;   // remembered so the DFS needs no global reads
       }
@@ -1109,13 +1099,16 @@ __device__ __noinline__ void sor_check_pass(bool act, unsigned meta, int gl, int
   }
 }
 
+// fc slot swizzle of the ring / pair sweep kernels (see SorRingSmem)
+__host__ __device__ __forceinline__ int ob_fc4(int b) { return 8 * b + ((b & 4) ? 4 : 0); }   // word offset of fc[0..3]
+__host__ __device__ __forceinline__ int ob_fc2(int b) { return 8 * b + ((b & 4) ? 0 : 4); }   // word offset of fc[4..5]
 // after the sweeps: cforce per body for k_post; lambda + joint feedback taps (quickstep.cpp:918-957)
 template <int G>
 __device__ __forceinline__ void sor_epilogue(const ObBatchDev &d, int taps, int wc, bool valid, int gl, int nb, int mtot, const int *si,
                                              const real *rows, const real *s_fc, const real *s_lam, int fcs = 8) {
   real *g_fc = d.tmp1 + (size_t)wc * d.NB * 8;   // tmp1 is dead after row assembly: reuse as cforce
   for (int b = gl; b < nb; b += G)
-    for (int k = 0; k < 6; k++) g_fc[8 * b + k] = s_fc[8 * b + k];
+    for (int k = 0; k < 6; k++) g_fc[8 * b + k] = fcs == 1 ? s_fc[(k < 4 ? ob_fc4(b) : ob_fc2(b) - 4) + k] : s_fc[8 * b + k];   // fcs == 1: swizzled slots (ring / pair kernels)
   if (taps && valid) {
     const int nij = si[SI_NIJ];
     const unsigned short *g_jrow = d.jrow + (size_t)wc * (d.NC + d.NJ + 1);
@@ -1287,10 +1280,15 @@ __global__ void __launch_bounds__(32) k_sor(ObBatchDev d, int taps) {
 //     results are dropped by selects and predicated stores (a select never lets a garbage NaN through).
 // The arithmetic of a row update is ob_sor_row()'s, operation for operation (same products, same association order):
 // bit-identical results, checked by the parity suite and the OB_CHECK pass-disjointness tap.
-struct SorRingSmem { size_t fc, lam, idx, hdr, ring, total; };
+struct SorRingSmem { size_t fc, invM, lam, idx, hdr, ring, total; };
+// fc slot of body b: 8 words.  Bank-conflict swizzle (r02c/r02e: the shared-memory pipe is the busiest unit of the sweep, 58-65 % of
+// its peak, half of the wavefronts are conflict replays): with the natural layout the 16-byte part of every body starts at bank
+// 8b mod 32 -- four start positions for the lanes of a wavefront.  Bodies with bit 2 of b set keep their halves swapped
+// ([4..7] = fc[0..3], [0..1] = fc[4..5]), which gives eight start positions for both the 16-byte and the 8-byte access.
 __host__ __device__ inline SorRingSmem sor_ring_smem(int NB, int NR, int G, int D) {
   SorRingSmem s; size_t o = 0;
-  s.fc = o; o = ob_al(o + sizeof(real) * 8 * NB, 16);                      // per body: fc[6], invMass, unused
+  s.fc = o; o = ob_al(o + sizeof(real) * 8 * NB, 16);                      // per body: fc[6] + 2 spare words, swizzled (ob_fc4 / ob_fc2)
+  s.invM = o; o = ob_al(o + sizeof(real) * NB, 16);                        // dense: bank = b mod 32
   s.lam = o; o = ob_al(o + sizeof(real) * NR, 16);
   s.idx = o; o = ob_al(o + sizeof(unsigned short) * (NR + G + 2), 16);     // schedule of the epoch + sentinels
   s.hdr = o; o = ob_al(o + sizeof(unsigned short) * D * G, 16);            // row index of every ring slot (0xffff: idle)
@@ -1315,11 +1313,11 @@ struct ObRowPrep {
   real iM2[3];      // invM2 * J1l
   real iMa[6];      // iMJ1a, iMJ2a as stored
   real b, adcfm, lo, hi;
-  int o1, o2;       // word offsets of the bodies' fc in s_fc (o2 == o1 for one-body rows)
+  int o1, o2;       // the bodies (o2 == o1 for one-body rows)
   int li, lf;       // lambda index of the row, of its friction normal (== li when none)
   bool act, has2, fric;
 };
-__device__ __forceinline__ void sor_prep(const real *slot, int ci, const real *s_fc, ObRowPrep &P) {
+__device__ __forceinline__ void sor_prep(const real *slot, int ci, const real *s_invM, ObRowPrep &P) {
   ObRowReg r;
 #if defined(dSINGLE)
   const float4 *q = (const float4 *)slot;
@@ -1338,10 +1336,10 @@ __device__ __forceinline__ void sor_prep(const real *slot, int ci, const real *s
   P.has2 = b2r != 255;
   P.fric = fio != 0;
   const int b2 = P.has2 ? b2r : b1;
-  P.o1 = 8 * b1; P.o2 = 8 * b2;
+  P.o1 = b1; P.o2 = b2;
   P.li = P.act ? ci : 0;
   P.lf = P.fric ? P.li - fio : P.li;
-  const real Ad = r.v[15], k1 = s_fc[8 * b1 + 6], k2 = s_fc[8 * b2 + 6];
+  const real Ad = r.v[15], k1 = s_invM[b1], k2 = s_invM[b2];
   const real bv = r.v[18];
   P.lo = bmode == 0 ? -bv : (bmode == 1 ? (real)0 : bv);
   P.hi = bmode == 2 ? (real)0 : bv;
@@ -1368,6 +1366,7 @@ __global__ void __launch_bounds__(32) k_sor_ring(ObBatchDev d, int taps) {
   const int gsh = grp * G;
   unsigned char *smem = smem_all + (size_t)grp * L.total;
   real *s_fc = (real *)(smem + L.fc);
+  real *s_invM = (real *)(smem + L.invM);
   real *s_lam = (real *)(smem + L.lam);
   unsigned short *s_idx = (unsigned short *)(smem + L.idx);
   unsigned short *s_hdr = (unsigned short *)(smem + L.hdr) + gl;   // this lane's column: slot k at k * G
@@ -1388,7 +1387,7 @@ __global__ void __launch_bounds__(32) k_sor_ring(ObBatchDev d, int taps) {
     for (int b = gl; b < d.NB; b += G) {
 #pragma unroll
       for (int k = 0; k < 8; k++) s_fc[8 * b + k] = 0;
-      if (b < nb) s_fc[8 * b + 6] = bc[b].invMass;
+      s_invM[b] = b < nb ? bc[b].invMass : (real)0;
     }
     for (int i = gl; i < mtot; i += G) s_lam[i] = 0;
     int nep = mtot > 0 ? (iters + 7) >> 3 : 0;
@@ -1440,7 +1439,7 @@ __global__ void __launch_bounds__(32) k_sor_ring(ObBatchDev d, int taps) {
       for (int k = 0; k < D - 1; k++) OB_RING_ISSUE()
       ObRowPrep pa, pb;
       ob_cp_async_wait<D - 2>();                // group 0 has landed
-      sor_prep((const real *)s_ring, (int)s_hdr[0], s_fc, pa);
+      sor_prep((const real *)s_ring, (int)s_hdr[0], s_invM, pa);
       int n_slot = 1;                           // ring slot of pass v + 1
       // one pass: CUR is applied, NXT is decoded meanwhile; the loop alternates (pa, pb) / (pb, pa) so no operand set is copied
 #define OB_RING_PASS(CUR, NXT)                                                                     \
@@ -1448,14 +1447,13 @@ __global__ void __launch_bounds__(32) k_sor_ring(ObBatchDev d, int taps) {
         OB_RING_ISSUE()                                                                            \
         /* (B) this pass's dependent loads: fc of both bodies, lambda, lambda of the friction normal */ \
         real f1[6], f2[6];                                                                         \
-        const real *fp1 = s_fc + CUR.o1, *fp2 = s_fc + CUR.o2;                                     \
-        OB_LOAD_FC(f1, fp1) OB_LOAD_FC(f2, fp2)                                                    \
+        OB_LOAD_FC(f1, CUR.o1) OB_LOAD_FC(f2, CUR.o2)                                              \
         const real old_lambda = s_lam[CUR.li], lam_f = s_lam[CUR.lf];                              \
         /* (C) meanwhile: decode the row of the next pass */                                       \
         ob_cp_async_wait<D - 2>();              /* this lane's copy of pass v + 1 has landed (groups complete in order) */ \
-        sor_prep((const real *)(s_ring + (size_t)n_slot * (G * ROWB)), (int)s_hdr[n_slot * G], s_fc, NXT); \
+        sor_prep((const real *)(s_ring + (size_t)n_slot * (G * ROWB)), (int)s_hdr[n_slot * G], s_invM, NXT); \
         if (++n_slot == D) n_slot = 0;                                                             \
-        if (taps & 4) sor_check_pass<G>(CUR.act, (unsigned)(CUR.o1 >> 3) | ((CUR.has2 ? (unsigned)(CUR.o2 >> 3) : 255u) << 8), gl, &d.world[wc].status); \
+        if (taps & 4) sor_check_pass<G>(CUR.act, (unsigned)CUR.o1 | ((CUR.has2 ? (unsigned)CUR.o2 : 255u) << 8), gl, &d.world[wc].status); \
         /* (D) the update, ob_sor_row() operation for operation (quickstep.cpp:490-581) */         \
         real delta = CUR.b - old_lambda * CUR.adcfm;                                               \
         delta -= f1[0] * CUR.Js[0] + f1[1] * CUR.Js[1] + f1[2] * CUR.Js[2] + f1[3] * CUR.Js[3] + f1[4] * CUR.Js[4] + f1[5] * CUR.Js[5]; \
@@ -1473,17 +1471,17 @@ __global__ void __launch_bounds__(32) k_sor_ring(ObBatchDev d, int taps) {
         f2[3] += delta * CUR.iMa[3]; f2[4] += delta * CUR.iMa[4]; f2[5] += delta * CUR.iMa[5];     \
         if (CUR.act) {                                                                             \
           s_lam[CUR.li] = out;                                                                     \
-          OB_STORE_FC(s_fc + CUR.o1, f1)                                                           \
-          if (CUR.has2) OB_STORE_FC(s_fc + CUR.o2, f2)                                             \
+          OB_STORE_FC(CUR.o1, f1)                                                                  \
+          if (CUR.has2) OB_STORE_FC(CUR.o2, f2)                                                    \
         }                                                                                          \
         __syncwarp();                                                                              \
       }
 #if defined(dSINGLE)
-#define OB_LOAD_FC(F, P) { const float4 a_ = *(const float4 *)(P); const float2 c_ = *(const float2 *)((P) + 4); F[0] = a_.x; F[1] = a_.y; F[2] = a_.z; F[3] = a_.w; F[4] = c_.x; F[5] = c_.y; }
-#define OB_STORE_FC(P, F) { real *w_ = (P); *(float4 *)w_ = make_float4(F[0], F[1], F[2], F[3]); *(float2 *)(w_ + 4) = make_float2(F[4], F[5]); }
+#define OB_LOAD_FC(F, B_) { const float4 a_ = *(const float4 *)(s_fc + ob_fc4(B_)); const float2 c_ = *(const float2 *)(s_fc + ob_fc2(B_)); F[0] = a_.x; F[1] = a_.y; F[2] = a_.z; F[3] = a_.w; F[4] = c_.x; F[5] = c_.y; }
+#define OB_STORE_FC(B_, F) { *(float4 *)(s_fc + ob_fc4(B_)) = make_float4(F[0], F[1], F[2], F[3]); *(float2 *)(s_fc + ob_fc2(B_)) = make_float2(F[4], F[5]); }
 #else
-#define OB_LOAD_FC(F, P) { _Pragma("unroll") for (int e_ = 0; e_ < 6; e_++) F[e_] = (P)[e_]; }
-#define OB_STORE_FC(P, F) { real *w_ = (P); _Pragma("unroll") for (int e_ = 0; e_ < 6; e_++) w_[e_] = F[e_]; }
+#define OB_LOAD_FC(F, B_) { const real *p4_ = s_fc + ob_fc4(B_), *p2_ = s_fc + ob_fc2(B_); F[0] = p4_[0]; F[1] = p4_[1]; F[2] = p4_[2]; F[3] = p4_[3]; F[4] = p2_[0]; F[5] = p2_[1]; }
+#define OB_STORE_FC(B_, F) { real *p4_ = s_fc + ob_fc4(B_), *p2_ = s_fc + ob_fc2(B_); p4_[0] = F[0]; p4_[1] = F[1]; p4_[2] = F[2]; p4_[3] = F[3]; p2_[0] = F[4]; p2_[1] = F[5]; }
 #endif
 #pragma unroll 1
       for (int v = 0; v < vmax; v += 2) {
@@ -1498,7 +1496,7 @@ __global__ void __launch_bounds__(32) k_sor_ring(ObBatchDev d, int taps) {
 #undef OB_RING_ISSUE
     }
     __syncwarp();
-    sor_epilogue<G>(d, taps, wc, valid, gl, nb, mtot, si, rows, s_fc, s_lam, 8);
+    sor_epilogue<G>(d, taps, wc, valid, gl, nb, mtot, si, rows, s_fc, s_lam, 1);
     __syncwarp();
   }
 }
@@ -1519,11 +1517,11 @@ struct ObHalfPrep {
   real Jo[6];       // this lane's half of the row's J, scaled by Ad (body 2: linear part negated)
   real iMo[6];      // this lane's half of iMJ (body 2: linear part negated)
   real b, adcfm, lo, hi;
-  int off;          // word offset of this lane's body in s_fc
+  int off;          // this lane's body
   int li, lf;       // lambda index of the row, of its friction normal (== li when none)
   bool act, has2, fric;
 };
-__device__ __forceinline__ void sor_prep_half(const real *slot, int ci, int h, const real *s_fc, ObHalfPrep &P) {
+__device__ __forceinline__ void sor_prep_half(const real *slot, int ci, int h, const real *s_invM, ObHalfPrep &P) {
   // words: [0-2 J1l][3-5 J1a][6-8 J2a][9-11 iMJ1a][12-14 iMJ2a][15 Ad][16 b][17 Ad*cfm][18 bound][19 meta]
   real lin[3], ang[3], ima[3];
 #pragma unroll
@@ -1541,10 +1539,10 @@ __device__ __forceinline__ void sor_prep_half(const real *slot, int ci, int h, c
   P.has2 = b2r != 255;
   P.fric = fio != 0;
   const int bo = (h && P.has2) ? b2r : b1;
-  P.off = 8 * bo;
+  P.off = bo;
   P.li = P.act ? ci : 0;
   P.lf = P.fric ? P.li - fio : P.li;
-  const real k = s_fc[8 * bo + 6];
+  const real k = s_invM[bo];
   P.lo = bmode == 0 ? -bv : (bmode == 1 ? (real)0 : bv);
   P.hi = bmode == 2 ? (real)0 : bv;
 #pragma unroll
@@ -1571,6 +1569,7 @@ __global__ void __launch_bounds__(32) k_sor_pair(ObBatchDev d, int taps) {
   const int gsh = grp * G;
   unsigned char *smem = smem_all + (size_t)grp * L.total;
   real *s_fc = (real *)(smem + L.fc);
+  real *s_invM = (real *)(smem + L.invM);
   real *s_lam = (real *)(smem + L.lam);
   unsigned short *s_idx = (unsigned short *)(smem + L.idx);
   unsigned short *s_hdr = (unsigned short *)(smem + L.hdr) + r;    // this row slot's column: ring slot k at k * R
@@ -1591,7 +1590,7 @@ __global__ void __launch_bounds__(32) k_sor_pair(ObBatchDev d, int taps) {
     for (int b = gl; b < d.NB; b += G) {
 #pragma unroll
       for (int k = 0; k < 8; k++) s_fc[8 * b + k] = 0;
-      if (b < nb) s_fc[8 * b + 6] = bc[b].invMass;
+      s_invM[b] = b < nb ? bc[b].invMass : (real)0;
     }
     for (int i = gl; i < mtot; i += G) s_lam[i] = 0;
     int nep = mtot > 0 ? (iters + 7) >> 3 : 0;
@@ -1643,17 +1642,16 @@ __global__ void __launch_bounds__(32) k_sor_pair(ObBatchDev d, int taps) {
       ObHalfPrep pa, pb;
       ob_cp_async_wait<D - 3>();                // groups 0 and 1 have landed (this lane's parts)
       __syncwarp();                             // ... and the partner's
-      sor_prep_half((const real *)s_ring, (int)s_hdr[0], h, s_fc, pa);
+      sor_prep_half((const real *)s_ring, (int)s_hdr[0], h, s_invM, pa);
       int n_slot = 1;
 #define OB_PAIR_PASS(CUR, NXT)                                                                     \
       {                                                                                            \
         OB_PAIR_ISSUE()                                                                            \
         real f[6];                                                                                 \
-        const real *fp = s_fc + CUR.off;                                                           \
-        OB_LOAD_FC(f, fp)                                                                          \
+        OB_LOAD_FC(f, CUR.off)                                                                     \
         const real old_lambda = s_lam[CUR.li], lam_f = s_lam[CUR.lf];                              \
         ob_cp_async_wait<D - 3>();              /* pass v + 2 landed; published by this pass's closing __syncwarp */ \
-        sor_prep_half((const real *)(s_ring + (size_t)n_slot * (R * ROWB)), (int)s_hdr[n_slot * R], h, s_fc, NXT); \
+        sor_prep_half((const real *)(s_ring + (size_t)n_slot * (R * ROWB)), (int)s_hdr[n_slot * R], h, s_invM, NXT); \
         if (++n_slot == D) n_slot = 0;                                                             \
         const real dot = f[0] * CUR.Jo[0] + f[1] * CUR.Jo[1] + f[2] * CUR.Jo[2] + f[3] * CUR.Jo[3] + f[4] * CUR.Jo[4] + f[5] * CUR.Jo[5]; \
         const real oth = __shfl_xor_sync(FULL, dot, 1);                                            \
@@ -1672,16 +1670,16 @@ __global__ void __launch_bounds__(32) k_sor_pair(ObBatchDev d, int taps) {
         f[3] += delta * CUR.iMo[3]; f[4] += delta * CUR.iMo[4]; f[5] += delta * CUR.iMo[5];        \
         if (CUR.act && (h == 0 || CUR.has2)) {                                                     \
           if (h == 0) s_lam[CUR.li] = out;                                                         \
-          OB_STORE_FC(s_fc + CUR.off, f)                                                           \
+          OB_STORE_FC(CUR.off, f)                                                                  \
         }                                                                                          \
         __syncwarp();                                                                              \
       }
 #if defined(dSINGLE)
-#define OB_LOAD_FC(F, P) { const float4 a_ = *(const float4 *)(P); const float2 c_ = *(const float2 *)((P) + 4); F[0] = a_.x; F[1] = a_.y; F[2] = a_.z; F[3] = a_.w; F[4] = c_.x; F[5] = c_.y; }
-#define OB_STORE_FC(P, F) { real *w_ = (P); *(float4 *)w_ = make_float4(F[0], F[1], F[2], F[3]); *(float2 *)(w_ + 4) = make_float2(F[4], F[5]); }
+#define OB_LOAD_FC(F, B_) { const float4 a_ = *(const float4 *)(s_fc + ob_fc4(B_)); const float2 c_ = *(const float2 *)(s_fc + ob_fc2(B_)); F[0] = a_.x; F[1] = a_.y; F[2] = a_.z; F[3] = a_.w; F[4] = c_.x; F[5] = c_.y; }
+#define OB_STORE_FC(B_, F) { *(float4 *)(s_fc + ob_fc4(B_)) = make_float4(F[0], F[1], F[2], F[3]); *(float2 *)(s_fc + ob_fc2(B_)) = make_float2(F[4], F[5]); }
 #else
-#define OB_LOAD_FC(F, P) { _Pragma("unroll") for (int e_ = 0; e_ < 6; e_++) F[e_] = (P)[e_]; }
-#define OB_STORE_FC(P, F) { real *w_ = (P); _Pragma("unroll") for (int e_ = 0; e_ < 6; e_++) w_[e_] = F[e_]; }
+#define OB_LOAD_FC(F, B_) { const real *p4_ = s_fc + ob_fc4(B_), *p2_ = s_fc + ob_fc2(B_); F[0] = p4_[0]; F[1] = p4_[1]; F[2] = p4_[2]; F[3] = p4_[3]; F[4] = p2_[0]; F[5] = p2_[1]; }
+#define OB_STORE_FC(B_, F) { real *p4_ = s_fc + ob_fc4(B_), *p2_ = s_fc + ob_fc2(B_); p4_[0] = F[0]; p4_[1] = F[1]; p4_[2] = F[2]; p4_[3] = F[3]; p2_[0] = F[4]; p2_[1] = F[5]; }
 #endif
 #pragma unroll 1
       for (int v = 0; v < vmax; v += 2) {
@@ -1696,7 +1694,7 @@ __global__ void __launch_bounds__(32) k_sor_pair(ObBatchDev d, int taps) {
 #undef OB_PAIR_ISSUE
     }
     __syncwarp();
-    sor_epilogue<G>(d, taps, wc, valid, gl, nb, mtot, si, rows, s_fc, s_lam, 8);
+    sor_epilogue<G>(d, taps, wc, valid, gl, nb, mtot, si, rows, s_fc, s_lam, 1);
     __syncwarp();
   }
 }

@@ -125,6 +125,7 @@ struct ObBatchDev {
   int NJ;       // permanent (non-contact) joints per world slot
   int dropin;   // 1: batch serves the classic per-call API (per-contact surfaces in csurf/cfdir1)
   int large;    // 1: one large world on the grid-wide path (ob_large.h); W == 1
+  int NADIS;    // auto-disable sample buffer depth per body (max average_samples of the bound bodies; 0: nobody averages)
   int wbeg, wend;   // world range [wbeg, wend) of THIS launch (a chunk of the batch; chunks run on their own streams)
   ObWorld *world;        // [W]
   ObBodyDyn *bdyn;       // [W*NB]
@@ -167,4 +168,6 @@ struct ObBatchDev {
   ObSurface *csurf;      // [W*NC] per-contact surface parameters (drop-in path only, else null: policy table)
   real *cfdir1;          // [W*NC*4] per-contact fdir1 (drop-in path only)
   ObCounters *counters;  // [1]
+  real *adisbuf;         // [W*NB*NADIS*6] auto-disable velocity samples (lvel, avel) per body, ring buffer (util.cpp:128-147)
+  int *adisctl;          // [W*NB*2] per body: write index, buffer-full flag
 };

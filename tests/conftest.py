@@ -39,6 +39,7 @@ GOLDEN = [  # (file stem, scene, steps, worlds, settle) — must match tests/gol
     ("bodyflags_settle50", "bodyflags", 30, 1, 50),     # finite rotation (both modes: glibc-exact sinf / cosf), damping + thresholds, max angular speed, gravity mode, gyroscopic off, contact max-correcting-vel / surface layer
     ("autodisable_settle150", "autodisable", 30, 1, 150),   # auto-disable (instantaneous samples) + re-enabling through the island walk
     ("contactmodes_settle60", "contactmodes", 30, 1, 60),   # Mu2, Motion1/2/N, Slip1/2, Bounce, SoftERP/CFM, Approx1_2
+    ("autodisable_avg_settle150", "autodisable_avg", 30, 1, 150),   # auto-disable on averaged velocity samples (5 / 3 / 1 samples per body)
 ]
 
 

@@ -1123,8 +1123,9 @@ static inline void scene_bodyflags(SceneWorld &sw, int w) {
 // Auto-disable (util.cpp:99-233, instantaneous-sample mode) and re-enabling through the island walk (util.cpp:447-451):
 // a small pile settles and falls asleep body by body; late spheres land on it and wake it; one body has auto-disable off,
 // one was put to sleep by hand, one has its own thresholds.
-static inline void scene_autodisable(SceneWorld &sw, int w) {
+static inline void scene_autodisable(SceneWorld &sw, int w, int avg = 0) {
   scene_world_base(sw, w);
+  if (avg) dWorldSetAutoDisableAverageSamplesCount(sw.world, 5);   // averaged mode: bodies created below inherit 5 samples
   xs32 rng(sw.seed ^ 0x51EE9u);
   dWorldSetAutoDisableFlag(sw.world, 1);
   dWorldSetAutoDisableLinearThreshold(sw.world, (dReal)0.05);
@@ -1136,6 +1137,8 @@ static inline void scene_autodisable(SceneWorld &sw, int w) {
     dBodyID b = scene_add_box(sw, 3, rng.uni(0.4, 0.7), rng.uni(0.4, 0.7), rng.uni(0.3, 0.5),
                               (dReal)((i % 3 - 1) * 0.75) + rng.uni(-0.03, 0.03), (dReal)((i / 3 - 1) * 0.75) + rng.uni(-0.03, 0.03), (dReal)0.3);
     if (i == 4) dBodySetAutoDisableFlag(b, 0);
+    if (avg && i == 2) dBodySetAutoDisableAverageSamplesCount(b, 3);
+    if (avg && i == 5) dBodySetAutoDisableAverageSamplesCount(b, 1);
     if (i == 7) { dBodySetAutoDisableLinearThreshold(b, (dReal)0.5); dBodySetAutoDisableSteps(b, 2); dBodySetAutoDisableTime(b, 0); }
     if (i == 8) dBodyDisable(b);
   }
@@ -1190,6 +1193,7 @@ static inline int scene_build(const char *name_in, SceneWorld &sw, int w, SceneP
   if (!strcmp(name, "mixed_varmaxc")) { scene_mixed(sw, w, 12, 6); pol.varmaxc = 1; return 0; }   // callback loop only
   if (!strcmp(name, "bodyflags")) { scene_bodyflags(sw, w); return 0; }
   if (!strcmp(name, "autodisable")) { scene_autodisable(sw, w); return 0; }
+  if (!strcmp(name, "autodisable_avg")) { scene_autodisable(sw, w, 1); return 0; }   // averaged samples (util.cpp:139-205)
   if (!strcmp(name, "contactmodes")) { scene_mixed(sw, w, 10, 5); pol = policy_contactmodes(0); return 0; }
   if (!strcmp(name, "contactmodes_fdir1")) { scene_mixed(sw, w, 10, 5); pol = policy_contactmodes(1); return 0; }   // callback loop only
   if (!strcmp(name, "chain")) { scene_chain(sw, w, 8); return 0; }

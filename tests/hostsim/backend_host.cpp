@@ -66,6 +66,8 @@ ObBackend *obk_create(const ObBatchDev &caps, int, char *, size_t) {
   d.csurf = d.dropin ? halloc<ObSurface>(b, W * d.NC) : 0;
   d.cfdir1 = d.dropin ? halloc<real>(b, W * d.NC * 4) : 0;
   d.counters = halloc<ObCounters>(b, 1);
+  d.adisbuf = 0; d.adisctl = 0;
+  if (d.NADIS > 0) { d.adisbuf = halloc<real>(b, (size_t)d.W * d.NB * d.NADIS * 6); d.adisctl = halloc<int>(b, (size_t)d.W * d.NB * 2); }
   if (d.large) { d.invIw = halloc<real>(b, (size_t)d.NB * 12); d.tmp1 = halloc<real>(b, (size_t)d.NB * 8); }
   return b;
 }
@@ -332,21 +334,11 @@ static void step_world(ObBatchDev &d, int w, real h, int taps) {
     const unsigned short *ps = d.padjstart + (size_t)w * (d.NB + 1), *pa = d.padj + (size_t)w * 2 * (d.NJ ? d.NJ : 1);
     for (int b = 0; b < nb; b++) for (int k = ps[b]; k < ps[b + 1]; k++) adj[b].push_back(nc + pa[k]);
   }
-  // auto-disable (util.cpp:99-233), instantaneous-sample mode only
+  // auto-disable (util.cpp:99-233)
   for (int b = 0; b < nb; b++) {
     if (adj[b].empty()) continue;
-    if ((bd[b].flags & (OB_BODY_AUTO_DISABLE | OB_BODY_DISABLED)) != OB_BODY_AUTO_DISABLE) continue;
-    if (bc[b].adis_samples == 0) continue;
-    int idle = 1;
-    real ls = ob_dot(bd[b].lvel, bd[b].lvel);
-    if (ls > bc[b].adis_lin_thr) idle = 0;
-    else { real as = ob_dot(bd[b].avel, bd[b].avel); if (as > bc[b].adis_ang_thr) idle = 0; }
-    if (idle) { bd[b].adis_stepsleft--; bd[b].adis_timeleft -= h; }
-    else { bd[b].adis_stepsleft = bc[b].adis_idle_steps; bd[b].adis_timeleft = bc[b].adis_idle_time; }
-    if (bd[b].adis_stepsleft <= 0 && bd[b].adis_timeleft <= 0) {
-      bd[b].flags |= OB_BODY_DISABLED;
-      for (int k = 0; k < 3; k++) { bd[b].lvel[k] = 0; bd[b].avel[k] = 0; }
-    }
+    const size_t bi = (size_t)w * d.NB + b;
+    ob_auto_disable(bd[b], bc[b], h, d.NADIS ? d.adisbuf + bi * d.NADIS * 6 : (real *)0, d.NADIS ? d.adisctl + bi * 2 : (int *)0);
   }
   // islands (util.cpp:411-487)
   std::vector<int> btag(nb, 0), jtag(njall, 0), ibody, ijoint, isz;
