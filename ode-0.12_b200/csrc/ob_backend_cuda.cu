@@ -69,7 +69,7 @@ ObBackend *obk_create(const ObBatchDev &caps, int device, char *err, size_t errl
   ObBackend *b = new ObBackend;
   b->d = caps; b->device = device; b->stream = 0; b->st_dev = 0; b->st_host = 0;
   b->ktiming = 0;
-  b->sched_gs = 0; b->smem_sched_tile = 0; b->sor_ring = 0; b->smem_sor_ring = 0; b->ring_resident = 0; b->ring_depth = 0; b->sor_pair = 0; b->smem_sor_pair = 0; b->pair_resident = 0; b->avg_rows = 0; b->cnt_host = 0;
+  b->sched_gs = 0; b->smem_sched_tile = 0; b->sor_ring = 0; b->smem_sor_ring = 0; b->ring_resident = 0; b->ring_depth = 0; b->sor_reg = 0; b->smem_sor_reg = 0; b->prep_split = 0; b->sstream = 0; b->sev[0] = b->sev[1] = 0; b->sor_pair = 0; b->smem_sor_pair = 0; b->pair_resident = 0; b->avg_rows = 0; b->cnt_host = 0;
   b->l2_target_bytes = 1e12;   // r02a on B200: limiting the worlds in flight to an L2-sized set costs whole waves (1.72 -> 2.5 -> 3.2 ms at 100 / 60 / 40 MB); off unless OB_SOR_L2MB asks
   for (int k = 0; k < OBK_NKERNELS; k++) { b->kms[k] = 0; b->klaunch[k] = 0; }
   for (int k = 0; k < 8; k++) b->ev[k] = 0;
@@ -136,6 +136,11 @@ ObBackend *obk_create(const ObBatchDev &caps, int device, char *err, size_t errl
   if (d.dropin) { CK(dalloc(b, &d.csurf, W * d.NC)); CK(dalloc(b, &d.cfdir1, W * d.NC * 4)); }
   CK(dalloc(b, &d.counters, (size_t)1));
   d.adisbuf = 0; d.adisctl = 0;
+  CK(dalloc(b, &d.rowmeta, W * d.NR));
+  CK(cudaStreamCreateWithFlags(&b->sstream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&b->sev[0], cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&b->sev[1], cudaEventDisableTiming));
+  { const char *e = getenv("OB_PREP_SPLIT"); b->prep_split = e ? atoi(e) != 0 : (W >= 256); }
   if (d.NADIS > 0) { CK(dalloc(b, &d.adisbuf, W * d.NB * d.NADIS * 6)); CK(dalloc(b, &d.adisctl, W * d.NB * 2)); }
   b->st_elems = W * d.NB;
   CK(dalloc(b, &b->st_dev, b->st_elems * 13));
@@ -177,6 +182,8 @@ void obk_destroy(ObBackend *b) {
   for (int k = 0; k < 8; k++) if (b->ev[k]) cudaEventDestroy(b->ev[k]);
   for (int k = 0; k < 8; k++) if (b->cstream[k]) cudaStreamDestroy(b->cstream[k]);
   for (int k = 0; k < 9; k++) if (b->cev[k]) cudaEventDestroy(b->cev[k]);
+  if (b->sstream) { cudaStreamSynchronize(b->sstream); cudaStreamDestroy(b->sstream); }
+  for (int k = 0; k < 2; k++) if (b->sev[k]) cudaEventDestroy(b->sev[k]);
   cudaStreamDestroy(b->stream);
   delete b;
 }

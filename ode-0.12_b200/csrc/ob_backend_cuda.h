@@ -111,6 +111,11 @@ struct ObBackend {
   size_t smem_sor_ring;
   int ring_resident;        // CTAs of k_sor_ring that fit the device at once
   int ring_depth;           // slots of the row ring (6 or 4; 0: ring kernel not in use)
+  int prep_split;           // 1: k_prep in two launches, the schedule on `sstream` beside the second (batches of >= 256 worlds)
+  cudaStream_t sstream;
+  cudaEvent_t sev[2];
+  int sor_reg;              // 1: k_sor_reg (pipelined pass, rows prefetched into registers)
+  size_t smem_sor_reg;
   int sor_pair;             // > 0: k_sor_pair (two lanes per row) with this ring depth
   size_t smem_sor_pair;
   int pair_resident;

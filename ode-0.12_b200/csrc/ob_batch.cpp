@@ -68,6 +68,17 @@ void ob_marshal_joint(const dxJoint *j, ObJoint &d) {
 
 void ob_marshal_geom(dxGeom *g, ObGeom &d) {
   memset(&d, 0, sizeof d);
+  if (g->is_space) {
+    // a sub-space is a member like any geom: enabled flag, category / collide bits and the union box of its members; the near
+    // callback decides what to do with the pair (dSpaceCollide2 / dCollide on the space), there is no collider for it
+    d.type = OB_GEOM_SPACE; d.body = -1; d.body_next = -1;
+    d.cat = (uint32_t)g->category_bits; d.col = (uint32_t)g->collide_bits;
+    d.flags = (g->gflags & GEOM_ENABLED) ? OB_GEOM_ENABLED : 0;
+    dReal a[6];
+    dGeomGetAABB(g, a);
+    for (int k = 0; k < 6; k++) d.R[k] = a[k];
+    return;
+  }
   // a geom transform is uploaded as its encapsulated geom: class, parameters and zero-size flag of the inner geom,
   // everything else (body, bits, enable flag) of the transform; the inner geom's own pose is the "offset"
   // (computeFinalTx, collision_transform.cpp:101-108, is the same arithmetic as computePosr)
@@ -222,7 +233,7 @@ dxBatch *ob_batch_create(int nworlds, const dWorldID *worlds, const dSpaceID *sp
     B->geoms[w].resize(ng);
     int pos = 0;
     for (dxGeom *g = S->first; g; g = g->next, pos++) {
-      if (g->is_space) { ob_set_last_error("dBatchCreate: world %d: nested spaces are not supported on this path", w); delete B; return 0; }
+      if (g->is_space && !dropin) { ob_set_last_error("dBatchCreate: world %d: nested spaces are served by the classic API (dSpaceCollide / dSpaceCollide2 / dCollide), not by a bound batch", w); delete B; return 0; }
       if (g->body && g->body->world != W) { ob_set_last_error("dBatchCreate: world %d: geom attached to a body of another world", w); delete B; return 0; }
       if (g->type == dRayClass && !dropin) { ob_set_last_error("dBatchCreate: world %d: ray geoms are served by dSpaceCollide / dCollide (a ray contact is a query result, not a contact joint)", w); delete B; return 0; }
       g->batch_index = ng - 1 - pos;

@@ -92,6 +92,9 @@ OB_HD void ob_aabb(const ObPose &g, real *aabb, const ObMeshDev *meshes = 0) {
         else { aabb[2 * k] = e; aabb[2 * k + 1] = g.pos[k]; }
       }
     } break;
+    case OB_GEOM_SPACE:   // dxSpace::computeAABB (collision_space.cpp:116-137) ran on the host: the union of the members' boxes
+      for (int k = 0; k < 6; k++) aabb[k] = g.R[k];
+      break;
     default:
       aabb[0] = aabb[2] = aabb[4] = -OB_INF; aabb[1] = aabb[3] = aabb[5] = OB_INF;
   }

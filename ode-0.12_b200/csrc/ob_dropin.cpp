@@ -59,11 +59,16 @@ void ob_dropin_forget_space(dxSpace *s) {
   for (size_t i = 0; i < g_ctx.size();) { if (g_ctx[i]->space == s && g_ctx[i]->own_space != s) ctx_drop(i); else i++; }
 }
 
+static void world_of_space_rec(dxSpace *s, dxWorld **w, bool *mixed) {
+  for (dxGeom *g = s->first; g; g = g->next) {
+    if (g->is_space) world_of_space_rec((dxSpace *)g, w, mixed);
+    else if (g->body) { if (!*w) *w = g->body->world; else if (*w != g->body->world) *mixed = true; }
+  }
+}
 static dxWorld *world_of_space(dxSpace *s, bool *mixed) {
   dxWorld *w = 0;
   *mixed = false;
-  for (dxGeom *g = s->first; g; g = g->next)
-    if (g->body) { if (!w) w = g->body->world; else if (w != g->body->world) *mixed = true; }
+  world_of_space_rec(s, &w, mixed);   // sub-spaces included (demo_buggy's car_space inside the main space)
   return w;
 }
 
@@ -88,7 +93,7 @@ static bool batch_matches(ObDropin *c, int need_contacts) {
   if (i != B->nb[0]) return false;
   if (c->space->count != B->ng[0]) return false;
   for (dxGeom *g = c->space->first; g; g = g->next)
-    if (g->is_space || g->batch_index < 0 || g->batch_index >= B->ng[0] || B->geoms[0][g->batch_index] != g) return false;
+    if (g->batch_index < 0 || g->batch_index >= B->ng[0] || B->geoms[0][g->batch_index] != g) return false;
   for (dxGeom *g = c->space->first; g; g = g->next)
     if (g->type == dTriMeshClass) {
       bool have = false;
@@ -200,8 +205,40 @@ static inline int shape_type(dxGeom *g) { dxGeom *sh = ob_geom_shape(g); return 
 
 #define OB_CONTACT_AT(p, skip, i) ((dContactGeom *)(((char *)(p)) + (size_t)(i) * (skip)))
 
+// dCollide with a space as an argument: dCollideSpaceGeom (collision_kernel.cpp:104-131) -- dSpaceCollide2 over the pair with a
+// collector callback that calls dCollide for every reported pair while contact slots remain
+struct SpaceGeomColliderData { int flags; dContactGeom *contact; int skip; };
+static void space_geom_collider(void *data, dGeomID o1, dGeomID o2) {
+  SpaceGeomColliderData *d = (SpaceGeomColliderData *)data;
+  if (d->flags & 0xffff) {
+    const int n = dCollide(o1, o2, d->flags, d->contact, d->skip);
+    d->contact = (dContactGeom *)(((char *)d->contact) + (size_t)d->skip * n);
+    d->flags -= n;
+  }
+}
+static int collide_space_geom(dxGeom *o1, dxGeom *o2, int flags, dContactGeom *contact, int skip) {
+  SpaceGeomColliderData data = {flags, contact, skip};
+  ob_dropin_space_collide2(o1, o2, &data, &space_geom_collider);
+  return (flags & 0xffff) - (data.flags & 0xffff);
+}
+
 int ob_dropin_collide(dxGeom *o1, dxGeom *o2, int flags, dContactGeom *contact, int skip) {
   const int want = flags & 0xffff;
+  if (o1->is_space || o2->is_space) {
+    // collider table of the space classes (dInitColliders, collision_kernel.cpp:177-182): (space, anything) straight, (geom, space)
+    // reversed, of two spaces the one of the higher class number is the reversed one
+    if (o1 == o2) return 0;
+    const bool rev = o1->is_space ? (o2->is_space && o1->type > o2->type) : true;
+    if (!rev) return collide_space_geom(o1, o2, flags, contact, skip);
+    const int n = collide_space_geom(o2, o1, flags, contact, skip);
+    for (int i = 0; i < n; i++) {
+      dContactGeom *c = (dContactGeom *)(((char *)contact) + (size_t)skip * i);
+      c->normal[0] = -c->normal[0]; c->normal[1] = -c->normal[1]; c->normal[2] = -c->normal[2];
+      dGeomID tg = c->g1; c->g1 = c->g2; c->g2 = tg;
+      const int ts = c->side1; c->side1 = c->side2; c->side2 = ts;
+    }
+    return n;
+  }
   if (!(o1->gflags & GEOM_ENABLED) || !(o2->gflags & GEOM_ENABLED)) { /* dCollide itself does not test enable flags */ }
   // (1) inside dSpaceCollide's callback: serve from the batch results when they are the same computation
   for (size_t i = 0; i < g_ctx.size(); i++) {
@@ -272,7 +309,16 @@ static void space_collide2(dxSpace *space, const std::vector<dxGeom *> &queries,
   std::vector<uint32_t> qcat(nq), qcol(nq);
   for (int i = 0; i < nq; i++) {
     dxGeom *g = queries[i];
-    if (g->is_space) { ob_error(0, "dSpaceCollide2: nested spaces are not supported on this path"); return; }
+    if (g->is_space) {   // a space as the query: its union box (dxSpace::computeAABB); no pose, no body
+      memset(&qp[i], 0, sizeof(ObPose));
+      qp[i].type = OB_GEOM_SPACE;
+      dReal a[6];
+      dGeomGetAABB(g, a);
+      for (int k = 0; k < 6; k++) qp[i].R[k] = a[k];
+      memset(&qm[i], 0, sizeof(ObMeshDev));
+      qb[i] = -1; qcat[i] = (uint32_t)g->category_bits; qcol[i] = (uint32_t)g->collide_bits;
+      continue;
+    }
     geom_pose_host(g, &qp[i]);
     memset(&qm[i], 0, sizeof(ObMeshDev));
     if (g->type == dTriMeshClass) {
@@ -302,9 +348,14 @@ static void space_collide2(dxSpace *space, const std::vector<dxGeom *> &queries,
   space->lock_count--;
 }
 
-// dSpaceCollide2, collision_space.cpp:772-833 (spaces are flat here: sublevels are all 0)
+// dSpaceCollide2, collision_space.cpp:772-833
 void ob_dropin_space_collide2(dxGeom *g1, dxGeom *g2, void *data, dNearCallback *cb) {
   dxSpace *s1 = g1->is_space ? (dxSpace *)g1 : 0, *s2 = g2->is_space ? (dxSpace *)g2 : 0;
+  if (s1 && s2) {
+    // sublevel rule (:778-788): of two spaces on different sublevels the deeper one is traversed, the other is taken as one geom
+    const int l1 = s1->sublevel, l2 = s2->sublevel;
+    if (l1 != l2) { if (l1 > l2) s2 = 0; else s1 = 0; }
+  }
   if (s1 && s2) {
     if (s1 == s2) { ob_dropin_space_collide(s1, data, cb); return; }
     // iterate through the space that has the fewest geoms, calling collide2 in the other space for each one

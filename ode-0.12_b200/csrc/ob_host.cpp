@@ -1007,7 +1007,20 @@ static void geom_host_pose(dxGeom *g, ObPose *o) {
   for (int i = 0; i < 12; i++) o->R[i] = f.R[i];
 }
 void dGeomGetAABB(dGeomID g, dReal aabb[6]) {
-  if (g->is_space) { for (int i = 0; i < 6; i++) aabb[i] = (i & 1) ? OB_INF : -OB_INF; return; }
+  if (g->is_space) {
+    // dxSpace::computeAABB (collision_space.cpp:116-137): union of the members' boxes, all zero for an empty space
+    dxSpace *sp = (dxSpace *)g;
+    if (!sp->first) { for (int i = 0; i < 6; i++) aabb[i] = 0; return; }
+    dReal a[6] = {OB_INF, -OB_INF, OB_INF, -OB_INF, OB_INF, -OB_INF};
+    for (dxGeom *m = sp->first; m; m = m->next) {
+      dReal b[6];
+      dGeomGetAABB(m, b);
+      for (int i = 0; i < 6; i += 2) if (b[i] < a[i]) a[i] = b[i];
+      for (int i = 1; i < 6; i += 2) if (b[i] > a[i]) a[i] = b[i];
+    }
+    for (int i = 0; i < 6; i++) aabb[i] = a[i];
+    return;
+  }
   if (!ob_geom_shape(g)) { for (int i = 0; i < 6; i++) aabb[i] = 0; return; }   // empty transform, collision_transform.cpp:83-86
   ObPose o;
   geom_host_pose(g, &o);

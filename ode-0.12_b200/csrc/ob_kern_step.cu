@@ -36,8 +36,12 @@ int obk_stepk_setup(ObBackend *b, const cudaDeviceProp &prop, char *err, size_t 
     goto fail;
   }
 #define OB_SETSMEM(GG) \
-  CK(cudaFuncSetAttribute(k_prep<GG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_prep)); \
-  CK(cudaFuncSetAttribute(k_prep<GG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_prep)); \
+  CK(cudaFuncSetAttribute(k_prep<GG, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_prep)); \
+  CK(cudaFuncSetAttribute(k_prep<GG, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_prep)); \
+  CK(cudaFuncSetAttribute(k_prep<GG, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_prep)); \
+  CK(cudaFuncSetAttribute(k_prep<GG, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_prep)); \
+  CK(cudaFuncSetAttribute(k_prep<GG, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_prep)); \
+  CK(cudaFuncSetAttribute(k_prep<GG, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_prep)); \
   CK(cudaFuncSetAttribute(k_sor<GG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sor)); \
   CK(cudaFuncSetAttribute(k_sor<GG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sor)); \
   CK(cudaFuncSetAttribute(k_post<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_post));
@@ -106,6 +110,20 @@ int obk_stepk_setup(ObBackend *b, const cudaDeviceProp &prop, char *err, size_t 
       }
       b->sor_ring = b->ring_depth != 0;
     }
+    // k_sor_reg: the pipelined pass with register row buffers (no ring): preferred over the ring when it fits
+    b->sor_reg = 0;
+    {
+      const char *re = getenv("OB_SOR_REG");
+      const bool wantr = want && (re ? atoi(re) != 0 : false);   // r02g on B200: 1.15 ms against the ring's 0.88 on configs[1] (the loads three passes ahead do not hide the global latency the way the 4-deep LDGSTS ring does): opt-in
+      b->smem_sor_reg = sor_reg_smem(d.NB, d.NR, b->tile).total * Tw;
+      if (wantr && b->smem_sor_reg <= (size_t)prop.sharedMemPerBlockOptin) {
+        if (b->tile == 4) CK(cudaFuncSetAttribute(k_sor_reg<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sor_reg));
+        if (b->tile == 8) CK(cudaFuncSetAttribute(k_sor_reg<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sor_reg));
+        if (b->tile == 16) CK(cudaFuncSetAttribute(k_sor_reg<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sor_reg));
+        if (b->tile == 32) CK(cudaFuncSetAttribute(k_sor_reg<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sor_reg));
+        b->sor_reg = 1;
+      }
+    }
     // k_sor_pair: two lanes per row (2 * tile lanes per world), on top of the ring's machinery; ring depth 5, or 4 when that keeps more CTAs resident
     b->sor_pair = 0;
     {
@@ -149,21 +167,41 @@ template <int G> static void stepk_launch_t(ObBackend *b, const ObBatchDev &d, r
     const int gstep = (W + T - 1) / T;
     int gsor = gstep;
     if (b->grid_sor < b->grid_step) gsor = gsor < b->grid_sor ? gsor : b->grid_sor;
-#define OB_LAUNCH_PREP(GP) { const int gp = (W + (32 / GP) - 1) / (32 / GP); \
-      if (d.NJ > 0) k_prep<GP, true><<<gp, 32, b->smem_prep, st>>>(d, h, taps); else k_prep<GP, false><<<gp, 32, b->smem_prep, st>>>(d, h, taps); }
-    if (b->prep_tile == 4) OB_LAUNCH_PREP(4) else if (b->prep_tile == 8) OB_LAUNCH_PREP(8) else if (b->prep_tile == 16) OB_LAUNCH_PREP(16) else OB_LAUNCH_PREP(32)
-#undef OB_LAUNCH_PREP
+    // k_prep in two halves with the schedule on a second stream beside the second half (it needs only what the first half
+    // leaves: island / row tables and the rows' body + findex bytes).  Per-kernel timing and small batches keep the single launch.
+    const bool split = b->prep_split && !timing && b->nchunks <= 1;
+    ObBatchDev dk = d;
+    dk.rowmeta = split ? d.rowmeta : (unsigned *)0;
+    cudaStream_t ss = split ? b->sstream : st;
+#define OB_LAUNCH_PREP(GP, PH) { const int gp = (W + (32 / GP) - 1) / (32 / GP); \
+      if (d.NJ > 0) k_prep<GP, true, PH><<<gp, 32, b->smem_prep, st>>>(dk, h, taps); else k_prep<GP, false, PH><<<gp, 32, b->smem_prep, st>>>(dk, h, taps); }
+#define OB_LAUNCH_PREP_G(PH) { if (b->prep_tile == 4) OB_LAUNCH_PREP(4, PH) else if (b->prep_tile == 8) OB_LAUNCH_PREP(8, PH) else if (b->prep_tile == 16) OB_LAUNCH_PREP(16, PH) else OB_LAUNCH_PREP(32, PH) }
+    if (split) {
+      OB_LAUNCH_PREP_G(1)
+      cudaEventRecord(b->sev[0], st);
+      cudaStreamWaitEvent(ss, b->sev[0], 0);
+    } else OB_LAUNCH_PREP_G(0)
     if (timing) cudaEventRecord(ev[2], st);
-    if (b->sched_gs == 2) k_sched_tile<2><<<(W + 15) / 16, 32, b->smem_sched_tile, st>>>(d, G);
-    else if (b->sched_gs == 4) k_sched_tile<4><<<(W + 7) / 8, 32, b->smem_sched_tile, st>>>(d, G);
-    else if (b->sched_gs == 8) k_sched_tile<8><<<(W + 3) / 4, 32, b->smem_sched_tile, st>>>(d, G);
-    else if (b->sched_gs == 16) k_sched_tile<16><<<(W + 1) / 2, 32, b->smem_sched_tile, st>>>(d, G);
-    else if (b->sched_lane) k_sched_lane<<<(W + 31) / 32, 32, b->smem_sched_lane, st>>>(d, G);
-    else if (d.NB <= 64) k_sched<2><<<W, 32, b->smem_sched, st>>>(d, G, taps);
-    else if (d.NB <= 128) k_sched<4><<<W, 32, b->smem_sched, st>>>(d, G, taps);
-    else k_sched<8><<<W, 32, b->smem_sched, st>>>(d, G, taps);
+    if (b->sched_gs == 2) k_sched_tile<2><<<(W + 15) / 16, 32, b->smem_sched_tile, ss>>>(dk, G);
+    else if (b->sched_gs == 4) k_sched_tile<4><<<(W + 7) / 8, 32, b->smem_sched_tile, ss>>>(dk, G);
+    else if (b->sched_gs == 8) k_sched_tile<8><<<(W + 3) / 4, 32, b->smem_sched_tile, ss>>>(dk, G);
+    else if (b->sched_gs == 16) k_sched_tile<16><<<(W + 1) / 2, 32, b->smem_sched_tile, ss>>>(dk, G);
+    else if (b->sched_lane) k_sched_lane<<<(W + 31) / 32, 32, b->smem_sched_lane, ss>>>(dk, G);
+    else if (d.NB <= 64) k_sched<2><<<W, 32, b->smem_sched, ss>>>(dk, G, taps);
+    else if (d.NB <= 128) k_sched<4><<<W, 32, b->smem_sched, ss>>>(dk, G, taps);
+    else k_sched<8><<<W, 32, b->smem_sched, ss>>>(dk, G, taps);
+    if (split) {
+      cudaEventRecord(b->sev[1], ss);
+      OB_LAUNCH_PREP_G(2)
+      cudaStreamWaitEvent(st, b->sev[1], 0);
+      g_launches++;
+    }
+#undef OB_LAUNCH_PREP_G
+#undef OB_LAUNCH_PREP
     if (timing) cudaEventRecord(ev[3], st);
-    if (b->sor_pair) {
+    if (b->sor_reg) {
+      k_sor_reg<G><<<gsor, 32, b->smem_sor_reg, st>>>(d, taps);
+    } else if (b->sor_pair) {
       constexpr int GP = G <= 16 ? 2 * G : 32, Tp = 32 / GP;
       const int gp = (W + Tp - 1) / Tp;
       long long cap = b->pair_resident > 0 ? b->pair_resident : gp;

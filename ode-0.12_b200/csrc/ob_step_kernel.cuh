@@ -129,7 +129,11 @@ __device__ __forceinline__ bool encode_bounds(real lo, real hi, real *v, unsigne
 // PJ = false: the batch has no permanent joints (contact joints only), the getInfo1/2 code of every joint type is compiled out
 // (tried on B200: capping the contact-only variant at 128 registers for 16 warps per SM instead of 11 -- spills in the row
 // assembly, config 2 k_prep 0.43 -> 0.58 ms; kept at 168 registers)
-template <int G, bool PJ>
+// PH = 0: the whole kernel.  PH = 1 / 2: its two halves as separate launches -- (1) joint graph, islands, body preamble, rows
+// per joint and everything k_sched* needs (island / row tables, the rows' body + findex bytes in d.rowmeta); (2) row assembly
+// and finalisation -- so that the schedule (k_sched*, which needs only the topology) runs on a second stream WHILE the rows
+// are assembled (ob_kern_step.cu).  Half 2 re-stages the few index tables it needs from what half 1 left in global memory.
+template <int G, bool PJ, int PH>
 __global__ void __launch_bounds__(32) k_prep(ObBatchDev d, real h, int taps) {
   constexpr int T = 32 / G;
   extern __shared__ __align__(16) unsigned char smem_all[];
@@ -179,6 +183,15 @@ __global__ void __launch_bounds__(32) k_prep(ObBatchDev d, real h, int taps) {
     const unsigned short *padjstart = d.padjstart + (size_t)wc * (d.NB + 1);
     const unsigned short *padj = d.padj + (size_t)wc * 2 * (d.NJ ? d.NJ : 1);
     const int njall_max = warp_max_i(njall);
+    int nis = 0, nib = 0, nij = 0, nib_max = 0, nij_max = 0, mtot = 0, anyball = 0;
+    bool have_rows = false;
+    const ObSurface surf0 = d.policy[0].surface;
+    const ObSurface *csurf = d.csurf ? d.csurf + (size_t)wc * d.NC : (const ObSurface *)0;   // drop-in: per-contact surfaces
+    unsigned char *g_ibody = d.ibody + (size_t)wc * d.NB;
+    unsigned short *g_jrow = d.jrow + (size_t)wc * (d.NC + d.NJ + 1);
+    unsigned short *g_ijoint = d.ijoint + (size_t)wc * (d.NC + d.NJ);
+    unsigned short *g_isz = d.isz + (size_t)wc * 4 * d.NB;
+    if constexpr (PH != 2) {
     for (int b = gl; b < nb; b += G) { s_cursor[b] = 0; s_btag[b] = 0; }
     __syncwarp();
     for (int base = 0; base < njall_max; base += G) {
@@ -272,11 +285,10 @@ __global__ void __launch_bounds__(32) k_prep(ObBatchDev d, real h, int taps) {
       s_misc[0] = nis; s_misc[1] = nib; s_misc[2] = nij;
     }
     __syncwarp();
-    const int nis = valid ? s_misc[0] : 0, nib = valid ? s_misc[1] : 0, nij = valid ? s_misc[2] : 0;
-    const int nib_max = warp_max_i(nib), nij_max = warp_max_i(nij), nis_max = warp_max_i(nis);
+      nis = valid ? s_misc[0] : 0; nib = valid ? s_misc[1] : 0; nij = valid ? s_misc[2] : 0;
+      nib_max = warp_max_i(nib); nij_max = warp_max_i(nij);
 
     // ---- (4) per-body preamble (quickstep.cpp:610-665), island bodies only
-    unsigned char *g_ibody = d.ibody + (size_t)wc * d.NB;
     for (int base = 0; base < nib_max; base += G) {
       const int i = base + gl;
       if (i < nib) {
@@ -293,9 +305,6 @@ __global__ void __launch_bounds__(32) k_prep(ObBatchDev d, real h, int taps) {
       }
     }
     // ---- (5) rows per joint (getInfo1) -> row offsets in island joint order (tile-wide scan)
-    const ObSurface surf0 = d.policy[0].surface;
-    const ObSurface *csurf = d.csurf ? d.csurf + (size_t)wc * d.NC : (const ObSurface *)0;   // drop-in: per-contact surfaces
-    int mtot = 0, anyball = 0;
     for (int base = 0; base < nij_max; base += G) {
       const int k = base + gl;
       int m = 0;
@@ -323,7 +332,61 @@ __global__ void __launch_bounds__(32) k_prep(ObBatchDev d, real h, int taps) {
       if (gl == 0) atomicOr(&W.status, OB_ERR_ROW_OVERFLOW);
       mtot = 0;
     }
-    const bool have_rows = mtot > 0;
+    have_rows = mtot > 0;
+    if constexpr (PH == 1) {
+      // hand-off: island / row tables for half 2 and k_sched*, the rows' body + findex bytes for k_sched*
+      unsigned *g_meta = d.rowmeta + (size_t)wc * d.NR;
+      for (int base = 0; base < nij_max; base += G) {
+        const int k = base + gl;
+        if (k < nij) {
+          const int j = s_ijoint[k];
+          g_ijoint[k] = s_ijoint[k]; g_jrow[k] = s_jrow[k];
+          if (have_rows) {
+            const int r0 = s_jrow[k], jm = s_jrow[k + 1] - r0;
+            const unsigned bb = (unsigned)s_jb1[j] | ((unsigned)s_jb2[j] << 8);
+            unsigned mode = 0;
+            if (!PJ || j < nc) { const ObSurface sf = csurf ? csurf[j] : surf0; mode = (unsigned)sf.mode; }
+            for (int q = 0; q < jm; q++) {
+              // findex offset of a contact's friction rows (contact.cpp:211, :235); every other row has findex -1
+              const unsigned fio = (q == 1 && (mode & 0x1000u)) ? 1u : ((q == 2 && (mode & 0x2000u)) ? 2u : 0u);
+              g_meta[r0 + q] = bb | (fio << 16);
+            }
+          }
+        }
+      }
+      if (gl == 0 && valid) {
+        g_jrow[nij] = (unsigned short)(have_rows ? mtot : 0);
+        si[SI_NIS] = nis; si[SI_NIB] = nib; si[SI_NIJ] = nij; si[SI_MTOT] = mtot; si[SI_HAVEROWS] = have_rows ? 1 : 0;
+        si[SI_ANYBALL] = anyball;
+        for (int i = 0; i < 4 * nis; i++) g_isz[i] = s_isz[i];
+      }
+      __syncwarp();
+      continue;
+    }
+    } else {
+      // half 2: re-stage what half 1 computed
+      nis = valid ? si[SI_NIS] : 0; nib = valid ? si[SI_NIB] : 0; nij = valid ? si[SI_NIJ] : 0;
+      mtot = valid ? si[SI_MTOT] : 0; have_rows = valid && si[SI_HAVEROWS] != 0; anyball = valid ? si[SI_ANYBALL] : 0;
+      anyball = __shfl_sync(FULL, anyball, 0, G);
+      nib_max = warp_max_i(nib); nij_max = warp_max_i(nij);
+      for (int b = gl; b < nb; b += G) s_invM[b] = bc[b].invMass;
+      for (int i = gl; i < nib; i += G) s_ibody[i] = g_ibody[i];
+      for (int k = gl; k <= nij; k += G) { s_jrow[k] = g_jrow[k]; if (k < nij) s_ijoint[k] = g_ijoint[k]; }
+      for (int i = gl; i < 4 * nis; i += G) s_isz[i] = g_isz[i];
+      for (int base = 0; base < njall_max; base += G) {
+        const int j = base + gl;
+        if (j < nc) {
+          int b1, b2;
+          if (d.dropin) { b1 = con[j].side1; b2 = con[j].side2; }
+          else { b1 = geoms[con[j].g1].body; b2 = geoms[con[j].g2].body; if (b1 < 0) { b1 = b2; b2 = -1; } }
+          s_jb1[j] = (unsigned char)b1; s_jb2[j] = (unsigned char)(b2 < 0 ? 255 : b2);
+        } else if (j < njall) {
+          const ObJoint &pj = pjoint[j - nc];
+          s_jb1[j] = (unsigned char)pj.b1; s_jb2[j] = (unsigned char)(pj.b2 < 0 ? 255 : pj.b2);
+        }
+      }
+      __syncwarp();
+    }
     // Info2.erp is one variable shared by all joints of an island and a ball joint overwrites it
     // (ball.cpp:60, quickstep.cpp:764-786): joint k sees the erp of the last ball joint before it
     if (anyball && gl == 0 && have_rows) {
@@ -340,8 +403,6 @@ __global__ void __launch_bounds__(32) k_prep(ObBatchDev d, real h, int taps) {
     __syncwarp();
     // ---- (6a) row assembly (getInfo2), one lane per joint: raw rows {J[12], c, cfm, lo, hi} staged in
     // the row records; motor-at-limit torques (joint.cpp:638-657) are collected and applied below
-    unsigned short *g_jrow = d.jrow + (size_t)wc * (d.NC + d.NJ + 1);
-    unsigned short *g_ijoint = d.ijoint + (size_t)wc * (d.NC + d.NJ);
     real *g_side = d.jside + (size_t)wc * (d.NJ ? d.NJ : 1) * 4 * OB_NSIDE;
     int anyside = 0;
     for (int base = 0; base < nij_max; base += G) {
@@ -465,7 +526,6 @@ __global__ void __launch_bounds__(32) k_prep(ObBatchDev d, real h, int taps) {
     // (7) the row order and the level schedule of every shuffle epoch are built by k_sched
     if (gl == 0 && valid) {
       si[SI_NIS] = nis; si[SI_NIB] = nib; si[SI_NIJ] = nij; si[SI_MTOT] = mtot; si[SI_HAVEROWS] = have_rows ? 1 : 0;
-      unsigned short *g_isz = d.isz + (size_t)wc * 4 * d.NB;
       for (int i = 0; i < 4 * nis; i++) g_isz[i] = s_isz[i];
     }
     __syncwarp();
@@ -481,6 +541,10 @@ __global__ void __launch_bounds__(32) k_prep(ObBatchDev d, real h, int taps) {
 // over the order; it runs with the per-body "last level" table spread over the lanes'
 // registers (body b -> lane b&31, register b>>5) so one step costs two shuffles, not a
 // shared-memory round trip.
+// the rows' body + findex bytes: from d.rowmeta when the split k_prep wrote them, else from the row records
+__device__ __forceinline__ unsigned ob_row_meta(const ObBatchDev &d, int w, const real *rows, int i) {
+  return d.rowmeta ? d.rowmeta[(size_t)w * d.NR + i] : *(const unsigned *)(rows + (size_t)i * OB_ROWW + OB_ROWF);
+}
 struct SchedSmem { size_t ord, rowb, fio, lvl, X, isl, last, total; };
 __host__ __device__ inline SchedSmem sched_smem(int NB, int NR) {
   SchedSmem s; size_t o = 0;
@@ -536,7 +600,7 @@ __global__ void __launch_bounds__(32) k_sched(ObBatchDev d, int G, int taps) {
     }
     nri = __shfl_sync(FULL, nri, 0);
     for (int i = lane; i < mtot; i += 32) {
-      const unsigned meta = *(const unsigned *)(rows + (size_t)i * OB_ROWW + OB_ROWF);   // low word of the meta slot
+      const unsigned meta = ob_row_meta(d, w, rows, i);
       s_rowb[i] = (unsigned short)(meta & 0xffffu);
       s_fio[i] = (unsigned char)((meta >> 16) & 255u);
     }
@@ -727,7 +791,7 @@ __global__ void __launch_bounds__(32) k_sched_lane(ObBatchDev d, int G) {
       if (m > 0) { LN(s_isl, 2 * nri) = (unsigned short)r0; LN(s_isl, 2 * nri + 1) = (unsigned short)m; nri++; }
     }
     for (int i = 0; i < mtot; i++) {
-      const unsigned meta = *(const unsigned *)(rows + (size_t)i * OB_ROWW + OB_ROWF);
+      const unsigned meta = ob_row_meta(d, w, rows, i);
       LN(s_rowb, i) = (unsigned short)(meta & 0xffffu);
       LN(s_fio, i) = (unsigned char)((meta >> 16) & 255u);
     }
@@ -876,7 +940,7 @@ __global__ void __launch_bounds__(32) k_sched_tile(ObBatchDev d, int G) {
     }
     nri = __shfl_sync(FULL, nri, 0, GS);
     for (int i = gl; i < mtot; i += GS) {
-      const unsigned meta = *(const unsigned *)(rows + (size_t)i * OB_ROWW + OB_ROWF);   // low word of the meta slot
+      const unsigned meta = ob_row_meta(d, wc, rows, i);
       s_rowb[i] = (unsigned short)(meta & 0xffffu);
       s_fio[i] = (unsigned char)((meta >> 16) & 255u);
     }
@@ -1494,6 +1558,206 @@ __global__ void __launch_bounds__(32) k_sor_ring(ObBatchDev d, int taps) {
 #undef OB_STORE_FC
       ob_cp_async_wait<0>();
 #undef OB_RING_ISSUE
+    }
+    __syncwarp();
+    sor_epilogue<G>(d, taps, wc, valid, gl, nb, mtot, si, rows, s_fc, s_lam, 1);
+    __syncwarp();
+  }
+}
+
+// =====================================================================================
+// k_sor_reg<G>: the pipelined, branch-free pass of k_sor_ring with the row records prefetched into REGISTERS again.
+// ncu of the ring kernel (r02c-r02f): the shared-memory pipe is its busiest unit (55-65 % of peak wavefronts) and more than
+// half of that is the ring itself -- every 80-byte record crosses the pipe twice (LDGSTS in, LDS out) -- while the loads
+// that depend on shared memory (short-scoreboard) top the stall list.  Here every lane loads ITS row of pass v + 3 with
+// five 16-byte LDG.cg straight into one of three rotating register buffers; the decode of pass v + 1 reads the buffer that was
+// filled two passes earlier (the hardware scoreboard is the only synchronisation).  What stays in shared memory is what
+// the dependency chain runs through (fc, lambda) plus the staged schedule.  The loop is unrolled 6x = lcm(3 buffers, 2
+// operand sets) so that every buffer and operand set is addressed statically.
+struct SorRegSmem { size_t fc, invM, lam, idx, total; };
+__host__ __device__ inline SorRegSmem sor_reg_smem(int NB, int NR, int G) {
+  SorRegSmem s; size_t o = 0;
+  s.fc = o; o = ob_al(o + sizeof(real) * 8 * NB, 16);
+  s.invM = o; o = ob_al(o + sizeof(real) * NB, 16);
+  s.lam = o; o = ob_al(o + sizeof(real) * NR, 16);
+  s.idx = o; o = ob_al(o + sizeof(unsigned short) * (NR + G + 2), 16);
+  s.total = ob_al(o, 16);
+  return s;
+}
+struct ObRowBuf { ObRowReg r; int ci; };   // a prefetched row + its index (0xffff: this lane idles in that pass)
+__device__ __forceinline__ void load_row_cg(const real *__restrict__ p, ObRowReg &r) {
+#if defined(dSINGLE)
+  const float4 *q = (const float4 *)p;
+#pragma unroll
+  for (int i = 0; i < 4; i++) { const float4 t = __ldcg(q + i); r.v[4 * i] = t.x; r.v[4 * i + 1] = t.y; r.v[4 * i + 2] = t.z; r.v[4 * i + 3] = t.w; }
+  const float4 t = __ldcg(q + 4);
+  r.v[16] = t.x; r.v[17] = t.y; r.v[18] = t.z; r.meta = __float_as_uint(t.w);
+#else
+  const double2 *q = (const double2 *)p;
+#pragma unroll
+  for (int i = 0; i < 9; i++) { const double2 t = __ldcg(q + i); r.v[2 * i] = t.x; r.v[2 * i + 1] = t.y; }
+  const double2 t = __ldcg(q + 9);
+  r.v[18] = t.x; r.meta = (unsigned)__double2loint(t.y);
+#endif
+}
+__device__ __forceinline__ void sor_prep_reg(const ObRowBuf &B, const real *s_invM, ObRowPrep &P) {
+  const ObRowReg &r = B.r;
+  const int ci = B.ci;
+  P.act = ci != 0xffff;
+  const unsigned meta = P.act ? r.meta : 0u;
+  const int b1 = meta & 255, b2r = (meta >> 8) & 255, fio = (meta >> 16) & 255, bmode = meta >> 24;
+  P.has2 = b2r != 255;
+  P.fric = fio != 0;
+  const int b2 = P.has2 ? b2r : b1;
+  P.o1 = b1; P.o2 = b2;
+  P.li = P.act ? ci : 0;
+  P.lf = P.fric ? P.li - fio : P.li;
+  const real Ad = r.v[15], k1 = s_invM[b1], k2 = s_invM[b2];
+  const real bv = r.v[18];
+  P.lo = bmode == 0 ? -bv : (bmode == 1 ? (real)0 : bv);
+  P.hi = bmode == 2 ? (real)0 : bv;
+  P.b = r.v[16]; P.adcfm = r.v[17];
+#pragma unroll
+  for (int e = 0; e < 9; e++) P.Js[e] = r.v[e] * Ad;
+#pragma unroll
+  for (int e = 0; e < 3; e++) { P.iM1[e] = k1 * r.v[e]; P.iM2[e] = k2 * r.v[e]; }
+#pragma unroll
+  for (int e = 0; e < 6; e++) P.iMa[e] = r.v[9 + e];
+}
+
+template <int G>
+__global__ void __launch_bounds__(32) k_sor_reg(ObBatchDev d, int taps) {
+  constexpr int T = 32 / G;
+  extern __shared__ __align__(16) unsigned char smem_all[];
+  const SorRegSmem L = sor_reg_smem(d.NB, d.NR, G);
+  int lane = threadIdx.x;
+  asm volatile("" : "+r"(lane));
+  const int grp = lane / G, gl = lane % G;
+  const unsigned FULL = 0xffffffffu;
+  const unsigned gmask = G == 32 ? FULL : ((1u << G) - 1u);
+  const int gsh = grp * G;
+  unsigned char *smem = smem_all + (size_t)grp * L.total;
+  real *s_fc = (real *)(smem + L.fc);
+  real *s_invM = (real *)(smem + L.invM);
+  real *s_lam = (real *)(smem + L.lam);
+  unsigned short *s_idx = (unsigned short *)(smem + L.idx);
+
+  for (int wbase = d.wbeg + blockIdx.x * T; wbase < d.wend; wbase += gridDim.x * T) {
+    const int w = wbase + grp;
+    const bool valid = w < d.wend;
+    const int wc = valid ? w : d.wbeg;
+    const int *si = d.stepinfo + (size_t)wc * SI_WORDS;
+    const int nb = valid ? d.world[wc].nb : 0;
+    const int iters = valid ? d.world[wc].iters : 0;
+    const int mtot = valid && si[SI_HAVEROWS] ? si[SI_MTOT] : 0;
+    const ObBodyConst *bc = d.bconst + (size_t)wc * d.NB;
+    const real *rows = d.rows + (size_t)wc * d.NR * OB_ROWW;
+    for (int b = gl; b < d.NB; b += G) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) s_fc[8 * b + k] = 0;
+      s_invM[b] = b < nb ? bc[b].invMass : (real)0;
+    }
+    for (int i = gl; i < mtot; i += G) s_lam[i] = 0;
+    int nep = mtot > 0 ? (iters + 7) >> 3 : 0;
+    if (nep > d.NEP) nep = d.NEP;
+    const int nep_max = warp_max_i(nep);
+    for (int ep = 0; ep < nep_max; ep++) {
+      const bool epv = ep < nep;
+      const int np = epv ? si[SI_NPASS0 + ep] : 0;
+      int nit = epv ? iters - 8 * ep : 0;
+      if (nit > 8) nit = 8;
+      __syncwarp();
+      if (epv) {
+        const unsigned short *sched = d.sched + ((size_t)wc * d.NEP + ep) * d.NR;
+        for (int i = gl; i < mtot; i += G) s_idx[i] = sched[i];
+        for (int i = gl; i <= G + 1; i += G) s_idx[mtot + i] = 0x8000;
+      }
+      __syncwarp();
+      if (epv) {
+        const unsigned short *pstart = d.pstart + ((size_t)wc * d.NEP + ep) * (d.NR + 1);
+        for (int i = gl; i < np; i += G) s_idx[pstart[i]] |= 0x8000;
+      }
+      __syncwarp();
+      const int vtot = np * nit;
+      const int vmax = warp_max_i(vtot);
+      int pf_v = 0, pf_s = 0;
+      // one prefetch step into buffer BUF: find this lane's row of the next pass and start its five 16-byte loads
+#define OB_REG_FETCH(BUF)                                                                          \
+      {                                                                                            \
+        const bool on_ = pf_v < vtot;                                                              \
+        const unsigned me_ = on_ ? (unsigned)s_idx[pf_s + gl] : 0u;                                \
+        const unsigned nx_ = on_ ? (unsigned)s_idx[pf_s + gl + 1] : 0x8000u;                       \
+        const unsigned bits_ = (__ballot_sync(FULL, (nx_ & 0x8000u) != 0) >> gsh) & gmask;         \
+        const int len_ = __ffs(bits_);                                                             \
+        const bool mine_ = on_ && gl < len_;                                                       \
+        const unsigned ri_ = mine_ ? (me_ & 0x7fffu) : 0u;   /* idle lanes load row 0 of their world (valid memory, result unused) */ \
+        load_row_cg(rows + (size_t)ri_ * OB_ROWW, BUF.r);                                          \
+        BUF.ci = mine_ ? (int)ri_ : 0xffff;                                                        \
+        if (on_) { pf_s += len_; if (pf_s >= mtot) pf_s = 0; }                                     \
+        pf_v++;                                                                                    \
+      }
+      ObRowBuf r0, r1, r2;
+      ObRowPrep pa, pb;
+      if (vmax > 0) {
+        OB_REG_FETCH(r0) OB_REG_FETCH(r1) OB_REG_FETCH(r2)
+        sor_prep_reg(r0, s_invM, pa);
+      }
+      // pass v: CUR is applied; FB (the buffer of pass v, already decoded) is refilled with the row of pass v + 3; NXT is decoded from NB
+#define OB_REG_PASS(CUR, NXT, FB, NBUF)                                                            \
+      {                                                                                            \
+        real f1[6], f2[6];                                                                         \
+        OB_LOAD_FC(f1, CUR.o1) OB_LOAD_FC(f2, CUR.o2)                                              \
+        const real old_lambda = s_lam[CUR.li], lam_f = s_lam[CUR.lf];                              \
+        OB_REG_FETCH(FB)                                                                           \
+        sor_prep_reg(NBUF, s_invM, NXT);                                                           \
+        if (taps & 4) sor_check_pass<G>(CUR.act, (unsigned)CUR.o1 | ((CUR.has2 ? (unsigned)CUR.o2 : 255u) << 8), gl, &d.world[wc].status); \
+        real delta = CUR.b - old_lambda * CUR.adcfm;                                               \
+        delta -= f1[0] * CUR.Js[0] + f1[1] * CUR.Js[1] + f1[2] * CUR.Js[2] + f1[3] * CUR.Js[3] + f1[4] * CUR.Js[4] + f1[5] * CUR.Js[5]; \
+        const real delta2 = delta - (f2[0] * -CUR.Js[0] + f2[1] * -CUR.Js[1] + f2[2] * -CUR.Js[2] + f2[3] * CUR.Js[6] + f2[4] * CUR.Js[7] + f2[5] * CUR.Js[8]); \
+        delta = CUR.has2 ? delta2 : delta;                                                         \
+        const real hf = ob_fabs(CUR.hi * lam_f);                                                   \
+        const real hi_act = CUR.fric ? hf : CUR.hi, lo_act = CUR.fric ? -hf : CUR.lo;              \
+        const real new_lambda = old_lambda + delta;                                                \
+        real out = new_lambda;                                                                     \
+        if (new_lambda < lo_act) { delta = lo_act - old_lambda; out = lo_act; }                    \
+        else if (new_lambda > hi_act) { delta = hi_act - old_lambda; out = hi_act; }               \
+        f1[0] += delta * CUR.iM1[0]; f1[1] += delta * CUR.iM1[1]; f1[2] += delta * CUR.iM1[2];     \
+        f1[3] += delta * CUR.iMa[0]; f1[4] += delta * CUR.iMa[1]; f1[5] += delta * CUR.iMa[2];     \
+        f2[0] += delta * -CUR.iM2[0]; f2[1] += delta * -CUR.iM2[1]; f2[2] += delta * -CUR.iM2[2];  \
+        f2[3] += delta * CUR.iMa[3]; f2[4] += delta * CUR.iMa[4]; f2[5] += delta * CUR.iMa[5];     \
+        if (CUR.act) {                                                                             \
+          s_lam[CUR.li] = out;                                                                     \
+          OB_STORE_FC(CUR.o1, f1)                                                                  \
+          if (CUR.has2) OB_STORE_FC(CUR.o2, f2)                                                    \
+        }                                                                                          \
+        __syncwarp();                                                                              \
+      }
+#if defined(dSINGLE)
+#define OB_LOAD_FC(F, B_) { const float4 a_ = *(const float4 *)(s_fc + ob_fc4(B_)); const float2 c_ = *(const float2 *)(s_fc + ob_fc2(B_)); F[0] = a_.x; F[1] = a_.y; F[2] = a_.z; F[3] = a_.w; F[4] = c_.x; F[5] = c_.y; }
+#define OB_STORE_FC(B_, F) { *(float4 *)(s_fc + ob_fc4(B_)) = make_float4(F[0], F[1], F[2], F[3]); *(float2 *)(s_fc + ob_fc2(B_)) = make_float2(F[4], F[5]); }
+#else
+#define OB_LOAD_FC(F, B_) { const real *p4_ = s_fc + ob_fc4(B_), *p2_ = s_fc + ob_fc2(B_); F[0] = p4_[0]; F[1] = p4_[1]; F[2] = p4_[2]; F[3] = p4_[3]; F[4] = p2_[0]; F[5] = p2_[1]; }
+#define OB_STORE_FC(B_, F) { real *p4_ = s_fc + ob_fc4(B_), *p2_ = s_fc + ob_fc2(B_); p4_[0] = F[0]; p4_[1] = F[1]; p4_[2] = F[2]; p4_[3] = F[3]; p2_[0] = F[4]; p2_[1] = F[5]; }
+#endif
+      // pass v: operands (pa, pb) alternate with v mod 2, buffers with v mod 3: pass v refills buffer v mod 3, decodes buffer (v + 1) mod 3
+#pragma unroll 1
+      for (int v = 0; v < vmax; v += 6) {
+        OB_REG_PASS(pa, pb, r0, r1)
+        if (v + 1 >= vmax) break;
+        OB_REG_PASS(pb, pa, r1, r2)
+        if (v + 2 >= vmax) break;
+        OB_REG_PASS(pa, pb, r2, r0)
+        if (v + 3 >= vmax) break;
+        OB_REG_PASS(pb, pa, r0, r1)
+        if (v + 4 >= vmax) break;
+        OB_REG_PASS(pa, pb, r1, r2)
+        if (v + 5 >= vmax) break;
+        OB_REG_PASS(pb, pa, r2, r0)
+      }
+#undef OB_REG_PASS
+#undef OB_LOAD_FC
+#undef OB_STORE_FC
+#undef OB_REG_FETCH
     }
     __syncwarp();
     sor_epilogue<G>(d, taps, wc, valid, gl, nb, mtot, si, rows, s_fc, s_lam, 1);

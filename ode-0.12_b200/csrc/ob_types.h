@@ -20,7 +20,8 @@ enum {  // body flags, ode/src/objects.h:38-48
   OB_BODY_AUTO_DISABLE = 16, OB_BODY_LIN_DAMP = 32, OB_BODY_ANG_DAMP = 64, OB_BODY_MAX_ANG_SPEED = 128,
   OB_BODY_GYROSCOPIC = 256
 };
-enum { OB_GEOM_SPHERE = 0, OB_GEOM_BOX = 1, OB_GEOM_CAPSULE = 2, OB_GEOM_CYLINDER = 3, OB_GEOM_PLANE = 4, OB_GEOM_RAY = 5, OB_GEOM_TRIMESH = 8 };
+enum { OB_GEOM_SPHERE = 0, OB_GEOM_BOX = 1, OB_GEOM_CAPSULE = 2, OB_GEOM_CYLINDER = 3, OB_GEOM_PLANE = 4, OB_GEOM_RAY = 5, OB_GEOM_TRIMESH = 8,
+       OB_GEOM_SPACE = 10 };   // a sub-space as a member of the bound space (drop-in path): an axis-aligned box given directly in R[0..5]; no collider
 enum { OB_GEOM_ENABLED = 1, OB_GEOM_HAS_OFFSET = 2, OB_GEOM_ZERO_SIZED = 4 };
 // ObGeom::mesh / ObPose::mesh of a primitive (non-trimesh, non-ray) geom: set when the record stands for a geom
 // transform (dCreateGeomTransform) served as its encapsulated geom; only the collider dispatch order depends on it
@@ -110,7 +111,7 @@ struct ObCounters {
 
 #define OB_MAXEPOCH 8   // shuffle epochs per step ((iters+7)/8)
 // per-world hand-off between the step kernels (ObBatchDev::stepinfo), ints
-enum { SI_NIS = 0, SI_NIB, SI_NIJ, SI_MTOT, SI_HAVEROWS, SI_NPASS0, SI_WORDS = SI_NPASS0 + OB_MAXEPOCH };
+enum { SI_NIS = 0, SI_NIB, SI_NIJ, SI_MTOT, SI_HAVEROWS, SI_ANYBALL, SI_NPASS0, SI_WORDS = SI_NPASS0 + OB_MAXEPOCH };
 
 // capacities + device pointers, passed by value to every kernel
 struct ObBatchDev {
@@ -170,4 +171,5 @@ struct ObBatchDev {
   ObCounters *counters;  // [1]
   real *adisbuf;         // [W*NB*NADIS*6] auto-disable velocity samples (lvel, avel) per body, ring buffer (util.cpp:128-147)
   int *adisctl;          // [W*NB*2] per body: write index, buffer-full flag
+  unsigned *rowmeta;     // [W*NR] b1 | b2<<8 | findex offset<<16 per row, written by the first half of k_prep for k_sched* (null: read the row records)
 };

@@ -51,6 +51,8 @@ GOLDEN_CALLBACK = [
     ("raycyl_settle40", "raycyl", 20, 1, 40),       # ray-cylinder (mantle and cap branches)
     ("contactmodes_fdir1_settle60", "contactmodes_fdir1", 25, 1, 60),   # dContactFDir1: per-contact first friction direction set by the callback
     ("mixed_varmaxc_settle40", "mixed_varmaxc", 30, 1, 40),             # max-contacts differs from dCollide call to call (cached batch results vs on-demand pairs)
+    ("nested_settle60", "nested", 25, 1, 60),                           # sub-spaces: dSpaceCollide2 recursion with the sublevel rule + interior dSpaceCollide (demo_buggy's car space)
+    ("nested_dcollide_settle60", "nested_dcollide", 25, 1, 60),         # dCollide on a (space, geom) pair: dCollideSpaceGeom
 ]
 
 
@@ -85,7 +87,7 @@ def _built():
 # from the reference's pre-step body state, SURVEY 8d parity protocol with K = 1) so that a
 # last-bit difference cannot be amplified by chaotic dynamics into a different contact set.
 ATAN2_SCENES = ("hinges", "buggy", "ragdoll", "buggy_terrain", "universals", "motors", "pistons", "pus",
-                "bodyflags")   # bodyflags: finite rotation calls sin / cos (dDOUBLE: platform libm, same tolerance class; dSINGLE: glibc-exact restatement)
+                "bodyflags", "nested", "nested_dcollide")   # nested: hinge2 buggies; bodyflags: finite rotation calls sin / cos (dDOUBLE: platform libm, same tolerance class; dSINGLE: glibc-exact restatement)
 
 
 # dDOUBLE on the GPU, scenes whose limit-motors bounce off their stops (restitution turns a last-bit atan2 difference

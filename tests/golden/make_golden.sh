@@ -45,6 +45,8 @@ for p in single double; do
   $d --scene raycyl --steps 20 --settle 40 --out tests/golden/raycyl_settle40_$p.trace
   $d --scene contactmodes_fdir1 --steps 25 --settle 60 --out tests/golden/contactmodes_fdir1_settle60_$p.trace
   $d --scene mixed_varmaxc --steps 30 --settle 40 --out tests/golden/mixed_varmaxc_settle40_$p.trace
+  $d --scene nested --steps 25 --settle 60 --out tests/golden/nested_settle60_$p.trace
+  $d --scene nested_dcollide --steps 25 --settle 60 --out tests/golden/nested_dcollide_settle60_$p.trace
   # large-world path (config 5): reference trace used in lock-step (--resync) by tests/test_large_world.py
   $d --scene pile_5x5x8 --steps 10 --settle 60 --out tests/golden/pile_5x5x8_large_settle60_$p.trace
 done

@@ -50,6 +50,14 @@ static void near_cb(void *data, dGeomID o1, dGeomID o2) {
     c->pairs.push_back((int)(intptr_t)dGeomGetData(o1));
     c->pairs.push_back((int)(intptr_t)dGeomGetData(o2));
   }
+  const bool sp1 = dGeomIsSpace(o1) != 0, sp2 = dGeomIsSpace(o2) != 0;
+  if ((sp1 || sp2) && c->pol->nested != 2) {
+    // the manual's idiom for sub-spaces: collide the pair, then the interior of each space
+    dSpaceCollide2(o1, o2, data, &near_cb);
+    if (sp1) dSpaceCollide((dSpaceID)o1, data, &near_cb);
+    if (sp2) dSpaceCollide((dSpaceID)o2, data, &near_cb);
+    return;
+  }
   dBodyID b1 = dGeomGetBody(o1), b2 = dGeomGetBody(o2);
   if (c->pol->skip_if_connected && b1 && b2 && dAreConnectedExcluding(b1, b2, dJointTypeContact)) return;
   enum { MAXC = 64 };
@@ -78,7 +86,7 @@ static void near_cb(void *data, dGeomID o1, dGeomID o2) {
   const bool ray = dGeomGetClass(o1) == dRayClass || dGeomGetClass(o2) == dRayClass;   // query result, not a contact joint
   // contact geom identity (collision_kernel.cpp:331-343, collision_transform.cpp:143-151): g1 / g2 name the geoms of the
   // call, a geom transform being replaced by its encapsulated geom unless its info mode is on
-  for (int i = 0; i < n; i++) {
+  for (int i = 0; i < n && !sp1 && !sp2; i++) {
     dGeomID e[2] = {o1, o2};
     for (int k = 0; k < 2; k++)
       if (dGeomGetClass(e[k]) == dGeomTransformClass && !dGeomTransformGetInfo(e[k])) e[k] = dGeomTransformGetGeom(e[k]);
@@ -87,6 +95,8 @@ static void near_cb(void *data, dGeomID o1, dGeomID o2) {
   for (int i = 0; i < n; i++) {
     dJointID j = 0;
     if (!ray) {
+      if (sp1 || sp2) { b1 = dGeomGetBody(contact[i].geom.g1); b2 = dGeomGetBody(contact[i].geom.g2); }   // demo_buggy.cpp:104-107: dCollide on a space names the member geoms
+      if (!b1 && !b2) continue;
       j = dJointCreateContact(c->sw->world, c->sw->cgroup, &contact[i]);
       dJointAttach(j, b1, b2);
     }

@@ -31,6 +31,8 @@ struct ScenePolicy {
   // knobs only a near callback can express (classic loop; the batched path's policy table has no equivalent):
   int fdir1;     // 1: dContactFDir1 with a first friction direction computed from the contact normal
   int varmaxc;   // 1: the max-contacts value passed to dCollide varies from call to call
+  int nested;    // sub-spaces among the pairs: 1 = the manual's idiom (dSpaceCollide2 on the pair, then dSpaceCollide on each space
+                 // for its interior pairs), 2 = demo_buggy's way (dCollide straight on the (space, geom) pair, bodies from the contacts)
 };
 
 struct xs32 {  // scene jitter RNG (not ODE's)
@@ -1172,6 +1174,69 @@ static inline ScenePolicy policy_contactmodes(int fdir1) {
   return p;
 }
 
+
+// Nested spaces (collision_space.cpp:772-833, collision_kernel.cpp:104-131), after demo_buggy.cpp:226-310: two cars, each in its own
+// simple space (sublevel 1) inside the main space, one of them carrying a further sub-space (sublevel 2) with two "antenna" spheres;
+// a ground plane and a ramp box in the main space; a few loose boxes.  The cars start close enough to run into each other:
+// space x space pairs, space x geom pairs and the sublevel rule all occur.
+static inline void scene_nested(SceneWorld &sw, int w) {
+  scene_world_base(sw, w);
+  xs32 rng(sw.seed ^ 0x0E57EDu);
+  scene_add_geom(sw, dCreatePlane(sw.space, 0, 0, 1, 0));
+  {
+    dGeomID ramp = scene_add_geom(sw, dCreateBox(sw.space, 2, (dReal)1.5, 1));
+    dMatrix3 R;
+    dRFromAxisAndAngle(R, 0, 1, 0, (dReal)-0.15);
+    dGeomSetPosition(ramp, 2, 0, (dReal)-0.34);
+    dGeomSetRotation(ramp, R);
+  }
+  const dReal L = (dReal)0.7, Wd = (dReal)0.5, H = (dReal)0.2, Rw = (dReal)0.18, Z = (dReal)0.5;
+  for (int car = 0; car < 2; car++) {
+    dSpaceID main_space = sw.space;
+    dSpaceID car_space = dSimpleSpaceCreate(main_space);
+    dSpaceSetCleanup(car_space, 0);
+    dSpaceSetSublevel(car_space, 1);
+    scene_add_geom(sw, (dGeomID)car_space);
+    const dReal x0 = (dReal)(car == 0 ? 0.0 : 1.35), y0 = rng.uni(-0.05, 0.05);
+    sw.space = car_space;   // scene_add_box / scene_add_sphere create their geoms in sw.space
+    dBodyID chassis = scene_add_box(sw, 1 / (L * Wd * H), L, Wd, H, x0, y0, Z);
+    for (int i = 0; i < 3; i++) {
+      const dReal wx = (dReal)(i == 0 ? 0.5 * L : -0.5 * L), wy = (dReal)(i == 0 ? 0 : (i == 1 ? 0.5 * Wd : -0.5 * Wd));
+      dBodyID wheel = scene_add_sphere(sw, (dReal)(0.2 / (4.0 / 3.0 * 3.14159265358979 * Rw * Rw * Rw)), Rw, x0 + wx, y0 + wy, Z - H * (dReal)0.5);
+      dQuaternion q;
+      dQFromAxisAndAngle(q, 1, 0, 0, (dReal)(3.14159265358979 * 0.5));
+      dBodySetQuaternion(wheel, q);
+      dJointID j = dJointCreateHinge2(sw.world, 0);
+      dJointAttach(j, chassis, wheel);
+      const dReal *a = dBodyGetPosition(wheel);
+      dJointSetHinge2Anchor(j, a[0], a[1], a[2]);
+      dJointSetHinge2Axis1(j, 0, 0, 1);
+      dJointSetHinge2Axis2(j, 0, 1, 0);
+      dJointSetHinge2Param(j, dParamSuspensionERP, (dReal)0.4);
+      dJointSetHinge2Param(j, dParamSuspensionCFM, (dReal)0.8);
+      if (i > 0) { dJointSetHinge2Param(j, dParamLoStop, 0); dJointSetHinge2Param(j, dParamHiStop, 0); }
+      dJointSetHinge2Param(j, dParamVel2, (dReal)(car == 0 ? -3.0 : 1.0)); dJointSetHinge2Param(j, dParamFMax2, (dReal)0.1);
+      sw.joints.push_back(j);
+    }
+    if (car == 0) {
+      dSpaceID ant = dHashSpaceCreate(car_space);
+      dSpaceSetCleanup(ant, 0);
+      dSpaceSetSublevel(ant, 2);
+      scene_add_geom(sw, (dGeomID)ant);
+      sw.space = ant;
+      for (int k = 0; k < 2; k++) {
+        dBodyID b = scene_add_sphere(sw, 1, (dReal)0.06, x0 + (dReal)(0.2 * k - 0.1), y0, Z + (dReal)0.4);
+        dJointID j = dJointCreateFixed(sw.world, 0);
+        dJointAttach(j, chassis, b);
+        dJointSetFixed(j);
+        sw.joints.push_back(j);
+      }
+    }
+    sw.space = main_space;
+  }
+  for (int i = 0; i < 4; i++) scene_add_box(sw, 1, (dReal)0.3, (dReal)0.3, (dReal)0.3, rng.uni(0.3, 1.2), rng.uni(-0.6, 0.6), (dReal)(1.2 + 0.5 * i));
+}
+
 static inline int scene_build(const char *name_in, SceneWorld &sw, int w, ScenePolicy &pol) {
   // suffixes select the space class: NAME@sap, NAME@sapz (axis order ZXY), NAME@simple
   char name[64];
@@ -1191,6 +1256,8 @@ static inline int scene_build(const char *name_in, SceneWorld &sw, int w, SceneP
   if (!strcmp(name, "mixed")) { scene_mixed(sw, w, 12, 6); return 0; }
   if (!strcmp(name, "mixed_maxc4")) { scene_mixed(sw, w, 12, 6); pol = policy_crash(); return 0; }
   if (!strcmp(name, "mixed_varmaxc")) { scene_mixed(sw, w, 12, 6); pol.varmaxc = 1; return 0; }   // callback loop only
+  if (!strcmp(name, "nested")) { scene_nested(sw, w); pol = policy_buggy(); pol.nested = 1; return 0; }          // callback loop only
+  if (!strcmp(name, "nested_dcollide")) { scene_nested(sw, w); pol = policy_buggy(); pol.nested = 2; return 0; } // callback loop only
   if (!strcmp(name, "bodyflags")) { scene_bodyflags(sw, w); return 0; }
   if (!strcmp(name, "autodisable")) { scene_autodisable(sw, w); return 0; }
   if (!strcmp(name, "autodisable_avg")) { scene_autodisable(sw, w, 1); return 0; }   // averaged samples (util.cpp:139-205)

@@ -66,7 +66,7 @@ ObBackend *obk_create(const ObBatchDev &caps, int, char *, size_t) {
   d.csurf = d.dropin ? halloc<ObSurface>(b, W * d.NC) : 0;
   d.cfdir1 = d.dropin ? halloc<real>(b, W * d.NC * 4) : 0;
   d.counters = halloc<ObCounters>(b, 1);
-  d.adisbuf = 0; d.adisctl = 0;
+  d.adisbuf = 0; d.adisctl = 0; d.rowmeta = 0;
   if (d.NADIS > 0) { d.adisbuf = halloc<real>(b, (size_t)d.W * d.NB * d.NADIS * 6); d.adisctl = halloc<int>(b, (size_t)d.W * d.NB * 2); }
   if (d.large) { d.invIw = halloc<real>(b, (size_t)d.NB * 12); d.tmp1 = halloc<real>(b, (size_t)d.NB * 8); }
   return b;

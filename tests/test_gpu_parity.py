@@ -51,7 +51,7 @@ def test_cuda_matches_live_reference(scene, steps, worlds, prec):
                                                 ("stack32@sap", 60, 2), ("mixed@simple", 100, 1), ("terrain_boxes", 80, 1), ("buggy_terrain", 100, 1),
                                                 ("raycast", 150, 2), ("raycast2", 120, 2), ("raycast2h", 120, 1), ("raycyl", 120, 1), ("sliders", 150, 1), ("universals", 150, 1), ("motors", 150, 1), ("pistons", 150, 1), ("pus", 150, 1), ("cylmix", 150, 1), ("kinematic", 150, 1), ("nulljoint", 150, 1), ("transforms", 150, 1),
                                                 ("hinges", 120, 1), ("buggy", 120, 1), ("ragdoll", 80, 1),
-                                                ("bodyflags", 150, 1), ("autodisable", 300, 1), ("autodisable_avg", 300, 1), ("contactmodes", 150, 1), ("contactmodes_fdir1", 150, 1), ("mixed_varmaxc", 200, 2)])
+                                                ("bodyflags", 150, 1), ("autodisable", 300, 1), ("autodisable_avg", 300, 1), ("contactmodes", 150, 1), ("contactmodes_fdir1", 150, 1), ("mixed_varmaxc", 200, 2), ("nested", 200, 2), ("nested_dcollide", 200, 1), ("nested@sap", 150, 1)])
 def test_dropin_classic_api_matches_live_reference(scene, steps, worlds, prec):
     """the drop-in boundary: unchanged user code (dSpaceCollide + near callback calling dCollide /
     dJointCreateContact / dJointSetFeedback + dWorldQuickStep + dJointGroupEmpty) linked against

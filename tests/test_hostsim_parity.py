@@ -45,7 +45,7 @@ def test_hostsim_matches_live_reference(scene, steps, worlds):
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
 @pytest.mark.parametrize("scene,steps,worlds", [("stack32", 80, 2), ("mixed_maxc4", 150, 1), ("hinges", 150, 1), ("buggy", 120, 2), ("ragdoll", 100, 1),
                                                 ("raycast", 250, 3), ("raycast2", 200, 2), ("raycast2h", 200, 2), ("raycyl", 200, 1), ("sliders", 200, 1), ("universals", 200, 1), ("motors", 200, 1), ("pistons", 200, 1), ("pus", 200, 1), ("cylmix", 200, 1), ("kinematic", 200, 1), ("nulljoint", 200, 1), ("transforms", 200, 1), ("transforms@sapz", 150, 1), ("transforms_rays", 200, 2),
-                                                ("bodyflags", 200, 1), ("autodisable", 400, 1), ("autodisable_avg", 400, 1), ("contactmodes", 200, 1), ("contactmodes_fdir1", 300, 2), ("mixed_varmaxc", 300, 2)])
+                                                ("bodyflags", 200, 1), ("autodisable", 400, 1), ("autodisable_avg", 400, 1), ("contactmodes", 200, 1), ("contactmodes_fdir1", 300, 2), ("mixed_varmaxc", 300, 2), ("nested", 300, 2), ("nested_dcollide", 300, 2), ("nested@sap", 200, 1), ("nested_dcollide@simple", 200, 1)])
 def test_hostsim_dropin_callback_loop_matches_live_reference(scene, steps, worlds):
     """host logic of the drop-in path (ob_dropin.cpp): the classic loop dSpaceCollide + near callback
     (dCollide, dJointCreateContact, dJointAttach, dJointSetFeedback) + dWorldQuickStep +
