@@ -825,6 +825,18 @@ int dBatchGetLargeWorldStats(dBatchID, dBatchLargeWorldStats *out);   /* -1 for 
 #define D_BATCH_SPLIT_HANDLE_BYTES 128
 int dBatchSplitExport(dBatchID, void *handle);
 int dBatchSplitAttach(dBatchID, int rank, int nranks, const void *handles);
+/* Ray queries against the bound worlds (the batched form of the ray-cast vehicle's wheel probe, demos/raycar/car.cpp:353-371:
+ * dGeomRaySet + dGeomRaySetParams + dGeomRaySetClosestHit + dSpaceCollide2(space, ray, callback keeping the nearest
+ * dCollide result)).  rays_per_world rays per world: origin3 / dir3 are [world][ray][3] (dir is normalised like dGeomRaySet
+ * does, ray.cpp:115-135), length [world][ray].  ray_flags: 1 first contact, 2 backface cull, 4 closest hit
+ * (dGeomRaySetParams / dGeomRaySetClosestHit; they only matter against trimeshes).  For every ray the result is the
+ * contact of smallest depth among dCollide(ray, g, 1, ...) over the enabled geoms g of the world's space whose AABB
+ * overlaps the ray's and whose category / collide bits pass collideAABBs (collision_space_internal.h:48-82); ties
+ * go to the geom that comes first in the space's list.  geom = creation index of that geom inside its space, -1 = no
+ * hit (depth = length then).  Bodies are taken where the device has them (after the steps run so far). */
+typedef struct dBatchRayHit { dReal pos[3]; dReal depth; dReal normal[3]; int geom; } dBatchRayHit;
+int dBatchRayCast(dBatchID, int rays_per_world, const dReal *origin3, const dReal *dir3, const dReal *length, int ray_flags,
+                  unsigned long category_bits, unsigned long collide_bits, dBatchRayHit *hits);
 /* the CUDA stream the batch launches on (cudaStream_t as void*), so callers can
  * time with events on the launching stream */
 void *dBatchGetStream(dBatchID);

@@ -34,6 +34,10 @@ int obk_collide_pair(const ObPose *a, const ObPose *b, int flags, ObCg *out, con
 // (collision_space_internal.h:48-82) would call the near callback for (geom g of the space, query q).
 int obk_collide2(ObBackend *, const ObPose *q, const int *qbody, const uint32_t *qcat, const uint32_t *qcol, const ObMeshDev *qmesh,
                  int nq, unsigned char *hit, char *err, size_t errlen);
+// dBatchRayCast: nrays rays per world against every world's geoms (host arrays in, host hits out); hit = {pos3, depth, normal3, geom index}
+struct ObRayHit { real pos[3]; real depth; real normal[3]; int geom; };
+int obk_raycast(ObBackend *, int nrays, const real *origin3, const real *dir3, const real *length, int ray_flags, uint32_t cat, uint32_t col,
+                ObRayHit *hits, char *err, size_t errlen);
 int obk_mesh_upload(const float *verts, int nverts, const int *tris, int ntris, const ObBvNode *nodes, const unsigned char *useflags /* [ntris] or null */, int device, ObMeshDev *io);
 void obk_mesh_free(ObMeshDev *m);
 int obk_sync(ObBackend *);

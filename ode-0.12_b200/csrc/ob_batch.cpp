@@ -558,6 +558,17 @@ int dBatchSplitAttach(dBatchID B, int rank, int nranks, const void *handles) {
   return 0;
 }
 void *dBatchGetStream(dBatchID B) { return obk_stream(B->bk); }
+int dBatchRayCast(dBatchID B, int rays_per_world, const dReal *origin3, const dReal *dir3, const dReal *length, int ray_flags,
+                  unsigned long category_bits, unsigned long collide_bits, dBatchRayHit *hits) {
+  if (!B || rays_per_world < 0 || !origin3 || !dir3 || !length || !hits) { ob_set_last_error("dBatchRayCast: bad arguments"); return -1; }
+  static_assert(sizeof(dBatchRayHit) == sizeof(ObRayHit), "dBatchRayHit layout");
+  char err[512] = "";
+  if (obk_raycast(B->bk, rays_per_world, origin3, dir3, length, ray_flags, (uint32_t)category_bits, (uint32_t)collide_bits, (ObRayHit *)hits, err, sizeof err)) {
+    ob_set_last_error("dBatchRayCast: %s", err);
+    return -1;
+  }
+  return 0;
+}
 long long dB200KernelLaunchCount(void) { return obk_launch_count(); }
 int dB200LibmHost(int fn, int n, const float *a, const float *b, float *out) {
   for (int i = 0; i < n; i++) out[i] = fn == 0 ? ob_atan2f_glibc(a[i], b[i]) : (fn == 1 ? ob_sinf_glibc(a[i]) : ob_cosf_glibc(a[i]));

@@ -1506,3 +1506,4 @@ OB_HD int ob_collide_pair(const ObPose &o1, const ObPose &o2, int flags, ObCg *c
                           int *bverr = 0) {
   return ob_collide_pair_xf_t<true, OB_MAXC_LOCAL>(&o1, &o2, 1, flags, c, swapped, meshes, bverr);
 }
+

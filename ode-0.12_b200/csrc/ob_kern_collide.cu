@@ -1,6 +1,7 @@
 // ob_kern_collide.cu — broadphase + narrowphase kernels of the batched path (k_collide, k_collide_tile), the
 // one-pair kernel behind dCollide and the dSpaceCollide2 filter kernel.
 #include "ob_backend_cuda.h"
+#include "ob_ray.h"
 
 // ------------------------------------------------------------------------------------
 // MESH: the batch has trimesh geoms (narrowphase with the BVH colliders, up to OB_MAXC_LOCAL contacts per
@@ -653,5 +654,72 @@ int obk_collide2(ObBackend *b, const ObPose *q, const int *qbody, const uint32_t
   if (dq) cudaFree(dq);
   if (dh) cudaFree(dh);
   if (e != cudaSuccess) { snprintf(err, errlen, "k_collide2 failed: %s", cudaGetErrorString(e)); return -1; }
+  return 0;
+}
+
+
+// dBatchRayCast: thread per (world, ray); the world's geoms are walked in the space's list order (SAP: GeomList then DirtyList,
+// what cleanGeoms leaves), so that of two equally near hits the first in list order wins, like a near callback keeping `depth <`
+__global__ void __launch_bounds__(128) k_raycast(ObBatchDev d, int nrays, const real *origin, const real *dir, const real *length, int ray_flags,
+                                                 uint32_t rcat, uint32_t rcol, ObRayHit *hits) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)d.W * nrays) return;
+  const int w = (int)(t / nrays);
+  ObWorld &W = d.world[w];
+  const int ng = W.ng;
+  const ObGeom *geoms = d.geom + (size_t)w * d.NG;
+  const ObBodyDyn *bd = d.bdyn + (size_t)w * d.NB;
+  const int *glist = d.glist + (size_t)w * d.NG;
+  const int rot = W.space_type == OB_SPACE_SAP ? W.sap_ndirty : 0;
+  ObPose ray;
+  ob_ray_pose(origin + 3 * t, dir + 3 * t, length[t], ray_flags, &ray);
+  real rab[6];
+  ob_aabb(ray, rab, d.meshes);
+  ObRayHit h;
+  for (int k = 0; k < 3; k++) { h.pos[k] = 0; h.normal[k] = 0; }
+  h.depth = length[t]; h.geom = -1;
+  bool have = false;
+  int bverr = 0;
+  for (int i = 0; i < ng; i++) {
+    const int gi = glist[i + rot < ng ? i + rot : i + rot - ng];
+    const ObGeom g = geoms[gi];
+    if (!(g.flags & OB_GEOM_ENABLED) || (g.flags & OB_GEOM_ZERO_SIZED) || g.type == OB_GEOM_RAY || g.type == OB_GEOM_SPACE) continue;
+    ObPose p;
+    geom_pose_dev(g, bd, &p);
+    ObCg c;
+    if (ob_ray_vs_geom(ray, rab, rcat, rcol, p, g.body, g.cat, g.col, d.meshes, &c, &bverr) && (!have || c.depth < h.depth)) {
+      have = true;
+      for (int k = 0; k < 3; k++) { h.pos[k] = c.pos[k]; h.normal[k] = c.normal[k]; }
+      h.depth = c.depth; h.geom = gi;
+    }
+  }
+  if (bverr) atomicOr(&W.status, OB_ERR_BVH_STACK);
+  ObRayHit &o = hits[t];   // field by field: the buffer was zeroed, so the padding of the dDOUBLE layout stays zero
+  for (int k = 0; k < 3; k++) { o.pos[k] = h.pos[k]; o.normal[k] = h.normal[k]; }
+  o.depth = h.depth; o.geom = h.geom;
+}
+int obk_raycast(ObBackend *b, int nrays, const real *origin3, const real *dir3, const real *length, int ray_flags, uint32_t cat, uint32_t col,
+                ObRayHit *hits, char *err, size_t errlen) {
+  cudaSetDevice(b->device);
+  if (b->large) { snprintf(err, errlen, "dBatchRayCast is not served on the large-world path"); return -1; }
+  const size_t n = (size_t)b->d.W * nrays;
+  if (n == 0) return 0;
+  real *dbuf = 0; ObRayHit *dh = 0;
+  cudaError_t e = cudaMalloc((void **)&dbuf, sizeof(real) * 7 * n);
+  if (e == cudaSuccess) e = cudaMalloc((void **)&dh, sizeof(ObRayHit) * n);
+  real *dor = dbuf, *ddir = dbuf + 3 * n, *dlen = dbuf + 6 * n;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dor, origin3, sizeof(real) * 3 * n, cudaMemcpyHostToDevice, b->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(ddir, dir3, sizeof(real) * 3 * n, cudaMemcpyHostToDevice, b->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dlen, length, sizeof(real) * n, cudaMemcpyHostToDevice, b->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(dh, 0, sizeof(ObRayHit) * n, b->stream);
+  if (e == cudaSuccess) {
+    k_raycast<<<(unsigned)((n + 127) / 128), 128, 0, b->stream>>>(b->d, nrays, dor, ddir, dlen, ray_flags, cat, col, dh);
+    g_launches++;
+    e = cudaMemcpyAsync(hits, dh, sizeof(ObRayHit) * n, cudaMemcpyDeviceToHost, b->stream);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
+  if (dbuf) cudaFree(dbuf);
+  if (dh) cudaFree(dh);
+  if (e != cudaSuccess) { snprintf(err, errlen, "k_raycast failed: %s", cudaGetErrorString(e)); return -1; }
   return 0;
 }

@@ -163,6 +163,36 @@ struct Resync {
   }
 };
 
+
+// --rays: the wheel probe of the ray-cast vehicle (demos/raycar/car.cpp:353-371) for a deterministic set of rays per world: a ray geom
+// outside any space, dGeomRaySet / SetParams / SetClosestHit, dSpaceCollide2(space, ray) with a callback keeping the nearest
+// dCollide(ray, geom, 1) result.  The batched build answers the same rays with ONE dBatchRayCast call; the two outputs must be equal.
+struct RayProbe { dReal o[3], d[3], len; };
+struct RayHitOut { dReal pos[3]; dReal depth; dReal normal[3]; int geom; };
+static void make_probes(int w, int n, std::vector<RayProbe> &out) {
+  xs32 rng(0xC0FFEEu ^ (uint32_t)(w * 7919 + 13));
+  out.resize(n);
+  for (int i = 0; i < n; i++) {
+    RayProbe &r = out[i];
+    r.o[0] = rng.uni(-2.5, 2.5); r.o[1] = rng.uni(-2.5, 2.5); r.o[2] = rng.uni(0.3, 4.0);
+    dVector3 d = {rng.uni(-0.6, 0.6), rng.uni(-0.6, 0.6), (dReal)(i % 5 == 4 ? 0.4 : -1.0), 0};
+    dNormalize3(d);
+    r.d[0] = d[0]; r.d[1] = d[1]; r.d[2] = d[2];
+    r.len = rng.uni(0.5, 6.0);
+  }
+}
+struct RayCb { dGeomID ray; RayHitOut best; bool have; };
+static void ray_cb(void *data, dGeomID o1, dGeomID o2) {
+  RayCb *c = (RayCb *)data;
+  dGeomID g = o1 == c->ray ? o2 : o1;
+  dContactGeom cg;
+  if (dCollide(c->ray, g, 1, &cg, sizeof cg) == 1 && (!c->have || cg.depth < c->best.depth)) {
+    c->have = true;
+    for (int k = 0; k < 3; k++) { c->best.pos[k] = cg.pos[k]; c->best.normal[k] = cg.normal[k]; }
+    c->best.depth = cg.depth; c->best.geom = (int)(intptr_t)dGeomGetData(g);
+  }
+}
+
 static double now_s() {
   struct timespec ts;
   clock_gettime(CLOCK_MONOTONIC, &ts);
@@ -178,6 +208,8 @@ int main(int argc, char **argv) {
   int nworlds = 1, nsteps = 10, world0 = 0, timing = 0, settle = 0, maxc_world = 0, large = 0;
   uint32_t seed_xor = 0;
   double h = 0.01;
+  int rays = 0;
+  std::string rays_out = "";
   for (int i = 1; i < argc; i++) {
     std::string a = argv[i];
     if (a == "--scene") scene = argv[++i];
@@ -195,6 +227,7 @@ int main(int argc, char **argv) {
     else if (a == "--moved-log") moved_log = argv[++i];                          // callback mode: order of the body moved-callbacks per step
     else if (a == "--export-dif") export_dif = argv[++i];                        // callback mode: dWorldExportDIF of every world inside the last step (contact joints alive)
     else if (a == "--large") large = 1;                                          // force the large-world path (batch mode)
+    else if (a == "--rays") { rays = atoi(argv[++i]); rays_out = argv[++i]; }    // after the steps: N probe rays per world, nearest hits written to a file
     else { fprintf(stderr, "unknown arg %s\n", a.c_str()); return 2; }
   }
   dInitODE2(0);
@@ -312,6 +345,30 @@ int main(int argc, char **argv) {
       }
     }
     contacts = ctx.ncontacts;
+    if (rays > 0) {
+      FILE *rf = fopen(rays_out.c_str(), "wb");
+      if (!rf) { perror("rays"); return 2; }
+      for (int w = 0; w < nworlds; w++) {
+        SceneWorld &sw = worlds[w];
+        std::vector<RayProbe> pr;
+        make_probes(world0 + w, rays, pr);
+        dGeomID ray = dCreateRay(0, 1);
+        for (int i = 0; i < rays; i++) {
+          dGeomRaySetLength(ray, pr[i].len);
+          dGeomRaySet(ray, pr[i].o[0], pr[i].o[1], pr[i].o[2], pr[i].d[0], pr[i].d[1], pr[i].d[2]);
+          dGeomRaySetParams(ray, 0, 0);
+          dGeomRaySetClosestHit(ray, 1);
+          RayCb cb;
+          cb.ray = ray; cb.have = false;
+          memset(&cb.best, 0, sizeof cb.best);
+          cb.best.depth = pr[i].len; cb.best.geom = -1;
+          dSpaceCollide2((dGeomID)sw.space, ray, &cb, &ray_cb);
+          fwrite(&cb.best, sizeof cb.best, 1, rf);
+        }
+        dGeomDestroy(ray);
+      }
+      fclose(rf);
+    }
   }
 #ifdef HAVE_BATCH
   else if (mode == "batch") {
@@ -416,6 +473,24 @@ int main(int argc, char **argv) {
           body_steps += nb; pairs += np; contacts += nc;
         }
       }
+    }
+    if (rays > 0) {
+      std::vector<dReal> ro((size_t)nworlds * rays * 3), rd((size_t)nworlds * rays * 3), rl((size_t)nworlds * rays);
+      for (int w = 0; w < nworlds; w++) {
+        std::vector<RayProbe> pr;
+        make_probes(world0 + w, rays, pr);
+        for (int i = 0; i < rays; i++) {
+          const size_t k = (size_t)w * rays + i;
+          for (int e = 0; e < 3; e++) { ro[3 * k + e] = pr[i].o[e]; rd[3 * k + e] = pr[i].d[e]; }
+          rl[k] = pr[i].len;
+        }
+      }
+      std::vector<dBatchRayHit> hits((size_t)nworlds * rays);
+      if (dBatchRayCast(B, rays, ro.data(), rd.data(), rl.data(), 4 /* closest hit */, ~0ul, ~0ul, hits.data())) { fprintf(stderr, "dBatchRayCast failed: %s\n", dB200LastError()); return 3; }
+      FILE *rf = fopen(rays_out.c_str(), "wb");
+      if (!rf) { perror("rays"); return 2; }
+      fwrite(hits.data(), sizeof(dBatchRayHit), hits.size(), rf);
+      fclose(rf);
     }
     dBatchDestroy(B);
   }

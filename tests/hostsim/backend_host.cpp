@@ -678,3 +678,44 @@ int obk_split_attach(ObBackend *b, int rank, int nranks, const void *handles, ch
 
 
 int obk_libm(int, int, const float *, const float *, float *) { return -1; }   // device-only diagnostic
+
+#include "../../ode-0.12_b200/csrc/ob_ray.h"
+int obk_raycast(ObBackend *b, int nrays, const real *origin3, const real *dir3, const real *length, int ray_flags, uint32_t cat, uint32_t col,
+                ObRayHit *hits, char *, size_t) {
+  ObBatchDev &d = b->d;
+  for (int w = 0; w < d.W; w++) {
+    ObWorld &W = d.world[w];
+    const int ng = W.ng;
+    const int *glist = d.glist + (size_t)w * d.NG;
+    const int rot = W.space_type == OB_SPACE_SAP ? W.sap_ndirty : 0;
+    for (int r = 0; r < nrays; r++) {
+      const size_t t = (size_t)w * nrays + r;
+      ObPose ray;
+      ob_ray_pose(origin3 + 3 * t, dir3 + 3 * t, length[t], ray_flags, &ray);
+      real rab[6];
+      ob_aabb(ray, rab, d.meshes);
+      ObRayHit h;
+      for (int k = 0; k < 3; k++) { h.pos[k] = 0; h.normal[k] = 0; }
+      h.depth = length[t]; h.geom = -1;
+      bool have = false;
+      int bverr = 0;
+      for (int i = 0; i < ng; i++) {
+        const int gi = glist[i + rot < ng ? i + rot : i + rot - ng];
+        const ObGeom &g = d.geom[(size_t)w * d.NG + gi];
+        if (!(g.flags & OB_GEOM_ENABLED) || (g.flags & OB_GEOM_ZERO_SIZED) || g.type == OB_GEOM_RAY || g.type == OB_GEOM_SPACE) continue;
+        ObPose p;
+        geom_pose(d, w, gi, &p);
+        ObCg c;
+        if (ob_ray_vs_geom(ray, rab, cat, col, p, g.body, g.cat, g.col, d.meshes, &c, &bverr) && (!have || c.depth < h.depth)) {
+          have = true;
+          for (int k = 0; k < 3; k++) { h.pos[k] = c.pos[k]; h.normal[k] = c.normal[k]; }
+          h.depth = c.depth; h.geom = gi;
+        }
+      }
+      memset(&hits[t], 0, sizeof(ObRayHit));
+      for (int k = 0; k < 3; k++) { hits[t].pos[k] = h.pos[k]; hits[t].normal[k] = h.normal[k]; }
+      hits[t].depth = h.depth; hits[t].geom = h.geom;
+    }
+  }
+  return 0;
+}
