@@ -485,7 +485,6 @@ int dBatchDebugFeedback(dBatchID B, int w, dReal *f1t1, int cap) {
   if (obk_d2h(B->bk, &n, B->caps.ncontacts + w, sizeof(int))) return -1;
   int m = std::min(n, cap);
   if (m <= 0) return n;
-  if (B->caps.large) { memset(f1t1, 0, sizeof(dReal) * 6 * (size_t)m); return n; }   // no feedback tap on the large-world path
   std::vector<dReal> fb((size_t)m * 12);
   if (obk_d2h(B->bk, fb.data(), B->caps.fback + (size_t)w * (B->caps.NC + B->caps.NJ) * 12, sizeof(dReal) * 12 * m)) return -1;
   for (int i = 0; i < m; i++) for (int k = 0; k < 6; k++) f1t1[6 * i + k] = fb[(size_t)12 * i + k];

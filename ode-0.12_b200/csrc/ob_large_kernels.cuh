@@ -672,6 +672,34 @@ __global__ void __launch_bounds__(LW_SOR_T) k_lw_sor_split(ObLargeDev L, ObLwSpl
     }
 }
 
+// parity tap (taps & 1): dJointFeedback of every contact joint, creation order -- f1 / t1 / f2 / t2 = J^T lambda of the contact's rows
+// (quickstep.cpp:918-957, Multiply1_12q1 order: rows of the contact in sequence)
+__global__ void __launch_bounds__(LW_T) k_lw_feedback(ObBatchDev d, ObLargeDev L, int ncp, int maxc, int m) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= ncp) return;
+  const ObLwPair P = L.cp[1][p];
+  const int nc = P.info & 255, col = (P.info >> 16) & 255;
+  const int *seg = L.segtab + col * (2 + OB_LW_MAXC);
+  const int i = p - seg[0];
+  for (int k = 0; k < nc; k++) {
+    const size_t cs = (size_t)seg[2 + k] + i;
+    if (cs >= (size_t)L.NC) break;
+    const size_t ci = (size_t)L.coff[P.src] + k;
+    if (ci >= (size_t)d.NC) continue;
+    real acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int q = 0; q < m; q++) {
+      real rw[OB_LW_ROWW];
+      unsigned meta;
+      lw_load_row(L, q, cs, rw, &meta);
+      const real lam = __ldcg(L.lambda + (size_t)q * L.NC + cs);
+      for (int e = 0; e < 6; e++) acc[e] += rw[e] * lam;
+      for (int e = 0; e < 3; e++) { acc[6 + e] += (-rw[e]) * lam; acc[9 + e] += rw[6 + e] * lam; }
+    }
+    if (P.b2 < 0) for (int e = 6; e < 12; e++) acc[e] = 0;
+    for (int e = 0; e < 12; e++) d.fback[ci * 12 + e] = acc[e];
+  }
+}
+
 __global__ void __launch_bounds__(LW_T) k_lw_body_post(ObBatchDev d, ObLargeDev L, real h) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   const ObWorld &W = d.world[0];
@@ -728,7 +756,8 @@ int lw_create(ObBackend *b, char *err, size_t errlen) {
   LWCK(dalloc(b, &d.counters, (size_t)1));
   d.joint = 0; d.padjstart = 0; d.padj = 0; d.sapstate = 0; d.rows = 0; d.stepinfo = 0; d.ibody = 0; d.isz = 0; d.jrow = 0;
   d.ijoint = 0; d.jside = 0; d.sched = 0; d.pstart = 0; d.rowJ = d.rowiMJ = d.rowJc = d.rowS = 0; d.rowI = 0; d.lambda = 0;
-  d.fback = 0; d.csurf = 0; d.cfdir1 = 0;
+  d.csurf = 0; d.cfdir1 = 0;
+  LWCK(dalloc(b, &d.fback, NC * 12));   // parity tap: joint feedback per contact (creation order), k_lw_feedback
   b->st_elems = NB;
   LWCK(dalloc(b, &b->st_dev, NB * 13));
   LWCK(dalloc(b, &L.pose, NG));
@@ -982,6 +1011,10 @@ int lw_step(ObBackend *b, real h, int taps, char *err, size_t errlen) {
       g_launches++; sor_launches++;
     }
   LW_MARK();
+  if ((taps & 1) && d.fback) {
+    LWCK(cudaMemsetAsync(d.fback, 0, sizeof(real) * 12 * (size_t)d.NC, st));
+    if (ncp > 0) { k_lw_feedback<<<lw_blocks(ncp), LW_T, 0, st>>>(d, L, ncp, maxc, m); g_launches++; }
+  }
   // (7) integrate
   k_lw_body_post<<<lw_blocks(nb), LW_T, 0, st>>>(d, L, h);
   g_launches++;

@@ -96,7 +96,6 @@ static void near_cb(void *data, dGeomID o1, dGeomID o2) {
     dJointID j = 0;
     if (!ray) {
       if (sp1 || sp2) { b1 = dGeomGetBody(contact[i].geom.g1); b2 = dGeomGetBody(contact[i].geom.g2); }   // demo_buggy.cpp:104-107: dCollide on a space names the member geoms
-      if (!b1 && !b2) continue;
       j = dJointCreateContact(c->sw->world, c->sw->cgroup, &contact[i]);
       dJointAttach(j, b1, b2);
     }

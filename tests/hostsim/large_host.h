@@ -261,6 +261,29 @@ static int large_step_host(ObBatchDev &d, real h, int taps, LargeHostStats *stat
           lam[ri] = ob_lw_row_update(rows[ri].v, rows[ri].meta, k1, k2, b2 >= 0, lam_f, lam[ri], f1, f2);
         }
     }
+  // parity tap: joint feedback per contact joint in creation order (as k_lw_feedback)
+  if ((taps & 1) && d.fback) {
+    memset(d.fback, 0, sizeof(real) * 12 * (size_t)d.NC);
+    std::vector<size_t> coff(np + 1, 0);
+    for (int p = 0; p < np; p++) coff[p + 1] = coff[p] + ncp[p];
+    for (int p = 0; p < ncpairs; p++) {
+      const ObLwPair &P = scp[p];
+      const int nc = P.info & 255;
+      for (int k = 0; k < nc; k++) {
+        const size_t ci = coff[P.src] + k;
+        if (ci >= (size_t)d.NC) continue;
+        real acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        for (int q = 0; q < m; q++) {
+          const size_t ri = rstart[p] + (size_t)k * m + q;
+          const real *rw = rows[ri].v;
+          for (int e = 0; e < 6; e++) acc[e] += rw[e] * lam[ri];
+          for (int e = 0; e < 3; e++) { acc[6 + e] += (-rw[e]) * lam[ri]; acc[9 + e] += rw[6 + e] * lam[ri]; }
+        }
+        if (P.b2 < 0) for (int e = 6; e < 12; e++) acc[e] = 0;
+        for (int e = 0; e < 12; e++) d.fback[ci * 12 + e] = acc[e];
+      }
+    }
+  }
   // (9) integrate
   for (int b = 0; b < nb; b++) {
     ObBodyDyn &B = d.bdyn[b];
