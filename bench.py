@@ -255,7 +255,7 @@ def measure_batched(ctx, cfg_id, steps, warmup, worlds=0, strong=False, cpu=Fals
     if os.path.exists(tf):
         tj = json.load(open(tf))
         # the capture is of configs[1] (stack32 x 4096 worlds, the bench's capacities): only that workload may quote it
-        if tj.get("kernel") == dom and SCENE == "stack32" and nworlds == 4096:
+        if str(tj.get("kernel", "")).startswith(dom) and SCENE == "stack32" and nworlds == 4096:
             traffic = tj.get("dram_bytes_per_launch")
 
     # end to end through the C ABI with HOST buffers every step (page-locked, from dBatchHostAlloc):

@@ -25,6 +25,21 @@
 
 long long g_launches = 0;
 
+#include <map>
+#include <mutex>
+cudaError_t ob_func_smem(const void *func, int bytes) {
+  static std::map<std::pair<int, const void *>, int> high;   // (device, kernel) -> largest size requested so far
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int &h = high[std::make_pair(dev, func)];
+  if (bytes <= h) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) h = bytes;
+  return e;
+}
+
 // ------------------------------------------------------------------------------------
 // bulk state I/O kernels: API order is [world][creation index], device order is newest-first
 __global__ void k_pack_state(ObBatchDev d, real *pos3, real *quat4, real *lvel3, real *avel3) {

@@ -149,6 +149,10 @@ struct ObBackend {
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { snprintf(err, errlen, "%s: %s", #call, cudaGetErrorString(e_)); goto fail; } } while (0)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a property of the kernel, not of a batch: several batches of different shapes
+// live side by side (one drop-in context per space of a nested scene), so the attribute only ever grows (ob_backend_cuda.cu)
+cudaError_t ob_func_smem(const void *func, int bytes);
+
 template <class T> static inline cudaError_t dalloc(ObBackend *b, T **p, size_t n) {
   void *q = 0;
   cudaError_t e = cudaMalloc(&q, (n ? n : 1) * sizeof(T));

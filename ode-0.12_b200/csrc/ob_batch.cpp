@@ -213,7 +213,7 @@ int ob_batch_upload(dxBatch *B) {
 dxBatch *ob_batch_create(int nworlds, const dWorldID *worlds, const dSpaceID *spaces, const dBatchDesc *desc, int dropin) {
   if (nworlds <= 0 || !worlds || !spaces) { ob_set_last_error("dBatchCreate: bad arguments"); return 0; }
   dxBatch *B = new dxBatch;
-  B->bk = 0; B->debug_taps = 1; B->dropin = dropin;
+  B->bk = 0; B->debug_taps = 1; B->dropin = dropin; B->invalid = 0;
   B->worlds.assign(worlds, worlds + nworlds);
   B->spaces.assign(spaces, spaces + nworlds);
   B->bodies.resize(nworlds); B->geoms.resize(nworlds); B->nb.resize(nworlds); B->ng.resize(nworlds);
@@ -319,6 +319,20 @@ dxBatch *ob_batch_create(int nworlds, const dWorldID *worlds, const dSpaceID *sp
   return B;
 }
 
+void ob_batch_invalidate(dxBatch *B, dxWorld *gone_world, dxSpace *gone_space) {
+  if (!B || B->dropin) return;
+  B->invalid = 1;
+  for (size_t w = 0; w < B->worlds.size(); w++) {
+    if (gone_world && B->worlds[w] == gone_world) B->worlds[w] = 0;
+    if (gone_space && B->spaces[w] == gone_space) B->spaces[w] = 0;
+  }
+}
+static bool batch_usable(dxBatch *B, const char *who) {
+  if (!B) { ob_set_last_error("%s: null batch", who); return false; }
+  if (B->invalid) { ob_set_last_error("%s: a world, space, body or geom bound into this batch was destroyed or added / removed after dBatchCreate; destroy the batch and create it again", who); return false; }
+  return true;
+}
+
 extern "C" {
 
 dBatchID dBatchCreate(int nworlds, const dWorldID *worlds, const dSpaceID *spaces, const dBatchDesc *desc) {
@@ -328,8 +342,8 @@ dBatchID dBatchCreate(int nworlds, const dWorldID *worlds, const dSpaceID *space
 void dBatchDestroy(dBatchID B) {
   if (!B) return;
   for (size_t w = 0; w < B->worlds.size() && !B->dropin; w++) {
-    if (B->worlds[w]->bound_batch == B) B->worlds[w]->bound_batch = 0;
-    if (B->spaces[w]->bound_batch == B) B->spaces[w]->bound_batch = 0;
+    if (B->worlds[w] && B->worlds[w]->bound_batch == B) B->worlds[w]->bound_batch = 0;
+    if (B->spaces[w] && B->spaces[w]->bound_batch == B) B->spaces[w]->bound_batch = 0;
   }
   if (B->bk) obk_destroy(B->bk);
   delete B;
@@ -363,6 +377,7 @@ int dBatchGetSeeds(dBatchID B, uint32_t *seeds) {
 
 int dBatchCollideAndQuickStep(dBatchID B, dReal h, int nsteps, int *status_per_world) {
   if (!B || !(h > 0) || nsteps < 0) { ob_set_last_error("dBatchCollideAndQuickStep: bad arguments"); return -1; }
+  if (!batch_usable(B, "dBatchCollideAndQuickStep")) return -1;
   char err[512] = "";
   int rc = obk_step(B->bk, h, nsteps, B->debug_taps, err, sizeof err);
   if (rc) { ob_set_last_error("dBatchCollideAndQuickStep: %s", err); return rc; }
@@ -389,6 +404,7 @@ void *dBatchHostAlloc(size_t bytes) { return obk_host_alloc(bytes); }
 void dBatchHostFree(void *p) { obk_host_free(p); }
 
 int dBatchDownload(dBatchID B) {
+  if (!batch_usable(B, "dBatchDownload")) return -1;
   int W = B->caps.W, NB = B->caps.NB, NG = B->caps.NG;
   std::vector<ObBodyDyn> hd((size_t)W * NB);
   std::vector<int> hl((size_t)W * NG);

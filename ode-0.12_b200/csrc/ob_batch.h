@@ -18,7 +18,11 @@ struct dxBatch {
   std::vector<uint32_t> seeds;                 // host mirror of the per-world LCG seeds as last set
   int debug_taps;
   int dropin;
+  int invalid;   // a bound world / space was destroyed or changed structurally: the host object tables are stale, every entry point that would read them refuses
 };
+// called by the host object model (ob_host.cpp) when an object owned by a user batch is destroyed or its world / space changes
+// structurally (body / geom added or removed): the batch is marked invalid and forgets the object pointers it must not touch again
+void ob_batch_invalidate(dxBatch *B, dxWorld *gone_world, dxSpace *gone_space);
 
 dxBatch *ob_batch_create(int nworlds, const dWorldID *worlds, const dSpaceID *spaces, const dBatchDesc *desc, int dropin);
 int ob_batch_upload(dxBatch *B);

@@ -203,38 +203,38 @@ OB_HD void ob_line_closest_approach(const real *pa, const real *ua, const real *
   }
 }
 
-// intersectRectQuad, box.cpp:187-238.  ret must hold 16 reals.
+// intersectRectQuad, box.cpp:187-238: the quad p[4] clipped against the rectangle |x| < h[0], |y| < h[1]; ret must
+// hold 16 reals.  Same clip arithmetic and point order as the reference; the control flow is structured for a warp:
+// the reference leaves all three loops with a goto when the 8th point is written, here a flag closes the loops so
+// that the lanes of a warp (each clipping its own pair) meet again after every pass.
 OB_HDN int ob_intersect_rect_quad(const real h[2], real p[8], real ret[16]) {
-  int nq = 4, nr = 0;
   real buffer[16];
-  real *q = p;
-  real *r = ret;
-  for (int dir = 0; dir <= 1; dir++) {
-    for (int sign = -1; sign <= 1; sign += 2) {
-      real *pq = q;
-      real *pr = r;
-      nr = 0;
-      for (int i = nq; i > 0; i--) {
-        if (sign * pq[dir] < h[dir]) {
-          pr[0] = pq[0]; pr[1] = pq[1];
-          pr += 2; nr++;
-          if (nr & 8) { q = r; goto done; }
-        }
-        real *nextq = (i > 1) ? pq + 2 : q;
-        if ((sign * pq[dir] < h[dir]) ^ (sign * nextq[dir] < h[dir])) {
-          pr[1 - dir] = pq[1 - dir] + (nextq[1 - dir] - pq[1 - dir]) / (nextq[dir] - pq[dir]) * (sign * h[dir] - pq[dir]);
-          pr[dir] = sign * h[dir];
-          pr += 2; nr++;
-          if (nr & 8) { q = r; goto done; }
-        }
-        pq += 2;
+  real *q = p, *r = ret;
+  int nq = 4, nr = 0;
+  bool full = false;
+  for (int pass = 0; pass < 4 && !full; pass++) {
+    const int dir = pass >> 1, sign = (pass & 1) ? 1 : -1;
+    real *pr = r;
+    nr = 0;
+    for (int i = nq; i > 0 && !full; i--) {
+      const real *pq = q + 2 * (nq - i);
+      const bool inside = sign * pq[dir] < h[dir];
+      if (inside) {
+        pr[0] = pq[0]; pr[1] = pq[1];
+        pr += 2; nr++;
+        full = (nr & 8) != 0;
       }
-      q = r;
-      r = (q == ret) ? buffer : ret;
-      nq = nr;
+      const real *nextq = (i > 1) ? pq + 2 : q;
+      if (!full && (inside ^ (sign * nextq[dir] < h[dir]))) {
+        pr[1 - dir] = pq[1 - dir] + (nextq[1 - dir] - pq[1 - dir]) / (nextq[dir] - pq[dir]) * (sign * h[dir] - pq[dir]);
+        pr[dir] = sign * h[dir];
+        pr += 2; nr++;
+        full = (nr & 8) != 0;
+      }
     }
+    q = r;
+    if (!full) { r = (q == ret) ? buffer : ret; nq = nr; }
   }
-done:
   if (q != ret) for (int i = 0; i < nr * 2; i++) ret[i] = q[i];
   return nr;
 }
@@ -282,21 +282,31 @@ OB_HDN void ob_cull_points(int n, const real p[], int m, int i0, int iret[]) {
   }
 }
 
+OB_HD real ob_sel3(real v0, real v1, real v2, int i) { return i == 0 ? v0 : (i == 1 ? v1 : v2); }
+
 // dBoxBox, box.cpp:331-712.  Returns number of contacts (pos/depth filled), normal, depth, code.
+//
+// The reference scans its 15 candidate separating axes with a macro that returns from the middle of the function on
+// a separating axis and breaks out on the first hit of an "unimportant" query.  One pair per lane, that control flow
+// leaves the lanes of a warp on their own for the rest of the scan (ncu r02d: the scan ran with 1.2 active threads
+// per instruction and was half of k_collide's issued instructions).  Here the scan is straight-line: every axis is
+// evaluated with the reference's expressions in the reference's order and three flags carry what the returns and
+// breaks did (sep: a separating axis was met while the scan was live; stop: the unimportant query took its first
+// hit; neither: keep the deepest axis so far).  The edge axes keep the winning unnormalised axis and its length and
+// normalise once after the scan -- the same three divisions the reference performs when that axis takes the lead.
+// The values compared and stored are the reference's, so the result is bit-identical (tests: every box scene).
 OB_HDN int ob_box_box(const real *p1, const real *R1, const real *side1, const real *p2, const real *R2,
                       const real *side2, real *normal, real *depth, int *return_code, int flags, ObCg *contact) {
   const real fudge_factor = OB_REAL(1.05);
-  real p[3], pp[3], normalC[3] = {0, 0, 0};
-  const real *normalR = 0;
-  real A[3], B[3], R11, R12, R13, R21, R22, R23, R31, R32, R33, Q11, Q12, Q13, Q21, Q22, Q23, Q31, Q32, Q33, s, s2, l,
-      expr1_val;
-  int i, j, invert_normal, code;
-  const int unimportant = (flags & 0x80000000u) != 0;
+  real p[3], pp[3];
+  real R11, R12, R13, R21, R22, R23, R31, R32, R33, Q11, Q12, Q13, Q21, Q22, Q23, Q31, Q32, Q33;
+  int i, j;
+  const bool unimportant = (flags & 0x80000000u) != 0;
 
   p[0] = p2[0] - p1[0]; p[1] = p2[1] - p1[1]; p[2] = p2[2] - p1[2];
   ob_mul1_331(pp, R1, p);
-  A[0] = side1[0] * OB_REAL(0.5); A[1] = side1[1] * OB_REAL(0.5); A[2] = side1[2] * OB_REAL(0.5);
-  B[0] = side2[0] * OB_REAL(0.5); B[1] = side2[1] * OB_REAL(0.5); B[2] = side2[2] * OB_REAL(0.5);
+  const real A0 = side1[0] * OB_REAL(0.5), A1 = side1[1] * OB_REAL(0.5), A2 = side1[2] * OB_REAL(0.5);
+  const real B0 = side2[0] * OB_REAL(0.5), B1 = side2[1] * OB_REAL(0.5), B2 = side2[2] * OB_REAL(0.5);
 
   R11 = ob_dot44(R1 + 0, R2 + 0); R12 = ob_dot44(R1 + 0, R2 + 1); R13 = ob_dot44(R1 + 0, R2 + 2);
   R21 = ob_dot44(R1 + 1, R2 + 0); R22 = ob_dot44(R1 + 1, R2 + 1); R23 = ob_dot44(R1 + 1, R2 + 2);
@@ -305,66 +315,69 @@ OB_HDN int ob_box_box(const real *p1, const real *R1, const real *side1, const r
   Q21 = ob_fabs(R21); Q22 = ob_fabs(R22); Q23 = ob_fabs(R23);
   Q31 = ob_fabs(R31); Q32 = ob_fabs(R32); Q33 = ob_fabs(R33);
 
-  do {
-#define OB_TST(expr1, expr2, norm, cc)        \
-  expr1_val = (expr1);                        \
-  s2 = ob_fabs(expr1_val) - (expr2);          \
-  if (s2 > 0) return 0;                       \
-  if (s2 > s) {                               \
-    s = s2;                                   \
-    normalR = norm;                           \
-    invert_normal = ((expr1_val) < 0);        \
-    code = (cc);                              \
-    if (unimportant) break;                   \
+  real s = -OB_INF;
+  int code = 0;
+  bool invert_normal = false, sep = false, stop = false;
+  real en1 = 0, en2 = 0, en3 = 0, el = 1;   // leading edge axis (unnormalised) and its length
+  // face axes (box.cpp:389-411)
+#define OB_TST(expr1, expr2, cc)                                   \
+  {                                                                \
+    const real e_ = (expr1);                                       \
+    const real s2_ = ob_fabs(e_) - (expr2);                        \
+    const bool live_ = !(sep | stop), out_ = s2_ > 0;              \
+    sep |= live_ & out_;                                           \
+    const bool upd_ = live_ & !out_ & (s2_ > s);                   \
+    if (upd_) { s = s2_; invert_normal = e_ < 0; code = (cc); }    \
+    stop |= upd_ & unimportant;                                    \
   }
-    s = -OB_INF;
-    invert_normal = 0;
-    code = 0;
-    OB_TST(pp[0], (A[0] + B[0] * Q11 + B[1] * Q12 + B[2] * Q13), R1 + 0, 1);
-    OB_TST(pp[1], (A[1] + B[0] * Q21 + B[1] * Q22 + B[2] * Q23), R1 + 1, 2);
-    OB_TST(pp[2], (A[2] + B[0] * Q31 + B[1] * Q32 + B[2] * Q33), R1 + 2, 3);
-    OB_TST(ob_dot41(R2 + 0, p), (A[0] * Q11 + A[1] * Q21 + A[2] * Q31 + B[0]), R2 + 0, 4);
-    OB_TST(ob_dot41(R2 + 1, p), (A[0] * Q12 + A[1] * Q22 + A[2] * Q32 + B[1]), R2 + 1, 5);
-    OB_TST(ob_dot41(R2 + 2, p), (A[0] * Q13 + A[1] * Q23 + A[2] * Q33 + B[2]), R2 + 2, 6);
+  OB_TST(pp[0], (A0 + B0 * Q11 + B1 * Q12 + B2 * Q13), 1);
+  OB_TST(pp[1], (A1 + B0 * Q21 + B1 * Q22 + B2 * Q23), 2);
+  OB_TST(pp[2], (A2 + B0 * Q31 + B1 * Q32 + B2 * Q33), 3);
+  OB_TST(ob_dot41(R2 + 0, p), (A0 * Q11 + A1 * Q21 + A2 * Q31 + B0), 4);
+  OB_TST(ob_dot41(R2 + 1, p), (A0 * Q12 + A1 * Q22 + A2 * Q32 + B1), 5);
+  OB_TST(ob_dot41(R2 + 2, p), (A0 * Q13 + A1 * Q23 + A2 * Q33 + B2), 6);
 #undef OB_TST
-#define OB_TST(expr1, expr2, n1, n2, n3, cc)                        \
-  expr1_val = (expr1);                                              \
-  s2 = ob_fabs(expr1_val) - (expr2);                                \
-  if (s2 > 0) return 0;                                             \
-  l = ob_sqrt((n1) * (n1) + (n2) * (n2) + (n3) * (n3));             \
-  if (l > 0) {                                                      \
-    s2 /= l;                                                        \
-    if (s2 * fudge_factor > s) {                                    \
-      s = s2;                                                       \
-      normalR = 0;                                                  \
-      normalC[0] = (n1) / l; normalC[1] = (n2) / l; normalC[2] = (n3) / l; \
-      invert_normal = ((expr1_val) < 0);                            \
-      code = (cc);                                                  \
-      if (unimportant) break;                                       \
-    }                                                               \
+  // edge x edge axes (box.cpp:413-452): the penetration is measured along the normalised axis
+#define OB_TST(expr1, expr2, n1, n2, n3, cc)                                                  \
+  {                                                                                           \
+    const real e_ = (expr1);                                                                  \
+    real s2_ = ob_fabs(e_) - (expr2);                                                         \
+    const bool live_ = !(sep | stop), out_ = s2_ > 0;                                         \
+    sep |= live_ & out_;                                                                      \
+    const real l_ = ob_sqrt((n1) * (n1) + (n2) * (n2) + (n3) * (n3));                         \
+    s2_ /= l_;                                                                                \
+    const bool upd_ = live_ & !out_ & (l_ > 0) & (s2_ * fudge_factor > s);                    \
+    if (upd_) { s = s2_; en1 = (n1); en2 = (n2); en3 = (n3); el = l_; invert_normal = e_ < 0; code = (cc); } \
+    stop |= upd_ & unimportant;                                                               \
   }
-    OB_TST(pp[2] * R21 - pp[1] * R31, (A[1] * Q31 + A[2] * Q21 + B[1] * Q13 + B[2] * Q12), 0, -R31, R21, 7);
-    OB_TST(pp[2] * R22 - pp[1] * R32, (A[1] * Q32 + A[2] * Q22 + B[0] * Q13 + B[2] * Q11), 0, -R32, R22, 8);
-    OB_TST(pp[2] * R23 - pp[1] * R33, (A[1] * Q33 + A[2] * Q23 + B[0] * Q12 + B[1] * Q11), 0, -R33, R23, 9);
-    OB_TST(pp[0] * R31 - pp[2] * R11, (A[0] * Q31 + A[2] * Q11 + B[1] * Q23 + B[2] * Q22), R31, 0, -R11, 10);
-    OB_TST(pp[0] * R32 - pp[2] * R12, (A[0] * Q32 + A[2] * Q12 + B[0] * Q23 + B[2] * Q21), R32, 0, -R12, 11);
-    OB_TST(pp[0] * R33 - pp[2] * R13, (A[0] * Q33 + A[2] * Q13 + B[0] * Q22 + B[1] * Q21), R33, 0, -R13, 12);
-    OB_TST(pp[1] * R11 - pp[0] * R21, (A[0] * Q21 + A[1] * Q11 + B[1] * Q33 + B[2] * Q32), -R21, R11, 0, 13);
-    OB_TST(pp[1] * R12 - pp[0] * R22, (A[0] * Q22 + A[1] * Q12 + B[0] * Q33 + B[2] * Q31), -R22, R12, 0, 14);
-    OB_TST(pp[1] * R13 - pp[0] * R23, (A[0] * Q23 + A[1] * Q13 + B[0] * Q32 + B[1] * Q31), -R23, R13, 0, 15);
+  OB_TST(pp[2] * R21 - pp[1] * R31, (A1 * Q31 + A2 * Q21 + B1 * Q13 + B2 * Q12), 0, -R31, R21, 7);
+  OB_TST(pp[2] * R22 - pp[1] * R32, (A1 * Q32 + A2 * Q22 + B0 * Q13 + B2 * Q11), 0, -R32, R22, 8);
+  OB_TST(pp[2] * R23 - pp[1] * R33, (A1 * Q33 + A2 * Q23 + B0 * Q12 + B1 * Q11), 0, -R33, R23, 9);
+  OB_TST(pp[0] * R31 - pp[2] * R11, (A0 * Q31 + A2 * Q11 + B1 * Q23 + B2 * Q22), R31, 0, -R11, 10);
+  OB_TST(pp[0] * R32 - pp[2] * R12, (A0 * Q32 + A2 * Q12 + B0 * Q23 + B2 * Q21), R32, 0, -R12, 11);
+  OB_TST(pp[0] * R33 - pp[2] * R13, (A0 * Q33 + A2 * Q13 + B0 * Q22 + B1 * Q21), R33, 0, -R13, 12);
+  OB_TST(pp[1] * R11 - pp[0] * R21, (A0 * Q21 + A1 * Q11 + B1 * Q33 + B2 * Q32), -R21, R11, 0, 13);
+  OB_TST(pp[1] * R12 - pp[0] * R22, (A0 * Q22 + A1 * Q12 + B0 * Q33 + B2 * Q31), -R22, R12, 0, 14);
+  OB_TST(pp[1] * R13 - pp[0] * R23, (A0 * Q23 + A1 * Q13 + B0 * Q32 + B1 * Q31), -R23, R13, 0, 15);
 #undef OB_TST
-  } while (0);
 
-  if (!code) return 0;
+  if (sep || !code) return 0;
 
-  if (normalR) { normal[0] = normalR[0]; normal[1] = normalR[4]; normal[2] = normalR[8]; }
-  else ob_mul0_331(normal, R1, normalC);
+  if (code <= 6) {
+    const real *normalR = code <= 3 ? R1 + (code - 1) : R2 + (code - 4);
+    normal[0] = normalR[0]; normal[1] = normalR[4]; normal[2] = normalR[8];
+  } else {
+    real normalC[3];
+    normalC[0] = en1 / el; normalC[1] = en2 / el; normalC[2] = en3 / el;
+    ob_mul0_331(normal, R1, normalC);
+  }
   if (invert_normal) { normal[0] = -normal[0]; normal[1] = -normal[1]; normal[2] = -normal[2]; }
   *depth = -s;
 
   if (code > 6) {
-    // edge-edge contact
+    // edge-edge contact: the point midway between the closest points of the two edges (box.cpp:474-512)
     real pa[3], pb[3], sign;
+    const real A[3] = {A0, A1, A2}, B[3] = {B0, B1, B2};
     for (i = 0; i < 3; i++) pa[i] = p1[i];
     for (j = 0; j < 3; j++) {
       sign = (ob_dot14(normal, R1 + j) > 0) ? OB_REAL(1.0) : OB_REAL(-1.0);
@@ -387,17 +400,20 @@ OB_HDN int ob_box_box(const real *p1, const real *R1, const real *side1, const r
     return 1;
   }
 
-  // face-something contact
-  const real *Ra, *Rb, *pa, *pb, *Sa, *Sb;
-  if (code <= 3) { Ra = R1; Rb = R2; pa = p1; pb = p2; Sa = A; Sb = B; }
-  else { Ra = R2; Rb = R1; pa = p2; pb = p1; Sa = B; Sb = A; }
+  // face-something contact (box.cpp:514-712): a = the box of the reference face, b = the other one.  The poses stay where
+  // they are (pointer selects into memory); the half sizes are selected by value so that they stay in registers
+  const bool face1 = code <= 3;
+  const real *Ra = face1 ? R1 : R2, *Rb = face1 ? R2 : R1, *pa = face1 ? p1 : p2, *pb = face1 ? p2 : p1;
+  const real Sa0 = face1 ? A0 : B0, Sa1 = face1 ? A1 : B1, Sa2 = face1 ? A2 : B2;
+  const real Sb0 = face1 ? B0 : A0, Sb1 = face1 ? B1 : A1, Sb2 = face1 ? B2 : A2;
 
   real normal2[3], nr[3], anr[3];
-  if (code <= 3) { normal2[0] = normal[0]; normal2[1] = normal[1]; normal2[2] = normal[2]; }
+  if (face1) { normal2[0] = normal[0]; normal2[1] = normal[1]; normal2[2] = normal[2]; }
   else { normal2[0] = -normal[0]; normal2[1] = -normal[1]; normal2[2] = -normal[2]; }
   ob_mul1_331(nr, Rb, normal2);
   anr[0] = ob_fabs(nr[0]); anr[1] = ob_fabs(nr[1]); anr[2] = ob_fabs(nr[2]);
 
+  // largest component of the normal in b's frame -> incident face lanr, its two in-plane axes a1, a2
   int lanr, a1, a2;
   if (anr[1] > anr[0]) {
     if (anr[1] > anr[2]) { a1 = 0; lanr = 1; a2 = 2; }
@@ -408,11 +424,12 @@ OB_HDN int ob_box_box(const real *p1, const real *R1, const real *side1, const r
   }
 
   real center[3];
-  if (nr[lanr] < 0) { for (i = 0; i < 3; i++) center[i] = pb[i] - pa[i] + Sb[lanr] * Rb[i * 4 + lanr]; }
-  else { for (i = 0; i < 3; i++) center[i] = pb[i] - pa[i] - Sb[lanr] * Rb[i * 4 + lanr]; }
+  const real Sbl = ob_sel3(Sb0, Sb1, Sb2, lanr), nrl = ob_sel3(nr[0], nr[1], nr[2], lanr);
+  if (nrl < 0) { for (i = 0; i < 3; i++) center[i] = pb[i] - pa[i] + Sbl * Rb[i * 4 + lanr]; }
+  else { for (i = 0; i < 3; i++) center[i] = pb[i] - pa[i] - Sbl * Rb[i * 4 + lanr]; }
 
   int codeN, code1, code2;
-  if (code <= 3) codeN = code - 1; else codeN = code - 4;
+  if (face1) codeN = code - 1; else codeN = code - 4;
   if (codeN == 0) { code1 = 1; code2 = 2; }
   else if (codeN == 1) { code1 = 0; code2 = 2; }
   else { code1 = 0; code2 = 1; }
@@ -426,13 +443,14 @@ OB_HDN int ob_box_box(const real *p1, const real *R1, const real *side1, const r
   m21 = ob_dot44(Ra + code2, Rb + a1);
   m22 = ob_dot44(Ra + code2, Rb + a2);
   {
-    real k1 = m11 * Sb[a1], k2 = m21 * Sb[a1], k3 = m12 * Sb[a2], k4 = m22 * Sb[a2];
+    const real Sba1 = ob_sel3(Sb0, Sb1, Sb2, a1), Sba2 = ob_sel3(Sb0, Sb1, Sb2, a2);
+    real k1 = m11 * Sba1, k2 = m21 * Sba1, k3 = m12 * Sba2, k4 = m22 * Sba2;
     quad[0] = c1 - k1 - k3; quad[1] = c2 - k2 - k4;
     quad[2] = c1 - k1 + k3; quad[3] = c2 - k2 + k4;
     quad[4] = c1 + k1 + k3; quad[5] = c2 + k2 + k4;
     quad[6] = c1 + k1 - k3; quad[7] = c2 + k2 - k4;
   }
-  real rect[2] = {Sa[code1], Sa[code2]};
+  real rect[2] = {ob_sel3(Sa0, Sa1, Sa2, code1), ob_sel3(Sa0, Sa1, Sa2, code2)};
   real ret[16];
   int n = ob_intersect_rect_quad(rect, quad, ret);
   if (n < 1) return 0;
@@ -441,12 +459,13 @@ OB_HDN int ob_box_box(const real *p1, const real *R1, const real *side1, const r
   real dep[8];
   real det1 = ob_recip(m11 * m22 - m12 * m21);
   m11 *= det1; m12 *= det1; m21 *= det1; m22 *= det1;
+  const real SaN = ob_sel3(Sa0, Sa1, Sa2, codeN);
   int cnum = 0;
   for (j = 0; j < n; j++) {
     real k1 = m22 * (ret[j * 2] - c1) - m12 * (ret[j * 2 + 1] - c2);
     real k2 = -m21 * (ret[j * 2] - c1) + m11 * (ret[j * 2 + 1] - c2);
     for (i = 0; i < 3; i++) point[cnum * 3 + i] = center[i] + k1 * Rb[i * 4 + a1] + k2 * Rb[i * 4 + a2];
-    dep[cnum] = Sa[codeN] - ob_dot(normal2, point + cnum * 3);
+    dep[cnum] = SaN - ob_dot(normal2, point + cnum * 3);
     if (dep[cnum] >= 0) {
       ret[cnum * 2] = ret[j * 2];
       ret[cnum * 2 + 1] = ret[j * 2 + 1];

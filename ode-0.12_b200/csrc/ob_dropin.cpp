@@ -34,6 +34,7 @@ struct ObDropin {
   int maxc_used;       // max-contacts value this frame's batched narrowphase actually ran with (what the cached contacts obey)
   int kcap;            // per-pair contact capacity of the collide kernel that produced them (8 without trimeshes, else OB_MAXC_LOCAL)
   bool in_collide;     // results below are valid (only while the callbacks run)
+  int pairs_cap;       // 0: the batch layer's default pair capacity; else the capacity to bind with (grown after an overflow)
   std::vector<int> pairs;              // (o1,o2) geom indices in callback order
   std::vector<ObContact> contacts;     // grouped by pair, pair order
   std::map<std::pair<int, int>, std::pair<int, int> > pair_contacts;   // (o1,o2) -> (first contact, count)
@@ -74,7 +75,7 @@ static dxWorld *world_of_space(dxSpace *s, bool *mixed) {
 
 static ObDropin *ctx_new(dxWorld *w, dxSpace *s) {
   ObDropin *c = new ObDropin;
-  c->B = 0; c->world = w; c->space = s; c->own_world = 0; c->own_space = 0; c->maxc_hint = 8; c->maxc_used = 8; c->kcap = 8; c->in_collide = false;
+  c->B = 0; c->world = w; c->space = s; c->own_world = 0; c->own_space = 0; c->maxc_hint = 8; c->maxc_used = 8; c->kcap = 8; c->in_collide = false; c->pairs_cap = 0;
   g_ctx.push_back(c);
   return c;
 }
@@ -115,6 +116,7 @@ static bool ctx_ensure(ObDropin *c, int need_contacts, const char *who) {
   int cap = std::max(64, 16 * std::max(1, c->space->count));
   while (cap < need_contacts) cap *= 2;
   desc.max_contacts_per_world = cap;
+  desc.max_pairs_per_world = c->pairs_cap;
   c->B = ob_batch_create(1, &c->world, &c->space, &desc, 1);
   if (!c->B) { ob_error(0, "%s: %s", who, dB200LastError()); return false; }
   return true;
@@ -161,7 +163,16 @@ void ob_dropin_space_collide(dxSpace *space, void *data, dNearCallback *cb) {
   rc |= obk_d2h(B->bk, &nc, B->caps.ncontacts, sizeof(int));
   rc |= obk_d2h(B->bk, &hw, B->caps.world, sizeof hw);
   if (rc) { ob_error(0, "dSpaceCollide: download failed"); return; }
-  if (hw.status & OB_ERR_PAIR_OVERFLOW) { ob_error(0, "dSpaceCollide: more than %d overlapping pairs", B->caps.NP); return; }
+  if (hw.status & OB_ERR_PAIR_OVERFLOW) {
+    // more overlapping pairs than the bound capacity (default max(256, 12 per geom)): the reference has no such limit, so rebind
+    // with room for every pair of the space and collide again
+    const long long all = (long long)c->space->count * (c->space->count - 1) / 2 + 1;
+    if (c->pairs_cap >= all || all > 60000000) { hw.status = 0; obk_h2d(B->bk, B->caps.world, &hw, sizeof hw); ob_error(0, "dSpaceCollide: more than %d overlapping pairs", B->caps.NP); return; }
+    c->pairs_cap = (int)all;
+    ctx_free_batch(c);
+    ob_dropin_space_collide(space, data, cb);
+    return;
+  }
   c->pairs.resize((size_t)2 * np);
   c->contacts.resize(nc);
   if (np) rc |= obk_d2h(B->bk, c->pairs.data(), B->caps.pairs, sizeof(int) * 2 * np);

@@ -1,9 +1,11 @@
 // ob_host.cpp — host object model + the non-compute part of the ODE C API.
 // See ob_host.h.  Reference behaviour cited per function group.
 #include "ob_host.h"
+#include "ob_batch.h"
 #include "ob_collide.h"
 #include "ob_trimesh_host.h"
 #include "ob_solver.h"
+#include <new>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -351,6 +353,7 @@ dWorldID dWorldCreate(void) {
 static void joint_unlink_bodies(dxJoint *j);
 void dWorldDestroy(dWorldID w) {
   OB_AASSERT(w);
+  if (w->bound_batch) { ob_batch_invalidate(w->bound_batch, w, 0); w->bound_batch = 0; }   // a user batch must never touch this world again
   ob_dropin_forget_world(w);
   dxBody *b = w->firstbody;
   while (b) { dxBody *nb = b->next; dBodyDestroy(b); b = nb; }
@@ -411,8 +414,10 @@ int dWorldQuickStep(dWorldID w, dReal stepsize) {
 static void body_geoms_moved(dxBody *b) { for (dxGeom *g = b->geom; g; g = g->body_next) ob_geom_moved(g); }
 dBodyID dBodyCreate(dWorldID w) {
   OB_AASSERT(w);
+  if (w->bound_batch) ob_batch_invalidate(w->bound_batch, 0, 0);
   dxBody *b = new dxBody;
   memset(b, 0, sizeof(*b));
+  new (&b->average_buf) std::vector<dReal>();   // the one non-trivial member: constructed again after the memset
   b->world = w;
   dMassSetParameters(&b->mass, 1, 0, 0, 0, 1, 1, 1, 0, 0, 0);
   b->invI[0] = 1; b->invI[5] = 1; b->invI[10] = 1;
@@ -436,6 +441,7 @@ dBodyID dBodyCreate(dWorldID w) {
 }
 void dBodyDestroy(dBodyID b) {
   OB_AASSERT(b);
+  if (b->world && b->world->bound_batch) ob_batch_invalidate(b->world->bound_batch, 0, 0);   // the batch's body table names this body
   dxGeom *next_geom = 0;
   for (dxGeom *g = b->geom; g; g = next_geom) { next_geom = g->body_next; dGeomSetBody(g, 0); }
   dxJointNode *n = b->firstjoint;
@@ -833,6 +839,7 @@ void dGeomDestroy(dGeomID g) {
   if (g->is_space) {
     dxSpace *s = (dxSpace *)g;
     CHECK_NOT_LOCKED(s);
+    if (s->bound_batch) { ob_batch_invalidate(s->bound_batch, 0, s); s->bound_batch = 0; }
     ob_dropin_forget_space(s);
     dxGeom *x, *n;
     for (x = s->first; x; x = n) {
@@ -1154,6 +1161,7 @@ void dSpaceSetSublevel(dSpaceID s, int sublevel) { s->sublevel = sublevel; }
 int dSpaceGetSublevel(dSpaceID s) { return s->sublevel; }
 static void space_add(dxSpace *s, dxGeom *g) {   // dxSpace::add, collision_space.cpp:162-182
   CHECK_NOT_LOCKED(s);
+  if (s->bound_batch) ob_batch_invalidate(s->bound_batch, 0, 0);
   OB_UASSERT(g->parent_space == 0 && g->next == 0, "geom is already in a space");
   g->parent_space = s;
   g->next = s->first; g->tome = &s->first;
@@ -1169,6 +1177,7 @@ static void space_add(dxSpace *s, dxGeom *g) {   // dxSpace::add, collision_spac
 }
 static void space_remove(dxSpace *s, dxGeom *g) {   // dxSpace::remove, :185-206
   CHECK_NOT_LOCKED(s);
+  if (s->bound_batch) ob_batch_invalidate(s->bound_batch, 0, (g->is_space && ((dxSpace *)g)->bound_batch == s->bound_batch) ? (dxSpace *)g : 0);
   OB_UASSERT(g->parent_space == s, "object is not in this space");
   if (g->next) g->next->tome = g->tome;
   *g->tome = g->next;

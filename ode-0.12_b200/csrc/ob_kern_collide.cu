@@ -6,6 +6,15 @@
 // ------------------------------------------------------------------------------------
 // MESH: the batch has trimesh geoms (narrowphase with the BVH colliders, up to OB_MAXC_LOCAL contacts per
 // pair); otherwise the primitive-only narrowphase with 8 contact slots per pair (box-box emits at most 8)
+// idx = b (b - 1) / 2 + a  ->  (a, b) with a < b: the strict lower triangle, so a candidate scan touches every unordered
+// pair once (the float square root is only a first guess, the two loops make it exact)
+__device__ __forceinline__ void tri_pair(int idx, int *a, int *b) {
+  int r = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)idx)) * 0.5f);
+  while (r * (r - 1) / 2 > idx) r--;
+  while ((r + 1) * r / 2 <= idx) r++;
+  *b = r; *a = idx - r * (r - 1) / 2;
+}
+
 template <bool MESH, bool XF>
 __global__ void __launch_bounds__(OB_THREADS) k_collide(ObBatchDev d) {
   constexpr int CGCAP = MESH ? OB_MAXC_LOCAL : 8;
@@ -114,9 +123,10 @@ __global__ void __launch_bounds__(OB_THREADS) k_collide(ObBatchDev d) {
       if (tid == 0) { st[1] = nbk; if (unsorted) st[0] = 1; else if (!valid) st[0] = 0; }
     }
     // (3) candidate pairs: the space's filter + the sequence key of the pair's callback
-    for (int idx = tid; idx < ng * ng; idx += nt) {
-      int a = idx / ng, b = idx - a * ng;
-      if (a >= b || !s_en[a] || !s_en[b]) continue;
+    for (int idx = tid; idx < ng * (ng - 1) / 2; idx += nt) {
+      int a, b;
+      tri_pair(idx, &a, &b);   // the idx-th pair a < b (any enumeration will do: the pairs are ordered by key below)
+      if (!s_en[a] || !s_en[b]) continue;
       ObPairKey key;
       int first_is_a;
       if (stype == OB_SPACE_HASH) {
@@ -363,9 +373,10 @@ __global__ void __launch_bounds__(32 * WPC) k_collide_tile(ObBatchDev d, int sta
       if (tid == 0) { st[1] = nbk; if (unsorted) st[0] = 1; else if (!valid) st[0] = 0; }
     }
     // (3) candidate pairs: the space's filter + the sequence key of the pair's callback
-    for (int idx = tid; idx < ng * ng; idx += nt) {
-      int a = idx / ng, b = idx - a * ng;
-      if (a >= b || !s_en[a] || !s_en[b]) continue;
+    for (int idx = tid; idx < ng * (ng - 1) / 2; idx += nt) {
+      int a, b;
+      tri_pair(idx, &a, &b);   // the idx-th pair a < b (any enumeration will do: the pairs are ordered by key below)
+      if (!s_en[a] || !s_en[b]) continue;
       ObPairKey key;
       int first_is_a;
       if (stype == OB_SPACE_HASH) {
@@ -537,9 +548,9 @@ int obk_collide_setup(ObBackend *b, const cudaDeviceProp &prop, char *err, size_
     snprintf(err, errlen, "world does not fit one CTA's shared memory (collide %zu B, limit %zu B)", b->smem_collide, (size_t)prop.sharedMemPerBlockOptin);
     goto fail;
   }
-  CK(cudaFuncSetAttribute(k_collide<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_collide));
-  CK(cudaFuncSetAttribute(k_collide<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_collide));
-  CK(cudaFuncSetAttribute(k_collide<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_collide));
+  CK(ob_func_smem((const void *)k_collide<false, false>, (int)b->smem_collide));
+  CK(ob_func_smem((const void *)k_collide<true, false>, (int)b->smem_collide));
+  CK(ob_func_smem((const void *)k_collide<true, true>, (int)b->smem_collide));
   // small worlds: OB_TILE_WPC worlds per CTA with a pooled, class-grouped narrowphase (k_collide_tile)
   b->collide_tile = 0;
   if (d.NG <= 8 && !getenv("OB_COLLIDE_NOTILE")) {
@@ -548,9 +559,9 @@ int obk_collide_setup(ObBackend *b, const cudaDeviceProp &prop, char *err, size_
     b->smem_collide_tile = (size_t)OB_TILE_WPC * collide_smem(d.NG, d.NP).total + collide_tile_smem(d.NG, d.NP, OB_TILE_WPC, b->tile_stage_cap).total;
     if (b->smem_collide_tile <= (size_t)prop.sharedMemPerBlockOptin && (long long)OB_TILE_WPC * d.NP < 65000) {
       b->collide_tile = 1;
-      CK(cudaFuncSetAttribute(k_collide_tile<false, false, OB_TILE_WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_collide_tile));
-      CK(cudaFuncSetAttribute(k_collide_tile<true, false, OB_TILE_WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_collide_tile));
-      CK(cudaFuncSetAttribute(k_collide_tile<true, true, OB_TILE_WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_collide_tile));
+      CK(ob_func_smem((const void *)k_collide_tile<false, false, OB_TILE_WPC>, (int)b->smem_collide_tile));
+      CK(ob_func_smem((const void *)k_collide_tile<true, false, OB_TILE_WPC>, (int)b->smem_collide_tile));
+      CK(ob_func_smem((const void *)k_collide_tile<true, true, OB_TILE_WPC>, (int)b->smem_collide_tile));
     }
   }
   return 0;

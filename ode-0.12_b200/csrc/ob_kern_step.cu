@@ -36,27 +36,27 @@ int obk_stepk_setup(ObBackend *b, const cudaDeviceProp &prop, char *err, size_t 
     goto fail;
   }
 #define OB_SETSMEM(GG) \
-  CK(cudaFuncSetAttribute(k_prep<GG, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_prep)); \
-  CK(cudaFuncSetAttribute(k_prep<GG, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_prep)); \
-  CK(cudaFuncSetAttribute(k_prep<GG, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_prep)); \
-  CK(cudaFuncSetAttribute(k_prep<GG, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_prep)); \
-  CK(cudaFuncSetAttribute(k_prep<GG, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_prep)); \
-  CK(cudaFuncSetAttribute(k_prep<GG, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_prep)); \
-  CK(cudaFuncSetAttribute(k_sor<GG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sor)); \
-  CK(cudaFuncSetAttribute(k_sor<GG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sor)); \
-  CK(cudaFuncSetAttribute(k_post<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_post));
+  CK(ob_func_smem((const void *)k_prep<GG, true, 0>, (int)b->smem_prep)); \
+  CK(ob_func_smem((const void *)k_prep<GG, false, 0>, (int)b->smem_prep)); \
+  CK(ob_func_smem((const void *)k_prep<GG, true, 1>, (int)b->smem_prep)); \
+  CK(ob_func_smem((const void *)k_prep<GG, false, 1>, (int)b->smem_prep)); \
+  CK(ob_func_smem((const void *)k_prep<GG, true, 2>, (int)b->smem_prep)); \
+  CK(ob_func_smem((const void *)k_prep<GG, false, 2>, (int)b->smem_prep)); \
+  CK(ob_func_smem((const void *)k_sor<GG, true>, (int)b->smem_sor)); \
+  CK(ob_func_smem((const void *)k_sor<GG, false>, (int)b->smem_sor)); \
+  CK(ob_func_smem((const void *)k_post<GG>, (int)b->smem_post));
   OB_SETSMEM(4) OB_SETSMEM(8) OB_SETSMEM(16) OB_SETSMEM(32)
 #undef OB_SETSMEM
-  CK(cudaFuncSetAttribute(k_sched<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sched));
-  CK(cudaFuncSetAttribute(k_sched<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sched));
-  CK(cudaFuncSetAttribute(k_sched<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sched));
+  CK(ob_func_smem((const void *)k_sched<2>, (int)b->smem_sched));
+  CK(ob_func_smem((const void *)k_sched<4>, (int)b->smem_sched));
+  CK(ob_func_smem((const void *)k_sched<8>, (int)b->smem_sched));
   b->sor_deep = d.NR > 256 ? 1 : 0;
   { const char *e = getenv("OB_SOR_DEEP"); if (e) b->sor_deep = atoi(e) != 0; }
   b->smem_sched_lane = sched_lane_smem(d.NB, d.NR).total;
   // measured on B200: one lane per world wins for many small worlds (config 3: 65536 worlds x 56 rows, 0.70 -> 0.43 ms),
   // the warp per world for fewer, larger ones (config 2: 4096 x 377 rows, 0.40 vs 2.7 ms: too few warps to hide the chain latency)
   b->sched_lane = b->smem_sched_lane <= (size_t)prop.sharedMemPerBlockOptin && ((W >= 8192 && d.NR <= 256) || getenv("OB_SCHED_LANE")) && !getenv("OB_SCHED_WARP");
-  if (b->sched_lane) CK(cudaFuncSetAttribute(k_sched_lane, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sched_lane));
+  if (b->sched_lane) CK(ob_func_smem((const void *)k_sched_lane, (int)b->smem_sched_lane));
   {
     // k_sched_tile: lanes per world by batch size (enough warps to hide the serial chains' latency, few enough lanes
     // per world that a warp instruction of the chains advances several worlds)
@@ -71,10 +71,10 @@ int obk_stepk_setup(ObBackend *b, const cudaDeviceProp &prop, char *err, size_t 
       b->smem_sched_tile = sched_tile_smem(d.NB, d.NR).total * (32 / gs);
       if (b->smem_sched_tile <= (size_t)prop.sharedMemPerBlockOptin) {
         b->sched_gs = gs;
-        if (gs == 2) CK(cudaFuncSetAttribute(k_sched_tile<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sched_tile));
-        if (gs == 4) CK(cudaFuncSetAttribute(k_sched_tile<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sched_tile));
-        if (gs == 8) CK(cudaFuncSetAttribute(k_sched_tile<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sched_tile));
-        if (gs == 16) CK(cudaFuncSetAttribute(k_sched_tile<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sched_tile));
+        if (gs == 2) CK(ob_func_smem((const void *)k_sched_tile<2>, (int)b->smem_sched_tile));
+        if (gs == 4) CK(ob_func_smem((const void *)k_sched_tile<4>, (int)b->smem_sched_tile));
+        if (gs == 8) CK(ob_func_smem((const void *)k_sched_tile<8>, (int)b->smem_sched_tile));
+        if (gs == 16) CK(ob_func_smem((const void *)k_sched_tile<16>, (int)b->smem_sched_tile));
       }
     }
   }
@@ -97,7 +97,7 @@ int obk_stepk_setup(ObBackend *b, const cudaDeviceProp &prop, char *err, size_t 
         const size_t sm = sor_ring_smem(d.NB, d.NR, b->tile, D).total * Tw;
         if (sm > (size_t)prop.sharedMemPerBlockOptin) continue;
         int per_sm = 0;
-#define OB_RING_SETUP(GG, DD) { CK(cudaFuncSetAttribute(k_sor_ring<GG, DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+#define OB_RING_SETUP(GG, DD) { CK(ob_func_smem((const void *)k_sor_ring<GG, DD>, (int)sm)); \
           CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sor_ring<GG, DD>, 32, sm)); }
 #define OB_RING_SETUP_G(DD) { if (b->tile == 4) OB_RING_SETUP(4, DD) else if (b->tile == 8) OB_RING_SETUP(8, DD) else if (b->tile == 16) OB_RING_SETUP(16, DD) else OB_RING_SETUP(32, DD) }
         if (D == 6) OB_RING_SETUP_G(6) else OB_RING_SETUP_G(4)
@@ -117,10 +117,10 @@ int obk_stepk_setup(ObBackend *b, const cudaDeviceProp &prop, char *err, size_t 
       const bool wantr = want && (re ? atoi(re) != 0 : false);   // r02g on B200: 1.15 ms against the ring's 0.88 on configs[1] (the loads three passes ahead do not hide the global latency the way the 4-deep LDGSTS ring does): opt-in
       b->smem_sor_reg = sor_reg_smem(d.NB, d.NR, b->tile).total * Tw;
       if (wantr && b->smem_sor_reg <= (size_t)prop.sharedMemPerBlockOptin) {
-        if (b->tile == 4) CK(cudaFuncSetAttribute(k_sor_reg<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sor_reg));
-        if (b->tile == 8) CK(cudaFuncSetAttribute(k_sor_reg<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sor_reg));
-        if (b->tile == 16) CK(cudaFuncSetAttribute(k_sor_reg<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sor_reg));
-        if (b->tile == 32) CK(cudaFuncSetAttribute(k_sor_reg<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_sor_reg));
+        if (b->tile == 4) CK(ob_func_smem((const void *)k_sor_reg<4>, (int)b->smem_sor_reg));
+        if (b->tile == 8) CK(ob_func_smem((const void *)k_sor_reg<8>, (int)b->smem_sor_reg));
+        if (b->tile == 16) CK(ob_func_smem((const void *)k_sor_reg<16>, (int)b->smem_sor_reg));
+        if (b->tile == 32) CK(ob_func_smem((const void *)k_sor_reg<32>, (int)b->smem_sor_reg));
         b->sor_reg = 1;
       }
     }
@@ -140,7 +140,7 @@ int obk_stepk_setup(ObBackend *b, const cudaDeviceProp &prop, char *err, size_t 
           const size_t sm = sor_ring_smem(d.NB, d.NR, b->tile, D).total * Tp;
           if (sm > (size_t)prop.sharedMemPerBlockOptin) continue;
           int per_sm = 0;
-#define OB_PAIR_SETUP(GG, DD) { CK(cudaFuncSetAttribute(k_sor_pair<GG, DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+#define OB_PAIR_SETUP(GG, DD) { CK(ob_func_smem((const void *)k_sor_pair<GG, DD>, (int)sm)); \
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sor_pair<GG, DD>, 32, sm)); }
 #define OB_PAIR_SETUP_G(DD) { if (GP == 8) OB_PAIR_SETUP(8, DD) else if (GP == 16) OB_PAIR_SETUP(16, DD) else OB_PAIR_SETUP(32, DD) }
           if (D == 5) OB_PAIR_SETUP_G(5) else OB_PAIR_SETUP_G(4)

@@ -177,11 +177,10 @@ OB_HD void ob_obb_query_init(ObObbQuery &q, const real *boxpos, const real *boxR
   q.BB[8] = E[0] * q.AR[1][2] + E[1] * q.AR[0][2];
 }
 
+// OB_EPSILON (dEpsilon) comes from ob_math.h
 #if defined(dSINGLE)
-#define OB_EPSILON 1.19209290e-07f
 #define OB_MAXVALUE 3.402823466e+38f
 #else
-#define OB_EPSILON 2.2204460492503131e-16
 #define OB_MAXVALUE 1.7976931348623157e+308
 #endif
 #define OB_CONTACTS_UNIMPORTANT 0x80000000u

@@ -69,8 +69,9 @@ def main(tag):
                 to_bytes(d["dram__bytes_write.sum"]["value"], d["dram__bytes_write.sum"]["unit"])
         except KeyError:
             pass
-    if "k_sor" in dom:
-        json.dump({"kernel": "k_sor", "dram_bytes_per_launch": dom["k_sor"], "source": f"profiles/{tag}_ncu_k_sor.json",
+    sor = [k for k in ("k_sor_ring", "k_sor_pair", "k_sor_reg", "k_sor") if k in dom]   # whichever sweep variant the capture ran
+    if sor:
+        json.dump({"kernel": sor[0], "dram_bytes_per_launch": dom[sor[0]], "source": f"profiles/{tag}_ncu_{sor[0]}.json",
                    "workload": "stack32 x 4096 worlds, step 306 (settled), one launch, ncu --set full --clock-control none"},
                   open(os.path.join(PROF, "dominant_kernel_traffic.json"), "w"), indent=1)
     print("wrote", sorted(os.listdir(PROF)))

@@ -67,3 +67,31 @@ def test_binding_and_snapshot_on_host_build():
 @pytest.mark.gpu
 def test_binding_and_snapshot_on_gpu():
     _check(_run(lib_path("single")))
+
+
+def test_batch_refuses_to_run_after_a_bound_world_changed():
+    """a user batch whose worlds are destroyed or restructured must fail with an error instead of touching freed objects (host logic, CPU build)"""
+    import ctypes
+
+    lib = ctypes.CDLL(HOSTSIM)
+    vp = ctypes.c_void_p
+    for n in ("dWorldCreate", "dHashSpaceCreate", "dBodyCreate", "dCreateSphere", "dBatchCreate"):
+        getattr(lib, n).restype = vp
+    lib.dB200LastError.restype = ctypes.c_char_p
+    lib.dHashSpaceCreate.argtypes = [vp]; lib.dBodyCreate.argtypes = [vp]; lib.dCreateSphere.argtypes = [vp, ctypes.c_float]
+    lib.dGeomSetBody.argtypes = [vp, vp]; lib.dBatchCreate.argtypes = [ctypes.c_int, vp, vp, vp]
+    lib.dBatchCollideAndQuickStep.argtypes = [vp, ctypes.c_float, ctypes.c_int, vp]
+    lib.dBatchDestroy.argtypes = [vp]; lib.dBatchDownload.argtypes = [vp]; lib.dWorldDestroy.argtypes = [vp]; lib.dSpaceDestroy.argtypes = [vp]
+    lib.dBodyDestroy.argtypes = [vp]
+    w, s = lib.dWorldCreate(), lib.dHashSpaceCreate(None)
+    b = lib.dBodyCreate(w)
+    lib.dGeomSetBody(lib.dCreateSphere(s, 0.5), b)
+    B = vp(lib.dBatchCreate(1, (vp * 1)(w), (vp * 1)(s), None))
+    assert B
+    assert lib.dBatchCollideAndQuickStep(B, 0.01, 2, None) == 0
+    b2 = lib.dBodyCreate(w)                                   # structural change of a bound world
+    assert lib.dBatchCollideAndQuickStep(B, 0.01, 1, None) != 0 and b"destroyed or added" in lib.dB200LastError()
+    assert lib.dBatchDownload(B) != 0
+    lib.dWorldDestroy(w)                                       # the batch must not dereference the dead world when it goes
+    lib.dBatchDestroy(B)
+    lib.dSpaceDestroy(s)
