@@ -347,8 +347,8 @@ class LargeStats(ctypes.Structure):
 
 def measure_large(ctx, steps, warmup, scene="", settle=-1, cpu=False):
     """configs[4]: one large world.  N = 1: one GPU.  N > 1 (torchrun, one process per GPU): every rank holds the whole
-    world, the SOR phase is split over the ranks with the fc exchange over NVLink inside the kernel
-    (dBatchSplitExport / dBatchSplitAttach) -- total work is fixed, "scaling": "strong"; NCCL only gathers
+    world; the pair sweep and the narrowphase are divided over the ranks by SAP-sorted position and their results written into every
+    rank's arrays over NVLink (dBatchSplitExport / dBatchSplitAttach) -- total work is fixed, "scaling": "strong"; NCCL only gathers
     the 128-byte buffer descriptions once and reduces the timing.  value = device-resident body-steps/s (max over ranks
     of the CUDA-event time); roofline on the SOR phase, algorithmic bytes D x iterations per row."""
     rank, world_size, local_rank, dist, lib, scenes = ctx.rank, ctx.world_size, ctx.local_rank, ctx.dist, ctx.lib, ctx.scenes
@@ -476,8 +476,14 @@ def measure_large(ctx, steps, warmup, scene="", settle=-1, cpu=False):
         "config": {"workload": LARGE["desc"].format(NB=nb) + f", scene {scene}, quickstep 20 it, h={H}, settled {settle} steps",
                    "bodies": nb, "pairs_per_step": st.pairs, "contacts_per_step": st.contacts, "rows_per_step": rows_per_step,
                    "colours": st.colours, "colouring_rounds": st.colouring_rounds, "sor_launches_per_step": st.sor_launches,
-                   "parallelism": "one GPU" if world_size == 1 else f"SOR phase split over {world_size} GPUs (fc exchange over NVLink peer stores inside "
-                                  "k_lw_sor_split, flag barrier per colour); the phases before it run on every rank",
+                   "parallelism": "one GPU" if world_size == 1 else (
+                       f"front end split over {world_size} GPUs: every rank sweeps and collides the pairs of its share of the SAP-sorted positions and "
+                       "stores counts / pairs / contacts into every rank's arrays through NVLink peer mappings (k_lw_sweep / k_lw_narrow, two flag "
+                       "barriers per step); sort, colouring, rows, SOR (latency-bound: one wave per colour) and integration run on every rank"
+                       if not os.environ.get("OB_LW_SPLIT_SOR") else
+                       f"front end + SOR phase split over {world_size} GPUs (fc exchange inside k_lw_sor_split, flag barrier per colour)"),
+                   "nvlink_bytes_per_step_per_rank": 0 if world_size == 1 else int(
+                       (world_size - 1) * (st.pairs * 16 + st.contacts * 48 + 8 * nb) / world_size),
                    "cache": "rows %.0f MB/step streamed every iteration (> 126 MB L2 at full size)" % (rows_per_step * 80 / 1e6),
                    "precision": "dSINGLE", "parity": "pairs+contacts exact, state within stated tolerance vs reference; bitwise vs sequential mirror (tests/test_large_world.py)"},
         "e2e": {"value": ce["body_steps"] / t_e2e, "unit": "body-steps/s", "h2d_bytes_per_step": int(forces[0].nbytes + torque.nbytes),
@@ -594,7 +600,7 @@ def brief(d):
         out["kernels_ms"] = {k: v["ms"] for k, v in r["kernels"].items()}
     if "phases_ms" in r:
         out["phases_ms"] = r["phases_ms"]
-    for k in ("rows_per_world_step", "contacts_per_world_step", "bodies", "contacts_per_step", "colours", "parallelism"):
+    for k in ("rows_per_world_step", "contacts_per_world_step", "bodies", "contacts_per_step", "colours", "parallelism", "nvlink_bytes_per_step_per_rank"):
         if k in d["config"]:
             out[k] = d["config"][k]
     if "cpu_baseline" in d:

@@ -95,7 +95,7 @@ ObBackend *obk_create(const ObBatchDev &caps, int device, char *err, size_t errl
   b->nchunks = 1;
   for (int k = 0; k < 8; k++) b->cstream[k] = 0;
   for (int k = 0; k < 9; k++) b->cev[k] = 0;
-  b->lw_flags = 0; b->lw_flags_off = 0; b->lw_split_on = 0; memset(&b->lw_split, 0, sizeof b->lw_split);
+  b->lw_flags = 0; b->lw_flags_off = 0; b->lw_split_on = 0; b->lw_split_front = 0; b->lw_split_sor = 0; memset(&b->lw_split, 0, sizeof b->lw_split);
   for (int k = 0; k < OB_LW_MAXRANKS; k++) b->lw_peer_base[k] = 0;
   b->large = d.large; b->lw_host = 0; b->lw_rounds = 0; b->lw_ncol = 0;
   for (int k = 0; k < 8; k++) b->lw_stat[k] = 0;

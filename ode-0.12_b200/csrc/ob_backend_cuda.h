@@ -23,7 +23,7 @@ extern long long g_launches;
 // ------------------------------------------------------------------------------------
 // shared-memory layouts (one function for host sizing and device carving)
 struct CollideSmem {
-  size_t pose, aabb, cb, gid, body, cat, col, en, hr, br, walk_of, sapkey, sapinit, sappos, sapwalk, key, o12, sorted, misc, total;
+  size_t pose, aabb, cb, gid, body, cat, col, en, hr, br, walk_of, sapkey, sapinit, sappos, sapwalk, key, o12, sorted, misc, grp, member, gstart, gcur, total;
 };
 __host__ __device__ inline size_t ob_al16(size_t x) { return (x + 15) & ~(size_t)15; }
 __host__ __device__ inline CollideSmem collide_smem(int NG, int NP) {
@@ -43,10 +43,14 @@ __host__ __device__ inline CollideSmem collide_smem(int NG, int NP) {
   s.sapinit = o; o = ob_al16(o + sizeof(int) * (NG + 1));
   s.sappos = o; o = ob_al16(o + sizeof(int) * (NG + 1));
   s.sapwalk = o; o = ob_al16(o + sizeof(int) * (NG + 1));
-  { const size_t kb = sizeof(ObPairKey) * NP, cb = sizeof(int) * 2 * OB_THREADS; s.key = o; o = ob_al16(o + (kb > cb ? kb : cb)); }   // keys; reused by the narrowphase for per-pair counts / offsets of a chunk
+  { const size_t kb = sizeof(int) * 5 * NP, cb = sizeof(int) * 2 * OB_THREADS; s.key = o; o = ob_al16(o + (kb > cb ? kb : cb)); }   // key tails (ObKeyTail, 5 words); reused by the narrowphase for per-pair counts / offsets of a chunk
   s.o12 = o; o = ob_al16(o + sizeof(int2) * NP);
   s.sorted = o; o = ob_al16(o + sizeof(int2) * NP);
   s.misc = o; o = ob_al16(o + sizeof(int) * 64);
+  s.grp = o; o = ob_al16(o + sizeof(unsigned short) * NP);          // group (stage, query rank) of a pair
+  s.member = o; o = ob_al16(o + sizeof(unsigned short) * NP);       // pairs listed group by group
+  s.gstart = o; o = ob_al16(o + sizeof(int) * (3 * (NG + 1) + 1));  // first member of a group
+  s.gcur = o; o = ob_al16(o + sizeof(int) * (3 * (NG + 1) + 1));    // count, then fill cursor, then end of a group
   s.total = o;
   return s;
 }
@@ -143,6 +147,7 @@ struct ObBackend {
   unsigned *lw_flags;
   size_t lw_flags_off;          // bytes from L.fc to lw_flags
   int lw_split_on, lw_split_grid[3], lw_split_threads;
+  int lw_split_front, lw_split_sor;   // what is divided over the ranks: pair sweep + narrowphase (default), the SOR sweep (OB_LW_SPLIT_SOR=1)
   ObLwSplit lw_split;
   void *lw_peer_base[OB_LW_MAXRANKS];   // cudaIpcOpenMemHandle mappings to close
 };

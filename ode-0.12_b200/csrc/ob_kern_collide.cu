@@ -4,8 +4,42 @@
 #include "ob_ray.h"
 
 // ------------------------------------------------------------------------------------
-// MESH: the batch has trimesh geoms (narrowphase with the BVH colliders, up to OB_MAXC_LOCAL contacts per
-// pair); otherwise the primitive-only narrowphase with 8 contact slots per pair (box-box emits at most 8)
+// Phases (1)-(4) of the collide kernels, shared by k_collide (one CTA per world, CTA = true) and k_collide_tile (one warp
+// per world, CTA = false): poses + AABBs + cell boxes in walk order, ranks, the space's candidate filter, the sequence key
+// of every surviving pair and the ordered pair list (V.sorted, d.pairs).  Returns the number of pairs.
+//   (3) runs in two steps so that lanes stay busy: (3a) the cheap overlap filter over the strict triangle of geom pairs,
+//       survivors compacted by warp ballots; (3b) the key of every survivor (ncu r02k: computing the key inside the scan
+//       left 3 of 32 lanes live in every iteration).
+//   (4) pairs are ranked inside their GROUP (stage, query rank) -- the two leading words of the key -- after a counting
+//       sort over the groups, so a pair is compared with the few pairs of its own query instead of all np (np^2 / 2
+//       seven-word compares before; ncu r02k: a quarter of the kernel's instructions).
+struct ObKeyTail { int k[5]; };   // level, cx, cy, cz, node walk index (words 2..6 of ObPairKey)
+__device__ __forceinline__ bool ob_tail_less(const ObKeyTail &a, const ObKeyTail &b) {
+#pragma unroll
+  for (int i = 0; i < 5; i++) {
+    if (a.k[i] < b.k[i]) return true;
+    if (a.k[i] > b.k[i]) return false;
+  }
+  return false;
+}
+struct CollideView {
+  ObPose *pose; real *aabb; ObCellBox *cb; int *gid, *body; uint32_t *cat, *col; int *en, *hr, *br, *walk_of;
+  float *sapkey; int *sapinit, *sappos, *sapwalk; ObKeyTail *key; int2 *o12, *sorted; int *misc;
+  unsigned short *grp, *member; int *gstart, *gcur;
+};
+__device__ __forceinline__ CollideView collide_view(unsigned char *smem, const CollideSmem &L) {
+  CollideView V;
+  V.pose = (ObPose *)(smem + L.pose); V.aabb = (real *)(smem + L.aabb); V.cb = (ObCellBox *)(smem + L.cb);
+  V.gid = (int *)(smem + L.gid); V.body = (int *)(smem + L.body); V.cat = (uint32_t *)(smem + L.cat); V.col = (uint32_t *)(smem + L.col);
+  V.en = (int *)(smem + L.en); V.hr = (int *)(smem + L.hr); V.br = (int *)(smem + L.br); V.walk_of = (int *)(smem + L.walk_of);
+  V.sapkey = (float *)(smem + L.sapkey); V.sapinit = (int *)(smem + L.sapinit); V.sappos = (int *)(smem + L.sappos); V.sapwalk = (int *)(smem + L.sapwalk);
+  V.key = (ObKeyTail *)(smem + L.key); V.o12 = (int2 *)(smem + L.o12); V.sorted = (int2 *)(smem + L.sorted);
+  V.misc = (int *)(smem + L.misc);   // [0]=npairs raw, [1]=nh, [2]=nbig, [3]=contact base, [4]=SAP unsorted, [5]=candidates, [8..40]=scan scratch
+  V.grp = (unsigned short *)(smem + L.grp); V.member = (unsigned short *)(smem + L.member);
+  V.gstart = (int *)(smem + L.gstart); V.gcur = (int *)(smem + L.gcur);
+  return V;
+}
+template <bool CTA> __device__ __forceinline__ void collide_sync() { if (CTA) __syncthreads(); else __syncwarp(); }
 // idx = b (b - 1) / 2 + a  ->  (a, b) with a < b: the strict lower triangle, so a candidate scan touches every unordered
 // pair once (the float square root is only a first guess, the two loops make it exact)
 __device__ __forceinline__ void tri_pair(int idx, int *a, int *b) {
@@ -14,34 +48,13 @@ __device__ __forceinline__ void tri_pair(int idx, int *a, int *b) {
   while ((r + 1) * r / 2 <= idx) r++;
   *b = r; *a = idx - r * (r - 1) / 2;
 }
-
-template <bool MESH, bool XF>
-__global__ void __launch_bounds__(OB_THREADS) k_collide(ObBatchDev d) {
-  constexpr int CGCAP = MESH ? OB_MAXC_LOCAL : 8;
-  extern __shared__ __align__(16) unsigned char smem[];
-  const CollideSmem L = collide_smem(d.NG, d.NP);
-  ObPose *s_pose = (ObPose *)(smem + L.pose);
-  real *s_aabb = (real *)(smem + L.aabb);
-  ObCellBox *s_cb = (ObCellBox *)(smem + L.cb);
-  int *s_gid = (int *)(smem + L.gid);
-  int *s_body = (int *)(smem + L.body);
-  uint32_t *s_cat = (uint32_t *)(smem + L.cat);
-  uint32_t *s_col = (uint32_t *)(smem + L.col);
-  int *s_en = (int *)(smem + L.en);
-  int *s_hr = (int *)(smem + L.hr);
-  int *s_br = (int *)(smem + L.br);
-  int *s_walk_of = (int *)(smem + L.walk_of);
-  float *s_sapkey = (float *)(smem + L.sapkey);
-  int *s_sapinit = (int *)(smem + L.sapinit);
-  int *s_sappos = (int *)(smem + L.sappos);
-  int *s_sapwalk = (int *)(smem + L.sapwalk);
-  ObPairKey *s_key = (ObPairKey *)(smem + L.key);
-  int2 *s_o12 = (int2 *)(smem + L.o12);
-  int2 *s_sorted = (int2 *)(smem + L.sorted);
-  int *s_misc = (int *)(smem + L.misc);   // [0]=npairs raw, [1]=nh, [2]=nbig, [3]=contact base, [8..40]=scan scratch
-  const int tid = threadIdx.x, nt = blockDim.x;
-
-  for (int w = d.wbeg + blockIdx.x; w < d.wend; w += gridDim.x) {
+template <bool CTA>
+__device__ __forceinline__ int collide_broad(const ObBatchDev &d, int w, const CollideView &V, int tid, int nt) {
+  ObPose *s_pose = V.pose; real *s_aabb = V.aabb; ObCellBox *s_cb = V.cb; int *s_gid = V.gid, *s_body = V.body;
+  uint32_t *s_cat = V.cat, *s_col = V.col; int *s_en = V.en, *s_hr = V.hr, *s_br = V.br, *s_walk_of = V.walk_of;
+  float *s_sapkey = V.sapkey; int *s_sapinit = V.sapinit, *s_sappos = V.sappos, *s_sapwalk = V.sapwalk;
+  int2 *s_o12 = V.o12, *s_sorted = V.sorted; int *s_misc = V.misc;
+  const unsigned FULL = 0xffffffffu;
     ObWorld &W = d.world[w];
     const int ng = W.ng;
     const ObGeom *geoms = d.geom + (size_t)w * d.NG;
@@ -74,7 +87,7 @@ __global__ void __launch_bounds__(OB_THREADS) k_collide(ObBatchDev d) {
       else if (stype == OB_SPACE_SAP && ab[ax0 + 1] == OB_INF) cb.level = OB_LEVEL_BIG;   // TmpInfGeomList (:446-449)
       s_cb[i] = cb;
     }
-    __syncthreads();
+    collide_sync<CTA>();
     if (stype == OB_SPACE_SAP) {
       int *gl = d.glist + (size_t)w * d.NG;
       for (int i = tid; i < ng; i += nt) gl[i] = s_gid[i];
@@ -92,7 +105,7 @@ __global__ void __launch_bounds__(OB_THREADS) k_collide(ObBatchDev d) {
         s_misc[1] = h; s_misc[2] = b;
       }
     }
-    __syncthreads();
+    collide_sync<CTA>();
     const int nh = s_misc[1], nbig = s_misc[2];
     // (2b) SAP: sorted position of every finite geom = RadixSort's output order (ob_broad.h)
     if (stype == OB_SPACE_SAP && nh > 0) {
@@ -101,12 +114,12 @@ __global__ void __launch_bounds__(OB_THREADS) k_collide(ObBatchDev d) {
       const bool valid = st[0] != 0 && st[1] == nbk;
       if (tid == 0) s_sapkey[nh] = 3.402823466e+38f;
       for (int p = tid; p < nbk; p += nt) { if (valid) s_sapinit[st[2 + p]] = p; else s_sapinit[p] = p; }
-      __syncthreads();
+      collide_sync<CTA>();
       for (int p = 1 + tid; p < nbk; p += nt) {
         const int e = valid ? st[2 + p] : p, e0 = valid ? st[1 + p] : p - 1;
         if (s_sapkey[e] < s_sapkey[e0]) s_misc[4] = 1;   // not already sorted
       }
-      __syncthreads();
+      collide_sync<CTA>();
       const bool unsorted = s_misc[4] != 0;
       for (int t = tid; t < nbk; t += nt) {
         int pos = s_sapinit[t];
@@ -118,58 +131,130 @@ __global__ void __launch_bounds__(OB_THREADS) k_collide(ObBatchDev d) {
         }
         s_sappos[t] = pos;
       }
-      __syncthreads();
+      collide_sync<CTA>();
       if (unsorted) for (int t = tid; t < nbk; t += nt) st[2 + s_sappos[t]] = t;
       if (tid == 0) { st[1] = nbk; if (unsorted) st[0] = 1; else if (!valid) st[0] = 0; }
     }
-    // (3) candidate pairs: the space's filter + the sequence key of the pair's callback
-    for (int idx = tid; idx < ng * (ng - 1) / 2; idx += nt) {
-      int a, b;
-      tri_pair(idx, &a, &b);   // the idx-th pair a < b (any enumeration will do: the pairs are ordered by key below)
-      if (!s_en[a] || !s_en[b]) continue;
+    // (3a) the space's overlap filter over every unordered geom pair; survivors compacted into a candidate list (in s_sorted,
+    // which the ordering step fills only after the candidates are consumed)
+    int *cand = (int *)s_sorted;
+    const int candcap = 2 * d.NP, T = ng * (ng - 1) / 2;
+    for (int base = 0; base < T; base += nt) {
+      const int idx = base + tid;
+      bool ok = false;
+      int a = 0, b = 0;
+      if (idx < T) {
+        tri_pair(idx, &a, &b);
+        if (s_en[a] && s_en[b]) {
+          if (stype == OB_SPACE_SAP) {
+            ok = ob_pair_filter_noaabb(s_body[a], s_body[b], s_cat[a], s_col[a], s_cat[b], s_col[b]);
+            if (ok && s_cb[a].level != OB_LEVEL_BIG && s_cb[b].level != OB_LEVEL_BIG) {
+              const bool fa = s_sappos[s_hr[a]] < s_sappos[s_hr[b]];
+              const int K = fa ? a : b, J = fa ? b : a;
+              ok = ob_sap_sweep_test(s_sapkey[s_hr[J]], s_aabb + 6 * K, s_aabb + 6 * J, ax0, ax1, ax2);
+            }
+          } else ok = ob_aabb_pair_filter(s_body[a], s_body[b], s_cat[a], s_col[a], s_cat[b], s_col[b], s_aabb + 6 * a, s_aabb + 6 * b);
+        }
+      }
+      const unsigned m = __ballot_sync(FULL, ok);
+      if (m) {
+        const int lane = tid & 31, leader = __ffs(m) - 1;
+        int pos = 0;
+        if (lane == leader) pos = atomicAdd(&s_misc[5], __popc(m));
+        pos = __shfl_sync(FULL, pos, leader) + __popc(m & ((1u << lane) - 1u));
+        if (ok && pos < candcap) cand[pos] = a | (b << 16);
+      }
+    }
+    collide_sync<CTA>();
+    int ncand = s_misc[5];
+    const bool cand_over = ncand > candcap;
+    if (cand_over) ncand = candcap;
+    // (3b) the sequence key of every candidate's callback: group = (stage, query rank), tail = the rest
+    for (int c = tid; c < ncand; c += nt) {
+      const int a = cand[c] & 0xffff, b = cand[c] >> 16;
       ObPairKey key;
       int first_is_a;
       if (stype == OB_SPACE_HASH) {
-        if (!ob_aabb_pair_filter(s_body[a], s_body[b], s_cat[a], s_col[a], s_cat[b], s_col[b], s_aabb + 6 * a, s_aabb + 6 * b))
-          continue;
         if (!ob_hash_pair_key(a, b, s_cb[a], s_cb[b], s_hr[a], s_hr[b], s_br[a], s_br[b], nh, nbig, &key, &first_is_a)) continue;
       } else if (stype == OB_SPACE_SAP) {
-        if (!ob_pair_filter_noaabb(s_body[a], s_body[b], s_cat[a], s_col[a], s_cat[b], s_col[b])) continue;
         const bool ia = s_cb[a].level == OB_LEVEL_BIG, ib = s_cb[b].level == OB_LEVEL_BIG;
         for (int k = 0; k < 7; k++) key.k[k] = 0;
         if (!ia && !ib) {
           const int pa = s_sappos[s_hr[a]], pb = s_sappos[s_hr[b]];
           first_is_a = pa < pb;
-          const int K = first_is_a ? a : b, J = first_is_a ? b : a;
-          if (!ob_sap_sweep_test(s_sapkey[s_hr[J]], s_aabb + 6 * K, s_aabb + 6 * J, ax0, ax1, ax2)) continue;
           key.k[1] = first_is_a ? pa : pb; key.k[2] = first_is_a ? pb : pa;
         } else if (ia && ib) { key.k[0] = 1; key.k[1] = s_br[a]; key.k[3] = s_br[b]; first_is_a = 1; }
         else { key.k[0] = 1; key.k[1] = ia ? s_br[a] : s_br[b]; key.k[2] = 1; key.k[3] = ia ? s_hr[b] : s_hr[a]; first_is_a = ia; }
       } else {   // dxSimpleSpace::collide (collision_space.cpp:247-268): nested walk of the list
-        if (!ob_aabb_pair_filter(s_body[a], s_body[b], s_cat[a], s_col[a], s_cat[b], s_col[b], s_aabb + 6 * a, s_aabb + 6 * b))
-          continue;
         for (int k = 0; k < 7; k++) key.k[k] = 0;
         key.k[1] = a; key.k[2] = b; first_is_a = 1;
       }
-      int slot = atomicAdd(&s_misc[0], 1);
+      const int slot = atomicAdd(&s_misc[0], 1);
       if (slot < d.NP) {
-        s_key[slot] = key;
+        ObKeyTail t;
+        for (int k = 0; k < 5; k++) t.k[k] = key.k[2 + k];
+        V.key[slot] = t;
+        V.grp[slot] = (unsigned short)(key.k[0] * (ng + 1) + key.k[1]);   // stage <= 2, query rank <= ng
         s_o12[slot] = first_is_a ? make_int2(s_gid[a], s_gid[b]) : make_int2(s_gid[b], s_gid[a]);
       }
     }
-    __syncthreads();
+    const int ngrp = 3 * (ng + 1);
+    for (int g = tid; g <= ngrp; g += nt) V.gcur[g] = 0;
+    collide_sync<CTA>();
     int np = s_misc[0];
-    if (np > d.NP) { np = d.NP; if (tid == 0) atomicOr(&W.status, OB_ERR_PAIR_OVERFLOW); }
-    // (4) order: rank of every pair = number of pairs with a smaller key (keys are unique)
+    if (np > d.NP || cand_over) { if (np > d.NP) np = d.NP; if (tid == 0) atomicOr(&W.status, OB_ERR_PAIR_OVERFLOW); }
+    // (4) order: counting sort over the groups, then the rank of a pair inside its group = the number of members with a
+    // smaller tail (keys are unique)
     int *gpairs = d.pairs + (size_t)w * d.NP * 2;
+    for (int p = tid; p < np; p += nt) atomicAdd(&V.gcur[V.grp[p]], 1);
+    collide_sync<CTA>();
+    if (tid < 32) {
+      int carry = 0;
+      for (int base = 0; base < ngrp; base += 32) {
+        const int g = base + tid;
+        const int v = g < ngrp ? V.gcur[g] : 0;
+        int x = v;
+#pragma unroll
+        for (int dd = 1; dd < 32; dd <<= 1) { const int y = __shfl_up_sync(FULL, x, dd); if (tid >= dd) x += y; }
+        if (g < ngrp) { V.gstart[g] = carry + x - v; V.gcur[g] = carry + x - v; }
+        carry += __shfl_sync(FULL, x, 31);
+      }
+    }
+    collide_sync<CTA>();
+    for (int p = tid; p < np; p += nt) V.member[atomicAdd(&V.gcur[V.grp[p]], 1)] = (unsigned short)p;
+    collide_sync<CTA>();
     for (int p = tid; p < np; p += nt) {
-      const ObPairKey kp = s_key[p];
-      int rank = 0;
-      for (int q = 0; q < np; q++) rank += ob_key_less(s_key[q], kp) ? 1 : 0;
+      const int g = V.grp[p];
+      const ObKeyTail kp = V.key[p];
+      const int g0 = V.gstart[g], g1 = V.gcur[g];
+      int rank = g0;
+      for (int mm = g0; mm < g1; mm++) rank += ob_tail_less(V.key[V.member[mm]], kp) ? 1 : 0;
       s_sorted[rank] = s_o12[p];
       gpairs[2 * rank] = s_o12[p].x; gpairs[2 * rank + 1] = s_o12[p].y;
     }
-    __syncthreads();
+    collide_sync<CTA>();
+    return np;
+}
+
+// ------------------------------------------------------------------------------------
+// MESH: the batch has trimesh geoms (narrowphase with the BVH colliders, up to OB_MAXC_LOCAL contacts per
+// pair); otherwise the primitive-only narrowphase with 8 contact slots per pair (box-box emits at most 8)
+template <bool MESH, bool XF>
+__global__ void __launch_bounds__(OB_THREADS) k_collide(ObBatchDev d) {
+  constexpr int CGCAP = MESH ? OB_MAXC_LOCAL : 8;
+  extern __shared__ __align__(16) unsigned char smem[];
+  const CollideSmem L = collide_smem(d.NG, d.NP);
+  const CollideView V = collide_view(smem, L);
+  ObPose *s_pose = V.pose;
+  int *s_walk_of = V.walk_of;
+  int2 *s_sorted = V.sorted;
+  int *s_misc = V.misc;
+  const int tid = threadIdx.x, nt = blockDim.x;
+
+  for (int w = d.wbeg + blockIdx.x; w < d.wend; w += gridDim.x) {
+    ObWorld &W = d.world[w];
+    const ObGeom *geoms = d.geom + (size_t)w * d.NG;
+    const int np = collide_broad<true>(d, w, V, tid, nt);
     // (5) narrowphase per pair in callback order, ordered compaction into contact joints
     const ObPolicy pol = d.policy[0];
     ObContact *cout = d.contacts + (size_t)w * d.NC;
@@ -254,25 +339,7 @@ __global__ void __launch_bounds__(32 * WPC) k_collide_tile(ObBatchDev d, int sta
   const CollideSmem L = collide_smem(d.NG, d.NP);
   const int warp = threadIdx.x >> 5;
   unsigned char *sm = smem + (size_t)warp * L.total;
-  ObPose *s_pose = (ObPose *)(sm + L.pose);
-  real *s_aabb = (real *)(sm + L.aabb);
-  ObCellBox *s_cb = (ObCellBox *)(sm + L.cb);
-  int *s_gid = (int *)(sm + L.gid);
-  int *s_body = (int *)(sm + L.body);
-  uint32_t *s_cat = (uint32_t *)(sm + L.cat);
-  uint32_t *s_col = (uint32_t *)(sm + L.col);
-  int *s_en = (int *)(sm + L.en);
-  int *s_hr = (int *)(sm + L.hr);
-  int *s_br = (int *)(sm + L.br);
-  int *s_walk_of = (int *)(sm + L.walk_of);
-  float *s_sapkey = (float *)(sm + L.sapkey);
-  int *s_sapinit = (int *)(sm + L.sapinit);
-  int *s_sappos = (int *)(sm + L.sappos);
-  int *s_sapwalk = (int *)(sm + L.sapwalk);
-  ObPairKey *s_key = (ObPairKey *)(sm + L.key);
-  int2 *s_o12 = (int2 *)(sm + L.o12);
-  int2 *s_sorted = (int2 *)(sm + L.sorted);
-  int *s_misc = (int *)(sm + L.misc);   // [0]=npairs raw, [1]=nh, [2]=nbig, [3]=contact base, [8..40]=scan scratch
+  const CollideView V = collide_view(sm, L);
   const int tid = threadIdx.x & 31, nt = 32;
   // CTA-wide area behind the WPC per-world slices
   const CollideTileSmem T = collide_tile_smem(d.NG, d.NP, WPC, stage_cap);
@@ -291,136 +358,7 @@ __global__ void __launch_bounds__(32 * WPC) k_collide_tile(ObBatchDev d, int sta
     const int w = wb + warp;
     const bool valid = w < d.wend;
     int np = 0;
-    if (valid) {
-    ObWorld &W = d.world[w];
-    const int ng = W.ng;
-    const ObGeom *geoms = d.geom + (size_t)w * d.NG;
-    const ObBodyDyn *bd = d.bdyn + (size_t)w * d.NB;
-    const int *glist = d.glist + (size_t)w * d.NG;
-    if (tid < 8) s_misc[tid] = 0;
-    const int stype = W.space_type;
-    // SAP: cleanGeoms appends the DirtyList to the GeomList (collision_sapspace.cpp:394-423), so the walk
-    // order is glist rotated by sap_ndirty; the cleaned order is written back below
-    const int rot = stype == OB_SPACE_SAP ? W.sap_ndirty : 0;
-    int ax0 = 0, ax1 = 2, ax2 = 4;
-    if (stype == OB_SPACE_SAP) ob_sap_axes(W.sap_axes, &ax0, &ax1, &ax2);
-    // (1) pose, AABB, cell box per geom in walk order
-    for (int i = tid; i < ng; i += nt) {
-      int gi = glist[i + rot < ng ? i + rot : i + rot - ng];
-      const ObGeom g = geoms[gi];
-      s_gid[i] = gi; s_body[i] = g.body; s_cat[i] = g.cat; s_col[i] = g.col;
-      s_walk_of[gi] = i;
-      s_en[i] = (g.flags & OB_GEOM_ENABLED) && !(g.flags & OB_GEOM_ZERO_SIZED);
-      ObPose p;
-      geom_pose_dev(g, bd, &p);
-      s_pose[i] = p;
-      real ab[6];
-      ob_aabb(p, ab, d.meshes);
-      for (int k = 0; k < 6; k++) s_aabb[6 * i + k] = ab[k];
-      ObCellBox cb;
-      cb.level = 0;
-      for (int k = 0; k < 6; k++) cb.db[k] = 0;
-      if (stype == OB_SPACE_HASH) ob_hash_cellbox(ab, W.hash_minlevel, W.hash_maxlevel, &cb);
-      else if (stype == OB_SPACE_SAP && ab[ax0 + 1] == OB_INF) cb.level = OB_LEVEL_BIG;   // TmpInfGeomList (:446-449)
-      s_cb[i] = cb;
-    }
-    __syncwarp();
-    if (stype == OB_SPACE_SAP) {
-      int *gl = d.glist + (size_t)w * d.NG;
-      for (int i = tid; i < ng; i += nt) gl[i] = s_gid[i];
-      if (tid == 0) W.sap_ndirty = 0;
-    }
-    // (2) ranks among hashed / big geoms in walk order (SAP: finite / infinite on axis 0)
-    for (int i = tid; i < ng; i += nt) {
-      int h = 0, b = 0;
-      for (int j = 0; j < i; j++)
-        if (s_en[j]) { if (s_cb[j].level == OB_LEVEL_BIG) b++; else h++; }
-      s_hr[i] = h; s_br[i] = b;
-      if (s_en[i] && s_cb[i].level != OB_LEVEL_BIG) { s_sapwalk[h] = i; s_sapkey[h] = (float)s_aabb[6 * i + ax0]; }
-      if (i == ng - 1) {
-        if (s_en[i]) { if (s_cb[i].level == OB_LEVEL_BIG) b++; else h++; }
-        s_misc[1] = h; s_misc[2] = b;
-      }
-    }
-    __syncwarp();
-    const int nh = s_misc[1], nbig = s_misc[2];
-    // (2b) SAP: sorted position of every finite geom = RadixSort's output order (ob_broad.h)
-    if (stype == OB_SPACE_SAP && nh > 0) {
-      int *st = d.sapstate + (size_t)w * (d.NG + 3);
-      const int nbk = nh + 1;                       // + FLT_MAX sentinel, element index nh
-      const bool valid = st[0] != 0 && st[1] == nbk;
-      if (tid == 0) s_sapkey[nh] = 3.402823466e+38f;
-      for (int p = tid; p < nbk; p += nt) { if (valid) s_sapinit[st[2 + p]] = p; else s_sapinit[p] = p; }
-      __syncwarp();
-      for (int p = 1 + tid; p < nbk; p += nt) {
-        const int e = valid ? st[2 + p] : p, e0 = valid ? st[1 + p] : p - 1;
-        if (s_sapkey[e] < s_sapkey[e0]) s_misc[4] = 1;   // not already sorted
-      }
-      __syncwarp();
-      const bool unsorted = s_misc[4] != 0;
-      for (int t = tid; t < nbk; t += nt) {
-        int pos = s_sapinit[t];
-        if (unsorted) {
-          const uint32_t ot = ob_sap_keyorder(s_sapkey[t]);
-          pos = 0;
-          for (int u = 0; u < nbk; u++)
-            if (u != t && ob_sap_precedes(ob_sap_keyorder(s_sapkey[u]), ot, s_sapinit[u], s_sapinit[t])) pos++;
-        }
-        s_sappos[t] = pos;
-      }
-      __syncwarp();
-      if (unsorted) for (int t = tid; t < nbk; t += nt) st[2 + s_sappos[t]] = t;
-      if (tid == 0) { st[1] = nbk; if (unsorted) st[0] = 1; else if (!valid) st[0] = 0; }
-    }
-    // (3) candidate pairs: the space's filter + the sequence key of the pair's callback
-    for (int idx = tid; idx < ng * (ng - 1) / 2; idx += nt) {
-      int a, b;
-      tri_pair(idx, &a, &b);   // the idx-th pair a < b (any enumeration will do: the pairs are ordered by key below)
-      if (!s_en[a] || !s_en[b]) continue;
-      ObPairKey key;
-      int first_is_a;
-      if (stype == OB_SPACE_HASH) {
-        if (!ob_aabb_pair_filter(s_body[a], s_body[b], s_cat[a], s_col[a], s_cat[b], s_col[b], s_aabb + 6 * a, s_aabb + 6 * b))
-          continue;
-        if (!ob_hash_pair_key(a, b, s_cb[a], s_cb[b], s_hr[a], s_hr[b], s_br[a], s_br[b], nh, nbig, &key, &first_is_a)) continue;
-      } else if (stype == OB_SPACE_SAP) {
-        if (!ob_pair_filter_noaabb(s_body[a], s_body[b], s_cat[a], s_col[a], s_cat[b], s_col[b])) continue;
-        const bool ia = s_cb[a].level == OB_LEVEL_BIG, ib = s_cb[b].level == OB_LEVEL_BIG;
-        for (int k = 0; k < 7; k++) key.k[k] = 0;
-        if (!ia && !ib) {
-          const int pa = s_sappos[s_hr[a]], pb = s_sappos[s_hr[b]];
-          first_is_a = pa < pb;
-          const int K = first_is_a ? a : b, J = first_is_a ? b : a;
-          if (!ob_sap_sweep_test(s_sapkey[s_hr[J]], s_aabb + 6 * K, s_aabb + 6 * J, ax0, ax1, ax2)) continue;
-          key.k[1] = first_is_a ? pa : pb; key.k[2] = first_is_a ? pb : pa;
-        } else if (ia && ib) { key.k[0] = 1; key.k[1] = s_br[a]; key.k[3] = s_br[b]; first_is_a = 1; }
-        else { key.k[0] = 1; key.k[1] = ia ? s_br[a] : s_br[b]; key.k[2] = 1; key.k[3] = ia ? s_hr[b] : s_hr[a]; first_is_a = ia; }
-      } else {   // dxSimpleSpace::collide (collision_space.cpp:247-268): nested walk of the list
-        if (!ob_aabb_pair_filter(s_body[a], s_body[b], s_cat[a], s_col[a], s_cat[b], s_col[b], s_aabb + 6 * a, s_aabb + 6 * b))
-          continue;
-        for (int k = 0; k < 7; k++) key.k[k] = 0;
-        key.k[1] = a; key.k[2] = b; first_is_a = 1;
-      }
-      int slot = atomicAdd(&s_misc[0], 1);
-      if (slot < d.NP) {
-        s_key[slot] = key;
-        s_o12[slot] = first_is_a ? make_int2(s_gid[a], s_gid[b]) : make_int2(s_gid[b], s_gid[a]);
-      }
-    }
-    __syncwarp();
-    np = s_misc[0];
-    if (np > d.NP) { np = d.NP; if (tid == 0) atomicOr(&W.status, OB_ERR_PAIR_OVERFLOW); }
-    // (4) order: rank of every pair = number of pairs with a smaller key (keys are unique)
-    int *gpairs = d.pairs + (size_t)w * d.NP * 2;
-    for (int p = tid; p < np; p += nt) {
-      const ObPairKey kp = s_key[p];
-      int rank = 0;
-      for (int q = 0; q < np; q++) rank += ob_key_less(s_key[q], kp) ? 1 : 0;
-      s_sorted[rank] = s_o12[p];
-      gpairs[2 * rank] = s_o12[p].x; gpairs[2 * rank + 1] = s_o12[p].y;
-    }
-    __syncwarp();
-    }   // valid
+    if (valid) np = collide_broad<false>(d, w, V, tid, nt);
     // (5) narrowphase over the pooled pairs of the CTA's worlds
     const ObPolicy pol = d.policy[0];
     const int maxc = pol.max_contacts > CGCAP ? CGCAP : pol.max_contacts;

@@ -91,12 +91,20 @@ struct ObLargeDev {
   uint32_t *tmp;               // scan / sort scratch
   size_t tmp_words;
 };
-// ---- split of the SOR phase over the GPUs of one box -------------------
-// Every rank (one process per GPU) holds the whole world and runs the phases before the solver
-// redundantly: they are deterministic, so all ranks hold the same pairs, colours and rows.  In the SOR
-// phase the pairs of a colour are dealt over the ranks; a rank writes the fc[] it produced into EVERY
-// rank's fc array (stores through NVLink peer mappings) and the ranks meet at a flag barrier after each
-// colour, so after the barrier each rank's fc equals the single-GPU array bit for bit.
+// ---- one large world over the GPUs of one box ---------------------------
+// Every rank (one process per GPU) holds the whole world.  What is divided, and what is not:
+//   * FRONT END (default after dBatchSplitAttach): the pair sweep and the narrowphase are throughput-bound and
+//     independent per sorted position, so rank r takes the sorted positions [ng r / N, ng (r + 1) / N): it counts
+//     their hits, and -- after one exchange of the counts -- fills and collides exactly the pairs those positions
+//     emit.  Counts, pairs and contacts are written into EVERY rank's arrays (plain stores through the NVLink peer
+//     mappings) and a flag barrier (k_lw_xbarrier) follows, so afterwards all ranks hold the single-GPU arrays bit for
+//     bit.  Two barriers per step.
+//   * sort, colouring, row assembly, SOR and integration run on every rank redundantly: they are deterministic, and the
+//     SOR phase is bound by the dependent row chain of one pair per colour (one wave of threads per colour at 200 k
+//     bodies), not by bytes, so dividing its pairs does not shorten it.
+//   * SOR split (OB_LW_SPLIT_SOR=1, the first design, kept as a measured negative result): the pairs of a colour are
+//     dealt over the ranks; a rank writes the fc[] it produced into every rank's fc array and the ranks meet at a flag
+//     barrier after each colour.
 #define OB_LW_MAXRANKS 8
 #define OB_LW_FLAG_WORDS 64      // per rank: [0..7] phase reached by rank r, [16] local release word, [17] timeout flag
 #define OB_LW_FLAG_RELEASE 16
@@ -107,12 +115,25 @@ struct ObLwSplit {
   unsigned timeout_ms;
   real *fc[OB_LW_MAXRANKS];            // every rank's fc array as mapped into THIS process (fc[rank] == ObLargeDev::fc)
   unsigned *flags[OB_LW_MAXRANKS];     // every rank's flag words (flags[rank] is local)
+  // front-end split: every rank's pair-count, pair and contact arrays (the local ones are ObLargeDev's)
+  uint32_t *cnt[OB_LW_MAXRANKS];
+  int *pairs[OB_LW_MAXRANKS];
+  uint32_t *ncp[OB_LW_MAXRANKS];
+  uint32_t *cpflag[OB_LW_MAXRANKS];
+  ObContact *pc[OB_LW_MAXRANKS];
 };
+// sorted positions [lo, hi) of rank r (multiples of 32 so that warps stay whole)
+OB_HD void ob_lw_split_range(int ng, int rank, int nranks, int *lo, int *hi) {
+  const int per = ((ng + nranks - 1) / nranks + 31) & ~31;
+  *lo = rank * per < ng ? rank * per : ng;
+  *hi = (rank + 1) * per < ng ? (rank + 1) * per : ng;
+}
 // which rank sweeps warp tile `tile` (32 consecutive pairs of a colour): tiles are dealt round-robin, like the
 // single-GPU kernel deals them over its CTAs, so every rank gets the same mix of heavy and light pairs
 OB_HD int ob_lw_split_owner(int pair_in_colour, int nranks) { return (pair_in_colour >> 5) % nranks; }
 
-enum { LW_NFIN = 0, LW_NBIG, LW_NP, LW_NCONTACTS, LW_NCP, LW_UNCOLOURED, LW_NCOL, LW_ERR, LW_NSOLVED, LW_BARRIER, LW_LEFT0 /* 16 per-round counters */, LW_WORDS = 32 };
+enum { LW_NFIN = 0, LW_NBIG, LW_NP, LW_NCONTACTS, LW_NCP, LW_UNCOLOURED, LW_NCOL, LW_ERR, LW_NSOLVED, LW_BARRIER, LW_LEFT0 /* 16 per-round counters */,
+       LW_SEG0 = 26 /* front-end split: start / length of this rank's two pair ranges */, LW_WORDS = 32 };
 
 // ---- broadphase --------------------------------------------------------------------------------
 // sort key of one geom (collision_sapspace.cpp:441-452, :531-535): float-cast axis-0 minimum

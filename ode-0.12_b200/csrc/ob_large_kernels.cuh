@@ -182,14 +182,20 @@ __global__ void __launch_bounds__(LW_T) k_lw_gather(ObBatchDev d, ObLargeDev L, 
 // ---- pairs ---------------------------------------------------------------------------------------
 // cnt / off layout: [0, ng) sweep hits of sorted position i; [ng, 2ng) hits of i against the infinite
 // list; [2ng] infinite x infinite.  Pair orientation: the geom met first is o1 (sapspace.cpp:478-493, :553).
-template <int FILL>
-__global__ void __launch_bounds__(LW_T) k_lw_sweep(ObBatchDev d, ObLargeDev L) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// SPLIT (several GPUs, ObLwSplit): this launch handles the sorted positions [i0, i1) only and writes its counts / pairs
+// into every rank's arrays; the infinite x infinite block is evaluated by every rank for itself.
+template <int FILL, bool SPLIT>
+__global__ void __launch_bounds__(LW_T) k_lw_sweep(ObBatchDev d, ObLargeDev L, int i0, int i1, ObLwSplit S) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = i0 + t;
   const int ng = d.world[0].ng;
+  const int nr = SPLIT ? S.nranks : 1;
+#define LW_PUT_PAIR(IDX, A, B) { const size_t x_ = (IDX); if (x_ < (size_t)L.NP) { if (SPLIT) { for (int r_ = 0; r_ < nr; r_++) *(int2 *)(S.pairs[r_] + 2 * x_) = make_int2((A), (B)); } else *(int2 *)(L.pairs + 2 * x_) = make_int2((A), (B)); } }
+#define LW_PUT_CNT(IDX, V) { if (SPLIT) { for (int r_ = 0; r_ < nr; r_++) S.cnt[r_][(IDX)] = (V); } else L.cnt[(IDX)] = (V); }
   const int nfin = L.scal[LW_NFIN];
   const int bigend = L.scal[LW_NBIG] > nfin ? L.scal[LW_NBIG] : nfin;
   const int *sidx = L.gidx[0];   // the 4-pass sort leaves the result in buffer 0
-  if (i == 0) {   // infinite x infinite (collideGeomsNoAABBs on the TmpInfGeomList, :479-485)
+  if (t == 0) {   // infinite x infinite (collideGeomsNoAABBs on the TmpInfGeomList, :479-485)
     uint32_t h = 0;
     const size_t o = FILL ? L.off[2 * ng] : 0;
     for (int a = nfin; a < bigend; a++)
@@ -206,10 +212,13 @@ __global__ void __launch_bounds__(LW_T) k_lw_sweep(ObBatchDev d, ObLargeDev L) {
       uint32_t np = L.off[2 * ng + 1];
       if (np > (uint32_t)L.NP) { np = (uint32_t)L.NP; atomicOr(&d.world[0].status, OB_ERR_PAIR_OVERFLOW); }
       L.scal[LW_NP] = (int)np;
+      // the pairs this launch fills: sweep hits of [i0, i1), then their hits against the infinite list
+      L.scal[LW_SEG0] = (int)L.off[i0]; L.scal[LW_SEG0 + 1] = (int)(L.off[i1] - L.off[i0]);
+      L.scal[LW_SEG0 + 2] = (int)L.off[ng + i0]; L.scal[LW_SEG0 + 3] = (int)(L.off[ng + i1] - L.off[ng + i0]);
     }
   }
-  if (i >= ng) return;
-  if (i >= nfin) { if (!FILL) { L.cnt[i] = 0; L.cnt[ng + i] = 0; } return; }
+  if (i >= i1) return;
+  if (i >= nfin) { if (!FILL) { LW_PUT_CNT(i, 0u) LW_PUT_CNT(ng + i, 0u) } return; }
   const real Kmaxx = L.smaxx[i];
   const real Kminy = L.syz[(size_t)4 * i], Kmaxy = L.syz[(size_t)4 * i + 1], Kminz = L.syz[(size_t)4 * i + 2], Kmaxz = L.syz[(size_t)4 * i + 3];
   const int4 Km = L.smeta[i];
@@ -233,12 +242,12 @@ __global__ void __launch_bounds__(LW_T) k_lw_sweep(ObBatchDev d, ObLargeDev L) {
       if (h < OB_LW_HITBUF) hb[h] = Jm.w;
       h++;
     }
-    L.cnt[i] = h;
+    LW_PUT_CNT(i, h)
   } else {
     const uint32_t n = L.cnt[i];
     const size_t o = L.off[i];
     if (n <= OB_LW_HITBUF) {
-      for (uint32_t h = 0; h < n; h++) if (o + h < (size_t)L.NP) { L.pairs[2 * (o + h)] = Km.w; L.pairs[2 * (o + h) + 1] = hb[h]; }
+      for (uint32_t h = 0; h < n; h++) LW_PUT_PAIR(o + h, Km.w, hb[h])
     } else {
       uint32_t h = 0;
       for (int j = i + 1; j < nfin; j++) {
@@ -248,7 +257,7 @@ __global__ void __launch_bounds__(LW_T) k_lw_sweep(ObBatchDev d, ObLargeDev L) {
         if (!(Kmaxz >= Jminz && Jmaxz >= Kminz)) continue;
         const int4 Jm = L.smeta[j];
         if (!ob_pair_filter_noaabb(Km.x, Jm.x, (uint32_t)Km.y, (uint32_t)Km.z, (uint32_t)Jm.y, (uint32_t)Jm.z)) continue;
-        if (o + h < (size_t)L.NP) { L.pairs[2 * (o + h)] = Km.w; L.pairs[2 * (o + h) + 1] = Jm.w; }
+        LW_PUT_PAIR(o + h, Km.w, Jm.w)
         h++;
       }
     }
@@ -259,32 +268,66 @@ __global__ void __launch_bounds__(LW_T) k_lw_sweep(ObBatchDev d, ObLargeDev L) {
     const int ga = sidx[a];
     const ObGeom &A = d.geom[ga];
     if (ob_pair_filter_noaabb(A.body, Km.x, A.cat, A.col, (uint32_t)Km.y, (uint32_t)Km.z)) {
-      if (FILL && o + h < (size_t)L.NP) { L.pairs[2 * (o + h)] = ga; L.pairs[2 * (o + h) + 1] = Km.w; }
+      if (FILL) LW_PUT_PAIR(o + h, ga, Km.w)
       h++;
     }
   }
-  if (!FILL) L.cnt[ng + i] = h;
+  if (!FILL) LW_PUT_CNT(ng + i, h)
+#undef LW_PUT_PAIR
+#undef LW_PUT_CNT
 }
 
-template <bool MESH, bool XF>
-__global__ void __launch_bounds__(LW_T) k_lw_narrow(ObBatchDev d, ObLargeDev L, int np, int maxc) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= np) return;
+// the pairs one launch collides: up to three ranges of the pair list (one GPU: [0, np); front-end split: the two ranges this
+// rank filled, written to every rank, and the infinite x infinite range, which every rank keeps to itself)
+struct ObLwSeg3 { int start[3], len[3], remote[3]; };
+template <bool MESH, bool XF, bool SPLIT>
+__global__ void __launch_bounds__(LW_T) k_lw_narrow(ObBatchDev d, ObLargeDev L, ObLwSeg3 G, int np, int maxc, ObLwSplit S) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  int p = -1, remote = 0;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    if (p < 0 && t < G.len[k]) { p = G.start[k] + t; remote = G.remote[k]; }
+    t -= G.len[k];
+  }
+  if (p < 0 || p >= np) return;
   const int o1 = L.pairs[2 * p], o2 = L.pairs[2 * p + 1];
   ObCg cg[OB_LW_MAXC];
   int swapped, bverr = 0;
   const int n = ob_collide_pair_sel_t<MESH, OB_LW_MAXC, XF>(&L.pose[o1], &L.pose[o2], maxc, cg, &swapped, d.meshes, &bverr);
   if (bverr) atomicOr(&d.world[0].status, OB_ERR_BVH_STACK);
-  ObContact *out = L.pc + (size_t)p * maxc;
-  for (int k = 0; k < n; k++) {
-    ObContact c;
-    for (int e = 0; e < 3; e++) { c.pos[e] = cg[k].pos[e]; c.normal[e] = cg[k].normal[e]; }
-    c.depth = cg[k].depth; c.g1 = o1; c.g2 = o2; c.side1 = cg[k].side1; c.side2 = cg[k].side2; c.policy = 0;
-    out[k] = c;
-  }
-  L.ncp[p] = (uint32_t)n;
   const int b1 = d.geom[o1].body, b2 = d.geom[o2].body;
-  L.cpflag[p] = (n > 0 && (b1 >= 0 || b2 >= 0)) ? 1u : 0u;
+  const uint32_t flag = (n > 0 && (b1 >= 0 || b2 >= 0)) ? 1u : 0u;
+  const int nr = (SPLIT && remote) ? S.nranks : 1;
+  for (int r = 0; r < nr; r++) {
+    ObContact *out = ((SPLIT && remote) ? S.pc[r] : L.pc) + (size_t)p * maxc;
+    for (int k = 0; k < n; k++) {
+      ObContact c;
+      for (int e = 0; e < 3; e++) { c.pos[e] = cg[k].pos[e]; c.normal[e] = cg[k].normal[e]; }
+      c.depth = cg[k].depth; c.g1 = o1; c.g2 = o2; c.side1 = cg[k].side1; c.side2 = cg[k].side2; c.policy = 0;
+      out[k] = c;
+    }
+    ((SPLIT && remote) ? S.ncp[r] : L.ncp)[p] = (uint32_t)n;
+    ((SPLIT && remote) ? S.cpflag[r] : L.cpflag)[p] = flag;
+  }
+}
+// Barrier of the ranks between two kernels of the step (front-end split): one thread.  The kernels before it have
+// completed, so their peer stores are performed; this rank raises its phase word in every peer's flag array and waits
+// until every peer has raised its own here.  The kernels behind it on the stream then read what the peers wrote into
+// this GPU's memory.  A peer that never arrives trips the timeout flag (the host reports it) instead of hanging the GPU.
+__device__ __forceinline__ unsigned long long lw_globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__global__ void k_lw_xbarrier(ObLwSplit S, unsigned phase) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  volatile unsigned *mine = (volatile unsigned *)S.flags[S.rank];
+  __threadfence_system();
+  for (int r = 0; r < S.nranks; r++) if (r != S.rank) *((volatile unsigned *)S.flags[r] + S.rank) = phase;
+  const unsigned long long t0 = lw_globaltimer();
+  for (int r = 0; r < S.nranks; r++) {
+    if (r == S.rank) continue;
+    while ((int)(mine[r] - phase) < 0 && !mine[OB_LW_FLAG_TIMEOUT]) {
+      if (lw_globaltimer() - t0 > (unsigned long long)S.timeout_ms * 1000000ull) mine[OB_LW_FLAG_TIMEOUT] = 1;
+    }
+  }
+  __threadfence_system();
 }
 __global__ void __launch_bounds__(LW_T) k_lw_cpairs(ObBatchDev d, ObLargeDev L, int np, int maxc, int taps) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -616,7 +659,6 @@ __global__ void __launch_bounds__(LW_SOR_T) k_lw_sor_all(ObLargeDev L, int iters
 // rank's phase word in every peer's flag array, waits until every peer has raised its own here, and then
 // releases the local CTAs.  A wait that outlasts timeout_ms (a rank that never launched) raises the
 // timeout flag, after which no barrier waits any more: the step finishes and the host reports the error.
-__device__ __forceinline__ unsigned long long lw_globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ void lw_split_barrier(unsigned *bar, unsigned local_target, const ObLwSplit &S, unsigned phase) {
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -732,6 +774,23 @@ __global__ void __launch_bounds__(LW_T) k_lw_body_post(ObBatchDev d, ObLargeDev 
 #define LWCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { snprintf(err, errlen, "%s: %s", #call, cudaGetErrorString(e_)); return -1; } } while (0)
 #define LW_HOST_WORDS (LW_WORDS + OB_LW_MAXCOL * (2 + OB_LW_MAXC))
 
+// layout of the peer-visible allocation: byte offsets from its start (= ObLargeDev::fc); a function of the capacities
+// only, so every rank derives a peer's pointers from that peer's base address
+struct ObLwArena { size_t flags, cnt, pairs, ncp, cpflag, pc, total; };
+static ObLwArena lw_arena(size_t NB, size_t NG, size_t NP) {
+  ObLwArena A; size_t o = 0;
+  auto take = [&o](size_t bytes) { const size_t at = o; o = (o + bytes + 255) & ~(size_t)255; return at; };
+  take(NB * 8 * sizeof(real));
+  A.flags = take(OB_LW_FLAG_WORDS * sizeof(unsigned));
+  A.cnt = take((2 * NG + 2) * sizeof(uint32_t));
+  A.pairs = take(NP * 2 * sizeof(int));
+  A.ncp = take((NP + 1) * sizeof(uint32_t));
+  A.cpflag = take((NP + 1) * sizeof(uint32_t));
+  A.pc = take(NP * OB_LW_MAXC * sizeof(ObContact));
+  A.total = o;
+  return A;
+}
+
 int lw_create(ObBackend *b, char *err, size_t errlen) {
   ObBatchDev &d = b->d;
   ObLargeDev &L = b->L;
@@ -747,7 +806,6 @@ int lw_create(ObBackend *b, char *err, size_t errlen) {
   LWCK(dalloc(b, &d.meshes, (size_t)(d.nmesh ? d.nmesh : 1)));
   LWCK(dalloc(b, &d.njoints, (size_t)1));
   LWCK(dalloc(b, &d.npairs, (size_t)1));
-  LWCK(dalloc(b, &d.pairs, NP * 2));
   LWCK(dalloc(b, &d.ncontacts, (size_t)1));
   LWCK(dalloc(b, &d.contacts, NC));
   LWCK(dalloc(b, &d.invIw, NB * 12));
@@ -770,13 +828,8 @@ int lw_create(ObBackend *b, char *err, size_t errlen) {
   LWCK(dalloc(b, &L.smeta, NG));
   LWCK(dalloc(b, &L.hits, NG * OB_LW_HITBUF));
   LWCK(dalloc(b, &L.scal, (size_t)LW_WORDS));
-  LWCK(dalloc(b, &L.cnt, 2 * NG + 2));
   LWCK(dalloc(b, &L.off, 2 * NG + 2));
-  L.pairs = d.pairs;
-  LWCK(dalloc(b, &L.pc, NP * OB_LW_MAXC));
-  LWCK(dalloc(b, &L.ncp, NP + 1));
   LWCK(dalloc(b, &L.coff, NP + 1));
-  LWCK(dalloc(b, &L.cpflag, NP + 1));
   LWCK(dalloc(b, &L.cpoff, NP + 1));
   for (int k = 0; k < 2; k++) { LWCK(dalloc(b, &L.cp[k], NP)); LWCK(dalloc(b, &L.pkey[k], NP)); LWCK(dalloc(b, &L.pidx[k], NP)); }
   LWCK(dalloc(b, &L.claim, NB));
@@ -784,11 +837,13 @@ int lw_create(ObBackend *b, char *err, size_t errlen) {
   LWCK(dalloc(b, &L.segtab, (size_t)OB_LW_MAXCOL * (2 + OB_LW_MAXC)));
   LWCK(dalloc(b, &L.rows, (size_t)3 * OB_LW_SLOTS * OB_LW_SLOTW * NC));
   LWCK(dalloc(b, &L.lambda, 3 * NC));
-  {   // fc and the split barrier's flag words share one allocation, so that one IPC handle exports both
-    const size_t fcb = (NB * 8 * sizeof(real) + 255) & ~(size_t)255;
+  {   // everything a peer rank writes into (ObLwSplit) lives in ONE allocation, so that one IPC handle exports it all
+    ObLwArena A = lw_arena(NB, NG, NP);
     unsigned char *raw = 0;
-    LWCK(dalloc(b, &raw, fcb + OB_LW_FLAG_WORDS * sizeof(unsigned)));
-    L.fc = (real *)raw; b->lw_flags = (unsigned *)(raw + fcb); b->lw_flags_off = fcb;
+    LWCK(dalloc(b, &raw, A.total));
+    L.fc = (real *)raw; b->lw_flags = (unsigned *)(raw + A.flags); b->lw_flags_off = A.flags;
+    L.cnt = (uint32_t *)(raw + A.cnt); L.pairs = (int *)(raw + A.pairs); d.pairs = L.pairs;
+    L.ncp = (uint32_t *)(raw + A.ncp); L.cpflag = (uint32_t *)(raw + A.cpflag); L.pc = (ObContact *)(raw + A.pc);
   }
   LWCK(dalloc(b, &L.invM, NB));
   LWCK(dalloc(b, &L.hasrow, NB));
@@ -829,7 +884,8 @@ struct ObLwSplitHandle {
   unsigned long long flags_off;  // flag words - L.fc
   unsigned long long nb;         // body capacity (must match)
   cudaIpcMemHandle_t ipc;        // 64 bytes
-  unsigned char pad[128 - 40 - sizeof(cudaIpcMemHandle_t)];
+  unsigned long long ng, np;     // geom and pair capacities (must match: they fix the layout behind fc, lw_arena)
+  unsigned char pad[128 - 56 - sizeof(cudaIpcMemHandle_t)];
 };
 static_assert(sizeof(ObLwSplitHandle) == OBK_SPLIT_HANDLE_BYTES, "split handle is 128 bytes");
 
@@ -838,7 +894,7 @@ int obk_split_export(ObBackend *b, void *handle128, char *err, size_t errlen) {
   cudaSetDevice(b->device);
   ObLwSplitHandle H;
   memset(&H, 0, sizeof H);
-  H.pid = (int)getpid(); H.device = b->device; H.ptr = (unsigned long long)(uintptr_t)b->L.fc; H.flags_off = b->lw_flags_off; H.nb = (unsigned long long)b->L.NB;
+  H.pid = (int)getpid(); H.device = b->device; H.ptr = (unsigned long long)(uintptr_t)b->L.fc; H.flags_off = b->lw_flags_off; H.nb = (unsigned long long)b->L.NB; H.ng = (unsigned long long)b->L.NG; H.np = (unsigned long long)b->L.NP;
   // the IPC handle names the whole block cudaMalloc carved the buffer from: find our offset in it
   typedef int (*getrange_t)(unsigned long long *, size_t *, unsigned long long);
   void *fn = 0;
@@ -864,7 +920,7 @@ int obk_split_attach(ObBackend *b, int rank, int nranks, const void *handles, ch
   const char *to = getenv("OB_LW_SPLIT_TIMEOUT_MS");
   S.timeout_ms = to && atoi(to) > 0 ? (unsigned)atoi(to) : 5000u;
   for (int r = 0; r < nranks; r++) {
-    if (H[r].nb != (unsigned long long)b->L.NB || H[r].flags_off != b->lw_flags_off) { snprintf(err, errlen, "rank %d holds a world of another size", r); return -1; }
+    if (H[r].nb != (unsigned long long)b->L.NB || H[r].flags_off != b->lw_flags_off || H[r].ng != (unsigned long long)b->L.NG || H[r].np != (unsigned long long)b->L.NP) { snprintf(err, errlen, "rank %d holds a world of another size", r); return -1; }
     real *fc = 0;
     if (r == rank) {
       if (H[r].ptr != (unsigned long long)(uintptr_t)b->L.fc || H[r].pid != (int)getpid()) { snprintf(err, errlen, "handle %d is not this batch's own export", r); return -1; }
@@ -884,7 +940,13 @@ int obk_split_attach(ObBackend *b, int rank, int nranks, const void *handles, ch
     }
     S.fc[r] = fc;
     S.flags[r] = (unsigned *)((unsigned char *)fc + H[r].flags_off);
+    const ObLwArena A = lw_arena((size_t)b->L.NB, (size_t)b->L.NG, (size_t)b->L.NP);
+    unsigned char *raw = (unsigned char *)fc;
+    S.cnt[r] = (uint32_t *)(raw + A.cnt); S.pairs[r] = (int *)(raw + A.pairs); S.ncp[r] = (uint32_t *)(raw + A.ncp);
+    S.cpflag[r] = (uint32_t *)(raw + A.cpflag); S.pc[r] = (ObContact *)(raw + A.pc);
   }
+  { const char *e = getenv("OB_LW_SPLIT_SOR"); b->lw_split_sor = e && atoi(e) != 0; }
+  { const char *e = getenv("OB_LW_SPLIT_FRONT"); b->lw_split_front = e ? atoi(e) != 0 : 1; }
   LWCK(cudaMemsetAsync(b->lw_flags, 0, OB_LW_FLAG_WORDS * sizeof(unsigned), b->stream));
   LWCK(cudaStreamSynchronize(b->stream));
   b->lw_split = S;
@@ -919,21 +981,53 @@ int lw_step(ObBackend *b, real h, int taps, char *err, size_t errlen) {
   k_lw_gather<<<lw_blocks(ng), LW_T, 0, st>>>(d, L, L.gkey[0], L.gidx[0]);
   g_launches += 2;
   LW_MARK();
-  // (2) pairs: count, scan, fill
-  k_lw_sweep<0><<<lw_blocks(ng), LW_T, 0, st>>>(d, L);
+  // (2) pairs: count, scan, fill.  Front-end split: this rank's share of the sorted positions, counts exchanged before the scan
+  const bool front = b->lw_split_on && b->lw_split_front;
+  ObLwSplit S = b->lw_split;
+  int i0 = 0, i1 = ng;
+  if (front) ob_lw_split_range(ng, S.rank, S.nranks, &i0, &i1);
+  const int nsw = i1 - i0 > 1 ? i1 - i0 : 1;   // thread 0 always runs (infinite x infinite block)
+  if (front) {
+    k_lw_sweep<0, true><<<lw_blocks(nsw), LW_T, 0, st>>>(d, L, i0, i1, S);
+    k_lw_xbarrier<<<1, 32, 0, st>>>(S, ++b->lw_split.base);
+    g_launches++;
+  } else k_lw_sweep<0, false><<<lw_blocks(nsw), LW_T, 0, st>>>(d, L, i0, i1, S);
   lw_scan(st, L.cnt, L.off, 2 * ng + 1, L.tmp);
-  k_lw_sweep<1><<<lw_blocks(ng), LW_T, 0, st>>>(d, L);
+  if (front) k_lw_sweep<1, true><<<lw_blocks(nsw), LW_T, 0, st>>>(d, L, i0, i1, S);
+  else k_lw_sweep<1, false><<<lw_blocks(nsw), LW_T, 0, st>>>(d, L, i0, i1, S);
   g_launches += 2;
   LWCK(cudaMemcpyAsync(hs, L.scal, sizeof(int) * LW_WORDS, cudaMemcpyDeviceToHost, st));
   LWCK(cudaStreamSynchronize(st));
   const int np = hs[LW_NP];
   LW_MARK();
-  // (3) narrowphase, contact pairs
-  if (np > 0) {
-    if (d.any_xf) k_lw_narrow<true, true><<<lw_blocks(np), LW_T, 0, st>>>(d, L, np, maxc);
-    else if (d.nmesh) k_lw_narrow<true, false><<<lw_blocks(np), LW_T, 0, st>>>(d, L, np, maxc);
-    else k_lw_narrow<false, false><<<lw_blocks(np), LW_T, 0, st>>>(d, L, np, maxc);
-    g_launches++;
+  // (3) narrowphase, contact pairs.  Front-end split: the pairs this rank has just filled (nobody else's are needed yet),
+  // results to every rank, then the second barrier of the step
+  {
+    ObLwSeg3 G;
+    memset(&G, 0, sizeof G);
+    if (front) {
+      G.start[0] = hs[LW_SEG0]; G.len[0] = hs[LW_SEG0 + 1]; G.remote[0] = 1;
+      G.start[1] = hs[LW_SEG0 + 2]; G.len[1] = hs[LW_SEG0 + 3]; G.remote[1] = 1;
+      // infinite x infinite: behind the two lists (off[2 ng] = end of the second one); every rank for itself
+      G.start[2] = 0; G.len[2] = 0;
+      LWCK(cudaMemcpyAsync(&G.start[2], L.off + 2 * ng, sizeof(int), cudaMemcpyDeviceToHost, st));
+      LWCK(cudaStreamSynchronize(st));
+      G.len[2] = np > G.start[2] ? np - G.start[2] : 0;
+    } else { G.start[0] = 0; G.len[0] = np; }
+    const int nt = G.len[0] + G.len[1] + G.len[2];
+    if (nt > 0) {
+      if (front) {
+        if (d.any_xf) k_lw_narrow<true, true, true><<<lw_blocks(nt), LW_T, 0, st>>>(d, L, G, np, maxc, S);
+        else if (d.nmesh) k_lw_narrow<true, false, true><<<lw_blocks(nt), LW_T, 0, st>>>(d, L, G, np, maxc, S);
+        else k_lw_narrow<false, false, true><<<lw_blocks(nt), LW_T, 0, st>>>(d, L, G, np, maxc, S);
+      } else {
+        if (d.any_xf) k_lw_narrow<true, true, false><<<lw_blocks(nt), LW_T, 0, st>>>(d, L, G, np, maxc, S);
+        else if (d.nmesh) k_lw_narrow<true, false, false><<<lw_blocks(nt), LW_T, 0, st>>>(d, L, G, np, maxc, S);
+        else k_lw_narrow<false, false, false><<<lw_blocks(nt), LW_T, 0, st>>>(d, L, G, np, maxc, S);
+      }
+      g_launches++;
+    }
+    if (front) { k_lw_xbarrier<<<1, 32, 0, st>>>(S, ++b->lw_split.base); g_launches++; }
   }
   lw_scan(st, L.ncp, L.coff, np, L.tmp);
   lw_scan(st, L.cpflag, L.cpoff, np, L.tmp);
@@ -990,7 +1084,7 @@ int lw_step(ObBackend *b, real h, int taps, char *err, size_t errlen) {
     int iters = hw.iters, nc_ = ncol;
     void *kargs[] = {(void *)&L, (void *)&iters, (void *)&nc_, (void *)&bar};
     const void *fn = m == 3 ? (const void *)k_lw_sor_all<3> : (m == 2 ? (const void *)k_lw_sor_all<2> : (const void *)k_lw_sor_all<1>);
-    if (b->lw_split_on) {
+    if (b->lw_split_on && b->lw_split_sor) {
       ObLwSplit S = b->lw_split;
       void *sargs[] = {(void *)&L, (void *)&S, (void *)&iters, (void *)&nc_, (void *)&bar};
       const void *sfn = m == 3 ? (const void *)k_lw_sor_split<3> : (m == 2 ? (const void *)k_lw_sor_split<2> : (const void *)k_lw_sor_split<1>);
@@ -1022,7 +1116,8 @@ int lw_step(ObBackend *b, real h, int taps, char *err, size_t errlen) {
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) { snprintf(err, errlen, "large-world step failed: %s", cudaGetErrorString(e)); return -1; }
-  if (b->lw_split_on && sor_launches && hs[LW_ERR]) { snprintf(err, errlen, "split SOR: a peer rank did not reach the barrier within the timeout (rank %d of %d)", b->lw_split.rank, b->lw_split.nranks); return -1; }
+  if (b->lw_split_on) { LWCK(cudaMemcpy(hs + LW_ERR, b->lw_flags + OB_LW_FLAG_TIMEOUT, sizeof(int), cudaMemcpyDeviceToHost)); }
+  if (b->lw_split_on && hs[LW_ERR]) { snprintf(err, errlen, "split step: a peer rank did not reach a barrier within the timeout (rank %d of %d)", b->lw_split.rank, b->lw_split.nranks); return -1; }
   if (tm) for (int k = 0; k + 1 < evi && k < 8; k++) { float ms = 0; cudaEventElapsedTime(&ms, b->lw_ev[k], b->lw_ev[k + 1]); b->lw_ms[k] += ms; }
   b->lw_stat[0] = np; b->lw_stat[1] = hs[LW_NCONTACTS]; b->lw_stat[2] = ncp; b->lw_stat[3] = ncp > 0 ? hs[LW_NSOLVED] : 0;
   b->lw_stat[4] = ncol; b->lw_stat[5] = rounds; b->lw_stat[6] = sor_launches; if (tm) b->lw_stat[7]++;

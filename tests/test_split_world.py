@@ -1,9 +1,10 @@
 """One large world over several GPUs (BASELINE.json configs[4] "2/4/8-GPU split"):
-dBatchSplitExport / dBatchSplitAttach (include/ode_b200/ode.h), k_lw_sor_split (ob_large_kernels.cuh).
+dBatchSplitExport / dBatchSplitAttach (include/ode_b200/ode.h); ob_large_kernels.cuh: front-end split (k_lw_sweep /
+k_lw_narrow by SAP-sorted position + k_lw_xbarrier, the default) and SOR split (k_lw_sor_split, OB_LW_SPLIT_SOR=1).
 
 Contract: every rank ends every step with the body state of the single-GPU coloured sweep, BIT FOR BIT
-(the split changes who executes a pair of a colour, never the order of dependent updates), and that
-single-GPU sweep is what tests/test_large_world.py holds against the reference.
+(the split changes who computes a pair or executes a pair of a colour, never a value or the order of dependent
+updates), and that single-GPU sweep is what tests/test_large_world.py holds against the reference.
 
   not gpu  the host mirror of the protocol (tests/hostsim/large_host.h: ranks are host threads, same dealing
            of warp tiles, same flag barrier) equals the unsplit mirror for 2, 3 and 4 ranks;
@@ -50,20 +51,24 @@ def _gpus():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["front", "front+sor"])
 @pytest.mark.parametrize("prec", ["single", "double"])
-def test_split_loopback_one_gpu(prec):
+def test_split_loopback_one_gpu(prec, mode):
     # two persistent cooperative kernels must be co-resident on one GPU: one CTA of 128 threads per SM each
     env = {"OB_LW_SOR_CTAS_PER_SM": "1", "OB_LW_SOR_THREADS": "128", "OB_LW_SPLIT_TIMEOUT_MS": "3000"}
+    if mode == "front+sor":
+        env["OB_LW_SPLIT_SOR"] = "1"
     if _run_split("b200", prec, 2, [0], env=env) == "timeout":
         pytest.skip("the two ranks' kernels were not scheduled together on this GPU (loop-back needs co-residency)")
 
 
 @pytest.mark.gpu
-def test_split_one_device_per_rank():
+@pytest.mark.parametrize("mode", ["front", "front+sor"])
+def test_split_one_device_per_rank(mode):
     n = _gpus()
     if n < 2:
         pytest.skip("needs two GPUs")
-    assert _run_split("b200", "single", min(n, 4), list(range(min(n, 4)))) == "equal"
+    assert _run_split("b200", "single", min(n, 4), list(range(min(n, 4))), env={"OB_LW_SPLIT_SOR": "1"} if mode == "front+sor" else None) == "equal"
 
 
 @pytest.mark.gpu
