@@ -82,16 +82,28 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def begin(self):
+        """the timed region starts now (the sampler has been running since before the settle / warm-up steps: nvidia-smi needs
+        longer to start than a short timed region lasts)"""
+        self.t0 = time.perf_counter()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        t1 = time.perf_counter()
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        t0 = getattr(self, "t0", 0.0)
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.12]
+        window = "timed region"
+        if not rows:   # a timed region shorter than the sampling period: the last samples of the same load (settle + warm-up steps) before it
+            rows = [r for (t, r) in self.rows if t <= t1 + 0.12][-5:]
+            window = "settle + warm-up steps of the same workload, up to the end of the timed region (region shorter than the 100 ms sampling period)"
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 for n, v in zip(names, r[3:7]):
@@ -100,7 +112,7 @@ class ClockSampler:
             except (ValueError, IndexError):
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def load_libs():
@@ -203,13 +215,14 @@ def measure_batched(ctx, cfg_id, steps, warmup, worlds=0, strong=False, cpu=Fals
             torch.cuda.synchronize()
             dist.barrier()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     step(SETTLE)                       # untimed: let the pile come to rest
     step(max(warmup, 3))          # warm-up steps proper
     lib.dBatchResetCounters(B)
     l0 = lib.dB200KernelLaunchCount()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     barrier()
+    sampler.begin()
     ms = ctypes.c_float()
     lib.dBatchTimerStart(B)
     step(steps)
@@ -399,13 +412,14 @@ def measure_large(ctx, steps, warmup, scene="", settle=-1, cpu=False):
             raise SystemExit("split attach failed: " + lib.dB200LastError().decode())
         barrier()
     settle = settle if settle >= 0 else LARGE["settle"]
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     step(settle)
     step(max(warmup, 3))
     lib.dBatchResetCounters(B)
     l0 = lib.dB200KernelLaunchCount()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     barrier()
+    sampler.begin()
     ms = ctypes.c_float()
     lib.dBatchTimerStart(B)
     step(steps)

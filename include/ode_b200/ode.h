@@ -706,8 +706,13 @@ typedef struct dxBatch *dBatchID;
  * demo_buggy.cpp:83-111): optionally skip pairs whose bodies are connected by
  * a non-contact joint, call dCollide with max_contacts, copy `surface` into
  * every contact and create+attach one contact joint per contact.
- * Row selection: first row with (cat(o1)&cat_mask1)&&(cat(o2)&cat_mask2) or the
- * swapped test; row 0 should be the catch-all {~0,~0}. */
+ * Row selection (1 to 8 rows): the first row with (cat(o1)&cat_mask1)&&(cat(o2)&cat_mask2)
+ * or the swapped test serves the pair -- put the specific rows first and a catch-all
+ * {~0,~0} last; a pair that no row accepts gets no contacts (a callback that returns
+ * early).  A table of ONE row serves every pair, whatever its masks say.  This is how
+ * demo_crash.cpp:128-131 (mu = 20 for pairs with a sphere, 0.5 otherwise) is written:
+ * the spheres get a category bit of their own, row 0 = {SPHERE_BIT, ~0, ..., mu 20},
+ * row 1 = {~0, ~0, ..., mu 0.5}.  The large-world path takes one row. */
 typedef struct dBatchContactPolicy {
   unsigned long cat_mask1, cat_mask2;
   int max_contacts;                 /* flags & 0xffff handed to dCollide */

@@ -281,7 +281,7 @@ dxBatch *ob_batch_create(int nworlds, const dWorldID *worlds, const dSpaceID *sp
   for (int w = 0; w < nworlds; w++)
     for (int i = 0; i < B->nb[w]; i++) { const int n = (int)B->bodies[w][i]->adis.average_samples; if (n > 1 && n > caps.NADIS) caps.NADIS = n; }
   caps.NR = 3 * caps.NC + 6 * NJ;
-  caps.npolicy = 1;
+  caps.npolicy = OB_MAXPOLICY;
   caps.dropin = dropin;
   {
     int it = 1;
@@ -350,14 +350,18 @@ void dBatchDestroy(dBatchID B) {
 }
 
 int dBatchSetContactPolicy(dBatchID B, const dBatchContactPolicy *table, int n) {
-  if (!B || !table || n != 1) { ob_set_last_error("dBatchSetContactPolicy: exactly one policy row is supported in this build"); return -1; }
-  ObPolicy pol;
-  memset(&pol, 0, sizeof pol);
-  pol.cat_mask1 = (uint32_t)table[0].cat_mask1; pol.cat_mask2 = (uint32_t)table[0].cat_mask2;
-  pol.max_contacts = table[0].max_contacts; pol.skip_if_connected = table[0].skip_if_connected;
-  pol.skip_static_pairs = table[0].skip_static_pairs;
-  ob_fill_surface(pol.surface, table[0].surface);
-  return obk_h2d(B->bk, B->caps.policy, &pol, sizeof pol);
+  if (!B || !table || n < 1 || n > OB_MAXPOLICY) { ob_set_last_error("dBatchSetContactPolicy: 1 to %d policy rows", OB_MAXPOLICY); return -1; }
+  if (n > 1 && B->caps.large) { ob_set_last_error("dBatchSetContactPolicy: the large-world path takes one policy row"); return -1; }
+  ObPolicy pol[OB_MAXPOLICY];
+  memset(pol, 0, sizeof pol);
+  for (int r = 0; r < n; r++) {
+    pol[r].cat_mask1 = (uint32_t)table[r].cat_mask1; pol[r].cat_mask2 = (uint32_t)table[r].cat_mask2;
+    pol[r].max_contacts = table[r].max_contacts; pol[r].skip_if_connected = table[r].skip_if_connected;
+    pol[r].skip_static_pairs = table[r].skip_static_pairs;
+    ob_fill_surface(pol[r].surface, table[r].surface);
+  }
+  pol[0].nrows = n;
+  return obk_h2d(B->bk, B->caps.policy, pol, sizeof(ObPolicy) * (B->caps.npolicy < OB_MAXPOLICY ? 1 : OB_MAXPOLICY));
 }
 
 int dBatchSetSeeds(dBatchID B, const uint32_t *seeds) {

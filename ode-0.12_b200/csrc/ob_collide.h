@@ -1516,6 +1516,18 @@ OB_HD int ob_collide_pair_xf_t(const ObPose *a1, const ObPose *a2, int any_xf, i
 // <true, true> instantiation): measured on B200, even a never-taken call to the flipped path cost k_collide 2 % (config 2)
 // to 7 % (config 4) through register allocation (80 -> 96 registers), so batches without transforms run the code they
 // had before (profiles/job_ab.sh).
+// Row of the contact-policy table that serves a pair (dBatchContactPolicy, ode.h): the first row whose category masks accept
+// the two geoms in either order; -1 = no row, the pair gets no contacts (a near callback that returns early).  A table of one
+// row serves every pair, as a callback without a class test does (the masks of a single row are not consulted).
+OB_HD int ob_policy_row(const ObPolicy *tab, uint32_t cat1, uint32_t cat2) {
+  const int n = tab[0].nrows;
+  if (n <= 1) return 0;
+  for (int r = 0; r < n && r < OB_MAXPOLICY; r++) {
+    const uint32_t m1 = tab[r].cat_mask1, m2 = tab[r].cat_mask2;
+    if (((cat1 & m1) && (cat2 & m2)) || ((cat2 & m1) && (cat1 & m2))) return r;
+  }
+  return -1;
+}
 template <bool MESH, int CGCAP, bool XF>
 OB_HD int ob_collide_pair_sel_t(const ObPose *a1, const ObPose *a2, int flags, ObCg *c, int *swapped, const ObMeshDev *meshes, int *bverr) {
   if (XF) return ob_collide_pair_xf_t<MESH, CGCAP>(a1, a2, 1, flags, c, swapped, meshes, bverr);

@@ -256,17 +256,19 @@ __global__ void __launch_bounds__(OB_THREADS) k_collide(ObBatchDev d) {
     const ObGeom *geoms = d.geom + (size_t)w * d.NG;
     const int np = collide_broad<true>(d, w, V, tid, nt);
     // (5) narrowphase per pair in callback order, ordered compaction into contact joints
-    const ObPolicy pol = d.policy[0];
+    const int nrows = d.policy[0].nrows;   // > 1: the row is chosen per pair by the geoms' category bits
     ObContact *cout = d.contacts + (size_t)w * d.NC;
-    const int maxc = pol.max_contacts > CGCAP ? CGCAP : pol.max_contacts;
     for (int base = 0; base < np; base += nt) {
       int p = base + tid;
       ObCg cg[CGCAP];
-      int n = 0, o1 = 0, o2 = 0;
+      int n = 0, o1 = 0, o2 = 0, row = 0;
       if (p < np) {
         o1 = s_sorted[p].x; o2 = s_sorted[p].y;
-        bool connected = false;
-        if (pol.skip_if_connected && d.NJ) {   // dAreConnectedExcluding(b1, b2, dJointTypeContact), ode.cpp:1529-1537
+        if (nrows > 1) row = ob_policy_row(d.policy, geoms[o1].cat, geoms[o2].cat);
+        const ObPolicy &pol = d.policy[row < 0 ? 0 : row];
+        const int maxc = pol.max_contacts > CGCAP ? CGCAP : pol.max_contacts;
+        bool connected = row < 0 || (pol.skip_static_pairs && geoms[o1].body < 0 && geoms[o2].body < 0);
+        if (!connected && pol.skip_if_connected && d.NJ) {   // dAreConnectedExcluding(b1, b2, dJointTypeContact), ode.cpp:1529-1537
           const int b1 = geoms[o1].body, b2 = geoms[o2].body;
           if (b1 >= 0 && b2 >= 0) {
             const unsigned short *ps = d.padjstart + (size_t)w * (d.NB + 1), *pa = d.padj + (size_t)w * 2 * d.NJ;
@@ -291,7 +293,7 @@ __global__ void __launch_bounds__(OB_THREADS) k_collide(ObBatchDev d) {
         if (j < d.NC) {
           ObContact c;
           for (int e = 0; e < 3; e++) { c.pos[e] = cg[k].pos[e]; c.normal[e] = cg[k].normal[e]; }
-          c.depth = cg[k].depth; c.g1 = o1; c.g2 = o2; c.side1 = cg[k].side1; c.side2 = cg[k].side2; c.policy = 0;
+          c.depth = cg[k].depth; c.g1 = o1; c.g2 = o2; c.side1 = cg[k].side1; c.side2 = cg[k].side2; c.policy = row;
           cout[j] = c;
         }
       }
@@ -360,8 +362,8 @@ __global__ void __launch_bounds__(32 * WPC) k_collide_tile(ObBatchDev d, int sta
     int np = 0;
     if (valid) np = collide_broad<false>(d, w, V, tid, nt);
     // (5) narrowphase over the pooled pairs of the CTA's worlds
-    const ObPolicy pol = d.policy[0];
-    const int maxc = pol.max_contacts > CGCAP ? CGCAP : pol.max_contacts;
+    const int nrows = d.policy[0].nrows;   // > 1: the row is chosen per pair by the geoms' category bits
+    const bool any_skip_connected = d.policy[0].skip_if_connected != 0;
     const int nthr = 32 * WPC;
     if (tid == 0) c_np[warp + 1] = np;
     if (threadIdx.x < 8) c_cls[threadIdx.x] = 0;
@@ -379,7 +381,7 @@ __global__ void __launch_bounds__(32 * WPC) k_collide_tile(ObBatchDev d, int sta
       const int t1 = gv[o12.x].type, t2 = gv[o12.y].type;
       const int lo = t1 < t2 ? t1 : t2, hi = t1 < t2 ? t2 : t1;
       int cls = hi == OB_GEOM_TRIMESH ? (lo == OB_GEOM_SPHERE ? 1 : (lo == OB_GEOM_BOX ? 2 : 3)) : ((lo == OB_GEOM_BOX && hi == OB_GEOM_BOX) ? 4 : 5);
-      if (pol.skip_if_connected && d.NJ && gv[o12.x].body >= 0 && gv[o12.y].body >= 0) cls = 0;   // mostly jointed pairs: the cheap test
+      if (any_skip_connected && d.NJ && gv[o12.x].body >= 0 && gv[o12.y].body >= 0) cls = 0;   // mostly jointed pairs: the cheap test
       c_n[f] = (unsigned char)cls;
       atomicAdd(&c_cls[cls], 1);
     }
@@ -403,8 +405,11 @@ __global__ void __launch_bounds__(32 * WPC) k_collide_tile(ObBatchDev d, int sta
         const ObGeom *gv = d.geom + (size_t)wv * d.NG;
         ObCg cg[CGCAP];
         int n = 0;
-        bool connected = false;
-        if (pol.skip_if_connected && d.NJ) {   // dAreConnectedExcluding(b1, b2, dJointTypeContact), ode.cpp:1529-1537
+        const int row = nrows > 1 ? ob_policy_row(d.policy, gv[o12.x].cat, gv[o12.y].cat) : 0;
+        const ObPolicy &pol = d.policy[row < 0 ? 0 : row];
+        const int maxc = pol.max_contacts > CGCAP ? CGCAP : pol.max_contacts;
+        bool connected = row < 0 || (pol.skip_static_pairs && gv[o12.x].body < 0 && gv[o12.y].body < 0);
+        if (!connected && pol.skip_if_connected && d.NJ) {   // dAreConnectedExcluding(b1, b2, dJointTypeContact), ode.cpp:1529-1537
           const int b1 = gv[o12.x].body, b2 = gv[o12.y].body;
           if (b1 >= 0 && b2 >= 0) {
             const unsigned short *ps = d.padjstart + (size_t)wv * (d.NB + 1), *pa = d.padj + (size_t)wv * 2 * d.NJ;
@@ -450,12 +455,14 @@ __global__ void __launch_bounds__(32 * WPC) k_collide_tile(ObBatchDev d, int sta
         const int2 o12 = ((const int2 *)(smv + L.sorted))[f - c_np[v]];
         ObContact *cout = d.contacts + (size_t)(wb + v) * d.NC;
         const ObCg *src = c_stage + c_stoff[f];
+        const ObGeom *gv = d.geom + (size_t)(wb + v) * d.NG;
+        const int row = (n > 0 && nrows > 1) ? ob_policy_row(d.policy, gv[o12.x].cat, gv[o12.y].cat) : 0;
         for (int k = 0; k < n; k++) {
           const int j = j0 + k;
           if (j < d.NC) {
             ObContact c;
             for (int e = 0; e < 3; e++) { c.pos[e] = src[k].pos[e]; c.normal[e] = src[k].normal[e]; }
-            c.depth = src[k].depth; c.g1 = o12.x; c.g2 = o12.y; c.side1 = src[k].side1; c.side2 = src[k].side2; c.policy = 0;
+            c.depth = src[k].depth; c.g1 = o12.x; c.g2 = o12.y; c.side1 = src[k].side1; c.side2 = src[k].side2; c.policy = row;
             cout[j] = c;
           }
         }

@@ -182,16 +182,15 @@ __global__ void __launch_bounds__(LW_T) k_lw_gather(ObBatchDev d, ObLargeDev L, 
 // ---- pairs ---------------------------------------------------------------------------------------
 // cnt / off layout: [0, ng) sweep hits of sorted position i; [ng, 2ng) hits of i against the infinite
 // list; [2ng] infinite x infinite.  Pair orientation: the geom met first is o1 (sapspace.cpp:478-493, :553).
-// SPLIT (several GPUs, ObLwSplit): this launch handles the sorted positions [i0, i1) only and writes its counts / pairs
-// into every rank's arrays; the infinite x infinite block is evaluated by every rank for itself.
-template <int FILL, bool SPLIT>
-__global__ void __launch_bounds__(LW_T) k_lw_sweep(ObBatchDev d, ObLargeDev L, int i0, int i1, ObLwSplit S) {
+// Front-end split (several GPUs, ObLwSplit): a launch handles the sorted positions [i0, i1) only; k_lw_push_cnt / k_lw_push_pairs
+// then copy what it produced into the peers' arrays.  The infinite x infinite block is evaluated by every rank for itself.
+template <int FILL>
+__global__ void __launch_bounds__(LW_T) k_lw_sweep(ObBatchDev d, ObLargeDev L, int i0, int i1) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int i = i0 + t;
   const int ng = d.world[0].ng;
-  const int nr = SPLIT ? S.nranks : 1;
-#define LW_PUT_PAIR(IDX, A, B) { const size_t x_ = (IDX); if (x_ < (size_t)L.NP) { if (SPLIT) { for (int r_ = 0; r_ < nr; r_++) *(int2 *)(S.pairs[r_] + 2 * x_) = make_int2((A), (B)); } else *(int2 *)(L.pairs + 2 * x_) = make_int2((A), (B)); } }
-#define LW_PUT_CNT(IDX, V) { if (SPLIT) { for (int r_ = 0; r_ < nr; r_++) S.cnt[r_][(IDX)] = (V); } else L.cnt[(IDX)] = (V); }
+#define LW_PUT_PAIR(IDX, A, B) { const size_t x_ = (IDX); if (x_ < (size_t)L.NP) *(int2 *)(L.pairs + 2 * x_) = make_int2((A), (B)); }
+#define LW_PUT_CNT(IDX, V) { L.cnt[(IDX)] = (V); }
   const int nfin = L.scal[LW_NFIN];
   const int bigend = L.scal[LW_NBIG] > nfin ? L.scal[LW_NBIG] : nfin;
   const int *sidx = L.gidx[0];   // the 4-pass sort leaves the result in buffer 0
@@ -279,35 +278,68 @@ __global__ void __launch_bounds__(LW_T) k_lw_sweep(ObBatchDev d, ObLargeDev L, i
 
 // the pairs one launch collides: up to three ranges of the pair list (one GPU: [0, np); front-end split: the two ranges this
 // rank filled, written to every rank, and the infinite x infinite range, which every rank keeps to itself)
-struct ObLwSeg3 { int start[3], len[3], remote[3]; };
-template <bool MESH, bool XF, bool SPLIT>
-__global__ void __launch_bounds__(LW_T) k_lw_narrow(ObBatchDev d, ObLargeDev L, ObLwSeg3 G, int np, int maxc, ObLwSplit S) {
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
-  int p = -1, remote = 0;
+struct ObLwSeg3 { int start[3], len[3]; };
+__device__ __forceinline__ int lw_seg_pair(const ObLwSeg3 &G, int t) {   // t-th pair of the ranges, -1 behind the end
+  int p = -1;
 #pragma unroll
   for (int k = 0; k < 3; k++) {
-    if (p < 0 && t < G.len[k]) { p = G.start[k] + t; remote = G.remote[k]; }
+    if (p < 0 && t >= 0 && t < G.len[k]) p = G.start[k] + t;
     t -= G.len[k];
   }
+  return p;
+}
+template <bool MESH, bool XF>
+__global__ void __launch_bounds__(LW_T) k_lw_narrow(ObBatchDev d, ObLargeDev L, ObLwSeg3 G, int np, int maxc) {
+  const int p = lw_seg_pair(G, blockIdx.x * blockDim.x + threadIdx.x);
   if (p < 0 || p >= np) return;
   const int o1 = L.pairs[2 * p], o2 = L.pairs[2 * p + 1];
   ObCg cg[OB_LW_MAXC];
   int swapped, bverr = 0;
   const int n = ob_collide_pair_sel_t<MESH, OB_LW_MAXC, XF>(&L.pose[o1], &L.pose[o2], maxc, cg, &swapped, d.meshes, &bverr);
   if (bverr) atomicOr(&d.world[0].status, OB_ERR_BVH_STACK);
+  ObContact *out = L.pc + (size_t)p * maxc;
+  for (int k = 0; k < n; k++) {
+    ObContact c;
+    for (int e = 0; e < 3; e++) { c.pos[e] = cg[k].pos[e]; c.normal[e] = cg[k].normal[e]; }
+    c.depth = cg[k].depth; c.g1 = o1; c.g2 = o2; c.side1 = cg[k].side1; c.side2 = cg[k].side2; c.policy = 0;
+    out[k] = c;
+  }
+  L.ncp[p] = (uint32_t)n;
   const int b1 = d.geom[o1].body, b2 = d.geom[o2].body;
-  const uint32_t flag = (n > 0 && (b1 >= 0 || b2 >= 0)) ? 1u : 0u;
-  const int nr = (SPLIT && remote) ? S.nranks : 1;
-  for (int r = 0; r < nr; r++) {
-    ObContact *out = ((SPLIT && remote) ? S.pc[r] : L.pc) + (size_t)p * maxc;
-    for (int k = 0; k < n; k++) {
-      ObContact c;
-      for (int e = 0; e < 3; e++) { c.pos[e] = cg[k].pos[e]; c.normal[e] = cg[k].normal[e]; }
-      c.depth = cg[k].depth; c.g1 = o1; c.g2 = o2; c.side1 = cg[k].side1; c.side2 = cg[k].side2; c.policy = 0;
-      out[k] = c;
+  L.cpflag[p] = (n > 0 && (b1 >= 0 || b2 >= 0)) ? 1u : 0u;
+}
+// ---- front-end split: what a rank computed goes to its peers as bulk copies -- consecutive threads store consecutive 4 / 8 / 16-byte
+// words through the NVLink peer mappings, so the links carry full lines (r02l: storing every count / pair / contact from inside the
+// sweep and narrowphase kernels cost more than the split saved).  The flag barrier behind a push makes the copies visible.
+__global__ void __launch_bounds__(LW_T) k_lw_push_cnt(ObLargeDev L, ObLwSplit S, int ng, int i0, int i1) {
+  const int n = i1 - i0;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < 2 * n; t += gridDim.x * blockDim.x) {
+    const int idx = t < n ? i0 + t : ng + i0 + (t - n);
+    const uint32_t v = L.cnt[idx];
+    for (int r = 0; r < S.nranks; r++) if (r != S.rank) S.cnt[r][idx] = v;
+  }
+}
+// thread (pair, j): j == 0 copies the pair's geom ids, contact count and solver flag; j >= 1 the (j - 1)-th 16-byte chunk of its contact slots
+__global__ void __launch_bounds__(LW_T) k_lw_push_pairs(ObLargeDev L, ObLwSplit S, ObLwSeg3 G, int np, int maxc) {
+  static_assert(sizeof(ObContact) % 16 == 0, "contacts are copied in 16-byte chunks");
+  constexpr int CC = (int)sizeof(ObContact) / 16;
+  const int per = 1 + CC * maxc;
+  const long long total = (long long)(G.len[0] + G.len[1]) * per;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(t / per), j = (int)(t - (long long)q * per);
+    const int p = lw_seg_pair(G, q);
+    if (p < 0 || p >= np) continue;
+    if (j == 0) {
+      const int2 o = *(const int2 *)(L.pairs + 2 * (size_t)p);
+      const uint32_t n = L.ncp[p], f = L.cpflag[p];
+      for (int r = 0; r < S.nranks; r++) if (r != S.rank) { *(int2 *)(S.pairs[r] + 2 * (size_t)p) = o; S.ncp[r][p] = n; S.cpflag[r][p] = f; }
+    } else {
+      const int k = (j - 1) / CC;
+      if ((uint32_t)k >= L.ncp[p]) continue;
+      const size_t off = ((size_t)p * maxc) * CC + (size_t)(j - 1);   // in 16-byte chunks from the start of pc
+      const float4 v = ((const float4 *)L.pc)[off];
+      for (int r = 0; r < S.nranks; r++) if (r != S.rank) ((float4 *)S.pc[r])[off] = v;
     }
-    ((SPLIT && remote) ? S.ncp[r] : L.ncp)[p] = (uint32_t)n;
-    ((SPLIT && remote) ? S.cpflag[r] : L.cpflag)[p] = flag;
   }
 }
 // Barrier of the ranks between two kernels of the step (front-end split): one thread.  The kernels before it have
@@ -849,7 +881,7 @@ int lw_create(ObBackend *b, char *err, size_t errlen) {
   LWCK(dalloc(b, &L.hasrow, NB));
   L.tmp_words = (NP > 2 * NG ? NP : 2 * NG) / 2 + 65536;
   LWCK(dalloc(b, &L.tmp, L.tmp_words));
-  LWCK(cudaMallocHost((void **)&b->lw_host, sizeof(int) * LW_HOST_WORDS));
+  LWCK(cudaMallocHost((void **)&b->lw_host, sizeof(int) * (LW_HOST_WORDS + 4)));
   for (int k = 0; k < 9; k++) LWCK(cudaEventCreate(&b->lw_ev[k]));
   {   // persistent SOR kernel: as many CTAs as are co-resident
     cudaDeviceProp prop;
@@ -987,47 +1019,45 @@ int lw_step(ObBackend *b, real h, int taps, char *err, size_t errlen) {
   int i0 = 0, i1 = ng;
   if (front) ob_lw_split_range(ng, S.rank, S.nranks, &i0, &i1);
   const int nsw = i1 - i0 > 1 ? i1 - i0 : 1;   // thread 0 always runs (infinite x infinite block)
+  k_lw_sweep<0><<<lw_blocks(nsw), LW_T, 0, st>>>(d, L, i0, i1);
   if (front) {
-    k_lw_sweep<0, true><<<lw_blocks(nsw), LW_T, 0, st>>>(d, L, i0, i1, S);
+    if (i1 > i0) k_lw_push_cnt<<<lw_blocks(2 * (size_t)(i1 - i0)), LW_T, 0, st>>>(L, S, ng, i0, i1);
     k_lw_xbarrier<<<1, 32, 0, st>>>(S, ++b->lw_split.base);
-    g_launches++;
-  } else k_lw_sweep<0, false><<<lw_blocks(nsw), LW_T, 0, st>>>(d, L, i0, i1, S);
+    g_launches += 2;
+  }
   lw_scan(st, L.cnt, L.off, 2 * ng + 1, L.tmp);
-  if (front) k_lw_sweep<1, true><<<lw_blocks(nsw), LW_T, 0, st>>>(d, L, i0, i1, S);
-  else k_lw_sweep<1, false><<<lw_blocks(nsw), LW_T, 0, st>>>(d, L, i0, i1, S);
+  k_lw_sweep<1><<<lw_blocks(nsw), LW_T, 0, st>>>(d, L, i0, i1);
   g_launches += 2;
   LWCK(cudaMemcpyAsync(hs, L.scal, sizeof(int) * LW_WORDS, cudaMemcpyDeviceToHost, st));
+  if (front) LWCK(cudaMemcpyAsync(hs + LW_HOST_WORDS, L.off + 2 * ng, sizeof(int), cudaMemcpyDeviceToHost, st));
   LWCK(cudaStreamSynchronize(st));
   const int np = hs[LW_NP];
   LW_MARK();
-  // (3) narrowphase, contact pairs.  Front-end split: the pairs this rank has just filled (nobody else's are needed yet),
-  // results to every rank, then the second barrier of the step
+  // (3) narrowphase, contact pairs.  Front-end split: the pairs this rank has just filled (nobody else's are needed yet), then
+  // pairs + contacts go to the peers in one bulk copy and the second barrier of the step follows
   {
     ObLwSeg3 G;
     memset(&G, 0, sizeof G);
     if (front) {
-      G.start[0] = hs[LW_SEG0]; G.len[0] = hs[LW_SEG0 + 1]; G.remote[0] = 1;
-      G.start[1] = hs[LW_SEG0 + 2]; G.len[1] = hs[LW_SEG0 + 3]; G.remote[1] = 1;
+      G.start[0] = hs[LW_SEG0]; G.len[0] = hs[LW_SEG0 + 1];
+      G.start[1] = hs[LW_SEG0 + 2]; G.len[1] = hs[LW_SEG0 + 3];
       // infinite x infinite: behind the two lists (off[2 ng] = end of the second one); every rank for itself
-      G.start[2] = 0; G.len[2] = 0;
-      LWCK(cudaMemcpyAsync(&G.start[2], L.off + 2 * ng, sizeof(int), cudaMemcpyDeviceToHost, st));
-      LWCK(cudaStreamSynchronize(st));
+      G.start[2] = hs[LW_HOST_WORDS];
       G.len[2] = np > G.start[2] ? np - G.start[2] : 0;
     } else { G.start[0] = 0; G.len[0] = np; }
     const int nt = G.len[0] + G.len[1] + G.len[2];
     if (nt > 0) {
-      if (front) {
-        if (d.any_xf) k_lw_narrow<true, true, true><<<lw_blocks(nt), LW_T, 0, st>>>(d, L, G, np, maxc, S);
-        else if (d.nmesh) k_lw_narrow<true, false, true><<<lw_blocks(nt), LW_T, 0, st>>>(d, L, G, np, maxc, S);
-        else k_lw_narrow<false, false, true><<<lw_blocks(nt), LW_T, 0, st>>>(d, L, G, np, maxc, S);
-      } else {
-        if (d.any_xf) k_lw_narrow<true, true, false><<<lw_blocks(nt), LW_T, 0, st>>>(d, L, G, np, maxc, S);
-        else if (d.nmesh) k_lw_narrow<true, false, false><<<lw_blocks(nt), LW_T, 0, st>>>(d, L, G, np, maxc, S);
-        else k_lw_narrow<false, false, false><<<lw_blocks(nt), LW_T, 0, st>>>(d, L, G, np, maxc, S);
-      }
+      if (d.any_xf) k_lw_narrow<true, true><<<lw_blocks(nt), LW_T, 0, st>>>(d, L, G, np, maxc);
+      else if (d.nmesh) k_lw_narrow<true, false><<<lw_blocks(nt), LW_T, 0, st>>>(d, L, G, np, maxc);
+      else k_lw_narrow<false, false><<<lw_blocks(nt), LW_T, 0, st>>>(d, L, G, np, maxc);
       g_launches++;
     }
-    if (front) { k_lw_xbarrier<<<1, 32, 0, st>>>(S, ++b->lw_split.base); g_launches++; }
+    if (front) {
+      const size_t work = (size_t)(G.len[0] + G.len[1]) * (1 + (sizeof(ObContact) / 16) * maxc);
+      if (work > 0) { k_lw_push_pairs<<<lw_blocks(work < ((size_t)1 << 24) ? work : ((size_t)1 << 24)), LW_T, 0, st>>>(L, S, G, np, maxc); g_launches++; }
+      k_lw_xbarrier<<<1, 32, 0, st>>>(S, ++b->lw_split.base);
+      g_launches++;
+    }
   }
   lw_scan(st, L.ncp, L.coff, np, L.tmp);
   lw_scan(st, L.cpflag, L.cpoff, np, L.tmp);

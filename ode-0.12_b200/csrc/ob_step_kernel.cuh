@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(32) k_prep(ObBatchDev d, real h, int taps) {
     const int njall_max = warp_max_i(njall);
     int nis = 0, nib = 0, nij = 0, nib_max = 0, nij_max = 0, mtot = 0, anyball = 0;
     bool have_rows = false;
-    const ObSurface surf0 = d.policy[0].surface;
+    const ObPolicy *ptab = d.policy;   // batched path: a contact carries the row of the policy table that made it (drop-in: per-contact surfaces)
     const ObSurface *csurf = d.csurf ? d.csurf + (size_t)wc * d.NC : (const ObSurface *)0;   // drop-in: per-contact surfaces
     unsigned char *g_ibody = d.ibody + (size_t)wc * d.NB;
     unsigned short *g_jrow = d.jrow + (size_t)wc * (d.NC + d.NJ + 1);
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(32) k_prep(ObBatchDev d, real h, int taps) {
       int m = 0;
       if (k < nij) {
         const int j = s_ijoint[k];
-        if (!PJ || j < nc) { ObSurface sf = csurf ? csurf[j] : surf0; m = ob_contact_info1(sf); }
+        if (!PJ || j < nc) { ObSurface sf = csurf ? csurf[j] : ptab[con[j].policy].surface; m = ob_contact_info1(sf); }
         else {
           ObJoint pj = pjoint[j - nc];
           const int b1 = pj.b1, b2 = pj.b2;
@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(32) k_prep(ObBatchDev d, real h, int taps) {
             const int r0 = s_jrow[k], jm = s_jrow[k + 1] - r0;
             const unsigned bb = (unsigned)s_jb1[j] | ((unsigned)s_jb2[j] << 8);
             unsigned mode = 0;
-            if (!PJ || j < nc) { const ObSurface sf = csurf ? csurf[j] : surf0; mode = (unsigned)sf.mode; }
+            if (!PJ || j < nc) { const ObSurface sf = csurf ? csurf[j] : ptab[con[j].policy].surface; mode = (unsigned)sf.mode; }
             for (int q = 0; q < jm; q++) {
               // findex offset of a contact's friction rows (contact.cpp:211, :235); every other row has findex -1
               const unsigned fio = (q == 1 && (mode & 0x1000u)) ? 1u : ((q == 2 && (mode & 0x2000u)) ? 2u : 0u);
@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(32) k_prep(ObBatchDev d, real h, int taps) {
         real erp_in = W.erp;
         if (anyball) { const int src = s_erpsrc[k]; if (src != 0xffff) erp_in = pjoint[s_ijoint[src] - nc].erp; }
         if (!PJ || j < nc) {
-          ObSurface sf = csurf ? csurf[j] : surf0;
+          ObSurface sf = csurf ? csurf[j] : ptab[con[j].policy].surface;
           const int jm = ob_contact_info1(sf);
           ObRowOut3 r;
           ob_rows_defaults(r, jm, W.cfm);

@@ -73,9 +73,10 @@ struct __attribute__((aligned(16))) ObSurface {
 };
 struct __attribute__((aligned(16))) ObPolicy {
   uint32_t cat_mask1, cat_mask2; int max_contacts; int skip_if_connected;
-  int skip_static_pairs; int pad[3];
+  int skip_static_pairs; int nrows /* row 0 only: rows in use (0 = 1) */; int pad[2];
   ObSurface surface;
 };
+#define OB_MAXPOLICY 8   // rows of the contact-policy table (dBatchContactPolicy, include/ode_b200/ode.h)
 // permanent joints (ball / hinge / hinge2), body-frame parameters as the host API maintains them
 struct __attribute__((aligned(16))) ObLimot {
   real vel, fmax, lostop, histop;

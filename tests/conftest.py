@@ -40,6 +40,7 @@ GOLDEN = [  # (file stem, scene, steps, worlds, settle) — must match tests/gol
     ("autodisable_settle150", "autodisable", 30, 1, 150),   # auto-disable (instantaneous samples) + re-enabling through the island walk
     ("contactmodes_settle60", "contactmodes", 30, 1, 60),   # Mu2, Motion1/2/N, Slip1/2, Bounce, SoftERP/CFM, Approx1_2
     ("autodisable_avg_settle150", "autodisable_avg", 30, 1, 150),   # auto-disable on averaged velocity samples (5 / 3 / 1 samples per body)
+    ("crashwall_settle45", "crashwall", 30, 1, 45),   # demo_crash as shipped: SAP space, brick wall, hinge2 car + fixed counterweight, cannon ball; TWO policy rows (mu by geom class)
 ]
 
 
@@ -87,7 +88,7 @@ def _built():
 # from the reference's pre-step body state, SURVEY 8d parity protocol with K = 1) so that a
 # last-bit difference cannot be amplified by chaotic dynamics into a different contact set.
 ATAN2_SCENES = ("hinges", "buggy", "ragdoll", "buggy_terrain", "universals", "motors", "pistons", "pus",
-                "bodyflags", "nested", "nested_dcollide")   # nested: hinge2 buggies; bodyflags: finite rotation calls sin / cos (dDOUBLE: platform libm, same tolerance class; dSINGLE: glibc-exact restatement)
+                "bodyflags", "nested", "nested_dcollide", "crashwall")   # nested: hinge2 buggies; bodyflags: finite rotation calls sin / cos (dDOUBLE: platform libm, same tolerance class; dSINGLE: glibc-exact restatement)
 
 
 # dDOUBLE on the GPU, scenes whose limit-motors bounce off their stops (restitution turns a last-bit atan2 difference

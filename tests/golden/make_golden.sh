@@ -38,6 +38,7 @@ for p in single double; do
   $d --scene bodyflags --steps 30 --settle 50 --out tests/golden/bodyflags_settle50_$p.trace
   $d --scene autodisable --steps 30 --settle 150 --out tests/golden/autodisable_settle150_$p.trace
   $d --scene contactmodes --steps 30 --settle 60 --out tests/golden/contactmodes_settle60_$p.trace
+  $d --scene crashwall --steps 30 --settle 45 --out tests/golden/crashwall_settle45_$p.trace
   $d --scene autodisable_avg --steps 30 --settle 150 --out tests/golden/autodisable_avg_settle150_$p.trace
   # drop-in (callback) path only: ray colliders + capsule-trimesh, FDir1, per-call max-contacts
   $d --scene raycast --steps 20 --settle 40 --out tests/golden/raycast_settle40_$p.trace

@@ -22,13 +22,21 @@ extern "C" dBatchID ob_scene_build_batch(const char *scene, int nworlds, int wor
   desc.device = device;
   dBatchID B = dBatchCreate(nworlds, wv.data(), sv.data(), &desc);
   if (!B) return 0;
-  dBatchContactPolicy bp;
-  memset(&bp, 0, sizeof(bp));
-  bp.cat_mask1 = bp.cat_mask2 = ~0ul;
-  bp.max_contacts = pol.max_contacts;
-  bp.skip_if_connected = pol.skip_if_connected;
-  bp.surface = pol.surface;
-  dBatchSetContactPolicy(B, &bp, 1);
+  dBatchContactPolicy bp[2];
+  memset(bp, 0, sizeof(bp));
+  int nrows = 0;
+  if (pol.sphere_mu > 0) {   // pairs with a sphere first (category bit SCENE_CAT_SPHERE), then the catch-all row
+    bp[0].cat_mask1 = SCENE_CAT_SPHERE; bp[0].cat_mask2 = ~0ul;
+    bp[0].max_contacts = pol.max_contacts; bp[0].skip_if_connected = pol.skip_if_connected;
+    bp[0].surface = pol.surface; bp[0].surface.mu = pol.sphere_mu;
+    nrows = 1;
+  }
+  bp[nrows].cat_mask1 = bp[nrows].cat_mask2 = ~0ul;
+  bp[nrows].max_contacts = pol.max_contacts;
+  bp[nrows].skip_if_connected = pol.skip_if_connected;
+  bp[nrows].surface = pol.surface;
+  nrows++;
+  dBatchSetContactPolicy(B, bp, nrows);
   dBatchSetSeeds(B, seeds.data());
   g_keep.push_back(worlds);
   return B;

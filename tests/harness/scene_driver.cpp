@@ -71,6 +71,8 @@ static void near_cb(void *data, dGeomID o1, dGeomID o2) {
     memset(&contact[i], 0, sizeof(dContact));
     contact[i].surface = c->pol->surface;
   }
+  if (c->pol->sphere_mu > 0 && (dGeomGetClass(o1) == dSphereClass || dGeomGetClass(o2) == dSphereClass))
+    for (int i = 0; i < maxc; i++) contact[i].surface.mu = c->pol->sphere_mu;   // demo_crash.cpp:128-131
   int n = dCollide(o1, o2, maxc, &contact[0].geom, sizeof(dContact));
   if (c->pol->fdir1)
     for (int i = 0; i < n; i++) {
@@ -381,13 +383,21 @@ int main(int argc, char **argv) {
     desc.large_world = large;
     dBatchID B = dBatchCreate(nworlds, wv.data(), sv.data(), &desc);
     if (!B) { fprintf(stderr, "dBatchCreate failed: %s\n", dB200LastError()); return 3; }
-    dBatchContactPolicy bp;
-    memset(&bp, 0, sizeof(bp));
-    bp.cat_mask1 = bp.cat_mask2 = ~0ul;
-    bp.max_contacts = pol.max_contacts;
-    bp.skip_if_connected = pol.skip_if_connected;
-    bp.surface = pol.surface;
-    dBatchSetContactPolicy(B, &bp, 1);
+    dBatchContactPolicy bp[2];
+    memset(bp, 0, sizeof(bp));
+    int nrows = 0;
+    if (pol.sphere_mu > 0) {   // pairs with a sphere first (category bit SCENE_CAT_SPHERE), then the catch-all row
+      bp[0].cat_mask1 = SCENE_CAT_SPHERE; bp[0].cat_mask2 = ~0ul;
+      bp[0].max_contacts = pol.max_contacts; bp[0].skip_if_connected = pol.skip_if_connected;
+      bp[0].surface = pol.surface; bp[0].surface.mu = pol.sphere_mu;
+      nrows = 1;
+    }
+    bp[nrows].cat_mask1 = bp[nrows].cat_mask2 = ~0ul;
+    bp[nrows].max_contacts = pol.max_contacts;
+    bp[nrows].skip_if_connected = pol.skip_if_connected;
+    bp[nrows].surface = pol.surface;
+    nrows++;
+    dBatchSetContactPolicy(B, bp, nrows);
     dBatchSetSeeds(B, seeds.data());
     int nb = dBatchNumBodies(B);
     std::vector<dReal> pos(nworlds * nb * 3), quat(nworlds * nb * 4), lv(nworlds * nb * 3), av(nworlds * nb * 3);

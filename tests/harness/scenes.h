@@ -31,6 +31,8 @@ struct ScenePolicy {
   // knobs only a near callback can express (classic loop; the batched path's policy table has no equivalent):
   int fdir1;     // 1: dContactFDir1 with a first friction direction computed from the contact normal
   int varmaxc;   // 1: the max-contacts value passed to dCollide varies from call to call
+  dReal sphere_mu;   // > 0: contacts of a pair with a sphere geom take this mu instead of surface.mu (demo_crash.cpp:128-131); the scene gives
+                     // its spheres category bit SCENE_CAT_SPHERE so that the batched path's policy table can tell them apart
   int nested;    // sub-spaces among the pairs: 1 = the manual's idiom (dSpaceCollide2 on the pair, then dSpaceCollide on each space
                  // for its interior pairs), 2 = demo_buggy's way (dCollide straight on the (space, geom) pair, bodies from the contacts)
 };
@@ -108,6 +110,7 @@ static inline ScenePolicy policy_boxstack() {
   return p;
 }
 
+#define SCENE_CAT_SPHERE 2ul
 static inline ScenePolicy policy_crash() {
   // ode/demo/demo_crash.cpp:128-137
   ScenePolicy p;
@@ -1075,6 +1078,100 @@ static inline void scene_raycast(SceneWorld &sw, int w, int two_spaces, bool cyl
   }
 }
 
+// ode/demo/demo_crash.cpp as shipped (CARS + WALL + CANNON, :47-78, :165-231, :252-290): dSweepAndPruneSpace XYZ, gravity -1.5,
+// a brick wall of unit boxes, a car (box chassis, four sphere wheels on hinge2 joints with the demo's suspension and motor
+// parameters, a counterweight body on a fixed joint below the chassis) driving into it and a cannon ball on its way to the wall.
+// The demo's callback gives pairs with a sphere mu = 20 and all others mu = 0.5 (:128-131): ScenePolicy::sphere_mu.  A smaller
+// wall than the demo's 12 x 10 keeps the trace short; the body count (wall + 6 car bodies + ball) stays on the CTA-per-world path.
+static inline void scene_crashwall(SceneWorld &sw, int w, int wallw, int wallh) {
+  sw.world = dWorldCreate();
+  sw.space2 = 0;
+  sw.space = dSweepAndPruneSpaceCreate(0, dSAP_AXES_XYZ);
+  sw.cgroup = dJointGroupCreate(0);
+  sw.seed = scene_world_seed(w);
+  dWorldSetGravity(sw.world, 0, 0, (dReal)-1.5);
+  dWorldSetCFM(sw.world, (dReal)1e-5);
+  dWorldSetERP(sw.world, (dReal)0.8);
+  dWorldSetQuickStepNumIterations(sw.world, 20);
+  xs32 rng(sw.seed ^ 0x00C8A54u);
+  dGeomSetCategoryBits(scene_add_geom(sw, dCreatePlane(sw.space, 0, 0, 1, 0)), 1);   // every geom that is not a sphere: category bit 1 only
+  const dReal LENGTH = (dReal)3.5, WIDTH = (dReal)2.5, HEIGHT = 1, RADIUS = (dReal)0.5, STARTZ = 1;
+  const dReal x = -12, y = rng.uni(-0.2, 0.2);
+  dMass m;
+  dBodyID chassis = dBodyCreate(sw.world);
+  dBodySetPosition(chassis, x, y, STARTZ);
+  dMassSetBox(&m, 1, LENGTH, WIDTH, HEIGHT);
+  dMassAdjust(&m, (dReal)0.5);
+  dBodySetMass(chassis, &m);
+  { dGeomID g = scene_add_geom(sw, dCreateBox(sw.space, LENGTH, WIDTH, HEIGHT)); dGeomSetCategoryBits(g, 1); dGeomSetBody(g, chassis); }
+  sw.bodies.push_back(chassis);
+  const dReal wx[4] = {(dReal)(x + 0.4 * LENGTH - 0.5 * RADIUS), (dReal)(x + 0.4 * LENGTH - 0.5 * RADIUS), (dReal)(x - 0.4 * LENGTH + 0.5 * RADIUS), (dReal)(x - 0.4 * LENGTH + 0.5 * RADIUS)};
+  const dReal wy[4] = {(dReal)(y + WIDTH * 0.5), (dReal)(y - WIDTH * 0.5), (dReal)(y + WIDTH * 0.5), (dReal)(y - WIDTH * 0.5)};
+  for (int i = 0; i < 4; i++) {
+    dBodyID wheel = dBodyCreate(sw.world);
+    dQuaternion q;
+    dQFromAxisAndAngle(q, 1, 0, 0, (dReal)(3.14159265358979 * 0.5));
+    dBodySetQuaternion(wheel, q);
+    dMassSetSphere(&m, 1, RADIUS);
+    dMassAdjust(&m, 1);
+    dBodySetMass(wheel, &m);
+    dGeomID g = scene_add_geom(sw, dCreateSphere(sw.space, RADIUS));
+    dGeomSetCategoryBits(g, SCENE_CAT_SPHERE);
+    dGeomSetBody(g, wheel);
+    dBodySetPosition(wheel, wx[i], wy[i], STARTZ - HEIGHT * (dReal)0.5);
+    sw.bodies.push_back(wheel);
+    dJointID j = dJointCreateHinge2(sw.world, 0);
+    dJointAttach(j, chassis, wheel);
+    const dReal *a = dBodyGetPosition(wheel);
+    dJointSetHinge2Anchor(j, a[0], a[1], a[2]);
+    dJointSetHinge2Axis1(j, 0, 0, (dReal)(i < 2 ? 1 : -1));
+    dJointSetHinge2Axis2(j, 0, 1, 0);
+    dJointSetHinge2Param(j, dParamSuspensionERP, (dReal)0.8);
+    dJointSetHinge2Param(j, dParamSuspensionCFM, (dReal)1e-5);
+    dJointSetHinge2Param(j, dParamVel2, (dReal)-6);       // the demo's 'a' key a few times: drive towards the wall (-x)
+    dJointSetHinge2Param(j, dParamFMax2, 25);
+    dJointSetHinge2Param(j, dParamLoStop, 0); dJointSetHinge2Param(j, dParamHiStop, 0);   // steering straight (simLoop's lock of the rear wheels, applied to all four)
+    dJointSetHinge2Param(j, dParamFudgeFactor, (dReal)0.1);
+    sw.joints.push_back(j);
+  }
+  {   // centre-of-mass offset body on a fixed joint (:214-222)
+    dBodyID b = dBodyCreate(sw.world);
+    dBodySetPosition(b, x, y, STARTZ - 5);
+    dMassSetBox(&m, 1, LENGTH, WIDTH, HEIGHT);
+    dMassAdjust(&m, (dReal)0.5);
+    dBodySetMass(b, &m);
+    sw.bodies.push_back(b);
+    dJointID j = dJointCreateFixed(sw.world, 0);
+    dJointAttach(j, chassis, b);
+    dJointSetFixed(j);
+    sw.joints.push_back(j);
+  }
+  bool offset = false;   // the wall (:274-291)
+  for (dReal z = (dReal)0.5; z <= (dReal)wallh; z += 1) {
+    offset = !offset;
+    for (dReal yy = (-(dReal)wallw + z) / 2; yy <= ((dReal)wallw - z) / 2; yy += 1) {
+      dBodyID b = dBodyCreate(sw.world);
+      dBodySetPosition(b, -20, yy, z);
+      dMassSetBox(&m, 1, 1, 1, 1);
+      dMassAdjust(&m, 1);
+      dBodySetMass(b, &m);
+      { dGeomID g = scene_add_geom(sw, dCreateBox(sw.space, 1, 1, 1)); dGeomSetCategoryBits(g, 1); dGeomSetBody(g, b); }
+      sw.bodies.push_back(b);
+    }
+  }
+  {   // the cannon ball in flight (:432-452: mass 10, radius 0.5, fired at the wall)
+    dBodyID b = dBodyCreate(sw.world);
+    dMassSetSphereTotal(&m, 10, (dReal)0.5);
+    dBodySetMass(b, &m);
+    dBodySetPosition(b, -14, rng.uni(-1.0, 1.0), (dReal)2.5);
+    dBodySetLinearVel(b, -10, 0, (dReal)0.5);
+    dGeomID g = scene_add_geom(sw, dCreateSphere(sw.space, (dReal)0.5));
+    dGeomSetCategoryBits(g, SCENE_CAT_SPHERE);
+    dGeomSetBody(g, b);
+    sw.bodies.push_back(b);
+  }
+}
+
 static inline ScenePolicy policy_buggy() {
   // ode/demo/demo_buggy.cpp:96-103
   ScenePolicy p;
@@ -1258,6 +1355,7 @@ static inline int scene_build(const char *name_in, SceneWorld &sw, int w, SceneP
   if (!strcmp(name, "mixed_varmaxc")) { scene_mixed(sw, w, 12, 6); pol.varmaxc = 1; return 0; }   // callback loop only
   if (!strcmp(name, "nested")) { scene_nested(sw, w); pol = policy_buggy(); pol.nested = 1; return 0; }          // callback loop only
   if (!strcmp(name, "nested_dcollide")) { scene_nested(sw, w); pol = policy_buggy(); pol.nested = 2; return 0; } // callback loop only
+  if (!strcmp(name, "crashwall")) { scene_crashwall(sw, w, 8, 6); pol = policy_crash(); pol.sphere_mu = 20; return 0; }
   if (!strcmp(name, "bodyflags")) { scene_bodyflags(sw, w); return 0; }
   if (!strcmp(name, "autodisable")) { scene_autodisable(sw, w); return 0; }
   if (!strcmp(name, "autodisable_avg")) { scene_autodisable(sw, w, 1); return 0; }   // averaged samples (util.cpp:139-205)

@@ -263,15 +263,19 @@ static void collide_world(ObBatchDev &d, int w) {
   for (int i = 0; i < np; i++) { pairs[2 * i] = recs[i].o1; pairs[2 * i + 1] = recs[i].o2; }
 
   // narrowphase + policy, contact joints in creation order
-  const ObPolicy &pol = d.policy[0];
   ObContact *cout = d.contacts + (size_t)w * d.NC;
   int nc = 0;
   std::vector<int> walk_of(d.NG, -1);
   for (int i = 0; i < ng; i++) walk_of[glist[i]] = i;
   for (int i = 0; i < np; i++) {
     int o1 = pairs[2 * i], o2 = pairs[2 * i + 1];
+    const ObGeom &G1 = d.geom[(size_t)w * d.NG + o1], &G2 = d.geom[(size_t)w * d.NG + o2];
+    const int row = ob_policy_row(d.policy, G1.cat, G2.cat);   // the row of the policy table that serves this pair
+    if (row < 0) continue;
+    const ObPolicy &pol = d.policy[row];
+    if (pol.skip_static_pairs && G1.body < 0 && G2.body < 0) continue;
     if (pol.skip_if_connected && d.NJ) {   // dAreConnectedExcluding(b1, b2, dJointTypeContact), ode.cpp:1529-1537
-      const int b1 = d.geom[(size_t)w * d.NG + o1].body, b2 = d.geom[(size_t)w * d.NG + o2].body;
+      const int b1 = G1.body, b2 = G2.body;
       bool connected = false;
       if (b1 >= 0 && b2 >= 0) {
         const unsigned short *ps = d.padjstart + (size_t)w * (d.NB + 1), *pa = d.padj + (size_t)w * 2 * d.NJ;
@@ -294,7 +298,7 @@ static void collide_world(ObBatchDev &d, int w) {
       if (nc >= d.NC) { W.status |= OB_ERR_CONTACT_OVERFLOW; break; }
       ObContact &c = cout[nc++];
       for (int j = 0; j < 3; j++) { c.pos[j] = cg[k].pos[j]; c.normal[j] = cg[k].normal[j]; }
-      c.depth = cg[k].depth; c.g1 = o1; c.g2 = o2; c.side1 = cg[k].side1; c.side2 = cg[k].side2; c.policy = 0;
+      c.depth = cg[k].depth; c.g1 = o1; c.g2 = o2; c.side1 = cg[k].side1; c.side2 = cg[k].side2; c.policy = row;
     }
   }
   d.ncontacts[w] = nc;

@@ -38,7 +38,7 @@ def test_cuda_dropin_matches_golden_reference_traces(stem, scene, steps, worlds,
                                                 ("mixed", 200, 2), ("mixed_maxc4", 300, 1), ("chain", 250, 2), ("hinges", 250, 1), ("buggy", 250, 3), ("capsmix", 250, 3), ("ragdoll", 250, 3),
                                                 ("block64@sap", 50, 1), ("stack32@sap", 200, 3), ("tower64@sapz", 250, 1), ("capsmix@simple", 200, 2),
                                                 ("terrain_spheres", 300, 3), ("terrain_boxes", 250, 2), ("buggy_terrain", 300, 4), ("terrain_capsules", 300, 2), ("terrain_plane", 200, 2), ("sliders", 300, 2), ("universals", 300, 2), ("terrain_capsules_pre", 250, 2), ("motors", 300, 2), ("pistons", 300, 2), ("pus", 300, 2), ("cylmix", 300, 2), ("cylspheres", 200, 1), ("kinematic", 300, 2), ("nulljoint", 250, 2), ("transforms", 250, 2),
-                                                ("bodyflags", 250, 2), ("autodisable", 400, 2), ("contactmodes", 250, 2), ("autodisable_avg", 400, 2)])
+                                                ("bodyflags", 250, 2), ("autodisable", 400, 2), ("contactmodes", 250, 2), ("autodisable_avg", 400, 2), ("crashwall", 250, 3)])
 def test_cuda_matches_live_reference(scene, steps, worlds, prec):
     # dDOUBLE scenes with atan2 on the path: lock-step protocol (SURVEY 8d, K = 1), see conftest.ATAN2_SCENES
     r = parity("b200", prec, scene, steps, worlds, lockstep=(prec == "double" and scene.split("@")[0] in ATAN2_SCENES))
@@ -51,7 +51,7 @@ def test_cuda_matches_live_reference(scene, steps, worlds, prec):
                                                 ("stack32@sap", 60, 2), ("mixed@simple", 100, 1), ("terrain_boxes", 80, 1), ("buggy_terrain", 100, 1),
                                                 ("raycast", 150, 2), ("raycast2", 120, 2), ("raycast2h", 120, 1), ("raycyl", 120, 1), ("sliders", 150, 1), ("universals", 150, 1), ("motors", 150, 1), ("pistons", 150, 1), ("pus", 150, 1), ("cylmix", 150, 1), ("kinematic", 150, 1), ("nulljoint", 150, 1), ("transforms", 150, 1),
                                                 ("hinges", 120, 1), ("buggy", 120, 1), ("ragdoll", 80, 1),
-                                                ("bodyflags", 150, 1), ("autodisable", 300, 1), ("autodisable_avg", 300, 1), ("contactmodes", 150, 1), ("contactmodes_fdir1", 150, 1), ("mixed_varmaxc", 200, 2), ("nested", 200, 2), ("nested_dcollide", 200, 1), ("nested@sap", 150, 1)])
+                                                ("bodyflags", 150, 1), ("autodisable", 300, 1), ("autodisable_avg", 300, 1), ("contactmodes", 150, 1), ("contactmodes_fdir1", 150, 1), ("mixed_varmaxc", 200, 2), ("nested", 200, 2), ("nested_dcollide", 200, 1), ("nested@sap", 150, 1), ("crashwall", 150, 1)])
 def test_dropin_classic_api_matches_live_reference(scene, steps, worlds, prec):
     """the drop-in boundary: unchanged user code (dSpaceCollide + near callback calling dCollide /
     dJointCreateContact / dJointSetFeedback + dWorldQuickStep + dJointGroupEmpty) linked against

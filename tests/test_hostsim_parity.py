@@ -35,7 +35,7 @@ def test_hostsim_dropin_matches_golden_reference_traces(stem, scene, steps, worl
                                                 ("mixed_maxc4", 400, 1), ("chain", 300, 2), ("hinges", 300, 1), ("buggy", 300, 2), ("capsmix", 300, 2), ("ragdoll", 300, 2),
                                                 ("block64@sap", 60, 1), ("stack32@sap", 200, 2), ("tower64@sapz", 250, 1), ("capsmix@simple", 200, 1),
                                                 ("terrain_spheres", 300, 2), ("terrain_boxes", 250, 1), ("buggy_terrain", 300, 3), ("terrain_capsules", 300, 2), ("terrain_plane", 200, 2), ("sliders", 300, 2), ("universals", 300, 2), ("terrain_capsules_pre", 250, 2), ("motors", 300, 2), ("pistons", 300, 2), ("pus", 300, 2), ("cylmix", 300, 2), ("cylspheres", 200, 1), ("kinematic", 300, 2), ("nulljoint", 250, 2), ("transforms", 250, 2), ("transforms@sap", 200, 1), ("transforms@simple", 200, 1),
-                                                ("bodyflags", 300, 2), ("autodisable", 400, 2), ("autodisable_avg", 400, 2), ("contactmodes", 300, 2), ("bodyflags@sap", 150, 1)])
+                                                ("bodyflags", 300, 2), ("autodisable", 400, 2), ("autodisable_avg", 400, 2), ("contactmodes", 300, 2), ("bodyflags@sap", 150, 1), ("crashwall", 250, 2)])
 def test_hostsim_matches_live_reference(scene, steps, worlds):
     r = parity("hostsim", "single", scene, steps, worlds)
     assert r["contacts"] > 0
@@ -45,7 +45,7 @@ def test_hostsim_matches_live_reference(scene, steps, worlds):
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
 @pytest.mark.parametrize("scene,steps,worlds", [("stack32", 80, 2), ("mixed_maxc4", 150, 1), ("hinges", 150, 1), ("buggy", 120, 2), ("ragdoll", 100, 1),
                                                 ("raycast", 250, 3), ("raycast2", 200, 2), ("raycast2h", 200, 2), ("raycyl", 200, 1), ("sliders", 200, 1), ("universals", 200, 1), ("motors", 200, 1), ("pistons", 200, 1), ("pus", 200, 1), ("cylmix", 200, 1), ("kinematic", 200, 1), ("nulljoint", 200, 1), ("transforms", 200, 1), ("transforms@sapz", 150, 1), ("transforms_rays", 200, 2),
-                                                ("bodyflags", 200, 1), ("autodisable", 400, 1), ("autodisable_avg", 400, 1), ("contactmodes", 200, 1), ("contactmodes_fdir1", 300, 2), ("mixed_varmaxc", 300, 2), ("nested", 300, 2), ("nested_dcollide", 300, 2), ("nested@sap", 200, 1), ("nested_dcollide@simple", 200, 1)])
+                                                ("bodyflags", 200, 1), ("autodisable", 400, 1), ("autodisable_avg", 400, 1), ("contactmodes", 200, 1), ("contactmodes_fdir1", 300, 2), ("mixed_varmaxc", 300, 2), ("nested", 300, 2), ("nested_dcollide", 300, 2), ("nested@sap", 200, 1), ("nested_dcollide@simple", 200, 1), ("crashwall", 200, 1)])
 def test_hostsim_dropin_callback_loop_matches_live_reference(scene, steps, worlds):
     """host logic of the drop-in path (ob_dropin.cpp): the classic loop dSpaceCollide + near callback
     (dCollide, dJointCreateContact, dJointAttach, dJointSetFeedback) + dWorldQuickStep +
