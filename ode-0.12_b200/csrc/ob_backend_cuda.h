@@ -106,6 +106,8 @@ struct ObBackend {
   size_t st_elems;   // W*NB
   size_t smem_collide, smem_prep, smem_sched, smem_sched_lane, smem_sor, smem_post, smem_collide_tile;
   int prep_tile;                      // tile width of k_prep (defaults to `tile`)
+  int collide_split, narrow_grid[3];   // decoupled narrowphase (k_broad / k_narrow / k_contacts) and k_narrow's persistent grid per instantiation
+  size_t smem_broad_tile;
   int collide_tile, tile_stage_cap;   // k_collide_tile serves the batch (worlds of <= 8 geoms)
   int sor_deep;     // 1: k_sor with the deep index prefetch (worlds with many rows)
   int sched_lane;   // 1: k_sched_lane (one lane per world) fits shared memory

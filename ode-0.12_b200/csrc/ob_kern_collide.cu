@@ -486,6 +486,208 @@ __global__ void __launch_bounds__(32 * WPC) k_collide_tile(ObBatchDev d, int sta
 }
 
 
+// =====================================================================================
+// Decoupled narrowphase: k_broad -> k_narrow -> k_contacts.
+//
+// ncu of the fused kernels (r02m): the warps of a CTA wait at the barrier behind the narrowphase for the slowest pair of
+// their world(s) -- 28 % (configs[1]), 39 % ([3]) and 66 % ([2]) of all warp samples sit there, at 25 % occupancy.  Here the
+// narrowphase is a kernel of its own that knows no worlds: k_broad (phases 1-4 per world as before) leaves the poses in
+// global memory and files every pair that needs a collider call into the work list of its collider class; k_narrow is a
+// persistent grid whose warps pull 32 items of ONE class at a time from a queue (heavy classes first), so a warp runs one
+// collider on full lanes and no warp ever waits for another; contacts go into the world's pool in order of completion
+// and k_contacts (a warp per world) moves them into the contact-joint array in callback order, which is what fixes
+// dJointCreateContact's creation order.
+__device__ __forceinline__ int collide_class(int t1, int t2) {
+  const int lo = t1 < t2 ? t1 : t2, hi = t1 < t2 ? t2 : t1;
+  return hi == OB_GEOM_TRIMESH ? (lo == OB_GEOM_SPHERE ? 1 : (lo == OB_GEOM_BOX ? 2 : 3)) : ((lo == OB_GEOM_BOX && hi == OB_GEOM_BOX) ? 4 : 5);
+}
+// class of pair p of world w (0: the policy makes no dCollide call for it) and the policy row that serves it
+__device__ __forceinline__ int collide_classify(const ObBatchDev &d, int w, int o1, int o2, int nrows, int *row_out) {
+  const ObGeom *geoms = d.geom + (size_t)w * d.NG;
+  const ObGeom &G1 = geoms[o1], &G2 = geoms[o2];
+  const int row = nrows > 1 ? ob_policy_row(d.policy, G1.cat, G2.cat) : 0;
+  *row_out = row < 0 ? 0 : row;
+  if (row < 0) return 0;
+  const ObPolicy &pol = d.policy[row];
+  if (pol.skip_static_pairs && G1.body < 0 && G2.body < 0) return 0;
+  if (pol.skip_if_connected && d.NJ) {   // dAreConnectedExcluding(b1, b2, dJointTypeContact), ode.cpp:1529-1537
+    const int b1 = G1.body, b2 = G2.body;
+    if (b1 >= 0 && b2 >= 0) {
+      const unsigned short *ps = d.padjstart + (size_t)w * (d.NB + 1), *pa = d.padj + (size_t)w * 2 * d.NJ;
+      const ObJoint *pj = d.joint + (size_t)w * d.NJ;
+      for (int k = ps[b1]; k < ps[b1 + 1]; k++) {
+        const ObJoint &jj = pj[pa[k]];
+        const int other = jj.b1 == b1 ? jj.b2 : jj.b1;
+        if (other == b2) return 0;
+      }
+    }
+  }
+  return collide_class(G1.type, G2.type);
+}
+// Filing the pairs of one world (ordered list in V.sorted, np of them) into the class lists, in three steps so that the
+// space in the lists can be reserved once per CTA: (A) classify, (B) reserve, (C) fill.  misc[41..46] = items per class,
+// [47..52] = first slot in the class list, [53..58] = fill cursor (misc[8..40] is scan scratch in the fused kernels).
+__device__ __forceinline__ void collide_emit_classify(const ObBatchDev &d, int w, const CollideView &V, int np, int tid, int nt, int nrows) {
+  int *s_cnt = V.misc + 41;
+  unsigned short *s_code = V.member;   // class | row << 4 per pair (the ranking step is done with its member list)
+  for (int p = tid; p < np; p += nt) {
+    int row;
+    const int cls = collide_classify(d, w, V.sorted[p].x, V.sorted[p].y, nrows, &row);
+    s_code[p] = (unsigned short)(cls | (row << 4));
+    if (cls) atomicAdd(&s_cnt[cls], 1);
+    else d.pn[(size_t)w * d.NP + p] = 0;
+  }
+  const int ng = d.world[w].ng;
+  for (int i = tid; i < ng; i += nt) d.gpose[(size_t)w * d.NG + V.gid[i]] = V.pose[i];
+}
+__device__ __forceinline__ void collide_emit_fill(const ObBatchDev &d, int w, const CollideView &V, int np, int tid, int nt) {
+  const int *s_base = V.misc + 47;
+  int *s_cur = V.misc + 53;
+  const unsigned short *s_code = V.member;
+  const size_t wlcap = (size_t)d.W * d.NP;
+  for (int p = tid; p < np; p += nt) {
+    const int code = s_code[p], cls = code & 15;
+    if (!cls) continue;
+    const size_t slot = (size_t)cls * wlcap + (size_t)s_base[cls] + (size_t)atomicAdd(&s_cur[cls], 1);
+    d.wl[2 * slot] = (unsigned)w; d.wl[2 * slot + 1] = (unsigned)p | ((unsigned)(code >> 4) << 24);
+  }
+  if (tid == 0) { d.pcount[w] = 0; d.npairs[w] = np; atomicAdd(&d.counters->pairs, (unsigned long long)np); }
+}
+// k_broad: one CTA per world
+__global__ void __launch_bounds__(OB_THREADS) k_broad(ObBatchDev d) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const CollideSmem L = collide_smem(d.NG, d.NP);
+  const CollideView V = collide_view(smem, L);
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int nrows = d.policy[0].nrows;
+  for (int w = d.wbeg + blockIdx.x; w < d.wend; w += gridDim.x) {
+    const int np = collide_broad<true>(d, w, V, tid, nt);
+    if (tid < 18) V.misc[41 + tid] = 0;
+    __syncthreads();
+    collide_emit_classify(d, w, V, np, tid, nt, nrows);
+    __syncthreads();
+    if (tid >= 1 && tid < OB_NCLS && V.misc[41 + tid]) V.misc[47 + tid] = (int)atomicAdd(&d.wlcnt[tid], (unsigned)V.misc[41 + tid]);
+    __syncthreads();
+    collide_emit_fill(d, w, V, np, tid, nt);
+    __syncthreads();
+  }
+}
+// k_broad_tile: a warp per world, WPC worlds per CTA (worlds of a handful of geoms); one reservation per class and CTA
+template <int WPC>
+__global__ void __launch_bounds__(32 * WPC) k_broad_tile(ObBatchDev d) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const CollideSmem L = collide_smem(d.NG, d.NP);
+  const int warp = threadIdx.x >> 5, tid = threadIdx.x & 31;
+  const CollideView V = collide_view(smem + (size_t)warp * L.total, L);
+  const int nrows = d.policy[0].nrows;
+  for (int wb = d.wbeg + blockIdx.x * WPC; wb < d.wend; wb += gridDim.x * WPC) {
+    const int w = wb + warp;
+    const bool valid = w < d.wend;
+    int np = 0;
+    if (valid) np = collide_broad<false>(d, w, V, tid, 32);
+    if (tid < 18) V.misc[41 + tid] = 0;
+    __syncwarp();
+    if (valid) collide_emit_classify(d, w, V, np, tid, 32, nrows);
+    __syncthreads();
+    if (threadIdx.x >= 1 && threadIdx.x < OB_NCLS) {   // thread c reserves class c for all WPC worlds of the CTA
+      const int c = threadIdx.x;
+      int tot = 0;
+      for (int v = 0; v < WPC; v++) tot += ((const int *)(smem + (size_t)v * L.total + L.misc))[41 + c];
+      if (tot) {
+        int base = (int)atomicAdd(&d.wlcnt[c], (unsigned)tot);
+        for (int v = 0; v < WPC; v++) { int *mv = (int *)(smem + (size_t)v * L.total + L.misc); mv[47 + c] = base; base += mv[41 + c]; }
+      }
+    }
+    __syncthreads();
+    if (valid) collide_emit_fill(d, w, V, np, tid, 32);
+    __syncthreads();
+  }
+}
+// k_narrow: persistent; a warp takes 32 items of one class at a time.  Queue order: the mesh classes, box-box, the rest.
+template <bool MESH, bool XF>
+__global__ void __launch_bounds__(128) k_narrow(ObBatchDev d) {
+  constexpr int CGCAP = MESH ? OB_MAXC_LOCAL : 8;
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const size_t wlcap = (size_t)d.W * d.NP;
+  const int order[OB_NCLS - 1] = {3, 2, 1, 4, 5};
+  unsigned cnt[OB_NCLS];
+#pragma unroll
+  for (int c = 1; c < OB_NCLS; c++) cnt[c] = d.wlcnt[c];
+  for (;;) {
+    unsigned v = 0;
+    if (lane == 0) v = atomicAdd(&d.wlcnt[8], 1u);
+    v = __shfl_sync(FULL, v, 0);
+    int cls = 0;
+#pragma unroll
+    for (int k = 0; k < OB_NCLS - 1; k++) {
+      const int c = order[k];
+      const unsigned nch = (cnt[c] + 31u) >> 5;
+      if (!cls) { if (v < nch) cls = c; else v -= nch; }
+    }
+    if (!cls) break;
+    const unsigned idx = v * 32u + (unsigned)lane;
+    if (idx < cnt[cls]) {
+      const size_t slot = (size_t)cls * wlcap + idx;
+      const int w = (int)d.wl[2 * slot];
+      const unsigned pw = d.wl[2 * slot + 1];
+      const int p = (int)(pw & 0xffffffu), row = (int)(pw >> 24);
+      const int *pr = d.pairs + ((size_t)w * d.NP + p) * 2;
+      const int o1 = pr[0], o2 = pr[1];
+      const ObPolicy &pol = d.policy[row];
+      const int maxc = pol.max_contacts > CGCAP ? CGCAP : pol.max_contacts;
+      const ObPose *gp = d.gpose + (size_t)w * d.NG;
+      ObCg cg[CGCAP];
+      int swapped, bverr = 0;
+      const int n = ob_collide_pair_sel_t<MESH, CGCAP, XF>(&gp[o1], &gp[o2], maxc, cg, &swapped, d.meshes, &bverr);
+      if (bverr) atomicOr(&d.world[w].status, OB_ERR_BVH_STACK);
+      int off = 0;
+      if (n > 0) {
+        off = atomicAdd(&d.pcount[w], n);
+        ObContact *out = d.pool + (size_t)w * d.NC;
+        for (int k = 0; k < n; k++) {
+          if (off + k >= d.NC) break;   // k_contacts reports the overflow
+          ObContact c;
+          for (int e = 0; e < 3; e++) { c.pos[e] = cg[k].pos[e]; c.normal[e] = cg[k].normal[e]; }
+          c.depth = cg[k].depth; c.g1 = o1; c.g2 = o2; c.side1 = cg[k].side1; c.side2 = cg[k].side2; c.policy = row;
+          out[off + k] = c;
+        }
+      }
+      d.pn[(size_t)w * d.NP + p] = (unsigned char)n;
+      d.poff[(size_t)w * d.NP + p] = off;
+    }
+  }
+}
+// k_contacts: a warp per world moves the pool into the contact-joint array, pairs in callback order
+__global__ void __launch_bounds__(128) k_contacts(ObBatchDev d) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int w = d.wbeg + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= d.wend) return;
+  const int np = d.npairs[w];
+  const unsigned char *pn = d.pn + (size_t)w * d.NP;
+  const int *poff = d.poff + (size_t)w * d.NP;
+  const ObContact *pool = d.pool + (size_t)w * d.NC;
+  ObContact *out = d.contacts + (size_t)w * d.NC;
+  int carry = 0;
+  for (int base = 0; base < np; base += 32) {
+    const int p = base + lane;
+    const int n = p < np ? (int)pn[p] : 0;
+    int x = n;
+#pragma unroll
+    for (int dd = 1; dd < 32; dd <<= 1) { const int y = __shfl_up_sync(FULL, x, dd); if (lane >= dd) x += y; }
+    const int dst = carry + x - n;
+    const int src = n ? poff[p] : 0;
+    for (int k = 0; k < n; k++) if (dst + k < d.NC && src + k < d.NC) out[dst + k] = pool[src + k];
+    carry += __shfl_sync(FULL, x, 31);
+  }
+  if (lane == 0) {
+    int nc = carry;
+    if (nc > d.NC || d.pcount[w] > d.NC) { if (nc > d.NC) nc = d.NC; atomicOr(&d.world[w].status, OB_ERR_CONTACT_OVERFLOW); }
+    d.ncontacts[w] = nc;
+  }
+}
+
 int obk_collide_setup(ObBackend *b, const cudaDeviceProp &prop, char *err, size_t errlen) {
   ObBatchDev &d = b->d;
   b->smem_collide = collide_smem(d.NG, d.NP).total;
@@ -509,12 +711,53 @@ int obk_collide_setup(ObBackend *b, const cudaDeviceProp &prop, char *err, size_
       CK(ob_func_smem((const void *)k_collide_tile<true, true, OB_TILE_WPC>, (int)b->smem_collide_tile));
     }
   }
+  // decoupled narrowphase (k_broad -> k_narrow -> k_contacts): the default; OB_COLLIDE_FUSED=1 keeps the one-kernel path
+  b->collide_split = 0;
+  { const char *e = getenv("OB_COLLIDE_FUSED"); if (!(e && atoi(e) != 0) && d.W < (1 << 24) && d.NP < (1 << 24) && b->nchunks <= 1) b->collide_split = 1; }
+  if (b->collide_split) {
+    CK(dalloc(b, &d.gpose, (size_t)d.W * d.NG));
+    CK(dalloc(b, &d.wl, (size_t)OB_NCLS * d.W * d.NP * 2));
+    CK(dalloc(b, &d.wlcnt, (size_t)16));
+    CK(dalloc(b, &d.pn, (size_t)d.W * d.NP));
+    CK(dalloc(b, &d.poff, (size_t)d.W * d.NP));
+    CK(dalloc(b, &d.pool, (size_t)d.W * d.NC));
+    CK(dalloc(b, &d.pcount, (size_t)d.W));
+    CK(ob_func_smem((const void *)k_broad, (int)b->smem_collide));
+    b->smem_broad_tile = (size_t)OB_TILE_WPC * collide_smem(d.NG, d.NP).total;
+    if (b->collide_tile && b->smem_broad_tile <= (size_t)prop.sharedMemPerBlockOptin) CK(ob_func_smem((const void *)k_broad_tile<OB_TILE_WPC>, (int)b->smem_broad_tile));
+    int per = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_narrow<true, true>, 128, 0));
+    b->narrow_grid[2] = per * prop.multiProcessorCount;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_narrow<true, false>, 128, 0));
+    b->narrow_grid[1] = per * prop.multiProcessorCount;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_narrow<false, false>, 128, 0));
+    b->narrow_grid[0] = per * prop.multiProcessorCount;
+  }
   return 0;
 fail:
   return -1;
 }
 
 void obk_collide_launch(ObBackend *b, const ObBatchDev &d, int W, int cap, cudaStream_t st) {
+  if (b->collide_split && b->nchunks <= 1) {   // chunks of the batch on streams of their own would share the work lists
+    cudaMemsetAsync(d.wlcnt, 0, 16 * sizeof(unsigned), st);
+    int ct = d.NG <= 8 ? 32 : (d.NG <= 20 ? 64 : OB_THREADS);
+    if (b->collide_tile) {
+      const int tiles = (W + OB_TILE_WPC - 1) / OB_TILE_WPC;
+      k_broad_tile<OB_TILE_WPC><<<tiles < cap ? tiles : cap, 32 * OB_TILE_WPC, b->smem_broad_tile, st>>>(d);
+    } else k_broad<<<W < cap ? W : cap, ct, b->smem_collide, st>>>(d);
+    // the queue is as long as the pairs that need a collider call; a grid that fills the machine drains it
+    const long long maxitems = (long long)W * d.NP;
+    int ngrid = d.any_xf ? b->narrow_grid[2] : (d.nmesh ? b->narrow_grid[1] : b->narrow_grid[0]);
+    if ((long long)ngrid * 128 > maxitems + 127) ngrid = (int)((maxitems + 127) / 128);
+    if (ngrid < 1) ngrid = 1;
+    if (d.any_xf) k_narrow<true, true><<<ngrid, 128, 0, st>>>(d);
+    else if (d.nmesh) k_narrow<true, false><<<ngrid, 128, 0, st>>>(d);
+    else k_narrow<false, false><<<ngrid, 128, 0, st>>>(d);
+    k_contacts<<<(W + 3) / 4, 128, 0, st>>>(d);
+    g_launches += 3;
+    return;
+  }
     // CTA width follows the world size: the widest loop is the ng*ng candidate-pair scan
     int ct = d.NG <= 8 ? 32 : (d.NG <= 20 ? 64 : OB_THREADS);
     { static const char *e = getenv("OB_COLLIDE_THREADS"); if (e && (atoi(e) == 32 || atoi(e) == 64 || atoi(e) == 96 || atoi(e) == 128)) ct = atoi(e); }

@@ -76,6 +76,7 @@ struct __attribute__((aligned(16))) ObPolicy {
   int skip_static_pairs; int nrows /* row 0 only: rows in use (0 = 1) */; int pad[2];
   ObSurface surface;
 };
+#define OB_NCLS 6         // collider classes of the decoupled narrowphase: 0 = no call, 1 sphere-mesh, 2 box-mesh, 3 other-mesh, 4 box-box, 5 other primitives
 #define OB_MAXPOLICY 8   // rows of the contact-policy table (dBatchContactPolicy, include/ode_b200/ode.h)
 // permanent joints (ball / hinge / hinge2), body-frame parameters as the host API maintains them
 struct __attribute__((aligned(16))) ObLimot {
@@ -173,4 +174,12 @@ struct ObBatchDev {
   real *adisbuf;         // [W*NB*NADIS*6] auto-disable velocity samples (lvel, avel) per body, ring buffer (util.cpp:128-147)
   int *adisctl;          // [W*NB*2] per body: write index, buffer-full flag
   unsigned *rowmeta;     // [W*NR] b1 | b2<<8 | findex offset<<16 per row, written by the first half of k_prep for k_sched* (null: read the row records)
+  // decoupled narrowphase of the CUDA path (k_broad -> k_narrow -> k_contacts, ob_kern_collide.cu); null on the other backends
+  struct ObPose *gpose;  // [W*NG] this step's geom poses by geom index
+  unsigned *wl;          // [OB_NCLS][W*NP][2] work items of the narrowphase per collider class: world, pair | policy row << 24
+  unsigned *wlcnt;       // [16] items per class ([1..OB_NCLS-1]), [8] = next chunk of the queue
+  unsigned char *pn;     // [W*NP] contacts of a pair
+  int *poff;             // [W*NP] where they are in the world's pool region
+  ObContact *pool;       // [W*NC] contacts in order of completion
+  int *pcount;           // [W] contacts in the pool
 };
