@@ -658,30 +658,37 @@ __global__ void __launch_bounds__(128) k_narrow(ObBatchDev d) {
     }
   }
 }
-// k_contacts: a warp per world moves the pool into the contact-joint array, pairs in callback order
+// k_contacts<G>: G lanes per world (32 / G worlds per warp) move the pool into the contact-joint array, pairs in callback order.
+// G follows the pair capacity: a warp per world would leave most lanes idle on worlds of a dozen pairs (configs[2]: 65536 worlds).
+template <int G>
 __global__ void __launch_bounds__(128) k_contacts(ObBatchDev d) {
+  constexpr int T = 32 / G;
   const unsigned FULL = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
-  const int w = d.wbeg + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (w >= d.wend) return;
-  const int np = d.npairs[w];
-  const unsigned char *pn = d.pn + (size_t)w * d.NP;
-  const int *poff = d.poff + (size_t)w * d.NP;
-  const ObContact *pool = d.pool + (size_t)w * d.NC;
-  ObContact *out = d.contacts + (size_t)w * d.NC;
+  const int lane = threadIdx.x & 31, grp = lane / G, gl = lane % G;
+  const int w = d.wbeg + (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * T + grp;
+  const bool valid = w < d.wend;
+  const int wc = valid ? w : d.wbeg;
+  const int np = valid ? d.npairs[wc] : 0;
+  const unsigned char *pn = d.pn + (size_t)wc * d.NP;
+  const int *poff = d.poff + (size_t)wc * d.NP;
+  const ObContact *pool = d.pool + (size_t)wc * d.NC;
+  ObContact *out = d.contacts + (size_t)wc * d.NC;
+  int np_max = np;   // warp-uniform trip count
+#pragma unroll
+  for (int dd = 16; dd >= 1; dd >>= 1) { const int o = __shfl_xor_sync(FULL, np_max, dd); np_max = o > np_max ? o : np_max; }
   int carry = 0;
-  for (int base = 0; base < np; base += 32) {
-    const int p = base + lane;
+  for (int base = 0; base < np_max; base += G) {
+    const int p = base + gl;
     const int n = p < np ? (int)pn[p] : 0;
     int x = n;
 #pragma unroll
-    for (int dd = 1; dd < 32; dd <<= 1) { const int y = __shfl_up_sync(FULL, x, dd); if (lane >= dd) x += y; }
+    for (int dd = 1; dd < G; dd <<= 1) { const int y = __shfl_up_sync(FULL, x, dd, G); if (gl >= dd) x += y; }
     const int dst = carry + x - n;
     const int src = n ? poff[p] : 0;
     for (int k = 0; k < n; k++) if (dst + k < d.NC && src + k < d.NC) out[dst + k] = pool[src + k];
-    carry += __shfl_sync(FULL, x, 31);
+    carry += __shfl_sync(FULL, x, G - 1, G);
   }
-  if (lane == 0) {
+  if (gl == 0 && valid) {
     int nc = carry;
     if (nc > d.NC || d.pcount[w] > d.NC) { if (nc > d.NC) nc = d.NC; atomicOr(&d.world[w].status, OB_ERR_CONTACT_OVERFLOW); }
     d.ncontacts[w] = nc;
@@ -754,7 +761,9 @@ void obk_collide_launch(ObBackend *b, const ObBatchDev &d, int W, int cap, cudaS
     if (d.any_xf) k_narrow<true, true><<<ngrid, 128, 0, st>>>(d);
     else if (d.nmesh) k_narrow<true, false><<<ngrid, 128, 0, st>>>(d);
     else k_narrow<false, false><<<ngrid, 128, 0, st>>>(d);
-    k_contacts<<<(W + 3) / 4, 128, 0, st>>>(d);
+    if (d.NP <= 16) k_contacts<8><<<(W + 15) / 16, 128, 0, st>>>(d);          // 4 worlds per warp
+    else if (d.NP <= 64) k_contacts<16><<<(W + 7) / 8, 128, 0, st>>>(d);    // 2 worlds per warp
+    else k_contacts<32><<<(W + 3) / 4, 128, 0, st>>>(d);
     g_launches += 3;
     return;
   }

@@ -21,6 +21,10 @@ int obk_stepk_setup(ObBackend *b, const cudaDeviceProp &prop, char *err, size_t 
     // jointed / tiny worlds (configs 3, 4) are fastest at the sweep's own width (config 3: 1.26 / 1.35 / 1.50 / 2.17 ms at 4 / 8 / 16 / 32)
     if (d.NJ == 0 && d.NC >= 96) b->prep_tile = 32;
     { const char *pe = getenv("OB_PREP_TILE"); if (pe && (atoi(pe) == 4 || atoi(pe) == 8 || atoi(pe) == 16 || atoi(pe) == 32)) b->prep_tile = atoi(pe); }
+    // the first half (graph, islands: serial per world on the tile's lane 0) may run on narrower tiles than the second (row assembly)
+    b->prep_tile1 = b->prep_tile;
+    { const char *pe = getenv("OB_PREP_TILE1"); if (pe && (atoi(pe) == 4 || atoi(pe) == 8 || atoi(pe) == 16 || atoi(pe) == 32)) b->prep_tile1 = atoi(pe); }
+    b->smem_prep1 = prep_tile_smem(d.NB, d.NC, d.NJ, d.NR).total * (32 / b->prep_tile1);
     b->smem_prep = prep_tile_smem(d.NB, d.NC, d.NJ, d.NR).total * (32 / b->prep_tile);
     b->smem_sor = sor_tile_smem(d.NB, d.NR).total * (32 / G);
     b->smem_sched = sched_smem(d.NB, d.NR).total;
@@ -30,6 +34,7 @@ int obk_stepk_setup(ObBackend *b, const cudaDeviceProp &prop, char *err, size_t 
     { const char *g = getenv("OB_GRID_SOR"); if (g && atoi(g) > 0 && atoi(g) < b->grid_sor) b->grid_sor = atoi(g); }
   }
   if (d.NB > 254 || d.NG > 255 || d.NC + d.NJ > 65000) { snprintf(err, errlen, "world too large for the tile-per-world step kernel (NB=%d NG=%d NR=%d)", d.NB, d.NG, d.NR); goto fail; }
+  if (b->smem_prep1 > (size_t)prop.sharedMemPerBlockOptin) { b->prep_tile1 = b->prep_tile; b->smem_prep1 = b->smem_prep; }
   if (b->smem_prep > (size_t)prop.sharedMemPerBlockOptin || b->smem_sor > (size_t)prop.sharedMemPerBlockOptin) {
     snprintf(err, errlen, "world does not fit one CTA's shared memory (prep %zu B, sor %zu B, limit %zu B)",
              b->smem_prep, b->smem_sor, (size_t)prop.sharedMemPerBlockOptin);
@@ -38,8 +43,8 @@ int obk_stepk_setup(ObBackend *b, const cudaDeviceProp &prop, char *err, size_t 
 #define OB_SETSMEM(GG) \
   CK(ob_func_smem((const void *)k_prep<GG, true, 0>, (int)b->smem_prep)); \
   CK(ob_func_smem((const void *)k_prep<GG, false, 0>, (int)b->smem_prep)); \
-  CK(ob_func_smem((const void *)k_prep<GG, true, 1>, (int)b->smem_prep)); \
-  CK(ob_func_smem((const void *)k_prep<GG, false, 1>, (int)b->smem_prep)); \
+  CK(ob_func_smem((const void *)k_prep<GG, true, 1>, (int)(b->smem_prep1 > b->smem_prep ? b->smem_prep1 : b->smem_prep))); \
+  CK(ob_func_smem((const void *)k_prep<GG, false, 1>, (int)(b->smem_prep1 > b->smem_prep ? b->smem_prep1 : b->smem_prep))); \
   CK(ob_func_smem((const void *)k_prep<GG, true, 2>, (int)b->smem_prep)); \
   CK(ob_func_smem((const void *)k_prep<GG, false, 2>, (int)b->smem_prep)); \
   CK(ob_func_smem((const void *)k_sor<GG, true>, (int)b->smem_sor)); \
@@ -50,6 +55,12 @@ int obk_stepk_setup(ObBackend *b, const cudaDeviceProp &prop, char *err, size_t 
   CK(ob_func_smem((const void *)k_sched<2>, (int)b->smem_sched));
   CK(ob_func_smem((const void *)k_sched<4>, (int)b->smem_sched));
   CK(ob_func_smem((const void *)k_sched<8>, (int)b->smem_sched));
+  // one lane per world for batches of many tiny worlds (k_sor_lane); OB_SOR_LANE=0 / 1 overrides
+  b->smem_sor_lane = sor_lane_smem(d.NB).total;
+  b->sor_lane = (W >= 8192 && d.NB <= 8) ? 1 : 0;
+  { const char *e = getenv("OB_SOR_LANE"); if (e) b->sor_lane = atoi(e) != 0; }
+  if (b->smem_sor_lane > (size_t)prop.sharedMemPerBlockOptin || d.NB > 254) b->sor_lane = 0;
+  if (b->sor_lane) CK(ob_func_smem((const void *)k_sor_lane, (int)b->smem_sor_lane));
   b->sor_deep = d.NR > 256 ? 1 : 0;
   { const char *e = getenv("OB_SOR_DEEP"); if (e) b->sor_deep = atoi(e) != 0; }
   b->smem_sched_lane = sched_lane_smem(d.NB, d.NR).total;
@@ -173,9 +184,9 @@ template <int G> static void stepk_launch_t(ObBackend *b, const ObBatchDev &d, r
     ObBatchDev dk = d;
     dk.rowmeta = split ? d.rowmeta : (unsigned *)0;
     cudaStream_t ss = split ? b->sstream : st;
-#define OB_LAUNCH_PREP(GP, PH) { const int gp = (W + (32 / GP) - 1) / (32 / GP); \
-      if (d.NJ > 0) k_prep<GP, true, PH><<<gp, 32, b->smem_prep, st>>>(dk, h, taps); else k_prep<GP, false, PH><<<gp, 32, b->smem_prep, st>>>(dk, h, taps); }
-#define OB_LAUNCH_PREP_G(PH) { if (b->prep_tile == 4) OB_LAUNCH_PREP(4, PH) else if (b->prep_tile == 8) OB_LAUNCH_PREP(8, PH) else if (b->prep_tile == 16) OB_LAUNCH_PREP(16, PH) else OB_LAUNCH_PREP(32, PH) }
+#define OB_LAUNCH_PREP(GP, PH) { const int gp = (W + (32 / GP) - 1) / (32 / GP); const size_t sm_ = PH == 1 ? b->smem_prep1 : b->smem_prep; \
+      if (d.NJ > 0) k_prep<GP, true, PH><<<gp, 32, sm_, st>>>(dk, h, taps); else k_prep<GP, false, PH><<<gp, 32, sm_, st>>>(dk, h, taps); }
+#define OB_LAUNCH_PREP_G(PH) { const int pt_ = PH == 1 ? b->prep_tile1 : b->prep_tile; if (pt_ == 4) OB_LAUNCH_PREP(4, PH) else if (pt_ == 8) OB_LAUNCH_PREP(8, PH) else if (pt_ == 16) OB_LAUNCH_PREP(16, PH) else OB_LAUNCH_PREP(32, PH) }
     if (split) {
       OB_LAUNCH_PREP_G(1)
       cudaEventRecord(b->sev[0], st);
@@ -199,7 +210,9 @@ template <int G> static void stepk_launch_t(ObBackend *b, const ObBatchDev &d, r
 #undef OB_LAUNCH_PREP_G
 #undef OB_LAUNCH_PREP
     if (timing) cudaEventRecord(ev[3], st);
-    if (b->sor_reg) {
+    if (b->sor_lane) {
+      k_sor_lane<<<(W + 31) / 32, 32, b->smem_sor_lane, st>>>(d, taps);
+    } else if (b->sor_reg) {
       k_sor_reg<G><<<gsor, 32, b->smem_sor_reg, st>>>(d, taps);
     } else if (b->sor_pair) {
       constexpr int GP = G <= 16 ? 2 * G : 32, Tp = 32 / GP;

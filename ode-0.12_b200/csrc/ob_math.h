@@ -14,6 +14,17 @@
 #include <math.h>
 #include <stdint.h>
 
+// Lock-step helpers for per-lane loops whose lanes would otherwise drift apart (a BVH walk followed by a triangle test: lanes
+// that `continue` early re-enter the walk while their neighbours are still in the test, and every region of the loop runs
+// with a fraction of the warp).  The lanes that enter such a loop together vote at the top of every iteration; the vote
+// reconverges them, and a lane that is done idles until all are.  On the host a lane is alone.
+#if defined(__CUDA_ARCH__)
+#define OB_LANES_TOGETHER() __activemask()
+#define OB_ALL_LANES(mask, pred) (__all_sync((mask), (pred)) != 0)
+#else
+#define OB_LANES_TOGETHER() 0u
+#define OB_ALL_LANES(mask, pred) (pred)
+#endif
 #if defined(__CUDACC__)
 #define OB_HD __host__ __device__ __forceinline__
 #define OB_HDN static __host__ __device__ __noinline__

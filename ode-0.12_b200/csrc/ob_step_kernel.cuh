@@ -401,65 +401,49 @@ __global__ void __launch_bounds__(32) k_prep(ObBatchDev d, real h, int taps) {
       }
     }
     __syncwarp();
-    // ---- (6a) row assembly (getInfo2), one lane per joint: raw rows {J[12], c, cfm, lo, hi} staged in
-    // the row records; motor-at-limit torques (joint.cpp:638-657) are collected and applied below
+    // ---- (6) row assembly + finalisation.  Order of the sub-steps (r02r): (6a) getInfo2 of the PERMANENT joints, one lane per joint,
+    // raw rows {J[12], c, cfm, lo, hi} staged in the row records, motor-at-limit side effects collected (joint.cpp:638-657); (6b) the side
+    // effects applied in joint order; (4b) tmp1 per body; (6c) CONTACT joints, one lane per joint: getInfo2 and the finalisation of its
+    // rows in one go (contacts have no side effects, so nothing they produce can change tmp1) -- their rows never pass through memory as
+    // raw rows and the bodies' tmp1 / invI are loaded once per contact instead of once per row; (6d) finalisation of the staged rows of
+    // the permanent joints.  Before r02r every row was staged raw and finalised by a lane per row: ncu (configs[3]) 66 % of the warp
+    // samples of this half waited on those L2 round trips at 11 % occupancy.
     real *g_side = d.jside + (size_t)wc * (d.NJ ? d.NJ : 1) * 4 * OB_NSIDE;
     int anyside = 0;
+    if (PJ) {
     for (int base = 0; base < nij_max; base += G) {
       const int k = base + gl;
-      if (k < nij && have_rows) {
+      if (k < nij && have_rows && (int)s_ijoint[k] >= nc) {
         const int j = s_ijoint[k];
         const int b1 = s_jb1[j], b2 = s_jb2[j] == 255 ? -1 : (int)s_jb2[j];
         const int r0 = s_jrow[k];
         const unsigned ub2 = (unsigned)(b2 < 0 ? 255 : b2);
         real erp_in = W.erp;
         if (anyball) { const int src = s_erpsrc[k]; if (src != 0xffff) erp_in = pjoint[s_ijoint[src] - nc].erp; }
-        if (!PJ || j < nc) {
-          ObSurface sf = csurf ? csurf[j] : ptab[con[j].policy].surface;
-          const int jm = ob_contact_info1(sf);
-          ObRowOut3 r;
-          ob_rows_defaults(r, jm, W.cfm);
-          const ObContact c = con[j];
-          const int rev = d.dropin ? c.policy : (geoms[c.g1].body < 0);   // dJOINT_REVERSE
-          real p1[3], l1[3], a1[3], p2[3] = {0, 0, 0}, l2[3] = {0, 0, 0}, a2[3] = {0, 0, 0};
-          for (int e = 0; e < 3; e++) { p1[e] = bd[b1].pos[e]; l1[e] = bd[b1].lvel[e]; a1[e] = bd[b1].avel[e]; }
-          if (b2 >= 0) for (int e = 0; e < 3; e++) { p2[e] = bd[b2].pos[e]; l2[e] = bd[b2].lvel[e]; a2[e] = bd[b2].avel[e]; }
-          real fdir1[3] = {0, 0, 0};
-          if (csurf) for (int e = 0; e < 3; e++) fdir1[e] = d.cfdir1[((size_t)wc * d.NC + j) * 4 + e];
-          ob_contact_info2(r, jm, sf, c.pos, c.normal, c.depth, fdir1, rev, p1, l1, a1, b2 >= 0, p2, l2, a2, stepsize1,
-                           erp_in, W.min_depth, W.max_vel);
-          for (int q = 0; q < jm; q++) {
-            real rw[OB_ROWW];
-            for (int e = 0; e < 12; e++) rw[e] = r.J[q][e];
-            rw[12] = r.c[q]; rw[13] = r.cfm[q]; rw[14] = r.lo[q]; rw[15] = r.hi[q]; rw[16] = rw[17] = rw[18] = 0;
-            const unsigned fio = (unsigned)(r.findex[q] >= 0 ? q - r.findex[q] : 0);
-            store_row(rows + (size_t)(r0 + q) * OB_ROWW, rw, (unsigned)b1 | (ub2 << 8) | (fio << 16));
-          }
-        } else {
-          ObJoint pj = pjoint[j - nc];
-          ObBodyView B1 = {bd[b1].pos, bd[b1].R, bd[b1].q, bd[b1].lvel, bd[b1].avel}, B2 = B1;
-          if (b2 >= 0) { B2.pos = bd[b2].pos; B2.R = bd[b2].R; B2.q = bd[b2].q; B2.lvel = bd[b2].lvel; B2.avel = bd[b2].avel; }
-          const int jm = ob_joint_info1(pj, B1, b2 >= 0 ? &B2 : (const ObBodyView *)0);
-          ObRowOut r;
-          ob_rows_defaults(r, jm, W.cfm);
-          real side[OB_NSIDE][4];
-          real erp_io = erp_in;
-          ob_joint_info2(r, pj, B1, b2 >= 0 ? &B2 : (const ObBodyView *)0, stepsize1, &erp_io, side);
-          for (int sx = 0; sx < OB_NSIDE; sx++) {
-            for (int e = 0; e < 4; e++) g_side[(size_t)(j - nc) * 4 * OB_NSIDE + 4 * sx + e] = side[sx][e];
-            if (side[sx][0] != 0) anyside = 1;
-          }
-          for (int q = 0; q < jm; q++) {
-            real rw[OB_ROWW];
-            for (int e = 0; e < 12; e++) rw[e] = r.J[q][e];
-            rw[12] = r.c[q]; rw[13] = r.cfm[q]; rw[14] = r.lo[q]; rw[15] = r.hi[q]; rw[16] = rw[17] = rw[18] = 0;
-            const unsigned fio = (unsigned)(r.findex[q] >= 0 ? q - r.findex[q] : 0);
-            store_row(rows + (size_t)(r0 + q) * OB_ROWW, rw, (unsigned)b1 | (ub2 << 8) | (fio << 16));
-          }
+        ObJoint pj = pjoint[j - nc];
+        ObBodyView B1 = {bd[b1].pos, bd[b1].R, bd[b1].q, bd[b1].lvel, bd[b1].avel}, B2 = B1;
+        if (b2 >= 0) { B2.pos = bd[b2].pos; B2.R = bd[b2].R; B2.q = bd[b2].q; B2.lvel = bd[b2].lvel; B2.avel = bd[b2].avel; }
+        const int jm = ob_joint_info1(pj, B1, b2 >= 0 ? &B2 : (const ObBodyView *)0);
+        ObRowOut r;
+        ob_rows_defaults(r, jm, W.cfm);
+        real side[OB_NSIDE][4];
+        real erp_io = erp_in;
+        ob_joint_info2(r, pj, B1, b2 >= 0 ? &B2 : (const ObBodyView *)0, stepsize1, &erp_io, side);
+        for (int sx = 0; sx < OB_NSIDE; sx++) {
+          for (int e = 0; e < 4; e++) g_side[(size_t)(j - nc) * 4 * OB_NSIDE + 4 * sx + e] = side[sx][e];
+          if (side[sx][0] != 0) anyside = 1;
+        }
+        for (int q = 0; q < jm; q++) {
+          real rw[OB_ROWW];
+          for (int e = 0; e < 12; e++) rw[e] = r.J[q][e];
+          rw[12] = r.c[q]; rw[13] = r.cfm[q]; rw[14] = r.lo[q]; rw[15] = r.hi[q]; rw[16] = rw[17] = rw[18] = 0;
+          const unsigned fio = (unsigned)(r.findex[q] >= 0 ? q - r.findex[q] : 0);
+          store_row(rows + (size_t)(r0 + q) * OB_ROWW, rw, (unsigned)b1 | (ub2 << 8) | (fio << 16));
         }
       }
-      if (k < nij) { g_ijoint[k] = s_ijoint[k]; g_jrow[k] = s_jrow[k]; }
     }
+    }
+    for (int k = gl; k < nij; k += G) { g_ijoint[k] = s_ijoint[k]; g_jrow[k] = s_jrow[k]; }
     if (gl == 0 && valid) g_jrow[nij] = (unsigned short)(have_rows ? mtot : 0);
     for (int dd = 1; dd < G; dd <<= 1) anyside |= __shfl_xor_sync(FULL, anyside, dd, G);
     __syncwarp();
@@ -491,36 +475,84 @@ __global__ void __launch_bounds__(32) k_prep(ObBatchDev d, real h, int taps) {
       }
     }
     __syncwarp();
-    // ---- (6c) finalisation, one lane per ROW: rhs, cfm/h, iMJ, Ad (quickstep.cpp:849-857, :355-402)
-    for (int base = 0; base < warp_max_i(mtot); base += G) {
-      const int ri = base + gl;
-      if (ri < mtot) {
-        real *rp = rows + (size_t)ri * OB_ROWW;
-        real raw[16];
-        for (int e = 0; e < 16; e++) raw[e] = __ldcg(rp + e);
-        const unsigned meta = *(const volatile unsigned *)(rp + OB_ROWF);
-        const int b1 = meta & 255, b2r = (meta >> 8) & 255;
-        const int b2 = b2r == 255 ? -1 : b2r;
-        real t1a[6], t1b[6], iw1[12], iw2[12];
-        for (int e = 0; e < 6; e++) t1a[e] = __ldcg(g_tmp1 + 8 * b1 + e);
-        for (int e = 0; e < 12; e++) iw1[e] = __ldcg(g_invIw + 12 * b1 + e);
-        if (b2 >= 0) {
-          for (int e = 0; e < 6; e++) t1b[e] = __ldcg(g_tmp1 + 8 * b2 + e);
-          for (int e = 0; e < 12; e++) iw2[e] = __ldcg(g_invIw + 12 * b2 + e);
+    // one raw row {J[12], c, cfm, lo, hi} -> the compact record (rhs, cfm/h, iMJ, Ad: quickstep.cpp:849-857, :355-402)
+#define OB_FINALIZE_ROW(RAW, RP, B1_, B2_, META_)                                                                               \
+    {                                                                                                                            \
+      real rw_[OB_ROWW];                                                                                                         \
+      for (int e = 0; e < 6; e++) rw_[e] = (RAW)[e];                                                                             \
+      for (int e = 0; e < 3; e++) rw_[6 + e] = (RAW)[9 + e];                                                                     \
+      real iMJ_[12], b_out_, adcfm_, Ad_;                                                                                        \
+      ob_row_finalize2((RAW), (RAW)[12], (RAW)[13], (B2_), t1a, t1b, s_invM[(B1_)], iw1, (B2_) >= 0 ? s_invM[(B2_)] : (real)0, iw2, stepsize1, \
+                       W.sor_w, iMJ_, &b_out_, &adcfm_, &Ad_);                                                                   \
+      for (int e = 0; e < 3; e++) { rw_[9 + e] = iMJ_[3 + e]; rw_[12 + e] = iMJ_[9 + e]; }                                       \
+      rw_[15] = Ad_; rw_[16] = b_out_; rw_[17] = adcfm_;                                                                         \
+      unsigned bmode_;                                                                                                           \
+      if (!encode_bounds((RAW)[14], (RAW)[15], &rw_[18], &bmode_)) atomicOr(&W.status, OB_ERR_ROW_OVERFLOW);                     \
+      store_row((RP), rw_, ((META_) & 0x00ffffffu) | (bmode_ << 24));                                                           \
+    }
+#define OB_LOAD_BODY_TERMS(B1_, B2_)                                                                                             \
+      real t1a[6], t1b[6], iw1[12], iw2[12];                                                                                     \
+      for (int e = 0; e < 6; e++) t1a[e] = __ldcg(g_tmp1 + 8 * (B1_) + e);                                                       \
+      for (int e = 0; e < 12; e++) iw1[e] = __ldcg(g_invIw + 12 * (B1_) + e);                                                    \
+      if ((B2_) >= 0) {                                                                                                          \
+        for (int e = 0; e < 6; e++) t1b[e] = __ldcg(g_tmp1 + 8 * (B2_) + e);                                                     \
+        for (int e = 0; e < 12; e++) iw2[e] = __ldcg(g_invIw + 12 * (B2_) + e);                                                  \
+      }
+    // ---- (6c) contact joints: getInfo2 + finalisation, one lane per joint
+    for (int base = 0; base < nij_max; base += G) {
+      const int k = base + gl;
+      if (k < nij && have_rows && (!PJ || (int)s_ijoint[k] < nc)) {
+        const int j = s_ijoint[k];
+        const int b1 = s_jb1[j], b2 = s_jb2[j] == 255 ? -1 : (int)s_jb2[j];
+        const int r0 = s_jrow[k];
+        const unsigned ub2 = (unsigned)(b2 < 0 ? 255 : b2);
+        real erp_in = W.erp;
+        if (anyball) { const int src = s_erpsrc[k]; if (src != 0xffff) erp_in = pjoint[s_ijoint[src] - nc].erp; }
+        ObSurface sf = csurf ? csurf[j] : ptab[con[j].policy].surface;
+        const int jm = ob_contact_info1(sf);
+        ObRowOut3 r;
+        ob_rows_defaults(r, jm, W.cfm);
+        const ObContact c = con[j];
+        const int rev = d.dropin ? c.policy : (geoms[c.g1].body < 0);   // dJOINT_REVERSE
+        real p1[3], l1[3], a1[3], p2[3] = {0, 0, 0}, l2[3] = {0, 0, 0}, a2[3] = {0, 0, 0};
+        for (int e = 0; e < 3; e++) { p1[e] = bd[b1].pos[e]; l1[e] = bd[b1].lvel[e]; a1[e] = bd[b1].avel[e]; }
+        if (b2 >= 0) for (int e = 0; e < 3; e++) { p2[e] = bd[b2].pos[e]; l2[e] = bd[b2].lvel[e]; a2[e] = bd[b2].avel[e]; }
+        real fdir1[3] = {0, 0, 0};
+        if (csurf) for (int e = 0; e < 3; e++) fdir1[e] = d.cfdir1[((size_t)wc * d.NC + j) * 4 + e];
+        ob_contact_info2(r, jm, sf, c.pos, c.normal, c.depth, fdir1, rev, p1, l1, a1, b2 >= 0, p2, l2, a2, stepsize1,
+                         erp_in, W.min_depth, W.max_vel);
+        OB_LOAD_BODY_TERMS(b1, b2)
+        for (int q = 0; q < jm; q++) {
+          real raw[16];
+          for (int e = 0; e < 12; e++) raw[e] = r.J[q][e];
+          raw[12] = r.c[q]; raw[13] = r.cfm[q]; raw[14] = r.lo[q]; raw[15] = r.hi[q];
+          const unsigned fio = (unsigned)(r.findex[q] >= 0 ? q - r.findex[q] : 0);
+          OB_FINALIZE_ROW(raw, rows + (size_t)(r0 + q) * OB_ROWW, b1, b2, (unsigned)b1 | (ub2 << 8) | (fio << 16))
         }
-        real rw[OB_ROWW];
-        for (int e = 0; e < 6; e++) rw[e] = raw[e];
-        for (int e = 0; e < 3; e++) rw[6 + e] = raw[9 + e];
-        real iMJ[12], b_out, adcfm, Ad;
-        ob_row_finalize2(raw, raw[12], raw[13], b2, t1a, t1b, s_invM[b1], iw1, b2 >= 0 ? s_invM[b2] : (real)0, iw2, stepsize1,
-                         W.sor_w, iMJ, &b_out, &adcfm, &Ad);
-        for (int e = 0; e < 3; e++) { rw[9 + e] = iMJ[3 + e]; rw[12 + e] = iMJ[9 + e]; }
-        rw[15] = Ad; rw[16] = b_out; rw[17] = adcfm;
-        unsigned bmode;
-        if (!encode_bounds(raw[14], raw[15], &rw[18], &bmode)) atomicOr(&W.status, OB_ERR_ROW_OVERFLOW);
-        store_row(rp, rw, (meta & 0x00ffffffu) | (bmode << 24));
       }
     }
+    // ---- (6d) the staged rows of the permanent joints, one lane per joint
+    if (PJ) {
+    __syncwarp();
+    for (int base = 0; base < nij_max; base += G) {
+      const int k = base + gl;
+      if (k < nij && have_rows && (int)s_ijoint[k] >= nc) {
+        const int j = s_ijoint[k];
+        const int b1 = s_jb1[j], b2 = s_jb2[j] == 255 ? -1 : (int)s_jb2[j];
+        const int r0 = s_jrow[k], jm = (int)s_jrow[k + 1] - r0;
+        OB_LOAD_BODY_TERMS(b1, b2)
+        for (int q = 0; q < jm; q++) {
+          real *rp = rows + (size_t)(r0 + q) * OB_ROWW;
+          real raw[16];
+          for (int e = 0; e < 16; e++) raw[e] = __ldcg(rp + e);
+          const unsigned meta = *(const volatile unsigned *)(rp + OB_ROWF);
+          OB_FINALIZE_ROW(raw, rp, b1, b2, meta)
+        }
+      }
+    }
+    }
+#undef OB_FINALIZE_ROW
+#undef OB_LOAD_BODY_TERMS
     __syncwarp();
 
     // (7) the row order and the level schedule of every shuffle epoch are built by k_sched
@@ -895,6 +927,10 @@ __host__ __device__ inline SchedTileSmem sched_tile_smem(int NB, int NR) {
   s.total = ob_al(o, 16);
   return s;
 }
+// Tried and rejected (r02p, B200): running the shuffle chain of epoch e + 1 and the level chain of epoch e interleaved in one serial
+// loop (two independent dependency chains, nep + 1 chain lengths instead of 2 nep, order[] double-buffered): 0.31 -> 0.54 ms on
+// configs[1], 0.82 -> 1.20 ms on configs[3] -- the longer loop body and 4 NR more bytes of shared memory per world cost more than the
+// overlap gains.
 template <int GS>
 __global__ void __launch_bounds__(32) k_sched_tile(ObBatchDev d, int G) {
   constexpr int T = 32 / GS;
@@ -1561,6 +1597,146 @@ __global__ void __launch_bounds__(32) k_sor_ring(ObBatchDev d, int taps) {
     }
     __syncwarp();
     sor_epilogue<G>(d, taps, wc, valid, gl, nb, mtot, si, rows, s_fc, s_lam, 1);
+    __syncwarp();
+  }
+}
+
+// =====================================================================================
+// k_sor_lane: ONE LANE PER WORLD, for batches of many tiny worlds (configs[2]: 65536 buggies of 5 bodies and ~56 rows).
+// A tile of lanes per world finds 1-3 rows per level there, so most of a pass's ~170 instructions serve idle lanes, and at 228
+// registers only 8 such warps fit an SM (r02o: 3.07 ms, 16 % of the issue slots).  Here a lane walks its world's rows one after the
+// other in the schedule's order -- levels in sequence, rows of a level in any order: exactly the values of the reference's sweep,
+// as in the tiled kernels -- so 32 worlds advance per warp instruction, no shuffles, no pass table.  fc and invMass sit in shared
+// memory interleaved by lane (word (8 b + k) * 32 + lane: every lane owns its bank, whichever body it touches); lambda stays in
+// global memory (each lane re-reads what it wrote itself); the row records are read straight from global memory, the index two
+// rows and the record one row ahead of their use.
+struct SorLaneSmem { size_t fc, invM, total; };
+__host__ __device__ inline SorLaneSmem sor_lane_smem(int NB) {
+  SorLaneSmem s; size_t o = 0;
+  s.fc = o; o = ob_al(o + sizeof(real) * 8 * NB * 32, 16);
+  s.invM = o; o = ob_al(o + sizeof(real) * NB * 32, 16);
+  s.total = ob_al(o, 16);
+  return s;
+}
+__device__ __forceinline__ void sor_pass_lane(const ObRowReg &cur, int cur_idx, real *s_fc, real *g_lam, const real *s_invM) {
+  const int b1 = cur.meta & 255, b2r = (cur.meta >> 8) & 255, fio = (cur.meta >> 16) & 255, bmode = cur.meta >> 24;
+  const int b2 = b2r == 255 ? -1 : b2r;
+  const int fi = fio ? cur_idx - fio : -1;
+  const real Ad = cur.v[15], k1 = s_invM[b1 * 32];
+  const real bv = cur.v[18];
+  const real lo = bmode == 0 ? -bv : (bmode == 1 ? (real)0 : bv);
+  const real hi = bmode == 2 ? (real)0 : bv;
+  real J[12], iMJ[12];
+  // rebuild what SOR_LCP keeps per row: J scaled by Ad (quickstep.cpp:393-401), iMJ (:117-136) -- as sor_pass does
+#pragma unroll
+  for (int e = 0; e < 3; e++) {
+    iMJ[e] = k1 * cur.v[e];
+    iMJ[3 + e] = cur.v[9 + e];
+    J[e] = cur.v[e] * Ad;
+    J[3 + e] = cur.v[3 + e] * Ad;
+  }
+  real f1[6], f2[6];
+  real *fp1 = s_fc + (size_t)(8 * b1) * 32;
+#pragma unroll
+  for (int e = 0; e < 6; e++) f1[e] = fp1[e * 32];
+  real *fp2 = s_fc;
+  if (b2 >= 0) {
+    const real k2 = s_invM[b2 * 32];
+#pragma unroll
+    for (int e = 0; e < 3; e++) {
+      const real j2l = -cur.v[e];
+      iMJ[6 + e] = k2 * j2l;
+      iMJ[9 + e] = cur.v[12 + e];
+      J[6 + e] = j2l * Ad;
+      J[9 + e] = cur.v[6 + e] * Ad;
+    }
+    fp2 = s_fc + (size_t)(8 * b2) * 32;
+#pragma unroll
+    for (int e = 0; e < 6; e++) f2[e] = fp2[e * 32];
+  }
+  const real lam_new = ob_sor_row(J, iMJ, cur.v[16], cur.v[17], lo, hi, fi, fi >= 0 ? g_lam[fi] : (real)0, g_lam[cur_idx], f1,
+                                  b2 >= 0 ? f2 : (real *)0);
+  g_lam[cur_idx] = lam_new;
+#pragma unroll
+  for (int e = 0; e < 6; e++) fp1[e * 32] = f1[e];
+  if (b2 >= 0) {
+#pragma unroll
+    for (int e = 0; e < 6; e++) fp2[e * 32] = f2[e];
+  }
+}
+__global__ void __launch_bounds__(32) k_sor_lane(ObBatchDev d, int taps) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const SorLaneSmem L = sor_lane_smem(d.NB);
+  const int lane = threadIdx.x;
+  real *s_fc = (real *)(smem + L.fc) + lane;
+  real *s_invM = (real *)(smem + L.invM) + lane;
+  for (int wbase = d.wbeg + blockIdx.x * 32; wbase < d.wend; wbase += gridDim.x * 32) {
+    const int w = wbase + lane;
+    const bool valid = w < d.wend;
+    const int wc = valid ? w : d.wbeg;
+    const int *si = d.stepinfo + (size_t)wc * SI_WORDS;
+    const int nb = valid ? d.world[wc].nb : 0;
+    const int iters = valid ? d.world[wc].iters : 0;
+    const int mtot = valid && si[SI_HAVEROWS] ? si[SI_MTOT] : 0;
+    const ObBodyConst *bc = d.bconst + (size_t)wc * d.NB;
+    const real *rows = d.rows + (size_t)wc * d.NR * OB_ROWW;
+    real *g_lam = d.lambda + (size_t)wc * d.NR;
+    for (int b = 0; b < d.NB; b++) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) s_fc[(size_t)(8 * b + k) * 32] = 0;
+      s_invM[b * 32] = b < nb ? bc[b].invMass : (real)0;
+    }
+    for (int i = 0; i < mtot; i++) g_lam[i] = 0;
+    const int iters_max = warp_max_i(mtot > 0 ? iters : 0);
+    for (int it = 0; it < iters_max; it++) {
+      const int ep = it >> 3;
+      const int m = (mtot > 0 && it < iters) ? mtot : 0;
+      const unsigned short *sched = d.sched + ((size_t)wc * d.NEP + (ep < d.NEP ? ep : d.NEP - 1)) * d.NR;
+      const int m_max = warp_max_i(m);
+      // the index two rows ahead, the record one row ahead
+      int i1 = m > 0 ? (int)sched[0] : 0, i2 = m > 1 ? (int)sched[1] : 0;
+      ObRowReg nxt;
+      load_row(rows + (size_t)i1 * OB_ROWW, nxt);
+      int ni = i1;
+      for (int sx = 0; sx < m_max; sx++) {
+        const ObRowReg cur = nxt;
+        const int ci = ni;
+        const int i3 = sx + 2 < m ? (int)sched[sx + 2] : 0;
+        ni = i2;
+        if (sx + 1 < m) load_row(rows + (size_t)i2 * OB_ROWW, nxt);
+        i2 = i3;
+        if (sx < m) sor_pass_lane(cur, ci, s_fc, g_lam, s_invM);
+      }
+    }
+    // cforce per body for k_post (tmp1 is dead after row assembly); lambda is where the taps expect it already
+    real *g_fc = d.tmp1 + (size_t)wc * d.NB * 8;
+    if (valid)
+      for (int b = 0; b < nb; b++)
+        for (int k = 0; k < 6; k++) g_fc[8 * b + k] = s_fc[(size_t)(8 * b + k) * 32];
+    if (taps && valid && mtot > 0) {   // joint feedback (quickstep.cpp:918-957, Multiply1_12q1), as sor_epilogue
+      const int nij = si[SI_NIJ];
+      const unsigned short *g_jrow = d.jrow + (size_t)wc * (d.NC + d.NJ + 1);
+      const unsigned short *g_ijoint = d.ijoint + (size_t)wc * (d.NC + d.NJ);
+      const int ncw = d.ncontacts[wc];
+      real *fb = d.fback + (size_t)wc * (d.NC + d.NJ) * 12;
+      for (int k = 0; k < nij; k++) {
+        const int jr0 = g_jrow[k], jm = g_jrow[k + 1] - jr0;
+        real acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        bool two = false;
+        for (int q = 0; q < jm; q++) {
+          const real *rp = rows + (size_t)(jr0 + q) * OB_ROWW;
+          const real sl = g_lam[jr0 + q];
+          const unsigned meta = *(const unsigned *)(rp + OB_ROWF);
+          two = ((meta >> 8) & 255u) != 255u;
+          for (int e = 0; e < 6; e++) acc[e] += rp[e] * sl;
+          for (int e = 0; e < 3; e++) { acc[6 + e] += (-rp[e]) * sl; acc[9 + e] += rp[6 + e] * sl; }
+        }
+        if (!two) for (int e = 6; e < 12; e++) acc[e] = 0;
+        const int jid = g_ijoint[k];
+        real *o = fb + (size_t)(jid < ncw ? jid : d.NC + (jid - ncw)) * 12;
+        for (int e = 0; e < 12; e++) o[e] = acc[e];
+      }
+    }
     __syncwarp();
   }
 }

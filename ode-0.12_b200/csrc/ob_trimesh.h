@@ -219,6 +219,36 @@ OB_HD bool ob_stl_contact_data(const real *Center, real Radius, const real *Orig
   return false;
 }
 
+// one candidate triangle of dCollideSTL's loop (collision_trimesh_sphere.cpp:318-420): 1 and the contact in *c, or 0
+OB_HD int ob_stl_triangle(const ObMeshDev &m, int tri, const real *TLPosition, const real *TLRotation, const real *Position, real Radius, ObCg *c) {
+  real dv[3][3];
+  ob_fetch_triangle(m, tri, TLPosition, TLRotation, dv);
+  const real *v0 = dv[0], *v1 = dv[1], *v2 = dv[2];
+  real vu[3] = {v1[0] - v0[0], v1[1] - v0[1], v1[2] - v0[2]};
+  real vv[3] = {v2[0] - v0[0], v2[1] - v0[1], v2[2] - v0[2]};
+  real Plane[3];
+  ob_cross(Plane, vu, vv);
+  if (!ob_safe_normalize3(Plane)) return 0;
+  const real side = ob_dot(Plane, Position) - ob_dot(Plane, v0);
+  if (side < OB_REAL(0.0)) return 0;
+  real Depth, u, v;
+  if (!ob_stl_contact_data(Position, Radius, v0, vu, vv, &Depth, &u, &v)) return 0;
+  if (Depth < OB_REAL(0.0)) return 0;
+  real ContactPos[3];
+  const real w = OB_REAL(1.0) - u - v;
+  ContactPos[0] = (v0[0] * w) + (v1[0] * u) + (v2[0] * v);
+  ContactPos[1] = (v0[1] * w) + (v1[1] * u) + (v2[1] * v);
+  ContactPos[2] = (v0[2] * w) + (v1[2] * u) + (v2[2] * v);
+  real dir[3] = {Position[0] - ContactPos[0], Position[1] - ContactPos[1], Position[2] - ContactPos[2]};
+  const real dirProj = ob_dot(dir, Plane) / ob_sqrt(ob_dot(dir, dir));
+  if (dirProj < OB_REAL(0.0)) return 0;
+  c->pos[0] = ContactPos[0]; c->pos[1] = ContactPos[1]; c->pos[2] = ContactPos[2];
+  c->normal[0] = -Plane[0]; c->normal[1] = -Plane[1]; c->normal[2] = -Plane[2];
+  c->depth = Depth * dirProj;
+  c->side1 = tri; c->side2 = -1;
+  return 1;
+}
+
 // dCollideSTL, collision_trimesh_sphere.cpp:244-538 (default: no contact merging,
 // collision_trimesh_internal.h:343-345).  o1 = trimesh, o2 = sphere.  *bverr: traversal stack overflow
 OB_HD int ob_collide_trimesh_sphere(const ObPose &o1, const ObPose &o2, const ObMeshDev &m, int flags, ObCg *contact, int *bverr) {
@@ -237,37 +267,18 @@ OB_HD int ob_collide_trimesh_sphere(const ObPose &o1, const ObPose &o2, const Ob
   ObBvIter it;
   ob_bv_begin(it);
   int out = 0;
+  // the walk and the triangle test alternate in lock-step over the lanes that came here together (OB_ALL_LANES): every lane
+  // visits its triangles in the reference's order, the warp runs each of the two regions with all the lanes that are in it
+  const unsigned together = OB_LANES_TOGETHER();
+  bool fin = false;
   for (;;) {
-    if (out == maxc) break;
-    const int tri = ob_bv_next(m, it, q);
-    if (tri < 0) break;
-    real dv[3][3];
-    ob_fetch_triangle(m, tri, TLPosition, TLRotation, dv);
-    const real *v0 = dv[0], *v1 = dv[1], *v2 = dv[2];
-    real vu[3] = {v1[0] - v0[0], v1[1] - v0[1], v1[2] - v0[2]};
-    real vv[3] = {v2[0] - v0[0], v2[1] - v0[1], v2[2] - v0[2]};
-    real Plane[3];
-    ob_cross(Plane, vu, vv);
-    if (!ob_safe_normalize3(Plane)) continue;
-    const real side = ob_dot(Plane, Position) - ob_dot(Plane, v0);
-    if (side < OB_REAL(0.0)) continue;
-    real Depth, u, v;
-    if (!ob_stl_contact_data(Position, Radius, v0, vu, vv, &Depth, &u, &v)) continue;
-    if (Depth < OB_REAL(0.0)) continue;
-    real ContactPos[3];
-    const real w = OB_REAL(1.0) - u - v;
-    ContactPos[0] = (v0[0] * w) + (v1[0] * u) + (v2[0] * v);
-    ContactPos[1] = (v0[1] * w) + (v1[1] * u) + (v2[1] * v);
-    ContactPos[2] = (v0[2] * w) + (v1[2] * u) + (v2[2] * v);
-    real dir[3] = {Position[0] - ContactPos[0], Position[1] - ContactPos[1], Position[2] - ContactPos[2]};
-    const real dirProj = ob_dot(dir, Plane) / ob_sqrt(ob_dot(dir, dir));
-    if (dirProj < OB_REAL(0.0)) continue;
-    ObCg *c = contact + out;
-    c->pos[0] = ContactPos[0]; c->pos[1] = ContactPos[1]; c->pos[2] = ContactPos[2];
-    c->normal[0] = -Plane[0]; c->normal[1] = -Plane[1]; c->normal[2] = -Plane[2];
-    c->depth = Depth * dirProj;
-    c->side1 = tri; c->side2 = -1;
-    out++;
+    int tri = -1;
+    if (!fin) {
+      if (out == maxc) fin = true;
+      else { tri = ob_bv_next(m, it, q); fin = tri < 0; }
+    }
+    if (OB_ALL_LANES(together, fin)) break;
+    if (tri >= 0) out += ob_stl_triangle(m, tri, TLPosition, TLRotation, Position, Radius, contact + out);
   }
   if (it.overflow) *bverr = 1;
   return out;

@@ -481,13 +481,19 @@ OB_HD int ob_collide_trimesh_box(const ObPose &o1, const ObPose &o2, const ObMes
   ob_obb_query_init(q, o2.pos, o2.R, D.half, o1.pos, o1.R);
   ObBvIter it;
   ob_bv_begin(it);
+  // walk and triangle test in lock-step over the lanes that came here together (ob_math.h: OB_ALL_LANES), as in the sphere collider
+  const unsigned together = OB_LANES_TOGETHER();
+  bool fin = false;
   for (;;) {
-    const int tri = ob_bv_next(m, it, q);
-    if (tri < 0) break;
-    real dv[3][3];
-    ob_fetch_triangle(m, tri, o1.pos, o1.R, dv);
-    if (ob_btl_separating_axes(D, dv[0], dv[1], dv[2]) && D.bestAxis != 0) ob_btl_clipping(D, dv[0], dv[1], dv[2], tri);
-    if (ob_btl_done(D)) break;
+    int tri = -1;
+    if (!fin) { tri = ob_bv_next(m, it, q); fin = tri < 0; }
+    if (OB_ALL_LANES(together, fin)) break;
+    if (tri >= 0) {
+      real dv[3][3];
+      ob_fetch_triangle(m, tri, o1.pos, o1.R, dv);
+      if (ob_btl_separating_axes(D, dv[0], dv[1], dv[2]) && D.bestAxis != 0) ob_btl_clipping(D, dv[0], dv[1], dv[2], tri);
+      if (ob_btl_done(D)) fin = true;
+    }
   }
   if (it.overflow) *bverr = 1;
   return D.ct;

@@ -72,6 +72,19 @@ def test_lane_per_world_scheduler_matches_golden(stem, scene, steps, worlds, set
     assert r["steps"] == steps
     assert_parity(r, f"{stem}/lane", scene, "single", "b200")
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec", ["single", "double"])
+@pytest.mark.parametrize("stem,scene,steps,worlds,settle", [g for g in GOLDEN if g[1] in ("stack32", "ragdoll", "buggy_terrain", "mixed_maxc4", "tower64", "hinges", "buggy", "crashwall", "contactmodes")])
+def test_lane_per_world_sweep_matches_golden(stem, scene, steps, worlds, settle, prec, monkeypatch):
+    """k_sor_lane (one lane walks its world's rows in the schedule's order; the default for batches of >= 8192 tiny worlds) forced on
+    the golden scenes: joint feedback (lambda tap) and body state bit for bit, like the tiled sweeps"""
+    monkeypatch.setenv("OB_SOR_LANE", "1")
+    g = os.path.join(ROOT, "tests", "golden", f"{stem}_{prec}.trace")
+    r = parity_golden("b200", g, scene, prec, steps, worlds, settle)
+    assert r["steps"] == steps
+    assert_parity(r, f"{stem}/sorlane/{prec}", scene, prec, "b200")
+
+
 
 @pytest.mark.parametrize("tile", ["4", "16", "32"])
 @pytest.mark.parametrize("stem,scene,steps,worlds,settle", [g for g in GOLDEN if g[1] in ("stack32", "ragdoll", "buggy_terrain", "universals", "tower64")])
