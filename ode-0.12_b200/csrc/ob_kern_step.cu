@@ -211,7 +211,10 @@ template <int G> static void stepk_launch_t(ObBackend *b, const ObBatchDev &d, r
 #undef OB_LAUNCH_PREP
     if (timing) cudaEventRecord(ev[3], st);
     if (b->sor_lane) {
-      k_sor_lane<<<(W + 31) / 32, 32, b->smem_sor_lane, st>>>(d, taps);
+      // whole waves of a size whose row records stay in the L2 between the iterations (OB_SOR_LANE_GRID overrides)
+      int gl_ = (W + 31) / 32;
+      { static const char *e = getenv("OB_SOR_LANE_GRID"); if (e && atoi(e) > 0 && atoi(e) < gl_) { const int waves = (gl_ + atoi(e) - 1) / atoi(e); gl_ = (gl_ + waves - 1) / waves; } }
+      k_sor_lane<<<gl_, 32, b->smem_sor_lane, st>>>(d, taps);
     } else if (b->sor_reg) {
       k_sor_reg<G><<<gsor, 32, b->smem_sor_reg, st>>>(d, taps);
     } else if (b->sor_pair) {

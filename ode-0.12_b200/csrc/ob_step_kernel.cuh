@@ -1608,8 +1608,10 @@ __global__ void __launch_bounds__(32) k_sor_ring(ObBatchDev d, int taps) {
 // other in the schedule's order -- levels in sequence, rows of a level in any order: exactly the values of the reference's sweep,
 // as in the tiled kernels -- so 32 worlds advance per warp instruction, no shuffles, no pass table.  fc and invMass sit in shared
 // memory interleaved by lane (word (8 b + k) * 32 + lane: every lane owns its bank, whichever body it touches); lambda stays in
-// global memory (each lane re-reads what it wrote itself); the row records are read straight from global memory, the index two
-// rows and the record one row ahead of their use.
+// global memory (each lane re-reads what it wrote itself; r02u: lambda in lane-interleaved shared memory costs the occupancy the
+// loads need -- 27 KB per warp -- and was slower, 2.84 -> 3.87 ms); the row records are read straight from global memory, the index
+// two rows and the record one row ahead of their use (r02v: an extra prefetch.global.L2 six rows ahead, 2.84 -> 3.75 ms; r02t: fewer
+// worlds in flight so that their records stay in the L2, 2.99 / 3.55 / 4.00 ms at 1024 / 683 / 512 warps -- the kernel wants every warp it can get).
 struct SorLaneSmem { size_t fc, invM, total; };
 __host__ __device__ inline SorLaneSmem sor_lane_smem(int NB) {
   SorLaneSmem s; size_t o = 0;
