@@ -106,6 +106,7 @@ struct ObBackend {
   size_t st_elems;   // W*NB
   size_t smem_collide, smem_prep, smem_sched, smem_sched_lane, smem_sor, smem_post, smem_collide_tile;
   int prep_tile;                      // tile width of k_prep (defaults to `tile`)
+  int post_tile;                      // tile width of k_post
   int sor_lane; size_t smem_sor_lane;   // k_sor_lane: one lane per world (many tiny worlds)
   int prep_tile1; size_t smem_prep1;   // tile width / shared memory of k_prep's first half (OB_PREP_TILE1)
   int collide_split, narrow_grid[3];   // decoupled narrowphase (k_broad / k_narrow / k_contacts) and k_narrow's persistent grid per instantiation

@@ -28,7 +28,12 @@ int obk_stepk_setup(ObBackend *b, const cudaDeviceProp &prop, char *err, size_t 
     b->smem_prep = prep_tile_smem(d.NB, d.NC, d.NJ, d.NR).total * (32 / b->prep_tile);
     b->smem_sor = sor_tile_smem(d.NB, d.NR).total * (32 / G);
     b->smem_sched = sched_smem(d.NB, d.NR).total;
-    b->smem_post = post_tile_smem(d.NG).total * (32 / G);
+    // integration (k_post) is a lane-per-body kernel of a few microseconds per world: it wants warps, not lane efficiency -- the widest
+    // tile that still gives ~4096 warps (r02z, configs[1]: 1024 warps, 5.5 % issue-active, 100 us on the critical path)
+    b->post_tile = G;
+    while (b->post_tile < 32 && (long long)W * (2 * b->post_tile) / 32 <= 4096) b->post_tile *= 2;
+    { const char *pe = getenv("OB_POST_TILE"); if (pe && (atoi(pe) == 4 || atoi(pe) == 8 || atoi(pe) == 16 || atoi(pe) == 32)) b->post_tile = atoi(pe); }
+    b->smem_post = post_tile_smem(d.NG).total * (32 / b->post_tile);
     b->grid_step = (int)((W + (32 / G) - 1) / (32 / G));
     b->grid_sor = b->grid_step;
     { const char *g = getenv("OB_GRID_SOR"); if (g && atoi(g) > 0 && atoi(g) < b->grid_sor) b->grid_sor = atoi(g); }
@@ -244,7 +249,11 @@ template <int G> static void stepk_launch_t(ObBackend *b, const ObBatchDev &d, r
     } else if (b->sor_deep) k_sor<G, true><<<gsor, 32, b->smem_sor, st>>>(d, taps);
     else k_sor<G, false><<<gsor, 32, b->smem_sor, st>>>(d, taps);
     if (timing) cudaEventRecord(ev[4], st);
-    k_post<G><<<gstep, 32, b->smem_post, st>>>(d, h);
+    { const int pt = b->post_tile, gpost = (W + (32 / pt) - 1) / (32 / pt);
+      if (pt == 4) k_post<4><<<gpost, 32, b->smem_post, st>>>(d, h);
+      else if (pt == 8) k_post<8><<<gpost, 32, b->smem_post, st>>>(d, h);
+      else if (pt == 16) k_post<16><<<gpost, 32, b->smem_post, st>>>(d, h);
+      else k_post<32><<<gpost, 32, b->smem_post, st>>>(d, h); }
   g_launches += 4;
 }
 void obk_stepk_launch(ObBackend *b, const ObBatchDev &d, real h, int taps, int W, cudaStream_t st, cudaEvent_t *ev, bool timing) {
