@@ -95,3 +95,27 @@ def test_batch_refuses_to_run_after_a_bound_world_changed():
     lib.dWorldDestroy(w)                                       # the batch must not dereference the dead world when it goes
     lib.dBatchDestroy(B)
     lib.dSpaceDestroy(s)
+
+
+def test_contact_policy_table_is_validated():
+    """dBatchSetContactPolicy takes 1 to 8 rows (host logic, CPU build); the rows themselves are exercised by the scene `crashwall`"""
+    import ctypes
+
+    lib = ctypes.CDLL(HOSTSIM)
+    vp = ctypes.c_void_p
+    for n in ("dWorldCreate", "dHashSpaceCreate", "dBodyCreate", "dCreateSphere", "dBatchCreate"):
+        getattr(lib, n).restype = vp
+    lib.dB200LastError.restype = ctypes.c_char_p
+    lib.dHashSpaceCreate.argtypes = [vp]; lib.dBodyCreate.argtypes = [vp]; lib.dCreateSphere.argtypes = [vp, ctypes.c_float]
+    lib.dGeomSetBody.argtypes = [vp, vp]; lib.dBatchCreate.argtypes = [ctypes.c_int, vp, vp, vp]
+    lib.dBatchSetContactPolicy.argtypes = [vp, vp, ctypes.c_int]; lib.dBatchDestroy.argtypes = [vp]
+    w, s = lib.dWorldCreate(), lib.dHashSpaceCreate(None)
+    lib.dGeomSetBody(lib.dCreateSphere(s, 0.5), lib.dBodyCreate(w))
+    B = vp(lib.dBatchCreate(1, (vp * 1)(w), (vp * 1)(s), None))
+    assert B
+    rows = ctypes.create_string_buffer(9 * 256)   # zeroed rows, larger than any dBatchContactPolicy
+    assert lib.dBatchSetContactPolicy(B, rows, 0) != 0
+    assert lib.dBatchSetContactPolicy(B, rows, 9) != 0 and b"policy rows" in lib.dB200LastError()
+    assert lib.dBatchSetContactPolicy(B, rows, 1) == 0
+    assert lib.dBatchSetContactPolicy(B, rows, 8) == 0
+    lib.dBatchDestroy(B)
