@@ -598,6 +598,12 @@ int dSpaceGetNumGeoms(dSpaceID);
 dGeomID dSpaceGetGeom(dSpaceID, int i);
 void dSpaceCollide(dSpaceID space, void *data, dNearCallback *callback);  /* collision_space.h:72-ish / collision.h:795 */
 void dSpaceCollide2(dGeomID space1, dGeomID space2, void *data, dNearCallback *callback);
+/* Contact capacity per pair (the one documented limit of this path): a collider call generates at most 16 contacts.  The
+ * reference returns up to (flags & 0xffff) contacts for trimesh-* and cylinder-box pairs; a larger request is served with 16
+ * and reported once through the message handler.  The batched narrowphase (dBatchCollideAndQuickStep, and the results
+ * dCollide serves from dSpaceCollide's batch) keeps at most 8 contacts per pair in batches without trimesh geoms or geom
+ * transforms -- every primitive collider but cylinder-box emits at most 8 -- and 16 otherwise; dCollide falls back to an
+ * on-demand collider call whenever the cached result was computed with another limit than the caller's. */
 int dCollide(dGeomID o1, dGeomID o2, int flags, dContactGeom *contact, int skip); /* collision.h:747 */
 
 void dGeomDestroy(dGeomID);
