@@ -119,3 +119,68 @@ def test_contact_policy_table_is_validated():
     assert lib.dBatchSetContactPolicy(B, rows, 1) == 0
     assert lib.dBatchSetContactPolicy(B, rows, 8) == 0
     lib.dBatchDestroy(B)
+
+
+def _policy_rows_check(libpath):
+    """semantics of the policy table on the batched path (ob_policy_row, the per-pair rule of k_broad / the host mirror):
+    first matching row serves the pair, no matching row = no contacts, a single row serves every pair, skip_static_pairs"""
+    import ctypes
+
+    import numpy as np
+
+    lib = ctypes.CDLL(libpath)
+    vp, ci, cf, ul = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_ulong
+
+    class Surface(ctypes.Structure):
+        _fields_ = [("mode", ci)] + [(n, cf) for n in ("mu", "mu2", "bounce", "bounce_vel", "soft_erp", "soft_cfm", "motion1", "motion2", "motionN", "slip1", "slip2")]
+
+    class Policy(ctypes.Structure):
+        _fields_ = [("cat_mask1", ul), ("cat_mask2", ul), ("max_contacts", ci), ("skip_if_connected", ci), ("skip_static_pairs", ci), ("surface", Surface)]
+
+    for n in ("dWorldCreate", "dSimpleSpaceCreate", "dBodyCreate", "dCreateSphere", "dCreateBox", "dCreatePlane", "dBatchCreate"):
+        getattr(lib, n).restype = vp
+    lib.dSimpleSpaceCreate.argtypes = [vp]; lib.dBodyCreate.argtypes = [vp]; lib.dCreateSphere.argtypes = [vp, cf]
+    lib.dCreateBox.argtypes = [vp, cf, cf, cf]; lib.dCreatePlane.argtypes = [vp, cf, cf, cf, cf]
+    lib.dGeomSetBody.argtypes = [vp, vp]; lib.dBodySetPosition.argtypes = [vp, cf, cf, cf]; lib.dGeomSetPosition.argtypes = [vp, cf, cf, cf]
+    lib.dGeomSetCategoryBits.argtypes = [vp, ul]; lib.dWorldSetGravity.argtypes = [vp, cf, cf, cf]
+    lib.dBatchCreate.argtypes = [ci, vp, vp, vp]; lib.dBatchSetContactPolicy.argtypes = [vp, vp, ci]
+    lib.dBatchCollideAndQuickStep.argtypes = [vp, cf, ci, vp]; lib.dBatchDebugContacts.argtypes = [vp, ci, vp, vp, ci]
+    lib.dBatchDestroy.argtypes = [vp]
+
+    def contacts(rows):
+        w, s = lib.dWorldCreate(), lib.dSimpleSpaceCreate(None)
+        lib.dWorldSetGravity(w, 0, 0, -9.81)
+        plane = lib.dCreatePlane(s, 0, 0, 1, 0); lib.dGeomSetCategoryBits(plane, 1)          # geom 0
+        bs = lib.dBodyCreate(w); lib.dBodySetPosition(bs, 0, 0, 0.49)
+        sph = lib.dCreateSphere(s, 0.5); lib.dGeomSetCategoryBits(sph, 2); lib.dGeomSetBody(sph, bs)   # geom 1: sphere on the plane
+        bb = lib.dBodyCreate(w); lib.dBodySetPosition(bb, 3, 0, 0.49)
+        box = lib.dCreateBox(s, 1, 1, 1); lib.dGeomSetCategoryBits(box, 4); lib.dGeomSetBody(box, bb)    # geom 2: box on the plane
+        stat = lib.dCreateBox(s, 1, 1, 1); lib.dGeomSetCategoryBits(stat, 8); lib.dGeomSetPosition(stat, -3, 0, 0.4)   # geom 3: static box in the plane
+        B = vp(lib.dBatchCreate(1, (vp * 1)(w), (vp * 1)(s), None))
+        assert B
+        tab = (Policy * len(rows))()
+        for i, (m1, m2, skip_static) in enumerate(rows):
+            tab[i].cat_mask1, tab[i].cat_mask2, tab[i].max_contacts, tab[i].skip_static_pairs = m1, m2, 8, skip_static
+            tab[i].surface.mu = 1.0
+        assert lib.dBatchSetContactPolicy(B, tab, len(rows)) == 0
+        assert lib.dBatchCollideAndQuickStep(B, 0.01, 1, None) == 0
+        g = np.zeros((64, 2), dtype=np.int32); pnd = np.zeros((64, 7), dtype=np.float32)
+        n = lib.dBatchDebugContacts(B, 0, pnd.ctypes.data, g.ctypes.data, 64)
+        lib.dBatchDestroy(B)
+        return sorted({tuple(sorted(map(int, g[i]))) for i in range(n)})
+
+    ALL = 0xFFFFFFFF
+    assert contacts([(ALL, ALL, 0)]) == [(0, 1), (0, 2), (0, 3)]                       # one row: every pair, the static pair included
+    assert contacts([(ALL, ALL, 1)]) == [(0, 1), (0, 2)]                               # skip_static_pairs
+    assert contacts([(2, ALL, 0), (4, 1, 0)]) == [(0, 1), (0, 2)]                      # two specific rows, no catch-all: the static pair has no row
+    assert contacts([(2, ALL, 0)] * 2) == [(0, 1)]                                     # only pairs with the sphere are served
+    assert contacts([(8, ALL, 1), (ALL, ALL, 0)]) == [(0, 1), (0, 2)]                  # the FIRST matching row decides (row 0 skips the static pair)
+
+
+def test_contact_policy_rows_select_pairs_by_category():
+    _policy_rows_check(HOSTSIM)
+
+
+@pytest.mark.gpu
+def test_contact_policy_rows_select_pairs_by_category_on_gpu():
+    _policy_rows_check(lib_path("single"))
