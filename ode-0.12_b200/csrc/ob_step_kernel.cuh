@@ -1071,7 +1071,6 @@ __global__ void __launch_bounds__(32) k_sched_tile(ObBatchDev d, int G) {
               s_last[b1] = (unsigned short)lv;
               s_last[b2 + (b2 == 255)] = (unsigned short)lv;
               s_lvl[kk] = (unsigned short)lv;
-              s_X[lv] = s_X[lv] + 1;                             // rows per level (off the dependent chain)
               nlev = lv > nlev ? lv : nlev;
             }
             rb = rbn;
@@ -1079,6 +1078,10 @@ __global__ void __launch_bounds__(32) k_sched_tile(ObBatchDev d, int G) {
         }
       }
       nlev = __shfl_sync(FULL, nlev, 0, GS);
+      __syncwarp();
+      // rows per level, counted by the tile's lanes afterwards: inside the serial loop the read-modify-write of s_X put a second
+      // shared-memory round trip into every step of an in-order instruction stream (ncu r02j: as many stall samples as the chain itself)
+      for (int k = gl; k < mtot_e; k += GS) atomicAdd(&s_X[s_lvl[k]], 1);
       __syncwarp();
       const int nlev_max = warp_max_i(nlev);
       // exclusive prefix over levels 1..nlev: s_X[l] = first slot of level l
